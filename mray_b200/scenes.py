@@ -1,0 +1,257 @@
+"""Deterministic procedural scenes for the BASELINE.json configs (numpy only, no GPU).
+
+The reference's Sponza-class scenes are an external download that is not available offline
+(SURVEY.md §8c), so config 2/3/5 use fixed generators:
+
+* ``arcade_mesh``   — "Sponza-scale" closed hall with two rows of columns, arches, displaced
+                      floor/walls and blob clutter; ~260 K triangles, coordinates in [-20,20]^3.
+* ``random_soup``   — uniformly random small triangles in the unit cube (BVH build sweep, config 5).
+* ``pinhole_rays``  — deterministic pixel-centre primary rays (config 2 batch A).
+* ``cornell_box``   — triangles-only Cornell box (config 1).
+
+All functions return C-contiguous float32 / uint32 arrays.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _grid(nu: int, nv: int):
+    """Index list of an (nu+1) x (nv+1) vertex grid -> 2*nu*nv triangles (CCW in u,v)."""
+    i, j = np.meshgrid(np.arange(nu), np.arange(nv), indexing="ij")
+    a = (i * (nv + 1) + j).ravel()
+    b = a + (nv + 1)
+    c = b + 1
+    d = a + 1
+    return np.stack([np.stack([a, b, c], 1), np.stack([a, c, d], 1)], 1).reshape(-1, 3)
+
+
+def _patch(origin, eu, ev, nu, nv, disp=None, normal=None):
+    u, v = np.meshgrid(np.linspace(0, 1, nu + 1), np.linspace(0, 1, nv + 1), indexing="ij")
+    p = (np.asarray(origin, np.float64)[None, None, :]
+         + u[..., None] * np.asarray(eu, np.float64) + v[..., None] * np.asarray(ev, np.float64))
+    if disp is not None:
+        n = np.asarray(normal, np.float64)
+        p = p + disp(u, v)[..., None] * n
+    return p.reshape(-1, 3), _grid(nu, nv)
+
+
+def _cylinder(center, radius, y0, y1, nseg, nh, flute=0.0):
+    th = np.linspace(0, 2 * np.pi, nseg + 1)
+    h = np.linspace(y0, y1, nh + 1)
+    T, H = np.meshgrid(th, h, indexing="ij")
+    r = radius * (1.0 + flute * np.cos(12 * T)) * (1.0 + 0.04 * np.cos(2 * np.pi * (H - y0) / (y1 - y0)))
+    p = np.stack([center[0] + r * np.cos(T), H, center[1] + r * np.sin(T)], -1)
+    return p.reshape(-1, 3), _grid(nseg, nh)
+
+
+def _sphere(center, radius, nu, nv, bump, rng):
+    th = np.linspace(0, 2 * np.pi, nu + 1)
+    ph = np.linspace(1e-3, np.pi - 1e-3, nv + 1)
+    T, P = np.meshgrid(th, ph, indexing="ij")
+    k = rng.integers(2, 6, size=3)
+    r = radius * (1.0 + bump * np.sin(k[0] * T) * np.sin(k[1] * P) + 0.5 * bump * np.cos(k[2] * P))
+    p = np.stack([center[0] + r * np.sin(P) * np.cos(T),
+                  center[1] + r * np.cos(P),
+                  center[2] + r * np.sin(P) * np.sin(T)], -1)
+    return p.reshape(-1, 3), _grid(nu, nv)
+
+
+def arcade_mesh(target_tris: int = 262144, seed: int = 1234):
+    """Closed hall (40 x 24 x 40, inside [-20,20]^3) with colonnades. Returns (positions[V,3] f32,
+    indices[T,3] u32). ``target_tris`` scales the tessellation; the default gives ~260 K."""
+    rng = np.random.default_rng(seed)
+    s = max(0.05, np.sqrt(target_tris / 288000.0))  # 288000: measured count at s = 1
+    parts = []
+
+    def q(n):
+        return max(2, int(round(n * s)))
+
+    ph = rng.uniform(0, 2 * np.pi, size=8)
+
+    def bumps(amp, f):
+        return lambda u, v: amp * (np.sin(f * u * 2 * np.pi + ph[0]) * np.cos(f * v * 2 * np.pi + ph[1])
+                                   + 0.35 * np.sin(3.1 * f * u * 2 * np.pi + ph[2]) * np.sin(2.7 * f * v * 2 * np.pi + ph[3]))
+
+    X, Y0, Y1, Z = 19.5, -12.0, 12.0, 19.5
+    # floor / ceiling / 4 walls (normals pointing inside)
+    parts.append(_patch([-X, Y0, -Z], [0, 0, 2 * Z], [2 * X, 0, 0], q(128), q(128), bumps(0.18, 9), [0, 1, 0]))
+    parts.append(_patch([-X, Y1, -Z], [2 * X, 0, 0], [0, 0, 2 * Z], q(64), q(64), bumps(0.25, 5), [0, -1, 0]))
+    parts.append(_patch([-X, Y0, -Z], [0, Y1 - Y0, 0], [0, 0, 2 * Z], q(72), q(96), bumps(0.22, 7), [1, 0, 0]))
+    parts.append(_patch([X, Y0, -Z], [0, 0, 2 * Z], [0, Y1 - Y0, 0], q(96), q(72), bumps(0.22, 7), [-1, 0, 0]))
+    parts.append(_patch([-X, Y0, -Z], [2 * X, 0, 0], [0, Y1 - Y0, 0], q(96), q(72), bumps(0.22, 6), [0, 0, 1]))
+    parts.append(_patch([-X, Y0, Z], [0, Y1 - Y0, 0], [2 * X, 0, 0], q(72), q(96), bumps(0.22, 6), [0, 0, -1]))
+    # two storeys of colonnades along z, plus arches (half tori) between neighbouring columns
+    col_x = [-9.0, 9.0]
+    col_z = np.linspace(-16.0, 16.0, 9)
+    for cx in col_x:
+        for cz in col_z:
+            parts.append(_cylinder((cx, cz), 0.85, Y0, 0.0, q(48), q(40), flute=0.05))
+            parts.append(_cylinder((cx, cz), 0.6, 0.8, 8.0, q(40), q(32), flute=0.04))
+        for z0, z1 in zip(col_z[:-1], col_z[1:]):
+            # arch: swept circle along a half circle in the (z,y) plane
+            nu, nv = q(28), q(12)
+            a = np.linspace(0, np.pi, nu + 1)
+            b = np.linspace(0, 2 * np.pi, nv + 1)
+            A, B = np.meshgrid(a, b, indexing="ij")
+            R, r = 0.5 * (z1 - z0), 0.35
+            zc = 0.5 * (z0 + z1)
+            p = np.stack([cx + r * np.cos(B),
+                          0.0 + (R + r * np.sin(B)) * np.sin(A) * 0.45,
+                          zc - (R + r * np.sin(B)) * np.cos(A)], -1).reshape(-1, 3)
+            parts.append((p, _grid(nu, nv)))
+        # gallery floor slab above the arches
+        parts.append(_patch([cx - 1.4, 0.75, -17.0], [0, 0, 34.0], [2.8, 0, 0], q(96), q(8), bumps(0.03, 11), [0, 1, 0]))
+    # clutter: bumpy blobs on the floor and hanging from the ceiling
+    for _ in range(14):
+        c = np.array([rng.uniform(-7, 7), rng.uniform(Y0 + 1.0, Y0 + 2.5), rng.uniform(-17, 17)])
+        parts.append(_sphere(c, rng.uniform(0.7, 1.6), q(40), q(28), 0.08, rng))
+    for _ in range(6):
+        c = np.array([rng.uniform(-6, 6), rng.uniform(5.0, 9.0), rng.uniform(-15, 15)])
+        parts.append(_sphere(c, rng.uniform(0.5, 1.2), q(32), q(24), 0.12, rng))
+    # hanging curtains (thin displaced sheets) across the nave
+    for zc in np.linspace(-12, 12, 4):
+        parts.append(_patch([-7.5, 1.0, zc], [15.0, 0, 0], [0, 9.5, 0], q(72), q(40),
+                            lambda u, v: 0.35 * np.sin(14 * np.pi * u + ph[4]) * (1.0 - 0.6 * v), [0, 0, 1]))
+
+    pos, idx, off = [], [], 0
+    for p, i in parts:
+        pos.append(p)
+        idx.append(i + off)
+        off += p.shape[0]
+    positions = np.ascontiguousarray(np.concatenate(pos).astype(np.float32))
+    indices = np.ascontiguousarray(np.concatenate(idx).astype(np.uint32))
+    assert np.abs(positions).max() <= 20.0
+    return positions, indices
+
+
+def random_soup(n_tris: int, seed: int | None = None, size: float = 0.01):
+    """Uniformly random small triangles in the unit cube (config 5 build sweep; seed defaults to N)."""
+    rng = np.random.default_rng(n_tris if seed is None else seed)
+    c = rng.random((n_tris, 1, 3), dtype=np.float32)
+    d = (rng.random((n_tris, 3, 3), dtype=np.float32) - 0.5) * np.float32(size)
+    positions = np.ascontiguousarray(np.clip(c + d, 0.0, 1.0).reshape(-1, 3).astype(np.float32))
+    indices = np.arange(3 * n_tris, dtype=np.uint32).reshape(-1, 3)
+    return positions, indices
+
+
+def pinhole_rays(width: int, height: int, eye, gaze, up, fov_y_deg: float,
+                 t_min: float = 0.0, t_max: float = np.float32(3.4028235e38)):
+    """Deterministic pixel-centre primary rays, RayGMem layout [pos(3), tMin, dir(3), tMax] float32
+    (Tracer/TracerTypes.h:L276-283). Row-major, pixel (0,0) first."""
+    eye = np.asarray(eye, np.float64)
+    w = np.asarray(gaze, np.float64) - eye
+    w /= np.linalg.norm(w)
+    u = np.cross(w, np.asarray(up, np.float64))
+    u /= np.linalg.norm(u)
+    v = np.cross(u, w)
+    th = np.tan(np.deg2rad(fov_y_deg) * 0.5)
+    aspect = width / height
+    px = ((np.arange(width) + 0.5) / width * 2.0 - 1.0) * th * aspect
+    py = (1.0 - (np.arange(height) + 0.5) / height * 2.0) * th
+    PX, PY = np.meshgrid(px, py, indexing="xy")
+    d = w[None, None, :] + PX[..., None] * u + PY[..., None] * v
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    rays = np.empty((height * width, 8), np.float32)
+    rays[:, 0:3] = eye.astype(np.float32)
+    rays[:, 3] = t_min
+    rays[:, 4:7] = d.reshape(-1, 3).astype(np.float32)
+    rays[:, 7] = t_max
+    return rays
+
+
+ARCADE_CAMERA = dict(eye=(0.0, -4.0, 18.5), gaze=(1.5, -3.0, 0.0), up=(0.0, 1.0, 0.0), fov_y_deg=60.0)
+
+
+def pcg32_floats(seeds: np.ndarray, n: int):
+    """n uniform floats in [0,1) per seed from PCG32 (XSH-RR 64/32, the generator family of the
+    reference's PermutedCG32, Tracer/Random.h:L763-771). Deterministic ray-batch helper only."""
+    mult = np.uint64(6364136223846793005)
+    inc = np.uint64(1442695040888963407)
+    state = (seeds.astype(np.uint64) + inc) * mult + inc
+    out = np.empty((seeds.shape[0], n), np.float32)
+    with np.errstate(over="ignore"):
+        for k in range(n):
+            old = state
+            state = old * mult + inc
+            xs = (((old >> np.uint64(18)) ^ old) >> np.uint64(27)).astype(np.uint32)
+            rot = (old >> np.uint64(59)).astype(np.uint32)
+            r = (xs >> rot) | (xs << ((np.uint32(32) - rot) & np.uint32(31)))
+            out[:, k] = np.minimum(r.astype(np.float64) * 2.0 ** -32, np.float64(np.nextafter(np.float32(1), np.float32(0))))
+    return out
+
+
+def ao_rays(rays: np.ndarray, prim: np.ndarray, t: np.ndarray, positions: np.ndarray,
+            indices: np.ndarray, t_max: float, seed_offset: int = 0):
+    """Config 2 batch B: from each primary hit one cosine-hemisphere direction about the geometric
+    normal (flipped towards the viewer), PCG32 seeded by pixel index. Misses produce tMax = 0 rays
+    (never hit anything). Origin is offset by 1e-3 along the normal."""
+    n = rays.shape[0]
+    hit = prim != 0xFFFFFFFF
+    pr = np.where(hit, prim, 0).astype(np.int64)
+    p0 = positions[indices[pr, 0]].astype(np.float64)
+    p1 = positions[indices[pr, 1]].astype(np.float64)
+    p2 = positions[indices[pr, 2]].astype(np.float64)
+    nrm = np.cross(p1 - p0, p2 - p0)
+    ln = np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm = nrm / np.where(ln > 0, ln, 1.0)
+    d = rays[:, 4:7].astype(np.float64)
+    nrm = np.where((np.sum(nrm * d, 1, keepdims=True) > 0), -nrm, nrm)
+    xi = pcg32_floats(np.arange(n, dtype=np.uint64) + np.uint64(seed_offset), 2).astype(np.float64)
+    r = np.sqrt(xi[:, 0])
+    phi = 2 * np.pi * xi[:, 1]
+    lx, ly, lz = r * np.cos(phi), r * np.sin(phi), np.sqrt(np.maximum(0.0, 1.0 - xi[:, 0]))
+    a = np.where(np.abs(nrm[:, 0:1]) > 0.9, np.array([[0.0, 1.0, 0.0]]), np.array([[1.0, 0.0, 0.0]]))
+    tx = np.cross(a, nrm)
+    tx /= np.linalg.norm(tx, axis=1, keepdims=True)
+    ty = np.cross(nrm, tx)
+    wdir = lx[:, None] * tx + ly[:, None] * ty + lz[:, None] * nrm
+    wdir /= np.linalg.norm(wdir, axis=1, keepdims=True)
+    tt = np.where(hit, t, 0.0).astype(np.float64)
+    org = rays[:, 0:3].astype(np.float64) + tt[:, None] * d + 1e-3 * nrm
+    out = np.empty((n, 8), np.float32)
+    out[:, 0:3] = org.astype(np.float32)
+    out[:, 3] = 0.0
+    out[:, 4:7] = wdir.astype(np.float32)
+    out[:, 7] = np.where(hit, np.float32(t_max), np.float32(0.0))
+    return out
+
+
+def cornell_box():
+    """Triangles-only Cornell box after the reference's documented scene
+    (Docs/markdown/scene/mrayScene.md:L310-553): walls from a unit plane, two boxes instead of the
+    spheres. Returns dict with positions, indices, per-triangle material id
+    (0 white, 1 red, 2 green, 3 light) and the camera."""
+    quads = []
+
+    def quad(a, b, c, d, m):
+        quads.append((np.array([a, b, c, d], np.float32), m))
+
+    # room spans x,z in [-1,1], y in [0,2]
+    quad([-1, 0, 1], [1, 0, 1], [1, 0, -1], [-1, 0, -1], 0)     # floor
+    quad([-1, 2, -1], [1, 2, -1], [1, 2, 1], [-1, 2, 1], 0)     # ceiling
+    quad([-1, 0, -1], [1, 0, -1], [1, 2, -1], [-1, 2, -1], 0)   # back
+    quad([-1, 0, 1], [-1, 0, -1], [-1, 2, -1], [-1, 2, 1], 1)   # left (red)
+    quad([1, 0, -1], [1, 0, 1], [1, 2, 1], [1, 2, -1], 2)       # right (green)
+    quad([-0.25, 1.98, -0.25], [0.25, 1.98, -0.25], [0.25, 1.98, 0.25], [-0.25, 1.98, 0.25], 3)  # light
+
+    def box(cx, cz, sx, sy, sz, ang):
+        ca, sa = np.cos(ang), np.sin(ang)
+        def P(x, y, z):
+            return [cx + ca * x * sx - sa * z * sz, y * sy, cz + sa * x * sx + ca * z * sz]
+        v = [P(-1, 0, -1), P(1, 0, -1), P(1, 0, 1), P(-1, 0, 1), P(-1, 1, -1), P(1, 1, -1), P(1, 1, 1), P(-1, 1, 1)]
+        for f in ([4, 7, 6, 5], [0, 1, 5, 4], [1, 2, 6, 5], [2, 3, 7, 6], [3, 0, 4, 7], [0, 3, 2, 1]):
+            quad(v[f[0]], v[f[1]], v[f[2]], v[f[3]], 0)
+
+    box(-0.35, -0.3, 0.3, 1.2, 0.3, 0.3)
+    box(0.4, 0.35, 0.3, 0.6, 0.3, -0.3)
+    pos, idx, mat = [], [], []
+    for k, (qv, m) in enumerate(quads):
+        pos.append(qv)
+        idx += [[4 * k, 4 * k + 1, 4 * k + 2], [4 * k, 4 * k + 2, 4 * k + 3]]
+        mat += [m, m]
+    return dict(positions=np.ascontiguousarray(np.concatenate(pos)),
+                indices=np.array(idx, np.uint32), material=np.array(mat, np.uint32),
+                albedo=np.array([[0.725, 0.71, 0.68], [0.63, 0.065, 0.05], [0.14, 0.45, 0.091], [0, 0, 0]], np.float32),
+                radiance=np.array([68.0, 48.0, 16.0], np.float32),
+                camera=dict(eye=(0.0, 1.0, 6.8), gaze=(0.0, 1.0, 0.0), up=(0.0, 1.0, 0.0), fov_y_deg=19.5))

@@ -73,3 +73,9 @@ printf '%s\n' "${SRCS[@]}" | xargs -P "$(nproc)" -I{} bash -c 'compile_one "$@"'
 
 g++ -shared -o "$OUT/libTracerDLL_CPU$SUF.so" "$W"/obj/*.o -lpthread -latomic -ldl
 echo "LINK_OK $OUT/libTracerDLL_CPU$SUF.so"
+
+# taps: a TU of ours that forwards C arrays to the reference's own kernels (see ref_taps.cpp)
+g++ $(cat "$W/cxxflags.txt") -c "$HERE/ref_taps.cpp" -o "$W/ref_taps.o"
+g++ -shared -o "$OUT/libref_taps$SUF.so" "$W/ref_taps.o" -L"$OUT" -lTracerDLL_CPU$SUF \
+    -Wl,-rpath,'$ORIGIN' -lpthread -latomic -ldl
+echo "LINK_OK $OUT/libref_taps$SUF.so"
