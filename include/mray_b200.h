@@ -1,0 +1,197 @@
+/* mray_b200.h — C-ABI of the B200-native (sm_100a) MRay hot path.
+ *
+ * This is the boundary a maintainer of yalcinerbora/mray binds behind the TracerDLL plugin
+ * (class Tracer : TracerBase implementing Core/TracerI.h:L150-376): the C++20 host object keeps
+ * the scene/group registries and calls these entry points where the reference calls its
+ * accelerator / renderer device code. Plain pointers and sizes only; no C++ or torch types.
+ * Every entry point names the reference interface it replaces (paths relative to
+ * /root/reference/Source). See INTEGRATION.md for the reference-side binding.
+ *
+ * Conventions
+ *   - every function returns MRB_OK (0) or a negative mrb_status; mrb_last_error() gives text.
+ *   - "memspace" says whether the array pointers of that call are host or device pointers.
+ *     Host variants copy in/out on the context stream and synchronise before returning.
+ *   - all device work is issued on the context stream (mrb_context_set_stream); device-pointer
+ *     calls are asynchronous with respect to the host unless stated otherwise.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     MRB_ERR_NO_DEVICE.
+ *
+ * Binary layouts are the reference's own (Tracer/TracerTypes.h):
+ *   RayGMem      32 B  { float pos[3]; float tMin; float dir[3]; float tMax; }      L276-283
+ *   HitKeyPack   16 B  { u32 primKey; u32 lightOrMatKey; u32 transKey; u32 accelKey } L201-209
+ *   MetaHit       8 B  { float a, b }  (triangle barycentrics (1-u-v, u))            Hit.h
+ *   PrimitiveKey  u32  batch:4 | index:28     AcceleratorKey u32 batch:12 | index:20  L164-175
+ */
+#ifndef MRAY_B200_H
+#define MRAY_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define MRB_API __declspec(dllexport)
+#else
+#define MRB_API __attribute__((visibility("default")))
+#endif
+
+typedef enum mrb_status
+{
+    MRB_OK = 0,
+    MRB_ERR_NO_DEVICE = -1,   /* no CUDA device / driver: the product path refuses to run */
+    MRB_ERR_INVALID_ARG = -2,
+    MRB_ERR_CUDA = -3,
+    MRB_ERR_OUT_OF_MEMORY = -4,
+    MRB_ERR_UNSUPPORTED = -5
+} mrb_status;
+
+typedef enum mrb_memspace { MRB_MEM_HOST = 0, MRB_MEM_DEVICE = 1 } mrb_memspace;
+
+typedef struct mrb_context_t* mrb_context;
+typedef struct mrb_accel_t* mrb_accel;
+
+typedef struct mrb_ray_gmem { float pos[3]; float tMin; float dir[3]; float tMax; } mrb_ray_gmem;
+typedef struct mrb_hit_key_pack { uint32_t primKey, lightOrMatKey, transKey, accelKey; } mrb_hit_key_pack;
+typedef struct mrb_meta_hit { float a, b; } mrb_meta_hit;
+
+#define MRB_INVALID_KEY 0xFFFFFFFFu
+
+/* ---- library / context ------------------------------------------------------------------ */
+
+/* ABI version of this header (major<<16 | minor). */
+MRB_API uint32_t mrb_abi_version(void);
+
+/* Replaces GPUSystem + GPUQueue ownership inside TracerBase (Device/CUDA/GPUSystemCUDA.cpp:L249-405:
+ * the reference always renders on BestDevice() with one queue). One context = one device, one
+ * stream, one device arena (the reference's DeviceMemory + MemAlloc::AllocateMultiData,
+ * Core/MemAlloc.h:L171-209: 256-byte aligned sub-allocation of a growing arena). */
+MRB_API mrb_status mrb_context_create(int device, mrb_context* out);
+MRB_API void       mrb_context_destroy(mrb_context ctx);
+/* Use an externally owned cudaStream_t (e.g. torch's current stream). NULL = context's own. */
+MRB_API mrb_status mrb_context_set_stream(mrb_context ctx, void* cuda_stream);
+MRB_API mrb_status mrb_context_synchronize(mrb_context ctx);
+/* TracerI::UsedDeviceMemory / TotalDeviceMemory (Core/TracerI.h:L372-373). */
+MRB_API size_t     mrb_context_used_device_memory(mrb_context ctx);
+MRB_API size_t     mrb_context_total_device_memory(mrb_context ctx);
+/* Number of kernels this library has launched on the context since creation (for the
+ * gpu_launches accounting of bench.py). */
+MRB_API uint64_t   mrb_context_launch_count(mrb_context ctx);
+MRB_API const char* mrb_last_error(mrb_context ctx); /* ctx may be NULL: last create error */
+
+/* ---- accelerator build ------------------------------------------------------------------ */
+
+typedef enum mrb_build_flags
+{
+    /* Default: Karras delta with the augmented key (64 + clz(i^j)) on EQUAL Morton codes. This is
+     * bit-identical to the reference whenever all codes of an accelerator are distinct
+     * (mrb_accel_info.duplicateCodes == 0) and stays a valid tree otherwise. */
+    MRB_BUILD_DEFAULT = 0,
+    /* Audit mode: the reference's literal equal-code fallback, which compares the raw indices
+     * without the +64 offset (AcceleratorLBVH.cu:L85-90) and can emit an ill-formed hierarchy when
+     * codes repeat. Implies MRB_BUILD_BINARY_ONLY; the topology arrays still match the reference
+     * node for node. */
+    MRB_BUILD_REFERENCE_DELTA = 1,
+    /* keep only the binary LBVH (skip the wide-BVH collapse) */
+    MRB_BUILD_BINARY_ONLY = 2
+} mrb_build_flags;
+
+/* One concrete accelerator over a triangle primitive group.
+ * Replaces AcceleratorGroupLBVH<PrimGroupTriangle>::Construct + MultiBuildLBVH
+ * (Tracer/AcceleratorLBVH.hpp:L433-899) for one concrete accelerator:
+ *   KCGeneratePrimitiveKeys (AcceleratorLinear.cu:L14)  leaf i -> PrimitiveKey
+ *   KCGeneratePrimAABBs / KCGenPrimCenters (AcceleratorWork.kt.h:L5-123)
+ *   SegmentedTransformReduce(UnionAABB3) (hpp:L764-769)
+ *   KCGenMortonCode (AcceleratorLBVH.cu:L96-168), SegmentedRadixSort<true,u64,u32> (hpp:L828-838)
+ *   KCConstructLBVHInternalNodes (cu:L170-299), KCUnionLBVHBoundingBoxes (cu:L301-435)
+ * then (unless MRB_BUILD_BINARY_ONLY) collapses the bit-exact binary tree into the 8-wide
+ * quantised BVH the traversal kernels use. */
+typedef struct mrb_accel_desc
+{
+    const float*    positions;    /* vertexCount * 3 floats (PrimGroupTriangle positions)          */
+    uint32_t        vertexCount;
+    const uint32_t* indices;      /* triangleCount * 3, already rebased to the group's vertex list */
+    uint32_t        triangleCount;/* triangles in the GROUP index list                             */
+    mrb_memspace    memspace;     /* of positions / indices                                        */
+    uint32_t        primGroupId;  /* batch portion of the PrimitiveKeys (4 bits)                   */
+    /* prim ranges of this accelerator inside the group (<= 8, TracerConstants::MaxPrimBatchPerSurface);
+     * leaves are numbered range by range. NULL/0 = one range covering the whole group. */
+    uint32_t        rangeCount;
+    const uint32_t* primRanges;   /* rangeCount * 2 : [begin, end) ; host memory                   */
+    const uint32_t* lightOrMatKeys;/* rangeCount ; host ; NULL = 0                                 */
+    const uint8_t*  cullBackface; /* rangeCount ; host ; NULL = 0 (two sided)                      */
+    uint32_t        flags;        /* mrb_build_flags                                               */
+} mrb_accel_desc;
+
+MRB_API mrb_status mrb_accel_build(mrb_context ctx, const mrb_accel_desc* desc, mrb_accel* out);
+MRB_API void       mrb_accel_destroy(mrb_context ctx, mrb_accel accel);
+
+typedef struct mrb_accel_info
+{
+    uint32_t leafCount;      /* triangles                                   */
+    uint32_t nodeCount;      /* binary LBVH nodes = max(1, leafCount-1)     */
+    uint32_t wideNodeCount;  /* 8-wide nodes (0 when BINARY_ONLY)           */
+    uint32_t duplicateCodes; /* 1 if the Morton codes were not all distinct */
+    float    aabb[6];        /* accelerator AABB (min xyz, max xyz)         */
+    float    buildMs;        /* device time of the last build (CUDA events) */
+    size_t   deviceBytes;
+} mrb_accel_info;
+MRB_API mrb_status mrb_accel_get_info(mrb_context ctx, mrb_accel accel, mrb_accel_info* info);
+
+/* Parity tap: copies the binary LBVH artefacts to HOST arrays in the reference's layout
+ * (any pointer may be NULL): morton[leaf] in leaf order, sortedMorton/sortedLeaf[leaf] after the
+ * stable sort, nodes[node*3] = LBVHNode{left,right,parent} with MSB = leaf flag and ORIGINAL leaf
+ * index payload (AcceleratorLBVH.h:L62-67), leafParent[leaf], nodeBoxes[node*6], leafAABBs[leaf*6]. */
+MRB_API mrb_status mrb_accel_export_lbvh(mrb_context ctx, mrb_accel accel,
+                                         uint64_t* morton, uint64_t* sortedMorton, uint32_t* sortedLeaf,
+                                         uint32_t* nodes, uint32_t* leafParent,
+                                         float* nodeBoxes, float* leafAABBs);
+
+/* ---- ray casting ------------------------------------------------------------------------ */
+
+typedef enum mrb_trace_mode
+{
+    MRB_TRACE_WIDE = 0,        /* product path: 8-wide quantised BVH                                   */
+    MRB_TRACE_BINARY_EXACT = 1 /* audit path: the reference's binary LBVH, left-first, exact slab test */
+} mrb_trace_mode;
+
+/* Closest hit. Replaces BaseAcceleratorLBVH::CastRays (Tracer/AcceleratorLBVH.cu:L760-896) +
+ * KCLocalRayCast (AcceleratorWork.kt.h:L177-244) + AcceleratorLBVH::ClosestHit
+ * (AcceleratorLBVH.hpp:L327-374) for an identity-transform triangle accelerator.
+ * For i in [0,rayCount): r = rayIndices ? rayIndices[i] : i ; on a hit writes hitKeys[r]
+ * {primKey, lightOrMatKey of the prim range, transKey = 0, accelKey}, metaHits[r] and shrinks
+ * rays[r].tMax ; on a miss leaves all three untouched (the caller pre-fills boundary keys,
+ * RendererCommon.cu:L68-81). */
+MRB_API mrb_status mrb_cast_rays(mrb_context ctx, mrb_accel accel,
+                                 mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits,
+                                 mrb_ray_gmem* rays, const uint32_t* rayIndices,
+                                 uint32_t rayCount, uint32_t totalRayCount,
+                                 mrb_memspace memspace, mrb_trace_mode mode);
+
+/* Any hit. Replaces BaseAcceleratorLBVH::CastVisibilityRays (AcceleratorLBVH.cu:L898-1035) +
+ * KCVisibilityRayCast (AcceleratorWork.kt.h:L246-296): clears bit r of isVisible (u32 words,
+ * Bitspan, Tracer/Bitspan.h:L108) when ray r hits anything in [tMin,tMax); never sets bits. */
+MRB_API mrb_status mrb_cast_visibility_rays(mrb_context ctx, mrb_accel accel,
+                                            uint32_t* isVisibleBits,
+                                            const mrb_ray_gmem* rays, const uint32_t* rayIndices,
+                                            uint32_t rayCount, uint32_t totalRayCount,
+                                            mrb_memspace memspace, mrb_trace_mode mode);
+
+/* ---- device algorithms (Device/GPUAlgRadixSort.h, exposed for parity tests) -------------- */
+
+/* Stable ascending LSD radix sort of (key,value) pairs over bits [bitBegin,bitEnd).
+ * Replaces DeviceAlgorithms::RadixSort<true,K,uint32_t> (Device/CUDA/AlgRadixSortCUDA.h:L60-116).
+ * In-place on the given arrays (internally double buffered). */
+MRB_API mrb_status mrb_radix_sort_pairs_u64(mrb_context ctx, uint64_t* keys, uint32_t* values,
+                                            uint32_t count, uint32_t bitBegin, uint32_t bitEnd,
+                                            mrb_memspace memspace);
+MRB_API mrb_status mrb_radix_sort_pairs_u32(mrb_context ctx, uint32_t* keys, uint32_t* values,
+                                            uint32_t count, uint32_t bitBegin, uint32_t bitEnd,
+                                            mrb_memspace memspace);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRAY_B200_H */

@@ -1,0 +1,272 @@
+"""ctypes mirror of include/mray_b200.h.
+
+Python-side names follow the reference's accelerator interface
+(``BaseAcceleratorI::CastRays / CastVisibilityRays``, Tracer/AcceleratorC.h; layouts of
+Tracer/TracerTypes.h) so that parity tests read like calls into the reference. Device arrays are
+``torch`` CUDA tensors (torch is plumbing for device memory and streams only); host arrays are
+numpy. The library is loaded from ``mray_b200/lib/libmray_b200.so`` — if it is missing or no CUDA
+device exists every compute call raises :class:`MrbError`; nothing falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmray_b200.so")
+
+MRB_MEM_HOST, MRB_MEM_DEVICE = 0, 1
+MRB_TRACE_WIDE, MRB_TRACE_BINARY_EXACT = 0, 1
+MRB_BUILD_DEFAULT, MRB_BUILD_REFERENCE_DELTA, MRB_BUILD_BINARY_ONLY = 0, 1, 2
+INVALID_KEY = 0xFFFFFFFF
+
+STATUS = {0: "MRB_OK", -1: "MRB_ERR_NO_DEVICE", -2: "MRB_ERR_INVALID_ARG", -3: "MRB_ERR_CUDA",
+          -4: "MRB_ERR_OUT_OF_MEMORY", -5: "MRB_ERR_UNSUPPORTED"}
+
+# numpy dtypes of the reference's device structs (Tracer/TracerTypes.h:L201-209,L276-283)
+RAY_DTYPE = np.dtype([("pos", np.float32, 3), ("tMin", np.float32), ("dir", np.float32, 3), ("tMax", np.float32)])
+HITKEY_DTYPE = np.dtype([("primKey", np.uint32), ("lightOrMatKey", np.uint32), ("transKey", np.uint32),
+                         ("accelKey", np.uint32)])
+
+
+class MrbError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"{STATUS.get(status, status)}: {message}")
+        self.status = status
+
+
+class AccelDesc(C.Structure):
+    _fields_ = [("positions", C.c_void_p), ("vertexCount", C.c_uint32),
+                ("indices", C.c_void_p), ("triangleCount", C.c_uint32),
+                ("memspace", C.c_int), ("primGroupId", C.c_uint32),
+                ("rangeCount", C.c_uint32), ("primRanges", C.c_void_p),
+                ("lightOrMatKeys", C.c_void_p), ("cullBackface", C.c_void_p),
+                ("flags", C.c_uint32)]
+
+
+class AccelInfo(C.Structure):
+    _fields_ = [("leafCount", C.c_uint32), ("nodeCount", C.c_uint32), ("wideNodeCount", C.c_uint32),
+                ("duplicateCodes", C.c_uint32), ("aabb", C.c_float * 6), ("buildMs", C.c_float),
+                ("deviceBytes", C.c_size_t)]
+
+
+# every symbol include/mray_b200.h declares (tests/test_capi_symbols.py checks the header against this)
+_PROTOTYPES = {
+    "mrb_abi_version": (C.c_uint32, []),
+    "mrb_context_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "mrb_context_destroy": (None, [C.c_void_p]),
+    "mrb_context_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mrb_context_synchronize": (C.c_int, [C.c_void_p]),
+    "mrb_context_used_device_memory": (C.c_size_t, [C.c_void_p]),
+    "mrb_context_total_device_memory": (C.c_size_t, [C.c_void_p]),
+    "mrb_context_launch_count": (C.c_uint64, [C.c_void_p]),
+    "mrb_last_error": (C.c_char_p, [C.c_void_p]),
+    "mrb_accel_build": (C.c_int, [C.c_void_p, C.POINTER(AccelDesc), C.POINTER(C.c_void_p)]),
+    "mrb_accel_destroy": (None, [C.c_void_p, C.c_void_p]),
+    "mrb_accel_get_info": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(AccelInfo)]),
+    "mrb_accel_export_lbvh": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_void_p] * 7),
+    "mrb_cast_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_uint32, C.c_uint32, C.c_int, C.c_int]),
+    "mrb_cast_visibility_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_uint32, C.c_uint32, C.c_int, C.c_int]),
+    "mrb_radix_sort_pairs_u64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
+    "mrb_radix_sort_pairs_u32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
+}
+
+_lib = None
+
+
+def build_library(verbose: bool = False) -> str:
+    """Compiles mray_b200/csrc for sm_100a into mray_b200/lib/libmray_b200.so (nvcc cross-compiles
+    without a GPU). Raises if nvcc fails."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose:
+        print(res.stdout)
+    if res.returncode != 0:
+        raise RuntimeError("building libmray_b200.so failed:\n" + res.stdout)
+    return LIB_PATH
+
+
+def load_library():
+    """Loads the CUDA extension. Fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MrbError(-1, f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
+                               "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _ptr(x):
+    """Raw pointer of a numpy array, torch tensor or None."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return x.ctypes.data
+    return x.data_ptr()  # torch tensor
+
+
+def _space(*xs):
+    spaces = set()
+    for x in xs:
+        if x is None:
+            continue
+        spaces.add(MRB_MEM_HOST if isinstance(x, np.ndarray) else
+                   (MRB_MEM_DEVICE if x.is_cuda else MRB_MEM_HOST))
+    if len(spaces) != 1:
+        raise ValueError("all arrays of one call must live in the same memory space")
+    return spaces.pop()
+
+
+class Context:
+    """One device + stream + scratch arena (mrb_context)."""
+
+    def __init__(self, device: int = 0, stream=None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        st = self.lib.mrb_context_create(device, C.byref(h))
+        if st != 0:
+            raise MrbError(st, (self.lib.mrb_last_error(None) or b"").decode())
+        self.handle = h
+        self.device = device
+        if stream is not None:
+            self.set_stream(stream)
+
+    def check(self, st):
+        if st != 0:
+            raise MrbError(st, (self.lib.mrb_last_error(self.handle) or b"").decode())
+
+    def set_stream(self, stream):
+        """``stream``: a torch.cuda.Stream, a raw cudaStream_t integer, or None (own stream)."""
+        raw = None if stream is None else getattr(stream, "cuda_stream", stream)
+        self.check(self.lib.mrb_context_set_stream(self.handle, C.c_void_p(raw)))
+
+    def synchronize(self):
+        self.check(self.lib.mrb_context_synchronize(self.handle))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.mrb_context_launch_count(self.handle))
+
+    @property
+    def used_device_memory(self) -> int:
+        return int(self.lib.mrb_context_used_device_memory(self.handle))
+
+    def radix_sort_pairs(self, keys, values, bit_begin=0, bit_end=None):
+        """DeviceAlgorithms::RadixSort<true,K,u32> (Device/CUDA/AlgRadixSortCUDA.h:L60-116), in place."""
+        space = _space(keys, values)
+        itemsize = keys.itemsize if isinstance(keys, np.ndarray) else keys.element_size()
+        n = keys.shape[0]
+        bit_end = itemsize * 8 if bit_end is None else bit_end
+        fn = self.lib.mrb_radix_sort_pairs_u64 if itemsize == 8 else self.lib.mrb_radix_sort_pairs_u32
+        self.check(fn(self.handle, _ptr(keys), _ptr(values), n, bit_begin, bit_end, space))
+
+    def close(self):
+        if self.handle:
+            self.lib.mrb_context_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Accelerator:
+    """One concrete triangle accelerator — AcceleratorGroupLBVH<PrimGroupTriangle> with a single
+    identity-transform instance (Tracer/AcceleratorLBVH.hpp:L433-899)."""
+
+    def __init__(self, ctx: Context, positions, indices, prim_ranges=None, light_or_mat_keys=None,
+                 cull_backface=None, prim_group_id: int = 0, flags: int = MRB_BUILD_DEFAULT):
+        self.ctx = ctx
+        d = AccelDesc()
+        d.positions = _ptr(positions)
+        d.vertexCount = positions.shape[0]
+        d.indices = _ptr(indices)
+        d.triangleCount = indices.shape[0]
+        d.memspace = _space(positions, indices)
+        d.primGroupId = prim_group_id
+        self._keep = []
+        if prim_ranges is not None:
+            pr = np.ascontiguousarray(prim_ranges, np.uint32).reshape(-1, 2)
+            d.rangeCount = pr.shape[0]
+            d.primRanges = pr.ctypes.data
+            self._keep.append(pr)
+        if light_or_mat_keys is not None:
+            lm = np.ascontiguousarray(light_or_mat_keys, np.uint32)
+            d.lightOrMatKeys = lm.ctypes.data
+            self._keep.append(lm)
+        if cull_backface is not None:
+            cb = np.ascontiguousarray(cull_backface, np.uint8)
+            d.cullBackface = cb.ctypes.data
+            self._keep.append(cb)
+        d.flags = flags
+        h = C.c_void_p()
+        ctx.check(ctx.lib.mrb_accel_build(ctx.handle, C.byref(d), C.byref(h)))
+        self.handle = h
+        info = AccelInfo()
+        ctx.check(ctx.lib.mrb_accel_get_info(ctx.handle, self.handle, C.byref(info)))
+        self.info = info
+
+    @property
+    def leaf_count(self):
+        return int(self.info.leafCount)
+
+    @property
+    def node_count(self):
+        return int(self.info.nodeCount)
+
+    def export_lbvh(self):
+        """Binary LBVH artefacts in the reference layout (host numpy arrays)."""
+        n, nn = self.leaf_count, self.node_count
+        out = dict(morton=np.zeros(n, np.uint64), sorted_morton=np.zeros(n, np.uint64),
+                   sorted_idx=np.zeros(n, np.uint32), nodes=np.zeros((nn, 3), np.uint32),
+                   leaf_parent=np.zeros(n, np.uint32), boxes=np.zeros((nn, 6), np.float32),
+                   leaf_aabb=np.zeros((n, 6), np.float32))
+        self.ctx.check(self.ctx.lib.mrb_accel_export_lbvh(
+            self.ctx.handle, self.handle, out["morton"].ctypes.data, out["sorted_morton"].ctypes.data,
+            out["sorted_idx"].ctypes.data, out["nodes"].ctypes.data, out["leaf_parent"].ctypes.data,
+            out["boxes"].ctypes.data, out["leaf_aabb"].ctypes.data))
+        out["accel_aabb"] = np.array(list(self.info.aabb), np.float32)
+        return out
+
+    def cast_rays(self, hit_keys, meta_hits, rays, ray_indices=None, mode=MRB_TRACE_WIDE):
+        """BaseAcceleratorLBVH::CastRays (Tracer/AcceleratorLBVH.cu:L760-896): closest hit; writes
+        hit_keys / meta_hits / rays.tMax at hit rays only."""
+        space = _space(hit_keys, meta_hits, rays, ray_indices)
+        total = rays.shape[0]
+        count = total if ray_indices is None else ray_indices.shape[0]
+        self.ctx.check(self.ctx.lib.mrb_cast_rays(self.ctx.handle, self.handle, _ptr(hit_keys), _ptr(meta_hits),
+                                                  _ptr(rays), _ptr(ray_indices), count, total, space, mode))
+
+    def cast_visibility_rays(self, visible_bits, rays, ray_indices=None, mode=MRB_TRACE_WIDE):
+        """BaseAcceleratorLBVH::CastVisibilityRays (AcceleratorLBVH.cu:L898-1035): clears bit r when
+        ray r is occluded."""
+        space = _space(visible_bits, rays, ray_indices)
+        total = rays.shape[0]
+        count = total if ray_indices is None else ray_indices.shape[0]
+        self.ctx.check(self.ctx.lib.mrb_cast_visibility_rays(self.ctx.handle, self.handle, _ptr(visible_bits),
+                                                             _ptr(rays), _ptr(ray_indices), count, total, space, mode))
+
+    def close(self):
+        if self.handle and self.ctx.handle:
+            self.ctx.lib.mrb_accel_destroy(self.ctx.handle, self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

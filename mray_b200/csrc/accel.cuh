@@ -1,0 +1,77 @@
+// accel.cuh — device-side data layout of one triangle accelerator (binary LBVH + 8-wide BVH).
+#pragma once
+#include "common.cuh"
+
+namespace mrb
+{
+
+// Reference layouts (Tracer/AcceleratorLBVH.h:L62-77)
+struct LBVHNode { uint32_t left, right, parent; };
+struct LBVHBox  { float min[3], max[3]; };
+
+// leaf -> primitive mapping of one accelerator (<= 8 prim ranges, AcceleratorC.h:L281-301)
+struct PrimRanges
+{
+    uint32_t count;
+    uint32_t leafStart[9]; // prefix sum of range sizes
+    uint32_t primBegin[8];
+    uint32_t lmKey[8];
+    uint32_t cull[8];
+    uint32_t primGroupId;
+};
+
+// 8-wide compressed node, 80 bytes = 5 x 128-bit loads (after Ylitie et al. 2017, "CWBVH").
+//   q0 : p.x, p.y, p.z (node origin, float bits), {ex, ey, ez, imask} bytes (2^e quantisation
+//        step per axis as a biased float exponent; imask = slots holding internal children)
+//   q1 : childBase (first internal child node), triBase (first triangle record),
+//        meta[0..3], meta[4..7]   meta = 0                      : empty slot
+//                                      = 0b001'11sss (0x38|slot): internal child
+//                                      = unary(count)<<5 | offset: leaf, `count` (1..3) triangle
+//                                        records starting at triBase + offset (offset < 24)
+//   q2 : qlo.x[0..7], qlo.y[0..7]   q3 : qlo.z[0..7], qhi.x[0..7]   q4 : qhi.y[0..7], qhi.z[0..7]
+struct alignas(16) WideNode { uint4 q[5]; };
+
+// Triangle record, 48 bytes = 3 x 128-bit loads. e0/e1 are the float differences p1-p0, p2-p0
+// exactly as Ray::IntersectsTriangle forms them (Core/Ray.hpp:L133-134), so the intersection
+// arithmetic stays bit-identical to the reference.
+//   v0 : p0.xyz, leaf index (position in the accelerator's leaf list)
+//   v1 : e0.xyz, rank (position after the Morton sort = the reference's visit order; tie-break)
+//   v2 : e1.xyz, flags (bit0 = cull back face) | range index << 8
+struct alignas(16) TriRecord { float4 v0, v1, v2; };
+
+struct AccelData
+{
+    // inputs (device copies owned by the accelerator)
+    const float*    positions = nullptr; // V*3
+    const uint32_t* indices = nullptr;   // T*3
+    PrimRanges      ranges = {};
+    uint32_t        leafCount = 0;
+    uint32_t        nodeCount = 0;
+    // binary LBVH (reference layout)
+    float*    leafAABB = nullptr;     // leaf*6
+    uint64_t* morton = nullptr;       // leaf (leaf order)
+    uint64_t* sortedMorton = nullptr; // leaf (sorted)
+    uint32_t* sortedLeaf = nullptr;   // leaf (sorted) -> leaf index
+    LBVHNode* nodes = nullptr;        // node
+    uint32_t* leafParent = nullptr;   // leaf
+    LBVHBox*  boxes = nullptr;        // node
+    uint2*    nodeRange = nullptr;    // node : [first,last] sorted positions covered
+    uint32_t* accelAABBEnc = nullptr; // 6 order-preserving encoded floats + 2 flags
+    // wide BVH
+    WideNode*  wideNodes = nullptr;
+    TriRecord* tris = nullptr;
+    uint32_t   wideNodeCapacity = 0;
+    uint32_t   wideNodeCount = 0;
+    uint32_t   wideDepth = 0;
+};
+
+} // namespace mrb
+
+struct mrb_accel_t
+{
+    mrb::AccelData   d;
+    mrb::DeviceBlock mem;
+    mrb_accel_info   info = {};
+    uint32_t         flags = 0;
+    uint32_t         accelKey = 0;
+};

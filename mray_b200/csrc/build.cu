@@ -1,0 +1,636 @@
+// build.cu — accelerator construction on the device.
+//
+//  Stage 1 (bit-exact with the reference; AcceleratorLBVH.hpp:L584-899):
+//     KLeafAABB    <- KCGeneratePrimitiveKeys + KCGeneratePrimAABBs + SegmentedTransformReduce
+//     KMorton      <- KCGenPrimCenters + KCGenMortonCode      (centroid recomputed, never stored)
+//     RadixSort    <- SegmentedIota + SegmentedRadixSort<true,u64,u32>
+//     KKarras      <- KCConstructLBVHInternalNodes
+//     KUnionBoxes  <- KCUnionLBVHBoundingBoxes
+//  Stage 2 (new): KCollapse + KFillTris turn the binary tree into the 8-wide quantised BVH.
+//
+// Floating point: every expression that feeds an integer artefact (Morton code) is written with
+// explicit round-to-nearest intrinsics so that nvcc cannot contract it into an FMA.
+#include "accel.cuh"
+#include <cfloat>
+#include <cstring>
+
+namespace mrb
+{
+namespace
+{
+
+constexpr int TPB = 256;
+
+__device__ __forceinline__ uint32_t EncodeOrdered(float f)
+{
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float DecodeOrdered(uint32_t u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+__device__ __forceinline__ uint32_t LeafToPrim(const PrimRanges& r, uint32_t leaf, uint32_t& rangeIdx)
+{
+    uint32_t k = 0;
+    #pragma unroll
+    for(uint32_t j = 1; j < 8; j++) if(j < r.count && leaf >= r.leafStart[j]) k = j;
+    rangeIdx = k;
+    return r.primBegin[k] + (leaf - r.leafStart[k]);
+}
+
+__device__ __forceinline__ void LoadTri(const float* __restrict__ pos, const uint32_t* __restrict__ idx,
+                                        uint32_t prim, float p[3][3])
+{
+    uint32_t i0 = idx[3 * size_t(prim) + 0], i1 = idx[3 * size_t(prim) + 1], i2 = idx[3 * size_t(prim) + 2];
+    #pragma unroll
+    for(int a = 0; a < 3; a++)
+    {
+        p[0][a] = pos[3 * size_t(i0) + a];
+        p[1][a] = pos[3 * size_t(i1) + a];
+        p[2][a] = pos[3 * size_t(i2) + a];
+    }
+}
+
+// Per-leaf AABB (Shape::Triangle::BoundingBox, Core/ShapeFunctions.h:L48-57) + accelerator AABB.
+__global__ void __launch_bounds__(TPB)
+KLeafAABB(AccelData a)
+{
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for(uint32_t leaf = blockIdx.x * TPB + threadIdx.x; leaf < a.leafCount; leaf += gridDim.x * TPB)
+    {
+        uint32_t ri; uint32_t prim = LeafToPrim(a.ranges, leaf, ri);
+        float p[3][3]; LoadTri(a.positions, a.indices, prim, p);
+        float lo[3], hi[3];
+        #pragma unroll
+        for(int k = 0; k < 3; k++)
+        {
+            float l = p[0][k], h = p[0][k];
+            l = (p[1][k] < l) ? p[1][k] : l; l = (p[2][k] < l) ? p[2][k] : l;
+            h = (h < p[1][k]) ? p[1][k] : h; h = (h < p[2][k]) ? p[2][k] : h;
+            lo[k] = l; hi[k] = h;
+            mn[k] = fminf(mn[k], l); mx[k] = fmaxf(mx[k], h);
+        }
+        float2* out = reinterpret_cast<float2*>(a.leafAABB + 6 * size_t(leaf));
+        out[0] = make_float2(lo[0], lo[1]); out[1] = make_float2(lo[2], hi[0]); out[2] = make_float2(hi[1], hi[2]);
+    }
+    #pragma unroll
+    for(int k = 0; k < 3; k++)
+    {
+        for(int o = 16; o > 0; o >>= 1)
+        {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+    }
+    if((threadIdx.x & 31) == 0)
+    {
+        #pragma unroll
+        for(int k = 0; k < 3; k++)
+        {
+            atomicMin(&a.accelAABBEnc[k], EncodeOrdered(mn[k]));
+            atomicMax(&a.accelAABBEnc[3 + k], EncodeOrdered(mx[k]));
+        }
+    }
+}
+
+// Interleave — Graphics::MortonCode::Compose3D<uint64_t> (Core/GraphicsFunctions.h:L606-625)
+__device__ __forceinline__ uint64_t Expand3D(uint32_t v)
+{
+    uint64_t x = v;
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x001f00000000ffffull;
+    x = (x | x << 16) & 0x001f0000ff0000ffull;
+    x = (x | x << 8)  & 0x100f00f00f00f00full;
+    x = (x | x << 4)  & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2)  & 0x1249249249249249ull;
+    return x;
+}
+
+// KCGenMortonCode (AcceleratorLBVH.cu:L96-168) on the centroid of Triangle::GetCenter
+// (PrimitiveDefaultTriangle.hpp:L109-115). Also seeds the identity permutation (SegmentedIota).
+__global__ void __launch_bounds__(TPB)
+KMorton(AccelData a)
+{
+    float bl[3], sz[3];
+    #pragma unroll
+    for(int k = 0; k < 3; k++)
+    {
+        bl[k] = DecodeOrdered(a.accelAABBEnc[k]);
+        sz[k] = __fsub_rn(DecodeOrdered(a.accelAABBEnc[3 + k]), bl[k]);
+    }
+    float maxSide = fmaxf(sz[0], fmaxf(sz[1], sz[2]));
+    const double deltaRecip = __ddiv_rn(2097152.0, double(maxSide));
+    const uint32_t lastValue = (1u << 21) - 1u;
+    const float third = 0.333333333f;
+    for(uint32_t leaf = blockIdx.x * TPB + threadIdx.x; leaf < a.leafCount; leaf += gridDim.x * TPB)
+    {
+        uint32_t ri; uint32_t prim = LeafToPrim(a.ranges, leaf, ri);
+        float p[3][3]; LoadTri(a.positions, a.indices, prim, p);
+        uint32_t q[3];
+        #pragma unroll
+        for(int k = 0; k < 3; k++)
+        {
+            float c = __fmul_rn(p[0][k], third);
+            c = __fadd_rn(c, __fmul_rn(p[1][k], third));
+            c = __fadd_rn(c, __fmul_rn(p[2][k], third));
+            float diff = __fsub_rn(c, bl[k]);
+            diff = (diff < 0.0f) ? 0.0f : diff;
+            float scaled = __double2float_rn(__dmul_rn(double(diff), deltaRecip));
+            int32_t r = int32_t(lroundf(scaled));
+            uint32_t u = uint32_t(r);
+            q[k] = (u > lastValue) ? lastValue : u;
+        }
+        uint64_t code = Expand3D(q[0]) | (Expand3D(q[1]) << 1) | (Expand3D(q[2]) << 2);
+        a.morton[leaf] = code;
+        a.sortedMorton[leaf] = code;
+        a.sortedLeaf[leaf] = leaf;
+    }
+}
+
+// Delta (AcceleratorLBVH.cu:L69-94); robust != 0 adds the +64 of Karras' augmented key.
+__device__ __forceinline__ int32_t Delta(const uint64_t* __restrict__ codes, int32_t n, int32_t i, uint64_t ci,
+                                         int32_t j, int robust)
+{
+    if(j < 0 || j >= n) return -1;
+    uint64_t cj = codes[j];
+    uint64_t l = ci, r = cj;
+    int32_t off = 0;
+    if(l == r) { l = uint64_t(i); r = uint64_t(j); off = robust ? 64 : 0; }
+    return __clzll(l ^ r) + off;
+}
+
+// KCConstructLBVHInternalNodes (AcceleratorLBVH.cu:L170-299), one accelerator. Additionally
+// records the sorted range each node covers (used by the wide collapse) and whether any two
+// neighbouring codes are equal.
+__global__ void __launch_bounds__(TPB)
+KKarras(AccelData a, int robust, uint32_t* dupFlag)
+{
+    const int32_t totalLeafs = int32_t(a.leafCount);
+    const uint64_t* __restrict__ codes = a.sortedMorton;
+    if(totalLeafs == 1)
+    {
+        if(blockIdx.x == 0 && threadIdx.x == 0)
+        {
+            a.nodes[0] = LBVHNode{LEAF_FLAG | 0u, INVALID_U32, INVALID_U32};
+            a.nodeRange[0] = make_uint2(0, 0);
+        }
+        return;
+    }
+    const int32_t totalNodes = totalLeafs - 1;
+    for(int32_t i = blockIdx.x * TPB + threadIdx.x; i < totalNodes; i += gridDim.x * TPB)
+    {
+        uint64_t ci = codes[i];
+        if(ci == codes[i + 1]) *dupFlag = 1u;
+        int32_t diff = Delta(codes, totalLeafs, i, ci, i + 1, robust) - Delta(codes, totalLeafs, i, ci, i - 1, robust);
+        int32_t d = (diff < 0) ? -1 : 1;
+        int32_t deltaMin = Delta(codes, totalLeafs, i, ci, i - d, robust);
+        int32_t lMax = 2;
+        while(Delta(codes, totalLeafs, i, ci, i + lMax * d, robust) > deltaMin) lMax <<= 1;
+        int32_t l = 0;
+        for(int32_t t = lMax >> 1; t != 0; t >>= 1)
+            if(Delta(codes, totalLeafs, i, ci, i + (l + t) * d, robust) > deltaMin) l += t;
+        int32_t j = i + l * d;
+        int32_t s = 0;
+        int32_t deltaNode = Delta(codes, totalLeafs, i, ci, j, robust);
+        for(int32_t t = (l + 1) / 2; t != 0; t = (t == 1) ? 0 : (t + 1) / 2)
+            if(Delta(codes, totalLeafs, i, ci, i + (s + t) * d, robust) > deltaNode) s += t;
+        int32_t gamma = i + s * d + min(d, 0);
+        int32_t lo = min(i, j), hi = max(i, j);
+        uint32_t left, right;
+        if(lo == gamma)
+        {
+            uint32_t leaf = a.sortedLeaf[gamma];
+            left = LEAF_FLAG | leaf; a.leafParent[leaf] = uint32_t(i);
+        }
+        else { left = uint32_t(gamma); a.nodes[gamma].parent = uint32_t(i); }
+        if(hi == gamma + 1)
+        {
+            uint32_t leaf = a.sortedLeaf[gamma + 1];
+            right = LEAF_FLAG | leaf; a.leafParent[leaf] = uint32_t(i);
+        }
+        else { right = uint32_t(gamma + 1); a.nodes[gamma + 1].parent = uint32_t(i); }
+        a.nodes[i].left = left;
+        a.nodes[i].right = right;
+        if(i == 0) a.nodes[i].parent = INVALID_U32;
+        a.nodeRange[i] = make_uint2(uint32_t(lo), uint32_t(hi));
+    }
+}
+
+// KCUnionLBVHBoundingBoxes (AcceleratorLBVH.cu:L301-435): the second arriver at a node unions
+// its children's boxes. Boxes cross threads through L2 (st.cg / ld.cg) with fences around the
+// counter atomic.
+__global__ void __launch_bounds__(TPB)
+KUnionBoxes(AccelData a, uint32_t* counters)
+{
+    const uint32_t totalLeafs = a.leafCount;
+    if(totalLeafs == 1)
+    {
+        if(blockIdx.x == 0 && threadIdx.x == 0)
+            for(int k = 0; k < 3; k++) { a.boxes[0].min[k] = a.leafAABB[k]; a.boxes[0].max[k] = a.leafAABB[3 + k]; }
+        return;
+    }
+    for(uint32_t i = blockIdx.x * TPB + threadIdx.x; i < totalLeafs; i += gridDim.x * TPB)
+    {
+        uint32_t ni = a.leafParent[i];
+        while(ni != INVALID_U32)
+        {
+            uint32_t prev = atomicAdd(&counters[ni], 1u);
+            if(prev != 1u) break;
+            __threadfence();
+            LBVHNode nd = a.nodes[ni];
+            float l[6], r[6];
+            const float* lp = (nd.left & LEAF_FLAG) ? a.leafAABB + 6 * size_t(nd.left & ~LEAF_FLAG)
+                                                    : reinterpret_cast<const float*>(a.boxes + nd.left);
+            const float* rp = (nd.right & LEAF_FLAG) ? a.leafAABB + 6 * size_t(nd.right & ~LEAF_FLAG)
+                                                     : reinterpret_cast<const float*>(a.boxes + nd.right);
+            #pragma unroll
+            for(int k = 0; k < 6; k++) { l[k] = __ldcg(lp + k); r[k] = __ldcg(rp + k); }
+            float* bp = reinterpret_cast<float*>(a.boxes + ni);
+            #pragma unroll
+            for(int k = 0; k < 3; k++)
+            {
+                __stcg(bp + k, (r[k] < l[k]) ? r[k] : l[k]);                     // Math::Min(l, r)
+                __stcg(bp + 3 + k, (l[3 + k] < r[3 + k]) ? r[3 + k] : l[3 + k]); // Math::Max(l, r)
+            }
+            __threadfence();
+            ni = nd.parent;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Wide collapse
+// ------------------------------------------------------------------------------------------------
+struct CollapseState
+{
+    uint32_t head;     // next ticket
+    uint32_t created;  // wide nodes allocated so far (root = 1)
+    uint32_t done;     // wide nodes finished
+    uint32_t triCount; // triangle records allocated
+    uint32_t maxDepth;
+    uint32_t error;
+};
+
+struct ChildRef { uint32_t lo, hi, node; float area; };
+
+__device__ __forceinline__ float HalfArea(const float* b)
+{
+    float dx = b[3] - b[0], dy = b[4] - b[1], dz = b[5] - b[2];
+    return dx * dy + dy * dz + dz * dx;
+}
+
+__device__ __forceinline__ ChildRef MakeRef(const AccelData& a, uint32_t child, uint32_t leafPos)
+{
+    ChildRef r;
+    if(child & LEAF_FLAG) { r.lo = r.hi = leafPos; r.node = INVALID_U32; r.area = -1.0f; }
+    else
+    {
+        uint2 rg = a.nodeRange[child];
+        r.lo = rg.x; r.hi = rg.y; r.node = child;
+        r.area = HalfArea(reinterpret_cast<const float*>(a.boxes + child));
+    }
+    return r;
+}
+
+__device__ void CollapseNode(const AccelData& a, CollapseState* st, unsigned long long* queue,
+                             uint32_t* triRank, uint32_t wideIdx, uint32_t binNode, uint32_t depth)
+{
+    constexpr uint32_t MAX_LEAF = 3;
+    ChildRef refs[8];
+    uint32_t n = 0;
+    if(a.leafCount == 1) { refs[0] = ChildRef{0, 0, INVALID_U32, -1.0f}; n = 1; }
+    else
+    {
+        LBVHNode nd = a.nodes[binNode];
+        uint2 rg = a.nodeRange[binNode];
+        refs[0] = MakeRef(a, nd.left, rg.x);
+        refs[1] = MakeRef(a, nd.right, rg.y);
+        n = 2;
+        while(n < 8)
+        {
+            int best = -1; float bestArea = -1.0f;
+            for(uint32_t c = 0; c < n; c++)
+                if(refs[c].node != INVALID_U32 && refs[c].area > bestArea) { bestArea = refs[c].area; best = int(c); }
+            if(best < 0) break;
+            ChildRef o = refs[best];
+            LBVHNode on = a.nodes[o.node];
+            refs[best] = MakeRef(a, on.left, o.lo);
+            refs[n++] = MakeRef(a, on.right, o.hi);
+        }
+    }
+    // child boxes, node bounds
+    float cb[8][6];
+    float nb[6] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+    bool isInner[8];
+    uint32_t numInner = 0, numTris = 0;
+    for(uint32_t c = 0; c < n; c++)
+    {
+        const float* src = (refs[c].node != INVALID_U32)
+                         ? reinterpret_cast<const float*>(a.boxes + refs[c].node)
+                         : a.leafAABB + 6 * size_t(a.sortedLeaf[refs[c].lo]);
+        for(int k = 0; k < 6; k++) cb[c][k] = src[k];
+        for(int k = 0; k < 3; k++) { nb[k] = fminf(nb[k], cb[c][k]); nb[3 + k] = fmaxf(nb[3 + k], cb[c][3 + k]); }
+        uint32_t size = refs[c].hi - refs[c].lo + 1;
+        isInner[c] = size > MAX_LEAF;
+        if(isInner[c]) numInner++; else numTris += size;
+    }
+    // slot assignment: greedy on cost[c][s] = dot(centroid_c - centre, dir_s), dir_s component is
+    // -1 where the slot bit is set (bit2 = x, bit1 = y, bit0 = z). A ray whose negative-direction
+    // octant is r visits slot s with priority (s ^ r): slot r^7 first (nearest), slot r last.
+    int slotOf[8]; bool slotUsed[8];
+    for(int s = 0; s < 8; s++) slotUsed[s] = false;
+    for(uint32_t c = 0; c < n; c++) slotOf[c] = -1;
+    float cen[3] = {0.5f * (nb[0] + nb[3]), 0.5f * (nb[1] + nb[4]), 0.5f * (nb[2] + nb[5])};
+    for(uint32_t it = 0; it < numInner; it++)
+    {
+        float bestCost = -FLT_MAX; int bc = -1, bs = -1;
+        for(uint32_t c = 0; c < n; c++)
+        {
+            if(!isInner[c] || slotOf[c] >= 0) continue;
+            float dx = 0.5f * (cb[c][0] + cb[c][3]) - cen[0];
+            float dy = 0.5f * (cb[c][1] + cb[c][4]) - cen[1];
+            float dz = 0.5f * (cb[c][2] + cb[c][5]) - cen[2];
+            for(int s = 0; s < 8; s++)
+            {
+                if(slotUsed[s]) continue;
+                float cost = ((s & 4) ? -dx : dx) + ((s & 2) ? -dy : dy) + ((s & 1) ? -dz : dz);
+                if(cost > bestCost) { bestCost = cost; bc = int(c); bs = s; }
+            }
+        }
+        slotOf[bc] = bs; slotUsed[bs] = true;
+    }
+    for(uint32_t c = 0; c < n; c++)
+    {
+        if(slotOf[c] >= 0) continue;
+        for(int s = 0; s < 8; s++) if(!slotUsed[s]) { slotOf[c] = s; slotUsed[s] = true; break; }
+    }
+    // allocation
+    uint32_t childBase = numInner ? atomicAdd(&st->created, numInner) : 0u;
+    uint32_t triBase = numTris ? atomicAdd(&st->triCount, numTris) : 0u;
+    if(numInner && childBase + numInner > a.wideNodeCapacity) { st->error = 2u; return; }
+    // quantisation frame
+    int ex[3]; double scale[3];
+    for(int k = 0; k < 3; k++)
+    {
+        float ext = nb[3 + k] - nb[k];
+        int e = -126;
+        if(ext > 0.0f)
+        {
+            int fe; float m = frexpf(ext / 255.0f, &fe);
+            e = (m == 0.5f) ? fe - 1 : fe;
+            while(ldexp(255.0, e) < double(nb[3 + k]) - double(nb[k])) e++;
+            e = max(-126, min(127, e));
+        }
+        ex[k] = e; scale[k] = ldexp(1.0, e);
+    }
+    uint32_t qlo[3][2] = {{0, 0}, {0, 0}, {0, 0}}, qhi[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    uint32_t meta[2] = {0, 0};
+    uint32_t imask = 0;
+    // empty slots get an inverted box
+    for(int k = 0; k < 3; k++) { qlo[k][0] = qlo[k][1] = 0xFFFFFFFFu; }
+    uint32_t triOff = 0;
+    for(int s = 0; s < 8; s++)
+    {
+        int c = -1;
+        for(uint32_t cc = 0; cc < n; cc++) if(slotOf[cc] == s) c = int(cc);
+        if(c < 0) continue;
+        for(int k = 0; k < 3; k++)
+        {
+            double p = double(nb[k]);
+            double lo = double(cb[c][k]), hi = double(cb[c][3 + k]);
+            int ql = int(floor((lo - p) / scale[k]));
+            ql = max(0, min(255, ql));
+            while(ql > 0 && p + ql * scale[k] > lo) ql--;
+            int qh = int(ceil((hi - p) / scale[k]));
+            qh = max(0, min(255, qh));
+            while(qh < 255 && p + qh * scale[k] < hi) qh++;
+            uint32_t sh = 8u * uint32_t(s & 3);
+            qlo[k][s >> 2] = (qlo[k][s >> 2] & ~(0xFFu << sh)) | (uint32_t(ql) << sh);
+            qhi[k][s >> 2] = (qhi[k][s >> 2] & ~(0xFFu << sh)) | (uint32_t(qh) << sh);
+        }
+        uint32_t m;
+        if(isInner[c]) { m = 0x20u | (24u + uint32_t(s)); imask |= 1u << s; }
+        else
+        {
+            uint32_t size = refs[c].hi - refs[c].lo + 1;
+            m = (((1u << size) - 1u) << 5) | triOff;
+            for(uint32_t j = 0; j < size; j++) triRank[triBase + triOff + j] = refs[c].lo + j;
+            triOff += size;
+        }
+        meta[s >> 2] |= m << (8u * uint32_t(s & 3));
+    }
+    WideNode w;
+    w.q[0] = make_uint4(__float_as_uint(nb[0]), __float_as_uint(nb[1]), __float_as_uint(nb[2]),
+                        uint32_t(ex[0] + 127) | (uint32_t(ex[1] + 127) << 8) | (uint32_t(ex[2] + 127) << 16) | (imask << 24));
+    w.q[1] = make_uint4(childBase, triBase, meta[0], meta[1]);
+    w.q[2] = make_uint4(qlo[0][0], qlo[0][1], qlo[1][0], qlo[1][1]);
+    w.q[3] = make_uint4(qlo[2][0], qlo[2][1], qhi[0][0], qhi[0][1]);
+    w.q[4] = make_uint4(qhi[1][0], qhi[1][1], qhi[2][0], qhi[2][1]);
+    a.wideNodes[wideIdx] = w;
+    // enqueue internal children in slot order
+    uint32_t rel = 0;
+    for(int s = 0; s < 8; s++)
+    {
+        if(!((imask >> s) & 1u)) continue;
+        int c = -1;
+        for(uint32_t cc = 0; cc < n; cc++) if(slotOf[cc] == s) c = int(cc);
+        unsigned long long item = (unsigned long long)(refs[c].node) | ((unsigned long long)(depth + 1) << 32);
+        atomicExch(&queue[childBase + rel], item);
+        rel++;
+    }
+    atomicMax(&st->maxDepth, depth);
+}
+
+// Persistent ticket queue: ticket k is wide node k; its work item is written by the thread that
+// processed its parent (always a smaller ticket, i.e. an already running thread).
+__global__ void __launch_bounds__(64)
+KCollapse(AccelData a, CollapseState* st, unsigned long long* queue, uint32_t* triRank)
+{
+    constexpr unsigned long long EMPTY = ~0ull;
+    while(true)
+    {
+        uint32_t k = atomicAdd(&st->head, 1u);
+        unsigned long long item = EMPTY;
+        uint32_t spins = 0;
+        while(true)
+        {
+            if(k < a.wideNodeCapacity)
+            {
+                item = *reinterpret_cast<volatile unsigned long long*>(queue + k);
+                if(item != EMPTY) break;
+            }
+            uint32_t done = atomicAdd(&st->done, 0u);
+            __threadfence();
+            uint32_t created = atomicAdd(&st->created, 0u);
+            if(done == created && k >= created) return;
+            if(*reinterpret_cast<volatile uint32_t*>(&st->error)) return;
+            if(++spins > (1u << 24)) { st->error = 1u; return; }
+            __nanosleep(64);
+        }
+        CollapseNode(a, st, queue, triRank, k, uint32_t(item & 0xFFFFFFFFull), uint32_t(item >> 32));
+        __threadfence();
+        atomicAdd(&st->done, 1u);
+    }
+}
+
+// One thread per triangle record.
+__global__ void __launch_bounds__(TPB)
+KFillTris(AccelData a, const uint32_t* __restrict__ triRank)
+{
+    for(uint32_t s = blockIdx.x * TPB + threadIdx.x; s < a.leafCount; s += gridDim.x * TPB)
+    {
+        uint32_t rank = triRank[s];
+        uint32_t leaf = a.sortedLeaf[rank];
+        uint32_t ri; uint32_t prim = LeafToPrim(a.ranges, leaf, ri);
+        float p[3][3]; LoadTri(a.positions, a.indices, prim, p);
+        TriRecord t;
+        t.v0 = make_float4(p[0][0], p[0][1], p[0][2], __uint_as_float(leaf));
+        t.v1 = make_float4(__fsub_rn(p[1][0], p[0][0]), __fsub_rn(p[1][1], p[0][1]), __fsub_rn(p[1][2], p[0][2]),
+                           __uint_as_float(rank));
+        t.v2 = make_float4(__fsub_rn(p[2][0], p[0][0]), __fsub_rn(p[2][1], p[0][1]), __fsub_rn(p[2][2], p[0][2]),
+                           __uint_as_float((a.ranges.cull[ri] ? 1u : 0u) | (ri << 8)));
+        a.tris[s] = t;
+    }
+}
+
+} // namespace
+
+// Sizes the persistent block of one accelerator (sub-arrays are 256-byte aligned).
+static void LayoutAccel(MultiAlloc& ma, AccelData& d, uint32_t vertexCount, uint32_t triCount, bool ownInputs, bool wide)
+{
+    if(ownInputs)
+    {
+        d.positions = ma.Take<float>(size_t(vertexCount) * 3);
+        d.indices = ma.Take<uint32_t>(size_t(triCount) * 3);
+    }
+    d.leafAABB = ma.Take<float>(size_t(d.leafCount) * 6);
+    d.morton = ma.Take<uint64_t>(d.leafCount);
+    d.sortedMorton = ma.Take<uint64_t>(d.leafCount);
+    d.sortedLeaf = ma.Take<uint32_t>(d.leafCount);
+    d.nodes = ma.Take<LBVHNode>(d.nodeCount);
+    d.leafParent = ma.Take<uint32_t>(d.leafCount);
+    d.boxes = ma.Take<LBVHBox>(d.nodeCount);
+    d.nodeRange = ma.Take<uint2>(d.nodeCount);
+    d.accelAABBEnc = ma.Take<uint32_t>(8);
+    if(wide)
+    {
+        d.wideNodeCapacity = d.leafCount / 3 + 2;
+        d.wideNodes = ma.Take<WideNode>(d.wideNodeCapacity);
+        d.tris = ma.Take<TriRecord>(d.leafCount);
+    }
+}
+
+void BuildAccel(Context& ctx, mrb_accel_t& acc, const mrb_accel_desc& desc)
+{
+    AccelData& d = acc.d;
+    const bool wide = !(desc.flags & (MRB_BUILD_BINARY_ONLY | MRB_BUILD_REFERENCE_DELTA));
+    const int robust = (desc.flags & MRB_BUILD_REFERENCE_DELTA) ? 0 : 1;
+    // ranges
+    PrimRanges& r = d.ranges;
+    r = PrimRanges{};
+    r.primGroupId = desc.primGroupId;
+    if(desc.rangeCount == 0 || desc.primRanges == nullptr)
+    {
+        r.count = 1; r.leafStart[0] = 0; r.leafStart[1] = desc.triangleCount; r.primBegin[0] = 0;
+    }
+    else
+    {
+        r.count = desc.rangeCount;
+        for(uint32_t i = 0; i < r.count; i++)
+        {
+            r.primBegin[i] = desc.primRanges[2 * i];
+            r.leafStart[i + 1] = r.leafStart[i] + (desc.primRanges[2 * i + 1] - desc.primRanges[2 * i]);
+        }
+    }
+    for(uint32_t i = 0; i < r.count; i++)
+    {
+        r.lmKey[i] = desc.lightOrMatKeys ? desc.lightOrMatKeys[i] : 0u;
+        r.cull[i] = (desc.cullBackface && desc.cullBackface[i]) ? 1u : 0u;
+    }
+    d.leafCount = r.leafStart[r.count];
+    d.nodeCount = d.leafCount > 1 ? d.leafCount - 1 : 1;
+
+    MultiAlloc sizing(nullptr);
+    LayoutAccel(sizing, d, desc.vertexCount, desc.triangleCount, true, wide);
+    acc.mem.Reserve(sizing.Total());
+    MultiAlloc ma(acc.mem.Base());
+    LayoutAccel(ma, d, desc.vertexCount, desc.triangleCount, true, wide);
+    ctx.persistentBytes += acc.mem.Capacity();
+
+    cudaMemcpyKind kind = (desc.memspace == MRB_MEM_HOST) ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<float*>(d.positions), desc.positions,
+                                 sizeof(float) * 3 * size_t(desc.vertexCount), kind, ctx.stream));
+    MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<uint32_t*>(d.indices), desc.indices,
+                                 sizeof(uint32_t) * 3 * size_t(desc.triangleCount), kind, ctx.stream));
+
+    // scratch: sort temp | union counters | collapse state | queue | triRank
+    size_t sortBytes = RadixSortTempBytes(d.leafCount, 8);
+    MultiAlloc ssz(nullptr);
+    ssz.Take<char>(sortBytes); ssz.Take<uint32_t>(d.nodeCount + 8); ssz.Take<CollapseState>(1);
+    ssz.Take<unsigned long long>(d.wideNodeCapacity + 1); ssz.Take<uint32_t>(d.leafCount);
+    ctx.scratch.Reserve(ssz.Total());
+    MultiAlloc sm(ctx.scratch.Base());
+    void* sortTemp = sm.Take<char>(sortBytes);
+    uint32_t* counters = sm.Take<uint32_t>(d.nodeCount + 8);
+    CollapseState* cst = sm.Take<CollapseState>(1);
+    unsigned long long* queue = sm.Take<unsigned long long>(d.wideNodeCapacity + 1);
+    uint32_t* triRank = sm.Take<uint32_t>(d.leafCount);
+    uint32_t* dupFlag = counters + d.nodeCount;
+
+    MRB_CUDA_TRY(cudaEventRecord(ctx.ev0, ctx.stream));
+    const uint32_t initEnc[8] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u, 0u};
+    MRB_CUDA_TRY(cudaMemcpyAsync(d.accelAABBEnc, initEnc, sizeof(initEnc), cudaMemcpyHostToDevice, ctx.stream));
+    MRB_CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * (d.nodeCount + 8), ctx.stream));
+
+    const uint32_t grid = GridFor(ctx, d.leafCount, TPB, 8);
+    MRB_LAUNCH(ctx, KLeafAABB, grid, TPB, 0, d);
+    MRB_LAUNCH(ctx, KMorton, grid, TPB, 0, d);
+    RadixSortPairs(ctx, d.sortedMorton, d.sortedLeaf, d.leafCount, 0, 64, sortTemp);
+    MRB_LAUNCH(ctx, KKarras, grid, TPB, 0, d, robust, dupFlag);
+    MRB_LAUNCH(ctx, KUnionBoxes, grid, TPB, 0, d, counters);
+    if(wide)
+    {
+        CollapseState init = {0u, 1u, 0u, 0u, 0u, 0u};
+        MRB_CUDA_TRY(cudaMemcpyAsync(cst, &init, sizeof(init), cudaMemcpyHostToDevice, ctx.stream));
+        MRB_CUDA_TRY(cudaMemsetAsync(queue, 0xFF, sizeof(unsigned long long) * (d.wideNodeCapacity + 1), ctx.stream));
+        unsigned long long rootItem = 0ull; // binary node 0, depth 0
+        MRB_CUDA_TRY(cudaMemcpyAsync(queue, &rootItem, sizeof(rootItem), cudaMemcpyHostToDevice, ctx.stream));
+        uint32_t cgrid = min(uint32_t(ctx.smCount) * 8u, max(1u, DivUp(d.wideNodeCapacity, 64u)));
+        MRB_LAUNCH(ctx, KCollapse, cgrid, 64, 0, d, cst, queue, triRank);
+        MRB_LAUNCH(ctx, KFillTris, grid, TPB, 0, d, triRank);
+    }
+    MRB_CUDA_TRY(cudaEventRecord(ctx.ev1, ctx.stream));
+
+    // results the host needs
+    uint32_t enc[8]; CollapseState hst = {};
+    MRB_CUDA_TRY(cudaMemcpyAsync(enc, d.accelAABBEnc, sizeof(uint32_t) * 6, cudaMemcpyDeviceToHost, ctx.stream));
+    uint32_t hDup = 0;
+    MRB_CUDA_TRY(cudaMemcpyAsync(&hDup, dupFlag, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx.stream));
+    if(wide) MRB_CUDA_TRY(cudaMemcpyAsync(&hst, cst, sizeof(hst), cudaMemcpyDeviceToHost, ctx.stream));
+    MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
+    float ms = 0.f; MRB_CUDA_TRY(cudaEventElapsedTime(&ms, ctx.ev0, ctx.ev1));
+
+    acc.info.leafCount = d.leafCount;
+    acc.info.nodeCount = d.nodeCount;
+    acc.info.duplicateCodes = hDup;
+    acc.info.buildMs = ms;
+    acc.info.deviceBytes = acc.mem.Capacity();
+    for(int k = 0; k < 6; k++)
+    {
+        uint32_t u = enc[k];
+        uint32_t b = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+        float f; memcpy(&f, &b, 4); acc.info.aabb[k] = f;
+    }
+    if(wide)
+    {
+        if(hst.error || hst.triCount != d.leafCount)
+            throw CudaError{cudaErrorUnknown, "wide collapse failed (queue stall / capacity)", int(hst.error)};
+        d.wideNodeCount = hst.created;
+        d.wideDepth = hst.maxDepth + 1;
+        acc.info.wideNodeCount = hst.created;
+    }
+}
+
+} // namespace mrb

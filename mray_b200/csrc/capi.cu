@@ -1,0 +1,309 @@
+// capi.cu — the C-ABI of include/mray_b200.h. Thin: argument checks, host<->device staging for the
+// MRB_MEM_HOST variants, exception -> status translation. No CPU fallback anywhere.
+#include "accel.cuh"
+#include <cstring>
+#include <cstdio>
+#include <new>
+
+namespace mrb
+{
+void BuildAccel(Context& ctx, mrb_accel_t& acc, const mrb_accel_desc& desc);
+void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode mode,
+               mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, uint32_t* visibleBits,
+               mrb_ray_gmem* rays, const uint32_t* rayIndices, uint32_t rayCount);
+}
+
+struct mrb_context_t { mrb::Context c; };
+
+static thread_local std::string gCreateError;
+
+template<class F>
+static mrb_status Guard(mrb_context ctx, F&& f)
+{
+    if(!ctx) return MRB_ERR_INVALID_ARG;
+    try
+    {
+        cudaError_t e = cudaSetDevice(ctx->c.device);
+        if(e != cudaSuccess) throw mrb::CudaError{e, __FILE__, __LINE__};
+        return f(ctx->c);
+    }
+    catch(const mrb::CudaError& e)
+    {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d", int(e.code), cudaGetErrorString(e.code), e.file, e.line);
+        ctx->c.error = buf;
+        cudaGetLastError();
+        return (e.code == cudaErrorMemoryAllocation) ? MRB_ERR_OUT_OF_MEMORY : MRB_ERR_CUDA;
+    }
+    catch(const std::bad_alloc&) { ctx->c.error = "host allocation failed"; return MRB_ERR_OUT_OF_MEMORY; }
+}
+
+static mrb_status Fail(mrb::Context& c, mrb_status s, const char* msg) { c.error = msg; return s; }
+
+extern "C"
+{
+
+uint32_t mrb_abi_version(void) { return (0u << 16) | 1u; }
+
+mrb_status mrb_context_create(int device, mrb_context* out)
+{
+    if(!out) return MRB_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if(e != cudaSuccess || count == 0)
+    {
+        gCreateError = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return MRB_ERR_NO_DEVICE; // the product path refuses to run without a GPU
+    }
+    if(device < 0 || device >= count) { gCreateError = "device index out of range"; return MRB_ERR_INVALID_ARG; }
+    mrb_context ctx = new(std::nothrow) mrb_context_t();
+    if(!ctx) return MRB_ERR_OUT_OF_MEMORY;
+    ctx->c.device = device;
+    try
+    {
+        MRB_CUDA_TRY(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        MRB_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        ctx->c.smCount = prop.multiProcessorCount;
+        ctx->c.totalMem = prop.totalGlobalMem;
+        MRB_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->c.ownStream, cudaStreamNonBlocking));
+        ctx->c.stream = ctx->c.ownStream;
+        MRB_CUDA_TRY(cudaEventCreate(&ctx->c.ev0));
+        MRB_CUDA_TRY(cudaEventCreate(&ctx->c.ev1));
+    }
+    catch(const mrb::CudaError& err)
+    {
+        gCreateError = std::string("context creation failed: ") + cudaGetErrorString(err.code);
+        delete ctx;
+        return MRB_ERR_CUDA;
+    }
+    *out = ctx;
+    return MRB_OK;
+}
+
+void mrb_context_destroy(mrb_context ctx)
+{
+    if(!ctx) return;
+    cudaSetDevice(ctx->c.device);
+    cudaStreamSynchronize(ctx->c.stream);
+    ctx->c.scratch.Free();
+    if(ctx->c.ev0) cudaEventDestroy(ctx->c.ev0);
+    if(ctx->c.ev1) cudaEventDestroy(ctx->c.ev1);
+    if(ctx->c.ownStream) cudaStreamDestroy(ctx->c.ownStream);
+    delete ctx;
+}
+
+mrb_status mrb_context_set_stream(mrb_context ctx, void* cuda_stream)
+{
+    if(!ctx) return MRB_ERR_INVALID_ARG;
+    ctx->c.stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->c.ownStream;
+    return MRB_OK;
+}
+
+mrb_status mrb_context_synchronize(mrb_context ctx)
+{
+    return Guard(ctx, [&](mrb::Context& c) { MRB_CUDA_TRY(cudaStreamSynchronize(c.stream)); return MRB_OK; });
+}
+
+size_t mrb_context_used_device_memory(mrb_context ctx) { return ctx ? ctx->c.persistentBytes + ctx->c.scratch.Capacity() : 0; }
+size_t mrb_context_total_device_memory(mrb_context ctx) { return ctx ? ctx->c.totalMem : 0; }
+uint64_t mrb_context_launch_count(mrb_context ctx) { return ctx ? ctx->c.launches : 0; }
+const char* mrb_last_error(mrb_context ctx) { return ctx ? ctx->c.error.c_str() : gCreateError.c_str(); }
+
+mrb_status mrb_accel_build(mrb_context ctx, const mrb_accel_desc* desc, mrb_accel* out)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!desc || !out) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        *out = nullptr;
+        if(!desc->positions || !desc->indices || desc->triangleCount == 0 || desc->vertexCount == 0)
+            return Fail(c, MRB_ERR_INVALID_ARG, "empty primitive group");
+        if(desc->rangeCount > 8) return Fail(c, MRB_ERR_INVALID_ARG, "more than 8 prim ranges (MaxPrimBatchPerSurface)");
+        if(desc->primGroupId > 15) return Fail(c, MRB_ERR_INVALID_ARG, "primGroupId exceeds PrimitiveKey batch bits (4)");
+        uint64_t leafs = 0;
+        if(desc->rangeCount && desc->primRanges)
+        {
+            for(uint32_t i = 0; i < desc->rangeCount; i++)
+            {
+                uint32_t b = desc->primRanges[2 * i], e = desc->primRanges[2 * i + 1];
+                if(e <= b || e > desc->triangleCount) return Fail(c, MRB_ERR_INVALID_ARG, "bad prim range");
+                leafs += e - b;
+            }
+        }
+        else leafs = desc->triangleCount;
+        if(leafs >= (1ull << 28)) return Fail(c, MRB_ERR_INVALID_ARG, "leaf count exceeds PrimitiveKey index bits (28)");
+        mrb_accel acc = new mrb_accel_t();
+        acc->flags = desc->flags;
+        try { mrb::BuildAccel(c, *acc, *desc); }
+        catch(...) { c.persistentBytes -= acc->mem.Capacity(); delete acc; throw; }
+        if(acc->d.wideDepth > 63)
+        {
+            c.persistentBytes -= acc->mem.Capacity(); delete acc;
+            return Fail(c, MRB_ERR_UNSUPPORTED, "wide BVH deeper than the traversal stack (63)");
+        }
+        *out = acc;
+        return MRB_OK;
+    });
+}
+
+void mrb_accel_destroy(mrb_context ctx, mrb_accel accel)
+{
+    if(!ctx || !accel) return;
+    cudaSetDevice(ctx->c.device);
+    cudaStreamSynchronize(ctx->c.stream);
+    ctx->c.persistentBytes -= accel->mem.Capacity();
+    delete accel;
+}
+
+mrb_status mrb_accel_get_info(mrb_context ctx, mrb_accel accel, mrb_accel_info* info)
+{
+    if(!ctx || !accel || !info) return MRB_ERR_INVALID_ARG;
+    *info = accel->info;
+    return MRB_OK;
+}
+
+mrb_status mrb_accel_export_lbvh(mrb_context ctx, mrb_accel accel,
+                                 uint64_t* morton, uint64_t* sortedMorton, uint32_t* sortedLeaf,
+                                 uint32_t* nodes, uint32_t* leafParent, float* nodeBoxes, float* leafAABBs)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!accel) return Fail(c, MRB_ERR_INVALID_ARG, "null accelerator");
+        const mrb::AccelData& d = accel->d;
+        auto D2H = [&](void* dst, const void* src, size_t bytes)
+        {
+            if(dst) MRB_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c.stream));
+        };
+        D2H(morton, d.morton, sizeof(uint64_t) * d.leafCount);
+        D2H(sortedMorton, d.sortedMorton, sizeof(uint64_t) * d.leafCount);
+        D2H(sortedLeaf, d.sortedLeaf, sizeof(uint32_t) * d.leafCount);
+        D2H(nodes, d.nodes, sizeof(mrb::LBVHNode) * d.nodeCount);
+        D2H(leafParent, d.leafParent, sizeof(uint32_t) * d.leafCount);
+        D2H(nodeBoxes, d.boxes, sizeof(mrb::LBVHBox) * d.nodeCount);
+        D2H(leafAABBs, d.leafAABB, sizeof(float) * 6 * d.leafCount);
+        MRB_CUDA_TRY(cudaStreamSynchronize(c.stream));
+        return MRB_OK;
+    });
+}
+
+} // extern "C"
+
+static mrb_status CastCommon(mrb_context ctx, mrb_accel accel, bool anyHit,
+                             mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, uint32_t* visibleBits,
+                             mrb_ray_gmem* rays, const uint32_t* rayIndices,
+                             uint32_t rayCount, uint32_t totalRayCount,
+                             mrb_memspace memspace, mrb_trace_mode mode)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!accel || !rays) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        if(anyHit ? !visibleBits : (!hitKeys || !metaHits)) return Fail(c, MRB_ERR_INVALID_ARG, "null output");
+        if(totalRayCount < rayCount && !rayIndices) return Fail(c, MRB_ERR_INVALID_ARG, "totalRayCount < rayCount");
+        if(mode == MRB_TRACE_WIDE && !accel->d.wideNodes) return Fail(c, MRB_ERR_UNSUPPORTED, "accelerator was built BINARY_ONLY");
+        if(rayCount == 0) return MRB_OK;
+        if(memspace == MRB_MEM_DEVICE)
+        {
+            mrb::TraceRays(c, *accel, anyHit, mode, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount);
+            return MRB_OK;
+        }
+        // host variant: stage through scratch, copies inside the stream, synchronous on return
+        const size_t words = (size_t(totalRayCount) + 31) / 32;
+        mrb::MultiAlloc sz(nullptr);
+        sz.Take<mrb_ray_gmem>(totalRayCount); sz.Take<uint32_t>(rayIndices ? rayCount : 0);
+        if(anyHit) sz.Take<uint32_t>(words); else { sz.Take<mrb_hit_key_pack>(totalRayCount); sz.Take<mrb_meta_hit>(totalRayCount); }
+        c.scratch.Reserve(sz.Total());
+        mrb::MultiAlloc ma(c.scratch.Base());
+        mrb_ray_gmem* dRays = ma.Take<mrb_ray_gmem>(totalRayCount);
+        uint32_t* dIdx = ma.Take<uint32_t>(rayIndices ? rayCount : 0);
+        MRB_CUDA_TRY(cudaMemcpyAsync(dRays, rays, sizeof(mrb_ray_gmem) * totalRayCount, cudaMemcpyHostToDevice, c.stream));
+        if(rayIndices) MRB_CUDA_TRY(cudaMemcpyAsync(dIdx, rayIndices, sizeof(uint32_t) * rayCount, cudaMemcpyHostToDevice, c.stream));
+        if(anyHit)
+        {
+            uint32_t* dBits = ma.Take<uint32_t>(words);
+            MRB_CUDA_TRY(cudaMemcpyAsync(dBits, visibleBits, sizeof(uint32_t) * words, cudaMemcpyHostToDevice, c.stream));
+            mrb::TraceRays(c, *accel, true, mode, nullptr, nullptr, dBits, dRays, rayIndices ? dIdx : nullptr, rayCount);
+            MRB_CUDA_TRY(cudaMemcpyAsync(visibleBits, dBits, sizeof(uint32_t) * words, cudaMemcpyDeviceToHost, c.stream));
+        }
+        else
+        {
+            mrb_hit_key_pack* dKeys = ma.Take<mrb_hit_key_pack>(totalRayCount);
+            mrb_meta_hit* dHits = ma.Take<mrb_meta_hit>(totalRayCount);
+            MRB_CUDA_TRY(cudaMemcpyAsync(dKeys, hitKeys, sizeof(mrb_hit_key_pack) * totalRayCount, cudaMemcpyHostToDevice, c.stream));
+            MRB_CUDA_TRY(cudaMemcpyAsync(dHits, metaHits, sizeof(mrb_meta_hit) * totalRayCount, cudaMemcpyHostToDevice, c.stream));
+            mrb::TraceRays(c, *accel, false, mode, dKeys, dHits, nullptr, dRays, rayIndices ? dIdx : nullptr, rayCount);
+            MRB_CUDA_TRY(cudaMemcpyAsync(hitKeys, dKeys, sizeof(mrb_hit_key_pack) * totalRayCount, cudaMemcpyDeviceToHost, c.stream));
+            MRB_CUDA_TRY(cudaMemcpyAsync(metaHits, dHits, sizeof(mrb_meta_hit) * totalRayCount, cudaMemcpyDeviceToHost, c.stream));
+            MRB_CUDA_TRY(cudaMemcpyAsync(rays, dRays, sizeof(mrb_ray_gmem) * totalRayCount, cudaMemcpyDeviceToHost, c.stream));
+        }
+        MRB_CUDA_TRY(cudaStreamSynchronize(c.stream));
+        return MRB_OK;
+    });
+}
+
+extern "C"
+{
+
+mrb_status mrb_cast_rays(mrb_context ctx, mrb_accel accel, mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits,
+                         mrb_ray_gmem* rays, const uint32_t* rayIndices, uint32_t rayCount, uint32_t totalRayCount,
+                         mrb_memspace memspace, mrb_trace_mode mode)
+{
+    return CastCommon(ctx, accel, false, hitKeys, metaHits, nullptr, rays, rayIndices, rayCount, totalRayCount, memspace, mode);
+}
+
+mrb_status mrb_cast_visibility_rays(mrb_context ctx, mrb_accel accel, uint32_t* isVisibleBits,
+                                    const mrb_ray_gmem* rays, const uint32_t* rayIndices,
+                                    uint32_t rayCount, uint32_t totalRayCount,
+                                    mrb_memspace memspace, mrb_trace_mode mode)
+{
+    return CastCommon(ctx, accel, true, nullptr, nullptr, isVisibleBits, const_cast<mrb_ray_gmem*>(rays), rayIndices,
+                      rayCount, totalRayCount, memspace, mode);
+}
+
+} // extern "C"
+
+template<class K>
+static mrb_status SortCommon(mrb_context ctx, K* keys, uint32_t* values, uint32_t count,
+                             uint32_t bitBegin, uint32_t bitEnd, mrb_memspace memspace)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(bitEnd > sizeof(K) * 8 || bitBegin > bitEnd) return Fail(c, MRB_ERR_INVALID_ARG, "bad bit range");
+        if(count == 0) return MRB_OK;
+        if(!keys || !values) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        if(count >= (1u << 30)) return Fail(c, MRB_ERR_UNSUPPORTED, "count >= 2^30");
+        size_t tempBytes = mrb::RadixSortTempBytes(count, sizeof(K));
+        mrb::MultiAlloc sz(nullptr);
+        sz.Take<char>(tempBytes); sz.Take<K>(count); sz.Take<uint32_t>(count);
+        c.scratch.Reserve(sz.Total());
+        mrb::MultiAlloc ma(c.scratch.Base());
+        void* temp = ma.Take<char>(tempBytes);
+        if(memspace == MRB_MEM_DEVICE) { mrb::RadixSortPairs(c, keys, values, count, bitBegin, bitEnd, temp); return MRB_OK; }
+        K* dk = ma.Take<K>(count); uint32_t* dv = ma.Take<uint32_t>(count);
+        MRB_CUDA_TRY(cudaMemcpyAsync(dk, keys, sizeof(K) * count, cudaMemcpyHostToDevice, c.stream));
+        MRB_CUDA_TRY(cudaMemcpyAsync(dv, values, sizeof(uint32_t) * count, cudaMemcpyHostToDevice, c.stream));
+        mrb::RadixSortPairs(c, dk, dv, count, bitBegin, bitEnd, temp);
+        MRB_CUDA_TRY(cudaMemcpyAsync(keys, dk, sizeof(K) * count, cudaMemcpyDeviceToHost, c.stream));
+        MRB_CUDA_TRY(cudaMemcpyAsync(values, dv, sizeof(uint32_t) * count, cudaMemcpyDeviceToHost, c.stream));
+        MRB_CUDA_TRY(cudaStreamSynchronize(c.stream));
+        return MRB_OK;
+    });
+}
+
+extern "C"
+{
+
+mrb_status mrb_radix_sort_pairs_u64(mrb_context ctx, uint64_t* keys, uint32_t* values, uint32_t count,
+                                    uint32_t bitBegin, uint32_t bitEnd, mrb_memspace memspace)
+{
+    return SortCommon<uint64_t>(ctx, keys, values, count, bitBegin, bitEnd, memspace);
+}
+
+mrb_status mrb_radix_sort_pairs_u32(mrb_context ctx, uint32_t* keys, uint32_t* values, uint32_t count,
+                                    uint32_t bitBegin, uint32_t bitEnd, mrb_memspace memspace)
+{
+    return SortCommon<uint32_t>(ctx, keys, values, count, bitBegin, bitEnd, memspace);
+}
+
+} // extern "C"

@@ -1,0 +1,275 @@
+// sort.cu — stable LSD radix sort of (key,value) pairs, onesweep style (one histogram pass over
+// the keys for all digits, then ONE read + ONE write of the pairs per 8-bit digit with a
+// decoupled look-back chained scan across tiles).
+//
+// Replaces the reference's DeviceAlgorithms::RadixSort / SegmentedRadixSort wrappers over
+// cub::DeviceRadixSort (Device/CUDA/AlgRadixSortCUDA.h:L60-156; CPU restatement
+// Device/CPU/AlgRadixSortCPU.h:L21-92). Semantics: ascending, stable, arbitrary bit range —
+// hence a unique permutation, which is what the parity tests pin.
+//
+// HBM traffic per element for P digit passes: histogram read sizeof(K) + P * 2 * (sizeof(K) + 4).
+#include "common.cuh"
+
+namespace mrb
+{
+namespace
+{
+
+constexpr int      SORT_TPB = 256;
+constexpr int      SORT_WARPS = SORT_TPB / 32;
+constexpr int      RADIX = 256;
+constexpr uint32_t FLAG_AGG = 1u << 30;
+constexpr uint32_t FLAG_PREFIX = 2u << 30;
+constexpr uint32_t FLAG_MASK = 3u << 30;
+constexpr uint32_t COUNT_MASK = ~FLAG_MASK;
+constexpr int      MAX_PASSES = 8;
+
+template<class K> struct SortCfg;
+template<> struct SortCfg<uint32_t> { static constexpr int ITEMS = 16; };
+template<> struct SortCfg<uint64_t> { static constexpr int ITEMS = 12; };
+
+__device__ __forceinline__ uint32_t LaneMaskLt()
+{
+    uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m;
+}
+
+// One read of the keys builds the digit histograms of every pass.
+template<class K>
+__global__ void __launch_bounds__(SORT_TPB)
+KSortHistogram(const K* __restrict__ keys, uint32_t n, uint32_t bitBegin, uint32_t bitEnd,
+               uint32_t* __restrict__ gHist)
+{
+    __shared__ uint32_t sHist[MAX_PASSES * RADIX];
+    const uint32_t passes = (bitEnd - bitBegin + 7) / 8;
+    for(uint32_t j = threadIdx.x; j < passes * RADIX; j += SORT_TPB) sHist[j] = 0;
+    __syncthreads();
+    for(uint32_t i = blockIdx.x * SORT_TPB + threadIdx.x; i < n; i += gridDim.x * SORT_TPB)
+    {
+        K k = keys[i];
+        for(uint32_t p = 0; p < passes; p++)
+        {
+            uint32_t shift = bitBegin + 8 * p;
+            uint32_t bits = min(8u, bitEnd - shift);
+            uint32_t d = uint32_t(k >> shift) & ((1u << bits) - 1u);
+            // warp-aggregate equal digits (Morton high digits are often uniform across a warp)
+            uint32_t peers = __match_any_sync(__activemask(), d);
+            if((peers & LaneMaskLt()) == 0) atomicAdd(&sHist[p * RADIX + d], __popc(peers));
+        }
+    }
+    __syncthreads();
+    for(uint32_t j = threadIdx.x; j < passes * RADIX; j += SORT_TPB)
+        if(sHist[j]) atomicAdd(&gHist[j], sHist[j]);
+}
+
+// Exclusive scan of each pass' 256-bin histogram (one block per pass).
+__global__ void __launch_bounds__(RADIX) KSortScan(uint32_t* __restrict__ gHist)
+{
+    __shared__ uint32_t sWarp[RADIX / 32];
+    uint32_t* h = gHist + blockIdx.x * RADIX;
+    uint32_t v = h[threadIdx.x];
+    uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+    for(int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if(lane >= o) inc += t; }
+    if(lane == 31) sWarp[warp] = inc;
+    __syncthreads();
+    if(warp == 0)
+    {
+        uint32_t w = (lane < RADIX / 32) ? sWarp[lane] : 0, wi = w;
+        for(int o = 1; o < RADIX / 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, wi, o); if(lane >= o) wi += t; }
+        if(lane < RADIX / 32) sWarp[lane] = wi - w;
+    }
+    __syncthreads();
+    h[threadIdx.x] = inc - v + sWarp[warp];
+}
+
+// One digit pass: rank inside the tile (stable), chained look-back for the cross-tile prefix,
+// stage in shared memory in sorted order, write out in per-digit runs.
+template<class K, int ITEMS>
+__global__ void __launch_bounds__(SORT_TPB)
+KOnesweepPass(const K* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
+              K* __restrict__ keysOut, uint32_t* __restrict__ valsOut,
+              uint32_t n, uint32_t shift, uint32_t mask,
+              const uint32_t* __restrict__ gBase, uint32_t* __restrict__ tileCounter,
+              volatile uint32_t* __restrict__ status)
+{
+    constexpr int TILE = SORT_TPB * ITEMS;
+    __shared__ K        sKeys[TILE];
+    __shared__ uint32_t sVals[TILE];
+    __shared__ uint32_t sWarpCnt[SORT_WARPS * RADIX];
+    __shared__ uint32_t sBinStart[RADIX];
+    __shared__ uint32_t sGlobalOff[RADIX];
+    __shared__ uint32_t sScan[RADIX / 32];
+    __shared__ uint32_t sTile;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if(tid == 0) sTile = atomicAdd(tileCounter, 1u); // dynamic tile id => look-back always makes progress
+    for(int j = tid; j < SORT_WARPS * RADIX; j += SORT_TPB) sWarpCnt[j] = 0;
+    __syncthreads();
+    const uint32_t tile = sTile;
+    const uint32_t base = tile * TILE;
+    const uint32_t warpBase = base + warp * 32 * ITEMS;
+
+    K        key[ITEMS];
+    uint32_t pos[ITEMS];
+    #pragma unroll
+    for(int i = 0; i < ITEMS; i++)
+    {
+        uint32_t idx = warpBase + i * 32 + lane;
+        key[i] = (idx < n) ? keysIn[idx] : K(~K(0));
+    }
+    uint32_t* myCnt = sWarpCnt + warp * RADIX;
+    const uint32_t ltMask = LaneMaskLt();
+    #pragma unroll
+    for(int i = 0; i < ITEMS; i++)
+    {
+        uint32_t idx = warpBase + i * 32 + lane;
+        bool valid = idx < n;
+        uint32_t d = uint32_t(key[i] >> shift) & mask;
+        uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xFFFFu);
+        uint32_t cnt = valid ? myCnt[d] : 0u;
+        pos[i] = cnt + __popc(peers & ltMask);
+        __syncwarp();
+        if(valid && (peers >> lane) == 1u) myCnt[d] = cnt + __popc(peers); // highest peer lane
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // thread d owns digit d: prefix over warps, publish, look back
+    uint32_t total = 0;
+    {
+        const uint32_t d = tid;
+        #pragma unroll
+        for(int w = 0; w < SORT_WARPS; w++) { uint32_t c = sWarpCnt[w * RADIX + d]; sWarpCnt[w * RADIX + d] = total; total += c; }
+        status[size_t(tile) * RADIX + d] = (tile == 0 ? FLAG_PREFIX : FLAG_AGG) | total;
+    }
+    // block exclusive scan of `total` over digits -> tile-local bin starts
+    {
+        uint32_t inc = total;
+        for(int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if(lane >= o) inc += t; }
+        if(lane == 31) sScan[warp] = inc;
+        __syncthreads();
+        if(warp == 0)
+        {
+            uint32_t w = (lane < RADIX / 32) ? sScan[lane] : 0, wi = w;
+            for(int o = 1; o < RADIX / 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, wi, o); if(lane >= o) wi += t; }
+            if(lane < RADIX / 32) sScan[lane] = wi - w;
+        }
+        __syncthreads();
+        sBinStart[tid] = inc - total + sScan[warp];
+    }
+    {
+        const uint32_t d = tid;
+        uint32_t excl = 0;
+        if(tile > 0)
+        {
+            int32_t t = int32_t(tile) - 1;
+            while(true)
+            {
+                uint32_t v = status[size_t(t) * RADIX + d];
+                uint32_t f = v & FLAG_MASK;
+                if(f == 0) continue;
+                excl += v & COUNT_MASK;
+                if(f == FLAG_PREFIX) break;
+                t--;
+            }
+            status[size_t(tile) * RADIX + d] = FLAG_PREFIX | (excl + total);
+        }
+        sGlobalOff[d] = gBase[d] + excl - sBinStart[d];
+    }
+    __syncthreads();
+
+    #pragma unroll
+    for(int i = 0; i < ITEMS; i++)
+    {
+        uint32_t idx = warpBase + i * 32 + lane;
+        if(idx < n)
+        {
+            uint32_t d = uint32_t(key[i] >> shift) & mask;
+            uint32_t p = sBinStart[d] + myCnt[d] + pos[i];
+            sKeys[p] = key[i];
+            sVals[p] = valsIn[idx];
+        }
+    }
+    __syncthreads();
+    const uint32_t tileCount = min(uint32_t(TILE), n - base);
+    for(uint32_t j = tid; j < tileCount; j += SORT_TPB)
+    {
+        K k = sKeys[j];
+        uint32_t d = uint32_t(k >> shift) & mask;
+        uint32_t o = sGlobalOff[d] + j;
+        keysOut[o] = k;
+        valsOut[o] = sVals[j];
+    }
+}
+
+template<class K>
+void RadixSortImpl(Context& ctx, K* keys, uint32_t* values, uint32_t count,
+                   uint32_t bitBegin, uint32_t bitEnd, void* temp)
+{
+    if(count == 0 || bitEnd <= bitBegin) return;
+    constexpr int ITEMS = SortCfg<K>::ITEMS;
+    constexpr uint32_t TILE = SORT_TPB * ITEMS;
+    const uint32_t passes = (bitEnd - bitBegin + 7) / 8;
+    const uint32_t numTiles = DivUp(count, TILE);
+
+    MultiAlloc ma(temp);
+    K*        keysAlt = ma.Take<K>(count);
+    uint32_t* valsAlt = ma.Take<uint32_t>(count);
+    uint32_t* gHist = ma.Take<uint32_t>(MAX_PASSES * RADIX + MAX_PASSES); // + tile counters
+    uint32_t* status = ma.Take<uint32_t>(size_t(passes) * numTiles * RADIX);
+    uint32_t* tileCounters = gHist + MAX_PASSES * RADIX;
+    // gHist .. status are contiguous up to alignment: clear them in one memset
+    size_t clearBytes = size_t(reinterpret_cast<char*>(status) - reinterpret_cast<char*>(gHist))
+                        + size_t(passes) * numTiles * RADIX * sizeof(uint32_t);
+    MRB_CUDA_TRY(cudaMemsetAsync(gHist, 0, clearBytes, ctx.stream));
+
+    MRB_LAUNCH(ctx, KSortHistogram<K>, GridFor(ctx, count, SORT_TPB * 4, 4), SORT_TPB, 0,
+               keys, count, bitBegin, bitEnd, gHist);
+    MRB_LAUNCH(ctx, KSortScan, passes, RADIX, 0, gHist);
+
+    K* kIn = keys; K* kOut = keysAlt; uint32_t* vIn = values; uint32_t* vOut = valsAlt;
+    for(uint32_t p = 0; p < passes; p++)
+    {
+        uint32_t shift = bitBegin + 8 * p;
+        uint32_t bits = (bitEnd - shift < 8u) ? (bitEnd - shift) : 8u;
+        uint32_t mask = (1u << bits) - 1u;
+        MRB_LAUNCH(ctx, (KOnesweepPass<K, ITEMS>), numTiles, SORT_TPB, 0,
+                   kIn, vIn, kOut, vOut, count, shift, mask,
+                   gHist + p * RADIX, tileCounters + p, status + size_t(p) * numTiles * RADIX);
+        K* tk = kIn; kIn = kOut; kOut = tk;
+        uint32_t* tv = vIn; vIn = vOut; vOut = tv;
+    }
+    if(kIn != keys)
+    {
+        MRB_CUDA_TRY(cudaMemcpyAsync(keys, kIn, sizeof(K) * count, cudaMemcpyDeviceToDevice, ctx.stream));
+        MRB_CUDA_TRY(cudaMemcpyAsync(values, vIn, sizeof(uint32_t) * count, cudaMemcpyDeviceToDevice, ctx.stream));
+    }
+}
+
+} // namespace
+
+size_t RadixSortTempBytes(uint32_t count, size_t keyBytes)
+{
+    uint32_t tile = SORT_TPB * (keyBytes == 8 ? SortCfg<uint64_t>::ITEMS : SortCfg<uint32_t>::ITEMS);
+    uint32_t numTiles = DivUp(count ? count : 1u, tile);
+    MultiAlloc ma(nullptr);
+    if(keyBytes == 8) ma.Take<uint64_t>(count); else ma.Take<uint32_t>(count);
+    ma.Take<uint32_t>(count);
+    ma.Take<uint32_t>(MAX_PASSES * RADIX + MAX_PASSES);
+    ma.Take<uint32_t>(size_t(MAX_PASSES) * numTiles * RADIX);
+    return ma.Total();
+}
+
+void RadixSortPairs(Context& ctx, uint64_t* keys, uint32_t* values, uint32_t count,
+                    uint32_t bitBegin, uint32_t bitEnd, void* temp)
+{
+    RadixSortImpl<uint64_t>(ctx, keys, values, count, bitBegin, bitEnd, temp);
+}
+
+void RadixSortPairs(Context& ctx, uint32_t* keys, uint32_t* values, uint32_t count,
+                    uint32_t bitBegin, uint32_t bitEnd, void* temp)
+{
+    RadixSortImpl<uint32_t>(ctx, keys, values, count, bitBegin, bitEnd, temp);
+}
+
+} // namespace mrb

@@ -1,0 +1,317 @@
+// trace.cu — closest-hit / any-hit ray casting.
+//
+//  KTraceWide   : product path. Per-thread traversal of the 8-wide quantised BVH (node = 5 x 128-bit
+//                 loads, triangle = 3 x 128-bit loads), octant-ordered child visits, node-group
+//                 stack. Box tests are CONSERVATIVE with respect to the reference's slab test on
+//                 the exact binary boxes (quantised boxes enclose them; a per-node slack covers the
+//                 rounding of both formulations), triangle tests are the reference's Moller-Trumbore
+//                 arithmetic bit for bit, and equal-t candidates are resolved towards the smaller
+//                 Morton rank = the reference's left-first visit order. Result: same primitive, same
+//                 t, same barycentrics as BaseAcceleratorLBVH::CastRays.
+//  KTraceBinary : audit path. The reference's own algorithm: binary LBVH, left-first stack
+//                 traversal (TraverseLBVHStack, AcceleratorLBVH.hpp:L109-167), Ray::IntersectsAABB
+//                 (Core/Ray.hpp:L192-219) with identical arithmetic.
+#include "accel.cuh"
+#include <cfloat>
+
+namespace mrb
+{
+namespace
+{
+
+constexpr int TRACE_TPB = 128;
+constexpr int WIDE_STACK = 64;
+
+struct HitRecord
+{
+    float    t;
+    float    u, v;   // Moller-Trumbore u, v
+    uint32_t leaf;
+    uint32_t rank;
+    uint32_t flags;
+};
+
+// Ray::IntersectsTriangle (Core/Ray.hpp:L121-167) with Math::Cross / Math::Dot exactly as
+// Core/Math.h:L1586-1596,L1627-1633 build them from (true) FMAs.
+__device__ __forceinline__ float Dot3(float ax, float ay, float az, float bx, float by, float bz)
+{
+    float r = __fmaf_rn(ax, bx, 0.0f);
+    r = __fmaf_rn(ay, by, r);
+    r = __fmaf_rn(az, bz, r);
+    return r;
+}
+
+__device__ __forceinline__ bool RayTriangle(float ox, float oy, float oz, float dx, float dy, float dz,
+                                            const float4& v0, const float4& e0, const float4& e1, bool cull,
+                                            float& tOut, float& uOut, float& vOut)
+{
+    const float eps = 1.0e-7f;
+    float px = __fmaf_rn(dy, e1.z, -__fmul_rn(dz, e1.y));
+    float py = __fmaf_rn(dz, e1.x, -__fmul_rn(dx, e1.z));
+    float pz = __fmaf_rn(dx, e1.y, -__fmul_rn(dy, e1.x));
+    float det = Dot3(e0.x, e0.y, e0.z, px, py, pz);
+    bool back = det < eps;
+    bool parallel = fabsf(det) < eps;
+    if((cull && back) || parallel) return false;
+    float invDet = __frcp_rn(det);
+    float tx = __fsub_rn(ox, v0.x), ty = __fsub_rn(oy, v0.y), tz = __fsub_rn(oz, v0.z);
+    float u = __fmul_rn(Dot3(tx, ty, tz, px, py, pz), invDet);
+    if(u < 0.0f || u > 1.0f) return false;
+    float qx = __fmaf_rn(ty, e0.z, -__fmul_rn(tz, e0.y));
+    float qy = __fmaf_rn(tz, e0.x, -__fmul_rn(tx, e0.z));
+    float qz = __fmaf_rn(tx, e0.y, -__fmul_rn(ty, e0.x));
+    float v = __fmul_rn(Dot3(dx, dy, dz, qx, qy, qz), invDet);
+    if(v < 0.0f || __fadd_rn(v, u) > 1.0f) return false;
+    float t = __fmul_rn(Dot3(e1.x, e1.y, e1.z, qx, qy, qz), invDet);
+    if(t <= eps) return false;
+    tOut = t; uOut = u; vOut = v;
+    return true;
+}
+
+__device__ __forceinline__ void WriteHit(const AccelData& a, uint32_t accelKey, uint32_t r, const HitRecord& h,
+                                         mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, mrb_ray_gmem* rays)
+{
+    uint32_t ri = h.flags >> 8;
+    uint32_t prim = a.ranges.primBegin[ri] + (h.leaf - a.ranges.leafStart[ri]);
+    uint4 keys = make_uint4((a.ranges.primGroupId << 28) | prim, a.ranges.lmKey[ri], 0u, accelKey);
+    *reinterpret_cast<uint4*>(hitKeys + r) = keys;
+    float w = __fsub_rn(__fsub_rn(1.0f, h.u), h.v);
+    *reinterpret_cast<float2*>(metaHits + r) = make_float2(w, h.u); // Vector2(baryCoords) = (1-u-v, u)
+    rays[r].tMax = h.t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Wide traversal
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ByteToFloat(uint32_t word, int j)
+{
+    // exact: 2^23 + byte, minus 2^23
+    return __uint_as_float(0x4B000000u | ((word >> (8 * j)) & 0xFFu)) - 8388608.0f;
+}
+
+template<bool ANY_HIT>
+__global__ void __launch_bounds__(TRACE_TPB)
+KTraceWide(AccelData a, uint32_t accelKey,
+           mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
+           uint32_t* __restrict__ visibleBits,
+           mrb_ray_gmem* rays, const uint32_t* __restrict__ rayIndices, uint32_t rayCount)
+{
+    const uint32_t i = blockIdx.x * TRACE_TPB + threadIdx.x;
+    if(i >= rayCount) return;
+    const uint32_t r = rayIndices ? rayIndices[i] : i;
+    const float4 r0 = reinterpret_cast<const float4*>(rays + r)[0];
+    const float4 r1 = reinterpret_cast<const float4*>(rays + r)[1];
+    const float ox = r0.x, oy = r0.y, oz = r0.z, tMin = r0.w;
+    const float dx = r1.x, dy = r1.y, dz = r1.z;
+    float tMax = r1.w;
+
+    // reciprocal direction; tiny components are clamped so that no inf/NaN enters the box tests
+    const float idx = (fabsf(dx) > 1e-30f) ? 1.0f / dx : copysignf(1e30f, dx);
+    const float idy = (fabsf(dy) > 1e-30f) ? 1.0f / dy : copysignf(1e30f, dy);
+    const float idz = (fabsf(dz) > 1e-30f) ? 1.0f / dz : copysignf(1e30f, dz);
+    const uint32_t oct = (dx < 0.0f ? 4u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 1u : 0u);
+    const uint32_t oct4 = oct * 0x01010101u;
+
+    HitRecord best; best.t = tMax; best.rank = 0u; best.leaf = INVALID_U32; best.u = best.v = 0.f; best.flags = 0u;
+
+    uint2 stack[WIDE_STACK];
+    int sp = 0;
+    uint2 G = make_uint2(0u, 0x80000000u);
+    const uint4* __restrict__ nodeBase = reinterpret_cast<const uint4*>(a.wideNodes);
+    const float4* __restrict__ triBase = reinterpret_cast<const float4*>(a.tris);
+
+    while(true)
+    {
+        uint32_t triMask = 0u, triFirst = 0u;
+        if(G.y & 0xFF000000u)
+        {
+            const uint32_t hitsImask = G.y;
+            const uint32_t bit = 31u - uint32_t(__clz(int(hitsImask)));
+            G.y &= ~(1u << bit);
+            if(G.y & 0xFF000000u) { stack[sp++] = G; }
+            const uint32_t slot = (bit - 24u) ^ oct;
+            const uint32_t rel = __popc(hitsImask & ~(0xFFFFFFFFu << slot));
+            const uint4* np = nodeBase + size_t(G.x + rel) * 5;
+            const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+
+            const float sx = __uint_as_float((n0.w & 0xFFu) << 23) * idx;
+            const float sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * idy;
+            const float sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23) * idz;
+            const float cx = (__uint_as_float(n0.x) - ox) * idx;
+            const float cy = (__uint_as_float(n0.y) - oy) * idy;
+            const float cz = (__uint_as_float(n0.z) - oz) * idz;
+            // slack covering the rounding of this formulation and of the reference's (see header)
+            const float slack = 9.5367431640625e-07f * // 2^-20
+                fmaxf(fmaxf(fabsf(cx) + 255.0f * fabsf(sx), fabsf(cy) + 255.0f * fabsf(sy)), fabsf(cz) + 255.0f * fabsf(sz));
+            const float tFarLimit = tMax + slack;
+
+            uint32_t hitmask = 0u;
+            #pragma unroll
+            for(int half = 0; half < 2; half++)
+            {
+                const uint32_t meta4 = half ? n1.w : n1.z;
+                const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+                const uint32_t innerMask4 = (isInner4 >> 4) * 0xFFu;
+                const uint32_t bitIndex4 = (meta4 ^ (oct4 & innerMask4)) & 0x1F1F1F1Fu;
+                const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+                const uint32_t qlx = half ? n2.y : n2.x, qly = half ? n2.w : n2.z, qlz = half ? n3.y : n3.x;
+                const uint32_t qhx = half ? n3.w : n3.z, qhy = half ? n4.y : n4.x, qhz = half ? n4.w : n4.z;
+                const uint32_t nx = (dx < 0.0f) ? qhx : qlx, fx = (dx < 0.0f) ? qlx : qhx;
+                const uint32_t ny = (dy < 0.0f) ? qhy : qly, fy = (dy < 0.0f) ? qly : qhy;
+                const uint32_t nz = (dz < 0.0f) ? qhz : qlz, fz = (dz < 0.0f) ? qlz : qhz;
+                #pragma unroll
+                for(int j = 0; j < 4; j++)
+                {
+                    float tnx = __fmaf_rn(ByteToFloat(nx, j), sx, cx), tfx = __fmaf_rn(ByteToFloat(fx, j), sx, cx);
+                    float tny = __fmaf_rn(ByteToFloat(ny, j), sy, cy), tfy = __fmaf_rn(ByteToFloat(fy, j), sy, cy);
+                    float tnz = __fmaf_rn(ByteToFloat(nz, j), sz, cz), tfz = __fmaf_rn(ByteToFloat(fz, j), sz, cz);
+                    float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tMin));
+                    float tf = fminf(fminf(tfx, tfy), fminf(tfz, tFarLimit));
+                    if(tn <= tf + slack)
+                    {
+                        uint32_t cbits = (childBits4 >> (8 * j)) & 0xFFu;
+                        uint32_t bidx = (bitIndex4 >> (8 * j)) & 0xFFu;
+                        hitmask |= cbits << bidx;
+                    }
+                }
+            }
+            G.x = n1.x;
+            G.y = (hitmask & 0xFF000000u) | (n0.w >> 24);
+            triFirst = n1.y;
+            triMask = hitmask & 0x00FFFFFFu;
+        }
+        while(triMask)
+        {
+            const uint32_t tb = uint32_t(__ffs(int(triMask))) - 1u;
+            triMask &= triMask - 1u;
+            const float4* tp = triBase + size_t(triFirst + tb) * 3;
+            const float4 v0 = __ldg(tp + 0), e0 = __ldg(tp + 1), e1 = __ldg(tp + 2);
+            const uint32_t flags = __float_as_uint(e1.w);
+            float t, u, v;
+            if(!RayTriangle(ox, oy, oz, dx, dy, dz, v0, e0, e1, (flags & 1u) != 0u, t, u, v)) continue;
+            if(!(t >= tMin)) continue;
+            const uint32_t rank = __float_as_uint(e0.w);
+            if(t < best.t || (t == best.t && rank < best.rank))
+            {
+                best.t = t; best.u = u; best.v = v; best.rank = rank;
+                best.leaf = __float_as_uint(v0.w); best.flags = flags;
+                tMax = t;
+                if(ANY_HIT) { sp = 0; G.y = 0u; triMask = 0u; }
+            }
+        }
+        if((G.y & 0xFF000000u) == 0u)
+        {
+            if(sp == 0) break;
+            G = stack[--sp];
+        }
+    }
+    if(best.leaf != INVALID_U32)
+    {
+        if(ANY_HIT) atomicAnd(&visibleBits[r >> 5], ~(1u << (r & 31u)));
+        else WriteHit(a, accelKey, r, best, hitKeys, metaHits, rays);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact binary traversal (audit path)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float StdMax(float a, float b) { return (a < b) ? b : a; }
+__device__ __forceinline__ float StdMin(float a, float b) { return (b < a) ? b : a; }
+
+template<bool ANY_HIT>
+__global__ void __launch_bounds__(TRACE_TPB)
+KTraceBinary(AccelData a, uint32_t accelKey,
+             mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
+             uint32_t* __restrict__ visibleBits,
+             mrb_ray_gmem* rays, const uint32_t* __restrict__ rayIndices, uint32_t rayCount)
+{
+    const uint32_t i = blockIdx.x * TRACE_TPB + threadIdx.x;
+    if(i >= rayCount) return;
+    const uint32_t r = rayIndices ? rayIndices[i] : i;
+    const float4 r0 = reinterpret_cast<const float4*>(rays + r)[0];
+    const float4 r1 = reinterpret_cast<const float4*>(rays + r)[1];
+    const float o[3] = {r0.x, r0.y, r0.z}, d[3] = {r1.x, r1.y, r1.z};
+    const float tMin = r0.w; float tMax = r1.w;
+    float invD[3];
+    #pragma unroll
+    for(int k = 0; k < 3; k++) invD[k] = __fdiv_rn(1.0f, d[k]);
+
+    HitRecord best; best.t = tMax; best.rank = 0u; best.leaf = INVALID_U32; best.u = best.v = 0.f; best.flags = 0u;
+    uint32_t stack[160];
+    int sp = 0;
+    stack[sp++] = 0u;
+    while(sp > 0)
+    {
+        uint32_t ni = stack[--sp];
+        if(ni == INVALID_U32) continue;
+        if(ni & LEAF_FLAG)
+        {
+            uint32_t leaf = ni & ~LEAF_FLAG;
+            uint32_t ri = 0;
+            #pragma unroll
+            for(uint32_t j = 1; j < 8; j++) if(j < a.ranges.count && leaf >= a.ranges.leafStart[j]) ri = j;
+            uint32_t prim = a.ranges.primBegin[ri] + (leaf - a.ranges.leafStart[ri]);
+            uint32_t i0 = a.indices[3 * size_t(prim)], i1 = a.indices[3 * size_t(prim) + 1], i2 = a.indices[3 * size_t(prim) + 2];
+            float4 v0, e0, e1;
+            const float* p0 = a.positions + 3 * size_t(i0);
+            const float* p1 = a.positions + 3 * size_t(i1);
+            const float* p2 = a.positions + 3 * size_t(i2);
+            v0 = make_float4(p0[0], p0[1], p0[2], 0.f);
+            e0 = make_float4(__fsub_rn(p1[0], p0[0]), __fsub_rn(p1[1], p0[1]), __fsub_rn(p1[2], p0[2]), 0.f);
+            e1 = make_float4(__fsub_rn(p2[0], p0[0]), __fsub_rn(p2[1], p0[1]), __fsub_rn(p2[2], p0[2]), 0.f);
+            float t, u, v;
+            if(!RayTriangle(o[0], o[1], o[2], d[0], d[1], d[2], v0, e0, e1, a.ranges.cull[ri] != 0u, t, u, v)) continue;
+            if(!(t >= tMin && t < tMax)) continue;
+            best.t = t; best.u = u; best.v = v; best.leaf = leaf; best.flags = ri << 8;
+            tMax = t;
+            if(ANY_HIT) break;
+        }
+        else
+        {
+            const float* b = reinterpret_cast<const float*>(a.boxes + ni);
+            float o0 = tMin, o1 = tMax;
+            #pragma unroll
+            for(int k = 0; k < 3; k++)
+            {
+                float t0 = __fmul_rn(__fsub_rn(b[k], o[k]), invD[k]);
+                float t1 = __fmul_rn(__fsub_rn(b[3 + k], o[k]), invD[k]);
+                if(invD[k] < 0.0f) { float t = t0; t0 = t1; t1 = t; }
+                o0 = StdMax(o0, StdMin(t0, t1));
+                o1 = StdMin(o1, StdMax(t0, t1));
+            }
+            if(o1 >= o0)
+            {
+                LBVHNode nd = a.nodes[ni];
+                stack[sp++] = nd.right;
+                stack[sp++] = nd.left;
+            }
+        }
+    }
+    if(best.leaf != INVALID_U32)
+    {
+        if(ANY_HIT) atomicAnd(&visibleBits[r >> 5], ~(1u << (r & 31u)));
+        else WriteHit(a, accelKey, r, best, hitKeys, metaHits, rays);
+    }
+}
+
+} // namespace
+
+void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode mode,
+               mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, uint32_t* visibleBits,
+               mrb_ray_gmem* rays, const uint32_t* rayIndices, uint32_t rayCount)
+{
+    if(rayCount == 0) return;
+    const uint32_t grid = DivUp(rayCount, TRACE_TPB);
+    if(mode == MRB_TRACE_WIDE)
+    {
+        if(anyHit) MRB_LAUNCH(ctx, KTraceWide<true>, grid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount);
+        else       MRB_LAUNCH(ctx, KTraceWide<false>, grid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount);
+    }
+    else
+    {
+        if(anyHit) MRB_LAUNCH(ctx, KTraceBinary<true>, grid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount);
+        else       MRB_LAUNCH(ctx, KTraceBinary<false>, grid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount);
+    }
+}
+
+} // namespace mrb
