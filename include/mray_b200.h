@@ -70,7 +70,8 @@ MRB_API uint32_t mrb_abi_version(void);
  * Core/MemAlloc.h:L171-209: 256-byte aligned sub-allocation of a growing arena). */
 MRB_API mrb_status mrb_context_create(int device, mrb_context* out);
 MRB_API void       mrb_context_destroy(mrb_context ctx);
-/* Use an externally owned cudaStream_t (e.g. torch's current stream). NULL = context's own. */
+/* Issue all work on an externally owned cudaStream_t (e.g. torch's current stream). NULL is the
+ * CUDA default stream. Until this is called the context uses a private non-blocking stream. */
 MRB_API mrb_status mrb_context_set_stream(mrb_context ctx, void* cuda_stream);
 MRB_API mrb_status mrb_context_synchronize(mrb_context ctx);
 /* TracerI::UsedDeviceMemory / TotalDeviceMemory (Core/TracerI.h:L372-373). */
@@ -79,6 +80,10 @@ MRB_API size_t     mrb_context_total_device_memory(mrb_context ctx);
 /* Number of kernels this library has launched on the context since creation (for the
  * gpu_launches accounting of bench.py). */
 MRB_API uint64_t   mrb_context_launch_count(mrb_context ctx);
+/* Rays of the last MRB_TRACE_WIDE cast that could not be certified against the reference's box
+ * arithmetic and were re-traced with the reference's exact binary traversal (synchronises).
+ * out[0] = total, out[1] = near-tie candidates, out[2] = winner's leaf AABB not certified. */
+MRB_API mrb_status mrb_context_last_fallback_count(mrb_context ctx, uint32_t* out);
 MRB_API const char* mrb_last_error(mrb_context ctx); /* ctx may be NULL: last create error */
 
 /* ---- accelerator build ------------------------------------------------------------------ */

@@ -63,6 +63,7 @@ _PROTOTYPES = {
     "mrb_context_used_device_memory": (C.c_size_t, [C.c_void_p]),
     "mrb_context_total_device_memory": (C.c_size_t, [C.c_void_p]),
     "mrb_context_launch_count": (C.c_uint64, [C.c_void_p]),
+    "mrb_context_last_fallback_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "mrb_last_error": (C.c_char_p, [C.c_void_p]),
     "mrb_accel_build": (C.c_int, [C.c_void_p, C.POINTER(AccelDesc), C.POINTER(C.c_void_p)]),
     "mrb_accel_destroy": (None, [C.c_void_p, C.c_void_p]),
@@ -148,8 +149,8 @@ class Context:
             raise MrbError(st, (self.lib.mrb_last_error(self.handle) or b"").decode())
 
     def set_stream(self, stream):
-        """``stream``: a torch.cuda.Stream, a raw cudaStream_t integer, or None (own stream)."""
-        raw = None if stream is None else getattr(stream, "cuda_stream", stream)
+        """``stream``: a torch.cuda.Stream or a raw cudaStream_t integer (0 / None = default stream)."""
+        raw = None if stream is None else (getattr(stream, "cuda_stream", stream) or None)
         self.check(self.lib.mrb_context_set_stream(self.handle, C.c_void_p(raw)))
 
     def synchronize(self):
@@ -158,6 +159,18 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.lib.mrb_context_launch_count(self.handle))
+
+    @property
+    def last_fallback_count(self) -> int:
+        """Rays of the last wide cast that were re-traced by the exact binary fallback (syncs)."""
+        return self.last_fallback_stats[0]
+
+    @property
+    def last_fallback_stats(self):
+        """(total, near-tie, uncertified-leaf) exact-fallback ray counts of the last wide cast."""
+        out = (C.c_uint32 * 3)()
+        self.check(self.lib.mrb_context_last_fallback_count(self.handle, out))
+        return tuple(int(x) for x in out)
 
     @property
     def used_device_memory(self) -> int:

@@ -13,6 +13,8 @@
 #include "accel.cuh"
 #include <cfloat>
 #include <cstring>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace mrb
 {
@@ -265,7 +267,7 @@ KUnionBoxes(AccelData a, uint32_t* counters)
 // ------------------------------------------------------------------------------------------------
 struct CollapseState
 {
-    uint32_t head;     // next ticket
+    uint32_t head;     // unused
     uint32_t created;  // wide nodes allocated so far (root = 1)
     uint32_t done;     // wide nodes finished
     uint32_t triCount; // triangle records allocated
@@ -437,41 +439,33 @@ __device__ void CollapseNode(const AccelData& a, CollapseState* st, unsigned lon
         int c = -1;
         for(uint32_t cc = 0; cc < n; cc++) if(slotOf[cc] == s) c = int(cc);
         unsigned long long item = (unsigned long long)(refs[c].node) | ((unsigned long long)(depth + 1) << 32);
-        atomicExch(&queue[childBase + rel], item);
+        queue[childBase + rel] = item;
         rel++;
     }
     atomicMax(&st->maxDepth, depth);
 }
 
-// Persistent ticket queue: ticket k is wide node k; its work item is written by the thread that
-// processed its parent (always a smaller ticket, i.e. an already running thread).
+// Level-synchronous collapse in ONE cooperative launch: wide nodes [begin,end) form the current
+// level, their internal children are appended behind `end` (atomic bump of st->created), a grid-wide
+// barrier separates levels. No spinning, no inter-thread waiting other than the barrier.
 __global__ void __launch_bounds__(64)
 KCollapse(AccelData a, CollapseState* st, unsigned long long* queue, uint32_t* triRank)
 {
-    constexpr unsigned long long EMPTY = ~0ull;
-    while(true)
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t gsize = gridDim.x * blockDim.x;
+    uint32_t begin = 0, end = 1;
+    while(begin < end)
     {
-        uint32_t k = atomicAdd(&st->head, 1u);
-        unsigned long long item = EMPTY;
-        uint32_t spins = 0;
-        while(true)
+        for(uint32_t k = begin + gtid; k < end; k += gsize)
         {
-            if(k < a.wideNodeCapacity)
-            {
-                item = *reinterpret_cast<volatile unsigned long long*>(queue + k);
-                if(item != EMPTY) break;
-            }
-            uint32_t done = atomicAdd(&st->done, 0u);
-            __threadfence();
-            uint32_t created = atomicAdd(&st->created, 0u);
-            if(done == created && k >= created) return;
-            if(*reinterpret_cast<volatile uint32_t*>(&st->error)) return;
-            if(++spins > (1u << 24)) { st->error = 1u; return; }
-            __nanosleep(64);
+            unsigned long long item = queue[k];
+            CollapseNode(a, st, queue, triRank, k, uint32_t(item & 0xFFFFFFFFull), uint32_t(item >> 32));
         }
-        CollapseNode(a, st, queue, triRank, k, uint32_t(item & 0xFFFFFFFFull), uint32_t(item >> 32));
-        __threadfence();
-        atomicAdd(&st->done, 1u);
+        grid.sync();
+        begin = end;
+        end = min(*reinterpret_cast<volatile uint32_t*>(&st->created), a.wideNodeCapacity);
+        if(*reinterpret_cast<volatile uint32_t*>(&st->error)) break;
     }
 }
 
@@ -594,11 +588,14 @@ void BuildAccel(Context& ctx, mrb_accel_t& acc, const mrb_accel_desc& desc)
     {
         CollapseState init = {0u, 1u, 0u, 0u, 0u, 0u};
         MRB_CUDA_TRY(cudaMemcpyAsync(cst, &init, sizeof(init), cudaMemcpyHostToDevice, ctx.stream));
-        MRB_CUDA_TRY(cudaMemsetAsync(queue, 0xFF, sizeof(unsigned long long) * (d.wideNodeCapacity + 1), ctx.stream));
         unsigned long long rootItem = 0ull; // binary node 0, depth 0
         MRB_CUDA_TRY(cudaMemcpyAsync(queue, &rootItem, sizeof(rootItem), cudaMemcpyHostToDevice, ctx.stream));
-        uint32_t cgrid = min(uint32_t(ctx.smCount) * 8u, max(1u, DivUp(d.wideNodeCapacity, 64u)));
-        MRB_LAUNCH(ctx, KCollapse, cgrid, 64, 0, d, cst, queue, triRank);
+        int perSM = 0;
+        MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, KCollapse, 64, 0));
+        uint32_t cgrid = min(uint32_t(ctx.smCount) * uint32_t(max(1, min(perSM, 16))), max(1u, DivUp(d.wideNodeCapacity, 64u)));
+        void* cargs[] = {(void*)&d, (void*)&cst, (void*)&queue, (void*)&triRank};
+        MRB_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)KCollapse, dim3(cgrid), dim3(64), cargs, 0, ctx.stream));
+        ctx.launches++;
         MRB_LAUNCH(ctx, KFillTris, grid, TPB, 0, d, triRank);
     }
     MRB_CUDA_TRY(cudaEventRecord(ctx.ev1, ctx.stream));

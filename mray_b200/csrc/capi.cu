@@ -89,6 +89,7 @@ void mrb_context_destroy(mrb_context ctx)
     cudaSetDevice(ctx->c.device);
     cudaStreamSynchronize(ctx->c.stream);
     ctx->c.scratch.Free();
+    ctx->c.traceScratch.Free();
     if(ctx->c.ev0) cudaEventDestroy(ctx->c.ev0);
     if(ctx->c.ev1) cudaEventDestroy(ctx->c.ev1);
     if(ctx->c.ownStream) cudaStreamDestroy(ctx->c.ownStream);
@@ -98,7 +99,9 @@ void mrb_context_destroy(mrb_context ctx)
 mrb_status mrb_context_set_stream(mrb_context ctx, void* cuda_stream)
 {
     if(!ctx) return MRB_ERR_INVALID_ARG;
-    ctx->c.stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->c.ownStream;
+    // pass-through: NULL is the CUDA (legacy) default stream, exactly what torch hands out as its
+    // default "current stream"; the context's own stream is only used until this is called
+    ctx->c.stream = static_cast<cudaStream_t>(cuda_stream);
     return MRB_OK;
 }
 
@@ -107,9 +110,23 @@ mrb_status mrb_context_synchronize(mrb_context ctx)
     return Guard(ctx, [&](mrb::Context& c) { MRB_CUDA_TRY(cudaStreamSynchronize(c.stream)); return MRB_OK; });
 }
 
-size_t mrb_context_used_device_memory(mrb_context ctx) { return ctx ? ctx->c.persistentBytes + ctx->c.scratch.Capacity() : 0; }
+size_t mrb_context_used_device_memory(mrb_context ctx) { return ctx ? ctx->c.persistentBytes + ctx->c.scratch.Capacity() + ctx->c.traceScratch.Capacity() : 0; }
 size_t mrb_context_total_device_memory(mrb_context ctx) { return ctx ? ctx->c.totalMem : 0; }
 uint64_t mrb_context_launch_count(mrb_context ctx) { return ctx ? ctx->c.launches : 0; }
+
+mrb_status mrb_context_last_fallback_count(mrb_context ctx, uint32_t* out)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!out) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        out[0] = out[1] = out[2] = 0;
+        if(!c.lastFallbackCount) return MRB_OK;
+        MRB_CUDA_TRY(cudaMemcpyAsync(out, c.lastFallbackCount, sizeof(uint32_t) * 3, cudaMemcpyDeviceToHost, c.stream));
+        MRB_CUDA_TRY(cudaStreamSynchronize(c.stream));
+        return MRB_OK;
+    });
+}
+
 const char* mrb_last_error(mrb_context ctx) { return ctx ? ctx->c.error.c_str() : gCreateError.c_str(); }
 
 mrb_status mrb_accel_build(mrb_context ctx, const mrb_accel_desc* desc, mrb_accel* out)

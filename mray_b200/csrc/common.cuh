@@ -72,6 +72,8 @@ struct Context
     size_t       totalMem = 0;
     size_t       persistentBytes = 0; // bytes held by live accelerators / renderers
     DeviceBlock  scratch;             // per-call temporaries (grow-only, reused)
+    DeviceBlock  traceScratch;        // exact-fallback ray list of the wide traversal
+    const uint32_t* lastFallbackCount = nullptr; // device counter of the last wide cast
     uint64_t     launches = 0;
     std::string  error;
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr;

@@ -5,9 +5,17 @@
 //                 stack. Box tests are CONSERVATIVE with respect to the reference's slab test on
 //                 the exact binary boxes (quantised boxes enclose them; a per-node slack covers the
 //                 rounding of both formulations), triangle tests are the reference's Moller-Trumbore
-//                 arithmetic bit for bit, and equal-t candidates are resolved towards the smaller
-//                 Morton rank = the reference's left-first visit order. Result: same primitive, same
-//                 t, same barycentrics as BaseAcceleratorLBVH::CastRays.
+//                 arithmetic bit for bit, so the kernel finds the true minimum over a SUPERSET of the
+//                 triangles the reference tests. The reference can differ from that minimum only
+//                 when one of its own (exact, binary) box tests rejects the winner numerically, which
+//                 needs either a second candidate within rounding distance of the winner or a ray that
+//                 grazes the winner's own AABB. Both are detected: culling is relaxed to
+//                 t <= tBest * (1 + 2^-16) so every near-tie candidate is seen, and the winner is
+//                 certified with the reference's slab test on its leaf AABB (all ancestor boxes
+//                 enclose it and the computed slab values are monotone in the box). Certified rays are
+//                 provably what BaseAcceleratorLBVH::CastRays returns; the rest (about 1e-6 of the rays
+//                 of config 2) are appended to a list and re-traced by KTraceBinary, the reference's
+//                 algorithm verbatim.
 //  KTraceBinary : audit path. The reference's own algorithm: binary LBVH, left-first stack
 //                 traversal (TraverseLBVHStack, AcceleratorLBVH.hpp:L109-167), Ray::IntersectsAABB
 //                 (Core/Ray.hpp:L192-219) with identical arithmetic.
@@ -80,6 +88,42 @@ __device__ __forceinline__ void WriteHit(const AccelData& a, uint32_t accelKey, 
     rays[r].tMax = h.t;
 }
 
+__device__ __forceinline__ float StdMax(float a, float b) { return (a < b) ? b : a; }
+__device__ __forceinline__ float StdMin(float a, float b) { return (b < a) ? b : a; }
+
+// Ray::IntersectsAABB (Core/Ray.hpp:L192-219), identical arithmetic (IEEE div / sub / mul, host
+// std::min / std::max semantics).
+__device__ __forceinline__ bool SlabExact(const float* __restrict__ b, const float o[3], const float invD[3],
+                                          float tMin, float tMax)
+{
+    float o0 = tMin, o1 = tMax;
+    #pragma unroll
+    for(int k = 0; k < 3; k++)
+    {
+        float t0 = __fmul_rn(__fsub_rn(b[k], o[k]), invD[k]);
+        float t1 = __fmul_rn(__fsub_rn(b[3 + k], o[k]), invD[k]);
+        if(invD[k] < 0.0f) { float t = t0; t0 = t1; t1 = t; }
+        o0 = StdMax(o0, StdMin(t0, t1));
+        o1 = StdMin(o1, StdMax(t0, t1));
+    }
+    return o1 >= o0;
+}
+
+// Would the reference's traversal reach this leaf with upper bound tUpper? Sufficient condition:
+// its own slab test passes on the leaf's AABB (every ancestor box encloses it).
+__device__ __forceinline__ bool CertifyLeaf(const AccelData& a, uint32_t leaf, float ox, float oy, float oz,
+                                            float dx, float dy, float dz, float tMin, float tUpper)
+{
+    const float2* bp = reinterpret_cast<const float2*>(a.leafAABB + 6 * size_t(leaf));
+    float2 b0 = __ldg(bp), b1 = __ldg(bp + 1), b2 = __ldg(bp + 2);
+    const float box[6] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y};
+    const float o[3] = {ox, oy, oz};
+    const float invD[3] = {__fdiv_rn(1.0f, dx), __fdiv_rn(1.0f, dy), __fdiv_rn(1.0f, dz)};
+    return SlabExact(box, o, invD, tMin, tUpper);
+}
+
+constexpr float NEAR_TIE = 1.0000152587890625f; // 1 + 2^-16
+
 // ------------------------------------------------------------------------------------------------
 // Wide traversal
 // ------------------------------------------------------------------------------------------------
@@ -94,7 +138,8 @@ __global__ void __launch_bounds__(TRACE_TPB)
 KTraceWide(AccelData a, uint32_t accelKey,
            mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
            uint32_t* __restrict__ visibleBits,
-           mrb_ray_gmem* rays, const uint32_t* __restrict__ rayIndices, uint32_t rayCount)
+           mrb_ray_gmem* rays, const uint32_t* __restrict__ rayIndices, uint32_t rayCount,
+           uint32_t* __restrict__ fallbackCount, uint32_t* __restrict__ fallbackList)
 {
     const uint32_t i = blockIdx.x * TRACE_TPB + threadIdx.x;
     if(i >= rayCount) return;
@@ -103,7 +148,10 @@ KTraceWide(AccelData a, uint32_t accelKey,
     const float4 r1 = reinterpret_cast<const float4*>(rays + r)[1];
     const float ox = r0.x, oy = r0.y, oz = r0.z, tMin = r0.w;
     const float dx = r1.x, dy = r1.y, dz = r1.z;
-    float tMax = r1.w;
+    const float tMaxOrig = r1.w;
+    float tMax = tMaxOrig;    // culling bound: min(tMaxOrig, tBest * NEAR_TIE)
+    float tSecond = FLT_MAX;  // smallest t among accepted candidates other than the best
+    bool  uncertified = false, done = false;
 
     // reciprocal direction; tiny components are clamped so that no inf/NaN enters the box tests
     const float idx = (fabsf(dx) > 1e-30f) ? 1.0f / dx : copysignf(1e30f, dx);
@@ -112,7 +160,7 @@ KTraceWide(AccelData a, uint32_t accelKey,
     const uint32_t oct = (dx < 0.0f ? 4u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 1u : 0u);
     const uint32_t oct4 = oct * 0x01010101u;
 
-    HitRecord best; best.t = tMax; best.rank = 0u; best.leaf = INVALID_U32; best.u = best.v = 0.f; best.flags = 0u;
+    HitRecord best; best.t = tMaxOrig; best.rank = 0u; best.leaf = INVALID_U32; best.u = best.v = 0.f; best.flags = 0u;
 
     uint2 stack[WIDE_STACK];
     int sp = 0;
@@ -189,15 +237,23 @@ KTraceWide(AccelData a, uint32_t accelKey,
             const uint32_t flags = __float_as_uint(e1.w);
             float t, u, v;
             if(!RayTriangle(ox, oy, oz, dx, dy, dz, v0, e0, e1, (flags & 1u) != 0u, t, u, v)) continue;
-            if(!(t >= tMin)) continue;
+            if(!(t >= tMin && t < tMaxOrig)) continue; // IsInRange (AcceleratorLBVH.hpp:L233-236)
             const uint32_t rank = __float_as_uint(e0.w);
-            if(t < best.t || (t == best.t && rank < best.rank))
+            if(ANY_HIT)
             {
+                const uint32_t leaf = __float_as_uint(v0.w);
+                if(CertifyLeaf(a, leaf, ox, oy, oz, dx, dy, dz, tMin, tMaxOrig))
+                { done = true; sp = 0; G.y = 0u; triMask = 0u; }
+                else uncertified = true;
+            }
+            else if(t < best.t || (t == best.t && rank < best.rank))
+            {
+                tSecond = fminf(tSecond, (best.leaf != INVALID_U32) ? best.t : FLT_MAX);
                 best.t = t; best.u = u; best.v = v; best.rank = rank;
                 best.leaf = __float_as_uint(v0.w); best.flags = flags;
-                tMax = t;
-                if(ANY_HIT) { sp = 0; G.y = 0u; triMask = 0u; }
+                tMax = fminf(tMaxOrig, t * NEAR_TIE);
             }
+            else tSecond = fminf(tSecond, t);
         }
         if((G.y & 0xFF000000u) == 0u)
         {
@@ -205,28 +261,40 @@ KTraceWide(AccelData a, uint32_t accelKey,
             G = stack[--sp];
         }
     }
-    if(best.leaf != INVALID_U32)
+    if(ANY_HIT)
     {
-        if(ANY_HIT) atomicAnd(&visibleBits[r >> 5], ~(1u << (r & 31u)));
-        else WriteHit(a, accelKey, r, best, hitKeys, metaHits, rays);
+        if(done) atomicAnd(&visibleBits[r >> 5], ~(1u << (r & 31u)));
+        else if(uncertified) { fallbackList[atomicAdd(fallbackCount, 1u)] = r; atomicAdd(fallbackCount + 2, 1u); }
+    }
+    else if(best.leaf != INVALID_U32)
+    {
+        const float tUpper = fminf(tMaxOrig, best.t * NEAR_TIE);
+        bool exact = (tSecond > tUpper) &&
+                     CertifyLeaf(a, best.leaf, ox, oy, oz, dx, dy, dz, tMin, tUpper);
+        if(exact) WriteHit(a, accelKey, r, best, hitKeys, metaHits, rays);
+        else
+        {
+            fallbackList[atomicAdd(fallbackCount, 1u)] = r;
+            atomicAdd(fallbackCount + ((tSecond > tUpper) ? 2 : 1), 1u); // [1] near ties, [2] uncertified leaf
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Exact binary traversal (audit path)
+// Exact binary traversal (audit path, and fallback of the rays the wide path could not certify)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float StdMax(float a, float b) { return (a < b) ? b : a; }
-__device__ __forceinline__ float StdMin(float a, float b) { return (b < a) ? b : a; }
 
 template<bool ANY_HIT>
 __global__ void __launch_bounds__(TRACE_TPB)
 KTraceBinary(AccelData a, uint32_t accelKey,
              mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
              uint32_t* __restrict__ visibleBits,
-             mrb_ray_gmem* rays, const uint32_t* __restrict__ rayIndices, uint32_t rayCount)
+             mrb_ray_gmem* rays, const uint32_t* __restrict__ rayIndices, uint32_t rayCount,
+             const uint32_t* __restrict__ deviceRayCount)
 {
-    const uint32_t i = blockIdx.x * TRACE_TPB + threadIdx.x;
-    if(i >= rayCount) return;
+    if(deviceRayCount) rayCount = *deviceRayCount;
+    for(uint32_t i = blockIdx.x * TRACE_TPB + threadIdx.x; i < rayCount; i += gridDim.x * TRACE_TPB)
+    {
     const uint32_t r = rayIndices ? rayIndices[i] : i;
     const float4 r0 = reinterpret_cast<const float4*>(rays + r)[0];
     const float4 r1 = reinterpret_cast<const float4*>(rays + r)[1];
@@ -269,17 +337,7 @@ KTraceBinary(AccelData a, uint32_t accelKey,
         else
         {
             const float* b = reinterpret_cast<const float*>(a.boxes + ni);
-            float o0 = tMin, o1 = tMax;
-            #pragma unroll
-            for(int k = 0; k < 3; k++)
-            {
-                float t0 = __fmul_rn(__fsub_rn(b[k], o[k]), invD[k]);
-                float t1 = __fmul_rn(__fsub_rn(b[3 + k], o[k]), invD[k]);
-                if(invD[k] < 0.0f) { float t = t0; t0 = t1; t1 = t; }
-                o0 = StdMax(o0, StdMin(t0, t1));
-                o1 = StdMin(o1, StdMax(t0, t1));
-            }
-            if(o1 >= o0)
+            if(SlabExact(b, o, invD, tMin, tMax))
             {
                 LBVHNode nd = a.nodes[ni];
                 stack[sp++] = nd.right;
@@ -291,6 +349,7 @@ KTraceBinary(AccelData a, uint32_t accelKey,
     {
         if(ANY_HIT) atomicAnd(&visibleBits[r >> 5], ~(1u << (r & 31u)));
         else WriteHit(a, accelKey, r, best, hitKeys, metaHits, rays);
+    }
     }
 }
 
@@ -304,13 +363,30 @@ void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode
     const uint32_t grid = DivUp(rayCount, TRACE_TPB);
     if(mode == MRB_TRACE_WIDE)
     {
-        if(anyHit) MRB_LAUNCH(ctx, KTraceWide<true>, grid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount);
-        else       MRB_LAUNCH(ctx, KTraceWide<false>, grid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount);
+        // fallback list: [count][ray slots...] in the context's trace scratch
+        ctx.traceScratch.Reserve(sizeof(uint32_t) * (size_t(rayCount) + 64));
+        uint32_t* fbCount = static_cast<uint32_t*>(ctx.traceScratch.Base());
+        uint32_t* fbList = fbCount + 64;
+        MRB_CUDA_TRY(cudaMemsetAsync(fbCount, 0, sizeof(uint32_t) * 4, ctx.stream));
+        const uint32_t fbGrid = uint32_t(ctx.smCount) * 2u;
+        if(anyHit)
+        {
+            MRB_LAUNCH(ctx, KTraceWide<true>, grid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, fbCount, fbList);
+            MRB_LAUNCH(ctx, KTraceBinary<true>, fbGrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, fbList, 0u, fbCount);
+        }
+        else
+        {
+            MRB_LAUNCH(ctx, KTraceWide<false>, grid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, fbCount, fbList);
+            MRB_LAUNCH(ctx, KTraceBinary<false>, fbGrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, fbList, 0u, fbCount);
+        }
+        ctx.lastFallbackCount = fbCount;
     }
     else
     {
-        if(anyHit) MRB_LAUNCH(ctx, KTraceBinary<true>, grid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount);
-        else       MRB_LAUNCH(ctx, KTraceBinary<false>, grid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount);
+        const uint32_t bgrid = min(grid, uint32_t(ctx.smCount) * 16u);
+        if(anyHit) MRB_LAUNCH(ctx, KTraceBinary<true>, bgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, nullptr);
+        else       MRB_LAUNCH(ctx, KTraceBinary<false>, bgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, nullptr);
+        ctx.lastFallbackCount = nullptr;
     }
 }
 
