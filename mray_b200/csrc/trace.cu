@@ -21,6 +21,7 @@
 //                 (Core/Ray.hpp:L192-219) with identical arithmetic.
 #include "accel.cuh"
 #include <cfloat>
+#include <cstdlib>
 
 namespace mrb
 {
@@ -127,156 +128,234 @@ constexpr float NEAR_TIE = 1.0000152587890625f; // 1 + 2^-16
 // ------------------------------------------------------------------------------------------------
 // Wide traversal
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float ByteToFloat(uint32_t word, int j)
+// Quantised byte j of `word` as the float 32768 + q (bits 0x4700qq00): ONE PRMT, no int->float
+// conversion. The 32768 offset is folded into the per-node constant (c - 32768 s), whose rounding
+// error (<= 2^-9 |s|, 0.002 quantisation cells) is covered by the node slack.
+__device__ __forceinline__ float QF(uint32_t word, int j)
 {
-    // exact: 2^23 + byte, minus 2^23
-    return __uint_as_float(0x4B000000u | ((word >> (8 * j)) & 0xFFu)) - 8388608.0f;
+    return __uint_as_float(__byte_perm(word, 0x47000000u, 0x7604u | (uint32_t(j) << 4)));
 }
 
+struct TraceParams
+{
+    uint32_t triDiv;    // triangle phase runs when lanesWithTriangles * triDiv >= liveLanes (or no lane has node work)
+    uint32_t fetchThr;  // refill idle lanes with new rays when fewer than this many lanes are live
+};
+
+// Persistent warps: every lane owns one ray at a time; finished lanes are refilled from a global
+// counter (dynamic fetch). Inside a warp the loop is phase-uniform — at most one triangle test and
+// one node step per iteration, each executed by all lanes that have that kind of work — so the
+// 200-instruction node step and the 60-instruction triangle test always run with as many lanes as
+// possible; triangle groups are postponed (kept / pushed on the stack) until enough lanes have one.
 template<bool ANY_HIT>
 __global__ void __launch_bounds__(TRACE_TPB)
 KTraceWide(AccelData a, uint32_t accelKey,
            mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
            uint32_t* __restrict__ visibleBits,
            mrb_ray_gmem* rays, const uint32_t* __restrict__ rayIndices, uint32_t rayCount,
-           uint32_t* __restrict__ fallbackCount, uint32_t* __restrict__ fallbackList)
+           uint32_t* __restrict__ counters, uint32_t* __restrict__ fallbackList, TraceParams prm)
 {
-    const uint32_t i = blockIdx.x * TRACE_TPB + threadIdx.x;
-    if(i >= rayCount) return;
-    const uint32_t r = rayIndices ? rayIndices[i] : i;
-    const float4 r0 = reinterpret_cast<const float4*>(rays + r)[0];
-    const float4 r1 = reinterpret_cast<const float4*>(rays + r)[1];
-    const float ox = r0.x, oy = r0.y, oz = r0.z, tMin = r0.w;
-    const float dx = r1.x, dy = r1.y, dz = r1.z;
-    const float tMaxOrig = r1.w;
-    float tMax = tMaxOrig;    // culling bound: min(tMaxOrig, tBest * NEAR_TIE)
-    float tSecond = FLT_MAX;  // smallest t among accepted candidates other than the best
-    bool  uncertified = false, done = false;
-
-    // reciprocal direction; tiny components are clamped so that no inf/NaN enters the box tests
-    const float idx = (fabsf(dx) > 1e-30f) ? 1.0f / dx : copysignf(1e30f, dx);
-    const float idy = (fabsf(dy) > 1e-30f) ? 1.0f / dy : copysignf(1e30f, dy);
-    const float idz = (fabsf(dz) > 1e-30f) ? 1.0f / dz : copysignf(1e30f, dz);
-    const uint32_t oct = (dx < 0.0f ? 4u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 1u : 0u);
-    const uint32_t oct4 = oct * 0x01010101u;
-
-    HitRecord best; best.t = tMaxOrig; best.rank = 0u; best.leaf = INVALID_U32; best.u = best.v = 0.f; best.flags = 0u;
-
-    uint2 stack[WIDE_STACK];
-    int sp = 0;
-    uint2 G = make_uint2(0u, 0x80000000u);
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t ltMask = (1u << lane) - 1u;
     const uint4* __restrict__ nodeBase = reinterpret_cast<const uint4*>(a.wideNodes);
     const float4* __restrict__ triBase = reinterpret_cast<const float4*>(a.tris);
 
+    bool hasRay = false, finished = false, exhausted = false;
+    uint32_t r = 0;
+    float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, idx = 0, idy = 0, idz = 0;
+    float tMin = 0, tMaxOrig = 0, tMax = 0, tSecond = 0;
+    uint32_t oct = 0;
+    bool uncertified = false, done = false;
+    HitRecord best; best.t = 0; best.u = best.v = 0; best.leaf = INVALID_U32; best.rank = 0; best.flags = 0;
+    uint2 G = make_uint2(0u, 0u), T = make_uint2(0u, 0u);
+    uint2 stack[WIDE_STACK];
+    int sp = 0;
+
     while(true)
     {
-        uint32_t triMask = 0u, triFirst = 0u;
-        if(G.y & 0xFF000000u)
+        // ------------------------------ epilogue of finished rays ------------------------------
+        if(finished)
         {
-            const uint32_t hitsImask = G.y;
-            const uint32_t bit = 31u - uint32_t(__clz(int(hitsImask)));
-            G.y &= ~(1u << bit);
-            if(G.y & 0xFF000000u) { stack[sp++] = G; }
-            const uint32_t slot = (bit - 24u) ^ oct;
-            const uint32_t rel = __popc(hitsImask & ~(0xFFFFFFFFu << slot));
-            const uint4* np = nodeBase + size_t(G.x + rel) * 5;
-            const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-
-            const float sx = __uint_as_float((n0.w & 0xFFu) << 23) * idx;
-            const float sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * idy;
-            const float sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23) * idz;
-            const float cx = (__uint_as_float(n0.x) - ox) * idx;
-            const float cy = (__uint_as_float(n0.y) - oy) * idy;
-            const float cz = (__uint_as_float(n0.z) - oz) * idz;
-            // slack covering the rounding of this formulation and of the reference's (see header)
-            const float slack = 9.5367431640625e-07f * // 2^-20
-                fmaxf(fmaxf(fabsf(cx) + 255.0f * fabsf(sx), fabsf(cy) + 255.0f * fabsf(sy)), fabsf(cz) + 255.0f * fabsf(sz));
-            const float tFarLimit = tMax + slack;
-
-            uint32_t hitmask = 0u;
-            #pragma unroll
-            for(int half = 0; half < 2; half++)
+            finished = false;
+            if(ANY_HIT)
             {
-                const uint32_t meta4 = half ? n1.w : n1.z;
-                const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-                const uint32_t innerMask4 = (isInner4 >> 4) * 0xFFu;
-                const uint32_t bitIndex4 = (meta4 ^ (oct4 & innerMask4)) & 0x1F1F1F1Fu;
-                const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
-                const uint32_t qlx = half ? n2.y : n2.x, qly = half ? n2.w : n2.z, qlz = half ? n3.y : n3.x;
-                const uint32_t qhx = half ? n3.w : n3.z, qhy = half ? n4.y : n4.x, qhz = half ? n4.w : n4.z;
-                const uint32_t nx = (dx < 0.0f) ? qhx : qlx, fx = (dx < 0.0f) ? qlx : qhx;
-                const uint32_t ny = (dy < 0.0f) ? qhy : qly, fy = (dy < 0.0f) ? qly : qhy;
-                const uint32_t nz = (dz < 0.0f) ? qhz : qlz, fz = (dz < 0.0f) ? qlz : qhz;
-                #pragma unroll
-                for(int j = 0; j < 4; j++)
+                if(done) atomicAnd(&visibleBits[r >> 5], ~(1u << (r & 31u)));
+                else if(uncertified) { fallbackList[atomicAdd(counters, 1u)] = r; atomicAdd(counters + 2, 1u); }
+            }
+            else if(best.leaf != INVALID_U32)
+            {
+                const float tUpper = fminf(tMaxOrig, best.t * NEAR_TIE);
+                bool exact = (tSecond > tUpper) &&
+                             CertifyLeaf(a, best.leaf, ox, oy, oz, dx, dy, dz, tMin, tUpper);
+                if(exact) WriteHit(a, accelKey, r, best, hitKeys, metaHits, rays);
+                else
                 {
-                    float tnx = __fmaf_rn(ByteToFloat(nx, j), sx, cx), tfx = __fmaf_rn(ByteToFloat(fx, j), sx, cx);
-                    float tny = __fmaf_rn(ByteToFloat(ny, j), sy, cy), tfy = __fmaf_rn(ByteToFloat(fy, j), sy, cy);
-                    float tnz = __fmaf_rn(ByteToFloat(nz, j), sz, cz), tfz = __fmaf_rn(ByteToFloat(fz, j), sz, cz);
-                    float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tMin));
-                    float tf = fminf(fminf(tfx, tfy), fminf(tfz, tFarLimit));
-                    if(tn <= tf + slack)
+                    fallbackList[atomicAdd(counters, 1u)] = r;
+                    atomicAdd(counters + ((tSecond > tUpper) ? 2 : 1), 1u); // [1] near ties, [2] uncertified leaf
+                }
+            }
+        }
+        // ------------------------------------ dynamic fetch ------------------------------------
+        if(!exhausted)
+        {
+            const uint32_t need = __ballot_sync(FULL, !hasRay);
+            if(need)
+            {
+                const int leader = __ffs(int(need)) - 1;
+                uint32_t base = 0;
+                if(int(lane) == leader) base = atomicAdd(counters + 3, uint32_t(__popc(need)));
+                base = __shfl_sync(FULL, base, leader);
+                if(!hasRay)
+                {
+                    const uint32_t i = base + uint32_t(__popc(need & ltMask));
+                    if(i < rayCount)
                     {
-                        uint32_t cbits = (childBits4 >> (8 * j)) & 0xFFu;
-                        uint32_t bidx = (bitIndex4 >> (8 * j)) & 0xFFu;
-                        hitmask |= cbits << bidx;
+                        r = rayIndices ? rayIndices[i] : i;
+                        const float4 r0 = reinterpret_cast<const float4*>(rays + r)[0];
+                        const float4 r1 = reinterpret_cast<const float4*>(rays + r)[1];
+                        ox = r0.x; oy = r0.y; oz = r0.z; tMin = r0.w;
+                        dx = r1.x; dy = r1.y; dz = r1.z; tMaxOrig = r1.w;
+                        // reciprocal direction; tiny components are clamped so no inf/NaN enters the box tests
+                        idx = (fabsf(dx) > 1e-30f) ? 1.0f / dx : copysignf(1e30f, dx);
+                        idy = (fabsf(dy) > 1e-30f) ? 1.0f / dy : copysignf(1e30f, dy);
+                        idz = (fabsf(dz) > 1e-30f) ? 1.0f / dz : copysignf(1e30f, dz);
+                        oct = (dx < 0.0f ? 4u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 1u : 0u);
+                        tMax = tMaxOrig; tSecond = FLT_MAX;
+                        best.t = tMaxOrig; best.rank = 0u; best.leaf = INVALID_U32; best.flags = 0u;
+                        uncertified = false; done = false;
+                        G = make_uint2(0u, 0x80000000u); T = make_uint2(0u, 0u); sp = 0;
+                        hasRay = true;
+                    }
+                }
+                if(base + uint32_t(__popc(need)) >= rayCount) exhausted = true;
+            }
+        }
+        uint32_t live = __ballot_sync(FULL, hasRay);
+        if(live == 0u) break;
+        const int fetchThr = exhausted ? 1 : int(prm.fetchThr);
+
+        // -------------------------------------- traversal --------------------------------------
+        do
+        {
+            const bool triWork = hasRay && (T.y != 0u);
+            const bool nodeWork = hasRay && ((G.y & 0xFF000000u) != 0u);
+            const uint32_t bT = __ballot_sync(FULL, triWork);
+            const uint32_t bN = __ballot_sync(FULL, nodeWork);
+
+            // ---- triangle phase: one triangle per lane ----
+            if(bT != 0u && (bN == 0u || uint32_t(__popc(bT)) * prm.triDiv >= uint32_t(__popc(live))))
+            {
+                if(triWork)
+                {
+                    const uint32_t tb = uint32_t(__ffs(int(T.y))) - 1u;
+                    T.y &= T.y - 1u;
+                    const float4* tp = triBase + size_t(T.x + tb) * 3;
+                    const float4 v0 = __ldg(tp + 0), e0 = __ldg(tp + 1), e1 = __ldg(tp + 2);
+                    const uint32_t flags = __float_as_uint(e1.w);
+                    float t, u, v;
+                    if(RayTriangle(ox, oy, oz, dx, dy, dz, v0, e0, e1, (flags & 1u) != 0u, t, u, v) &&
+                       (t >= tMin && t < tMaxOrig)) // IsInRange (AcceleratorLBVH.hpp:L233-236)
+                    {
+                        const uint32_t rank = __float_as_uint(e0.w);
+                        if(ANY_HIT)
+                        {
+                            if(CertifyLeaf(a, __float_as_uint(v0.w), ox, oy, oz, dx, dy, dz, tMin, tMaxOrig))
+                            { done = true; hasRay = false; finished = true; }
+                            else uncertified = true;
+                        }
+                        else if(t < best.t || (t == best.t && rank < best.rank))
+                        {
+                            tSecond = fminf(tSecond, (best.leaf != INVALID_U32) ? best.t : FLT_MAX);
+                            best.t = t; best.u = u; best.v = v; best.rank = rank;
+                            best.leaf = __float_as_uint(v0.w); best.flags = flags;
+                            tMax = fminf(tMaxOrig, t * NEAR_TIE);
+                        }
+                        else tSecond = fminf(tSecond, t);
                     }
                 }
             }
-            G.x = n1.x;
-            G.y = (hitmask & 0xFF000000u) | (n0.w >> 24);
-            triFirst = n1.y;
-            triMask = hitmask & 0x00FFFFFFu;
-        }
-        while(triMask)
-        {
-            const uint32_t tb = uint32_t(__ffs(int(triMask))) - 1u;
-            triMask &= triMask - 1u;
-            const float4* tp = triBase + size_t(triFirst + tb) * 3;
-            const float4 v0 = __ldg(tp + 0), e0 = __ldg(tp + 1), e1 = __ldg(tp + 2);
-            const uint32_t flags = __float_as_uint(e1.w);
-            float t, u, v;
-            if(!RayTriangle(ox, oy, oz, dx, dy, dz, v0, e0, e1, (flags & 1u) != 0u, t, u, v)) continue;
-            if(!(t >= tMin && t < tMaxOrig)) continue; // IsInRange (AcceleratorLBVH.hpp:L233-236)
-            const uint32_t rank = __float_as_uint(e0.w);
-            if(ANY_HIT)
+            // ---- node phase: one node per lane ----
+            if(bN != 0u)
             {
-                const uint32_t leaf = __float_as_uint(v0.w);
-                if(CertifyLeaf(a, leaf, ox, oy, oz, dx, dy, dz, tMin, tMaxOrig))
-                { done = true; sp = 0; G.y = 0u; triMask = 0u; }
-                else uncertified = true;
+                if(nodeWork && hasRay)
+                {
+                    if(T.y != 0u) { stack[sp++] = T; T.y = 0u; } // postponed triangle group
+                    const uint32_t hitsImask = G.y;
+                    const uint32_t bit = 31u - uint32_t(__clz(int(hitsImask)));
+                    G.y &= ~(1u << bit);
+                    if(G.y & 0xFF000000u) { stack[sp++] = G; }
+                    const uint32_t slot = (bit - 24u) ^ oct;
+                    const uint32_t rel = __popc(hitsImask & ~(0xFFFFFFFFu << slot));
+                    const uint4* np = nodeBase + size_t(G.x + rel) * 5;
+                    const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+
+                    const float sx = __uint_as_float((n0.w & 0xFFu) << 23) * idx;
+                    const float sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * idy;
+                    const float sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23) * idz;
+                    const float cx = (__uint_as_float(n0.x) - ox) * idx;
+                    const float cy = (__uint_as_float(n0.y) - oy) * idy;
+                    const float cz = (__uint_as_float(n0.z) - oz) * idz;
+                    // per-axis slack covering the rounding of this formulation and of the reference's
+                    // slab test: 2^-20 (|c| + 255 |s|) + 2^-8 |s|. It must stay per axis: a ray almost
+                    // parallel to one axis has huge |s|, |c| there, which says nothing about the others.
+                    const float kx = __fmaf_rn(0.0042f, fabsf(sx), 9.5367431640625e-07f * fabsf(cx));
+                    const float ky = __fmaf_rn(0.0042f, fabsf(sy), 9.5367431640625e-07f * fabsf(cy));
+                    const float kz = __fmaf_rn(0.0042f, fabsf(sz), 9.5367431640625e-07f * fabsf(cz));
+                    const float bx = __fmaf_rn(-32768.0f, sx, cx), by = __fmaf_rn(-32768.0f, sy, cy), bz = __fmaf_rn(-32768.0f, sz, cz);
+                    const float cnx = bx - kx, cny = by - ky, cnz = bz - kz;
+                    const float cfx = bx + kx, cfy = by + ky, cfz = bz + kz;
+                    const float tFarLimit = tMax;
+
+                    uint32_t hitmask = 0u;
+                    const uint32_t oct4 = oct * 0x01010101u;
+                    #pragma unroll
+                    for(int half = 0; half < 2; half++)
+                    {
+                        const uint32_t meta4 = half ? n1.w : n1.z;
+                        const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+                        const uint32_t innerMask4 = (isInner4 >> 4) * 0xFFu;
+                        const uint32_t bitIndex4 = (meta4 ^ (oct4 & innerMask4)) & 0x1F1F1F1Fu;
+                        const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+                        const uint32_t qlx = half ? n2.y : n2.x, qly = half ? n2.w : n2.z, qlz = half ? n3.y : n3.x;
+                        const uint32_t qhx = half ? n3.w : n3.z, qhy = half ? n4.y : n4.x, qhz = half ? n4.w : n4.z;
+                        const uint32_t nx = (dx < 0.0f) ? qhx : qlx, fx = (dx < 0.0f) ? qlx : qhx;
+                        const uint32_t ny = (dy < 0.0f) ? qhy : qly, fy = (dy < 0.0f) ? qly : qhy;
+                        const uint32_t nz = (dz < 0.0f) ? qhz : qlz, fz = (dz < 0.0f) ? qlz : qhz;
+                        #pragma unroll
+                        for(int j = 0; j < 4; j++)
+                        {
+                            const float tnx = __fmaf_rn(QF(nx, j), sx, cnx), tfx = __fmaf_rn(QF(fx, j), sx, cfx);
+                            const float tny = __fmaf_rn(QF(ny, j), sy, cny), tfy = __fmaf_rn(QF(fy, j), sy, cfy);
+                            const float tnz = __fmaf_rn(QF(nz, j), sz, cnz), tfz = __fmaf_rn(QF(fz, j), sz, cfz);
+                            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tMin));
+                            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tFarLimit));
+                            if(tn <= tf)
+                            {
+                                const uint32_t cbits = (childBits4 >> (8 * j)) & 0xFFu;
+                                const uint32_t bidx = (bitIndex4 >> (8 * j)) & 0xFFu;
+                                hitmask |= cbits << bidx;
+                            }
+                        }
+                    }
+                    G.x = n1.x;
+                    G.y = (hitmask & 0xFF000000u) | (n0.w >> 24);
+                    T.x = n1.y;
+                    T.y = hitmask & 0x00FFFFFFu;
+                }
             }
-            else if(t < best.t || (t == best.t && rank < best.rank))
+            // ---- pop / finish ----
+            if(hasRay && (G.y & 0xFF000000u) == 0u && T.y == 0u)
             {
-                tSecond = fminf(tSecond, (best.leaf != INVALID_U32) ? best.t : FLT_MAX);
-                best.t = t; best.u = u; best.v = v; best.rank = rank;
-                best.leaf = __float_as_uint(v0.w); best.flags = flags;
-                tMax = fminf(tMaxOrig, t * NEAR_TIE);
+                if(sp == 0) { hasRay = false; finished = true; }
+                else
+                {
+                    const uint2 e = stack[--sp];
+                    if(e.y & 0xFF000000u) G = e; else T = e;
+                }
             }
-            else tSecond = fminf(tSecond, t);
-        }
-        if((G.y & 0xFF000000u) == 0u)
-        {
-            if(sp == 0) break;
-            G = stack[--sp];
-        }
-    }
-    if(ANY_HIT)
-    {
-        if(done) atomicAnd(&visibleBits[r >> 5], ~(1u << (r & 31u)));
-        else if(uncertified) { fallbackList[atomicAdd(fallbackCount, 1u)] = r; atomicAdd(fallbackCount + 2, 1u); }
-    }
-    else if(best.leaf != INVALID_U32)
-    {
-        const float tUpper = fminf(tMaxOrig, best.t * NEAR_TIE);
-        bool exact = (tSecond > tUpper) &&
-                     CertifyLeaf(a, best.leaf, ox, oy, oz, dx, dy, dz, tMin, tUpper);
-        if(exact) WriteHit(a, accelKey, r, best, hitKeys, metaHits, rays);
-        else
-        {
-            fallbackList[atomicAdd(fallbackCount, 1u)] = r;
-            atomicAdd(fallbackCount + ((tSecond > tUpper) ? 2 : 1), 1u); // [1] near ties, [2] uncertified leaf
-        }
+            live = __ballot_sync(FULL, hasRay);
+        } while(__popc(live) >= fetchThr);
     }
 }
 
@@ -369,14 +448,28 @@ void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode
         uint32_t* fbList = fbCount + 64;
         MRB_CUDA_TRY(cudaMemsetAsync(fbCount, 0, sizeof(uint32_t) * 4, ctx.stream));
         const uint32_t fbGrid = uint32_t(ctx.smCount) * 2u;
+        static int occClosest = 0, occAny = 0;
+        if(!occClosest)
+        {
+            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occClosest, KTraceWide<false>, TRACE_TPB, 0));
+            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occAny, KTraceWide<true>, TRACE_TPB, 0));
+        }
+        static TraceParams prm = []
+        {
+            TraceParams p{5u, 24u};
+            if(const char* e = getenv("MRB_TRI_DIV")) p.triDiv = uint32_t(atoi(e));
+            if(const char* e = getenv("MRB_FETCH_THR")) p.fetchThr = uint32_t(atoi(e));
+            return p;
+        }();
+        const uint32_t pgrid = min(grid, uint32_t(ctx.smCount) * uint32_t(anyHit ? occAny : occClosest));
         if(anyHit)
         {
-            MRB_LAUNCH(ctx, KTraceWide<true>, grid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, fbCount, fbList);
+            MRB_LAUNCH(ctx, KTraceWide<true>, pgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, fbCount, fbList, prm);
             MRB_LAUNCH(ctx, KTraceBinary<true>, fbGrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, fbList, 0u, fbCount);
         }
         else
         {
-            MRB_LAUNCH(ctx, KTraceWide<false>, grid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, fbCount, fbList);
+            MRB_LAUNCH(ctx, KTraceWide<false>, pgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, fbCount, fbList, prm);
             MRB_LAUNCH(ctx, KTraceBinary<false>, fbGrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, fbList, 0u, fbCount);
         }
         ctx.lastFallbackCount = fbCount;
