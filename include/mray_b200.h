@@ -81,8 +81,10 @@ MRB_API size_t     mrb_context_total_device_memory(mrb_context ctx);
  * gpu_launches accounting of bench.py). */
 MRB_API uint64_t   mrb_context_launch_count(mrb_context ctx);
 /* Rays of the last MRB_TRACE_WIDE cast that could not be certified against the reference's box
- * arithmetic and were re-traced with the reference's exact binary traversal (synchronises).
- * out[0] = total, out[1] = near-tie candidates, out[2] = winner's leaf AABB not certified. */
+ * arithmetic by the traversal kernel itself (synchronises). out[4]:
+ * [0] total, [1] of which near-tie candidates, [2] of which winner's leaf AABB not certified,
+ * [3] rays that needed the full exact binary re-traversal (the others were settled by replaying the
+ *     reference's box tests on the candidates' ancestor chains). */
 MRB_API mrb_status mrb_context_last_fallback_count(mrb_context ctx, uint32_t* out);
 MRB_API const char* mrb_last_error(mrb_context ctx); /* ctx may be NULL: last create error */
 

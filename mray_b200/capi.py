@@ -167,8 +167,8 @@ class Context:
 
     @property
     def last_fallback_stats(self):
-        """(total, near-tie, uncertified-leaf) exact-fallback ray counts of the last wide cast."""
-        out = (C.c_uint32 * 3)()
+        """(uncertified total, near-tie, uncertified-leaf, full binary re-traversals) of the last wide cast."""
+        out = (C.c_uint32 * 4)()
         self.check(self.lib.mrb_context_last_fallback_count(self.handle, out))
         return tuple(int(x) for x in out)
 

@@ -177,6 +177,7 @@ KKarras(AccelData a, int robust, uint32_t* dupFlag)
         {
             a.nodes[0] = LBVHNode{LEAF_FLAG | 0u, INVALID_U32, INVALID_U32};
             a.nodeRange[0] = make_uint2(0, 0);
+            a.leafParent[0] = 0u; // (the reference leaves it unset; KResolveExact walks it)
         }
         return;
     }

@@ -119,10 +119,12 @@ mrb_status mrb_context_last_fallback_count(mrb_context ctx, uint32_t* out)
     return Guard(ctx, [&](mrb::Context& c)
     {
         if(!out) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
-        out[0] = out[1] = out[2] = 0;
+        out[0] = out[1] = out[2] = out[3] = 0;
         if(!c.lastFallbackCount) return MRB_OK;
-        MRB_CUDA_TRY(cudaMemcpyAsync(out, c.lastFallbackCount, sizeof(uint32_t) * 3, cudaMemcpyDeviceToHost, c.stream));
+        uint32_t h[5];
+        MRB_CUDA_TRY(cudaMemcpyAsync(h, c.lastFallbackCount, sizeof(uint32_t) * 5, cudaMemcpyDeviceToHost, c.stream));
         MRB_CUDA_TRY(cudaStreamSynchronize(c.stream));
+        out[0] = h[0]; out[1] = h[1]; out[2] = h[2]; out[3] = h[4];
         return MRB_OK;
     });
 }

@@ -124,6 +124,9 @@ __device__ __forceinline__ bool CertifyLeaf(const AccelData& a, uint32_t leaf, f
 }
 
 constexpr float NEAR_TIE = 1.0000152587890625f; // 1 + 2^-16
+constexpr uint32_t RESOLVE_CAPACITY = 1u << 16;  // candidate records KResolveExact can take per cast
+// counters of one wide cast: [0] uncertified rays, [1] of which near ties, [2] of which leaf-AABB
+// certification failures, [3] dynamic-fetch cursor, [4] rays handed to the full binary fallback
 
 // ------------------------------------------------------------------------------------------------
 // Wide traversal
@@ -153,7 +156,8 @@ KTraceWide(AccelData a, uint32_t accelKey,
            mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
            uint32_t* __restrict__ visibleBits,
            mrb_ray_gmem* rays, const uint32_t* __restrict__ rayIndices, uint32_t rayCount,
-           uint32_t* __restrict__ counters, uint32_t* __restrict__ fallbackList, TraceParams prm)
+           uint32_t* __restrict__ counters, uint32_t* __restrict__ fallbackList,
+           uint4* __restrict__ resolveRecords, TraceParams prm)
 {
     constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
@@ -164,10 +168,12 @@ KTraceWide(AccelData a, uint32_t accelKey,
     bool hasRay = false, finished = false, exhausted = false;
     uint32_t r = 0;
     float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, idx = 0, idy = 0, idz = 0;
-    float tMin = 0, tMaxOrig = 0, tMax = 0, tSecond = 0;
+    float tMin = 0, tMaxOrig = 0, tMax = 0;
+    bool overflow = false; // more than two candidates inside the near-tie window
     uint32_t oct = 0;
     bool uncertified = false, done = false;
     HitRecord best; best.t = 0; best.u = best.v = 0; best.leaf = INVALID_U32; best.rank = 0; best.flags = 0;
+    HitRecord second = best; // runner-up inside the near-tie window of `best`
     uint2 G = make_uint2(0u, 0u), T = make_uint2(0u, 0u);
     uint2 stack[WIDE_STACK];
     int sp = 0;
@@ -181,18 +187,28 @@ KTraceWide(AccelData a, uint32_t accelKey,
             if(ANY_HIT)
             {
                 if(done) atomicAnd(&visibleBits[r >> 5], ~(1u << (r & 31u)));
-                else if(uncertified) { fallbackList[atomicAdd(counters, 1u)] = r; atomicAdd(counters + 2, 1u); }
+                else if(uncertified) { fallbackList[atomicAdd(counters + 4, 1u)] = r; atomicAdd(counters, 1u); atomicAdd(counters + 2, 1u); }
             }
             else if(best.leaf != INVALID_U32)
             {
                 const float tUpper = fminf(tMaxOrig, best.t * NEAR_TIE);
-                bool exact = (tSecond > tUpper) &&
-                             CertifyLeaf(a, best.leaf, ox, oy, oz, dx, dy, dz, tMin, tUpper);
-                if(exact) WriteHit(a, accelKey, r, best, hitKeys, metaHits, rays);
+                const bool hasSecond = second.leaf != INVALID_U32 && second.t <= tUpper;
+                if(!hasSecond && !overflow && CertifyLeaf(a, best.leaf, ox, oy, oz, dx, dy, dz, tMin, tUpper))
+                    WriteHit(a, accelKey, r, best, hitKeys, metaHits, rays);
                 else
                 {
-                    fallbackList[atomicAdd(counters, 1u)] = r;
-                    atomicAdd(counters + ((tSecond > tUpper) ? 2 : 1), 1u); // [1] near ties, [2] uncertified leaf
+                    // hand the candidates to KResolveExact (or, past its capacity, to the full fallback)
+                    const uint32_t slot = atomicAdd(counters, 1u);
+                    atomicAdd(counters + ((hasSecond || overflow) ? 1 : 2), 1u); // [1] near ties, [2] uncertified leaf
+                    if(slot < RESOLVE_CAPACITY)
+                    {
+                        uint4* rec = resolveRecords + size_t(slot) * 4;
+                        rec[0] = make_uint4(r, (overflow ? 1u : 0u) | (hasSecond ? 2u : 0u), 0u, 0u);
+                        rec[1] = make_uint4(__float_as_uint(best.t), __float_as_uint(best.u), __float_as_uint(best.v), best.leaf);
+                        rec[2] = make_uint4(best.rank, best.flags, __float_as_uint(second.t), __float_as_uint(second.u));
+                        rec[3] = make_uint4(__float_as_uint(second.v), second.leaf, second.rank, second.flags);
+                    }
+                    else fallbackList[atomicAdd(counters + 4, 1u)] = r;
                 }
             }
         }
@@ -221,8 +237,9 @@ KTraceWide(AccelData a, uint32_t accelKey,
                         idy = (fabsf(dy) > 1e-30f) ? 1.0f / dy : copysignf(1e30f, dy);
                         idz = (fabsf(dz) > 1e-30f) ? 1.0f / dz : copysignf(1e30f, dz);
                         oct = (dx < 0.0f ? 4u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 1u : 0u);
-                        tMax = tMaxOrig; tSecond = FLT_MAX;
+                        tMax = tMaxOrig; overflow = false;
                         best.t = tMaxOrig; best.rank = 0u; best.leaf = INVALID_U32; best.flags = 0u;
+                        second.leaf = INVALID_U32;
                         uncertified = false; done = false;
                         G = make_uint2(0u, 0x80000000u); T = make_uint2(0u, 0u); sp = 0;
                         hasRay = true;
@@ -266,12 +283,26 @@ KTraceWide(AccelData a, uint32_t accelKey,
                         }
                         else if(t < best.t || (t == best.t && rank < best.rank))
                         {
-                            tSecond = fminf(tSecond, (best.leaf != INVALID_U32) ? best.t : FLT_MAX);
+                            if(best.leaf != INVALID_U32)
+                            {
+                                const float win = t * NEAR_TIE;
+                                const bool bestIn = best.t <= win;
+                                if(bestIn && second.leaf != INVALID_U32 && second.t <= win) overflow = true;
+                                if(bestIn) second = best; else second.leaf = INVALID_U32;
+                            }
                             best.t = t; best.u = u; best.v = v; best.rank = rank;
                             best.leaf = __float_as_uint(v0.w); best.flags = flags;
                             tMax = fminf(tMaxOrig, t * NEAR_TIE);
                         }
-                        else tSecond = fminf(tSecond, t);
+                        else if(t <= best.t * NEAR_TIE)
+                        {
+                            if(second.leaf != INVALID_U32) overflow = true;
+                            else
+                            {
+                                second.t = t; second.u = u; second.v = v; second.rank = rank;
+                                second.leaf = __float_as_uint(v0.w); second.flags = flags;
+                            }
+                        }
                     }
                 }
             }
@@ -432,6 +463,64 @@ KTraceBinary(AccelData a, uint32_t accelKey,
     }
 }
 
+// Exact resolution of the rays the wide path could not certify, WITHOUT a full re-traversal: the
+// reference's answer is decided by the (at most two) candidates inside the near-tie window, by the
+// order it visits them (Morton rank) and by its box tests on their ancestor chains, evaluated with
+// the tMax the reference holds when it first enters each node: the t of an already accepted
+// candidate whose rank lies left of the node's range, else anything >= tUpper. A box that fails
+// with a real candidate's t is a genuine cull; a box that fails with tUpper is undecidable here and
+// the ray goes to the full binary traversal (KTraceBinary), as do rays with three or more
+// candidates in the window.
+__global__ void __launch_bounds__(TRACE_TPB)
+KResolveExact(AccelData a, uint32_t accelKey,
+              mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
+              mrb_ray_gmem* rays, uint32_t* __restrict__ counters, uint32_t* __restrict__ fallbackList,
+              const uint4* __restrict__ resolveRecords)
+{
+    const uint32_t count = min(counters[0], RESOLVE_CAPACITY);
+    for(uint32_t k = blockIdx.x * TRACE_TPB + threadIdx.x; k < count; k += gridDim.x * TRACE_TPB)
+    {
+        const uint4 q0 = resolveRecords[size_t(k) * 4 + 0], q1 = resolveRecords[size_t(k) * 4 + 1];
+        const uint4 q2 = resolveRecords[size_t(k) * 4 + 2], q3 = resolveRecords[size_t(k) * 4 + 3];
+        const uint32_t r = q0.x;
+        bool full = (q0.y & 1u) != 0u;
+        HitRecord c[2];
+        c[0].t = __uint_as_float(q1.x); c[0].u = __uint_as_float(q1.y); c[0].v = __uint_as_float(q1.z); c[0].leaf = q1.w;
+        c[0].rank = q2.x; c[0].flags = q2.y;
+        c[1].t = __uint_as_float(q2.z); c[1].u = __uint_as_float(q2.w); c[1].v = __uint_as_float(q3.x); c[1].leaf = q3.y;
+        c[1].rank = q3.z; c[1].flags = q3.w;
+        const int n = (q0.y & 2u) ? 2 : 1;
+        const float4 r0 = reinterpret_cast<const float4*>(rays + r)[0];
+        const float4 r1 = reinterpret_cast<const float4*>(rays + r)[1];
+        const float o[3] = {r0.x, r0.y, r0.z};
+        const float invD[3] = {__fdiv_rn(1.0f, r1.x), __fdiv_rn(1.0f, r1.y), __fdiv_rn(1.0f, r1.z)};
+        const float tMin = r0.w;
+        const float tUpper = fminf(r1.w, c[0].t * NEAR_TIE);
+        const int first = (n == 2 && c[1].rank < c[0].rank) ? 1 : 0;
+        int accepted = -1;
+        for(int s = 0; s < n && !full; s++)
+        {
+            const HitRecord& z = c[s == 0 ? first : 1 - first];
+            bool reach = true;
+            uint32_t ni = a.leafParent[z.leaf];
+            while(ni != INVALID_U32)
+            {
+                const bool usePrior = accepted >= 0 && c[accepted].rank < a.nodeRange[ni].x;
+                const float tcur = usePrior ? c[accepted].t : tUpper;
+                if(!SlabExact(reinterpret_cast<const float*>(a.boxes + ni), o, invD, tMin, tcur))
+                {
+                    if(usePrior) reach = false; else full = true;
+                    break;
+                }
+                ni = a.nodes[ni].parent;
+            }
+            if(!full && reach && (accepted < 0 || z.t < c[accepted].t)) accepted = (s == 0 ? first : 1 - first);
+        }
+        if(full || accepted < 0) fallbackList[atomicAdd(counters + 4, 1u)] = r;
+        else WriteHit(a, accelKey, r, c[accepted], hitKeys, metaHits, rays);
+    }
+}
+
 } // namespace
 
 void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode mode,
@@ -442,12 +531,15 @@ void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode
     const uint32_t grid = DivUp(rayCount, TRACE_TPB);
     if(mode == MRB_TRACE_WIDE)
     {
-        // fallback list: [count][ray slots...] in the context's trace scratch
-        ctx.traceScratch.Reserve(sizeof(uint32_t) * (size_t(rayCount) + 64));
-        uint32_t* fbCount = static_cast<uint32_t*>(ctx.traceScratch.Base());
-        uint32_t* fbList = fbCount + 64;
-        MRB_CUDA_TRY(cudaMemsetAsync(fbCount, 0, sizeof(uint32_t) * 4, ctx.stream));
-        const uint32_t fbGrid = uint32_t(ctx.smCount) * 2u;
+        // trace scratch: [counters (64 words)][resolve records][full-fallback ray list]
+        MultiAlloc sz(nullptr);
+        sz.Take<uint32_t>(64); sz.Take<uint4>(size_t(RESOLVE_CAPACITY) * 4); sz.Take<uint32_t>(rayCount);
+        ctx.traceScratch.Reserve(sz.Total());
+        MultiAlloc ma(ctx.traceScratch.Base());
+        uint32_t* counters = ma.Take<uint32_t>(64);
+        uint4* records = ma.Take<uint4>(size_t(RESOLVE_CAPACITY) * 4);
+        uint32_t* fbList = ma.Take<uint32_t>(rayCount);
+        MRB_CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 8, ctx.stream));
         static int occClosest = 0, occAny = 0;
         if(!occClosest)
         {
@@ -462,17 +554,19 @@ void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode
             return p;
         }();
         const uint32_t pgrid = min(grid, uint32_t(ctx.smCount) * uint32_t(anyHit ? occAny : occClosest));
+        const uint32_t fbGrid = uint32_t(ctx.smCount);
         if(anyHit)
         {
-            MRB_LAUNCH(ctx, KTraceWide<true>, pgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, fbCount, fbList, prm);
-            MRB_LAUNCH(ctx, KTraceBinary<true>, fbGrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, fbList, 0u, fbCount);
+            MRB_LAUNCH(ctx, KTraceWide<true>, pgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, fbList, records, prm);
+            MRB_LAUNCH(ctx, KTraceBinary<true>, fbGrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, fbList, 0u, counters + 4);
         }
         else
         {
-            MRB_LAUNCH(ctx, KTraceWide<false>, pgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, fbCount, fbList, prm);
-            MRB_LAUNCH(ctx, KTraceBinary<false>, fbGrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, fbList, 0u, fbCount);
+            MRB_LAUNCH(ctx, KTraceWide<false>, pgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, fbList, records, prm);
+            MRB_LAUNCH(ctx, KResolveExact, fbGrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, rays, counters, fbList, records);
+            MRB_LAUNCH(ctx, KTraceBinary<false>, fbGrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, fbList, 0u, counters + 4);
         }
-        ctx.lastFallbackCount = fbCount;
+        ctx.lastFallbackCount = counters;
     }
     else
     {
