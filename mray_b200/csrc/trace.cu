@@ -134,15 +134,29 @@ constexpr uint32_t RESOLVE_CAPACITY = 1u << 16;  // candidate records KResolveEx
 // Quantised byte j of `word` as the float 32768 + q (bits 0x4700qq00): ONE PRMT, no int->float
 // conversion. The 32768 offset is folded into the per-node constant (c - 32768 s), whose rounding
 // error (<= 2^-9 |s|, 0.002 quantisation cells) is covered by the node slack.
-__device__ __forceinline__ float QF(uint32_t word, int j)
+template<int J>
+__device__ __forceinline__ float QFI(uint32_t word, uint32_t magic)
 {
-    return __uint_as_float(__byte_perm(word, 0x47000000u, 0x7604u | (uint32_t(j) << 4)));
+    uint32_t d; // selector must stay an immediate: {magic.b3, magic.b2, word.bJ, magic.b0}
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(word), "r"(magic), "n"(0x7604 | (J << 4)));
+    return __uint_as_float(d);
+}
+__device__ __forceinline__ float QF(uint32_t word, int j, uint32_t magic)
+{
+    switch(j)
+    {
+        case 0: return QFI<0>(word, magic);
+        case 1: return QFI<1>(word, magic);
+        case 2: return QFI<2>(word, magic);
+        default: return QFI<3>(word, magic);
+    }
 }
 
 struct TraceParams
 {
     uint32_t triDiv;    // triangle phase runs when lanesWithTriangles * triDiv >= liveLanes (or no lane has node work)
     uint32_t fetchThr;  // refill idle lanes with new rays when fewer than this many lanes are live
+    uint32_t magic;     // 0x47000000 (float 32768): see QF
 };
 
 // Persistent warps: every lane owns one ray at a time; finished lanes are refilled from a global
@@ -340,6 +354,7 @@ KTraceWide(AccelData a, uint32_t accelKey,
 
                     uint32_t hitmask = 0u;
                     const uint32_t oct4 = oct * 0x01010101u;
+                    const uint32_t magic = prm.magic; // 0x47000000, kept opaque so ptxas keeps the PRMT selectors immediate
                     #pragma unroll
                     for(int half = 0; half < 2; half++)
                     {
@@ -356,9 +371,9 @@ KTraceWide(AccelData a, uint32_t accelKey,
                         #pragma unroll
                         for(int j = 0; j < 4; j++)
                         {
-                            const float tnx = __fmaf_rn(QF(nx, j), sx, cnx), tfx = __fmaf_rn(QF(fx, j), sx, cfx);
-                            const float tny = __fmaf_rn(QF(ny, j), sy, cny), tfy = __fmaf_rn(QF(fy, j), sy, cfy);
-                            const float tnz = __fmaf_rn(QF(nz, j), sz, cnz), tfz = __fmaf_rn(QF(fz, j), sz, cfz);
+                            const float tnx = __fmaf_rn(QF(nx, j, magic), sx, cnx), tfx = __fmaf_rn(QF(fx, j, magic), sx, cfx);
+                            const float tny = __fmaf_rn(QF(ny, j, magic), sy, cny), tfy = __fmaf_rn(QF(fy, j, magic), sy, cfy);
+                            const float tnz = __fmaf_rn(QF(nz, j, magic), sz, cnz), tfz = __fmaf_rn(QF(fz, j, magic), sz, cfz);
                             const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tMin));
                             const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tFarLimit));
                             if(tn <= tf)
@@ -548,7 +563,7 @@ void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode
         }
         static TraceParams prm = []
         {
-            TraceParams p{5u, 24u};
+            TraceParams p{5u, 24u, 0x47000000u};
             if(const char* e = getenv("MRB_TRI_DIV")) p.triDiv = uint32_t(atoi(e));
             if(const char* e = getenv("MRB_FETCH_THR")) p.fetchThr = uint32_t(atoi(e));
             return p;
