@@ -18,6 +18,7 @@ if [ ! -d "$R" ]; then echo "reference not present at $REF; keeping prebuilt ora
 case $MODE in
   parity)  OPT="-O2"; SUF="" ;;
   release) OPT="-O3 -funsafe-math-optimizations -fno-math-errno"; SUF="_rel" ;;
+  safe)    OPT="-O1 -fno-strict-aliasing -fwrapv -fno-delete-null-pointer-checks"; SUF="_safe" ;;
   *) echo "bad mode"; exit 1 ;;
 esac
 W=$OUT/work$SUF

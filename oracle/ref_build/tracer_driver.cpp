@@ -1,0 +1,406 @@
+// tracer_driver.cpp — drives ANY TracerDLL (the reference's libTracerDLL_CPU.so, or our
+// libTracerDLL_B200.so) through the reference's own plugin interface Core/TracerI.h, exactly as
+// MRay's TracerThread / SceneLoaderMRay / RunCommand do (MRay/TracerThread.cpp:L149-300,L855-876,
+// SceneLoaderMRay/SceneLoaderMRay.cpp:L335-460,L2136-2260, MRay/RunCommand.cpp:L293-345).
+//
+// TEST / BASELINE INFRASTRUCTURE ONLY. Compiled against the unmodified reference headers in the
+// authoring container; exposes one C entry point so Python (ctypes) can feed it numpy arrays.
+#include "Core/TracerI.h"
+#include "Core/ThreadPool.h"
+#include "Core/TimelineSemaphore.h"
+#include "Core/Error.h"
+#include "Core/TypeNameGenerators.h"
+#include "TransientPool/TransientPool.h"
+#include "Core/GraphicsFunctions.h"
+
+#include <dlfcn.h>
+#include <chrono>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cstdio>
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+#include <ucontext.h>
+
+extern "C"
+{
+
+struct DriverScene
+{
+    // geometry: `batchCount` triangle batches, each with its own vertex list
+    uint32_t        batchCount;
+    const uint32_t* batchVertexOffsets; // batchCount + 1 (into positions / normals)
+    const uint32_t* batchTriOffsets;    // batchCount + 1 (into indices; indices are batch-local)
+    const float*    positions;          // V * 3
+    const float*    normals;            // V * 3 (unit shading normals)
+    const uint32_t* indices;            // T * 3
+    const int32_t*  batchMaterial;      // batchCount : Lambert material index, or -1 for an emissive batch
+    const int32_t*  batchLight;         // batchCount : light index, or -1
+    uint32_t        materialCount;
+    const float*    albedo;             // materialCount * 3
+    uint32_t        lightCount;
+    const float*    radiance;           // lightCount * 3
+    // camera (pinhole)
+    float           camPos[3], camGaze[3], camUp[3];
+    float           fovXY[2];           // radians
+    float           nearFar[2];
+};
+
+struct DriverRender
+{
+    const char* rendererName;   // "PathTracerRGB" | "PathTracerSpectral"
+    uint32_t    width, height;
+    uint32_t    totalSPP;
+    const char* sampleMode;     // "Pure" | "WithNextEventEstimation" | "WithNEEAndMIS"
+    uint32_t    rrRange[2];
+    uint64_t    seed;
+    uint32_t    accelMode;      // AcceleratorType: 0 SOFTWARE_NONE(linear), 1 SOFTWARE_BASIC_BVH, 2 HARDWARE
+    uint32_t    parallelHint;   // 0 = default (2^21)
+    uint32_t    threads;        // host thread pool size (0 = hardware)
+};
+
+struct DriverStats
+{
+    double commitSeconds;   // CommitSurfaces (BVH build)
+    double renderSeconds;   // DoRenderWork loop
+    double totalPaths;      // sum of section weights (approx. completed paths)
+    uint32_t iterations;
+    float  sceneAABB[6];
+};
+
+static void SegvInfo(int, siginfo_t* si, void* ctx)
+{
+    ucontext_t* uc = static_cast<ucontext_t*>(ctx);
+    void* rip = reinterpret_cast<void*>(uc->uc_mcontext.gregs[REG_RIP]);
+    Dl_info info; memset(&info, 0, sizeof(info));
+    dladdr(rip, &info);
+    char buf[1024];
+    int n = snprintf(buf, sizeof(buf), "SEGV addr=%p rip=%p module=%s base=%p off=0x%lx sym=%s\n", si->si_addr, rip,
+                     info.dli_fname ? info.dli_fname : "?", info.dli_fbase,
+                     (unsigned long)((char*)rip - (char*)info.dli_fbase), info.dli_sname ? info.dli_sname : "?");
+    write(2, buf, n);
+    // walk a few frames by frame pointer-less heuristic: dump return addresses found on the stack that lie in the module
+    unsigned long* sp = reinterpret_cast<unsigned long*>(uc->uc_mcontext.gregs[REG_RSP]);
+    for(int i = 0, found = 0; i < 4096 && found < 12; i++)
+    {
+        Dl_info fi; memset(&fi, 0, sizeof(fi));
+        if(dladdr(reinterpret_cast<void*>(sp[i]), &fi) && fi.dli_fbase == info.dli_fbase && fi.dli_sname)
+        {
+            n = snprintf(buf, sizeof(buf), "  stack[%d] off=0x%lx %s\n", i, (unsigned long)((char*)sp[i] - (char*)fi.dli_fbase), fi.dli_sname);
+            write(2, buf, n); found++;
+        }
+    }
+    _exit(98);
+}
+
+static void AlarmBacktrace(int)
+{
+    void* frames[64];
+    int n = backtrace(frames, 64);
+    backtrace_symbols_fd(frames, n, 2);
+    _exit(99);
+}
+
+static void Fail(char* err, size_t n, const std::string& s)
+{
+    std::snprintf(err, n, "%s", s.c_str());
+}
+
+// Returns 0 on success. outRGB: width*height*3 floats (row 0 = bottom row, as the tracer delivers),
+// accumulated in double like RunCommand (out = (out*W + in)/(W + w)).
+int tracer_driver_render(const char* dllPath, const DriverScene* sc, const DriverRender* rd,
+                         float* outRGB, float* outWeight, DriverStats* stats, char* err, size_t errLen)
+{
+    using namespace std::string_literals;
+    if(getenv("DRIVER_ALARM"))
+    {
+        static char altStack[1 << 16];
+        stack_t ss; ss.ss_sp = altStack; ss.ss_size = sizeof(altStack); ss.ss_flags = 0;
+        sigaltstack(&ss, nullptr);
+        struct sigaction sa; memset(&sa, 0, sizeof(sa));
+        sa.sa_sigaction = SegvInfo; sa.sa_flags = SA_SIGINFO;
+        sigaction(SIGSEGV, &sa, nullptr);
+    }
+    void* lib = dlopen(dllPath, RTLD_NOW | RTLD_GLOBAL);
+    if(!lib) { Fail(err, errLen, "dlopen failed: "s + dlerror()); return 1; }
+    using ConstructF = TracerI* (*)(const TracerParameters&);
+    using DestroyF = void (*)(TracerI*);
+    auto construct = reinterpret_cast<ConstructF>(dlsym(lib, "ConstructTracer"));
+    auto destroy = reinterpret_cast<DestroyF>(dlsym(lib, "DestroyTracer"));
+    if(!construct || !destroy) { Fail(err, errLen, "ConstructTracer/DestroyTracer not exported"); return 2; }
+
+    TracerI* tracer = nullptr;
+    try
+    {
+        TracerParameters tp;
+        tp.seed = rd->seed;
+        tp.accelMode = AcceleratorType(rd->accelMode);
+        if(rd->parallelHint) tp.parallelizationHint = rd->parallelHint;
+        tracer = construct(tp);
+        // as MRay/RunCommand.cpp:L1015-1025: worker threads run the tracer's device-init function
+        ThreadPool pool;
+        auto threadInit = tracer->GetThreadInitFunction();
+        pool.RestartThreads(rd->threads ? rd->threads : std::thread::hardware_concurrency(),
+                            [threadInit](std::thread::native_handle_type, uint32_t) { threadInit(); });
+        tracer->SetThreadPool(pool);
+        threadInit();
+
+        // ---- primitives ----
+        PrimGroupId pg = tracer->CreatePrimitiveGroup("(P)Triangle");
+        std::vector<PrimCount> counts;
+        for(uint32_t b = 0; b < sc->batchCount; b++)
+            counts.push_back(PrimCount{sc->batchTriOffsets[b + 1] - sc->batchTriOffsets[b],
+                                       sc->batchVertexOffsets[b + 1] - sc->batchVertexOffsets[b]});
+        PrimBatchIdList batches = tracer->ReservePrimitiveBatches(pg, counts);
+        tracer->CommitPrimReservations(pg);
+        PrimAttributeInfoList pInfo = tracer->AttributeInfo(pg);
+        for(uint32_t b = 0; b < sc->batchCount; b++)
+        {
+            uint32_t v0 = sc->batchVertexOffsets[b], vN = counts[b].attributeCount;
+            uint32_t t0 = sc->batchTriOffsets[b], tN = counts[b].primCount;
+            for(uint32_t a = 0; a < pInfo.size(); a++)
+            {
+                using enum PrimitiveAttributeLogic::E;
+                switch(pInfo[a].logic.e)
+                {
+                    case POSITION:
+                    {
+                        TransientData d(std::in_place_type_t<Vector3>{}, vN);
+                        d.Push(Span<const Vector3>(reinterpret_cast<const Vector3*>(sc->positions) + v0, vN));
+                        tracer->PushPrimAttribute(pg, batches[b], a, std::move(d));
+                        break;
+                    }
+                    case NORMAL:
+                    {
+                        // normals travel as tangent-space rotations (SceneLoaderMRay.cpp:L395-436)
+                        TransientData d(std::in_place_type_t<Quaternion>{}, vN);
+                        for(uint32_t i = 0; i < vN; i++)
+                        {
+                            Vector3 n = Math::Normalize(reinterpret_cast<const Vector3*>(sc->normals)[v0 + i]);
+                            Vector3 bt = Graphics::OrthogonalVector(n);
+                            Vector3 t = Math::Cross(bt, n);
+                            Quaternion q = TransformGen::ToSpaceQuat(t, bt, n);
+                            d.Push(Span<const Quaternion>(&q, 1));
+                        }
+                        tracer->PushPrimAttribute(pg, batches[b], a, std::move(d));
+                        break;
+                    }
+                    case UV0:
+                    {
+                        TransientData d(std::in_place_type_t<Vector2>{}, vN);
+                        std::vector<Vector2> z(vN, Vector2::Zero());
+                        d.Push(Span<const Vector2>(z));
+                        tracer->PushPrimAttribute(pg, batches[b], a, std::move(d));
+                        break;
+                    }
+                    case INDEX:
+                    {
+                        TransientData d(std::in_place_type_t<Vector3ui>{}, tN);
+                        d.Push(Span<const Vector3ui>(reinterpret_cast<const Vector3ui*>(sc->indices) + t0, tN));
+                        tracer->PushPrimAttribute(pg, batches[b], a, std::move(d));
+                        break;
+                    }
+                    default: break;
+                }
+            }
+        }
+        // ---- materials (Lambert, constant albedo) ----
+        MatGroupId mg = tracer->CreateMaterialGroup("(Mt)Lambert");
+        MatAttributeInfoList mInfo = tracer->AttributeInfo(mg);
+        std::vector<AttributeCountList> mCounts(sc->materialCount);
+        for(auto& c : mCounts) { c = AttributeCountList(StaticVecSize(mInfo.size())); c[0] = 1; for(size_t k = 1; k < mInfo.size(); k++) c[k] = 0; }
+        MaterialIdList mats = tracer->ReserveMaterials(mg, mCounts);
+        tracer->CommitMatReservations(mg);
+        {
+            auto range = CommonIdRange(std::bit_cast<CommonId>(mats.front()), std::bit_cast<CommonId>(mats.back()));
+            TransientData d(std::in_place_type_t<Vector3>{}, sc->materialCount);
+            d.Push(Span<const Vector3>(reinterpret_cast<const Vector3*>(sc->albedo), sc->materialCount));
+            tracer->PushMatAttribute(mg, range, 0, std::move(d),
+                                     std::vector<Optional<TextureId>>(sc->materialCount, std::nullopt));
+            // attribute 1 (optional texture-only normal map) is left unset
+        }
+        // ---- lights (prim backed) ----
+        LightGroupId lg = sc->lightCount ? tracer->CreateLightGroup("(L)Prim(P)Triangle", pg) : LightGroupId(0);
+        LightAttributeInfoList lInfo = tracer->AttributeInfo(lg);
+        std::vector<AttributeCountList> lCounts(sc->lightCount);
+        for(auto& c : lCounts) { c = AttributeCountList(StaticVecSize(lInfo.size())); for(size_t k = 0; k < lInfo.size(); k++) c[k] = 1; }
+        std::vector<PrimBatchId> lightBatches(sc->lightCount);
+        for(uint32_t b = 0; b < sc->batchCount; b++)
+            if(sc->batchLight[b] >= 0) lightBatches[size_t(sc->batchLight[b])] = batches[b];
+        LightIdList lights;
+        if(sc->lightCount)
+        {
+            lights = tracer->ReserveLights(lg, lCounts, lightBatches);
+            tracer->CommitLightReservations(lg);
+            auto range = CommonIdRange(std::bit_cast<CommonId>(lights.front()), std::bit_cast<CommonId>(lights.back()));
+            for(uint32_t a = 0; a < lInfo.size(); a++)
+            {
+                if(lInfo[a].dataType.Name() == MRayDataEnum::MR_VECTOR_3)
+                {
+                    TransientData d(std::in_place_type_t<Vector3>{}, sc->lightCount);
+                    d.Push(Span<const Vector3>(reinterpret_cast<const Vector3*>(sc->radiance), sc->lightCount));
+                    tracer->PushLightAttribute(lg, range, a, std::move(d),
+                                               std::vector<Optional<TextureId>>(sc->lightCount, std::nullopt));
+                }
+                else
+                {
+                    TransientData d(std::in_place_type_t<bool>{}, sc->lightCount);
+                    std::vector<uint8_t> f(sc->lightCount, 0);
+                    d.Push(Span<const bool>(reinterpret_cast<const bool*>(f.data()), sc->lightCount));
+                    tracer->PushLightAttribute(lg, range, a, std::move(d));
+                }
+            }
+        }
+        // ---- camera ----
+        CameraGroupId cg = tracer->CreateCameraGroup("(C)Pinhole");
+        CamAttributeInfoList cInfo = tracer->AttributeInfo(cg);
+        AttributeCountList cCount(StaticVecSize(cInfo.size()));
+        for(size_t k = 0; k < cInfo.size(); k++) cCount[k] = 1;
+        CameraId cam = tracer->ReserveCamera(cg, cCount);
+        tracer->CommitCamReservations(cg);
+        {
+            auto range = CommonIdRange(std::bit_cast<CommonId>(cam), std::bit_cast<CommonId>(cam));
+            // attribute order of CameraGroupPinhole: FovAndPlanes, gaze, position, up
+            Vector4 fp(sc->fovXY[0], sc->fovXY[1], sc->nearFar[0], sc->nearFar[1]);
+            Vector3 v[3] = {Vector3(sc->camGaze[0], sc->camGaze[1], sc->camGaze[2]),
+                            Vector3(sc->camPos[0], sc->camPos[1], sc->camPos[2]),
+                            Vector3(sc->camUp[0], sc->camUp[1], sc->camUp[2])};
+            TransientData d0(std::in_place_type_t<Vector4>{}, 1); d0.Push(Span<const Vector4>(&fp, 1));
+            tracer->PushCamAttribute(cg, range, 0, std::move(d0));
+            for(uint32_t a = 1; a < 4; a++)
+            {
+                TransientData d(std::in_place_type_t<Vector3>{}, 1); d.Push(Span<const Vector3>(&v[a - 1], 1));
+                tracer->PushCamAttribute(cg, range, a, std::move(d));
+            }
+        }
+        // ---- surfaces ----
+        for(uint32_t b = 0; b < sc->batchCount; b++)
+        {
+            if(sc->batchMaterial[b] < 0) continue;
+            SurfaceParams sp;
+            sp.primBatches.push_back(batches[b]);
+            sp.materials.push_back(mats[size_t(sc->batchMaterial[b])]);
+            sp.transformId = TracerConstants::IdentityTransformId;
+            sp.alphaMaps.push_back(std::nullopt);
+            sp.cullFaceFlags.push_back(false);
+            sp.volumes.push_back(TracerConstants::InvalidVolume);
+            tracer->CreateSurface(sp);
+        }
+        for(uint32_t l = 0; l < sc->lightCount; l++)
+            tracer->CreateLightSurface(LightSurfaceParams{lights[l], TracerConstants::IdentityTransformId, {}});
+        CamSurfaceId camSurf = tracer->CreateCameraSurface(CameraSurfaceParams{cam, TracerConstants::IdentityTransformId, {}});
+        tracer->SetBoundarySurface(TracerConstants::NullLightId, TracerConstants::IdentityTransformId);
+        VolumeId bVol = tracer->RegisterVolume(VolumeParams{TracerConstants::VacuumMediumId,
+                                                            TracerConstants::IdentityTransformId, 0});
+        tracer->SetBoundaryVolume(bVol);
+
+        auto c0 = std::chrono::steady_clock::now();
+        SurfaceCommitResult cr = tracer->CommitSurfaces();
+        auto c1 = std::chrono::steady_clock::now();
+        stats->commitSeconds = std::chrono::duration<double>(c1 - c0).count();
+        for(int k = 0; k < 3; k++) { stats->sceneAABB[k] = cr.aabb.Min()[k]; stats->sceneAABB[3 + k] = cr.aabb.Max()[k]; }
+
+        // ---- renderer ----
+        TimelineSemaphore sem(0);
+        tracer->SetupRenderEnv(&sem, 4096, 0);
+        RendererId rid = tracer->CreateRenderer(std::string("(R)") + rd->rendererName);
+        RendererAttributeInfoList rInfo = tracer->AttributeInfo(rid);
+        for(uint32_t a = 0; a < rInfo.size(); a++)
+        {
+            std::string_view name = rInfo[a].name;
+            MRayDataTypeRT dt = rInfo[a].dataType;
+            auto PushU32 = [&](uint32_t v)
+            { TransientData d(std::in_place_type_t<uint32_t>{}, 1); d.Push(Span<const uint32_t>(&v, 1)); tracer->PushRendererAttribute(rid, a, std::move(d)); };
+            auto PushStr = [&](std::string_view s)
+            {   // as MRay/TracerThread.cpp:L205-216
+                TransientData d = AllocateTransientData(dt, s.size());
+                d.ReserveAll();
+                Span<char> o = d.AccessAsString();
+                std::copy(s.cbegin(), s.cend(), o.begin());
+                tracer->PushRendererAttribute(rid, a, std::move(d));
+            };
+            if(name == "totalSPP") PushU32(rd->totalSPP);
+            else if(name == "burstSize") PushU32(1);
+            else if(name == "renderMode") PushStr("Throughput");
+            else if(name == "sampleMode") PushStr(rd->sampleMode);
+            else if(name == "rrRange")
+            {
+                Vector2ui v(rd->rrRange[0], rd->rrRange[1]);
+                TransientData d(std::in_place_type_t<Vector2ui>{}, 1); d.Push(Span<const Vector2ui>(&v, 1));
+                tracer->PushRendererAttribute(rid, a, std::move(d));
+            }
+            else if(name == "neeSamplerType") PushStr("Uniform");
+            else if(rInfo[a].isOptional == AttributeOptionality::MR_MANDATORY)
+                throw MRayError("driver: unknown mandatory renderer attribute {}", name);
+            (void)dt;
+        }
+        RenderImageParams rip{Vector2ui(rd->width, rd->height), Vector2ui(0, 0), Vector2ui(rd->width, rd->height)};
+        if(getenv("DRIVER_VERBOSE")) std::fprintf(stderr, "StartRender...\n");
+        if(const char* a = getenv("DRIVER_ALARM")) { signal(SIGALRM, AlarmBacktrace); alarm(unsigned(atoi(a))); }
+        RenderBufferInfo rbi = tracer->StartRender(rid, camSurf, rip, std::nullopt, std::nullopt);
+        if(getenv("DRIVER_VERBOSE")) std::fprintf(stderr, "StartRender done, buffer %zu bytes\n", rbi.totalSize);
+
+        size_t pix = size_t(rd->width) * rd->height;
+        std::vector<double> acc(pix * 4, 0.0);
+        auto r0 = std::chrono::steady_clock::now();
+        uint32_t iters = 0;
+        while(true)
+        {
+            RendererOutput out = tracer->DoRenderWork();
+            iters++;
+            if(getenv("DRIVER_VERBOSE")) std::fprintf(stderr, "iter %u img %d save %d\n", iters, int(out.imageOut.has_value()), int(out.triggerSave));
+            if(out.imageOut)
+            {
+                const RenderImageSection& s = *out.imageOut;
+                if(!sem.Acquire(s.waitCounter)) break;
+                const float* R = reinterpret_cast<const float*>(rbi.data + s.pixStartOffsets[0]);
+                const float* G = reinterpret_cast<const float*>(rbi.data + s.pixStartOffsets[1]);
+                const float* B = reinterpret_cast<const float*>(rbi.data + s.pixStartOffsets[2]);
+                const float* Wt = reinterpret_cast<const float*>(rbi.data + s.weightStartOffset);
+                uint32_t w = s.pixelMax[0] - s.pixelMin[0], h = s.pixelMax[1] - s.pixelMin[1];
+                for(uint32_t y = 0; y < h; y++)
+                for(uint32_t x = 0; x < w; x++)
+                {
+                    size_t src = size_t(y) * w + x;
+                    size_t dst = (size_t(y + s.pixelMin[1]) * rd->width + (x + s.pixelMin[0])) * 4;
+                    // RunCommand keeps a running weighted mean; summing numerator and weight is the same value
+                    acc[dst + 0] += R[src]; acc[dst + 1] += G[src]; acc[dst + 2] += B[src]; acc[dst + 3] += double(Wt[src]) * s.globalWeight;
+                }
+                sem.Release();
+            }
+            if(out.triggerSave) break;
+            if(iters > 100000000u) break;
+        }
+        auto r1 = std::chrono::steady_clock::now();
+        tracer->StopRender();
+        stats->renderSeconds = std::chrono::duration<double>(r1 - r0).count();
+        stats->iterations = iters;
+        double tw = 0;
+        for(size_t p = 0; p < pix; p++)
+        {
+            double w = acc[p * 4 + 3];
+            tw += w;
+            for(int c = 0; c < 3; c++) outRGB[p * 3 + c] = float(w > 0 ? acc[p * 4 + c] / w : 0.0);
+            if(outWeight) outWeight[p] = float(w);
+        }
+        stats->totalPaths = tw;
+        tracer->DestroyRenderer(rid);
+        destroy(tracer);
+        tracer = nullptr;
+    }
+    catch(const MRayError& e)
+    {
+        Fail(err, errLen, "MRayError: "s + e.GetError());
+        return 3;
+    }
+    catch(const std::exception& e)
+    {
+        Fail(err, errLen, "exception: "s + e.what());
+        return 4;
+    }
+    return 0;
+}
+
+} // extern "C"

@@ -151,3 +151,94 @@ def ref_trace(positions, indices, bvh: LBVH, rays, mode=0, cull=0):
     ref().ref_lbvh_trace(positions, positions.shape[0], indices, indices.shape[0], bvh.nodes, bvh.boxes,
                          bvh.nodes.shape[0], np.ascontiguousarray(rays), n, mode, cull, prim, t, bary, back)
     return prim, t, bary, back
+
+
+# ------------------------------------------------------------------------------------------------
+# tracer driver (TracerI protocol) — renders a scene through any TracerDLL
+# ------------------------------------------------------------------------------------------------
+class _DriverScene(C.Structure):
+    _fields_ = [("batchCount", C.c_uint32), ("batchVertexOffsets", C.c_void_p), ("batchTriOffsets", C.c_void_p),
+                ("positions", C.c_void_p), ("normals", C.c_void_p), ("indices", C.c_void_p),
+                ("batchMaterial", C.c_void_p), ("batchLight", C.c_void_p),
+                ("materialCount", C.c_uint32), ("albedo", C.c_void_p),
+                ("lightCount", C.c_uint32), ("radiance", C.c_void_p),
+                ("camPos", C.c_float * 3), ("camGaze", C.c_float * 3), ("camUp", C.c_float * 3),
+                ("fovXY", C.c_float * 2), ("nearFar", C.c_float * 2)]
+
+
+class _DriverRender(C.Structure):
+    _fields_ = [("rendererName", C.c_char_p), ("width", C.c_uint32), ("height", C.c_uint32), ("totalSPP", C.c_uint32),
+                ("sampleMode", C.c_char_p), ("rrRange", C.c_uint32 * 2), ("seed", C.c_uint64),
+                ("accelMode", C.c_uint32), ("parallelHint", C.c_uint32), ("threads", C.c_uint32)]
+
+
+class _DriverStats(C.Structure):
+    _fields_ = [("commitSeconds", C.c_double), ("renderSeconds", C.c_double), ("totalPaths", C.c_double),
+                ("iterations", C.c_uint32), ("sceneAABB", C.c_float * 6)]
+
+
+def driver_available():
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libtracer_driver.so"))
+
+
+def batched_scene(positions, indices, tri_material, normals=None):
+    """Splits a flat mesh into one batch per material id (own compacted vertex list, local indices) — the
+    shape TracerI::ReservePrimitiveBatches wants. Returns dict of arrays."""
+    mats = np.unique(tri_material)
+    vo, to, P, N, I = [0], [0], [], [], []
+    if normals is None:  # flat per-vertex normals only make sense for unshared vertices; compute smooth ones
+        fn = np.cross(positions[indices[:, 1]] - positions[indices[:, 0]], positions[indices[:, 2]] - positions[indices[:, 0]])
+        normals = np.zeros_like(positions, dtype=np.float64)
+        for k in range(3):
+            np.add.at(normals, indices[:, k], fn)
+        ln = np.linalg.norm(normals, axis=1, keepdims=True)
+        normals = (normals / np.where(ln > 0, ln, 1)).astype(np.float32)
+    for m in mats:
+        tris = indices[tri_material == m]
+        used, inv = np.unique(tris.ravel(), return_inverse=True)
+        P.append(positions[used]); N.append(normals[used]); I.append(inv.reshape(-1, 3).astype(np.uint32))
+        vo.append(vo[-1] + used.size); to.append(to[-1] + tris.shape[0])
+    return dict(materials=mats, vertex_offsets=np.array(vo, np.uint32), tri_offsets=np.array(to, np.uint32),
+                positions=np.ascontiguousarray(np.concatenate(P), np.float32),
+                normals=np.ascontiguousarray(np.concatenate(N), np.float32),
+                indices=np.ascontiguousarray(np.concatenate(I), np.uint32))
+
+
+def driver_render(dll_path, batched, albedo, light_material, radiance, camera, width, height, spp,
+                  renderer="PathTracerRGB", sample_mode="WithNEEAndMIS", rr_range=(2, 20), seed=0,
+                  accel_mode=1, threads=0, parallel_hint=0, near_far=(0.01, 1000.0)):
+    """Renders through TracerI. `light_material`: material id whose batch is the prim-backed light.
+    Returns (image[h,w,3] float32 with row 0 = bottom, weight[h,w], stats dict)."""
+    L = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libtracer_driver.so"))
+    L.tracer_driver_render.restype = C.c_int
+    mats = list(batched["materials"])
+    lambert = [m for m in mats if m != light_material]
+    bm = np.array([lambert.index(m) if m != light_material else -1 for m in mats], np.int32)
+    bl = np.array([0 if m == light_material else -1 for m in mats], np.int32)
+    alb = np.ascontiguousarray(np.asarray(albedo, np.float32)[lambert])
+    rad = np.ascontiguousarray(np.asarray(radiance, np.float32).reshape(1, 3))
+    sc = _DriverScene()
+    sc.batchCount = len(mats)
+    keep = [batched["vertex_offsets"], batched["tri_offsets"], batched["positions"], batched["normals"],
+            batched["indices"], bm, bl, alb, rad]
+    sc.batchVertexOffsets, sc.batchTriOffsets = keep[0].ctypes.data, keep[1].ctypes.data
+    sc.positions, sc.normals, sc.indices = keep[2].ctypes.data, keep[3].ctypes.data, keep[4].ctypes.data
+    sc.batchMaterial, sc.batchLight = bm.ctypes.data, bl.ctypes.data
+    sc.materialCount, sc.albedo = len(lambert), alb.ctypes.data
+    sc.lightCount, sc.radiance = (1 if light_material in mats else 0), rad.ctypes.data
+    sc.camPos = (C.c_float * 3)(*camera["eye"]); sc.camGaze = (C.c_float * 3)(*camera["gaze"]); sc.camUp = (C.c_float * 3)(*camera["up"])
+    fy = np.deg2rad(camera["fov_y_deg"])
+    fx = 2 * np.arctan(np.tan(fy / 2) * width / height)
+    sc.fovXY = (C.c_float * 2)(fx, fy); sc.nearFar = (C.c_float * 2)(*near_far)
+    rd = _DriverRender(renderer.encode(), width, height, spp, sample_mode.encode(), (C.c_uint32 * 2)(*rr_range), seed,
+                       accel_mode, parallel_hint, threads)
+    img = np.zeros((height, width, 3), np.float32)
+    wgt = np.zeros((height, width), np.float32)
+    st = _DriverStats()
+    err = C.create_string_buffer(1024)
+    rc = L.tracer_driver_render(dll_path.encode(), C.byref(sc), C.byref(rd), img.ctypes.data_as(C.c_void_p),
+                                wgt.ctypes.data_as(C.c_void_p), C.byref(st), err, 1024)
+    if rc != 0:
+        raise RuntimeError(f"tracer driver failed ({rc}): {err.value.decode()}")
+    return img, wgt, dict(commit_s=st.commitSeconds, render_s=st.renderSeconds, paths=st.totalPaths,
+                          iterations=st.iterations, aabb=list(st.sceneAABB))
