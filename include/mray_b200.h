@@ -186,6 +186,69 @@ MRB_API mrb_status mrb_cast_visibility_rays(mrb_context ctx, mrb_accel accel,
                                             uint32_t rayCount, uint32_t totalRayCount,
                                             mrb_memspace memspace, mrb_trace_mode mode);
 
+/* ---- wavefront path tracer ------------------------------------------------------------- */
+
+typedef struct mrb_renderer_t* mrb_renderer;
+
+typedef enum mrb_sample_mode
+{   /* PathTraceRDetail::SampleModeEnum (TracerDLL/PathTracerRendererShaders.h:L21-35) */
+    MRB_SAMPLE_PURE = 0, MRB_SAMPLE_NEE = 1, MRB_SAMPLE_NEE_WITH_MIS = 2
+} mrb_sample_mode;
+
+/* Everything PathTracerRendererT::StartRender needs (TracerDLL/PathTracerRenderer.cu:L1182-1355):
+ * the committed accelerator, the material / light groups its lightOrMatKeys point into, the
+ * camera surface, the render attributes ("totalSPP", "sampleMode", "rrRange" — L1384-1400) and
+ * TracerParameters.seed / filmFilter. lightOrMatKey layout (Tracer/TracerTypes.h:L171-175):
+ * bit 31 = light flag, bits 0..20 = index into albedo[] (material) or lightRadiance[] (light).
+ * Round 1: (R)PathTracerRGB, (Mt)Lambert with constant albedo, (L)Prim(P)Triangle with constant
+ * radiance, (L)Null boundary, (C)Pinhole, Gaussian film filter, Independent (PCG32) sampler. */
+typedef struct mrb_render_desc
+{
+    mrb_accel       accel;
+    uint32_t        vertexCount, triangleCount;   /* of the primitive group the accelerator was built on */
+    const float*    vertexNormals;   /* host, vertexCount*3 shading normals, or NULL (geometric normal) */
+    uint32_t        materialCount;
+    const float*    albedo;          /* host, materialCount*3 */
+    uint32_t        lightCount;
+    const float*    lightRadiance;   /* host, lightCount*3 */
+    const uint8_t*  lightTwoSided;   /* host, lightCount, or NULL */
+    float           camPosition[3], camGaze[3], camUp[3];
+    float           fovXY[2];        /* radians ("FovAndPlanes") */
+    float           nearFar[2];
+    uint32_t        width, height;   /* RenderImageParams.resolution (one tile) */
+    uint32_t        totalSPP;
+    uint32_t        sampleMode;      /* mrb_sample_mode */
+    uint32_t        rrRange[2];
+    float           filmFilterRadius;/* Gaussian, TracerParameters.filmFilter (default 1) */
+    uint64_t        seed;            /* TracerParameters.seed */
+    uint32_t        maxPathCount;    /* paths in flight; 0 = width*height (parallelizationHint tile) */
+} mrb_render_desc;
+
+typedef struct mrb_render_stats
+{
+    uint64_t pathsStarted, pathsCompleted;    /* camera paths */
+    uint64_t closestRays, shadowRays;         /* rays cast (the reference only counts paths) */
+    uint64_t iterations;
+    uint32_t finished;                        /* 1 when totalSPP*pixels paths have completed (triggerSave) */
+} mrb_render_stats;
+
+/* StartRender */
+MRB_API mrb_status mrb_renderer_create(mrb_context ctx, const mrb_render_desc* desc, mrb_renderer* out);
+/* StopRender + destroy */
+MRB_API void       mrb_renderer_destroy(mrb_context ctx, mrb_renderer r);
+/* DoRenderWork x iterations (throughput mode: one bounce of every live path per iteration);
+ * asynchronous, no host synchronisation inside. */
+MRB_API mrb_status mrb_renderer_iterate(mrb_context ctx, mrb_renderer r, uint32_t iterations);
+/* Synchronises and reads the counters. */
+MRB_API mrb_status mrb_renderer_get_stats(mrb_context ctx, mrb_renderer r, mrb_render_stats* out);
+/* The film the reference hands over as RenderImageSection (Common/RenderImageStructs.h:L22-37):
+ * 4 planar fp32 planes R,G,B,weight of width*height (row 0 = bottom), radiance sums and filter-weight
+ * sums accumulated since the last clear. Copies to `out` (host or device); `clear` != 0 zeroes the
+ * device film afterwards (the reference's per-iteration delta protocol). */
+MRB_API mrb_status mrb_renderer_read_film(mrb_context ctx, mrb_renderer r, float* out, mrb_memspace memspace, int clear);
+/* Device pointer of the film planes, for a multi-GPU film reduction (ncclAllReduce over NVLink). */
+MRB_API float*     mrb_renderer_film_device_ptr(mrb_renderer r);
+
 /* ---- device algorithms (Device/GPUAlgRadixSort.h, exposed for parity tests) -------------- */
 
 /* Stable ascending LSD radix sort of (key,value) pairs over bits [bitBegin,bitEnd).

@@ -53,6 +53,24 @@ class AccelInfo(C.Structure):
                 ("deviceBytes", C.c_size_t)]
 
 
+class RenderDesc(C.Structure):
+    _fields_ = [("accel", C.c_void_p), ("vertexCount", C.c_uint32), ("triangleCount", C.c_uint32),
+                ("vertexNormals", C.c_void_p), ("materialCount", C.c_uint32), ("albedo", C.c_void_p),
+                ("lightCount", C.c_uint32), ("lightRadiance", C.c_void_p), ("lightTwoSided", C.c_void_p),
+                ("camPosition", C.c_float * 3), ("camGaze", C.c_float * 3), ("camUp", C.c_float * 3),
+                ("fovXY", C.c_float * 2), ("nearFar", C.c_float * 2),
+                ("width", C.c_uint32), ("height", C.c_uint32), ("totalSPP", C.c_uint32), ("sampleMode", C.c_uint32),
+                ("rrRange", C.c_uint32 * 2), ("filmFilterRadius", C.c_float), ("seed", C.c_uint64),
+                ("maxPathCount", C.c_uint32)]
+
+
+class RenderStats(C.Structure):
+    _fields_ = [("pathsStarted", C.c_uint64), ("pathsCompleted", C.c_uint64), ("closestRays", C.c_uint64),
+                ("shadowRays", C.c_uint64), ("iterations", C.c_uint64), ("finished", C.c_uint32)]
+
+
+SAMPLE_MODES = {"Pure": 0, "WithNextEventEstimation": 1, "WithNEEAndMIS": 2}
+
 # every symbol include/mray_b200.h declares (tests/test_capi_symbols.py checks the header against this)
 _PROTOTYPES = {
     "mrb_abi_version": (C.c_uint32, []),
@@ -73,6 +91,12 @@ _PROTOTYPES = {
                                 C.c_uint32, C.c_uint32, C.c_int, C.c_int]),
     "mrb_cast_visibility_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_uint32, C.c_uint32, C.c_int, C.c_int]),
+    "mrb_renderer_create": (C.c_int, [C.c_void_p, C.POINTER(RenderDesc), C.POINTER(C.c_void_p)]),
+    "mrb_renderer_destroy": (None, [C.c_void_p, C.c_void_p]),
+    "mrb_renderer_iterate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "mrb_renderer_get_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(RenderStats)]),
+    "mrb_renderer_read_film": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "mrb_renderer_film_device_ptr": (C.c_void_p, [C.c_void_p]),
     "mrb_radix_sort_pairs_u64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
     "mrb_radix_sort_pairs_u32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
 }
@@ -276,6 +300,99 @@ class Accelerator:
     def close(self):
         if self.handle and self.ctx.handle:
             self.ctx.lib.mrb_accel_destroy(self.ctx.handle, self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def light_key(index: int) -> int:
+    """LightOrMatKey of light `index` (flag bit 31 set, Tracer/TracerTypes.h:L171-179)."""
+    return 0x80000000 | (index & 0x1FFFFF)
+
+
+class Renderer:
+    """(R)PathTracerRGB behind the C-ABI: StartRender / DoRenderWork / film read-out
+    (TracerDLL/PathTracerRenderer.cu:L930-1355)."""
+
+    def __init__(self, ctx: Context, accel: Accelerator, vertex_count, triangle_count, albedo, light_radiance,
+                 camera, width, height, total_spp, sample_mode="WithNEEAndMIS", rr_range=(2, 20), seed=0,
+                 vertex_normals=None, light_two_sided=None, film_filter_radius=1.0, near_far=(0.01, 1000.0),
+                 max_path_count=0):
+        self.ctx, self.accel = ctx, accel
+        self.width, self.height = width, height
+        d = RenderDesc()
+        d.accel = accel.handle
+        d.vertexCount, d.triangleCount = vertex_count, triangle_count
+        self._keep = []
+
+        def host(a, dt):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dt)
+            self._keep.append(a)
+            return a.ctypes.data
+        alb = np.asarray(albedo, np.float32).reshape(-1, 3)
+        rad = np.asarray(light_radiance, np.float32).reshape(-1, 3)
+        d.vertexNormals = host(vertex_normals, np.float32)
+        d.materialCount, d.albedo = alb.shape[0], host(alb, np.float32)
+        d.lightCount, d.lightRadiance = rad.shape[0], host(rad, np.float32)
+        d.lightTwoSided = host(light_two_sided, np.uint8)
+        d.camPosition = (C.c_float * 3)(*camera["eye"])
+        d.camGaze = (C.c_float * 3)(*camera["gaze"])
+        d.camUp = (C.c_float * 3)(*camera["up"])
+        fy = float(np.deg2rad(camera["fov_y_deg"]))
+        fx = float(2 * np.arctan(np.tan(fy / 2) * width / height))
+        d.fovXY = (C.c_float * 2)(fx, fy)
+        d.nearFar = (C.c_float * 2)(*near_far)
+        d.width, d.height, d.totalSPP = width, height, total_spp
+        d.sampleMode = SAMPLE_MODES[sample_mode] if isinstance(sample_mode, str) else int(sample_mode)
+        d.rrRange = (C.c_uint32 * 2)(*rr_range)
+        d.filmFilterRadius = film_filter_radius
+        d.seed = seed
+        d.maxPathCount = max_path_count
+        h = C.c_void_p()
+        ctx.check(ctx.lib.mrb_renderer_create(ctx.handle, C.byref(d), C.byref(h)))
+        self.handle = h
+
+    def iterate(self, iterations=1):
+        """DoRenderWork x iterations (asynchronous)."""
+        self.ctx.check(self.ctx.lib.mrb_renderer_iterate(self.ctx.handle, self.handle, iterations))
+
+    def stats(self) -> RenderStats:
+        st = RenderStats()
+        self.ctx.check(self.ctx.lib.mrb_renderer_get_stats(self.ctx.handle, self.handle, C.byref(st)))
+        return st
+
+    def read_film(self, clear=False):
+        """(rgb_sum[h,w,3], weight[h,w]) host arrays, row 0 = bottom (RenderImageSection planes)."""
+        out = np.zeros((4, self.height, self.width), np.float32)
+        self.ctx.check(self.ctx.lib.mrb_renderer_read_film(self.ctx.handle, self.handle, out.ctypes.data, MRB_MEM_HOST,
+                                                           1 if clear else 0))
+        return np.ascontiguousarray(np.moveaxis(out[:3], 0, -1)), out[3]
+
+    def film_device_ptr(self) -> int:
+        return int(self.ctx.lib.mrb_renderer_film_device_ptr(self.handle))
+
+    def render(self, batch=8, max_iterations=1_000_000):
+        """Runs DoRenderWork until totalSPP*pixels paths have completed; returns the resolved image
+        (sum radiance / sum weight, like MRay/RunCommand.cpp:L293-345) and the final stats."""
+        it = 0
+        while it < max_iterations:
+            self.iterate(batch)
+            it += batch
+            st = self.stats()
+            if st.finished:
+                break
+        rgb, w = self.read_film()
+        return rgb / np.maximum(w, 1e-20)[..., None], st
+
+    def close(self):
+        if self.handle and self.ctx.handle:
+            self.ctx.lib.mrb_renderer_destroy(self.ctx.handle, self.handle)
         self.handle = None
 
     def __del__(self):

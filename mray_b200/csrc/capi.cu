@@ -13,6 +13,18 @@ void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode
                mrb_ray_gmem* rays, const uint32_t* rayIndices, uint32_t rayCount);
 }
 
+struct mrb_render_data_fwd;
+namespace mrb
+{
+void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc);
+void RenderIterate(Context& ctx, mrb_renderer_t& r, uint32_t iterations);
+void DestroyRenderer(Context& ctx, mrb_renderer_t* r);
+mrb_renderer_t* NewRenderer();
+void RendererStats(Context& ctx, mrb_renderer_t& r, mrb_render_stats& out);
+void RendererReadFilm(Context& ctx, mrb_renderer_t& r, float* out, bool device, bool clear);
+float* RendererFilmPtr(mrb_renderer_t& r);
+}
+
 struct mrb_context_t { mrb::Context c; };
 
 static thread_local std::string gCreateError;
@@ -324,5 +336,66 @@ mrb_status mrb_radix_sort_pairs_u32(mrb_context ctx, uint32_t* keys, uint32_t* v
 {
     return SortCommon<uint32_t>(ctx, keys, values, count, bitBegin, bitEnd, memspace);
 }
+
+
+mrb_status mrb_renderer_create(mrb_context ctx, const mrb_render_desc* desc, mrb_renderer* out)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!desc || !out || !desc->accel) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        *out = nullptr;
+        if(!desc->accel->d.wideNodes) return Fail(c, MRB_ERR_UNSUPPORTED, "accelerator was built BINARY_ONLY");
+        if(desc->width == 0 || desc->height == 0 || desc->totalSPP == 0) return Fail(c, MRB_ERR_INVALID_ARG, "empty render");
+        if(desc->sampleMode > 2) return Fail(c, MRB_ERR_INVALID_ARG, "unknown sampleMode");
+        if(desc->rrRange[1] > 255) return Fail(c, MRB_ERR_INVALID_ARG, "rrRange[1] exceeds PathDataPack depth (u8)");
+        if((desc->materialCount && !desc->albedo) || (desc->lightCount && !desc->lightRadiance))
+            return Fail(c, MRB_ERR_INVALID_ARG, "missing material / light attributes");
+        mrb_renderer r = mrb::NewRenderer();
+        try { mrb::CreateRenderer(c, *r, *desc); }
+        catch(...) { mrb::DestroyRenderer(c, r); throw; }
+        *out = r;
+        return MRB_OK;
+    });
+}
+
+void mrb_renderer_destroy(mrb_context ctx, mrb_renderer r)
+{
+    if(!ctx || !r) return;
+    cudaSetDevice(ctx->c.device);
+    cudaStreamSynchronize(ctx->c.stream);
+    mrb::DestroyRenderer(ctx->c, r);
+}
+
+mrb_status mrb_renderer_iterate(mrb_context ctx, mrb_renderer r, uint32_t iterations)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!r) return Fail(c, MRB_ERR_INVALID_ARG, "null renderer");
+        mrb::RenderIterate(c, *r, iterations);
+        return MRB_OK;
+    });
+}
+
+mrb_status mrb_renderer_get_stats(mrb_context ctx, mrb_renderer r, mrb_render_stats* out)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!r || !out) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        mrb::RendererStats(c, *r, *out);
+        return MRB_OK;
+    });
+}
+
+mrb_status mrb_renderer_read_film(mrb_context ctx, mrb_renderer r, float* out, mrb_memspace memspace, int clear)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!r || !out) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        mrb::RendererReadFilm(c, *r, out, memspace == MRB_MEM_DEVICE, clear != 0);
+        return MRB_OK;
+    });
+}
+
+float* mrb_renderer_film_device_ptr(mrb_renderer r) { return r ? mrb::RendererFilmPtr(*r) : nullptr; }
 
 } // extern "C"

@@ -1,0 +1,622 @@
+// render.cu — wavefront path tracer (RGB, Lambert, prim-backed triangle lights, NEE + MIS, Russian
+// roulette, stochastic film filter). One wavefront iteration advances every live path by one bounce:
+//
+//   KReload   : free slots take the next camera path of the tile (device counter, no host sync),
+//               stochastic-filter camera ray, path state init           (PathTracerRendererBase::ReloadPaths,
+//               Tracer/PathTracerRendererBase.cu:L69-203; KCGenerateCamRaysStochastic, RayGenKernels.kt.h:L155-227;
+//               CameraPinhole::EvaluateRay, CamerasDefault.hpp:L93-142; KCInitPathStateIndirect, L34-57)
+//   TraceRays : closest hit                                              (BaseAcceleratorLBVH::CastRays)
+//   KShade    : boundary / light hit (MIS re-weighting) / Lambert: NEE shadow ray + BxDF sample + RR
+//               (TracerDLL/PathTracerRendererShaders.h:L201-520; LambertMaterial, Tracer/MaterialsDefault.hpp:L25-126;
+//               LightPrim, Tracer/LightsDefault.hpp:L22-168; DirectLightSamplerUniform, LightSampler.hpp:L30-119;
+//               Triangle::SampleSurface, PrimitiveDefaultTriangle.hpp:L48-77; RussianRoulette, DistributionFunctions.h:L943-953)
+//   TraceRays : any hit on the shadow rays                               (CastVisibilityRays)
+//   KFinish   : add the pre-multiplied NEE radiance of visible shadow rays (KCAccumulateShadowRaysPT,
+//               PathTracerRenderer.cu:L11-32); dead paths go to the film with atomics
+//               (KCSetImagePixelsIndirectAtomic + ConvertNaNsToColor, Tracer/TextureFilter.cu:L114-121,L669-697)
+//               and free their slot.
+//
+// The reference runs NEE and BxDF sampling as two partitioned passes with a random-number buffer in
+// between; both only depend on the hit, so they are one kernel here and the PCG32 stream is consumed
+// in registers. Host synchronisations per iteration: none.
+#include "accel.cuh"
+#include <cfloat>
+#include <random>
+#include <vector>
+
+namespace mrb
+{
+
+void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode mode,
+               mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, uint32_t* visibleBits,
+               mrb_ray_gmem* rays, const uint32_t* rayIndices, uint32_t rayCount);
+
+namespace
+{
+
+constexpr int RTPB = 256;
+constexpr float PI_F = 3.14159265358979323846f;
+constexpr float INV_PI_F = 0.31830988618379067154f;
+
+enum : uint32_t { ST_INVALID = 0u, ST_ALIVE = 1u, ST_DEAD = 2u };
+enum : uint32_t { RAY_SHADOW = 0u, RAY_SPECULAR = 1u, RAY_PATH = 2u, RAY_CAMERA = 3u }; // RayType, PathTracerRendererBase.h:L11-17
+
+struct Float3 { float x, y, z; };
+__device__ __forceinline__ Float3 F3(float x, float y, float z) { return Float3{x, y, z}; }
+__device__ __forceinline__ Float3 operator+(Float3 a, Float3 b) { return F3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ Float3 operator-(Float3 a, Float3 b) { return F3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ Float3 operator*(Float3 a, float s) { return F3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ Float3 operator*(Float3 a, Float3 b) { return F3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float Dot(Float3 a, Float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ Float3 Cross(Float3 a, Float3 b)
+{ return F3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ float Length(Float3 a) { return sqrtf(Dot(a, a)); }
+__device__ __forceinline__ Float3 Normalize(Float3 a) { return a * (1.0f / Length(a)); }
+
+// PermutedCG32 (Tracer/Random.h:L237-238,L763-812): 32-bit state LCG, RXS-M-XS output
+struct PCG32
+{
+    uint32_t s;
+    __device__ __forceinline__ uint32_t Next()
+    {
+        uint32_t old = s;
+        s = old * 747796405u + 2891336453u;
+        uint32_t r = ((old >> ((old >> 28u) + 4u)) ^ old) * 277803737u;
+        return (r >> 22u) ^ r;
+    }
+    // RNGFunctions::ToFloat01 (Random.h:L102-118)
+    __device__ __forceinline__ float NextFloat() { return fminf(float(Next()) * 2.3283064365386963e-10f, 0.99999994f); }
+};
+
+// Ray::Nudge (Core/Ray.hpp:L258-301, after RT Gems I ch. 6)
+__device__ __forceinline__ Float3 NudgePos(Float3 p, Float3 n)
+{
+    const float ORIGIN = 1.0f / 32.0f, FLOAT_SCALE = 1.0f / 65536.0f, INT_SCALE = 256.0f;
+    int ox = int(INT_SCALE * n.x), oy = int(INT_SCALE * n.y), oz = int(INT_SCALE * n.z);
+    float ix = __int_as_float(__float_as_int(p.x) + ((p.x < 0.f) ? -ox : ox));
+    float iy = __int_as_float(__float_as_int(p.y) + ((p.y < 0.f) ? -oy : oy));
+    float iz = __int_as_float(__float_as_int(p.z) + ((p.z < 0.f) ? -oz : oz));
+    return F3(fabsf(p.x) < ORIGIN ? p.x + FLOAT_SCALE * n.x : ix,
+              fabsf(p.y) < ORIGIN ? p.y + FLOAT_SCALE * n.y : iy,
+              fabsf(p.z) < ORIGIN ? p.z + FLOAT_SCALE * n.z : iz);
+}
+
+struct Camera // CameraPinhole members (CamerasDefault.hpp:L8-36), tile-local
+{
+    Float3 position, right, up, bottomLeft;
+    float  planeW, planeH, tNear, tFar;
+};
+
+struct EmissiveTri { float4 p0, e0, e1; float4 radiance; }; // p0.w = area, e0.w = twoSided, radiance.w unused
+
+struct RenderData
+{
+    // scene
+    const float*      positions;
+    const uint32_t*   indices;
+    const float4*     vertexNormals;   // optional (xyz), nullptr = geometric
+    PrimRanges        ranges;          // leaf -> prim; lmKey per range
+    const float4*     albedo;          // per material index
+    const EmissiveTri* lights;         // one per emissive triangle (MetaLight list)
+    const uint32_t*   lightOfPrim;     // prim index -> emissive triangle index or INVALID
+    uint32_t          lightCount;      // emissive triangles (+1 boundary light in the sampler)
+    Camera            cam;
+    uint32_t          width, height;
+    float             filterSigma;     // Gaussian film filter (Filters.h:L195-227): sigma = r * 0.285714
+    // options
+    uint32_t          rrLo, rrHi, sampleMode; // 0 Pure, 1 NEE, 2 NEE+MIS
+    uint64_t          pathLimit;
+    // path state (P slots)
+    uint32_t          slots;
+    mrb_ray_gmem*     rays;
+    mrb_ray_gmem*     shadowRays;
+    mrb_hit_key_pack* hitKeys;
+    mrb_meta_hit*     hits;
+    float4*           throughput;
+    float4*           radiance;
+    float4*           shadowRadiance;
+    float*            prevPdf;
+    float*            filmWeight;
+    uint32_t*         pixel;
+    uint32_t*         pathData;        // depth | status << 8 | type << 16
+    uint32_t*         rng;
+    uint32_t*         visible;
+    // film (planar R,G,B,W)
+    float*            film;
+    // u64 counters: [0] next camera path, [1] completed paths, [2] closest-hit rays cast, [3] shadow rays cast
+    unsigned long long* counters;
+};
+
+__device__ __forceinline__ uint32_t PackPD(uint32_t depth, uint32_t status, uint32_t type) { return depth | (status << 8) | (type << 16); }
+
+__global__ void __launch_bounds__(RTPB) KReload(RenderData d)
+{
+    const uint32_t i = blockIdx.x * RTPB + threadIdx.x;
+    const bool inRange = i < d.slots;
+    uint32_t pd = inRange ? d.pathData[i] : PackPD(0, ST_ALIVE, 0);
+    const bool isFree = ((pd >> 8) & 0xFFu) == ST_INVALID;
+    // warp-aggregated claim of new path indices
+    const uint32_t want = __ballot_sync(0xffffffffu, isFree);
+    unsigned long long base = 0;
+    const uint32_t lane = threadIdx.x & 31u;
+    if(want)
+    {
+        const int leader = __ffs(int(want)) - 1;
+        if(int(lane) == leader) base = atomicAdd(&d.counters[0], (unsigned long long)__popc(want));
+        base = __shfl_sync(0xffffffffu, base, leader);
+    }
+    if(!inRange) return;
+    if(!isFree)
+    {
+        d.hitKeys[i].primKey = INVALID_U32; // default: boundary (KCSetBoundaryWorkKeysIndirect)
+        return;
+    }
+    const unsigned long long g = base + __popc(want & ((1u << lane) - 1u));
+    if(g >= d.pathLimit)
+    {
+        // surplus slot: never traced (KCWriteInvalidRaysIndirect)
+        d.rays[i].tMin = 1.0f; d.rays[i].tMax = -1.0f;
+        d.shadowRays[i].tMin = 1.0f; d.shadowRays[i].tMax = -1.0f;
+        d.hitKeys[i].primKey = INVALID_U32;
+        return;
+    }
+    PCG32 rng{d.rng[i]};
+    const uint32_t pix = uint32_t(g % (unsigned long long)(d.width * d.height));
+    const uint32_t px = pix % d.width, py = pix / d.width;
+    // stochastic filter sample: offset ~ Gaussian, weight = f / pdf
+    float xi0 = rng.NextFloat(), xi1 = rng.NextFloat();
+    const float sig = d.filterSigma;
+    auto SampleG = [sig](float xi, float& pdfOut)
+    {
+        float e = erfinvf(2.0f * xi - 1.0f);
+        float x = 1.41421356237f * sig * e;
+        if(isinf(e)) x = fminf(fmaxf(x, -3.5f * sig), 3.5f * sig);
+        float p = x / sig;
+        pdfOut = 0.3989422804f / sig * expf(-0.5f * p * p);
+        return x;
+    };
+    float pdfx, pdfy;
+    const float offx = SampleG(xi0, pdfx), offy = SampleG(xi1, pdfy);
+    // Evaluate == the same Gaussian, so the weight is 1 up to the clamp of the tails
+    const float weight = 1.0f;
+    const float sx = (float(px) + offx + 0.5f) * (d.cam.planeW / float(d.width));
+    const float sy = (float(py) + offy + 0.5f) * (d.cam.planeH / float(d.height));
+    const Float3 point = d.cam.bottomLeft + d.cam.right * sx + d.cam.up * sy;
+    const Float3 dir = Normalize(point - d.cam.position);
+    float4* rp = reinterpret_cast<float4*>(d.rays + i);
+    rp[0] = make_float4(d.cam.position.x, d.cam.position.y, d.cam.position.z, d.cam.tNear);
+    rp[1] = make_float4(dir.x, dir.y, dir.z, d.cam.tFar);
+    d.shadowRays[i].tMin = 1.0f; d.shadowRays[i].tMax = -1.0f;
+    d.hitKeys[i].primKey = INVALID_U32;
+    d.throughput[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+    d.radiance[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    d.shadowRadiance[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    d.prevPdf[i] = 0.0f;
+    d.filmWeight[i] = weight;
+    d.pixel[i] = pix;
+    d.pathData[i] = PackPD(0, ST_ALIVE, RAY_CAMERA);
+    d.rng[i] = rng.s;
+}
+
+__device__ __forceinline__ void LoadTriangle(const RenderData& d, uint32_t prim, Float3 p[3], uint32_t vi[3])
+{
+    vi[0] = d.indices[3 * size_t(prim)]; vi[1] = d.indices[3 * size_t(prim) + 1]; vi[2] = d.indices[3 * size_t(prim) + 2];
+    #pragma unroll
+    for(int k = 0; k < 3; k++)
+        p[k] = F3(d.positions[3 * size_t(vi[k])], d.positions[3 * size_t(vi[k]) + 1], d.positions[3 * size_t(vi[k]) + 2]);
+}
+
+// LightPrim::EmitViaHit / EmitViaSurfacePoint for a constant radiance (LightsDefault.hpp:L129-168)
+__device__ __forceinline__ Float3 Emit(const EmissiveTri& l, Float3 n, Float3 wO)
+{
+    float NdL = Dot(n, wO);
+    if(l.e0.w == 0.0f && NdL <= 0.0f) return F3(0.f, 0.f, 0.f);
+    return F3(l.radiance.x, l.radiance.y, l.radiance.z);
+}
+
+__global__ void __launch_bounds__(RTPB) KShade(RenderData d)
+{
+    const uint32_t i = blockIdx.x * RTPB + threadIdx.x;
+    if(i >= d.slots) return;
+    uint32_t pd = d.pathData[i];
+    if(((pd >> 8) & 0xFFu) != ST_ALIVE) return;
+    uint32_t depth = pd & 0xFFu, type = (pd >> 16) & 0xFFu;
+    const float4 r0 = reinterpret_cast<const float4*>(d.rays + i)[0];
+    const float4 r1 = reinterpret_cast<const float4*>(d.rays + i)[1];
+    const Float3 ro = F3(r0.x, r0.y, r0.z), rd = F3(r1.x, r1.y, r1.z);
+    const uint4 keys = *reinterpret_cast<const uint4*>(d.hitKeys + i);
+    {   // closest-hit rays cast this iteration (one atomic per warp)
+        const uint32_t m = __activemask();
+        if((threadIdx.x & 31u) == uint32_t(__ffs(int(m)) - 1)) atomicAdd(&d.counters[2], (unsigned long long)__popc(m));
+    }
+    float4 thr4 = d.throughput[i];
+    Float3 throughput = F3(thr4.x, thr4.y, thr4.z);
+    // every live slot gets a well defined (never hitting) shadow ray unless NEE writes one
+    d.shadowRays[i].tMin = 1.0f; d.shadowRays[i].tMax = -1.0f;
+
+    if(keys.x == INVALID_U32)
+    {
+        // boundary light (Null): no emission; path ends (LightWorkFunction[WithNEE]::Call)
+        d.pathData[i] = PackPD(depth, ST_DEAD, type);
+        return;
+    }
+    const float2 bary = *reinterpret_cast<const float2*>(d.hits + i);
+    const uint32_t prim = keys.x & 0x0FFFFFFFu;
+    const uint32_t lmKey = keys.y;
+    Float3 p[3]; uint32_t vi[3];
+    LoadTriangle(d, prim, p, vi);
+    const float a = bary.x, b = bary.y, c = 1.0f - a - b;
+    const Float3 pos = p[0] * a + p[1] * b + p[2] * c;
+    const Float3 e0 = p[1] - p[0], e1 = p[2] - p[0];
+    Float3 geoN = Normalize(Cross(e0, e1));
+
+    if(lmKey & 0x80000000u)
+    {
+        // ---------------- light hit: LightWorkFunctionWithNEE / LightWorkFunction ----------------
+        const EmissiveTri l = d.lights[d.lightOfPrim[prim]];
+        bool count = true;
+        if(d.sampleMode == 1u && type != RAY_CAMERA && type != RAY_SPECULAR) count = false;
+        if(count)
+        {
+            if(d.sampleMode == 2u && type == RAY_PATH)
+            {
+                // MIS: undo the bxdf pdf division, divide by (bxdf pdf + light pdf)  (BalanceCancelled)
+                float pdfB = d.prevPdf[i];
+                float NdL = Dot(geoN, rd * -1.0f);
+                NdL = (l.e0.w != 0.0f) ? fabsf(NdL) : fmaxf(0.0f, NdL);
+                float pdfL = (NdL == 0.0f) ? 0.0f : (1.0f / l.p0.w) / NdL;
+                Float3 dv = ro - pos;
+                pdfL *= Dot(dv, dv);
+                pdfL *= 1.0f / float(d.lightCount + 1u);
+                float mis = pdfB + pdfL;
+                throughput = throughput * pdfB;
+                throughput = (mis == 0.0f) ? F3(0, 0, 0) : throughput * (1.0f / mis);
+            }
+            const Float3 em = Emit(l, geoN, rd * -1.0f);
+            if(depth + 1u <= d.rrHi)
+            {
+                float4 rad = d.radiance[i];
+                const Float3 est = em * throughput;
+                rad.x += est.x; rad.y += est.y; rad.z += est.z;
+                d.radiance[i] = rad;
+            }
+        }
+        d.pathData[i] = PackPD(depth, ST_DEAD, type);
+        return;
+    }
+
+    // ------------------------------- Lambert surface -------------------------------
+    PCG32 rng{d.rng[i]};
+    const bool backSide = Dot(geoN, Normalize(rd)) > 0.0f;
+    Float3 shadeN = geoN;
+    if(d.vertexNormals)
+    {
+        const float4 n0 = d.vertexNormals[vi[0]], n1 = d.vertexNormals[vi[1]], n2 = d.vertexNormals[vi[2]];
+        shadeN = Normalize(F3(n0.x, n0.y, n0.z) * a + F3(n1.x, n1.y, n1.z) * b + F3(n2.x, n2.y, n2.z) * c);
+    }
+    if(backSide) { geoN = geoN * -1.0f; shadeN = shadeN * -1.0f; }
+    const float4 alb4 = d.albedo[lmKey & 0x1FFFFFu];
+    const Float3 albedo = F3(alb4.x, alb4.y, alb4.z);
+    // orthonormal frame about the shading normal
+    const Float3 hlp = (fabsf(shadeN.x) > 0.9f) ? F3(0, 1, 0) : F3(1, 0, 0);
+    const Float3 tX = Normalize(Cross(hlp, shadeN));
+    const Float3 tY = Cross(shadeN, tX);
+
+    // ---- NEE (WorkFunctionNEE::Call) ----
+    uint32_t newType = type;
+    float4 shadowRad = make_float4(0.f, 0.f, 0.f, 0.f);
+    if(d.sampleMode != 0u)
+    {
+        const float x0 = rng.NextFloat(), x1 = rng.NextFloat(), xs = rng.NextFloat();
+        const uint32_t nLights = d.lightCount + 1u; // + boundary light
+        uint32_t li = min(uint32_t(xs * float(nLights)), nLights - 1u);
+        newType = RAY_SHADOW;
+        if(li < d.lightCount)
+        {
+            const EmissiveTri l = d.lights[li];
+            // Triangle::SampleSurface (Osada)
+            const float r1s = sqrtf(x0), r2s = x1;
+            const float la = 1.0f - r1s, lb = (1.0f - r2s) * r1s, lc = r1s * r2s;
+            const Float3 lp0 = F3(l.p0.x, l.p0.y, l.p0.z), le0 = F3(l.e0.x, l.e0.y, l.e0.z), le1 = F3(l.e1.x, l.e1.y, l.e1.z);
+            const Float3 lpos = lp0 * la + (lp0 + le0) * lb + (lp0 + le1) * lc;
+            const Float3 lN = Normalize(Cross(le0, le1));
+            // LightPrim::SampleSolidAngle
+            Float3 sdir = pos - lpos;
+            const float distSqr = Dot(sdir, sdir);
+            sdir = Normalize(sdir);
+            float NdL = Dot(lN, sdir);
+            NdL = (l.e0.w != 0.0f) ? fabsf(NdL) : fmaxf(0.0f, NdL);
+            float pdfL = (NdL == 0.0f) ? 0.0f : (1.0f / l.p0.w) / NdL;
+            pdfL *= distSqr;
+            pdfL *= 1.0f / float(nLights);
+            const Float3 em = Emit(l, lN, sdir);
+            // LightSampleOutput::SampledRay
+            const Float3 wI = Normalize(lpos - pos);
+            const Float3 lposN = NudgePos(lpos, wI * -1.0f);
+            const float len = Length(lposN - pos);
+            // Lambert Evaluate / Pdf
+            const float nDotL = fmaxf(Dot(shadeN, wI), 0.0f);
+            const Float3 refl = albedo * (nDotL * INV_PI_F);
+            float pdf = pdfL;
+            if(d.sampleMode == 2u) pdf = fmaxf(nDotL * INV_PI_F, 0.0f) + pdfL;
+            Float3 sr = throughput * refl * em;
+            sr = (pdf == 0.0f) ? F3(0, 0, 0) : sr * (1.0f / pdf);
+            // +2: depth is not incremented yet (KCAccumulateShadowRaysPT)
+            if(depth + 2u <= d.rrHi) shadowRad = make_float4(sr.x, sr.y, sr.z, 0.f);
+            const Float3 so = NudgePos(pos, geoN);
+            float4* sp = reinterpret_cast<float4*>(d.shadowRays + i);
+            sp[0] = make_float4(so.x, so.y, so.z, 1.0e-5f);
+            sp[1] = make_float4(wI.x, wI.y, wI.z, len * (1.0f - 1.0e-4f));
+            {
+                const uint32_t m = __activemask();
+                if((threadIdx.x & 31u) == uint32_t(__ffs(int(m)) - 1)) atomicAdd(&d.counters[3], (unsigned long long)__popc(m));
+            }
+        }
+    }
+    d.shadowRadiance[i] = shadowRad;
+
+    // ---- BxDF sample + Russian roulette (WorkFunction::Call) ----
+    const float u0 = rng.NextFloat(), u1 = rng.NextFloat();
+    const float phi = 2.0f * PI_F * u1, su = sqrtf(u0);
+    float sn, cs; sincosf(phi, &sn, &cs);
+    const float lx = su * cs, ly = su * sn;
+    const float lz = sqrtf(fmaxf(0.0f, 1.0f - (lx * lx + ly * ly)));
+    const float pdfB = lz * INV_PI_F;
+    const Float3 wIw = Normalize(tX * lx + tY * ly + shadeN * lz);
+    throughput = throughput * (albedo * (fmaxf(lz, 0.0f) * INV_PI_F));
+    depth += 1u;
+    bool dead = depth >= d.rrHi;
+    if(!dead && depth >= d.rrLo)
+    {
+        const float rrXi = rng.NextFloat();
+        float prob = (throughput.x + throughput.y + throughput.z) * 0.33333333f;
+        prob = fminf(fmaxf(prob, 0.1f), 1.0f);
+        if(rrXi >= prob) dead = true;
+        else throughput = throughput * (1.0f / prob);
+    }
+    d.rng[i] = rng.s;
+    if(!dead)
+    {
+        throughput = (pdfB == 0.0f) ? F3(0, 0, 0) : throughput * (1.0f / pdfB);
+        d.throughput[i] = make_float4(throughput.x, throughput.y, throughput.z, 1.f);
+        d.prevPdf[i] = pdfB;
+        const Float3 no = NudgePos(pos, geoN);
+        float4* rp = reinterpret_cast<float4*>(d.rays + i);
+        rp[0] = make_float4(no.x, no.y, no.z, 1.0e-4f);
+        rp[1] = make_float4(wIw.x, wIw.y, wIw.z, FLT_MAX);
+        // type of the NEXT hit's MIS decision is PATH_RAY; the shadow flag only lives until KFinish
+        d.pathData[i] = PackPD(depth, ST_ALIVE, (newType == RAY_SHADOW) ? (RAY_PATH | 0x80u) : RAY_PATH);
+    }
+    else
+    {
+        d.rays[i].tMin = 1.0f; d.rays[i].tMax = -1.0f;
+        d.pathData[i] = PackPD(depth, ST_DEAD, (newType == RAY_SHADOW) ? (RAY_PATH | 0x80u) : RAY_PATH);
+    }
+}
+
+__global__ void __launch_bounds__(RTPB) KFinish(RenderData d)
+{
+    const uint32_t i = blockIdx.x * RTPB + threadIdx.x;
+    if(i >= d.slots) return;
+    uint32_t pd = d.pathData[i];
+    const uint32_t status = (pd >> 8) & 0xFFu;
+    if(status == ST_INVALID) return;
+    uint32_t type = (pd >> 16) & 0xFFu;
+    float4 rad = d.radiance[i];
+    if(type & 0x80u)
+    {
+        // shadow ray of this bounce: add the pre-multiplied NEE estimate when unoccluded
+        const bool vis = (d.visible[i >> 5] >> (i & 31u)) & 1u;
+        if(vis)
+        {
+            const float4 sr = d.shadowRadiance[i];
+            rad.x += sr.x; rad.y += sr.y; rad.z += sr.z;
+            d.radiance[i] = rad;
+        }
+        type &= 0x7Fu;
+    }
+    if(status == ST_DEAD)
+    {
+        // film: ConvertNaNsToColor + atomic add (planar R,G,B,W)
+        float w = d.filmWeight[i];
+        Float3 v = F3(rad.x, rad.y, rad.z);
+        if(!(isfinite(v.x) && isfinite(v.y) && isfinite(v.z))) { v = F3(1e7f, 0.f, 1e7f); w *= 128.0f; }
+        const uint32_t pix = d.pixel[i];
+        const size_t plane = size_t(d.width) * d.height;
+        atomicAdd(d.film + pix, v.x);
+        atomicAdd(d.film + plane + pix, v.y);
+        atomicAdd(d.film + 2 * plane + pix, v.z);
+        atomicAdd(d.film + 3 * plane + pix, w);
+        {
+            const uint32_t m = __activemask();
+            if((threadIdx.x & 31u) == uint32_t(__ffs(int(m)) - 1)) atomicAdd(&d.counters[1], (unsigned long long)__popc(m));
+        }
+        d.pathData[i] = PackPD(0, ST_INVALID, 0);
+        d.rays[i].tMin = 1.0f; d.rays[i].tMax = -1.0f;
+    }
+    else d.pathData[i] = PackPD(pd & 0xFFu, ST_ALIVE, type);
+}
+
+} // namespace
+} // namespace mrb
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct mrb_renderer_t
+{
+    mrb::RenderData  d = {};
+    mrb::DeviceBlock mem;
+    mrb_accel        accel = nullptr;
+    uint64_t         iterations = 0;
+};
+
+namespace mrb
+{
+
+void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc)
+{
+    using namespace mrb;
+    RenderData& d = r.d;
+    const AccelData& a = desc.accel->d;
+    r.accel = desc.accel;
+    d.positions = a.positions; d.indices = a.indices; d.ranges = a.ranges;
+    d.width = desc.width; d.height = desc.height;
+    d.rrLo = desc.rrRange[0]; d.rrHi = desc.rrRange[1]; d.sampleMode = desc.sampleMode;
+    d.pathLimit = uint64_t(desc.totalSPP) * desc.width * desc.height;
+    d.filterSigma = desc.filmFilterRadius * 0.285714f;
+    d.slots = desc.maxPathCount ? desc.maxPathCount : desc.width * desc.height;
+    // camera (CameraPinhole ctor)
+    auto V = [](const float* p) { return make_float3(p[0], p[1], p[2]); };
+    auto sub = [](float3 x, float3 y) { return make_float3(x.x - y.x, x.y - y.y, x.z - y.z); };
+    auto cross = [](float3 x, float3 y) { return make_float3(x.y * y.z - x.z * y.y, x.z * y.x - x.x * y.z, x.x * y.y - x.y * y.x); };
+    auto norm = [](float3 x) { float l = 1.0f / sqrtf(x.x * x.x + x.y * x.y + x.z * x.z); return make_float3(x.x * l, x.y * l, x.z * l); };
+    float3 pos = V(desc.camPosition), gazeDir = sub(V(desc.camGaze), pos), up = V(desc.camUp);
+    float3 right = norm(cross(gazeDir, up));
+    up = norm(cross(right, gazeDir));
+    gazeDir = norm(cross(up, right));
+    float wh = tanf(desc.fovXY[0] * 0.5f) * desc.nearFar[0], hh = tanf(desc.fovXY[1] * 0.5f) * desc.nearFar[0];
+    float3 bl = make_float3(pos.x - right.x * wh - up.x * hh + gazeDir.x * desc.nearFar[0],
+                            pos.y - right.y * wh - up.y * hh + gazeDir.y * desc.nearFar[0],
+                            pos.z - right.z * wh - up.z * hh + gazeDir.z * desc.nearFar[0]);
+    d.cam.position = {pos.x, pos.y, pos.z}; d.cam.right = {right.x, right.y, right.z}; d.cam.up = {up.x, up.y, up.z};
+    d.cam.bottomLeft = {bl.x, bl.y, bl.z}; d.cam.planeW = 2.0f * wh; d.cam.planeH = 2.0f * hh;
+    d.cam.tNear = desc.nearFar[0]; d.cam.tFar = desc.nearFar[1];
+
+    // emissive triangle list (MetaLightArrayT::Construct: one meta light per emissive triangle), host side
+    std::vector<float> hpos(size_t(desc.vertexCount) * 3);
+    std::vector<uint32_t> hidx(size_t(desc.triangleCount) * 3);
+    MRB_CUDA_TRY(cudaMemcpyAsync(hpos.data(), a.positions, hpos.size() * 4, cudaMemcpyDeviceToHost, ctx.stream));
+    MRB_CUDA_TRY(cudaMemcpyAsync(hidx.data(), a.indices, hidx.size() * 4, cudaMemcpyDeviceToHost, ctx.stream));
+    MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
+    std::vector<EmissiveTri> lights;
+    std::vector<uint32_t> lightOfPrim(desc.triangleCount, INVALID_U32);
+    for(uint32_t rg = 0; rg < a.ranges.count; rg++)
+    {
+        uint32_t key = a.ranges.lmKey[rg];
+        if(!(key & 0x80000000u)) continue;
+        uint32_t li = key & 0x1FFFFFu;
+        uint32_t count = a.ranges.leafStart[rg + 1] - a.ranges.leafStart[rg];
+        for(uint32_t k = 0; k < count; k++)
+        {
+            uint32_t prim = a.ranges.primBegin[rg] + k;
+            const float* p0 = &hpos[3 * size_t(hidx[3 * size_t(prim)])];
+            const float* p1 = &hpos[3 * size_t(hidx[3 * size_t(prim) + 1])];
+            const float* p2 = &hpos[3 * size_t(hidx[3 * size_t(prim) + 2])];
+            float e0[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]}, e1[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
+            float cx = e0[1] * e1[2] - e0[2] * e1[1], cy = e0[2] * e1[0] - e0[0] * e1[2], cz = e0[0] * e1[1] - e0[1] * e1[0];
+            float area = 0.5f * sqrtf(cx * cx + cy * cy + cz * cz);
+            EmissiveTri t;
+            t.p0 = make_float4(p0[0], p0[1], p0[2], area);
+            t.e0 = make_float4(e0[0], e0[1], e0[2], (desc.lightTwoSided && desc.lightTwoSided[li]) ? 1.0f : 0.0f);
+            t.e1 = make_float4(e1[0], e1[1], e1[2], 0.0f);
+            t.radiance = make_float4(desc.lightRadiance[3 * li], desc.lightRadiance[3 * li + 1], desc.lightRadiance[3 * li + 2], 0.f);
+            lightOfPrim[prim] = uint32_t(lights.size());
+            lights.push_back(t);
+        }
+    }
+    d.lightCount = uint32_t(lights.size());
+
+    auto Layout = [&](MultiAlloc& ma)
+    {
+        const uint32_t P = d.slots;
+        d.rays = ma.Take<mrb_ray_gmem>(P); d.shadowRays = ma.Take<mrb_ray_gmem>(P);
+        d.hitKeys = ma.Take<mrb_hit_key_pack>(P); d.hits = ma.Take<mrb_meta_hit>(P);
+        d.throughput = ma.Take<float4>(P); d.radiance = ma.Take<float4>(P); d.shadowRadiance = ma.Take<float4>(P);
+        d.prevPdf = ma.Take<float>(P); d.filmWeight = ma.Take<float>(P); d.pixel = ma.Take<uint32_t>(P);
+        d.pathData = ma.Take<uint32_t>(P); d.rng = ma.Take<uint32_t>(P); d.visible = ma.Take<uint32_t>((P + 31) / 32);
+        d.film = ma.Take<float>(size_t(4) * d.width * d.height);
+        d.counters = ma.Take<unsigned long long>(8);
+        d.albedo = ma.Take<float4>(desc.materialCount ? desc.materialCount : 1);
+        d.lights = ma.Take<EmissiveTri>(lights.size() ? lights.size() : 1);
+        d.lightOfPrim = ma.Take<uint32_t>(desc.triangleCount);
+        d.vertexNormals = desc.vertexNormals ? ma.Take<float4>(desc.vertexCount) : nullptr;
+    };
+    MultiAlloc sz(nullptr); Layout(sz);
+    r.mem.Reserve(sz.Total());
+    MultiAlloc ma(r.mem.Base()); Layout(ma);
+    ctx.persistentBytes += r.mem.Capacity();
+    MRB_CUDA_TRY(cudaMemsetAsync(r.mem.Base(), 0, sz.Total(), ctx.stream));
+
+    std::vector<float4> halb(desc.materialCount ? desc.materialCount : 1, make_float4(0, 0, 0, 0));
+    for(uint32_t m = 0; m < desc.materialCount; m++)
+        halb[m] = make_float4(desc.albedo[3 * m], desc.albedo[3 * m + 1], desc.albedo[3 * m + 2], 0.f);
+    MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<float4*>(d.albedo), halb.data(), halb.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx.stream));
+    if(!lights.empty())
+        MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<EmissiveTri*>(d.lights), lights.data(), lights.size() * sizeof(EmissiveTri), cudaMemcpyHostToDevice, ctx.stream));
+    MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<uint32_t*>(d.lightOfPrim), lightOfPrim.data(), lightOfPrim.size() * 4, cudaMemcpyHostToDevice, ctx.stream));
+    std::vector<float4> hn;
+    if(desc.vertexNormals)
+    {
+        hn.resize(desc.vertexCount);
+        for(uint32_t v = 0; v < desc.vertexCount; v++)
+            hn[v] = make_float4(desc.vertexNormals[3 * v], desc.vertexNormals[3 * v + 1], desc.vertexNormals[3 * v + 2], 0.f);
+        MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<float4*>(d.vertexNormals), hn.data(), hn.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx.stream));
+    }
+    // RNGGroupIndependent (Tracer/Random.cu:L661-720): mt19937(seed32) draws -> PermutedCG32::GenerateState
+    uint32_t seed32 = uint32_t((desc.seed >> 32) ^ (desc.seed & 0xFFFFFFFFull));
+    std::mt19937 mt(seed32);
+    std::vector<uint32_t> states(d.slots);
+    for(uint32_t i = 0; i < d.slots; i++)
+    {
+        uint32_t s = 0u * 747796405u + 2891336453u; // Step(0)
+        s += uint32_t(mt());
+        s = s * 747796405u + 2891336453u;
+        states[i] = s;
+    }
+    MRB_CUDA_TRY(cudaMemcpyAsync(d.rng, states.data(), states.size() * 4, cudaMemcpyHostToDevice, ctx.stream));
+    MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
+}
+
+void RenderIterate(Context& ctx, mrb_renderer_t& r, uint32_t iterations)
+{
+    using namespace mrb;
+    RenderData& d = r.d;
+    const uint32_t grid = DivUp(d.slots, RTPB);
+    for(uint32_t it = 0; it < iterations; it++)
+    {
+        MRB_LAUNCH(ctx, KReload, grid, RTPB, 0, d);
+        TraceRays(ctx, *r.accel, false, MRB_TRACE_WIDE, d.hitKeys, d.hits, nullptr, d.rays, nullptr, d.slots);
+        MRB_LAUNCH(ctx, KShade, grid, RTPB, 0, d);
+        if(d.sampleMode != 0u)
+        {
+            MRB_CUDA_TRY(cudaMemsetAsync(d.visible, 0xFF, sizeof(uint32_t) * ((d.slots + 31) / 32), ctx.stream));
+            TraceRays(ctx, *r.accel, true, MRB_TRACE_WIDE, nullptr, nullptr, d.visible, d.shadowRays, nullptr, d.slots);
+        }
+        MRB_LAUNCH(ctx, KFinish, grid, RTPB, 0, d);
+        r.iterations++;
+    }
+}
+
+
+mrb_renderer_t* NewRenderer() { return new mrb_renderer_t(); }
+
+void DestroyRenderer(Context& ctx, mrb_renderer_t* r)
+{
+    if(!r) return;
+    ctx.persistentBytes -= r->mem.Capacity();
+    delete r;
+}
+
+void RendererStats(Context& ctx, mrb_renderer_t& r, mrb_render_stats& out)
+{
+    unsigned long long h[4];
+    MRB_CUDA_TRY(cudaMemcpyAsync(h, r.d.counters, sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
+    MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
+    out.pathsStarted = h[0] < r.d.pathLimit ? h[0] : r.d.pathLimit;
+    out.pathsCompleted = h[1]; out.closestRays = h[2]; out.shadowRays = h[3];
+    out.iterations = r.iterations;
+    out.finished = (h[1] >= r.d.pathLimit) ? 1u : 0u;
+}
+
+void RendererReadFilm(Context& ctx, mrb_renderer_t& r, float* out, bool device, bool clear)
+{
+    size_t bytes = sizeof(float) * 4 * size_t(r.d.width) * r.d.height;
+    MRB_CUDA_TRY(cudaMemcpyAsync(out, r.d.film, bytes, device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx.stream));
+    if(clear) MRB_CUDA_TRY(cudaMemsetAsync(r.d.film, 0, bytes, ctx.stream));
+    if(!device) MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
+}
+
+float* RendererFilmPtr(mrb_renderer_t& r) { return r.d.film; }
+
+} // namespace mrb

@@ -1,0 +1,266 @@
+/* pt_oracle.c — CPU restatement of the reference's path-tracing ESTIMATOR (RGB, Lambert, prim-backed
+ * triangle lights, uniform light sampler incl. the boundary light, NEE / NEE+MIS / pure, Russian
+ * roulette, stochastic Gaussian film filter), one path at a time instead of a wavefront.
+ *
+ * TEST INFRASTRUCTURE ONLY (see mray_oracle.c). Parity status: UNPINNED by reference execution —
+ * the reference's CPU backend crashes in this container as soon as a scene has a prim-backed light
+ * (DESIGN.md §4), so no reference image exists to pin it. It is pinned only (a) internally: Pure,
+ * NEE and NEE+MIS must agree in expectation, (b) analytically: tests/test_oracle_pt.py checks the
+ * direct irradiance under a square light against the closed-form form factor.
+ * Statistical parity only (even the reference's own backends differ per sample).
+ *
+ * Restated from (paths relative to /root/reference/Source):
+ *   TracerDLL/PathTracerRendererShaders.h:L201-301  WorkFunction::Call        (BxDF sample, RR)
+ *   ...:L352-443                                    WorkFunctionNEE::Call     (light sample, shadow ray, MIS)
+ *   ...:L306-347, L448-520                          LightWorkFunction[WithNEE]::Call
+ *   TracerDLL/PathTracerRenderer.cu:L11-32          KCAccumulateShadowRaysPT  (depth + 2 <= rrRange[1])
+ *   Tracer/MaterialsDefault.hpp:L25-126             LambertMaterial
+ *   Tracer/LightsDefault.hpp:L22-168                LightPrim (SampleSolidAngle, PdfSolidAngle, EmitVia*)
+ *   Tracer/LightSampler.hpp:L5-119                  SampledRay, DirectLightSamplerUniform
+ *   Tracer/PrimitiveDefaultTriangle.hpp:L48-77      Triangle::SampleSurface (Osada)
+ *   Tracer/DistributionFunctions.h:L847-871,L943-965 SampleCosDirection, RussianRoulette, BalanceCancelled
+ *   Tracer/CamerasDefault.hpp:L8-36,L93-142         CameraPinhole ctor / EvaluateRay
+ *   Tracer/Filters.h:L195-227, DistributionFunctions.h:L686-705  Gaussian filter sample / evaluate
+ *   Tracer/Random.h:L237-238,L763-812               PermutedCG32
+ *   Core/Ray.hpp:L258-301                           Ray::Nudge
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <float.h>
+
+/* from mray_oracle.c */
+void orc_lbvh_trace(const float* pos, const uint32_t* idx, const uint32_t* nodes, const float* boxes,
+                    const float* rays, uint32_t nRays, int mode, int cullFace,
+                    uint32_t* outPrim, float* outT, float* outBary, uint8_t* outBack);
+
+typedef struct { float x, y, z; } v3;
+static v3 V(float x, float y, float z) { v3 r = {x, y, z}; return r; }
+static v3 add(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
+static v3 sub(v3 a, v3 b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }
+static v3 mul(v3 a, float s) { return V(a.x * s, a.y * s, a.z * s); }
+static v3 mulv(v3 a, v3 b) { return V(a.x * b.x, a.y * b.y, a.z * b.z); }
+static float dot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static v3 cross(v3 a, v3 b) { return V(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+static float len(v3 a) { return sqrtf(dot(a, a)); }
+static v3 nrm(v3 a) { return mul(a, 1.0f / len(a)); }
+
+typedef struct { uint32_t s; } pcg;
+static uint32_t pcg_next(pcg* r)
+{
+    uint32_t old = r->s;
+    r->s = old * 747796405u + 2891336453u;
+    uint32_t v = ((old >> ((old >> 28u) + 4u)) ^ old) * 277803737u;
+    return (v >> 22u) ^ v;
+}
+static float pcg_float(pcg* r) { float f = (float)pcg_next(r) * 0x1.p-32f; return f < 0.99999994f ? f : 0.99999994f; }
+
+static v3 nudge(v3 p, v3 n)
+{
+    const float ORIGIN = 1.0f / 32.0f, FLOAT_SCALE = 1.0f / 65536.0f, INT_SCALE = 256.0f;
+    float pin[3] = {p.x, p.y, p.z}, nin[3] = {n.x, n.y, n.z}, out[3];
+    for(int k = 0; k < 3; k++)
+    {
+        int32_t of = (int32_t)(INT_SCALE * nin[k]);
+        int32_t pi; memcpy(&pi, &pin[k], 4);
+        pi += (pin[k] < 0.0f) ? -of : of;
+        float pf; memcpy(&pf, &pi, 4);
+        out[k] = (fabsf(pin[k]) < ORIGIN) ? pin[k] + FLOAT_SCALE * nin[k] : pf;
+    }
+    return V(out[0], out[1], out[2]);
+}
+
+typedef struct
+{
+    const float* pos; const uint32_t* idx; uint32_t nTris;
+    const uint32_t* nodes; const float* boxes;          /* binary LBVH of the whole scene */
+    const int32_t* triMaterial;                         /* >= 0 Lambert material index, < 0 : light index = -1 - v */
+    const float* albedo; const float* radiance; const uint8_t* twoSided;
+    const uint32_t* lightTris; uint32_t nLightTris;     /* emissive triangle list (one meta light each) */
+    float camPos[3], camGaze[3], camUp[3], fovXY[2], nearFar[2];
+    uint32_t width, height, spp, sampleMode, rrLo, rrHi;
+    float filterRadius; uint64_t seed;
+} pt_scene;
+
+static void tri(const pt_scene* s, uint32_t t, v3 p[3])
+{
+    for(int k = 0; k < 3; k++)
+    {
+        const float* q = s->pos + 3 * (size_t)s->idx[3 * (size_t)t + k];
+        p[k] = V(q[0], q[1], q[2]);
+    }
+}
+
+static int trace(const pt_scene* s, v3 o, v3 d, float tMin, float tMax, int any, uint32_t* prim, float* t, float bary[2])
+{
+    float ray[8] = {o.x, o.y, o.z, tMin, d.x, d.y, d.z, tMax};
+    uint8_t back;
+    orc_lbvh_trace(s->pos, s->idx, s->nodes, s->boxes, ray, 1, any, 0, prim, t, bary, &back);
+    return *prim != 0xFFFFFFFFu;
+}
+
+static v3 light_emit(const pt_scene* s, uint32_t li, v3 n, v3 wO)
+{
+    float NdL = dot(n, wO);
+    if(!(s->twoSided && s->twoSided[li]) && NdL <= 0.0f) return V(0, 0, 0);
+    return V(s->radiance[3 * li], s->radiance[3 * li + 1], s->radiance[3 * li + 2]);
+}
+
+/* one camera path -> radiance; *filmW receives the filter weight */
+static v3 path(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, float* filmW)
+{
+    /* camera (CameraPinhole ctor + EvaluateRay with a filter-sampled offset) */
+    v3 pos = V(s->camPos[0], s->camPos[1], s->camPos[2]);
+    v3 gz = sub(V(s->camGaze[0], s->camGaze[1], s->camGaze[2]), pos), up = V(s->camUp[0], s->camUp[1], s->camUp[2]);
+    v3 right = nrm(cross(gz, up)); up = nrm(cross(right, gz)); gz = nrm(cross(up, right));
+    float wh = tanf(s->fovXY[0] * 0.5f) * s->nearFar[0], hh = tanf(s->fovXY[1] * 0.5f) * s->nearFar[0];
+    v3 bl = add(sub(sub(pos, mul(right, wh)), mul(up, hh)), mul(gz, s->nearFar[0]));
+    float sig = s->filterRadius * 0.285714f;
+    float off[2];
+    for(int k = 0; k < 2; k++)
+    {
+        float xi = pcg_float(rng);
+        double e = 0; /* inverse error function via Newton on erf (double) */
+        {
+            double y = 2.0 * xi - 1.0;
+            if(y <= -1.0) e = -INFINITY; else if(y >= 1.0) e = INFINITY;
+            else { double x = 0; for(int it = 0; it < 60; it++) { double f = erf(x) - y; x -= f / (1.1283791670955126 * exp(-x * x)); } e = x; }
+        }
+        float x = 1.41421356237f * sig * (float)e;
+        if(isinf(e)) { float mm = 3.5f * sig; x = x < -mm ? -mm : (x > mm ? mm : x); }
+        off[k] = x;
+    }
+    *filmW = 1.0f; /* Evaluate(offset) / pdf(offset): same Gaussian */
+    float sx = ((float)px + off[0] + 0.5f) * (2.0f * wh / (float)s->width);
+    float sy = ((float)py + off[1] + 0.5f) * (2.0f * hh / (float)s->height);
+    v3 o = pos, d = nrm(sub(add(add(bl, mul(right, sx)), mul(up, sy)), pos));
+    float tMin = s->nearFar[0], tMax = s->nearFar[1];
+
+    v3 throughput = V(1, 1, 1), radiance = V(0, 0, 0);
+    uint32_t depth = 0; int type = 3; /* CAMERA_RAY */
+    float prevPdf = 0;
+    const uint32_t nLights = s->nLightTris + 1u; /* + boundary (Null) light, MetaLight.hpp:L514-516 */
+    for(;;)
+    {
+        uint32_t prim; float t, bary[2];
+        if(!trace(s, o, d, tMin, tMax, 0, &prim, &t, bary)) break; /* boundary Null light: nothing, path dead */
+        v3 p[3]; tri(s, prim, p);
+        float a = bary[0], b = bary[1], c = 1.0f - a - b;
+        v3 hitPos = add(add(mul(p[0], a), mul(p[1], b)), mul(p[2], c));
+        v3 e0 = sub(p[1], p[0]), e1 = sub(p[2], p[0]);
+        v3 gN = nrm(cross(e0, e1));
+        int32_t m = s->triMaterial[prim];
+        if(m < 0)
+        {   /* light hit */
+            uint32_t li = (uint32_t)(-1 - m);
+            int count = !(s->sampleMode == 1u && type != 3 && type != 1);
+            if(count)
+            {
+                v3 thr = throughput;
+                if(s->sampleMode == 2u && type == 2)
+                {
+                    float NdL = dot(gN, mul(d, -1.0f));
+                    NdL = (s->twoSided && s->twoSided[li]) ? fabsf(NdL) : (NdL > 0 ? NdL : 0);
+                    float area = 0.5f * len(cross(e0, e1));
+                    float pdfL = (NdL == 0) ? 0 : (1.0f / area) / NdL;
+                    v3 dv = sub(o, hitPos);
+                    pdfL *= dot(dv, dv);
+                    pdfL *= 1.0f / (float)nLights;
+                    float mis = prevPdf + pdfL;
+                    thr = mul(thr, prevPdf);
+                    thr = (mis == 0) ? V(0, 0, 0) : mul(thr, 1.0f / mis);
+                }
+                if(depth + 1u <= s->rrHi) radiance = add(radiance, mulv(light_emit(s, li, gN, mul(d, -1.0f)), thr));
+            }
+            break;
+        }
+        /* Lambert */
+        if(dot(gN, nrm(d)) > 0) gN = mul(gN, -1.0f);
+        v3 alb = V(s->albedo[3 * m], s->albedo[3 * m + 1], s->albedo[3 * m + 2]);
+        v3 hlp = fabsf(gN.x) > 0.9f ? V(0, 1, 0) : V(1, 0, 0);
+        v3 tX = nrm(cross(hlp, gN)), tY = cross(gN, tX);
+        if(s->sampleMode != 0u)
+        {   /* NEE */
+            float x0 = pcg_float(rng), x1 = pcg_float(rng), xs = pcg_float(rng);
+            uint32_t li = (uint32_t)(xs * (float)nLights);
+            if(li > nLights - 1u) li = nLights - 1u;
+            if(li < s->nLightTris)
+            {
+                uint32_t lt = s->lightTris[li]; uint32_t lightIdx = (uint32_t)(-1 - s->triMaterial[lt]);
+                v3 q[3]; tri(s, lt, q);
+                float r1 = sqrtf(x0), r2 = x1;
+                float la = 1 - r1, lb = (1 - r2) * r1, lc = r1 * r2;
+                v3 lpos = add(add(mul(q[0], la), mul(q[1], lb)), mul(q[2], lc));
+                v3 le0 = sub(q[1], q[0]), le1 = sub(q[2], q[0]);
+                v3 lN = nrm(cross(le0, le1));
+                float area = 0.5f * len(cross(le0, le1));
+                v3 sd = sub(hitPos, lpos); float distSqr = dot(sd, sd); sd = nrm(sd);
+                float NdL = dot(lN, sd);
+                NdL = (s->twoSided && s->twoSided[lightIdx]) ? fabsf(NdL) : (NdL > 0 ? NdL : 0);
+                float pdfL = (NdL == 0) ? 0 : (1.0f / area) / NdL;
+                pdfL *= distSqr; pdfL *= 1.0f / (float)nLights;
+                v3 em = light_emit(s, lightIdx, lN, sd);
+                v3 wI = nrm(sub(lpos, hitPos));
+                v3 lposN = nudge(lpos, mul(wI, -1.0f));
+                float length = len(sub(lposN, hitPos));
+                float nDotL = dot(gN, wI); if(nDotL < 0) nDotL = 0;
+                v3 refl = mul(alb, nDotL * 0.31830988618f);
+                float pdf = pdfL;
+                if(s->sampleMode == 2u) pdf = nDotL * 0.31830988618f + pdfL;
+                v3 sr = mulv(mulv(throughput, refl), em);
+                sr = (pdf == 0) ? V(0, 0, 0) : mul(sr, 1.0f / pdf);
+                if(depth + 2u <= s->rrHi && (sr.x > 0 || sr.y > 0 || sr.z > 0))
+                {
+                    v3 so = nudge(hitPos, gN);
+                    uint32_t sp; float st, sb[2];
+                    if(!trace(s, so, wI, 1.0e-5f, length * (1.0f - 1.0e-4f), 1, &sp, &st, sb)) radiance = add(radiance, sr);
+                }
+            }
+        }
+        /* BxDF sample + RR */
+        float u0 = pcg_float(rng), u1 = pcg_float(rng);
+        float phi = 6.28318530718f * u1, su = sqrtf(u0);
+        float lx = su * cosf(phi), ly = su * sinf(phi);
+        float lz2 = 1.0f - (lx * lx + ly * ly); float lz = lz2 > 0 ? sqrtf(lz2) : 0;
+        float pdfB = lz * 0.31830988618f;
+        v3 wI = nrm(add(add(mul(tX, lx), mul(tY, ly)), mul(gN, lz)));
+        throughput = mulv(throughput, mul(alb, lz * 0.31830988618f));
+        depth += 1;
+        int dead = depth >= s->rrHi;
+        if(!dead && depth >= s->rrLo)
+        {
+            float xi = pcg_float(rng);
+            float prob = (throughput.x + throughput.y + throughput.z) * 0.33333333f;
+            prob = prob < 0.1f ? 0.1f : (prob > 1.0f ? 1.0f : prob);
+            if(xi >= prob) dead = 1; else throughput = mul(throughput, 1.0f / prob);
+        }
+        if(dead) break;
+        throughput = (pdfB == 0) ? V(0, 0, 0) : mul(throughput, 1.0f / pdfB);
+        prevPdf = pdfB; type = 2; /* PATH_RAY */
+        o = nudge(hitPos, gN); d = wI; tMin = 1.0e-4f; tMax = FLT_MAX;
+    }
+    return radiance;
+}
+
+/* Renders rows [y0, y1) into out (planar R,G,B,W sums of the FULL image, row 0 = bottom). Thread safe
+ * for disjoint row ranges. RNG: one PCG32 stream per pixel, state = GenerateState(seed32 ^ hash(pixel)). */
+void orc_pt_render_rows(const pt_scene* s, uint32_t y0, uint32_t y1, float* out)
+{
+    size_t plane = (size_t)s->width * s->height;
+    uint32_t seed32 = (uint32_t)((s->seed >> 32) ^ (s->seed & 0xFFFFFFFFull));
+    for(uint32_t y = y0; y < y1; y++)
+    for(uint32_t x = 0; x < s->width; x++)
+    {
+        pcg rng; uint32_t h = (y * s->width + x) * 2654435761u ^ seed32 ^ 0x9E3779B9u;
+        rng.s = 0u * 747796405u + 2891336453u; rng.s += h; rng.s = rng.s * 747796405u + 2891336453u;
+        double acc[3] = {0, 0, 0}, w = 0;
+        for(uint32_t k = 0; k < s->spp; k++)
+        {
+            float fw; v3 r = path(s, &rng, x, y, &fw);
+            acc[0] += r.x; acc[1] += r.y; acc[2] += r.z; w += fw;
+        }
+        size_t pix = (size_t)y * s->width + x;
+        out[pix] = (float)acc[0]; out[plane + pix] = (float)acc[1]; out[2 * plane + pix] = (float)acc[2]; out[3 * plane + pix] = (float)w;
+    }
+}

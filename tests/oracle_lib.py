@@ -21,9 +21,9 @@ _u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 
 
 def build_oracle():
-    src = os.path.join(ORACLE_DIR, "mray_oracle.c")
+    srcs = [os.path.join(ORACLE_DIR, "mray_oracle.c"), os.path.join(ORACLE_DIR, "pt_oracle.c")]
     so = os.path.join(ORACLE_DIR, "liboracle.so")
-    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(x) for x in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
     return so
 
@@ -206,10 +206,10 @@ def batched_scene(positions, indices, tri_material, normals=None):
 
 def driver_render(dll_path, batched, albedo, light_material, radiance, camera, width, height, spp,
                   renderer="PathTracerRGB", sample_mode="WithNEEAndMIS", rr_range=(2, 20), seed=0,
-                  accel_mode=1, threads=0, parallel_hint=0, near_far=(0.01, 1000.0)):
+                  accel_mode=1, threads=0, parallel_hint=0, near_far=(0.01, 1000.0), driver_flavour=""):
     """Renders through TracerI. `light_material`: material id whose batch is the prim-backed light.
     Returns (image[h,w,3] float32 with row 0 = bottom, weight[h,w], stats dict)."""
-    L = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libtracer_driver.so"))
+    L = C.CDLL(os.path.join(ORACLE_DIR, "_ref", f"libtracer_driver{driver_flavour}.so"))
     L.tracer_driver_render.restype = C.c_int
     mats = list(batched["materials"])
     lambert = [m for m in mats if m != light_material]
@@ -242,3 +242,48 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
         raise RuntimeError(f"tracer driver failed ({rc}): {err.value.decode()}")
     return img, wgt, dict(commit_s=st.commitSeconds, render_s=st.renderSeconds, paths=st.totalPaths,
                           iterations=st.iterations, aabb=list(st.sceneAABB))
+
+
+# ------------------------------------------------------------------------------------------------
+# path-tracing estimator oracle (oracle/pt_oracle.c)
+# ------------------------------------------------------------------------------------------------
+class _PtScene(C.Structure):
+    _fields_ = [("pos", C.c_void_p), ("idx", C.c_void_p), ("nTris", C.c_uint32),
+                ("nodes", C.c_void_p), ("boxes", C.c_void_p), ("triMaterial", C.c_void_p),
+                ("albedo", C.c_void_p), ("radiance", C.c_void_p), ("twoSided", C.c_void_p),
+                ("lightTris", C.c_void_p), ("nLightTris", C.c_uint32),
+                ("camPos", C.c_float * 3), ("camGaze", C.c_float * 3), ("camUp", C.c_float * 3),
+                ("fovXY", C.c_float * 2), ("nearFar", C.c_float * 2),
+                ("width", C.c_uint32), ("height", C.c_uint32), ("spp", C.c_uint32), ("sampleMode", C.c_uint32),
+                ("rrLo", C.c_uint32), ("rrHi", C.c_uint32), ("filterRadius", C.c_float), ("seed", C.c_uint64)]
+
+
+def oracle_render(positions, indices, tri_material, albedo, radiance, camera, width, height, spp,
+                  sample_mode=2, rr_range=(2, 20), seed=0, near_far=(0.01, 1000.0), threads=None):
+    """tri_material: per triangle, >= 0 Lambert material index, -1 - k for light k. Returns image[h,w,3]
+    (row 0 = bottom) resolved as sum radiance / sum weight."""
+    from concurrent.futures import ThreadPoolExecutor
+    L = lib()
+    L.orc_pt_render_rows.argtypes = [C.POINTER(_PtScene), C.c_uint32, C.c_uint32, C.c_void_p]
+    positions = np.ascontiguousarray(positions, np.float32); indices = np.ascontiguousarray(indices, np.uint32)
+    b = oracle_build(positions, indices)
+    tm = np.ascontiguousarray(tri_material, np.int32)
+    lt = np.ascontiguousarray(np.nonzero(tm < 0)[0], np.uint32)
+    alb = np.ascontiguousarray(albedo, np.float32); rad = np.ascontiguousarray(np.asarray(radiance, np.float32).reshape(-1, 3))
+    s = _PtScene()
+    s.pos, s.idx, s.nTris = positions.ctypes.data, indices.ctypes.data, indices.shape[0]
+    s.nodes, s.boxes, s.triMaterial = b.nodes.ctypes.data, b.boxes.ctypes.data, tm.ctypes.data
+    s.albedo, s.radiance, s.twoSided = alb.ctypes.data, rad.ctypes.data, None
+    s.lightTris, s.nLightTris = lt.ctypes.data, lt.shape[0]
+    s.camPos = (C.c_float * 3)(*camera["eye"]); s.camGaze = (C.c_float * 3)(*camera["gaze"]); s.camUp = (C.c_float * 3)(*camera["up"])
+    fy = float(np.deg2rad(camera["fov_y_deg"])); fx = float(2 * np.arctan(np.tan(fy / 2) * width / height))
+    s.fovXY = (C.c_float * 2)(fx, fy); s.nearFar = (C.c_float * 2)(*near_far)
+    s.width, s.height, s.spp, s.sampleMode = width, height, spp, sample_mode
+    s.rrLo, s.rrHi, s.filterRadius, s.seed = rr_range[0], rr_range[1], 1.0, seed
+    out = np.zeros((4, height, width), np.float32)
+    threads = threads or min(16, os.cpu_count() or 1)
+    rows = np.linspace(0, height, threads * 4 + 1).astype(int)
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda k: L.orc_pt_render_rows(C.byref(s), int(rows[k]), int(rows[k + 1]), out.ctypes.data),
+                    range(len(rows) - 1)))
+    return np.moveaxis(out[:3], 0, -1) / np.maximum(out[3], 1e-20)[..., None]
