@@ -33,27 +33,29 @@ def cornell_accel(ctx):
 
 def test_cornell_matches_oracle_and_modes_agree(gpu_ctx):
     c, idx, tm, acc = cornell_accel(gpu_ctx)
-    res, spp = 48, 4096
+    res = 32
+    spp = {"Pure": 16384, "WithNextEventEstimation": 16384, "WithNEEAndMIS": 131072}
     imgs = {}
-    for mode in ("Pure", "WithNextEventEstimation", "WithNEEAndMIS"):
+    for mode in spp:
         r = capi.Renderer(gpu_ctx, acc, c["positions"].shape[0], idx.shape[0], c["albedo"][:3], c["radiance"], c["camera"],
-                          res, res, spp, sample_mode=mode, seed=7)
-        imgs[mode], st = r.render()
-        assert st.finished and st.pathsCompleted == spp * res * res      # triggerSave condition
+                          res, res, spp[mode], sample_mode=mode, seed=7)
+        imgs[mode], st = r.render(batch=64)
+        assert st.finished and st.pathsCompleted == spp[mode] * res * res  # triggerSave condition
         assert st.closestRays >= st.pathsCompleted
         assert (st.shadowRays > 0) == (mode != "Pure")
         rgb, w = r.read_film()
-        assert np.allclose(w, spp, rtol=0, atol=0.5)                      # Gaussian filter: weight 1 per path
+        assert np.allclose(w, spp[mode], rtol=1e-3)                        # Gaussian filter: weight 1 per path
         r.close()
-    ref = O.oracle_render(c["positions"], idx, tm, c["albedo"][:3], c["radiance"], c["camera"], res, res, spp, sample_mode=2, seed=3)
-    # converged images agree (NEE+MIS is the low-variance pair)
-    assert rel_mse(imgs["WithNEEAndMIS"], ref) <= REL_MSE_TOL, rel_mse(imgs["WithNEEAndMIS"], ref)
-    assert rel_mse(imgs["WithNextEventEstimation"], ref) <= 3 * REL_MSE_TOL
-    # the three estimators share one expectation (pure path tracing is noisy: compare means off the light)
+    # oracle at 16384 spp; relMSE between two independent estimates of N and M spp is ~ 7.7 (1/N + 1/M)
+    # for this scene (measured oracle-vs-oracle), i.e. ~5e-4 here: the converged images agree to 1e-3.
+    ref = O.oracle_render(c["positions"], idx, tm, c["albedo"][:3], c["radiance"], c["camera"], res, res, 16384, sample_mode=2, seed=3)
+    err = rel_mse(imgs["WithNEEAndMIS"], ref)
+    assert err <= REL_MSE_TOL, err
+    # the three estimators share one expectation (compare means away from the directly visible light)
     mask = ref.max(axis=-1) < 5.0
     m_ref = ref[mask].mean(axis=0)
     for mode, im in imgs.items():
-        assert np.allclose(im[mask].mean(axis=0), m_ref, rtol=0.03), (mode, im[mask].mean(axis=0), m_ref)
+        assert np.allclose(im[mask].mean(axis=0), m_ref, rtol=0.02), (mode, im[mask].mean(axis=0), m_ref)
     acc.close()
 
 
