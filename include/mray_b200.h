@@ -123,8 +123,10 @@ typedef struct mrb_accel_desc
     uint32_t        triangleCount;/* triangles in the GROUP index list                             */
     mrb_memspace    memspace;     /* of positions / indices                                        */
     uint32_t        primGroupId;  /* batch portion of the PrimitiveKeys (4 bits)                   */
-    /* prim ranges of this accelerator inside the group (<= 8, TracerConstants::MaxPrimBatchPerSurface);
-     * leaves are numbered range by range. NULL/0 = one range covering the whole group. */
+    /* prim ranges of this accelerator inside the group; leaves are numbered range by range. One
+     * reference surface has <= 8 (TracerConstants::MaxPrimBatchPerSurface); surfaces sharing the
+     * identity transform may be flattened into one accelerator, so any count is accepted.
+     * NULL/0 = one range covering the whole group. */
     uint32_t        rangeCount;
     const uint32_t* primRanges;   /* rangeCount * 2 : [begin, end) ; host memory                   */
     const uint32_t* lightOrMatKeys;/* rangeCount ; host ; NULL = 0                                 */

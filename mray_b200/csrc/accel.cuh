@@ -1,6 +1,7 @@
 // accel.cuh — device-side data layout of one triangle accelerator (binary LBVH + 8-wide BVH).
 #pragma once
 #include "common.cuh"
+#include <vector>
 
 namespace mrb
 {
@@ -9,16 +10,30 @@ namespace mrb
 struct LBVHNode { uint32_t left, right, parent; };
 struct LBVHBox  { float min[3], max[3]; };
 
-// leaf -> primitive mapping of one accelerator (<= 8 prim ranges, AcceleratorC.h:L281-301)
+// leaf -> primitive mapping of one accelerator: the prim ranges of the surfaces it was built from
+// (the reference allows <= 8 per surface, AcceleratorC.h:L281-301; surfaces that share the identity
+// transform may be flattened into one accelerator here, so the list lives in device memory and is
+// searched by bisection).
 struct PrimRanges
 {
-    uint32_t count;
-    uint32_t leafStart[9]; // prefix sum of range sizes
-    uint32_t primBegin[8];
-    uint32_t lmKey[8];
-    uint32_t cull[8];
-    uint32_t primGroupId;
+    uint32_t        count;
+    uint32_t        primGroupId;
+    const uint32_t* leafStart; // count + 1, prefix sum of range sizes
+    const uint32_t* primBegin; // count
+    const uint32_t* lmKey;     // count
+    const uint32_t* cull;      // count
 };
+
+__host__ __device__ __forceinline__ uint32_t FindRange(const PrimRanges& r, uint32_t leaf)
+{
+    uint32_t lo = 0, hi = r.count; // invariant: leafStart[lo] <= leaf < leafStart[hi]
+    while(hi - lo > 1u)
+    {
+        uint32_t mid = (lo + hi) >> 1;
+        if(leaf >= r.leafStart[mid]) lo = mid; else hi = mid;
+    }
+    return lo;
+}
 
 // 8-wide compressed node, 80 bytes = 5 x 128-bit loads (after Ylitie et al. 2017, "CWBVH").
 //   q0 : p.x, p.y, p.z (node origin, float bits), {ex, ey, ez, imask} bytes (2^e quantisation
@@ -70,6 +85,8 @@ struct AccelData
 struct mrb_accel_t
 {
     mrb::AccelData   d;
+    // host copies of the prim-range table (d.ranges points at the device copy)
+    std::vector<uint32_t> hLeafStart, hPrimBegin, hLmKey, hCull;
     mrb::DeviceBlock mem;
     mrb_accel_info   info = {};
     uint32_t         flags = 0;

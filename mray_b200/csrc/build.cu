@@ -35,9 +35,7 @@ __device__ __forceinline__ float DecodeOrdered(uint32_t u)
 
 __device__ __forceinline__ uint32_t LeafToPrim(const PrimRanges& r, uint32_t leaf, uint32_t& rangeIdx)
 {
-    uint32_t k = 0;
-    #pragma unroll
-    for(uint32_t j = 1; j < 8; j++) if(j < r.count && leaf >= r.leafStart[j]) k = j;
+    const uint32_t k = (r.count == 1u) ? 0u : FindRange(r, leaf);
     rangeIdx = k;
     return r.primBegin[k] + (leaf - r.leafStart[k]);
 }
@@ -509,6 +507,10 @@ static void LayoutAccel(MultiAlloc& ma, AccelData& d, uint32_t vertexCount, uint
     d.boxes = ma.Take<LBVHBox>(d.nodeCount);
     d.nodeRange = ma.Take<uint2>(d.nodeCount);
     d.accelAABBEnc = ma.Take<uint32_t>(8);
+    d.ranges.leafStart = ma.Take<uint32_t>(d.ranges.count + 1);
+    d.ranges.primBegin = ma.Take<uint32_t>(d.ranges.count);
+    d.ranges.lmKey = ma.Take<uint32_t>(d.ranges.count);
+    d.ranges.cull = ma.Take<uint32_t>(d.ranges.count);
     if(wide)
     {
         d.wideNodeCapacity = d.leafCount / 3 + 2;
@@ -522,29 +524,23 @@ void BuildAccel(Context& ctx, mrb_accel_t& acc, const mrb_accel_desc& desc)
     AccelData& d = acc.d;
     const bool wide = !(desc.flags & (MRB_BUILD_BINARY_ONLY | MRB_BUILD_REFERENCE_DELTA));
     const int robust = (desc.flags & MRB_BUILD_REFERENCE_DELTA) ? 0 : 1;
-    // ranges
+    // ranges (host table, then device copy inside the accelerator block)
     PrimRanges& r = d.ranges;
     r = PrimRanges{};
     r.primGroupId = desc.primGroupId;
-    if(desc.rangeCount == 0 || desc.primRanges == nullptr)
-    {
-        r.count = 1; r.leafStart[0] = 0; r.leafStart[1] = desc.triangleCount; r.primBegin[0] = 0;
-    }
-    else
-    {
-        r.count = desc.rangeCount;
-        for(uint32_t i = 0; i < r.count; i++)
-        {
-            r.primBegin[i] = desc.primRanges[2 * i];
-            r.leafStart[i + 1] = r.leafStart[i] + (desc.primRanges[2 * i + 1] - desc.primRanges[2 * i]);
-        }
-    }
+    const bool whole = (desc.rangeCount == 0 || desc.primRanges == nullptr);
+    r.count = whole ? 1u : desc.rangeCount;
+    acc.hLeafStart.assign(r.count + 1, 0u); acc.hPrimBegin.assign(r.count, 0u);
+    acc.hLmKey.assign(r.count, 0u); acc.hCull.assign(r.count, 0u);
     for(uint32_t i = 0; i < r.count; i++)
     {
-        r.lmKey[i] = desc.lightOrMatKeys ? desc.lightOrMatKeys[i] : 0u;
-        r.cull[i] = (desc.cullBackface && desc.cullBackface[i]) ? 1u : 0u;
+        uint32_t b = whole ? 0u : desc.primRanges[2 * i], e = whole ? desc.triangleCount : desc.primRanges[2 * i + 1];
+        acc.hPrimBegin[i] = b;
+        acc.hLeafStart[i + 1] = acc.hLeafStart[i] + (e - b);
+        acc.hLmKey[i] = desc.lightOrMatKeys ? desc.lightOrMatKeys[i] : 0u;
+        acc.hCull[i] = (desc.cullBackface && desc.cullBackface[i]) ? 1u : 0u;
     }
-    d.leafCount = r.leafStart[r.count];
+    d.leafCount = acc.hLeafStart[r.count];
     d.nodeCount = d.leafCount > 1 ? d.leafCount - 1 : 1;
 
     MultiAlloc sizing(nullptr);
@@ -554,6 +550,10 @@ void BuildAccel(Context& ctx, mrb_accel_t& acc, const mrb_accel_desc& desc)
     LayoutAccel(ma, d, desc.vertexCount, desc.triangleCount, true, wide);
     ctx.persistentBytes += acc.mem.Capacity();
 
+    MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<uint32_t*>(r.leafStart), acc.hLeafStart.data(), 4 * (r.count + 1), cudaMemcpyHostToDevice, ctx.stream));
+    MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<uint32_t*>(r.primBegin), acc.hPrimBegin.data(), 4 * r.count, cudaMemcpyHostToDevice, ctx.stream));
+    MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<uint32_t*>(r.lmKey), acc.hLmKey.data(), 4 * r.count, cudaMemcpyHostToDevice, ctx.stream));
+    MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<uint32_t*>(r.cull), acc.hCull.data(), 4 * r.count, cudaMemcpyHostToDevice, ctx.stream));
     cudaMemcpyKind kind = (desc.memspace == MRB_MEM_HOST) ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<float*>(d.positions), desc.positions,
                                  sizeof(float) * 3 * size_t(desc.vertexCount), kind, ctx.stream));

@@ -151,7 +151,7 @@ mrb_status mrb_accel_build(mrb_context ctx, const mrb_accel_desc* desc, mrb_acce
         *out = nullptr;
         if(!desc->positions || !desc->indices || desc->triangleCount == 0 || desc->vertexCount == 0)
             return Fail(c, MRB_ERR_INVALID_ARG, "empty primitive group");
-        if(desc->rangeCount > 8) return Fail(c, MRB_ERR_INVALID_ARG, "more than 8 prim ranges (MaxPrimBatchPerSurface)");
+        if(desc->rangeCount > (1u << 20)) return Fail(c, MRB_ERR_INVALID_ARG, "too many prim ranges");
         if(desc->primGroupId > 15) return Fail(c, MRB_ERR_INVALID_ARG, "primGroupId exceeds PrimitiveKey batch bits (4)");
         uint64_t leafs = 0;
         if(desc->rangeCount && desc->primRanges)

@@ -491,15 +491,16 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
     MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
     std::vector<EmissiveTri> lights;
     std::vector<uint32_t> lightOfPrim(desc.triangleCount, INVALID_U32);
+    const mrb_accel_t& hacc = *desc.accel;
     for(uint32_t rg = 0; rg < a.ranges.count; rg++)
     {
-        uint32_t key = a.ranges.lmKey[rg];
+        uint32_t key = hacc.hLmKey[rg];
         if(!(key & 0x80000000u)) continue;
         uint32_t li = key & 0x1FFFFFu;
-        uint32_t count = a.ranges.leafStart[rg + 1] - a.ranges.leafStart[rg];
+        uint32_t count = hacc.hLeafStart[rg + 1] - hacc.hLeafStart[rg];
         for(uint32_t k = 0; k < count; k++)
         {
-            uint32_t prim = a.ranges.primBegin[rg] + k;
+            uint32_t prim = hacc.hPrimBegin[rg] + k;
             const float* p0 = &hpos[3 * size_t(hidx[3 * size_t(prim)])];
             const float* p1 = &hpos[3 * size_t(hidx[3 * size_t(prim) + 1])];
             const float* p2 = &hpos[3 * size_t(hidx[3 * size_t(prim) + 2])];

@@ -440,9 +440,7 @@ KTraceBinary(AccelData a, uint32_t accelKey,
         if(ni & LEAF_FLAG)
         {
             uint32_t leaf = ni & ~LEAF_FLAG;
-            uint32_t ri = 0;
-            #pragma unroll
-            for(uint32_t j = 1; j < 8; j++) if(j < a.ranges.count && leaf >= a.ranges.leafStart[j]) ri = j;
+            const uint32_t ri = (a.ranges.count == 1u) ? 0u : FindRange(a.ranges, leaf);
             uint32_t prim = a.ranges.primBegin[ri] + (leaf - a.ranges.leafStart[ri]);
             uint32_t i0 = a.indices[3 * size_t(prim)], i1 = a.indices[3 * size_t(prim) + 1], i2 = a.indices[3 * size_t(prim) + 2];
             float4 v0, e0, e1;

@@ -143,6 +143,28 @@ def test_build_device_pointers_and_prim_ranges(gpu_ctx):
     acc.close()
 
 
+def test_many_prim_ranges_flattened_surfaces(gpu_ctx):
+    """More than 8 prim ranges in one accelerator (identity-transform surfaces flattened): every range
+    keeps its own lightOrMatKey / cull flag; hits report the ORIGINAL prim index of the group."""
+    p, i = scenes.arcade_mesh(6000)
+    n = i.shape[0]
+    cuts = np.linspace(0, n, 41).astype(np.uint32)
+    ranges = np.stack([cuts[:-1], cuts[1:]], 1)
+    lm = (np.arange(40) * 3 + 1).astype(np.uint32)
+    acc = capi.Accelerator(gpu_ctx, p, i, prim_ranges=ranges, light_or_mat_keys=lm)
+    b = O.oracle_build(p, i)
+    assert np.array_equal(acc.export_lbvh()["nodes"], b.nodes)
+    rays = scenes.pinhole_rays(96, 54, **scenes.ARCADE_CAMERA)
+    for mode in (capi.MRB_TRACE_WIDE, capi.MRB_TRACE_BINARY_EXACT):
+        keys, hits, rout = gpu_cast(acc, rays, mode)
+        prim, t, bary, _ = O.oracle_trace(p, i, b, rays)
+        assert np.array_equal(keys[:, 0], prim)
+        hit = prim != O.INVALID
+        expect_lm = lm[np.searchsorted(cuts, prim[hit], side="right") - 1]
+        assert np.array_equal(keys[hit, 1], expect_lm)
+    acc.close()
+
+
 def test_build_large_soup_matches_oracle(gpu_ctx):
     p, i = scenes.random_soup(1_000_000)
     acc = capi.Accelerator(gpu_ctx, p, i)
