@@ -1,0 +1,604 @@
+// tracer_b200.cpp — the TracerDLL plugin object: `TracerI` (Core/TracerI.h:L150-376) implemented on
+// top of the C-ABI of include/mray_b200.h. Exports the two symbols MRay's TracerThread resolves
+// (TracerDLL/EntryPoint.h:L15-18). Host-side C++20, compiled against the reference's own headers so
+// that the vtable order and the layouts of TransientData / StaticVector / Optional match.
+//
+// Scope of round 1 (everything else throws MRayError, as the reference does for unknown types):
+//   (P)Triangle  (Mt)Lambert [constant albedo]  (L)Prim(P)Triangle [constant radiance]  (L)Null
+//   (T)Identity  (C)Pinhole  (Md)Vacuum  (R)PathTracerRGB   — i.e. BASELINE config 1 / 3-style scenes.
+// All identity-transform surfaces are flattened into ONE accelerator (one prim range per
+// prim-batch / material pair); ids are Key-typed bit casts like the reference's (Tracer/Key.h).
+#include "Core/TracerI.h"
+#include "Core/Error.h"
+#include "Core/TimelineSemaphore.h"
+#include "Core/Quaternion.h"
+#include "TransientPool/TransientPool.h"
+#include "mray_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace
+{
+
+using namespace std::string_view_literals;
+
+constexpr uint32_t PRIM_ID_BITS = 28, MAT_ID_BITS = 21, TRANS_ID_BITS = 24, CAM_ID_BITS = 24;
+template<class Id> uint32_t Raw(Id id) { return static_cast<uint32_t>(id); }
+
+struct PrimBatch { uint32_t primCount, vertexCount, primOffset, vertexOffset; };
+struct PrimGroupB200
+{
+    std::string type; bool committed = false;
+    std::vector<PrimBatch> batches;
+    std::vector<Vector3> positions; std::vector<Vector3> normals; std::vector<Vector3ui> indices;
+    uint32_t primTotal = 0, vertexTotal = 0;
+};
+struct MatGroupB200 { std::string type; bool committed = false; std::vector<Vector3> albedo; };
+struct LightGroupB200
+{
+    std::string type; bool committed = false; uint32_t primGroup = 0;
+    std::vector<Vector3> radiance; std::vector<uint8_t> twoSided; std::vector<uint32_t> primBatch;
+};
+struct CamGroupB200 { std::string type; bool committed = false; std::vector<Vector4> fovPlanes; std::vector<Vector3> gaze, position, up; };
+struct RendererB200
+{
+    std::string type;
+    uint32_t totalSPP = 16384, burstSize = 1, sampleMode = 0; Vector2ui rrRange = Vector2ui(4, 20);
+};
+
+class TracerB200 final : public TracerI
+{
+    TracerParameters params;
+    mrb_context ctx = nullptr;
+    mrb_accel accel = nullptr;
+    mrb_renderer renderer = nullptr;
+    std::mutex mtx; // scene-loading calls arrive concurrently from pool threads (TracerBase.h:L97-130)
+
+    std::vector<PrimGroupB200> prims; std::vector<MatGroupB200> mats; std::vector<LightGroupB200> lights;
+    std::vector<CamGroupB200> cams; std::vector<RendererB200> renderers;
+    std::vector<SurfaceParams> surfaces; std::vector<LightSurfaceParams> lightSurfaces;
+    std::vector<CameraSurfaceParams> camSurfaces; std::vector<VolumeParams> volumes;
+    LightSurfaceParams boundary{};
+    // flattened scene
+    uint32_t flatPrimGroup = 0; std::vector<float> flatLightRadiance; std::vector<uint8_t> flatLightTwoSided;
+    std::vector<float> flatAlbedo;
+    // render hand-off
+    TimelineSemaphore* sem = nullptr; uint64_t acquireValue = 0;
+    std::vector<float> staging; Vector2ui resolution = Vector2ui::Zero();
+    uint32_t curRenderer = 0; ThreadPool* pool = nullptr;
+
+    void Check(mrb_status s) const { if(s != MRB_OK) throw MRayError("{}", mrb_last_error(ctx)); }
+    template<class G> G& Get(std::vector<G>& v, uint32_t id, std::string_view what)
+    { if(id >= v.size()) throw MRayError("Unable to find {}({})", what, id); return v[id]; }
+    template<class G> const G& Get(const std::vector<G>& v, uint32_t id, std::string_view what) const
+    { if(id >= v.size()) throw MRayError("Unable to find {}({})", what, id); return v[id]; }
+
+    public:
+    explicit TracerB200(const TracerParameters& p) : params(p)
+    {
+        mrb_status s = mrb_context_create(0, &ctx);
+        if(s != MRB_OK) throw MRayError("mray_b200: {}", mrb_last_error(nullptr)); // no CPU fallback
+        // implicit groups, id 0 of every kind (Core/TracerI.h:L99-124)
+        prims.push_back(PrimGroupB200{std::string(TracerConstants::EmptyPrimName), true});
+        mats.push_back(MatGroupB200{std::string(TracerConstants::PassthroughMatName), true});
+        lights.push_back(LightGroupB200{std::string(TracerConstants::NullLightName), true});
+        lights[0].radiance.push_back(Vector3::Zero()); lights[0].twoSided.push_back(0); lights[0].primBatch.push_back(0);
+    }
+    ~TracerB200() override
+    {
+        if(renderer) mrb_renderer_destroy(ctx, renderer);
+        if(accel) mrb_accel_destroy(ctx, accel);
+        mrb_context_destroy(ctx);
+    }
+
+    // ------------------------------- generic -------------------------------
+    TypeNameList PrimitiveGroups() const override { return {"(P)Triangle"sv, "(P)Empty"sv}; }
+    TypeNameList MaterialGroups() const override { return {"(Mt)Lambert"sv, "(Mt)Passthrough"sv}; }
+    TypeNameList TransformGroups() const override { return {"(T)Identity"sv}; }
+    TypeNameList CameraGroups() const override { return {"(C)Pinhole"sv}; }
+    TypeNameList MediumGroups() const override { return {"(Md)Vacuum"sv}; }
+    TypeNameList LightGroups() const override { return {"(L)Null"sv, "(L)Prim(P)Triangle"sv}; }
+    TypeNameList Renderers() const override { return {"(R)PathTracerRGB"sv}; }
+
+    PrimAttributeInfoList AttributeInfoPrim(std::string_view name) const override
+    {
+        using enum MRayDataEnum; using enum AttributeIsArray; using enum AttributeOptionality;
+        using L = PrimitiveAttributeLogic;
+        if(name != "(P)Triangle"sv) return {};
+        // Tracer/PrimitiveDefaultTriangle.cu:L169-184
+        return PrimAttributeInfoList
+        {
+            PrimAttributeInfo(L::POSITION, MRayDataTypeRT(MR_VECTOR_3), IS_SCALAR, MR_MANDATORY),
+            PrimAttributeInfo(L::NORMAL,   MRayDataTypeRT(MR_QUATERNION), IS_SCALAR, MR_OPTIONAL),
+            PrimAttributeInfo(L::UV0,      MRayDataTypeRT(MR_VECTOR_2), IS_SCALAR, MR_OPTIONAL),
+            PrimAttributeInfo(L::INDEX,    MRayDataTypeRT(MR_VECTOR_3UI), IS_SCALAR, MR_MANDATORY)
+        };
+    }
+    MatAttributeInfoList AttributeInfoMat(std::string_view name) const override
+    {
+        using enum MRayDataEnum; using enum AttributeIsArray; using enum AttributeOptionality; using enum AttributeTexturable; using enum AttributeIsColor;
+        if(name != "(Mt)Lambert"sv) return {};
+        return MatAttributeInfoList
+        {
+            MatAttributeInfo("albedo", MRayDataTypeRT(MR_VECTOR_3), IS_SCALAR, MR_MANDATORY, MR_TEXTURE_OR_CONSTANT, IS_COLOR),
+            MatAttributeInfo("normalMap", MRayDataTypeRT(MR_VECTOR_3), IS_SCALAR, MR_OPTIONAL, MR_TEXTURE_ONLY, IS_PURE_DATA)
+        };
+    }
+    LightAttributeInfoList AttributeInfoLight(std::string_view name) const override
+    {
+        using enum MRayDataEnum; using enum AttributeIsArray; using enum AttributeOptionality; using enum AttributeTexturable; using enum AttributeIsColor;
+        if(name != "(L)Prim(P)Triangle"sv) return {};
+        return LightAttributeInfoList // Tracer/LightsDefault.hpp:L547-562
+        {
+            LightAttributeInfo("radiance", MRayDataTypeRT(MR_VECTOR_3), IS_SCALAR, MR_MANDATORY, MR_TEXTURE_OR_CONSTANT, IS_COLOR),
+            LightAttributeInfo("isTwoSided", MRayDataTypeRT(MR_BOOL), IS_SCALAR, MR_MANDATORY, MR_CONSTANT_ONLY, IS_PURE_DATA)
+        };
+    }
+    CamAttributeInfoList AttributeInfoCam(std::string_view name) const override
+    {
+        using enum MRayDataEnum; using enum AttributeIsArray; using enum AttributeOptionality;
+        if(name != "(C)Pinhole"sv) return {};
+        return CamAttributeInfoList
+        {
+            CamAttributeInfo("FovAndPlanes", MRayDataTypeRT(MR_VECTOR_4), IS_SCALAR, MR_MANDATORY),
+            CamAttributeInfo("gaze", MRayDataTypeRT(MR_VECTOR_3), IS_SCALAR, MR_MANDATORY),
+            CamAttributeInfo("position", MRayDataTypeRT(MR_VECTOR_3), IS_SCALAR, MR_MANDATORY),
+            CamAttributeInfo("up", MRayDataTypeRT(MR_VECTOR_3), IS_SCALAR, MR_MANDATORY)
+        };
+    }
+    MediumAttributeInfoList AttributeInfoMedium(std::string_view) const override { return {}; }
+    TransAttributeInfoList AttributeInfoTrans(std::string_view) const override { return {}; }
+    RendererAttributeInfoList AttributeInfoRenderer(std::string_view name) const override
+    {
+        using enum MRayDataEnum; using enum AttributeIsArray; using enum AttributeOptionality;
+        if(name != "(R)PathTracerRGB"sv) return {};
+        return RendererAttributeInfoList // TracerDLL/PathTracerRenderer.cu:L1384-1400
+        {
+            RendererAttributeInfo("totalSPP", MRayDataTypeRT(MR_UINT32), IS_SCALAR, MR_MANDATORY),
+            RendererAttributeInfo("burstSize", MRayDataTypeRT(MR_UINT32), IS_SCALAR, MR_OPTIONAL),
+            RendererAttributeInfo("renderMode", MRayDataTypeRT(MR_STRING), IS_SCALAR, MR_MANDATORY),
+            RendererAttributeInfo("sampleMode", MRayDataTypeRT(MR_STRING), IS_SCALAR, MR_MANDATORY),
+            RendererAttributeInfo("rrRange", MRayDataTypeRT(MR_VECTOR_2UI), IS_SCALAR, MR_MANDATORY),
+            RendererAttributeInfo("neeSamplerType", MRayDataTypeRT(MR_STRING), IS_SCALAR, MR_MANDATORY)
+        };
+    }
+    PrimAttributeInfoList AttributeInfo(PrimGroupId id) const override { return AttributeInfoPrim(Get(prims, Raw(id), "PrimitiveGroup").type); }
+    CamAttributeInfoList AttributeInfo(CameraGroupId id) const override { return AttributeInfoCam(Get(cams, Raw(id), "CameraGroup").type); }
+    MediumAttributeInfoList AttributeInfo(MediumGroupId) const override { return {}; }
+    MatAttributeInfoList AttributeInfo(MatGroupId id) const override { return AttributeInfoMat(Get(mats, Raw(id), "MaterialGroup").type); }
+    TransAttributeInfoList AttributeInfo(TransGroupId) const override { return {}; }
+    LightAttributeInfoList AttributeInfo(LightGroupId id) const override { return AttributeInfoLight(Get(lights, Raw(id), "LightGroup").type); }
+    RendererAttributeInfoList AttributeInfo(RendererId id) const override { return AttributeInfoRenderer(Get(renderers, Raw(id), "Renderer").type); }
+    std::string TypeName(PrimGroupId id) const override { return Get(prims, Raw(id), "PrimitiveGroup").type; }
+    std::string TypeName(CameraGroupId id) const override { return Get(cams, Raw(id), "CameraGroup").type; }
+    std::string TypeName(MediumGroupId) const override { return std::string(TracerConstants::VacuumMediumName); }
+    std::string TypeName(MatGroupId id) const override { return Get(mats, Raw(id), "MaterialGroup").type; }
+    std::string TypeName(TransGroupId) const override { return std::string(TracerConstants::IdentityTransName); }
+    std::string TypeName(LightGroupId id) const override { return Get(lights, Raw(id), "LightGroup").type; }
+    std::string TypeName(RendererId id) const override { return Get(renderers, Raw(id), "Renderer").type; }
+
+    // ------------------------------- primitives -------------------------------
+    PrimGroupId CreatePrimitiveGroup(std::string typeName) override
+    {
+        std::lock_guard lk(mtx);
+        if(typeName != "(P)Triangle") throw MRayError("Unable to find generator for {}", typeName);
+        prims.push_back(PrimGroupB200{typeName});
+        return PrimGroupId(uint32_t(prims.size() - 1));
+    }
+    PrimBatchId ReservePrimitiveBatch(PrimGroupId g, PrimCount c) override { return ReservePrimitiveBatches(g, {c}).front(); }
+    PrimBatchIdList ReservePrimitiveBatches(PrimGroupId g, std::vector<PrimCount> counts) override
+    {
+        std::lock_guard lk(mtx);
+        PrimGroupB200& pg = Get(prims, Raw(g), "PrimitiveGroup");
+        if(pg.committed) throw MRayError("{}: reservations are already committed", pg.type);
+        PrimBatchIdList out;
+        for(const PrimCount& c : counts)
+        {
+            pg.batches.push_back(PrimBatch{c.primCount, c.attributeCount, pg.primTotal, pg.vertexTotal});
+            pg.primTotal += c.primCount; pg.vertexTotal += c.attributeCount;
+            out.push_back(PrimBatchId((Raw(g) << PRIM_ID_BITS) | uint32_t(pg.batches.size() - 1)));
+        }
+        return out;
+    }
+    void CommitPrimReservations(PrimGroupId g) override
+    {
+        std::lock_guard lk(mtx);
+        PrimGroupB200& pg = Get(prims, Raw(g), "PrimitiveGroup");
+        pg.positions.assign(pg.vertexTotal, Vector3::Zero());
+        pg.normals.assign(pg.vertexTotal, Vector3::Zero());
+        pg.indices.assign(pg.primTotal, Vector3ui::Zero());
+        pg.committed = true;
+    }
+    bool IsPrimCommitted(PrimGroupId g) const override { return Get(prims, Raw(g), "PrimitiveGroup").committed; }
+    void PushPrimAttribute(PrimGroupId g, PrimBatchId b, uint32_t attributeIndex, TransientData data) override
+    {
+        PrimGroupB200& pg = Get(prims, Raw(g), "PrimitiveGroup");
+        uint32_t bi = Raw(b) & ((1u << PRIM_ID_BITS) - 1u);
+        if(!pg.committed || bi >= pg.batches.size()) throw MRayError("{}: unknown / uncommitted batch {}", pg.type, bi);
+        const PrimBatch& pb = pg.batches[bi];
+        switch(attributeIndex)
+        {
+            case 0: { auto s = data.AccessAs<const Vector3>(); if(s.size() != pb.vertexCount) throw MRayError("position count mismatch");
+                      std::copy(s.begin(), s.end(), pg.positions.begin() + pb.vertexOffset); break; }
+            case 1: { auto s = data.AccessAs<const Quaternion>(); if(s.size() != pb.vertexCount) throw MRayError("normal count mismatch");
+                      // the attribute is the to-tangent-space rotation; its Z basis is the shading normal
+                      for(size_t i = 0; i < s.size(); i++) pg.normals[pb.vertexOffset + i] = s[i].OrthoBasisZ(); break; }
+            case 2: break; // uv: constant albedo only in round 1
+            case 3: { auto s = data.AccessAs<const Vector3ui>(); if(s.size() != pb.primCount) throw MRayError("index count mismatch");
+                      // KCAdjustIndices (Tracer/PrimitiveDefaultTriangle.cu:L9): rebase batch-local indices
+                      for(size_t i = 0; i < s.size(); i++) pg.indices[pb.primOffset + i] = s[i] + Vector3ui(pb.vertexOffset); break; }
+            default: throw MRayError("{}: unknown attribute index {}", pg.type, attributeIndex);
+        }
+    }
+    void PushPrimAttribute(PrimGroupId, PrimBatchId, uint32_t, Vector2ui, TransientData) override
+    { throw MRayError("(P)Triangle: sub-batch attribute push is not supported"); }
+    void TransformPrimitives(PrimGroupId, std::vector<PrimBatchId>, std::vector<Matrix3x4>) override
+    { throw MRayError("TransformPrimitives is not supported"); }
+
+    // ------------------------------- materials -------------------------------
+    MatGroupId CreateMaterialGroup(std::string typeName) override
+    {
+        std::lock_guard lk(mtx);
+        if(typeName != "(Mt)Lambert") throw MRayError("Unable to find generator for {}", typeName);
+        mats.push_back(MatGroupB200{typeName});
+        return MatGroupId(uint32_t(mats.size() - 1));
+    }
+    MaterialId ReserveMaterial(MatGroupId g, AttributeCountList c) override { return ReserveMaterials(g, {c}).front(); }
+    MaterialIdList ReserveMaterials(MatGroupId g, std::vector<AttributeCountList> counts) override
+    {
+        std::lock_guard lk(mtx);
+        MatGroupB200& mg = Get(mats, Raw(g), "MaterialGroup");
+        MaterialIdList out;
+        for(size_t i = 0; i < counts.size(); i++)
+        {
+            mg.albedo.push_back(Vector3::Zero());
+            out.push_back(MaterialId((Raw(g) << MAT_ID_BITS) | uint32_t(mg.albedo.size() - 1)));
+        }
+        return out;
+    }
+    void CommitMatReservations(MatGroupId g) override { Get(mats, Raw(g), "MaterialGroup").committed = true; }
+    bool IsMatCommitted(MatGroupId g) const override { return Get(mats, Raw(g), "MaterialGroup").committed; }
+    void PushMatAttribute(MatGroupId, CommonIdRange, uint32_t attributeIndex, TransientData) override
+    { throw MRayError("(Mt)Lambert: Attribute {:d} is not \"ConstantOnly\", wrong function is called", attributeIndex); }
+    void PushMatAttribute(MatGroupId g, CommonIdRange range, uint32_t attributeIndex, TransientData data,
+                          std::vector<Optional<TextureId>> tex) override
+    {
+        MatGroupB200& mg = Get(mats, Raw(g), "MaterialGroup");
+        if(attributeIndex != 0) throw MRayError("{}: Attribute {:d} is not \"ParamVarying\"", mg.type, attributeIndex);
+        for(const auto& t : tex) if(t.has_value()) throw MRayError("{}: textured albedo is not supported yet", mg.type);
+        uint32_t lo = range[0] & ((1u << MAT_ID_BITS) - 1u), hi = range[1] & ((1u << MAT_ID_BITS) - 1u);
+        auto s = data.AccessAs<const Vector3>();
+        if(hi >= mg.albedo.size() || s.size() != hi - lo + 1) throw MRayError("{}: albedo range mismatch", mg.type);
+        std::copy(s.begin(), s.end(), mg.albedo.begin() + lo);
+    }
+    void PushMatAttribute(MatGroupId, CommonIdRange, uint32_t, std::vector<TextureId>) override
+    { throw MRayError("(Mt)Lambert: texture-only attributes (normalMap) are not supported yet"); }
+
+    // ------------------------------- textures -------------------------------
+    TextureId CreateTexture2D(Vector2ui, uint32_t, MRayTextureParameters) override { throw MRayError("textures are not supported yet"); }
+    TextureId CreateTexture3D(Vector3ui, uint32_t, MRayTextureParameters) override { throw MRayError("textures are not supported yet"); }
+    void CommitTextures() override {}
+    void PushTextureData(TextureId, uint32_t, TransientData) override { throw MRayError("textures are not supported yet"); }
+
+    // ------------------------------- transforms -------------------------------
+    TransGroupId CreateTransformGroup(std::string typeName) override
+    { throw MRayError("Unable to find generator for {} (round 1: (T)Identity only)", typeName); }
+    TransformId ReserveTransformation(TransGroupId, AttributeCountList) override { throw MRayError("only (T)Identity exists"); }
+    TransformIdList ReserveTransformations(TransGroupId, std::vector<AttributeCountList>) override { throw MRayError("only (T)Identity exists"); }
+    void CommitTransReservations(TransGroupId) override {}
+    bool IsTransCommitted(TransGroupId) const override { return true; }
+    void PushTransAttribute(TransGroupId, CommonIdRange, uint32_t, TransientData) override { throw MRayError("only (T)Identity exists"); }
+
+    // ------------------------------- lights -------------------------------
+    LightGroupId CreateLightGroup(std::string typeName, PrimGroupId pg) override
+    {
+        std::lock_guard lk(mtx);
+        if(typeName != "(L)Prim(P)Triangle") throw MRayError("Unable to find generator for {}", typeName);
+        lights.push_back(LightGroupB200{typeName, false, Raw(pg)});
+        return LightGroupId(uint32_t(lights.size() - 1));
+    }
+    LightId ReserveLight(LightGroupId g, AttributeCountList c, PrimBatchId b) override { return ReserveLights(g, {c}, {b}).front(); }
+    LightIdList ReserveLights(LightGroupId g, std::vector<AttributeCountList> counts, std::vector<PrimBatchId> batches) override
+    {
+        std::lock_guard lk(mtx);
+        LightGroupB200& lg = Get(lights, Raw(g), "LightGroup");
+        if(batches.size() != counts.size()) throw MRayError("{}: prim-backed lights need one prim batch each", lg.type);
+        LightIdList out;
+        for(size_t i = 0; i < counts.size(); i++)
+        {
+            lg.radiance.push_back(Vector3::Zero()); lg.twoSided.push_back(0);
+            lg.primBatch.push_back(Raw(batches[i]) & ((1u << PRIM_ID_BITS) - 1u));
+            out.push_back(LightId((Raw(g) << MAT_ID_BITS) | uint32_t(lg.radiance.size() - 1)));
+        }
+        return out;
+    }
+    void CommitLightReservations(LightGroupId g) override { Get(lights, Raw(g), "LightGroup").committed = true; }
+    bool IsLightCommitted(LightGroupId g) const override { return Get(lights, Raw(g), "LightGroup").committed; }
+    void PushLightAttribute(LightGroupId g, CommonIdRange range, uint32_t attributeIndex, TransientData data) override
+    {
+        LightGroupB200& lg = Get(lights, Raw(g), "LightGroup");
+        if(attributeIndex != 1) throw MRayError("{}: Attribute {:d} is not \"ConstantOnly\", wrong function is called", lg.type, attributeIndex);
+        uint32_t lo = range[0] & ((1u << MAT_ID_BITS) - 1u), hi = range[1] & ((1u << MAT_ID_BITS) - 1u);
+        auto s = data.AccessAs<const bool>();
+        if(hi >= lg.twoSided.size() || s.size() != hi - lo + 1) throw MRayError("{}: isTwoSided range mismatch", lg.type);
+        for(size_t i = 0; i < s.size(); i++) lg.twoSided[lo + i] = s[i] ? 1 : 0;
+    }
+    void PushLightAttribute(LightGroupId g, CommonIdRange range, uint32_t attributeIndex, TransientData data,
+                            std::vector<Optional<TextureId>> tex) override
+    {
+        LightGroupB200& lg = Get(lights, Raw(g), "LightGroup");
+        if(attributeIndex != 0) throw MRayError("{}: Attribute {:d} is not \"ParamVarying\", wrong function is called", lg.type, attributeIndex);
+        for(const auto& t : tex) if(t.has_value()) throw MRayError("{}: textured radiance is not supported yet", lg.type);
+        uint32_t lo = range[0] & ((1u << MAT_ID_BITS) - 1u), hi = range[1] & ((1u << MAT_ID_BITS) - 1u);
+        auto s = data.AccessAs<const Vector3>();
+        if(hi >= lg.radiance.size() || s.size() != hi - lo + 1) throw MRayError("{}: radiance range mismatch", lg.type);
+        std::copy(s.begin(), s.end(), lg.radiance.begin() + lo);
+    }
+    void PushLightAttribute(LightGroupId, CommonIdRange, uint32_t, std::vector<TextureId>) override
+    { throw MRayError("textured lights are not supported yet"); }
+
+    // ------------------------------- cameras -------------------------------
+    CameraGroupId CreateCameraGroup(std::string typeName) override
+    {
+        std::lock_guard lk(mtx);
+        if(typeName != "(C)Pinhole") throw MRayError("Unable to find generator for {}", typeName);
+        cams.push_back(CamGroupB200{typeName});
+        return CameraGroupId(uint32_t(cams.size() - 1));
+    }
+    CameraId ReserveCamera(CameraGroupId g, AttributeCountList c) override { return ReserveCameras(g, {c}).front(); }
+    CameraIdList ReserveCameras(CameraGroupId g, std::vector<AttributeCountList> counts) override
+    {
+        std::lock_guard lk(mtx);
+        CamGroupB200& cg = Get(cams, Raw(g), "CameraGroup");
+        CameraIdList out;
+        for(size_t i = 0; i < counts.size(); i++)
+        {
+            cg.fovPlanes.push_back(Vector4::Zero()); cg.gaze.push_back(Vector3::Zero());
+            cg.position.push_back(Vector3::Zero()); cg.up.push_back(Vector3::YAxis());
+            out.push_back(CameraId((Raw(g) << CAM_ID_BITS) | uint32_t(cg.gaze.size() - 1)));
+        }
+        return out;
+    }
+    void CommitCamReservations(CameraGroupId g) override { Get(cams, Raw(g), "CameraGroup").committed = true; }
+    bool IsCamCommitted(CameraGroupId g) const override { return Get(cams, Raw(g), "CameraGroup").committed; }
+    void PushCamAttribute(CameraGroupId g, CommonIdRange range, uint32_t attributeIndex, TransientData data) override
+    {
+        CamGroupB200& cg = Get(cams, Raw(g), "CameraGroup");
+        uint32_t lo = range[0] & ((1u << CAM_ID_BITS) - 1u);
+        if(lo >= cg.gaze.size()) throw MRayError("{}: unknown camera {}", cg.type, lo);
+        if(attributeIndex == 0) cg.fovPlanes[lo] = data.AccessAs<const Vector4>().front();
+        else if(attributeIndex == 1) cg.gaze[lo] = data.AccessAs<const Vector3>().front();
+        else if(attributeIndex == 2) cg.position[lo] = data.AccessAs<const Vector3>().front();
+        else if(attributeIndex == 3) cg.up[lo] = data.AccessAs<const Vector3>().front();
+        else throw MRayError("{}: unknown attribute index {}", cg.type, attributeIndex);
+    }
+
+    // ------------------------------- mediums -------------------------------
+    MediumGroupId CreateMediumGroup(std::string typeName) override { throw MRayError("Unable to find generator for {}", typeName); }
+    MediumId ReserveMedium(MediumGroupId, AttributeCountList) override { throw MRayError("only (Md)Vacuum exists"); }
+    MediumIdList ReserveMediums(MediumGroupId, std::vector<AttributeCountList>) override { throw MRayError("only (Md)Vacuum exists"); }
+    void CommitMediumReservations(MediumGroupId) override {}
+    bool IsMediumCommitted(MediumGroupId) const override { return true; }
+    void PushMediumAttribute(MediumGroupId, CommonIdRange, uint32_t, TransientData) override { throw MRayError("only (Md)Vacuum exists"); }
+    void PushMediumAttribute(MediumGroupId, CommonIdRange, uint32_t, TransientData, std::vector<Optional<TextureId>>) override { throw MRayError("only (Md)Vacuum exists"); }
+    void PushMediumAttribute(MediumGroupId, CommonIdRange, uint32_t, std::vector<TextureId>) override { throw MRayError("only (Md)Vacuum exists"); }
+
+    // ------------------------------- surfaces -------------------------------
+    SurfaceId CreateSurface(SurfaceParams p) override { std::lock_guard lk(mtx); surfaces.push_back(p); return SurfaceId(uint32_t(surfaces.size() - 1)); }
+    LightSurfaceId SetBoundarySurface(LightId l, TransformId t) override { boundary = LightSurfaceParams{l, t, {}}; return LightSurfaceId(0xFFFFFFFEu); }
+    LightSurfaceId CreateLightSurface(LightSurfaceParams p) override { std::lock_guard lk(mtx); lightSurfaces.push_back(p); return LightSurfaceId(uint32_t(lightSurfaces.size() - 1)); }
+    CamSurfaceId CreateCameraSurface(CameraSurfaceParams p) override { std::lock_guard lk(mtx); camSurfaces.push_back(p); return CamSurfaceId(uint32_t(camSurfaces.size() - 1)); }
+    VolumeId RegisterVolume(VolumeParams v) override { std::lock_guard lk(mtx); volumes.push_back(v); return VolumeId(uint32_t(volumes.size() - 1)); }
+    VolumeIdList RegisterVolumes(std::vector<VolumeParams> v) override { VolumeIdList o; for(auto& x : v) o.push_back(RegisterVolume(x)); return o; }
+    void SetBoundaryVolume(VolumeId) override {}
+
+    SurfaceCommitResult CommitSurfaces() override
+    {
+        // TracerBase::CommitSurfaces (Tracer/TracerBase.cpp:L1529-1674) + BaseAccelerator::Construct:
+        // every surface here has the identity transform, so they become the prim ranges of one accelerator.
+        if(Raw(boundary.lightId) != 0) throw MRayError("round 1: the boundary light must be (L)Null");
+        std::vector<uint32_t> ranges, lmKeys; std::vector<uint8_t> cull;
+        flatAlbedo.clear(); flatLightRadiance.clear(); flatLightTwoSided.clear();
+        int32_t pgUsed = -1;
+        auto UsePrimGroup = [&](uint32_t g)
+        {
+            if(pgUsed >= 0 && uint32_t(pgUsed) != g) throw MRayError("round 1: one triangle primitive group per scene");
+            pgUsed = int32_t(g);
+        };
+        // material table: flat index = running index over (group, id) pairs in first-use order
+        std::vector<uint32_t> matKeyOf;
+        auto FlatMat = [&](MaterialId m)
+        {
+            for(size_t i = 0; i < matKeyOf.size(); i++) if(matKeyOf[i] == Raw(m)) return uint32_t(i);
+            const MatGroupB200& mg = Get(mats, Raw(m) >> MAT_ID_BITS, "MaterialGroup");
+            uint32_t idx = Raw(m) & ((1u << MAT_ID_BITS) - 1u);
+            if(idx >= mg.albedo.size()) throw MRayError("Unable to find Material({})", Raw(m));
+            matKeyOf.push_back(Raw(m));
+            flatAlbedo.insert(flatAlbedo.end(), {mg.albedo[idx][0], mg.albedo[idx][1], mg.albedo[idx][2]});
+            return uint32_t(matKeyOf.size() - 1);
+        };
+        for(const SurfaceParams& s : surfaces)
+        {
+            if(Raw(s.transformId) != 0) throw MRayError("round 1: surfaces must use (T)Identity");
+            for(size_t k = 0; k < s.primBatches.size(); k++)
+            {
+                uint32_t g = Raw(s.primBatches[k]) >> PRIM_ID_BITS, bi = Raw(s.primBatches[k]) & ((1u << PRIM_ID_BITS) - 1u);
+                UsePrimGroup(g);
+                const PrimBatch& pb = Get(Get(prims, g, "PrimitiveGroup").batches, bi, "PrimitiveBatch");
+                ranges.insert(ranges.end(), {pb.primOffset, pb.primOffset + pb.primCount});
+                lmKeys.push_back(FlatMat(s.materials[k]));
+                cull.push_back(s.cullFaceFlags[k] ? 1 : 0);
+            }
+        }
+        for(const LightSurfaceParams& ls : lightSurfaces)
+        {
+            if(Raw(ls.transformId) != 0) throw MRayError("round 1: light surfaces must use (T)Identity");
+            const LightGroupB200& lg = Get(lights, Raw(ls.lightId) >> MAT_ID_BITS, "LightGroup");
+            uint32_t li = Raw(ls.lightId) & ((1u << MAT_ID_BITS) - 1u);
+            if(li >= lg.radiance.size()) throw MRayError("Unable to find Light({})", Raw(ls.lightId));
+            UsePrimGroup(lg.primGroup);
+            const PrimBatch& pb = Get(Get(prims, lg.primGroup, "PrimitiveGroup").batches, lg.primBatch[li], "PrimitiveBatch");
+            ranges.insert(ranges.end(), {pb.primOffset, pb.primOffset + pb.primCount});
+            lmKeys.push_back(0x80000000u | uint32_t(flatLightTwoSided.size()));
+            cull.push_back(0);
+            flatLightRadiance.insert(flatLightRadiance.end(), {lg.radiance[li][0], lg.radiance[li][1], lg.radiance[li][2]});
+            flatLightTwoSided.push_back(lg.twoSided[li]);
+        }
+        if(pgUsed < 0 || lmKeys.empty()) throw MRayError("empty scene");
+        flatPrimGroup = uint32_t(pgUsed);
+        const PrimGroupB200& pg = prims[flatPrimGroup];
+        if(accel) { mrb_accel_destroy(ctx, accel); accel = nullptr; }
+        mrb_accel_desc d = {};
+        d.positions = reinterpret_cast<const float*>(pg.positions.data()); d.vertexCount = pg.vertexTotal;
+        d.indices = reinterpret_cast<const uint32_t*>(pg.indices.data()); d.triangleCount = pg.primTotal;
+        d.memspace = MRB_MEM_HOST; d.primGroupId = flatPrimGroup;
+        d.rangeCount = uint32_t(lmKeys.size()); d.primRanges = ranges.data();
+        d.lightOrMatKeys = lmKeys.data(); d.cullBackface = cull.data(); d.flags = MRB_BUILD_DEFAULT;
+        Check(mrb_accel_build(ctx, &d, &accel));
+        mrb_accel_info info; Check(mrb_accel_get_info(ctx, accel, &info));
+        return SurfaceCommitResult
+        {
+            .aabb = AABB3(Vector3(info.aabb[0], info.aabb[1], info.aabb[2]), Vector3(info.aabb[3], info.aabb[4], info.aabb[5])),
+            .instanceCount = surfaces.size() + lightSurfaces.size(),
+            .acceleratorCount = 1
+        };
+    }
+    CameraTransform GetCamTransform(CamSurfaceId id) const override
+    {
+        const CameraSurfaceParams& cs = Get(camSurfaces, Raw(id), "CameraSurface");
+        const CamGroupB200& cg = Get(cams, Raw(cs.cameraId) >> CAM_ID_BITS, "CameraGroup");
+        uint32_t ci = Raw(cs.cameraId) & ((1u << CAM_ID_BITS) - 1u);
+        return CameraTransform{cg.position[ci], cg.gaze[ci], cg.up[ci]};
+    }
+
+    // ------------------------------- renderers -------------------------------
+    RendererId CreateRenderer(std::string typeName) override
+    {
+        std::lock_guard lk(mtx);
+        if(typeName != "(R)PathTracerRGB") throw MRayError("Unable to find generator for {}", typeName);
+        renderers.push_back(RendererB200{typeName});
+        return RendererId(uint32_t(renderers.size() - 1));
+    }
+    void DestroyRenderer(RendererId id) override
+    {
+        if(Raw(id) >= renderers.size()) throw MRayError("Unable to find renderer ({})", Raw(id));
+        if(Raw(id) == curRenderer && renderer) { mrb_renderer_destroy(ctx, renderer); renderer = nullptr; }
+    }
+    void PushRendererAttribute(RendererId id, uint32_t attributeIndex, TransientData dataIn) override
+    {
+        const TransientData& data = dataIn;
+        RendererB200& r = Get(renderers, Raw(id), "Renderer");
+        switch(attributeIndex) // PathTracerRendererT::PushAttribute (TracerDLL/PathTracerRenderer.cu)
+        {
+            case 0: r.totalSPP = data.AccessAs<const uint32_t>().front(); break;
+            case 1: r.burstSize = data.AccessAs<const uint32_t>().front(); break;
+            case 2: { std::string_view m = data.AccessAsString();
+                      if(m != "Throughput"sv && m != "Latency"sv) throw MRayError("Bad enum name"); break; }
+            case 3: { std::string_view m = data.AccessAsString();
+                      if(m == "Pure"sv) r.sampleMode = 0; else if(m == "WithNextEventEstimation"sv) r.sampleMode = 1;
+                      else if(m == "WithNEEAndMIS"sv) r.sampleMode = 2; else throw MRayError("Bad enum name"); break; }
+            case 4: r.rrRange = data.AccessAs<const Vector2ui>().front(); break;
+            case 5: { if(data.AccessAsString() != "Uniform"sv) throw MRayError("Bad enum name"); break; }
+            default: throw MRayError("{}: unknown attribute index {}", r.type, attributeIndex);
+        }
+    }
+
+    // ------------------------------- rendering -------------------------------
+    void SetupRenderEnv(TimelineSemaphore* s, uint32_t, uint64_t initialAcquireValue) override { sem = s; acquireValue = initialAcquireValue; }
+    RenderBufferInfo StartRender(RendererId id, CamSurfaceId camSurf, RenderImageParams rip, Optional<uint32_t> logic0, Optional<uint32_t>) override
+    {
+        if(!sem) throw MRayError("Render environment is not set properly! Please provide a semaphore to the tracer.");
+        if(!accel) throw MRayError("CommitSurfaces must be called before StartRender");
+        const RendererB200& r = Get(renderers, Raw(id), "Renderer");
+        const CameraSurfaceParams& cs = Get(camSurfaces, Raw(camSurf), "CameraSurface");
+        const CamGroupB200& cg = Get(cams, Raw(cs.cameraId) >> CAM_ID_BITS, "CameraGroup");
+        uint32_t ci = Raw(cs.cameraId) & ((1u << CAM_ID_BITS) - 1u);
+        const PrimGroupB200& pg = prims[flatPrimGroup];
+        if(renderer) { mrb_renderer_destroy(ctx, renderer); renderer = nullptr; }
+        Vector2ui tile = rip.regionMax - rip.regionMin;
+        if(tile != rip.resolution) throw MRayError("round 1: the render region must be the whole image");
+        mrb_render_desc d = {};
+        d.accel = accel; d.vertexCount = pg.vertexTotal; d.triangleCount = pg.primTotal;
+        bool hasNormals = std::any_of(pg.normals.begin(), pg.normals.end(), [](const Vector3& n) { return n != Vector3::Zero(); });
+        d.vertexNormals = hasNormals ? reinterpret_cast<const float*>(pg.normals.data()) : nullptr;
+        d.materialCount = uint32_t(flatAlbedo.size() / 3); d.albedo = flatAlbedo.data();
+        d.lightCount = uint32_t(flatLightTwoSided.size()); d.lightRadiance = flatLightRadiance.data(); d.lightTwoSided = flatLightTwoSided.data();
+        for(int k = 0; k < 3; k++) { d.camPosition[k] = cg.position[ci][k]; d.camGaze[k] = cg.gaze[ci][k]; d.camUp[k] = cg.up[ci][k]; }
+        d.fovXY[0] = cg.fovPlanes[ci][0]; d.fovXY[1] = cg.fovPlanes[ci][1];
+        d.nearFar[0] = cg.fovPlanes[ci][2]; d.nearFar[1] = cg.fovPlanes[ci][3];
+        d.width = tile[0]; d.height = tile[1]; d.totalSPP = r.totalSPP;
+        // render logic 0 rolls the sample mode like PathTracerRendererT::StartRender (L1192-1200)
+        d.sampleMode = (r.sampleMode + logic0.value_or(0)) % 3u;
+        d.rrRange[0] = r.rrRange[0]; d.rrRange[1] = r.rrRange[1];
+        d.filmFilterRadius = params.filmFilter.radius; d.seed = params.seed;
+        uint64_t pixels = uint64_t(tile[0]) * tile[1];
+        d.maxPathCount = uint32_t(std::min<uint64_t>(pixels, std::max<uint32_t>(params.parallelizationHint, 1u)));
+        Check(mrb_renderer_create(ctx, &d, &renderer));
+        curRenderer = Raw(id); resolution = tile;
+        staging.assign(size_t(4) * pixels, 0.0f);
+        return RenderBufferInfo
+        {
+            .data = reinterpret_cast<const Byte*>(staging.data()), .totalSize = staging.size() * sizeof(float),
+            .renderColorSpace = params.globalTextureColorSpace, .resolution = rip.resolution,
+            .curRenderLogic0 = logic0.value_or(0), .curRenderLogic1 = 0
+        };
+    }
+    void SetCameraTransform(RendererId, CameraTransform) override { throw MRayError("SetCameraTransform is not supported yet"); }
+    void StopRender() override { if(renderer) { mrb_renderer_destroy(ctx, renderer); renderer = nullptr; } }
+    RendererOutput DoRenderWork() override
+    {
+        if(!renderer) return RendererOutput{};
+        // one wavefront iteration (DoThroughputSingleTileRender), then the film delta hand-off of
+        // RenderImage::TransferToHost (Tracer/RenderImage.cpp:L163-219): acquire, copy, release, next state
+        Check(mrb_renderer_iterate(ctx, renderer, std::max(1u, renderers[curRenderer].burstSize)));
+        mrb_render_stats st; Check(mrb_renderer_get_stats(ctx, renderer, &st));
+        if(!sem->Acquire(acquireValue)) return RendererOutput{};
+        Check(mrb_renderer_read_film(ctx, renderer, staging.data(), MRB_MEM_HOST, 1));
+        sem->Release();
+        acquireValue += 2;
+        size_t plane = size_t(resolution[0]) * resolution[1] * sizeof(float);
+        RendererOutput out;
+        out.imageOut = RenderImageSection
+        {
+            .pixelMin = Vector2ui::Zero(), .pixelMax = resolution, .globalWeight = Float(1),
+            .waitCounter = acquireValue - 1,
+            .pixStartOffsets = {0, plane, 2 * plane}, .weightStartOffset = 3 * plane
+        };
+        out.analytics = RendererAnalyticData
+        {
+            .throughput = 0.0, .throughputSuffix = "M path/s",
+            .workPerPixel = double(st.pathsCompleted) / double(resolution[0] * resolution[1]),
+            .wppLimit = double(renderers[curRenderer].totalSPP), .workPerPixelSuffix = "spp",
+            .iterationTimeMS = 0.0f, .renderResolution = resolution,
+            .outputColorSpace = params.globalTextureColorSpace,
+            .usedGPUMemoryBytes = mrb_context_used_device_memory(ctx)
+        };
+        out.triggerSave = st.finished != 0;
+        return out;
+    }
+
+    // ------------------------------- misc -------------------------------
+    void ClearAll() override
+    {
+        StopRender();
+        if(accel) { mrb_accel_destroy(ctx, accel); accel = nullptr; }
+        prims.resize(1); mats.resize(1); lights.resize(1); cams.clear(); renderers.clear();
+        surfaces.clear(); lightSurfaces.clear(); camSurfaces.clear(); volumes.clear();
+    }
+    void Flush() const override { mrb_context_synchronize(ctx); }
+    GPUThreadInitFunction GetThreadInitFunction() const override { return []() {}; } // the C-ABI selects its device per call
+    void SetThreadPool(ThreadPool& tp) override { pool = &tp; }
+    size_t TotalDeviceMemory() const override { return mrb_context_total_device_memory(ctx); }
+    size_t UsedDeviceMemory() const override { return mrb_context_used_device_memory(ctx); }
+    const TracerParameters& Parameters() const override { return params; }
+};
+
+} // namespace
+
+extern "C" __attribute__((visibility("default"))) TracerI* ConstructTracer(const TracerParameters& p) { return new TracerB200(p); }
+extern "C" __attribute__((visibility("default"))) void DestroyTracer(TracerI* t) { delete t; }
