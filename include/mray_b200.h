@@ -263,6 +263,26 @@ MRB_API mrb_status mrb_radix_sort_pairs_u32(mrb_context ctx, uint32_t* keys, uin
                                             uint32_t count, uint32_t bitBegin, uint32_t bitEnd,
                                             mrb_memspace memspace);
 
+/* RayPartitioner::MultiPartition (Tracer/RayPartitioner.cu:L263-411): sorts (keys, indices) in place —
+ * stable, by the data bit range then the batch bit range (batch-only when onlySortForBatches) — and
+ * writes the partition table: partitionCount[0], partitionOffsets[count+1] (start of each run of equal
+ * batch bits, closed by `count`), partitionKeys[count] (first sorted key of each run). At most
+ * maxPartitions entries are written; batch range <= 16 bits. With MRB_MEM_DEVICE nothing synchronises
+ * (the reference reads this table on the host every iteration). */
+MRB_API mrb_status mrb_multi_partition(mrb_context ctx, uint32_t* keys, uint32_t* indices, uint32_t count,
+                                       const uint32_t dataBitRange[2], const uint32_t batchBitRange[2],
+                                       int onlySortForBatches, uint32_t maxPartitions,
+                                       uint32_t* partitionCount, uint32_t* partitionOffsets, uint32_t* partitionKeys,
+                                       mrb_memspace memspace);
+
+/* RayPartitioner::BinaryPartition (Tracer/RayPartitioner.h:L154-200; cub::DevicePartition::If /
+ * Device/CPU/AlgBinaryPartitionCPU.h): stable two-way split of an index list. indicesOut =
+ * [indices i of indicesIn with flags[i] != 0, in order][the rest, in order]; leftCount[0] = size of the
+ * first part. flags is indexed by the VALUE of the index (like IsAliveFunctor over dPathDataPack). */
+MRB_API mrb_status mrb_binary_partition(mrb_context ctx, uint32_t* indicesOut, uint32_t* leftCount,
+                                        const uint32_t* indicesIn, const uint8_t* flags, uint32_t flagCount,
+                                        uint32_t count, mrb_memspace memspace);
+
 #ifdef __cplusplus
 }
 #endif

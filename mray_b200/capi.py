@@ -97,6 +97,9 @@ _PROTOTYPES = {
     "mrb_renderer_get_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(RenderStats)]),
     "mrb_renderer_read_film": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "mrb_renderer_film_device_ptr": (C.c_void_p, [C.c_void_p]),
+    "mrb_multi_partition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                      C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "mrb_binary_partition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]),
     "mrb_radix_sort_pairs_u64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
     "mrb_radix_sort_pairs_u32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
 }
@@ -208,6 +211,26 @@ class Context:
         bit_end = itemsize * 8 if bit_end is None else bit_end
         fn = self.lib.mrb_radix_sort_pairs_u64 if itemsize == 8 else self.lib.mrb_radix_sort_pairs_u32
         self.check(fn(self.handle, _ptr(keys), _ptr(values), n, bit_begin, bit_end, space))
+
+    def multi_partition(self, keys, indices, data_bits, batch_bits, max_partitions, only_batches=False):
+        """RayPartitioner::MultiPartition on HOST numpy arrays (sorted in place). Returns
+        (count, offsets[count+1], partition_keys[count])."""
+        n = keys.shape[0]
+        cnt = np.zeros(1, np.uint32); ofs = np.zeros(max_partitions + 1, np.uint32); pk = np.zeros(max_partitions, np.uint32)
+        self.check(self.lib.mrb_multi_partition(self.handle, _ptr(keys), _ptr(indices), n, (C.c_uint32 * 2)(*data_bits),
+                                                (C.c_uint32 * 2)(*batch_bits), 1 if only_batches else 0, max_partitions,
+                                                cnt.ctypes.data, ofs.ctypes.data, pk.ctypes.data, MRB_MEM_HOST))
+        c = int(cnt[0])
+        return c, ofs[:c + 1].copy(), pk[:c].copy()
+
+    def binary_partition(self, indices, flags):
+        """RayPartitioner::BinaryPartition on HOST arrays: (partitioned indices, left count)."""
+        n = indices.shape[0]
+        out = np.zeros(n, np.uint32); left = np.zeros(1, np.uint32)
+        flags = np.ascontiguousarray(flags, np.uint8)
+        self.check(self.lib.mrb_binary_partition(self.handle, out.ctypes.data, left.ctypes.data, _ptr(indices), _ptr(flags),
+                                                 flags.shape[0], n, MRB_MEM_HOST))
+        return out, int(left[0])
 
     def close(self):
         if self.handle:

@@ -25,6 +25,17 @@ void RendererReadFilm(Context& ctx, mrb_renderer_t& r, float* out, bool device, 
 float* RendererFilmPtr(mrb_renderer_t& r);
 }
 
+namespace mrb
+{
+size_t MultiPartitionTempBytes(uint32_t count, uint32_t batchBits);
+void MultiPartition(Context& ctx, uint32_t* keys, uint32_t* indices, uint32_t count,
+                    const uint32_t dataBits[2], const uint32_t batchBits[2], bool onlySortForBatches,
+                    uint32_t maxPartitions, uint32_t* outCount, uint32_t* outOffsets, uint32_t* outKeys, void* temp);
+size_t BinaryPartitionTempBytes(uint32_t count);
+void BinaryPartition(Context& ctx, uint32_t* indicesOut, uint32_t* leftCount, const uint32_t* indicesIn,
+                     const uint8_t* flags, uint32_t count, void* temp);
+}
+
 struct mrb_context_t { mrb::Context c; };
 
 static thread_local std::string gCreateError;
@@ -397,5 +408,79 @@ mrb_status mrb_renderer_read_film(mrb_context ctx, mrb_renderer r, float* out, m
 }
 
 float* mrb_renderer_film_device_ptr(mrb_renderer r) { return r ? mrb::RendererFilmPtr(*r) : nullptr; }
+
+
+mrb_status mrb_multi_partition(mrb_context ctx, uint32_t* keys, uint32_t* indices, uint32_t count,
+                               const uint32_t dataBitRange[2], const uint32_t batchBitRange[2],
+                               int onlySortForBatches, uint32_t maxPartitions,
+                               uint32_t* partitionCount, uint32_t* partitionOffsets, uint32_t* partitionKeys,
+                               mrb_memspace memspace)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!dataBitRange || !batchBitRange || !partitionCount || !partitionOffsets || !partitionKeys)
+            return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        if(count && (!keys || !indices)) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        if(batchBitRange[1] <= batchBitRange[0] || batchBitRange[1] > 32 || batchBitRange[1] - batchBitRange[0] > 16)
+            return Fail(c, MRB_ERR_INVALID_ARG, "batch bit range must be 1..16 bits");
+        if(dataBitRange[1] < dataBitRange[0] || dataBitRange[1] > 32) return Fail(c, MRB_ERR_INVALID_ARG, "bad data bit range");
+        if(maxPartitions == 0) return Fail(c, MRB_ERR_INVALID_ARG, "maxPartitions == 0");
+        const uint32_t bb = batchBitRange[1] - batchBitRange[0];
+        size_t tempBytes = mrb::MultiPartitionTempBytes(count, bb);
+        mrb::MultiAlloc sz(nullptr);
+        sz.Take<char>(tempBytes); sz.Take<uint32_t>(count); sz.Take<uint32_t>(count);
+        sz.Take<uint32_t>(4); sz.Take<uint32_t>(maxPartitions + 1); sz.Take<uint32_t>(maxPartitions);
+        c.scratch.Reserve(sz.Total());
+        mrb::MultiAlloc ma(c.scratch.Base());
+        void* temp = ma.Take<char>(tempBytes);
+        const bool batchOnly = onlySortForBatches != 0 || dataBitRange[1] == dataBitRange[0];
+        if(memspace == MRB_MEM_DEVICE)
+        {
+            mrb::MultiPartition(c, keys, indices, count, dataBitRange, batchBitRange, batchOnly, maxPartitions,
+                                partitionCount, partitionOffsets, partitionKeys, temp);
+            return MRB_OK;
+        }
+        uint32_t* dk = ma.Take<uint32_t>(count); uint32_t* di = ma.Take<uint32_t>(count);
+        uint32_t* dc = ma.Take<uint32_t>(4); uint32_t* dofs = ma.Take<uint32_t>(maxPartitions + 1); uint32_t* dpk = ma.Take<uint32_t>(maxPartitions);
+        MRB_CUDA_TRY(cudaMemcpyAsync(dk, keys, 4 * size_t(count), cudaMemcpyHostToDevice, c.stream));
+        MRB_CUDA_TRY(cudaMemcpyAsync(di, indices, 4 * size_t(count), cudaMemcpyHostToDevice, c.stream));
+        mrb::MultiPartition(c, dk, di, count, dataBitRange, batchBitRange, batchOnly, maxPartitions, dc, dofs, dpk, temp);
+        MRB_CUDA_TRY(cudaMemcpyAsync(keys, dk, 4 * size_t(count), cudaMemcpyDeviceToHost, c.stream));
+        MRB_CUDA_TRY(cudaMemcpyAsync(indices, di, 4 * size_t(count), cudaMemcpyDeviceToHost, c.stream));
+        MRB_CUDA_TRY(cudaMemcpyAsync(partitionCount, dc, 4, cudaMemcpyDeviceToHost, c.stream));
+        MRB_CUDA_TRY(cudaStreamSynchronize(c.stream));
+        uint32_t n = partitionCount[0];
+        MRB_CUDA_TRY(cudaMemcpyAsync(partitionOffsets, dofs, 4 * size_t(n + 1), cudaMemcpyDeviceToHost, c.stream));
+        MRB_CUDA_TRY(cudaMemcpyAsync(partitionKeys, dpk, 4 * size_t(n), cudaMemcpyDeviceToHost, c.stream));
+        MRB_CUDA_TRY(cudaStreamSynchronize(c.stream));
+        return MRB_OK;
+    });
+}
+
+mrb_status mrb_binary_partition(mrb_context ctx, uint32_t* indicesOut, uint32_t* leftCount,
+                                const uint32_t* indicesIn, const uint8_t* flags, uint32_t flagCount,
+                                uint32_t count, mrb_memspace memspace)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!leftCount || (count && (!indicesOut || !indicesIn || !flags))) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        size_t tempBytes = mrb::BinaryPartitionTempBytes(count);
+        mrb::MultiAlloc sz(nullptr);
+        sz.Take<char>(tempBytes); sz.Take<uint32_t>(count); sz.Take<uint32_t>(count); sz.Take<uint8_t>(flagCount); sz.Take<uint32_t>(4);
+        c.scratch.Reserve(sz.Total());
+        mrb::MultiAlloc ma(c.scratch.Base());
+        void* temp = ma.Take<char>(tempBytes);
+        if(memspace == MRB_MEM_DEVICE) { mrb::BinaryPartition(c, indicesOut, leftCount, indicesIn, flags, count, temp); return MRB_OK; }
+        uint32_t* dout = ma.Take<uint32_t>(count); uint32_t* din = ma.Take<uint32_t>(count);
+        uint8_t* df = ma.Take<uint8_t>(flagCount); uint32_t* dc = ma.Take<uint32_t>(4);
+        MRB_CUDA_TRY(cudaMemcpyAsync(din, indicesIn, 4 * size_t(count), cudaMemcpyHostToDevice, c.stream));
+        MRB_CUDA_TRY(cudaMemcpyAsync(df, flags, flagCount, cudaMemcpyHostToDevice, c.stream));
+        mrb::BinaryPartition(c, dout, dc, din, df, count, temp);
+        MRB_CUDA_TRY(cudaMemcpyAsync(indicesOut, dout, 4 * size_t(count), cudaMemcpyDeviceToHost, c.stream));
+        MRB_CUDA_TRY(cudaMemcpyAsync(leftCount, dc, 4, cudaMemcpyDeviceToHost, c.stream));
+        MRB_CUDA_TRY(cudaStreamSynchronize(c.stream));
+        return MRB_OK;
+    });
+}
 
 } // extern "C"

@@ -288,3 +288,58 @@ def test_full_size_config2_parity(gpu_ctx):
     bkeys, _, bout = gpu_cast(acc, rays, capi.MRB_TRACE_BINARY_EXACT)
     assert np.array_equal(bkeys[:, 0], prim) and np.array_equal(bout[:, 7], t)
     acc.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# RayPartitioner
+# ---------------------------------------------------------------------------------------------
+def test_multi_partition_like_reference_test(gpu_ctx):
+    """Tests/Tracer/T_RayPartitioner.cu:L12-188 (SimulateBasicPathTracer): 500 000 rays, 16 batches x 256 data
+    values, seed 333 — every partition non-empty, all rays visited, order = stable sort by (batch, data)."""
+    import random
+    rng = random.Random(333)
+    n, batch_bits, data_bits = 500_000, 4, 8
+    keys = np.array([(rng.randrange(16) << data_bits) | rng.randrange(256) for _ in range(n)], np.uint32)
+    idx = np.arange(n, dtype=np.uint32)
+    k, i = keys.copy(), idx.copy()
+    count, ofs, pk = gpu_ctx.multi_partition(k, i, (0, data_bits), (data_bits, data_bits + batch_bits), 64)
+    expect = np.argsort(keys, kind="stable").astype(np.uint32)
+    assert np.array_equal(i, expect) and np.array_equal(k, keys[expect])        # permutation: bit exact
+    assert count == 16 and ofs[0] == 0 and ofs[-1] == n
+    assert np.all(np.diff(ofs.astype(np.int64)) > 0)                             # every partition non-empty
+    assert np.array_equal(pk >> data_bits, np.arange(16, dtype=np.uint32))
+    visited = np.zeros(n, bool)
+    for p in range(count):
+        part = i[ofs[p]:ofs[p + 1]]
+        assert np.all((keys[part] >> data_bits) == (pk[p] >> data_bits))
+        visited[part] = True
+    assert visited.all()
+
+
+def test_multi_partition_noncontiguous_ranges_and_batch_only(gpu_ctx):
+    rng = np.random.default_rng(4)
+    n = 70_000
+    data = rng.integers(0, 32, n).astype(np.uint32); batch = rng.choice([1, 5, 6, 200], n).astype(np.uint32)
+    keys = (batch << 20) | (data << 3) | rng.integers(0, 8, n).astype(np.uint32)  # junk in bits 0..2 and 8..19
+    k, i = keys.copy(), np.arange(n, dtype=np.uint32)
+    count, ofs, pk = gpu_ctx.multi_partition(k, i, (3, 8), (20, 28), 16)
+    expect = np.lexsort((np.arange(n), data, batch)).astype(np.uint32)
+    assert np.array_equal(i, expect)
+    assert count == 4 and list(pk >> 20) == [1, 5, 6, 200]
+    k, i = keys.copy(), np.arange(n, dtype=np.uint32)
+    count, ofs, pk = gpu_ctx.multi_partition(k, i, (3, 8), (20, 28), 16, only_batches=True)
+    assert np.array_equal(i, np.argsort(batch, kind="stable").astype(np.uint32))
+    # empty input
+    count, ofs, pk = gpu_ctx.multi_partition(np.zeros(0, np.uint32), np.zeros(0, np.uint32), (0, 4), (4, 8), 4)
+    assert count == 0 and ofs[0] == 0
+
+
+def test_binary_partition_is_stable(gpu_ctx):
+    rng = np.random.default_rng(8)
+    slots = 300_000
+    flags = (rng.random(slots) < 0.3).astype(np.uint8)
+    indices = rng.permutation(slots)[:200_000].astype(np.uint32)
+    out, left = gpu_ctx.binary_partition(indices, flags)
+    alive = flags[indices] != 0
+    assert left == int(alive.sum())
+    assert np.array_equal(out[:left], indices[alive]) and np.array_equal(out[left:], indices[~alive])
