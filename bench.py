@@ -230,6 +230,31 @@ def run_ours(args):
     h2d = 3 * ray_b + 2 * (key_b + hit_b) + words * 4
     d2h = 2 * (ray_b + key_b + hit_b) + words * 4
 
+    # ---- config 3 flavour: the full wavefront path tracer (NEE+MIS, rrRange [3,8]) at 1080p on the same mesh ----
+    pt = None
+    if os.environ.get("MRB_BENCH_SKIP_PT") is None:
+        pidx, pranges, pkeys, palb, prad, _ = scenes.arcade_materials(p, i)
+        pacc = mray_b200.Accelerator(ctx, dp, torch.from_numpy(pidx.view(np.int32)).cuda(), prim_ranges=pranges, light_or_mat_keys=pkeys)
+        pt_spp = 8
+        pr = mray_b200.Renderer(ctx, pacc, p.shape[0], pidx.shape[0], palb, prad, scenes.ARCADE_CAMERA, W, H, pt_spp,
+                                sample_mode="WithNEEAndMIS", rr_range=(3, 8), seed=rank, partition_rays=True)
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pr.iterate(2); torch.cuda.synchronize()      # warm
+        l0 = ctx.launch_count
+        pe0.record(stream)
+        while True:
+            pr.iterate(8)
+            pst = pr.stats()
+            if pst.finished:
+                break
+        pe1.record(stream); torch.cuda.synchronize()
+        pms = pe0.elapsed_time(pe1)
+        pt = {"workload": "arcade mesh, 64 Lambert + 200 emissive tris, PathTracerRGB WithNEEAndMIS rr[3,8], %dx%d, %d spp, material-key ray sort on" % (W, H, pt_spp),
+              "ms_per_spp_1080p": round(pms / pt_spp, 3), "mrays_s": round((pst.closestRays + pst.shadowRays) / pms / 1e3, 1),
+              "mpaths_s": round(pst.pathsCompleted / pms / 1e3, 1), "iterations": int(pst.iterations),
+              "gpu_launches": int(ctx.launch_count - l0)}
+        pr.close(); pacc.close()
+
     peak, peak_src = measured_peak()
     closest_bytes = 2 * n * BYTES_CLOSEST * args.steps
     achieved = closest_bytes / ((t_primary + t_ao) * 1e-3) / 1e9
@@ -249,6 +274,7 @@ def run_ours(args):
             "bvh_build_ms": round(build_best, 4), "bvh_build_mtris_s": round(i.shape[0] / (build_best * 1e-3) / 1e6, 1),
             "wide_nodes": int(acc.info.wideNodeCount), "exact_fallback_rays_last_cast": fallback,
             "parallelism": "independent ranks, BVH replicated" if world > 1 else "single GPU",
+            "path_tracer_1080p": pt,
         },
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -224,6 +224,8 @@ typedef struct mrb_render_desc
     float           filmFilterRadius;/* Gaussian, TracerParameters.filmFilter (default 1) */
     uint64_t        seed;            /* TracerParameters.seed */
     uint32_t        maxPathCount;    /* paths in flight; 0 = width*height (parallelizationHint tile) */
+    uint32_t        partitionRays;   /* 1 = sort live rays by (work batch, material) key before shading
+                                      * (RenderSurfaceWorkHasher + RayPartitioner::MultiPartition) */
 } mrb_render_desc;
 
 typedef struct mrb_render_stats

@@ -61,7 +61,7 @@ class RenderDesc(C.Structure):
                 ("fovXY", C.c_float * 2), ("nearFar", C.c_float * 2),
                 ("width", C.c_uint32), ("height", C.c_uint32), ("totalSPP", C.c_uint32), ("sampleMode", C.c_uint32),
                 ("rrRange", C.c_uint32 * 2), ("filmFilterRadius", C.c_float), ("seed", C.c_uint64),
-                ("maxPathCount", C.c_uint32)]
+                ("maxPathCount", C.c_uint32), ("partitionRays", C.c_uint32)]
 
 
 class RenderStats(C.Structure):
@@ -344,7 +344,7 @@ class Renderer:
     def __init__(self, ctx: Context, accel: Accelerator, vertex_count, triangle_count, albedo, light_radiance,
                  camera, width, height, total_spp, sample_mode="WithNEEAndMIS", rr_range=(2, 20), seed=0,
                  vertex_normals=None, light_two_sided=None, film_filter_radius=1.0, near_far=(0.01, 1000.0),
-                 max_path_count=0):
+                 max_path_count=0, partition_rays=False):
         self.ctx, self.accel = ctx, accel
         self.width, self.height = width, height
         d = RenderDesc()
@@ -377,6 +377,7 @@ class Renderer:
         d.filmFilterRadius = film_filter_radius
         d.seed = seed
         d.maxPathCount = max_path_count
+        d.partitionRays = 1 if partition_rays else 0
         h = C.c_void_p()
         ctx.check(ctx.lib.mrb_renderer_create(ctx.handle, C.byref(d), C.byref(h)))
         self.handle = h

@@ -30,6 +30,10 @@ namespace mrb
 void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode mode,
                mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, uint32_t* visibleBits,
                mrb_ray_gmem* rays, const uint32_t* rayIndices, uint32_t rayCount);
+size_t MultiPartitionTempBytes(uint32_t count, uint32_t batchBits);
+void MultiPartition(Context& ctx, uint32_t* keys, uint32_t* indices, uint32_t count,
+                    const uint32_t dataBits[2], const uint32_t batchBits[2], bool onlySortForBatches,
+                    uint32_t maxPartitions, uint32_t* outCount, uint32_t* outOffsets, uint32_t* outKeys, void* temp);
 
 namespace
 {
@@ -121,6 +125,12 @@ struct RenderData
     uint32_t*         pathData;        // depth | status << 8 | type << 16
     uint32_t*         rng;
     uint32_t*         visible;
+    // material-key ray partitioning (RenderSurfaceWorkHasher + RayPartitioner::MultiPartition)
+    uint32_t*         workKeys;        // per slot sort key
+    uint32_t*         workIndices;     // slot indices, sorted by work key
+    uint32_t*         partTable;       // [0] count, [1..] offsets (count+1), then first keys
+    uint32_t          partitionRays;   // 0 = shade in slot order
+    uint32_t          matBits;         // data bits of the work key (material index)
     // film (planar R,G,B,W)
     float*            film;
     // u64 counters: [0] next camera path, [1] completed paths, [2] closest-hit rays cast, [3] shadow rays cast
@@ -214,10 +224,29 @@ __device__ __forceinline__ Float3 Emit(const EmissiveTri& l, Float3 n, Float3 wO
     return F3(l.radiance.x, l.radiance.y, l.radiance.z);
 }
 
-__global__ void __launch_bounds__(RTPB) KShade(RenderData d)
+// KCGenerateSurfaceWorkKeysIndirect / KCSetBoundaryWorkKeysIndirect (Tracer/RendererCommon.cu:L23-81):
+// 32-bit sort key = [work batch : MSBs][data bits]. Work batches here: 0 = Lambert surface work,
+// 1 = prim-light work, 2 = boundary (miss) work, 3 = idle slot; data bits = material / light index, so
+// rays of one material are contiguous after the sort.
+__global__ void __launch_bounds__(RTPB) KGenWorkKeys(RenderData d)
 {
     const uint32_t i = blockIdx.x * RTPB + threadIdx.x;
     if(i >= d.slots) return;
+    const uint32_t status = (d.pathData[i] >> 8) & 0xFFu;
+    const uint4 keys = *reinterpret_cast<const uint4*>(d.hitKeys + i);
+    uint32_t batch, data = 0;
+    if(status != ST_ALIVE) batch = 3u;
+    else if(keys.x == INVALID_U32) batch = 2u;
+    else { batch = (keys.y & 0x80000000u) ? 1u : 0u; data = keys.y & ((1u << d.matBits) - 1u); }
+    d.workKeys[i] = (batch << d.matBits) | data;
+    d.workIndices[i] = i;
+}
+
+__global__ void __launch_bounds__(RTPB) KShade(RenderData d)
+{
+    const uint32_t tidx = blockIdx.x * RTPB + threadIdx.x;
+    if(tidx >= d.slots) return;
+    const uint32_t i = d.partitionRays ? d.workIndices[tidx] : tidx;
     uint32_t pd = d.pathData[i];
     if(((pd >> 8) & 0xFFu) != ST_ALIVE) return;
     uint32_t depth = pd & 0xFFu, type = (pd >> 16) & 0xFFu;
@@ -466,6 +495,11 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
     d.pathLimit = uint64_t(desc.totalSPP) * desc.width * desc.height;
     d.filterSigma = desc.filmFilterRadius * 0.285714f;
     d.slots = desc.maxPathCount ? desc.maxPathCount : desc.width * desc.height;
+    d.partitionRays = desc.partitionRays ? 1u : 0u;
+    {   // bits needed for the larger of the material / light tables (Bit::RequiredBitsToRepresent)
+        uint32_t m = desc.materialCount > desc.lightCount ? desc.materialCount : desc.lightCount;
+        d.matBits = 1; while((1u << d.matBits) < m) d.matBits++;
+    }
     // camera (CameraPinhole ctor)
     auto V = [](const float* p) { return make_float3(p[0], p[1], p[2]); };
     auto sub = [](float3 x, float3 y) { return make_float3(x.x - y.x, x.y - y.y, x.z - y.z); };
@@ -532,6 +566,7 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
         d.lights = ma.Take<EmissiveTri>(lights.size() ? lights.size() : 1);
         d.lightOfPrim = ma.Take<uint32_t>(desc.triangleCount);
         d.vertexNormals = desc.vertexNormals ? ma.Take<float4>(desc.vertexCount) : nullptr;
+        d.workKeys = ma.Take<uint32_t>(P); d.workIndices = ma.Take<uint32_t>(P); d.partTable = ma.Take<uint32_t>(32);
     };
     MultiAlloc sz(nullptr); Layout(sz);
     r.mem.Reserve(sz.Total());
@@ -578,6 +613,14 @@ void RenderIterate(Context& ctx, mrb_renderer_t& r, uint32_t iterations)
     {
         MRB_LAUNCH(ctx, KReload, grid, RTPB, 0, d);
         TraceRays(ctx, *r.accel, false, MRB_TRACE_WIDE, d.hitKeys, d.hits, nullptr, d.rays, nullptr, d.slots);
+        if(d.partitionRays)
+        {
+            const uint32_t dataBits[2] = {0u, d.matBits}, batchBits[2] = {d.matBits, d.matBits + 2u};
+            ctx.scratch.Reserve(MultiPartitionTempBytes(d.slots, 2));
+            MRB_LAUNCH(ctx, KGenWorkKeys, grid, RTPB, 0, d);
+            MultiPartition(ctx, d.workKeys, d.workIndices, d.slots, dataBits, batchBits, false, 4,
+                           d.partTable, d.partTable + 1, d.partTable + 8, ctx.scratch.Base());
+        }
         MRB_LAUNCH(ctx, KShade, grid, RTPB, 0, d);
         if(d.sampleMode != 0u)
         {

@@ -538,6 +538,7 @@ class TracerB200 final : public TracerI
         d.filmFilterRadius = params.filmFilter.radius; d.seed = params.seed;
         uint64_t pixels = uint64_t(tile[0]) * tile[1];
         d.maxPathCount = uint32_t(std::min<uint64_t>(pixels, std::max<uint32_t>(params.parallelizationHint, 1u)));
+        d.partitionRays = d.materialCount > 1 ? 1u : 0u;
         Check(mrb_renderer_create(ctx, &d, &renderer));
         curRenderer = Raw(id); resolution = tile;
         staging.assign(size_t(4) * pixels, 0.0f);

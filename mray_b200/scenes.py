@@ -255,3 +255,34 @@ def cornell_box():
                 albedo=np.array([[0.725, 0.71, 0.68], [0.63, 0.065, 0.05], [0.14, 0.45, 0.091], [0, 0, 0]], np.float32),
                 radiance=np.array([68.0, 48.0, 16.0], np.float32),
                 camera=dict(eye=(0.0, 1.0, 6.8), gaze=(0.0, 1.0, 0.0), up=(0.0, 1.0, 0.0), fov_y_deg=19.5))
+
+
+def arcade_materials(positions, indices, material_count: int = 64, seed: int = 1234):
+    """Config 3 material assignment for ``arcade_mesh``: ``material_count`` Lambert albedos assigned to
+    contiguous triangle blocks, plus one emissive patch (~200 ceiling triangles around the nave centre).
+    Returns (indices sorted by material, prim_ranges, light_or_mat_keys, albedo[material_count,3], radiance[3],
+    tri_material[int32, -1 = light]) with the triangles reordered so that each material is one prim range."""
+    rng = np.random.default_rng(seed)
+    n = indices.shape[0]
+    block = max(1, n // (material_count * 8))
+    mat = ((np.arange(n) // block) % material_count).astype(np.int32)
+    cen = positions[indices].mean(axis=1)
+    nrm = np.cross(positions[indices[:, 1]] - positions[indices[:, 0]], positions[indices[:, 2]] - positions[indices[:, 0]])
+    ceiling = (cen[:, 1] > 11.0) & (nrm[:, 1] < 0)
+    d2 = cen[:, 0] ** 2 + cen[:, 2] ** 2
+    cand = np.nonzero(ceiling)[0]
+    light = cand[np.argsort(d2[cand])[:200]]
+    mat[light] = -1
+    order = np.argsort(np.where(mat < 0, material_count, mat), kind="stable")
+    idx = np.ascontiguousarray(indices[order])
+    m = mat[order]
+    ranges, keys = [], []
+    for k in list(range(material_count)) + [-1]:
+        w = np.nonzero(m == k)[0]
+        if w.size == 0:
+            continue
+        ranges.append([int(w[0]), int(w[-1]) + 1])
+        keys.append((0x80000000 | 0) if k < 0 else k)
+    albedo = (0.25 + 0.6 * rng.random((material_count, 3))).astype(np.float32)
+    radiance = np.array([40.0, 36.0, 30.0], np.float32)
+    return idx, np.array(ranges, np.uint32), np.array(keys, np.uint32), albedo, radiance, m

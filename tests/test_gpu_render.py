@@ -83,7 +83,7 @@ def test_film_delta_protocol_and_partial_path_pool(gpu_ctx):
     c, idx, tm, acc = cornell_accel(gpu_ctx)
     res, spp = 32, 64
     r = capi.Renderer(gpu_ctx, acc, c["positions"].shape[0], idx.shape[0], c["albedo"][:3], c["radiance"], c["camera"],
-                      res, res, spp, max_path_count=300)
+                      res, res, spp, max_path_count=300, partition_rays=True)  # + material-key ray sort
     total_rgb = np.zeros((res, res, 3)); total_w = np.zeros((res, res))
     for _ in range(100000):
         r.iterate(16)
