@@ -188,6 +188,49 @@ MRB_API mrb_status mrb_cast_visibility_rays(mrb_context ctx, mrb_accel accel,
                                             uint32_t rayCount, uint32_t totalRayCount,
                                             mrb_memspace memspace, mrb_trace_mode mode);
 
+/* ---- two-level scene ------------------------------------------------------------------- */
+
+typedef struct mrb_scene_t* mrb_scene;
+
+/* One accelerator instance: a concrete accelerator + the transform of its surface
+ * (AcceleratorGroup::WriteInstanceKeysAndAABBsInternal, Tracer/AcceleratorCommon.cu:L452-572).
+ * transform / invTransform: row-major 3x4 (Matrix3x4), local->world and world->local — both are
+ * supplied by the host object, which owns the TransformGroup ((T)Single stores both,
+ * Tracer/TransformsDefault.hpp). Rays are taken to local space WITHOUT renormalising the direction
+ * (KCLocalRayCast, AcceleratorWork.kt.h:L207-218), so t stays in world units. */
+typedef struct mrb_instance_desc
+{
+    mrb_accel accel;
+    float     transform[12];
+    float     invTransform[12];
+    uint32_t  isIdentity;     /* (T)Identity: no ray transform, world AABB = accelerator AABB */
+    uint32_t  transformKey;   /* reported in HitKeyPack.transKey */
+    uint32_t  accelKey;       /* reported in HitKeyPack.accelKey (batch:12 | index:20) */
+} mrb_instance_desc;
+
+/* BaseAcceleratorLBVH::InternalConstruct (Tracer/AcceleratorLBVH.cu:L537-740): top-level LBVH over the
+ * instances' world AABBs (same Morton / sort / Karras / union chain) + its wide collapse. The
+ * accelerators must outlive the scene. */
+MRB_API mrb_status mrb_scene_build(mrb_context ctx, const mrb_instance_desc* instances, uint32_t instanceCount, mrb_scene* out);
+MRB_API void       mrb_scene_destroy(mrb_context ctx, mrb_scene scene);
+/* Parity tap (host arrays, any may be NULL): world AABBs [n*6], scene AABB [6], top-level Morton codes,
+ * sorted instance order, binary nodes [max(1,n-1)*3], node boxes [..*6]. */
+MRB_API mrb_status mrb_scene_export_tlas(mrb_context ctx, mrb_scene scene, float* instanceAABBs, float* sceneAABB,
+                                         uint64_t* morton, uint32_t* sortedInstance, uint32_t* nodes, float* nodeBoxes);
+/* BaseAcceleratorLBVH::CastRays / CastVisibilityRays over the whole scene in ONE launch (the reference
+ * alternates top-level traversal, a ray sort by instance key, a host read-back and per-instance
+ * launches until every ray has left the top-level tree, AcceleratorLBVH.cu:L806-895). Same buffer
+ * contract as mrb_cast_rays; hitKeys carry the instance's transKey / accelKey. */
+MRB_API mrb_status mrb_scene_cast_rays(mrb_context ctx, mrb_scene scene,
+                                       mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits,
+                                       mrb_ray_gmem* rays, const uint32_t* rayIndices,
+                                       uint32_t rayCount, uint32_t totalRayCount,
+                                       mrb_memspace memspace, mrb_trace_mode mode);
+MRB_API mrb_status mrb_scene_cast_visibility_rays(mrb_context ctx, mrb_scene scene, uint32_t* isVisibleBits,
+                                                  const mrb_ray_gmem* rays, const uint32_t* rayIndices,
+                                                  uint32_t rayCount, uint32_t totalRayCount,
+                                                  mrb_memspace memspace, mrb_trace_mode mode);
+
 /* ---- wavefront path tracer ------------------------------------------------------------- */
 
 typedef struct mrb_renderer_t* mrb_renderer;

@@ -53,6 +53,11 @@ class AccelInfo(C.Structure):
                 ("deviceBytes", C.c_size_t)]
 
 
+class InstanceDesc(C.Structure):
+    _fields_ = [("accel", C.c_void_p), ("transform", C.c_float * 12), ("invTransform", C.c_float * 12),
+                ("isIdentity", C.c_uint32), ("transformKey", C.c_uint32), ("accelKey", C.c_uint32)]
+
+
 class RenderDesc(C.Structure):
     _fields_ = [("accel", C.c_void_p), ("vertexCount", C.c_uint32), ("triangleCount", C.c_uint32),
                 ("vertexNormals", C.c_void_p), ("materialCount", C.c_uint32), ("albedo", C.c_void_p),
@@ -91,6 +96,13 @@ _PROTOTYPES = {
                                 C.c_uint32, C.c_uint32, C.c_int, C.c_int]),
     "mrb_cast_visibility_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_uint32, C.c_uint32, C.c_int, C.c_int]),
+    "mrb_scene_build": (C.c_int, [C.c_void_p, C.POINTER(InstanceDesc), C.c_uint32, C.POINTER(C.c_void_p)]),
+    "mrb_scene_destroy": (None, [C.c_void_p, C.c_void_p]),
+    "mrb_scene_export_tlas": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_void_p] * 6),
+    "mrb_scene_cast_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_uint32, C.c_uint32, C.c_int, C.c_int]),
+    "mrb_scene_cast_visibility_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_uint32, C.c_uint32, C.c_int, C.c_int]),
     "mrb_renderer_create": (C.c_int, [C.c_void_p, C.POINTER(RenderDesc), C.POINTER(C.c_void_p)]),
     "mrb_renderer_destroy": (None, [C.c_void_p, C.c_void_p]),
     "mrb_renderer_iterate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
@@ -417,6 +429,68 @@ class Renderer:
     def close(self):
         if self.handle and self.ctx.handle:
             self.ctx.lib.mrb_renderer_destroy(self.ctx.handle, self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Scene:
+    """Two-level scene = BaseAcceleratorLBVH over accelerator instances (Tracer/AcceleratorLBVH.cu:L537-1035).
+    instances: list of (Accelerator, transform 3x4 or None for identity). accelKey of instance i = i,
+    transformKey = i + 1 (0 for identity)."""
+
+    def __init__(self, ctx: Context, instances):
+        self.ctx = ctx
+        self._keep = [a for a, _ in instances]
+        arr = (InstanceDesc * len(instances))()
+        self.transforms = []
+        for i, (acc, m) in enumerate(instances):
+            d = arr[i]
+            d.accel = acc.handle
+            ident = m is None
+            m34 = np.eye(4, dtype=np.float64)[:3] if ident else np.asarray(m, np.float64).reshape(3, 4)
+            inv = np.linalg.inv(np.vstack([m34, [0, 0, 0, 1]]))[:3]
+            m32, i32 = m34.astype(np.float32), inv.astype(np.float32)
+            d.transform = (C.c_float * 12)(*m32.ravel()); d.invTransform = (C.c_float * 12)(*i32.ravel())
+            d.isIdentity = 1 if ident else 0
+            d.transformKey = 0 if ident else i + 1
+            d.accelKey = i
+            self.transforms.append((m32, i32, ident))
+        h = C.c_void_p()
+        ctx.check(ctx.lib.mrb_scene_build(ctx.handle, arr, len(instances), C.byref(h)))
+        self.handle = h
+        self.count = len(instances)
+
+    def export_tlas(self):
+        n, nn = self.count, max(1, self.count - 1)
+        out = dict(instance_aabb=np.zeros((n, 6), np.float32), scene_aabb=np.zeros(6, np.float32), morton=np.zeros(n, np.uint64),
+                   sorted_idx=np.zeros(n, np.uint32), nodes=np.zeros((nn, 3), np.uint32), boxes=np.zeros((nn, 6), np.float32))
+        self.ctx.check(self.ctx.lib.mrb_scene_export_tlas(self.ctx.handle, self.handle, out["instance_aabb"].ctypes.data,
+                                                          out["scene_aabb"].ctypes.data, out["morton"].ctypes.data,
+                                                          out["sorted_idx"].ctypes.data, out["nodes"].ctypes.data, out["boxes"].ctypes.data))
+        return out
+
+    def cast_rays(self, hit_keys, meta_hits, rays, ray_indices=None, mode=MRB_TRACE_WIDE):
+        space = _space(hit_keys, meta_hits, rays, ray_indices)
+        total = rays.shape[0]
+        count = total if ray_indices is None else ray_indices.shape[0]
+        self.ctx.check(self.ctx.lib.mrb_scene_cast_rays(self.ctx.handle, self.handle, _ptr(hit_keys), _ptr(meta_hits), _ptr(rays),
+                                                        _ptr(ray_indices), count, total, space, mode))
+
+    def cast_visibility_rays(self, visible_bits, rays, ray_indices=None, mode=MRB_TRACE_WIDE):
+        space = _space(visible_bits, rays, ray_indices)
+        total = rays.shape[0]
+        count = total if ray_indices is None else ray_indices.shape[0]
+        self.ctx.check(self.ctx.lib.mrb_scene_cast_visibility_rays(self.ctx.handle, self.handle, _ptr(visible_bits), _ptr(rays),
+                                                                   _ptr(ray_indices), count, total, space, mode))
+
+    def close(self):
+        if self.handle and self.ctx.handle:
+            self.ctx.lib.mrb_scene_destroy(self.ctx.handle, self.handle)
         self.handle = None
 
     def __del__(self):

@@ -78,6 +78,31 @@ struct AccelData
     uint32_t   wideNodeCapacity = 0;
     uint32_t   wideNodeCount = 0;
     uint32_t   wideDepth = 0;
+    uint32_t   maxLeafSize = 3;       // leaves per wide leaf child (3 triangles; 1 instance in a top-level tree)
+    uint32_t*  leafOfSlot = nullptr;  // top-level tree only: leaf record slot -> instance index
+};
+
+// One instance of a two-level scene (AcceleratorGroup instance + transform, AcceleratorCommon.cu:L452-572).
+struct InstanceRec
+{
+    float            invTransform[12];   // world -> local, row-major 3x4 (TransformContextSingle::InvApply)
+    float            worldAABB[6];       // leaf AABB of the top-level tree
+    const WideNode*  wideNodes;
+    const TriRecord* tris;
+    const float*     leafAABB;
+    const float*     positions;          // audit / exact fallback
+    const uint32_t*  indices;
+    const LBVHNode*  nodes;
+    const LBVHBox*   boxes;
+    PrimRanges       ranges;
+    uint32_t         accelKey, transKey, identity, leafCount;
+};
+
+struct SceneData
+{
+    AccelData          tlas;              // leaves = instances (leafAABB = world AABBs)
+    const InstanceRec* instances = nullptr;
+    uint32_t           instanceCount = 0;
 };
 
 } // namespace mrb
@@ -91,4 +116,13 @@ struct mrb_accel_t
     mrb_accel_info   info = {};
     uint32_t         flags = 0;
     uint32_t         accelKey = 0;
+};
+
+struct mrb_scene_t
+{
+    mrb::SceneData   d;
+    mrb::DeviceBlock mem;
+    std::vector<mrb_accel> accels;
+    float            aabb[6] = {};
+    float            buildMs = 0.f;
 };

@@ -298,7 +298,7 @@ __device__ __forceinline__ ChildRef MakeRef(const AccelData& a, uint32_t child, 
 __device__ void CollapseNode(const AccelData& a, CollapseState* st, unsigned long long* queue,
                              uint32_t* triRank, uint32_t wideIdx, uint32_t binNode, uint32_t depth)
 {
-    constexpr uint32_t MAX_LEAF = 3;
+    const uint32_t MAX_LEAF = a.maxLeafSize;
     ChildRef refs[8];
     uint32_t n = 0;
     if(a.leafCount == 1) { refs[0] = ChildRef{0, 0, INVALID_U32, -1.0f}; n = 1; }
@@ -489,6 +489,205 @@ KFillTris(AccelData a, const uint32_t* __restrict__ triRank)
 }
 
 } // namespace
+
+namespace
+{
+
+// Matrix3x4::TransformAABB (Core/Matrix.hpp:L915-932; Math::Dot FMA chains) with the homogeneous
+// coordinate held at 1 for all eight corners: the reference reassigns its Vector4 from an operator*
+// (L777-787) that never writes the 4th lane, so its w is indeterminate after the first corner.
+// Identity instances copy the accelerator AABB (TransformContextIdentity::Apply) and stay bit exact.
+struct InstanceBuildIn { float transform[12]; const uint32_t* accelAABBEnc; uint32_t identity; uint32_t pad; };
+
+__global__ void __launch_bounds__(TPB)
+KInstanceAABB(AccelData a, const InstanceBuildIn* __restrict__ in, InstanceRec* __restrict__ recs)
+{
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for(uint32_t i = blockIdx.x * TPB + threadIdx.x; i < a.leafCount; i += gridDim.x * TPB)
+    {
+        float box[6];
+        #pragma unroll
+        for(int k = 0; k < 6; k++) box[k] = DecodeOrdered(in[i].accelAABBEnc[k]);
+        float lo[3], hi[3];
+        if(in[i].identity) { for(int k = 0; k < 3; k++) { lo[k] = box[k]; hi[k] = box[3 + k]; } }
+        else
+        {
+            for(int k = 0; k < 3; k++) { lo[k] = FLT_MAX; hi[k] = -FLT_MAX; }
+            const float* m = in[i].transform;
+            for(uint32_t c = 0; c < 8; c++)
+            {
+                float v[3];
+                for(uint32_t j = 0; j < 3; j++) v[j] = ((c >> j) & 1u) ? box[3 + j] : box[j];
+                #pragma unroll
+                for(int r = 0; r < 3; r++)
+                {
+                    float d = __fmaf_rn(m[4 * r + 0], v[0], 0.0f);
+                    d = __fmaf_rn(m[4 * r + 1], v[1], d);
+                    d = __fmaf_rn(m[4 * r + 2], v[2], d);
+                    d = __fmaf_rn(m[4 * r + 3], 1.0f, d);
+                    lo[r] = (d < lo[r]) ? d : lo[r];
+                    hi[r] = (hi[r] < d) ? d : hi[r];
+                }
+            }
+        }
+        for(int k = 0; k < 3; k++)
+        {
+            a.leafAABB[6 * size_t(i) + k] = lo[k]; a.leafAABB[6 * size_t(i) + 3 + k] = hi[k];
+            recs[i].worldAABB[k] = lo[k]; recs[i].worldAABB[3 + k] = hi[k];
+            mn[k] = fminf(mn[k], lo[k]); mx[k] = fmaxf(mx[k], hi[k]);
+        }
+    }
+    for(int k = 0; k < 3; k++)
+        for(int o = 16; o > 0; o >>= 1)
+        {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+    if((threadIdx.x & 31) == 0)
+        for(int k = 0; k < 3; k++)
+        {
+            atomicMin(&a.accelAABBEnc[k], EncodeOrdered(mn[k]));
+            atomicMax(&a.accelAABBEnc[3 + k], EncodeOrdered(mx[k]));
+        }
+}
+
+// KCGenAABBCenters (AABB::Centroid = min + (max - min) * 0.5) + KCGenMortonCode over the scene AABB.
+__global__ void __launch_bounds__(TPB)
+KMortonBoxes(AccelData a)
+{
+    float bl[3], sz[3];
+    for(int k = 0; k < 3; k++)
+    {
+        bl[k] = DecodeOrdered(a.accelAABBEnc[k]);
+        sz[k] = __fsub_rn(DecodeOrdered(a.accelAABBEnc[3 + k]), bl[k]);
+    }
+    float maxSide = fmaxf(sz[0], fmaxf(sz[1], sz[2]));
+    const double deltaRecip = __ddiv_rn(2097152.0, double(maxSide));
+    const uint32_t lastValue = (1u << 21) - 1u;
+    for(uint32_t leaf = blockIdx.x * TPB + threadIdx.x; leaf < a.leafCount; leaf += gridDim.x * TPB)
+    {
+        uint32_t q[3];
+        for(int k = 0; k < 3; k++)
+        {
+            float lo = a.leafAABB[6 * size_t(leaf) + k], hi = a.leafAABB[6 * size_t(leaf) + 3 + k];
+            float c = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), 0.5f));
+            float diff = __fsub_rn(c, bl[k]);
+            diff = (diff < 0.0f) ? 0.0f : diff;
+            float scaled = __double2float_rn(__dmul_rn(double(diff), deltaRecip));
+            uint32_t u = uint32_t(int32_t(lroundf(scaled)));
+            q[k] = (u > lastValue) ? lastValue : u;
+        }
+        uint64_t code = Expand3D(q[0]) | (Expand3D(q[1]) << 1) | (Expand3D(q[2]) << 2);
+        a.morton[leaf] = code; a.sortedMorton[leaf] = code; a.sortedLeaf[leaf] = leaf;
+    }
+}
+
+__global__ void __launch_bounds__(TPB)
+KFillInstanceSlots(AccelData a, const uint32_t* __restrict__ slotRank)
+{
+    for(uint32_t s = blockIdx.x * TPB + threadIdx.x; s < a.leafCount; s += gridDim.x * TPB)
+        a.leafOfSlot[s] = a.sortedLeaf[slotRank[s]];
+}
+
+} // namespace
+
+// BaseAcceleratorLBVH::InternalConstruct (Tracer/AcceleratorLBVH.cu:L537-740): top-level LBVH over the
+// instances' world AABBs, then the same wide collapse as a bottom-level tree (one instance per leaf).
+void BuildScene(Context& ctx, mrb_scene_t& sc, const mrb_instance_desc* inst, uint32_t n)
+{
+    SceneData& s = sc.d;
+    AccelData& d = s.tlas;
+    d = AccelData{};
+    d.leafCount = n; d.nodeCount = n > 1 ? n - 1 : 1; d.maxLeafSize = 1;
+    d.ranges = PrimRanges{};
+    auto Layout = [&](MultiAlloc& ma)
+    {
+        d.leafAABB = ma.Take<float>(size_t(n) * 6);
+        d.morton = ma.Take<uint64_t>(n); d.sortedMorton = ma.Take<uint64_t>(n); d.sortedLeaf = ma.Take<uint32_t>(n);
+        d.nodes = ma.Take<LBVHNode>(d.nodeCount); d.leafParent = ma.Take<uint32_t>(n);
+        d.boxes = ma.Take<LBVHBox>(d.nodeCount); d.nodeRange = ma.Take<uint2>(d.nodeCount);
+        d.accelAABBEnc = ma.Take<uint32_t>(8);
+        d.wideNodeCapacity = n + 2;
+        d.wideNodes = ma.Take<WideNode>(d.wideNodeCapacity);
+        d.leafOfSlot = ma.Take<uint32_t>(n);
+        s.instances = ma.Take<InstanceRec>(n);
+    };
+    MultiAlloc sz(nullptr); Layout(sz);
+    sc.mem.Reserve(sz.Total());
+    MultiAlloc ma(sc.mem.Base()); Layout(ma);
+    ctx.persistentBytes += sc.mem.Capacity();
+    s.instanceCount = n;
+
+    std::vector<InstanceRec> recs(n);
+    std::vector<InstanceBuildIn> bin(n);
+    sc.accels.assign(n, nullptr);
+    for(uint32_t i = 0; i < n; i++)
+    {
+        const mrb_accel_t& a = *inst[i].accel;
+        sc.accels[i] = inst[i].accel;
+        InstanceRec& r = recs[i];
+        memcpy(r.invTransform, inst[i].invTransform, sizeof(r.invTransform));
+        r.wideNodes = a.d.wideNodes; r.tris = a.d.tris; r.leafAABB = a.d.leafAABB;
+        r.positions = a.d.positions; r.indices = a.d.indices; r.nodes = a.d.nodes; r.boxes = a.d.boxes;
+        r.ranges = a.d.ranges; r.accelKey = inst[i].accelKey; r.transKey = inst[i].transformKey;
+        r.identity = inst[i].isIdentity ? 1u : 0u; r.leafCount = a.d.leafCount;
+        memcpy(bin[i].transform, inst[i].transform, sizeof(bin[i].transform));
+        bin[i].accelAABBEnc = a.d.accelAABBEnc; bin[i].identity = r.identity; bin[i].pad = 0;
+    }
+    // scratch: instance inputs | sort temp | counters | collapse state | queue | slot ranks
+    size_t sortBytes = RadixSortTempBytes(n, 8);
+    MultiAlloc ssz(nullptr);
+    ssz.Take<InstanceBuildIn>(n); ssz.Take<char>(sortBytes); ssz.Take<uint32_t>(d.nodeCount + 8); ssz.Take<CollapseState>(1);
+    ssz.Take<unsigned long long>(d.wideNodeCapacity + 1); ssz.Take<uint32_t>(n);
+    ctx.scratch.Reserve(ssz.Total());
+    MultiAlloc sm(ctx.scratch.Base());
+    InstanceBuildIn* dIn = sm.Take<InstanceBuildIn>(n);
+    void* sortTemp = sm.Take<char>(sortBytes);
+    uint32_t* counters = sm.Take<uint32_t>(d.nodeCount + 8);
+    CollapseState* cst = sm.Take<CollapseState>(1);
+    unsigned long long* queue = sm.Take<unsigned long long>(d.wideNodeCapacity + 1);
+    uint32_t* slotRank = sm.Take<uint32_t>(n);
+    uint32_t* dupFlag = counters + d.nodeCount;
+
+    MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<InstanceRec*>(s.instances), recs.data(), sizeof(InstanceRec) * n, cudaMemcpyHostToDevice, ctx.stream));
+    MRB_CUDA_TRY(cudaMemcpyAsync(dIn, bin.data(), sizeof(InstanceBuildIn) * n, cudaMemcpyHostToDevice, ctx.stream));
+    MRB_CUDA_TRY(cudaEventRecord(ctx.ev0, ctx.stream));
+    const uint32_t initEnc[8] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u, 0u};
+    MRB_CUDA_TRY(cudaMemcpyAsync(d.accelAABBEnc, initEnc, sizeof(initEnc), cudaMemcpyHostToDevice, ctx.stream));
+    MRB_CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * (d.nodeCount + 8), ctx.stream));
+    const uint32_t grid = GridFor(ctx, n, TPB, 8);
+    MRB_LAUNCH(ctx, KInstanceAABB, grid, TPB, 0, d, dIn, const_cast<InstanceRec*>(s.instances));
+    MRB_LAUNCH(ctx, KMortonBoxes, grid, TPB, 0, d);
+    RadixSortPairs(ctx, d.sortedMorton, d.sortedLeaf, n, 0, 64, sortTemp);
+    MRB_LAUNCH(ctx, KKarras, grid, TPB, 0, d, 1, dupFlag);
+    MRB_LAUNCH(ctx, KUnionBoxes, grid, TPB, 0, d, counters);
+    {
+        CollapseState init = {0u, 1u, 0u, 0u, 0u, 0u};
+        MRB_CUDA_TRY(cudaMemcpyAsync(cst, &init, sizeof(init), cudaMemcpyHostToDevice, ctx.stream));
+        unsigned long long rootItem = 0ull;
+        MRB_CUDA_TRY(cudaMemcpyAsync(queue, &rootItem, sizeof(rootItem), cudaMemcpyHostToDevice, ctx.stream));
+        int perSM = 0;
+        MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, KCollapse, 64, 0));
+        uint32_t cgrid = min(uint32_t(ctx.smCount) * uint32_t(max(1, min(perSM, 16))), max(1u, DivUp(d.wideNodeCapacity, 64u)));
+        void* cargs[] = {(void*)&d, (void*)&cst, (void*)&queue, (void*)&slotRank};
+        MRB_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)KCollapse, dim3(cgrid), dim3(64), cargs, 0, ctx.stream));
+        ctx.launches++;
+        MRB_LAUNCH(ctx, KFillInstanceSlots, grid, TPB, 0, d, slotRank);
+    }
+    MRB_CUDA_TRY(cudaEventRecord(ctx.ev1, ctx.stream));
+    uint32_t enc[8]; CollapseState hst = {};
+    MRB_CUDA_TRY(cudaMemcpyAsync(enc, d.accelAABBEnc, sizeof(uint32_t) * 6, cudaMemcpyDeviceToHost, ctx.stream));
+    MRB_CUDA_TRY(cudaMemcpyAsync(&hst, cst, sizeof(hst), cudaMemcpyDeviceToHost, ctx.stream));
+    MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
+    MRB_CUDA_TRY(cudaEventElapsedTime(&sc.buildMs, ctx.ev0, ctx.ev1));
+    if(hst.error || hst.triCount != n) throw CudaError{cudaErrorUnknown, "top-level collapse failed", int(hst.error)};
+    d.wideNodeCount = hst.created; d.wideDepth = hst.maxDepth + 1;
+    for(int k = 0; k < 6; k++)
+    {
+        uint32_t u = enc[k]; uint32_t b = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+        memcpy(&sc.aabb[k], &b, 4);
+    }
+}
 
 // Sizes the persistent block of one accelerator (sub-arrays are 256-byte aligned).
 static void LayoutAccel(MultiAlloc& ma, AccelData& d, uint32_t vertexCount, uint32_t triCount, bool ownInputs, bool wide)

@@ -36,6 +36,14 @@ void BinaryPartition(Context& ctx, uint32_t* indicesOut, uint32_t* leftCount, co
                      const uint8_t* flags, uint32_t count, void* temp);
 }
 
+namespace mrb
+{
+void BuildScene(Context& ctx, mrb_scene_t& sc, const mrb_instance_desc* inst, uint32_t n);
+void TraceScene(Context& ctx, const mrb_scene_t& scn, bool anyHit, mrb_trace_mode mode,
+                mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, uint32_t* visibleBits,
+                mrb_ray_gmem* rays, const uint32_t* rayIndices, uint32_t rayCount);
+}
+
 struct mrb_context_t { mrb::Context c; };
 
 static thread_local std::string gCreateError;
@@ -231,6 +239,52 @@ mrb_status mrb_accel_export_lbvh(mrb_context ctx, mrb_accel accel,
 }
 
 } // extern "C"
+
+template<class TraceF>
+static mrb_status CastGeneric(mrb_context ctx, bool anyHit,
+                              mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, uint32_t* visibleBits,
+                              mrb_ray_gmem* rays, const uint32_t* rayIndices,
+                              uint32_t rayCount, uint32_t totalRayCount, mrb_memspace memspace, TraceF&& trace)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!rays) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        if(anyHit ? !visibleBits : (!hitKeys || !metaHits)) return Fail(c, MRB_ERR_INVALID_ARG, "null output");
+        if(totalRayCount < rayCount && !rayIndices) return Fail(c, MRB_ERR_INVALID_ARG, "totalRayCount < rayCount");
+        if(rayCount == 0) return MRB_OK;
+        if(memspace == MRB_MEM_DEVICE) { trace(c, hitKeys, metaHits, visibleBits, rays, rayIndices); return MRB_OK; }
+        const size_t words = (size_t(totalRayCount) + 31) / 32;
+        mrb::MultiAlloc sz(nullptr);
+        sz.Take<mrb_ray_gmem>(totalRayCount); sz.Take<uint32_t>(rayIndices ? rayCount : 0);
+        if(anyHit) sz.Take<uint32_t>(words); else { sz.Take<mrb_hit_key_pack>(totalRayCount); sz.Take<mrb_meta_hit>(totalRayCount); }
+        c.scratch.Reserve(sz.Total());
+        mrb::MultiAlloc ma(c.scratch.Base());
+        mrb_ray_gmem* dRays = ma.Take<mrb_ray_gmem>(totalRayCount);
+        uint32_t* dIdx = ma.Take<uint32_t>(rayIndices ? rayCount : 0);
+        MRB_CUDA_TRY(cudaMemcpyAsync(dRays, rays, sizeof(mrb_ray_gmem) * totalRayCount, cudaMemcpyHostToDevice, c.stream));
+        if(rayIndices) MRB_CUDA_TRY(cudaMemcpyAsync(dIdx, rayIndices, sizeof(uint32_t) * rayCount, cudaMemcpyHostToDevice, c.stream));
+        if(anyHit)
+        {
+            uint32_t* dBits = ma.Take<uint32_t>(words);
+            MRB_CUDA_TRY(cudaMemcpyAsync(dBits, visibleBits, sizeof(uint32_t) * words, cudaMemcpyHostToDevice, c.stream));
+            trace(c, nullptr, nullptr, dBits, dRays, rayIndices ? dIdx : nullptr);
+            MRB_CUDA_TRY(cudaMemcpyAsync(visibleBits, dBits, sizeof(uint32_t) * words, cudaMemcpyDeviceToHost, c.stream));
+        }
+        else
+        {
+            mrb_hit_key_pack* dKeys = ma.Take<mrb_hit_key_pack>(totalRayCount);
+            mrb_meta_hit* dHits = ma.Take<mrb_meta_hit>(totalRayCount);
+            MRB_CUDA_TRY(cudaMemcpyAsync(dKeys, hitKeys, sizeof(mrb_hit_key_pack) * totalRayCount, cudaMemcpyHostToDevice, c.stream));
+            MRB_CUDA_TRY(cudaMemcpyAsync(dHits, metaHits, sizeof(mrb_meta_hit) * totalRayCount, cudaMemcpyHostToDevice, c.stream));
+            trace(c, dKeys, dHits, nullptr, dRays, rayIndices ? dIdx : nullptr);
+            MRB_CUDA_TRY(cudaMemcpyAsync(hitKeys, dKeys, sizeof(mrb_hit_key_pack) * totalRayCount, cudaMemcpyDeviceToHost, c.stream));
+            MRB_CUDA_TRY(cudaMemcpyAsync(metaHits, dHits, sizeof(mrb_meta_hit) * totalRayCount, cudaMemcpyDeviceToHost, c.stream));
+            MRB_CUDA_TRY(cudaMemcpyAsync(rays, dRays, sizeof(mrb_ray_gmem) * totalRayCount, cudaMemcpyDeviceToHost, c.stream));
+        }
+        MRB_CUDA_TRY(cudaStreamSynchronize(c.stream));
+        return MRB_OK;
+    });
+}
 
 static mrb_status CastCommon(mrb_context ctx, mrb_accel accel, bool anyHit,
                              mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, uint32_t* visibleBits,
@@ -481,6 +535,77 @@ mrb_status mrb_binary_partition(mrb_context ctx, uint32_t* indicesOut, uint32_t*
         MRB_CUDA_TRY(cudaStreamSynchronize(c.stream));
         return MRB_OK;
     });
+}
+
+
+mrb_status mrb_scene_build(mrb_context ctx, const mrb_instance_desc* instances, uint32_t instanceCount, mrb_scene* out)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!instances || !out || instanceCount == 0) return Fail(c, MRB_ERR_INVALID_ARG, "empty scene");
+        *out = nullptr;
+        if(instanceCount >= (1u << 20)) return Fail(c, MRB_ERR_INVALID_ARG, "instance count exceeds AcceleratorKey index bits (20)");
+        for(uint32_t i = 0; i < instanceCount; i++)
+        {
+            if(!instances[i].accel) return Fail(c, MRB_ERR_INVALID_ARG, "null accelerator in instance list");
+            if(!instances[i].accel->d.wideNodes) return Fail(c, MRB_ERR_UNSUPPORTED, "instance of a BINARY_ONLY accelerator");
+        }
+        mrb_scene sc = new mrb_scene_t();
+        try { mrb::BuildScene(c, *sc, instances, instanceCount); }
+        catch(...) { c.persistentBytes -= sc->mem.Capacity(); delete sc; throw; }
+        if(sc->d.tlas.wideDepth > 30) { c.persistentBytes -= sc->mem.Capacity(); delete sc; return Fail(c, MRB_ERR_UNSUPPORTED, "top-level tree too deep"); }
+        *out = sc;
+        return MRB_OK;
+    });
+}
+
+void mrb_scene_destroy(mrb_context ctx, mrb_scene scene)
+{
+    if(!ctx || !scene) return;
+    cudaSetDevice(ctx->c.device);
+    cudaStreamSynchronize(ctx->c.stream);
+    ctx->c.persistentBytes -= scene->mem.Capacity();
+    delete scene;
+}
+
+mrb_status mrb_scene_export_tlas(mrb_context ctx, mrb_scene scene, float* instanceAABBs, float* sceneAABB,
+                                 uint64_t* morton, uint32_t* sortedInstance, uint32_t* nodes, float* nodeBoxes)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!scene) return Fail(c, MRB_ERR_INVALID_ARG, "null scene");
+        const mrb::AccelData& d = scene->d.tlas;
+        auto D2H = [&](void* dst, const void* src, size_t bytes)
+        { if(dst) MRB_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c.stream)); };
+        D2H(instanceAABBs, d.leafAABB, sizeof(float) * 6 * d.leafCount);
+        D2H(morton, d.morton, sizeof(uint64_t) * d.leafCount);
+        D2H(sortedInstance, d.sortedLeaf, sizeof(uint32_t) * d.leafCount);
+        D2H(nodes, d.nodes, sizeof(mrb::LBVHNode) * d.nodeCount);
+        D2H(nodeBoxes, d.boxes, sizeof(mrb::LBVHBox) * d.nodeCount);
+        MRB_CUDA_TRY(cudaStreamSynchronize(c.stream));
+        if(sceneAABB) memcpy(sceneAABB, scene->aabb, sizeof(float) * 6);
+        return MRB_OK;
+    });
+}
+
+mrb_status mrb_scene_cast_rays(mrb_context ctx, mrb_scene scene, mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits,
+                               mrb_ray_gmem* rays, const uint32_t* rayIndices, uint32_t rayCount, uint32_t totalRayCount,
+                               mrb_memspace memspace, mrb_trace_mode mode)
+{
+    if(!scene) return MRB_ERR_INVALID_ARG;
+    return CastGeneric(ctx, false, hitKeys, metaHits, nullptr, rays, rayIndices, rayCount, totalRayCount, memspace,
+        [&](mrb::Context& c, mrb_hit_key_pack* k, mrb_meta_hit* h, uint32_t* b, mrb_ray_gmem* r, const uint32_t* idx)
+        { mrb::TraceScene(c, *scene, false, mode, k, h, b, r, idx, rayCount); });
+}
+
+mrb_status mrb_scene_cast_visibility_rays(mrb_context ctx, mrb_scene scene, uint32_t* isVisibleBits,
+                                          const mrb_ray_gmem* rays, const uint32_t* rayIndices,
+                                          uint32_t rayCount, uint32_t totalRayCount, mrb_memspace memspace, mrb_trace_mode mode)
+{
+    if(!scene) return MRB_ERR_INVALID_ARG;
+    return CastGeneric(ctx, true, nullptr, nullptr, isVisibleBits, const_cast<mrb_ray_gmem*>(rays), rayIndices, rayCount, totalRayCount, memspace,
+        [&](mrb::Context& c, mrb_hit_key_pack* k, mrb_meta_hit* h, uint32_t* b, mrb_ray_gmem* r, const uint32_t* idx)
+        { mrb::TraceScene(c, *scene, true, mode, k, h, b, r, idx, rayCount); });
 }
 
 } // extern "C"

@@ -534,6 +534,385 @@ KResolveExact(AccelData a, uint32_t accelKey,
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Two-level scenes
+// ------------------------------------------------------------------------------------------------
+// Matrix3x4::TransformRay (Core/Matrix.hpp:L905-912) with Math::Dot's FMA chains: dir' = M dir,
+// pos' = M (pos, 1); no renormalisation.
+__device__ __forceinline__ void TransformRayExact(const float* __restrict__ m, float ox, float oy, float oz,
+                                                  float dx, float dy, float dz, float lo[3], float ld[3])
+{
+    #pragma unroll
+    for(int r = 0; r < 3; r++)
+    {
+        float d = __fmaf_rn(m[4 * r + 0], dx, 0.0f);
+        d = __fmaf_rn(m[4 * r + 1], dy, d);
+        d = __fmaf_rn(m[4 * r + 2], dz, d);
+        ld[r] = d;
+        float p = __fmaf_rn(m[4 * r + 0], ox, 0.0f);
+        p = __fmaf_rn(m[4 * r + 1], oy, p);
+        p = __fmaf_rn(m[4 * r + 2], oz, p);
+        p = __fmaf_rn(m[4 * r + 3], 1.0f, p);
+        lo[r] = p;
+    }
+}
+
+__device__ __forceinline__ void WriteHit2(const InstanceRec& in, uint32_t r, const HitRecord& h,
+                                          mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, mrb_ray_gmem* rays)
+{
+    uint32_t ri = h.flags >> 8;
+    uint32_t prim = in.ranges.primBegin[ri] + (h.leaf - in.ranges.leafStart[ri]);
+    uint4 keys = make_uint4((in.ranges.primGroupId << 28) | prim, in.ranges.lmKey[ri], in.transKey, in.accelKey);
+    *reinterpret_cast<uint4*>(hitKeys + r) = keys;
+    float w = __fsub_rn(__fsub_rn(1.0f, h.u), h.v);
+    *reinterpret_cast<float2*>(metaHits + r) = make_float2(w, h.u);
+    rays[r].tMax = h.t;
+}
+
+// Reference reaches (instance, leaf) if its slab test passes on the instance's world AABB with the world
+// ray (every top-level ancestor encloses it) and on the leaf AABB with the local ray.
+__device__ __forceinline__ bool CertifyLeaf2(const InstanceRec& in, uint32_t leaf, const float wo[3], const float wd[3],
+                                             float tMin, float tUpper)
+{
+    const float winv[3] = {__fdiv_rn(1.0f, wd[0]), __fdiv_rn(1.0f, wd[1]), __fdiv_rn(1.0f, wd[2])};
+    if(!SlabExact(in.worldAABB, wo, winv, tMin, tUpper)) return false;
+    float lo[3] = {wo[0], wo[1], wo[2]}, ld[3] = {wd[0], wd[1], wd[2]};
+    if(!in.identity) TransformRayExact(in.invTransform, wo[0], wo[1], wo[2], wd[0], wd[1], wd[2], lo, ld);
+    const float linv[3] = {__fdiv_rn(1.0f, ld[0]), __fdiv_rn(1.0f, ld[1]), __fdiv_rn(1.0f, ld[2])};
+    const float* b = in.leafAABB + 6 * size_t(leaf);
+    const float box[6] = {b[0], b[1], b[2], b[3], b[4], b[5]};
+    return SlabExact(box, lo, linv, tMin, tUpper);
+}
+
+// Same phase-uniform persistent loop as KTraceWide with one more kind of leaf: in the top-level tree a
+// leaf record is an instance; entering it pushes the pending top-level groups and a sentinel, switches the
+// lane to the instance's local ray / node arrays, and the sentinel pop switches back.
+template<bool ANY_HIT>
+__global__ void __launch_bounds__(TRACE_TPB)
+KTraceWide2(SceneData sc,
+            mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
+            uint32_t* __restrict__ visibleBits,
+            mrb_ray_gmem* rays, const uint32_t* __restrict__ rayIndices, uint32_t rayCount,
+            uint32_t* __restrict__ counters, uint32_t* __restrict__ fallbackList, TraceParams prm)
+{
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t ltMask = (1u << lane) - 1u;
+    const uint4* const tlasNodes = reinterpret_cast<const uint4*>(sc.tlas.wideNodes);
+
+    bool hasRay = false, finished = false, exhausted = false;
+    uint32_t r = 0, level = 0, inst = 0;
+    const uint4* nodeBase = tlasNodes;
+    const float4* triBase = nullptr;
+    float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, idx = 0, idy = 0, idz = 0;
+    float tMin = 0, tMaxOrig = 0, tMax = 0;
+    bool overflow = false, uncertified = false, done = false;
+    uint32_t oct = 0, bestInst = 0, secondSeen = 0;
+    HitRecord best; best.t = 0; best.u = best.v = 0; best.leaf = INVALID_U32; best.rank = 0; best.flags = 0;
+    uint2 G = make_uint2(0u, 0u), T = make_uint2(0u, 0u);
+    uint2 stack[WIDE_STACK];
+    int sp = 0;
+
+    auto SetRay = [&](float nox, float noy, float noz, float ndx, float ndy, float ndz)
+    {
+        ox = nox; oy = noy; oz = noz; dx = ndx; dy = ndy; dz = ndz;
+        idx = (fabsf(dx) > 1e-30f) ? 1.0f / dx : copysignf(1e30f, dx);
+        idy = (fabsf(dy) > 1e-30f) ? 1.0f / dy : copysignf(1e30f, dy);
+        idz = (fabsf(dz) > 1e-30f) ? 1.0f / dz : copysignf(1e30f, dz);
+        oct = (dx < 0.0f ? 4u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 1u : 0u);
+    };
+
+    while(true)
+    {
+        if(finished)
+        {
+            finished = false;
+            const float4 w0 = reinterpret_cast<const float4*>(rays + r)[0];
+            const float4 w1 = reinterpret_cast<const float4*>(rays + r)[1];
+            const float wo[3] = {w0.x, w0.y, w0.z}, wd[3] = {w1.x, w1.y, w1.z};
+            if(ANY_HIT)
+            {
+                if(done) atomicAnd(&visibleBits[r >> 5], ~(1u << (r & 31u)));
+                else if(uncertified) { fallbackList[atomicAdd(counters + 4, 1u)] = r; atomicAdd(counters, 1u); atomicAdd(counters + 2, 1u); }
+            }
+            else if(best.leaf != INVALID_U32)
+            {
+                const float tUpper = fminf(tMaxOrig, best.t * NEAR_TIE);
+                const InstanceRec& in = sc.instances[bestInst];
+                if(!secondSeen && !overflow && CertifyLeaf2(in, best.leaf, wo, wd, tMin, tUpper))
+                    WriteHit2(in, r, best, hitKeys, metaHits, rays);
+                else
+                {
+                    fallbackList[atomicAdd(counters + 4, 1u)] = r;
+                    atomicAdd(counters, 1u);
+                    atomicAdd(counters + ((secondSeen || overflow) ? 1 : 2), 1u);
+                }
+            }
+        }
+        if(!exhausted)
+        {
+            const uint32_t need = __ballot_sync(FULL, !hasRay);
+            if(need)
+            {
+                const int leader = __ffs(int(need)) - 1;
+                uint32_t base = 0;
+                if(int(lane) == leader) base = atomicAdd(counters + 3, uint32_t(__popc(need)));
+                base = __shfl_sync(FULL, base, leader);
+                if(!hasRay)
+                {
+                    const uint32_t i = base + uint32_t(__popc(need & ltMask));
+                    if(i < rayCount)
+                    {
+                        r = rayIndices ? rayIndices[i] : i;
+                        const float4 r0 = reinterpret_cast<const float4*>(rays + r)[0];
+                        const float4 r1 = reinterpret_cast<const float4*>(rays + r)[1];
+                        SetRay(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
+                        tMin = r0.w; tMaxOrig = r1.w; tMax = tMaxOrig; overflow = false; secondSeen = 0u;
+                        best.t = tMaxOrig; best.rank = 0u; best.leaf = INVALID_U32; best.flags = 0u; bestInst = 0u;
+                        uncertified = false; done = false;
+                        G = make_uint2(0u, 0x80000000u); T = make_uint2(0u, 0u); sp = 0;
+                        level = 0u; nodeBase = tlasNodes; triBase = nullptr;
+                        hasRay = true;
+                    }
+                }
+                if(base + uint32_t(__popc(need)) >= rayCount) exhausted = true;
+            }
+        }
+        uint32_t live = __ballot_sync(FULL, hasRay);
+        if(live == 0u) break;
+        const int fetchThr = exhausted ? 1 : int(prm.fetchThr);
+        do
+        {
+            const bool triWork = hasRay && (T.y != 0u);
+            const bool nodeWork = hasRay && ((G.y & 0xFF000000u) != 0u);
+            const uint32_t bT = __ballot_sync(FULL, triWork);
+            const uint32_t bN = __ballot_sync(FULL, nodeWork);
+            if(bT != 0u && (bN == 0u || uint32_t(__popc(bT)) * prm.triDiv >= uint32_t(__popc(live))))
+            {
+                if(triWork)
+                {
+                    const uint32_t tb = uint32_t(__ffs(int(T.y))) - 1u;
+                    T.y &= T.y - 1u;
+                    if(level == 0u)
+                    {
+                        // ---- enter an instance ----
+                        const uint32_t ii = sc.tlas.leafOfSlot[T.x + tb];
+                        const InstanceRec* in = sc.instances + ii;
+                        if(G.y & 0xFF000000u) stack[sp++] = G;
+                        if(T.y != 0u) stack[sp++] = T;
+                        stack[sp++] = make_uint2(0xFFFFFFFFu, 0u); // sentinel: back to the top level
+                        if(!in->identity)
+                        {
+                            float lo[3], ld[3];
+                            TransformRayExact(in->invTransform, ox, oy, oz, dx, dy, dz, lo, ld);
+                            SetRay(lo[0], lo[1], lo[2], ld[0], ld[1], ld[2]);
+                        }
+                        nodeBase = reinterpret_cast<const uint4*>(in->wideNodes);
+                        triBase = reinterpret_cast<const float4*>(in->tris);
+                        inst = ii; level = 1u;
+                        G = make_uint2(0u, 0x80000000u); T = make_uint2(0u, 0u);
+                    }
+                    else
+                    {
+                        const float4* tp = triBase + size_t(T.x + tb) * 3;
+                        const float4 v0 = __ldg(tp + 0), e0 = __ldg(tp + 1), e1 = __ldg(tp + 2);
+                        const uint32_t flags = __float_as_uint(e1.w);
+                        float t, u, v;
+                        if(RayTriangle(ox, oy, oz, dx, dy, dz, v0, e0, e1, (flags & 1u) != 0u, t, u, v) &&
+                           (t >= tMin && t < tMaxOrig))
+                        {
+                            const uint32_t rank = __float_as_uint(e0.w);
+                            if(ANY_HIT)
+                            {
+                                const float4 w0 = reinterpret_cast<const float4*>(rays + r)[0];
+                                const float4 w1 = reinterpret_cast<const float4*>(rays + r)[1];
+                                const float wo[3] = {w0.x, w0.y, w0.z}, wd[3] = {w1.x, w1.y, w1.z};
+                                if(CertifyLeaf2(sc.instances[inst], __float_as_uint(v0.w), wo, wd, tMin, tMaxOrig))
+                                { done = true; hasRay = false; finished = true; }
+                                else uncertified = true;
+                            }
+                            else if(t < best.t)
+                            {
+                                // any earlier candidate inside the new window makes the ray a near tie
+                                if(best.leaf != INVALID_U32 && best.t <= t * NEAR_TIE) secondSeen = 1u;
+                                best.t = t; best.u = u; best.v = v; best.rank = rank;
+                                best.leaf = __float_as_uint(v0.w); best.flags = flags; bestInst = inst;
+                                tMax = fminf(tMaxOrig, t * NEAR_TIE);
+                            }
+                            else if(t <= best.t * NEAR_TIE) secondSeen = 1u;
+                        }
+                    }
+                }
+            }
+            if(bN != 0u)
+            {
+                if(nodeWork && hasRay && ((G.y & 0xFF000000u) != 0u))
+                {
+                    if(T.y != 0u) { stack[sp++] = T; T.y = 0u; }
+                    const uint32_t hitsImask = G.y;
+                    const uint32_t bit = 31u - uint32_t(__clz(int(hitsImask)));
+                    G.y &= ~(1u << bit);
+                    if(G.y & 0xFF000000u) { stack[sp++] = G; }
+                    const uint32_t slot = (bit - 24u) ^ oct;
+                    const uint32_t rel = __popc(hitsImask & ~(0xFFFFFFFFu << slot));
+                    const uint4* np = nodeBase + size_t(G.x + rel) * 5;
+                    const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+                    const float sx = __uint_as_float((n0.w & 0xFFu) << 23) * idx;
+                    const float sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * idy;
+                    const float sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23) * idz;
+                    const float cx = (__uint_as_float(n0.x) - ox) * idx;
+                    const float cy = (__uint_as_float(n0.y) - oy) * idy;
+                    const float cz = (__uint_as_float(n0.z) - oz) * idz;
+                    const float kx = __fmaf_rn(0.0042f, fabsf(sx), 9.5367431640625e-07f * fabsf(cx));
+                    const float ky = __fmaf_rn(0.0042f, fabsf(sy), 9.5367431640625e-07f * fabsf(cy));
+                    const float kz = __fmaf_rn(0.0042f, fabsf(sz), 9.5367431640625e-07f * fabsf(cz));
+                    const float bx = __fmaf_rn(-32768.0f, sx, cx), by = __fmaf_rn(-32768.0f, sy, cy), bz = __fmaf_rn(-32768.0f, sz, cz);
+                    const float cnx = bx - kx, cny = by - ky, cnz = bz - kz;
+                    const float cfx = bx + kx, cfy = by + ky, cfz = bz + kz;
+                    const float tFarLimit = tMax;
+                    uint32_t hitmask = 0u;
+                    const uint32_t oct4 = oct * 0x01010101u;
+                    const uint32_t magic = prm.magic;
+                    #pragma unroll
+                    for(int half = 0; half < 2; half++)
+                    {
+                        const uint32_t meta4 = half ? n1.w : n1.z;
+                        const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+                        const uint32_t innerMask4 = (isInner4 >> 4) * 0xFFu;
+                        const uint32_t bitIndex4 = (meta4 ^ (oct4 & innerMask4)) & 0x1F1F1F1Fu;
+                        const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+                        const uint32_t qlx = half ? n2.y : n2.x, qly = half ? n2.w : n2.z, qlz = half ? n3.y : n3.x;
+                        const uint32_t qhx = half ? n3.w : n3.z, qhy = half ? n4.y : n4.x, qhz = half ? n4.w : n4.z;
+                        const uint32_t nx = (dx < 0.0f) ? qhx : qlx, fx = (dx < 0.0f) ? qlx : qhx;
+                        const uint32_t ny = (dy < 0.0f) ? qhy : qly, fy = (dy < 0.0f) ? qly : qhy;
+                        const uint32_t nz = (dz < 0.0f) ? qhz : qlz, fz = (dz < 0.0f) ? qlz : qhz;
+                        #pragma unroll
+                        for(int j = 0; j < 4; j++)
+                        {
+                            const float tnx = __fmaf_rn(QF(nx, j, magic), sx, cnx), tfx = __fmaf_rn(QF(fx, j, magic), sx, cfx);
+                            const float tny = __fmaf_rn(QF(ny, j, magic), sy, cny), tfy = __fmaf_rn(QF(fy, j, magic), sy, cfy);
+                            const float tnz = __fmaf_rn(QF(nz, j, magic), sz, cnz), tfz = __fmaf_rn(QF(fz, j, magic), sz, cfz);
+                            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tMin));
+                            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tFarLimit));
+                            if(tn <= tf)
+                            {
+                                const uint32_t cbits = (childBits4 >> (8 * j)) & 0xFFu;
+                                const uint32_t bidx = (bitIndex4 >> (8 * j)) & 0xFFu;
+                                hitmask |= cbits << bidx;
+                            }
+                        }
+                    }
+                    G.x = n1.x;
+                    G.y = (hitmask & 0xFF000000u) | (n0.w >> 24);
+                    T.x = n1.y;
+                    T.y = hitmask & 0x00FFFFFFu;
+                }
+            }
+            if(hasRay && (G.y & 0xFF000000u) == 0u && T.y == 0u)
+            {
+                if(sp == 0) { hasRay = false; finished = true; }
+                else
+                {
+                    const uint2 e = stack[--sp];
+                    if(e.y == 0u)
+                    {
+                        // sentinel: leave the instance, restore the world ray
+                        const float4 r0 = reinterpret_cast<const float4*>(rays + r)[0];
+                        const float4 r1 = reinterpret_cast<const float4*>(rays + r)[1];
+                        SetRay(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
+                        level = 0u; nodeBase = tlasNodes;
+                    }
+                    else if(e.y & 0xFF000000u) G = e; else T = e;
+                }
+            }
+            live = __ballot_sync(FULL, hasRay);
+        } while(__popc(live) >= fetchThr);
+    }
+}
+
+// Exact two-level traversal (audit path and fallback): KCIntersectBaseLBVH semantics on the top level
+// (internal boxes and the instance leaf AABB slab-tested with the current tMax, left-first), the
+// bottom-level ClosestHit / FirstHit in local space, tMax shrinking across instances.
+template<bool ANY_HIT>
+__global__ void __launch_bounds__(TRACE_TPB)
+KTraceBinary2(SceneData sc,
+              mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
+              uint32_t* __restrict__ visibleBits,
+              mrb_ray_gmem* rays, const uint32_t* __restrict__ rayIndices, uint32_t rayCount,
+              const uint32_t* __restrict__ deviceRayCount)
+{
+    if(deviceRayCount) rayCount = *deviceRayCount;
+    for(uint32_t i = blockIdx.x * TRACE_TPB + threadIdx.x; i < rayCount; i += gridDim.x * TRACE_TPB)
+    {
+        const uint32_t r = rayIndices ? rayIndices[i] : i;
+        const float4 r0 = reinterpret_cast<const float4*>(rays + r)[0];
+        const float4 r1 = reinterpret_cast<const float4*>(rays + r)[1];
+        const float wo[3] = {r0.x, r0.y, r0.z}, wd[3] = {r1.x, r1.y, r1.z};
+        const float winv[3] = {__fdiv_rn(1.0f, wd[0]), __fdiv_rn(1.0f, wd[1]), __fdiv_rn(1.0f, wd[2])};
+        const float tMin = r0.w; float tMax = r1.w;
+        HitRecord best; best.t = tMax; best.rank = 0u; best.leaf = INVALID_U32; best.u = best.v = 0.f; best.flags = 0u;
+        uint32_t bestInst = 0; bool done = false;
+        uint32_t tstack[96]; int tsp = 0;
+        tstack[tsp++] = 0u;
+        while(tsp > 0 && !done)
+        {
+            uint32_t tn = tstack[--tsp];
+            if(tn == INVALID_U32) continue;
+            if(!(tn & LEAF_FLAG))
+            {
+                if(SlabExact(reinterpret_cast<const float*>(sc.tlas.boxes + tn), wo, winv, tMin, tMax))
+                {
+                    LBVHNode nd = sc.tlas.nodes[tn];
+                    tstack[tsp++] = nd.right; tstack[tsp++] = nd.left;
+                }
+                continue;
+            }
+            const uint32_t ii = tn & ~LEAF_FLAG;
+            const InstanceRec& in = sc.instances[ii];
+            if(!SlabExact(in.worldAABB, wo, winv, tMin, tMax)) continue;
+            float o[3] = {wo[0], wo[1], wo[2]}, d[3] = {wd[0], wd[1], wd[2]};
+            if(!in.identity) TransformRayExact(in.invTransform, wo[0], wo[1], wo[2], wd[0], wd[1], wd[2], o, d);
+            const float invD[3] = {__fdiv_rn(1.0f, d[0]), __fdiv_rn(1.0f, d[1]), __fdiv_rn(1.0f, d[2])};
+            uint32_t stack[128]; int sp = 0;
+            stack[sp++] = 0u;
+            while(sp > 0)
+            {
+                uint32_t ni = stack[--sp];
+                if(ni == INVALID_U32) continue;
+                if(ni & LEAF_FLAG)
+                {
+                    uint32_t leaf = ni & ~LEAF_FLAG;
+                    const uint32_t ri = (in.ranges.count == 1u) ? 0u : FindRange(in.ranges, leaf);
+                    uint32_t prim = in.ranges.primBegin[ri] + (leaf - in.ranges.leafStart[ri]);
+                    uint32_t i0 = in.indices[3 * size_t(prim)], i1 = in.indices[3 * size_t(prim) + 1], i2 = in.indices[3 * size_t(prim) + 2];
+                    const float* p0 = in.positions + 3 * size_t(i0);
+                    const float* p1 = in.positions + 3 * size_t(i1);
+                    const float* p2 = in.positions + 3 * size_t(i2);
+                    float4 v0 = make_float4(p0[0], p0[1], p0[2], 0.f);
+                    float4 e0 = make_float4(__fsub_rn(p1[0], p0[0]), __fsub_rn(p1[1], p0[1]), __fsub_rn(p1[2], p0[2]), 0.f);
+                    float4 e1 = make_float4(__fsub_rn(p2[0], p0[0]), __fsub_rn(p2[1], p0[1]), __fsub_rn(p2[2], p0[2]), 0.f);
+                    float t, u, v;
+                    if(!RayTriangle(o[0], o[1], o[2], d[0], d[1], d[2], v0, e0, e1, in.ranges.cull[ri] != 0u, t, u, v)) continue;
+                    if(!(t >= tMin && t < tMax)) continue;
+                    best.t = t; best.u = u; best.v = v; best.leaf = leaf; best.flags = ri << 8; bestInst = ii;
+                    tMax = t;
+                    if(ANY_HIT) { done = true; break; }
+                }
+                else if(SlabExact(reinterpret_cast<const float*>(in.boxes + ni), o, invD, tMin, tMax))
+                {
+                    LBVHNode nd = in.nodes[ni];
+                    stack[sp++] = nd.right; stack[sp++] = nd.left;
+                }
+            }
+        }
+        if(best.leaf != INVALID_U32)
+        {
+            if(ANY_HIT) atomicAnd(&visibleBits[r >> 5], ~(1u << (r & 31u)));
+            else WriteHit2(sc.instances[bestInst], r, best, hitKeys, metaHits, rays);
+        }
+    }
+}
+
 } // namespace
 
 void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode mode,
@@ -586,6 +965,53 @@ void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode
         const uint32_t bgrid = min(grid, uint32_t(ctx.smCount) * 16u);
         if(anyHit) MRB_LAUNCH(ctx, KTraceBinary<true>, bgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, nullptr);
         else       MRB_LAUNCH(ctx, KTraceBinary<false>, bgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, nullptr);
+        ctx.lastFallbackCount = nullptr;
+    }
+}
+
+
+void TraceScene(Context& ctx, const mrb_scene_t& scn, bool anyHit, mrb_trace_mode mode,
+                mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, uint32_t* visibleBits,
+                mrb_ray_gmem* rays, const uint32_t* rayIndices, uint32_t rayCount)
+{
+    if(rayCount == 0) return;
+    const uint32_t grid = DivUp(rayCount, TRACE_TPB);
+    if(mode == MRB_TRACE_WIDE)
+    {
+        MultiAlloc sz(nullptr);
+        sz.Take<uint32_t>(64); sz.Take<uint4>(size_t(RESOLVE_CAPACITY) * 4); sz.Take<uint32_t>(rayCount);
+        ctx.traceScratch.Reserve(sz.Total());
+        MultiAlloc ma(ctx.traceScratch.Base());
+        uint32_t* counters = ma.Take<uint32_t>(64);
+        ma.Take<uint4>(size_t(RESOLVE_CAPACITY) * 4);
+        uint32_t* fbList = ma.Take<uint32_t>(rayCount);
+        MRB_CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 8, ctx.stream));
+        static int occClosest = 0, occAny = 0;
+        if(!occClosest)
+        {
+            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occClosest, KTraceWide2<false>, TRACE_TPB, 0));
+            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occAny, KTraceWide2<true>, TRACE_TPB, 0));
+        }
+        TraceParams prm{5u, 24u, 0x47000000u};
+        const uint32_t pgrid = min(grid, uint32_t(ctx.smCount) * uint32_t(anyHit ? occAny : occClosest));
+        const uint32_t fbGrid = uint32_t(ctx.smCount);
+        if(anyHit)
+        {
+            MRB_LAUNCH(ctx, KTraceWide2<true>, pgrid, TRACE_TPB, 0, scn.d, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, fbList, prm);
+            MRB_LAUNCH(ctx, KTraceBinary2<true>, fbGrid, TRACE_TPB, 0, scn.d, hitKeys, metaHits, visibleBits, rays, fbList, 0u, counters + 4);
+        }
+        else
+        {
+            MRB_LAUNCH(ctx, KTraceWide2<false>, pgrid, TRACE_TPB, 0, scn.d, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, fbList, prm);
+            MRB_LAUNCH(ctx, KTraceBinary2<false>, fbGrid, TRACE_TPB, 0, scn.d, hitKeys, metaHits, visibleBits, rays, fbList, 0u, counters + 4);
+        }
+        ctx.lastFallbackCount = counters;
+    }
+    else
+    {
+        const uint32_t bgrid = min(grid, uint32_t(ctx.smCount) * 16u);
+        if(anyHit) MRB_LAUNCH(ctx, KTraceBinary2<true>, bgrid, TRACE_TPB, 0, scn.d, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, nullptr);
+        else       MRB_LAUNCH(ctx, KTraceBinary2<false>, bgrid, TRACE_TPB, 0, scn.d, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, nullptr);
         ctx.lastFallbackCount = nullptr;
     }
 }

@@ -443,3 +443,127 @@ void orc_brute_trace(const float* pos, const uint32_t* idx, uint32_t nTris, cons
         outPrim[r] = best; outT[r] = bestT;
     }
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Two-level accelerator (BaseAcceleratorLBVH, Tracer/AcceleratorLBVH.cu:L537-1035)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Top-level LBVH over instance AABBs — InternalConstruct (AcceleratorLBVH.cu:L537-740): scene AABB =
+ * union, centres = AABB::Centroid() = min + (max - min) * 0.5 (Core/AABB.hpp:L62-65, KCGenAABBCenters
+ * L497-510), then the same Morton / sort / Karras / union chain as a bottom-level accelerator. */
+void orc_tlas_build(const float* instAABB, uint32_t n, int robust,
+                    float* sceneAABB, uint64_t* morton, uint64_t* sortedMorton, uint32_t* sortedIdx,
+                    uint32_t* nodes, uint32_t* leafParent, float* boxes)
+{
+    float* centers = (float*)malloc(sizeof(float) * 3 * (size_t)n);
+    for(uint32_t i = 0; i < n; i++)
+        for(int a = 0; a < 3; a++)
+        {
+            float span = instAABB[6 * i + 3 + a] - instAABB[6 * i + a];
+            centers[3 * i + a] = instAABB[6 * i + a] + span * 0.5f;
+        }
+    orc_aabb_union(instAABB, n, sceneAABB);
+    orc_morton63(centers, n, sceneAABB, morton);
+    memcpy(sortedMorton, morton, sizeof(uint64_t) * n);
+    for(uint32_t i = 0; i < n; i++) sortedIdx[i] = i;
+    orc_radix_sort_u64(sortedMorton, sortedIdx, n, 0, 64);
+    orc_karras(sortedMorton, sortedIdx, n, nodes, leafParent, robust);
+    orc_union_boxes(nodes, leafParent, instAABB, n, boxes);
+    free(centers);
+}
+
+/* Matrix3x4::TransformAABB (Core/Matrix.hpp:L915-932) with the homogeneous coordinate held at 1 for all
+ * eight corners. (The reference reassigns its Vector4 `vertex` from an operator* whose 4th lane is never
+ * written — L777-787 — so for corners 1..7 its w is indeterminate; identity-transform instances do not go
+ * through this function.) Dot = Math::Dot FMA chain. m: row-major 3x4. */
+void orc_transform_aabb(const float m[12], const float aabb[6], float out[6])
+{
+    for(int a = 0; a < 3; a++) { out[a] = FLT_MAX; out[3 + a] = -FLT_MAX; }
+    for(unsigned i = 0; i < 8; i++)
+    {
+        float v[4];
+        for(unsigned j = 0; j < 3; j++) v[j] = ((i >> j) & 1u) ? aabb[3 + j] : aabb[j];
+        v[3] = 1.0f;
+        for(int r = 0; r < 3; r++)
+        {
+            float d = fmaf(m[4 * r + 0], v[0], 0.0f);
+            d = fmaf(m[4 * r + 1], v[1], d);
+            d = fmaf(m[4 * r + 2], v[2], d);
+            d = fmaf(m[4 * r + 3], v[3], d);
+            out[r] = (d < out[r]) ? d : out[r];
+            out[3 + r] = (out[3 + r] < d) ? d : out[3 + r];
+        }
+    }
+}
+
+/* Matrix3x4::TransformRay (Core/Matrix.hpp:L905-912): dir' = M * dir (3-dot), pos' = M * (pos, 1) (4-dot);
+ * no renormalisation, so t stays in world units (KCLocalRayCast, AcceleratorWork.kt.h:L207-218). */
+static void transform_ray(const float m[12], const float* ray, float* out)
+{
+    for(int r = 0; r < 3; r++)
+    {
+        float d = fmaf(m[4 * r + 0], ray[4], 0.0f);
+        d = fmaf(m[4 * r + 1], ray[5], d);
+        d = fmaf(m[4 * r + 2], ray[6], d);
+        out[4 + r] = d;
+        float p = fmaf(m[4 * r + 0], ray[0], 0.0f);
+        p = fmaf(m[4 * r + 1], ray[1], p);
+        p = fmaf(m[4 * r + 2], ray[2], p);
+        p = fmaf(m[4 * r + 3], 1.0f, p);
+        out[r] = p;
+    }
+    out[3] = ray[3]; out[7] = ray[7];
+}
+
+typedef struct
+{
+    const float* pos; const uint32_t* idx; const uint32_t* nodes; const float* boxes; /* bottom-level accelerator */
+    float invTransform[12];
+    int identity;
+} orc_instance;
+
+/* CastRays / CastVisibilityRays over a two-level scene: left-first traversal of the top-level tree
+ * (KCIntersectBaseLBVH: internal boxes AND the instance leaf AABB are slab-tested with the current
+ * [tMin,tMax]); every reached instance runs the bottom-level ClosestHit / FirstHit in its local space and
+ * shrinks tMax (the reference interleaves this per top-level round over all rays — per ray the visit order
+ * is the same). mode 0 closest, 1 any. outInst = instance index or ORC_INVALID. */
+void orc_scene_trace(const orc_instance* inst, const float* instAABB,
+                     const uint32_t* tNodes, const float* tBoxes, uint32_t nInst,
+                     const float* rays, uint32_t nRays, int mode, int cullFace,
+                     uint32_t* outInst, uint32_t* outPrim, float* outT, float* outBary)
+{
+    for(uint32_t r = 0; r < nRays; r++)
+    {
+        const float* ray = rays + 8 * (size_t)r;
+        float tMin = ray[3], tMax = ray[7];
+        uint32_t bestI = ORC_INVALID, bestP = ORC_INVALID; float bb[2] = {0, 0};
+        uint32_t stack[160]; int sp = 0; int done = 0;
+        stack[sp++] = 0;
+        while(sp > 0 && !done)
+        {
+            uint32_t ni = stack[--sp];
+            if(ni == ORC_INVALID) continue;
+            if(ni & ORC_LEAF_FLAG)
+            {
+                uint32_t ii = ni & ~ORC_LEAF_FLAG;
+                if(!slab_test(ray, ray + 4, instAABB + 6 * (size_t)ii, tMin, tMax)) continue;
+                float local[8];
+                if(inst[ii].identity) memcpy(local, ray, sizeof(local)); else transform_ray(inst[ii].invTransform, ray, local);
+                local[3] = tMin; local[7] = tMax;
+                uint32_t prim; float t, b2[2]; uint8_t back;
+                orc_lbvh_trace(inst[ii].pos, inst[ii].idx, inst[ii].nodes, inst[ii].boxes, local, 1, mode, cullFace, &prim, &t, b2, &back);
+                if(prim != ORC_INVALID)
+                {
+                    bestI = ii; bestP = prim; tMax = t; bb[0] = b2[0]; bb[1] = b2[1];
+                    if(mode == 1) done = 1;
+                }
+            }
+            else if(slab_test(ray, ray + 4, tBoxes + 6 * (size_t)ni, tMin, tMax))
+            {
+                stack[sp++] = tNodes[3 * (size_t)ni + 1];
+                stack[sp++] = tNodes[3 * (size_t)ni + 0];
+            }
+        }
+        outInst[r] = bestI; outPrim[r] = bestP; outT[r] = tMax; outBary[2 * r] = bb[0]; outBary[2 * r + 1] = bb[1];
+    }
+}

@@ -287,3 +287,45 @@ def oracle_render(positions, indices, tri_material, albedo, radiance, camera, wi
         list(ex.map(lambda k: L.orc_pt_render_rows(C.byref(s), int(rows[k]), int(rows[k + 1]), out.ctypes.data),
                     range(len(rows) - 1)))
     return np.moveaxis(out[:3], 0, -1) / np.maximum(out[3], 1e-20)[..., None]
+
+
+# ------------------------------------------------------------------------------------------------
+# two-level scenes
+# ------------------------------------------------------------------------------------------------
+class _OrcInstance(C.Structure):
+    _fields_ = [("pos", C.c_void_p), ("idx", C.c_void_p), ("nodes", C.c_void_p), ("boxes", C.c_void_p),
+                ("invTransform", C.c_float * 12), ("identity", C.c_int)]
+
+
+def oracle_transform_aabb(m34, aabb):
+    L = lib()
+    L.orc_transform_aabb.argtypes = [_f32p, _f32p, _f32p]
+    out = np.zeros(6, np.float32)
+    L.orc_transform_aabb(np.ascontiguousarray(m34, np.float32).ravel(), np.ascontiguousarray(aabb, np.float32), out)
+    return out
+
+
+def oracle_tlas_build(inst_aabb) -> LBVH:
+    L = lib()
+    L.orc_tlas_build.argtypes = [_f32p, C.c_uint32, C.c_int, _f32p, _u64p, _u64p, _u32p, _u32p, _u32p, _f32p]
+    n = inst_aabb.shape[0]
+    b = LBVH(n)
+    b.leaf_aabb = np.ascontiguousarray(inst_aabb, np.float32)
+    L.orc_tlas_build(b.leaf_aabb, n, 1, b.accel_aabb, b.morton, b.sorted_morton, b.sorted_idx, b.nodes, b.leaf_parent, b.boxes)
+    return b
+
+
+def oracle_scene_trace(instances, tlas: LBVH, rays, mode=0, cull=0):
+    """instances: list of (positions, indices, LBVH, inv34 float32, identity)."""
+    L = lib()
+    L.orc_scene_trace.argtypes = [C.POINTER(_OrcInstance), _f32p, _u32p, _f32p, C.c_uint32, _f32p, C.c_uint32, C.c_int, C.c_int,
+                                  _u32p, _u32p, _f32p, _f32p]
+    arr = (_OrcInstance * len(instances))()
+    for i, (p, idx, b, inv, ident) in enumerate(instances):
+        arr[i].pos, arr[i].idx, arr[i].nodes, arr[i].boxes = p.ctypes.data, idx.ctypes.data, b.nodes.ctypes.data, b.boxes.ctypes.data
+        arr[i].invTransform = (C.c_float * 12)(*np.asarray(inv, np.float32).ravel())
+        arr[i].identity = 1 if ident else 0
+    n = rays.shape[0]
+    oi = np.zeros(n, np.uint32); op = np.zeros(n, np.uint32); ot = np.zeros(n, np.float32); ob = np.zeros((n, 2), np.float32)
+    L.orc_scene_trace(arr, tlas.leaf_aabb, tlas.nodes, tlas.boxes, len(instances), np.ascontiguousarray(rays), n, mode, cull, oi, op, ot, ob)
+    return oi, op, ot, ob
