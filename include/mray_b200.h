@@ -269,6 +269,14 @@ typedef struct mrb_render_desc
     uint32_t        maxPathCount;    /* paths in flight; 0 = width*height (parallelizationHint tile) */
     uint32_t        partitionRays;   /* 1 = sort live rays by (work batch, material) key before shading
                                       * (RenderSurfaceWorkHasher + RayPartitioner::MultiPartition) */
+    /* Two-level scenes: when `scene` is non-NULL it replaces `accel` (which must then be NULL) and
+     * vertexCount / triangleCount / vertexNormals are ignored. Surfaces are generated in the instance's
+     * local space and moved to world space with the instance transform (TransformContextSingle,
+     * Tracer/TransformsDefault.h); emissive triangles are listed per instance in world space.
+     * instanceVertexNormals: NULL, or one host pointer per instance (NULL entries = geometric normal),
+     * each with as many normals as the instance's accelerator has vertices. */
+    mrb_scene       scene;
+    const float* const* instanceVertexNormals;
 } mrb_render_desc;
 
 typedef struct mrb_render_stats

@@ -66,7 +66,8 @@ class RenderDesc(C.Structure):
                 ("fovXY", C.c_float * 2), ("nearFar", C.c_float * 2),
                 ("width", C.c_uint32), ("height", C.c_uint32), ("totalSPP", C.c_uint32), ("sampleMode", C.c_uint32),
                 ("rrRange", C.c_uint32 * 2), ("filmFilterRadius", C.c_float), ("seed", C.c_uint64),
-                ("maxPathCount", C.c_uint32), ("partitionRays", C.c_uint32)]
+                ("maxPathCount", C.c_uint32), ("partitionRays", C.c_uint32),
+                ("scene", C.c_void_p), ("instanceVertexNormals", C.POINTER(C.c_void_p))]
 
 
 class RenderStats(C.Structure):
@@ -353,16 +354,29 @@ class Renderer:
     """(R)PathTracerRGB behind the C-ABI: StartRender / DoRenderWork / film read-out
     (TracerDLL/PathTracerRenderer.cu:L930-1355)."""
 
-    def __init__(self, ctx: Context, accel: Accelerator, vertex_count, triangle_count, albedo, light_radiance,
+    def __init__(self, ctx: Context, accel, vertex_count, triangle_count, albedo, light_radiance,
                  camera, width, height, total_spp, sample_mode="WithNEEAndMIS", rr_range=(2, 20), seed=0,
                  vertex_normals=None, light_two_sided=None, film_filter_radius=1.0, near_far=(0.01, 1000.0),
-                 max_path_count=0, partition_rays=False):
+                 max_path_count=0, partition_rays=False, instance_vertex_normals=None):
+        """`accel` is an Accelerator, or a Scene (two-level; vertex_count / triangle_count / vertex_normals
+        are then ignored and instance_vertex_normals may hold one array or None per instance)."""
         self.ctx, self.accel = ctx, accel
         self.width, self.height = width, height
         d = RenderDesc()
-        d.accel = accel.handle
-        d.vertexCount, d.triangleCount = vertex_count, triangle_count
         self._keep = []
+        if isinstance(accel, Scene):
+            d.scene = accel.handle
+            if instance_vertex_normals is not None:
+                ptrs = (C.c_void_p * accel.count)()
+                for k, nrm in enumerate(instance_vertex_normals):
+                    if nrm is not None:
+                        a = np.ascontiguousarray(nrm, np.float32); self._keep.append(a); ptrs[k] = a.ctypes.data
+                self._keep.append(ptrs)
+                d.instanceVertexNormals = C.cast(ptrs, C.POINTER(C.c_void_p))
+            vertex_normals = None
+        else:
+            d.accel = accel.handle
+            d.vertexCount, d.triangleCount = vertex_count, triangle_count
 
         def host(a, dt):
             if a is None:

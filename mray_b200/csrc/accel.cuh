@@ -116,6 +116,7 @@ struct mrb_accel_t
     mrb_accel_info   info = {};
     uint32_t         flags = 0;
     uint32_t         accelKey = 0;
+    uint32_t         vertexCount = 0, triangleCount = 0;   // of the primitive group (ranges may cover a subset)
 };
 
 struct mrb_scene_t
@@ -123,6 +124,7 @@ struct mrb_scene_t
     mrb::SceneData   d;
     mrb::DeviceBlock mem;
     std::vector<mrb_accel> accels;
+    std::vector<mrb_instance_desc> hInstances;   // host copy (renderer: forward transforms, keys)
     float            aabb[6] = {};
     float            buildMs = 0.f;
 };

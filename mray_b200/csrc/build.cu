@@ -309,16 +309,26 @@ __device__ void CollapseNode(const AccelData& a, CollapseState* st, unsigned lon
         refs[0] = MakeRef(a, nd.left, rg.x);
         refs[1] = MakeRef(a, nd.right, rg.y);
         n = 2;
-        while(n < 8)
+        // phase 1: open (largest surface area first) only subtrees that cannot be a leaf child, so slots go to
+        // shrinking the internal children; phase 2: left-over slots split multi-triangle leaves for tighter boxes
+        for(int phase = 0; phase < 2 && n < 8; phase++)
         {
-            int best = -1; float bestArea = -1.0f;
-            for(uint32_t c = 0; c < n; c++)
-                if(refs[c].node != INVALID_U32 && refs[c].area > bestArea) { bestArea = refs[c].area; best = int(c); }
-            if(best < 0) break;
-            ChildRef o = refs[best];
-            LBVHNode on = a.nodes[o.node];
-            refs[best] = MakeRef(a, on.left, o.lo);
-            refs[n++] = MakeRef(a, on.right, o.hi);
+            while(n < 8)
+            {
+                int best = -1; float bestArea = -1.0f;
+                for(uint32_t c = 0; c < n; c++)
+                {
+                    if(refs[c].node == INVALID_U32) continue;
+                    const uint32_t size = refs[c].hi - refs[c].lo + 1;
+                    if(phase == 0 && size <= MAX_LEAF) continue;
+                    if(refs[c].area > bestArea) { bestArea = refs[c].area; best = int(c); }
+                }
+                if(best < 0) break;
+                ChildRef o = refs[best];
+                LBVHNode on = a.nodes[o.node];
+                refs[best] = MakeRef(a, on.left, o.lo);
+                refs[n++] = MakeRef(a, on.right, o.hi);
+            }
         }
     }
     // child boxes, node bounds
@@ -621,6 +631,7 @@ void BuildScene(Context& ctx, mrb_scene_t& sc, const mrb_instance_desc* inst, ui
     std::vector<InstanceRec> recs(n);
     std::vector<InstanceBuildIn> bin(n);
     sc.accels.assign(n, nullptr);
+    sc.hInstances.assign(inst, inst + n);
     for(uint32_t i = 0; i < n; i++)
     {
         const mrb_accel_t& a = *inst[i].accel;
@@ -730,6 +741,7 @@ void BuildAccel(Context& ctx, mrb_accel_t& acc, const mrb_accel_desc& desc)
     const bool whole = (desc.rangeCount == 0 || desc.primRanges == nullptr);
     r.count = whole ? 1u : desc.rangeCount;
     acc.hLeafStart.assign(r.count + 1, 0u); acc.hPrimBegin.assign(r.count, 0u);
+    acc.vertexCount = desc.vertexCount; acc.triangleCount = desc.triangleCount;
     acc.hLmKey.assign(r.count, 0u); acc.hCull.assign(r.count, 0u);
     for(uint32_t i = 0; i < r.count; i++)
     {

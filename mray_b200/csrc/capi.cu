@@ -39,7 +39,7 @@ void BinaryPartition(Context& ctx, uint32_t* indicesOut, uint32_t* leftCount, co
 namespace mrb
 {
 void BuildScene(Context& ctx, mrb_scene_t& sc, const mrb_instance_desc* inst, uint32_t n);
-void TraceScene(Context& ctx, const mrb_scene_t& scn, bool anyHit, mrb_trace_mode mode,
+void TraceScene(Context& ctx, const SceneData& scn, bool anyHit, mrb_trace_mode mode,
                 mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, uint32_t* visibleBits,
                 mrb_ray_gmem* rays, const uint32_t* rayIndices, uint32_t rayCount);
 }
@@ -407,9 +407,11 @@ mrb_status mrb_renderer_create(mrb_context ctx, const mrb_render_desc* desc, mrb
 {
     return Guard(ctx, [&](mrb::Context& c)
     {
-        if(!desc || !out || !desc->accel) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        if(!desc || !out) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
         *out = nullptr;
-        if(!desc->accel->d.wideNodes) return Fail(c, MRB_ERR_UNSUPPORTED, "accelerator was built BINARY_ONLY");
+        if((desc->accel != nullptr) == (desc->scene != nullptr))
+            return Fail(c, MRB_ERR_INVALID_ARG, "exactly one of accel / scene must be set");
+        if(desc->accel && !desc->accel->d.wideNodes) return Fail(c, MRB_ERR_UNSUPPORTED, "accelerator was built BINARY_ONLY");
         if(desc->width == 0 || desc->height == 0 || desc->totalSPP == 0) return Fail(c, MRB_ERR_INVALID_ARG, "empty render");
         if(desc->sampleMode > 2) return Fail(c, MRB_ERR_INVALID_ARG, "unknown sampleMode");
         if(desc->rrRange[1] > 255) return Fail(c, MRB_ERR_INVALID_ARG, "rrRange[1] exceeds PathDataPack depth (u8)");
@@ -595,7 +597,7 @@ mrb_status mrb_scene_cast_rays(mrb_context ctx, mrb_scene scene, mrb_hit_key_pac
     if(!scene) return MRB_ERR_INVALID_ARG;
     return CastGeneric(ctx, false, hitKeys, metaHits, nullptr, rays, rayIndices, rayCount, totalRayCount, memspace,
         [&](mrb::Context& c, mrb_hit_key_pack* k, mrb_meta_hit* h, uint32_t* b, mrb_ray_gmem* r, const uint32_t* idx)
-        { mrb::TraceScene(c, *scene, false, mode, k, h, b, r, idx, rayCount); });
+        { mrb::TraceScene(c, scene->d, false, mode, k, h, b, r, idx, rayCount); });
 }
 
 mrb_status mrb_scene_cast_visibility_rays(mrb_context ctx, mrb_scene scene, uint32_t* isVisibleBits,
@@ -605,7 +607,7 @@ mrb_status mrb_scene_cast_visibility_rays(mrb_context ctx, mrb_scene scene, uint
     if(!scene) return MRB_ERR_INVALID_ARG;
     return CastGeneric(ctx, true, nullptr, nullptr, isVisibleBits, const_cast<mrb_ray_gmem*>(rays), rayIndices, rayCount, totalRayCount, memspace,
         [&](mrb::Context& c, mrb_hit_key_pack* k, mrb_meta_hit* h, uint32_t* b, mrb_ray_gmem* r, const uint32_t* idx)
-        { mrb::TraceScene(c, *scene, true, mode, k, h, b, r, idx, rayCount); });
+        { mrb::TraceScene(c, scene->d, true, mode, k, h, b, r, idx, rayCount); });
 }
 
 } // extern "C"

@@ -22,6 +22,8 @@
 #include "accel.cuh"
 #include <cfloat>
 #include <random>
+#include <stdexcept>
+#include <cstring>
 #include <vector>
 
 namespace mrb
@@ -30,6 +32,9 @@ namespace mrb
 void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode mode,
                mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, uint32_t* visibleBits,
                mrb_ray_gmem* rays, const uint32_t* rayIndices, uint32_t rayCount);
+void TraceScene(Context& ctx, const SceneData& scn, bool anyHit, mrb_trace_mode mode,
+                mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, uint32_t* visibleBits,
+                mrb_ray_gmem* rays, const uint32_t* rayIndices, uint32_t rayCount);
 size_t MultiPartitionTempBytes(uint32_t count, uint32_t batchBits);
 void MultiPartition(Context& ctx, uint32_t* keys, uint32_t* indices, uint32_t count,
                     const uint32_t dataBits[2], const uint32_t batchBits[2], bool onlySortForBatches,
@@ -93,16 +98,27 @@ struct Camera // CameraPinhole members (CamerasDefault.hpp:L8-36), tile-local
 
 struct EmissiveTri { float4 p0, e0, e1; float4 radiance; }; // p0.w = area, e0.w = twoSided, radiance.w unused
 
+// Per-instance shading inputs: the primitive group's arrays plus the instance transform
+// (PrimitiveC::GenerateSurface in local space + TransformContextSingle::Apply / ApplyN).
+struct RenderInstance
+{
+    const float*    positions;
+    const uint32_t* indices;
+    const float4*   vertexNormals;   // optional (xyz), nullptr = geometric
+    const uint32_t* lightOfPrim;     // prim index -> emissive triangle index or INVALID
+    float           transform[12];   // local -> world, row-major 3x4
+    float           invTransform[12];
+    uint32_t        identity;
+    uint32_t        pad[3];
+};
+
 struct RenderData
 {
-    // scene
-    const float*      positions;
-    const uint32_t*   indices;
-    const float4*     vertexNormals;   // optional (xyz), nullptr = geometric
-    PrimRanges        ranges;          // leaf -> prim; lmKey per range
+    // scene: one record per instance (a single record when rendering one accelerator)
+    const RenderInstance* instances;
+    uint32_t          sceneMode;       // 1 = hitKeys.accelKey holds the instance index
     const float4*     albedo;          // per material index
-    const EmissiveTri* lights;         // one per emissive triangle (MetaLight list)
-    const uint32_t*   lightOfPrim;     // prim index -> emissive triangle index or INVALID
+    const EmissiveTri* lights;         // one per emissive triangle (MetaLight list), world space
     uint32_t          lightCount;      // emissive triangles (+1 boundary light in the sampler)
     Camera            cam;
     uint32_t          width, height;
@@ -208,12 +224,26 @@ __global__ void __launch_bounds__(RTPB) KReload(RenderData d)
     d.rng[i] = rng.s;
 }
 
-__device__ __forceinline__ void LoadTriangle(const RenderData& d, uint32_t prim, Float3 p[3], uint32_t vi[3])
+__device__ __forceinline__ Float3 ApplyP(const float* m, Float3 p)
 {
-    vi[0] = d.indices[3 * size_t(prim)]; vi[1] = d.indices[3 * size_t(prim) + 1]; vi[2] = d.indices[3 * size_t(prim) + 2];
+    return F3(m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3],
+              m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7],
+              m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]);
+}
+// normals move with the inverse transpose (TransformContextSingle::ApplyN)
+__device__ __forceinline__ Float3 ApplyN(const float* inv, Float3 n)
+{
+    return F3(inv[0] * n.x + inv[4] * n.y + inv[8] * n.z,
+              inv[1] * n.x + inv[5] * n.y + inv[9] * n.z,
+              inv[2] * n.x + inv[6] * n.y + inv[10] * n.z);
+}
+
+__device__ __forceinline__ void LoadTriangle(const RenderInstance& in, uint32_t prim, Float3 p[3], uint32_t vi[3])
+{
+    vi[0] = in.indices[3 * size_t(prim)]; vi[1] = in.indices[3 * size_t(prim) + 1]; vi[2] = in.indices[3 * size_t(prim) + 2];
     #pragma unroll
     for(int k = 0; k < 3; k++)
-        p[k] = F3(d.positions[3 * size_t(vi[k])], d.positions[3 * size_t(vi[k]) + 1], d.positions[3 * size_t(vi[k]) + 2]);
+        p[k] = F3(in.positions[3 * size_t(vi[k])], in.positions[3 * size_t(vi[k]) + 1], in.positions[3 * size_t(vi[k]) + 2]);
 }
 
 // LightPrim::EmitViaHit / EmitViaSurfacePoint for a constant radiance (LightsDefault.hpp:L129-168)
@@ -272,17 +302,20 @@ __global__ void __launch_bounds__(RTPB) KShade(RenderData d)
     const float2 bary = *reinterpret_cast<const float2*>(d.hits + i);
     const uint32_t prim = keys.x & 0x0FFFFFFFu;
     const uint32_t lmKey = keys.y;
+    const RenderInstance& in = d.instances[d.sceneMode ? keys.w : 0u];
     Float3 p[3]; uint32_t vi[3];
-    LoadTriangle(d, prim, p, vi);
+    LoadTriangle(in, prim, p, vi);
     const float a = bary.x, b = bary.y, c = 1.0f - a - b;
-    const Float3 pos = p[0] * a + p[1] * b + p[2] * c;
+    Float3 pos = p[0] * a + p[1] * b + p[2] * c;
     const Float3 e0 = p[1] - p[0], e1 = p[2] - p[0];
-    Float3 geoN = Normalize(Cross(e0, e1));
+    Float3 geoN = Cross(e0, e1);
+    if(!in.identity) { pos = ApplyP(in.transform, pos); geoN = ApplyN(in.invTransform, geoN); }
+    geoN = Normalize(geoN);
 
     if(lmKey & 0x80000000u)
     {
         // ---------------- light hit: LightWorkFunctionWithNEE / LightWorkFunction ----------------
-        const EmissiveTri l = d.lights[d.lightOfPrim[prim]];
+        const EmissiveTri l = d.lights[in.lightOfPrim[prim]];
         bool count = true;
         if(d.sampleMode == 1u && type != RAY_CAMERA && type != RAY_SPECULAR) count = false;
         if(count)
@@ -318,10 +351,12 @@ __global__ void __launch_bounds__(RTPB) KShade(RenderData d)
     PCG32 rng{d.rng[i]};
     const bool backSide = Dot(geoN, Normalize(rd)) > 0.0f;
     Float3 shadeN = geoN;
-    if(d.vertexNormals)
+    if(in.vertexNormals)
     {
-        const float4 n0 = d.vertexNormals[vi[0]], n1 = d.vertexNormals[vi[1]], n2 = d.vertexNormals[vi[2]];
-        shadeN = Normalize(F3(n0.x, n0.y, n0.z) * a + F3(n1.x, n1.y, n1.z) * b + F3(n2.x, n2.y, n2.z) * c);
+        const float4 n0 = in.vertexNormals[vi[0]], n1 = in.vertexNormals[vi[1]], n2 = in.vertexNormals[vi[2]];
+        shadeN = F3(n0.x, n0.y, n0.z) * a + F3(n1.x, n1.y, n1.z) * b + F3(n2.x, n2.y, n2.z) * c;
+        if(!in.identity) shadeN = ApplyN(in.invTransform, shadeN);
+        shadeN = Normalize(shadeN);
     }
     if(backSide) { geoN = geoN * -1.0f; shadeN = shadeN * -1.0f; }
     const float4 alb4 = d.albedo[lmKey & 0x1FFFFFu];
@@ -423,6 +458,12 @@ __global__ void __launch_bounds__(RTPB) KShade(RenderData d)
     }
 }
 
+__global__ void KIndexInstances(InstanceRec* inst, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) inst[i].accelKey = i;
+}
+
 __global__ void __launch_bounds__(RTPB) KFinish(RenderData d)
 {
     const uint32_t i = blockIdx.x * RTPB + threadIdx.x;
@@ -477,6 +518,8 @@ struct mrb_renderer_t
     mrb::RenderData  d = {};
     mrb::DeviceBlock mem;
     mrb_accel        accel = nullptr;
+    mrb_scene        scene = nullptr;
+    mrb::SceneData   sceneData;        // scene->d with the renderer's instance records (accelKey = instance index)
     uint64_t         iterations = 0;
 };
 
@@ -487,9 +530,8 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
 {
     using namespace mrb;
     RenderData& d = r.d;
-    const AccelData& a = desc.accel->d;
-    r.accel = desc.accel;
-    d.positions = a.positions; d.indices = a.indices; d.ranges = a.ranges;
+    r.accel = desc.accel; r.scene = desc.scene;
+    d.sceneMode = desc.scene ? 1u : 0u;
     d.width = desc.width; d.height = desc.height;
     d.rrLo = desc.rrRange[0]; d.rrHi = desc.rrRange[1]; d.sampleMode = desc.sampleMode;
     d.pathLimit = uint64_t(desc.totalSPP) * desc.width * desc.height;
@@ -517,41 +559,82 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
     d.cam.bottomLeft = {bl.x, bl.y, bl.z}; d.cam.planeW = 2.0f * wh; d.cam.planeH = 2.0f * hh;
     d.cam.tNear = desc.nearFar[0]; d.cam.tFar = desc.nearFar[1];
 
-    // emissive triangle list (MetaLightArrayT::Construct: one meta light per emissive triangle), host side
-    std::vector<float> hpos(size_t(desc.vertexCount) * 3);
-    std::vector<uint32_t> hidx(size_t(desc.triangleCount) * 3);
-    MRB_CUDA_TRY(cudaMemcpyAsync(hpos.data(), a.positions, hpos.size() * 4, cudaMemcpyDeviceToHost, ctx.stream));
-    MRB_CUDA_TRY(cudaMemcpyAsync(hidx.data(), a.indices, hidx.size() * 4, cudaMemcpyDeviceToHost, ctx.stream));
-    MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
-    std::vector<EmissiveTri> lights;
-    std::vector<uint32_t> lightOfPrim(desc.triangleCount, INVALID_U32);
-    const mrb_accel_t& hacc = *desc.accel;
-    for(uint32_t rg = 0; rg < a.ranges.count; rg++)
-    {
-        uint32_t key = hacc.hLmKey[rg];
-        if(!(key & 0x80000000u)) continue;
-        uint32_t li = key & 0x1FFFFFu;
-        uint32_t count = hacc.hLeafStart[rg + 1] - hacc.hLeafStart[rg];
-        for(uint32_t k = 0; k < count; k++)
+    // instance list: the scene's instances, or one identity instance of the single accelerator
+    struct HostInst { const mrb_accel_t* acc; const float* m; const float* inv; bool identity; const float* normals; };
+    static const float IDENTITY[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    std::vector<HostInst> hinst;
+    if(desc.scene)
+        for(size_t k = 0; k < desc.scene->hInstances.size(); k++)
         {
-            uint32_t prim = hacc.hPrimBegin[rg] + k;
-            const float* p0 = &hpos[3 * size_t(hidx[3 * size_t(prim)])];
-            const float* p1 = &hpos[3 * size_t(hidx[3 * size_t(prim) + 1])];
-            const float* p2 = &hpos[3 * size_t(hidx[3 * size_t(prim) + 2])];
-            float e0[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]}, e1[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
-            float cx = e0[1] * e1[2] - e0[2] * e1[1], cy = e0[2] * e1[0] - e0[0] * e1[2], cz = e0[0] * e1[1] - e0[1] * e1[0];
-            float area = 0.5f * sqrtf(cx * cx + cy * cy + cz * cz);
-            EmissiveTri t;
-            t.p0 = make_float4(p0[0], p0[1], p0[2], area);
-            t.e0 = make_float4(e0[0], e0[1], e0[2], (desc.lightTwoSided && desc.lightTwoSided[li]) ? 1.0f : 0.0f);
-            t.e1 = make_float4(e1[0], e1[1], e1[2], 0.0f);
-            t.radiance = make_float4(desc.lightRadiance[3 * li], desc.lightRadiance[3 * li + 1], desc.lightRadiance[3 * li + 2], 0.f);
-            lightOfPrim[prim] = uint32_t(lights.size());
-            lights.push_back(t);
+            const mrb_instance_desc& id = desc.scene->hInstances[k];
+            hinst.push_back({id.accel, id.transform, id.invTransform, id.isIdentity != 0,
+                             desc.instanceVertexNormals ? desc.instanceVertexNormals[k] : nullptr});
+        }
+    else hinst.push_back({desc.accel, IDENTITY, IDENTITY, true, desc.vertexNormals});
+    const uint32_t instCount = uint32_t(hinst.size());
+
+    // emissive triangle list (MetaLightArrayT::Construct: one meta light per emissive triangle of every
+    // instance, in world space), host side
+    std::vector<EmissiveTri> lights;
+    std::vector<std::vector<uint32_t>> lightOfPrim(instCount);
+    {
+        std::vector<float> hpos; std::vector<uint32_t> hidx;
+        const mrb_accel_t* loaded = nullptr;
+        for(uint32_t k = 0; k < instCount; k++)
+        {
+            const mrb_accel_t& hacc = *hinst[k].acc;
+            const AccelData& a = hacc.d;
+            lightOfPrim[k].assign(hacc.triangleCount, INVALID_U32);
+            bool anyLight = false;
+            for(uint32_t rg = 0; rg < a.ranges.count; rg++) anyLight |= (hacc.hLmKey[rg] & 0x80000000u) != 0;
+            if(!anyLight) continue;
+            if(loaded != &hacc)
+            {
+                hpos.resize(size_t(hacc.vertexCount) * 3); hidx.resize(size_t(hacc.triangleCount) * 3);
+                MRB_CUDA_TRY(cudaMemcpyAsync(hpos.data(), a.positions, hpos.size() * 4, cudaMemcpyDeviceToHost, ctx.stream));
+                MRB_CUDA_TRY(cudaMemcpyAsync(hidx.data(), a.indices, hidx.size() * 4, cudaMemcpyDeviceToHost, ctx.stream));
+                MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
+                loaded = &hacc;
+            }
+            const float* m = hinst[k].m;
+            auto World = [&](const float* p, float* o)
+            {
+                if(hinst[k].identity) { o[0] = p[0]; o[1] = p[1]; o[2] = p[2]; return; }
+                for(int rrow = 0; rrow < 3; rrow++)
+                    o[rrow] = m[4 * rrow] * p[0] + m[4 * rrow + 1] * p[1] + m[4 * rrow + 2] * p[2] + m[4 * rrow + 3];
+            };
+            for(uint32_t rg = 0; rg < a.ranges.count; rg++)
+            {
+                uint32_t key = hacc.hLmKey[rg];
+                if(!(key & 0x80000000u)) continue;
+                uint32_t li = key & 0x1FFFFFu;
+                if(li >= desc.lightCount) throw std::runtime_error("light key index exceeds lightCount");
+                uint32_t count = hacc.hLeafStart[rg + 1] - hacc.hLeafStart[rg];
+                for(uint32_t q = 0; q < count; q++)
+                {
+                    uint32_t prim = hacc.hPrimBegin[rg] + q;
+                    float p0[3], p1[3], p2[3];
+                    World(&hpos[3 * size_t(hidx[3 * size_t(prim)])], p0);
+                    World(&hpos[3 * size_t(hidx[3 * size_t(prim) + 1])], p1);
+                    World(&hpos[3 * size_t(hidx[3 * size_t(prim) + 2])], p2);
+                    float e0[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]}, e1[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
+                    float cx = e0[1] * e1[2] - e0[2] * e1[1], cy = e0[2] * e1[0] - e0[0] * e1[2], cz = e0[0] * e1[1] - e0[1] * e1[0];
+                    float area = 0.5f * sqrtf(cx * cx + cy * cy + cz * cz);
+                    EmissiveTri t;
+                    t.p0 = make_float4(p0[0], p0[1], p0[2], area);
+                    t.e0 = make_float4(e0[0], e0[1], e0[2], (desc.lightTwoSided && desc.lightTwoSided[li]) ? 1.0f : 0.0f);
+                    t.e1 = make_float4(e1[0], e1[1], e1[2], 0.0f);
+                    t.radiance = make_float4(desc.lightRadiance[3 * li], desc.lightRadiance[3 * li + 1], desc.lightRadiance[3 * li + 2], 0.f);
+                    lightOfPrim[k][prim] = uint32_t(lights.size());
+                    lights.push_back(t);
+                }
+            }
         }
     }
     d.lightCount = uint32_t(lights.size());
 
+    std::vector<RenderInstance> hri(instCount);
+    InstanceRec* dSceneInst = nullptr;
     auto Layout = [&](MultiAlloc& ma)
     {
         const uint32_t P = d.slots;
@@ -564,8 +647,13 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
         d.counters = ma.Take<unsigned long long>(8);
         d.albedo = ma.Take<float4>(desc.materialCount ? desc.materialCount : 1);
         d.lights = ma.Take<EmissiveTri>(lights.size() ? lights.size() : 1);
-        d.lightOfPrim = ma.Take<uint32_t>(desc.triangleCount);
-        d.vertexNormals = desc.vertexNormals ? ma.Take<float4>(desc.vertexCount) : nullptr;
+        d.instances = ma.Take<RenderInstance>(instCount);
+        dSceneInst = desc.scene ? ma.Take<InstanceRec>(instCount) : nullptr;
+        for(uint32_t k = 0; k < instCount; k++)
+        {
+            hri[k].lightOfPrim = ma.Take<uint32_t>(hinst[k].acc->triangleCount);
+            hri[k].vertexNormals = hinst[k].normals ? ma.Take<float4>(hinst[k].acc->vertexCount) : nullptr;
+        }
         d.workKeys = ma.Take<uint32_t>(P); d.workIndices = ma.Take<uint32_t>(P); d.partTable = ma.Take<uint32_t>(32);
     };
     MultiAlloc sz(nullptr); Layout(sz);
@@ -580,14 +668,34 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
     MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<float4*>(d.albedo), halb.data(), halb.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx.stream));
     if(!lights.empty())
         MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<EmissiveTri*>(d.lights), lights.data(), lights.size() * sizeof(EmissiveTri), cudaMemcpyHostToDevice, ctx.stream));
-    MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<uint32_t*>(d.lightOfPrim), lightOfPrim.data(), lightOfPrim.size() * 4, cudaMemcpyHostToDevice, ctx.stream));
     std::vector<float4> hn;
-    if(desc.vertexNormals)
+    for(uint32_t k = 0; k < instCount; k++)
     {
-        hn.resize(desc.vertexCount);
-        for(uint32_t v = 0; v < desc.vertexCount; v++)
-            hn[v] = make_float4(desc.vertexNormals[3 * v], desc.vertexNormals[3 * v + 1], desc.vertexNormals[3 * v + 2], 0.f);
-        MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<float4*>(d.vertexNormals), hn.data(), hn.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx.stream));
+        const mrb_accel_t& hacc = *hinst[k].acc;
+        RenderInstance& ri = hri[k];
+        ri.positions = hacc.d.positions; ri.indices = hacc.d.indices;
+        memcpy(ri.transform, hinst[k].m, sizeof(ri.transform));
+        memcpy(ri.invTransform, hinst[k].inv, sizeof(ri.invTransform));
+        ri.identity = hinst[k].identity ? 1u : 0u;
+        MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<uint32_t*>(ri.lightOfPrim), lightOfPrim[k].data(), lightOfPrim[k].size() * 4, cudaMemcpyHostToDevice, ctx.stream));
+        if(hinst[k].normals)
+        {
+            hn.resize(hacc.vertexCount);
+            for(uint32_t v = 0; v < hacc.vertexCount; v++)
+                hn[v] = make_float4(hinst[k].normals[3 * v], hinst[k].normals[3 * v + 1], hinst[k].normals[3 * v + 2], 0.f);
+            MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<float4*>(ri.vertexNormals), hn.data(), hn.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx.stream));
+            MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream)); // hn is reused
+        }
+    }
+    MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<RenderInstance*>(d.instances), hri.data(), hri.size() * sizeof(RenderInstance), cudaMemcpyHostToDevice, ctx.stream));
+    if(desc.scene)
+    {
+        // the scene's instance records with accelKey = instance index, so the shading kernel finds the
+        // instance of a hit without a key lookup (world AABBs are filled by the scene build: device copy)
+        r.sceneData = desc.scene->d;
+        MRB_CUDA_TRY(cudaMemcpyAsync(dSceneInst, desc.scene->d.instances, sizeof(InstanceRec) * instCount, cudaMemcpyDeviceToDevice, ctx.stream));
+        MRB_LAUNCH(ctx, KIndexInstances, DivUp(instCount, 256u), 256, 0, dSceneInst, instCount);
+        r.sceneData.instances = dSceneInst;
     }
     // RNGGroupIndependent (Tracer/Random.cu:L661-720): mt19937(seed32) draws -> PermutedCG32::GenerateState
     uint32_t seed32 = uint32_t((desc.seed >> 32) ^ (desc.seed & 0xFFFFFFFFull));
@@ -612,7 +720,8 @@ void RenderIterate(Context& ctx, mrb_renderer_t& r, uint32_t iterations)
     for(uint32_t it = 0; it < iterations; it++)
     {
         MRB_LAUNCH(ctx, KReload, grid, RTPB, 0, d);
-        TraceRays(ctx, *r.accel, false, MRB_TRACE_WIDE, d.hitKeys, d.hits, nullptr, d.rays, nullptr, d.slots);
+        if(r.scene) TraceScene(ctx, r.sceneData, false, MRB_TRACE_WIDE, d.hitKeys, d.hits, nullptr, d.rays, nullptr, d.slots);
+        else TraceRays(ctx, *r.accel, false, MRB_TRACE_WIDE, d.hitKeys, d.hits, nullptr, d.rays, nullptr, d.slots);
         if(d.partitionRays)
         {
             const uint32_t dataBits[2] = {0u, d.matBits}, batchBits[2] = {d.matBits, d.matBits + 2u};
@@ -625,7 +734,8 @@ void RenderIterate(Context& ctx, mrb_renderer_t& r, uint32_t iterations)
         if(d.sampleMode != 0u)
         {
             MRB_CUDA_TRY(cudaMemsetAsync(d.visible, 0xFF, sizeof(uint32_t) * ((d.slots + 31) / 32), ctx.stream));
-            TraceRays(ctx, *r.accel, true, MRB_TRACE_WIDE, nullptr, nullptr, d.visible, d.shadowRays, nullptr, d.slots);
+            if(r.scene) TraceScene(ctx, r.sceneData, true, MRB_TRACE_WIDE, nullptr, nullptr, d.visible, d.shadowRays, nullptr, d.slots);
+            else TraceRays(ctx, *r.accel, true, MRB_TRACE_WIDE, nullptr, nullptr, d.visible, d.shadowRays, nullptr, d.slots);
         }
         MRB_LAUNCH(ctx, KFinish, grid, RTPB, 0, d);
         r.iterations++;

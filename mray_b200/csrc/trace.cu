@@ -970,7 +970,7 @@ void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode
 }
 
 
-void TraceScene(Context& ctx, const mrb_scene_t& scn, bool anyHit, mrb_trace_mode mode,
+void TraceScene(Context& ctx, const SceneData& scnData, bool anyHit, mrb_trace_mode mode,
                 mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, uint32_t* visibleBits,
                 mrb_ray_gmem* rays, const uint32_t* rayIndices, uint32_t rayCount)
 {
@@ -997,21 +997,21 @@ void TraceScene(Context& ctx, const mrb_scene_t& scn, bool anyHit, mrb_trace_mod
         const uint32_t fbGrid = uint32_t(ctx.smCount);
         if(anyHit)
         {
-            MRB_LAUNCH(ctx, KTraceWide2<true>, pgrid, TRACE_TPB, 0, scn.d, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, fbList, prm);
-            MRB_LAUNCH(ctx, KTraceBinary2<true>, fbGrid, TRACE_TPB, 0, scn.d, hitKeys, metaHits, visibleBits, rays, fbList, 0u, counters + 4);
+            MRB_LAUNCH(ctx, KTraceWide2<true>, pgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, fbList, prm);
+            MRB_LAUNCH(ctx, KTraceBinary2<true>, fbGrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, fbList, 0u, counters + 4);
         }
         else
         {
-            MRB_LAUNCH(ctx, KTraceWide2<false>, pgrid, TRACE_TPB, 0, scn.d, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, fbList, prm);
-            MRB_LAUNCH(ctx, KTraceBinary2<false>, fbGrid, TRACE_TPB, 0, scn.d, hitKeys, metaHits, visibleBits, rays, fbList, 0u, counters + 4);
+            MRB_LAUNCH(ctx, KTraceWide2<false>, pgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, fbList, prm);
+            MRB_LAUNCH(ctx, KTraceBinary2<false>, fbGrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, fbList, 0u, counters + 4);
         }
         ctx.lastFallbackCount = counters;
     }
     else
     {
         const uint32_t bgrid = min(grid, uint32_t(ctx.smCount) * 16u);
-        if(anyHit) MRB_LAUNCH(ctx, KTraceBinary2<true>, bgrid, TRACE_TPB, 0, scn.d, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, nullptr);
-        else       MRB_LAUNCH(ctx, KTraceBinary2<false>, bgrid, TRACE_TPB, 0, scn.d, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, nullptr);
+        if(anyHit) MRB_LAUNCH(ctx, KTraceBinary2<true>, bgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, nullptr);
+        else       MRB_LAUNCH(ctx, KTraceBinary2<false>, bgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, nullptr);
         ctx.lastFallbackCount = nullptr;
     }
 }

@@ -18,6 +18,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <array>
+#include <cmath>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -44,6 +46,7 @@ struct LightGroupB200
     std::string type; bool committed = false; uint32_t primGroup = 0;
     std::vector<Vector3> radiance; std::vector<uint8_t> twoSided; std::vector<uint32_t> primBatch;
 };
+struct TransGroupB200 { std::string type; bool committed = false; std::vector<Matrix3x4> matrices; };
 struct CamGroupB200 { std::string type; bool committed = false; std::vector<Vector4> fovPlanes; std::vector<Vector3> gaze, position, up; };
 struct RendererB200
 {
@@ -51,16 +54,43 @@ struct RendererB200
     uint32_t totalSPP = 16384, burstSize = 1, sampleMode = 0; Vector2ui rrRange = Vector2ui(4, 20);
 };
 
+// Inverse of an affine 3x4 matrix by Laplace expansion, the arithmetic of Matrix3x4T::Inverse
+// (Core/Matrix.hpp:L853-903) term for term, EXCEPT element (1,2): the reference writes +s1 where the
+// cofactor is -s1 (Matrix.hpp:L892), which only cancels when m00*m12 == m02*m10 (axis-aligned scales,
+// rotations about z) and otherwise yields a matrix that is not the inverse. The corrected sign is used
+// here; for every matrix the reference inverts correctly the result is bit-identical.
+std::array<float, 12> InverseAffine(const Matrix3x4& mat)
+{
+    float m[12];
+    for(unsigned r = 0; r < 3; r++) for(unsigned c = 0; c < 4; c++) m[4 * r + c] = mat(r, c);
+    auto Det2x2 = [](float m00, float m01, float m10, float m11) { return std::fma(m00, m11, -m01 * m10); };
+    float s0 = Det2x2(m[0], m[1], m[4], m[5]), s1 = Det2x2(m[0], m[2], m[4], m[6]), s2 = Det2x2(m[0], m[3], m[4], m[7]);
+    float s3 = Det2x2(m[1], m[2], m[5], m[6]), s4 = Det2x2(m[1], m[3], m[5], m[7]), s5 = Det2x2(m[2], m[3], m[6], m[7]);
+    float c5 = m[10], c4 = m[9], c2 = m[8];
+    float det = ((s0 * c5) - (s1 * c4) + (s3 * c2));
+    float detInv = 1.0f / det;
+    std::array<float, 12> inv =
+    {
+        (+m[5] * c5 - m[6] * c4), (-m[1] * c5 + m[2] * c4), s3, (-m[9] * s5 + m[10] * s4 - m[11] * s3),
+        (-m[4] * c5 + m[6] * c2), (+m[0] * c5 - m[2] * c2), -s1, (+m[8] * s5 - m[10] * s2 + m[11] * s1),
+        (+m[4] * c4 - m[5] * c2), (-m[0] * c4 + m[1] * c2), s0, (-m[8] * s4 + m[9] * s2 - m[11] * s0)
+    };
+    for(float& v : inv) v *= detInv;
+    return inv;
+}
+
 class TracerB200 final : public TracerI
 {
     TracerParameters params;
     mrb_context ctx = nullptr;
-    mrb_accel accel = nullptr;
+    mrb_accel accel = nullptr;           // all (T)Identity surfaces
+    std::vector<mrb_accel> instAccels;   // one per distinct (T)Single transform in use
+    mrb_scene scene = nullptr;           // set when any surface is transformed
     mrb_renderer renderer = nullptr;
     std::mutex mtx; // scene-loading calls arrive concurrently from pool threads (TracerBase.h:L97-130)
 
     std::vector<PrimGroupB200> prims; std::vector<MatGroupB200> mats; std::vector<LightGroupB200> lights;
-    std::vector<CamGroupB200> cams; std::vector<RendererB200> renderers;
+    std::vector<CamGroupB200> cams; std::vector<RendererB200> renderers; std::vector<TransGroupB200> transforms;
     std::vector<SurfaceParams> surfaces; std::vector<LightSurfaceParams> lightSurfaces;
     std::vector<CameraSurfaceParams> camSurfaces; std::vector<VolumeParams> volumes;
     LightSurfaceParams boundary{};
@@ -88,18 +118,27 @@ class TracerB200 final : public TracerI
         mats.push_back(MatGroupB200{std::string(TracerConstants::PassthroughMatName), true});
         lights.push_back(LightGroupB200{std::string(TracerConstants::NullLightName), true});
         lights[0].radiance.push_back(Vector3::Zero()); lights[0].twoSided.push_back(0); lights[0].primBatch.push_back(0);
+        transforms.push_back(TransGroupB200{std::string(TracerConstants::IdentityTransName), true});
+        transforms[0].matrices.push_back(Matrix3x4::Identity());
+    }
+    void ReleaseAccels()
+    {
+        if(scene) { mrb_scene_destroy(ctx, scene); scene = nullptr; }
+        for(mrb_accel a : instAccels) mrb_accel_destroy(ctx, a);
+        instAccels.clear();
+        if(accel) { mrb_accel_destroy(ctx, accel); accel = nullptr; }
     }
     ~TracerB200() override
     {
         if(renderer) mrb_renderer_destroy(ctx, renderer);
-        if(accel) mrb_accel_destroy(ctx, accel);
+        ReleaseAccels();
         mrb_context_destroy(ctx);
     }
 
     // ------------------------------- generic -------------------------------
     TypeNameList PrimitiveGroups() const override { return {"(P)Triangle"sv, "(P)Empty"sv}; }
     TypeNameList MaterialGroups() const override { return {"(Mt)Lambert"sv, "(Mt)Passthrough"sv}; }
-    TypeNameList TransformGroups() const override { return {"(T)Identity"sv}; }
+    TypeNameList TransformGroups() const override { return {"(T)Identity"sv, "(T)Single"sv}; }
     TypeNameList CameraGroups() const override { return {"(C)Pinhole"sv}; }
     TypeNameList MediumGroups() const override { return {"(Md)Vacuum"sv}; }
     TypeNameList LightGroups() const override { return {"(L)Null"sv, "(L)Prim(P)Triangle"sv}; }
@@ -152,7 +191,13 @@ class TracerB200 final : public TracerI
         };
     }
     MediumAttributeInfoList AttributeInfoMedium(std::string_view) const override { return {}; }
-    TransAttributeInfoList AttributeInfoTrans(std::string_view) const override { return {}; }
+    TransAttributeInfoList AttributeInfoTrans(std::string_view name) const override
+    {
+        using enum MRayDataEnum; using enum AttributeIsArray; using enum AttributeOptionality;
+        if(name != "(T)Single"sv) return {};
+        // Tracer/TransformsDefault.cu:L27-37 (declared 4x4; the loader pushes Matrix3x4, SceneLoaderMRay.cpp:L492-576)
+        return TransAttributeInfoList{TransAttributeInfo("Transform", MRayDataTypeRT(MR_MATRIX_4x4), IS_SCALAR, MR_MANDATORY)};
+    }
     RendererAttributeInfoList AttributeInfoRenderer(std::string_view name) const override
     {
         using enum MRayDataEnum; using enum AttributeIsArray; using enum AttributeOptionality;
@@ -171,14 +216,14 @@ class TracerB200 final : public TracerI
     CamAttributeInfoList AttributeInfo(CameraGroupId id) const override { return AttributeInfoCam(Get(cams, Raw(id), "CameraGroup").type); }
     MediumAttributeInfoList AttributeInfo(MediumGroupId) const override { return {}; }
     MatAttributeInfoList AttributeInfo(MatGroupId id) const override { return AttributeInfoMat(Get(mats, Raw(id), "MaterialGroup").type); }
-    TransAttributeInfoList AttributeInfo(TransGroupId) const override { return {}; }
+    TransAttributeInfoList AttributeInfo(TransGroupId id) const override { return AttributeInfoTrans(Get(transforms, Raw(id), "TransformGroup").type); }
     LightAttributeInfoList AttributeInfo(LightGroupId id) const override { return AttributeInfoLight(Get(lights, Raw(id), "LightGroup").type); }
     RendererAttributeInfoList AttributeInfo(RendererId id) const override { return AttributeInfoRenderer(Get(renderers, Raw(id), "Renderer").type); }
     std::string TypeName(PrimGroupId id) const override { return Get(prims, Raw(id), "PrimitiveGroup").type; }
     std::string TypeName(CameraGroupId id) const override { return Get(cams, Raw(id), "CameraGroup").type; }
     std::string TypeName(MediumGroupId) const override { return std::string(TracerConstants::VacuumMediumName); }
     std::string TypeName(MatGroupId id) const override { return Get(mats, Raw(id), "MaterialGroup").type; }
-    std::string TypeName(TransGroupId) const override { return std::string(TracerConstants::IdentityTransName); }
+    std::string TypeName(TransGroupId id) const override { return Get(transforms, Raw(id), "TransformGroup").type; }
     std::string TypeName(LightGroupId id) const override { return Get(lights, Raw(id), "LightGroup").type; }
     std::string TypeName(RendererId id) const override { return Get(renderers, Raw(id), "Renderer").type; }
 
@@ -287,12 +332,38 @@ class TracerB200 final : public TracerI
 
     // ------------------------------- transforms -------------------------------
     TransGroupId CreateTransformGroup(std::string typeName) override
-    { throw MRayError("Unable to find generator for {} (round 1: (T)Identity only)", typeName); }
-    TransformId ReserveTransformation(TransGroupId, AttributeCountList) override { throw MRayError("only (T)Identity exists"); }
-    TransformIdList ReserveTransformations(TransGroupId, std::vector<AttributeCountList>) override { throw MRayError("only (T)Identity exists"); }
-    void CommitTransReservations(TransGroupId) override {}
-    bool IsTransCommitted(TransGroupId) const override { return true; }
-    void PushTransAttribute(TransGroupId, CommonIdRange, uint32_t, TransientData) override { throw MRayError("only (T)Identity exists"); }
+    {
+        std::lock_guard lk(mtx);
+        if(typeName != "(T)Single") throw MRayError("Unable to find generator for {}", typeName);
+        transforms.push_back(TransGroupB200{typeName});
+        return TransGroupId(uint32_t(transforms.size() - 1));
+    }
+    TransformId ReserveTransformation(TransGroupId g, AttributeCountList c) override { return ReserveTransformations(g, {c}).front(); }
+    TransformIdList ReserveTransformations(TransGroupId g, std::vector<AttributeCountList> counts) override
+    {
+        std::lock_guard lk(mtx);
+        TransGroupB200& tg = Get(transforms, Raw(g), "TransformGroup");
+        if(Raw(g) == 0 || tg.committed) throw MRayError("{}: reservations are already committed", tg.type);
+        TransformIdList out;
+        for(size_t i = 0; i < counts.size(); i++)
+        {
+            tg.matrices.push_back(Matrix3x4::Identity());
+            out.push_back(TransformId((Raw(g) << TRANS_ID_BITS) | uint32_t(tg.matrices.size() - 1)));
+        }
+        return out;
+    }
+    void CommitTransReservations(TransGroupId g) override { Get(transforms, Raw(g), "TransformGroup").committed = true; }
+    bool IsTransCommitted(TransGroupId g) const override { return Get(transforms, Raw(g), "TransformGroup").committed; }
+    void PushTransAttribute(TransGroupId g, CommonIdRange range, uint32_t attributeIndex, TransientData data) override
+    {
+        TransGroupB200& tg = Get(transforms, Raw(g), "TransformGroup");
+        if(Raw(g) == 0) throw MRayError("(T)Identity has no attributes");
+        if(attributeIndex != 0) throw MRayError("{:s}: Unknown AttributeIndex {:d}", tg.type, attributeIndex);
+        uint32_t lo = range[0] & ((1u << TRANS_ID_BITS) - 1u), hi = range[1] & ((1u << TRANS_ID_BITS) - 1u);
+        Span<const Matrix3x4> m = data.AccessAs<const Matrix3x4>();
+        if(hi >= tg.matrices.size() || m.size() != size_t(hi - lo + 1)) throw MRayError("{}: transform range / data size mismatch", tg.type);
+        for(uint32_t i = lo; i <= hi; i++) tg.matrices[i] = m[i - lo];
+    }
 
     // ------------------------------- lights -------------------------------
     LightGroupId CreateLightGroup(std::string typeName, PrimGroupId pg) override
@@ -400,9 +471,19 @@ class TracerB200 final : public TracerI
     SurfaceCommitResult CommitSurfaces() override
     {
         // TracerBase::CommitSurfaces (Tracer/TracerBase.cpp:L1529-1674) + BaseAccelerator::Construct:
-        // every surface here has the identity transform, so they become the prim ranges of one accelerator.
+        // surfaces sharing a transform become the prim ranges of one accelerator; (T)Identity-only scenes
+        // are a single accelerator, anything else a two-level scene with one instance per transform.
         if(Raw(boundary.lightId) != 0) throw MRayError("round 1: the boundary light must be (L)Null");
-        std::vector<uint32_t> ranges, lmKeys; std::vector<uint8_t> cull;
+        struct Group { uint32_t transformId; std::vector<uint32_t> ranges, lmKeys; std::vector<uint8_t> cull; };
+        std::vector<Group> groups;
+        auto GroupOf = [&](TransformId t) -> Group&
+        {
+            for(Group& g : groups) if(g.transformId == Raw(t)) return g;
+            const TransGroupB200& tg = Get(transforms, Raw(t) >> TRANS_ID_BITS, "TransformGroup");
+            if((Raw(t) & ((1u << TRANS_ID_BITS) - 1u)) >= tg.matrices.size()) throw MRayError("Unable to find Transform({})", Raw(t));
+            groups.push_back(Group{Raw(t), {}, {}, {}});
+            return groups.back();
+        };
         flatAlbedo.clear(); flatLightRadiance.clear(); flatLightTwoSided.clear();
         int32_t pgUsed = -1;
         auto UsePrimGroup = [&](uint32_t g)
@@ -424,50 +505,85 @@ class TracerB200 final : public TracerI
         };
         for(const SurfaceParams& s : surfaces)
         {
-            if(Raw(s.transformId) != 0) throw MRayError("round 1: surfaces must use (T)Identity");
+            Group& grp = GroupOf(s.transformId);
             for(size_t k = 0; k < s.primBatches.size(); k++)
             {
                 uint32_t g = Raw(s.primBatches[k]) >> PRIM_ID_BITS, bi = Raw(s.primBatches[k]) & ((1u << PRIM_ID_BITS) - 1u);
                 UsePrimGroup(g);
                 const PrimBatch& pb = Get(Get(prims, g, "PrimitiveGroup").batches, bi, "PrimitiveBatch");
-                ranges.insert(ranges.end(), {pb.primOffset, pb.primOffset + pb.primCount});
-                lmKeys.push_back(FlatMat(s.materials[k]));
-                cull.push_back(s.cullFaceFlags[k] ? 1 : 0);
+                grp.ranges.insert(grp.ranges.end(), {pb.primOffset, pb.primOffset + pb.primCount});
+                grp.lmKeys.push_back(FlatMat(s.materials[k]));
+                grp.cull.push_back(s.cullFaceFlags[k] ? 1 : 0);
             }
         }
         for(const LightSurfaceParams& ls : lightSurfaces)
         {
-            if(Raw(ls.transformId) != 0) throw MRayError("round 1: light surfaces must use (T)Identity");
+            Group& grp = GroupOf(ls.transformId);
             const LightGroupB200& lg = Get(lights, Raw(ls.lightId) >> MAT_ID_BITS, "LightGroup");
             uint32_t li = Raw(ls.lightId) & ((1u << MAT_ID_BITS) - 1u);
             if(li >= lg.radiance.size()) throw MRayError("Unable to find Light({})", Raw(ls.lightId));
             UsePrimGroup(lg.primGroup);
             const PrimBatch& pb = Get(Get(prims, lg.primGroup, "PrimitiveGroup").batches, lg.primBatch[li], "PrimitiveBatch");
-            ranges.insert(ranges.end(), {pb.primOffset, pb.primOffset + pb.primCount});
-            lmKeys.push_back(0x80000000u | uint32_t(flatLightTwoSided.size()));
-            cull.push_back(0);
+            grp.ranges.insert(grp.ranges.end(), {pb.primOffset, pb.primOffset + pb.primCount});
+            grp.lmKeys.push_back(0x80000000u | uint32_t(flatLightTwoSided.size()));
+            grp.cull.push_back(0);
             flatLightRadiance.insert(flatLightRadiance.end(), {lg.radiance[li][0], lg.radiance[li][1], lg.radiance[li][2]});
             flatLightTwoSided.push_back(lg.twoSided[li]);
         }
-        if(pgUsed < 0 || lmKeys.empty()) throw MRayError("empty scene");
+        if(pgUsed < 0 || groups.empty()) throw MRayError("empty scene");
         flatPrimGroup = uint32_t(pgUsed);
         const PrimGroupB200& pg = prims[flatPrimGroup];
-        if(accel) { mrb_accel_destroy(ctx, accel); accel = nullptr; }
-        mrb_accel_desc d = {};
-        d.positions = reinterpret_cast<const float*>(pg.positions.data()); d.vertexCount = pg.vertexTotal;
-        d.indices = reinterpret_cast<const uint32_t*>(pg.indices.data()); d.triangleCount = pg.primTotal;
-        d.memspace = MRB_MEM_HOST; d.primGroupId = flatPrimGroup;
-        d.rangeCount = uint32_t(lmKeys.size()); d.primRanges = ranges.data();
-        d.lightOrMatKeys = lmKeys.data(); d.cullBackface = cull.data(); d.flags = MRB_BUILD_DEFAULT;
-        Check(mrb_accel_build(ctx, &d, &accel));
-        mrb_accel_info info; Check(mrb_accel_get_info(ctx, accel, &info));
+        ReleaseAccels();
+        auto BuildGroup = [&](const Group& g)
+        {
+            mrb_accel_desc d = {};
+            d.positions = reinterpret_cast<const float*>(pg.positions.data()); d.vertexCount = pg.vertexTotal;
+            d.indices = reinterpret_cast<const uint32_t*>(pg.indices.data()); d.triangleCount = pg.primTotal;
+            d.memspace = MRB_MEM_HOST; d.primGroupId = flatPrimGroup;
+            d.rangeCount = uint32_t(g.lmKeys.size()); d.primRanges = g.ranges.data();
+            d.lightOrMatKeys = g.lmKeys.data(); d.cullBackface = g.cull.data(); d.flags = MRB_BUILD_DEFAULT;
+            mrb_accel a = nullptr;
+            Check(mrb_accel_build(ctx, &d, &a));
+            return a;
+        };
+        AABB3 aabb;
+        if(groups.size() == 1 && groups[0].transformId == 0)
+        {
+            accel = BuildGroup(groups[0]);
+            mrb_accel_info info; Check(mrb_accel_get_info(ctx, accel, &info));
+            aabb = AABB3(Vector3(info.aabb[0], info.aabb[1], info.aabb[2]), Vector3(info.aabb[3], info.aabb[4], info.aabb[5]));
+        }
+        else
+        {
+            std::vector<mrb_instance_desc> inst(groups.size());
+            for(size_t k = 0; k < groups.size(); k++)
+            {
+                mrb_accel a = BuildGroup(groups[k]);
+                if(groups[k].transformId == 0) accel = a; else instAccels.push_back(a);
+                const uint32_t tid = groups[k].transformId;
+                const Matrix3x4& m = transforms[tid >> TRANS_ID_BITS].matrices[tid & ((1u << TRANS_ID_BITS) - 1u)];
+                const std::array<float, 12> inv = InverseAffine(m);  // KCInvertTransforms (Tracer/TransformC.h:L119-123)
+                mrb_instance_desc& d = inst[k];
+                d = {};
+                d.accel = a;
+                for(unsigned r = 0; r < 3; r++) for(unsigned c = 0; c < 4; c++)
+                { d.transform[4 * r + c] = m(r, c); d.invTransform[4 * r + c] = inv[4 * r + c]; }
+                d.isIdentity = (tid == 0) ? 1 : 0;
+                d.transformKey = tid; d.accelKey = uint32_t(k);
+            }
+            Check(mrb_scene_build(ctx, inst.data(), uint32_t(inst.size()), &scene));
+            float box[6];
+            Check(mrb_scene_export_tlas(ctx, scene, nullptr, box, nullptr, nullptr, nullptr, nullptr));
+            aabb = AABB3(Vector3(box[0], box[1], box[2]), Vector3(box[3], box[4], box[5]));
+        }
         return SurfaceCommitResult
         {
-            .aabb = AABB3(Vector3(info.aabb[0], info.aabb[1], info.aabb[2]), Vector3(info.aabb[3], info.aabb[4], info.aabb[5])),
+            .aabb = aabb,
             .instanceCount = surfaces.size() + lightSurfaces.size(),
-            .acceleratorCount = 1
+            .acceleratorCount = uint32_t(groups.size())
         };
     }
+
     CameraTransform GetCamTransform(CamSurfaceId id) const override
     {
         const CameraSurfaceParams& cs = Get(camSurfaces, Raw(id), "CameraSurface");
@@ -513,7 +629,7 @@ class TracerB200 final : public TracerI
     RenderBufferInfo StartRender(RendererId id, CamSurfaceId camSurf, RenderImageParams rip, Optional<uint32_t> logic0, Optional<uint32_t>) override
     {
         if(!sem) throw MRayError("Render environment is not set properly! Please provide a semaphore to the tracer.");
-        if(!accel) throw MRayError("CommitSurfaces must be called before StartRender");
+        if(!accel && !scene) throw MRayError("CommitSurfaces must be called before StartRender");
         const RendererB200& r = Get(renderers, Raw(id), "Renderer");
         const CameraSurfaceParams& cs = Get(camSurfaces, Raw(camSurf), "CameraSurface");
         const CamGroupB200& cg = Get(cams, Raw(cs.cameraId) >> CAM_ID_BITS, "CameraGroup");
@@ -523,9 +639,11 @@ class TracerB200 final : public TracerI
         Vector2ui tile = rip.regionMax - rip.regionMin;
         if(tile != rip.resolution) throw MRayError("round 1: the render region must be the whole image");
         mrb_render_desc d = {};
-        d.accel = accel; d.vertexCount = pg.vertexTotal; d.triangleCount = pg.primTotal;
         bool hasNormals = std::any_of(pg.normals.begin(), pg.normals.end(), [](const Vector3& n) { return n != Vector3::Zero(); });
-        d.vertexNormals = hasNormals ? reinterpret_cast<const float*>(pg.normals.data()) : nullptr;
+        const float* normals = hasNormals ? reinterpret_cast<const float*>(pg.normals.data()) : nullptr;
+        std::vector<const float*> instNormals((accel ? 1 : 0) + instAccels.size(), normals);
+        if(scene) { d.scene = scene; d.instanceVertexNormals = instNormals.data(); }
+        else { d.accel = accel; d.vertexCount = pg.vertexTotal; d.triangleCount = pg.primTotal; d.vertexNormals = normals; }
         d.materialCount = uint32_t(flatAlbedo.size() / 3); d.albedo = flatAlbedo.data();
         d.lightCount = uint32_t(flatLightTwoSided.size()); d.lightRadiance = flatLightRadiance.data(); d.lightTwoSided = flatLightTwoSided.data();
         for(int k = 0; k < 3; k++) { d.camPosition[k] = cg.position[ci][k]; d.camGaze[k] = cg.gaze[ci][k]; d.camUp[k] = cg.up[ci][k]; }

@@ -46,6 +46,9 @@ struct DriverScene
     float           camPos[3], camGaze[3], camUp[3];
     float           fovXY[2];           // radians
     float           nearFar[2];
+    // optional: batchCount row-major 3x4 local->world matrices; every batch then gets its own (T)Single
+    // transform (positions are local-space). NULL = all surfaces use (T)Identity.
+    const float*    batchTransforms;
 };
 
 struct DriverRender
@@ -275,6 +278,26 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
                 tracer->PushCamAttribute(cg, range, a, std::move(d));
             }
         }
+        // ---- transforms ----
+        std::vector<TransformId> batchTrans(sc->batchCount, TracerConstants::IdentityTransformId);
+        if(sc->batchTransforms)
+        {
+            TransGroupId tg = tracer->CreateTransformGroup("(T)Single");
+            std::vector<AttributeCountList> tCounts(sc->batchCount);
+            for(auto& c : tCounts) { c = AttributeCountList(StaticVecSize(1)); c[0] = 1; }
+            TransformIdList tids = tracer->ReserveTransformations(tg, tCounts);
+            tracer->CommitTransReservations(tg);
+            std::vector<Matrix3x4> ms;
+            for(uint32_t b = 0; b < sc->batchCount; b++)
+            {
+                const float* m = sc->batchTransforms + 12 * size_t(b);
+                ms.push_back(Matrix3x4(Vector4(m[0], m[1], m[2], m[3]), Vector4(m[4], m[5], m[6], m[7]), Vector4(m[8], m[9], m[10], m[11])));
+                batchTrans[b] = tids[b];
+            }
+            TransientData d(std::in_place_type_t<Matrix3x4>{}, ms.size());
+            d.Push(Span<const Matrix3x4>(ms.data(), ms.size()));
+            tracer->PushTransAttribute(tg, CommonIdRange(std::bit_cast<CommonId>(tids.front()), std::bit_cast<CommonId>(tids.back())), 0, std::move(d));
+        }
         // ---- surfaces ----
         for(uint32_t b = 0; b < sc->batchCount; b++)
         {
@@ -282,14 +305,15 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
             SurfaceParams sp;
             sp.primBatches.push_back(batches[b]);
             sp.materials.push_back(mats[size_t(sc->batchMaterial[b])]);
-            sp.transformId = TracerConstants::IdentityTransformId;
+            sp.transformId = batchTrans[b];
             sp.alphaMaps.push_back(std::nullopt);
             sp.cullFaceFlags.push_back(false);
             sp.volumes.push_back(TracerConstants::InvalidVolume);
             tracer->CreateSurface(sp);
         }
-        for(uint32_t l = 0; l < sc->lightCount; l++)
-            tracer->CreateLightSurface(LightSurfaceParams{lights[l], TracerConstants::IdentityTransformId, {}});
+        for(uint32_t b = 0; b < sc->batchCount; b++)
+            if(sc->batchLight[b] >= 0)
+                tracer->CreateLightSurface(LightSurfaceParams{lights[size_t(sc->batchLight[b])], batchTrans[b], {}});
         CamSurfaceId camSurf = tracer->CreateCameraSurface(CameraSurfaceParams{cam, TracerConstants::IdentityTransformId, {}});
         tracer->SetBoundarySurface(TracerConstants::NullLightId, TracerConstants::IdentityTransformId);
         VolumeId bVol = tracer->RegisterVolume(VolumeParams{TracerConstants::VacuumMediumId,

@@ -163,7 +163,7 @@ class _DriverScene(C.Structure):
                 ("materialCount", C.c_uint32), ("albedo", C.c_void_p),
                 ("lightCount", C.c_uint32), ("radiance", C.c_void_p),
                 ("camPos", C.c_float * 3), ("camGaze", C.c_float * 3), ("camUp", C.c_float * 3),
-                ("fovXY", C.c_float * 2), ("nearFar", C.c_float * 2)]
+                ("fovXY", C.c_float * 2), ("nearFar", C.c_float * 2), ("batchTransforms", C.c_void_p)]
 
 
 class _DriverRender(C.Structure):
@@ -206,8 +206,10 @@ def batched_scene(positions, indices, tri_material, normals=None):
 
 def driver_render(dll_path, batched, albedo, light_material, radiance, camera, width, height, spp,
                   renderer="PathTracerRGB", sample_mode="WithNEEAndMIS", rr_range=(2, 20), seed=0,
-                  accel_mode=1, threads=0, parallel_hint=0, near_far=(0.01, 1000.0), driver_flavour=""):
+                  accel_mode=1, threads=0, parallel_hint=0, near_far=(0.01, 1000.0), driver_flavour="",
+                  batch_transforms=None):
     """Renders through TracerI. `light_material`: material id whose batch is the prim-backed light.
+    batch_transforms: optional [batch, 3, 4] local->world matrices ((T)Single per batch; positions local).
     Returns (image[h,w,3] float32 with row 0 = bottom, weight[h,w], stats dict)."""
     L = C.CDLL(os.path.join(ORACLE_DIR, "_ref", f"libtracer_driver{driver_flavour}.so"))
     L.tracer_driver_render.restype = C.c_int
@@ -230,6 +232,9 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
     fy = np.deg2rad(camera["fov_y_deg"])
     fx = 2 * np.arctan(np.tan(fy / 2) * width / height)
     sc.fovXY = (C.c_float * 2)(fx, fy); sc.nearFar = (C.c_float * 2)(*near_far)
+    if batch_transforms is not None:
+        bt = np.ascontiguousarray(batch_transforms, np.float32).reshape(len(mats), 12)
+        keep.append(bt); sc.batchTransforms = bt.ctypes.data
     rd = _DriverRender(renderer.encode(), width, height, spp, sample_mode.encode(), (C.c_uint32 * 2)(*rr_range), seed,
                        accel_mode, parallel_hint, threads)
     img = np.zeros((height, width, 3), np.float32)

@@ -31,3 +31,37 @@ def test_cornell_through_tracer_interface():
     assert np.allclose(img[mask].mean(axis=0), ref[mask].mean(axis=0), rtol=0.02)
     # two independent 4096-spp estimates of this scene differ by relMSE ~ 3.8e-3 (oracle vs oracle)
     assert float(np.mean((img - ref) ** 2 / (ref ** 2 + 1e-2))) < 6e-3
+
+
+@pytest.mark.skipif(not (os.path.exists(PLUGIN) and O.driver_available()), reason="plugin / driver were not prebuilt")
+def test_cornell_with_single_transforms_through_tracer_interface():
+    """Every batch is uploaded in its own local space with a (T)Single transform that puts it back: the
+    plugin commits a two-level scene (one instance per transform) and the image matches the flat oracle."""
+    from test_gpu_render import _rigid
+    c = scenes.cornell_box()
+    b = O.batched_scene(c["positions"], c["indices"], c["material"])
+    rng = np.random.default_rng(17)
+    nb = len(b["materials"])
+    mats34 = np.stack([_rigid(rng) for _ in range(nb)])
+    pos = b["positions"].astype(np.float64).copy()
+    for k in range(nb):
+        lo, hi = int(b["vertex_offsets"][k]), int(b["vertex_offsets"][k + 1])
+        inv = np.linalg.inv(np.vstack([mats34[k], [0, 0, 0, 1]]))
+        pos[lo:hi] = pos[lo:hi] @ inv[:3, :3].T + inv[:3, 3]
+        # similarity transforms: normals rotate with the inverse transpose; local normal = R^T n (up to scale)
+        n = b["normals"][lo:hi].astype(np.float64) @ mats34[k][:, :3]
+        b["normals"][lo:hi] = (n / np.linalg.norm(n, axis=1, keepdims=True)).astype(np.float32)
+    b["positions"] = np.ascontiguousarray(pos, np.float32)
+    res, spp = 32, 4096
+    img, w, st = O.driver_render(PLUGIN, b, c["albedo"], 3, c["radiance"], c["camera"], res, res, spp,
+                                 sample_mode="WithNEEAndMIS", rr_range=(2, 20), seed=2, batch_transforms=mats34)
+    assert np.allclose(w, spp, rtol=1e-3)
+    # instance world boxes are the transformed LOCAL boxes (8 corners), so the scene box encloses the true one
+    box = np.array(st["aabb"])
+    assert np.all(box[:3] <= np.array([-1.0, 0.0, -1.0]) + 1e-4) and np.all(box[3:] >= np.array([1.0, 2.0, 1.0]) - 1e-4)
+    assert np.all(np.abs(box) < 4.0)
+    tm = np.where(c["material"] == 3, -1, c["material"]).astype(np.int32)
+    ref = O.oracle_render(c["positions"], c["indices"], tm, c["albedo"][:3], c["radiance"], c["camera"], res, res, spp, sample_mode=2, seed=9)
+    mask = ref.max(axis=-1) < 5.0
+    assert np.allclose(img[mask].mean(axis=0), ref[mask].mean(axis=0), rtol=0.02)
+    assert float(np.mean((img - ref) ** 2 / (ref ** 2 + 1e-2))) < 6e-3
