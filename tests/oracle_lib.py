@@ -21,7 +21,7 @@ _u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 
 
 def build_oracle():
-    srcs = [os.path.join(ORACLE_DIR, "mray_oracle.c"), os.path.join(ORACLE_DIR, "pt_oracle.c")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("mray_oracle.c", "pt_oracle.c", "spectrum_oracle.c")]
     so = os.path.join(ORACLE_DIR, "liboracle.so")
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(x) for x in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
@@ -334,3 +334,40 @@ def oracle_scene_trace(instances, tlas: LBVH, rays, mode=0, cull=0):
     oi = np.zeros(n, np.uint32); op = np.zeros(n, np.uint32); ot = np.zeros(n, np.float32); ob = np.zeros((n, 2), np.float32)
     L.orc_scene_trace(arr, tlas.leaf_aabb, tlas.nodes, tlas.boxes, len(instances), np.ascontiguousarray(rays), n, mode, cull, oi, op, ot, ob)
     return oi, op, ot, ob
+
+
+# ---- spectral restatement (oracle/spectrum_oracle.c) ----
+class _SpectrumTables(C.Structure):
+    _fields_ = [("lut", C.c_void_p), ("n", C.c_uint32), ("observer", C.c_void_p), ("illuminant", C.c_void_p),
+                ("xyzToRGB", C.c_float * 9)]
+
+
+def spectrum_tables(data):
+    """data = mray_b200.spectral.load(); returns (ctypes struct, keep-alive list)."""
+    t = _SpectrumTables()
+    keep = [np.ascontiguousarray(data["lut"], np.float32), np.ascontiguousarray(data["observer"], np.float32),
+            np.ascontiguousarray(data["illuminant"], np.float32)]
+    t.lut, t.n, t.observer, t.illuminant = keep[0].ctypes.data, data["resolution"], keep[1].ctypes.data, keep[2].ctypes.data
+    t.xyzToRGB = (C.c_float * 9)(*np.asarray(data["xyz_to_rgb"], np.float32).ravel())
+    return t, keep
+
+
+def oracle_sample_wavelengths(mode, randoms):
+    L = lib()
+    rn = np.ascontiguousarray(randoms, np.uint32)
+    waves = np.zeros((rn.size, 4), np.float32); pdfs = np.zeros((rn.size, 4), np.float32)
+    L.orc_sample_wavelengths(C.c_int(mode), rn.ctypes.data_as(C.c_void_p), C.c_uint32(rn.size),
+                             waves.ctypes.data_as(C.c_void_p), pdfs.ctypes.data_as(C.c_void_p))
+    return waves, pdfs
+
+
+def oracle_convert_batch(data, rgb, waves, pdfs, radiance_scale):
+    L = lib()
+    t, keep = spectrum_tables(data)
+    n = waves.shape[0]
+    w = np.ascontiguousarray(waves, np.float32); p = np.ascontiguousarray(pdfs, np.float32)
+    outs = [np.zeros((n, 4), np.float32) for _ in range(4)]
+    c = (C.c_float * 3)(*[float(x) for x in rgb])
+    L.orc_convert_batch(C.byref(t), c, w.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p), C.c_uint32(n),
+                        C.c_float(radiance_scale), *[o.ctypes.data_as(C.c_void_p) for o in outs])
+    return outs
