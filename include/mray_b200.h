@@ -231,6 +231,47 @@ MRB_API mrb_status mrb_scene_cast_visibility_rays(mrb_context ctx, mrb_scene sce
                                                   uint32_t rayCount, uint32_t totalRayCount,
                                                   mrb_memspace memspace, mrb_trace_mode mode);
 
+/* ---- hero-wavelength spectral transport ------------------------------------------------- */
+
+typedef struct mrb_spectrum_t* mrb_spectrum;
+
+typedef enum mrb_wavelength_sample_mode
+{   /* WavelengthSampleMode (Core/TracerEnums.h:L133-150), TracerParameters.wavelengthSampleMode */
+    MRB_WAVELENGTH_UNIFORM = 0, MRB_WAVELENGTH_GAUSSIAN_MIS = 1, MRB_WAVELENGTH_HYPERBOLIC_PBRT = 2
+} mrb_wavelength_sample_mode;
+
+/* What SpectrumContextJakob2019's constructor loads (Tracer/SpectrumContext.cu:L354-520), passed as
+ * HOST data by the plugin: the payload of "SpectraLUT/<COLORSPACE>.mrspectra" (9 blocks of res^3 fp32:
+ * for max-channel table t = 0..2 the coefficients c0, c1, c2; texel (x,y,z) at z*res*res + y*res + x),
+ * the CIE-1931 observer divided by its X/Y/Z integrals, the colour space's standard illuminant SPD
+ * scaled by CIE_1931_Y_INTEGRAL / SelectIlluminantSPDNormFactor, both 471 entries for 360..830 nm,
+ * and the XYZ->RGB matrix (row-major). */
+typedef struct mrb_spectrum_desc
+{
+    const float* lut;
+    uint32_t     lutResolution;        /* must be 64 (Jakob2019Detail::Data::N) */
+    const float* observerXYZ;          /* 471 * 3 */
+    const float* illuminantSPD;        /* 471 */
+    float        xyzToRGB[9];
+    uint32_t     wavelengthSampleMode; /* mrb_wavelength_sample_mode */
+} mrb_spectrum_desc;
+
+MRB_API mrb_status mrb_spectrum_create(mrb_context ctx, const mrb_spectrum_desc* desc, mrb_spectrum* out);
+MRB_API void       mrb_spectrum_destroy(mrb_context ctx, mrb_spectrum spectrum);
+/* SpectrumContextJakob2019::SampleSpectrumWavelengths (SpectrumContext.cu:L14-135,L173-196): one random
+ * number per element -> 4 wavelengths (nm) + 4 pdfs. waves / pdfs: count * 4 floats. */
+MRB_API mrb_status mrb_spectrum_sample_wavelengths(mrb_context ctx, mrb_spectrum spectrum, float* waves, float* pdfs,
+                                                   const uint32_t* randomNumbers, uint32_t count, mrb_memspace memspace);
+/* SpectrumContextJakob2019::ConvertSpectrumToRGB (SpectrumContext.cu:L137-171,L225-254), in place:
+ * values[i] (4 spectral samples) -> (r, g, b, 0). */
+MRB_API mrb_status mrb_spectrum_convert_to_rgb(mrb_context ctx, mrb_spectrum spectrum, float* values, const float* waves,
+                                               const float* pdfs, uint32_t count, mrb_memspace memspace);
+/* Jakob2019Detail::Converter::ConvertAlbedo (isRadiance = 0) / ConvertRadiance (1) per element
+ * (SpectrumContext.hpp:L37-150). rgb: count * 3 floats, or 3 floats shared by all when rgbIsUniform != 0. */
+MRB_API mrb_status mrb_spectrum_upsample(mrb_context ctx, mrb_spectrum spectrum, float* outSpectra, const float* rgb,
+                                         int rgbIsUniform, const float* waves, uint32_t count, int isRadiance,
+                                         mrb_memspace memspace);
+
 /* ---- wavefront path tracer ------------------------------------------------------------- */
 
 typedef struct mrb_renderer_t* mrb_renderer;
@@ -277,6 +318,11 @@ typedef struct mrb_render_desc
      * each with as many normals as the instance's accelerator has vertices. */
     mrb_scene       scene;
     const float* const* instanceVertexNormals;
+    /* NULL = (R)PathTracerRGB. Non-NULL = (R)PathTracerSpectral: albedo / lightRadiance are upsampled to
+     * spectra over 4 hero wavelengths per path (sampled at path start from one extra random number),
+     * transport runs on the 4 samples, the film receives ConvertSpectrumToRGB of each finished path
+     * (Tracer/PathTracerRendererBase.cu:L139-168,L228-241). The spectrum object must outlive the renderer. */
+    mrb_spectrum    spectrum;
 } mrb_render_desc;
 
 typedef struct mrb_render_stats

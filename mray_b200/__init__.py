@@ -6,6 +6,6 @@ ctypes mirror used by tests and bench.py. There is no CPU fallback: importing wo
 every compute entry point raises when the CUDA extension or a CUDA device is missing.
 """
 from . import scenes  # noqa: F401
-from .capi import Accelerator, Context, MrbError, Renderer, Scene, load_library  # noqa: F401
+from .capi import Accelerator, Context, MrbError, Renderer, Scene, Spectrum, load_library  # noqa: F401
 
-__all__ = ["scenes", "Accelerator", "Context", "MrbError", "Renderer", "Scene", "load_library"]
+__all__ = ["scenes", "Accelerator", "Context", "MrbError", "Renderer", "Scene", "Spectrum", "load_library"]

@@ -58,6 +58,11 @@ class InstanceDesc(C.Structure):
                 ("isIdentity", C.c_uint32), ("transformKey", C.c_uint32), ("accelKey", C.c_uint32)]
 
 
+class SpectrumDesc(C.Structure):
+    _fields_ = [("lut", C.c_void_p), ("lutResolution", C.c_uint32), ("observerXYZ", C.c_void_p),
+                ("illuminantSPD", C.c_void_p), ("xyzToRGB", C.c_float * 9), ("wavelengthSampleMode", C.c_uint32)]
+
+
 class RenderDesc(C.Structure):
     _fields_ = [("accel", C.c_void_p), ("vertexCount", C.c_uint32), ("triangleCount", C.c_uint32),
                 ("vertexNormals", C.c_void_p), ("materialCount", C.c_uint32), ("albedo", C.c_void_p),
@@ -67,7 +72,7 @@ class RenderDesc(C.Structure):
                 ("width", C.c_uint32), ("height", C.c_uint32), ("totalSPP", C.c_uint32), ("sampleMode", C.c_uint32),
                 ("rrRange", C.c_uint32 * 2), ("filmFilterRadius", C.c_float), ("seed", C.c_uint64),
                 ("maxPathCount", C.c_uint32), ("partitionRays", C.c_uint32),
-                ("scene", C.c_void_p), ("instanceVertexNormals", C.POINTER(C.c_void_p))]
+                ("scene", C.c_void_p), ("instanceVertexNormals", C.POINTER(C.c_void_p)), ("spectrum", C.c_void_p)]
 
 
 class RenderStats(C.Structure):
@@ -104,6 +109,12 @@ _PROTOTYPES = {
                                       C.c_uint32, C.c_uint32, C.c_int, C.c_int]),
     "mrb_scene_cast_visibility_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                  C.c_uint32, C.c_uint32, C.c_int, C.c_int]),
+    "mrb_spectrum_create": (C.c_int, [C.c_void_p, C.POINTER(SpectrumDesc), C.POINTER(C.c_void_p)]),
+    "mrb_spectrum_destroy": (None, [C.c_void_p, C.c_void_p]),
+    "mrb_spectrum_sample_wavelengths": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]),
+    "mrb_spectrum_convert_to_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]),
+    "mrb_spectrum_upsample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32,
+                                        C.c_int, C.c_int]),
     "mrb_renderer_create": (C.c_int, [C.c_void_p, C.POINTER(RenderDesc), C.POINTER(C.c_void_p)]),
     "mrb_renderer_destroy": (None, [C.c_void_p, C.c_void_p]),
     "mrb_renderer_iterate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
@@ -350,6 +361,53 @@ def light_key(index: int) -> int:
     return 0x80000000 | (index & 0x1FFFFF)
 
 
+class Spectrum:
+    """SpectrumContextJakob2019 behind the C-ABI (Tracer/SpectrumContext.h:L76-155). `data` =
+    mray_b200.spectral.load(); arrays are host numpy or device torch tensors like everywhere else."""
+
+    def __init__(self, ctx: Context, data, wavelength_sample_mode="HyperbolicPBRT"):
+        from . import spectral
+        self.ctx = ctx
+        d = SpectrumDesc()
+        self._keep = [np.ascontiguousarray(data["lut"], np.float32), np.ascontiguousarray(data["observer"], np.float32),
+                      np.ascontiguousarray(data["illuminant"], np.float32)]
+        d.lut, d.lutResolution = self._keep[0].ctypes.data, int(data["resolution"])
+        d.observerXYZ, d.illuminantSPD = self._keep[1].ctypes.data, self._keep[2].ctypes.data
+        d.xyzToRGB = (C.c_float * 9)(*np.asarray(data["xyz_to_rgb"], np.float32).ravel())
+        d.wavelengthSampleMode = (spectral.WAVELENGTH_SAMPLE_MODES[wavelength_sample_mode]
+                                  if isinstance(wavelength_sample_mode, str) else int(wavelength_sample_mode))
+        h = C.c_void_p()
+        ctx.check(ctx.lib.mrb_spectrum_create(ctx.handle, C.byref(d), C.byref(h)))
+        self.handle = h
+
+    def sample_wavelengths(self, waves, pdfs, random_numbers):
+        space = _space(waves, pdfs, random_numbers)
+        self.ctx.check(self.ctx.lib.mrb_spectrum_sample_wavelengths(self.ctx.handle, self.handle, _ptr(waves), _ptr(pdfs),
+                                                                    _ptr(random_numbers), random_numbers.shape[0], space))
+
+    def convert_to_rgb(self, values, waves, pdfs):
+        space = _space(values, waves, pdfs)
+        self.ctx.check(self.ctx.lib.mrb_spectrum_convert_to_rgb(self.ctx.handle, self.handle, _ptr(values), _ptr(waves), _ptr(pdfs),
+                                                                values.shape[0], space))
+
+    def upsample(self, out, rgb, waves, is_radiance=False):
+        space = _space(out, rgb, waves)
+        uniform = 1 if rgb.ndim == 1 else 0
+        self.ctx.check(self.ctx.lib.mrb_spectrum_upsample(self.ctx.handle, self.handle, _ptr(out), _ptr(rgb), uniform, _ptr(waves),
+                                                          waves.shape[0], 1 if is_radiance else 0, space))
+
+    def close(self):
+        if self.handle and self.ctx.handle:
+            self.ctx.lib.mrb_spectrum_destroy(self.ctx.handle, self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Renderer:
     """(R)PathTracerRGB behind the C-ABI: StartRender / DoRenderWork / film read-out
     (TracerDLL/PathTracerRenderer.cu:L930-1355)."""
@@ -357,13 +415,15 @@ class Renderer:
     def __init__(self, ctx: Context, accel, vertex_count, triangle_count, albedo, light_radiance,
                  camera, width, height, total_spp, sample_mode="WithNEEAndMIS", rr_range=(2, 20), seed=0,
                  vertex_normals=None, light_two_sided=None, film_filter_radius=1.0, near_far=(0.01, 1000.0),
-                 max_path_count=0, partition_rays=False, instance_vertex_normals=None):
+                 max_path_count=0, partition_rays=False, instance_vertex_normals=None, spectrum=None):
         """`accel` is an Accelerator, or a Scene (two-level; vertex_count / triangle_count / vertex_normals
         are then ignored and instance_vertex_normals may hold one array or None per instance)."""
-        self.ctx, self.accel = ctx, accel
+        self.ctx, self.accel, self.spectrum = ctx, accel, spectrum
         self.width, self.height = width, height
         d = RenderDesc()
         self._keep = []
+        if spectrum is not None:
+            d.spectrum = spectrum.handle   # (R)PathTracerSpectral
         if isinstance(accel, Scene):
             d.scene = accel.handle
             if instance_vertex_normals is not None:

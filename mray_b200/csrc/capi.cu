@@ -1,7 +1,10 @@
 // capi.cu — the C-ABI of include/mray_b200.h. Thin: argument checks, host<->device staging for the
 // MRB_MEM_HOST variants, exception -> status translation. No CPU fallback anywhere.
 #include "accel.cuh"
+#include "spectrum.cuh"
 #include <cstring>
+#include <initializer_list>
+#include <vector>
 #include <cstdio>
 #include <new>
 
@@ -39,6 +42,11 @@ void BinaryPartition(Context& ctx, uint32_t* indicesOut, uint32_t* leftCount, co
 namespace mrb
 {
 void BuildScene(Context& ctx, mrb_scene_t& sc, const mrb_instance_desc* inst, uint32_t n);
+void CreateSpectrum(Context& ctx, mrb_spectrum_t& sp, const mrb_spectrum_desc& desc);
+void SpectrumSampleWavelengths(Context& ctx, const mrb_spectrum_t& sp, const uint32_t* randoms, uint32_t n, float* waves, float* pdfs);
+void SpectrumToRGB(Context& ctx, const mrb_spectrum_t& sp, float* values, const float* waves, const float* pdfs, uint32_t n);
+void SpectrumUpsample(Context& ctx, const mrb_spectrum_t& sp, const float* rgb, uint32_t rgbStride, const float* waves, uint32_t n,
+                      bool isRadiance, float* out);
 void TraceScene(Context& ctx, const SceneData& scn, bool anyHit, mrb_trace_mode mode,
                 mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, uint32_t* visibleBits,
                 mrb_ray_gmem* rays, const uint32_t* rayIndices, uint32_t rayCount);
@@ -402,6 +410,105 @@ mrb_status mrb_radix_sort_pairs_u32(mrb_context ctx, uint32_t* keys, uint32_t* v
     return SortCommon<uint32_t>(ctx, keys, values, count, bitBegin, bitEnd, memspace);
 }
 
+
+mrb_status mrb_spectrum_create(mrb_context ctx, const mrb_spectrum_desc* desc, mrb_spectrum* out)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!desc || !out || !desc->lut || !desc->observerXYZ || !desc->illuminantSPD) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        *out = nullptr;
+        if(desc->lutResolution != 64) return Fail(c, MRB_ERR_INVALID_ARG, "Wrong size, spectra lut size must be 64!");
+        if(desc->wavelengthSampleMode > 2) return Fail(c, MRB_ERR_INVALID_ARG, "Unkown wavelength sample mode!");
+        mrb_spectrum sp = new mrb_spectrum_t();
+        try { mrb::CreateSpectrum(c, *sp, *desc); }
+        catch(...) { c.persistentBytes -= sp->mem.Capacity(); delete sp; throw; }
+        *out = sp;
+        return MRB_OK;
+    });
+}
+
+void mrb_spectrum_destroy(mrb_context ctx, mrb_spectrum spectrum)
+{
+    if(!ctx || !spectrum) return;
+    cudaSetDevice(ctx->c.device);
+    cudaStreamSynchronize(ctx->c.stream);
+    ctx->c.persistentBytes -= spectrum->mem.Capacity();
+    delete spectrum;
+}
+
+} // extern "C"
+
+// Runs `work(devicePointers...)` on device copies of host arrays (or directly on device arrays).
+struct StagedArray { void* user; size_t bytes; bool in, out; void* dev; };
+template<class F>
+static mrb_status Staged(mrb::Context& c, mrb_memspace memspace, std::initializer_list<StagedArray> list, F&& work)
+{
+    std::vector<StagedArray> a(list);
+    if(memspace == MRB_MEM_DEVICE) { for(auto& x : a) x.dev = x.user; work(a); return MRB_OK; }
+    mrb::MultiAlloc sz(nullptr);
+    for(auto& x : a) sz.Take<char>(mrb::AlignUp(x.bytes, 256));
+    c.scratch.Reserve(sz.Total());
+    mrb::MultiAlloc ma(c.scratch.Base());
+    for(auto& x : a)
+    {
+        x.dev = ma.Take<char>(mrb::AlignUp(x.bytes, 256));
+        if(x.in && x.bytes) MRB_CUDA_TRY(cudaMemcpyAsync(x.dev, x.user, x.bytes, cudaMemcpyHostToDevice, c.stream));
+    }
+    work(a);
+    for(auto& x : a) if(x.out && x.bytes) MRB_CUDA_TRY(cudaMemcpyAsync(x.user, x.dev, x.bytes, cudaMemcpyDeviceToHost, c.stream));
+    MRB_CUDA_TRY(cudaStreamSynchronize(c.stream));
+    return MRB_OK;
+}
+
+extern "C" {
+
+mrb_status mrb_spectrum_sample_wavelengths(mrb_context ctx, mrb_spectrum spectrum, float* waves, float* pdfs,
+                                           const uint32_t* randomNumbers, uint32_t count, mrb_memspace memspace)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!spectrum || !waves || !pdfs || !randomNumbers) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        if(count == 0) return MRB_OK;
+        return Staged(c, memspace, {{waves, size_t(count) * 16, false, true, nullptr}, {pdfs, size_t(count) * 16, false, true, nullptr},
+                                    {const_cast<uint32_t*>(randomNumbers), size_t(count) * 4, true, false, nullptr}},
+                      [&](std::vector<StagedArray>& a)
+                      { mrb::SpectrumSampleWavelengths(c, *spectrum, static_cast<const uint32_t*>(a[2].dev), count,
+                                                       static_cast<float*>(a[0].dev), static_cast<float*>(a[1].dev)); });
+    });
+}
+
+mrb_status mrb_spectrum_convert_to_rgb(mrb_context ctx, mrb_spectrum spectrum, float* values, const float* waves,
+                                       const float* pdfs, uint32_t count, mrb_memspace memspace)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!spectrum || !values || !waves || !pdfs) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        if(count == 0) return MRB_OK;
+        return Staged(c, memspace, {{values, size_t(count) * 16, true, true, nullptr},
+                                    {const_cast<float*>(waves), size_t(count) * 16, true, false, nullptr},
+                                    {const_cast<float*>(pdfs), size_t(count) * 16, true, false, nullptr}},
+                      [&](std::vector<StagedArray>& a)
+                      { mrb::SpectrumToRGB(c, *spectrum, static_cast<float*>(a[0].dev), static_cast<const float*>(a[1].dev),
+                                           static_cast<const float*>(a[2].dev), count); });
+    });
+}
+
+mrb_status mrb_spectrum_upsample(mrb_context ctx, mrb_spectrum spectrum, float* outSpectra, const float* rgb,
+                                 int rgbIsUniform, const float* waves, uint32_t count, int isRadiance, mrb_memspace memspace)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!spectrum || !outSpectra || !rgb || !waves) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        if(count == 0) return MRB_OK;
+        const size_t rgbBytes = rgbIsUniform ? 12 : size_t(count) * 12;
+        return Staged(c, memspace, {{outSpectra, size_t(count) * 16, false, true, nullptr},
+                                    {const_cast<float*>(rgb), rgbBytes, true, false, nullptr},
+                                    {const_cast<float*>(waves), size_t(count) * 16, true, false, nullptr}},
+                      [&](std::vector<StagedArray>& a)
+                      { mrb::SpectrumUpsample(c, *spectrum, static_cast<const float*>(a[1].dev), rgbIsUniform ? 0u : 3u,
+                                              static_cast<const float*>(a[2].dev), count, isRadiance != 0, static_cast<float*>(a[0].dev)); });
+    });
+}
 
 mrb_status mrb_renderer_create(mrb_context ctx, const mrb_render_desc* desc, mrb_renderer* out)
 {

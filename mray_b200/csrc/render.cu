@@ -20,6 +20,7 @@
 // between; both only depend on the hit, so they are one kernel here and the PCG32 stream is consumed
 // in registers. Host synchronisations per iteration: none.
 #include "accel.cuh"
+#include "spectrum.cuh"
 #include <cfloat>
 #include <random>
 #include <stdexcept>
@@ -61,6 +62,16 @@ __device__ __forceinline__ Float3 Cross(Float3 a, Float3 b)
 { return F3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 __device__ __forceinline__ float Length(Float3 a) { return sqrtf(Dot(a, a)); }
 __device__ __forceinline__ Float3 Normalize(Float3 a) { return a * (1.0f / Length(a)); }
+
+// Spectrum = Vector<4, Float> (Core/Definitions.h:L238-240): (r, g, b, 0) for the RGB renderer, 4 hero
+// wavelength samples for the spectral one
+struct Spec { float x, y, z, w; };
+__device__ __forceinline__ Spec S4(float x, float y, float z, float w) { return Spec{x, y, z, w}; }
+__device__ __forceinline__ Spec S4(float4 v) { return Spec{v.x, v.y, v.z, v.w}; }
+__device__ __forceinline__ float4 F4(Spec v) { return make_float4(v.x, v.y, v.z, v.w); }
+__device__ __forceinline__ Spec operator*(Spec a, Spec b) { return S4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ Spec operator*(Spec a, float s) { return S4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ Spec operator+(Spec a, Spec b) { return S4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 // PermutedCG32 (Tracer/Random.h:L237-238,L763-812): 32-bit state LCG, RXS-M-XS output
 struct PCG32
@@ -117,7 +128,12 @@ struct RenderData
     // scene: one record per instance (a single record when rendering one accelerator)
     const RenderInstance* instances;
     uint32_t          sceneMode;       // 1 = hitKeys.accelKey holds the instance index
-    const float4*     albedo;          // per material index
+    const float4*     albedo;          // per material index: (r, g, b, 0), or Jakob coefficients (c0, c1, c2, -) when spectral
+    // hero-wavelength spectral transport ((R)PathTracerSpectral); lights carry (c0, c1, c2, scale) in .radiance
+    SpectrumData      spec;
+    uint32_t          spectral;
+    float4*           waves;           // per slot: 4 wavelengths (nm)
+    float4*           wavePdf;         // per slot: their pdfs
     const EmissiveTri* lights;         // one per emissive triangle (MetaLight list), world space
     uint32_t          lightCount;      // emissive triangles (+1 boundary light in the sampler)
     Camera            cam;
@@ -221,6 +237,14 @@ __global__ void __launch_bounds__(RTPB) KReload(RenderData d)
     d.filmWeight[i] = weight;
     d.pixel[i] = pix;
     d.pathData[i] = PackPD(0, ST_ALIVE, RAY_CAMERA);
+    if(d.spectral)
+    {
+        // one more dimension after the camera sample (PathTracerRendererBase.cu:L139-168)
+        float w[4], p[4];
+        SampleWavelengths(d.spec.mode, rng.NextFloat(), w, p);
+        d.waves[i] = make_float4(w[0], w[1], w[2], w[3]);
+        d.wavePdf[i] = make_float4(p[0], p[1], p[2], p[3]);
+    }
     d.rng[i] = rng.s;
 }
 
@@ -246,12 +270,26 @@ __device__ __forceinline__ void LoadTriangle(const RenderInstance& in, uint32_t 
         p[k] = F3(in.positions[3 * size_t(vi[k])], in.positions[3 * size_t(vi[k]) + 1], in.positions[3 * size_t(vi[k]) + 2]);
 }
 
+// Material / light colour at the path's wavelengths: Converter::ConvertAlbedo / ConvertRadiance with the
+// coefficient fetch hoisted to StartRender (constant attributes), or the RGB pass-through converter.
+__device__ __forceinline__ Spec AlbedoAt(const RenderData& d, float4 a, float4 w)
+{
+    if(!d.spectral) return S4(a.x, a.y, a.z, 0.0f);
+    const float3 c = make_float3(a.x, a.y, a.z);
+    return S4(EvalSpectrum(c, w.x), EvalSpectrum(c, w.y), EvalSpectrum(c, w.z), EvalSpectrum(c, w.w));
+}
+__device__ __forceinline__ Spec RadianceAt(const RenderData& d, float4 r, float4 w)
+{
+    if(!d.spectral) return S4(r.x, r.y, r.z, 0.0f);
+    return S4(EvalRadiance(d.spec, r, w.x), EvalRadiance(d.spec, r, w.y), EvalRadiance(d.spec, r, w.z), EvalRadiance(d.spec, r, w.w));
+}
+
 // LightPrim::EmitViaHit / EmitViaSurfacePoint for a constant radiance (LightsDefault.hpp:L129-168)
-__device__ __forceinline__ Float3 Emit(const EmissiveTri& l, Float3 n, Float3 wO)
+__device__ __forceinline__ Spec Emit(const RenderData& d, const EmissiveTri& l, Float3 n, Float3 wO, float4 waves)
 {
     float NdL = Dot(n, wO);
-    if(l.e0.w == 0.0f && NdL <= 0.0f) return F3(0.f, 0.f, 0.f);
-    return F3(l.radiance.x, l.radiance.y, l.radiance.z);
+    if(l.e0.w == 0.0f && NdL <= 0.0f) return S4(0.f, 0.f, 0.f, 0.f);
+    return RadianceAt(d, l.radiance, waves);
 }
 
 // KCGenerateSurfaceWorkKeysIndirect / KCSetBoundaryWorkKeysIndirect (Tracer/RendererCommon.cu:L23-81):
@@ -288,8 +326,8 @@ __global__ void __launch_bounds__(RTPB) KShade(RenderData d)
         const uint32_t m = __activemask();
         if((threadIdx.x & 31u) == uint32_t(__ffs(int(m)) - 1)) atomicAdd(&d.counters[2], (unsigned long long)__popc(m));
     }
-    float4 thr4 = d.throughput[i];
-    Float3 throughput = F3(thr4.x, thr4.y, thr4.z);
+    Spec throughput = S4(d.throughput[i]);
+    const float4 waves = d.spectral ? d.waves[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     // every live slot gets a well defined (never hitting) shadow ray unless NEE writes one
     d.shadowRays[i].tMin = 1.0f; d.shadowRays[i].tMax = -1.0f;
 
@@ -332,16 +370,11 @@ __global__ void __launch_bounds__(RTPB) KShade(RenderData d)
                 pdfL *= 1.0f / float(d.lightCount + 1u);
                 float mis = pdfB + pdfL;
                 throughput = throughput * pdfB;
-                throughput = (mis == 0.0f) ? F3(0, 0, 0) : throughput * (1.0f / mis);
+                throughput = (mis == 0.0f) ? S4(0, 0, 0, 0) : throughput * (1.0f / mis);
             }
-            const Float3 em = Emit(l, geoN, rd * -1.0f);
+            const Spec em = Emit(d, l, geoN, rd * -1.0f, waves);
             if(depth + 1u <= d.rrHi)
-            {
-                float4 rad = d.radiance[i];
-                const Float3 est = em * throughput;
-                rad.x += est.x; rad.y += est.y; rad.z += est.z;
-                d.radiance[i] = rad;
-            }
+                d.radiance[i] = F4(S4(d.radiance[i]) + em * throughput);
         }
         d.pathData[i] = PackPD(depth, ST_DEAD, type);
         return;
@@ -359,8 +392,7 @@ __global__ void __launch_bounds__(RTPB) KShade(RenderData d)
         shadeN = Normalize(shadeN);
     }
     if(backSide) { geoN = geoN * -1.0f; shadeN = shadeN * -1.0f; }
-    const float4 alb4 = d.albedo[lmKey & 0x1FFFFFu];
-    const Float3 albedo = F3(alb4.x, alb4.y, alb4.z);
+    const Spec albedo = AlbedoAt(d, d.albedo[lmKey & 0x1FFFFFu], waves);
     // orthonormal frame about the shading normal
     const Float3 hlp = (fabsf(shadeN.x) > 0.9f) ? F3(0, 1, 0) : F3(1, 0, 0);
     const Float3 tX = Normalize(Cross(hlp, shadeN));
@@ -393,20 +425,20 @@ __global__ void __launch_bounds__(RTPB) KShade(RenderData d)
             float pdfL = (NdL == 0.0f) ? 0.0f : (1.0f / l.p0.w) / NdL;
             pdfL *= distSqr;
             pdfL *= 1.0f / float(nLights);
-            const Float3 em = Emit(l, lN, sdir);
+            const Spec em = Emit(d, l, lN, sdir, waves);
             // LightSampleOutput::SampledRay
             const Float3 wI = Normalize(lpos - pos);
             const Float3 lposN = NudgePos(lpos, wI * -1.0f);
             const float len = Length(lposN - pos);
             // Lambert Evaluate / Pdf
             const float nDotL = fmaxf(Dot(shadeN, wI), 0.0f);
-            const Float3 refl = albedo * (nDotL * INV_PI_F);
+            const Spec refl = albedo * (nDotL * INV_PI_F);
             float pdf = pdfL;
             if(d.sampleMode == 2u) pdf = fmaxf(nDotL * INV_PI_F, 0.0f) + pdfL;
-            Float3 sr = throughput * refl * em;
-            sr = (pdf == 0.0f) ? F3(0, 0, 0) : sr * (1.0f / pdf);
+            Spec sr = throughput * refl * em;
+            sr = (pdf == 0.0f) ? S4(0, 0, 0, 0) : sr * (1.0f / pdf);
             // +2: depth is not incremented yet (KCAccumulateShadowRaysPT)
-            if(depth + 2u <= d.rrHi) shadowRad = make_float4(sr.x, sr.y, sr.z, 0.f);
+            if(depth + 2u <= d.rrHi) shadowRad = F4(sr);
             const Float3 so = NudgePos(pos, geoN);
             float4* sp = reinterpret_cast<float4*>(d.shadowRays + i);
             sp[0] = make_float4(so.x, so.y, so.z, 1.0e-5f);
@@ -433,7 +465,8 @@ __global__ void __launch_bounds__(RTPB) KShade(RenderData d)
     if(!dead && depth >= d.rrLo)
     {
         const float rrXi = rng.NextFloat();
-        float prob = (throughput.x + throughput.y + throughput.z) * 0.33333333f;
+        // rrFactor = throughput.Sum() * ChannelCountInv (PathTracerRendererShaders.h:L251-256)
+        float prob = (throughput.x + throughput.y + throughput.z + throughput.w) * (d.spectral ? 0.25f : 0.33333333f);
         prob = fminf(fmaxf(prob, 0.1f), 1.0f);
         if(rrXi >= prob) dead = true;
         else throughput = throughput * (1.0f / prob);
@@ -441,8 +474,8 @@ __global__ void __launch_bounds__(RTPB) KShade(RenderData d)
     d.rng[i] = rng.s;
     if(!dead)
     {
-        throughput = (pdfB == 0.0f) ? F3(0, 0, 0) : throughput * (1.0f / pdfB);
-        d.throughput[i] = make_float4(throughput.x, throughput.y, throughput.z, 1.f);
+        throughput = (pdfB == 0.0f) ? S4(0, 0, 0, 0) : throughput * (1.0f / pdfB);
+        d.throughput[i] = F4(throughput);
         d.prevPdf[i] = pdfB;
         const Float3 no = NudgePos(pos, geoN);
         float4* rp = reinterpret_cast<float4*>(d.rays + i);
@@ -455,6 +488,23 @@ __global__ void __launch_bounds__(RTPB) KShade(RenderData d)
     {
         d.rays[i].tMin = 1.0f; d.rays[i].tMax = -1.0f;
         d.pathData[i] = PackPD(depth, ST_DEAD, (newType == RAY_SHADOW) ? (RAY_PATH | 0x80u) : RAY_PATH);
+    }
+}
+
+// Converter::ConvertAlbedo / ConvertRadiance, LUT half: RGB attributes -> Jakob coefficients, once per render
+__global__ void KPrepareSpectral(SpectrumData s, float4* albedo, uint32_t materialCount, EmissiveTri* lights, uint32_t lightCount)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < materialCount)
+    {
+        const float4 a = albedo[i];
+        const float3 c = FetchAlbedoCoeffs(s, a.x, a.y, a.z);
+        albedo[i] = make_float4(c.x, c.y, c.z, 0.0f);
+    }
+    else if(i < materialCount + lightCount)
+    {
+        EmissiveTri& l = lights[i - materialCount];
+        l.radiance = FetchRadianceCoeffs(s, l.radiance.x, l.radiance.y, l.radiance.z);
     }
 }
 
@@ -480,7 +530,7 @@ __global__ void __launch_bounds__(RTPB) KFinish(RenderData d)
         if(vis)
         {
             const float4 sr = d.shadowRadiance[i];
-            rad.x += sr.x; rad.y += sr.y; rad.z += sr.z;
+            rad.x += sr.x; rad.y += sr.y; rad.z += sr.z; rad.w += sr.w;
             d.radiance[i] = rad;
         }
         type &= 0x7Fu;
@@ -490,6 +540,14 @@ __global__ void __launch_bounds__(RTPB) KFinish(RenderData d)
         // film: ConvertNaNsToColor + atomic add (planar R,G,B,W)
         float w = d.filmWeight[i];
         Float3 v = F3(rad.x, rad.y, rad.z);
+        if(d.spectral)
+        {
+            // ConvertSpectrumToRGBIndirect on the dead paths (PathTracerRendererBase.cu:L228-241)
+            const float4 w4 = d.waves[i], p4 = d.wavePdf[i];
+            const float val[4] = {rad.x, rad.y, rad.z, rad.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w}, pp[4] = {p4.x, p4.y, p4.z, p4.w};
+            const float3 rgb = SpectraToRGB(d.spec, val, wv, pp);
+            v = F3(rgb.x, rgb.y, rgb.z);
+        }
         if(!(isfinite(v.x) && isfinite(v.y) && isfinite(v.z))) { v = F3(1e7f, 0.f, 1e7f); w *= 128.0f; }
         const uint32_t pix = d.pixel[i];
         const size_t plane = size_t(d.width) * d.height;
@@ -655,6 +713,7 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
             hri[k].vertexNormals = hinst[k].normals ? ma.Take<float4>(hinst[k].acc->vertexCount) : nullptr;
         }
         d.workKeys = ma.Take<uint32_t>(P); d.workIndices = ma.Take<uint32_t>(P); d.partTable = ma.Take<uint32_t>(32);
+        d.waves = desc.spectrum ? ma.Take<float4>(P) : nullptr; d.wavePdf = desc.spectrum ? ma.Take<float4>(P) : nullptr;
     };
     MultiAlloc sz(nullptr); Layout(sz);
     r.mem.Reserve(sz.Total());
@@ -668,6 +727,14 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
     MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<float4*>(d.albedo), halb.data(), halb.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx.stream));
     if(!lights.empty())
         MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<EmissiveTri*>(d.lights), lights.data(), lights.size() * sizeof(EmissiveTri), cudaMemcpyHostToDevice, ctx.stream));
+    d.spectral = desc.spectrum ? 1u : 0u;
+    if(desc.spectrum)
+    {
+        d.spec = desc.spectrum->d;
+        const uint32_t total = desc.materialCount + uint32_t(lights.size());
+        if(total) MRB_LAUNCH(ctx, KPrepareSpectral, DivUp(total, 128u), 128, 0, d.spec, const_cast<float4*>(d.albedo), desc.materialCount,
+                             const_cast<EmissiveTri*>(d.lights), uint32_t(lights.size()));
+    }
     std::vector<float4> hn;
     for(uint32_t k = 0; k < instCount; k++)
     {

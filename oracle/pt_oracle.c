@@ -81,7 +81,28 @@ typedef struct
     float camPos[3], camGaze[3], camUp[3], fovXY[2], nearFar[2];
     uint32_t width, height, spp, sampleMode, rrLo, rrHi;
     float filterRadius; uint64_t seed;
+    /* (R)PathTracerSpectral when non-NULL: tables of spectrum_oracle.c + WavelengthSampleMode */
+    const struct orc_spectrum_tables* spectrum; uint32_t wavelengthMode;
 } pt_scene;
+
+/* spectrum_oracle.c */
+struct orc_spectrum_tables;
+void orc_sample_wavelengths(int mode, const uint32_t* randoms, uint32_t n, float* waves, float* pdfs);
+void orc_convert_albedo(const struct orc_spectrum_tables* t, const float rgb[3], const float waves[4], float out[4]);
+void orc_convert_radiance(const struct orc_spectrum_tables* t, const float radiance[3], const float waves[4], float out[4]);
+void orc_spectra_to_rgb(const struct orc_spectrum_tables* t, const float value[4], const float waves[4], const float pdf[4], float out[4]);
+
+/* Spectrum = 4 floats: (r, g, b, 0) for the RGB renderer, 4 hero-wavelength samples for the spectral one */
+typedef struct { float v[4]; } s4;
+static s4 S(float a, float b, float c, float d) { s4 r = {{a, b, c, d}}; return r; }
+static s4 s_mul(s4 a, float k) { return S(a.v[0] * k, a.v[1] * k, a.v[2] * k, a.v[3] * k); }
+static s4 s_mulv(s4 a, s4 b) { return S(a.v[0] * b.v[0], a.v[1] * b.v[1], a.v[2] * b.v[2], a.v[3] * b.v[3]); }
+static s4 s_add(s4 a, s4 b) { return S(a.v[0] + b.v[0], a.v[1] + b.v[1], a.v[2] + b.v[2], a.v[3] + b.v[3]); }
+static s4 albedo_at(const pt_scene* s, uint32_t m, const float waves[4])
+{
+    if(!s->spectrum) return S(s->albedo[3 * m], s->albedo[3 * m + 1], s->albedo[3 * m + 2], 0.0f);
+    s4 o; orc_convert_albedo(s->spectrum, s->albedo + 3 * m, waves, o.v); return o;
+}
 
 static void tri(const pt_scene* s, uint32_t t, v3 p[3])
 {
@@ -100,15 +121,28 @@ static int trace(const pt_scene* s, v3 o, v3 d, float tMin, float tMax, int any,
     return *prim != 0xFFFFFFFFu;
 }
 
-static v3 light_emit(const pt_scene* s, uint32_t li, v3 n, v3 wO)
+static s4 light_emit(const pt_scene* s, uint32_t li, v3 n, v3 wO, const float waves[4])
 {
     float NdL = dot(n, wO);
-    if(!(s->twoSided && s->twoSided[li]) && NdL <= 0.0f) return V(0, 0, 0);
-    return V(s->radiance[3 * li], s->radiance[3 * li + 1], s->radiance[3 * li + 2]);
+    if(!(s->twoSided && s->twoSided[li]) && NdL <= 0.0f) return S(0, 0, 0, 0);
+    if(!s->spectrum) return S(s->radiance[3 * li], s->radiance[3 * li + 1], s->radiance[3 * li + 2], 0.0f);
+    s4 o; orc_convert_radiance(s->spectrum, s->radiance + 3 * li, waves, o.v); return o;
 }
 
-/* one camera path -> radiance; *filmW receives the filter weight */
+/* one camera path -> radiance (RGB; spectral paths are converted with their wavelengths at the end, as
+ * ConvertSpectrumToRGBIndirect does on dead paths); *filmW receives the filter weight */
+static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, float* filmW, float waves[4], float wavePdf[4]);
 static v3 path(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, float* filmW)
+{
+    float waves[4] = {0, 0, 0, 0}, wavePdf[4] = {1, 1, 1, 1};
+    s4 r = path_spectrum(s, rng, px, py, filmW, waves, wavePdf);
+    if(!s->spectrum) return V(r.v[0], r.v[1], r.v[2]);
+    float rgb[4];
+    orc_spectra_to_rgb(s->spectrum, r.v, waves, wavePdf, rgb);
+    return V(rgb[0], rgb[1], rgb[2]);
+}
+
+static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, float* filmW, float waves[4], float wavePdf[4])
 {
     /* camera (CameraPinhole ctor + EvaluateRay with a filter-sampled offset) */
     v3 pos = V(s->camPos[0], s->camPos[1], s->camPos[2]);
@@ -137,7 +171,12 @@ static v3 path(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, float* fil
     v3 o = pos, d = nrm(sub(add(add(bl, mul(right, sx)), mul(up, sy)), pos));
     float tMin = s->nearFar[0], tMax = s->nearFar[1];
 
-    v3 throughput = V(1, 1, 1), radiance = V(0, 0, 0);
+    if(s->spectrum)
+    {   /* one more dimension after the camera sample (PathTracerRendererBase.cu:L139-168) */
+        uint32_t rn = pcg_next(rng);
+        orc_sample_wavelengths((int)s->wavelengthMode, &rn, 1, waves, wavePdf);
+    }
+    s4 throughput = S(1, 1, 1, 1), radiance = S(0, 0, 0, 0);
     uint32_t depth = 0; int type = 3; /* CAMERA_RAY */
     float prevPdf = 0;
     const uint32_t nLights = s->nLightTris + 1u; /* + boundary (Null) light, MetaLight.hpp:L514-516 */
@@ -157,7 +196,7 @@ static v3 path(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, float* fil
             int count = !(s->sampleMode == 1u && type != 3 && type != 1);
             if(count)
             {
-                v3 thr = throughput;
+                s4 thr = throughput;
                 if(s->sampleMode == 2u && type == 2)
                 {
                     float NdL = dot(gN, mul(d, -1.0f));
@@ -168,16 +207,16 @@ static v3 path(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, float* fil
                     pdfL *= dot(dv, dv);
                     pdfL *= 1.0f / (float)nLights;
                     float mis = prevPdf + pdfL;
-                    thr = mul(thr, prevPdf);
-                    thr = (mis == 0) ? V(0, 0, 0) : mul(thr, 1.0f / mis);
+                    thr = s_mul(thr, prevPdf);
+                    thr = (mis == 0) ? S(0, 0, 0, 0) : s_mul(thr, 1.0f / mis);
                 }
-                if(depth + 1u <= s->rrHi) radiance = add(radiance, mulv(light_emit(s, li, gN, mul(d, -1.0f)), thr));
+                if(depth + 1u <= s->rrHi) radiance = s_add(radiance, s_mulv(light_emit(s, li, gN, mul(d, -1.0f), waves), thr));
             }
             break;
         }
         /* Lambert */
         if(dot(gN, nrm(d)) > 0) gN = mul(gN, -1.0f);
-        v3 alb = V(s->albedo[3 * m], s->albedo[3 * m + 1], s->albedo[3 * m + 2]);
+        s4 alb = albedo_at(s, (uint32_t)m, waves);
         v3 hlp = fabsf(gN.x) > 0.9f ? V(0, 1, 0) : V(1, 0, 0);
         v3 tX = nrm(cross(hlp, gN)), tY = cross(gN, tX);
         if(s->sampleMode != 0u)
@@ -200,21 +239,21 @@ static v3 path(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, float* fil
                 NdL = (s->twoSided && s->twoSided[lightIdx]) ? fabsf(NdL) : (NdL > 0 ? NdL : 0);
                 float pdfL = (NdL == 0) ? 0 : (1.0f / area) / NdL;
                 pdfL *= distSqr; pdfL *= 1.0f / (float)nLights;
-                v3 em = light_emit(s, lightIdx, lN, sd);
+                s4 em = light_emit(s, lightIdx, lN, sd, waves);
                 v3 wI = nrm(sub(lpos, hitPos));
                 v3 lposN = nudge(lpos, mul(wI, -1.0f));
                 float length = len(sub(lposN, hitPos));
                 float nDotL = dot(gN, wI); if(nDotL < 0) nDotL = 0;
-                v3 refl = mul(alb, nDotL * 0.31830988618f);
+                s4 refl = s_mul(alb, nDotL * 0.31830988618f);
                 float pdf = pdfL;
                 if(s->sampleMode == 2u) pdf = nDotL * 0.31830988618f + pdfL;
-                v3 sr = mulv(mulv(throughput, refl), em);
-                sr = (pdf == 0) ? V(0, 0, 0) : mul(sr, 1.0f / pdf);
-                if(depth + 2u <= s->rrHi && (sr.x > 0 || sr.y > 0 || sr.z > 0))
+                s4 sr = s_mulv(s_mulv(throughput, refl), em);
+                sr = (pdf == 0) ? S(0, 0, 0, 0) : s_mul(sr, 1.0f / pdf);
+                if(depth + 2u <= s->rrHi && (sr.v[0] > 0 || sr.v[1] > 0 || sr.v[2] > 0 || sr.v[3] > 0))
                 {
                     v3 so = nudge(hitPos, gN);
                     uint32_t sp; float st, sb[2];
-                    if(!trace(s, so, wI, 1.0e-5f, length * (1.0f - 1.0e-4f), 1, &sp, &st, sb)) radiance = add(radiance, sr);
+                    if(!trace(s, so, wI, 1.0e-5f, length * (1.0f - 1.0e-4f), 1, &sp, &st, sb)) radiance = s_add(radiance, sr);
                 }
             }
         }
@@ -225,18 +264,18 @@ static v3 path(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, float* fil
         float lz2 = 1.0f - (lx * lx + ly * ly); float lz = lz2 > 0 ? sqrtf(lz2) : 0;
         float pdfB = lz * 0.31830988618f;
         v3 wI = nrm(add(add(mul(tX, lx), mul(tY, ly)), mul(gN, lz)));
-        throughput = mulv(throughput, mul(alb, lz * 0.31830988618f));
+        throughput = s_mulv(throughput, s_mul(alb, lz * 0.31830988618f));
         depth += 1;
         int dead = depth >= s->rrHi;
         if(!dead && depth >= s->rrLo)
         {
             float xi = pcg_float(rng);
-            float prob = (throughput.x + throughput.y + throughput.z) * 0.33333333f;
+            float prob = (throughput.v[0] + throughput.v[1] + throughput.v[2] + throughput.v[3]) * (s->spectrum ? 0.25f : 0.33333333f);
             prob = prob < 0.1f ? 0.1f : (prob > 1.0f ? 1.0f : prob);
-            if(xi >= prob) dead = 1; else throughput = mul(throughput, 1.0f / prob);
+            if(xi >= prob) dead = 1; else throughput = s_mul(throughput, 1.0f / prob);
         }
         if(dead) break;
-        throughput = (pdfB == 0) ? V(0, 0, 0) : mul(throughput, 1.0f / pdfB);
+        throughput = (pdfB == 0) ? S(0, 0, 0, 0) : s_mul(throughput, 1.0f / pdfB);
         prevPdf = pdfB; type = 2; /* PATH_RAY */
         o = nudge(hitPos, gN); d = wI; tMin = 1.0e-4f; tMax = FLT_MAX;
     }

@@ -260,13 +260,16 @@ class _PtScene(C.Structure):
                 ("camPos", C.c_float * 3), ("camGaze", C.c_float * 3), ("camUp", C.c_float * 3),
                 ("fovXY", C.c_float * 2), ("nearFar", C.c_float * 2),
                 ("width", C.c_uint32), ("height", C.c_uint32), ("spp", C.c_uint32), ("sampleMode", C.c_uint32),
-                ("rrLo", C.c_uint32), ("rrHi", C.c_uint32), ("filterRadius", C.c_float), ("seed", C.c_uint64)]
+                ("rrLo", C.c_uint32), ("rrHi", C.c_uint32), ("filterRadius", C.c_float), ("seed", C.c_uint64),
+                ("spectrum", C.c_void_p), ("wavelengthMode", C.c_uint32)]
 
 
 def oracle_render(positions, indices, tri_material, albedo, radiance, camera, width, height, spp,
-                  sample_mode=2, rr_range=(2, 20), seed=0, near_far=(0.01, 1000.0), threads=None):
+                  sample_mode=2, rr_range=(2, 20), seed=0, near_far=(0.01, 1000.0), threads=None,
+                  spectral_data=None, wavelength_mode=2):
     """tri_material: per triangle, >= 0 Lambert material index, -1 - k for light k. Returns image[h,w,3]
-    (row 0 = bottom) resolved as sum radiance / sum weight."""
+    (row 0 = bottom) resolved as sum radiance / sum weight. spectral_data (mray_b200.spectral.load())
+    switches to the hero-wavelength spectral estimator."""
     from concurrent.futures import ThreadPoolExecutor
     L = lib()
     L.orc_pt_render_rows.argtypes = [C.POINTER(_PtScene), C.c_uint32, C.c_uint32, C.c_void_p]
@@ -285,6 +288,9 @@ def oracle_render(positions, indices, tri_material, albedo, radiance, camera, wi
     s.fovXY = (C.c_float * 2)(fx, fy); s.nearFar = (C.c_float * 2)(*near_far)
     s.width, s.height, s.spp, s.sampleMode = width, height, spp, sample_mode
     s.rrLo, s.rrHi, s.filterRadius, s.seed = rr_range[0], rr_range[1], 1.0, seed
+    if spectral_data is not None:
+        tables, keep_tables = spectrum_tables(spectral_data)
+        s.spectrum, s.wavelengthMode = C.addressof(tables), wavelength_mode
     out = np.zeros((4, height, width), np.float32)
     threads = threads or min(16, os.cpu_count() or 1)
     rows = np.linspace(0, height, threads * 4 + 1).astype(int)
