@@ -236,24 +236,34 @@ def run_ours(args):
         pidx, pranges, pkeys, palb, prad, _ = scenes.arcade_materials(p, i)
         pacc = mray_b200.Accelerator(ctx, dp, torch.from_numpy(pidx.view(np.int32)).cuda(), prim_ranges=pranges, light_or_mat_keys=pkeys)
         pt_spp = 8
-        pr = mray_b200.Renderer(ctx, pacc, p.shape[0], pidx.shape[0], palb, prad, scenes.ARCADE_CAMERA, W, H, pt_spp,
-                                sample_mode="WithNEEAndMIS", rr_range=(3, 8), seed=rank, partition_rays=True)
-        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        pr.iterate(2); torch.cuda.synchronize()      # warm
-        l0 = ctx.launch_count
-        pe0.record(stream)
-        while True:
-            pr.iterate(8)
-            pst = pr.stats()
-            if pst.finished:
-                break
-        pe1.record(stream); torch.cuda.synchronize()
-        pms = pe0.elapsed_time(pe1)
-        pt = {"workload": "arcade mesh, 64 Lambert + 200 emissive tris, PathTracerRGB WithNEEAndMIS rr[3,8], %dx%d, %d spp, material-key ray sort on" % (W, H, pt_spp),
-              "ms_per_spp_1080p": round(pms / pt_spp, 3), "mrays_s": round((pst.closestRays + pst.shadowRays) / pms / 1e3, 1),
-              "mpaths_s": round(pst.pathsCompleted / pms / 1e3, 1), "iterations": int(pst.iterations),
-              "gpu_launches": int(ctx.launch_count - l0)}
-        pr.close(); pacc.close()
+
+        def run_pt(spectrum):
+            pr = mray_b200.Renderer(ctx, pacc, p.shape[0], pidx.shape[0], palb, prad, scenes.ARCADE_CAMERA, W, H, pt_spp,
+                                    sample_mode="WithNEEAndMIS", rr_range=(3, 8), seed=rank, partition_rays=True, spectrum=spectrum)
+            pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            pr.iterate(2); torch.cuda.synchronize()      # warm
+            l0 = ctx.launch_count
+            pe0.record(stream)
+            while True:
+                pr.iterate(8)
+                pst = pr.stats()
+                if pst.finished:
+                    break
+            pe1.record(stream); torch.cuda.synchronize()
+            pms = pe0.elapsed_time(pe1)
+            res = {"ms_per_spp_1080p": round(pms / pt_spp, 3), "mrays_s": round((pst.closestRays + pst.shadowRays) / pms / 1e3, 1),
+                   "mpaths_s": round(pst.pathsCompleted / pms / 1e3, 1), "iterations": int(pst.iterations),
+                   "gpu_launches": int(ctx.launch_count - l0)}
+            pr.close()
+            return res
+        pt = {"workload": "arcade mesh, 64 Lambert + 200 emissive tris, WithNEEAndMIS rr[3,8], %dx%d, %d spp, material-key ray sort on" % (W, H, pt_spp),
+              "PathTracerRGB": run_pt(None)}
+        from mray_b200 import spectral
+        if spectral.available():
+            spec = mray_b200.Spectrum(ctx, spectral.load(), "HyperbolicPBRT")
+            pt["PathTracerSpectral"] = run_pt(spec)      # config 3: hero-wavelength spectral transport, ACES_CG LUT
+            spec.close()
+        pacc.close()
 
     peak, peak_src = measured_peak()
     closest_bytes = 2 * n * BYTES_CLOSEST * args.steps

@@ -13,7 +13,13 @@
 #include "Core/TimelineSemaphore.h"
 #include "Core/Quaternion.h"
 #include "TransientPool/TransientPool.h"
+#include "Core/ColorFunctions.h"
+#include "Core/System.h"
 #include "mray_b200.h"
+#include <dlfcn.h>
+#include <filesystem>
+#include <fstream>
+#include <cstdlib>
 
 #include <algorithm>
 #include <cmath>
@@ -87,6 +93,7 @@ class TracerB200 final : public TracerI
     std::vector<mrb_accel> instAccels;   // one per distinct (T)Single transform in use
     mrb_scene scene = nullptr;           // set when any surface is transformed
     mrb_renderer renderer = nullptr;
+    mrb_spectrum spectrum = nullptr;     // SpectrumContextJakob2019 of params.globalTextureColorSpace, made on first use
     std::mutex mtx; // scene-loading calls arrive concurrently from pool threads (TracerBase.h:L97-130)
 
     std::vector<PrimGroupB200> prims; std::vector<MatGroupB200> mats; std::vector<LightGroupB200> lights;
@@ -121,6 +128,50 @@ class TracerB200 final : public TracerI
         transforms.push_back(TransGroupB200{std::string(TracerConstants::IdentityTransName), true});
         transforms[0].matrices.push_back(Matrix3x4::Identity());
     }
+    // SpectrumContextJakob2019 ctor (Tracer/SpectrumContext.cu:L354-532): LUT file + normalised CIE tables
+    void EnsureSpectrum()
+    {
+        if(spectrum) return;
+        const MRayColorSpaceEnum cs = params.globalTextureColorSpace;
+        const std::string fileName = std::string(MRayColorSpaceStringifier::ToString(cs)) + std::string(Color::LUT_FILE_EXT);
+        namespace fs = std::filesystem;
+        std::vector<fs::path> candidates;
+        if(const char* e = std::getenv("MRB_SPECTRA_LUT_DIR")) candidates.push_back(fs::path(e) / fileName);
+        candidates.push_back(fs::path(GetProcessPath()) / fs::path(Color::LUT_FOLDER_NAME) / fileName);   // the reference's location
+        Dl_info info;
+        if(dladdr(reinterpret_cast<const void*>(&InverseAffine), &info) && info.dli_fname)
+            candidates.push_back(fs::path(info.dli_fname).parent_path().parent_path() / "data" / fileName);
+        fs::path found;
+        for(const fs::path& c : candidates) if(fs::exists(c)) { found = c; break; }
+        if(found.empty()) throw MRayError("Unable to open spectra lut file {}!", candidates[candidates.size() > 1 ? 1 : 0].string());
+        std::ifstream f(found, std::ios_base::binary);
+        char cc[10]; uint32_t res = 0, mode = 0;
+        f.read(cc, 10);
+        if(!f || std::string_view(cc, 10) != Color::LUT_FILE_CC) throw MRayError("Wrong character code in .mrspectra file!");
+        f.read(reinterpret_cast<char*>(&res), 4);
+        if(!f || res != 64) throw MRayError("Wrong size ({}), spectra lut size must be {}!", res, 64);
+        f.read(reinterpret_cast<char*>(&mode), 4);
+        if(!f || mode != 1) throw MRayError("Wrong mode ({}), spectra lut must have mode \"1\" (aka. Float)!", mode);
+        std::vector<float> lut(size_t(9) * 64 * 64 * 64);
+        if(!f.read(reinterpret_cast<char*>(lut.data()), std::streamsize(lut.size() * sizeof(float)))) throw MRayError("Unable to read sprectum lut file!");
+        std::vector<float> observer(Color::CIE_1931_N * 3), illum(Color::CIE_1931_N);
+        const auto& spd = Color::SelectIlluminantSPD(cs);
+        Float illumNorm = Color::CIE_1931_Y_INTEGRAL;
+        illumNorm /= Color::SelectIlluminantSPDNormFactor(cs);
+        const Vector3 weight = Vector3(1) / Vector3(Color::CIE_1931_X_INTEGRAL, Color::CIE_1931_Y_INTEGRAL, Color::CIE_1931_Z_INTEGRAL);
+        for(uint32_t i = 0; i < Color::CIE_1931_N; i++)
+        {
+            Vector3 v = Color::CIE_1931_XYZ[i] * weight;
+            observer[3 * i] = v[0]; observer[3 * i + 1] = v[1]; observer[3 * i + 2] = v[2];
+            illum[i] = spd[i] * illumNorm;
+        }
+        const Matrix3x3 xyzToRGB = Color::SelectRGBToXYZMatrix(cs).Inverse();
+        mrb_spectrum_desc d = {};
+        d.lut = lut.data(); d.lutResolution = res; d.observerXYZ = observer.data(); d.illuminantSPD = illum.data();
+        for(unsigned i = 0; i < 9; i++) d.xyzToRGB[i] = xyzToRGB[i];
+        d.wavelengthSampleMode = uint32_t(params.wavelengthSampleMode.e);
+        Check(mrb_spectrum_create(ctx, &d, &spectrum));
+    }
     void ReleaseAccels()
     {
         if(scene) { mrb_scene_destroy(ctx, scene); scene = nullptr; }
@@ -131,6 +182,7 @@ class TracerB200 final : public TracerI
     ~TracerB200() override
     {
         if(renderer) mrb_renderer_destroy(ctx, renderer);
+        if(spectrum) mrb_spectrum_destroy(ctx, spectrum);
         ReleaseAccels();
         mrb_context_destroy(ctx);
     }
@@ -142,7 +194,7 @@ class TracerB200 final : public TracerI
     TypeNameList CameraGroups() const override { return {"(C)Pinhole"sv}; }
     TypeNameList MediumGroups() const override { return {"(Md)Vacuum"sv}; }
     TypeNameList LightGroups() const override { return {"(L)Null"sv, "(L)Prim(P)Triangle"sv}; }
-    TypeNameList Renderers() const override { return {"(R)PathTracerRGB"sv}; }
+    TypeNameList Renderers() const override { return {"(R)PathTracerRGB"sv, "(R)PathTracerSpectral"sv}; }
 
     PrimAttributeInfoList AttributeInfoPrim(std::string_view name) const override
     {
@@ -201,7 +253,7 @@ class TracerB200 final : public TracerI
     RendererAttributeInfoList AttributeInfoRenderer(std::string_view name) const override
     {
         using enum MRayDataEnum; using enum AttributeIsArray; using enum AttributeOptionality;
-        if(name != "(R)PathTracerRGB"sv) return {};
+        if(name != "(R)PathTracerRGB"sv && name != "(R)PathTracerSpectral"sv) return {};
         return RendererAttributeInfoList // TracerDLL/PathTracerRenderer.cu:L1384-1400
         {
             RendererAttributeInfo("totalSPP", MRayDataTypeRT(MR_UINT32), IS_SCALAR, MR_MANDATORY),
@@ -596,7 +648,7 @@ class TracerB200 final : public TracerI
     RendererId CreateRenderer(std::string typeName) override
     {
         std::lock_guard lk(mtx);
-        if(typeName != "(R)PathTracerRGB") throw MRayError("Unable to find generator for {}", typeName);
+        if(typeName != "(R)PathTracerRGB" && typeName != "(R)PathTracerSpectral") throw MRayError("Unable to find generator for {}", typeName);
         renderers.push_back(RendererB200{typeName});
         return RendererId(uint32_t(renderers.size() - 1));
     }
@@ -657,6 +709,7 @@ class TracerB200 final : public TracerI
         uint64_t pixels = uint64_t(tile[0]) * tile[1];
         d.maxPathCount = uint32_t(std::min<uint64_t>(pixels, std::max<uint32_t>(params.parallelizationHint, 1u)));
         d.partitionRays = d.materialCount > 1 ? 1u : 0u;
+        if(r.type == "(R)PathTracerSpectral") { EnsureSpectrum(); d.spectrum = spectrum; }
         Check(mrb_renderer_create(ctx, &d, &renderer));
         curRenderer = Raw(id); resolution = tile;
         staging.assign(size_t(4) * pixels, 0.0f);

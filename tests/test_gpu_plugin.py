@@ -65,3 +65,24 @@ def test_cornell_with_single_transforms_through_tracer_interface():
     mask = ref.max(axis=-1) < 5.0
     assert np.allclose(img[mask].mean(axis=0), ref[mask].mean(axis=0), rtol=0.02)
     assert float(np.mean((img - ref) ** 2 / (ref ** 2 + 1e-2))) < 6e-3
+
+
+@pytest.mark.skipif(not (os.path.exists(PLUGIN) and O.driver_available()), reason="plugin / driver were not prebuilt")
+def test_spectral_renderer_through_tracer_interface():
+    """(R)PathTracerSpectral: the plugin builds SpectrumContextJakob2019's inputs from the reference's own colour
+    tables + the .mrspectra file and the image matches the spectral estimator oracle."""
+    from mray_b200 import spectral
+    if not spectral.available():
+        pytest.skip("spectral LUT was not generated")
+    c = scenes.cornell_box()
+    b = O.batched_scene(c["positions"], c["indices"], c["material"])
+    res, spp = 32, 4096
+    img, w, st = O.driver_render(PLUGIN, b, c["albedo"], 3, c["radiance"], c["camera"], res, res, spp,
+                                 renderer="PathTracerSpectral", sample_mode="WithNEEAndMIS", rr_range=(2, 20), seed=4)
+    assert np.allclose(w, spp, rtol=1e-3)
+    tm = np.where(c["material"] == 3, -1, c["material"]).astype(np.int32)
+    ref = O.oracle_render(c["positions"], c["indices"], tm, c["albedo"][:3], c["radiance"], c["camera"], res, res, spp,
+                          sample_mode=2, seed=9, spectral_data=spectral.load(), wavelength_mode=2)
+    mask = ref.max(axis=-1) < 5.0
+    assert np.allclose(img[mask].mean(axis=0), ref[mask].mean(axis=0), rtol=0.03), (img[mask].mean(axis=0), ref[mask].mean(axis=0))
+    assert float(np.mean((img - ref) ** 2 / (ref ** 2 + 1e-2))) < 1e-2
