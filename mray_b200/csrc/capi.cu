@@ -129,6 +129,14 @@ void mrb_context_destroy(mrb_context ctx)
     cudaStreamSynchronize(ctx->c.stream);
     ctx->c.scratch.Free();
     ctx->c.traceScratch.Free();
+    if(ctx->c.copyIn) cudaStreamDestroy(ctx->c.copyIn);
+    if(ctx->c.copyOut) cudaStreamDestroy(ctx->c.copyOut);
+    if(ctx->c.evStart) cudaEventDestroy(ctx->c.evStart);
+    for(int k = 0; k < mrb::Context::PIPE_CHUNKS; k++)
+    {
+        if(ctx->c.evIn[k]) cudaEventDestroy(ctx->c.evIn[k]);
+        if(ctx->c.evDone[k]) cudaEventDestroy(ctx->c.evDone[k]);
+    }
     if(ctx->c.ev0) cudaEventDestroy(ctx->c.ev0);
     if(ctx->c.ev1) cudaEventDestroy(ctx->c.ev1);
     if(ctx->c.ownStream) cudaStreamDestroy(ctx->c.ownStream);
@@ -248,6 +256,10 @@ mrb_status mrb_accel_export_lbvh(mrb_context ctx, mrb_accel accel,
 
 } // extern "C"
 
+// Host-pointer casts (the boundary a TracerI host uses before its buffers live on the device): the rays are
+// cut into chunks; chunk k+1 uploads and chunk k-1 downloads while chunk k is traced, on three streams, so
+// the call costs max(H2D, D2H, trace) instead of their sum (PCIe is full duplex). Indirect casts
+// (rayIndices) need every ray resident and take the unpipelined route.
 template<class TraceF>
 static mrb_status CastGeneric(mrb_context ctx, bool anyHit,
                               mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, uint32_t* visibleBits,
@@ -260,7 +272,7 @@ static mrb_status CastGeneric(mrb_context ctx, bool anyHit,
         if(anyHit ? !visibleBits : (!hitKeys || !metaHits)) return Fail(c, MRB_ERR_INVALID_ARG, "null output");
         if(totalRayCount < rayCount && !rayIndices) return Fail(c, MRB_ERR_INVALID_ARG, "totalRayCount < rayCount");
         if(rayCount == 0) return MRB_OK;
-        if(memspace == MRB_MEM_DEVICE) { trace(c, hitKeys, metaHits, visibleBits, rays, rayIndices); return MRB_OK; }
+        if(memspace == MRB_MEM_DEVICE) { trace(c, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount); return MRB_OK; }
         const size_t words = (size_t(totalRayCount) + 31) / 32;
         mrb::MultiAlloc sz(nullptr);
         sz.Take<mrb_ray_gmem>(totalRayCount); sz.Take<uint32_t>(rayIndices ? rayCount : 0);
@@ -269,22 +281,74 @@ static mrb_status CastGeneric(mrb_context ctx, bool anyHit,
         mrb::MultiAlloc ma(c.scratch.Base());
         mrb_ray_gmem* dRays = ma.Take<mrb_ray_gmem>(totalRayCount);
         uint32_t* dIdx = ma.Take<uint32_t>(rayIndices ? rayCount : 0);
+        uint32_t* dBits = anyHit ? ma.Take<uint32_t>(words) : nullptr;
+        mrb_hit_key_pack* dKeys = anyHit ? nullptr : ma.Take<mrb_hit_key_pack>(totalRayCount);
+        mrb_meta_hit* dHits = anyHit ? nullptr : ma.Take<mrb_meta_hit>(totalRayCount);
+
+        constexpr uint32_t MIN_CHUNK = 1u << 16;   // rays; chunk starts stay multiples of 32 (visibility words)
+        if(!rayIndices && rayCount >= 2 * MIN_CHUNK)
+        {
+            if(!c.copyIn)
+            {
+                MRB_CUDA_TRY(cudaStreamCreateWithFlags(&c.copyIn, cudaStreamNonBlocking));
+                MRB_CUDA_TRY(cudaStreamCreateWithFlags(&c.copyOut, cudaStreamNonBlocking));
+                MRB_CUDA_TRY(cudaEventCreateWithFlags(&c.evStart, cudaEventDisableTiming));
+                for(int k = 0; k < mrb::Context::PIPE_CHUNKS; k++)
+                {
+                    MRB_CUDA_TRY(cudaEventCreateWithFlags(&c.evIn[k], cudaEventDisableTiming));
+                    MRB_CUDA_TRY(cudaEventCreateWithFlags(&c.evDone[k], cudaEventDisableTiming));
+                }
+            }
+            uint32_t chunks = rayCount / MIN_CHUNK;
+            if(chunks > uint32_t(mrb::Context::PIPE_CHUNKS)) chunks = uint32_t(mrb::Context::PIPE_CHUNKS);
+            const uint32_t per = ((rayCount + chunks - 1) / chunks + 1023u) & ~1023u;
+            // whatever the caller queued on the context stream (a build, a previous cast) comes first
+            MRB_CUDA_TRY(cudaEventRecord(c.evStart, c.stream));
+            MRB_CUDA_TRY(cudaStreamWaitEvent(c.copyIn, c.evStart, 0));
+            MRB_CUDA_TRY(cudaStreamWaitEvent(c.copyOut, c.evStart, 0));
+            uint32_t k = 0;
+            for(uint32_t b = 0; b < rayCount; b += per, k++)
+            {
+                const uint32_t n = (rayCount - b < per) ? rayCount - b : per;
+                const size_t w0 = b / 32, wn = (size_t(n) + 31) / 32;
+                MRB_CUDA_TRY(cudaMemcpyAsync(dRays + b, rays + b, sizeof(mrb_ray_gmem) * n, cudaMemcpyHostToDevice, c.copyIn));
+                if(anyHit) MRB_CUDA_TRY(cudaMemcpyAsync(dBits + w0, visibleBits + w0, sizeof(uint32_t) * wn, cudaMemcpyHostToDevice, c.copyIn));
+                else
+                {
+                    MRB_CUDA_TRY(cudaMemcpyAsync(dKeys + b, hitKeys + b, sizeof(mrb_hit_key_pack) * n, cudaMemcpyHostToDevice, c.copyIn));
+                    MRB_CUDA_TRY(cudaMemcpyAsync(dHits + b, metaHits + b, sizeof(mrb_meta_hit) * n, cudaMemcpyHostToDevice, c.copyIn));
+                }
+                MRB_CUDA_TRY(cudaEventRecord(c.evIn[k], c.copyIn));
+                MRB_CUDA_TRY(cudaStreamWaitEvent(c.stream, c.evIn[k], 0));
+                trace(c, anyHit ? nullptr : dKeys + b, anyHit ? nullptr : dHits + b, anyHit ? dBits + w0 : nullptr, dRays + b, nullptr, n);
+                MRB_CUDA_TRY(cudaEventRecord(c.evDone[k], c.stream));
+                MRB_CUDA_TRY(cudaStreamWaitEvent(c.copyOut, c.evDone[k], 0));
+                if(anyHit) MRB_CUDA_TRY(cudaMemcpyAsync(visibleBits + w0, dBits + w0, sizeof(uint32_t) * wn, cudaMemcpyDeviceToHost, c.copyOut));
+                else
+                {
+                    MRB_CUDA_TRY(cudaMemcpyAsync(hitKeys + b, dKeys + b, sizeof(mrb_hit_key_pack) * n, cudaMemcpyDeviceToHost, c.copyOut));
+                    MRB_CUDA_TRY(cudaMemcpyAsync(metaHits + b, dHits + b, sizeof(mrb_meta_hit) * n, cudaMemcpyDeviceToHost, c.copyOut));
+                    MRB_CUDA_TRY(cudaMemcpyAsync(rays + b, dRays + b, sizeof(mrb_ray_gmem) * n, cudaMemcpyDeviceToHost, c.copyOut));
+                }
+            }
+            MRB_CUDA_TRY(cudaStreamSynchronize(c.copyOut));
+            MRB_CUDA_TRY(cudaStreamSynchronize(c.stream));
+            return MRB_OK;
+        }
+
         MRB_CUDA_TRY(cudaMemcpyAsync(dRays, rays, sizeof(mrb_ray_gmem) * totalRayCount, cudaMemcpyHostToDevice, c.stream));
         if(rayIndices) MRB_CUDA_TRY(cudaMemcpyAsync(dIdx, rayIndices, sizeof(uint32_t) * rayCount, cudaMemcpyHostToDevice, c.stream));
         if(anyHit)
         {
-            uint32_t* dBits = ma.Take<uint32_t>(words);
             MRB_CUDA_TRY(cudaMemcpyAsync(dBits, visibleBits, sizeof(uint32_t) * words, cudaMemcpyHostToDevice, c.stream));
-            trace(c, nullptr, nullptr, dBits, dRays, rayIndices ? dIdx : nullptr);
+            trace(c, nullptr, nullptr, dBits, dRays, rayIndices ? dIdx : nullptr, rayCount);
             MRB_CUDA_TRY(cudaMemcpyAsync(visibleBits, dBits, sizeof(uint32_t) * words, cudaMemcpyDeviceToHost, c.stream));
         }
         else
         {
-            mrb_hit_key_pack* dKeys = ma.Take<mrb_hit_key_pack>(totalRayCount);
-            mrb_meta_hit* dHits = ma.Take<mrb_meta_hit>(totalRayCount);
             MRB_CUDA_TRY(cudaMemcpyAsync(dKeys, hitKeys, sizeof(mrb_hit_key_pack) * totalRayCount, cudaMemcpyHostToDevice, c.stream));
             MRB_CUDA_TRY(cudaMemcpyAsync(dHits, metaHits, sizeof(mrb_meta_hit) * totalRayCount, cudaMemcpyHostToDevice, c.stream));
-            trace(c, dKeys, dHits, nullptr, dRays, rayIndices ? dIdx : nullptr);
+            trace(c, dKeys, dHits, nullptr, dRays, rayIndices ? dIdx : nullptr, rayCount);
             MRB_CUDA_TRY(cudaMemcpyAsync(hitKeys, dKeys, sizeof(mrb_hit_key_pack) * totalRayCount, cudaMemcpyDeviceToHost, c.stream));
             MRB_CUDA_TRY(cudaMemcpyAsync(metaHits, dHits, sizeof(mrb_meta_hit) * totalRayCount, cudaMemcpyDeviceToHost, c.stream));
             MRB_CUDA_TRY(cudaMemcpyAsync(rays, dRays, sizeof(mrb_ray_gmem) * totalRayCount, cudaMemcpyDeviceToHost, c.stream));
@@ -300,50 +364,12 @@ static mrb_status CastCommon(mrb_context ctx, mrb_accel accel, bool anyHit,
                              uint32_t rayCount, uint32_t totalRayCount,
                              mrb_memspace memspace, mrb_trace_mode mode)
 {
-    return Guard(ctx, [&](mrb::Context& c)
-    {
-        if(!accel || !rays) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
-        if(anyHit ? !visibleBits : (!hitKeys || !metaHits)) return Fail(c, MRB_ERR_INVALID_ARG, "null output");
-        if(totalRayCount < rayCount && !rayIndices) return Fail(c, MRB_ERR_INVALID_ARG, "totalRayCount < rayCount");
-        if(mode == MRB_TRACE_WIDE && !accel->d.wideNodes) return Fail(c, MRB_ERR_UNSUPPORTED, "accelerator was built BINARY_ONLY");
-        if(rayCount == 0) return MRB_OK;
-        if(memspace == MRB_MEM_DEVICE)
-        {
-            mrb::TraceRays(c, *accel, anyHit, mode, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount);
-            return MRB_OK;
-        }
-        // host variant: stage through scratch, copies inside the stream, synchronous on return
-        const size_t words = (size_t(totalRayCount) + 31) / 32;
-        mrb::MultiAlloc sz(nullptr);
-        sz.Take<mrb_ray_gmem>(totalRayCount); sz.Take<uint32_t>(rayIndices ? rayCount : 0);
-        if(anyHit) sz.Take<uint32_t>(words); else { sz.Take<mrb_hit_key_pack>(totalRayCount); sz.Take<mrb_meta_hit>(totalRayCount); }
-        c.scratch.Reserve(sz.Total());
-        mrb::MultiAlloc ma(c.scratch.Base());
-        mrb_ray_gmem* dRays = ma.Take<mrb_ray_gmem>(totalRayCount);
-        uint32_t* dIdx = ma.Take<uint32_t>(rayIndices ? rayCount : 0);
-        MRB_CUDA_TRY(cudaMemcpyAsync(dRays, rays, sizeof(mrb_ray_gmem) * totalRayCount, cudaMemcpyHostToDevice, c.stream));
-        if(rayIndices) MRB_CUDA_TRY(cudaMemcpyAsync(dIdx, rayIndices, sizeof(uint32_t) * rayCount, cudaMemcpyHostToDevice, c.stream));
-        if(anyHit)
-        {
-            uint32_t* dBits = ma.Take<uint32_t>(words);
-            MRB_CUDA_TRY(cudaMemcpyAsync(dBits, visibleBits, sizeof(uint32_t) * words, cudaMemcpyHostToDevice, c.stream));
-            mrb::TraceRays(c, *accel, true, mode, nullptr, nullptr, dBits, dRays, rayIndices ? dIdx : nullptr, rayCount);
-            MRB_CUDA_TRY(cudaMemcpyAsync(visibleBits, dBits, sizeof(uint32_t) * words, cudaMemcpyDeviceToHost, c.stream));
-        }
-        else
-        {
-            mrb_hit_key_pack* dKeys = ma.Take<mrb_hit_key_pack>(totalRayCount);
-            mrb_meta_hit* dHits = ma.Take<mrb_meta_hit>(totalRayCount);
-            MRB_CUDA_TRY(cudaMemcpyAsync(dKeys, hitKeys, sizeof(mrb_hit_key_pack) * totalRayCount, cudaMemcpyHostToDevice, c.stream));
-            MRB_CUDA_TRY(cudaMemcpyAsync(dHits, metaHits, sizeof(mrb_meta_hit) * totalRayCount, cudaMemcpyHostToDevice, c.stream));
-            mrb::TraceRays(c, *accel, false, mode, dKeys, dHits, nullptr, dRays, rayIndices ? dIdx : nullptr, rayCount);
-            MRB_CUDA_TRY(cudaMemcpyAsync(hitKeys, dKeys, sizeof(mrb_hit_key_pack) * totalRayCount, cudaMemcpyDeviceToHost, c.stream));
-            MRB_CUDA_TRY(cudaMemcpyAsync(metaHits, dHits, sizeof(mrb_meta_hit) * totalRayCount, cudaMemcpyDeviceToHost, c.stream));
-            MRB_CUDA_TRY(cudaMemcpyAsync(rays, dRays, sizeof(mrb_ray_gmem) * totalRayCount, cudaMemcpyDeviceToHost, c.stream));
-        }
-        MRB_CUDA_TRY(cudaStreamSynchronize(c.stream));
-        return MRB_OK;
-    });
+    if(ctx && !accel) return Guard(ctx, [&](mrb::Context& c) { return Fail(c, MRB_ERR_INVALID_ARG, "null argument"); });
+    if(ctx && mode == MRB_TRACE_WIDE && !accel->d.wideNodes)
+        return Guard(ctx, [&](mrb::Context& c) { return Fail(c, MRB_ERR_UNSUPPORTED, "accelerator was built BINARY_ONLY"); });
+    return CastGeneric(ctx, anyHit, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, totalRayCount, memspace,
+                       [&](mrb::Context& c, mrb_hit_key_pack* k, mrb_meta_hit* h, uint32_t* b, mrb_ray_gmem* r, const uint32_t* idx, uint32_t n)
+                       { mrb::TraceRays(c, *accel, anyHit, mode, k, h, b, r, idx, n); });
 }
 
 extern "C"
@@ -703,8 +729,8 @@ mrb_status mrb_scene_cast_rays(mrb_context ctx, mrb_scene scene, mrb_hit_key_pac
 {
     if(!scene) return MRB_ERR_INVALID_ARG;
     return CastGeneric(ctx, false, hitKeys, metaHits, nullptr, rays, rayIndices, rayCount, totalRayCount, memspace,
-        [&](mrb::Context& c, mrb_hit_key_pack* k, mrb_meta_hit* h, uint32_t* b, mrb_ray_gmem* r, const uint32_t* idx)
-        { mrb::TraceScene(c, scene->d, false, mode, k, h, b, r, idx, rayCount); });
+        [&](mrb::Context& c, mrb_hit_key_pack* k, mrb_meta_hit* h, uint32_t* b, mrb_ray_gmem* r, const uint32_t* idx, uint32_t n)
+        { mrb::TraceScene(c, scene->d, false, mode, k, h, b, r, idx, n); });
 }
 
 mrb_status mrb_scene_cast_visibility_rays(mrb_context ctx, mrb_scene scene, uint32_t* isVisibleBits,
@@ -713,8 +739,8 @@ mrb_status mrb_scene_cast_visibility_rays(mrb_context ctx, mrb_scene scene, uint
 {
     if(!scene) return MRB_ERR_INVALID_ARG;
     return CastGeneric(ctx, true, nullptr, nullptr, isVisibleBits, const_cast<mrb_ray_gmem*>(rays), rayIndices, rayCount, totalRayCount, memspace,
-        [&](mrb::Context& c, mrb_hit_key_pack* k, mrb_meta_hit* h, uint32_t* b, mrb_ray_gmem* r, const uint32_t* idx)
-        { mrb::TraceScene(c, scene->d, true, mode, k, h, b, r, idx, rayCount); });
+        [&](mrb::Context& c, mrb_hit_key_pack* k, mrb_meta_hit* h, uint32_t* b, mrb_ray_gmem* r, const uint32_t* idx, uint32_t n)
+        { mrb::TraceScene(c, scene->d, true, mode, k, h, b, r, idx, n); });
 }
 
 } // extern "C"

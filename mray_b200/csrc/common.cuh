@@ -77,6 +77,11 @@ struct Context
     uint64_t     launches = 0;
     std::string  error;
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+    // host-pointer casts: upload / trace / download of consecutive ray chunks overlap on three streams
+    static constexpr int PIPE_CHUNKS = 16;
+    cudaStream_t copyIn = nullptr, copyOut = nullptr;
+    cudaEvent_t  evIn[PIPE_CHUNKS] = {}, evDone[PIPE_CHUNKS] = {};
+    cudaEvent_t  evStart = nullptr;
 };
 
 inline uint32_t DivUp(uint32_t a, uint32_t b) { return (a + b - 1) / b; }

@@ -290,6 +290,27 @@ def test_full_size_config2_parity(gpu_ctx):
     acc.close()
 
 
+def test_host_pointer_casts_are_pipelined_and_identical(gpu_ctx):
+    """Host-buffer casts large enough to take the chunked upload / trace / download pipeline return exactly
+    what the device-pointer call returns (ragged last chunk, pre-set miss values untouched, visibility words)."""
+    p, i = scenes.arcade_mesh(60_000)
+    acc = capi.Accelerator(gpu_ctx, p, i)
+    rays = scenes.pinhole_rays(801, 517, **scenes.ARCADE_CAMERA)        # 414 117 rays: not a multiple of anything
+    n = rays.shape[0]
+    rays[::7, 7] = 0.5                                                   # short rays: plenty of misses
+    dkeys, dhits, drays = gpu_cast(acc, rays, capi.MRB_TRACE_WIDE)
+    hkeys = np.full((n, 4), 0xFFFFFFFF, np.uint32); hhits = np.zeros((n, 2), np.float32); hrays = rays.copy()
+    acc.cast_rays(hkeys, hhits, hrays, None, capi.MRB_TRACE_WIDE)
+    assert np.array_equal(hkeys, dkeys) and np.array_equal(hhits, dhits) and np.array_equal(hrays, drays)
+    assert (hkeys[:, 0] == 0xFFFFFFFF).any() and (hkeys[:, 0] != 0xFFFFFFFF).any()
+    dvis = gpu_visibility(acc, rays, capi.MRB_TRACE_WIDE)
+    bits = np.full(((n + 31) // 32,), 0xFFFFFFFF, np.uint32)
+    acc.cast_visibility_rays(bits, rays.copy(), None, capi.MRB_TRACE_WIDE)
+    hvis = ((bits[np.arange(n) // 32] >> (np.arange(n) % 32).astype(np.uint32)) & 1).astype(bool)
+    assert np.array_equal(hvis, dvis)
+    acc.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # RayPartitioner
 # ---------------------------------------------------------------------------------------------
