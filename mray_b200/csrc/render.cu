@@ -151,10 +151,7 @@ struct RenderData
     float4*           throughput;
     float4*           radiance;
     float4*           shadowRadiance;
-    float*            prevPdf;
-    float*            filmWeight;
-    uint32_t*         pixel;
-    uint32_t*         pathData;        // depth | status << 8 | type << 16
+    uint4*            meta;            // x: pathData (depth | status << 8 | type << 16), y: pixel, z: film weight, w: previous bxdf pdf
     uint32_t*         rng;
     uint32_t*         visible;
     // material-key ray partitioning (RenderSurfaceWorkHasher + RayPartitioner::MultiPartition)
@@ -171,22 +168,28 @@ struct RenderData
 
 __device__ __forceinline__ uint32_t PackPD(uint32_t depth, uint32_t status, uint32_t type) { return depth | (status << 8) | (type << 16); }
 
-__global__ void __launch_bounds__(RTPB) KReload(RenderData d)
+// Reload of one slot; must be called by all 32 lanes of a warp (warp-aggregated claim). `isFree`: the slot
+// holds no path (its meta.x status is INVALID).
+__device__ __forceinline__ void ReloadSlot(const RenderData& d, uint32_t i, bool inRange, bool isFree)
 {
-    const uint32_t i = blockIdx.x * RTPB + threadIdx.x;
-    const bool inRange = i < d.slots;
-    uint32_t pd = inRange ? d.pathData[i] : PackPD(0, ST_ALIVE, 0);
-    const bool isFree = ((pd >> 8) & 0xFFu) == ST_INVALID;
-    // warp-aggregated claim of new path indices
+    // block-aggregated claim of new path indices: ONE atomic per block on the global counter (same-address
+    // atomics serialise in L2; one per warp was the bottleneck of this kernel), ranks by ballot + a
+    // per-warp prefix in shared memory. Must be reached by every thread of the block.
+    __shared__ uint32_t sWarpFree[RTPB / 32];
+    __shared__ unsigned long long sBlockBase;
     const uint32_t want = __ballot_sync(0xffffffffu, isFree);
-    unsigned long long base = 0;
-    const uint32_t lane = threadIdx.x & 31u;
-    if(want)
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if(lane == 0) sWarpFree[warp] = uint32_t(__popc(want));
+    __syncthreads();
+    if(threadIdx.x == 0)
     {
-        const int leader = __ffs(int(want)) - 1;
-        if(int(lane) == leader) base = atomicAdd(&d.counters[0], (unsigned long long)__popc(want));
-        base = __shfl_sync(0xffffffffu, base, leader);
+        uint32_t total = 0;
+        #pragma unroll
+        for(int k = 0; k < RTPB / 32; k++) { const uint32_t c = sWarpFree[k]; sWarpFree[k] = total; total += c; }
+        sBlockBase = total ? atomicAdd(&d.counters[0], (unsigned long long)total) : 0ull;
     }
+    __syncthreads();
+    const unsigned long long base = sBlockBase + sWarpFree[warp];
     if(!inRange) return;
     if(!isFree)
     {
@@ -233,10 +236,7 @@ __global__ void __launch_bounds__(RTPB) KReload(RenderData d)
     d.throughput[i] = make_float4(1.f, 1.f, 1.f, 1.f);
     d.radiance[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     d.shadowRadiance[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    d.prevPdf[i] = 0.0f;
-    d.filmWeight[i] = weight;
-    d.pixel[i] = pix;
-    d.pathData[i] = PackPD(0, ST_ALIVE, RAY_CAMERA);
+    d.meta[i] = make_uint4(PackPD(0, ST_ALIVE, RAY_CAMERA), pix, __float_as_uint(weight), __float_as_uint(0.0f));
     if(d.spectral)
     {
         // one more dimension after the camera sample (PathTracerRendererBase.cu:L139-168)
@@ -270,6 +270,14 @@ __device__ __forceinline__ void LoadTriangle(const RenderInstance& in, uint32_t 
         p[k] = F3(in.positions[3 * size_t(vi[k])], in.positions[3 * size_t(vi[k]) + 1], in.positions[3 * size_t(vi[k]) + 2]);
 }
 
+__global__ void __launch_bounds__(RTPB) KReload(RenderData d)
+{
+    const uint32_t i = blockIdx.x * RTPB + threadIdx.x;
+    const bool inRange = i < d.slots;
+    const uint32_t pd = inRange ? d.meta[i].x : PackPD(0, ST_ALIVE, 0);
+    ReloadSlot(d, i, inRange, ((pd >> 8) & 0xFFu) == ST_INVALID);
+}
+
 // Material / light colour at the path's wavelengths: Converter::ConvertAlbedo / ConvertRadiance with the
 // coefficient fetch hoisted to StartRender (constant attributes), or the RGB pass-through converter.
 __device__ __forceinline__ Spec AlbedoAt(const RenderData& d, float4 a, float4 w)
@@ -300,7 +308,7 @@ __global__ void __launch_bounds__(RTPB) KGenWorkKeys(RenderData d)
 {
     const uint32_t i = blockIdx.x * RTPB + threadIdx.x;
     if(i >= d.slots) return;
-    const uint32_t status = (d.pathData[i] >> 8) & 0xFFu;
+    const uint32_t status = (d.meta[i].x >> 8) & 0xFFu;
     const uint4 keys = *reinterpret_cast<const uint4*>(d.hitKeys + i);
     uint32_t batch, data = 0;
     if(status != ST_ALIVE) batch = 3u;
@@ -310,23 +318,23 @@ __global__ void __launch_bounds__(RTPB) KGenWorkKeys(RenderData d)
     d.workIndices[i] = i;
 }
 
-__global__ void __launch_bounds__(RTPB) KShade(RenderData d)
+// Shading of one slot. Returns true when the slot held a live path (= one closest-hit ray was cast for it
+// this bounce); castShadow reports an NEE shadow ray.
+__device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool& castShadow)
 {
-    const uint32_t tidx = blockIdx.x * RTPB + threadIdx.x;
-    if(tidx >= d.slots) return;
-    const uint32_t i = d.partitionRays ? d.workIndices[tidx] : tidx;
-    uint32_t pd = d.pathData[i];
-    if(((pd >> 8) & 0xFFu) != ST_ALIVE) return;
-    uint32_t depth = pd & 0xFFu, type = (pd >> 16) & 0xFFu;
+    // every per-slot input is requested before the first use, so one round trip covers them all
+    const uint4 meta = d.meta[i];
     const float4 r0 = reinterpret_cast<const float4*>(d.rays + i)[0];
     const float4 r1 = reinterpret_cast<const float4*>(d.rays + i)[1];
-    const Float3 ro = F3(r0.x, r0.y, r0.z), rd = F3(r1.x, r1.y, r1.z);
     const uint4 keys = *reinterpret_cast<const uint4*>(d.hitKeys + i);
-    {   // closest-hit rays cast this iteration (one atomic per warp)
-        const uint32_t m = __activemask();
-        if((threadIdx.x & 31u) == uint32_t(__ffs(int(m)) - 1)) atomicAdd(&d.counters[2], (unsigned long long)__popc(m));
-    }
-    Spec throughput = S4(d.throughput[i]);
+    const float2 bary = *reinterpret_cast<const float2*>(d.hits + i);
+    const float4 thr4 = d.throughput[i];
+    const uint32_t rngState = d.rng[i];
+    const uint32_t pd = meta.x;
+    if(((pd >> 8) & 0xFFu) != ST_ALIVE) return false;
+    uint32_t depth = pd & 0xFFu, type = (pd >> 16) & 0xFFu;
+    const Float3 ro = F3(r0.x, r0.y, r0.z), rd = F3(r1.x, r1.y, r1.z);
+    Spec throughput = S4(thr4);
     const float4 waves = d.spectral ? d.waves[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     // every live slot gets a well defined (never hitting) shadow ray unless NEE writes one
     d.shadowRays[i].tMin = 1.0f; d.shadowRays[i].tMax = -1.0f;
@@ -334,10 +342,9 @@ __global__ void __launch_bounds__(RTPB) KShade(RenderData d)
     if(keys.x == INVALID_U32)
     {
         // boundary light (Null): no emission; path ends (LightWorkFunction[WithNEE]::Call)
-        d.pathData[i] = PackPD(depth, ST_DEAD, type);
-        return;
+        d.meta[i].x = PackPD(depth, ST_DEAD, type);
+        return true;
     }
-    const float2 bary = *reinterpret_cast<const float2*>(d.hits + i);
     const uint32_t prim = keys.x & 0x0FFFFFFFu;
     const uint32_t lmKey = keys.y;
     const RenderInstance& in = d.instances[d.sceneMode ? keys.w : 0u];
@@ -361,7 +368,7 @@ __global__ void __launch_bounds__(RTPB) KShade(RenderData d)
             if(d.sampleMode == 2u && type == RAY_PATH)
             {
                 // MIS: undo the bxdf pdf division, divide by (bxdf pdf + light pdf)  (BalanceCancelled)
-                float pdfB = d.prevPdf[i];
+                float pdfB = __uint_as_float(meta.w);
                 float NdL = Dot(geoN, rd * -1.0f);
                 NdL = (l.e0.w != 0.0f) ? fabsf(NdL) : fmaxf(0.0f, NdL);
                 float pdfL = (NdL == 0.0f) ? 0.0f : (1.0f / l.p0.w) / NdL;
@@ -376,12 +383,12 @@ __global__ void __launch_bounds__(RTPB) KShade(RenderData d)
             if(depth + 1u <= d.rrHi)
                 d.radiance[i] = F4(S4(d.radiance[i]) + em * throughput);
         }
-        d.pathData[i] = PackPD(depth, ST_DEAD, type);
-        return;
+        d.meta[i].x = PackPD(depth, ST_DEAD, type);
+        return true;
     }
 
     // ------------------------------- Lambert surface -------------------------------
-    PCG32 rng{d.rng[i]};
+    PCG32 rng{rngState};
     const bool backSide = Dot(geoN, Normalize(rd)) > 0.0f;
     Float3 shadeN = geoN;
     if(in.vertexNormals)
@@ -443,10 +450,7 @@ __global__ void __launch_bounds__(RTPB) KShade(RenderData d)
             float4* sp = reinterpret_cast<float4*>(d.shadowRays + i);
             sp[0] = make_float4(so.x, so.y, so.z, 1.0e-5f);
             sp[1] = make_float4(wI.x, wI.y, wI.z, len * (1.0f - 1.0e-4f));
-            {
-                const uint32_t m = __activemask();
-                if((threadIdx.x & 31u) == uint32_t(__ffs(int(m)) - 1)) atomicAdd(&d.counters[3], (unsigned long long)__popc(m));
-            }
+            castShadow = true;
         }
     }
     d.shadowRadiance[i] = shadowRad;
@@ -476,18 +480,33 @@ __global__ void __launch_bounds__(RTPB) KShade(RenderData d)
     {
         throughput = (pdfB == 0.0f) ? S4(0, 0, 0, 0) : throughput * (1.0f / pdfB);
         d.throughput[i] = F4(throughput);
-        d.prevPdf[i] = pdfB;
+        d.meta[i].w = __float_as_uint(pdfB);
         const Float3 no = NudgePos(pos, geoN);
         float4* rp = reinterpret_cast<float4*>(d.rays + i);
         rp[0] = make_float4(no.x, no.y, no.z, 1.0e-4f);
         rp[1] = make_float4(wIw.x, wIw.y, wIw.z, FLT_MAX);
         // type of the NEXT hit's MIS decision is PATH_RAY; the shadow flag only lives until KFinish
-        d.pathData[i] = PackPD(depth, ST_ALIVE, (newType == RAY_SHADOW) ? (RAY_PATH | 0x80u) : RAY_PATH);
+        d.meta[i].x = PackPD(depth, ST_ALIVE, (newType == RAY_SHADOW) ? (RAY_PATH | 0x80u) : RAY_PATH);
     }
     else
     {
         d.rays[i].tMin = 1.0f; d.rays[i].tMax = -1.0f;
-        d.pathData[i] = PackPD(depth, ST_DEAD, (newType == RAY_SHADOW) ? (RAY_PATH | 0x80u) : RAY_PATH);
+        d.meta[i].x = PackPD(depth, ST_DEAD, (newType == RAY_SHADOW) ? (RAY_PATH | 0x80u) : RAY_PATH);
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(RTPB) KShade(RenderData d)
+{
+    const uint32_t tidx = blockIdx.x * RTPB + threadIdx.x;
+    bool alive = false, castShadow = false;
+    if(tidx < d.slots) alive = ShadeSlot(d, d.partitionRays ? d.workIndices[tidx] : tidx, castShadow);
+    // ray statistics: one atomic per block per counter
+    const int nAlive = __syncthreads_count(alive), nShadow = __syncthreads_count(castShadow);
+    if(threadIdx.x == 0)
+    {
+        if(nAlive) atomicAdd(&d.counters[2], (unsigned long long)nAlive);
+        if(nShadow) atomicAdd(&d.counters[3], (unsigned long long)nShadow);
     }
 }
 
@@ -514,55 +533,78 @@ __global__ void KIndexInstances(InstanceRec* inst, uint32_t n)
     if(i < n) inst[i].accelKey = i;
 }
 
-__global__ void __launch_bounds__(RTPB) KFinish(RenderData d)
+// End of a bounce for one slot: add the NEE estimate of an unoccluded shadow ray, put finished paths on the
+// film. All inputs are requested up front (one memory round trip). Returns true when the slot is free
+// afterwards; `died` reports a path that finished in this call.
+__device__ __forceinline__ bool FinishSlot(const RenderData& d, uint32_t i, bool& died)
 {
-    const uint32_t i = blockIdx.x * RTPB + threadIdx.x;
-    if(i >= d.slots) return;
-    uint32_t pd = d.pathData[i];
-    const uint32_t status = (pd >> 8) & 0xFFu;
-    if(status == ST_INVALID) return;
-    uint32_t type = (pd >> 16) & 0xFFu;
+    const uint4 meta = d.meta[i];
     float4 rad = d.radiance[i];
+    const uint32_t visWord = d.visible[i >> 5];
+    const float4 sr = d.shadowRadiance[i];
+    float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f), p4 = w4;
+    if(d.spectral) { w4 = d.waves[i]; p4 = d.wavePdf[i]; }
+    const uint32_t pd = meta.x;
+    const uint32_t status = (pd >> 8) & 0xFFu;
+    if(status == ST_INVALID) return true;
+    uint32_t type = (pd >> 16) & 0xFFu;
     if(type & 0x80u)
     {
         // shadow ray of this bounce: add the pre-multiplied NEE estimate when unoccluded
-        const bool vis = (d.visible[i >> 5] >> (i & 31u)) & 1u;
-        if(vis)
+        if((visWord >> (i & 31u)) & 1u)
         {
-            const float4 sr = d.shadowRadiance[i];
             rad.x += sr.x; rad.y += sr.y; rad.z += sr.z; rad.w += sr.w;
-            d.radiance[i] = rad;
+            if(status != ST_DEAD) d.radiance[i] = rad;
         }
         type &= 0x7Fu;
     }
-    if(status == ST_DEAD)
+    if(status != ST_DEAD)
     {
-        // film: ConvertNaNsToColor + atomic add (planar R,G,B,W)
-        float w = d.filmWeight[i];
-        Float3 v = F3(rad.x, rad.y, rad.z);
-        if(d.spectral)
-        {
-            // ConvertSpectrumToRGBIndirect on the dead paths (PathTracerRendererBase.cu:L228-241)
-            const float4 w4 = d.waves[i], p4 = d.wavePdf[i];
-            const float val[4] = {rad.x, rad.y, rad.z, rad.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w}, pp[4] = {p4.x, p4.y, p4.z, p4.w};
-            const float3 rgb = SpectraToRGB(d.spec, val, wv, pp);
-            v = F3(rgb.x, rgb.y, rgb.z);
-        }
-        if(!(isfinite(v.x) && isfinite(v.y) && isfinite(v.z))) { v = F3(1e7f, 0.f, 1e7f); w *= 128.0f; }
-        const uint32_t pix = d.pixel[i];
-        const size_t plane = size_t(d.width) * d.height;
-        atomicAdd(d.film + pix, v.x);
-        atomicAdd(d.film + plane + pix, v.y);
-        atomicAdd(d.film + 2 * plane + pix, v.z);
-        atomicAdd(d.film + 3 * plane + pix, w);
-        {
-            const uint32_t m = __activemask();
-            if((threadIdx.x & 31u) == uint32_t(__ffs(int(m)) - 1)) atomicAdd(&d.counters[1], (unsigned long long)__popc(m));
-        }
-        d.pathData[i] = PackPD(0, ST_INVALID, 0);
-        d.rays[i].tMin = 1.0f; d.rays[i].tMax = -1.0f;
+        d.meta[i].x = PackPD(pd & 0xFFu, ST_ALIVE, type);
+        return false;
     }
-    else d.pathData[i] = PackPD(pd & 0xFFu, ST_ALIVE, type);
+    // film: ConvertNaNsToColor + atomic add (planar R,G,B,W)
+    float w = __uint_as_float(meta.z);
+    Float3 v = F3(rad.x, rad.y, rad.z);
+    if(d.spectral)
+    {
+        // ConvertSpectrumToRGBIndirect on the dead paths (PathTracerRendererBase.cu:L228-241)
+        const float val[4] = {rad.x, rad.y, rad.z, rad.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w}, pp[4] = {p4.x, p4.y, p4.z, p4.w};
+        const float3 rgb = SpectraToRGB(d.spec, val, wv, pp);
+        v = F3(rgb.x, rgb.y, rgb.z);
+    }
+    if(!(isfinite(v.x) && isfinite(v.y) && isfinite(v.z))) { v = F3(1e7f, 0.f, 1e7f); w *= 128.0f; }
+    const uint32_t pix = meta.y;
+    const size_t plane = size_t(d.width) * d.height;
+    atomicAdd(d.film + pix, v.x);
+    atomicAdd(d.film + plane + pix, v.y);
+    atomicAdd(d.film + 2 * plane + pix, v.z);
+    atomicAdd(d.film + 3 * plane + pix, w);
+    died = true;
+    d.meta[i].x = PackPD(0, ST_INVALID, 0);
+    d.rays[i].tMin = 1.0f; d.rays[i].tMax = -1.0f;
+    return true;
+}
+
+__global__ void __launch_bounds__(RTPB) KFinish(RenderData d)
+{
+    const uint32_t i = blockIdx.x * RTPB + threadIdx.x;
+    bool died = false;
+    if(i < d.slots) FinishSlot(d, i, died);
+    const int nDied = __syncthreads_count(died);   // completed paths: one atomic per block
+    if(threadIdx.x == 0 && nDied) atomicAdd(&d.counters[1], (unsigned long long)nDied);
+}
+
+// KFinish of bounce k fused with KReload of bounce k+1: the slot a path just left is refilled in the same pass
+__global__ void __launch_bounds__(RTPB) KFinishReload(RenderData d)
+{
+    const uint32_t i = blockIdx.x * RTPB + threadIdx.x;
+    const bool inRange = i < d.slots;
+    bool died = false;
+    const bool isFree = inRange ? FinishSlot(d, i, died) : false;
+    const int nDied = __syncthreads_count(died);
+    if(threadIdx.x == 0 && nDied) atomicAdd(&d.counters[1], (unsigned long long)nDied);
+    ReloadSlot(d, i, inRange, isFree);
 }
 
 } // namespace
@@ -699,8 +741,7 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
         d.rays = ma.Take<mrb_ray_gmem>(P); d.shadowRays = ma.Take<mrb_ray_gmem>(P);
         d.hitKeys = ma.Take<mrb_hit_key_pack>(P); d.hits = ma.Take<mrb_meta_hit>(P);
         d.throughput = ma.Take<float4>(P); d.radiance = ma.Take<float4>(P); d.shadowRadiance = ma.Take<float4>(P);
-        d.prevPdf = ma.Take<float>(P); d.filmWeight = ma.Take<float>(P); d.pixel = ma.Take<uint32_t>(P);
-        d.pathData = ma.Take<uint32_t>(P); d.rng = ma.Take<uint32_t>(P); d.visible = ma.Take<uint32_t>((P + 31) / 32);
+        d.meta = ma.Take<uint4>(P); d.rng = ma.Take<uint32_t>(P); d.visible = ma.Take<uint32_t>((P + 31) / 32);
         d.film = ma.Take<float>(size_t(4) * d.width * d.height);
         d.counters = ma.Take<unsigned long long>(8);
         d.albedo = ma.Take<float4>(desc.materialCount ? desc.materialCount : 1);
@@ -786,7 +827,7 @@ void RenderIterate(Context& ctx, mrb_renderer_t& r, uint32_t iterations)
     const uint32_t grid = DivUp(d.slots, RTPB);
     for(uint32_t it = 0; it < iterations; it++)
     {
-        MRB_LAUNCH(ctx, KReload, grid, RTPB, 0, d);
+        if(it == 0) MRB_LAUNCH(ctx, KReload, grid, RTPB, 0, d);   // later bounces: fused into the previous KFinishReload
         if(r.scene) TraceScene(ctx, r.sceneData, false, MRB_TRACE_WIDE, d.hitKeys, d.hits, nullptr, d.rays, nullptr, d.slots);
         else TraceRays(ctx, *r.accel, false, MRB_TRACE_WIDE, d.hitKeys, d.hits, nullptr, d.rays, nullptr, d.slots);
         if(d.partitionRays)
@@ -804,7 +845,8 @@ void RenderIterate(Context& ctx, mrb_renderer_t& r, uint32_t iterations)
             if(r.scene) TraceScene(ctx, r.sceneData, true, MRB_TRACE_WIDE, nullptr, nullptr, d.visible, d.shadowRays, nullptr, d.slots);
             else TraceRays(ctx, *r.accel, true, MRB_TRACE_WIDE, nullptr, nullptr, d.visible, d.shadowRays, nullptr, d.slots);
         }
-        MRB_LAUNCH(ctx, KFinish, grid, RTPB, 0, d);
+        if(it + 1 < iterations) MRB_LAUNCH(ctx, KFinishReload, grid, RTPB, 0, d);
+        else MRB_LAUNCH(ctx, KFinish, grid, RTPB, 0, d);
         r.iterations++;
     }
 }

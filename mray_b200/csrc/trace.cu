@@ -514,11 +514,19 @@ KResolveExact(AccelData a, uint32_t accelKey,
         for(int s = 0; s < n && !full; s++)
         {
             const HitRecord& z = c[s == 0 ? first : 1 - first];
+            // a later-visited candidate only matters when it is strictly closer than the accepted one
+            if(accepted >= 0 && !(z.t < c[accepted].t)) continue;
             bool reach = true;
+            // every ancestor box encloses the leaf box and the slab values are monotone in the box: if the leaf
+            // box passes with tUpper, so does every ancestor tested with tUpper, and once an ancestor contains
+            // the accepted candidate (range start <= its rank) all higher ones do too, so the walk can stop at
+            // the first ancestor that is not tested with the accepted t (the common ancestor, a few levels up)
+            const bool leafPasses = SlabExact(a.leafAABB + 6 * size_t(z.leaf), o, invD, tMin, tUpper);
             uint32_t ni = a.leafParent[z.leaf];
             while(ni != INVALID_U32)
             {
                 const bool usePrior = accepted >= 0 && c[accepted].rank < a.nodeRange[ni].x;
+                if(!usePrior && leafPasses) break;
                 const float tcur = usePrior ? c[accepted].t : tUpper;
                 if(!SlabExact(reinterpret_cast<const float*>(a.boxes + ni), o, invD, tMin, tcur))
                 {
