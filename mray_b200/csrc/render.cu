@@ -446,13 +446,21 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
             sr = (pdf == 0.0f) ? S4(0, 0, 0, 0) : sr * (1.0f / pdf);
             // +2: depth is not incremented yet (KCAccumulateShadowRaysPT)
             if(depth + 2u <= d.rrHi) shadowRad = F4(sr);
-            const Float3 so = NudgePos(pos, geoN);
-            float4* sp = reinterpret_cast<float4*>(d.shadowRays + i);
-            sp[0] = make_float4(so.x, so.y, so.z, 1.0e-5f);
-            sp[1] = make_float4(wI.x, wI.y, wI.z, len * (1.0f - 1.0e-4f));
-            castShadow = true;
+            // The reference casts every shadow ray and adds the pre-multiplied estimate if visible; an
+            // estimate that is exactly zero (light facing away, surface facing away, depth limit) adds
+            // nothing either way, so its visibility ray is not cast at all (about a third of them on the
+            // arcade scene). NaNs compare unequal to zero and keep the reference's behaviour.
+            if(shadowRad.x != 0.0f || shadowRad.y != 0.0f || shadowRad.z != 0.0f || shadowRad.w != 0.0f)
+            {
+                const Float3 so = NudgePos(pos, geoN);
+                float4* sp = reinterpret_cast<float4*>(d.shadowRays + i);
+                sp[0] = make_float4(so.x, so.y, so.z, 1.0e-5f);
+                sp[1] = make_float4(wI.x, wI.y, wI.z, len * (1.0f - 1.0e-4f));
+                castShadow = true;
+            }
         }
     }
+    if(!castShadow) newType = type;
     d.shadowRadiance[i] = shadowRad;
 
     // ---- BxDF sample + Russian roulette (WorkFunction::Call) ----
