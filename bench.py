@@ -292,7 +292,10 @@ def run_ours(args):
                 "steps": e2e_steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "KTraceWide<closest>", "achieved": round(achieved, 1), "peak": peak,
-                     "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                     "unit": "GB/s", "frac": round(achieved / peak, 4),
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the primary and the AO closest-hit
+                     # launch in the ncu --set full capture profiles/r1_ktracewide_f.md (142.1 MB and 132.1 MB)
+                     "traffic": 137.1e6, "algorithmic_bytes_per_launch": n * BYTES_CLOSEST,
                      "bytes_per_ray": BYTES_CLOSEST, "peak_source": peak_src},
     }
     if rank == 0:
