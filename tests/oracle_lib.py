@@ -21,7 +21,7 @@ _u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 
 
 def build_oracle():
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("mray_oracle.c", "pt_oracle.c", "spectrum_oracle.c")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("mray_oracle.c", "pt_oracle.c", "spectrum_oracle.c", "sobol_oracle.c")]
     so = os.path.join(ORACLE_DIR, "liboracle.so")
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(x) for x in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
@@ -377,3 +377,16 @@ def oracle_convert_batch(data, rgb, waves, pdfs, radiance_scale):
     L.orc_convert_batch(C.byref(t), c, w.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p), C.c_uint32(n),
                         C.c_float(radiance_scale), *[o.ctypes.data_as(C.c_void_p) for o in outs])
     return outs
+
+
+# ---- low-discrepancy samplers (oracle/sobol_oracle.c) ----
+def oracle_rng_generate(kind, matrices, seeds, sample_index, width, height, initial_max_spp, dim_start, requests):
+    """kind 1 Sobol, 2 ZSobol; returns u32[sum(requests), width*height] (dimension-major like the reference)."""
+    L = lib()
+    m = np.ascontiguousarray(matrices, np.uint32); s = np.ascontiguousarray(seeds, np.uint32)
+    req = (C.c_int * len(requests))(*[int(r) for r in requests])
+    out = np.zeros((int(sum(requests)), width * height), np.uint32)
+    L.orc_rng_generate(C.c_int(kind), m.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p), C.c_uint32(sample_index),
+                       C.c_uint32(width), C.c_uint32(height), C.c_uint32(initial_max_spp), C.c_uint32(dim_start), req,
+                       C.c_int(len(requests)), out.ctypes.data_as(C.c_void_p))
+    return out
