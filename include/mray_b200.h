@@ -272,6 +272,31 @@ MRB_API mrb_status mrb_spectrum_upsample(mrb_context ctx, mrb_spectrum spectrum,
                                          int rgbIsUniform, const float* waves, uint32_t count, int isRadiance,
                                          mrb_memspace memspace);
 
+/* ---- samplers --------------------------------------------------------------------------- */
+
+typedef enum mrb_sampler_type
+{   /* SamplerType (Core/TracerEnums.h), TracerParameters.samplerType */
+    MRB_SAMPLER_INDEPENDENT = 0, MRB_SAMPLER_SOBOL = 1, MRB_SAMPLER_ZSOBOL = 2,
+    /* OR-ed flag: scramble exactly like the reference. SobolCommon::ScambleOwenFast (Tracer/Random.cu:L152-162)
+     * hashes the bit-reversed value but never reverses it back, which leaves the stratified digits in the low
+     * bits: its points are no better than random. Without this flag the final bit reversal is applied (a proper
+     * Owen-scrambled net); with it the numbers equal the reference's bit for bit. */
+    MRB_SAMPLER_REFERENCE_SCRAMBLE = 0x100
+} mrb_sampler_type;
+
+/* RNGGroupSobol / RNGGroupZSobol::GenerateNumbers (Tracer/Random.cu:L1017-1042,L1293-1318 ->
+ * KCGenRandomNumbersGeneric + GenerateRNFromList, L439-555) for a width x height grid of generators
+ * (generator i = pixel (i % width, i / width), LocalState.seed = generatorSeeds[i]) that all stand at
+ * `sampleIndex`: for every request of requestDims[] (each 1, 2 or 3 = Next / Next2D / Next3D) starting at
+ * dimension dimensionStart, writes the raw 32-bit numbers dimension-major: out[i + width*height * o].
+ * sobolMatrices = SobolDetail::SobolMatrices (256 * 52 u32; ZSobol uses its first three rows).
+ * requestDims is a HOST array (<= 32 entries); the other arrays live in `memspace`. Bit-exact. */
+MRB_API mrb_status mrb_sampler_generate(mrb_context ctx, uint32_t samplerType, const uint32_t* sobolMatrices,
+                                        const uint32_t* generatorSeeds, uint32_t width, uint32_t height,
+                                        uint32_t sampleIndex, uint32_t initialMaxSPP, uint32_t dimensionStart,
+                                        const uint32_t* requestDims, uint32_t requestCount, uint32_t* numbersOut,
+                                        mrb_memspace memspace);
+
 /* ---- wavefront path tracer ------------------------------------------------------------- */
 
 typedef struct mrb_renderer_t* mrb_renderer;
@@ -323,6 +348,13 @@ typedef struct mrb_render_desc
      * transport runs on the 4 samples, the film receives ConvertSpectrumToRGB of each finished path
      * (Tracer/PathTracerRendererBase.cu:L139-168,L228-241). The spectrum object must outlive the renderer. */
     mrb_spectrum    spectrum;
+    /* TracerParameters.samplerType: mrb_sampler_type. Sobol / ZSobol need sobolMatrices (host, 256 * 52 u32,
+     * SobolDetail::SobolMatrices); one generator per PIXEL, seeded like RNGGroupSobol / RNGGroupZSobol
+     * (Tracer/Random.cu:L884-1408): the k-th path of a pixel draws sample index k, dimensions advance per
+     * request (filter 2-D, wavelength 1-D, then per bounce light 3-D, BxDF 2-D, roulette 1-D);
+     * ZSobol's initialMaxSPP = totalSPP. */
+    uint32_t        samplerType;
+    const uint32_t* sobolMatrices;
 } mrb_render_desc;
 
 typedef struct mrb_render_stats

@@ -72,7 +72,8 @@ class RenderDesc(C.Structure):
                 ("width", C.c_uint32), ("height", C.c_uint32), ("totalSPP", C.c_uint32), ("sampleMode", C.c_uint32),
                 ("rrRange", C.c_uint32 * 2), ("filmFilterRadius", C.c_float), ("seed", C.c_uint64),
                 ("maxPathCount", C.c_uint32), ("partitionRays", C.c_uint32),
-                ("scene", C.c_void_p), ("instanceVertexNormals", C.POINTER(C.c_void_p)), ("spectrum", C.c_void_p)]
+                ("scene", C.c_void_p), ("instanceVertexNormals", C.POINTER(C.c_void_p)), ("spectrum", C.c_void_p),
+                ("samplerType", C.c_uint32), ("sobolMatrices", C.c_void_p)]
 
 
 class RenderStats(C.Structure):
@@ -115,6 +116,8 @@ _PROTOTYPES = {
     "mrb_spectrum_convert_to_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]),
     "mrb_spectrum_upsample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32,
                                         C.c_int, C.c_int]),
+    "mrb_sampler_generate": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                       C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, C.c_void_p, C.c_int]),
     "mrb_renderer_create": (C.c_int, [C.c_void_p, C.POINTER(RenderDesc), C.POINTER(C.c_void_p)]),
     "mrb_renderer_destroy": (None, [C.c_void_p, C.c_void_p]),
     "mrb_renderer_iterate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
@@ -226,6 +229,15 @@ class Context:
     @property
     def used_device_memory(self) -> int:
         return int(self.lib.mrb_context_used_device_memory(self.handle))
+
+    def sampler_generate(self, sampler_type, matrices, seeds, width, height, sample_index, initial_max_spp, dim_start, requests, out):
+        """RNGGroupSobol / RNGGroupZSobol::GenerateNumbers (Tracer/Random.cu:L1017-1042,L1293-1318); out: u32[sum(requests), w*h]."""
+        from . import sampling
+        space = _space(matrices, seeds, out)
+        t = sampling.sampler_code(sampler_type)
+        req = (C.c_uint32 * len(requests))(*[int(r) for r in requests])
+        self.check(self.lib.mrb_sampler_generate(self.handle, t, _ptr(matrices), _ptr(seeds), width, height, sample_index, initial_max_spp,
+                                                 dim_start, req, len(requests), _ptr(out), space))
 
     def radix_sort_pairs(self, keys, values, bit_begin=0, bit_end=None):
         """DeviceAlgorithms::RadixSort<true,K,u32> (Device/CUDA/AlgRadixSortCUDA.h:L60-116), in place."""
@@ -415,7 +427,7 @@ class Renderer:
     def __init__(self, ctx: Context, accel, vertex_count, triangle_count, albedo, light_radiance,
                  camera, width, height, total_spp, sample_mode="WithNEEAndMIS", rr_range=(2, 20), seed=0,
                  vertex_normals=None, light_two_sided=None, film_filter_radius=1.0, near_far=(0.01, 1000.0),
-                 max_path_count=0, partition_rays=False, instance_vertex_normals=None, spectrum=None):
+                 max_path_count=0, partition_rays=False, instance_vertex_normals=None, spectrum=None, sampler="Independent"):
         """`accel` is an Accelerator, or a Scene (two-level; vertex_count / triangle_count / vertex_normals
         are then ignored and instance_vertex_normals may hold one array or None per instance)."""
         self.ctx, self.accel, self.spectrum = ctx, accel, spectrum
@@ -424,6 +436,12 @@ class Renderer:
         self._keep = []
         if spectrum is not None:
             d.spectrum = spectrum.handle   # (R)PathTracerSpectral
+        from . import sampling
+        d.samplerType = sampling.sampler_code(sampler)
+        if d.samplerType & 0xFF:
+            mats = np.ascontiguousarray(sampling.sobol_matrices(), np.uint32)
+            self._keep.append(mats)
+            d.sobolMatrices = mats.ctypes.data
         if isinstance(accel, Scene):
             d.scene = accel.handle
             if instance_vertex_normals is not None:

@@ -42,6 +42,8 @@ void BinaryPartition(Context& ctx, uint32_t* indicesOut, uint32_t* leftCount, co
 namespace mrb
 {
 void BuildScene(Context& ctx, mrb_scene_t& sc, const mrb_instance_desc* inst, uint32_t n);
+void SamplerGenerate(Context& ctx, uint32_t type, const uint32_t* matrices, const uint32_t* seeds, uint32_t width, uint32_t height,
+                     uint32_t sampleIndex, uint32_t initialMaxSPP, uint32_t dimStart, uint64_t requests, uint32_t requestCount, uint32_t* out);
 void CreateSpectrum(Context& ctx, mrb_spectrum_t& sp, const mrb_spectrum_desc& desc);
 void SpectrumSampleWavelengths(Context& ctx, const mrb_spectrum_t& sp, const uint32_t* randoms, uint32_t n, float* waves, float* pdfs);
 void SpectrumToRGB(Context& ctx, const mrb_spectrum_t& sp, float* values, const float* waves, const float* pdfs, uint32_t n);
@@ -536,6 +538,36 @@ mrb_status mrb_spectrum_upsample(mrb_context ctx, mrb_spectrum spectrum, float* 
     });
 }
 
+mrb_status mrb_sampler_generate(mrb_context ctx, uint32_t samplerType, const uint32_t* sobolMatrices,
+                                const uint32_t* generatorSeeds, uint32_t width, uint32_t height,
+                                uint32_t sampleIndex, uint32_t initialMaxSPP, uint32_t dimensionStart,
+                                const uint32_t* requestDims, uint32_t requestCount, uint32_t* numbersOut, mrb_memspace memspace)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!sobolMatrices || !generatorSeeds || !requestDims || !numbersOut) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        const uint32_t baseType = samplerType & 0xFFu;
+        if((baseType != MRB_SAMPLER_SOBOL && baseType != MRB_SAMPLER_ZSOBOL) || (samplerType & ~0x1FFu))
+            return Fail(c, MRB_ERR_INVALID_ARG, "sampler type must be Sobol or ZSobol");
+        if(requestCount > 32) return Fail(c, MRB_ERR_INVALID_ARG, "RNRequestList holds at most 32 requests");
+        if(baseType == MRB_SAMPLER_ZSOBOL && initialMaxSPP == 0) return Fail(c, MRB_ERR_INVALID_ARG, "initialMaxSPP must be positive");
+        uint64_t packed = 0; uint32_t total = 0;
+        for(uint32_t r = 0; r < requestCount; r++)
+        {
+            if(requestDims[r] < 1 || requestDims[r] > 3) return Fail(c, MRB_ERR_INVALID_ARG, "a request draws 1, 2 or 3 dimensions");
+            packed |= uint64_t(requestDims[r]) << (2u * r); total += requestDims[r];
+        }
+        const size_t n = size_t(width) * height;
+        if(n == 0 || total == 0) return MRB_OK;
+        return Staged(c, memspace, {{numbersOut, n * total * 4, false, true, nullptr},
+                                    {const_cast<uint32_t*>(sobolMatrices), size_t(256) * 52 * 4, true, false, nullptr},
+                                    {const_cast<uint32_t*>(generatorSeeds), n * 4, true, false, nullptr}},
+                      [&](std::vector<StagedArray>& a)
+                      { mrb::SamplerGenerate(c, samplerType, static_cast<const uint32_t*>(a[1].dev), static_cast<const uint32_t*>(a[2].dev), width, height,
+                                             sampleIndex, initialMaxSPP, dimensionStart, packed, requestCount, static_cast<uint32_t*>(a[0].dev)); });
+    });
+}
+
 mrb_status mrb_renderer_create(mrb_context ctx, const mrb_render_desc* desc, mrb_renderer* out)
 {
     return Guard(ctx, [&](mrb::Context& c)
@@ -548,6 +580,8 @@ mrb_status mrb_renderer_create(mrb_context ctx, const mrb_render_desc* desc, mrb
         if(desc->width == 0 || desc->height == 0 || desc->totalSPP == 0) return Fail(c, MRB_ERR_INVALID_ARG, "empty render");
         if(desc->sampleMode > 2) return Fail(c, MRB_ERR_INVALID_ARG, "unknown sampleMode");
         if(desc->rrRange[1] > 255) return Fail(c, MRB_ERR_INVALID_ARG, "rrRange[1] exceeds PathDataPack depth (u8)");
+        if((desc->samplerType & 0xFFu) > 2 || (desc->samplerType & ~0x1FFu)) return Fail(c, MRB_ERR_INVALID_ARG, "unknown samplerType");
+        if((desc->samplerType & 0xFFu) && !desc->sobolMatrices) return Fail(c, MRB_ERR_INVALID_ARG, "Sobol / ZSobol need sobolMatrices");
         if((desc->materialCount && !desc->albedo) || (desc->lightCount && !desc->lightRadiance))
             return Fail(c, MRB_ERR_INVALID_ARG, "missing material / light attributes");
         mrb_renderer r = mrb::NewRenderer();

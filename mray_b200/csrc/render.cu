@@ -21,6 +21,7 @@
 // in registers. Host synchronisations per iteration: none.
 #include "accel.cuh"
 #include "spectrum.cuh"
+#include "sampler.cuh"
 #include <cfloat>
 #include <random>
 #include <stdexcept>
@@ -88,6 +89,44 @@ struct PCG32
     __device__ __forceinline__ float NextFloat() { return fminf(float(Next()) * 2.3283064365386963e-10f, 0.99999994f); }
 };
 
+// The sample source of one path slot: the independent PCG32 stream, or dimension-indexed (Z-)Sobol points
+// (request sizes follow RNRequestList: a 2-D / 3-D request draws correlated dimensions from one scramble hash).
+struct SlotSampler
+{
+    uint32_t type, state, sampleIndex, dim;
+    bool reverseBack;
+    uint64_t morton;
+    const uint32_t* matrices;
+    ZSobolGlobals g;
+    template<int N>
+    __device__ __forceinline__ void Next(float* out)
+    {
+        if(type == SAMPLER_INDEPENDENT)
+        {
+            PCG32 pcg{state};
+            #pragma unroll
+            for(int k = 0; k < N; k++) out[k] = pcg.NextFloat();
+            state = pcg.s;
+            return;
+        }
+        uint32_t v[3];
+        if(type == SAMPLER_SOBOL) SobolNext(matrices, state, sampleIndex, dim, N, v, reverseBack);
+        else ZSobolNext(matrices, state, sampleIndex, morton, g, dim, N, v, reverseBack);
+        dim += uint32_t(N);
+        #pragma unroll
+        for(int k = 0; k < N; k++) out[k] = fminf(float(v[k]) * 2.3283064365386963e-10f, 0.99999994f);
+    }
+};
+__device__ __forceinline__ SlotSampler LoadSampler(uint32_t type, uint32_t state, uint2 ss, uint32_t pixel, uint32_t width,
+                                                   const uint32_t* matrices, ZSobolGlobals g)
+{
+    SlotSampler s;
+    s.reverseBack = (type & SAMPLER_REFERENCE_SCRAMBLE) == 0u; type &= SAMPLER_TYPE_MASK;
+    s.type = type; s.state = state; s.sampleIndex = ss.x; s.dim = ss.y; s.matrices = matrices; s.g = g;
+    s.morton = (type == SAMPLER_ZSOBOL) ? Morton2D(pixel % width, pixel / width) : 0ull;
+    return s;
+}
+
 // Ray::Nudge (Core/Ray.hpp:L258-301, after RT Gems I ch. 6)
 __device__ __forceinline__ Float3 NudgePos(Float3 p, Float3 n)
 {
@@ -152,7 +191,16 @@ struct RenderData
     float4*           radiance;
     float4*           shadowRadiance;
     uint4*            meta;            // x: pathData (depth | status << 8 | type << 16), y: pixel, z: film weight, w: previous bxdf pdf
-    uint32_t*         rng;
+    uint32_t*         rng;             // Independent: PCG32 state; Sobol / ZSobol: the generator's scramble seed (constant)
+    // low-discrepancy samplers (samplerType != 0): one generator per PIXEL, seeded like RNGGroupSobol /
+    // RNGGroupZSobol; path g renders pixel g % N as that pixel's sample g / N, so the generator state is implicit
+    // (the reference keeps its generators per path slot, which only coincides with the pixel while slots and
+    // pixels stay aligned; per pixel keeps the stratification of the sequence inside every pixel)
+    uint32_t          samplerType;     // 0 Independent (PCG32), 1 Sobol, 2 ZSobol
+    const uint32_t*   pixelSeeds;      // per pixel: LocalState.seed
+    uint2*            sampleState;     // per slot: x = sample index of the current path, y = next free dimension
+    const uint32_t*   sobolMatrices;   // 256 x 52 Joe-Kuo generator matrices
+    ZSobolGlobals     zsobol;
     uint32_t*         visible;
     // material-key ray partitioning (RenderSurfaceWorkHasher + RayPartitioner::MultiPartition)
     uint32_t*         workKeys;        // per slot sort key
@@ -205,11 +253,15 @@ __device__ __forceinline__ void ReloadSlot(const RenderData& d, uint32_t i, bool
         d.hitKeys[i].primKey = INVALID_U32;
         return;
     }
-    PCG32 rng{d.rng[i]};
     const uint32_t pix = uint32_t(g % (unsigned long long)(d.width * d.height));
+    // a new path = the next sample of its pixel's generator, dimension 0
+    const bool lowDisc = d.samplerType != SAMPLER_INDEPENDENT;
+    const uint2 ss = make_uint2(lowDisc ? uint32_t(g / (unsigned long long)(d.width * d.height)) : 0u, 0u);
+    SlotSampler rng = LoadSampler(d.samplerType, lowDisc ? d.pixelSeeds[pix] : d.rng[i], ss, pix, d.width, d.sobolMatrices, d.zsobol);
     const uint32_t px = pix % d.width, py = pix / d.width;
     // stochastic filter sample: offset ~ Gaussian, weight = f / pdf
-    float xi0 = rng.NextFloat(), xi1 = rng.NextFloat();
+    float xiF[2]; rng.Next<2>(xiF);
+    float xi0 = xiF[0], xi1 = xiF[1];
     const float sig = d.filterSigma;
     auto SampleG = [sig](float xi, float& pdfOut)
     {
@@ -241,11 +293,13 @@ __device__ __forceinline__ void ReloadSlot(const RenderData& d, uint32_t i, bool
     {
         // one more dimension after the camera sample (PathTracerRendererBase.cu:L139-168)
         float w[4], p[4];
-        SampleWavelengths(d.spec.mode, rng.NextFloat(), w, p);
+        float xiW[1]; rng.Next<1>(xiW);
+        SampleWavelengths(d.spec.mode, xiW[0], w, p);
         d.waves[i] = make_float4(w[0], w[1], w[2], w[3]);
         d.wavePdf[i] = make_float4(p[0], p[1], p[2], p[3]);
     }
-    d.rng[i] = rng.s;
+    if(!lowDisc) d.rng[i] = rng.state;
+    else { d.rng[i] = rng.state; d.sampleState[i] = make_uint2(rng.sampleIndex, rng.dim); }   // rng[i] = the pixel's seed for the bounces
 }
 
 __device__ __forceinline__ Float3 ApplyP(const float* m, Float3 p)
@@ -388,7 +442,8 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
     }
 
     // ------------------------------- Lambert surface -------------------------------
-    PCG32 rng{rngState};
+    SlotSampler rng = LoadSampler(d.samplerType, rngState, d.samplerType != SAMPLER_INDEPENDENT ? d.sampleState[i] : make_uint2(0u, 0u),
+                                  meta.y, d.width, d.sobolMatrices, d.zsobol);
     const bool backSide = Dot(geoN, Normalize(rd)) > 0.0f;
     Float3 shadeN = geoN;
     if(in.vertexNormals)
@@ -410,7 +465,8 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
     float4 shadowRad = make_float4(0.f, 0.f, 0.f, 0.f);
     if(d.sampleMode != 0u)
     {
-        const float x0 = rng.NextFloat(), x1 = rng.NextFloat(), xs = rng.NextFloat();
+        float xiL[3]; rng.Next<3>(xiL);   // light sample (2-D) + light selection
+        const float x0 = xiL[0], x1 = xiL[1], xs = xiL[2];
         const uint32_t nLights = d.lightCount + 1u; // + boundary light
         uint32_t li = min(uint32_t(xs * float(nLights)), nLights - 1u);
         newType = RAY_SHADOW;
@@ -464,7 +520,8 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
     d.shadowRadiance[i] = shadowRad;
 
     // ---- BxDF sample + Russian roulette (WorkFunction::Call) ----
-    const float u0 = rng.NextFloat(), u1 = rng.NextFloat();
+    float xiB[2]; rng.Next<2>(xiB);
+    const float u0 = xiB[0], u1 = xiB[1];
     const float phi = 2.0f * PI_F * u1, su = sqrtf(u0);
     float sn, cs; sincosf(phi, &sn, &cs);
     const float lx = su * cs, ly = su * sn;
@@ -476,14 +533,16 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
     bool dead = depth >= d.rrHi;
     if(!dead && depth >= d.rrLo)
     {
-        const float rrXi = rng.NextFloat();
+        float xiR[1]; rng.Next<1>(xiR);
+        const float rrXi = xiR[0];
         // rrFactor = throughput.Sum() * ChannelCountInv (PathTracerRendererShaders.h:L251-256)
         float prob = (throughput.x + throughput.y + throughput.z + throughput.w) * (d.spectral ? 0.25f : 0.33333333f);
         prob = fminf(fmaxf(prob, 0.1f), 1.0f);
         if(rrXi >= prob) dead = true;
         else throughput = throughput * (1.0f / prob);
     }
-    d.rng[i] = rng.s;
+    if(d.samplerType == SAMPLER_INDEPENDENT) d.rng[i] = rng.state;
+    else d.sampleState[i].y = rng.dim;
     if(!dead)
     {
         throughput = (pdfB == 0.0f) ? S4(0, 0, 0, 0) : throughput * (1.0f / pdfB);
@@ -749,7 +808,10 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
         d.rays = ma.Take<mrb_ray_gmem>(P); d.shadowRays = ma.Take<mrb_ray_gmem>(P);
         d.hitKeys = ma.Take<mrb_hit_key_pack>(P); d.hits = ma.Take<mrb_meta_hit>(P);
         d.throughput = ma.Take<float4>(P); d.radiance = ma.Take<float4>(P); d.shadowRadiance = ma.Take<float4>(P);
-        d.meta = ma.Take<uint4>(P); d.rng = ma.Take<uint32_t>(P); d.visible = ma.Take<uint32_t>((P + 31) / 32);
+        d.meta = ma.Take<uint4>(P); d.rng = ma.Take<uint32_t>(P);
+        d.sampleState = (desc.samplerType & 0xFFu) ? ma.Take<uint2>(P) : nullptr;
+        d.pixelSeeds = (desc.samplerType & 0xFFu) ? ma.Take<uint32_t>(size_t(d.width) * d.height) : nullptr;
+        d.sobolMatrices = (desc.samplerType & 0xFFu) ? ma.Take<uint32_t>(SOBOL_DIM_COUNT * SOBOL_MATRIX_WIDTH) : nullptr; d.visible = ma.Take<uint32_t>((P + 31) / 32);
         d.film = ma.Take<float>(size_t(4) * d.width * d.height);
         d.counters = ma.Take<unsigned long long>(8);
         d.albedo = ma.Take<float4>(desc.materialCount ? desc.materialCount : 1);
@@ -816,15 +878,30 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
     // RNGGroupIndependent (Tracer/Random.cu:L661-720): mt19937(seed32) draws -> PermutedCG32::GenerateState
     uint32_t seed32 = uint32_t((desc.seed >> 32) ^ (desc.seed & 0xFFFFFFFFull));
     std::mt19937 mt(seed32);
-    std::vector<uint32_t> states(d.slots);
-    for(uint32_t i = 0; i < d.slots; i++)
+    const bool lowDisc = (desc.samplerType & 0xFFu) != 0u;
+    d.samplerType = lowDisc ? desc.samplerType : 0u;
+    const uint32_t generators = lowDisc ? d.width * d.height : d.slots;
+    std::vector<uint32_t> states(generators);
+    for(uint32_t i = 0; i < generators; i++)
     {
+        const uint32_t xi = uint32_t(mt());
+        if(lowDisc) { states[i] = xi; continue; }   // RNGGroupSobol / ZSobol: LocalState.seed = the draw itself (Random.cu:L917-945)
         uint32_t s = 0u * 747796405u + 2891336453u; // Step(0)
-        s += uint32_t(mt());
+        s += xi;
         s = s * 747796405u + 2891336453u;
         states[i] = s;
     }
-    MRB_CUDA_TRY(cudaMemcpyAsync(d.rng, states.data(), states.size() * 4, cudaMemcpyHostToDevice, ctx.stream));
+    MRB_CUDA_TRY(cudaMemcpyAsync(lowDisc ? const_cast<uint32_t*>(d.pixelSeeds) : d.rng, states.data(), states.size() * 4,
+                                 cudaMemcpyHostToDevice, ctx.stream));
+    if(lowDisc)
+    {
+        MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<uint32_t*>(d.sobolMatrices), desc.sobolMatrices,
+                                     sizeof(uint32_t) * SOBOL_DIM_COUNT * SOBOL_MATRIX_WIDTH, cudaMemcpyHostToDevice, ctx.stream));
+        // ZSobol globals (Random.cu:L1172-1176): initialMaxSPP = the render's sample budget, resMaxBits from the larger image side
+        uint32_t maxRes = desc.width > desc.height ? desc.width : desc.height, p2 = 1u, bits = 0u;
+        while(p2 < maxRes) { p2 <<= 1; bits++; }
+        d.zsobol.initialMaxSPP = desc.totalSPP; d.zsobol.resMaxBits = bits;
+    }
     MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
 }
 

@@ -8,6 +8,15 @@ import numpy as np
 DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 SAMPLER_TYPES = {"Independent": 0, "Sobol": 1, "ZSobol": 2}     # SamplerType (Core/TracerEnums.h)
 SOBOL_DIM_COUNT, SOBOL_MATRIX_WIDTH = 256, 52
+REFERENCE_SCRAMBLE = 0x100     # MRB_SAMPLER_REFERENCE_SCRAMBLE: the reference's scramble without the final bit reversal
+
+
+def sampler_code(sampler):
+    """'Sobol' / 'ZSobol' / 'Independent', optionally suffixed '+reference' for the reference's exact scramble."""
+    if not isinstance(sampler, str):
+        return int(sampler)
+    name, _, flag = sampler.partition("+")
+    return SAMPLER_TYPES[name] | (REFERENCE_SCRAMBLE if flag == "reference" else 0)
 
 
 def sobol_matrices():
