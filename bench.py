@@ -239,9 +239,10 @@ def run_ours(args):
         pacc = mray_b200.Accelerator(ctx, dp, torch.from_numpy(pidx.view(np.int32)).cuda(), prim_ranges=pranges, light_or_mat_keys=pkeys)
         pt_spp = 8
 
-        def run_pt(spectrum, partition=False):
+        def run_pt(spectrum, partition=False, sampler="Independent"):
             pr = mray_b200.Renderer(ctx, pacc, p.shape[0], pidx.shape[0], palb, prad, scenes.ARCADE_CAMERA, W, H, pt_spp,
-                                    sample_mode="WithNEEAndMIS", rr_range=(3, 8), seed=rank, partition_rays=partition, spectrum=spectrum)
+                                    sample_mode="WithNEEAndMIS", rr_range=(3, 8), seed=rank, partition_rays=partition, spectrum=spectrum,
+                                    sampler=sampler)
             pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             pr.iterate(2); torch.cuda.synchronize()      # warm
             l0 = ctx.launch_count
@@ -260,7 +261,8 @@ def run_ours(args):
             return res
         pt = {"workload": "arcade mesh, 64 Lambert + 200 emissive tris, WithNEEAndMIS rr[3,8], %dx%d, %d spp" % (W, H, pt_spp),
               "PathTracerRGB": run_pt(None),
-              "PathTracerRGB_material_key_sort": run_pt(None, True)}   # RayPartitioner on: not needed by the fused shading kernel
+              "PathTracerRGB_material_key_sort": run_pt(None, True),   # RayPartitioner on: not needed by the fused shading kernel
+              "PathTracerRGB_ZSobol": run_pt(None, False, "ZSobol")}
         from mray_b200 import spectral
         if spectral.available():
             spec = mray_b200.Spectrum(ctx, spectral.load(), "HyperbolicPBRT")

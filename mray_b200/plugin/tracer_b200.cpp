@@ -172,6 +172,27 @@ class TracerB200 final : public TracerI
         d.wavelengthSampleMode = uint32_t(params.wavelengthSampleMode.e);
         Check(mrb_spectrum_create(ctx, &d, &spectrum));
     }
+    // SobolDetail::SobolMatrices as data (mray_b200/data/sobol_matrices.bin, or $MRB_DATA_DIR)
+    std::vector<uint32_t> sobolMatrices;
+    void EnsureSobolMatrices()
+    {
+        if(!sobolMatrices.empty()) return;
+        namespace fs = std::filesystem;
+        std::vector<fs::path> candidates;
+        if(const char* e = std::getenv("MRB_DATA_DIR")) candidates.push_back(fs::path(e) / "sobol_matrices.bin");
+        Dl_info info;
+        if(dladdr(reinterpret_cast<const void*>(&InverseAffine), &info) && info.dli_fname)
+            candidates.push_back(fs::path(info.dli_fname).parent_path().parent_path() / "data" / "sobol_matrices.bin");
+        for(const fs::path& c : candidates)
+        {
+            std::ifstream f(c, std::ios_base::binary);
+            if(!f) continue;
+            sobolMatrices.resize(size_t(256) * 52);
+            if(f.read(reinterpret_cast<char*>(sobolMatrices.data()), std::streamsize(sobolMatrices.size() * 4))) return;
+            sobolMatrices.clear();
+        }
+        throw MRayError("Unable to open the Sobol generator matrices (sobol_matrices.bin)");
+    }
     void ReleaseAccels()
     {
         if(scene) { mrb_scene_destroy(ctx, scene); scene = nullptr; }
@@ -714,6 +735,15 @@ class TracerB200 final : public TracerI
         const char* pr = std::getenv("MRB_PARTITION_RAYS");
         d.partitionRays = (pr && pr[0] == '1') ? 1u : 0u;
         if(r.type == "(R)PathTracerSpectral") { EnsureSpectrum(); d.spectrum = spectrum; }
+        if(params.samplerType.e != SamplerType::INDEPENDENT)
+        {
+            // the scramble's final bit reversal is applied unless MRB_REFERENCE_SCRAMBLE=1 (see include/mray_b200.h)
+            EnsureSobolMatrices();
+            d.samplerType = (params.samplerType.e == SamplerType::SOBOL) ? MRB_SAMPLER_SOBOL : MRB_SAMPLER_ZSOBOL;
+            const char* rs = std::getenv("MRB_REFERENCE_SCRAMBLE");
+            if(rs && rs[0] == '1') d.samplerType |= MRB_SAMPLER_REFERENCE_SCRAMBLE;
+            d.sobolMatrices = sobolMatrices.data();
+        }
         Check(mrb_renderer_create(ctx, &d, &renderer));
         curRenderer = Raw(id); resolution = tile;
         staging.assign(size_t(4) * pixels, 0.0f);

@@ -20,4 +20,6 @@ if [ ! -f "$OUT/SpectraLUT/ACES_CG.mrspectra" ]; then
 fi
 cp -u "$OUT/SpectraLUT/ACES_CG.mrspectra" "$ROOT/mray_b200/data/ACES_CG.mrspectra"
 g++ $FLAGS "$HERE/ref_spectrum_tap.cpp" -o "$OUT/ref_spectrum_tap" -L"$OUT" -lTracerDLL_CPU -Wl,-rpath,'$ORIGIN' -lpthread -latomic -ldl
+# sampler tap (RNGGroupSobol / RNGGroupZSobol on the reference's CPU backend; golden vectors + generator matrices)
+g++ $FLAGS "$HERE/ref_rng_tap.cpp" -o "$OUT/ref_rng_tap" -L"$OUT" -lTracerDLL_CPU -Wl,-rpath,'$ORIGIN' -lpthread -latomic -ldl
 echo "SPECTRAL_DATA_OK"

@@ -62,6 +62,7 @@ struct DriverRender
     uint32_t    accelMode;      // AcceleratorType: 0 SOFTWARE_NONE(linear), 1 SOFTWARE_BASIC_BVH, 2 HARDWARE
     uint32_t    parallelHint;   // 0 = default (2^21)
     uint32_t    threads;        // host thread pool size (0 = hardware)
+    uint32_t    samplerType;    // SamplerType::E: 0 Independent, 1 ZSobol, 2 Sobol
 };
 
 struct DriverStats
@@ -141,6 +142,7 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
         tp.seed = rd->seed;
         tp.accelMode = AcceleratorType(rd->accelMode);
         if(rd->parallelHint) tp.parallelizationHint = rd->parallelHint;
+        tp.samplerType = SamplerType::E(rd->samplerType);
         tracer = construct(tp);
         // as MRay/RunCommand.cpp:L1015-1025: worker threads run the tracer's device-init function
         ThreadPool pool;

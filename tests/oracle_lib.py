@@ -169,7 +169,7 @@ class _DriverScene(C.Structure):
 class _DriverRender(C.Structure):
     _fields_ = [("rendererName", C.c_char_p), ("width", C.c_uint32), ("height", C.c_uint32), ("totalSPP", C.c_uint32),
                 ("sampleMode", C.c_char_p), ("rrRange", C.c_uint32 * 2), ("seed", C.c_uint64),
-                ("accelMode", C.c_uint32), ("parallelHint", C.c_uint32), ("threads", C.c_uint32)]
+                ("accelMode", C.c_uint32), ("parallelHint", C.c_uint32), ("threads", C.c_uint32), ("samplerType", C.c_uint32)]
 
 
 class _DriverStats(C.Structure):
@@ -207,7 +207,7 @@ def batched_scene(positions, indices, tri_material, normals=None):
 def driver_render(dll_path, batched, albedo, light_material, radiance, camera, width, height, spp,
                   renderer="PathTracerRGB", sample_mode="WithNEEAndMIS", rr_range=(2, 20), seed=0,
                   accel_mode=1, threads=0, parallel_hint=0, near_far=(0.01, 1000.0), driver_flavour="",
-                  batch_transforms=None):
+                  batch_transforms=None, sampler="Independent"):
     """Renders through TracerI. `light_material`: material id whose batch is the prim-backed light.
     batch_transforms: optional [batch, 3, 4] local->world matrices ((T)Single per batch; positions local).
     Returns (image[h,w,3] float32 with row 0 = bottom, weight[h,w], stats dict)."""
@@ -236,7 +236,7 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
         bt = np.ascontiguousarray(batch_transforms, np.float32).reshape(len(mats), 12)
         keep.append(bt); sc.batchTransforms = bt.ctypes.data
     rd = _DriverRender(renderer.encode(), width, height, spp, sample_mode.encode(), (C.c_uint32 * 2)(*rr_range), seed,
-                       accel_mode, parallel_hint, threads)
+                       accel_mode, parallel_hint, threads, {"Independent": 0, "ZSobol": 1, "Sobol": 2}[sampler])
     img = np.zeros((height, width, 3), np.float32)
     wgt = np.zeros((height, width), np.float32)
     st = _DriverStats()

@@ -86,3 +86,20 @@ def test_spectral_renderer_through_tracer_interface():
     mask = ref.max(axis=-1) < 5.0
     assert np.allclose(img[mask].mean(axis=0), ref[mask].mean(axis=0), rtol=0.03), (img[mask].mean(axis=0), ref[mask].mean(axis=0))
     assert float(np.mean((img - ref) ** 2 / (ref ** 2 + 1e-2))) < 1e-2
+
+
+@pytest.mark.skipif(not (os.path.exists(PLUGIN) and O.driver_available()), reason="plugin / driver were not prebuilt")
+@pytest.mark.parametrize("sampler", ["ZSobol", "Sobol"])
+def test_low_discrepancy_sampler_through_tracer_interface(sampler):
+    """TracerParameters.samplerType reaches the renderer: same converged image as the oracle."""
+    c = scenes.cornell_box()
+    b = O.batched_scene(c["positions"], c["indices"], c["material"])
+    res, spp = 32, 4096
+    img, w, st = O.driver_render(PLUGIN, b, c["albedo"], 3, c["radiance"], c["camera"], res, res, spp,
+                                 sample_mode="WithNEEAndMIS", rr_range=(2, 20), seed=6, sampler=sampler)
+    assert np.allclose(w, spp, rtol=1e-3)
+    tm = np.where(c["material"] == 3, -1, c["material"]).astype(np.int32)
+    ref = O.oracle_render(c["positions"], c["indices"], tm, c["albedo"][:3], c["radiance"], c["camera"], res, res, spp, sample_mode=2, seed=9)
+    mask = ref.max(axis=-1) < 5.0
+    assert np.allclose(img[mask].mean(axis=0), ref[mask].mean(axis=0), rtol=0.02)
+    assert float(np.mean((img - ref) ** 2 / (ref ** 2 + 1e-2))) < 6e-3
