@@ -165,7 +165,7 @@ __device__ __forceinline__ int32_t Delta(const uint64_t* __restrict__ codes, int
 // records the sorted range each node covers (used by the wide collapse) and whether any two
 // neighbouring codes are equal.
 __global__ void __launch_bounds__(TPB)
-KKarras(AccelData a, int robust, uint32_t* dupFlag)
+KKarras(AccelData a, int robust, uint32_t* dupFlag, uint32_t* __restrict__ sortedLeafParent)
 {
     const int32_t totalLeafs = int32_t(a.leafCount);
     const uint64_t* __restrict__ codes = a.sortedMorton;
@@ -203,13 +203,13 @@ KKarras(AccelData a, int robust, uint32_t* dupFlag)
         if(lo == gamma)
         {
             uint32_t leaf = a.sortedLeaf[gamma];
-            left = LEAF_FLAG | leaf; a.leafParent[leaf] = uint32_t(i);
+            left = LEAF_FLAG | leaf; a.leafParent[leaf] = uint32_t(i); sortedLeafParent[gamma] = uint32_t(i);
         }
         else { left = uint32_t(gamma); a.nodes[gamma].parent = uint32_t(i); }
         if(hi == gamma + 1)
         {
             uint32_t leaf = a.sortedLeaf[gamma + 1];
-            right = LEAF_FLAG | leaf; a.leafParent[leaf] = uint32_t(i);
+            right = LEAF_FLAG | leaf; a.leafParent[leaf] = uint32_t(i); sortedLeafParent[gamma + 1] = uint32_t(i);
         }
         else { right = uint32_t(gamma + 1); a.nodes[gamma + 1].parent = uint32_t(i); }
         a.nodes[i].left = left;
@@ -223,7 +223,7 @@ KKarras(AccelData a, int robust, uint32_t* dupFlag)
 // its children's boxes. Boxes cross threads through L2 (st.cg / ld.cg) with fences around the
 // counter atomic.
 __global__ void __launch_bounds__(TPB)
-KUnionBoxes(AccelData a, uint32_t* counters)
+KUnionBoxes(AccelData a, uint32_t* counters, const uint32_t* __restrict__ sortedLeafParent)
 {
     const uint32_t totalLeafs = a.leafCount;
     if(totalLeafs == 1)
@@ -232,9 +232,11 @@ KUnionBoxes(AccelData a, uint32_t* counters)
             for(int k = 0; k < 3; k++) { a.boxes[0].min[k] = a.leafAABB[k]; a.boxes[0].max[k] = a.leafAABB[3 + k]; }
         return;
     }
+    // threads walk up from the leaves in SORTED order: Karras' node i sits next to sorted position i, so the
+    // counters, node records and boxes a warp touches are neighbours even when the input order is random
     for(uint32_t i = blockIdx.x * TPB + threadIdx.x; i < totalLeafs; i += gridDim.x * TPB)
     {
-        uint32_t ni = a.leafParent[i];
+        uint32_t ni = sortedLeafParent[i];
         while(ni != INVALID_U32)
         {
             uint32_t prev = atomicAdd(&counters[ni], 1u);
@@ -670,8 +672,8 @@ void BuildScene(Context& ctx, mrb_scene_t& sc, const mrb_instance_desc* inst, ui
     MRB_LAUNCH(ctx, KInstanceAABB, grid, TPB, 0, d, dIn, const_cast<InstanceRec*>(s.instances));
     MRB_LAUNCH(ctx, KMortonBoxes, grid, TPB, 0, d);
     RadixSortPairs(ctx, d.sortedMorton, d.sortedLeaf, n, 0, 64, sortTemp);
-    MRB_LAUNCH(ctx, KKarras, grid, TPB, 0, d, 1, dupFlag);
-    MRB_LAUNCH(ctx, KUnionBoxes, grid, TPB, 0, d, counters);
+    MRB_LAUNCH(ctx, KKarras, grid, TPB, 0, d, 1, dupFlag, slotRank);   // slotRank doubles as the sorted-position -> parent table until the collapse
+    MRB_LAUNCH(ctx, KUnionBoxes, grid, TPB, 0, d, counters, slotRank);
     {
         CollapseState init = {0u, 1u, 0u, 0u, 0u, 0u};
         MRB_CUDA_TRY(cudaMemcpyAsync(cst, &init, sizeof(init), cudaMemcpyHostToDevice, ctx.stream));
@@ -794,8 +796,8 @@ void BuildAccel(Context& ctx, mrb_accel_t& acc, const mrb_accel_desc& desc)
     MRB_LAUNCH(ctx, KLeafAABB, grid, TPB, 0, d);
     MRB_LAUNCH(ctx, KMorton, grid, TPB, 0, d);
     RadixSortPairs(ctx, d.sortedMorton, d.sortedLeaf, d.leafCount, 0, 64, sortTemp);
-    MRB_LAUNCH(ctx, KKarras, grid, TPB, 0, d, robust, dupFlag);
-    MRB_LAUNCH(ctx, KUnionBoxes, grid, TPB, 0, d, counters);
+    MRB_LAUNCH(ctx, KKarras, grid, TPB, 0, d, robust, dupFlag, triRank);   // triRank doubles as the sorted-position -> parent table until the collapse
+    MRB_LAUNCH(ctx, KUnionBoxes, grid, TPB, 0, d, counters, triRank);
     if(wide)
     {
         CollapseState init = {0u, 1u, 0u, 0u, 0u, 0u};

@@ -111,7 +111,9 @@ __device__ __forceinline__ void ZSobolNext(const uint32_t* __restrict__ matrices
         const uint32_t digitShift = uint32_t(2 * i - (pow2 ? 1 : 0));
         uint32_t digit = uint32_t(mortonIndex >> digitShift) & 3u;
         const uint64_t higher = mortonIndex >> (digitShift + 2u);
-        const uint32_t p = uint32_t((MixBits(higher ^ uint64_t(dimMixer)) >> 24) % 24ull);
+        // (x >> 24) % 24 on the 40-bit value without a 64-bit division: 2^32 = 16 (mod 24)
+        const uint64_t mixed = MixBits(higher ^ uint64_t(dimMixer)) >> 24;
+        const uint32_t p = (uint32_t(mixed >> 32) * 16u + uint32_t(mixed & 0xFFFFFFFFull) % 24u) % 24u;
         digit = ZSobolPermute(p, digit);
         sampleIndex |= uint64_t(digit) << digitShift;
     }

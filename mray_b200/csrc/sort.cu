@@ -51,9 +51,13 @@ KSortHistogram(const K* __restrict__ keys, uint32_t n, uint32_t bitBegin, uint32
             uint32_t shift = bitBegin + 8 * p;
             uint32_t bits = min(8u, bitEnd - shift);
             uint32_t d = uint32_t(k >> shift) & ((1u << bits) - 1u);
-            // warp-aggregate equal digits (Morton high digits are often uniform across a warp)
-            uint32_t peers = __match_any_sync(__activemask(), d);
-            if((peers & LaneMaskLt()) == 0) atomicAdd(&sHist[p * RADIX + d], __popc(peers));
+            // Morton high digits are usually uniform across a warp (one aggregated add); anything else goes
+            // straight to shared atomics: match.any costs one round per distinct digit, which is the worst
+            // case exactly when the digits are random and conflict-free
+            const uint32_t m = __activemask();
+            const uint32_t d0 = __shfl_sync(m, d, __ffs(int(m)) - 1);
+            if(__all_sync(m, d == d0)) { if((m & LaneMaskLt()) == 0) atomicAdd(&sHist[p * RADIX + d0], __popc(m)); }
+            else atomicAdd(&sHist[p * RADIX + d], 1u);
         }
     }
     __syncthreads();
