@@ -20,6 +20,7 @@
 //                 traversal (TraverseLBVHStack, AcceleratorLBVH.hpp:L109-167), Ray::IntersectsAABB
 //                 (Core/Ray.hpp:L192-219) with identical arithmetic.
 #include "accel.cuh"
+#include <cstdio>
 #include <cfloat>
 #include <cstdlib>
 
@@ -273,10 +274,16 @@ KTraceWide(AccelData a, uint32_t accelKey,
             const bool nodeWork = hasRay && ((G.y & 0xFF000000u) != 0u);
             const uint32_t bT = __ballot_sync(FULL, triWork);
             const uint32_t bN = __ballot_sync(FULL, nodeWork);
+#ifdef MRB_TRACE_STATS
+            if(lane == 0) { atomicAdd(counters + 12, 1u); atomicAdd(counters + 13, uint32_t(__popc(live))); }
+#endif
 
             // ---- triangle phase: one triangle per lane ----
             if(bT != 0u && (bN == 0u || uint32_t(__popc(bT)) * prm.triDiv >= uint32_t(__popc(live))))
             {
+#ifdef MRB_TRACE_STATS
+                if(lane == 0) { atomicAdd(counters + 10, 1u); atomicAdd(counters + 11, uint32_t(__popc(bT))); }
+#endif
                 if(triWork)
                 {
                     const uint32_t tb = uint32_t(__ffs(int(T.y))) - 1u;
@@ -323,6 +330,9 @@ KTraceWide(AccelData a, uint32_t accelKey,
             // ---- node phase: one node per lane ----
             if(bN != 0u)
             {
+#ifdef MRB_TRACE_STATS
+                if(lane == 0) { atomicAdd(counters + 8, 1u); atomicAdd(counters + 9, uint32_t(__popc(bN))); }
+#endif
                 if(nodeWork && hasRay)
                 {
                     if(T.y != 0u) { stack[sp++] = T; T.y = 0u; } // postponed triangle group
@@ -939,7 +949,11 @@ void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode
         uint32_t* counters = ma.Take<uint32_t>(64);
         uint4* records = ma.Take<uint4>(size_t(RESOLVE_CAPACITY) * 4);
         uint32_t* fbList = ma.Take<uint32_t>(rayCount);
+#ifdef MRB_TRACE_STATS
+        MRB_CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 16, ctx.stream));
+#else
         MRB_CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 8, ctx.stream));
+#endif
         static int occClosest = 0, occAny = 0;
         if(!occClosest)
         {
@@ -967,6 +981,16 @@ void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode
             MRB_LAUNCH(ctx, KTraceBinary<false>, fbGrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, fbList, 0u, counters + 4);
         }
         ctx.lastFallbackCount = counters;
+#ifdef MRB_TRACE_STATS
+        {   // diagnostic build only: warp-step statistics of this cast
+            uint32_t h[16];
+            MRB_CUDA_TRY(cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
+            MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
+            fprintf(stderr, "[trace stats] rays %u anyHit %d | loop iters %u (live lanes %.1f) | node steps %u (lanes %.1f, per ray %.2f) | tri steps %u (lanes %.1f, per ray %.2f)\n",
+                    rayCount, int(anyHit), h[12], double(h[13]) / double(h[12] ? h[12] : 1), h[8], double(h[9]) / double(h[8] ? h[8] : 1), double(h[9]) / rayCount,
+                    h[10], double(h[11]) / double(h[10] ? h[10] : 1), double(h[11]) / rayCount);
+        }
+#endif
     }
     else
     {
