@@ -271,15 +271,14 @@ KTraceWide(AccelData a, uint32_t accelKey,
         do
         {
             const bool triWork = hasRay && (T.y != 0u);
-            const bool nodeWork = hasRay && ((G.y & 0xFF000000u) != 0u);
             const uint32_t bT = __ballot_sync(FULL, triWork);
-            const uint32_t bN = __ballot_sync(FULL, nodeWork);
+            const uint32_t bN0 = __ballot_sync(FULL, hasRay && ((G.y & 0xFF000000u) != 0u));
 #ifdef MRB_TRACE_STATS
             if(lane == 0) { atomicAdd(counters + 12, 1u); atomicAdd(counters + 13, uint32_t(__popc(live))); }
 #endif
 
             // ---- triangle phase: one triangle per lane ----
-            if(bT != 0u && (bN == 0u || uint32_t(__popc(bT)) * prm.triDiv >= uint32_t(__popc(live))))
+            if(bT != 0u && (bN0 == 0u || uint32_t(__popc(bT)) * prm.triDiv >= uint32_t(__popc(live))))
             {
 #ifdef MRB_TRACE_STATS
                 if(lane == 0) { atomicAdd(counters + 10, 1u); atomicAdd(counters + 11, uint32_t(__popc(bT))); }
@@ -327,6 +326,15 @@ KTraceWide(AccelData a, uint32_t accelKey,
                     }
                 }
             }
+            // lanes whose triangle group just ran dry and that hold no node group take their next stack entry
+            // now, so that they can join this iteration's node phase instead of idling through it
+            if(hasRay && (G.y & 0xFF000000u) == 0u && T.y == 0u && sp > 0)
+            {
+                const uint2 e = stack[--sp];
+                if(e.y & 0xFF000000u) G = e; else T = e;
+            }
+            const bool nodeWork = hasRay && ((G.y & 0xFF000000u) != 0u);
+            const uint32_t bN = __ballot_sync(FULL, nodeWork);
             // ---- node phase: one node per lane ----
             if(bN != 0u)
             {
@@ -702,10 +710,9 @@ KTraceWide2(SceneData sc,
         do
         {
             const bool triWork = hasRay && (T.y != 0u);
-            const bool nodeWork = hasRay && ((G.y & 0xFF000000u) != 0u);
             const uint32_t bT = __ballot_sync(FULL, triWork);
-            const uint32_t bN = __ballot_sync(FULL, nodeWork);
-            if(bT != 0u && (bN == 0u || uint32_t(__popc(bT)) * prm.triDiv >= uint32_t(__popc(live))))
+            const uint32_t bN0 = __ballot_sync(FULL, hasRay && ((G.y & 0xFF000000u) != 0u));
+            if(bT != 0u && (bN0 == 0u || uint32_t(__popc(bT)) * prm.triDiv >= uint32_t(__popc(live))))
             {
                 if(triWork)
                 {
@@ -762,6 +769,15 @@ KTraceWide2(SceneData sc,
                     }
                 }
             }
+            // as in KTraceWide: lanes that just ran out of triangles pop now (unless the next entry is the
+            // level sentinel, which the regular pop below handles) and join this iteration's node phase
+            if(hasRay && (G.y & 0xFF000000u) == 0u && T.y == 0u && sp > 0)
+            {
+                const uint2 e = stack[sp - 1];
+                if(e.y != 0u) { sp--; if(e.y & 0xFF000000u) G = e; else T = e; }
+            }
+            const bool nodeWork = hasRay && ((G.y & 0xFF000000u) != 0u);
+            const uint32_t bN = __ballot_sync(FULL, nodeWork);
             if(bN != 0u)
             {
                 if(nodeWork && hasRay && ((G.y & 0xFF000000u) != 0u))
@@ -962,7 +978,7 @@ void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode
         }
         static TraceParams prm = []
         {
-            TraceParams p{5u, 24u, 0x47000000u};
+            TraceParams p{8u, 24u, 0x47000000u};
             if(const char* e = getenv("MRB_TRI_DIV")) p.triDiv = uint32_t(atoi(e));
             if(const char* e = getenv("MRB_FETCH_THR")) p.fetchThr = uint32_t(atoi(e));
             return p;
@@ -1024,7 +1040,7 @@ void TraceScene(Context& ctx, const SceneData& scnData, bool anyHit, mrb_trace_m
             MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occClosest, KTraceWide2<false>, TRACE_TPB, 0));
             MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occAny, KTraceWide2<true>, TRACE_TPB, 0));
         }
-        TraceParams prm{5u, 24u, 0x47000000u};
+        TraceParams prm{8u, 24u, 0x47000000u};
         const uint32_t pgrid = min(grid, uint32_t(ctx.smCount) * uint32_t(anyHit ? occAny : occClosest));
         const uint32_t fbGrid = uint32_t(ctx.smCount);
         if(anyHit)
