@@ -297,13 +297,19 @@ __device__ __forceinline__ ChildRef MakeRef(const AccelData& a, uint32_t child, 
     return r;
 }
 
+// One wide node. Everything per-child lives in registers: the loops over the (at most 8) children and slots
+// are fully unrolled with predicates and the child <-> slot maps are packed nibbles, because a lone thread
+// indexing local-memory arrays dynamically made this routine cost 60-140 K cycles per node — and the level
+// loop below pays one node latency per level.
 __device__ void CollapseNode(const AccelData& a, CollapseState* st, unsigned long long* queue,
                              uint32_t* triRank, uint32_t wideIdx, uint32_t binNode, uint32_t depth)
 {
     const uint32_t MAX_LEAF = a.maxLeafSize;
     ChildRef refs[8];
+    #pragma unroll
+    for(int c = 0; c < 8; c++) refs[c] = ChildRef{0u, 0u, INVALID_U32, -1.0f};
     uint32_t n = 0;
-    if(a.leafCount == 1) { refs[0] = ChildRef{0, 0, INVALID_U32, -1.0f}; n = 1; }
+    if(a.leafCount == 1) { n = 1; }
     else
     {
         LBVHNode nd = a.nodes[binNode];
@@ -318,73 +324,99 @@ __device__ void CollapseNode(const AccelData& a, CollapseState* st, unsigned lon
             while(n < 8)
             {
                 int best = -1; float bestArea = -1.0f;
-                for(uint32_t c = 0; c < n; c++)
+                #pragma unroll
+                for(int c = 0; c < 8; c++)
                 {
-                    if(refs[c].node == INVALID_U32) continue;
+                    if(uint32_t(c) >= n || refs[c].node == INVALID_U32) continue;
                     const uint32_t size = refs[c].hi - refs[c].lo + 1;
                     if(phase == 0 && size <= MAX_LEAF) continue;
-                    if(refs[c].area > bestArea) { bestArea = refs[c].area; best = int(c); }
+                    if(refs[c].area > bestArea) { bestArea = refs[c].area; best = c; }
                 }
                 if(best < 0) break;
-                ChildRef o = refs[best];
-                LBVHNode on = a.nodes[o.node];
-                refs[best] = MakeRef(a, on.left, o.lo);
-                refs[n++] = MakeRef(a, on.right, o.hi);
+                ChildRef o = refs[0];
+                #pragma unroll
+                for(int c = 1; c < 8; c++) if(c == best) o = refs[c];
+                const LBVHNode on = a.nodes[o.node];
+                const ChildRef l = MakeRef(a, on.left, o.lo), r = MakeRef(a, on.right, o.hi);
+                #pragma unroll
+                for(int c = 0; c < 8; c++) { if(c == best) refs[c] = l; if(uint32_t(c) == n) refs[c] = r; }
+                n++;
             }
         }
     }
     // child boxes, node bounds
     float cb[8][6];
     float nb[6] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
-    bool isInner[8];
-    uint32_t numInner = 0, numTris = 0;
-    for(uint32_t c = 0; c < n; c++)
+    uint32_t innerMask = 0u, numInner = 0, numTris = 0;
+    #pragma unroll
+    for(int c = 0; c < 8; c++)
     {
+        if(uint32_t(c) >= n) continue;
         const float* src = (refs[c].node != INVALID_U32)
                          ? reinterpret_cast<const float*>(a.boxes + refs[c].node)
                          : a.leafAABB + 6 * size_t(a.sortedLeaf[refs[c].lo]);
+        #pragma unroll
         for(int k = 0; k < 6; k++) cb[c][k] = src[k];
+    }
+    #pragma unroll
+    for(int c = 0; c < 8; c++)
+    {
+        if(uint32_t(c) >= n) continue;
+        #pragma unroll
         for(int k = 0; k < 3; k++) { nb[k] = fminf(nb[k], cb[c][k]); nb[3 + k] = fmaxf(nb[3 + k], cb[c][3 + k]); }
-        uint32_t size = refs[c].hi - refs[c].lo + 1;
-        isInner[c] = size > MAX_LEAF;
-        if(isInner[c]) numInner++; else numTris += size;
+        const uint32_t size = refs[c].hi - refs[c].lo + 1;
+        if(size > MAX_LEAF) { innerMask |= 1u << c; numInner++; } else numTris += size;
     }
     // slot assignment: greedy on cost[c][s] = dot(centroid_c - centre, dir_s), dir_s component is
     // -1 where the slot bit is set (bit2 = x, bit1 = y, bit0 = z). A ray whose negative-direction
     // octant is r visits slot s with priority (s ^ r): slot r^7 first (nearest), slot r last.
-    int slotOf[8]; bool slotUsed[8];
-    for(int s = 0; s < 8; s++) slotUsed[s] = false;
-    for(uint32_t c = 0; c < n; c++) slotOf[c] = -1;
-    float cen[3] = {0.5f * (nb[0] + nb[3]), 0.5f * (nb[1] + nb[4]), 0.5f * (nb[2] + nb[5])};
+    uint32_t slotOfChild = 0xFFFFFFFFu;   // nibble c = slot of child c (0xF = none yet)
+    uint32_t childOfSlot = 0xFFFFFFFFu;   // nibble s = child in slot s (0xF = empty)
+    uint32_t slotFree = 0xFFu, innerLeft = innerMask;
+    const float cen[3] = {0.5f * (nb[0] + nb[3]), 0.5f * (nb[1] + nb[4]), 0.5f * (nb[2] + nb[5])};
+    float ddx[8], ddy[8], ddz[8];
+    #pragma unroll
+    for(int c = 0; c < 8; c++)
+    {
+        ddx[c] = 0.5f * (cb[c][0] + cb[c][3]) - cen[0];
+        ddy[c] = 0.5f * (cb[c][1] + cb[c][4]) - cen[1];
+        ddz[c] = 0.5f * (cb[c][2] + cb[c][5]) - cen[2];
+    }
     for(uint32_t it = 0; it < numInner; it++)
     {
-        float bestCost = -FLT_MAX; int bc = -1, bs = -1;
-        for(uint32_t c = 0; c < n; c++)
+        float bestCost = -FLT_MAX; uint32_t bc = 0, bs = 0;
+        #pragma unroll
+        for(int c = 0; c < 8; c++)
         {
-            if(!isInner[c] || slotOf[c] >= 0) continue;
-            float dx = 0.5f * (cb[c][0] + cb[c][3]) - cen[0];
-            float dy = 0.5f * (cb[c][1] + cb[c][4]) - cen[1];
-            float dz = 0.5f * (cb[c][2] + cb[c][5]) - cen[2];
-            for(int s = 0; s < 8; s++)
+            if(!((innerLeft >> c) & 1u)) continue;
+            #pragma unroll
+            for(int sl = 0; sl < 8; sl++)
             {
-                if(slotUsed[s]) continue;
-                float cost = ((s & 4) ? -dx : dx) + ((s & 2) ? -dy : dy) + ((s & 1) ? -dz : dz);
-                if(cost > bestCost) { bestCost = cost; bc = int(c); bs = s; }
+                if(!((slotFree >> sl) & 1u)) continue;
+                const float cost = ((sl & 4) ? -ddx[c] : ddx[c]) + ((sl & 2) ? -ddy[c] : ddy[c]) + ((sl & 1) ? -ddz[c] : ddz[c]);
+                if(cost > bestCost) { bestCost = cost; bc = uint32_t(c); bs = uint32_t(sl); }
             }
         }
-        slotOf[bc] = bs; slotUsed[bs] = true;
+        innerLeft &= ~(1u << bc); slotFree &= ~(1u << bs);
+        slotOfChild = (slotOfChild & ~(0xFu << (4u * bc))) | (bs << (4u * bc));
+        childOfSlot = (childOfSlot & ~(0xFu << (4u * bs))) | (bc << (4u * bs));
     }
-    for(uint32_t c = 0; c < n; c++)
+    #pragma unroll
+    for(int c = 0; c < 8; c++)
     {
-        if(slotOf[c] >= 0) continue;
-        for(int s = 0; s < 8; s++) if(!slotUsed[s]) { slotOf[c] = s; slotUsed[s] = true; break; }
+        if(uint32_t(c) >= n || ((innerMask >> c) & 1u)) continue;
+        const uint32_t sl = uint32_t(__ffs(int(slotFree))) - 1u;   // leaf children take the free slots in order
+        slotFree &= ~(1u << sl);
+        slotOfChild = (slotOfChild & ~(0xFu << (4u * uint32_t(c)))) | (sl << (4u * uint32_t(c)));
+        childOfSlot = (childOfSlot & ~(0xFu << (4u * sl))) | (uint32_t(c) << (4u * sl));
     }
     // allocation
     uint32_t childBase = numInner ? atomicAdd(&st->created, numInner) : 0u;
     uint32_t triBase = numTris ? atomicAdd(&st->triCount, numTris) : 0u;
     if(numInner && childBase + numInner > a.wideNodeCapacity) { st->error = 2u; return; }
-    // quantisation frame
-    int ex[3]; double scale[3];
+    // quantisation frame: per axis the smallest power-of-two cell such that 255 cells cover the node
+    int ex[3]; double scale[3], invScale[3];
+    #pragma unroll
     for(int k = 0; k < 3; k++)
     {
         float ext = nb[3 + k] - nb[k];
@@ -396,61 +428,65 @@ __device__ void CollapseNode(const AccelData& a, CollapseState* st, unsigned lon
             while(ldexp(255.0, e) < double(nb[3 + k]) - double(nb[k])) e++;
             e = max(-126, min(127, e));
         }
-        ex[k] = e; scale[k] = ldexp(1.0, e);
+        ex[k] = e; scale[k] = ldexp(1.0, e); invScale[k] = ldexp(1.0, -e);
     }
-    uint32_t qlo[3][2] = {{0, 0}, {0, 0}, {0, 0}}, qhi[3][2] = {{0, 0}, {0, 0}, {0, 0}};
-    uint32_t meta[2] = {0, 0};
+    // child boxes on the grid. (lo - p) and the scaling by a power of two are exact in fp64, so floor / ceil give
+    // the tightest enclosing cells directly; the comparisons only guard the clamped ends.
+    unsigned long long qlo[3] = {~0ull, ~0ull, ~0ull}, qhi[3] = {0ull, 0ull, 0ull}, meta = 0ull;   // empty slots: inverted box
     uint32_t imask = 0;
-    // empty slots get an inverted box
-    for(int k = 0; k < 3; k++) { qlo[k][0] = qlo[k][1] = 0xFFFFFFFFu; }
-    uint32_t triOff = 0;
-    for(int s = 0; s < 8; s++)
+    #pragma unroll
+    for(int c = 0; c < 8; c++)
     {
-        int c = -1;
-        for(uint32_t cc = 0; cc < n; cc++) if(slotOf[cc] == s) c = int(cc);
-        if(c < 0) continue;
+        if(uint32_t(c) >= n) continue;
+        const uint32_t sl = (slotOfChild >> (4u * uint32_t(c))) & 0xFu, sh = 8u * sl;
+        #pragma unroll
         for(int k = 0; k < 3; k++)
         {
-            double p = double(nb[k]);
-            double lo = double(cb[c][k]), hi = double(cb[c][3 + k]);
-            int ql = int(floor((lo - p) / scale[k]));
+            const double p = double(nb[k]), lo = double(cb[c][k]), hi = double(cb[c][3 + k]);
+            int ql = __double2int_rd((lo - p) * invScale[k]);
             ql = max(0, min(255, ql));
-            while(ql > 0 && p + ql * scale[k] > lo) ql--;
-            int qh = int(ceil((hi - p) / scale[k]));
+            if(ql > 0 && p + ql * scale[k] > lo) ql--;
+            int qh = __double2int_ru((hi - p) * invScale[k]);
             qh = max(0, min(255, qh));
-            while(qh < 255 && p + qh * scale[k] < hi) qh++;
-            uint32_t sh = 8u * uint32_t(s & 3);
-            qlo[k][s >> 2] = (qlo[k][s >> 2] & ~(0xFFu << sh)) | (uint32_t(ql) << sh);
-            qhi[k][s >> 2] = (qhi[k][s >> 2] & ~(0xFFu << sh)) | (uint32_t(qh) << sh);
+            if(qh < 255 && p + qh * scale[k] < hi) qh++;
+            qlo[k] = (qlo[k] & ~(0xFFull << sh)) | ((unsigned long long)(uint32_t(ql)) << sh);
+            qhi[k] = (qhi[k] & ~(0xFFull << sh)) | ((unsigned long long)(uint32_t(qh)) << sh);
         }
-        uint32_t m;
-        if(isInner[c]) { m = 0x20u | (24u + uint32_t(s)); imask |= 1u << s; }
-        else
-        {
-            uint32_t size = refs[c].hi - refs[c].lo + 1;
-            m = (((1u << size) - 1u) << 5) | triOff;
-            for(uint32_t j = 0; j < size; j++) triRank[triBase + triOff + j] = refs[c].lo + j;
-            triOff += size;
-        }
-        meta[s >> 2] |= m << (8u * uint32_t(s & 3));
+        if((innerMask >> c) & 1u) { meta |= (unsigned long long)(0x20u | (24u + sl)) << sh; imask |= 1u << sl; }
+    }
+    // triangle groups take their record offsets in slot order
+    uint32_t triOff = 0;
+    #pragma unroll
+    for(int sl = 0; sl < 8; sl++)
+    {
+        const uint32_t c = (childOfSlot >> (4u * uint32_t(sl))) & 0xFu;
+        if(c == 0xFu || ((innerMask >> c) & 1u)) continue;
+        uint32_t lo = 0, size = 0;
+        #pragma unroll
+        for(int cc = 0; cc < 8; cc++) if(uint32_t(cc) == c) { lo = refs[cc].lo; size = refs[cc].hi - refs[cc].lo + 1; }
+        meta |= (unsigned long long)((((1u << size) - 1u) << 5) | triOff) << (8u * uint32_t(sl));
+        for(uint32_t j = 0; j < size; j++) triRank[triBase + triOff + j] = lo + j;
+        triOff += size;
     }
     WideNode w;
     w.q[0] = make_uint4(__float_as_uint(nb[0]), __float_as_uint(nb[1]), __float_as_uint(nb[2]),
                         uint32_t(ex[0] + 127) | (uint32_t(ex[1] + 127) << 8) | (uint32_t(ex[2] + 127) << 16) | (imask << 24));
-    w.q[1] = make_uint4(childBase, triBase, meta[0], meta[1]);
-    w.q[2] = make_uint4(qlo[0][0], qlo[0][1], qlo[1][0], qlo[1][1]);
-    w.q[3] = make_uint4(qlo[2][0], qlo[2][1], qhi[0][0], qhi[0][1]);
-    w.q[4] = make_uint4(qhi[1][0], qhi[1][1], qhi[2][0], qhi[2][1]);
+    w.q[1] = make_uint4(childBase, triBase, uint32_t(meta), uint32_t(meta >> 32));
+    w.q[2] = make_uint4(uint32_t(qlo[0]), uint32_t(qlo[0] >> 32), uint32_t(qlo[1]), uint32_t(qlo[1] >> 32));
+    w.q[3] = make_uint4(uint32_t(qlo[2]), uint32_t(qlo[2] >> 32), uint32_t(qhi[0]), uint32_t(qhi[0] >> 32));
+    w.q[4] = make_uint4(uint32_t(qhi[1]), uint32_t(qhi[1] >> 32), uint32_t(qhi[2]), uint32_t(qhi[2] >> 32));
     a.wideNodes[wideIdx] = w;
     // enqueue internal children in slot order
     uint32_t rel = 0;
-    for(int s = 0; s < 8; s++)
+    #pragma unroll
+    for(int sl = 0; sl < 8; sl++)
     {
-        if(!((imask >> s) & 1u)) continue;
-        int c = -1;
-        for(uint32_t cc = 0; cc < n; cc++) if(slotOf[cc] == s) c = int(cc);
-        unsigned long long item = (unsigned long long)(refs[c].node) | ((unsigned long long)(depth + 1) << 32);
-        queue[childBase + rel] = item;
+        if(!((imask >> sl) & 1u)) continue;
+        const uint32_t c = (childOfSlot >> (4u * uint32_t(sl))) & 0xFu;
+        uint32_t node = 0;
+        #pragma unroll
+        for(int cc = 0; cc < 8; cc++) if(uint32_t(cc) == c) node = refs[cc].node;
+        queue[childBase + rel] = (unsigned long long)(node) | ((unsigned long long)(depth + 1) << 32);
         rel++;
     }
     atomicMax(&st->maxDepth, depth);
