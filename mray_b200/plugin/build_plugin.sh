@@ -10,11 +10,13 @@ REF=${MRAY_REFERENCE:-/root/reference}
 W=$ROOT/oracle/_ref/work
 if [ ! -d "$REF/Source" ] || [ ! -f "$W/cxxflags.txt" ]; then echo "reference not present; keeping prebuilt plugin"; exit 0; fi
 mkdir -p "$ROOT/mray_b200/lib"
-# the reference's Core + TransientPool objects as one shared library (MRay ships them as libCore / libTransientPool)
-g++ -shared -o "$ROOT/oracle/_ref/libmray_refcore.so" "$W"/obj/*Source_Core_*.o "$W"/obj/*TransientPool*.o -lpthread -latomic -ldl
+# the reference's Core + TransientPool objects as one shared library (MRay ships them as libCore / libTransientPool):
+# the HOST's runtime the plugin is loaded into, so it sits next to the plugin; the test-side driver keeps its own copy
+g++ -shared -o "$ROOT/mray_b200/lib/libmray_refcore.so" "$W"/obj/*Source_Core_*.o "$W"/obj/*TransientPool*.o -lpthread -latomic -ldl
+cp "$ROOT/mray_b200/lib/libmray_refcore.so" "$ROOT/oracle/_ref/libmray_refcore.so"
 g++ $(cat "$W/cxxflags.txt") -I"$ROOT/include" -c "$HERE/tracer_b200.cpp" -o "$W/tracer_b200.o"
 g++ -shared -o "$ROOT/mray_b200/lib/libTracerDLL_B200.so" "$W/tracer_b200.o" -L"$ROOT/mray_b200/lib" -lmray_b200 \
-    -L"$ROOT/oracle/_ref" -lmray_refcore -Wl,-rpath,'$ORIGIN' -Wl,-rpath,'$ORIGIN/../../oracle/_ref' -Wl,--no-undefined
+    -lmray_refcore -Wl,-rpath,'$ORIGIN' -Wl,--no-undefined
 # the TracerI driver (test side) shares the same Core library
 g++ $(cat "$W/cxxflags.txt") -c "$ROOT/oracle/ref_build/tracer_driver.cpp" -o "$W/tracer_driver.o"
 g++ -shared -rdynamic -o "$ROOT/oracle/_ref/libtracer_driver.so" "$W/tracer_driver.o" -L"$ROOT/oracle/_ref" -lmray_refcore \
