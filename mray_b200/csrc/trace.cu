@@ -483,6 +483,18 @@ KTraceBinary(AccelData a, uint32_t accelKey,
                 LBVHNode nd = a.nodes[ni];
                 stack[sp++] = nd.right;
                 stack[sp++] = nd.left;
+                // this kernel is a dependent chain of (node, box) loads for a handful of rays: pull the records
+                // the next pops will need towards L1 while the current step finishes
+                if(!(nd.left & LEAF_FLAG))
+                {
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(a.boxes + nd.left));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(a.nodes + nd.left));
+                }
+                if(!(nd.right & LEAF_FLAG))
+                {
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(a.boxes + nd.right));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(a.nodes + nd.right));
+                }
             }
         }
     }

@@ -12,6 +12,6 @@ pidx, pranges, pkeys, palb, prad, _ = scenes.arcade_materials(p, i)
 acc = mray_b200.Accelerator(ctx, torch.from_numpy(p).cuda(), torch.from_numpy(pidx.view(np.int32)).cuda(), prim_ranges=pranges, light_or_mat_keys=pkeys)
 spec = mray_b200.Spectrum(ctx, spectral.load()) if (len(sys.argv) > 2 and sys.argv[2] == "spectral") else None
 r = mray_b200.Renderer(ctx, acc, p.shape[0], pidx.shape[0], palb, prad, scenes.ARCADE_CAMERA, 1920, 1080, 64, sample_mode="WithNEEAndMIS",
-                       rr_range=(3, 8), seed=0, partition_rays=True, spectrum=spec)
+                       rr_range=(3, 8), seed=0, partition_rays=("sort" in sys.argv), spectrum=spec)
 r.iterate(iters); torch.cuda.synchronize()
 print("done", r.stats().pathsCompleted)
