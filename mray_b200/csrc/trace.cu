@@ -563,6 +563,9 @@ KResolveExact(AccelData a, uint32_t accelKey,
                     if(usePrior) reach = false; else full = true;
                     break;
                 }
+                // a box that passes with tUpper is enclosed by every remaining ancestor, which therefore pass too
+                // (edge hits make the flat leaf boxes marginal, not the boxes above them)
+                if(!usePrior) break;
                 ni = a.nodes[ni].parent;
             }
             if(!full && reach && (accepted < 0 || z.t < c[accepted].t)) accepted = (s == 0 ? first : 1 - first);
