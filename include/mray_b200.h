@@ -163,7 +163,12 @@ MRB_API mrb_status mrb_accel_export_lbvh(mrb_context ctx, mrb_accel accel,
 typedef enum mrb_trace_mode
 {
     MRB_TRACE_WIDE = 0,        /* product path: 8-wide quantised BVH                                   */
-    MRB_TRACE_BINARY_EXACT = 1 /* audit path: the reference's binary LBVH, left-first, exact slab test */
+    MRB_TRACE_BINARY_EXACT = 1,/* audit path: the reference's binary LBVH, left-first, exact slab test */
+    /* OR-ed flag: the caller does not care what hitKeys / metaHits / isVisibleBits hold on entry. Rays that miss
+     * then get {INVALID, INVALID, INVALID, INVALID} keys, zero barycentrics and a set visibility bit instead of
+     * keeping the caller's values, so a host-pointer call uploads the rays only (keys and hits are 43 % of the
+     * bytes a closest-hit call sends over PCIe). */
+    MRB_TRACE_FRESH_OUTPUTS = 0x100
 } mrb_trace_mode;
 
 /* Closest hit. Replaces BaseAcceleratorLBVH::CastRays (Tracer/AcceleratorLBVH.cu:L760-896) +

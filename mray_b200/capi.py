@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmray_b200.so")
 
 MRB_MEM_HOST, MRB_MEM_DEVICE = 0, 1
 MRB_TRACE_WIDE, MRB_TRACE_BINARY_EXACT = 0, 1
+MRB_TRACE_FRESH_OUTPUTS = 0x100   # OR-ed flag: outputs need not be read, misses get INVALID keys / zero hits / set bits
 MRB_BUILD_DEFAULT, MRB_BUILD_REFERENCE_DELTA, MRB_BUILD_BINARY_ONLY = 0, 1, 2
 INVALID_KEY = 0xFFFFFFFF
 

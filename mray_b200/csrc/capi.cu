@@ -266,7 +266,7 @@ template<class TraceF>
 static mrb_status CastGeneric(mrb_context ctx, bool anyHit,
                               mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, uint32_t* visibleBits,
                               mrb_ray_gmem* rays, const uint32_t* rayIndices,
-                              uint32_t rayCount, uint32_t totalRayCount, mrb_memspace memspace, TraceF&& trace)
+                              uint32_t rayCount, uint32_t totalRayCount, mrb_memspace memspace, bool fresh, TraceF&& trace)
 {
     return Guard(ctx, [&](mrb::Context& c)
     {
@@ -274,8 +274,20 @@ static mrb_status CastGeneric(mrb_context ctx, bool anyHit,
         if(anyHit ? !visibleBits : (!hitKeys || !metaHits)) return Fail(c, MRB_ERR_INVALID_ARG, "null output");
         if(totalRayCount < rayCount && !rayIndices) return Fail(c, MRB_ERR_INVALID_ARG, "totalRayCount < rayCount");
         if(rayCount == 0) return MRB_OK;
-        if(memspace == MRB_MEM_DEVICE) { trace(c, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount); return MRB_OK; }
         const size_t words = (size_t(totalRayCount) + 31) / 32;
+        // MRB_TRACE_FRESH_OUTPUTS: outputs are initialised on the device instead of being read from the caller
+        auto Fresh = [&](mrb_hit_key_pack* k, mrb_meta_hit* h, uint32_t* b, size_t rayN, size_t wordN, cudaStream_t st)
+        {
+            if(b) MRB_CUDA_TRY(cudaMemsetAsync(b, 0xFF, sizeof(uint32_t) * wordN, st));
+            if(k) MRB_CUDA_TRY(cudaMemsetAsync(k, 0xFF, sizeof(mrb_hit_key_pack) * rayN, st));
+            if(h) MRB_CUDA_TRY(cudaMemsetAsync(h, 0, sizeof(mrb_meta_hit) * rayN, st));
+        };
+        if(memspace == MRB_MEM_DEVICE)
+        {
+            if(fresh) Fresh(anyHit ? nullptr : hitKeys, anyHit ? nullptr : metaHits, anyHit ? visibleBits : nullptr, totalRayCount, words, c.stream);
+            trace(c, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount);
+            return MRB_OK;
+        }
         mrb::MultiAlloc sz(nullptr);
         sz.Take<mrb_ray_gmem>(totalRayCount); sz.Take<uint32_t>(rayIndices ? rayCount : 0);
         if(anyHit) sz.Take<uint32_t>(words); else { sz.Take<mrb_hit_key_pack>(totalRayCount); sz.Take<mrb_meta_hit>(totalRayCount); }
@@ -314,7 +326,8 @@ static mrb_status CastGeneric(mrb_context ctx, bool anyHit,
                 const uint32_t n = (rayCount - b < per) ? rayCount - b : per;
                 const size_t w0 = b / 32, wn = (size_t(n) + 31) / 32;
                 MRB_CUDA_TRY(cudaMemcpyAsync(dRays + b, rays + b, sizeof(mrb_ray_gmem) * n, cudaMemcpyHostToDevice, c.copyIn));
-                if(anyHit) MRB_CUDA_TRY(cudaMemcpyAsync(dBits + w0, visibleBits + w0, sizeof(uint32_t) * wn, cudaMemcpyHostToDevice, c.copyIn));
+                if(fresh) Fresh(anyHit ? nullptr : dKeys + b, anyHit ? nullptr : dHits + b, anyHit ? dBits + w0 : nullptr, n, wn, c.copyIn);
+                else if(anyHit) MRB_CUDA_TRY(cudaMemcpyAsync(dBits + w0, visibleBits + w0, sizeof(uint32_t) * wn, cudaMemcpyHostToDevice, c.copyIn));
                 else
                 {
                     MRB_CUDA_TRY(cudaMemcpyAsync(dKeys + b, hitKeys + b, sizeof(mrb_hit_key_pack) * n, cudaMemcpyHostToDevice, c.copyIn));
@@ -340,16 +353,20 @@ static mrb_status CastGeneric(mrb_context ctx, bool anyHit,
 
         MRB_CUDA_TRY(cudaMemcpyAsync(dRays, rays, sizeof(mrb_ray_gmem) * totalRayCount, cudaMemcpyHostToDevice, c.stream));
         if(rayIndices) MRB_CUDA_TRY(cudaMemcpyAsync(dIdx, rayIndices, sizeof(uint32_t) * rayCount, cudaMemcpyHostToDevice, c.stream));
+        if(fresh) Fresh(dKeys, dHits, dBits, totalRayCount, words, c.stream);
         if(anyHit)
         {
-            MRB_CUDA_TRY(cudaMemcpyAsync(dBits, visibleBits, sizeof(uint32_t) * words, cudaMemcpyHostToDevice, c.stream));
+            if(!fresh) MRB_CUDA_TRY(cudaMemcpyAsync(dBits, visibleBits, sizeof(uint32_t) * words, cudaMemcpyHostToDevice, c.stream));
             trace(c, nullptr, nullptr, dBits, dRays, rayIndices ? dIdx : nullptr, rayCount);
             MRB_CUDA_TRY(cudaMemcpyAsync(visibleBits, dBits, sizeof(uint32_t) * words, cudaMemcpyDeviceToHost, c.stream));
         }
         else
         {
-            MRB_CUDA_TRY(cudaMemcpyAsync(dKeys, hitKeys, sizeof(mrb_hit_key_pack) * totalRayCount, cudaMemcpyHostToDevice, c.stream));
-            MRB_CUDA_TRY(cudaMemcpyAsync(dHits, metaHits, sizeof(mrb_meta_hit) * totalRayCount, cudaMemcpyHostToDevice, c.stream));
+            if(!fresh)
+            {
+                MRB_CUDA_TRY(cudaMemcpyAsync(dKeys, hitKeys, sizeof(mrb_hit_key_pack) * totalRayCount, cudaMemcpyHostToDevice, c.stream));
+                MRB_CUDA_TRY(cudaMemcpyAsync(dHits, metaHits, sizeof(mrb_meta_hit) * totalRayCount, cudaMemcpyHostToDevice, c.stream));
+            }
             trace(c, dKeys, dHits, nullptr, dRays, rayIndices ? dIdx : nullptr, rayCount);
             MRB_CUDA_TRY(cudaMemcpyAsync(hitKeys, dKeys, sizeof(mrb_hit_key_pack) * totalRayCount, cudaMemcpyDeviceToHost, c.stream));
             MRB_CUDA_TRY(cudaMemcpyAsync(metaHits, dHits, sizeof(mrb_meta_hit) * totalRayCount, cudaMemcpyDeviceToHost, c.stream));
@@ -366,10 +383,12 @@ static mrb_status CastCommon(mrb_context ctx, mrb_accel accel, bool anyHit,
                              uint32_t rayCount, uint32_t totalRayCount,
                              mrb_memspace memspace, mrb_trace_mode mode)
 {
+    const bool fresh = (uint32_t(mode) & uint32_t(MRB_TRACE_FRESH_OUTPUTS)) != 0u;
+    mode = mrb_trace_mode(uint32_t(mode) & 0xFFu);
     if(ctx && !accel) return Guard(ctx, [&](mrb::Context& c) { return Fail(c, MRB_ERR_INVALID_ARG, "null argument"); });
     if(ctx && mode == MRB_TRACE_WIDE && !accel->d.wideNodes)
         return Guard(ctx, [&](mrb::Context& c) { return Fail(c, MRB_ERR_UNSUPPORTED, "accelerator was built BINARY_ONLY"); });
-    return CastGeneric(ctx, anyHit, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, totalRayCount, memspace,
+    return CastGeneric(ctx, anyHit, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, totalRayCount, memspace, fresh,
                        [&](mrb::Context& c, mrb_hit_key_pack* k, mrb_meta_hit* h, uint32_t* b, mrb_ray_gmem* r, const uint32_t* idx, uint32_t n)
                        { mrb::TraceRays(c, *accel, anyHit, mode, k, h, b, r, idx, n); });
 }
@@ -762,7 +781,9 @@ mrb_status mrb_scene_cast_rays(mrb_context ctx, mrb_scene scene, mrb_hit_key_pac
                                mrb_memspace memspace, mrb_trace_mode mode)
 {
     if(!scene) return MRB_ERR_INVALID_ARG;
-    return CastGeneric(ctx, false, hitKeys, metaHits, nullptr, rays, rayIndices, rayCount, totalRayCount, memspace,
+    const bool fresh = (uint32_t(mode) & uint32_t(MRB_TRACE_FRESH_OUTPUTS)) != 0u;
+    mode = mrb_trace_mode(uint32_t(mode) & 0xFFu);
+    return CastGeneric(ctx, false, hitKeys, metaHits, nullptr, rays, rayIndices, rayCount, totalRayCount, memspace, fresh,
         [&](mrb::Context& c, mrb_hit_key_pack* k, mrb_meta_hit* h, uint32_t* b, mrb_ray_gmem* r, const uint32_t* idx, uint32_t n)
         { mrb::TraceScene(c, scene->d, false, mode, k, h, b, r, idx, n); });
 }
@@ -772,7 +793,9 @@ mrb_status mrb_scene_cast_visibility_rays(mrb_context ctx, mrb_scene scene, uint
                                           uint32_t rayCount, uint32_t totalRayCount, mrb_memspace memspace, mrb_trace_mode mode)
 {
     if(!scene) return MRB_ERR_INVALID_ARG;
-    return CastGeneric(ctx, true, nullptr, nullptr, isVisibleBits, const_cast<mrb_ray_gmem*>(rays), rayIndices, rayCount, totalRayCount, memspace,
+    const bool fresh = (uint32_t(mode) & uint32_t(MRB_TRACE_FRESH_OUTPUTS)) != 0u;
+    mode = mrb_trace_mode(uint32_t(mode) & 0xFFu);
+    return CastGeneric(ctx, true, nullptr, nullptr, isVisibleBits, const_cast<mrb_ray_gmem*>(rays), rayIndices, rayCount, totalRayCount, memspace, fresh,
         [&](mrb::Context& c, mrb_hit_key_pack* k, mrb_meta_hit* h, uint32_t* b, mrb_ray_gmem* r, const uint32_t* idx, uint32_t n)
         { mrb::TraceScene(c, scene->d, true, mode, k, h, b, r, idx, n); });
 }

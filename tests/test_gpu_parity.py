@@ -308,6 +308,14 @@ def test_host_pointer_casts_are_pipelined_and_identical(gpu_ctx):
     acc.cast_visibility_rays(bits, rays.copy(), None, capi.MRB_TRACE_WIDE)
     hvis = ((bits[np.arange(n) // 32] >> (np.arange(n) % 32).astype(np.uint32)) & 1).astype(bool)
     assert np.array_equal(hvis, dvis)
+    # MRB_TRACE_FRESH_OUTPUTS: whatever the output buffers held is ignored; misses come back INVALID / zero / visible
+    fkeys = np.full((n, 4), 0x12345678, np.uint32); fhits = np.full((n, 2), 7.0, np.float32); frays = rays.copy()
+    acc.cast_rays(fkeys, fhits, frays, None, capi.MRB_TRACE_WIDE | capi.MRB_TRACE_FRESH_OUTPUTS)
+    assert np.array_equal(fkeys, dkeys) and np.array_equal(fhits, dhits) and np.array_equal(frays, drays)
+    fbits = np.zeros(((n + 31) // 32,), np.uint32)
+    acc.cast_visibility_rays(fbits, rays.copy(), None, capi.MRB_TRACE_WIDE | capi.MRB_TRACE_FRESH_OUTPUTS)
+    tail = (1 << (n % 32)) - 1 if n % 32 else 0xFFFFFFFF
+    assert np.array_equal(fbits[:-1], bits[:-1]) and (fbits[-1] & tail) == (bits[-1] & tail)
     acc.close()
 
 
