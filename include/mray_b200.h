@@ -211,6 +211,13 @@ typedef struct mrb_instance_desc
     uint32_t  isIdentity;     /* (T)Identity: no ray transform, world AABB = accelerator AABB */
     uint32_t  transformKey;   /* reported in HitKeyPack.transKey */
     uint32_t  accelKey;       /* reported in HitKeyPack.accelKey (batch:12 | index:20) */
+    /* Optional (host pointer, one entry per prim range of `accel`, NULL = the accelerator's own keys):
+     * the reference keeps LightOrMatKeys per INSTANCE while surfaces with the same primitive batches and
+     * cull flags share one concrete accelerator (AcceleratorGroupLBVH::PreConstruct ->
+     * AcceleratorGroup partitions, Tracer/AcceleratorC.h:L780-905: `concreteIndicesOfInstances`,
+     * `dAllLeafs` per concrete accelerator, `dMatKeys` per instance), so N instances of one mesh with N
+     * different materials cost one BVH. Copied at build time. */
+    const uint32_t* lightOrMatKeys;
 } mrb_instance_desc;
 
 /* BaseAcceleratorLBVH::InternalConstruct (Tracer/AcceleratorLBVH.cu:L537-740): top-level LBVH over the

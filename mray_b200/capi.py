@@ -56,7 +56,8 @@ class AccelInfo(C.Structure):
 
 class InstanceDesc(C.Structure):
     _fields_ = [("accel", C.c_void_p), ("transform", C.c_float * 12), ("invTransform", C.c_float * 12),
-                ("isIdentity", C.c_uint32), ("transformKey", C.c_uint32), ("accelKey", C.c_uint32)]
+                ("isIdentity", C.c_uint32), ("transformKey", C.c_uint32), ("accelKey", C.c_uint32),
+                ("lightOrMatKeys", C.c_void_p)]
 
 
 class SpectrumDesc(C.Structure):
@@ -533,17 +534,23 @@ class Renderer:
 
 class Scene:
     """Two-level scene = BaseAcceleratorLBVH over accelerator instances (Tracer/AcceleratorLBVH.cu:L537-1035).
-    instances: list of (Accelerator, transform 3x4 or None for identity). accelKey of instance i = i,
-    transformKey = i + 1 (0 for identity)."""
+    instances: list of (Accelerator, transform 3x4 or None for identity[, light_or_mat_keys]). accelKey of
+    instance i = i, transformKey = i + 1 (0 for identity). The optional third entry gives the instance its own
+    LightOrMatKey per prim range (instances of one accelerator with different materials)."""
 
     def __init__(self, ctx: Context, instances):
         self.ctx = ctx
-        self._keep = [a for a, _ in instances]
+        self._keep = [t[0] for t in instances]
         arr = (InstanceDesc * len(instances))()
         self.transforms = []
-        for i, (acc, m) in enumerate(instances):
+        for i, t in enumerate(instances):
+            acc, m = t[0], t[1]
             d = arr[i]
             d.accel = acc.handle
+            if len(t) > 2 and t[2] is not None:
+                k = np.ascontiguousarray(t[2], np.uint32)
+                self._keep.append(k)
+                d.lightOrMatKeys = k.ctypes.data
             ident = m is None
             m34 = np.eye(4, dtype=np.float64)[:3] if ident else np.asarray(m, np.float64).reshape(3, 4)
             inv = np.linalg.inv(np.vstack([m34, [0, 0, 0, 1]]))[:3]

@@ -125,6 +125,7 @@ struct mrb_scene_t
     mrb::DeviceBlock mem;
     std::vector<mrb_accel> accels;
     std::vector<mrb_instance_desc> hInstances;   // host copy (renderer: forward transforms, keys)
+    std::vector<std::vector<uint32_t>> hInstanceKeys; // per instance: LightOrMatKey override per prim range (empty = accelerator's)
     float            aabb[6] = {};
     float            buildMs = 0.f;
 };

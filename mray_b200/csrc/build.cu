@@ -648,6 +648,10 @@ void BuildScene(Context& ctx, mrb_scene_t& sc, const mrb_instance_desc* inst, ui
     d = AccelData{};
     d.leafCount = n; d.nodeCount = n > 1 ? n - 1 : 1; d.maxLeafSize = 1;
     d.ranges = PrimRanges{};
+    // per-instance LightOrMatKey overrides (instances of one accelerator with different materials)
+    size_t overrideKeyCount = 0;
+    for(uint32_t i = 0; i < n; i++) if(inst[i].lightOrMatKeys) overrideKeyCount += inst[i].accel->d.ranges.count;
+    uint32_t* dInstKeys = nullptr;
     auto Layout = [&](MultiAlloc& ma)
     {
         d.leafAABB = ma.Take<float>(size_t(n) * 6);
@@ -659,6 +663,7 @@ void BuildScene(Context& ctx, mrb_scene_t& sc, const mrb_instance_desc* inst, ui
         d.wideNodes = ma.Take<WideNode>(d.wideNodeCapacity);
         d.leafOfSlot = ma.Take<uint32_t>(n);
         s.instances = ma.Take<InstanceRec>(n);
+        dInstKeys = ma.Take<uint32_t>(overrideKeyCount);
     };
     MultiAlloc sz(nullptr); Layout(sz);
     sc.mem.Reserve(sz.Total());
@@ -670,6 +675,8 @@ void BuildScene(Context& ctx, mrb_scene_t& sc, const mrb_instance_desc* inst, ui
     std::vector<InstanceBuildIn> bin(n);
     sc.accels.assign(n, nullptr);
     sc.hInstances.assign(inst, inst + n);
+    sc.hInstanceKeys.assign(n, {});
+    std::vector<uint32_t> flatKeys; flatKeys.reserve(overrideKeyCount);
     for(uint32_t i = 0; i < n; i++)
     {
         const mrb_accel_t& a = *inst[i].accel;
@@ -680,6 +687,13 @@ void BuildScene(Context& ctx, mrb_scene_t& sc, const mrb_instance_desc* inst, ui
         r.positions = a.d.positions; r.indices = a.d.indices; r.nodes = a.d.nodes; r.boxes = a.d.boxes;
         r.ranges = a.d.ranges; r.accelKey = inst[i].accelKey; r.transKey = inst[i].transformKey;
         r.identity = inst[i].isIdentity ? 1u : 0u; r.leafCount = a.d.leafCount;
+        if(inst[i].lightOrMatKeys)
+        {
+            r.ranges.lmKey = dInstKeys + flatKeys.size();
+            sc.hInstanceKeys[i].assign(inst[i].lightOrMatKeys, inst[i].lightOrMatKeys + a.d.ranges.count);
+            flatKeys.insert(flatKeys.end(), sc.hInstanceKeys[i].begin(), sc.hInstanceKeys[i].end());
+            sc.hInstances[i].lightOrMatKeys = nullptr;   // the caller's array need not outlive the call
+        }
         memcpy(bin[i].transform, inst[i].transform, sizeof(bin[i].transform));
         bin[i].accelAABBEnc = a.d.accelAABBEnc; bin[i].identity = r.identity; bin[i].pad = 0;
     }
@@ -699,6 +713,8 @@ void BuildScene(Context& ctx, mrb_scene_t& sc, const mrb_instance_desc* inst, ui
     uint32_t* dupFlag = counters + d.nodeCount;
 
     MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<InstanceRec*>(s.instances), recs.data(), sizeof(InstanceRec) * n, cudaMemcpyHostToDevice, ctx.stream));
+    if(!flatKeys.empty())
+        MRB_CUDA_TRY(cudaMemcpyAsync(dInstKeys, flatKeys.data(), sizeof(uint32_t) * flatKeys.size(), cudaMemcpyHostToDevice, ctx.stream));
     MRB_CUDA_TRY(cudaMemcpyAsync(dIn, bin.data(), sizeof(InstanceBuildIn) * n, cudaMemcpyHostToDevice, ctx.stream));
     MRB_CUDA_TRY(cudaEventRecord(ctx.ev0, ctx.stream));
     const uint32_t initEnc[8] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u, 0u};

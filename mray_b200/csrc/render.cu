@@ -753,7 +753,9 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
             const AccelData& a = hacc.d;
             lightOfPrim[k].assign(hacc.triangleCount, INVALID_U32);
             bool anyLight = false;
-            for(uint32_t rg = 0; rg < a.ranges.count; rg++) anyLight |= (hacc.hLmKey[rg] & 0x80000000u) != 0;
+            // an instance may carry its own keys (mrb_instance_desc.lightOrMatKeys)
+            const std::vector<uint32_t>& lmKeys = (desc.scene && !desc.scene->hInstanceKeys[k].empty()) ? desc.scene->hInstanceKeys[k] : hacc.hLmKey;
+            for(uint32_t rg = 0; rg < a.ranges.count; rg++) anyLight |= (lmKeys[rg] & 0x80000000u) != 0;
             if(!anyLight) continue;
             if(loaded != &hacc)
             {
@@ -772,7 +774,7 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
             };
             for(uint32_t rg = 0; rg < a.ranges.count; rg++)
             {
-                uint32_t key = hacc.hLmKey[rg];
+                uint32_t key = lmKeys[rg];
                 if(!(key & 0x80000000u)) continue;
                 uint32_t li = key & 0x1FFFFFu;
                 if(li >= desc.lightCount) throw std::runtime_error("light key index exceeds lightCount");

@@ -90,7 +90,8 @@ class TracerB200 final : public TracerI
     TracerParameters params;
     mrb_context ctx = nullptr;
     mrb_accel accel = nullptr;           // all (T)Identity surfaces
-    std::vector<mrb_accel> instAccels;   // one per distinct (T)Single transform in use
+    std::vector<mrb_accel> instAccels;   // two-level scenes: one per distinct (prim ranges, cull flags) set
+    uint32_t sceneInstanceCount = 0, uniqueAccelCount = 0;
     mrb_scene scene = nullptr;           // set when any surface is transformed
     mrb_renderer renderer = nullptr;
     mrb_spectrum spectrum = nullptr;     // SpectrumContextJakob2019 of params.globalTextureColorSpace, made on first use
@@ -387,6 +388,14 @@ class TracerB200 final : public TracerI
                           std::vector<Optional<TextureId>> tex) override
     {
         MatGroupB200& mg = Get(mats, Raw(g), "MaterialGroup");
+        // An EMPTY TransientData routes to the optional texture-only overload (TracerBase.cpp:L843-867): the
+        // scene loader always pushes Lambert's optional `normalMap` this way, with nullopt where a material has none.
+        if(data.IsEmpty())
+        {
+            if(attributeIndex != 1) throw MRayError("{}: Attribute {:d} is not \"Optional Texture\"", mg.type, attributeIndex);
+            for(const auto& t : tex) if(t.has_value()) throw MRayError("{}: normal maps are not supported yet", mg.type);
+            return;
+        }
         if(attributeIndex != 0) throw MRayError("{}: Attribute {:d} is not \"ParamVarying\"", mg.type, attributeIndex);
         for(const auto& t : tex) if(t.has_value()) throw MRayError("{}: textured albedo is not supported yet", mg.type);
         uint32_t lo = range[0] & ((1u << MAT_ID_BITS) - 1u), hi = range[1] & ((1u << MAT_ID_BITS) - 1u);
@@ -628,11 +637,16 @@ class TracerB200 final : public TracerI
         }
         else
         {
+            // Groups with the same prim ranges and cull flags share ONE accelerator and differ only in transform and
+            // LightOrMatKeys — the reference's concrete-accelerator / instance split (Tracer/AcceleratorC.h:L780-905).
             std::vector<mrb_instance_desc> inst(groups.size());
+            std::vector<size_t> builtFor;   // group index each unique accelerator was built from
             for(size_t k = 0; k < groups.size(); k++)
             {
-                mrb_accel a = BuildGroup(groups[k]);
-                if(groups[k].transformId == 0) accel = a; else instAccels.push_back(a);
+                mrb_accel a = nullptr;
+                for(size_t u = 0; u < builtFor.size() && !a; u++)
+                    if(groups[builtFor[u]].ranges == groups[k].ranges && groups[builtFor[u]].cull == groups[k].cull) a = instAccels[u];
+                if(!a) { a = BuildGroup(groups[k]); instAccels.push_back(a); builtFor.push_back(k); }
                 const uint32_t tid = groups[k].transformId;
                 const Matrix3x4& m = transforms[tid >> TRANS_ID_BITS].matrices[tid & ((1u << TRANS_ID_BITS) - 1u)];
                 const std::array<float, 12> inv = InverseAffine(m);  // KCInvertTransforms (Tracer/TransformC.h:L119-123)
@@ -643,8 +657,10 @@ class TracerB200 final : public TracerI
                 { d.transform[4 * r + c] = m(r, c); d.invTransform[4 * r + c] = inv[4 * r + c]; }
                 d.isIdentity = (tid == 0) ? 1 : 0;
                 d.transformKey = tid; d.accelKey = uint32_t(k);
+                d.lightOrMatKeys = groups[k].lmKeys.data();
             }
             Check(mrb_scene_build(ctx, inst.data(), uint32_t(inst.size()), &scene));
+            sceneInstanceCount = uint32_t(inst.size()); uniqueAccelCount = uint32_t(instAccels.size());
             float box[6];
             Check(mrb_scene_export_tlas(ctx, scene, nullptr, box, nullptr, nullptr, nullptr, nullptr));
             aabb = AABB3(Vector3(box[0], box[1], box[2]), Vector3(box[3], box[4], box[5]));
@@ -653,7 +669,7 @@ class TracerB200 final : public TracerI
         {
             .aabb = aabb,
             .instanceCount = surfaces.size() + lightSurfaces.size(),
-            .acceleratorCount = uint32_t(groups.size())
+            .acceleratorCount = scene ? uniqueAccelCount : 1u
         };
     }
 
@@ -714,7 +730,7 @@ class TracerB200 final : public TracerI
         mrb_render_desc d = {};
         bool hasNormals = std::any_of(pg.normals.begin(), pg.normals.end(), [](const Vector3& n) { return n != Vector3::Zero(); });
         const float* normals = hasNormals ? reinterpret_cast<const float*>(pg.normals.data()) : nullptr;
-        std::vector<const float*> instNormals((accel ? 1 : 0) + instAccels.size(), normals);
+        std::vector<const float*> instNormals(scene ? sceneInstanceCount : 1u, normals);
         if(scene) { d.scene = scene; d.instanceVertexNormals = instNormals.data(); }
         else { d.accel = accel; d.vertexCount = pg.vertexTotal; d.triangleCount = pg.primTotal; d.vertexNormals = normals; }
         d.materialCount = uint32_t(flatAlbedo.size() / 3); d.albedo = flatAlbedo.data();

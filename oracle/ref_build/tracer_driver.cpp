@@ -49,6 +49,9 @@ struct DriverScene
     // optional: batchCount row-major 3x4 local->world matrices; every batch then gets its own (T)Single
     // transform (positions are local-space). NULL = all surfaces use (T)Identity.
     const float*    batchTransforms;
+    // optional: batchCount entries; batchInstanceOf[b] = a >= 0 makes the SURFACE of batch b use the primitive batch
+    // of batch a (instancing: same geometry, own material and transform; b's own geometry stays unused). -1 = itself.
+    const int32_t*  batchInstanceOf;
 };
 
 struct DriverRender
@@ -224,7 +227,18 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
             d.Push(Span<const Vector3>(reinterpret_cast<const Vector3*>(sc->albedo), sc->materialCount));
             tracer->PushMatAttribute(mg, range, 0, std::move(d),
                                      std::vector<Optional<TextureId>>(sc->materialCount, std::nullopt));
-            // attribute 1 (optional texture-only normal map) is left unset
+            // Optional texture-only attributes (Lambert: 1 = normalMap) are pushed with an EMPTY TransientData and
+            // nullopt ids, as SceneLoaderMRay does (SceneLoaderMRay.cpp:L190-245; TracerBase::PushMatAttribute routes
+            // data.IsEmpty() to the texture-only overload, TracerBase.cpp:L843-867). The reference allocates the
+            // Optional<TracerTexView> array uninitialised, so leaving this out makes it read garbage.
+            for(uint32_t a = 1; a < mInfo.size(); a++)
+                if(mInfo[a].isTexturable == AttributeTexturable::MR_TEXTURE_ONLY &&
+                   mInfo[a].isOptional == AttributeOptionality::MR_OPTIONAL)
+                {
+                    TransientData e(std::in_place_type_t<Vector3>{}, 0);
+                    tracer->PushMatAttribute(mg, range, a, std::move(e),
+                                             std::vector<Optional<TextureId>>(sc->materialCount, std::nullopt));
+                }
         }
         // ---- lights (prim backed) ----
         LightGroupId lg = sc->lightCount ? tracer->CreateLightGroup("(L)Prim(P)Triangle", pg) : LightGroupId(0);
@@ -305,7 +319,7 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
         {
             if(sc->batchMaterial[b] < 0) continue;
             SurfaceParams sp;
-            sp.primBatches.push_back(batches[b]);
+            sp.primBatches.push_back(batches[(sc->batchInstanceOf && sc->batchInstanceOf[b] >= 0) ? uint32_t(sc->batchInstanceOf[b]) : b]);
             sp.materials.push_back(mats[size_t(sc->batchMaterial[b])]);
             sp.transformId = batchTrans[b];
             sp.alphaMaps.push_back(std::nullopt);

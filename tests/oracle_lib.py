@@ -163,7 +163,8 @@ class _DriverScene(C.Structure):
                 ("materialCount", C.c_uint32), ("albedo", C.c_void_p),
                 ("lightCount", C.c_uint32), ("radiance", C.c_void_p),
                 ("camPos", C.c_float * 3), ("camGaze", C.c_float * 3), ("camUp", C.c_float * 3),
-                ("fovXY", C.c_float * 2), ("nearFar", C.c_float * 2), ("batchTransforms", C.c_void_p)]
+                ("fovXY", C.c_float * 2), ("nearFar", C.c_float * 2), ("batchTransforms", C.c_void_p),
+                ("batchInstanceOf", C.c_void_p)]
 
 
 class _DriverRender(C.Structure):
@@ -207,18 +208,53 @@ def batched_scene(positions, indices, tri_material, normals=None):
 def driver_render(dll_path, batched, albedo, light_material, radiance, camera, width, height, spp,
                   renderer="PathTracerRGB", sample_mode="WithNEEAndMIS", rr_range=(2, 20), seed=0,
                   accel_mode=1, threads=0, parallel_hint=0, near_far=(0.01, 1000.0), driver_flavour="",
-                  batch_transforms=None, sampler="Independent"):
+                  batch_transforms=None, sampler="Independent", host_exe=False, instance_of=None):
     """Renders through TracerI. `light_material`: material id whose batch is the prim-backed light.
     batch_transforms: optional [batch, 3, 4] local->world matrices ((T)Single per batch; positions local).
+    instance_of: optional int per batch; a >= 0 makes that batch's surface an instance of batch a's geometry.
+    host_exe: run the driver inside oracle/_ref/ref_render_host (its own process, so that the reference's
+    spectral renderer finds SpectraLUT/ next to the executable) instead of in this interpreter.
     Returns (image[h,w,3] float32 with row 0 = bottom, weight[h,w], stats dict)."""
-    L = C.CDLL(os.path.join(ORACLE_DIR, "_ref", f"libtracer_driver{driver_flavour}.so"))
-    L.tracer_driver_render.restype = C.c_int
     mats = list(batched["materials"])
     lambert = [m for m in mats if m != light_material]
     bm = np.array([lambert.index(m) if m != light_material else -1 for m in mats], np.int32)
     bl = np.array([0 if m == light_material else -1 for m in mats], np.int32)
     alb = np.ascontiguousarray(np.asarray(albedo, np.float32)[lambert])
     rad = np.ascontiguousarray(np.asarray(radiance, np.float32).reshape(1, 3))
+    fy = np.deg2rad(camera["fov_y_deg"])
+    fx = 2 * np.arctan(np.tan(fy / 2) * width / height)
+    bt = None if batch_transforms is None else np.ascontiguousarray(batch_transforms, np.float32).reshape(len(mats), 12)
+    sampler_id = {"Independent": 0, "ZSobol": 1, "Sobol": 2}[sampler]
+    io = None if instance_of is None else np.ascontiguousarray(instance_of, np.int32)
+    n_lights = 1 if light_material in mats else 0
+    if host_exe:
+        import subprocess
+        import tempfile
+        u = np.array([len(mats), len(lambert), n_lights, width, height, spp, rr_range[0], rr_range[1], accel_mode,
+                      parallel_hint, threads, sampler_id], np.uint32)
+        cam = np.array(list(camera["eye"]) + list(camera["gaze"]) + list(camera["up"]) + [fx, fy] + list(near_far), np.float32)
+        secs = [dll_path.encode(), renderer.encode(), sample_mode.encode(), u.tobytes(), np.uint64(seed).tobytes(),
+                cam.tobytes(), batched["vertex_offsets"].astype(np.uint32).tobytes(), batched["tri_offsets"].astype(np.uint32).tobytes(),
+                np.ascontiguousarray(batched["positions"], np.float32).tobytes(), np.ascontiguousarray(batched["normals"], np.float32).tobytes(),
+                np.ascontiguousarray(batched["indices"], np.uint32).tobytes(), bm.tobytes(), bl.tobytes(), alb.tobytes(), rad.tobytes(),
+                b"" if bt is None else bt.tobytes(), b"" if io is None else io.tobytes()]
+        with tempfile.TemporaryDirectory() as td:
+            with open(os.path.join(td, "in.blob"), "wb") as f:
+                f.write(np.uint64(len(secs)).tobytes())
+                for b in secs:
+                    f.write(np.uint64(len(b)).tobytes()); f.write(b + b"\0" * (-len(b) % 8))
+            exe = os.path.join(ORACLE_DIR, "_ref", "ref_render_host")
+            r = subprocess.run([exe, os.path.join(td, "in.blob"), os.path.join(td, "out.bin")], capture_output=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"ref_render_host failed ({r.returncode}): {r.stderr.decode(errors='replace')[-600:]}")
+            raw = open(os.path.join(td, "out.bin"), "rb").read()
+        pix = width * height
+        img = np.frombuffer(raw, np.float32, pix * 3).reshape(height, width, 3).copy()
+        wgt = np.frombuffer(raw, np.float32, pix, pix * 12).reshape(height, width).copy()
+        sd = np.frombuffer(raw, np.float64, 4, pix * 16); box = np.frombuffer(raw, np.float32, 6, pix * 16 + 32)
+        return img, wgt, dict(commit_s=float(sd[0]), render_s=float(sd[1]), paths=float(sd[2]), iterations=int(sd[3]), aabb=[float(x) for x in box])
+    L = C.CDLL(os.path.join(ORACLE_DIR, "_ref", f"libtracer_driver{driver_flavour}.so"))
+    L.tracer_driver_render.restype = C.c_int
     sc = _DriverScene()
     sc.batchCount = len(mats)
     keep = [batched["vertex_offsets"], batched["tri_offsets"], batched["positions"], batched["normals"],
@@ -227,16 +263,15 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
     sc.positions, sc.normals, sc.indices = keep[2].ctypes.data, keep[3].ctypes.data, keep[4].ctypes.data
     sc.batchMaterial, sc.batchLight = bm.ctypes.data, bl.ctypes.data
     sc.materialCount, sc.albedo = len(lambert), alb.ctypes.data
-    sc.lightCount, sc.radiance = (1 if light_material in mats else 0), rad.ctypes.data
+    sc.lightCount, sc.radiance = n_lights, rad.ctypes.data
     sc.camPos = (C.c_float * 3)(*camera["eye"]); sc.camGaze = (C.c_float * 3)(*camera["gaze"]); sc.camUp = (C.c_float * 3)(*camera["up"])
-    fy = np.deg2rad(camera["fov_y_deg"])
-    fx = 2 * np.arctan(np.tan(fy / 2) * width / height)
     sc.fovXY = (C.c_float * 2)(fx, fy); sc.nearFar = (C.c_float * 2)(*near_far)
-    if batch_transforms is not None:
-        bt = np.ascontiguousarray(batch_transforms, np.float32).reshape(len(mats), 12)
+    if bt is not None:
         keep.append(bt); sc.batchTransforms = bt.ctypes.data
+    if io is not None:
+        keep.append(io); sc.batchInstanceOf = io.ctypes.data
     rd = _DriverRender(renderer.encode(), width, height, spp, sample_mode.encode(), (C.c_uint32 * 2)(*rr_range), seed,
-                       accel_mode, parallel_hint, threads, {"Independent": 0, "ZSobol": 1, "Sobol": 2}[sampler])
+                       accel_mode, parallel_hint, threads, sampler_id)
     img = np.zeros((height, width, 3), np.float32)
     wgt = np.zeros((height, width), np.float32)
     st = _DriverStats()

@@ -88,3 +88,26 @@ def test_two_level_scene(gpu_ctx, n_inst, identity_only):
     sc.close()
     for a in accs:
         a.close()
+
+
+def test_instances_of_one_accelerator_with_their_own_material_keys(gpu_ctx):
+    """mrb_instance_desc.lightOrMatKeys: the reference keeps material keys per INSTANCE while surfaces with the same
+    primitive batches share one concrete accelerator (Tracer/AcceleratorC.h:L780-905)."""
+    p, i = scenes.arcade_mesh(1500)
+    half = i.shape[0] // 2
+    acc = capi.Accelerator(gpu_ctx, p, i, light_or_mat_keys=[7, 8], prim_ranges=[[0, half], [half, i.shape[0]]])
+    rng = np.random.default_rng(3)
+    n_inst = 24
+    inst = [(acc, None if k == 0 else trs(rng), None if k % 4 == 0 else [100 + 2 * k, 101 + 2 * k]) for k in range(n_inst)]
+    sc = capi.Scene(gpu_ctx, inst)
+    rays = scene_rays(20000, seed=9)
+    for mode in (capi.MRB_TRACE_WIDE, capi.MRB_TRACE_BINARY_EXACT):
+        keys, hits, rout, vis = gpu_scene_cast(sc, rays, mode)
+        hit = keys[:, 0] != O.INVALID
+        assert hit.mean() > 0.2
+        k_inst, prim = keys[hit, 3].astype(np.int64), (keys[hit, 0] & 0x0FFFFFFF).astype(np.int64)
+        second = (prim >= half).astype(np.int64)
+        expect = np.where(k_inst % 4 == 0, 7 + second, 100 + 2 * k_inst + second)
+        assert np.array_equal(keys[hit, 1].astype(np.int64), expect)
+        assert len(np.unique(k_inst)) > n_inst // 2
+    sc.close(); acc.close()
