@@ -397,11 +397,30 @@ def run_reference(args):
     cnt = 3 * sel.size
     value = cnt * len(times) / sum(times) / 1e6
     sample = "every %d-th ray of the 3 batches (%d rays/step); %s" % (stride, cnt, desc)
+    # config 3 side by side: the UNMODIFIED reference path tracer (its CPU backend, through TracerI) on the same mesh,
+    # materials and lights at 1080p, 1 spp (wall time of its DoRenderWork loop, all host threads)
+    ref_pt = None
+    if os.environ.get("MRB_BENCH_SKIP_PT") is None and kind == "reference" and O.driver_available():
+        try:
+            pidx, pranges, pkeys, palb, prad, tri_mat = scenes.arcade_materials(p, i)
+            mat = np.where(tri_mat < 0, len(palb), tri_mat).astype(np.uint32)
+            bsc = O.batched_scene(p, pidx, mat)
+            dll = os.path.join(ROOT, "oracle", "_ref", "libTracerDLL_CPU.so")
+            alb = np.concatenate([palb, np.zeros((1, 3), np.float32)])
+            _, wgt, st = O.driver_render(dll, bsc, alb, len(palb), prad, scenes.ARCADE_CAMERA, W, H, 1, renderer="PathTracerRGB",
+                                         sample_mode="WithNEEAndMIS", rr_range=(3, 8), seed=0, threads=0, host_exe=True)
+            ref_pt = {"workload": "arcade mesh, 64 Lambert + 200 emissive tris, WithNEEAndMIS rr[3,8], %dx%d, 1 spp" % (W, H),
+                      "PathTracerRGB": {"ms_per_spp_1080p": round(1e3 * st["render_s"], 1), "mpaths_s": round(st["paths"] / st["render_s"] / 1e6, 3),
+                                        "bvh_build_ms": round(1e3 * st["commit_s"], 1), "iterations": st["iterations"]},
+                      "kind": "reference TracerDLL (CPU backend) through TracerI", "cores": cores}
+        except Exception as e:   # a baseline leg must not take the headline line down
+            ref_pt = {"error": str(e)[:200]}
     out = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "Mrays/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * sum(times) / len(times), 3),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "config 2: procedural arcade mesh %d tris, %dx%d primary closest-hit + AO closest-hit + "
-                                  "AO any-hit (bounded sample)" % (i.shape[0], W, H)},
+                                  "AO any-hit (bounded sample)" % (i.shape[0], W, H),
+                      "path_tracer_1080p": ref_pt},
            "cpu_baseline": {"value": round(value, 4), "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": round(value, 4), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)

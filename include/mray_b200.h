@@ -325,6 +325,23 @@ typedef enum mrb_sample_mode
  * bit 31 = light flag, bits 0..20 = index into albedo[] (material) or lightRadiance[] (light).
  * Round 1: (R)PathTracerRGB, (Mt)Lambert with constant albedo, (L)Prim(P)Triangle with constant
  * radiance, (L)Null boundary, (C)Pinhole, Gaussian film filter, Independent (PCG32) sampler. */
+/* One 2-D texture of the renderer (first slice): what TracerI::CreateTexture2D +
+ * PushTextureData + CommitTextures hand to TextureMemory (Tracer/TextureMemory.cpp), restricted to ONE mip
+ * level, 3 / 4 channels of fp32 or unorm8, already in the global colour space (MRayTextureParameters.colorSpace
+ * = MR_DEFAULT, gamma 1: TextureMemory::ConvertColorspaces skips such textures). Sampling restates the reference's
+ * host-backend texture view (Device/CPU/TextureViewCPU.h:L172-470): normalised coordinates, texel centres at
+ * +0.5, nearest or bilinear with unfused lerps, wrap / clamp / mirror edge resolve; with one mip level the
+ * ray-cone gradient of TracerTexView::operator()(uv, dpdx, dpdy) clamps to level 0. */
+typedef struct mrb_texture_desc
+{
+    const void* data;        /* host; row-major, width*height texels, `channels` values each */
+    uint32_t    width, height;
+    uint32_t    channels;    /* 3 or 4 (a 4th channel is ignored by Vector3 reads) */
+    uint32_t    format;      /* 0 = fp32, 1 = unorm8 (NormConversion::FromUNorm: v * (1/255)) */
+    uint32_t    interp;      /* MRayTextureInterpEnum: 0 NEAREST, 1 LINEAR */
+    uint32_t    edge;        /* MRayTextureEdgeResolveEnum: 0 WRAP, 1 CLAMP, 2 MIRROR */
+} mrb_texture_desc;
+
 typedef struct mrb_render_desc
 {
     mrb_accel       accel;
@@ -367,6 +384,16 @@ typedef struct mrb_render_desc
      * ZSobol's initialMaxSPP = totalSPP. */
     uint32_t        samplerType;
     const uint32_t* sobolMatrices;
+    /* Textured Lambert albedo (ParamVaryingData<2, Vector3>, Tracer/ParamVaryingData.h + MaterialsDefault.hpp:L17-25):
+     * albedoTexture: NULL, or host int32 per material, -1 = constant `albedo`, else an index into `textures`; the
+     * texture is read at the hit's interpolated UV0 (uv0 a + uv1 b + uv2 c, PrimitiveDefaultTriangle.hpp:L472-476)
+     * and, in the spectral renderer, upsampled per hit (Converter::ConvertAlbedo). vertexUVs: host, vertexCount*2
+     * (single accelerator); instanceVertexUVs: one host pointer per instance (two-level scenes); missing = uv (0,0). */
+    uint32_t        textureCount;
+    const mrb_texture_desc* textures;
+    const int32_t*  albedoTexture;
+    const float*    vertexUVs;
+    const float* const* instanceVertexUVs;
 } mrb_render_desc;
 
 typedef struct mrb_render_stats
@@ -393,6 +420,10 @@ MRB_API mrb_status mrb_renderer_get_stats(mrb_context ctx, mrb_renderer r, mrb_r
 MRB_API mrb_status mrb_renderer_read_film(mrb_context ctx, mrb_renderer r, float* out, mrb_memspace memspace, int clear);
 /* Device pointer of the film planes, for a multi-GPU film reduction (ncclAllReduce over NVLink). */
 MRB_API float*     mrb_renderer_film_device_ptr(mrb_renderer r);
+/* Parity tap: the renderer's texture filter on its own — TracerTexView<2, Vector3>::operator()(uv, dpdx, dpdy) of a
+ * single-level texture (Tracer/TextureView.hpp:L70-85 -> Device/CPU/TextureViewCPU.h:L397-470). Host pointers:
+ * uv[count*2] -> rgbOut[count*3]. */
+MRB_API mrb_status mrb_texture_sample(mrb_context ctx, const mrb_texture_desc* texture, const float* uv, uint32_t count, float* rgbOut);
 
 /* ---- device algorithms (Device/GPUAlgRadixSort.h, exposed for parity tests) -------------- */
 

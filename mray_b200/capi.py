@@ -75,7 +75,18 @@ class RenderDesc(C.Structure):
                 ("rrRange", C.c_uint32 * 2), ("filmFilterRadius", C.c_float), ("seed", C.c_uint64),
                 ("maxPathCount", C.c_uint32), ("partitionRays", C.c_uint32),
                 ("scene", C.c_void_p), ("instanceVertexNormals", C.POINTER(C.c_void_p)), ("spectrum", C.c_void_p),
-                ("samplerType", C.c_uint32), ("sobolMatrices", C.c_void_p)]
+                ("samplerType", C.c_uint32), ("sobolMatrices", C.c_void_p),
+                ("textureCount", C.c_uint32), ("textures", C.c_void_p), ("albedoTexture", C.c_void_p),
+                ("vertexUVs", C.c_void_p), ("instanceVertexUVs", C.POINTER(C.c_void_p))]
+
+
+class TextureDesc(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("channels", C.c_uint32),
+                ("format", C.c_uint32), ("interp", C.c_uint32), ("edge", C.c_uint32)]
+
+
+TEX_INTERP = {"Nearest": 0, "Linear": 1}
+TEX_EDGE = {"Wrap": 0, "Clamp": 1, "Mirror": 2}
 
 
 class RenderStats(C.Structure):
@@ -126,6 +137,7 @@ _PROTOTYPES = {
     "mrb_renderer_get_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(RenderStats)]),
     "mrb_renderer_read_film": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "mrb_renderer_film_device_ptr": (C.c_void_p, [C.c_void_p]),
+    "mrb_texture_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "mrb_multi_partition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                       C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "mrb_binary_partition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]),
@@ -429,9 +441,13 @@ class Renderer:
     def __init__(self, ctx: Context, accel, vertex_count, triangle_count, albedo, light_radiance,
                  camera, width, height, total_spp, sample_mode="WithNEEAndMIS", rr_range=(2, 20), seed=0,
                  vertex_normals=None, light_two_sided=None, film_filter_radius=1.0, near_far=(0.01, 1000.0),
-                 max_path_count=0, partition_rays=False, instance_vertex_normals=None, spectrum=None, sampler="Independent"):
+                 max_path_count=0, partition_rays=False, instance_vertex_normals=None, spectrum=None, sampler="Independent",
+                 textures=None, albedo_texture=None, vertex_uvs=None, instance_vertex_uvs=None):
         """`accel` is an Accelerator, or a Scene (two-level; vertex_count / triangle_count / vertex_normals
-        are then ignored and instance_vertex_normals may hold one array or None per instance)."""
+        are then ignored and instance_vertex_normals may hold one array or None per instance).
+        textures: list of dict(data=[h, w, 3|4] float32 or uint8 array, interp="Linear"|"Nearest",
+        edge="Wrap"|"Clamp"|"Mirror"); albedo_texture: per material, -1 or an index into `textures`;
+        vertex_uvs [V, 2] (instance_vertex_uvs: one array or None per instance of a Scene)."""
         self.ctx, self.accel, self.spectrum = ctx, accel, spectrum
         self.width, self.height = width, height
         d = RenderDesc()
@@ -484,6 +500,31 @@ class Renderer:
         d.seed = seed
         d.maxPathCount = max_path_count
         d.partitionRays = 1 if partition_rays else 0
+        if textures:
+            tarr = (TextureDesc * len(textures))()
+            for k, t in enumerate(textures):
+                a = np.ascontiguousarray(t["data"])
+                if a.dtype != np.uint8:
+                    a = np.ascontiguousarray(a, np.float32)
+                self._keep.append(a)
+                tarr[k].data = a.ctypes.data
+                tarr[k].height, tarr[k].width, tarr[k].channels = a.shape
+                tarr[k].format = 1 if a.dtype == np.uint8 else 0
+                tarr[k].interp = TEX_INTERP[t.get("interp", "Linear")]
+                tarr[k].edge = TEX_EDGE[t.get("edge", "Wrap")]
+            self._keep.append(tarr)
+            d.textureCount, d.textures = len(textures), C.cast(tarr, C.c_void_p)
+            d.albedoTexture = host(albedo_texture, np.int32)
+        if isinstance(accel, Scene):
+            if instance_vertex_uvs is not None:
+                uptrs = (C.c_void_p * accel.count)()
+                for k, uv in enumerate(instance_vertex_uvs):
+                    if uv is not None:
+                        a = np.ascontiguousarray(uv, np.float32); self._keep.append(a); uptrs[k] = a.ctypes.data
+                self._keep.append(uptrs)
+                d.instanceVertexUVs = C.cast(uptrs, C.POINTER(C.c_void_p))
+        else:
+            d.vertexUVs = host(vertex_uvs, np.float32)
         h = C.c_void_p()
         ctx.check(ctx.lib.mrb_renderer_create(ctx.handle, C.byref(d), C.byref(h)))
         self.handle = h
@@ -598,3 +639,19 @@ class Scene:
             self.close()
         except Exception:
             pass
+
+
+def texture_sample(ctx: Context, texture, uv):
+    """mrb_texture_sample: texture = dict(data=[h, w, 3|4] float32 / uint8, interp=, edge=), uv[n, 2] -> rgb[n, 3]."""
+    a = np.ascontiguousarray(texture["data"])
+    if a.dtype != np.uint8:
+        a = np.ascontiguousarray(a, np.float32)
+    t = TextureDesc()
+    t.data = a.ctypes.data
+    t.height, t.width, t.channels = a.shape
+    t.format = 1 if a.dtype == np.uint8 else 0
+    t.interp, t.edge = TEX_INTERP[texture.get("interp", "Linear")], TEX_EDGE[texture.get("edge", "Wrap")]
+    uv = np.ascontiguousarray(uv, np.float32)
+    out = np.zeros((uv.shape[0], 3), np.float32)
+    ctx.check(ctx.lib.mrb_texture_sample(ctx.handle, C.byref(t), uv.ctypes.data, uv.shape[0], out.ctypes.data))
+    return out

@@ -7,6 +7,7 @@
 #include <vector>
 #include <cstdio>
 #include <new>
+#include <stdexcept>
 
 namespace mrb
 {
@@ -26,6 +27,7 @@ mrb_renderer_t* NewRenderer();
 void RendererStats(Context& ctx, mrb_renderer_t& r, mrb_render_stats& out);
 void RendererReadFilm(Context& ctx, mrb_renderer_t& r, float* out, bool device, bool clear);
 float* RendererFilmPtr(mrb_renderer_t& r);
+void TextureSampleHost(Context& ctx, const mrb_texture_desc& td, const float* uv, uint32_t n, float* rgbOut);
 }
 
 namespace mrb
@@ -77,6 +79,7 @@ static mrb_status Guard(mrb_context ctx, F&& f)
         return (e.code == cudaErrorMemoryAllocation) ? MRB_ERR_OUT_OF_MEMORY : MRB_ERR_CUDA;
     }
     catch(const std::bad_alloc&) { ctx->c.error = "host allocation failed"; return MRB_ERR_OUT_OF_MEMORY; }
+    catch(const std::exception& e) { ctx->c.error = e.what(); return MRB_ERR_INVALID_ARG; }   // descriptor validation of the builders
 }
 
 static mrb_status Fail(mrb::Context& c, mrb_status s, const char* msg) { c.error = msg; return s; }
@@ -650,6 +653,16 @@ mrb_status mrb_renderer_read_film(mrb_context ctx, mrb_renderer r, float* out, m
 }
 
 float* mrb_renderer_film_device_ptr(mrb_renderer r) { return r ? mrb::RendererFilmPtr(*r) : nullptr; }
+
+mrb_status mrb_texture_sample(mrb_context ctx, const mrb_texture_desc* texture, const float* uv, uint32_t count, float* rgbOut)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!texture || (count && (!uv || !rgbOut))) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        mrb::TextureSampleHost(c, *texture, uv, count, rgbOut);
+        return MRB_OK;
+    });
+}
 
 
 mrb_status mrb_multi_partition(mrb_context ctx, uint32_t* keys, uint32_t* indices, uint32_t count,

@@ -146,6 +146,9 @@ struct Camera // CameraPinhole members (CamerasDefault.hpp:L8-36), tile-local
     float  planeW, planeH, tNear, tFar;
 };
 
+// One 2-D texture (single mip level) as the reference's host-backend view sees it (Device/CPU/TextureViewCPU.h)
+struct TexRec { const void* data; uint32_t w, h, channels, format, interp, edge, pad; };
+
 struct EmissiveTri { float4 p0, e0, e1; float4 radiance; }; // p0.w = area, e0.w = twoSided, radiance.w unused
 
 // Per-instance shading inputs: the primitive group's arrays plus the instance transform
@@ -156,10 +159,11 @@ struct RenderInstance
     const uint32_t* indices;
     const float4*   vertexNormals;   // optional (xyz), nullptr = geometric
     const uint32_t* lightOfPrim;     // prim index -> emissive triangle index or INVALID
+    const float2*   vertexUVs;       // optional UV0 per vertex, nullptr = (0, 0)
     float           transform[12];   // local -> world, row-major 3x4
     float           invTransform[12];
     uint32_t        identity;
-    uint32_t        pad[3];
+    uint32_t        pad[1];
 };
 
 struct RenderData
@@ -167,6 +171,8 @@ struct RenderData
     // scene: one record per instance (a single record when rendering one accelerator)
     const RenderInstance* instances;
     uint32_t          sceneMode;       // 1 = hitKeys.accelKey holds the instance index
+    const TexRec*     textures;        // textured albedo (ParamVaryingData): texture table ...
+    const int32_t*    albedoTex;       // ... and per material index: texture or -1; nullptr = no material is textured
     const float4*     albedo;          // per material index: (r, g, b, 0), or Jakob coefficients (c0, c1, c2, -) when spectral
     // hero-wavelength spectral transport ((R)PathTracerSpectral); lights carry (c0, c1, c2, scale) in .radiance
     SpectrumData      spec;
@@ -332,6 +338,58 @@ __global__ void __launch_bounds__(RTPB) KReload(RenderData d)
     ReloadSlot(d, i, inRange, ((pd >> 8) & 0xFFu) == ST_INVALID);
 }
 
+// TextureViewCPU<2, Vector3> restated (Device/CPU/TextureViewCPU.h): ResolveEdge L196-246 (C++ truncating / and %),
+// ReadPixel + Convert L120-170,L305-340, FindInterpolants L262-300 (a negative texel keeps |frac|, as the reference
+// does), ReadInterpolatedPixel L352-385 with Math::Lerp unfused, NearestPixel L248-260.
+__device__ __forceinline__ int TexResolveEdge(int i, int n, uint32_t edge)
+{
+    if(edge == 1u) return min(max(i, 0), n - 1);
+    if(edge == 2u)
+    {
+        const int dim = i / n;
+        i = i % n;
+        if(i < 0) i += n;
+        if((dim & 1) == 1) i = n - i;
+        return min(i, n - 1);   // the reference's mirror can produce n (out of bounds there)
+    }
+    i = i % n;
+    if(i < 0) i += n;
+    return i;
+}
+__device__ __forceinline__ Float3 TexReadPixel(const TexRec& t, int x, int y)
+{
+    const size_t o = (size_t(y) * t.w + size_t(x)) * t.channels;
+    if(t.format == 0u)
+    {
+        const float* f = static_cast<const float*>(t.data) + o;
+        return F3(__ldg(f), __ldg(f + 1), __ldg(f + 2));
+    }
+    const uint8_t* b = static_cast<const uint8_t*>(t.data) + o;
+    const float DELTA = 1.0f / 255.0f;
+    return F3(__fmul_rn(float(__ldg(b)), DELTA), __fmul_rn(float(__ldg(b + 1)), DELTA), __fmul_rn(float(__ldg(b + 2)), DELTA));
+}
+__device__ __forceinline__ Float3 TexLerp(Float3 a, Float3 b, float t)
+{ return F3(SpecLerp(a.x, b.x, t), SpecLerp(a.y, b.y, t), SpecLerp(a.z, b.z, t)); }
+__device__ __forceinline__ Float3 SampleTexture(const TexRec& t, float u, float v)
+{
+    const float tu = __fmul_rn(u, float(t.w)), tv = __fmul_rn(v, float(t.h));
+    if(t.interp == 0u)
+    {
+        const int x = int(roundf(tu - 0.5f)), y = int(roundf(tv - 0.5f));
+        return TexReadPixel(t, TexResolveEdge(x, int(t.w), t.edge), TexResolveEdge(y, int(t.h), t.edge));
+    }
+    float bx, by;
+    float fx = modff(tu - 0.5f, &bx), fy = modff(tv - 0.5f, &by);
+    int x0 = int(bx), y0 = int(by);
+    if(fx < 0.0f) { x0 -= 1; fx = fabsf(fx); }
+    if(fy < 0.0f) { y0 -= 1; fy = fabsf(fy); }
+    const int xa = TexResolveEdge(x0, int(t.w), t.edge), xb = TexResolveEdge(x0 + 1, int(t.w), t.edge);
+    const int ya = TexResolveEdge(y0, int(t.h), t.edge), yb = TexResolveEdge(y0 + 1, int(t.h), t.edge);
+    const Float3 p0 = TexLerp(TexReadPixel(t, xa, ya), TexReadPixel(t, xb, ya), fx);
+    const Float3 p1 = TexLerp(TexReadPixel(t, xa, yb), TexReadPixel(t, xb, yb), fx);
+    return TexLerp(p0, p1, fy);
+}
+
 // Material / light colour at the path's wavelengths: Converter::ConvertAlbedo / ConvertRadiance with the
 // coefficient fetch hoisted to StartRender (constant attributes), or the RGB pass-through converter.
 __device__ __forceinline__ Spec AlbedoAt(const RenderData& d, float4 a, float4 w)
@@ -454,7 +512,23 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
         shadeN = Normalize(shadeN);
     }
     if(backSide) { geoN = geoN * -1.0f; shadeN = shadeN * -1.0f; }
-    const Spec albedo = AlbedoAt(d, d.albedo[lmKey & 0x1FFFFFu], waves);
+    const uint32_t matIndex = lmKey & 0x1FFFFFu;
+    float4 albedoRaw = d.albedo[matIndex];
+    const int32_t texIndex = d.albedoTex ? d.albedoTex[matIndex] : -1;
+    if(texIndex >= 0)
+    {
+        // ParamVaryingData<2, Vector3>: albedo texture at the interpolated UV0 (LambertMaterial ctor, MaterialsDefault.hpp:L17-25)
+        float2 uv = make_float2(0.f, 0.f);
+        if(in.vertexUVs)
+        {
+            const float2 t0 = in.vertexUVs[vi[0]], t1 = in.vertexUVs[vi[1]], t2 = in.vertexUVs[vi[2]];
+            uv = make_float2(t0.x * a + t1.x * b + t2.x * c, t0.y * a + t1.y * b + t2.y * c);
+        }
+        const Float3 rgb = SampleTexture(d.textures[texIndex], uv.x, uv.y);
+        if(d.spectral) { const float3 cf = FetchAlbedoCoeffs(d.spec, rgb.x, rgb.y, rgb.z); albedoRaw = make_float4(cf.x, cf.y, cf.z, 0.f); }
+        else albedoRaw = make_float4(rgb.x, rgb.y, rgb.z, 0.f);
+    }
+    const Spec albedo = AlbedoAt(d, albedoRaw, waves);
     // orthonormal frame about the shading normal
     const Float3 hlp = (fabsf(shadeN.x) > 0.9f) ? F3(0, 1, 0) : F3(1, 0, 0);
     const Float3 tX = Normalize(Cross(hlp, shadeN));
@@ -727,7 +801,7 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
     d.cam.tNear = desc.nearFar[0]; d.cam.tFar = desc.nearFar[1];
 
     // instance list: the scene's instances, or one identity instance of the single accelerator
-    struct HostInst { const mrb_accel_t* acc; const float* m; const float* inv; bool identity; const float* normals; };
+    struct HostInst { const mrb_accel_t* acc; const float* m; const float* inv; bool identity; const float* normals; const float* uvs; };
     static const float IDENTITY[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
     std::vector<HostInst> hinst;
     if(desc.scene)
@@ -735,9 +809,10 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
         {
             const mrb_instance_desc& id = desc.scene->hInstances[k];
             hinst.push_back({id.accel, id.transform, id.invTransform, id.isIdentity != 0,
-                             desc.instanceVertexNormals ? desc.instanceVertexNormals[k] : nullptr});
+                             desc.instanceVertexNormals ? desc.instanceVertexNormals[k] : nullptr,
+                             desc.instanceVertexUVs ? desc.instanceVertexUVs[k] : nullptr});
         }
-    else hinst.push_back({desc.accel, IDENTITY, IDENTITY, true, desc.vertexNormals});
+    else hinst.push_back({desc.accel, IDENTITY, IDENTITY, true, desc.vertexNormals, desc.vertexUVs});
     const uint32_t instCount = uint32_t(hinst.size());
 
     // emissive triangle list (MetaLightArrayT::Construct: one meta light per emissive triangle of every
@@ -803,6 +878,17 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
     d.lightCount = uint32_t(lights.size());
 
     std::vector<RenderInstance> hri(instCount);
+    std::vector<TexRec> htex(desc.textureCount);
+    for(uint32_t t = 0; t < desc.textureCount; t++)
+    {
+        const mrb_texture_desc& td = desc.textures[t];
+        if(!td.data || td.width == 0 || td.height == 0 || (td.channels != 3 && td.channels != 4) || td.format > 1u || td.interp > 1u || td.edge > 2u)
+            throw std::runtime_error("bad texture descriptor");
+        htex[t] = TexRec{nullptr, td.width, td.height, td.channels, td.format, td.interp, td.edge, 0u};
+    }
+    if(desc.albedoTexture)
+        for(uint32_t m = 0; m < desc.materialCount; m++)
+            if(desc.albedoTexture[m] >= int32_t(desc.textureCount)) throw std::runtime_error("albedoTexture index exceeds textureCount");
     InstanceRec* dSceneInst = nullptr;
     auto Layout = [&](MultiAlloc& ma)
     {
@@ -824,8 +910,14 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
         {
             hri[k].lightOfPrim = ma.Take<uint32_t>(hinst[k].acc->triangleCount);
             hri[k].vertexNormals = hinst[k].normals ? ma.Take<float4>(hinst[k].acc->vertexCount) : nullptr;
+            hri[k].vertexUVs = hinst[k].uvs ? ma.Take<float2>(hinst[k].acc->vertexCount) : nullptr;
         }
         d.workKeys = ma.Take<uint32_t>(P); d.workIndices = ma.Take<uint32_t>(P); d.partTable = ma.Take<uint32_t>(32);
+        d.albedoTex = desc.albedoTexture ? ma.Take<int32_t>(desc.materialCount ? desc.materialCount : 1) : nullptr;
+        d.textures = desc.textureCount ? ma.Take<TexRec>(desc.textureCount) : nullptr;
+        for(uint32_t t = 0; t < desc.textureCount; t++)
+            htex[t].data = ma.Take<char>(size_t(desc.textures[t].width) * desc.textures[t].height * desc.textures[t].channels *
+                                         (desc.textures[t].format == 0u ? 4u : 1u));
         d.waves = desc.spectrum ? ma.Take<float4>(P) : nullptr; d.wavePdf = desc.spectrum ? ma.Take<float4>(P) : nullptr;
     };
     MultiAlloc sz(nullptr); Layout(sz);
@@ -838,6 +930,13 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
     for(uint32_t m = 0; m < desc.materialCount; m++)
         halb[m] = make_float4(desc.albedo[3 * m], desc.albedo[3 * m + 1], desc.albedo[3 * m + 2], 0.f);
     MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<float4*>(d.albedo), halb.data(), halb.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx.stream));
+    if(desc.albedoTexture)
+        MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<int32_t*>(d.albedoTex), desc.albedoTexture, sizeof(int32_t) * desc.materialCount, cudaMemcpyHostToDevice, ctx.stream));
+    for(uint32_t t = 0; t < desc.textureCount; t++)
+        MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<void*>(htex[t].data), desc.textures[t].data,
+                                     size_t(htex[t].w) * htex[t].h * htex[t].channels * (htex[t].format == 0u ? 4u : 1u), cudaMemcpyHostToDevice, ctx.stream));
+    if(desc.textureCount)
+        MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<TexRec*>(d.textures), htex.data(), htex.size() * sizeof(TexRec), cudaMemcpyHostToDevice, ctx.stream));
     if(!lights.empty())
         MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<EmissiveTri*>(d.lights), lights.data(), lights.size() * sizeof(EmissiveTri), cudaMemcpyHostToDevice, ctx.stream));
     d.spectral = desc.spectrum ? 1u : 0u;
@@ -858,6 +957,8 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
         memcpy(ri.invTransform, hinst[k].inv, sizeof(ri.invTransform));
         ri.identity = hinst[k].identity ? 1u : 0u;
         MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<uint32_t*>(ri.lightOfPrim), lightOfPrim[k].data(), lightOfPrim[k].size() * 4, cudaMemcpyHostToDevice, ctx.stream));
+        if(hinst[k].uvs)
+            MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<float2*>(ri.vertexUVs), hinst[k].uvs, size_t(hacc.vertexCount) * sizeof(float2), cudaMemcpyHostToDevice, ctx.stream));
         if(hinst[k].normals)
         {
             hn.resize(hacc.vertexCount);
@@ -968,5 +1069,31 @@ void RendererReadFilm(Context& ctx, mrb_renderer_t& r, float* out, bool device, 
 }
 
 float* RendererFilmPtr(mrb_renderer_t& r) { return r.d.film; }
+
+// mrb_texture_sample: the shading kernel's texture filter on its own (parity tap of SampleTexture)
+__global__ void KSampleTexture(TexRec t, const float2* __restrict__ uv, uint32_t n, float* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const Float3 c = SampleTexture(t, uv[i].x, uv[i].y);
+    out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z;
+}
+
+void TextureSampleHost(Context& ctx, const mrb_texture_desc& td, const float* uv, uint32_t n, float* rgbOut)
+{
+    if(!td.data || td.width == 0 || td.height == 0 || (td.channels != 3 && td.channels != 4) || td.format > 1u || td.interp > 1u || td.edge > 2u)
+        throw std::runtime_error("bad texture descriptor");
+    const size_t texBytes = size_t(td.width) * td.height * td.channels * (td.format == 0u ? 4u : 1u);
+    MultiAlloc sz(nullptr); sz.Take<char>(texBytes); sz.Take<float2>(n); sz.Take<float>(size_t(n) * 3);
+    ctx.scratch.Reserve(sz.Total());
+    MultiAlloc ma(ctx.scratch.Base());
+    char* dTex = ma.Take<char>(texBytes); float2* dUV = ma.Take<float2>(n); float* dOut = ma.Take<float>(size_t(n) * 3);
+    MRB_CUDA_TRY(cudaMemcpyAsync(dTex, td.data, texBytes, cudaMemcpyHostToDevice, ctx.stream));
+    MRB_CUDA_TRY(cudaMemcpyAsync(dUV, uv, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx.stream));
+    const TexRec t{dTex, td.width, td.height, td.channels, td.format, td.interp, td.edge, 0u};
+    if(n) MRB_LAUNCH(ctx, KSampleTexture, DivUp(n, 256u), 256, 0, t, dUV, n, dOut);
+    MRB_CUDA_TRY(cudaMemcpyAsync(rgbOut, dOut, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx.stream));
+    MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
+}
 
 } // namespace mrb

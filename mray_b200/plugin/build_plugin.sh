@@ -21,4 +21,6 @@ g++ -shared -o "$ROOT/mray_b200/lib/libTracerDLL_B200.so" "$W/tracer_b200.o" -L"
 g++ $(cat "$W/cxxflags.txt") -c "$ROOT/oracle/ref_build/tracer_driver.cpp" -o "$W/tracer_driver.o"
 g++ -shared -rdynamic -o "$ROOT/oracle/_ref/libtracer_driver.so" "$W/tracer_driver.o" -L"$ROOT/oracle/_ref" -lmray_refcore \
     -Wl,-rpath,'$ORIGIN' -lpthread -latomic -ldl
+# a process to host the driver in (the reference's spectral renderer looks for SpectraLUT/ next to the executable)
+g++ -O1 -std=c++17 "$ROOT/oracle/ref_build/ref_render_host.cpp" -o "$ROOT/oracle/_ref/ref_render_host" -ldl
 echo "PLUGIN_OK"

@@ -286,3 +286,77 @@ def arcade_materials(positions, indices, material_count: int = 64, seed: int = 1
     albedo = (0.25 + 0.6 * rng.random((material_count, 3))).astype(np.float32)
     radiance = np.array([40.0, 36.0, 30.0], np.float32)
     return idx, np.array(ranges, np.uint32), np.array(keys, np.uint32), albedo, radiance, m
+
+
+def instanced_field(seed: int = 99, instance_count: int = 1000, target_tris: int = 10_000_000, material_count: int = 64,
+                    light_panels: int = 16):
+    """BASELINE config 4: ``instance_count`` instances ((T)Single, random rotation * scale * translation) of 10
+    distinct meshes of 1 K .. 100 K triangles (bumpy spheres / fluted columns, log-spaced sizes; the smaller meshes
+    get more instances so that the instanced total is ~``target_tris``), one of ``material_count`` Lambert
+    materials per INSTANCE (round-robin), a ground plane and ``light_panels`` emissive quads above the field.
+
+    Returns dict(meshes=[(positions, indices)], instances=[(mesh, 3x4 transform or None, material or -1 for the
+    light)], albedo[material_count,3], radiance[3], camera, triangles_instanced)."""
+    rng = np.random.default_rng(seed)
+    sizes = np.round(1000.0 * 10.0 ** (2.0 * np.arange(10) / 9.0)).astype(int)
+    meshes = []
+    for k, s in enumerate(sizes):
+        if k % 2 == 0:
+            nv = max(4, int(np.sqrt(s / 4.0))); nu = max(8, int(round(s / (2.0 * nv))))
+            p, i = _sphere((0.0, 0.0, 0.0), 1.0, nu, nv, 0.08 + 0.02 * k, rng)
+        else:
+            nh = max(4, int(np.sqrt(s / 8.0))); nseg = max(8, int(round(s / (2.0 * nh))))
+            p, i = _cylinder((0.0, 0.0), 0.5, -1.5, 1.5, nseg, nh, flute=0.05)
+        meshes.append((np.ascontiguousarray(p, np.float32), np.ascontiguousarray(i, np.uint32)))
+    tris = np.array([m[1].shape[0] for m in meshes], np.float64)
+    # instance counts n_k ~ tris_k^-a with sum n_k = instance_count and sum n_k tris_k ~ target_tris (bisection on a)
+    lo, hi = 0.0, 3.0
+    for _ in range(60):
+        a = 0.5 * (lo + hi)
+        w = tris ** -a; n = instance_count * w / w.sum()
+        if (n * tris).sum() > target_tris: lo = a
+        else: hi = a
+    n = np.maximum(1, np.floor(instance_count * w / w.sum())).astype(int)
+    n[0] += instance_count - n.sum()
+    which = np.repeat(np.arange(10), n); rng.shuffle(which)
+    extent = 60.0
+    instances = []
+    for k, m in enumerate(which):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        w_, x, y, z = q
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w_), 2 * (x * z + y * w_)],
+                      [2 * (x * y + z * w_), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w_)],
+                      [2 * (x * z - y * w_), 2 * (y * z + x * w_), 1 - 2 * (x * x + y * y)]])
+        s = rng.uniform(0.8, 2.2)
+        t = np.array([rng.uniform(-extent, extent), rng.uniform(1.0, 14.0), rng.uniform(-extent, extent)])
+        instances.append((int(m), np.hstack([R * s, t[:, None]]), k % material_count))
+    # ground (two triangles, identity) and light panels (one quad mesh, instanced)
+    g = 1.5 * extent
+    meshes.append((np.array([[-g, 0, g], [g, 0, g], [g, 0, -g], [-g, 0, -g]], np.float32), np.array([[0, 1, 2], [0, 2, 3]], np.uint32)))
+    instances.append((10, None, 0))
+    meshes.append((np.array([[-1, 0, -1], [1, 0, -1], [1, 0, 1], [-1, 0, 1]], np.float32), np.array([[0, 1, 2], [0, 2, 3]], np.uint32)))
+    for k in range(light_panels):
+        t = np.array([rng.uniform(-extent, extent), 24.0, rng.uniform(-extent, extent)])
+        instances.append((11, np.hstack([np.eye(3) * 5.0, t[:, None]]), -1))
+    albedo = (0.25 + 0.6 * rng.random((material_count, 3))).astype(np.float32)
+    camera = dict(eye=(0.0, 22.0, 1.45 * extent), gaze=(0.0, 4.0, 0.0), up=(0.0, 1.0, 0.0), fov_y_deg=50.0)
+    total = int(sum(meshes[m][1].shape[0] for m, _, _ in instances))
+    return dict(meshes=meshes, instances=instances, albedo=albedo, radiance=np.array([60.0, 54.0, 45.0], np.float32),
+                camera=camera, triangles_instanced=total)
+
+
+def cornell_textures(seed: int = 5):
+    """UV0 + albedo textures for ``cornell_box`` (every quad owns its 4 vertices): the white material reads an 8x8
+    fp32 RGB texture (bilinear, wrap) over uv in [-0.75, 1.75]^2 — wrap-around and the negative-texel path of the
+    reference's filter both occur —, the red one a 4x4 unorm8 RGBA texture (nearest, clamp), green stays constant.
+    Returns (vertex_uvs[V, 2], textures, albedo_texture[4])."""
+    rng = np.random.default_rng(seed)
+    c = cornell_box()
+    nq = c["positions"].shape[0] // 4
+    corner = np.array([[-0.75, -0.75], [1.75, -0.75], [1.75, 1.75], [-0.75, 1.75]], np.float32)
+    uvs = np.tile(corner, (nq, 1)).astype(np.float32)
+    t0 = (0.1 + 0.8 * rng.random((8, 8, 3))).astype(np.float32)
+    t1 = rng.integers(40, 230, size=(4, 4, 4), dtype=np.uint8)
+    t1[..., 1:3] //= 4          # keep it reddish
+    textures = [dict(data=t0, interp="Linear", edge="Wrap"), dict(data=t1, interp="Nearest", edge="Clamp")]
+    return uvs, textures, np.array([0, 1, -1, -1], np.int32)

@@ -40,28 +40,30 @@ ITEMS = {
     # converged comparison at relMSE <= 1e-3 needs > 1e4 spp on BOTH sides: done at 128x128
     "cornell128_spp16384": (128, 16384, 11, "WithNEEAndMIS", (2, 20), False, np.float32, RGB),
     "cornell128_spectral_spp16384": (128, 16384, 12, "WithNEEAndMIS", (2, 20), False, np.float32, SPECTRAL),
-    # small images for the CPU tests of the estimator oracle, one per sample mode
-    "cornell32_spp65536":      (32, 65536, 3, "WithNEEAndMIS", (2, 20), False, np.float32, RGB),
-    "cornell32_nee_spp65536":  (32, 65536, 4, "WithNextEventEstimation", (2, 20), False, np.float32, RGB),
-    "cornell32_pure_spp65536": (32, 65536, 5, "Pure", (2, 20), False, np.float32, RGB),
-    "cornell32_spectral_spp65536": (32, 65536, 8, "WithNEEAndMIS", (2, 20), False, np.float32, SPECTRAL),
+    # small images for the CPU tests of the estimator oracle, one per sample mode. 64x64 at 16384 spp: the tests
+    # compare 2x2 block means (65536 samples per block); the reference pays per ITERATION, so a 32x32 image at
+    # 65536 spp would take four times as long for the same statistics.
+    "cornell64_spp16384":      (64, 16384, 3, "WithNEEAndMIS", (2, 20), False, np.float32, RGB),
+    "cornell64_nee_spp16384":  (64, 16384, 4, "WithNextEventEstimation", (2, 20), False, np.float32, RGB),
+    "cornell64_pure_spp16384": (64, 16384, 5, "Pure", (2, 20), False, np.float32, RGB),
+    "cornell64_spectral_spp16384": (64, 16384, 8, "WithNEEAndMIS", (2, 20), False, np.float32, SPECTRAL),
     # two-level scene: every batch in its own local space under a (T)Single transform
-    "cornell32_single_spp65536": (32, 65536, 6, "WithNEEAndMIS", (2, 20), True, np.float32, RGB),
+    "cornell64_single_spp16384": (64, 16384, 6, "WithNEEAndMIS", (2, 20), True, np.float32, RGB),
 }
 
 
 def rigid(rng):
-    """Translation + proper axis-permutation rotation, 3x4. The reference is only self-consistent for this
-    transform family: it leaves the shading frame in LOCAL space (PrimitiveDefaultTriangle.hpp:L610-613,
-    "we can't apply a transform to tbn") and its affine inverse has a cofactor sign slip (Core/Matrix.hpp:L892),
-    so general rotations / scales change ITS image of an unchanged world (measured: Cornell mean 1.09 -> 0.24
-    under random rotations). With this family its two-level image equals its flat image."""
+    """Translation + proper axis-permutation rotation with s1 = m00 m12 - m02 m10 = 0, 3x4. The reference is only
+    self-consistent for such transforms: its affine inverse (Core/Matrix.hpp:L860-905) writes +s1 where the cofactor
+    is -s1, so any rotation with s1 != 0 (every rotation about X, for one) sends rays to a mirrored local space, and
+    the reference's image of an UNCHANGED world changes (measured: Cornell mean 1.09 -> 0.24 under random rotations,
+    -> 0.93 under uniform scales). With this family its two-level image equals its flat image."""
     while True:
         perm, sg = rng.permutation(3), rng.choice([-1.0, 1.0], size=3)
         R = np.zeros((3, 3))
         for i in range(3):
             R[i, perm[i]] = sg[i]
-        if np.linalg.det(R) > 0:
+        if np.linalg.det(R) > 0 and R[0, 0] * R[1, 2] - R[0, 2] * R[1, 0] == 0:
             break
     return np.hstack([R, rng.uniform(-3, 3, size=(3, 1))])
 

@@ -2,11 +2,12 @@
  * triangle lights, uniform light sampler incl. the boundary light, NEE / NEE+MIS / pure, Russian
  * roulette, stochastic Gaussian film filter), one path at a time instead of a wavefront.
  *
- * TEST INFRASTRUCTURE ONLY (see mray_oracle.c). Parity status: UNPINNED by reference execution —
- * the reference's CPU backend crashes in this container as soon as a scene has a prim-backed light
- * (DESIGN.md §4), so no reference image exists to pin it. It is pinned only (a) internally: Pure,
- * NEE and NEE+MIS must agree in expectation, (b) analytically: tests/test_oracle_pt.py checks the
- * direct irradiance under a square light against the closed-form form factor.
+ * TEST INFRASTRUCTURE ONLY (see mray_oracle.c). Parity status: PINNED by reference execution — the unmodified
+ * reference (CPU backend, driven through TracerI by oracle/ref_build/tracer_driver.cpp) rendered the Cornell box
+ * in all three sample modes, as a two-level scene and with the spectral renderer (oracle/gen_golden_render.py ->
+ * tests/golden/render_*.npz); tests/test_oracle_pt.py holds this restatement to those images at the north-star
+ * tolerance (relMSE <= 1e-3 on converged images), plus (a) Pure / NEE / NEE+MIS agreeing in expectation and
+ * (b) the closed-form direct irradiance under a square light.
  * Statistical parity only (even the reference's own backends differ per sample).
  *
  * Restated from (paths relative to /root/reference/Source):
@@ -83,7 +84,65 @@ typedef struct
     float filterRadius; uint64_t seed;
     /* (R)PathTracerSpectral when non-NULL: tables of spectrum_oracle.c + WavelengthSampleMode */
     const struct orc_spectrum_tables* spectrum; uint32_t wavelengthMode;
+    /* textured Lambert albedo (all NULL / 0 = none): per-vertex UV0, texture table, per-material texture index or -1 */
+    const float* uv; const struct orc_texture* textures; const int32_t* albedoTexture; uint32_t nTextures;
 } pt_scene;
+
+/* One single-level 2-D texture as the reference's host-backend view reads it (Device/CPU/TextureViewCPU.h):
+ * format 0 = fp32, 1 = unorm8; interp 0 = nearest, 1 = linear; edge 0 = wrap, 1 = clamp, 2 = mirror. */
+struct orc_texture { const void* data; uint32_t w, h, channels, format, interp, edge; };
+
+/* TextureViewCPU::ResolveEdge (TextureViewCPU.h:L196-246); C's / and % truncate like the reference's */
+static int tex_edge(int i, int n, uint32_t edge)
+{
+    if(edge == 1u) return i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
+    if(edge == 2u)
+    {
+        int dim = i / n;
+        i = i % n;
+        if(i < 0) i += n;
+        if((dim & 1) == 1) i = n - i;
+        return i > n - 1 ? n - 1 : i;   /* the reference can produce n here (out of bounds there) */
+    }
+    i = i % n;
+    if(i < 0) i += n;
+    return i;
+}
+/* ReadPixel + Convert (L120-170,L305-340): FromUNorm = v * (1 / 255) */
+static void tex_pixel(const struct orc_texture* t, int x, int y, float out[3])
+{
+    size_t o = ((size_t)y * t->w + (size_t)x) * t->channels;
+    if(t->format == 0u) { const float* f = (const float*)t->data + o; out[0] = f[0]; out[1] = f[1]; out[2] = f[2]; return; }
+    const uint8_t* b = (const uint8_t*)t->data + o;
+    const float DELTA = 1.0f / 255.0f;
+    for(int k = 0; k < 3; k++) out[k] = (float)b[k] * DELTA;
+}
+/* Math::Lerp (Core/Math.h): a * (1 - t) + b * t, unfused */
+static float tex_lerp(float a, float b, float t) { volatile float x = a * (1.0f - t); volatile float y = b * t; return x + y; }
+/* TracerTexView<2, Vector3>::operator()(uv, dpdx, dpdy) for a texture with ONE mip level: the mip level computed
+ * from the gradients clamps to 0 (L429-470), leaving NearestPixel (L248-260) or FindInterpolants +
+ * ReadInterpolatedPixel (L262-300,L352-385) on the base level. */
+void orc_texture_sample(const struct orc_texture* t, float u, float v, float out[3])
+{
+    float tu = u * (float)t->w, tv = v * (float)t->h;
+    if(t->interp == 0u)
+    {
+        int x = (int)roundf(tu - 0.5f), y = (int)roundf(tv - 0.5f);
+        tex_pixel(t, tex_edge(x, (int)t->w, t->edge), tex_edge(y, (int)t->h, t->edge), out);
+        return;
+    }
+    float bx, by;
+    float fx = modff(tu - 0.5f, &bx), fy = modff(tv - 0.5f, &by);
+    int x0 = (int)bx, y0 = (int)by;
+    if(fx < 0.0f) { x0 -= 1; fx = fabsf(fx); }   /* as the reference: |frac|, not 1 - |frac| */
+    if(fy < 0.0f) { y0 -= 1; fy = fabsf(fy); }
+    int xa = tex_edge(x0, (int)t->w, t->edge), xb = tex_edge(x0 + 1, (int)t->w, t->edge);
+    int ya = tex_edge(y0, (int)t->h, t->edge), yb = tex_edge(y0 + 1, (int)t->h, t->edge);
+    float p00[3], p10[3], p01[3], p11[3];
+    tex_pixel(t, xa, ya, p00); tex_pixel(t, xb, ya, p10); tex_pixel(t, xa, yb, p01); tex_pixel(t, xb, yb, p11);
+    for(int k = 0; k < 3; k++)
+        out[k] = tex_lerp(tex_lerp(p00[k], p10[k], fx), tex_lerp(p01[k], p11[k], fx), fy);
+}
 
 /* spectrum_oracle.c */
 struct orc_spectrum_tables;
@@ -98,10 +157,23 @@ static s4 S(float a, float b, float c, float d) { s4 r = {{a, b, c, d}}; return 
 static s4 s_mul(s4 a, float k) { return S(a.v[0] * k, a.v[1] * k, a.v[2] * k, a.v[3] * k); }
 static s4 s_mulv(s4 a, s4 b) { return S(a.v[0] * b.v[0], a.v[1] * b.v[1], a.v[2] * b.v[2], a.v[3] * b.v[3]); }
 static s4 s_add(s4 a, s4 b) { return S(a.v[0] + b.v[0], a.v[1] + b.v[1], a.v[2] + b.v[2], a.v[3] + b.v[3]); }
-static s4 albedo_at(const pt_scene* s, uint32_t m, const float waves[4])
+/* LambertMaterial ctor (MaterialsDefault.hpp:L17-25): albedo = ConvertAlbedo(albedoMap(uv, dpdx, dpdy)) */
+static s4 albedo_at(const pt_scene* s, uint32_t m, const float waves[4], uint32_t prim, float a, float b, float c)
 {
-    if(!s->spectrum) return S(s->albedo[3 * m], s->albedo[3 * m + 1], s->albedo[3 * m + 2], 0.0f);
-    s4 o; orc_convert_albedo(s->spectrum, s->albedo + 3 * m, waves, o.v); return o;
+    float rgb[3] = {s->albedo[3 * m], s->albedo[3 * m + 1], s->albedo[3 * m + 2]};
+    if(s->albedoTexture && s->albedoTexture[m] >= 0)
+    {
+        float u = 0.0f, v = 0.0f;
+        if(s->uv)
+        {
+            const uint32_t* ix = s->idx + 3 * (size_t)prim;
+            u = s->uv[2 * ix[0]] * a + s->uv[2 * ix[1]] * b + s->uv[2 * ix[2]] * c;
+            v = s->uv[2 * ix[0] + 1] * a + s->uv[2 * ix[1] + 1] * b + s->uv[2 * ix[2] + 1] * c;
+        }
+        orc_texture_sample(s->textures + s->albedoTexture[m], u, v, rgb);
+    }
+    if(!s->spectrum) return S(rgb[0], rgb[1], rgb[2], 0.0f);
+    s4 o; orc_convert_albedo(s->spectrum, rgb, waves, o.v); return o;
 }
 
 static void tri(const pt_scene* s, uint32_t t, v3 p[3])
@@ -216,7 +288,7 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
         }
         /* Lambert */
         if(dot(gN, nrm(d)) > 0) gN = mul(gN, -1.0f);
-        s4 alb = albedo_at(s, (uint32_t)m, waves);
+        s4 alb = albedo_at(s, (uint32_t)m, waves, prim, a, b, c);
         v3 hlp = fabsf(gN.x) > 0.9f ? V(0, 1, 0) : V(1, 0, 0);
         v3 tX = nrm(cross(hlp, gN)), tY = cross(gN, tX);
         if(s->sampleMode != 0u)

@@ -296,12 +296,51 @@ class _PtScene(C.Structure):
                 ("fovXY", C.c_float * 2), ("nearFar", C.c_float * 2),
                 ("width", C.c_uint32), ("height", C.c_uint32), ("spp", C.c_uint32), ("sampleMode", C.c_uint32),
                 ("rrLo", C.c_uint32), ("rrHi", C.c_uint32), ("filterRadius", C.c_float), ("seed", C.c_uint64),
-                ("spectrum", C.c_void_p), ("wavelengthMode", C.c_uint32)]
+                ("spectrum", C.c_void_p), ("wavelengthMode", C.c_uint32),
+                ("uv", C.c_void_p), ("textures", C.c_void_p), ("albedoTexture", C.c_void_p), ("nTextures", C.c_uint32)]
+
+
+class _OrcTexture(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("w", C.c_uint32), ("h", C.c_uint32), ("channels", C.c_uint32),
+                ("format", C.c_uint32), ("interp", C.c_uint32), ("edge", C.c_uint32)]
+
+
+_TEX_INTERP = {"Nearest": 0, "Linear": 1}
+_TEX_EDGE = {"Wrap": 0, "Clamp": 1, "Mirror": 2}
+
+
+def _orc_textures(textures):
+    """list of dict(data=[h, w, 3|4] float32 / uint8, interp=, edge=) -> (ctypes array, keep-alive list)"""
+    arr = (_OrcTexture * len(textures))()
+    keep = []
+    for k, t in enumerate(textures):
+        a = np.ascontiguousarray(t["data"])
+        if a.dtype != np.uint8:
+            a = np.ascontiguousarray(a, np.float32)
+        keep.append(a)
+        arr[k].data = a.ctypes.data
+        arr[k].h, arr[k].w, arr[k].channels = a.shape
+        arr[k].format = 1 if a.dtype == np.uint8 else 0
+        arr[k].interp = _TEX_INTERP[t.get("interp", "Linear")]
+        arr[k].edge = _TEX_EDGE[t.get("edge", "Wrap")]
+    return arr, keep
+
+
+def oracle_texture_sample(texture, uv):
+    """TextureViewCPU restatement (oracle/pt_oracle.c::orc_texture_sample) at uv[n, 2] -> rgb[n, 3]."""
+    L = lib()
+    arr, keep = _orc_textures([texture])
+    uv = np.ascontiguousarray(uv, np.float32)
+    out = np.zeros((uv.shape[0], 3), np.float32)
+    L.orc_texture_sample.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+    for k in range(uv.shape[0]):
+        L.orc_texture_sample(C.addressof(arr), float(uv[k, 0]), float(uv[k, 1]), out[k].ctypes.data)
+    return out
 
 
 def oracle_render(positions, indices, tri_material, albedo, radiance, camera, width, height, spp,
                   sample_mode=2, rr_range=(2, 20), seed=0, near_far=(0.01, 1000.0), threads=None,
-                  spectral_data=None, wavelength_mode=2):
+                  spectral_data=None, wavelength_mode=2, textures=None, albedo_texture=None, vertex_uvs=None):
     """tri_material: per triangle, >= 0 Lambert material index, -1 - k for light k. Returns image[h,w,3]
     (row 0 = bottom) resolved as sum radiance / sum weight. spectral_data (mray_b200.spectral.load())
     switches to the hero-wavelength spectral estimator."""
@@ -326,6 +365,12 @@ def oracle_render(positions, indices, tri_material, albedo, radiance, camera, wi
     if spectral_data is not None:
         tables, keep_tables = spectrum_tables(spectral_data)
         s.spectrum, s.wavelengthMode = C.addressof(tables), wavelength_mode
+    if textures:
+        tarr, keep_tex = _orc_textures(textures)
+        at = np.ascontiguousarray(albedo_texture, np.int32)
+        uvs = None if vertex_uvs is None else np.ascontiguousarray(vertex_uvs, np.float32)
+        s.textures, s.nTextures, s.albedoTexture = C.addressof(tarr), len(textures), at.ctypes.data
+        s.uv = None if uvs is None else uvs.ctypes.data
     out = np.zeros((4, height, width), np.float32)
     threads = threads or min(16, os.cpu_count() or 1)
     rows = np.linspace(0, height, threads * 4 + 1).astype(int)
