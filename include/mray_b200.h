@@ -394,6 +394,11 @@ typedef struct mrb_render_desc
     const int32_t*  albedoTexture;
     const float*    vertexUVs;
     const float* const* instanceVertexUVs;
+    /* RenderImageParams{resolution, regionMin, regionMax} (Core/TracerI.h:L38-43): width x height above is the REGION
+     * rendered by this renderer; fullResolution (0,0 = the region is the whole image) and regionMin place it in the
+     * image the camera spans, so several renderers (tiles, GPUs) can share one image. */
+    uint32_t        fullResolution[2];
+    uint32_t        regionMin[2];
 } mrb_render_desc;
 
 typedef struct mrb_render_stats

@@ -182,7 +182,8 @@ struct RenderData
     const EmissiveTri* lights;         // one per emissive triangle (MetaLight list), world space
     uint32_t          lightCount;      // emissive triangles (+1 boundary light in the sampler)
     Camera            cam;
-    uint32_t          width, height;
+    uint32_t          width, height;   // the tile
+    uint32_t          fullWidth, fullHeight, regionX, regionY; // the image it is a region of
     float             filterSigma;     // Gaussian film filter (Filters.h:L195-227): sigma = r * 0.285714
     // options
     uint32_t          rrLo, rrHi, sampleMode; // 0 Pure, 1 NEE, 2 NEE+MIS
@@ -282,8 +283,9 @@ __device__ __forceinline__ void ReloadSlot(const RenderData& d, uint32_t i, bool
     const float offx = SampleG(xi0, pdfx), offy = SampleG(xi1, pdfy);
     // Evaluate == the same Gaussian, so the weight is 1 up to the clamp of the tails
     const float weight = 1.0f;
-    const float sx = (float(px) + offx + 0.5f) * (d.cam.planeW / float(d.width));
-    const float sy = (float(py) + offy + 0.5f) * (d.cam.planeH / float(d.height));
+    // the tile may be a region of a larger image (RenderImageParams.regionMin / resolution)
+    const float sx = (float(px + d.regionX) + offx + 0.5f) * (d.cam.planeW / float(d.fullWidth));
+    const float sy = (float(py + d.regionY) + offy + 0.5f) * (d.cam.planeH / float(d.fullHeight));
     const Float3 point = d.cam.bottomLeft + d.cam.right * sx + d.cam.up * sy;
     const Float3 dir = Normalize(point - d.cam.position);
     float4* rp = reinterpret_cast<float4*>(d.rays + i);
@@ -774,6 +776,10 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
     r.accel = desc.accel; r.scene = desc.scene;
     d.sceneMode = desc.scene ? 1u : 0u;
     d.width = desc.width; d.height = desc.height;
+    d.fullWidth = desc.fullResolution[0] ? desc.fullResolution[0] : desc.width;
+    d.fullHeight = desc.fullResolution[1] ? desc.fullResolution[1] : desc.height;
+    d.regionX = desc.regionMin[0]; d.regionY = desc.regionMin[1];
+    if(d.regionX + d.width > d.fullWidth || d.regionY + d.height > d.fullHeight) throw std::runtime_error("render region exceeds the image");
     d.rrLo = desc.rrRange[0]; d.rrHi = desc.rrRange[1]; d.sampleMode = desc.sampleMode;
     d.pathLimit = uint64_t(desc.totalSPP) * desc.width * desc.height;
     d.filterSigma = desc.filmFilterRadius * 0.285714f;

@@ -43,10 +43,17 @@ struct PrimGroupB200
 {
     std::string type; bool committed = false;
     std::vector<PrimBatch> batches;
-    std::vector<Vector3> positions; std::vector<Vector3> normals; std::vector<Vector3ui> indices;
+    std::vector<Vector3> positions; std::vector<Vector3> normals; std::vector<Vector2> uvs; std::vector<Vector3ui> indices;
     uint32_t primTotal = 0, vertexTotal = 0;
 };
-struct MatGroupB200 { std::string type; bool committed = false; std::vector<Vector3> albedo; };
+struct MatGroupB200 { std::string type; bool committed = false; std::vector<Vector3> albedo; std::vector<int32_t> albedoTex; /* TextureId or -1 */ };
+// One 2-D texture as TracerI::CreateTexture2D / PushTextureData deliver it (first slice: one mip level, 4-channel
+// fp32 or unorm8 pixels, already in the global colour space)
+struct TextureB200
+{
+    Vector2ui size; MRayTextureParameters params; uint32_t channels = 4, format = 0;
+    std::vector<Byte> pixels; bool loaded = false;
+};
 struct LightGroupB200
 {
     std::string type; bool committed = false; uint32_t primGroup = 0;
@@ -105,9 +112,12 @@ class TracerB200 final : public TracerI
     // flattened scene
     uint32_t flatPrimGroup = 0; std::vector<float> flatLightRadiance; std::vector<uint8_t> flatLightTwoSided;
     std::vector<float> flatAlbedo;
+    std::vector<int32_t> flatAlbedoTex;             // per flat material: index into flatTextures or -1
+    std::vector<uint32_t> flatTextures;             // TextureIds in use, in first-use order
+    std::vector<TextureB200> textures;              // TextureId = index + 1 (0 = InvalidTexture)
     // render hand-off
     TimelineSemaphore* sem = nullptr; uint64_t acquireValue = 0;
-    std::vector<float> staging; Vector2ui resolution = Vector2ui::Zero();
+    std::vector<float> staging; Vector2ui resolution = Vector2ui::Zero(), regionMin = Vector2ui::Zero();
     uint32_t curRenderer = 0; ThreadPool* pool = nullptr;
 
     void Check(mrb_status s) const { if(s != MRB_OK) throw MRayError("{}", mrb_last_error(ctx)); }
@@ -330,6 +340,7 @@ class TracerB200 final : public TracerI
         PrimGroupB200& pg = Get(prims, Raw(g), "PrimitiveGroup");
         pg.positions.assign(pg.vertexTotal, Vector3::Zero());
         pg.normals.assign(pg.vertexTotal, Vector3::Zero());
+        pg.uvs.assign(pg.vertexTotal, Vector2::Zero());
         pg.indices.assign(pg.primTotal, Vector3ui::Zero());
         pg.committed = true;
     }
@@ -347,7 +358,8 @@ class TracerB200 final : public TracerI
             case 1: { auto s = data.AccessAs<const Quaternion>(); if(s.size() != pb.vertexCount) throw MRayError("normal count mismatch");
                       // the attribute is the to-tangent-space rotation; its Z basis is the shading normal
                       for(size_t i = 0; i < s.size(); i++) pg.normals[pb.vertexOffset + i] = s[i].OrthoBasisZ(); break; }
-            case 2: break; // uv: constant albedo only in round 1
+            case 2: { auto s = data.AccessAs<const Vector2>(); if(s.size() != pb.vertexCount) throw MRayError("uv count mismatch");
+                      std::copy(s.begin(), s.end(), pg.uvs.begin() + pb.vertexOffset); break; }
             case 3: { auto s = data.AccessAs<const Vector3ui>(); if(s.size() != pb.primCount) throw MRayError("index count mismatch");
                       // KCAdjustIndices (Tracer/PrimitiveDefaultTriangle.cu:L9): rebase batch-local indices
                       for(size_t i = 0; i < s.size(); i++) pg.indices[pb.primOffset + i] = s[i] + Vector3ui(pb.vertexOffset); break; }
@@ -375,7 +387,7 @@ class TracerB200 final : public TracerI
         MaterialIdList out;
         for(size_t i = 0; i < counts.size(); i++)
         {
-            mg.albedo.push_back(Vector3::Zero());
+            mg.albedo.push_back(Vector3::Zero()); mg.albedoTex.push_back(-1);
             out.push_back(MaterialId((Raw(g) << MAT_ID_BITS) | uint32_t(mg.albedo.size() - 1)));
         }
         return out;
@@ -397,20 +409,72 @@ class TracerB200 final : public TracerI
             return;
         }
         if(attributeIndex != 0) throw MRayError("{}: Attribute {:d} is not \"ParamVarying\"", mg.type, attributeIndex);
-        for(const auto& t : tex) if(t.has_value()) throw MRayError("{}: textured albedo is not supported yet", mg.type);
+        // GenericTexturedGroupT::GenericPushTexAttribute (Tracer/GenericGroup.cpp:L243-288): one Optional<TextureId>
+        // AND one constant per material of the range; the constant is used where there is no texture
         uint32_t lo = range[0] & ((1u << MAT_ID_BITS) - 1u), hi = range[1] & ((1u << MAT_ID_BITS) - 1u);
         auto s = data.AccessAs<const Vector3>();
-        if(hi >= mg.albedo.size() || s.size() != hi - lo + 1) throw MRayError("{}: albedo range mismatch", mg.type);
-        std::copy(s.begin(), s.end(), mg.albedo.begin() + lo);
+        if(hi >= mg.albedo.size() || tex.size() != hi - lo + 1 || s.size() != tex.size()) throw MRayError("{}: albedo range mismatch", mg.type);
+        for(size_t k = 0; k < tex.size(); k++)
+        {
+            mg.albedo[lo + k] = s[k];
+            mg.albedoTex[lo + k] = -1;
+            if(tex[k].has_value())
+            {
+                const uint32_t tid = Raw(*tex[k]);
+                if(tid == 0 || tid > textures.size()) throw MRayError("{}: Given texture({}) is not found", mg.type, tid);
+                // GenericTexturedGroupT::ConvertToView: the albedo wants a TracerTexView<2, Vector3>
+                if(textures[tid - 1].channels != 4 || textures[tid - 1].params.readMode != MRayTextureReadMode::MR_DROP_1)
+                    throw MRayError("{}: Given texture({}) does not have a correct type for, Attribute {}", mg.type, tid, attributeIndex);
+                mg.albedoTex[lo + k] = int32_t(tid);
+            }
+        }
     }
     void PushMatAttribute(MatGroupId, CommonIdRange, uint32_t, std::vector<TextureId>) override
     { throw MRayError("(Mt)Lambert: texture-only attributes (normalMap) are not supported yet"); }
 
     // ------------------------------- textures -------------------------------
-    TextureId CreateTexture2D(Vector2ui, uint32_t, MRayTextureParameters) override { throw MRayError("textures are not supported yet"); }
-    TextureId CreateTexture3D(Vector3ui, uint32_t, MRayTextureParameters) override { throw MRayError("textures are not supported yet"); }
+    // TextureMemory::CreateTexture2D / PushTextureData / CommitTextures (Tracer/TextureMemory.cpp:L655-800), first slice
+    TextureId CreateTexture2D(Vector2ui size, uint32_t mipCount, MRayTextureParameters p) override
+    {
+        std::lock_guard lk(mtx);
+        if(mipCount != 1) throw MRayError("textures: mip chains are not supported yet (mipCount {})", mipCount);
+        if(size[0] == 0 || size[1] == 0) throw MRayError("textures: empty texture");
+        TextureB200 t; t.size = size; t.params = p;
+        switch(p.pixelType.Name())
+        {
+            case MRayPixelEnum::MR_RGBA_FLOAT:  t.channels = 4; t.format = 0; break;
+            case MRayPixelEnum::MR_RGBA8_UNORM: t.channels = 4; t.format = 1; break;
+            default: throw MRayError("textures: only MR_RGBA_FLOAT and MR_RGBA8_UNORM pixels are supported yet");
+        }
+        // TextureMemory::ConvertColorspaces leaves a texture alone when it is not a colour, or already global + linear
+        const bool needsConversion = p.isColor == AttributeIsColor::IS_COLOR &&
+            ((p.colorSpace != MRayColorSpaceEnum::MR_DEFAULT && p.colorSpace != params.globalTextureColorSpace) || p.gamma != Float(1));
+        if(needsConversion) throw MRayError("textures: colour space / gamma conversion is not supported yet");
+        // the view type follows DetermineReadMode (Tracer/TextureMemory.cpp:L329-396): 4 channels + MR_DROP_1 read as Vector3
+        if(p.readMode != MRayTextureReadMode::MR_PASSTHROUGH && p.readMode != MRayTextureReadMode::MR_DROP_1)
+            throw MRayError("textures: only MR_PASSTHROUGH / MR_DROP_1 reads are supported yet");
+        if(params.genMips) throw MRayError("textures: genMips is not supported yet");
+        if(!p.ignoreResClamp && std::max(size[0], size[1]) > params.clampedTexRes) throw MRayError("textures: clampedTexRes is not supported yet");
+        textures.push_back(std::move(t));
+        return TextureId(uint32_t(textures.size()));
+    }
+    TextureId CreateTexture3D(Vector3ui, uint32_t, MRayTextureParameters) override { throw MRayError("3-D textures are not supported yet"); }
     void CommitTextures() override {}
-    void PushTextureData(TextureId, uint32_t, TransientData) override { throw MRayError("textures are not supported yet"); }
+    void PushTextureData(TextureId id, uint32_t mipLevel, TransientData data) override
+    {
+        const uint32_t tid = Raw(id);
+        if(tid == 0 || tid > textures.size()) throw MRayError("Unable to find texture({})", tid);
+        TextureB200& t = textures[tid - 1];
+        if(mipLevel != 0) throw MRayError("textures: mip level {} of a single-level texture", mipLevel);
+        // the TransientData is typed by the pixel (MRayPixelType<E>::Type): Vector4 / Vector4uc here
+        const size_t pixels = size_t(t.size[0]) * t.size[1];
+        const Byte* src = nullptr; size_t got = 0;
+        if(t.format == 0) { auto s = data.AccessAs<const Vector4>(); src = reinterpret_cast<const Byte*>(s.data()); got = s.size(); }
+        else { auto s = data.AccessAs<const Vector4uc>(); src = reinterpret_cast<const Byte*>(s.data()); got = s.size(); }
+        if(got != pixels) throw MRayError("textures: {} pixels pushed, {} expected", got, pixels);
+        t.pixels.assign(src, src + pixels * t.channels * (t.format == 0 ? 4u : 1u));
+        t.loaded = true;
+    }
 
     // ------------------------------- transforms -------------------------------
     TransGroupId CreateTransformGroup(std::string typeName) override
@@ -566,7 +630,7 @@ class TracerB200 final : public TracerI
             groups.push_back(Group{Raw(t), {}, {}, {}});
             return groups.back();
         };
-        flatAlbedo.clear(); flatLightRadiance.clear(); flatLightTwoSided.clear();
+        flatAlbedo.clear(); flatAlbedoTex.clear(); flatTextures.clear(); flatLightRadiance.clear(); flatLightTwoSided.clear();
         int32_t pgUsed = -1;
         auto UsePrimGroup = [&](uint32_t g)
         {
@@ -583,6 +647,16 @@ class TracerB200 final : public TracerI
             if(idx >= mg.albedo.size()) throw MRayError("Unable to find Material({})", Raw(m));
             matKeyOf.push_back(Raw(m));
             flatAlbedo.insert(flatAlbedo.end(), {mg.albedo[idx][0], mg.albedo[idx][1], mg.albedo[idx][2]});
+            int32_t ft = -1;
+            if(mg.albedoTex[idx] >= 0)
+            {
+                const uint32_t tid = uint32_t(mg.albedoTex[idx]);
+                if(!textures[tid - 1].loaded) throw MRayError("texture({}) has no data", tid);
+                auto it = std::find(flatTextures.begin(), flatTextures.end(), tid);
+                ft = int32_t(it - flatTextures.begin());
+                if(it == flatTextures.end()) flatTextures.push_back(tid);
+            }
+            flatAlbedoTex.push_back(ft);
             return uint32_t(matKeyOf.size() - 1);
         };
         for(const SurfaceParams& s : surfaces)
@@ -726,7 +800,9 @@ class TracerB200 final : public TracerI
         const PrimGroupB200& pg = prims[flatPrimGroup];
         if(renderer) { mrb_renderer_destroy(ctx, renderer); renderer = nullptr; }
         Vector2ui tile = rip.regionMax - rip.regionMin;
-        if(tile != rip.resolution) throw MRayError("round 1: the render region must be the whole image");
+        if(rip.regionMax[0] > rip.resolution[0] || rip.regionMax[1] > rip.resolution[1] || tile[0] == 0 || tile[1] == 0 ||
+           rip.regionMin[0] >= rip.regionMax[0] || rip.regionMin[1] >= rip.regionMax[1])
+            throw MRayError("StartRender: bad render region");
         mrb_render_desc d = {};
         bool hasNormals = std::any_of(pg.normals.begin(), pg.normals.end(), [](const Vector3& n) { return n != Vector3::Zero(); });
         const float* normals = hasNormals ? reinterpret_cast<const float*>(pg.normals.data()) : nullptr;
@@ -734,11 +810,26 @@ class TracerB200 final : public TracerI
         if(scene) { d.scene = scene; d.instanceVertexNormals = instNormals.data(); }
         else { d.accel = accel; d.vertexCount = pg.vertexTotal; d.triangleCount = pg.primTotal; d.vertexNormals = normals; }
         d.materialCount = uint32_t(flatAlbedo.size() / 3); d.albedo = flatAlbedo.data();
+        std::vector<mrb_texture_desc> texDescs(flatTextures.size());
+        std::vector<const float*> instUVs(scene ? sceneInstanceCount : 1u, reinterpret_cast<const float*>(pg.uvs.data()));
+        if(!flatTextures.empty())
+        {
+            for(size_t k = 0; k < flatTextures.size(); k++)
+            {
+                const TextureB200& t = textures[flatTextures[k] - 1];
+                texDescs[k] = mrb_texture_desc{t.pixels.data(), t.size[0], t.size[1], t.channels, t.format,
+                                               uint32_t(t.params.interpolation), uint32_t(t.params.edgeResolve)};
+            }
+            d.textureCount = uint32_t(texDescs.size()); d.textures = texDescs.data(); d.albedoTexture = flatAlbedoTex.data();
+            if(scene) d.instanceVertexUVs = instUVs.data(); else d.vertexUVs = instUVs[0];
+        }
         d.lightCount = uint32_t(flatLightTwoSided.size()); d.lightRadiance = flatLightRadiance.data(); d.lightTwoSided = flatLightTwoSided.data();
         for(int k = 0; k < 3; k++) { d.camPosition[k] = cg.position[ci][k]; d.camGaze[k] = cg.gaze[ci][k]; d.camUp[k] = cg.up[ci][k]; }
         d.fovXY[0] = cg.fovPlanes[ci][0]; d.fovXY[1] = cg.fovPlanes[ci][1];
         d.nearFar[0] = cg.fovPlanes[ci][2]; d.nearFar[1] = cg.fovPlanes[ci][3];
         d.width = tile[0]; d.height = tile[1]; d.totalSPP = r.totalSPP;
+        d.fullResolution[0] = rip.resolution[0]; d.fullResolution[1] = rip.resolution[1];
+        d.regionMin[0] = rip.regionMin[0]; d.regionMin[1] = rip.regionMin[1];
         // render logic 0 rolls the sample mode like PathTracerRendererT::StartRender (L1192-1200)
         d.sampleMode = (r.sampleMode + logic0.value_or(0)) % 3u;
         d.rrRange[0] = r.rrRange[0]; d.rrRange[1] = r.rrRange[1];
@@ -761,7 +852,7 @@ class TracerB200 final : public TracerI
             d.sobolMatrices = sobolMatrices.data();
         }
         Check(mrb_renderer_create(ctx, &d, &renderer));
-        curRenderer = Raw(id); resolution = tile;
+        curRenderer = Raw(id); resolution = tile; regionMin = rip.regionMin;
         staging.assign(size_t(4) * pixels, 0.0f);
         return RenderBufferInfo
         {
@@ -787,7 +878,7 @@ class TracerB200 final : public TracerI
         RendererOutput out;
         out.imageOut = RenderImageSection
         {
-            .pixelMin = Vector2ui::Zero(), .pixelMax = resolution, .globalWeight = Float(1),
+            .pixelMin = regionMin, .pixelMax = regionMin + resolution, .globalWeight = Float(1),
             .waitCounter = acquireValue - 1,
             .pixStartOffsets = {0, plane, 2 * plane}, .weightStartOffset = 3 * plane
         };
@@ -810,7 +901,7 @@ class TracerB200 final : public TracerI
         StopRender();
         if(accel) { mrb_accel_destroy(ctx, accel); accel = nullptr; }
         prims.resize(1); mats.resize(1); lights.resize(1); cams.clear(); renderers.clear();
-        surfaces.clear(); lightSurfaces.clear(); camSurfaces.clear(); volumes.clear();
+        surfaces.clear(); lightSurfaces.clear(); camSurfaces.clear(); volumes.clear(); textures.clear();
     }
     void Flush() const override { mrb_context_synchronize(ctx); }
     GPUThreadInitFunction GetThreadInitFunction() const override { return []() {}; } // the C-ABI selects its device per call

@@ -347,7 +347,7 @@ def instanced_field(seed: int = 99, instance_count: int = 1000, target_tris: int
 
 def cornell_textures(seed: int = 5):
     """UV0 + albedo textures for ``cornell_box`` (every quad owns its 4 vertices): the white material reads an 8x8
-    fp32 RGB texture (bilinear, wrap) over uv in [-0.75, 1.75]^2 — wrap-around and the negative-texel path of the
+    fp32 RGBA texture (bilinear, wrap) over uv in [-0.75, 1.75]^2 — wrap-around and the negative-texel path of the
     reference's filter both occur —, the red one a 4x4 unorm8 RGBA texture (nearest, clamp), green stays constant.
     Returns (vertex_uvs[V, 2], textures, albedo_texture[4])."""
     rng = np.random.default_rng(seed)
@@ -355,7 +355,8 @@ def cornell_textures(seed: int = 5):
     nq = c["positions"].shape[0] // 4
     corner = np.array([[-0.75, -0.75], [1.75, -0.75], [1.75, 1.75], [-0.75, 1.75]], np.float32)
     uvs = np.tile(corner, (nq, 1)).astype(np.float32)
-    t0 = (0.1 + 0.8 * rng.random((8, 8, 3))).astype(np.float32)
+    t0 = (0.1 + 0.8 * rng.random((8, 8, 4))).astype(np.float32)   # RGBA: TracerI textures are pushed as 4-channel pixels
+    t0[..., 3] = 1.0
     t1 = rng.integers(40, 230, size=(4, 4, 4), dtype=np.uint8)
     t1[..., 1:3] //= 4          # keep it reddish
     textures = [dict(data=t0, interp="Linear", edge="Wrap"), dict(data=t1, interp="Nearest", edge="Clamp")]

@@ -47,6 +47,9 @@ ITEMS = {
     "cornell64_nee_spp16384":  (64, 16384, 4, "WithNextEventEstimation", (2, 20), False, np.float32, RGB),
     "cornell64_pure_spp16384": (64, 16384, 5, "Pure", (2, 20), False, np.float32, RGB),
     "cornell64_spectral_spp16384": (64, 16384, 8, "WithNEEAndMIS", (2, 20), False, np.float32, SPECTRAL),
+    # textured Lambert albedo (scenes.cornell_textures: an 8x8 fp32 bilinear/wrap texture on the white material, a 4x4
+    # unorm8 nearest/clamp one on the red material; single-level RGBA textures read as Vector3 through MR_DROP_1)
+    "cornell64_textured_spp16384": (64, 16384, 9, "WithNEEAndMIS", (2, 20), "textured", np.float32, RGB),
     # two-level scene: every batch in its own local space under a (T)Single transform
     "cornell64_single_spp16384": (64, 16384, 6, "WithNEEAndMIS", (2, 20), True, np.float32, RGB),
 }
@@ -87,12 +90,19 @@ def localise(b, seed=17):
 def render(name):
     res, spp, seed, mode, rr, single, dt, renderer = ITEMS[name]
     c = scenes.cornell_box()
-    b = O.batched_scene(c["positions"], c["indices"], c["material"])
-    bt = localise(b) if single else None
+    kw = {}
+    if single == "textured":
+        uvs, textures, at = scenes.cornell_textures()
+        b = O.batched_scene(c["positions"], c["indices"], c["material"], uvs=uvs)
+        kw = dict(textures=textures, material_texture=at)
+        bt = None
+    else:
+        b = O.batched_scene(c["positions"], c["indices"], c["material"])
+        bt = localise(b) if single else None
     t0 = time.time()
     img, w, st = O.driver_render(REF_DLL, b, c["albedo"], 3, c["radiance"], c["camera"], res, res, spp,
                                  sample_mode=mode, rr_range=rr, seed=seed, threads=0, batch_transforms=bt,
-                                 renderer=renderer, host_exe=True)
+                                 renderer=renderer, host_exe=True, **kw)
     assert np.allclose(w, spp, rtol=1e-3), (w.min(), w.max())
     np.savez_compressed(os.path.join(GOLDEN, f"render_{name}.npz"), img=img.astype(dt), spp=spp, seed=seed,
                         sample_mode=mode, rr_range=np.array(rr), iterations=st["iterations"])

@@ -26,11 +26,12 @@ struct DriverScene
     uint32_t materialCount; const float* albedo; uint32_t lightCount; const float* radiance;
     float camPos[3], camGaze[3], camUp[3]; float fovXY[2]; float nearFar[2];
     const float* batchTransforms; const int32_t* batchInstanceOf;
+    uint32_t textureCount; const uint32_t* textureInfo; const uint8_t* textureBytes; const int32_t* materialTexture; const float* uvs;
 };
 struct DriverRender
 {
     const char* rendererName; uint32_t width, height; uint32_t totalSPP; const char* sampleMode;
-    uint32_t rrRange[2]; uint64_t seed; uint32_t accelMode; uint32_t parallelHint; uint32_t threads; uint32_t samplerType;
+    uint32_t rrRange[2]; uint64_t seed; uint32_t accelMode; uint32_t parallelHint; uint32_t threads; uint32_t samplerType; uint32_t region[4];
 };
 struct DriverStats { double commitSeconds, renderSeconds, totalPaths; uint32_t iterations; float sceneAABB[6]; };
 using RenderF = int (*)(const char*, const DriverScene*, const DriverRender*, float*, float*, DriverStats*, char*, size_t);
@@ -41,7 +42,7 @@ int main(int argc, char** argv)
     FILE* f = std::fopen(argv[1], "rb");
     if(!f) { std::perror("blob"); return 65; }
     uint64_t n = 0;
-    if(std::fread(&n, 8, 1, f) != 1 || n != 17) { std::fprintf(stderr, "bad blob\n"); return 66; }
+    if(std::fread(&n, 8, 1, f) != 1 || n != 21) { std::fprintf(stderr, "bad blob\n"); return 66; }
     std::vector<std::vector<uint64_t>> sec(n);     // 8-byte aligned storage
     std::vector<uint64_t> bytes(n);
     for(uint64_t i = 0; i < n; i++)
@@ -53,9 +54,10 @@ int main(int argc, char** argv)
     std::fclose(f);
     auto P = [&](int i) { return bytes[i] ? reinterpret_cast<const void*>(sec[i].data()) : nullptr; };
     // sections: 0 dll path, 1 renderer name, 2 sample mode (NUL-terminated by the zero padding),
-    // 3 u32[12] {batchCount, materialCount, lightCount, width, height, spp, rr0, rr1, accelMode, parallelHint, threads, sampler},
+    // 3 u32[16] {batchCount, materialCount, lightCount, width, height, spp, rr0, rr1, accelMode, parallelHint, threads, sampler, region[4]},
     // 4 u64 seed, 5 f32[13] camera {pos, gaze, up, fovXY, nearFar}, 6 vertexOffsets, 7 triOffsets, 8 positions,
-    // 9 normals, 10 indices, 11 batchMaterial, 12 batchLight, 13 albedo, 14 radiance, 15 batchTransforms (may be empty), 16 batchInstanceOf (may be empty)
+    // 9 normals, 10 indices, 11 batchMaterial, 12 batchLight, 13 albedo, 14 radiance, 15 batchTransforms (may be empty), 16 batchInstanceOf (may be empty),
+    // 17 textureInfo (6 u32 per texture; may be empty), 18 textureBytes, 19 materialTexture, 20 uvs (may be empty)
     const uint32_t* u = static_cast<const uint32_t*>(P(3));
     const float* cam = static_cast<const float*>(P(5));
     DriverScene sc{};
@@ -66,6 +68,9 @@ int main(int argc, char** argv)
     sc.batchMaterial = static_cast<const int32_t*>(P(11)); sc.batchLight = static_cast<const int32_t*>(P(12));
     sc.albedo = static_cast<const float*>(P(13)); sc.radiance = static_cast<const float*>(P(14));
     sc.batchTransforms = static_cast<const float*>(P(15)); sc.batchInstanceOf = static_cast<const int32_t*>(P(16));
+    sc.textureCount = uint32_t(bytes[17] / 24); sc.textureInfo = static_cast<const uint32_t*>(P(17));
+    sc.textureBytes = static_cast<const uint8_t*>(P(18)); sc.materialTexture = static_cast<const int32_t*>(P(19));
+    sc.uvs = static_cast<const float*>(P(20));
     std::memcpy(sc.camPos, cam, 12); std::memcpy(sc.camGaze, cam + 3, 12); std::memcpy(sc.camUp, cam + 6, 12);
     std::memcpy(sc.fovXY, cam + 9, 8); std::memcpy(sc.nearFar, cam + 11, 8);
     DriverRender rd{};
@@ -73,6 +78,7 @@ int main(int argc, char** argv)
     rd.width = u[3]; rd.height = u[4]; rd.totalSPP = u[5]; rd.rrRange[0] = u[6]; rd.rrRange[1] = u[7];
     rd.seed = *static_cast<const uint64_t*>(P(4));
     rd.accelMode = u[8]; rd.parallelHint = u[9]; rd.threads = u[10]; rd.samplerType = u[11];
+    for(int k = 0; k < 4; k++) rd.region[k] = u[12 + k];
 
     char self[PATH_MAX]; ssize_t k = readlink("/proc/self/exe", self, sizeof(self) - 1);
     if(k <= 0) return 67;

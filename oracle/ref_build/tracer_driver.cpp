@@ -52,6 +52,14 @@ struct DriverScene
     // optional: batchCount entries; batchInstanceOf[b] = a >= 0 makes the SURFACE of batch b use the primitive batch
     // of batch a (instancing: same geometry, own material and transform; b's own geometry stays unused). -1 = itself.
     const int32_t*  batchInstanceOf;
+    // optional textured albedo: per texture 6 x u32 {width, height, format (0 = MR_RGBA_FLOAT, 1 = MR_RGBA8_UNORM),
+    // MRayTextureInterpEnum, MRayTextureEdgeResolveEnum, byte offset into textureBytes}; materialTexture: per material
+    // -1 or a texture index; uvs: V * 2 (UV0), NULL = zeros
+    uint32_t        textureCount;
+    const uint32_t* textureInfo;
+    const uint8_t*  textureBytes;
+    const int32_t*  materialTexture;
+    const float*    uvs;
 };
 
 struct DriverRender
@@ -66,6 +74,7 @@ struct DriverRender
     uint32_t    parallelHint;   // 0 = default (2^21)
     uint32_t    threads;        // host thread pool size (0 = hardware)
     uint32_t    samplerType;    // SamplerType::E: 0 Independent, 1 ZSobol, 2 Sobol
+    uint32_t    region[4];      // regionMin.xy, regionMax.xy of RenderImageParams; all 0 = the whole image
 };
 
 struct DriverStats
@@ -199,6 +208,7 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
                     {
                         TransientData d(std::in_place_type_t<Vector2>{}, vN);
                         std::vector<Vector2> z(vN, Vector2::Zero());
+                        if(sc->uvs) for(uint32_t i = 0; i < vN; i++) z[i] = Vector2(sc->uvs[2 * size_t(v0 + i)], sc->uvs[2 * size_t(v0 + i) + 1]);
                         d.Push(Span<const Vector2>(z));
                         tracer->PushPrimAttribute(pg, batches[b], a, std::move(d));
                         break;
@@ -214,7 +224,39 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
                 }
             }
         }
-        // ---- materials (Lambert, constant albedo) ----
+        // ---- textures (SceneLoaderMRay.cpp:L1040-1105: CreateTexture2D for all -> CommitTextures (allocation) -> PushTextureData) ----
+        std::vector<TextureId> texIds;
+        for(uint32_t t = 0; t < sc->textureCount; t++)
+        {
+            const uint32_t* ti = sc->textureInfo + 6 * size_t(t);
+            MRayTextureParameters tp;
+            tp.pixelType = MRayPixelTypeRT(ti[2] == 0 ? MRayPixelEnum::MR_RGBA_FLOAT : MRayPixelEnum::MR_RGBA8_UNORM);
+            tp.colorSpace = MRayColorSpaceEnum::MR_DEFAULT; tp.gamma = Float(1);
+            tp.interpolation = MRayTextureInterpEnum(ti[3]); tp.edgeResolve = MRayTextureEdgeResolveEnum(ti[4]);
+            tp.readMode = MRayTextureReadMode::MR_DROP_1;   // RGBA pixels read as Vector3 (TextureReadMode::TO_3C_FROM_4C): the albedo's view type
+            texIds.push_back(tracer->CreateTexture2D(Vector2ui(ti[0], ti[1]), 1, tp));
+        }
+        tracer->CommitTextures();
+        for(uint32_t t = 0; t < sc->textureCount; t++)
+        {
+            const uint32_t* ti = sc->textureInfo + 6 * size_t(t);
+            const Byte* src = reinterpret_cast<const Byte*>(sc->textureBytes) + ti[5];
+            size_t pixels = size_t(ti[0]) * ti[1];
+            // TransientData is typed by the pixel (the reference reads it back with AccessAs<PixelType>)
+            if(ti[2] == 0)
+            {
+                TransientData d(std::in_place_type_t<Vector4>{}, pixels);
+                d.Push(Span<const Vector4>(reinterpret_cast<const Vector4*>(src), pixels));
+                tracer->PushTextureData(texIds[t], 0, std::move(d));
+            }
+            else
+            {
+                TransientData d(std::in_place_type_t<Vector4uc>{}, pixels);
+                d.Push(Span<const Vector4uc>(reinterpret_cast<const Vector4uc*>(src), pixels));
+                tracer->PushTextureData(texIds[t], 0, std::move(d));
+            }
+        }
+        // ---- materials (Lambert, constant or textured albedo) ----
         MatGroupId mg = tracer->CreateMaterialGroup("(Mt)Lambert");
         MatAttributeInfoList mInfo = tracer->AttributeInfo(mg);
         std::vector<AttributeCountList> mCounts(sc->materialCount);
@@ -225,8 +267,11 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
             auto range = CommonIdRange(std::bit_cast<CommonId>(mats.front()), std::bit_cast<CommonId>(mats.back()));
             TransientData d(std::in_place_type_t<Vector3>{}, sc->materialCount);
             d.Push(Span<const Vector3>(reinterpret_cast<const Vector3*>(sc->albedo), sc->materialCount));
-            tracer->PushMatAttribute(mg, range, 0, std::move(d),
-                                     std::vector<Optional<TextureId>>(sc->materialCount, std::nullopt));
+            std::vector<Optional<TextureId>> albedoTex(sc->materialCount, std::nullopt);
+            if(sc->textureCount && sc->materialTexture)
+                for(uint32_t m = 0; m < sc->materialCount; m++)
+                    if(sc->materialTexture[m] >= 0) albedoTex[m] = texIds[size_t(sc->materialTexture[m])];
+            tracer->PushMatAttribute(mg, range, 0, std::move(d), std::move(albedoTex));
             // Optional texture-only attributes (Lambert: 1 = normalMap) are pushed with an EMPTY TransientData and
             // nullopt ids, as SceneLoaderMRay does (SceneLoaderMRay.cpp:L190-245; TracerBase::PushMatAttribute routes
             // data.IsEmpty() to the texture-only overload, TracerBase.cpp:L843-867). The reference allocates the
@@ -377,6 +422,7 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
             (void)dt;
         }
         RenderImageParams rip{Vector2ui(rd->width, rd->height), Vector2ui(0, 0), Vector2ui(rd->width, rd->height)};
+        if(rd->region[2] | rd->region[3]) { rip.regionMin = Vector2ui(rd->region[0], rd->region[1]); rip.regionMax = Vector2ui(rd->region[2], rd->region[3]); }
         if(getenv("DRIVER_VERBOSE")) std::fprintf(stderr, "StartRender...\n");
         if(const char* a = getenv("DRIVER_ALARM")) { signal(SIGALRM, AlarmBacktrace); alarm(unsigned(atoi(a))); }
         RenderBufferInfo rbi = tracer->StartRender(rid, camSurf, rip, std::nullopt, std::nullopt);

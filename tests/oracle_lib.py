@@ -164,13 +164,16 @@ class _DriverScene(C.Structure):
                 ("lightCount", C.c_uint32), ("radiance", C.c_void_p),
                 ("camPos", C.c_float * 3), ("camGaze", C.c_float * 3), ("camUp", C.c_float * 3),
                 ("fovXY", C.c_float * 2), ("nearFar", C.c_float * 2), ("batchTransforms", C.c_void_p),
-                ("batchInstanceOf", C.c_void_p)]
+                ("batchInstanceOf", C.c_void_p),
+                ("textureCount", C.c_uint32), ("textureInfo", C.c_void_p), ("textureBytes", C.c_void_p),
+                ("materialTexture", C.c_void_p), ("uvs", C.c_void_p)]
 
 
 class _DriverRender(C.Structure):
     _fields_ = [("rendererName", C.c_char_p), ("width", C.c_uint32), ("height", C.c_uint32), ("totalSPP", C.c_uint32),
                 ("sampleMode", C.c_char_p), ("rrRange", C.c_uint32 * 2), ("seed", C.c_uint64),
-                ("accelMode", C.c_uint32), ("parallelHint", C.c_uint32), ("threads", C.c_uint32), ("samplerType", C.c_uint32)]
+                ("accelMode", C.c_uint32), ("parallelHint", C.c_uint32), ("threads", C.c_uint32), ("samplerType", C.c_uint32),
+                ("region", C.c_uint32 * 4)]
 
 
 class _DriverStats(C.Structure):
@@ -182,11 +185,11 @@ def driver_available():
     return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libtracer_driver.so"))
 
 
-def batched_scene(positions, indices, tri_material, normals=None):
+def batched_scene(positions, indices, tri_material, normals=None, uvs=None):
     """Splits a flat mesh into one batch per material id (own compacted vertex list, local indices) — the
     shape TracerI::ReservePrimitiveBatches wants. Returns dict of arrays."""
     mats = np.unique(tri_material)
-    vo, to, P, N, I = [0], [0], [], [], []
+    vo, to, P, N, I, U = [0], [0], [], [], [], []
     if normals is None:  # flat per-vertex normals only make sense for unshared vertices; compute smooth ones
         fn = np.cross(positions[indices[:, 1]] - positions[indices[:, 0]], positions[indices[:, 2]] - positions[indices[:, 0]])
         normals = np.zeros_like(positions, dtype=np.float64)
@@ -198,19 +201,26 @@ def batched_scene(positions, indices, tri_material, normals=None):
         tris = indices[tri_material == m]
         used, inv = np.unique(tris.ravel(), return_inverse=True)
         P.append(positions[used]); N.append(normals[used]); I.append(inv.reshape(-1, 3).astype(np.uint32))
+        if uvs is not None:
+            U.append(np.asarray(uvs, np.float32)[used])
         vo.append(vo[-1] + used.size); to.append(to[-1] + tris.shape[0])
     return dict(materials=mats, vertex_offsets=np.array(vo, np.uint32), tri_offsets=np.array(to, np.uint32),
                 positions=np.ascontiguousarray(np.concatenate(P), np.float32),
                 normals=np.ascontiguousarray(np.concatenate(N), np.float32),
-                indices=np.ascontiguousarray(np.concatenate(I), np.uint32))
+                indices=np.ascontiguousarray(np.concatenate(I), np.uint32),
+                uvs=np.ascontiguousarray(np.concatenate(U), np.float32) if U else None)
 
 
 def driver_render(dll_path, batched, albedo, light_material, radiance, camera, width, height, spp,
                   renderer="PathTracerRGB", sample_mode="WithNEEAndMIS", rr_range=(2, 20), seed=0,
                   accel_mode=1, threads=0, parallel_hint=0, near_far=(0.01, 1000.0), driver_flavour="",
-                  batch_transforms=None, sampler="Independent", host_exe=False, instance_of=None):
+                  batch_transforms=None, sampler="Independent", host_exe=False, instance_of=None,
+                  textures=None, material_texture=None, region=None):
     """Renders through TracerI. `light_material`: material id whose batch is the prim-backed light.
     batch_transforms: optional [batch, 3, 4] local->world matrices ((T)Single per batch; positions local).
+    textures: list of dict(data=[h, w, 4] float32 / uint8 (RGBA), interp=, edge=); material_texture: per material id
+    (an index into `albedo`) -1 or a texture index; UV0 comes from batched["uvs"] (zeros when absent).
+    region: optional (minX, minY, maxX, maxY) of RenderImageParams; pixels outside it come back with weight 0.
     instance_of: optional int per batch; a >= 0 makes that batch's surface an instance of batch a's geometry.
     host_exe: run the driver inside oracle/_ref/ref_render_host (its own process, so that the reference's
     spectral renderer finds SpectraLUT/ next to the executable) instead of in this interpreter.
@@ -226,18 +236,35 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
     bt = None if batch_transforms is None else np.ascontiguousarray(batch_transforms, np.float32).reshape(len(mats), 12)
     sampler_id = {"Independent": 0, "ZSobol": 1, "Sobol": 2}[sampler]
     io = None if instance_of is None else np.ascontiguousarray(instance_of, np.int32)
+    tinfo = tbytes = mtex = None
+    uvs = None if batched.get("uvs") is None else np.ascontiguousarray(batched["uvs"], np.float32)
+    if textures:
+        info, blobs, off = [], [], 0
+        for t in textures:
+            a = np.ascontiguousarray(t["data"])
+            if a.dtype != np.uint8:
+                a = np.ascontiguousarray(a, np.float32)
+            assert a.shape[2] == 4, "the TracerI driver pushes RGBA pixels"
+            info.append([a.shape[1], a.shape[0], 1 if a.dtype == np.uint8 else 0, _TEX_INTERP[t.get("interp", "Linear")],
+                         _TEX_EDGE[t.get("edge", "Wrap")], off])
+            blobs.append(a.tobytes()); off += len(blobs[-1]) + (-len(blobs[-1]) % 16)
+            blobs[-1] += b"\0" * (-len(blobs[-1]) % 16)
+        tinfo = np.array(info, np.uint32); tbytes = np.frombuffer(b"".join(blobs), np.uint8).copy()
+        mtex = np.ascontiguousarray(np.asarray(material_texture, np.int32)[lambert])
     n_lights = 1 if light_material in mats else 0
     if host_exe:
         import subprocess
         import tempfile
         u = np.array([len(mats), len(lambert), n_lights, width, height, spp, rr_range[0], rr_range[1], accel_mode,
-                      parallel_hint, threads, sampler_id], np.uint32)
+                      parallel_hint, threads, sampler_id] + list(region or (0, 0, 0, 0)), np.uint32)
         cam = np.array(list(camera["eye"]) + list(camera["gaze"]) + list(camera["up"]) + [fx, fy] + list(near_far), np.float32)
         secs = [dll_path.encode(), renderer.encode(), sample_mode.encode(), u.tobytes(), np.uint64(seed).tobytes(),
                 cam.tobytes(), batched["vertex_offsets"].astype(np.uint32).tobytes(), batched["tri_offsets"].astype(np.uint32).tobytes(),
                 np.ascontiguousarray(batched["positions"], np.float32).tobytes(), np.ascontiguousarray(batched["normals"], np.float32).tobytes(),
                 np.ascontiguousarray(batched["indices"], np.uint32).tobytes(), bm.tobytes(), bl.tobytes(), alb.tobytes(), rad.tobytes(),
-                b"" if bt is None else bt.tobytes(), b"" if io is None else io.tobytes()]
+                b"" if bt is None else bt.tobytes(), b"" if io is None else io.tobytes(),
+                b"" if tinfo is None else tinfo.tobytes(), b"" if tbytes is None else tbytes.tobytes(),
+                b"" if mtex is None else mtex.tobytes(), b"" if uvs is None else uvs.tobytes()]
         with tempfile.TemporaryDirectory() as td:
             with open(os.path.join(td, "in.blob"), "wb") as f:
                 f.write(np.uint64(len(secs)).tobytes())
@@ -270,8 +297,13 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
         keep.append(bt); sc.batchTransforms = bt.ctypes.data
     if io is not None:
         keep.append(io); sc.batchInstanceOf = io.ctypes.data
+    if tinfo is not None:
+        keep += [tinfo, tbytes, mtex]
+        sc.textureCount, sc.textureInfo, sc.textureBytes, sc.materialTexture = len(textures), tinfo.ctypes.data, tbytes.ctypes.data, mtex.ctypes.data
+    if uvs is not None:
+        keep.append(uvs); sc.uvs = uvs.ctypes.data
     rd = _DriverRender(renderer.encode(), width, height, spp, sample_mode.encode(), (C.c_uint32 * 2)(*rr_range), seed,
-                       accel_mode, parallel_hint, threads, sampler_id)
+                       accel_mode, parallel_hint, threads, sampler_id, (C.c_uint32 * 4)(*(region or (0, 0, 0, 0))))
     img = np.zeros((height, width, 3), np.float32)
     wgt = np.zeros((height, width), np.float32)
     st = _DriverStats()
