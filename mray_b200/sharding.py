@@ -18,6 +18,24 @@ def shard_tiles(tile_count: int, world: int, rank: int) -> list[int]:
     return list(range(rank, tile_count, world))
 
 
+def shard_region(resolution: tuple[int, int], world: int, rank: int) -> tuple[int, int, int, int]:
+    """(minX, minY, maxX, maxY) of the horizontal band of the image rank renders — the reference's
+    RenderImageParams{resolution, regionMin, regionMax} hook (Core/TracerI.h:L38-43; mrb_render_desc.fullResolution /
+    regionMin): bands are contiguous, cover the image exactly once and differ by at most one row. With region
+    sharding every rank renders ALL samples of its own pixels, so the film needs a gather, not a sum."""
+    w, h = resolution
+    base, extra = divmod(h, world)
+    y0 = rank * base + min(rank, extra)
+    return 0, y0, w, y0 + base + (1 if rank < extra else 0)
+
+
+def place_region(full_film: np.ndarray, region_film: np.ndarray, region: tuple[int, int, int, int]) -> np.ndarray:
+    """Writes a rank's (4, h, w) region film into the (4, H, W) image film (RenderImageSection.pixelMin / pixelMax)."""
+    x0, y0, x1, y1 = region
+    full_film[:, y0:y1, x0:x1] = region_film
+    return full_film
+
+
 def rank_seed(seed: int, rank: int) -> int:
     """Per-rank RNG seed: ranks must draw independent streams (statistical, not bitwise, equivalence
     across world sizes)."""

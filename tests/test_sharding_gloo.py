@@ -63,3 +63,39 @@ def test_two_rank_film_reduce(tmp_path):
     img = sharding.resolve(film)
     mask = ref.max(axis=-1) < 5.0
     assert np.allclose(img[mask].mean(axis=0), ref[mask].mean(axis=0), rtol=0.08)
+
+
+def test_shard_region_partition():
+    for res in ((1920, 1080), (64, 64), (5, 7)):
+        for world in (1, 2, 3, 8):
+            if world > res[1]:
+                continue
+            regs = [sharding.shard_region(res, world, r) for r in range(world)]
+            assert regs[0][1] == 0 and regs[-1][3] == res[1]
+            assert all(a[3] == b[1] for a, b in zip(regs, regs[1:]))                 # contiguous, no overlap
+            assert all(r[0] == 0 and r[2] == res[0] for r in regs)
+            rows = [r[3] - r[1] for r in regs]
+            assert max(rows) - min(rows) <= 1
+
+
+def _region_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res = (12, 9)
+    reg = sharding.shard_region(res, world, rank)
+    band = np.full((4, reg[3] - reg[1], reg[2] - reg[0]), float(rank + 1), np.float32)   # this rank's region film
+    film = sharding.place_region(np.zeros((4, res[1], res[0]), np.float32), band, reg)
+    t = torch.from_numpy(film)
+    sharding.reduce_film(t)            # disjoint regions: the sum over ranks is the gather
+    if rank == 0:
+        np.save(os.path.join(out_dir, "regions.npy"), t.numpy())
+    dist.destroy_process_group()
+
+
+def test_two_rank_region_gather(tmp_path):
+    world, port = 2, 31000 + os.getpid() % 2000
+    mp.spawn(_region_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    film = np.load(tmp_path / "regions.npy")
+    r0, r1 = sharding.shard_region((12, 9), 2, 0), sharding.shard_region((12, 9), 2, 1)
+    assert np.all(film[:, r0[1]:r0[3]] == 1.0) and np.all(film[:, r1[1]:r1[3]] == 2.0)
