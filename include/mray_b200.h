@@ -325,6 +325,8 @@ typedef enum mrb_sample_mode
  * bit 31 = light flag, bits 0..20 = index into albedo[] (material) or lightRadiance[] (light).
  * Round 1: (R)PathTracerRGB, (Mt)Lambert with constant albedo, (L)Prim(P)Triangle with constant
  * radiance, (L)Null boundary, (C)Pinhole, Gaussian film filter, Independent (PCG32) sampler. */
+typedef enum mrb_material_type { MRB_MATERIAL_LAMBERT = 0, MRB_MATERIAL_REFLECT = 1 } mrb_material_type;
+
 /* One 2-D texture of the renderer (first slice): what TracerI::CreateTexture2D +
  * PushTextureData + CommitTextures hand to TextureMemory (Tracer/TextureMemory.cpp), restricted to ONE mip
  * level, 3 / 4 channels of fp32 or unorm8, already in the global colour space (MRayTextureParameters.colorSpace
@@ -399,6 +401,10 @@ typedef struct mrb_render_desc
      * image the camera spans, so several renderers (tiles, GPUs) can share one image. */
     uint32_t        fullResolution[2];
     uint32_t        regionMin[2];
+    /* NULL (every material is (Mt)Lambert), or host u8 per material: mrb_material_type. (Mt)Reflect
+     * (Tracer/MaterialsDefault.hpp:L132-215) is a perfect mirror: no NEE shadow ray, no Russian roulette, the next ray is
+     * a SPECULAR_RAY (PathTracerRendererShaders.h:L245-262,L415-424); its `albedo` entry is ignored. */
+    const uint8_t*  materialType;
 } mrb_render_desc;
 
 typedef struct mrb_render_stats

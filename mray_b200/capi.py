@@ -78,7 +78,7 @@ class RenderDesc(C.Structure):
                 ("samplerType", C.c_uint32), ("sobolMatrices", C.c_void_p),
                 ("textureCount", C.c_uint32), ("textures", C.c_void_p), ("albedoTexture", C.c_void_p),
                 ("vertexUVs", C.c_void_p), ("instanceVertexUVs", C.POINTER(C.c_void_p)),
-                ("fullResolution", C.c_uint32 * 2), ("regionMin", C.c_uint32 * 2)]
+                ("fullResolution", C.c_uint32 * 2), ("regionMin", C.c_uint32 * 2), ("materialType", C.c_void_p)]
 
 
 class TextureDesc(C.Structure):
@@ -444,7 +444,7 @@ class Renderer:
                  vertex_normals=None, light_two_sided=None, film_filter_radius=1.0, near_far=(0.01, 1000.0),
                  max_path_count=0, partition_rays=False, instance_vertex_normals=None, spectrum=None, sampler="Independent",
                  textures=None, albedo_texture=None, vertex_uvs=None, instance_vertex_uvs=None,
-                 full_resolution=None, region_min=(0, 0)):
+                 full_resolution=None, region_min=(0, 0), material_type=None):
         """`accel` is an Accelerator, or a Scene (two-level; vertex_count / triangle_count / vertex_normals
         are then ignored and instance_vertex_normals may hold one array or None per instance).
         textures: list of dict(data=[h, w, 3|4] float32 or uint8 array, interp="Linear"|"Nearest",
@@ -502,6 +502,7 @@ class Renderer:
         d.seed = seed
         d.maxPathCount = max_path_count
         d.partitionRays = 1 if partition_rays else 0
+        d.materialType = host(material_type, np.uint8)   # per material: 0 (Mt)Lambert, 1 (Mt)Reflect
         if full_resolution is not None:   # width x height is a region of a larger image
             d.fullResolution = (C.c_uint32 * 2)(*full_resolution)
             d.regionMin = (C.c_uint32 * 2)(*region_min)

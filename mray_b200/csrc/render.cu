@@ -173,6 +173,7 @@ struct RenderData
     uint32_t          sceneMode;       // 1 = hitKeys.accelKey holds the instance index
     const TexRec*     textures;        // textured albedo (ParamVaryingData): texture table ...
     const int32_t*    albedoTex;       // ... and per material index: texture or -1; nullptr = no material is textured
+    const uint8_t*    materialType;    // per material index: 0 (Mt)Lambert, 1 (Mt)Reflect; nullptr = all Lambert
     const float4*     albedo;          // per material index: (r, g, b, 0), or Jakob coefficients (c0, c1, c2, -) when spectral
     // hero-wavelength spectral transport ((R)PathTracerSpectral); lights carry (c0, c1, c2, scale) in .radiance
     SpectrumData      spec;
@@ -515,6 +516,34 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
     }
     if(backSide) { geoN = geoN * -1.0f; shadeN = shadeN * -1.0f; }
     const uint32_t matIndex = lmKey & 0x1FFFFFu;
+    if(d.materialType && d.materialType[matIndex] == 1u)
+    {
+        // (Mt)Reflect (MaterialsDefault.hpp:L132-215): WorkFunctionNEE draws its light sample but casts no shadow ray for a
+        // specular material; WorkFunction reflects wO about the shading normal (reflectance 1, pdf 1), skips the
+        // roulette and marks the next ray SPECULAR_RAY, so a light it hits counts in full
+        if(d.sampleMode != 0u) { float skip[3]; rng.Next<3>(skip); }
+        const Float3 wO = Normalize(rd) * -1.0f;
+        const Float3 wIr = Normalize(shadeN * (2.0f * Dot(wO, shadeN)) - wO);
+        d.shadowRadiance[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        depth += 1u;
+        if(d.samplerType == SAMPLER_INDEPENDENT) d.rng[i] = rng.state;
+        else d.sampleState[i].y = rng.dim;
+        if(depth < d.rrHi)
+        {
+            d.meta[i].w = __float_as_uint(1.0f);
+            const Float3 no = NudgePos(pos, geoN);
+            float4* rp = reinterpret_cast<float4*>(d.rays + i);
+            rp[0] = make_float4(no.x, no.y, no.z, 1.0e-4f);
+            rp[1] = make_float4(wIr.x, wIr.y, wIr.z, FLT_MAX);
+            d.meta[i].x = PackPD(depth, ST_ALIVE, RAY_SPECULAR);
+        }
+        else
+        {
+            d.rays[i].tMin = 1.0f; d.rays[i].tMax = -1.0f;
+            d.meta[i].x = PackPD(depth, ST_DEAD, RAY_SPECULAR);
+        }
+        return true;
+    }
     float4 albedoRaw = d.albedo[matIndex];
     const int32_t texIndex = d.albedoTex ? d.albedoTex[matIndex] : -1;
     if(texIndex >= 0)
@@ -920,6 +949,7 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
         }
         d.workKeys = ma.Take<uint32_t>(P); d.workIndices = ma.Take<uint32_t>(P); d.partTable = ma.Take<uint32_t>(32);
         d.albedoTex = desc.albedoTexture ? ma.Take<int32_t>(desc.materialCount ? desc.materialCount : 1) : nullptr;
+        d.materialType = desc.materialType ? ma.Take<uint8_t>(desc.materialCount ? desc.materialCount : 1) : nullptr;
         d.textures = desc.textureCount ? ma.Take<TexRec>(desc.textureCount) : nullptr;
         for(uint32_t t = 0; t < desc.textureCount; t++)
             htex[t].data = ma.Take<char>(size_t(desc.textures[t].width) * desc.textures[t].height * desc.textures[t].channels *
@@ -936,6 +966,8 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
     for(uint32_t m = 0; m < desc.materialCount; m++)
         halb[m] = make_float4(desc.albedo[3 * m], desc.albedo[3 * m + 1], desc.albedo[3 * m + 2], 0.f);
     MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<float4*>(d.albedo), halb.data(), halb.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx.stream));
+    if(desc.materialType)
+        MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<uint8_t*>(d.materialType), desc.materialType, desc.materialCount, cudaMemcpyHostToDevice, ctx.stream));
     if(desc.albedoTexture)
         MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<int32_t*>(d.albedoTex), desc.albedoTexture, sizeof(int32_t) * desc.materialCount, cudaMemcpyHostToDevice, ctx.stream));
     for(uint32_t t = 0; t < desc.textureCount; t++)

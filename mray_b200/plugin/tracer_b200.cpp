@@ -112,6 +112,7 @@ class TracerB200 final : public TracerI
     // flattened scene
     uint32_t flatPrimGroup = 0; std::vector<float> flatLightRadiance; std::vector<uint8_t> flatLightTwoSided;
     std::vector<float> flatAlbedo;
+    std::vector<uint8_t> flatMaterialType;          // per flat material: mrb_material_type
     std::vector<int32_t> flatAlbedoTex;             // per flat material: index into flatTextures or -1
     std::vector<uint32_t> flatTextures;             // TextureIds in use, in first-use order
     std::vector<TextureB200> textures;              // TextureId = index + 1 (0 = InvalidTexture)
@@ -221,7 +222,7 @@ class TracerB200 final : public TracerI
 
     // ------------------------------- generic -------------------------------
     TypeNameList PrimitiveGroups() const override { return {"(P)Triangle"sv, "(P)Empty"sv}; }
-    TypeNameList MaterialGroups() const override { return {"(Mt)Lambert"sv, "(Mt)Passthrough"sv}; }
+    TypeNameList MaterialGroups() const override { return {"(Mt)Lambert"sv, "(Mt)Passthrough"sv, "(Mt)Reflect"sv}; }
     TypeNameList TransformGroups() const override { return {"(T)Identity"sv, "(T)Single"sv}; }
     TypeNameList CameraGroups() const override { return {"(C)Pinhole"sv}; }
     TypeNameList MediumGroups() const override { return {"(Md)Vacuum"sv}; }
@@ -375,7 +376,8 @@ class TracerB200 final : public TracerI
     MatGroupId CreateMaterialGroup(std::string typeName) override
     {
         std::lock_guard lk(mtx);
-        if(typeName != "(Mt)Lambert") throw MRayError("Unable to find generator for {}", typeName);
+        // (Mt)Reflect has no attributes (MatGroupReflect::AttributeInfo returns an empty list, MaterialsDefault.cpp:L161-164)
+        if(typeName != "(Mt)Lambert" && typeName != "(Mt)Reflect") throw MRayError("Unable to find generator for {}", typeName);
         mats.push_back(MatGroupB200{typeName});
         return MatGroupId(uint32_t(mats.size() - 1));
     }
@@ -400,6 +402,7 @@ class TracerB200 final : public TracerI
                           std::vector<Optional<TextureId>> tex) override
     {
         MatGroupB200& mg = Get(mats, Raw(g), "MaterialGroup");
+        if(mg.type == "(Mt)Reflect") throw MRayError("{} group does not have any attributes!", mg.type);
         // An EMPTY TransientData routes to the optional texture-only overload (TracerBase.cpp:L843-867): the
         // scene loader always pushes Lambert's optional `normalMap` this way, with nullopt where a material has none.
         if(data.IsEmpty())
@@ -630,7 +633,7 @@ class TracerB200 final : public TracerI
             groups.push_back(Group{Raw(t), {}, {}, {}});
             return groups.back();
         };
-        flatAlbedo.clear(); flatAlbedoTex.clear(); flatTextures.clear(); flatLightRadiance.clear(); flatLightTwoSided.clear();
+        flatAlbedo.clear(); flatAlbedoTex.clear(); flatMaterialType.clear(); flatTextures.clear(); flatLightRadiance.clear(); flatLightTwoSided.clear();
         int32_t pgUsed = -1;
         auto UsePrimGroup = [&](uint32_t g)
         {
@@ -657,6 +660,7 @@ class TracerB200 final : public TracerI
                 if(it == flatTextures.end()) flatTextures.push_back(tid);
             }
             flatAlbedoTex.push_back(ft);
+            flatMaterialType.push_back(mg.type == "(Mt)Reflect" ? uint8_t(MRB_MATERIAL_REFLECT) : uint8_t(MRB_MATERIAL_LAMBERT));
             return uint32_t(matKeyOf.size() - 1);
         };
         for(const SurfaceParams& s : surfaces)
@@ -810,6 +814,7 @@ class TracerB200 final : public TracerI
         if(scene) { d.scene = scene; d.instanceVertexNormals = instNormals.data(); }
         else { d.accel = accel; d.vertexCount = pg.vertexTotal; d.triangleCount = pg.primTotal; d.vertexNormals = normals; }
         d.materialCount = uint32_t(flatAlbedo.size() / 3); d.albedo = flatAlbedo.data();
+        d.materialType = flatMaterialType.data();
         std::vector<mrb_texture_desc> texDescs(flatTextures.size());
         std::vector<const float*> instUVs(scene ? sceneInstanceCount : 1u, reinterpret_cast<const float*>(pg.uvs.data()));
         if(!flatTextures.empty())

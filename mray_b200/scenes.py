@@ -361,3 +361,16 @@ def cornell_textures(seed: int = 5):
     t1[..., 1:3] //= 4          # keep it reddish
     textures = [dict(data=t0, interp="Linear", edge="Wrap"), dict(data=t1, interp="Nearest", edge="Clamp")]
     return uvs, textures, np.array([0, 1, -1, -1], np.int32)
+
+
+def cornell_mirror():
+    """``cornell_box`` with the tall box turned into a perfect mirror: material 4 = (Mt)Reflect (triangles 12..23).
+    Returns the cornell dict with `material` updated, a 5-row albedo table and `material_type` (0 Lambert, 1 Reflect)
+    per material id (id 3 is the light)."""
+    c = cornell_box()
+    m = c["material"].copy()
+    m[12:24] = 4
+    c["material"] = m
+    c["albedo"] = np.concatenate([c["albedo"], np.zeros((1, 3), np.float32)])
+    c["material_type"] = np.array([0, 0, 0, 0, 1], np.uint8)
+    return c

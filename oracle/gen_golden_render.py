@@ -50,6 +50,8 @@ ITEMS = {
     # textured Lambert albedo (scenes.cornell_textures: an 8x8 fp32 bilinear/wrap texture on the white material, a 4x4
     # unorm8 nearest/clamp one on the red material; single-level RGBA textures read as Vector3 through MR_DROP_1)
     "cornell64_textured_spp16384": (64, 16384, 9, "WithNEEAndMIS", (2, 20), "textured", np.float32, RGB),
+    # (Mt)Reflect: the tall box is a perfect mirror (scenes.cornell_mirror); a much noisier scene (caustic paths)
+    "cornell64_mirror_spp16384": (64, 16384, 10, "WithNEEAndMIS", (2, 20), "mirror", np.float32, RGB),
     # two-level scene: every batch in its own local space under a (T)Single transform
     "cornell64_single_spp16384": (64, 16384, 6, "WithNEEAndMIS", (2, 20), True, np.float32, RGB),
 }
@@ -89,9 +91,13 @@ def localise(b, seed=17):
 
 def render(name):
     res, spp, seed, mode, rr, single, dt, renderer = ITEMS[name]
-    c = scenes.cornell_box()
+    c = scenes.cornell_mirror() if single == "mirror" else scenes.cornell_box()
     kw = {}
-    if single == "textured":
+    if single == "mirror":
+        b = O.batched_scene(c["positions"], c["indices"], c["material"])
+        kw = dict(material_kind=c["material_type"])
+        bt = None
+    elif single == "textured":
         uvs, textures, at = scenes.cornell_textures()
         b = O.batched_scene(c["positions"], c["indices"], c["material"], uvs=uvs)
         kw = dict(textures=textures, material_texture=at)

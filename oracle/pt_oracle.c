@@ -86,6 +86,8 @@ typedef struct
     const struct orc_spectrum_tables* spectrum; uint32_t wavelengthMode;
     /* textured Lambert albedo (all NULL / 0 = none): per-vertex UV0, texture table, per-material texture index or -1 */
     const float* uv; const struct orc_texture* textures; const int32_t* albedoTexture; uint32_t nTextures;
+    /* per material: 0 = (Mt)Lambert, 1 = (Mt)Reflect (NULL = all Lambert) */
+    const uint8_t* materialType;
 } pt_scene;
 
 /* One single-level 2-D texture as the reference's host-backend view reads it (Device/CPU/TextureViewCPU.h):
@@ -286,8 +288,22 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
             }
             break;
         }
-        /* Lambert */
         if(dot(gN, nrm(d)) > 0) gN = mul(gN, -1.0f);
+        if(s->materialType && s->materialType[m] == 1u)
+        {   /* (Mt)Reflect (MaterialsDefault.hpp:L132-215): a perfect mirror, Specularity() = 1. WorkFunctionNEE samples
+             * a light (three random numbers) but casts no shadow ray for a specular material; WorkFunction reflects
+             * wO about the shading normal (Graphics::Reflect: 2 (v.n) n - v), reflectance 1, pdf 1, NO Russian roulette,
+             * and marks the ray SPECULAR_RAY so that a light it hits counts in full (no MIS, counted under pure NEE). */
+            if(s->sampleMode != 0u) { pcg_float(rng); pcg_float(rng); pcg_float(rng); }
+            v3 wO = mul(nrm(d), -1.0f);
+            v3 wI = nrm(sub(mul(gN, 2.0f * dot(wO, gN)), wO));
+            depth += 1;
+            if(depth >= s->rrHi) break;
+            prevPdf = 1.0f; type = 1; /* SPECULAR_RAY */
+            o = nudge(hitPos, gN); d = wI; tMin = 1.0e-4f; tMax = FLT_MAX;
+            continue;
+        }
+        /* Lambert */
         s4 alb = albedo_at(s, (uint32_t)m, waves, prim, a, b, c);
         v3 hlp = fabsf(gN.x) > 0.9f ? V(0, 1, 0) : V(1, 0, 0);
         v3 tX = nrm(cross(hlp, gN)), tY = cross(gN, tX);

@@ -60,6 +60,8 @@ struct DriverScene
     const uint8_t*  textureBytes;
     const int32_t*  materialTexture;
     const float*    uvs;
+    // optional: per material 0 = (Mt)Lambert, 1 = (Mt)Reflect (its albedo entry is unused); NULL = all Lambert
+    const uint8_t*  materialKind;
 };
 
 struct DriverRender
@@ -256,21 +258,32 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
                 tracer->PushTextureData(texIds[t], 0, std::move(d));
             }
         }
-        // ---- materials (Lambert, constant or textured albedo) ----
-        MatGroupId mg = tracer->CreateMaterialGroup("(Mt)Lambert");
-        MatAttributeInfoList mInfo = tracer->AttributeInfo(mg);
-        std::vector<AttributeCountList> mCounts(sc->materialCount);
-        for(auto& c : mCounts) { c = AttributeCountList(StaticVecSize(mInfo.size())); c[0] = 1; for(size_t k = 1; k < mInfo.size(); k++) c[k] = 0; }
-        MaterialIdList mats = tracer->ReserveMaterials(mg, mCounts);
-        tracer->CommitMatReservations(mg);
+        // ---- materials: (Mt)Lambert (constant or textured albedo) and, where materialKind says so, (Mt)Reflect ----
+        std::vector<uint32_t> lambertOf, reflectOf;                 // scene material index per group entry
+        for(uint32_t m = 0; m < sc->materialCount; m++)
+            ((sc->materialKind && sc->materialKind[m] == 1) ? reflectOf : lambertOf).push_back(m);
+        MaterialIdList mats(sc->materialCount);
+        if(!lambertOf.empty())
         {
-            auto range = CommonIdRange(std::bit_cast<CommonId>(mats.front()), std::bit_cast<CommonId>(mats.back()));
-            TransientData d(std::in_place_type_t<Vector3>{}, sc->materialCount);
-            d.Push(Span<const Vector3>(reinterpret_cast<const Vector3*>(sc->albedo), sc->materialCount));
-            std::vector<Optional<TextureId>> albedoTex(sc->materialCount, std::nullopt);
-            if(sc->textureCount && sc->materialTexture)
-                for(uint32_t m = 0; m < sc->materialCount; m++)
-                    if(sc->materialTexture[m] >= 0) albedoTex[m] = texIds[size_t(sc->materialTexture[m])];
+            const uint32_t n = uint32_t(lambertOf.size());
+            MatGroupId mg = tracer->CreateMaterialGroup("(Mt)Lambert");
+            MatAttributeInfoList mInfo = tracer->AttributeInfo(mg);
+            std::vector<AttributeCountList> mCounts(n);
+            for(auto& c : mCounts) { c = AttributeCountList(StaticVecSize(mInfo.size())); c[0] = 1; for(size_t k = 1; k < mInfo.size(); k++) c[k] = 0; }
+            MaterialIdList ids = tracer->ReserveMaterials(mg, mCounts);
+            tracer->CommitMatReservations(mg);
+            for(uint32_t k = 0; k < n; k++) mats[lambertOf[k]] = ids[k];
+            auto range = CommonIdRange(std::bit_cast<CommonId>(ids.front()), std::bit_cast<CommonId>(ids.back()));
+            std::vector<Vector3> alb(n);
+            std::vector<Optional<TextureId>> albedoTex(n, std::nullopt);
+            for(uint32_t k = 0; k < n; k++)
+            {
+                const uint32_t m = lambertOf[k];
+                alb[k] = reinterpret_cast<const Vector3*>(sc->albedo)[m];
+                if(sc->textureCount && sc->materialTexture && sc->materialTexture[m] >= 0) albedoTex[k] = texIds[size_t(sc->materialTexture[m])];
+            }
+            TransientData d(std::in_place_type_t<Vector3>{}, n);
+            d.Push(Span<const Vector3>(alb.data(), n));
             tracer->PushMatAttribute(mg, range, 0, std::move(d), std::move(albedoTex));
             // Optional texture-only attributes (Lambert: 1 = normalMap) are pushed with an EMPTY TransientData and
             // nullopt ids, as SceneLoaderMRay does (SceneLoaderMRay.cpp:L190-245; TracerBase::PushMatAttribute routes
@@ -281,9 +294,17 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
                    mInfo[a].isOptional == AttributeOptionality::MR_OPTIONAL)
                 {
                     TransientData e(std::in_place_type_t<Vector3>{}, 0);
-                    tracer->PushMatAttribute(mg, range, a, std::move(e),
-                                             std::vector<Optional<TextureId>>(sc->materialCount, std::nullopt));
+                    tracer->PushMatAttribute(mg, range, a, std::move(e), std::vector<Optional<TextureId>>(n, std::nullopt));
                 }
+        }
+        if(!reflectOf.empty())
+        {
+            MatGroupId rg = tracer->CreateMaterialGroup("(Mt)Reflect");      // no attributes
+            MatAttributeInfoList rInfoM = tracer->AttributeInfo(rg);
+            std::vector<AttributeCountList> rCounts(reflectOf.size(), AttributeCountList(StaticVecSize(rInfoM.size())));
+            MaterialIdList ids = tracer->ReserveMaterials(rg, rCounts);
+            tracer->CommitMatReservations(rg);
+            for(size_t k = 0; k < reflectOf.size(); k++) mats[reflectOf[k]] = ids[k];
         }
         // ---- lights (prim backed) ----
         LightGroupId lg = sc->lightCount ? tracer->CreateLightGroup("(L)Prim(P)Triangle", pg) : LightGroupId(0);

@@ -166,7 +166,7 @@ class _DriverScene(C.Structure):
                 ("fovXY", C.c_float * 2), ("nearFar", C.c_float * 2), ("batchTransforms", C.c_void_p),
                 ("batchInstanceOf", C.c_void_p),
                 ("textureCount", C.c_uint32), ("textureInfo", C.c_void_p), ("textureBytes", C.c_void_p),
-                ("materialTexture", C.c_void_p), ("uvs", C.c_void_p)]
+                ("materialTexture", C.c_void_p), ("uvs", C.c_void_p), ("materialKind", C.c_void_p)]
 
 
 class _DriverRender(C.Structure):
@@ -215,11 +215,12 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
                   renderer="PathTracerRGB", sample_mode="WithNEEAndMIS", rr_range=(2, 20), seed=0,
                   accel_mode=1, threads=0, parallel_hint=0, near_far=(0.01, 1000.0), driver_flavour="",
                   batch_transforms=None, sampler="Independent", host_exe=False, instance_of=None,
-                  textures=None, material_texture=None, region=None):
+                  textures=None, material_texture=None, region=None, material_kind=None):
     """Renders through TracerI. `light_material`: material id whose batch is the prim-backed light.
     batch_transforms: optional [batch, 3, 4] local->world matrices ((T)Single per batch; positions local).
     textures: list of dict(data=[h, w, 4] float32 / uint8 (RGBA), interp=, edge=); material_texture: per material id
     (an index into `albedo`) -1 or a texture index; UV0 comes from batched["uvs"] (zeros when absent).
+    material_kind: per material id (an index into `albedo`) 0 = (Mt)Lambert, 1 = (Mt)Reflect.
     region: optional (minX, minY, maxX, maxY) of RenderImageParams; pixels outside it come back with weight 0.
     instance_of: optional int per batch; a >= 0 makes that batch's surface an instance of batch a's geometry.
     host_exe: run the driver inside oracle/_ref/ref_render_host (its own process, so that the reference's
@@ -237,6 +238,7 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
     sampler_id = {"Independent": 0, "ZSobol": 1, "Sobol": 2}[sampler]
     io = None if instance_of is None else np.ascontiguousarray(instance_of, np.int32)
     tinfo = tbytes = mtex = None
+    mkind = None if material_kind is None else np.ascontiguousarray(np.asarray(material_kind, np.uint8)[lambert])
     uvs = None if batched.get("uvs") is None else np.ascontiguousarray(batched["uvs"], np.float32)
     if textures:
         info, blobs, off = [], [], 0
@@ -264,7 +266,8 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
                 np.ascontiguousarray(batched["indices"], np.uint32).tobytes(), bm.tobytes(), bl.tobytes(), alb.tobytes(), rad.tobytes(),
                 b"" if bt is None else bt.tobytes(), b"" if io is None else io.tobytes(),
                 b"" if tinfo is None else tinfo.tobytes(), b"" if tbytes is None else tbytes.tobytes(),
-                b"" if mtex is None else mtex.tobytes(), b"" if uvs is None else uvs.tobytes()]
+                b"" if mtex is None else mtex.tobytes(), b"" if uvs is None else uvs.tobytes(),
+                b"" if mkind is None else mkind.tobytes()]
         with tempfile.TemporaryDirectory() as td:
             with open(os.path.join(td, "in.blob"), "wb") as f:
                 f.write(np.uint64(len(secs)).tobytes())
@@ -302,6 +305,8 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
         sc.textureCount, sc.textureInfo, sc.textureBytes, sc.materialTexture = len(textures), tinfo.ctypes.data, tbytes.ctypes.data, mtex.ctypes.data
     if uvs is not None:
         keep.append(uvs); sc.uvs = uvs.ctypes.data
+    if mkind is not None:
+        keep.append(mkind); sc.materialKind = mkind.ctypes.data
     rd = _DriverRender(renderer.encode(), width, height, spp, sample_mode.encode(), (C.c_uint32 * 2)(*rr_range), seed,
                        accel_mode, parallel_hint, threads, sampler_id, (C.c_uint32 * 4)(*(region or (0, 0, 0, 0))))
     img = np.zeros((height, width, 3), np.float32)
@@ -329,7 +334,8 @@ class _PtScene(C.Structure):
                 ("width", C.c_uint32), ("height", C.c_uint32), ("spp", C.c_uint32), ("sampleMode", C.c_uint32),
                 ("rrLo", C.c_uint32), ("rrHi", C.c_uint32), ("filterRadius", C.c_float), ("seed", C.c_uint64),
                 ("spectrum", C.c_void_p), ("wavelengthMode", C.c_uint32),
-                ("uv", C.c_void_p), ("textures", C.c_void_p), ("albedoTexture", C.c_void_p), ("nTextures", C.c_uint32)]
+                ("uv", C.c_void_p), ("textures", C.c_void_p), ("albedoTexture", C.c_void_p), ("nTextures", C.c_uint32),
+                ("materialType", C.c_void_p)]
 
 
 class _OrcTexture(C.Structure):
@@ -372,7 +378,8 @@ def oracle_texture_sample(texture, uv):
 
 def oracle_render(positions, indices, tri_material, albedo, radiance, camera, width, height, spp,
                   sample_mode=2, rr_range=(2, 20), seed=0, near_far=(0.01, 1000.0), threads=None,
-                  spectral_data=None, wavelength_mode=2, textures=None, albedo_texture=None, vertex_uvs=None):
+                  spectral_data=None, wavelength_mode=2, textures=None, albedo_texture=None, vertex_uvs=None,
+                  material_type=None):
     """tri_material: per triangle, >= 0 Lambert material index, -1 - k for light k. Returns image[h,w,3]
     (row 0 = bottom) resolved as sum radiance / sum weight. spectral_data (mray_b200.spectral.load())
     switches to the hero-wavelength spectral estimator."""
@@ -403,6 +410,9 @@ def oracle_render(positions, indices, tri_material, albedo, radiance, camera, wi
         uvs = None if vertex_uvs is None else np.ascontiguousarray(vertex_uvs, np.float32)
         s.textures, s.nTextures, s.albedoTexture = C.addressof(tarr), len(textures), at.ctypes.data
         s.uv = None if uvs is None else uvs.ctypes.data
+    if material_type is not None:     # per material: 0 (Mt)Lambert, 1 (Mt)Reflect
+        mt = np.ascontiguousarray(material_type, np.uint8)
+        s.materialType = mt.ctypes.data
     out = np.zeros((4, height, width), np.float32)
     threads = threads or min(16, os.cpu_count() or 1)
     rows = np.linspace(0, height, threads * 4 + 1).astype(int)
