@@ -233,3 +233,30 @@ def test_render_regions_through_tracer_interface_against_reference():
         img[inside] = part[inside]
     err = rel_mse(block_mean(img, 2), block_mean(ref, 2))
     assert err <= REL_MSE_TOL, err
+
+
+def test_mirror_cornell_against_reference(gpu_ctx):
+    """(Mt)Reflect through the C-ABI renderer against the reference's render (4x4 block means: the scene is ~5x noisier)."""
+    from test_gpu_render import mirror_accel
+    ref, spp_ref = ref_image("cornell64_mirror_spp16384")
+    c, idx, tm, acc, alb, mtype = mirror_accel(gpu_ctx)
+    r = capi.Renderer(gpu_ctx, acc, c["positions"].shape[0], idx.shape[0], alb, c["radiance"], c["camera"], 64, 64, 65536,
+                      sample_mode="WithNEEAndMIS", rr_range=(2, 20), seed=14, material_type=mtype)
+    ours, st = r.render(batch=64); r.close(); acc.close()
+    err = rel_mse(block_mean(ours, 4), block_mean(ref, 4))
+    assert err <= REL_MSE_TOL, err
+    assert np.allclose(ours.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=5e-3), (ours.mean(axis=(0, 1)), ref.mean(axis=(0, 1)))
+
+
+@pytest.mark.skipif(not (os.path.exists(PLUGIN) and O.driver_available()), reason="plugin / driver were not prebuilt")
+def test_mirror_cornell_through_tracer_interface_against_reference():
+    """CreateMaterialGroup("(Mt)Reflect") through TracerI on the B200 plugin."""
+    ref, spp_ref = ref_image("cornell64_mirror_spp16384")
+    c = scenes.cornell_mirror()
+    b = O.batched_scene(c["positions"], c["indices"], c["material"])
+    img, w, st = O.driver_render(os.path.abspath(PLUGIN), b, c["albedo"], 3, c["radiance"], c["camera"], 64, 64, 32768,
+                                 sample_mode="WithNEEAndMIS", rr_range=(2, 20), seed=15, material_kind=c["material_type"])
+    assert np.allclose(w, 32768, rtol=1e-3)
+    err = rel_mse(block_mean(img, 4), block_mean(ref, 4))
+    assert err <= REL_MSE_TOL, err
+    assert np.allclose(img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=5e-3)

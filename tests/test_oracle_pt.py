@@ -134,3 +134,46 @@ def test_textured_oracle_matches_reference_render():
     assert np.allclose(img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=5e-3), (img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)))
     # the textures matter: the untextured reference image is far away
     assert rel_mse(block_mean(ref), block_mean(ref_image("cornell64_spp16384"))) > 2e-2
+
+
+def test_mirror_shows_the_light_exactly():
+    """(Mt)Reflect closed form: a camera looking at a mirror floor that reflects a one-sided light sees exactly the
+    light's radiance (reflectance 1, pdf 1, SPECULAR_RAY hits count in full in every sample mode)."""
+    L = 7.0
+    floor = np.array([[-5, 0, 5], [5, 0, 5], [5, 0, -5], [-5, 0, -5]], np.float32)
+    light = np.array([[-30, 4, -30], [30, 4, -30], [30, 4, 30], [-30, 4, 30]], np.float32)   # faces down
+    pos = np.concatenate([floor, light]); idx = np.array([[0, 1, 2], [0, 2, 3], [4, 5, 6], [4, 6, 7]], np.uint32)
+    tm = np.array([0, 0, -1, -1], np.int32)
+    cam = dict(eye=(0.0, 1.0, 2.0), gaze=(0.0, 0.0, 0.0), up=(0.0, 1.0, 0.0), fov_y_deg=10.0)
+    for mode in (0, 1, 2):
+        img = O.oracle_render(pos, idx, tm, [[0.5, 0.5, 0.5]], [L, L, L], cam, 8, 8, 16, sample_mode=mode, material_type=[1])
+        assert np.allclose(img, L, rtol=1e-5), (mode, img.min(), img.max())
+
+
+def test_mirror_box_changes_the_image_but_not_the_energy_scale():
+    from mray_b200 import scenes
+    c = scenes.cornell_mirror()
+    tm = np.where(c["material"] == 3, -1, np.where(c["material"] == 4, 3, c["material"])).astype(np.int32)
+    alb = c["albedo"][[0, 1, 2, 4]]
+    img = O.oracle_render(c["positions"], c["indices"], tm, alb, c["radiance"], c["camera"], 32, 32, 512, sample_mode=2, seed=3,
+                          material_type=[0, 0, 0, 1])
+    plain = ref_image("cornell64_spp16384")
+    plain32 = block_mean(plain)
+    assert np.isfinite(img).all()
+    assert rel_mse(img, plain32) > 1e-2                       # the mirror is visible
+    assert 0.7 < img.mean() / plain32.mean() < 1.4
+
+
+def test_mirror_oracle_matches_reference_render():
+    """(Mt)Reflect against the reference's render of the mirror-box Cornell. The scene is ~5x noisier than the diffuse
+    one (reference-vs-reference relMSE ~ 43 (1/N + 1/M)), so 8x8 block means carry the converged comparison."""
+    from mray_b200 import scenes
+    c = scenes.cornell_mirror()
+    tm = np.where(c["material"] == 3, -1, np.where(c["material"] == 4, 3, c["material"])).astype(np.int32)
+    ref = ref_image("cornell64_mirror_spp16384")
+    img = O.oracle_render(c["positions"], c["indices"], tm, c["albedo"][[0, 1, 2, 4]], c["radiance"], c["camera"], 64, 64, 1024,
+                          sample_mode=2, seed=45, material_type=[0, 0, 0, 1])
+    err = rel_mse(block_mean(img, 8), block_mean(ref, 8))
+    assert err <= 1e-3, err
+    assert np.allclose(img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=0.01), (img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)))
+    assert rel_mse(block_mean(ref, 8), block_mean(ref_image("cornell64_spp16384"), 8)) > 5e-3     # the mirror is visible
