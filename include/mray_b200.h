@@ -422,6 +422,11 @@ MRB_API void       mrb_renderer_destroy(mrb_context ctx, mrb_renderer r);
 /* DoRenderWork x iterations (throughput mode: one bounce of every live path per iteration);
  * asynchronous, no host synchronisation inside. */
 MRB_API mrb_status mrb_renderer_iterate(mrb_context ctx, mrb_renderer r, uint32_t iterations);
+/* Latency render mode (PathTracerRendererT::DoLatencyRender, TracerDLL/PathTracerRenderer.cu:L1078-1160): camera paths
+ * are only started up to sppLimit samples per pixel (<= totalSPP; a new renderer starts at totalSPP = throughput mode).
+ * The caller lowers it right after create, iterates until stats.finished, reads the film and raises it for the next
+ * pass; raising requires the current pass to have finished. Synchronises. */
+MRB_API mrb_status mrb_renderer_set_spp_limit(mrb_context ctx, mrb_renderer r, uint32_t sppLimit);
 /* Synchronises and reads the counters. */
 MRB_API mrb_status mrb_renderer_get_stats(mrb_context ctx, mrb_renderer r, mrb_render_stats* out);
 /* The film the reference hands over as RenderImageSection (Common/RenderImageStructs.h:L22-37):

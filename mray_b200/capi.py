@@ -138,6 +138,7 @@ _PROTOTYPES = {
     "mrb_renderer_get_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(RenderStats)]),
     "mrb_renderer_read_film": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "mrb_renderer_film_device_ptr": (C.c_void_p, [C.c_void_p]),
+    "mrb_renderer_set_spp_limit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "mrb_texture_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "mrb_multi_partition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                       C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
@@ -538,6 +539,10 @@ class Renderer:
     def iterate(self, iterations=1):
         """DoRenderWork x iterations (asynchronous)."""
         self.ctx.check(self.ctx.lib.mrb_renderer_iterate(self.ctx.handle, self.handle, iterations))
+
+    def set_spp_limit(self, spp_limit: int):
+        """Latency mode: start camera paths only up to spp_limit samples per pixel (see mrb_renderer_set_spp_limit)."""
+        self.ctx.check(self.ctx.lib.mrb_renderer_set_spp_limit(self.ctx.handle, self.handle, spp_limit))
 
     def stats(self) -> RenderStats:
         st = RenderStats()

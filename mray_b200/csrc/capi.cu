@@ -27,6 +27,7 @@ mrb_renderer_t* NewRenderer();
 void RendererStats(Context& ctx, mrb_renderer_t& r, mrb_render_stats& out);
 void RendererReadFilm(Context& ctx, mrb_renderer_t& r, float* out, bool device, bool clear);
 float* RendererFilmPtr(mrb_renderer_t& r);
+void RendererSetSppLimit(Context& ctx, mrb_renderer_t& r, uint32_t sppLimit);
 void TextureSampleHost(Context& ctx, const mrb_texture_desc& td, const float* uv, uint32_t n, float* rgbOut);
 }
 
@@ -628,6 +629,16 @@ mrb_status mrb_renderer_iterate(mrb_context ctx, mrb_renderer r, uint32_t iterat
     {
         if(!r) return Fail(c, MRB_ERR_INVALID_ARG, "null renderer");
         mrb::RenderIterate(c, *r, iterations);
+        return MRB_OK;
+    });
+}
+
+mrb_status mrb_renderer_set_spp_limit(mrb_context ctx, mrb_renderer r, uint32_t sppLimit)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!r) return Fail(c, MRB_ERR_INVALID_ARG, "null renderer");
+        mrb::RendererSetSppLimit(c, *r, sppLimit);
         return MRB_OK;
     });
 }

@@ -793,6 +793,8 @@ struct mrb_renderer_t
     mrb_scene        scene = nullptr;
     mrb::SceneData   sceneData;        // scene->d with the renderer's instance records (accelKey = instance index)
     uint64_t         iterations = 0;
+    uint64_t         totalPaths = 0;   // totalSPP * pixels
+    bool             needReload = false;
 };
 
 namespace mrb
@@ -811,6 +813,7 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
     if(d.regionX + d.width > d.fullWidth || d.regionY + d.height > d.fullHeight) throw std::runtime_error("render region exceeds the image");
     d.rrLo = desc.rrRange[0]; d.rrHi = desc.rrRange[1]; d.sampleMode = desc.sampleMode;
     d.pathLimit = uint64_t(desc.totalSPP) * desc.width * desc.height;
+    r.totalPaths = d.pathLimit;
     d.filterSigma = desc.filmFilterRadius * 0.285714f;
     d.slots = desc.maxPathCount ? desc.maxPathCount : desc.width * desc.height;
     d.partitionRays = desc.partitionRays ? 1u : 0u;
@@ -1053,7 +1056,7 @@ void RenderIterate(Context& ctx, mrb_renderer_t& r, uint32_t iterations)
     const uint32_t grid = DivUp(d.slots, RTPB);
     for(uint32_t it = 0; it < iterations; it++)
     {
-        if(it == 0) MRB_LAUNCH(ctx, KReload, grid, RTPB, 0, d);   // later bounces: fused into the previous KFinishReload
+        if(it == 0 || r.needReload) { MRB_LAUNCH(ctx, KReload, grid, RTPB, 0, d); r.needReload = false; }   // later bounces: fused into the previous KFinishReload
         if(r.scene) TraceScene(ctx, r.sceneData, false, MRB_TRACE_WIDE, d.hitKeys, d.hits, nullptr, d.rays, nullptr, d.slots);
         else TraceRays(ctx, *r.accel, false, MRB_TRACE_WIDE, d.hitKeys, d.hits, nullptr, d.rays, nullptr, d.slots);
         if(d.partitionRays)
@@ -1107,6 +1110,30 @@ void RendererReadFilm(Context& ctx, mrb_renderer_t& r, float* out, bool device, 
 }
 
 float* RendererFilmPtr(mrb_renderer_t& r) { return r.d.film; }
+
+// Latency mode (PathTracerRendererT::DoLatencyRender, TracerDLL/PathTracerRenderer.cu:L1078-1160): paths are only
+// started up to `sppLimit` samples per pixel; the caller iterates until they have all died, hands the film over and
+// raises the limit for the next pass. Slots that found no sample to claim kept incrementing the claim counter, so it is
+// put back to the number of paths really started (= the old limit, all of which have completed).
+void RendererSetSppLimit(Context& ctx, mrb_renderer_t& r, uint32_t sppLimit)
+{
+    const uint64_t pixels = uint64_t(r.d.width) * r.d.height;
+    const uint64_t limit = uint64_t(sppLimit) * pixels;
+    if(limit > r.totalPaths) throw std::runtime_error("spp limit exceeds totalSPP");
+    unsigned long long h[2];
+    MRB_CUDA_TRY(cudaMemcpyAsync(h, r.d.counters, sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
+    MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
+    if(limit < r.d.pathLimit && h[0] > limit) throw std::runtime_error("spp limit below the samples already started");
+    if(h[0] > r.d.pathLimit)
+    {
+        if(h[1] < r.d.pathLimit) throw std::runtime_error("the current pass has not finished");
+        const unsigned long long started = r.d.pathLimit;
+        MRB_CUDA_TRY(cudaMemcpyAsync(r.d.counters, &started, sizeof(started), cudaMemcpyHostToDevice, ctx.stream));
+        MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
+    }
+    r.d.pathLimit = limit;
+    r.needReload = true;   // the next iteration starts with KReload again (free slots claim the new samples)
+}
 
 // mrb_texture_sample: the shading kernel's texture filter on its own (parity tap of SampleTexture)
 __global__ void KSampleTexture(TexRec t, const float2* __restrict__ uv, uint32_t n, float* __restrict__ out)

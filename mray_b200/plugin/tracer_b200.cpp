@@ -65,6 +65,7 @@ struct RendererB200
 {
     std::string type;
     uint32_t totalSPP = 16384, burstSize = 1, sampleMode = 0; Vector2ui rrRange = Vector2ui(4, 20);
+    bool latency = false;      // renderMode "Latency": every DoRenderWork finishes burstSize samples per pixel
 };
 
 // Inverse of an affine 3x4 matrix by Laplace expansion, the arithmetic of Matrix3x4T::Inverse
@@ -119,6 +120,9 @@ class TracerB200 final : public TracerI
     // render hand-off
     TimelineSemaphore* sem = nullptr; uint64_t acquireValue = 0;
     std::vector<float> staging; Vector2ui resolution = Vector2ui::Zero(), regionMin = Vector2ui::Zero();
+    struct StartArgs { RendererId id; CamSurfaceId camSurf; RenderImageParams rip; Optional<uint32_t> logic0; };
+    Optional<StartArgs> lastStart; Optional<CameraTransform> camOverride, pendingCam; bool rebuilding = false;
+    uint32_t latencySPP = 0;
     uint32_t curRenderer = 0; ThreadPool* pool = nullptr;
 
     void Check(mrb_status s) const { if(s != MRB_OK) throw MRayError("{}", mrb_last_error(ctx)); }
@@ -781,7 +785,7 @@ class TracerB200 final : public TracerI
             case 0: r.totalSPP = data.AccessAs<const uint32_t>().front(); break;
             case 1: r.burstSize = data.AccessAs<const uint32_t>().front(); break;
             case 2: { std::string_view m = data.AccessAsString();
-                      if(m != "Throughput"sv && m != "Latency"sv) throw MRayError("Bad enum name"); break; }
+                      if(m != "Throughput"sv && m != "Latency"sv) throw MRayError("Bad enum name"); r.latency = (m == "Latency"sv); break; }
             case 3: { std::string_view m = data.AccessAsString();
                       if(m == "Pure"sv) r.sampleMode = 0; else if(m == "WithNextEventEstimation"sv) r.sampleMode = 1;
                       else if(m == "WithNEEAndMIS"sv) r.sampleMode = 2; else throw MRayError("Bad enum name"); break; }
@@ -797,6 +801,8 @@ class TracerB200 final : public TracerI
     {
         if(!sem) throw MRayError("Render environment is not set properly! Please provide a semaphore to the tracer.");
         if(!accel && !scene) throw MRayError("CommitSurfaces must be called before StartRender");
+        if(!rebuilding) { camOverride.reset(); pendingCam.reset(); }
+        lastStart = StartArgs{id, camSurf, rip, logic0};
         const RendererB200& r = Get(renderers, Raw(id), "Renderer");
         const CameraSurfaceParams& cs = Get(camSurfaces, Raw(camSurf), "CameraSurface");
         const CamGroupB200& cg = Get(cams, Raw(cs.cameraId) >> CAM_ID_BITS, "CameraGroup");
@@ -830,6 +836,8 @@ class TracerB200 final : public TracerI
         }
         d.lightCount = uint32_t(flatLightTwoSided.size()); d.lightRadiance = flatLightRadiance.data(); d.lightTwoSided = flatLightTwoSided.data();
         for(int k = 0; k < 3; k++) { d.camPosition[k] = cg.position[ci][k]; d.camGaze[k] = cg.gaze[ci][k]; d.camUp[k] = cg.up[ci][k]; }
+        if(camOverride)   // SetCameraTransform: position / gaze point / up replace the camera's own, fov and planes stay
+            for(int k = 0; k < 3; k++) { d.camPosition[k] = camOverride->position[k]; d.camGaze[k] = camOverride->gazePoint[k]; d.camUp[k] = camOverride->up[k]; }
         d.fovXY[0] = cg.fovPlanes[ci][0]; d.fovXY[1] = cg.fovPlanes[ci][1];
         d.nearFar[0] = cg.fovPlanes[ci][2]; d.nearFar[1] = cg.fovPlanes[ci][3];
         d.width = tile[0]; d.height = tile[1]; d.totalSPP = r.totalSPP;
@@ -857,6 +865,8 @@ class TracerB200 final : public TracerI
             d.sobolMatrices = sobolMatrices.data();
         }
         Check(mrb_renderer_create(ctx, &d, &renderer));
+        latencySPP = 0;
+        if(r.latency || r.burstSize > 1) Check(mrb_renderer_set_spp_limit(ctx, renderer, 0));   // pass mode, see DoRenderWork
         curRenderer = Raw(id); resolution = tile; regionMin = rip.regionMin;
         staging.assign(size_t(4) * pixels, 0.0f);
         return RenderBufferInfo
@@ -866,15 +876,44 @@ class TracerB200 final : public TracerI
             .curRenderLogic0 = logic0.value_or(0), .curRenderLogic1 = 0
         };
     }
-    void SetCameraTransform(RendererId, CameraTransform) override { throw MRayError("SetCameraTransform is not supported yet"); }
+    // RendererI::SetCameraTransform (Tracer/PathTracerRendererBase.cu:L495-512): taken up by the next DoRenderWork, which
+    // restarts the accumulation with position / gaze point / up replaced
+    void SetCameraTransform(RendererId id, CameraTransform t) override
+    {
+        if(Raw(id) >= renderers.size()) throw MRayError("Unable to find Renderer({})", Raw(id));
+        pendingCam = t;
+    }
     void StopRender() override { if(renderer) { mrb_renderer_destroy(ctx, renderer); renderer = nullptr; } }
     RendererOutput DoRenderWork() override
     {
         if(!renderer) return RendererOutput{};
-        // one wavefront iteration (DoThroughputSingleTileRender), then the film delta hand-off of
-        // RenderImage::TransferToHost (Tracer/RenderImage.cpp:L163-219): acquire, copy, release, next state
-        Check(mrb_renderer_iterate(ctx, renderer, std::max(1u, renderers[curRenderer].burstSize)));
-        mrb_render_stats st; Check(mrb_renderer_get_stats(ctx, renderer, &st));
+        if(pendingCam && lastStart)
+        {
+            camOverride = pendingCam; pendingCam.reset();
+            rebuilding = true;
+            try { StartRender(lastStart->id, lastStart->camSurf, lastStart->rip, lastStart->logic0, std::nullopt); }
+            catch(...) { rebuilding = false; throw; }
+            rebuilding = false;
+        }
+        const RendererB200& rr = renderers[curRenderer];
+        mrb_render_stats st;
+        if(rr.latency || rr.burstSize > 1)
+        {
+            // PathTracerRendererBase::DoRender (Tracer/PathTracerRendererBase.cu:L515-533): renderMode Latency runs
+            // DoLatencyRender(1), Throughput with burstSize > 1 runs DoLatencyRender(burstSize) — that many more samples
+            // of every pixel, traced to completion before the film is handed over (PathTracerRenderer.cu:L1078-1160)
+            latencySPP = std::min(rr.totalSPP, latencySPP + (rr.latency ? 1u : rr.burstSize));
+            Check(mrb_renderer_set_spp_limit(ctx, renderer, latencySPP));
+            do { Check(mrb_renderer_iterate(ctx, renderer, 4)); Check(mrb_renderer_get_stats(ctx, renderer, &st)); } while(!st.finished);
+            st.finished = (latencySPP >= rr.totalSPP) ? 1u : 0u;
+        }
+        else
+        {
+            // one wavefront iteration (DoThroughputSingleTileRender), then the film delta hand-off of
+            // RenderImage::TransferToHost (Tracer/RenderImage.cpp:L163-219): acquire, copy, release, next state
+            Check(mrb_renderer_iterate(ctx, renderer, 1));
+            Check(mrb_renderer_get_stats(ctx, renderer, &st));
+        }
         if(!sem->Acquire(acquireValue)) return RendererOutput{};
         Check(mrb_renderer_read_film(ctx, renderer, staging.data(), MRB_MEM_HOST, 1));
         sem->Release();

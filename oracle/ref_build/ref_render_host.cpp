@@ -31,7 +31,7 @@ struct DriverScene
 struct DriverRender
 {
     const char* rendererName; uint32_t width, height; uint32_t totalSPP; const char* sampleMode;
-    uint32_t rrRange[2]; uint64_t seed; uint32_t accelMode; uint32_t parallelHint; uint32_t threads; uint32_t samplerType; uint32_t region[4];
+    uint32_t rrRange[2]; uint64_t seed; uint32_t accelMode; uint32_t parallelHint; uint32_t threads; uint32_t samplerType; uint32_t region[4]; uint32_t latency; uint32_t burstSize; uint32_t camSwitchAfter; float camSwitch[9];
 };
 struct DriverStats { double commitSeconds, renderSeconds, totalPaths; uint32_t iterations; float sceneAABB[6]; };
 using RenderF = int (*)(const char*, const DriverScene*, const DriverRender*, float*, float*, DriverStats*, char*, size_t);
@@ -54,7 +54,8 @@ int main(int argc, char** argv)
     std::fclose(f);
     auto P = [&](int i) { return bytes[i] ? reinterpret_cast<const void*>(sec[i].data()) : nullptr; };
     // sections: 0 dll path, 1 renderer name, 2 sample mode (NUL-terminated by the zero padding),
-    // 3 u32[16] {batchCount, materialCount, lightCount, width, height, spp, rr0, rr1, accelMode, parallelHint, threads, sampler, region[4]},
+    // 3 u32[28] {batchCount, materialCount, lightCount, width, height, spp, rr0, rr1, accelMode, parallelHint, threads, sampler, region[4],
+    //   latency, burstSize, camSwitchAfter, camSwitch[9] (float bits)},
     // 4 u64 seed, 5 f32[13] camera {pos, gaze, up, fovXY, nearFar}, 6 vertexOffsets, 7 triOffsets, 8 positions,
     // 9 normals, 10 indices, 11 batchMaterial, 12 batchLight, 13 albedo, 14 radiance, 15 batchTransforms (may be empty), 16 batchInstanceOf (may be empty),
     // 17 textureInfo (6 u32 per texture; may be empty), 18 textureBytes, 19 materialTexture, 20 uvs (may be empty), 21 materialKind (may be empty)
@@ -79,6 +80,8 @@ int main(int argc, char** argv)
     rd.seed = *static_cast<const uint64_t*>(P(4));
     rd.accelMode = u[8]; rd.parallelHint = u[9]; rd.threads = u[10]; rd.samplerType = u[11];
     for(int k = 0; k < 4; k++) rd.region[k] = u[12 + k];
+    rd.latency = u[16]; rd.burstSize = u[17]; rd.camSwitchAfter = u[18];
+    std::memcpy(rd.camSwitch, u + 19, sizeof(rd.camSwitch));
 
     char self[PATH_MAX]; ssize_t k = readlink("/proc/self/exe", self, sizeof(self) - 1);
     if(k <= 0) return 67;

@@ -77,6 +77,12 @@ struct DriverRender
     uint32_t    threads;        // host thread pool size (0 = hardware)
     uint32_t    samplerType;    // SamplerType::E: 0 Independent, 1 ZSobol, 2 Sobol
     uint32_t    region[4];      // regionMin.xy, regionMax.xy of RenderImageParams; all 0 = the whole image
+    uint32_t    latency;        // 1 = renderMode "Latency" (every DoRenderWork completes burstSize samples per pixel)
+    uint32_t    burstSize;      // 0 = 1
+    // optional SetCameraTransform exercise: after `camSwitchAfter` DoRenderWork calls (0 = never) the camera is moved to
+    // camSwitch{Pos,Gaze,Up} and the accumulation restarts (the driver clears its own accumulator, like Visor does)
+    uint32_t    camSwitchAfter;
+    float       camSwitch[9];
 };
 
 struct DriverStats
@@ -428,8 +434,8 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
                 tracer->PushRendererAttribute(rid, a, std::move(d));
             };
             if(name == "totalSPP") PushU32(rd->totalSPP);
-            else if(name == "burstSize") PushU32(1);
-            else if(name == "renderMode") PushStr("Throughput");
+            else if(name == "burstSize") PushU32(rd->burstSize ? rd->burstSize : 1u);
+            else if(name == "renderMode") PushStr(rd->latency ? "Latency" : "Throughput");
             else if(name == "sampleMode") PushStr(rd->sampleMode);
             else if(name == "rrRange")
             {
@@ -455,6 +461,14 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
         uint32_t iters = 0;
         while(true)
         {
+            if(rd->camSwitchAfter && iters == rd->camSwitchAfter)
+            {
+                CameraTransform ct{Vector3(rd->camSwitch[0], rd->camSwitch[1], rd->camSwitch[2]),
+                                   Vector3(rd->camSwitch[3], rd->camSwitch[4], rd->camSwitch[5]),
+                                   Vector3(rd->camSwitch[6], rd->camSwitch[7], rd->camSwitch[8])};
+                tracer->SetCameraTransform(rid, ct);
+                std::fill(acc.begin(), acc.end(), 0.0);
+            }
             RendererOutput out = tracer->DoRenderWork();
             iters++;
             if(getenv("DRIVER_VERBOSE")) std::fprintf(stderr, "iter %u img %d save %d\n", iters, int(out.imageOut.has_value()), int(out.triggerSave));

@@ -173,7 +173,8 @@ class _DriverRender(C.Structure):
     _fields_ = [("rendererName", C.c_char_p), ("width", C.c_uint32), ("height", C.c_uint32), ("totalSPP", C.c_uint32),
                 ("sampleMode", C.c_char_p), ("rrRange", C.c_uint32 * 2), ("seed", C.c_uint64),
                 ("accelMode", C.c_uint32), ("parallelHint", C.c_uint32), ("threads", C.c_uint32), ("samplerType", C.c_uint32),
-                ("region", C.c_uint32 * 4)]
+                ("region", C.c_uint32 * 4), ("latency", C.c_uint32), ("burstSize", C.c_uint32),
+                ("camSwitchAfter", C.c_uint32), ("camSwitch", C.c_float * 9)]
 
 
 class _DriverStats(C.Structure):
@@ -215,11 +216,14 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
                   renderer="PathTracerRGB", sample_mode="WithNEEAndMIS", rr_range=(2, 20), seed=0,
                   accel_mode=1, threads=0, parallel_hint=0, near_far=(0.01, 1000.0), driver_flavour="",
                   batch_transforms=None, sampler="Independent", host_exe=False, instance_of=None,
-                  textures=None, material_texture=None, region=None, material_kind=None):
+                  textures=None, material_texture=None, region=None, material_kind=None,
+                  latency=False, burst_size=1, cam_switch=None):
     """Renders through TracerI. `light_material`: material id whose batch is the prim-backed light.
     batch_transforms: optional [batch, 3, 4] local->world matrices ((T)Single per batch; positions local).
     textures: list of dict(data=[h, w, 4] float32 / uint8 (RGBA), interp=, edge=); material_texture: per material id
     (an index into `albedo`) -1 or a texture index; UV0 comes from batched["uvs"] (zeros when absent).
+    latency / burst_size: renderMode "Latency" and burstSize. cam_switch: (after_iterations, camera dict): calls
+    SetCameraTransform after that many DoRenderWork calls and restarts the accumulation.
     material_kind: per material id (an index into `albedo`) 0 = (Mt)Lambert, 1 = (Mt)Reflect.
     region: optional (minX, minY, maxX, maxY) of RenderImageParams; pixels outside it come back with weight 0.
     instance_of: optional int per batch; a >= 0 makes that batch's surface an instance of batch a's geometry.
@@ -258,7 +262,12 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
         import subprocess
         import tempfile
         u = np.array([len(mats), len(lambert), n_lights, width, height, spp, rr_range[0], rr_range[1], accel_mode,
-                      parallel_hint, threads, sampler_id] + list(region or (0, 0, 0, 0)), np.uint32)
+                      parallel_hint, threads, sampler_id] + list(region or (0, 0, 0, 0)) +
+                     [1 if latency else 0, burst_size, cam_switch[0] if cam_switch else 0], np.uint32)
+        cs = np.zeros(9, np.float32)
+        if cam_switch:
+            cs[:] = list(cam_switch[1]["eye"]) + list(cam_switch[1]["gaze"]) + list(cam_switch[1]["up"])
+        u = np.concatenate([u, cs.view(np.uint32)])
         cam = np.array(list(camera["eye"]) + list(camera["gaze"]) + list(camera["up"]) + [fx, fy] + list(near_far), np.float32)
         secs = [dll_path.encode(), renderer.encode(), sample_mode.encode(), u.tobytes(), np.uint64(seed).tobytes(),
                 cam.tobytes(), batched["vertex_offsets"].astype(np.uint32).tobytes(), batched["tri_offsets"].astype(np.uint32).tobytes(),
@@ -308,7 +317,9 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
     if mkind is not None:
         keep.append(mkind); sc.materialKind = mkind.ctypes.data
     rd = _DriverRender(renderer.encode(), width, height, spp, sample_mode.encode(), (C.c_uint32 * 2)(*rr_range), seed,
-                       accel_mode, parallel_hint, threads, sampler_id, (C.c_uint32 * 4)(*(region or (0, 0, 0, 0))))
+                       accel_mode, parallel_hint, threads, sampler_id, (C.c_uint32 * 4)(*(region or (0, 0, 0, 0))),
+                       1 if latency else 0, burst_size, cam_switch[0] if cam_switch else 0,
+                       (C.c_float * 9)(*((list(cam_switch[1]["eye"]) + list(cam_switch[1]["gaze"]) + list(cam_switch[1]["up"])) if cam_switch else [0.0] * 9)))
     img = np.zeros((height, width, 3), np.float32)
     wgt = np.zeros((height, width), np.float32)
     st = _DriverStats()

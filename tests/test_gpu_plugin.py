@@ -103,3 +103,29 @@ def test_low_discrepancy_sampler_through_tracer_interface(sampler):
     mask = ref.max(axis=-1) < 5.0
     assert np.allclose(img[mask].mean(axis=0), ref[mask].mean(axis=0), rtol=0.02)
     assert float(np.mean((img - ref) ** 2 / (ref ** 2 + 1e-2))) < 6e-3
+
+
+@pytest.mark.skipif(not (os.path.exists(PLUGIN) and O.driver_available()), reason="plugin / driver were not prebuilt")
+def test_latency_mode_burst_and_camera_switch_through_tracer_interface():
+    """renderMode Latency (one sample per pixel per DoRenderWork, traced to completion), Throughput with burstSize > 1
+    (burstSize samples per call) — PathTracerRendererBase::DoRender's dispatch — and SetCameraTransform (the next
+    DoRenderWork restarts the accumulation with the new camera). Iteration counts are the reference's own
+    (64 calls for 64 spp in Latency mode); images are compared with the reference's golden image."""
+    golden = np.load(os.path.join(ROOT, "tests", "golden", "render_cornell64_spp16384.npz"))["img"].astype(np.float32)
+    bm = lambda x, k: x.reshape(x.shape[0] // k, k, x.shape[1] // k, k, 3).mean(axis=(1, 3))
+    c = scenes.cornell_box()
+    b = O.batched_scene(c["positions"], c["indices"], c["material"])
+    spp = 256
+    img, w, st = O.driver_render(PLUGIN, b, c["albedo"], 3, c["radiance"], c["camera"], 64, 64, spp, seed=5, latency=True)
+    assert st["iterations"] == spp and np.allclose(w, spp, rtol=1e-3)
+    img_b, w_b, st_b = O.driver_render(PLUGIN, b, c["albedo"], 3, c["radiance"], c["camera"], 64, 64, spp, seed=6, burst_size=32)
+    assert st_b["iterations"] == spp // 32 and np.allclose(w_b, spp, rtol=1e-3)
+    for im in (img, img_b):      # 8x8 blocks: 16384 samples each vs 1 M in the golden image
+        assert float(np.mean((bm(im, 8) - bm(golden, 8)) ** 2 / (bm(golden, 8) ** 2 + 1e-2))) <= 1e-3
+    # camera switch after 5 calls: the final image is the second camera's, with the full sample count
+    cam2 = dict(eye=(0.5, 1.2, 5.0), gaze=(0.0, 0.8, 0.0), up=(0.0, 1.0, 0.0), fov_y_deg=c["camera"]["fov_y_deg"])
+    img_s, w_s, st_s = O.driver_render(PLUGIN, b, c["albedo"], 3, c["radiance"], c["camera"], 32, 32, 4096, seed=7, cam_switch=(5, cam2))
+    img_d, w_d, st_d = O.driver_render(PLUGIN, b, c["albedo"], 3, c["radiance"], cam2, 32, 32, 4096, seed=8)
+    assert np.allclose(w_s, 4096, rtol=1e-3)
+    assert float(np.mean((bm(img_s, 4) - bm(img_d, 4)) ** 2 / (bm(img_d, 4) ** 2 + 1e-2))) <= 1e-3
+    assert float(np.mean((img_s - bm(golden, 2)) ** 2 / (bm(golden, 2) ** 2 + 1e-2))) > 1e-2     # not the first camera's image

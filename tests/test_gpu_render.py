@@ -198,3 +198,30 @@ def test_reflect_material_matches_oracle_and_closed_form(gpu_ctx):
         img, st = r.render(); r.close()
         assert np.allclose(img, L, rtol=1e-5), (mode, img.min(), img.max())
     acc.close()
+
+
+def test_spp_limit_passes(gpu_ctx):
+    """mrb_renderer_set_spp_limit (DoLatencyRender): every pass completes exactly its samples of every pixel."""
+    c, idx, tm, acc = cornell_accel(gpu_ctx)
+    res, total = 32, 16
+    r = capi.Renderer(gpu_ctx, acc, c["positions"].shape[0], idx.shape[0], c["albedo"][:3], c["radiance"], c["camera"], res, res, total, seed=2)
+    r.set_spp_limit(0)
+    for k in range(1, 5):
+        r.set_spp_limit(4 * k)
+        while True:
+            r.iterate(4)
+            st = r.stats()
+            if st.finished:
+                break
+        assert st.pathsCompleted == 4 * k * res * res
+        rgb, w = r.read_film()
+        assert np.allclose(w, 4 * k, rtol=1e-4), (k, w.min(), w.max())
+    with pytest.raises(capi.MrbError):
+        r.set_spp_limit(total + 1)
+    img = rgb / w[..., None]
+    r.close()
+    r2 = capi.Renderer(gpu_ctx, acc, c["positions"].shape[0], idx.shape[0], c["albedo"][:3], c["radiance"], c["camera"], res, res, total, seed=3)
+    img2, st2 = r2.render(); r2.close()
+    mask = img2.max(axis=-1) < 5.0
+    assert np.allclose(img[mask].mean(axis=0), img2[mask].mean(axis=0), rtol=0.05)
+    acc.close()
