@@ -205,6 +205,86 @@ static s4 light_emit(const pt_scene* s, uint32_t li, v3 n, v3 wO, const float wa
 
 /* one camera path -> radiance (RGB; spectral paths are converted with their wavelengths at the end, as
  * ConvertSpectrumToRGBIndirect does on dead paths); *filmW receives the filter weight */
+/* Distribution::Common::SampleGaussian (DistributionFunctions.h:L686-705): x = sqrt2 sigma erfinv(2 xi - 1), clamped to
+ * +-3.5 sigma where erfinv overflows; the inverse error function by Newton iterations on erf in double */
+static float gauss_sample(float xi, float sig)
+{
+    double e = 0;
+    double y = 2.0 * xi - 1.0;
+    if(y <= -1.0) e = -INFINITY; else if(y >= 1.0) e = INFINITY;
+    else { double x = 0; for(int it = 0; it < 60; it++) { double f = erf(x) - y; x -= f / (1.1283791670955126 * exp(-x * x)); } e = x; }
+    float x = 1.41421356237f * sig * (float)e;
+    if(isinf(e)) { float mm = 3.5f * sig; x = x < -mm ? -mm : (x > mm ? mm : x); }
+    return x;
+}
+/* Math::Gaussian(x, sigma) = PDFGaussian = GaussianFilter::Evaluate per axis (Filters.h:L195-227) */
+static float gauss_pdf(float x, float sig) { float p = x / sig; return 0.3989422804f / sig * expf(-0.5f * p * p); }
+/* GaussianFilter(radius): out = {offset x, offset y, Sample().pdf, Pdf(offset), Evaluate(offset)} */
+void orc_pt_filter_sample(float radius, float xi0, float xi1, float out[5])
+{
+    float sig = radius * 0.285714f;
+    out[0] = gauss_sample(xi0, sig); out[1] = gauss_sample(xi1, sig);
+    out[2] = gauss_pdf(out[0], sig) * gauss_pdf(out[1], sig);
+    out[3] = out[2];
+    out[4] = gauss_pdf(out[0], sig) * gauss_pdf(out[1], sig);
+}
+
+/* Distribution::Common::SampleCosDirection (DistributionFunctions.h:L847-871), +Z hemisphere: out = {x, y, z, pdf} */
+static void cos_direction(float u0, float u1, float out[4])
+{
+    float phi = 6.28318530718f * u1, su = sqrtf(u0);
+    float lx = su * cosf(phi), ly = su * sinf(phi);
+    float lz2 = 1.0f - (lx * lx + ly * ly); float lz = lz2 > 0 ? sqrtf(lz2) : 0;
+    out[0] = lx; out[1] = ly; out[2] = lz; out[3] = lz * 0.31830988618f;
+}
+void orc_pt_sample_cos_direction(float u0, float u1, float out[4]) { cos_direction(u0, u1, out); }
+
+/* LightPrim<Triangle>::SampleSolidAngle (LightsDefault.hpp:L22-46) over Triangle::SampleSurface (Osada,
+ * PrimitiveDefaultTriangle.hpp:L48-77): q = the triangle, from = the shaded point; outputs the sampled position, the light's
+ * geometric normal, the area and the solid-angle pdf (NOT yet divided by the light count). */
+static float light_sample(const v3 q[3], int twoSided, float x0, float x1, v3 from, v3* lposOut, v3* lNOut, v3* sdOut)
+{
+    float r1 = sqrtf(x0), r2 = x1;
+    float la = 1 - r1, lb = (1 - r2) * r1, lc = r1 * r2;
+    v3 lpos = add(add(mul(q[0], la), mul(q[1], lb)), mul(q[2], lc));
+    v3 le0 = sub(q[1], q[0]), le1 = sub(q[2], q[0]);
+    v3 lN = nrm(cross(le0, le1));
+    float area = 0.5f * len(cross(le0, le1));
+    v3 sd = sub(from, lpos); float distSqr = dot(sd, sd); sd = nrm(sd);
+    float NdL = dot(lN, sd);
+    NdL = twoSided ? fabsf(NdL) : (NdL > 0 ? NdL : 0);
+    float pdfL = (NdL == 0) ? 0 : (1.0f / area) / NdL;
+    pdfL *= distSqr;
+    *lposOut = lpos; *lNOut = lN; *sdOut = sd;
+    return pdfL;
+}
+/* LightPrim::PdfSolidAngle (LightsDefault.hpp:L48-68) for a hit at `hitPos` on the triangle seen from `from` along dir */
+static float light_pdf(const v3 q[3], int twoSided, v3 hitPos, v3 from, v3 dir)
+{
+    v3 le0 = sub(q[1], q[0]), le1 = sub(q[2], q[0]);
+    v3 lN = nrm(cross(le0, le1));
+    float area = 0.5f * len(cross(le0, le1));
+    float NdL = dot(lN, mul(dir, -1.0f));
+    NdL = twoSided ? fabsf(NdL) : (NdL > 0 ? NdL : 0);
+    float pdfL = (NdL == 0) ? 0 : (1.0f / area) / NdL;
+    v3 dv = sub(from, hitPos);
+    return pdfL * dot(dv, dv);
+}
+/* test entry: tri[9], xi[2], from[3] -> out = {sampled pos xyz, pdf of SampleSolidAngle, PdfSolidAngle of the ray from
+ * `from` towards the sample, evaluated at its own intersection with the triangle's plane} */
+void orc_pt_light_sample(const float* triv, int twoSided, float x0, float x1, const float* fromv, float out[5])
+{
+    v3 q[3] = {V(triv[0], triv[1], triv[2]), V(triv[3], triv[4], triv[5]), V(triv[6], triv[7], triv[8])};
+    v3 from = V(fromv[0], fromv[1], fromv[2]), lpos, lN, sd;
+    out[3] = light_sample(q, twoSided, x0, x1, from, &lpos, &lN, &sd);
+    out[0] = lpos.x; out[1] = lpos.y; out[2] = lpos.z;
+    v3 dir = nrm(sub(lpos, from));
+    /* intersect the plane of the triangle along dir (Triangle::Intersects gives the same point up to rounding) */
+    float tt = dot(sub(q[0], from), lN) / dot(dir, lN);
+    v3 hit = add(from, mul(dir, tt));
+    out[4] = light_pdf(q, twoSided, hit, from, dir);
+}
+
 static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, float* filmW, float waves[4], float wavePdf[4]);
 static v3 path(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, float* filmW)
 {
@@ -226,19 +306,7 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
     v3 bl = add(sub(sub(pos, mul(right, wh)), mul(up, hh)), mul(gz, s->nearFar[0]));
     float sig = s->filterRadius * 0.285714f;
     float off[2];
-    for(int k = 0; k < 2; k++)
-    {
-        float xi = pcg_float(rng);
-        double e = 0; /* inverse error function via Newton on erf (double) */
-        {
-            double y = 2.0 * xi - 1.0;
-            if(y <= -1.0) e = -INFINITY; else if(y >= 1.0) e = INFINITY;
-            else { double x = 0; for(int it = 0; it < 60; it++) { double f = erf(x) - y; x -= f / (1.1283791670955126 * exp(-x * x)); } e = x; }
-        }
-        float x = 1.41421356237f * sig * (float)e;
-        if(isinf(e)) { float mm = 3.5f * sig; x = x < -mm ? -mm : (x > mm ? mm : x); }
-        off[k] = x;
-    }
+    for(int k = 0; k < 2; k++) off[k] = gauss_sample(pcg_float(rng), sig);
     *filmW = 1.0f; /* Evaluate(offset) / pdf(offset): same Gaussian */
     float sx = ((float)px + off[0] + 0.5f) * (2.0f * wh / (float)s->width);
     float sy = ((float)py + off[1] + 0.5f) * (2.0f * hh / (float)s->height);
@@ -273,12 +341,7 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
                 s4 thr = throughput;
                 if(s->sampleMode == 2u && type == 2)
                 {
-                    float NdL = dot(gN, mul(d, -1.0f));
-                    NdL = (s->twoSided && s->twoSided[li]) ? fabsf(NdL) : (NdL > 0 ? NdL : 0);
-                    float area = 0.5f * len(cross(e0, e1));
-                    float pdfL = (NdL == 0) ? 0 : (1.0f / area) / NdL;
-                    v3 dv = sub(o, hitPos);
-                    pdfL *= dot(dv, dv);
+                    float pdfL = light_pdf(p, s->twoSided && s->twoSided[li], hitPos, o, d);
                     pdfL *= 1.0f / (float)nLights;
                     float mis = prevPdf + pdfL;
                     thr = s_mul(thr, prevPdf);
@@ -316,17 +379,9 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
             {
                 uint32_t lt = s->lightTris[li]; uint32_t lightIdx = (uint32_t)(-1 - s->triMaterial[lt]);
                 v3 q[3]; tri(s, lt, q);
-                float r1 = sqrtf(x0), r2 = x1;
-                float la = 1 - r1, lb = (1 - r2) * r1, lc = r1 * r2;
-                v3 lpos = add(add(mul(q[0], la), mul(q[1], lb)), mul(q[2], lc));
-                v3 le0 = sub(q[1], q[0]), le1 = sub(q[2], q[0]);
-                v3 lN = nrm(cross(le0, le1));
-                float area = 0.5f * len(cross(le0, le1));
-                v3 sd = sub(hitPos, lpos); float distSqr = dot(sd, sd); sd = nrm(sd);
-                float NdL = dot(lN, sd);
-                NdL = (s->twoSided && s->twoSided[lightIdx]) ? fabsf(NdL) : (NdL > 0 ? NdL : 0);
-                float pdfL = (NdL == 0) ? 0 : (1.0f / area) / NdL;
-                pdfL *= distSqr; pdfL *= 1.0f / (float)nLights;
+                v3 lpos, lN, sd;
+                float pdfL = light_sample(q, s->twoSided && s->twoSided[lightIdx], x0, x1, hitPos, &lpos, &lN, &sd);
+                pdfL *= 1.0f / (float)nLights;
                 s4 em = light_emit(s, lightIdx, lN, sd, waves);
                 v3 wI = nrm(sub(lpos, hitPos));
                 v3 lposN = nudge(lpos, mul(wI, -1.0f));
@@ -347,10 +402,8 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
         }
         /* BxDF sample + RR */
         float u0 = pcg_float(rng), u1 = pcg_float(rng);
-        float phi = 6.28318530718f * u1, su = sqrtf(u0);
-        float lx = su * cosf(phi), ly = su * sinf(phi);
-        float lz2 = 1.0f - (lx * lx + ly * ly); float lz = lz2 > 0 ? sqrtf(lz2) : 0;
-        float pdfB = lz * 0.31830988618f;
+        float cd[4]; cos_direction(u0, u1, cd);
+        float lx = cd[0], ly = cd[1], lz = cd[2], pdfB = cd[3];
         v3 wI = nrm(add(add(mul(tX, lx), mul(tY, ly)), mul(gN, lz)));
         throughput = s_mulv(throughput, s_mul(alb, lz * 0.31830988618f));
         depth += 1;

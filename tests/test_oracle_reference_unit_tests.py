@@ -1,0 +1,76 @@
+"""CPU: the reference's own unit tests for this path, restated as plain asserts against the functions
+the estimator oracle is built from (oracle/pt_oracle.c):
+  Tests/Tracer/T_Filters.cu:L10-96           Filter_Gaussian ZeroVariance (Sample / Pdf / Evaluate agree, estimate == 1)
+  Tests/Tracer/T_Distributions.cu:L622-676   Dist_CosineHemisphere Sample (furnace: cos/pi over pdf == 1) and PDF
+  Tests/Tracer/T_DefaultLights.cu:L322-392   PrimLight_Triangle (SampleSolidAngle pdf == PdfSolidAngle of the same ray)
+  Tests/Tracer/T_Random.cu / Random.h        PermutedCG32 is exercised through tests/golden/rng_*.npz already"""
+import ctypes as C
+
+import numpy as np
+
+import oracle_lib as O
+
+
+def _lib():
+    L = O.lib()
+    L.orc_pt_filter_sample.argtypes = [C.c_float, C.c_float, C.c_float, C.c_void_p]
+    L.orc_pt_sample_cos_direction.argtypes = [C.c_float, C.c_float, C.c_void_p]
+    L.orc_pt_light_sample.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    return L
+
+
+def test_gaussian_filter_zero_variance():
+    """TestFilter<GaussianFilter>(true): 16 radii in (0, 5], 128 samples each incl. xi = 0 and xi = prev(1)."""
+    L = _lib()
+    rng = np.random.default_rng(123)
+    out = np.zeros(5, np.float32)
+    for f in range(16):
+        r = 1e-2 if f == 0 else float(rng.uniform(0.05, 5.0))
+        total = 0.0
+        for i in range(128):
+            xi = (0.0, 0.0) if i == 0 else ((np.nextafter(np.float32(1), np.float32(0)),) * 2 if i == 1 else rng.random(2))
+            L.orc_pt_filter_sample(r, float(xi[0]), float(xi[1]), out.ctypes.data)
+            sample_pdf, pdf, ev = float(out[2]), float(out[3]), float(out[4])
+            assert abs(pdf - sample_pdf) <= 1e-2 * max(1.0, pdf)           # EXPECT_NEAR(pdfFromFunc, result.pdf, HugeEpsilon)
+            assert abs(ev / sample_pdf - 1.0) <= 1e-3                      # zero variance: integral 1 per sample
+            assert np.isfinite(out).all()                                  # xi = 0 clamps to -3.5 sigma instead of -inf
+            total += ev / sample_pdf
+        assert abs(total / 128 - 1.0) <= 1e-4
+
+
+def test_cosine_hemisphere_furnace_and_pdf():
+    L = _lib()
+    rng0, rng1 = np.random.default_rng(123), np.random.default_rng(321)
+    out = np.zeros(4, np.float32)
+    total = 0.0
+    n = 50_000
+    for _ in range(n):
+        L.orc_pt_sample_cos_direction(float(rng0.random(dtype=np.float32)), float(rng1.random(dtype=np.float32)), out.ctypes.data)
+        d, pdf = out[:3].astype(np.float64), float(out[3])
+        assert abs(np.linalg.norm(d) - 1.0) < 1e-5 and d[2] >= 0.0
+        if pdf > 0:
+            total += (d[2] / np.pi) / pdf                                  # integral of cos(theta)/pi d(omega)
+        # PDFCosDirection(v) == InvPi * dot(v, Z)
+        assert pdf == np.float32(np.float32(out[2]) * np.float32(0.31830988618))
+    assert abs(total / n - 1.0) < 1e-4
+
+
+def test_prim_light_triangle_sample_pdf_consistency():
+    """The two triangles of the reference test's quad at z = -2, seen from the origin, one-sided lights facing +Z."""
+    L = _lib()
+    pos = np.array([[-0.5, -0.5, -2], [0.5, -0.5, -2], [0.5, 0.5, -2], [-0.5, 0.5, -2]], np.float32)
+    tris = [np.ascontiguousarray(pos[[0, 1, 2]].ravel()), np.ascontiguousarray(pos[[0, 2, 3]].ravel())]
+    origin = np.zeros(3, np.float32)
+    rng = np.random.default_rng(5)
+    out = np.zeros(5, np.float32)
+    for i in range(4096):
+        for t in tris:
+            x0, x1 = rng.random(2)
+            L.orc_pt_light_sample(t.ctypes.data, 0, float(x0), float(x1), origin.ctypes.data, out.ctypes.data)
+            assert out[3] > 0 and np.isclose(out[4], out[3], rtol=1e-4)    # EXPECT_FLOAT_EQ(pdf, sample.pdf)
+            assert abs(out[2] + 2.0) < 1e-6                               # sample lies on the triangle's plane
+    # facing away: pdf 0
+    L.orc_pt_light_sample(tris[0].ctypes.data, 0, 0.3, 0.6, np.array([0, 0, -4], np.float32).ctypes.data, out.ctypes.data)
+    assert out[3] == 0.0
+    L.orc_pt_light_sample(tris[0].ctypes.data, 1, 0.3, 0.6, np.array([0, 0, -4], np.float32).ctypes.data, out.ctypes.data)
+    assert out[3] > 0.0                                                   # two-sided
