@@ -52,6 +52,8 @@ ITEMS = {
     "cornell64_textured_spp16384": (64, 16384, 9, "WithNEEAndMIS", (2, 20), "textured", np.float32, RGB),
     # (Mt)Reflect: the tall box is a perfect mirror (scenes.cornell_mirror); a much noisier scene (caustic paths)
     "cornell64_mirror_spp16384": (64, 16384, 10, "WithNEEAndMIS", (2, 20), "mirror", np.float32, RGB),
+    # (L)Prim's isTwoSided attribute: the light also shines on the ceiling 2 cm above it
+    "cornell64_twosided_spp16384": (64, 16384, 15, "WithNEEAndMIS", (2, 20), "twosided", np.float32, RGB),
     # low-discrepancy samplers of the reference (TracerParameters.samplerType)
     "cornell64_sobol_spp4096":  (64, 4096, 13, "WithNEEAndMIS", (2, 20), "Sobol", np.float32, RGB),
     "cornell64_zsobol_spp4096": (64, 4096, 14, "WithNEEAndMIS", (2, 20), "ZSobol", np.float32, RGB),
@@ -96,7 +98,11 @@ def render(name):
     res, spp, seed, mode, rr, single, dt, renderer = ITEMS[name]
     c = scenes.cornell_mirror() if single == "mirror" else scenes.cornell_box()
     kw = {}
-    if single in ("Sobol", "ZSobol"):
+    if single == "twosided":
+        b = O.batched_scene(c["positions"], c["indices"], c["material"])
+        kw = dict(light_two_sided=True)
+        bt = None
+    elif single in ("Sobol", "ZSobol"):
         b = O.batched_scene(c["positions"], c["indices"], c["material"])
         kw = dict(sampler=single)
         bt = None

@@ -26,7 +26,7 @@ struct DriverScene
     uint32_t materialCount; const float* albedo; uint32_t lightCount; const float* radiance;
     float camPos[3], camGaze[3], camUp[3]; float fovXY[2]; float nearFar[2];
     const float* batchTransforms; const int32_t* batchInstanceOf;
-    uint32_t textureCount; const uint32_t* textureInfo; const uint8_t* textureBytes; const int32_t* materialTexture; const float* uvs; const uint8_t* materialKind;
+    uint32_t textureCount; const uint32_t* textureInfo; const uint8_t* textureBytes; const int32_t* materialTexture; const float* uvs; const uint8_t* materialKind; const uint8_t* lightTwoSided;
 };
 struct DriverRender
 {
@@ -42,7 +42,7 @@ int main(int argc, char** argv)
     FILE* f = std::fopen(argv[1], "rb");
     if(!f) { std::perror("blob"); return 65; }
     uint64_t n = 0;
-    if(std::fread(&n, 8, 1, f) != 1 || n != 22) { std::fprintf(stderr, "bad blob\n"); return 66; }
+    if(std::fread(&n, 8, 1, f) != 1 || n != 23) { std::fprintf(stderr, "bad blob\n"); return 66; }
     std::vector<std::vector<uint64_t>> sec(n);     // 8-byte aligned storage
     std::vector<uint64_t> bytes(n);
     for(uint64_t i = 0; i < n; i++)
@@ -58,7 +58,7 @@ int main(int argc, char** argv)
     //   latency, burstSize, camSwitchAfter, camSwitch[9] (float bits)},
     // 4 u64 seed, 5 f32[13] camera {pos, gaze, up, fovXY, nearFar}, 6 vertexOffsets, 7 triOffsets, 8 positions,
     // 9 normals, 10 indices, 11 batchMaterial, 12 batchLight, 13 albedo, 14 radiance, 15 batchTransforms (may be empty), 16 batchInstanceOf (may be empty),
-    // 17 textureInfo (6 u32 per texture; may be empty), 18 textureBytes, 19 materialTexture, 20 uvs (may be empty), 21 materialKind (may be empty)
+    // 17 textureInfo (6 u32 per texture; may be empty), 18 textureBytes, 19 materialTexture, 20 uvs (may be empty), 21 materialKind (may be empty), 22 lightTwoSided (may be empty)
     const uint32_t* u = static_cast<const uint32_t*>(P(3));
     const float* cam = static_cast<const float*>(P(5));
     DriverScene sc{};
@@ -72,6 +72,7 @@ int main(int argc, char** argv)
     sc.textureCount = uint32_t(bytes[17] / 24); sc.textureInfo = static_cast<const uint32_t*>(P(17));
     sc.textureBytes = static_cast<const uint8_t*>(P(18)); sc.materialTexture = static_cast<const int32_t*>(P(19));
     sc.uvs = static_cast<const float*>(P(20)); sc.materialKind = static_cast<const uint8_t*>(P(21));
+    sc.lightTwoSided = static_cast<const uint8_t*>(P(22));
     std::memcpy(sc.camPos, cam, 12); std::memcpy(sc.camGaze, cam + 3, 12); std::memcpy(sc.camUp, cam + 6, 12);
     std::memcpy(sc.fovXY, cam + 9, 8); std::memcpy(sc.nearFar, cam + 11, 8);
     DriverRender rd{};

@@ -62,6 +62,8 @@ struct DriverScene
     const float*    uvs;
     // optional: per material 0 = (Mt)Lambert, 1 = (Mt)Reflect (its albedo entry is unused); NULL = all Lambert
     const uint8_t*  materialKind;
+    // optional: per light the isTwoSided attribute of (L)Prim(P)Triangle; NULL = one-sided
+    const uint8_t*  lightTwoSided;
 };
 
 struct DriverRender
@@ -339,6 +341,7 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
                 {
                     TransientData d(std::in_place_type_t<bool>{}, sc->lightCount);
                     std::vector<uint8_t> f(sc->lightCount, 0);
+                    if(sc->lightTwoSided) for(uint32_t l = 0; l < sc->lightCount; l++) f[l] = sc->lightTwoSided[l] ? 1 : 0;
                     d.Push(Span<const bool>(reinterpret_cast<const bool*>(f.data()), sc->lightCount));
                     tracer->PushLightAttribute(lg, range, a, std::move(d));
                 }

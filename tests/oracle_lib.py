@@ -166,7 +166,7 @@ class _DriverScene(C.Structure):
                 ("fovXY", C.c_float * 2), ("nearFar", C.c_float * 2), ("batchTransforms", C.c_void_p),
                 ("batchInstanceOf", C.c_void_p),
                 ("textureCount", C.c_uint32), ("textureInfo", C.c_void_p), ("textureBytes", C.c_void_p),
-                ("materialTexture", C.c_void_p), ("uvs", C.c_void_p), ("materialKind", C.c_void_p)]
+                ("materialTexture", C.c_void_p), ("uvs", C.c_void_p), ("materialKind", C.c_void_p), ("lightTwoSided", C.c_void_p)]
 
 
 class _DriverRender(C.Structure):
@@ -217,7 +217,7 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
                   accel_mode=1, threads=0, parallel_hint=0, near_far=(0.01, 1000.0), driver_flavour="",
                   batch_transforms=None, sampler="Independent", host_exe=False, instance_of=None,
                   textures=None, material_texture=None, region=None, material_kind=None,
-                  latency=False, burst_size=1, cam_switch=None):
+                  latency=False, burst_size=1, cam_switch=None, light_two_sided=False):
     """Renders through TracerI. `light_material`: material id whose batch is the prim-backed light.
     batch_transforms: optional [batch, 3, 4] local->world matrices ((T)Single per batch; positions local).
     textures: list of dict(data=[h, w, 4] float32 / uint8 (RGBA), interp=, edge=); material_texture: per material id
@@ -242,6 +242,7 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
     sampler_id = {"Independent": 0, "ZSobol": 1, "Sobol": 2}[sampler]
     io = None if instance_of is None else np.ascontiguousarray(instance_of, np.int32)
     tinfo = tbytes = mtex = None
+    lts = np.array([1 if light_two_sided else 0], np.uint8)
     mkind = None if material_kind is None else np.ascontiguousarray(np.asarray(material_kind, np.uint8)[lambert])
     uvs = None if batched.get("uvs") is None else np.ascontiguousarray(batched["uvs"], np.float32)
     if textures:
@@ -276,7 +277,7 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
                 b"" if bt is None else bt.tobytes(), b"" if io is None else io.tobytes(),
                 b"" if tinfo is None else tinfo.tobytes(), b"" if tbytes is None else tbytes.tobytes(),
                 b"" if mtex is None else mtex.tobytes(), b"" if uvs is None else uvs.tobytes(),
-                b"" if mkind is None else mkind.tobytes()]
+                b"" if mkind is None else mkind.tobytes(), lts.tobytes() if light_two_sided else b""]
         with tempfile.TemporaryDirectory() as td:
             with open(os.path.join(td, "in.blob"), "wb") as f:
                 f.write(np.uint64(len(secs)).tobytes())
@@ -316,6 +317,8 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
         keep.append(uvs); sc.uvs = uvs.ctypes.data
     if mkind is not None:
         keep.append(mkind); sc.materialKind = mkind.ctypes.data
+    if light_two_sided:
+        keep.append(lts); sc.lightTwoSided = lts.ctypes.data
     rd = _DriverRender(renderer.encode(), width, height, spp, sample_mode.encode(), (C.c_uint32 * 2)(*rr_range), seed,
                        accel_mode, parallel_hint, threads, sampler_id, (C.c_uint32 * 4)(*(region or (0, 0, 0, 0))),
                        1 if latency else 0, burst_size, cam_switch[0] if cam_switch else 0,
@@ -390,7 +393,7 @@ def oracle_texture_sample(texture, uv):
 def oracle_render(positions, indices, tri_material, albedo, radiance, camera, width, height, spp,
                   sample_mode=2, rr_range=(2, 20), seed=0, near_far=(0.01, 1000.0), threads=None,
                   spectral_data=None, wavelength_mode=2, textures=None, albedo_texture=None, vertex_uvs=None,
-                  material_type=None):
+                  material_type=None, light_two_sided=None):
     """tri_material: per triangle, >= 0 Lambert material index, -1 - k for light k. Returns image[h,w,3]
     (row 0 = bottom) resolved as sum radiance / sum weight. spectral_data (mray_b200.spectral.load())
     switches to the hero-wavelength spectral estimator."""
@@ -406,6 +409,9 @@ def oracle_render(positions, indices, tri_material, albedo, radiance, camera, wi
     s.pos, s.idx, s.nTris = positions.ctypes.data, indices.ctypes.data, indices.shape[0]
     s.nodes, s.boxes, s.triMaterial = b.nodes.ctypes.data, b.boxes.ctypes.data, tm.ctypes.data
     s.albedo, s.radiance, s.twoSided = alb.ctypes.data, rad.ctypes.data, None
+    if light_two_sided is not None:       # per light: (L)Prim's isTwoSided
+        ts = np.ascontiguousarray(light_two_sided, np.uint8)
+        s.twoSided = ts.ctypes.data
     s.lightTris, s.nLightTris = lt.ctypes.data, lt.shape[0]
     s.camPos = (C.c_float * 3)(*camera["eye"]); s.camGaze = (C.c_float * 3)(*camera["gaze"]); s.camUp = (C.c_float * 3)(*camera["up"])
     fy = float(np.deg2rad(camera["fov_y_deg"])); fx = float(2 * np.arctan(np.tan(fy / 2) * width / height))

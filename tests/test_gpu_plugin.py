@@ -149,3 +149,17 @@ def test_low_discrepancy_sampler_against_reference_images(sampler, name):
     assert np.allclose(ref_ld.mean(axis=(0, 1)), conv.mean(axis=(0, 1)), rtol=0.01)
     e_ours, e_ref = rel(img, conv), rel(ref_ld, conv)
     assert e_ours <= 1.2 * e_ref, (e_ours, e_ref)
+
+
+@pytest.mark.skipif(not (os.path.exists(PLUGIN) and O.driver_available()), reason="plugin / driver were not prebuilt")
+def test_two_sided_light_through_tracer_interface_against_reference():
+    """PushLightAttribute(isTwoSided = true) through TracerI against the reference's render of the same calls."""
+    ref = np.load(os.path.join(ROOT, "tests", "golden", "render_cornell64_twosided_spp16384.npz"))["img"].astype(np.float32)
+    bm = lambda x, k: x.reshape(x.shape[0] // k, k, x.shape[1] // k, k, 3).mean(axis=(1, 3))
+    c = scenes.cornell_box()
+    b = O.batched_scene(c["positions"], c["indices"], c["material"])
+    img, w, st = O.driver_render(PLUGIN, b, c["albedo"], 3, c["radiance"], c["camera"], 64, 64, 32768, seed=17, light_two_sided=True)
+    assert np.allclose(w, 32768, rtol=1e-3)
+    # a noisy scene (the ceiling 2 cm above the emitter): 8x8 block means
+    assert float(np.mean((bm(img, 8) - bm(ref, 8)) ** 2 / (bm(ref, 8) ** 2 + 1e-2))) <= 1e-3
+    assert np.allclose(img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=5e-3)
