@@ -61,7 +61,8 @@ typedef struct mrb_meta_hit { float a, b; } mrb_meta_hit;
 
 /* ---- library / context ------------------------------------------------------------------ */
 
-/* ABI version of this header (major<<16 | minor). */
+/* ABI version of this header (major<<16 | minor); the descriptor struct layouts are part of it. */
+#define MRB_ABI_VERSION ((0u << 16) | 2u)
 MRB_API uint32_t mrb_abi_version(void);
 
 /* Replaces GPUSystem + GPUQueue ownership inside TracerBase (Device/CUDA/GPUSystemCUDA.cpp:L249-405:

@@ -88,7 +88,7 @@ static mrb_status Fail(mrb::Context& c, mrb_status s, const char* msg) { c.error
 extern "C"
 {
 
-uint32_t mrb_abi_version(void) { return (0u << 16) | 1u; }
+uint32_t mrb_abi_version(void) { return MRB_ABI_VERSION; }   // 2: mrb_instance_desc / mrb_render_desc grew (instance keys, textures, regions, material types)
 
 mrb_status mrb_context_create(int device, mrb_context* out)
 {

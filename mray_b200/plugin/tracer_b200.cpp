@@ -134,6 +134,8 @@ class TracerB200 final : public TracerI
     public:
     explicit TracerB200(const TracerParameters& p) : params(p)
     {
+        if(mrb_abi_version() != MRB_ABI_VERSION)   // descriptor layouts must match the header this object was compiled against
+            throw MRayError("mray_b200: libmray_b200.so has ABI {:#x}, the plugin was built for {:#x}", mrb_abi_version(), uint32_t(MRB_ABI_VERSION));
         mrb_status s = mrb_context_create(0, &ctx);
         if(s != MRB_OK) throw MRayError("mray_b200: {}", mrb_last_error(nullptr)); // no CPU fallback
         // implicit groups, id 0 of every kind (Core/TracerI.h:L99-124)

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(capi.LIB_PATH)
     for s in header_symbols():
         assert hasattr(lib, s), f"{s} not exported"
-    assert lib.mrb_abi_version() == 1
+    assert lib.mrb_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_device():
