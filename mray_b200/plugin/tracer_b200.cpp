@@ -3,11 +3,14 @@
 // (TracerDLL/EntryPoint.h:L15-18). Host-side C++20, compiled against the reference's own headers so
 // that the vtable order and the layouts of TransientData / StaticVector / Optional match.
 //
-// Scope of round 1 (everything else throws MRayError, as the reference does for unknown types):
-//   (P)Triangle  (Mt)Lambert [constant albedo]  (L)Prim(P)Triangle [constant radiance]  (L)Null
-//   (T)Identity  (C)Pinhole  (Md)Vacuum  (R)PathTracerRGB   — i.e. BASELINE config 1 / 3-style scenes.
-// All identity-transform surfaces are flattened into ONE accelerator (one prim range per
-// prim-batch / material pair); ids are Key-typed bit casts like the reference's (Tracer/Key.h).
+// Scope (everything else throws MRayError, as the reference does for unknown types):
+//   (P)Triangle  (Mt)Lambert [constant or textured albedo]  (Mt)Reflect  (L)Prim(P)Triangle [constant radiance,
+//   isTwoSided]  (L)Null  (T)Identity  (T)Single  (C)Pinhole  (Md)Vacuum  (R)PathTracerRGB  (R)PathTracerSpectral,
+//   single-level RGBA textures, samplerType Independent / Sobol / ZSobol, render regions, Throughput / Latency modes,
+//   SetCameraTransform — i.e. BASELINE config 1 / 3 / 4-style scenes.
+// Identity-transform surfaces are flattened into ONE accelerator (one prim range per prim-batch / material pair);
+// scenes with (T)Single transforms become two-level scenes whose instances share accelerators where their prim
+// batches and cull flags agree; ids are Key-typed bit casts like the reference's (Tracer/Key.h).
 #include "Core/TracerI.h"
 #include "Core/Error.h"
 #include "Core/TimelineSemaphore.h"
@@ -628,7 +631,7 @@ class TracerB200 final : public TracerI
         // TracerBase::CommitSurfaces (Tracer/TracerBase.cpp:L1529-1674) + BaseAccelerator::Construct:
         // surfaces sharing a transform become the prim ranges of one accelerator; (T)Identity-only scenes
         // are a single accelerator, anything else a two-level scene with one instance per transform.
-        if(Raw(boundary.lightId) != 0) throw MRayError("round 1: the boundary light must be (L)Null");
+        if(Raw(boundary.lightId) != 0) throw MRayError("boundary lights other than (L)Null are not supported yet");
         struct Group { uint32_t transformId; std::vector<uint32_t> ranges, lmKeys; std::vector<uint8_t> cull; };
         std::vector<Group> groups;
         auto GroupOf = [&](TransformId t) -> Group&
@@ -643,7 +646,7 @@ class TracerB200 final : public TracerI
         int32_t pgUsed = -1;
         auto UsePrimGroup = [&](uint32_t g)
         {
-            if(pgUsed >= 0 && uint32_t(pgUsed) != g) throw MRayError("round 1: one triangle primitive group per scene");
+            if(pgUsed >= 0 && uint32_t(pgUsed) != g) throw MRayError("more than one triangle primitive group per scene is not supported yet");
             pgUsed = int32_t(g);
         };
         // material table: flat index = running index over (group, id) pairs in first-use order
