@@ -62,7 +62,7 @@ typedef struct mrb_meta_hit { float a, b; } mrb_meta_hit;
 /* ---- library / context ------------------------------------------------------------------ */
 
 /* ABI version of this header (major<<16 | minor); the descriptor struct layouts are part of it. */
-#define MRB_ABI_VERSION ((0u << 16) | 2u)
+#define MRB_ABI_VERSION ((0u << 16) | 3u)
 MRB_API uint32_t mrb_abi_version(void);
 
 /* Replaces GPUSystem + GPUQueue ownership inside TracerBase (Device/CUDA/GPUSystemCUDA.cpp:L249-405:
@@ -88,6 +88,14 @@ MRB_API uint64_t   mrb_context_launch_count(mrb_context ctx);
  *     reference's box tests on the candidates' ancestor chains). */
 MRB_API mrb_status mrb_context_last_fallback_count(mrb_context ctx, uint32_t* out);
 MRB_API const char* mrb_last_error(mrb_context ctx); /* ctx may be NULL: last create error */
+/* Sampled kernel timing for measurement (bench.py's roofline): with profiling on, every iterationStride-th wavefront
+ * iteration of a renderer records CUDA-event pairs on the context stream around its kernels; mrb_context_get_profile
+ * synchronises and returns the accumulated times / sample counts per kind:
+ * [0] wide closest-hit traversal kernel, [1] shading kernel, [2] wide any-hit traversal kernel, [3] finish + reload kernel,
+ * [4] the exact-resolution tail of a cast (KResolveExact + KTraceBinary). The reference's counterpart is its NVTX ranges. */
+typedef struct mrb_kernel_profile { double ms[5]; uint64_t samples[5]; } mrb_kernel_profile;
+MRB_API mrb_status mrb_context_set_profiling(mrb_context ctx, int enabled, uint32_t iterationStride);
+MRB_API mrb_status mrb_context_get_profile(mrb_context ctx, mrb_kernel_profile* out);
 
 /* ---- accelerator build ------------------------------------------------------------------ */
 
@@ -324,9 +332,11 @@ typedef enum mrb_sample_mode
  * camera surface, the render attributes ("totalSPP", "sampleMode", "rrRange" — L1384-1400) and
  * TracerParameters.seed / filmFilter. lightOrMatKey layout (Tracer/TracerTypes.h:L171-175):
  * bit 31 = light flag, bits 0..20 = index into albedo[] (material) or lightRadiance[] (light).
- * Round 1: (R)PathTracerRGB, (Mt)Lambert with constant albedo, (L)Prim(P)Triangle with constant
- * radiance, (L)Null boundary, (C)Pinhole, Gaussian film filter, Independent (PCG32) sampler. */
+ * Scope: (R)PathTracerRGB / Spectral, (Mt)Lambert (constant or textured albedo), (Mt)Reflect, (L)Prim(P)Triangle with
+ * constant radiance, (L)Null boundary, (C)Pinhole, the four film filters, Independent / Sobol / ZSobol samplers. */
 typedef enum mrb_material_type { MRB_MATERIAL_LAMBERT = 0, MRB_MATERIAL_REFLECT = 1 } mrb_material_type;
+/* FilterType::E (Core/TracerEnums.h:L162-173) */
+typedef enum mrb_film_filter { MRB_FILTER_BOX = 0, MRB_FILTER_TENT = 1, MRB_FILTER_GAUSSIAN = 2, MRB_FILTER_MITCHELL_NETRAVALI = 3 } mrb_film_filter;
 
 /* One 2-D texture of the renderer (first slice): what TracerI::CreateTexture2D +
  * PushTextureData + CommitTextures hand to TextureMemory (Tracer/TextureMemory.cpp), restricted to ONE mip
@@ -362,7 +372,7 @@ typedef struct mrb_render_desc
     uint32_t        totalSPP;
     uint32_t        sampleMode;      /* mrb_sample_mode */
     uint32_t        rrRange[2];
-    float           filmFilterRadius;/* Gaussian, TracerParameters.filmFilter (default 1) */
+    float           filmFilterRadius;/* TracerParameters.filmFilter.radius (default 1); the type is filmFilterType below */
     uint64_t        seed;            /* TracerParameters.seed */
     uint32_t        maxPathCount;    /* paths in flight; 0 = width*height (parallelizationHint tile) */
     uint32_t        partitionRays;   /* 1 = sort live rays by (work batch, material) key before shading
@@ -406,6 +416,16 @@ typedef struct mrb_render_desc
      * (Tracer/MaterialsDefault.hpp:L132-215) is a perfect mirror: no NEE shadow ray, no Russian roulette, the next ray is
      * a SPECULAR_RAY (PathTracerRendererShaders.h:L245-262,L415-424); its `albedo` entry is ignored. */
     const uint8_t*  materialType;
+    /* TracerParameters.filmFilter.type (FilterType::E, Core/TracerEnums.h:L162-173; Tracer/Filters.h): the sampler of the
+     * camera sample's sub-pixel offset and its film weight Evaluate / pdf. filmFilterRadius above is its radius. */
+    uint32_t        filmFilterType;  /* mrb_film_filter; 0 = Box — set MRB_FILTER_GAUSSIAN for the reference's default */
+    /* Sample-range sharding: this renderer produces samples [sampleOffset, sampleOffset + totalSPP) of
+     * every pixel. Random numbers are a function of (seed, full-image pixel, sample index) only, so the ranges of several
+     * renderers (GPUs, passes, tiles) add up to exactly the image one renderer would produce with jobSPP samples (up to
+     * the order of the film's float additions). jobSPP: sample budget of the whole job (ZSobol's initialMaxSPP);
+     * 0 = sampleOffset + totalSPP. */
+    uint32_t        sampleOffset;
+    uint32_t        jobSPP;
 } mrb_render_desc;
 
 typedef struct mrb_render_stats
@@ -413,7 +433,9 @@ typedef struct mrb_render_stats
     uint64_t pathsStarted, pathsCompleted;    /* camera paths */
     uint64_t closestRays, shadowRays;         /* rays cast (the reference only counts paths) */
     uint64_t iterations;
-    uint32_t finished;                        /* 1 when totalSPP*pixels paths have completed (triggerSave) */
+    uint64_t neeSamples;                      /* NEE light samples taken = the shadow rays the REFERENCE casts (it also
+                                               * traces samples whose estimate is exactly zero; shadowRays omits those) */
+    uint32_t finished;                        /* 1 when every pass begun so far has completed (triggerSave at the last one) */
 } mrb_render_stats;
 
 /* StartRender */
@@ -430,6 +452,42 @@ MRB_API mrb_status mrb_renderer_iterate(mrb_context ctx, mrb_renderer r, uint32_
 MRB_API mrb_status mrb_renderer_set_spp_limit(mrb_context ctx, mrb_renderer r, uint32_t sppLimit);
 /* Synchronises and reads the counters. */
 MRB_API mrb_status mrb_renderer_get_stats(mrb_context ctx, mrb_renderer r, mrb_render_stats* out);
+/* Begins the pass "samples [sampleStart, sampleStart + sampleCount) of every pixel of the region regionMin .. regionMin +
+ * regionSize" — one step of the tile / burst loop of PathTracerRendererT::DoLatencyRender
+ * (TracerDLL/PathTracerRenderer.cu:L1078-1160) with ImageTiler::NextTile (Tracer/RenderImage.cpp:L20-136). The region must
+ * fit the width x height the renderer was created with (its film) and the full image. Asynchronous; the previous pass
+ * must have finished (mrb_renderer_run_pass / get_stats.finished). The film keeps accumulating: hand it over (or read it
+ * with clear) before a pass with a different region. */
+MRB_API mrb_status mrb_renderer_begin_pass(mrb_context ctx, mrb_renderer r, const uint32_t regionMin[2], const uint32_t regionSize[2],
+                                           uint32_t sampleStart, uint32_t sampleCount);
+/* DoRenderWork until the current pass has finished: `chunk` wavefront iterations (0 = 4) stay queued while the path
+ * counters of the previous chunk are polled from pinned memory, so the device never idles on the host
+ * (the reference synchronises after every iteration to read its dead-path count). Returns the final counters. */
+MRB_API mrb_status mrb_renderer_run_pass(mrb_context ctx, mrb_renderer r, uint32_t chunk, mrb_render_stats* out);
+/* Non-blocking counters for callers that iterate once per call (throughput mode, one bounce per DoRenderWork): returns
+ * the latest snapshot that has landed in pinned host memory (zeros before the first one) and queues the next snapshot
+ * behind the work issued so far — `finished` shows up an iteration or two after the last path died, without ever
+ * draining the stream. */
+MRB_API mrb_status mrb_renderer_poll_stats(mrb_context ctx, mrb_renderer r, mrb_render_stats* out);
+/* RenderImage::TransferToHost (Tracer/RenderImage.cpp:L163-219): hands the film accumulated since the last hand-off to
+ * hostDst (4 planar planes of the current region; pinned memory — mrb_host_alloc — makes the copy asynchronous) on a
+ * copy stream, clears it there and calls onComplete(user) from a CUDA host callback once the data has landed (the
+ * reference releases its timeline semaphore this way); rendering continues immediately into a second film buffer.
+ * onComplete may be NULL; it must not call back into this library. */
+typedef void (*mrb_host_fn)(void* user);
+MRB_API mrb_status mrb_renderer_film_handoff(mrb_context ctx, mrb_renderer r, float* hostDst, mrb_host_fn onComplete, void* user);
+/* Multi-GPU film reduction inside one process: adds the films of `peers` — renderers with the same
+ * region that live on OTHER devices (peerCtx[k] is the context peers[k] was created on) — to r's film and clears them,
+ * in one kernel on r's device that reads the peers' HBM over NVLink (peer access is enabled on demand). Stream-ordered on
+ * both sides: the peers' pending iterations are joined before the read, their next ones wait for the clear. */
+MRB_API mrb_status mrb_renderer_reduce_peers(mrb_context ctx, mrb_renderer r, const mrb_context* peerCtx, const mrb_renderer* peers,
+                                             uint32_t peerCount);
+/* Page-locked host memory for film staging (the reference's RenderImage staging memory, Tracer/RenderImage.cpp:L233-282). */
+MRB_API mrb_status mrb_host_alloc(mrb_context ctx, size_t bytes, void** out);
+MRB_API void       mrb_host_free(mrb_context ctx, void* ptr);
+/* Parity tap: the film filter on its own (Tests/Tracer/T_Filters.cu). Host pointers: xi[count*2] ->
+ * out[count*4] = {offset x, offset y, pdf of Sample(), Evaluate(offset)}. */
+MRB_API mrb_status mrb_filter_sample(mrb_context ctx, uint32_t filterType, float radius, const float* xi, uint32_t count, float* out);
 /* The film the reference hands over as RenderImageSection (Common/RenderImageStructs.h:L22-37):
  * 4 planar fp32 planes R,G,B,weight of width*height (row 0 = bottom), radiance sums and filter-weight
  * sums accumulated since the last clear. Copies to `out` (host or device); `clear` != 0 zeroes the

@@ -78,7 +78,8 @@ class RenderDesc(C.Structure):
                 ("samplerType", C.c_uint32), ("sobolMatrices", C.c_void_p),
                 ("textureCount", C.c_uint32), ("textures", C.c_void_p), ("albedoTexture", C.c_void_p),
                 ("vertexUVs", C.c_void_p), ("instanceVertexUVs", C.POINTER(C.c_void_p)),
-                ("fullResolution", C.c_uint32 * 2), ("regionMin", C.c_uint32 * 2), ("materialType", C.c_void_p)]
+                ("fullResolution", C.c_uint32 * 2), ("regionMin", C.c_uint32 * 2), ("materialType", C.c_void_p),
+                ("filmFilterType", C.c_uint32), ("sampleOffset", C.c_uint32), ("jobSPP", C.c_uint32)]
 
 
 class TextureDesc(C.Structure):
@@ -92,10 +93,19 @@ TEX_EDGE = {"Wrap": 0, "Clamp": 1, "Mirror": 2}
 
 class RenderStats(C.Structure):
     _fields_ = [("pathsStarted", C.c_uint64), ("pathsCompleted", C.c_uint64), ("closestRays", C.c_uint64),
-                ("shadowRays", C.c_uint64), ("iterations", C.c_uint64), ("finished", C.c_uint32)]
+                ("shadowRays", C.c_uint64), ("iterations", C.c_uint64), ("neeSamples", C.c_uint64), ("finished", C.c_uint32)]
 
 
+class KernelProfile(C.Structure):
+    _fields_ = [("ms", C.c_double * 5), ("samples", C.c_uint64 * 5)]
+
+
+PROFILE_KINDS = ["trace_closest", "shade", "trace_any", "finish_reload", "trace_tail"]
 SAMPLE_MODES = {"Pure": 0, "WithNextEventEstimation": 1, "WithNEEAndMIS": 2}
+FILM_FILTERS = {"Box": 0, "Tent": 1, "Gaussian": 2, "Mitchell-Netravali": 3}   # FilterType::E (Core/TracerEnums.h:L162-173)
+HOST_FN = C.CFUNCTYPE(None, C.c_void_p)
+# the descriptor mirrors above are written for this ABI (include/mray_b200.h: MRB_ABI_VERSION)
+MRB_ABI_VERSION = (0 << 16) | 3
 
 # every symbol include/mray_b200.h declares (tests/test_capi_symbols.py checks the header against this)
 _PROTOTYPES = {
@@ -109,6 +119,8 @@ _PROTOTYPES = {
     "mrb_context_launch_count": (C.c_uint64, [C.c_void_p]),
     "mrb_context_last_fallback_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "mrb_last_error": (C.c_char_p, [C.c_void_p]),
+    "mrb_context_set_profiling": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32]),
+    "mrb_context_get_profile": (C.c_int, [C.c_void_p, C.POINTER(KernelProfile)]),
     "mrb_accel_build": (C.c_int, [C.c_void_p, C.POINTER(AccelDesc), C.POINTER(C.c_void_p)]),
     "mrb_accel_destroy": (None, [C.c_void_p, C.c_void_p]),
     "mrb_accel_get_info": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(AccelInfo)]),
@@ -139,6 +151,14 @@ _PROTOTYPES = {
     "mrb_renderer_read_film": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "mrb_renderer_film_device_ptr": (C.c_void_p, [C.c_void_p]),
     "mrb_renderer_set_spp_limit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "mrb_renderer_begin_pass": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32]),
+    "mrb_renderer_run_pass": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(RenderStats)]),
+    "mrb_renderer_poll_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(RenderStats)]),
+    "mrb_renderer_film_handoff": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mrb_renderer_reduce_peers": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint32]),
+    "mrb_host_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "mrb_host_free": (None, [C.c_void_p, C.c_void_p]),
+    "mrb_filter_sample": (C.c_int, [C.c_void_p, C.c_uint32, C.c_float, C.c_void_p, C.c_uint32, C.c_void_p]),
     "mrb_texture_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "mrb_multi_partition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                       C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
@@ -174,6 +194,9 @@ def load_library():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
+        got = int(lib.mrb_abi_version())
+        if got != MRB_ABI_VERSION:   # a stale prebuilt .so would be driven with mismatched descriptor layouts
+            raise MrbError(-5, f"{LIB_PATH} has ABI {got:#x}, this module was written for {MRB_ABI_VERSION:#x}: rebuild it")
         _lib = lib
     return _lib
 
@@ -241,6 +264,16 @@ class Context:
         out = (C.c_uint32 * 4)()
         self.check(self.lib.mrb_context_last_fallback_count(self.handle, out))
         return tuple(int(x) for x in out)
+
+    def set_profiling(self, enabled: bool, iteration_stride: int = 16):
+        """Sampled CUDA-event timing of the renderer's kernels (mrb_context_set_profiling)."""
+        self.check(self.lib.mrb_context_set_profiling(self.handle, 1 if enabled else 0, iteration_stride))
+
+    def get_profile(self):
+        """{kind: (accumulated ms, samples)} since profiling was switched on (synchronises)."""
+        p = KernelProfile()
+        self.check(self.lib.mrb_context_get_profile(self.handle, C.byref(p)))
+        return {k: (float(p.ms[i]), int(p.samples[i])) for i, k in enumerate(PROFILE_KINDS)}
 
     @property
     def used_device_memory(self) -> int:
@@ -445,7 +478,8 @@ class Renderer:
                  vertex_normals=None, light_two_sided=None, film_filter_radius=1.0, near_far=(0.01, 1000.0),
                  max_path_count=0, partition_rays=False, instance_vertex_normals=None, spectrum=None, sampler="Independent",
                  textures=None, albedo_texture=None, vertex_uvs=None, instance_vertex_uvs=None,
-                 full_resolution=None, region_min=(0, 0), material_type=None):
+                 full_resolution=None, region_min=(0, 0), material_type=None, film_filter="Gaussian",
+                 sample_offset=0, job_spp=0):
         """`accel` is an Accelerator, or a Scene (two-level; vertex_count / triangle_count / vertex_normals
         are then ignored and instance_vertex_normals may hold one array or None per instance).
         textures: list of dict(data=[h, w, 3|4] float32 or uint8 array, interp="Linear"|"Nearest",
@@ -500,6 +534,8 @@ class Renderer:
         d.sampleMode = SAMPLE_MODES[sample_mode] if isinstance(sample_mode, str) else int(sample_mode)
         d.rrRange = (C.c_uint32 * 2)(*rr_range)
         d.filmFilterRadius = film_filter_radius
+        d.filmFilterType = FILM_FILTERS[film_filter] if isinstance(film_filter, str) else int(film_filter)
+        d.sampleOffset, d.jobSPP = sample_offset, job_spp   # samples [sample_offset, sample_offset + total_spp) of a job_spp job
         d.seed = seed
         d.maxPathCount = max_path_count
         d.partitionRays = 1 if partition_rays else 0
@@ -549,6 +585,38 @@ class Renderer:
         self.ctx.check(self.ctx.lib.mrb_renderer_get_stats(self.ctx.handle, self.handle, C.byref(st)))
         return st
 
+    def begin_pass(self, region_min, region_size, sample_start, sample_count):
+        """Samples [sample_start, sample_start + sample_count) of every pixel of the region (see mrb_renderer_begin_pass)."""
+        rm = (C.c_uint32 * 2)(*region_min); rs = (C.c_uint32 * 2)(*region_size)
+        self.ctx.check(self.ctx.lib.mrb_renderer_begin_pass(self.ctx.handle, self.handle, rm, rs, sample_start, sample_count))
+        self.width, self.height = int(region_size[0]), int(region_size[1])
+
+    def run_pass(self, chunk=4) -> RenderStats:
+        """DoRenderWork until the current pass has finished (pipelined polling, no stream drain between polls)."""
+        st = RenderStats()
+        self.ctx.check(self.ctx.lib.mrb_renderer_run_pass(self.ctx.handle, self.handle, chunk, C.byref(st)))
+        return st
+
+    def poll_stats(self) -> RenderStats:
+        """Non-blocking: the latest counter snapshot that has landed on the host (see mrb_renderer_poll_stats)."""
+        st = RenderStats()
+        self.ctx.check(self.ctx.lib.mrb_renderer_poll_stats(self.ctx.handle, self.handle, C.byref(st)))
+        return st
+
+    def film_handoff(self, host_dst, on_complete=None):
+        """Asynchronous film hand-off into `host_dst` (a pinned numpy / torch host array of 4 x h x w floats)."""
+        cb = HOST_FN(on_complete) if on_complete is not None else None
+        if cb is not None:
+            self._keep.append(cb)
+        self.ctx.check(self.ctx.lib.mrb_renderer_film_handoff(self.ctx.handle, self.handle, _ptr(host_dst),
+                                                              C.cast(cb, C.c_void_p) if cb is not None else None, None))
+
+    def reduce_peers(self, peers):
+        """Adds (and clears) the films of `peers` — Renderers of other devices — into this one's, over peer memory."""
+        n = len(peers)
+        pc = (C.c_void_p * n)(*[p.ctx.handle for p in peers]); pr = (C.c_void_p * n)(*[p.handle for p in peers])
+        self.ctx.check(self.ctx.lib.mrb_renderer_reduce_peers(self.ctx.handle, self.handle, pc, pr, n))
+
     def read_film(self, clear=False):
         """(rgb_sum[h,w,3], weight[h,w]) host arrays, row 0 = bottom (RenderImageSection planes)."""
         out = np.zeros((4, self.height, self.width), np.float32)
@@ -562,13 +630,7 @@ class Renderer:
     def render(self, batch=8, max_iterations=1_000_000):
         """Runs DoRenderWork until totalSPP*pixels paths have completed; returns the resolved image
         (sum radiance / sum weight, like MRay/RunCommand.cpp:L293-345) and the final stats."""
-        it = 0
-        while it < max_iterations:
-            self.iterate(batch)
-            it += batch
-            st = self.stats()
-            if st.finished:
-                break
+        st = self.run_pass(batch)
         rgb, w = self.read_film()
         return rgb / np.maximum(w, 1e-20)[..., None], st
 
@@ -665,4 +727,13 @@ def texture_sample(ctx: Context, texture, uv):
     uv = np.ascontiguousarray(uv, np.float32)
     out = np.zeros((uv.shape[0], 3), np.float32)
     ctx.check(ctx.lib.mrb_texture_sample(ctx.handle, C.byref(t), uv.ctypes.data, uv.shape[0], out.ctypes.data))
+    return out
+
+
+def filter_sample(ctx: Context, film_filter, radius, xi):
+    """The film filter on its own (mrb_filter_sample): xi [n, 2] -> [n, 4] = (offset x, offset y, pdf, Evaluate(offset))."""
+    xi = np.ascontiguousarray(xi, np.float32).reshape(-1, 2)
+    out = np.zeros((xi.shape[0], 4), np.float32)
+    t = FILM_FILTERS[film_filter] if isinstance(film_filter, str) else int(film_filter)
+    ctx.check(ctx.lib.mrb_filter_sample(ctx.handle, t, float(radius), xi.ctypes.data, xi.shape[0], out.ctypes.data))
     return out

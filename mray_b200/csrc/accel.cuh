@@ -6,6 +6,9 @@
 namespace mrb
 {
 
+// entries of the per-thread stack of the wide traversal kernels (trace.cu); the builders refuse trees that could overflow it
+static constexpr uint32_t WIDE_STACK_ENTRIES = 64;
+
 // Reference layouts (Tracer/AcceleratorLBVH.h:L62-77)
 struct LBVHNode { uint32_t left, right, parent; };
 struct LBVHBox  { float min[3], max[3]; };

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <new>
 #include <stdexcept>
+#include <algorithm>
 
 namespace mrb
 {
@@ -29,6 +30,13 @@ void RendererReadFilm(Context& ctx, mrb_renderer_t& r, float* out, bool device, 
 float* RendererFilmPtr(mrb_renderer_t& r);
 void RendererSetSppLimit(Context& ctx, mrb_renderer_t& r, uint32_t sppLimit);
 void TextureSampleHost(Context& ctx, const mrb_texture_desc& td, const float* uv, uint32_t n, float* rgbOut);
+void RendererBeginPass(Context& ctx, mrb_renderer_t& r, const uint32_t regionMin[2], const uint32_t regionSize[2],
+                       uint32_t sampleStart, uint32_t sampleCount);
+void RendererRunPass(Context& ctx, mrb_renderer_t& r, uint32_t chunk, mrb_render_stats& out);
+void RendererPollStats(Context& ctx, mrb_renderer_t& r, mrb_render_stats& out);
+void RendererFilmHandoff(Context& ctx, mrb_renderer_t& r, float* hostDst, void (*onComplete)(void*), void* user);
+void RendererReducePeers(Context& ctx, mrb_renderer_t& r, Context* const* peerCtx, mrb_renderer_t* const* peers, uint32_t n);
+void FilterSampleHost(Context& ctx, uint32_t type, float radius, const float* xi, uint32_t n, float* out);
 }
 
 namespace mrb
@@ -88,7 +96,7 @@ static mrb_status Fail(mrb::Context& c, mrb_status s, const char* msg) { c.error
 extern "C"
 {
 
-uint32_t mrb_abi_version(void) { return MRB_ABI_VERSION; }   // 2: mrb_instance_desc / mrb_render_desc grew (instance keys, textures, regions, material types)
+uint32_t mrb_abi_version(void) { return MRB_ABI_VERSION; }   // 3: film filter type, sample offsets, passes, NEE sample counter
 
 mrb_status mrb_context_create(int device, mrb_context* out)
 {
@@ -143,6 +151,7 @@ void mrb_context_destroy(mrb_context ctx)
         if(ctx->c.evIn[k]) cudaEventDestroy(ctx->c.evIn[k]);
         if(ctx->c.evDone[k]) cudaEventDestroy(ctx->c.evDone[k]);
     }
+    for(int k = 0; k < ctx->c.prof.created; k++) { cudaEventDestroy(ctx->c.prof.ev[k][0]); cudaEventDestroy(ctx->c.prof.ev[k][1]); }
     if(ctx->c.ev0) cudaEventDestroy(ctx->c.ev0);
     if(ctx->c.ev1) cudaEventDestroy(ctx->c.ev1);
     if(ctx->c.ownStream) cudaStreamDestroy(ctx->c.ownStream);
@@ -184,6 +193,33 @@ mrb_status mrb_context_last_fallback_count(mrb_context ctx, uint32_t* out)
 
 const char* mrb_last_error(mrb_context ctx) { return ctx ? ctx->c.error.c_str() : gCreateError.c_str(); }
 
+mrb_status mrb_context_set_profiling(mrb_context ctx, int enabled, uint32_t iterationStride)
+{
+    if(!ctx) return MRB_ERR_INVALID_ARG;
+    ctx->c.prof.enabled = enabled != 0;
+    ctx->c.prof.stride = iterationStride ? iterationStride : 16u;
+    return MRB_OK;
+}
+
+mrb_status mrb_context_get_profile(mrb_context ctx, mrb_kernel_profile* out)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!out) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        mrb::KernelProfile& p = c.prof;
+        MRB_CUDA_TRY(cudaStreamSynchronize(c.stream));
+        for(int k = 0; k < p.used; k++)
+        {
+            float ms = 0.f;
+            if(cudaEventElapsedTime(&ms, p.ev[k][0], p.ev[k][1]) == cudaSuccess) { p.ms[p.kind[k]] += ms; p.samples[p.kind[k]]++; }
+        }
+        cudaGetLastError();
+        p.used = 0;
+        for(int k = 0; k < mrb::PROF_KINDS; k++) { out->ms[k] = p.ms[k]; out->samples[k] = p.samples[k]; }
+        return MRB_OK;
+    });
+}
+
 mrb_status mrb_accel_build(mrb_context ctx, const mrb_accel_desc* desc, mrb_accel* out)
 {
     return Guard(ctx, [&](mrb::Context& c)
@@ -210,10 +246,13 @@ mrb_status mrb_accel_build(mrb_context ctx, const mrb_accel_desc* desc, mrb_acce
         acc->flags = desc->flags;
         try { mrb::BuildAccel(c, *acc, *desc); }
         catch(...) { c.persistentBytes -= acc->mem.Capacity(); delete acc; throw; }
-        if(acc->d.wideDepth > 63)
+        // The wide traversal keeps at most TWO stack entries per level of the path it is on (the postponed triangle
+        // group and the rest of the node group, trace.cu) on a 64-entry stack: a tree of wideDepth levels needs
+        // 2 * wideDepth entries. Deeper (pathologically skewed) trees are refused here instead of corrupting the stack.
+        if(2u * acc->d.wideDepth > mrb::WIDE_STACK_ENTRIES)
         {
             c.persistentBytes -= acc->mem.Capacity(); delete acc;
-            return Fail(c, MRB_ERR_UNSUPPORTED, "wide BVH deeper than the traversal stack (63)");
+            return Fail(c, MRB_ERR_UNSUPPORTED, "wide BVH deeper than the traversal stack (2 * depth > 64)");
         }
         *out = acc;
         return MRB_OK;
@@ -665,6 +704,92 @@ mrb_status mrb_renderer_read_film(mrb_context ctx, mrb_renderer r, float* out, m
 
 float* mrb_renderer_film_device_ptr(mrb_renderer r) { return r ? mrb::RendererFilmPtr(*r) : nullptr; }
 
+mrb_status mrb_renderer_begin_pass(mrb_context ctx, mrb_renderer r, const uint32_t regionMin[2], const uint32_t regionSize[2],
+                                   uint32_t sampleStart, uint32_t sampleCount)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!r || !regionMin || !regionSize) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        mrb::RendererBeginPass(c, *r, regionMin, regionSize, sampleStart, sampleCount);
+        return MRB_OK;
+    });
+}
+
+mrb_status mrb_renderer_run_pass(mrb_context ctx, mrb_renderer r, uint32_t chunk, mrb_render_stats* out)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!r || !out) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        mrb::RendererRunPass(c, *r, chunk, *out);
+        return MRB_OK;
+    });
+}
+
+mrb_status mrb_renderer_poll_stats(mrb_context ctx, mrb_renderer r, mrb_render_stats* out)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!r || !out) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        mrb::RendererPollStats(c, *r, *out);
+        return MRB_OK;
+    });
+}
+
+mrb_status mrb_renderer_film_handoff(mrb_context ctx, mrb_renderer r, float* hostDst, mrb_host_fn onComplete, void* user)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!r || !hostDst) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        mrb::RendererFilmHandoff(c, *r, hostDst, onComplete, user);
+        return MRB_OK;
+    });
+}
+
+mrb_status mrb_renderer_reduce_peers(mrb_context ctx, mrb_renderer r, const mrb_context* peerCtx, const mrb_renderer* peers, uint32_t peerCount)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!r || (peerCount && (!peerCtx || !peers))) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        std::vector<mrb::Context*> pc(peerCount); std::vector<mrb_renderer_t*> pr(peerCount);
+        for(uint32_t k = 0; k < peerCount; k++)
+        {
+            if(!peerCtx[k] || !peers[k]) return Fail(c, MRB_ERR_INVALID_ARG, "null peer");
+            pc[k] = &peerCtx[k]->c; pr[k] = peers[k];
+        }
+        try { mrb::RendererReducePeers(c, *r, pc.data(), pr.data(), peerCount); }
+        catch(...) { cudaSetDevice(c.device); throw; }
+        return MRB_OK;
+    });
+}
+
+mrb_status mrb_host_alloc(mrb_context ctx, size_t bytes, void** out)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!out || bytes == 0) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        *out = nullptr;
+        MRB_CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+        return MRB_OK;
+    });
+}
+
+void mrb_host_free(mrb_context ctx, void* ptr)
+{
+    if(!ctx || !ptr) return;
+    cudaSetDevice(ctx->c.device);
+    cudaFreeHost(ptr);
+}
+
+mrb_status mrb_filter_sample(mrb_context ctx, uint32_t filterType, float radius, const float* xi, uint32_t count, float* out)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(count && (!xi || !out)) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        mrb::FilterSampleHost(c, filterType, radius, xi, count, out);
+        return MRB_OK;
+    });
+}
+
 mrb_status mrb_texture_sample(mrb_context ctx, const mrb_texture_desc* texture, const float* uv, uint32_t count, float* rgbOut)
 {
     return Guard(ctx, [&](mrb::Context& c)
@@ -765,7 +890,12 @@ mrb_status mrb_scene_build(mrb_context ctx, const mrb_instance_desc* instances, 
         mrb_scene sc = new mrb_scene_t();
         try { mrb::BuildScene(c, *sc, instances, instanceCount); }
         catch(...) { c.persistentBytes -= sc->mem.Capacity(); delete sc; throw; }
-        if(sc->d.tlas.wideDepth > 30) { c.persistentBytes -= sc->mem.Capacity(); delete sc; return Fail(c, MRB_ERR_UNSUPPORTED, "top-level tree too deep"); }
+        // two-level traversal: 2 entries per top-level level + the 3 entries pushed on entering an instance (pending node
+        // group, pending instance group, sentinel) + 2 per level of the deepest instance
+        uint32_t deepest = 0;
+        for(uint32_t i = 0; i < instanceCount; i++) deepest = std::max(deepest, instances[i].accel->d.wideDepth);
+        if(2u * sc->d.tlas.wideDepth + 3u + 2u * deepest > mrb::WIDE_STACK_ENTRIES)
+        { c.persistentBytes -= sc->mem.Capacity(); delete sc; return Fail(c, MRB_ERR_UNSUPPORTED, "scene deeper than the traversal stack (2 * top + 3 + 2 * bottom > 64)"); }
         *out = sc;
         return MRB_OK;
     });

@@ -63,6 +63,21 @@ class MultiAlloc
     size_t Total() const { return offset; }
 };
 
+// Sampled kernel timing (mrb_context_set_profiling): pairs of CUDA events recorded on the context stream around the
+// kernels of every `stride`-th wavefront iteration, read back by mrb_context_get_profile. Off by default.
+enum ProfileKind : int { PROF_TRACE_CLOSEST = 0, PROF_SHADE = 1, PROF_TRACE_ANY = 2, PROF_FINISH_RELOAD = 3, PROF_TRACE_TAIL = 4, PROF_KINDS = 5 };
+struct KernelProfile
+{
+    static constexpr int POOL = 320;
+    bool        enabled = false, sampleNow = false;
+    uint32_t    stride = 16;
+    cudaEvent_t ev[POOL][2] = {};
+    int         kind[POOL] = {};
+    int         used = 0, created = 0;
+    double      ms[PROF_KINDS] = {};
+    uint64_t    samples[PROF_KINDS] = {};
+};
+
 struct Context
 {
     int          device = 0;
@@ -82,6 +97,29 @@ struct Context
     cudaStream_t copyIn = nullptr, copyOut = nullptr;
     cudaEvent_t  evIn[PIPE_CHUNKS] = {}, evDone[PIPE_CHUNKS] = {};
     cudaEvent_t  evStart = nullptr;
+    KernelProfile prof;
+    // occupancy of the persistent traversal kernels on THIS device (blocks per SM), filled on first use
+    int          occWide[2] = {0, 0}, occWide2[2] = {0, 0};
+};
+
+// Brackets the launches issued inside its scope with a sampled event pair (no-op unless profiling samples this iteration)
+struct ProfileScope
+{
+    Context& ctx; int slot = -1;
+    ProfileScope(Context& c, int kind) : ctx(c)
+    {
+        KernelProfile& p = c.prof;
+        if(!p.enabled || !p.sampleNow || p.used >= KernelProfile::POOL) return;
+        if(p.used >= p.created)
+        {
+            if(cudaEventCreate(&p.ev[p.created][0]) != cudaSuccess || cudaEventCreate(&p.ev[p.created][1]) != cudaSuccess) return;
+            p.created++;
+        }
+        slot = p.used++;
+        p.kind[slot] = kind;
+        cudaEventRecord(p.ev[slot][0], c.stream);
+    }
+    ~ProfileScope() { if(slot >= 0) cudaEventRecord(ctx.prof.ev[slot][1], ctx.stream); }
 };
 
 inline uint32_t DivUp(uint32_t a, uint32_t b) { return (a + b - 1) / b; }

@@ -23,7 +23,6 @@
 #include "spectrum.cuh"
 #include "sampler.cuh"
 #include <cfloat>
-#include <random>
 #include <stdexcept>
 #include <cstring>
 #include <vector>
@@ -57,7 +56,6 @@ __device__ __forceinline__ Float3 F3(float x, float y, float z) { return Float3{
 __device__ __forceinline__ Float3 operator+(Float3 a, Float3 b) { return F3(a.x + b.x, a.y + b.y, a.z + b.z); }
 __device__ __forceinline__ Float3 operator-(Float3 a, Float3 b) { return F3(a.x - b.x, a.y - b.y, a.z - b.z); }
 __device__ __forceinline__ Float3 operator*(Float3 a, float s) { return F3(a.x * s, a.y * s, a.z * s); }
-__device__ __forceinline__ Float3 operator*(Float3 a, Float3 b) { return F3(a.x * b.x, a.y * b.y, a.z * b.z); }
 __device__ __forceinline__ float Dot(Float3 a, Float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ Float3 Cross(Float3 a, Float3 b)
 { return F3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
@@ -117,14 +115,37 @@ struct SlotSampler
         for(int k = 0; k < N; k++) out[k] = fminf(float(v[k]) * 2.3283064365386963e-10f, 0.99999994f);
     }
 };
-__device__ __forceinline__ SlotSampler LoadSampler(uint32_t type, uint32_t state, uint2 ss, uint32_t pixel, uint32_t width,
+// `gpx, gpy`: the pixel in FULL-image coordinates (a tile / region renders the same points as the whole image would)
+__device__ __forceinline__ SlotSampler LoadSampler(uint32_t type, uint32_t state, uint2 ss, uint32_t gpx, uint32_t gpy,
                                                    const uint32_t* matrices, ZSobolGlobals g)
 {
     SlotSampler s;
     s.reverseBack = (type & SAMPLER_REFERENCE_SCRAMBLE) == 0u; type &= SAMPLER_TYPE_MASK;
     s.type = type; s.state = state; s.sampleIndex = ss.x; s.dim = ss.y; s.matrices = matrices; s.g = g;
-    s.morton = (type == SAMPLER_ZSOBOL) ? Morton2D(pixel % width, pixel / width) : 0ull;
+    s.morton = (type == SAMPLER_ZSOBOL) ? Morton2D(gpx, gpy) : 0ull;
     return s;
+}
+
+// Seeding. The reference seeds one generator per path SLOT from a host std::mt19937 (RNGGroupIndependent,
+// Tracer/Random.cu:L661-720) and lets it run on from path to path, so which numbers a sample sees depends on
+// which slot happened to pick it up. Here every (pixel, sample index) pair owns its numbers: the PCG32 state of
+// a new path (Independent) or the pixel's scramble seed (Sobol / ZSobol) is a hash of (seed, full-image pixel,
+// sample index), so a fixed seed gives a fixed image whatever the slot scheduling, the tiling or the number of
+// GPUs the sample range is split over (statistical parity with the reference, as SURVEY.md §8a-16 allows).
+__device__ __forceinline__ uint64_t Mix64(uint64_t z)
+{   // splitmix64 finaliser
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint32_t PixelSeed(uint64_t seed, uint32_t gpix)
+{ return uint32_t(Mix64(seed ^ (uint64_t(gpix) * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull)) >> 32); }
+__device__ __forceinline__ uint32_t PathState(uint64_t seed, uint32_t gpix, uint32_t sample)
+{
+    const uint32_t xi = uint32_t(Mix64(Mix64(seed + uint64_t(gpix) * 0x9E3779B97F4A7C15ull) ^ (uint64_t(sample) * 0xD1B54A32D192ED03ull)) >> 32);
+    uint32_t s = 2891336453u;            // PermutedCG32::GenerateState (Random.h:L763-771): Step(0), += xi, Step
+    s += xi;
+    return s * 747796405u + 2891336453u;
 }
 
 // Ray::Nudge (Core/Ray.hpp:L258-301, after RT Gems I ch. 6)
@@ -138,6 +159,104 @@ __device__ __forceinline__ Float3 NudgePos(Float3 p, Float3 n)
     return F3(fabsf(p.x) < ORIGIN ? p.x + FLOAT_SCALE * n.x : ix,
               fabsf(p.y) < ORIGIN ? p.y + FLOAT_SCALE * n.y : iy,
               fabsf(p.z) < ORIGIN ? p.z + FLOAT_SCALE * n.z : iz);
+}
+
+// Film filters (Tracer/Filters.h): Sample(xi) -> offset + pdf, Evaluate(offset); the film weight of a camera sample is
+// Evaluate / pdf (KCGenerateCamRaysStochastic, RayGenKernels.kt.h:L195-225). Box, Tent and Gaussian are sampled from
+// their own shape (weight 1 up to rounding); Mitchell-Netravali is sampled from a 3-Gaussian mixture, so its weight
+// varies and can be negative.
+enum : uint32_t { FILTER_BOX = 0u, FILTER_TENT = 1u, FILTER_GAUSSIAN = 2u, FILTER_MITCHELL = 3u };   // FilterType::E (Core/TracerEnums.h:L162-173)
+constexpr float PREV_ONE = 0.99999994f;
+
+__device__ __forceinline__ float GaussPdf(float x, float sigma, float mu = 0.0f)
+{   // Math::Gaussian (Core/Math.h:L1032-1042)
+    const float si = 1.0f / sigma, p = (x - mu) * si;
+    return 0.3989422804f * si * expf(-0.5f * p * p);
+}
+__device__ __forceinline__ float GaussSample(float xi, float sigma, float mu, float& pdf)
+{   // Distribution::Common::SampleGaussian (DistributionFunctions.h:L686-705)
+    const float e = erfinvf(2.0f * xi - 1.0f);
+    float x = 1.41421356237f * sigma * e + mu;
+    if(isinf(e)) x = fminf(fmaxf(x, -3.5f * sigma), 3.5f * sigma);
+    pdf = GaussPdf(x, sigma, mu);
+    return x;
+}
+__device__ __forceinline__ float LerpU(float a, float b, float t) { return __fadd_rn(__fmul_rn(a, 1.0f - t), __fmul_rn(b, t)); }   // Math::Lerp
+__device__ __forceinline__ float TentSample(float xi, float r, float& pdf)
+{   // Distribution::Common::SampleTent(xi, -r, r) (DistributionFunctions.h:L785-805) over BisectSample2 + SampleLine(., 1, 0)
+    const float a = -r, b = r;
+    if(b - a < 1.0e-5f) { pdf = 1.0f / (b - a); return 0.0f; }
+    const float w = r / (r + r);                                  // weights[0] / weights.Sum()
+    const bool left = xi < w;
+    float lxi = left ? xi / w : (xi - w) / (1.0f - w);
+    lxi = fminf(lxi, PREV_ONE);
+    if(left) lxi = PREV_ONE - lxi;
+    const float denom = 1.0f + sqrtf(fmaxf(LerpU(1.0f, 0.0f, lxi), 0.0f));
+    const float x = fminf(lxi / denom, PREV_ONE);
+    pdf = 2.0f * LerpU(1.0f, 0.0f, x) * (1.0f / (b - a));
+    return left ? x * a : x * b;
+}
+__device__ __forceinline__ float Mitchell1D(float x, float radiusRecip)
+{   // MitchellNetravaliFilter::Evaluate, b = c = 0.33333 (Filters.h:L258-300)
+    const float B = 0.33333f, C = 0.33333f, F = 1.0f / 6.0f;
+    x = fabsf(2.0f * x * radiusRecip);
+    const float x2 = x * x, x3 = x2 * x;
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+    if(x < 1.0f) { c0 = F * (12.0f - 9.0f * B - 6.0f * C); c1 = F * (-18.0f + 12.0f * B + 6.0f * C); c3 = F * (6.0f - 2.0f * B); }
+    else if(x < 2.0f) { c0 = F * (-B - 6.0f * C); c1 = F * (6.0f * B + 30.0f * C); c2 = F * (-12.0f * B - 48.0f * C); c3 = F * (8.0f * B + 24.0f * C); }
+    return (c0 * x3 + c1 * x2 + c2 * x + c3) * 2.0f * radiusRecip;
+}
+__device__ __forceinline__ float MitchellSampleDim(float xi, float r, float& pdf)
+{   // MitchellNetravaliFilter::Sample, one axis (Filters.h:L302-346): balance-heuristic mixture of three Gaussians
+    const float MIS_MID = 0.960566188838f, MIS_SIDES = 0.0197169055809f;
+    const float midSigma = 0.528f * r * 0.5f, sideSigma = 0.2f * r * 0.5f, sideMean = 1.3f * r * 0.5f;
+    // BisectSample<3>(xi, {SIDES, MID, SIDES}, normalised) (DistributionFunctions.h:L645-683)
+    uint32_t index; float lo, wsel;
+    if(xi < MIS_SIDES) { index = 0u; lo = 0.0f; wsel = MIS_SIDES; }
+    else if(xi < MIS_SIDES + MIS_MID) { index = 1u; lo = MIS_SIDES; wsel = MIS_MID; }
+    else { index = 2u; lo = MIS_SIDES + MIS_MID; wsel = MIS_SIDES; }
+    const float lxi = fminf((xi - lo) / wsel, PREV_ONE);
+    float own, x;
+    if(index == 0u) x = GaussSample(lxi, sideSigma, -sideMean, own);
+    else if(index == 1u) x = GaussSample(lxi, midSigma, 0.0f, own);
+    else x = GaussSample(lxi, sideSigma, sideMean, own);
+    const float p0 = (index == 0u) ? own : GaussPdf(x, sideSigma, -sideMean);
+    const float p1 = (index == 1u) ? own : GaussPdf(x, midSigma);
+    const float p2 = (index == 2u) ? own : GaussPdf(x, sideSigma, sideMean);
+    pdf = p0 * MIS_SIDES + p1 * MIS_MID + p2 * MIS_SIDES;          // MIS::BalanceCancelled<3>
+    return x;
+}
+// out: offset (x, y), pdf of Sample(), Evaluate(offset)
+__device__ __forceinline__ void FilterSample(uint32_t type, float r, float xi0, float xi1, float& ox, float& oy, float& pdf, float& eval)
+{
+    float px, py;
+    if(type == FILTER_BOX)
+    {   // Common::SampleUniformRange(xi, -r, r) per axis; Evaluate = 1 / (4 r^2) inside the square (Filters.h:L112-146)
+        const float range = r - (-r);
+        ox = xi0 * range + (-r); oy = xi1 * range + (-r);
+        px = py = 1.0f / range;
+        const float rr = 1.0f / r;
+        eval = (fabsf(ox) <= r && fabsf(oy) <= r) ? 0.25f * rr * rr : 0.0f;
+    }
+    else if(type == FILTER_TENT)
+    {   // Evaluate = Lerp(1/r, 0, |x| / r) Lerp(1/r, 0, |y| / r) (Filters.h:L160-172)
+        ox = TentSample(xi0, r, px); oy = TentSample(xi1, r, py);
+        const float rcp = 1.0f / r, cap = 1.0f / r;
+        eval = LerpU(cap, 0.0f, fminf(fabsf(ox * rcp), 1.0f)) * LerpU(cap, 0.0f, fminf(fabsf(oy * rcp), 1.0f));
+    }
+    else if(type == FILTER_MITCHELL)
+    {
+        ox = MitchellSampleDim(xi0, r, px); oy = MitchellSampleDim(xi1, r, py);
+        const float rcp = 1.0f / r;
+        eval = Mitchell1D(ox, rcp) * Mitchell1D(oy, rcp);
+    }
+    else
+    {   // GaussianFilter: sigma = 0.285714 r; Evaluate is the sampling density itself (Filters.h:L195-227)
+        const float sigma = r * 0.285714f;
+        ox = GaussSample(xi0, sigma, 0.0f, px); oy = GaussSample(xi1, sigma, 0.0f, py);
+        eval = px * py;
+    }
+    pdf = px * py;
 }
 
 struct Camera // CameraPinhole members (CamerasDefault.hpp:L8-36), tile-local
@@ -183,12 +302,15 @@ struct RenderData
     const EmissiveTri* lights;         // one per emissive triangle (MetaLight list), world space
     uint32_t          lightCount;      // emissive triangles (+1 boundary light in the sampler)
     Camera            cam;
-    uint32_t          width, height;   // the tile
+    uint32_t          width, height;   // the tile (region) of the current pass
     uint32_t          fullWidth, fullHeight, regionX, regionY; // the image it is a region of
-    float             filterSigma;     // Gaussian film filter (Filters.h:L195-227): sigma = r * 0.285714
+    uint32_t          filterType;      // FilterType::E: Box, Tent, Gaussian, Mitchell-Netravali (TracerParameters.filmFilter)
+    float             filterRadius;
     // options
     uint32_t          rrLo, rrHi, sampleMode; // 0 Pure, 1 NEE, 2 NEE+MIS
-    uint64_t          pathLimit;
+    uint64_t          pathLimit;       // camera paths of the current pass (samples x tile pixels)
+    uint32_t          sampleBase;      // sample index of the pass's first sample of every pixel
+    uint64_t          seed;            // TracerParameters.seed
     // path state (P slots)
     uint32_t          slots;
     mrb_ray_gmem*     rays;
@@ -200,12 +322,11 @@ struct RenderData
     float4*           shadowRadiance;
     uint4*            meta;            // x: pathData (depth | status << 8 | type << 16), y: pixel, z: film weight, w: previous bxdf pdf
     uint32_t*         rng;             // Independent: PCG32 state; Sobol / ZSobol: the generator's scramble seed (constant)
-    // low-discrepancy samplers (samplerType != 0): one generator per PIXEL, seeded like RNGGroupSobol /
-    // RNGGroupZSobol; path g renders pixel g % N as that pixel's sample g / N, so the generator state is implicit
+    // low-discrepancy samplers (samplerType != 0): one generator per PIXEL (LocalState.seed = PixelSeed());
+    // path g renders pixel g % N as that pixel's sample sampleBase + g / N, so the generator state is implicit
     // (the reference keeps its generators per path slot, which only coincides with the pixel while slots and
     // pixels stay aligned; per pixel keeps the stratification of the sequence inside every pixel)
     uint32_t          samplerType;     // 0 Independent (PCG32), 1 Sobol, 2 ZSobol
-    const uint32_t*   pixelSeeds;      // per pixel: LocalState.seed
     uint2*            sampleState;     // per slot: x = sample index of the current path, y = next free dimension
     const uint32_t*   sobolMatrices;   // 256 x 52 Joe-Kuo generator matrices
     ZSobolGlobals     zsobol;
@@ -218,7 +339,8 @@ struct RenderData
     uint32_t          matBits;         // data bits of the work key (material index)
     // film (planar R,G,B,W)
     float*            film;
-    // u64 counters: [0] next camera path, [1] completed paths, [2] closest-hit rays cast, [3] shadow rays cast
+    // u64 counters: [0] next camera path of the pass, [1] completed paths, [2] closest-hit rays cast, [3] shadow rays cast,
+    // [4] NEE light samples taken (= the shadow rays the reference casts: it also traces the zero-valued ones)
     unsigned long long* counters;
 };
 
@@ -261,29 +383,22 @@ __device__ __forceinline__ void ReloadSlot(const RenderData& d, uint32_t i, bool
         d.hitKeys[i].primKey = INVALID_U32;
         return;
     }
-    const uint32_t pix = uint32_t(g % (unsigned long long)(d.width * d.height));
-    // a new path = the next sample of its pixel's generator, dimension 0
-    const bool lowDisc = d.samplerType != SAMPLER_INDEPENDENT;
-    const uint2 ss = make_uint2(lowDisc ? uint32_t(g / (unsigned long long)(d.width * d.height)) : 0u, 0u);
-    SlotSampler rng = LoadSampler(d.samplerType, lowDisc ? d.pixelSeeds[pix] : d.rng[i], ss, pix, d.width, d.sobolMatrices, d.zsobol);
+    const unsigned long long tilePixels = (unsigned long long)(d.width * d.height);
+    const uint32_t pix = uint32_t(g % tilePixels);
+    const uint32_t sample = d.sampleBase + uint32_t(g / tilePixels);
     const uint32_t px = pix % d.width, py = pix / d.width;
-    // stochastic filter sample: offset ~ Gaussian, weight = f / pdf
+    const uint32_t gpx = px + d.regionX, gpy = py + d.regionY, gpix = gpy * d.fullWidth + gpx;
+    // a new path = sample `sample` of its pixel, dimension 0: numbers depend on (seed, pixel, sample) only
+    const bool lowDisc = d.samplerType != SAMPLER_INDEPENDENT;
+    const uint2 ss = make_uint2(lowDisc ? sample : 0u, 0u);
+    SlotSampler rng = LoadSampler(d.samplerType, lowDisc ? PixelSeed(d.seed, gpix) : PathState(d.seed, gpix, sample), ss, gpx, gpy,
+                                  d.sobolMatrices, d.zsobol);
+    // stochastic filter sample: offset ~ filter sampler, film weight = Evaluate / pdf
     float xiF[2]; rng.Next<2>(xiF);
-    float xi0 = xiF[0], xi1 = xiF[1];
-    const float sig = d.filterSigma;
-    auto SampleG = [sig](float xi, float& pdfOut)
-    {
-        float e = erfinvf(2.0f * xi - 1.0f);
-        float x = 1.41421356237f * sig * e;
-        if(isinf(e)) x = fminf(fmaxf(x, -3.5f * sig), 3.5f * sig);
-        float p = x / sig;
-        pdfOut = 0.3989422804f / sig * expf(-0.5f * p * p);
-        return x;
-    };
-    float pdfx, pdfy;
-    const float offx = SampleG(xi0, pdfx), offy = SampleG(xi1, pdfy);
-    // Evaluate == the same Gaussian, so the weight is 1 up to the clamp of the tails
-    const float weight = 1.0f;
+    float offx, offy, fPdf, fEval;
+    FilterSample(d.filterType, d.filterRadius, xiF[0], xiF[1], offx, offy, fPdf, fEval);
+    // Gaussian: Evaluate is the sampling density itself, the quotient is exactly 1
+    const float weight = (d.filterType == FILTER_GAUSSIAN) ? 1.0f : fEval / fPdf;
     // the tile may be a region of a larger image (RenderImageParams.regionMin / resolution)
     const float sx = (float(px + d.regionX) + offx + 0.5f) * (d.cam.planeW / float(d.fullWidth));
     const float sy = (float(py + d.regionY) + offy + 0.5f) * (d.cam.planeH / float(d.fullHeight));
@@ -435,7 +550,7 @@ __global__ void __launch_bounds__(RTPB) KGenWorkKeys(RenderData d)
 
 // Shading of one slot. Returns true when the slot held a live path (= one closest-hit ray was cast for it
 // this bounce); castShadow reports an NEE shadow ray.
-__device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool& castShadow)
+__device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool& castShadow, bool& neeSample)
 {
     // every per-slot input is requested before the first use, so one round trip covers them all
     const uint4 meta = d.meta[i];
@@ -504,7 +619,7 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
 
     // ------------------------------- Lambert surface -------------------------------
     SlotSampler rng = LoadSampler(d.samplerType, rngState, d.samplerType != SAMPLER_INDEPENDENT ? d.sampleState[i] : make_uint2(0u, 0u),
-                                  meta.y, d.width, d.sobolMatrices, d.zsobol);
+                                  meta.y % d.width + d.regionX, meta.y / d.width + d.regionY, d.sobolMatrices, d.zsobol);
     const bool backSide = Dot(geoN, Normalize(rd)) > 0.0f;
     Float3 shadeN = geoN;
     if(in.vertexNormals)
@@ -575,6 +690,7 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
         const uint32_t nLights = d.lightCount + 1u; // + boundary light
         uint32_t li = min(uint32_t(xs * float(nLights)), nLights - 1u);
         newType = RAY_SHADOW;
+        neeSample = true;
         if(li < d.lightCount)
         {
             const EmissiveTri l = d.lights[li];
@@ -671,14 +787,15 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
 __global__ void __launch_bounds__(RTPB) KShade(RenderData d)
 {
     const uint32_t tidx = blockIdx.x * RTPB + threadIdx.x;
-    bool alive = false, castShadow = false;
-    if(tidx < d.slots) alive = ShadeSlot(d, d.partitionRays ? d.workIndices[tidx] : tidx, castShadow);
+    bool alive = false, castShadow = false, neeSample = false;
+    if(tidx < d.slots) alive = ShadeSlot(d, d.partitionRays ? d.workIndices[tidx] : tidx, castShadow, neeSample);
     // ray statistics: one atomic per block per counter
-    const int nAlive = __syncthreads_count(alive), nShadow = __syncthreads_count(castShadow);
+    const int nAlive = __syncthreads_count(alive), nShadow = __syncthreads_count(castShadow), nNee = __syncthreads_count(neeSample);
     if(threadIdx.x == 0)
     {
         if(nAlive) atomicAdd(&d.counters[2], (unsigned long long)nAlive);
         if(nShadow) atomicAdd(&d.counters[3], (unsigned long long)nShadow);
+        if(nNee) atomicAdd(&d.counters[4], (unsigned long long)nNee);
     }
 }
 
@@ -758,16 +875,7 @@ __device__ __forceinline__ bool FinishSlot(const RenderData& d, uint32_t i, bool
     return true;
 }
 
-__global__ void __launch_bounds__(RTPB) KFinish(RenderData d)
-{
-    const uint32_t i = blockIdx.x * RTPB + threadIdx.x;
-    bool died = false;
-    if(i < d.slots) FinishSlot(d, i, died);
-    const int nDied = __syncthreads_count(died);   // completed paths: one atomic per block
-    if(threadIdx.x == 0 && nDied) atomicAdd(&d.counters[1], (unsigned long long)nDied);
-}
-
-// KFinish of bounce k fused with KReload of bounce k+1: the slot a path just left is refilled in the same pass
+// The end of bounce k (shadow accumulate, film) fused with the reload of bounce k+1: the slot a path just left is refilled in the same pass
 __global__ void __launch_bounds__(RTPB) KFinishReload(RenderData d)
 {
     const uint32_t i = blockIdx.x * RTPB + threadIdx.x;
@@ -793,8 +901,31 @@ struct mrb_renderer_t
     mrb_scene        scene = nullptr;
     mrb::SceneData   sceneData;        // scene->d with the renderer's instance records (accelKey = instance index)
     uint64_t         iterations = 0;
-    uint64_t         totalPaths = 0;   // totalSPP * pixels
-    bool             needReload = false;
+    bool             needReload = true;   // the next iteration starts with KReload (first one, or a pass has just begun)
+    // passes: samples [sampleBase, sampleBase + passSamples) of every pixel of the current region
+    uint32_t         maxWidth = 0, maxHeight = 0;      // the film allocation (the largest region a pass may take)
+    uint32_t         totalSPP = 0, sampleOffset = 0;
+    uint32_t         sppStarted = 0;                   // set_spp_limit bookkeeping: samples per pixel handed out so far
+    uint64_t         startedBefore = 0;                // camera paths of the finished passes
+    uint64_t         completedTarget = 0;              // counters[1] when every pass begun so far has finished
+    // film double buffer + asynchronous hand-off (RenderImage::TransferToHost, Tracer/RenderImage.cpp:L163-219)
+    float*           film[2] = {nullptr, nullptr};
+    int              cur = 0;
+    cudaStream_t     copyStream = nullptr;
+    cudaEvent_t      evCompute = nullptr, evCopied[2] = {nullptr, nullptr};
+    bool             copied[2] = {false, false};
+    // pipelined completion polling of run_pass (pinned host copies of the counters)
+    unsigned long long* hCounters = nullptr;           // 2 x 8
+    cudaEvent_t      evPoll[2] = {nullptr, nullptr};
+    unsigned long long lastCounters[8] = {};           // poll_stats: the latest snapshot that has landed
+    bool             pollPending = false;
+    ~mrb_renderer_t()
+    {
+        if(copyStream) { cudaStreamSynchronize(copyStream); cudaStreamDestroy(copyStream); }
+        if(evCompute) cudaEventDestroy(evCompute);
+        for(int k = 0; k < 2; k++) { if(evCopied[k]) cudaEventDestroy(evCopied[k]); if(evPoll[k]) cudaEventDestroy(evPoll[k]); }
+        if(hCounters) cudaFreeHost(hCounters);
+    }
 };
 
 namespace mrb
@@ -812,9 +943,15 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
     d.regionX = desc.regionMin[0]; d.regionY = desc.regionMin[1];
     if(d.regionX + d.width > d.fullWidth || d.regionY + d.height > d.fullHeight) throw std::runtime_error("render region exceeds the image");
     d.rrLo = desc.rrRange[0]; d.rrHi = desc.rrRange[1]; d.sampleMode = desc.sampleMode;
+    // a new renderer stands at the start of ONE pass over all of its samples (throughput mode)
     d.pathLimit = uint64_t(desc.totalSPP) * desc.width * desc.height;
-    r.totalPaths = d.pathLimit;
-    d.filterSigma = desc.filmFilterRadius * 0.285714f;
+    d.sampleBase = desc.sampleOffset; d.seed = desc.seed;
+    r.totalSPP = desc.totalSPP; r.sampleOffset = desc.sampleOffset; r.sppStarted = desc.totalSPP;
+    r.maxWidth = desc.width; r.maxHeight = desc.height;
+    r.completedTarget = d.pathLimit;
+    if(desc.filmFilterType > FILTER_MITCHELL) throw std::runtime_error("unknown film filter type");
+    if(!(desc.filmFilterRadius > 0.0f)) throw std::runtime_error("film filter radius must be positive");
+    d.filterType = desc.filmFilterType; d.filterRadius = desc.filmFilterRadius;
     d.slots = desc.maxPathCount ? desc.maxPathCount : desc.width * desc.height;
     d.partitionRays = desc.partitionRays ? 1u : 0u;
     {   // bits needed for the larger of the material / light tables (Bit::RequiredBitsToRepresent)
@@ -868,7 +1005,13 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
             bool anyLight = false;
             // an instance may carry its own keys (mrb_instance_desc.lightOrMatKeys)
             const std::vector<uint32_t>& lmKeys = (desc.scene && !desc.scene->hInstanceKeys[k].empty()) ? desc.scene->hInstanceKeys[k] : hacc.hLmKey;
-            for(uint32_t rg = 0; rg < a.ranges.count; rg++) anyLight |= (lmKeys[rg] & 0x80000000u) != 0;
+            for(uint32_t rg = 0; rg < a.ranges.count; rg++)
+            {
+                anyLight |= (lmKeys[rg] & 0x80000000u) != 0;
+                // a material key indexes albedo / materialType / albedoTexture in the shading kernel
+                if(!(lmKeys[rg] & 0x80000000u) && (lmKeys[rg] & 0x1FFFFFu) >= desc.materialCount)
+                    throw std::runtime_error("material key index exceeds materialCount");
+            }
             if(!anyLight) continue;
             if(loaded != &hacc)
             {
@@ -936,9 +1079,9 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
         d.throughput = ma.Take<float4>(P); d.radiance = ma.Take<float4>(P); d.shadowRadiance = ma.Take<float4>(P);
         d.meta = ma.Take<uint4>(P); d.rng = ma.Take<uint32_t>(P);
         d.sampleState = (desc.samplerType & 0xFFu) ? ma.Take<uint2>(P) : nullptr;
-        d.pixelSeeds = (desc.samplerType & 0xFFu) ? ma.Take<uint32_t>(size_t(d.width) * d.height) : nullptr;
         d.sobolMatrices = (desc.samplerType & 0xFFu) ? ma.Take<uint32_t>(SOBOL_DIM_COUNT * SOBOL_MATRIX_WIDTH) : nullptr; d.visible = ma.Take<uint32_t>((P + 31) / 32);
-        d.film = ma.Take<float>(size_t(4) * d.width * d.height);
+        r.film[0] = ma.Take<float>(size_t(4) * d.width * d.height); r.film[1] = ma.Take<float>(size_t(4) * d.width * d.height);
+        d.film = r.film[0];
         d.counters = ma.Take<unsigned long long>(8);
         d.albedo = ma.Take<float4>(desc.materialCount ? desc.materialCount : 1);
         d.lights = ma.Take<EmissiveTri>(lights.size() ? lights.size() : 1);
@@ -1019,36 +1162,33 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
         MRB_LAUNCH(ctx, KIndexInstances, DivUp(instCount, 256u), 256, 0, dSceneInst, instCount);
         r.sceneData.instances = dSceneInst;
     }
-    // RNGGroupIndependent (Tracer/Random.cu:L661-720): mt19937(seed32) draws -> PermutedCG32::GenerateState
-    uint32_t seed32 = uint32_t((desc.seed >> 32) ^ (desc.seed & 0xFFFFFFFFull));
-    std::mt19937 mt(seed32);
+    // samplers: no host-side generator table — every path derives its numbers from (seed, pixel, sample), see PathState()
     const bool lowDisc = (desc.samplerType & 0xFFu) != 0u;
     d.samplerType = lowDisc ? desc.samplerType : 0u;
-    const uint32_t generators = lowDisc ? d.width * d.height : d.slots;
-    std::vector<uint32_t> states(generators);
-    for(uint32_t i = 0; i < generators; i++)
-    {
-        const uint32_t xi = uint32_t(mt());
-        if(lowDisc) { states[i] = xi; continue; }   // RNGGroupSobol / ZSobol: LocalState.seed = the draw itself (Random.cu:L917-945)
-        uint32_t s = 0u * 747796405u + 2891336453u; // Step(0)
-        s += xi;
-        s = s * 747796405u + 2891336453u;
-        states[i] = s;
-    }
-    MRB_CUDA_TRY(cudaMemcpyAsync(lowDisc ? const_cast<uint32_t*>(d.pixelSeeds) : d.rng, states.data(), states.size() * 4,
-                                 cudaMemcpyHostToDevice, ctx.stream));
     if(lowDisc)
     {
         MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<uint32_t*>(d.sobolMatrices), desc.sobolMatrices,
                                      sizeof(uint32_t) * SOBOL_DIM_COUNT * SOBOL_MATRIX_WIDTH, cudaMemcpyHostToDevice, ctx.stream));
-        // ZSobol globals (Random.cu:L1172-1176): initialMaxSPP = the render's sample budget, resMaxBits from the larger image side
-        uint32_t maxRes = desc.width > desc.height ? desc.width : desc.height, p2 = 1u, bits = 0u;
+        // ZSobol globals (Random.cu:L1172-1176): initialMaxSPP = the render's sample budget (of the WHOLE job when the
+        // samples are split over GPUs), resMaxBits from the larger side of the full image
+        uint32_t maxRes = d.fullWidth > d.fullHeight ? d.fullWidth : d.fullHeight, p2 = 1u, bits = 0u;
         while(p2 < maxRes) { p2 <<= 1; bits++; }
-        d.zsobol.initialMaxSPP = desc.totalSPP; d.zsobol.resMaxBits = bits;
+        d.zsobol.initialMaxSPP = desc.jobSPP ? desc.jobSPP : desc.sampleOffset + desc.totalSPP; d.zsobol.resMaxBits = bits;
     }
+    MRB_CUDA_TRY(cudaStreamCreateWithFlags(&r.copyStream, cudaStreamNonBlocking));
+    MRB_CUDA_TRY(cudaEventCreateWithFlags(&r.evCompute, cudaEventDisableTiming));
+    for(int k = 0; k < 2; k++)
+    {
+        MRB_CUDA_TRY(cudaEventCreateWithFlags(&r.evCopied[k], cudaEventDisableTiming));
+        MRB_CUDA_TRY(cudaEventCreateWithFlags(&r.evPoll[k], cudaEventDisableTiming));
+    }
+    MRB_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&r.hCounters), sizeof(unsigned long long) * 16, cudaHostAllocPortable));
     MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
 }
 
+// One wavefront iteration = one bounce of every live path. Every iteration ends with KFinishReload, so the slots
+// freed by a bounce hold their next camera ray when the following iteration (of this or the next call) starts; the
+// separate KReload only runs on the first iteration of a pass.
 void RenderIterate(Context& ctx, mrb_renderer_t& r, uint32_t iterations)
 {
     using namespace mrb;
@@ -1056,7 +1196,8 @@ void RenderIterate(Context& ctx, mrb_renderer_t& r, uint32_t iterations)
     const uint32_t grid = DivUp(d.slots, RTPB);
     for(uint32_t it = 0; it < iterations; it++)
     {
-        if(it == 0 || r.needReload) { MRB_LAUNCH(ctx, KReload, grid, RTPB, 0, d); r.needReload = false; }   // later bounces: fused into the previous KFinishReload
+        ctx.prof.sampleNow = ctx.prof.enabled && (r.iterations % ctx.prof.stride) == 0;
+        if(r.needReload) { MRB_LAUNCH(ctx, KReload, grid, RTPB, 0, d); r.needReload = false; }
         if(r.scene) TraceScene(ctx, r.sceneData, false, MRB_TRACE_WIDE, d.hitKeys, d.hits, nullptr, d.rays, nullptr, d.slots);
         else TraceRays(ctx, *r.accel, false, MRB_TRACE_WIDE, d.hitKeys, d.hits, nullptr, d.rays, nullptr, d.slots);
         if(d.partitionRays)
@@ -1067,17 +1208,17 @@ void RenderIterate(Context& ctx, mrb_renderer_t& r, uint32_t iterations)
             MultiPartition(ctx, d.workKeys, d.workIndices, d.slots, dataBits, batchBits, false, 4,
                            d.partTable, d.partTable + 1, d.partTable + 8, ctx.scratch.Base());
         }
-        MRB_LAUNCH(ctx, KShade, grid, RTPB, 0, d);
+        { ProfileScope ps(ctx, PROF_SHADE); MRB_LAUNCH(ctx, KShade, grid, RTPB, 0, d); }
         if(d.sampleMode != 0u)
         {
             MRB_CUDA_TRY(cudaMemsetAsync(d.visible, 0xFF, sizeof(uint32_t) * ((d.slots + 31) / 32), ctx.stream));
             if(r.scene) TraceScene(ctx, r.sceneData, true, MRB_TRACE_WIDE, nullptr, nullptr, d.visible, d.shadowRays, nullptr, d.slots);
             else TraceRays(ctx, *r.accel, true, MRB_TRACE_WIDE, nullptr, nullptr, d.visible, d.shadowRays, nullptr, d.slots);
         }
-        if(it + 1 < iterations) MRB_LAUNCH(ctx, KFinishReload, grid, RTPB, 0, d);
-        else MRB_LAUNCH(ctx, KFinish, grid, RTPB, 0, d);
+        { ProfileScope ps(ctx, PROF_FINISH_RELOAD); MRB_LAUNCH(ctx, KFinishReload, grid, RTPB, 0, d); }
         r.iterations++;
     }
+    ctx.prof.sampleNow = false;
 }
 
 
@@ -1090,15 +1231,89 @@ void DestroyRenderer(Context& ctx, mrb_renderer_t* r)
     delete r;
 }
 
+static void FillStats(const mrb_renderer_t& r, const unsigned long long* h, mrb_render_stats& out)
+{
+    out.pathsStarted = r.startedBefore + (h[0] < r.d.pathLimit ? h[0] : r.d.pathLimit);
+    out.pathsCompleted = h[1]; out.closestRays = h[2]; out.shadowRays = h[3]; out.neeSamples = h[4];
+    out.iterations = r.iterations;
+    out.finished = (h[1] >= r.completedTarget) ? 1u : 0u;
+}
+
 void RendererStats(Context& ctx, mrb_renderer_t& r, mrb_render_stats& out)
 {
-    unsigned long long h[4];
+    unsigned long long h[8];
     MRB_CUDA_TRY(cudaMemcpyAsync(h, r.d.counters, sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
     MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
-    out.pathsStarted = h[0] < r.d.pathLimit ? h[0] : r.d.pathLimit;
-    out.pathsCompleted = h[1]; out.closestRays = h[2]; out.shadowRays = h[3];
+    FillStats(r, h, out);
+}
+
+// Begins the pass "samples [sampleStart, sampleStart + sampleCount) of every pixel of the region": the tile loop of
+// PathTracerRendererT::DoLatencyRender (TracerDLL/PathTracerRenderer.cu:L1078-1160) + ImageTiler::NextTile
+// (Tracer/RenderImage.cpp:L20-136). Asynchronous: the claim counter is reset in stream order; the caller must have seen
+// the previous pass finish (run_pass / get_stats), because paths of two passes cannot share the slots of one region.
+void RendererBeginPass(Context& ctx, mrb_renderer_t& r, const uint32_t regionMin[2], const uint32_t regionSize[2],
+                       uint32_t sampleStart, uint32_t sampleCount)
+{
+    RenderData& d = r.d;
+    if(regionSize[0] == 0 || regionSize[1] == 0 || regionSize[0] > r.maxWidth || regionSize[1] > r.maxHeight ||
+       uint64_t(regionSize[0]) * regionSize[1] > uint64_t(r.maxWidth) * r.maxHeight)
+        throw std::runtime_error("pass region exceeds the renderer's tile");
+    if(regionMin[0] + regionSize[0] > d.fullWidth || regionMin[1] + regionSize[1] > d.fullHeight)
+        throw std::runtime_error("pass region exceeds the image");
+    r.startedBefore += d.pathLimit;
+    d.regionX = regionMin[0]; d.regionY = regionMin[1]; d.width = regionSize[0]; d.height = regionSize[1];
+    d.sampleBase = sampleStart;
+    d.pathLimit = uint64_t(sampleCount) * regionSize[0] * regionSize[1];
+    r.completedTarget += d.pathLimit;
+    MRB_CUDA_TRY(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long), ctx.stream));
+    r.needReload = true;
+}
+
+// Iterates until the current pass has finished, without draining the stream between polls: `chunk` iterations are
+// always in flight while the counters of the previous chunk travel to pinned host memory (the reference reads its dead
+// path count on the host after every single iteration, PathTracerRenderer.cu:L1046-1061). The iterations queued
+// behind the one that finished the pass find no live path and cost ~0.1 ms each at 1080p.
+void RendererRunPass(Context& ctx, mrb_renderer_t& r, uint32_t chunk, mrb_render_stats& out)
+{
+    if(chunk == 0) chunk = 4;
+    int k = 0; bool havePrev = false;
+    for(;;)
+    {
+        RenderIterate(ctx, r, chunk);
+        MRB_CUDA_TRY(cudaMemcpyAsync(r.hCounters + 8 * k, r.d.counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, ctx.stream));
+        MRB_CUDA_TRY(cudaEventRecord(r.evPoll[k], ctx.stream));
+        if(havePrev)
+        {
+            MRB_CUDA_TRY(cudaEventSynchronize(r.evPoll[k ^ 1]));
+            if(r.hCounters[8 * (k ^ 1) + 1] >= r.completedTarget) break;
+        }
+        havePrev = true; k ^= 1;
+    }
+    // the chunk still in flight completes no path; its counters equal the ones just read except for the claim counter
+    FillStats(r, r.hCounters + 8 * (k ^ 1), out);
     out.iterations = r.iterations;
-    out.finished = (h[1] >= r.d.pathLimit) ? 1u : 0u;
+    memcpy(r.lastCounters, r.hCounters + 8 * (k ^ 1), sizeof(r.lastCounters));
+    r.pollPending = false;
+}
+
+// Non-blocking counters: returns the latest snapshot that has reached pinned host memory and queues the next one behind
+// the work issued so far, so a caller that iterates once per call (throughput mode) learns about the end of the render
+// an iteration or two late instead of draining the stream every bounce.
+void RendererPollStats(Context& ctx, mrb_renderer_t& r, mrb_render_stats& out)
+{
+    if(r.pollPending && cudaEventQuery(r.evPoll[0]) == cudaSuccess)
+    {
+        memcpy(r.lastCounters, r.hCounters, sizeof(r.lastCounters));
+        r.pollPending = false;
+    }
+    cudaGetLastError();   // cudaErrorNotReady is not an error
+    if(!r.pollPending)
+    {
+        MRB_CUDA_TRY(cudaMemcpyAsync(r.hCounters, r.d.counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, ctx.stream));
+        MRB_CUDA_TRY(cudaEventRecord(r.evPoll[0], ctx.stream));
+        r.pollPending = true;
+    }
+    FillStats(r, r.lastCounters, out);
 }
 
 void RendererReadFilm(Context& ctx, mrb_renderer_t& r, float* out, bool device, bool clear)
@@ -1109,30 +1324,135 @@ void RendererReadFilm(Context& ctx, mrb_renderer_t& r, float* out, bool device, 
     if(!device) MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
 }
 
+// RenderImage::TransferToHost (Tracer/RenderImage.cpp:L163-219): the film accumulated since the last hand-off travels
+// to (pinned) host memory on a copy stream and is cleared there, `onComplete` runs when the copy has landed (the
+// reference issues its semaphore release the same way), and rendering continues at once into the other film buffer.
+void RendererFilmHandoff(Context& ctx, mrb_renderer_t& r, float* hostDst, void (*onComplete)(void*), void* user)
+{
+    const size_t bytes = sizeof(float) * 4 * size_t(r.d.width) * r.d.height;
+    const int c = r.cur;
+    MRB_CUDA_TRY(cudaEventRecord(r.evCompute, ctx.stream));
+    MRB_CUDA_TRY(cudaStreamWaitEvent(r.copyStream, r.evCompute, 0));
+    MRB_CUDA_TRY(cudaMemcpyAsync(hostDst, r.film[c], bytes, cudaMemcpyDeviceToHost, r.copyStream));
+    MRB_CUDA_TRY(cudaMemsetAsync(r.film[c], 0, bytes, r.copyStream));
+    MRB_CUDA_TRY(cudaEventRecord(r.evCopied[c], r.copyStream));
+    r.copied[c] = true;
+    if(onComplete) MRB_CUDA_TRY(cudaLaunchHostFunc(r.copyStream, onComplete, user));
+    // continue into the other buffer once ITS previous hand-off (two calls ago) has been copied and cleared
+    r.cur = c ^ 1;
+    if(r.copied[r.cur]) MRB_CUDA_TRY(cudaStreamWaitEvent(ctx.stream, r.evCopied[r.cur], 0));
+    r.d.film = r.film[r.cur];
+}
+
 float* RendererFilmPtr(mrb_renderer_t& r) { return r.d.film; }
 
-// Latency mode (PathTracerRendererT::DoLatencyRender, TracerDLL/PathTracerRenderer.cu:L1078-1160): paths are only
-// started up to `sppLimit` samples per pixel; the caller iterates until they have all died, hands the film over and
-// raises the limit for the next pass. Slots that found no sample to claim kept incrementing the claim counter, so it is
-// put back to the number of paths really started (= the old limit, all of which have completed).
+// Sums the films of `peers` (renderers of OTHER devices with the same tile) into r's film over peer memory and clears
+// them: the film reduction of SURVEY.md §8e fused with the "clear tile film" step. Each peer's stream is joined
+// through an event; the kernel runs on r's device and reads the peers' HBM over NVLink.
+__global__ void KReduceFilms(float4* __restrict__ dst, const float4* const* __restrict__ srcs, uint32_t nSrc, size_t count4)
+{
+    for(size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < count4; i += size_t(gridDim.x) * blockDim.x)
+    {
+        float4 acc = dst[i];
+        for(uint32_t s = 0; s < nSrc; s++)
+        {
+            float4* sp = const_cast<float4*>(srcs[s]) + i;
+            const float4 v = *sp;
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            *sp = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        dst[i] = acc;
+    }
+}
+
+void RendererReducePeers(Context& ctx, mrb_renderer_t& r, Context* const* peerCtx, mrb_renderer_t* const* peers, uint32_t n)
+{
+    if(n == 0) return;
+    if(n > 15) throw std::runtime_error("too many peer renderers");
+    const size_t floats = size_t(4) * r.d.width * r.d.height;
+    if(floats % 4) throw std::runtime_error("film size must be a multiple of 4 floats");
+    std::vector<const float4*> h(n);
+    for(uint32_t k = 0; k < n; k++)
+    {
+        if(peers[k]->d.width != r.d.width || peers[k]->d.height != r.d.height) throw std::runtime_error("peer renderer has a different tile");
+        if(peerCtx[k]->device != ctx.device)
+        {
+            int can = 0;
+            MRB_CUDA_TRY(cudaDeviceCanAccessPeer(&can, ctx.device, peerCtx[k]->device));
+            if(!can) throw std::runtime_error("no peer access between the devices");
+            cudaError_t e = cudaDeviceEnablePeerAccess(peerCtx[k]->device, 0);
+            if(e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) throw CudaError{e, __FILE__, __LINE__};
+            cudaGetLastError();
+        }
+        // join the peer's stream: record on its device, wait on ours
+        MRB_CUDA_TRY(cudaSetDevice(peerCtx[k]->device));
+        MRB_CUDA_TRY(cudaEventRecord(peers[k]->evCompute, peerCtx[k]->stream));
+        MRB_CUDA_TRY(cudaSetDevice(ctx.device));
+        MRB_CUDA_TRY(cudaStreamWaitEvent(ctx.stream, peers[k]->evCompute, 0));
+        h[k] = reinterpret_cast<const float4*>(peers[k]->d.film);
+    }
+    ctx.scratch.Reserve(sizeof(float4*) * 16);
+    const float4** dPtrs = static_cast<const float4**>(ctx.scratch.Base());
+    MRB_CUDA_TRY(cudaMemcpyAsync(dPtrs, h.data(), sizeof(float4*) * n, cudaMemcpyHostToDevice, ctx.stream));
+    MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));   // h is a stack vector
+    const size_t count4 = floats / 4;
+    MRB_LAUNCH(ctx, KReduceFilms, GridFor(ctx, uint32_t(count4), 256, 8), 256, 0, reinterpret_cast<float4*>(r.d.film), dPtrs, n, count4);
+    // the peers may only go on once their films have been read and cleared
+    MRB_CUDA_TRY(cudaEventRecord(r.evCompute, ctx.stream));
+    for(uint32_t k = 0; k < n; k++)
+    {
+        MRB_CUDA_TRY(cudaSetDevice(peerCtx[k]->device));
+        MRB_CUDA_TRY(cudaStreamWaitEvent(peerCtx[k]->stream, r.evCompute, 0));
+    }
+    MRB_CUDA_TRY(cudaSetDevice(ctx.device));
+}
+
+// Latency mode (PathTracerRendererT::DoLatencyRender, TracerDLL/PathTracerRenderer.cu:L1078-1160) on top of passes:
+// raising the limit from a to b begins the pass "samples [a, b) of every pixel".
 void RendererSetSppLimit(Context& ctx, mrb_renderer_t& r, uint32_t sppLimit)
 {
-    const uint64_t pixels = uint64_t(r.d.width) * r.d.height;
-    const uint64_t limit = uint64_t(sppLimit) * pixels;
-    if(limit > r.totalPaths) throw std::runtime_error("spp limit exceeds totalSPP");
+    if(sppLimit > r.totalSPP) throw std::runtime_error("spp limit exceeds totalSPP");
     unsigned long long h[2];
     MRB_CUDA_TRY(cudaMemcpyAsync(h, r.d.counters, sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
     MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
-    if(limit < r.d.pathLimit && h[0] > limit) throw std::runtime_error("spp limit below the samples already started");
-    if(h[0] > r.d.pathLimit)
+    const unsigned long long started = r.startedBefore + (h[0] < r.d.pathLimit ? h[0] : r.d.pathLimit);
+    const uint32_t regionMin[2] = {r.d.regionX, r.d.regionY}, regionSize[2] = {r.d.width, r.d.height};
+    if(started == 0 && h[1] == 0)
     {
-        if(h[1] < r.d.pathLimit) throw std::runtime_error("the current pass has not finished");
-        const unsigned long long started = r.d.pathLimit;
-        MRB_CUDA_TRY(cudaMemcpyAsync(r.d.counters, &started, sizeof(started), cudaMemcpyHostToDevice, ctx.stream));
-        MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
+        // nothing has been started yet: the initial all-samples pass shrinks to [0, sppLimit)
+        r.completedTarget = 0; r.d.pathLimit = 0;
+        RendererBeginPass(ctx, r, regionMin, regionSize, r.sampleOffset, sppLimit);
+        r.sppStarted = sppLimit;
+        return;
     }
-    r.d.pathLimit = limit;
-    r.needReload = true;   // the next iteration starts with KReload again (free slots claim the new samples)
+    if(sppLimit < r.sppStarted) throw std::runtime_error("spp limit below the samples already started");
+    if(h[1] < r.completedTarget) throw std::runtime_error("the current pass has not finished");
+    RendererBeginPass(ctx, r, regionMin, regionSize, r.sampleOffset + r.sppStarted, sppLimit - r.sppStarted);
+    r.sppStarted = sppLimit;
+}
+
+// mrb_filter_sample: the film filter on its own (parity tap of FilterSample; Tests/Tracer/T_Filters.cu)
+__global__ void KFilterSample(uint32_t type, float radius, const float2* __restrict__ xi, uint32_t n, float4* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    float ox, oy, pdf, eval;
+    FilterSample(type, radius, xi[i].x, xi[i].y, ox, oy, pdf, eval);
+    out[i] = make_float4(ox, oy, pdf, eval);
+}
+
+void FilterSampleHost(Context& ctx, uint32_t type, float radius, const float* xi, uint32_t n, float* out)
+{
+    if(type > FILTER_MITCHELL) throw std::runtime_error("unknown film filter type");
+    if(!(radius > 0.0f)) throw std::runtime_error("film filter radius must be positive");
+    MultiAlloc sz(nullptr); sz.Take<float2>(n); sz.Take<float4>(n);
+    ctx.scratch.Reserve(sz.Total());
+    MultiAlloc ma(ctx.scratch.Base());
+    float2* dXi = ma.Take<float2>(n); float4* dOut = ma.Take<float4>(n);
+    MRB_CUDA_TRY(cudaMemcpyAsync(dXi, xi, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx.stream));
+    if(n) MRB_LAUNCH(ctx, KFilterSample, DivUp(n, 256u), 256, 0, type, radius, dXi, n, dOut);
+    MRB_CUDA_TRY(cudaMemcpyAsync(out, dOut, sizeof(float4) * n, cudaMemcpyDeviceToHost, ctx.stream));
+    MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
 }
 
 // mrb_texture_sample: the shading kernel's texture filter on its own (parity tap of SampleTexture)

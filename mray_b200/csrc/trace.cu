@@ -30,7 +30,7 @@ namespace
 {
 
 constexpr int TRACE_TPB = 128;
-constexpr int WIDE_STACK = 64;
+constexpr int WIDE_STACK = int(WIDE_STACK_ENTRIES);   // capi.cu refuses trees with 2 * depth (+ 3 + 2 * top-level depth) above it
 
 struct HitRecord
 {
@@ -962,6 +962,20 @@ KTraceBinary2(SceneData sc,
     }
 }
 
+// Scheduling knobs of the wide kernels, shared by single-accelerator and scene casts (MRB_TRI_DIV / MRB_FETCH_THR
+// override them for parameter sweeps)
+const TraceParams& WideTraceParams()
+{
+    static const TraceParams prm = []
+    {
+        TraceParams p{8u, 24u, 0x47000000u};
+        if(const char* e = getenv("MRB_TRI_DIV")) p.triDiv = uint32_t(atoi(e));
+        if(const char* e = getenv("MRB_FETCH_THR")) p.fetchThr = uint32_t(atoi(e));
+        return p;
+    }();
+    return prm;
+}
+
 } // namespace
 
 void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode mode,
@@ -985,29 +999,26 @@ void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode
 #else
         MRB_CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 8, ctx.stream));
 #endif
-        static int occClosest = 0, occAny = 0;
-        if(!occClosest)
+        if(!ctx.occWide[0])   // per context: a process may drive several devices
         {
-            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occClosest, KTraceWide<false>, TRACE_TPB, 0));
-            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occAny, KTraceWide<true>, TRACE_TPB, 0));
+            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx.occWide[0], KTraceWide<false>, TRACE_TPB, 0));
+            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx.occWide[1], KTraceWide<true>, TRACE_TPB, 0));
         }
-        static TraceParams prm = []
-        {
-            TraceParams p{8u, 24u, 0x47000000u};
-            if(const char* e = getenv("MRB_TRI_DIV")) p.triDiv = uint32_t(atoi(e));
-            if(const char* e = getenv("MRB_FETCH_THR")) p.fetchThr = uint32_t(atoi(e));
-            return p;
-        }();
-        const uint32_t pgrid = min(grid, uint32_t(ctx.smCount) * uint32_t(anyHit ? occAny : occClosest));
+        const TraceParams prm = WideTraceParams();
+        const uint32_t pgrid = min(grid, uint32_t(ctx.smCount) * uint32_t(ctx.occWide[anyHit ? 1 : 0]));
         const uint32_t fbGrid = uint32_t(ctx.smCount);
         if(anyHit)
         {
-            MRB_LAUNCH(ctx, KTraceWide<true>, pgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, fbList, records, prm);
+            { ProfileScope ps(ctx, PROF_TRACE_ANY);
+              MRB_LAUNCH(ctx, KTraceWide<true>, pgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, fbList, records, prm); }
+            ProfileScope pt(ctx, PROF_TRACE_TAIL);
             MRB_LAUNCH(ctx, KTraceBinary<true>, fbGrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, fbList, 0u, counters + 4);
         }
         else
         {
-            MRB_LAUNCH(ctx, KTraceWide<false>, pgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, fbList, records, prm);
+            { ProfileScope ps(ctx, PROF_TRACE_CLOSEST);
+              MRB_LAUNCH(ctx, KTraceWide<false>, pgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, fbList, records, prm); }
+            ProfileScope pt(ctx, PROF_TRACE_TAIL);
             MRB_LAUNCH(ctx, KResolveExact, fbGrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, rays, counters, fbList, records);
             MRB_LAUNCH(ctx, KTraceBinary<false>, fbGrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, fbList, 0u, counters + 4);
         }
@@ -1049,23 +1060,26 @@ void TraceScene(Context& ctx, const SceneData& scnData, bool anyHit, mrb_trace_m
         ma.Take<uint4>(size_t(RESOLVE_CAPACITY) * 4);
         uint32_t* fbList = ma.Take<uint32_t>(rayCount);
         MRB_CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 8, ctx.stream));
-        static int occClosest = 0, occAny = 0;
-        if(!occClosest)
+        if(!ctx.occWide2[0])
         {
-            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occClosest, KTraceWide2<false>, TRACE_TPB, 0));
-            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occAny, KTraceWide2<true>, TRACE_TPB, 0));
+            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx.occWide2[0], KTraceWide2<false>, TRACE_TPB, 0));
+            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx.occWide2[1], KTraceWide2<true>, TRACE_TPB, 0));
         }
-        TraceParams prm{8u, 24u, 0x47000000u};
-        const uint32_t pgrid = min(grid, uint32_t(ctx.smCount) * uint32_t(anyHit ? occAny : occClosest));
+        const TraceParams prm = WideTraceParams();
+        const uint32_t pgrid = min(grid, uint32_t(ctx.smCount) * uint32_t(ctx.occWide2[anyHit ? 1 : 0]));
         const uint32_t fbGrid = uint32_t(ctx.smCount);
         if(anyHit)
         {
-            MRB_LAUNCH(ctx, KTraceWide2<true>, pgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, fbList, prm);
+            { ProfileScope ps(ctx, PROF_TRACE_ANY);
+              MRB_LAUNCH(ctx, KTraceWide2<true>, pgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, fbList, prm); }
+            ProfileScope pt(ctx, PROF_TRACE_TAIL);
             MRB_LAUNCH(ctx, KTraceBinary2<true>, fbGrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, fbList, 0u, counters + 4);
         }
         else
         {
-            MRB_LAUNCH(ctx, KTraceWide2<false>, pgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, fbList, prm);
+            { ProfileScope ps(ctx, PROF_TRACE_CLOSEST);
+              MRB_LAUNCH(ctx, KTraceWide2<false>, pgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, fbList, prm); }
+            ProfileScope pt(ctx, PROF_TRACE_TAIL);
             MRB_LAUNCH(ctx, KTraceBinary2<false>, fbGrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, fbList, 0u, counters + 4);
         }
         ctx.lastFallbackCount = counters;

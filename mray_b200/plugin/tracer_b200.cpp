@@ -29,8 +29,10 @@
 #include <cstring>
 #include <array>
 #include <cmath>
+#include <chrono>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace
@@ -96,16 +98,28 @@ std::array<float, 12> InverseAffine(const Matrix3x4& mat)
     return inv;
 }
 
-class TracerB200 final : public TracerI
+// Everything that lives on ONE GPU. The reference renders on GPUSystem::BestDevice() only
+// (Device/CUDA/GPUSystemCUDA.cpp:L287-289); here one TracerB200 drives `MRB_DEVICES` GPUs of the box:
+// scene buffers, BVHs and LUTs are replicated per device, every pass's sample range is split over the devices, and
+// the per-device films are summed into device 0's over NVLink peer memory before the single RenderImageSection
+// is handed to the caller.
+struct DeviceB200
 {
-    TracerParameters params;
     mrb_context ctx = nullptr;
     mrb_accel accel = nullptr;           // all (T)Identity surfaces
     std::vector<mrb_accel> instAccels;   // two-level scenes: one per distinct (prim ranges, cull flags) set
-    uint32_t sceneInstanceCount = 0, uniqueAccelCount = 0;
     mrb_scene scene = nullptr;           // set when any surface is transformed
     mrb_renderer renderer = nullptr;
     mrb_spectrum spectrum = nullptr;     // SpectrumContextJakob2019 of params.globalTextureColorSpace, made on first use
+};
+
+class TracerB200 final : public TracerI
+{
+    TracerParameters params;
+    std::vector<DeviceB200> devs;        // devs[0] owns the film hand-off
+    mrb_context ctx = nullptr;           // = devs[0].ctx
+    uint32_t sceneInstanceCount = 0, uniqueAccelCount = 0;
+    bool committed = false, twoLevel = false;
     std::mutex mtx; // scene-loading calls arrive concurrently from pool threads (TracerBase.h:L97-130)
 
     std::vector<PrimGroupB200> prims; std::vector<MatGroupB200> mats; std::vector<LightGroupB200> lights;
@@ -120,15 +134,27 @@ class TracerB200 final : public TracerI
     std::vector<int32_t> flatAlbedoTex;             // per flat material: index into flatTextures or -1
     std::vector<uint32_t> flatTextures;             // TextureIds in use, in first-use order
     std::vector<TextureB200> textures;              // TextureId = index + 1 (0 = InvalidTexture)
-    // render hand-off
+    // render hand-off: pinned staging the caller reads between semaphore acquire / release
     TimelineSemaphore* sem = nullptr; uint64_t acquireValue = 0;
-    std::vector<float> staging; Vector2ui resolution = Vector2ui::Zero(), regionMin = Vector2ui::Zero();
+    float* staging = nullptr; size_t stagingBytes = 0;
     struct StartArgs { RendererId id; CamSurfaceId camSurf; RenderImageParams rip; Optional<uint32_t> logic0; };
     Optional<StartArgs> lastStart; Optional<CameraTransform> camOverride, pendingCam; bool rebuilding = false;
-    uint32_t latencySPP = 0;
     uint32_t curRenderer = 0; ThreadPool* pool = nullptr;
+    // ImageTiler state (Tracer/RenderImage.h:L56-110): the region is cut into tiles of at most ~parallelizationHint pixels
+    Vector2ui fullResolution = Vector2ui::Zero(), regionMin = Vector2ui::Zero(), regionSize = Vector2ui::Zero();
+    Vector2ui coveringTile = Vector2ui::Zero(), tileCount = Vector2ui::Zero();
+    uint32_t currentTile = 0; std::vector<uint32_t> tileSPPs;
+    // the sample range [jobBegin, jobEnd) of totalSPP this process renders (MRB_SPP_SHARD = "rank/world": sample-range
+    // sharding across processes, the caller sums the images); a single process renders [0, totalSPP)
+    uint32_t jobBegin = 0, jobEnd = 0;
+    bool throughputSingle = false, saveImage = true;
+    uint64_t completedPaths = 0;
+    // one burst pass: samples [tileSPP, tileSPP + count) of tile `tile`
+    struct PassPlan { uint32_t tile = 0, tileSPP = 0, count = 0; bool operator==(const PassPlan&) const = default; };
+    bool primed = false; PassPlan primedPlan;   // the next pass has been begun (and its first iterations queued) already
 
     void Check(mrb_status s) const { if(s != MRB_OK) throw MRayError("{}", mrb_last_error(ctx)); }
+    static void CheckOn(const DeviceB200& d, mrb_status s) { if(s != MRB_OK) throw MRayError("{}", mrb_last_error(d.ctx)); }
     template<class G> G& Get(std::vector<G>& v, uint32_t id, std::string_view what)
     { if(id >= v.size()) throw MRayError("Unable to find {}({})", what, id); return v[id]; }
     template<class G> const G& Get(const std::vector<G>& v, uint32_t id, std::string_view what) const
@@ -139,8 +165,28 @@ class TracerB200 final : public TracerI
     {
         if(mrb_abi_version() != MRB_ABI_VERSION)   // descriptor layouts must match the header this object was compiled against
             throw MRayError("mray_b200: libmray_b200.so has ABI {:#x}, the plugin was built for {:#x}", mrb_abi_version(), uint32_t(MRB_ABI_VERSION));
-        mrb_status s = mrb_context_create(0, &ctx);
-        if(s != MRB_OK) throw MRayError("mray_b200: {}", mrb_last_error(nullptr)); // no CPU fallback
+        // MRB_DEVICES = "N" (devices 0..N-1) or a comma list; default: one device, MRB_DEVICE (0)
+        std::vector<int> ids;
+        if(const char* e = std::getenv("MRB_DEVICES"))
+        {
+            const std::string v(e);
+            if(v.find(',') == std::string::npos) { int n = std::atoi(e); for(int k = 0; k < n; k++) ids.push_back(k); }
+            else for(size_t b = 0; b < v.size();) { size_t c = v.find(',', b); if(c == std::string::npos) c = v.size(); ids.push_back(std::atoi(v.substr(b, c - b).c_str())); b = c + 1; }
+        }
+        if(ids.empty()) { const char* e = std::getenv("MRB_DEVICE"); ids.push_back(e ? std::atoi(e) : 0); }
+        for(int id : ids)
+        {
+            DeviceB200 d;
+            mrb_status s = mrb_context_create(id, &d.ctx);
+            if(s != MRB_OK)
+            {
+                const std::string msg = mrb_last_error(nullptr);
+                for(DeviceB200& o : devs) mrb_context_destroy(o.ctx);
+                throw MRayError("mray_b200: {}", msg); // no CPU fallback
+            }
+            devs.push_back(d);
+        }
+        ctx = devs[0].ctx;
         // implicit groups, id 0 of every kind (Core/TracerI.h:L99-124)
         prims.push_back(PrimGroupB200{std::string(TracerConstants::EmptyPrimName), true});
         mats.push_back(MatGroupB200{std::string(TracerConstants::PassthroughMatName), true});
@@ -152,7 +198,7 @@ class TracerB200 final : public TracerI
     // SpectrumContextJakob2019 ctor (Tracer/SpectrumContext.cu:L354-532): LUT file + normalised CIE tables
     void EnsureSpectrum()
     {
-        if(spectrum) return;
+        if(devs[0].spectrum) return;
         const MRayColorSpaceEnum cs = params.globalTextureColorSpace;
         const std::string fileName = std::string(MRayColorSpaceStringifier::ToString(cs)) + std::string(Color::LUT_FILE_EXT);
         namespace fs = std::filesystem;
@@ -191,7 +237,7 @@ class TracerB200 final : public TracerI
         d.lut = lut.data(); d.lutResolution = res; d.observerXYZ = observer.data(); d.illuminantSPD = illum.data();
         for(unsigned i = 0; i < 9; i++) d.xyzToRGB[i] = xyzToRGB[i];
         d.wavelengthSampleMode = uint32_t(params.wavelengthSampleMode.e);
-        Check(mrb_spectrum_create(ctx, &d, &spectrum));
+        for(DeviceB200& dv : devs) CheckOn(dv, mrb_spectrum_create(dv.ctx, &d, &dv.spectrum));
     }
     // SobolDetail::SobolMatrices as data (mray_b200/data/sobol_matrices.bin, or $MRB_DATA_DIR)
     std::vector<uint32_t> sobolMatrices;
@@ -214,19 +260,28 @@ class TracerB200 final : public TracerI
         }
         throw MRayError("Unable to open the Sobol generator matrices (sobol_matrices.bin)");
     }
+    void ReleaseRenderers()
+    {
+        for(DeviceB200& d : devs) if(d.renderer) { mrb_renderer_destroy(d.ctx, d.renderer); d.renderer = nullptr; }
+    }
     void ReleaseAccels()
     {
-        if(scene) { mrb_scene_destroy(ctx, scene); scene = nullptr; }
-        for(mrb_accel a : instAccels) mrb_accel_destroy(ctx, a);
-        instAccels.clear();
-        if(accel) { mrb_accel_destroy(ctx, accel); accel = nullptr; }
+        for(DeviceB200& d : devs)
+        {
+            if(d.scene) { mrb_scene_destroy(d.ctx, d.scene); d.scene = nullptr; }
+            for(mrb_accel a : d.instAccels) mrb_accel_destroy(d.ctx, a);
+            d.instAccels.clear();
+            if(d.accel) { mrb_accel_destroy(d.ctx, d.accel); d.accel = nullptr; }
+        }
+        committed = false; twoLevel = false; sceneInstanceCount = 0; uniqueAccelCount = 0;
     }
     ~TracerB200() override
     {
-        if(renderer) mrb_renderer_destroy(ctx, renderer);
-        if(spectrum) mrb_spectrum_destroy(ctx, spectrum);
+        ReleaseRenderers();
+        if(staging) mrb_host_free(ctx, staging);
+        for(DeviceB200& d : devs) if(d.spectrum) mrb_spectrum_destroy(d.ctx, d.spectrum);
         ReleaseAccels();
-        mrb_context_destroy(ctx);
+        for(DeviceB200& d : devs) mrb_context_destroy(d.ctx);
     }
 
     // ------------------------------- generic -------------------------------
@@ -702,8 +757,9 @@ class TracerB200 final : public TracerI
         if(pgUsed < 0 || groups.empty()) throw MRayError("empty scene");
         flatPrimGroup = uint32_t(pgUsed);
         const PrimGroupB200& pg = prims[flatPrimGroup];
+        ReleaseRenderers();
         ReleaseAccels();
-        auto BuildGroup = [&](const Group& g)
+        auto BuildGroup = [&](const DeviceB200& dv, const Group& g)
         {
             mrb_accel_desc d = {};
             d.positions = reinterpret_cast<const float*>(pg.positions.data()); d.vertexCount = pg.vertexTotal;
@@ -712,51 +768,57 @@ class TracerB200 final : public TracerI
             d.rangeCount = uint32_t(g.lmKeys.size()); d.primRanges = g.ranges.data();
             d.lightOrMatKeys = g.lmKeys.data(); d.cullBackface = g.cull.data(); d.flags = MRB_BUILD_DEFAULT;
             mrb_accel a = nullptr;
-            Check(mrb_accel_build(ctx, &d, &a));
+            CheckOn(dv, mrb_accel_build(dv.ctx, &d, &a));
             return a;
         };
         AABB3 aabb;
         if(groups.size() == 1 && groups[0].transformId == 0)
         {
-            accel = BuildGroup(groups[0]);
-            mrb_accel_info info; Check(mrb_accel_get_info(ctx, accel, &info));
+            // the scene is replicated: every device builds its own copy of the BVH (264 K triangles: 0.5 ms)
+            for(DeviceB200& dv : devs) dv.accel = BuildGroup(dv, groups[0]);
+            mrb_accel_info info; Check(mrb_accel_get_info(ctx, devs[0].accel, &info));
             aabb = AABB3(Vector3(info.aabb[0], info.aabb[1], info.aabb[2]), Vector3(info.aabb[3], info.aabb[4], info.aabb[5]));
         }
         else
         {
             // Groups with the same prim ranges and cull flags share ONE accelerator and differ only in transform and
             // LightOrMatKeys — the reference's concrete-accelerator / instance split (Tracer/AcceleratorC.h:L780-905).
-            std::vector<mrb_instance_desc> inst(groups.size());
-            std::vector<size_t> builtFor;   // group index each unique accelerator was built from
-            for(size_t k = 0; k < groups.size(); k++)
+            for(DeviceB200& dv : devs)
             {
-                mrb_accel a = nullptr;
-                for(size_t u = 0; u < builtFor.size() && !a; u++)
-                    if(groups[builtFor[u]].ranges == groups[k].ranges && groups[builtFor[u]].cull == groups[k].cull) a = instAccels[u];
-                if(!a) { a = BuildGroup(groups[k]); instAccels.push_back(a); builtFor.push_back(k); }
-                const uint32_t tid = groups[k].transformId;
-                const Matrix3x4& m = transforms[tid >> TRANS_ID_BITS].matrices[tid & ((1u << TRANS_ID_BITS) - 1u)];
-                const std::array<float, 12> inv = InverseAffine(m);  // KCInvertTransforms (Tracer/TransformC.h:L119-123)
-                mrb_instance_desc& d = inst[k];
-                d = {};
-                d.accel = a;
-                for(unsigned r = 0; r < 3; r++) for(unsigned c = 0; c < 4; c++)
-                { d.transform[4 * r + c] = m(r, c); d.invTransform[4 * r + c] = inv[4 * r + c]; }
-                d.isIdentity = (tid == 0) ? 1 : 0;
-                d.transformKey = tid; d.accelKey = uint32_t(k);
-                d.lightOrMatKeys = groups[k].lmKeys.data();
+                std::vector<mrb_instance_desc> inst(groups.size());
+                std::vector<size_t> builtFor;   // group index each unique accelerator was built from
+                for(size_t k = 0; k < groups.size(); k++)
+                {
+                    mrb_accel a = nullptr;
+                    for(size_t u = 0; u < builtFor.size() && !a; u++)
+                        if(groups[builtFor[u]].ranges == groups[k].ranges && groups[builtFor[u]].cull == groups[k].cull) a = dv.instAccels[u];
+                    if(!a) { a = BuildGroup(dv, groups[k]); dv.instAccels.push_back(a); builtFor.push_back(k); }
+                    const uint32_t tid = groups[k].transformId;
+                    const Matrix3x4& m = transforms[tid >> TRANS_ID_BITS].matrices[tid & ((1u << TRANS_ID_BITS) - 1u)];
+                    const std::array<float, 12> inv = InverseAffine(m);  // KCInvertTransforms (Tracer/TransformC.h:L119-123)
+                    mrb_instance_desc& d = inst[k];
+                    d = {};
+                    d.accel = a;
+                    for(unsigned r = 0; r < 3; r++) for(unsigned c = 0; c < 4; c++)
+                    { d.transform[4 * r + c] = m(r, c); d.invTransform[4 * r + c] = inv[4 * r + c]; }
+                    d.isIdentity = (tid == 0) ? 1 : 0;
+                    d.transformKey = tid; d.accelKey = uint32_t(k);
+                    d.lightOrMatKeys = groups[k].lmKeys.data();
+                }
+                CheckOn(dv, mrb_scene_build(dv.ctx, inst.data(), uint32_t(inst.size()), &dv.scene));
+                sceneInstanceCount = uint32_t(inst.size()); uniqueAccelCount = uint32_t(dv.instAccels.size());
             }
-            Check(mrb_scene_build(ctx, inst.data(), uint32_t(inst.size()), &scene));
-            sceneInstanceCount = uint32_t(inst.size()); uniqueAccelCount = uint32_t(instAccels.size());
+            twoLevel = true;
             float box[6];
-            Check(mrb_scene_export_tlas(ctx, scene, nullptr, box, nullptr, nullptr, nullptr, nullptr));
+            Check(mrb_scene_export_tlas(ctx, devs[0].scene, nullptr, box, nullptr, nullptr, nullptr, nullptr));
             aabb = AABB3(Vector3(box[0], box[1], box[2]), Vector3(box[3], box[4], box[5]));
         }
+        committed = true;
         return SurfaceCommitResult
         {
             .aabb = aabb,
             .instanceCount = surfaces.size() + lightSurfaces.size(),
-            .acceleratorCount = scene ? uniqueAccelCount : 1u
+            .acceleratorCount = twoLevel ? uniqueAccelCount : 1u
         };
     }
 
@@ -779,7 +841,7 @@ class TracerB200 final : public TracerI
     void DestroyRenderer(RendererId id) override
     {
         if(Raw(id) >= renderers.size()) throw MRayError("Unable to find renderer ({})", Raw(id));
-        if(Raw(id) == curRenderer && renderer) { mrb_renderer_destroy(ctx, renderer); renderer = nullptr; }
+        if(Raw(id) == curRenderer) ReleaseRenderers();
     }
     void PushRendererAttribute(RendererId id, uint32_t attributeIndex, TransientData dataIn) override
     {
@@ -802,10 +864,40 @@ class TracerB200 final : public TracerI
 
     // ------------------------------- rendering -------------------------------
     void SetupRenderEnv(TimelineSemaphore* s, uint32_t, uint64_t initialAcquireValue) override { sem = s; acquireValue = initialAcquireValue; }
+
+    // ImageTiler::FindOptimumTileSize (Tracer/RenderImage.cpp:L20-52): a tile of about `parallelizationHint` pixels with
+    // the region's aspect ratio, adjusted so that an integer number of equal tiles covers each side
+    static Vector2ui FindOptimumTileSize(Vector2ui fbSize, uint32_t hint)
+    {
+        const Float aspect = Float(fbSize[0]) / Float(fbSize[1]);
+        const Float factor = std::sqrt(Float(hint) / aspect);
+        const Vector2ui tileHint(uint32_t(std::round(aspect * factor)), uint32_t(std::round(factor)));
+        auto Adjust = [&](unsigned i) -> uint32_t
+        {
+            if(fbSize[i] < tileHint[i]) return fbSize[i];
+            uint32_t count = uint32_t(std::round(Float(fbSize[i]) / Float(tileHint[i])));
+            uint32_t result = fbSize[i] / count, residual = fbSize[i] % count;
+            return result + (residual + count - 1) / count;
+        };
+        return Vector2ui(Adjust(0), Adjust(1));
+    }
+    Vector2ui TileStart(uint32_t t) const { return Vector2ui((t % tileCount[0]) * coveringTile[0], (t / tileCount[0]) * coveringTile[1]); }
+    Vector2ui TileEnd(uint32_t t) const
+    {
+        Vector2ui e((t % tileCount[0] + 1) * coveringTile[0], (t / tileCount[0] + 1) * coveringTile[1]);
+        return Vector2ui(std::min(e[0], regionSize[0]), std::min(e[1], regionSize[1]));
+    }
+    // [begin, end) of `count` items for part `k` of `n`: contiguous, sizes differ by at most one
+    static std::pair<uint32_t, uint32_t> Share(uint32_t count, uint32_t n, uint32_t k)
+    {
+        uint32_t base = count / n, extra = count % n, b = k * base + std::min(k, extra);
+        return {b, b + base + (k < extra ? 1u : 0u)};
+    }
+
     RenderBufferInfo StartRender(RendererId id, CamSurfaceId camSurf, RenderImageParams rip, Optional<uint32_t> logic0, Optional<uint32_t>) override
     {
         if(!sem) throw MRayError("Render environment is not set properly! Please provide a semaphore to the tracer.");
-        if(!accel && !scene) throw MRayError("CommitSurfaces must be called before StartRender");
+        if(!committed) throw MRayError("CommitSurfaces must be called before StartRender");
         if(!rebuilding) { camOverride.reset(); pendingCam.reset(); }
         lastStart = StartArgs{id, camSurf, rip, logic0};
         const RendererB200& r = Get(renderers, Raw(id), "Renderer");
@@ -813,21 +905,48 @@ class TracerB200 final : public TracerI
         const CamGroupB200& cg = Get(cams, Raw(cs.cameraId) >> CAM_ID_BITS, "CameraGroup");
         uint32_t ci = Raw(cs.cameraId) & ((1u << CAM_ID_BITS) - 1u);
         const PrimGroupB200& pg = prims[flatPrimGroup];
-        if(renderer) { mrb_renderer_destroy(ctx, renderer); renderer = nullptr; }
-        Vector2ui tile = rip.regionMax - rip.regionMin;
-        if(rip.regionMax[0] > rip.resolution[0] || rip.regionMax[1] > rip.resolution[1] || tile[0] == 0 || tile[1] == 0 ||
+        ReleaseRenderers();
+        if(rip.regionMax[0] > rip.resolution[0] || rip.regionMax[1] > rip.resolution[1] ||
            rip.regionMin[0] >= rip.regionMax[0] || rip.regionMin[1] >= rip.regionMax[1])
             throw MRayError("StartRender: bad render region");
+        // TracerParameters.filmFilter (Core/TracerI.h:L45-68): an unknown type is an error, not a Gaussian
+        uint32_t filterType;
+        switch(params.filmFilter.type)
+        {
+            case FilterType::BOX: filterType = MRB_FILTER_BOX; break;
+            case FilterType::TENT: filterType = MRB_FILTER_TENT; break;
+            case FilterType::GAUSSIAN: filterType = MRB_FILTER_GAUSSIAN; break;
+            case FilterType::MITCHELL_NETRAVALI: filterType = MRB_FILTER_MITCHELL_NETRAVALI; break;
+            default: throw MRayError("Unknown film filter type ({})", uint32_t(params.filmFilter.type));
+        }
+        // tiles (ImageTiler ctor, Tracer/RenderImage.cpp:L54-76)
+        fullResolution = rip.resolution; regionMin = rip.regionMin; regionSize = rip.regionMax - rip.regionMin;
+        coveringTile = FindOptimumTileSize(regionSize, std::max<uint32_t>(params.parallelizationHint, 1u));
+        tileCount = Vector2ui((regionSize[0] + coveringTile[0] - 1) / coveringTile[0], (regionSize[1] + coveringTile[1] - 1) / coveringTile[1]);
+        currentTile = 0; tileSPPs.assign(size_t(tileCount[0]) * tileCount[1], 0u);
+        // the samples this process is responsible for
+        jobBegin = 0; jobEnd = r.totalSPP;
+        if(const char* e = std::getenv("MRB_SPP_SHARD"))
+        {
+            unsigned rank = 0, world = 1;
+            if(std::sscanf(e, "%u/%u", &rank, &world) != 2 || world == 0 || rank >= world) throw MRayError("MRB_SPP_SHARD must be \"rank/world\"");
+            auto [b, en] = Share(r.totalSPP, world, rank);
+            jobBegin = b; jobEnd = en;
+        }
+        const uint32_t jobSamples = jobEnd - jobBegin;
+        const bool singleTile = tileSPPs.size() == 1;
+        // PathTracerRendererBase::DoRender's dispatch (Tracer/PathTracerRendererBase.cu:L515-533)
+        throughputSingle = !r.latency && singleTile && r.burstSize <= 1;
+        saveImage = true; completedPaths = 0; primed = false;
+
         mrb_render_desc d = {};
         bool hasNormals = std::any_of(pg.normals.begin(), pg.normals.end(), [](const Vector3& n) { return n != Vector3::Zero(); });
         const float* normals = hasNormals ? reinterpret_cast<const float*>(pg.normals.data()) : nullptr;
-        std::vector<const float*> instNormals(scene ? sceneInstanceCount : 1u, normals);
-        if(scene) { d.scene = scene; d.instanceVertexNormals = instNormals.data(); }
-        else { d.accel = accel; d.vertexCount = pg.vertexTotal; d.triangleCount = pg.primTotal; d.vertexNormals = normals; }
+        std::vector<const float*> instNormals(twoLevel ? sceneInstanceCount : 1u, normals);
         d.materialCount = uint32_t(flatAlbedo.size() / 3); d.albedo = flatAlbedo.data();
         d.materialType = flatMaterialType.data();
         std::vector<mrb_texture_desc> texDescs(flatTextures.size());
-        std::vector<const float*> instUVs(scene ? sceneInstanceCount : 1u, reinterpret_cast<const float*>(pg.uvs.data()));
+        std::vector<const float*> instUVs(twoLevel ? sceneInstanceCount : 1u, reinterpret_cast<const float*>(pg.uvs.data()));
         if(!flatTextures.empty())
         {
             for(size_t k = 0; k < flatTextures.size(); k++)
@@ -837,7 +956,6 @@ class TracerB200 final : public TracerI
                                                uint32_t(t.params.interpolation), uint32_t(t.params.edgeResolve)};
             }
             d.textureCount = uint32_t(texDescs.size()); d.textures = texDescs.data(); d.albedoTexture = flatAlbedoTex.data();
-            if(scene) d.instanceVertexUVs = instUVs.data(); else d.vertexUVs = instUVs[0];
         }
         d.lightCount = uint32_t(flatLightTwoSided.size()); d.lightRadiance = flatLightRadiance.data(); d.lightTwoSided = flatLightTwoSided.data();
         for(int k = 0; k < 3; k++) { d.camPosition[k] = cg.position[ci][k]; d.camGaze[k] = cg.gaze[ci][k]; d.camUp[k] = cg.up[ci][k]; }
@@ -845,21 +963,22 @@ class TracerB200 final : public TracerI
             for(int k = 0; k < 3; k++) { d.camPosition[k] = camOverride->position[k]; d.camGaze[k] = camOverride->gazePoint[k]; d.camUp[k] = camOverride->up[k]; }
         d.fovXY[0] = cg.fovPlanes[ci][0]; d.fovXY[1] = cg.fovPlanes[ci][1];
         d.nearFar[0] = cg.fovPlanes[ci][2]; d.nearFar[1] = cg.fovPlanes[ci][3];
-        d.width = tile[0]; d.height = tile[1]; d.totalSPP = r.totalSPP;
+        // the renderer's film is one (covering) tile; passes move it over the region
+        d.width = coveringTile[0]; d.height = coveringTile[1];
         d.fullResolution[0] = rip.resolution[0]; d.fullResolution[1] = rip.resolution[1];
         d.regionMin[0] = rip.regionMin[0]; d.regionMin[1] = rip.regionMin[1];
         // render logic 0 rolls the sample mode like PathTracerRendererT::StartRender (L1192-1200)
         d.sampleMode = (r.sampleMode + logic0.value_or(0)) % 3u;
         d.rrRange[0] = r.rrRange[0]; d.rrRange[1] = r.rrRange[1];
-        d.filmFilterRadius = params.filmFilter.radius; d.seed = params.seed;
-        uint64_t pixels = uint64_t(tile[0]) * tile[1];
+        d.filmFilterRadius = params.filmFilter.radius; d.filmFilterType = filterType; d.seed = params.seed;
+        uint64_t pixels = uint64_t(coveringTile[0]) * coveringTile[1];
         d.maxPathCount = uint32_t(std::min<uint64_t>(pixels, std::max<uint32_t>(params.parallelizationHint, 1u)));
         // every material of this plugin is shaded by one fused kernel, so the material-key ray sort
         // (RayPartitioner::MultiPartition) only costs: 8.74 -> 7.74 ms/spp at 1080p without it. It stays
         // available (MRB_PARTITION_RAYS=1) for parity with the reference's per-material work batches.
         const char* pr = std::getenv("MRB_PARTITION_RAYS");
         d.partitionRays = (pr && pr[0] == '1') ? 1u : 0u;
-        if(r.type == "(R)PathTracerSpectral") { EnsureSpectrum(); d.spectrum = spectrum; }
+        if(r.type == "(R)PathTracerSpectral") EnsureSpectrum();
         if(params.samplerType.e != SamplerType::INDEPENDENT)
         {
             // the scramble's final bit reversal is applied unless MRB_REFERENCE_SCRAMBLE=1 (see include/mray_b200.h)
@@ -869,14 +988,35 @@ class TracerB200 final : public TracerI
             if(rs && rs[0] == '1') d.samplerType |= MRB_SAMPLER_REFERENCE_SCRAMBLE;
             d.sobolMatrices = sobolMatrices.data();
         }
-        Check(mrb_renderer_create(ctx, &d, &renderer));
-        latencySPP = 0;
-        if(r.latency || r.burstSize > 1) Check(mrb_renderer_set_spp_limit(ctx, renderer, 0));   // pass mode, see DoRenderWork
-        curRenderer = Raw(id); resolution = tile; regionMin = rip.regionMin;
-        staging.assign(size_t(4) * pixels, 0.0f);
+        d.jobSPP = r.totalSPP;
+        const uint32_t nDev = uint32_t(devs.size());
+        for(uint32_t k = 0; k < nDev; k++)
+        {
+            DeviceB200& dv = devs[k];
+            if(twoLevel) { d.scene = dv.scene; d.accel = nullptr; d.instanceVertexNormals = instNormals.data(); if(!flatTextures.empty()) d.instanceVertexUVs = instUVs.data(); }
+            else { d.accel = dv.accel; d.vertexCount = pg.vertexTotal; d.triangleCount = pg.primTotal; d.vertexNormals = normals; if(!flatTextures.empty()) d.vertexUVs = instUVs[0]; }
+            d.spectrum = (r.type == "(R)PathTracerSpectral") ? dv.spectrum : nullptr;
+            // throughput mode: the renderer's initial pass is this device's share of the job's samples; pass modes
+            // (re)define the range with every pass
+            auto [b, e] = Share(jobSamples, nDev, k);
+            d.sampleOffset = jobBegin + b; d.totalSPP = std::max(e - b, 1u);
+            CheckOn(dv, mrb_renderer_create(dv.ctx, &d, &dv.renderer));
+            if(!throughputSingle || e == b)
+                CheckOn(dv, mrb_renderer_set_spp_limit(dv.ctx, dv.renderer, 0));   // pass modes start empty (DoRenderWork begins the passes); so does a device without samples
+        }
+        curRenderer = Raw(id);
+        const size_t need = size_t(4) * pixels * sizeof(float);
+        if(need > stagingBytes)
+        {
+            if(staging) { mrb_host_free(ctx, staging); staging = nullptr; stagingBytes = 0; }
+            void* ptr = nullptr;
+            Check(mrb_host_alloc(ctx, need, &ptr));
+            staging = static_cast<float*>(ptr); stagingBytes = need;
+        }
+        std::memset(staging, 0, need);
         return RenderBufferInfo
         {
-            .data = reinterpret_cast<const Byte*>(staging.data()), .totalSize = staging.size() * sizeof(float),
+            .data = reinterpret_cast<const Byte*>(staging), .totalSize = need,
             .renderColorSpace = params.globalTextureColorSpace, .resolution = rip.resolution,
             .curRenderLogic0 = logic0.value_or(0), .curRenderLogic1 = 0
         };
@@ -888,10 +1028,50 @@ class TracerB200 final : public TracerI
         if(Raw(id) >= renderers.size()) throw MRayError("Unable to find Renderer({})", Raw(id));
         pendingCam = t;
     }
-    void StopRender() override { if(renderer) { mrb_renderer_destroy(ctx, renderer); renderer = nullptr; } }
+    void StopRender() override { ReleaseRenderers(); }
+
+    static void ReleaseSemaphore(void* user) { static_cast<TimelineSemaphore*>(user)->Release(); }
+
+    // the pass DoLatencyRender would run next on the current tile (TracerDLL/PathTracerRenderer.cu:L1100-1112)
+    PassPlan PlanPass(const RendererB200& rr, uint32_t jobSamples) const
+    {
+        const uint32_t passCount = rr.latency ? 1u : std::max(rr.burstSize, 1u);
+        PassPlan p; p.tile = currentTile; p.tileSPP = tileSPPs[currentTile];
+        uint32_t sppLimit = p.tileSPP + passCount;
+        if(saveImage) sppLimit = std::min(sppLimit, jobSamples);
+        p.count = sppLimit - p.tileSPP;
+        return p;
+    }
+    // every device moves to the pass's tile (the film layout follows the region) and takes its share of the samples
+    void BeginPassOnAll(const PassPlan& plan)
+    {
+        const Vector2ui ts = TileStart(plan.tile), te = TileEnd(plan.tile);
+        const uint32_t rm[2] = {regionMin[0] + ts[0], regionMin[1] + ts[1]}, rs[2] = {te[0] - ts[0], te[1] - ts[1]};
+        const uint32_t nDev = uint32_t(devs.size());
+        for(uint32_t k = 0; k < nDev; k++)
+        {
+            auto [b, e] = Share(plan.count, nDev, k);
+            CheckOn(devs[k], mrb_renderer_begin_pass(devs[k].ctx, devs[k].renderer, rm, rs, jobBegin + plan.tileSPP + b, e - b));
+        }
+    }
+
+    // Runs `work(deviceIndex)` for every device concurrently (device 0 on the calling thread) and rethrows the first failure
+    template<class F> void OnAllDevices(F&& work)
+    {
+        const size_t n = devs.size();
+        if(n == 1) { work(0u); return; }
+        std::vector<std::string> errors(n);
+        std::vector<std::thread> threads;
+        for(size_t k = 1; k < n; k++)
+            threads.emplace_back([&, k]() { try { work(uint32_t(k)); } catch(const MRayError& e) { errors[k] = std::string(e.GetError()); if(errors[k].empty()) errors[k] = "error"; } });
+        try { work(0u); } catch(const MRayError& e) { errors[0] = std::string(e.GetError()); if(errors[0].empty()) errors[0] = "error"; }
+        for(std::thread& t : threads) t.join();
+        for(const std::string& e : errors) if(!e.empty()) throw MRayError("{}", e);
+    }
+
     RendererOutput DoRenderWork() override
     {
-        if(!renderer) return RendererOutput{};
+        if(!devs[0].renderer) return RendererOutput{};
         if(pendingCam && lastStart)
         {
             camOverride = pendingCam; pendingCam.reset();
@@ -900,63 +1080,128 @@ class TracerB200 final : public TracerI
             catch(...) { rebuilding = false; throw; }
             rebuilding = false;
         }
+        const auto t0 = std::chrono::steady_clock::now();
         const RendererB200& rr = renderers[curRenderer];
-        mrb_render_stats st;
-        if(rr.latency || rr.burstSize > 1)
+        const uint32_t nDev = uint32_t(devs.size());
+        const uint32_t jobSamples = jobEnd - jobBegin;
+        Vector2ui secMin, secMax;
+        uint64_t passPaths = 0;
+        bool triggerSave = false;
+        if(throughputSingle)
         {
-            // PathTracerRendererBase::DoRender (Tracer/PathTracerRendererBase.cu:L515-533): renderMode Latency runs
-            // DoLatencyRender(1), Throughput with burstSize > 1 runs DoLatencyRender(burstSize) — that many more samples
-            // of every pixel, traced to completion before the film is handed over (PathTracerRenderer.cu:L1078-1160)
-            latencySPP = std::min(rr.totalSPP, latencySPP + (rr.latency ? 1u : rr.burstSize));
-            Check(mrb_renderer_set_spp_limit(ctx, renderer, latencySPP));
-            do { Check(mrb_renderer_iterate(ctx, renderer, 4)); Check(mrb_renderer_get_stats(ctx, renderer, &st)); } while(!st.finished);
-            st.finished = (latencySPP >= rr.totalSPP) ? 1u : 0u;
+            // DoThroughputSingleTileRender (TracerDLL/PathTracerRenderer.cu:L1010-1076): one wavefront iteration, then the
+            // film delta. The reference synchronises to count the dead paths; here the counters of EARLIER iterations
+            // are polled from pinned memory, so triggerSave follows the last path by an iteration or two (empty ones).
+            secMin = regionMin; secMax = regionMin + regionSize;
+            std::vector<mrb_render_stats> st(nDev);
+            OnAllDevices([&](uint32_t k)
+            {
+                CheckOn(devs[k], mrb_renderer_iterate(devs[k].ctx, devs[k].renderer, 1));
+                CheckOn(devs[k], mrb_renderer_poll_stats(devs[k].ctx, devs[k].renderer, &st[k]));
+            });
+            uint64_t done = 0; bool all = true;
+            for(uint32_t k = 0; k < nDev; k++) { done += st[k].pathsCompleted; all = all && st[k].finished; }
+            passPaths = done - completedPaths; completedPaths = done;
+            triggerSave = saveImage && all;
         }
         else
         {
-            // one wavefront iteration (DoThroughputSingleTileRender), then the film delta hand-off of
-            // RenderImage::TransferToHost (Tracer/RenderImage.cpp:L163-219): acquire, copy, release, next state
-            Check(mrb_renderer_iterate(ctx, renderer, 1));
-            Check(mrb_renderer_get_stats(ctx, renderer, &st));
+            // DoLatencyRender(passCount) (TracerDLL/PathTracerRenderer.cu:L1078-1160): passCount more samples of every pixel
+            // of the current tile, traced to completion; then the tile's film is handed over and the next tile is up
+            const PassPlan plan = PlanPass(rr, jobSamples);
+            const Vector2ui ts = TileStart(plan.tile), te = TileEnd(plan.tile);
+            secMin = regionMin + ts; secMax = regionMin + te;
+            passPaths = uint64_t(plan.count) * (te[0] - ts[0]) * (te[1] - ts[1]);
+            if(!(primed && primedPlan == plan)) BeginPassOnAll(plan);
+            primed = false;
+            OnAllDevices([&](uint32_t k)
+            {
+                auto [b, e] = Share(plan.count, nDev, k);
+                if(e == b) return;
+                mrb_render_stats st;
+                CheckOn(devs[k], mrb_renderer_run_pass(devs[k].ctx, devs[k].renderer, 4, &st));
+            });
+            tileSPPs[plan.tile] = plan.tileSPP + plan.count;
+            completedPaths += passPaths;
+            currentTile = (currentTile + 1) % uint32_t(tileSPPs.size());
+            uint64_t sum = 0; for(uint32_t v : tileSPPs) sum += v;
+            triggerSave = saveImage && sum == uint64_t(jobSamples) * tileSPPs.size();
         }
+        if(triggerSave) saveImage = false;
+        // multi-GPU: the peers' films are added to device 0's (and cleared) over NVLink peer memory
+        if(nDev > 1)
+        {
+            std::vector<mrb_context> pc; std::vector<mrb_renderer> prs;
+            for(uint32_t k = 1; k < nDev; k++) { pc.push_back(devs[k].ctx); prs.push_back(devs[k].renderer); }
+            Check(mrb_renderer_reduce_peers(ctx, devs[0].renderer, pc.data(), prs.data(), uint32_t(prs.size())));
+        }
+        // RenderImage::TransferToHost (Tracer/RenderImage.cpp:L163-219): wait until the caller has read the previous
+        // section, queue the copy into the pinned staging buffer on the copy stream, release the semaphore from a host
+        // callback when it has landed; the next DoRenderWork's kernels overlap the copy (second film buffer)
         if(!sem->Acquire(acquireValue)) return RendererOutput{};
-        Check(mrb_renderer_read_film(ctx, renderer, staging.data(), MRB_MEM_HOST, 1));
-        sem->Release();
+        Check(mrb_renderer_film_handoff(ctx, devs[0].renderer, staging, &TracerB200::ReleaseSemaphore, sem));
         acquireValue += 2;
-        size_t plane = size_t(resolution[0]) * resolution[1] * sizeof(float);
+        if(!throughputSingle && !triggerSave)
+        {
+            // Keep the devices busy while the caller consumes this section: begin the NEXT pass now and queue its first
+            // iterations (they accumulate into the second film buffer); the next DoRenderWork picks the pass up.
+            const PassPlan next = PlanPass(rr, jobSamples);
+            if(next.count > 0)
+            {
+                BeginPassOnAll(next);
+                for(uint32_t k = 0; k < nDev; k++)
+                {
+                    auto [b, e] = Share(next.count, nDev, k);
+                    if(e > b) CheckOn(devs[k], mrb_renderer_iterate(devs[k].ctx, devs[k].renderer, 8));
+                }
+                primed = true; primedPlan = next;
+            }
+        }
+        const Vector2ui secSize = secMax - secMin;
+        size_t plane = size_t(secSize[0]) * secSize[1] * sizeof(float);
         RendererOutput out;
         out.imageOut = RenderImageSection
         {
-            .pixelMin = regionMin, .pixelMax = regionMin + resolution, .globalWeight = Float(1),
+            .pixelMin = secMin, .pixelMax = secMax, .globalWeight = Float(1),
             .waitCounter = acquireValue - 1,
             .pixStartOffsets = {0, plane, 2 * plane}, .weightStartOffset = 3 * plane
         };
+        // CalculateAnalyticDataThroughput / Latency (Tracer/PathTracerRendererBase.cu:L301-360): paths completed by this
+        // call over the CPU time of the call
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        size_t usedMem = 0; for(const DeviceB200& dv : devs) usedMem += mrb_context_used_device_memory(dv.ctx);
         out.analytics = RendererAnalyticData
         {
-            .throughput = 0.0, .throughputSuffix = "M path/s",
-            .workPerPixel = double(st.pathsCompleted) / double(resolution[0] * resolution[1]),
-            .wppLimit = double(renderers[curRenderer].totalSPP), .workPerPixelSuffix = "spp",
-            .iterationTimeMS = 0.0f, .renderResolution = resolution,
+            .throughput = (sec > 0.0) ? double(passPaths) / sec / 1.0e6 : 0.0, .throughputSuffix = "M path/s",
+            .workPerPixel = double(completedPaths) / (double(regionSize[0]) * double(regionSize[1])),
+            .wppLimit = double(jobSamples), .workPerPixelSuffix = "spp",
+            .iterationTimeMS = float(sec * 1.0e3), .renderResolution = fullResolution,
             .outputColorSpace = params.globalTextureColorSpace,
-            .usedGPUMemoryBytes = mrb_context_used_device_memory(ctx)
+            .usedGPUMemoryBytes = usedMem
         };
-        out.triggerSave = st.finished != 0;
+        out.triggerSave = triggerSave;
         return out;
     }
 
     // ------------------------------- misc -------------------------------
     void ClearAll() override
     {
-        StopRender();
-        if(accel) { mrb_accel_destroy(ctx, accel); accel = nullptr; }
-        prims.resize(1); mats.resize(1); lights.resize(1); cams.clear(); renderers.clear();
+        // TracerBase::ClearAll (Tracer/TracerBase.cpp): back to the freshly constructed state, implicit groups only
+        ReleaseRenderers();
+        ReleaseAccels();
+        prims.resize(1); mats.resize(1); lights.resize(1); transforms.resize(1);
+        cams.clear(); renderers.clear();
         surfaces.clear(); lightSurfaces.clear(); camSurfaces.clear(); volumes.clear(); textures.clear();
+        boundary = LightSurfaceParams{};
+        flatPrimGroup = 0; flatLightRadiance.clear(); flatLightTwoSided.clear(); flatAlbedo.clear();
+        flatMaterialType.clear(); flatAlbedoTex.clear(); flatTextures.clear();
+        lastStart.reset(); camOverride.reset(); pendingCam.reset(); tileSPPs.clear(); currentTile = 0;
     }
-    void Flush() const override { mrb_context_synchronize(ctx); }
+    void Flush() const override { for(const DeviceB200& d : devs) mrb_context_synchronize(d.ctx); }
     GPUThreadInitFunction GetThreadInitFunction() const override { return []() {}; } // the C-ABI selects its device per call
     void SetThreadPool(ThreadPool& tp) override { pool = &tp; }
     size_t TotalDeviceMemory() const override { return mrb_context_total_device_memory(ctx); }
-    size_t UsedDeviceMemory() const override { return mrb_context_used_device_memory(ctx); }
+    size_t UsedDeviceMemory() const override { size_t u = 0; for(const DeviceB200& d : devs) u += mrb_context_used_device_memory(d.ctx); return u; }
     const TracerParameters& Parameters() const override { return params; }
 };
 

@@ -57,6 +57,11 @@ ITEMS = {
     # low-discrepancy samplers of the reference (TracerParameters.samplerType)
     "cornell64_sobol_spp4096":  (64, 4096, 13, "WithNEEAndMIS", (2, 20), "Sobol", np.float32, RGB),
     "cornell64_zsobol_spp4096": (64, 4096, 14, "WithNEEAndMIS", (2, 20), "ZSobol", np.float32, RGB),
+    # TracerParameters.filmFilter: the other three film filters (Tracer/Filters.h). Mitchell-Netravali's film weight varies
+    # per sample (its sampler is a Gaussian mixture), so the weight plane is stored with the image.
+    "cornell64_box_spp16384":      (64, 16384, 21, "WithNEEAndMIS", (2, 20), ("filter", "Box", 1.0), np.float32, RGB),
+    "cornell64_tent_spp16384":     (64, 16384, 22, "WithNEEAndMIS", (2, 20), ("filter", "Tent", 1.5), np.float32, RGB),
+    "cornell64_mitchell_spp16384": (64, 16384, 23, "WithNEEAndMIS", (2, 20), ("filter", "Mitchell-Netravali", 2.0), np.float32, RGB),
     # two-level scene: every batch in its own local space under a (T)Single transform
     "cornell64_single_spp16384": (64, 16384, 6, "WithNEEAndMIS", (2, 20), True, np.float32, RGB),
 }
@@ -110,6 +115,10 @@ def render(name):
         b = O.batched_scene(c["positions"], c["indices"], c["material"])
         kw = dict(material_kind=c["material_type"])
         bt = None
+    elif isinstance(single, tuple) and single[0] == "filter":
+        b = O.batched_scene(c["positions"], c["indices"], c["material"])
+        kw = dict(film_filter=single[1], film_filter_radius=single[2])
+        bt = None
     elif single == "textured":
         uvs, textures, at = scenes.cornell_textures()
         b = O.batched_scene(c["positions"], c["indices"], c["material"], uvs=uvs)
@@ -122,9 +131,15 @@ def render(name):
     img, w, st = O.driver_render(REF_DLL, b, c["albedo"], 3, c["radiance"], c["camera"], res, res, spp,
                                  sample_mode=mode, rr_range=rr, seed=seed, threads=0, batch_transforms=bt,
                                  renderer=renderer, host_exe=True, **kw)
-    assert np.allclose(w, spp, rtol=1e-3), (w.min(), w.max())
+    extra = {}
+    if isinstance(single, tuple) and single[0] == "filter":
+        extra = dict(weight=w.astype(np.float32), film_filter=single[1], film_filter_radius=single[2])
+        if single[1] != "Mitchell-Netravali":
+            assert np.allclose(w, spp, rtol=1e-3), (w.min(), w.max())
+    else:
+        assert np.allclose(w, spp, rtol=1e-3), (w.min(), w.max())
     np.savez_compressed(os.path.join(GOLDEN, f"render_{name}.npz"), img=img.astype(dt), spp=spp, seed=seed,
-                        sample_mode=mode, rr_range=np.array(rr), iterations=st["iterations"])
+                        sample_mode=mode, rr_range=np.array(rr), iterations=st["iterations"], **extra)
     print(f"{name}: {time.time() - t0:.1f} s, mean {img.mean(axis=(0, 1))}", flush=True)
 
 

@@ -88,6 +88,9 @@ typedef struct
     const float* uv; const struct orc_texture* textures; const int32_t* albedoTexture; uint32_t nTextures;
     /* per material: 0 = (Mt)Lambert, 1 = (Mt)Reflect (NULL = all Lambert) */
     const uint8_t* materialType;
+    /* TracerParameters.filmFilter.type: 0 = the default (Gaussian), else FilterType::E + 1 (1 Box, 2 Tent, 3 Gaussian,
+     * 4 Mitchell-Netravali); the radius is filterRadius */
+    uint32_t filmFilter;
 } pt_scene;
 
 /* One single-level 2-D texture as the reference's host-backend view reads it (Device/CPU/TextureViewCPU.h):
@@ -229,6 +232,102 @@ void orc_pt_filter_sample(float radius, float xi0, float xi1, float out[5])
     out[4] = gauss_pdf(out[0], sig) * gauss_pdf(out[1], sig);
 }
 
+/* ---- the four film filters of Tracer/Filters.h ---- */
+static float gauss_pdf_mu(float x, float sig, float mu) { float si = 1.0f / sig, p = (x - mu) * si; return 0.3989422804f * si * expf(-0.5f * p * p); }
+static float gauss_sample_mu(float xi, float sig, float mu, float* pdf)
+{   /* Common::SampleGaussian(xi, sigma, mu) (DistributionFunctions.h:L686-705) */
+    double e, y = 2.0 * xi - 1.0;
+    if(y <= -1.0) e = -INFINITY; else if(y >= 1.0) e = INFINITY;
+    else { double x = 0; for(int it = 0; it < 60; it++) { double f = erf(x) - y; x -= f / (1.1283791670955126 * exp(-x * x)); } e = x; }
+    float x = 1.41421356237f * sig * (float)e + mu;
+    if(isinf(e)) { float mm = 3.5f * sig; x = x < -mm ? -mm : (x > mm ? mm : x); }
+    *pdf = gauss_pdf_mu(x, sig, mu);
+    return x;
+}
+static float lerp_u(float a, float b, float t) { volatile float x = a * (1.0f - t); volatile float y = b * t; return x + y; }
+static const float PREV_ONE = 0.99999994f;
+/* Common::SampleTent(xi, -r, r) (DistributionFunctions.h:L785-805): BisectSample2 picks the side, SampleLine(., 1, 0) the
+ * distance (L627-643, L745-765) */
+static float tent_sample(float xi, float r, float* pdf)
+{
+    float a = -r, b = r;
+    if(b - a < 1.0e-5f) { *pdf = 1.0f / (b - a); return 0.0f; }
+    float w = r / (r + r);
+    int left = xi < w;
+    float lxi = left ? xi / w : (xi - w) / (1.0f - w);
+    if(lxi > PREV_ONE) lxi = PREV_ONE;
+    if(left) lxi = PREV_ONE - lxi;
+    float den = lerp_u(1.0f, 0.0f, lxi); if(den < 0) den = 0;
+    float x = lxi / (1.0f + sqrtf(den)); if(x > PREV_ONE) x = PREV_ONE;
+    *pdf = 2.0f * lerp_u(1.0f, 0.0f, x) * (1.0f / (b - a));
+    return left ? x * a : x * b;
+}
+/* Common::PDFTent (L807-821) */
+static float tent_pdf(float x, float r) { float x01 = (x < 0) ? x / -r : x / r; return (1.0f / (r + r)) * 2.0f * lerp_u(1.0f, 0.0f, x01); }
+/* MitchellNetravaliFilter (Filters.h:L234-380), b = c = 0.33333 */
+static float mitchell_1d(float x, float rr)
+{
+    const float B = 0.33333f, Cc = 0.33333f, F = 1.0f / 6.0f;
+    x = fabsf(2.0f * x * rr);
+    float x2 = x * x, x3 = x2 * x, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    if(x < 1.0f) { c0 = F * (12.0f - 9.0f * B - 6.0f * Cc); c1 = F * (-18.0f + 12.0f * B + 6.0f * Cc); c3 = F * (6.0f - 2.0f * B); }
+    else if(x < 2.0f) { c0 = F * (-B - 6.0f * Cc); c1 = F * (6.0f * B + 30.0f * Cc); c2 = F * (-12.0f * B - 48.0f * Cc); c3 = F * (8.0f * B + 24.0f * Cc); }
+    return (c0 * x3 + c1 * x2 + c2 * x + c3) * 2.0f * rr;
+}
+static const float MN_MID = 0.960566188838f, MN_SIDES = 0.0197169055809f;
+static float mitchell_pdf_1d(float x, float r)
+{
+    float midS = 0.528f * r * 0.5f, sideS = 0.2f * r * 0.5f, sideM = 1.3f * r * 0.5f;
+    return gauss_pdf_mu(x, sideS, -sideM) * MN_SIDES + gauss_pdf_mu(x, midS, 0) * MN_MID + gauss_pdf_mu(x, sideS, sideM) * MN_SIDES;
+}
+static float mitchell_sample_1d(float xi, float r, float* pdf)
+{
+    float midS = 0.528f * r * 0.5f, sideS = 0.2f * r * 0.5f, sideM = 1.3f * r * 0.5f;
+    int index; float lo, wsel;
+    if(xi < MN_SIDES) { index = 0; lo = 0; wsel = MN_SIDES; }
+    else if(xi < MN_SIDES + MN_MID) { index = 1; lo = MN_SIDES; wsel = MN_MID; }
+    else { index = 2; lo = MN_SIDES + MN_MID; wsel = MN_SIDES; }
+    float lxi = (xi - lo) / wsel; if(lxi > PREV_ONE) lxi = PREV_ONE;
+    float own, x;
+    if(index == 0) x = gauss_sample_mu(lxi, sideS, -sideM, &own);
+    else if(index == 1) x = gauss_sample_mu(lxi, midS, 0, &own);
+    else x = gauss_sample_mu(lxi, sideS, sideM, &own);
+    float p0 = index == 0 ? own : gauss_pdf_mu(x, sideS, -sideM);
+    float p1 = index == 1 ? own : gauss_pdf_mu(x, midS, 0);
+    float p2 = index == 2 ? own : gauss_pdf_mu(x, sideS, sideM);
+    *pdf = p0 * MN_SIDES + p1 * MN_MID + p2 * MN_SIDES;
+    return x;
+}
+/* type = FilterType::E (0 Box, 1 Tent, 2 Gaussian, 3 Mitchell-Netravali):
+ * out = {offset x, offset y, Sample().pdf, Pdf(offset), Evaluate(offset)} */
+void orc_pt_filter_sample_typed(uint32_t type, float radius, float xi0, float xi1, float out[5])
+{
+    float px, py;
+    if(type == 0u)
+    {   /* BoxFilter (Filters.h:L106-146) */
+        float range = radius - (-radius), rr = 1.0f / radius;
+        out[0] = xi0 * range + (-radius); out[1] = xi1 * range + (-radius);
+        px = py = 1.0f / range;
+        out[3] = (1.0f / range) * (1.0f / range);
+        out[4] = (fabsf(out[0]) <= radius && fabsf(out[1]) <= radius) ? 0.25f * rr * rr : 0.0f;
+    }
+    else if(type == 1u)
+    {   /* TentFilter (Filters.h:L148-193) */
+        out[0] = tent_sample(xi0, radius, &px); out[1] = tent_sample(xi1, radius, &py);
+        out[3] = tent_pdf(out[0], radius) * tent_pdf(out[1], radius);
+        float rcp = 1.0f / radius, cap = 1.0f / radius, tx = fabsf(out[0] * rcp), ty = fabsf(out[1] * rcp);
+        out[4] = lerp_u(cap, 0.0f, tx > 1 ? 1 : tx) * lerp_u(cap, 0.0f, ty > 1 ? 1 : ty);
+    }
+    else if(type == 3u)
+    {
+        out[0] = mitchell_sample_1d(xi0, radius, &px); out[1] = mitchell_sample_1d(xi1, radius, &py);
+        out[3] = mitchell_pdf_1d(out[0], radius) * mitchell_pdf_1d(out[1], radius);
+        out[4] = mitchell_1d(out[0], 1.0f / radius) * mitchell_1d(out[1], 1.0f / radius);
+    }
+    else { orc_pt_filter_sample(radius, xi0, xi1, out); return; }
+    out[2] = px * py;
+}
+
 /* Distribution::Common::SampleCosDirection (DistributionFunctions.h:L847-871), +Z hemisphere: out = {x, y, z, pdf} */
 static void cos_direction(float u0, float u1, float out[4])
 {
@@ -304,10 +403,20 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
     v3 right = nrm(cross(gz, up)); up = nrm(cross(right, gz)); gz = nrm(cross(up, right));
     float wh = tanf(s->fovXY[0] * 0.5f) * s->nearFar[0], hh = tanf(s->fovXY[1] * 0.5f) * s->nearFar[0];
     v3 bl = add(sub(sub(pos, mul(right, wh)), mul(up, hh)), mul(gz, s->nearFar[0]));
-    float sig = s->filterRadius * 0.285714f;
     float off[2];
-    for(int k = 0; k < 2; k++) off[k] = gauss_sample(pcg_float(rng), sig);
-    *filmW = 1.0f; /* Evaluate(offset) / pdf(offset): same Gaussian */
+    if(s->filmFilter == 0u || s->filmFilter == 3u)
+    {
+        float sig = s->filterRadius * 0.285714f;
+        for(int k = 0; k < 2; k++) off[k] = gauss_sample(pcg_float(rng), sig);
+        *filmW = 1.0f; /* Evaluate(offset) / pdf(offset): same Gaussian */
+    }
+    else
+    {   /* KCGenerateCamRaysStochastic (RayGenKernels.kt.h:L195-225): weight = Evaluate(offset) / Sample().pdf */
+        float fo[5], x0 = pcg_float(rng), x1 = pcg_float(rng);
+        orc_pt_filter_sample_typed(s->filmFilter - 1u, s->filterRadius, x0, x1, fo);
+        off[0] = fo[0]; off[1] = fo[1];
+        *filmW = fo[4] / fo[2];
+    }
     float sx = ((float)px + off[0] + 0.5f) * (2.0f * wh / (float)s->width);
     float sy = ((float)py + off[1] + 0.5f) * (2.0f * hh / (float)s->height);
     v3 o = pos, d = nrm(sub(add(add(bl, mul(right, sx)), mul(up, sy)), pos));

@@ -32,8 +32,9 @@ struct DriverRender
 {
     const char* rendererName; uint32_t width, height; uint32_t totalSPP; const char* sampleMode;
     uint32_t rrRange[2]; uint64_t seed; uint32_t accelMode; uint32_t parallelHint; uint32_t threads; uint32_t samplerType; uint32_t region[4]; uint32_t latency; uint32_t burstSize; uint32_t camSwitchAfter; float camSwitch[9];
+    uint32_t filmFilter; float filmFilterRadius;
 };
-struct DriverStats { double commitSeconds, renderSeconds, totalPaths; uint32_t iterations; float sceneAABB[6]; };
+struct DriverStats { double commitSeconds, renderSeconds, totalPaths; uint32_t iterations; float sceneAABB[6]; double startSeconds; };
 using RenderF = int (*)(const char*, const DriverScene*, const DriverRender*, float*, float*, DriverStats*, char*, size_t);
 
 int main(int argc, char** argv)
@@ -54,7 +55,7 @@ int main(int argc, char** argv)
     std::fclose(f);
     auto P = [&](int i) { return bytes[i] ? reinterpret_cast<const void*>(sec[i].data()) : nullptr; };
     // sections: 0 dll path, 1 renderer name, 2 sample mode (NUL-terminated by the zero padding),
-    // 3 u32[28] {batchCount, materialCount, lightCount, width, height, spp, rr0, rr1, accelMode, parallelHint, threads, sampler, region[4],
+    // 3 u32[30] {..., filmFilter, filmFilterRadius (float bits)} after: {batchCount, materialCount, lightCount, width, height, spp, rr0, rr1, accelMode, parallelHint, threads, sampler, region[4],
     //   latency, burstSize, camSwitchAfter, camSwitch[9] (float bits)},
     // 4 u64 seed, 5 f32[13] camera {pos, gaze, up, fovXY, nearFar}, 6 vertexOffsets, 7 triOffsets, 8 positions,
     // 9 normals, 10 indices, 11 batchMaterial, 12 batchLight, 13 albedo, 14 radiance, 15 batchTransforms (may be empty), 16 batchInstanceOf (may be empty),
@@ -83,6 +84,7 @@ int main(int argc, char** argv)
     for(int k = 0; k < 4; k++) rd.region[k] = u[12 + k];
     rd.latency = u[16]; rd.burstSize = u[17]; rd.camSwitchAfter = u[18];
     std::memcpy(rd.camSwitch, u + 19, sizeof(rd.camSwitch));
+    if(bytes[3] >= 30 * 4) { rd.filmFilter = u[28]; std::memcpy(&rd.filmFilterRadius, u + 29, 4); }
 
     char self[PATH_MAX]; ssize_t k = readlink("/proc/self/exe", self, sizeof(self) - 1);
     if(k <= 0) return 67;
@@ -101,7 +103,7 @@ int main(int argc, char** argv)
     if(!o) return 71;
     std::fwrite(rgb.data(), 4, rgb.size(), o); std::fwrite(wgt.data(), 4, wgt.size(), o);
     double s[4] = {st.commitSeconds, st.renderSeconds, st.totalPaths, double(st.iterations)};
-    std::fwrite(s, 8, 4, o); std::fwrite(st.sceneAABB, 4, 6, o);
+    std::fwrite(s, 8, 4, o); std::fwrite(st.sceneAABB, 4, 6, o); std::fwrite(&st.startSeconds, 8, 1, o);
     std::fclose(o);
     return 0;
 }

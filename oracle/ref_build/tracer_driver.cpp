@@ -85,6 +85,10 @@ struct DriverRender
     // camSwitch{Pos,Gaze,Up} and the accumulation restarts (the driver clears its own accumulator, like Visor does)
     uint32_t    camSwitchAfter;
     float       camSwitch[9];
+    // TracerParameters.filmFilter: filmFilter = 0 keeps the default (Gaussian, radius 1), else FilterType::E + 1
+    // (1 Box, 2 Tent, 3 Gaussian, 4 Mitchell-Netravali); filmFilterRadius = 0 keeps the default radius
+    uint32_t    filmFilter;
+    float       filmFilterRadius;
 };
 
 struct DriverStats
@@ -94,6 +98,7 @@ struct DriverStats
     double totalPaths;      // sum of section weights (approx. completed paths)
     uint32_t iterations;
     float  sceneAABB[6];
+    double startSeconds;    // StartRender
 };
 
 static void SegvInfo(int, siginfo_t* si, void* ctx)
@@ -165,6 +170,8 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
         tp.accelMode = AcceleratorType(rd->accelMode);
         if(rd->parallelHint) tp.parallelizationHint = rd->parallelHint;
         tp.samplerType = SamplerType::E(rd->samplerType);
+        if(rd->filmFilter) tp.filmFilter.type = FilterType::E(rd->filmFilter - 1u);
+        if(rd->filmFilterRadius > 0.0f) tp.filmFilter.radius = rd->filmFilterRadius;
         tracer = construct(tp);
         // as MRay/RunCommand.cpp:L1015-1025: worker threads run the tracer's device-init function
         ThreadPool pool;
@@ -455,7 +462,9 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
         if(rd->region[2] | rd->region[3]) { rip.regionMin = Vector2ui(rd->region[0], rd->region[1]); rip.regionMax = Vector2ui(rd->region[2], rd->region[3]); }
         if(getenv("DRIVER_VERBOSE")) std::fprintf(stderr, "StartRender...\n");
         if(const char* a = getenv("DRIVER_ALARM")) { signal(SIGALRM, AlarmBacktrace); alarm(unsigned(atoi(a))); }
+        auto s0 = std::chrono::steady_clock::now();
         RenderBufferInfo rbi = tracer->StartRender(rid, camSurf, rip, std::nullopt, std::nullopt);
+        stats->startSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - s0).count();
         if(getenv("DRIVER_VERBOSE")) std::fprintf(stderr, "StartRender done, buffer %zu bytes\n", rbi.totalSize);
 
         size_t pix = size_t(rd->width) * rd->height;

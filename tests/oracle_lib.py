@@ -174,12 +174,13 @@ class _DriverRender(C.Structure):
                 ("sampleMode", C.c_char_p), ("rrRange", C.c_uint32 * 2), ("seed", C.c_uint64),
                 ("accelMode", C.c_uint32), ("parallelHint", C.c_uint32), ("threads", C.c_uint32), ("samplerType", C.c_uint32),
                 ("region", C.c_uint32 * 4), ("latency", C.c_uint32), ("burstSize", C.c_uint32),
-                ("camSwitchAfter", C.c_uint32), ("camSwitch", C.c_float * 9)]
+                ("camSwitchAfter", C.c_uint32), ("camSwitch", C.c_float * 9),
+                ("filmFilter", C.c_uint32), ("filmFilterRadius", C.c_float)]
 
 
 class _DriverStats(C.Structure):
     _fields_ = [("commitSeconds", C.c_double), ("renderSeconds", C.c_double), ("totalPaths", C.c_double),
-                ("iterations", C.c_uint32), ("sceneAABB", C.c_float * 6)]
+                ("iterations", C.c_uint32), ("sceneAABB", C.c_float * 6), ("startSeconds", C.c_double)]
 
 
 def driver_available():
@@ -217,7 +218,7 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
                   accel_mode=1, threads=0, parallel_hint=0, near_far=(0.01, 1000.0), driver_flavour="",
                   batch_transforms=None, sampler="Independent", host_exe=False, instance_of=None,
                   textures=None, material_texture=None, region=None, material_kind=None,
-                  latency=False, burst_size=1, cam_switch=None, light_two_sided=False):
+                  latency=False, burst_size=1, cam_switch=None, light_two_sided=False, film_filter=None, film_filter_radius=0.0):
     """Renders through TracerI. `light_material`: material id whose batch is the prim-backed light.
     batch_transforms: optional [batch, 3, 4] local->world matrices ((T)Single per batch; positions local).
     textures: list of dict(data=[h, w, 4] float32 / uint8 (RGBA), interp=, edge=); material_texture: per material id
@@ -240,6 +241,8 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
     fx = 2 * np.arctan(np.tan(fy / 2) * width / height)
     bt = None if batch_transforms is None else np.ascontiguousarray(batch_transforms, np.float32).reshape(len(mats), 12)
     sampler_id = {"Independent": 0, "ZSobol": 1, "Sobol": 2}[sampler]
+    # TracerParameters.filmFilter: None keeps the default (Gaussian, radius 1)
+    filter_id = 0 if film_filter is None else 1 + {"Box": 0, "Tent": 1, "Gaussian": 2, "Mitchell-Netravali": 3}[film_filter]
     io = None if instance_of is None else np.ascontiguousarray(instance_of, np.int32)
     tinfo = tbytes = mtex = None
     lts = np.array([1 if light_two_sided else 0], np.uint8)
@@ -268,7 +271,7 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
         cs = np.zeros(9, np.float32)
         if cam_switch:
             cs[:] = list(cam_switch[1]["eye"]) + list(cam_switch[1]["gaze"]) + list(cam_switch[1]["up"])
-        u = np.concatenate([u, cs.view(np.uint32)])
+        u = np.concatenate([u, cs.view(np.uint32), np.array([filter_id], np.uint32), np.array([film_filter_radius], np.float32).view(np.uint32)])
         cam = np.array(list(camera["eye"]) + list(camera["gaze"]) + list(camera["up"]) + [fx, fy] + list(near_far), np.float32)
         secs = [dll_path.encode(), renderer.encode(), sample_mode.encode(), u.tobytes(), np.uint64(seed).tobytes(),
                 cam.tobytes(), batched["vertex_offsets"].astype(np.uint32).tobytes(), batched["tri_offsets"].astype(np.uint32).tobytes(),
@@ -292,7 +295,9 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
         img = np.frombuffer(raw, np.float32, pix * 3).reshape(height, width, 3).copy()
         wgt = np.frombuffer(raw, np.float32, pix, pix * 12).reshape(height, width).copy()
         sd = np.frombuffer(raw, np.float64, 4, pix * 16); box = np.frombuffer(raw, np.float32, 6, pix * 16 + 32)
-        return img, wgt, dict(commit_s=float(sd[0]), render_s=float(sd[1]), paths=float(sd[2]), iterations=int(sd[3]), aabb=[float(x) for x in box])
+        start_s = float(np.frombuffer(raw, np.float64, 1, pix * 16 + 56)[0]) if len(raw) >= pix * 16 + 64 else 0.0
+        return img, wgt, dict(commit_s=float(sd[0]), render_s=float(sd[1]), paths=float(sd[2]), iterations=int(sd[3]), aabb=[float(x) for x in box],
+                              start_s=start_s)
     L = C.CDLL(os.path.join(ORACLE_DIR, "_ref", f"libtracer_driver{driver_flavour}.so"))
     L.tracer_driver_render.restype = C.c_int
     sc = _DriverScene()
@@ -322,7 +327,8 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
     rd = _DriverRender(renderer.encode(), width, height, spp, sample_mode.encode(), (C.c_uint32 * 2)(*rr_range), seed,
                        accel_mode, parallel_hint, threads, sampler_id, (C.c_uint32 * 4)(*(region or (0, 0, 0, 0))),
                        1 if latency else 0, burst_size, cam_switch[0] if cam_switch else 0,
-                       (C.c_float * 9)(*((list(cam_switch[1]["eye"]) + list(cam_switch[1]["gaze"]) + list(cam_switch[1]["up"])) if cam_switch else [0.0] * 9)))
+                       (C.c_float * 9)(*((list(cam_switch[1]["eye"]) + list(cam_switch[1]["gaze"]) + list(cam_switch[1]["up"])) if cam_switch else [0.0] * 9)),
+                       filter_id, float(film_filter_radius))
     img = np.zeros((height, width, 3), np.float32)
     wgt = np.zeros((height, width), np.float32)
     st = _DriverStats()
@@ -332,7 +338,7 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
     if rc != 0:
         raise RuntimeError(f"tracer driver failed ({rc}): {err.value.decode()}")
     return img, wgt, dict(commit_s=st.commitSeconds, render_s=st.renderSeconds, paths=st.totalPaths,
-                          iterations=st.iterations, aabb=list(st.sceneAABB))
+                          iterations=st.iterations, aabb=list(st.sceneAABB), start_s=st.startSeconds)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -349,7 +355,7 @@ class _PtScene(C.Structure):
                 ("rrLo", C.c_uint32), ("rrHi", C.c_uint32), ("filterRadius", C.c_float), ("seed", C.c_uint64),
                 ("spectrum", C.c_void_p), ("wavelengthMode", C.c_uint32),
                 ("uv", C.c_void_p), ("textures", C.c_void_p), ("albedoTexture", C.c_void_p), ("nTextures", C.c_uint32),
-                ("materialType", C.c_void_p)]
+                ("materialType", C.c_void_p), ("filmFilter", C.c_uint32)]
 
 
 class _OrcTexture(C.Structure):
@@ -393,7 +399,7 @@ def oracle_texture_sample(texture, uv):
 def oracle_render(positions, indices, tri_material, albedo, radiance, camera, width, height, spp,
                   sample_mode=2, rr_range=(2, 20), seed=0, near_far=(0.01, 1000.0), threads=None,
                   spectral_data=None, wavelength_mode=2, textures=None, albedo_texture=None, vertex_uvs=None,
-                  material_type=None, light_two_sided=None):
+                  material_type=None, light_two_sided=None, film_filter=None, film_filter_radius=1.0):
     """tri_material: per triangle, >= 0 Lambert material index, -1 - k for light k. Returns image[h,w,3]
     (row 0 = bottom) resolved as sum radiance / sum weight. spectral_data (mray_b200.spectral.load())
     switches to the hero-wavelength spectral estimator."""
@@ -417,7 +423,8 @@ def oracle_render(positions, indices, tri_material, albedo, radiance, camera, wi
     fy = float(np.deg2rad(camera["fov_y_deg"])); fx = float(2 * np.arctan(np.tan(fy / 2) * width / height))
     s.fovXY = (C.c_float * 2)(fx, fy); s.nearFar = (C.c_float * 2)(*near_far)
     s.width, s.height, s.spp, s.sampleMode = width, height, spp, sample_mode
-    s.rrLo, s.rrHi, s.filterRadius, s.seed = rr_range[0], rr_range[1], 1.0, seed
+    s.rrLo, s.rrHi, s.filterRadius, s.seed = rr_range[0], rr_range[1], float(film_filter_radius), seed
+    s.filmFilter = 0 if film_filter is None else 1 + {"Box": 0, "Tent": 1, "Gaussian": 2, "Mitchell-Netravali": 3}[film_filter]
     if spectral_data is not None:
         tables, keep_tables = spectrum_tables(spectral_data)
         s.spectrum, s.wavelengthMode = C.addressof(tables), wavelength_mode

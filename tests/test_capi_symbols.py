@@ -28,7 +28,11 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(capi.LIB_PATH)
     for s in header_symbols():
         assert hasattr(lib, s), f"{s} not exported"
-    assert lib.mrb_abi_version() == 2
+    # the header, the library and the ctypes mirror agree on the ABI version
+    header = open(os.path.join(ROOT, "include", "mray_b200.h")).read()
+    m = re.search(r"#define MRB_ABI_VERSION \(\((\d+)u << 16\) \| (\d+)u\)", header)
+    assert m, "MRB_ABI_VERSION not found in the header"
+    assert lib.mrb_abi_version() == (int(m.group(1)) << 16 | int(m.group(2))) == capi.MRB_ABI_VERSION
 
 
 def test_no_cpu_fallback_without_device():
