@@ -34,7 +34,7 @@ struct DriverRender
     uint32_t rrRange[2]; uint64_t seed; uint32_t accelMode; uint32_t parallelHint; uint32_t threads; uint32_t samplerType; uint32_t region[4]; uint32_t latency; uint32_t burstSize; uint32_t camSwitchAfter; float camSwitch[9];
     uint32_t filmFilter; float filmFilterRadius;
 };
-struct DriverStats { double commitSeconds, renderSeconds, totalPaths; uint32_t iterations; float sceneAABB[6]; double startSeconds; };
+struct DriverStats { double commitSeconds, renderSeconds, totalPaths; uint32_t iterations; float sceneAABB[6]; double startSeconds, sceneSeconds, closeSeconds, totalSeconds; };
 using RenderF = int (*)(const char*, const DriverScene*, const DriverRender*, float*, float*, DriverStats*, char*, size_t);
 
 int main(int argc, char** argv)

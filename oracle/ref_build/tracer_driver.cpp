@@ -99,6 +99,9 @@ struct DriverStats
     uint32_t iterations;
     float  sceneAABB[6];
     double startSeconds;    // StartRender
+    double sceneSeconds;    // ConstructTracer + scene upload calls (everything before CommitSurfaces)
+    double closeSeconds;    // StopRender + DestroyRenderer + DestroyTracer
+    double totalSeconds;    // the whole call
 };
 
 static void SegvInfo(int, siginfo_t* si, void* ctx)
@@ -145,6 +148,7 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
                          float* outRGB, float* outWeight, DriverStats* stats, char* err, size_t errLen)
 {
     using namespace std::string_literals;
+    const auto callStart = std::chrono::steady_clock::now();
     if(getenv("DRIVER_ALARM"))
     {
         static char altStack[1 << 16];
@@ -419,6 +423,7 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
         tracer->SetBoundaryVolume(bVol);
 
         auto c0 = std::chrono::steady_clock::now();
+        stats->sceneSeconds = std::chrono::duration<double>(c0 - callStart).count();
         SurfaceCommitResult cr = tracer->CommitSurfaces();
         auto c1 = std::chrono::steady_clock::now();
         stats->commitSeconds = std::chrono::duration<double>(c1 - c0).count();
@@ -522,6 +527,9 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
         tracer->DestroyRenderer(rid);
         destroy(tracer);
         tracer = nullptr;
+        const auto callEnd = std::chrono::steady_clock::now();
+        stats->closeSeconds = std::chrono::duration<double>(callEnd - r1).count();
+        stats->totalSeconds = std::chrono::duration<double>(callEnd - callStart).count();
     }
     catch(const MRayError& e)
     {

@@ -180,7 +180,8 @@ class _DriverRender(C.Structure):
 
 class _DriverStats(C.Structure):
     _fields_ = [("commitSeconds", C.c_double), ("renderSeconds", C.c_double), ("totalPaths", C.c_double),
-                ("iterations", C.c_uint32), ("sceneAABB", C.c_float * 6), ("startSeconds", C.c_double)]
+                ("iterations", C.c_uint32), ("sceneAABB", C.c_float * 6), ("startSeconds", C.c_double),
+                ("sceneSeconds", C.c_double), ("closeSeconds", C.c_double), ("totalSeconds", C.c_double)]
 
 
 def driver_available():
@@ -338,7 +339,8 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
     if rc != 0:
         raise RuntimeError(f"tracer driver failed ({rc}): {err.value.decode()}")
     return img, wgt, dict(commit_s=st.commitSeconds, render_s=st.renderSeconds, paths=st.totalPaths,
-                          iterations=st.iterations, aabb=list(st.sceneAABB), start_s=st.startSeconds)
+                          iterations=st.iterations, aabb=list(st.sceneAABB), start_s=st.startSeconds,
+                          scene_s=st.sceneSeconds, close_s=st.closeSeconds, total_s=st.totalSeconds)
 
 
 # ------------------------------------------------------------------------------------------------
