@@ -184,8 +184,10 @@ def build_library(verbose: bool = False) -> str:
 
 def load_library():
     """Loads the CUDA extension. Fails loudly when it has not been built."""
-    global _lib
+    global _lib, LIB_PATH
     if _lib is None:
+        if os.environ.get("MRB_LIB_PATH"):      # experiment builds (csrc/Makefile VARIANT=...)
+            LIB_PATH = os.environ["MRB_LIB_PATH"]
         if not os.path.exists(LIB_PATH):
             raise MrbError(-1, f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
                                "(there is no CPU fallback)")

@@ -100,6 +100,8 @@ struct Context
     KernelProfile prof;
     // occupancy of the persistent traversal kernels on THIS device (blocks per SM), filled on first use
     int          occWide[2] = {0, 0}, occWide2[2] = {0, 0};
+    const void*  persistBase = nullptr;   // accelerator the stream's L2 access-policy window currently covers
+    cudaStream_t persistStream = nullptr;
 };
 
 // Brackets the launches issued inside its scope with a sampled event pair (no-op unless profiling samples this iteration)

@@ -30,6 +30,14 @@ namespace
 {
 
 constexpr int TRACE_TPB = 128;
+// resident blocks per SM the wide kernels are compiled for (register budget 65536 / (128 x blocks)): the exact-resolution
+// code is called out of line from the epilogue, and without a cap its register needs would set the kernel's
+#ifndef MRB_WIDE_BLOCKS_CLOSEST
+#define MRB_WIDE_BLOCKS_CLOSEST 7
+#endif
+#ifndef MRB_WIDE_BLOCKS_ANY
+#define MRB_WIDE_BLOCKS_ANY 8
+#endif
 constexpr int WIDE_STACK = int(WIDE_STACK_ENTRIES);   // capi.cu refuses trees with 2 * depth (+ 3 + 2 * top-level depth) above it
 
 struct HitRecord
@@ -125,9 +133,163 @@ __device__ __forceinline__ bool CertifyLeaf(const AccelData& a, uint32_t leaf, f
 }
 
 constexpr float NEAR_TIE = 1.0000152587890625f; // 1 + 2^-16
-constexpr uint32_t RESOLVE_CAPACITY = 1u << 16;  // candidate records KResolveExact can take per cast
 // counters of one wide cast: [0] uncertified rays, [1] of which near ties, [2] of which leaf-AABB
 // certification failures, [3] dynamic-fetch cursor, [4] rays handed to the full binary fallback
+
+// ------------------------------------------------------------------------------------------------
+// Exact binary traversal (audit path, and fallback of the rays the wide path could not certify)
+// ------------------------------------------------------------------------------------------------
+// One ray through the reference's own algorithm: binary LBVH, left-first stack traversal
+// (TraverseLBVHStack, AcceleratorLBVH.hpp:L109-167), Ray::IntersectsAABB arithmetic.
+template<bool ANY_HIT>
+__device__ __forceinline__ void TraceBinaryRayBody(const AccelData& a, uint32_t accelKey,
+                                                   mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
+                                                   uint32_t* __restrict__ visibleBits, mrb_ray_gmem* rays, uint32_t r)
+{
+    const float4 r0 = reinterpret_cast<const float4*>(rays + r)[0];
+    const float4 r1 = reinterpret_cast<const float4*>(rays + r)[1];
+    const float o[3] = {r0.x, r0.y, r0.z}, d[3] = {r1.x, r1.y, r1.z};
+    const float tMin = r0.w; float tMax = r1.w;
+    float invD[3];
+    #pragma unroll
+    for(int k = 0; k < 3; k++) invD[k] = __fdiv_rn(1.0f, d[k]);
+
+    HitRecord best; best.t = tMax; best.rank = 0u; best.leaf = INVALID_U32; best.u = best.v = 0.f; best.flags = 0u;
+    uint32_t stack[160];
+    int sp = 0;
+    stack[sp++] = 0u;
+    while(sp > 0)
+    {
+        uint32_t ni = stack[--sp];
+        if(ni == INVALID_U32) continue;
+        if(ni & LEAF_FLAG)
+        {
+            uint32_t leaf = ni & ~LEAF_FLAG;
+            const uint32_t ri = (a.ranges.count == 1u) ? 0u : FindRange(a.ranges, leaf);
+            uint32_t prim = a.ranges.primBegin[ri] + (leaf - a.ranges.leafStart[ri]);
+            uint32_t i0 = a.indices[3 * size_t(prim)], i1 = a.indices[3 * size_t(prim) + 1], i2 = a.indices[3 * size_t(prim) + 2];
+            float4 v0, e0, e1;
+            const float* p0 = a.positions + 3 * size_t(i0);
+            const float* p1 = a.positions + 3 * size_t(i1);
+            const float* p2 = a.positions + 3 * size_t(i2);
+            v0 = make_float4(p0[0], p0[1], p0[2], 0.f);
+            e0 = make_float4(__fsub_rn(p1[0], p0[0]), __fsub_rn(p1[1], p0[1]), __fsub_rn(p1[2], p0[2]), 0.f);
+            e1 = make_float4(__fsub_rn(p2[0], p0[0]), __fsub_rn(p2[1], p0[1]), __fsub_rn(p2[2], p0[2]), 0.f);
+            float t, u, v;
+            if(!RayTriangle(o[0], o[1], o[2], d[0], d[1], d[2], v0, e0, e1, a.ranges.cull[ri] != 0u, t, u, v)) continue;
+            if(!(t >= tMin && t < tMax)) continue;
+            best.t = t; best.u = u; best.v = v; best.leaf = leaf; best.flags = ri << 8;
+            tMax = t;
+            if(ANY_HIT) break;
+        }
+        else
+        {
+            const float* b = reinterpret_cast<const float*>(a.boxes + ni);
+            if(SlabExact(b, o, invD, tMin, tMax))
+            {
+                LBVHNode nd = a.nodes[ni];
+                stack[sp++] = nd.right;
+                stack[sp++] = nd.left;
+                // a dependent chain of (node, box) loads for a handful of rays: pull the records
+                // the next pops will need towards L1 while the current step finishes
+                if(!(nd.left & LEAF_FLAG))
+                {
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(a.boxes + nd.left));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(a.nodes + nd.left));
+                }
+                if(!(nd.right & LEAF_FLAG))
+                {
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(a.boxes + nd.right));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(a.nodes + nd.right));
+                }
+            }
+        }
+    }
+    if(best.leaf != INVALID_U32)
+    {
+        if(ANY_HIT) atomicAnd(&visibleBits[r >> 5], ~(1u << (r & 31u)));
+        else WriteHit(a, accelKey, r, best, hitKeys, metaHits, rays);
+    }
+}
+
+// Out-of-line copies for the wide kernels: a call costs nothing until one of the ~1e-4 rays that need it shows up,
+// and keeps the 160-entry stack and the registers of this code out of the hot loop.
+__device__ __noinline__ void TraceBinaryRayClosest(const AccelData& a, uint32_t accelKey, mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits,
+                                                   mrb_ray_gmem* rays, uint32_t r)
+{ TraceBinaryRayBody<false>(a, accelKey, hitKeys, metaHits, nullptr, rays, r); }
+__device__ __noinline__ void TraceBinaryRayAny(const AccelData& a, uint32_t* visibleBits, mrb_ray_gmem* rays, uint32_t r)
+{ TraceBinaryRayBody<true>(a, 0u, nullptr, nullptr, visibleBits, rays, r); }
+
+template<bool ANY_HIT>
+__global__ void __launch_bounds__(TRACE_TPB)
+KTraceBinary(const __grid_constant__ AccelData a, uint32_t accelKey,
+             mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
+             uint32_t* __restrict__ visibleBits,
+             mrb_ray_gmem* rays, const uint32_t* __restrict__ rayIndices, uint32_t rayCount)
+{
+    for(uint32_t i = blockIdx.x * TRACE_TPB + threadIdx.x; i < rayCount; i += gridDim.x * TRACE_TPB)
+        TraceBinaryRayBody<ANY_HIT>(a, accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices ? rayIndices[i] : i);
+}
+
+// Exact resolution of a ray the wide path could not certify, WITHOUT a full re-traversal: the
+// reference's answer is decided by the (at most two) candidates inside the near-tie window, by the
+// order it visits them (Morton rank) and by its box tests on their ancestor chains, evaluated with
+// the tMax the reference holds when it first enters each node: the t of an already accepted
+// candidate whose rank lies left of the node's range, else anything >= tUpper. A box that fails
+// with a real candidate's t is a genuine cull; a box that fails with tUpper is undecidable here and
+// the ray goes to the full binary traversal (TraceBinaryRay), as do rays with three or more
+// candidates in the window. Called by the lane that owns the ray, straight from the wide kernel's epilogue
+// (round 1 ran this and the binary fallback as two more launches per cast: ~17 us of fixed cost each).
+__device__ __noinline__ void ResolveExactRay(const AccelData& a, uint32_t accelKey,
+                                             mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, mrb_ray_gmem* rays,
+                                             uint32_t* counters, uint32_t r, bool full, HitRecord c0, HitRecord c1, bool hasSecond)
+{
+    HitRecord c[2] = {c0, c1};   // by value: the caller's records must stay in registers
+    const int n = hasSecond ? 2 : 1;
+    const float4 r0 = reinterpret_cast<const float4*>(rays + r)[0];
+    const float4 r1 = reinterpret_cast<const float4*>(rays + r)[1];
+    const float o[3] = {r0.x, r0.y, r0.z};
+    const float invD[3] = {__fdiv_rn(1.0f, r1.x), __fdiv_rn(1.0f, r1.y), __fdiv_rn(1.0f, r1.z)};
+    const float tMin = r0.w;
+    const float tUpper = fminf(r1.w, c[0].t * NEAR_TIE);
+    const int first = (n == 2 && c[1].rank < c[0].rank) ? 1 : 0;
+    int accepted = -1;
+    for(int s = 0; s < n && !full; s++)
+    {
+        const HitRecord& z = c[s == 0 ? first : 1 - first];
+        // a later-visited candidate only matters when it is strictly closer than the accepted one
+        if(accepted >= 0 && !(z.t < c[accepted].t)) continue;
+        bool reach = true;
+        // every ancestor box encloses the leaf box and the slab values are monotone in the box: if the leaf
+        // box passes with tUpper, so does every ancestor tested with tUpper, and once an ancestor contains
+        // the accepted candidate (range start <= its rank) all higher ones do too, so the walk can stop at
+        // the first ancestor that is not tested with the accepted t (the common ancestor, a few levels up)
+        const bool leafPasses = SlabExact(a.leafAABB + 6 * size_t(z.leaf), o, invD, tMin, tUpper);
+        uint32_t ni = a.leafParent[z.leaf];
+        while(ni != INVALID_U32)
+        {
+            const bool usePrior = accepted >= 0 && c[accepted].rank < a.nodeRange[ni].x;
+            if(!usePrior && leafPasses) break;
+            const float tcur = usePrior ? c[accepted].t : tUpper;
+            if(!SlabExact(reinterpret_cast<const float*>(a.boxes + ni), o, invD, tMin, tcur))
+            {
+                if(usePrior) reach = false; else full = true;
+                break;
+            }
+            // a box that passes with tUpper is enclosed by every remaining ancestor, which therefore pass too
+            // (edge hits make the flat leaf boxes marginal, not the boxes above them)
+            if(!usePrior) break;
+            ni = a.nodes[ni].parent;
+        }
+        if(!full && reach && (accepted < 0 || z.t < c[accepted].t)) accepted = (s == 0 ? first : 1 - first);
+    }
+    if(full || accepted < 0)
+    {
+        atomicAdd(counters + 4, 1u);
+        TraceBinaryRayClosest(a, accelKey, hitKeys, metaHits, rays, r);
+    }
+    else WriteHit(a, accelKey, r, c[accepted], hitKeys, metaHits, rays);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Wide traversal
@@ -166,13 +328,12 @@ struct TraceParams
 // 200-instruction node step and the 60-instruction triangle test always run with as many lanes as
 // possible; triangle groups are postponed (kept / pushed on the stack) until enough lanes have one.
 template<bool ANY_HIT>
-__global__ void __launch_bounds__(TRACE_TPB)
-KTraceWide(AccelData a, uint32_t accelKey,
+__global__ void __launch_bounds__(TRACE_TPB, ANY_HIT ? MRB_WIDE_BLOCKS_ANY : MRB_WIDE_BLOCKS_CLOSEST)
+KTraceWide(const __grid_constant__ AccelData a, uint32_t accelKey,
            mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
            uint32_t* __restrict__ visibleBits,
            mrb_ray_gmem* rays, const uint32_t* __restrict__ rayIndices, uint32_t rayCount,
-           uint32_t* __restrict__ counters, uint32_t* __restrict__ fallbackList,
-           uint4* __restrict__ resolveRecords, TraceParams prm)
+           uint32_t* __restrict__ counters, TraceParams prm)
 {
     constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
@@ -202,7 +363,11 @@ KTraceWide(AccelData a, uint32_t accelKey,
             if(ANY_HIT)
             {
                 if(done) atomicAnd(&visibleBits[r >> 5], ~(1u << (r & 31u)));
-                else if(uncertified) { fallbackList[atomicAdd(counters + 4, 1u)] = r; atomicAdd(counters, 1u); atomicAdd(counters + 2, 1u); }
+                else if(uncertified)
+                {   // a hit whose leaf box the reference's own slab test might reject: ask the reference's algorithm
+                    atomicAdd(counters, 1u); atomicAdd(counters + 2, 1u); atomicAdd(counters + 4, 1u);
+                    TraceBinaryRayAny(a, visibleBits, rays, r);
+                }
             }
             else if(best.leaf != INVALID_U32)
             {
@@ -212,18 +377,10 @@ KTraceWide(AccelData a, uint32_t accelKey,
                     WriteHit(a, accelKey, r, best, hitKeys, metaHits, rays);
                 else
                 {
-                    // hand the candidates to KResolveExact (or, past its capacity, to the full fallback)
-                    const uint32_t slot = atomicAdd(counters, 1u);
+                    // settle it here and now with the reference's own box arithmetic (out of line, ~1e-4 of the rays)
+                    atomicAdd(counters, 1u);
                     atomicAdd(counters + ((hasSecond || overflow) ? 1 : 2), 1u); // [1] near ties, [2] uncertified leaf
-                    if(slot < RESOLVE_CAPACITY)
-                    {
-                        uint4* rec = resolveRecords + size_t(slot) * 4;
-                        rec[0] = make_uint4(r, (overflow ? 1u : 0u) | (hasSecond ? 2u : 0u), 0u, 0u);
-                        rec[1] = make_uint4(__float_as_uint(best.t), __float_as_uint(best.u), __float_as_uint(best.v), best.leaf);
-                        rec[2] = make_uint4(best.rank, best.flags, __float_as_uint(second.t), __float_as_uint(second.u));
-                        rec[3] = make_uint4(__float_as_uint(second.v), second.leaf, second.rank, second.flags);
-                    }
-                    else fallbackList[atomicAdd(counters + 4, 1u)] = r;
+                    ResolveExactRay(a, accelKey, hitKeys, metaHits, rays, counters, r, overflow, best, second, hasSecond);
                 }
             }
         }
@@ -424,158 +581,6 @@ KTraceWide(AccelData a, uint32_t accelKey,
 }
 
 // ------------------------------------------------------------------------------------------------
-// Exact binary traversal (audit path, and fallback of the rays the wide path could not certify)
-// ------------------------------------------------------------------------------------------------
-
-template<bool ANY_HIT>
-__global__ void __launch_bounds__(TRACE_TPB)
-KTraceBinary(AccelData a, uint32_t accelKey,
-             mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
-             uint32_t* __restrict__ visibleBits,
-             mrb_ray_gmem* rays, const uint32_t* __restrict__ rayIndices, uint32_t rayCount,
-             const uint32_t* __restrict__ deviceRayCount)
-{
-    if(deviceRayCount) rayCount = *deviceRayCount;
-    for(uint32_t i = blockIdx.x * TRACE_TPB + threadIdx.x; i < rayCount; i += gridDim.x * TRACE_TPB)
-    {
-    const uint32_t r = rayIndices ? rayIndices[i] : i;
-    const float4 r0 = reinterpret_cast<const float4*>(rays + r)[0];
-    const float4 r1 = reinterpret_cast<const float4*>(rays + r)[1];
-    const float o[3] = {r0.x, r0.y, r0.z}, d[3] = {r1.x, r1.y, r1.z};
-    const float tMin = r0.w; float tMax = r1.w;
-    float invD[3];
-    #pragma unroll
-    for(int k = 0; k < 3; k++) invD[k] = __fdiv_rn(1.0f, d[k]);
-
-    HitRecord best; best.t = tMax; best.rank = 0u; best.leaf = INVALID_U32; best.u = best.v = 0.f; best.flags = 0u;
-    uint32_t stack[160];
-    int sp = 0;
-    stack[sp++] = 0u;
-    while(sp > 0)
-    {
-        uint32_t ni = stack[--sp];
-        if(ni == INVALID_U32) continue;
-        if(ni & LEAF_FLAG)
-        {
-            uint32_t leaf = ni & ~LEAF_FLAG;
-            const uint32_t ri = (a.ranges.count == 1u) ? 0u : FindRange(a.ranges, leaf);
-            uint32_t prim = a.ranges.primBegin[ri] + (leaf - a.ranges.leafStart[ri]);
-            uint32_t i0 = a.indices[3 * size_t(prim)], i1 = a.indices[3 * size_t(prim) + 1], i2 = a.indices[3 * size_t(prim) + 2];
-            float4 v0, e0, e1;
-            const float* p0 = a.positions + 3 * size_t(i0);
-            const float* p1 = a.positions + 3 * size_t(i1);
-            const float* p2 = a.positions + 3 * size_t(i2);
-            v0 = make_float4(p0[0], p0[1], p0[2], 0.f);
-            e0 = make_float4(__fsub_rn(p1[0], p0[0]), __fsub_rn(p1[1], p0[1]), __fsub_rn(p1[2], p0[2]), 0.f);
-            e1 = make_float4(__fsub_rn(p2[0], p0[0]), __fsub_rn(p2[1], p0[1]), __fsub_rn(p2[2], p0[2]), 0.f);
-            float t, u, v;
-            if(!RayTriangle(o[0], o[1], o[2], d[0], d[1], d[2], v0, e0, e1, a.ranges.cull[ri] != 0u, t, u, v)) continue;
-            if(!(t >= tMin && t < tMax)) continue;
-            best.t = t; best.u = u; best.v = v; best.leaf = leaf; best.flags = ri << 8;
-            tMax = t;
-            if(ANY_HIT) break;
-        }
-        else
-        {
-            const float* b = reinterpret_cast<const float*>(a.boxes + ni);
-            if(SlabExact(b, o, invD, tMin, tMax))
-            {
-                LBVHNode nd = a.nodes[ni];
-                stack[sp++] = nd.right;
-                stack[sp++] = nd.left;
-                // this kernel is a dependent chain of (node, box) loads for a handful of rays: pull the records
-                // the next pops will need towards L1 while the current step finishes
-                if(!(nd.left & LEAF_FLAG))
-                {
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(a.boxes + nd.left));
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(a.nodes + nd.left));
-                }
-                if(!(nd.right & LEAF_FLAG))
-                {
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(a.boxes + nd.right));
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(a.nodes + nd.right));
-                }
-            }
-        }
-    }
-    if(best.leaf != INVALID_U32)
-    {
-        if(ANY_HIT) atomicAnd(&visibleBits[r >> 5], ~(1u << (r & 31u)));
-        else WriteHit(a, accelKey, r, best, hitKeys, metaHits, rays);
-    }
-    }
-}
-
-// Exact resolution of the rays the wide path could not certify, WITHOUT a full re-traversal: the
-// reference's answer is decided by the (at most two) candidates inside the near-tie window, by the
-// order it visits them (Morton rank) and by its box tests on their ancestor chains, evaluated with
-// the tMax the reference holds when it first enters each node: the t of an already accepted
-// candidate whose rank lies left of the node's range, else anything >= tUpper. A box that fails
-// with a real candidate's t is a genuine cull; a box that fails with tUpper is undecidable here and
-// the ray goes to the full binary traversal (KTraceBinary), as do rays with three or more
-// candidates in the window.
-__global__ void __launch_bounds__(TRACE_TPB)
-KResolveExact(AccelData a, uint32_t accelKey,
-              mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
-              mrb_ray_gmem* rays, uint32_t* __restrict__ counters, uint32_t* __restrict__ fallbackList,
-              const uint4* __restrict__ resolveRecords)
-{
-    const uint32_t count = min(counters[0], RESOLVE_CAPACITY);
-    for(uint32_t k = blockIdx.x * TRACE_TPB + threadIdx.x; k < count; k += gridDim.x * TRACE_TPB)
-    {
-        const uint4 q0 = resolveRecords[size_t(k) * 4 + 0], q1 = resolveRecords[size_t(k) * 4 + 1];
-        const uint4 q2 = resolveRecords[size_t(k) * 4 + 2], q3 = resolveRecords[size_t(k) * 4 + 3];
-        const uint32_t r = q0.x;
-        bool full = (q0.y & 1u) != 0u;
-        HitRecord c[2];
-        c[0].t = __uint_as_float(q1.x); c[0].u = __uint_as_float(q1.y); c[0].v = __uint_as_float(q1.z); c[0].leaf = q1.w;
-        c[0].rank = q2.x; c[0].flags = q2.y;
-        c[1].t = __uint_as_float(q2.z); c[1].u = __uint_as_float(q2.w); c[1].v = __uint_as_float(q3.x); c[1].leaf = q3.y;
-        c[1].rank = q3.z; c[1].flags = q3.w;
-        const int n = (q0.y & 2u) ? 2 : 1;
-        const float4 r0 = reinterpret_cast<const float4*>(rays + r)[0];
-        const float4 r1 = reinterpret_cast<const float4*>(rays + r)[1];
-        const float o[3] = {r0.x, r0.y, r0.z};
-        const float invD[3] = {__fdiv_rn(1.0f, r1.x), __fdiv_rn(1.0f, r1.y), __fdiv_rn(1.0f, r1.z)};
-        const float tMin = r0.w;
-        const float tUpper = fminf(r1.w, c[0].t * NEAR_TIE);
-        const int first = (n == 2 && c[1].rank < c[0].rank) ? 1 : 0;
-        int accepted = -1;
-        for(int s = 0; s < n && !full; s++)
-        {
-            const HitRecord& z = c[s == 0 ? first : 1 - first];
-            // a later-visited candidate only matters when it is strictly closer than the accepted one
-            if(accepted >= 0 && !(z.t < c[accepted].t)) continue;
-            bool reach = true;
-            // every ancestor box encloses the leaf box and the slab values are monotone in the box: if the leaf
-            // box passes with tUpper, so does every ancestor tested with tUpper, and once an ancestor contains
-            // the accepted candidate (range start <= its rank) all higher ones do too, so the walk can stop at
-            // the first ancestor that is not tested with the accepted t (the common ancestor, a few levels up)
-            const bool leafPasses = SlabExact(a.leafAABB + 6 * size_t(z.leaf), o, invD, tMin, tUpper);
-            uint32_t ni = a.leafParent[z.leaf];
-            while(ni != INVALID_U32)
-            {
-                const bool usePrior = accepted >= 0 && c[accepted].rank < a.nodeRange[ni].x;
-                if(!usePrior && leafPasses) break;
-                const float tcur = usePrior ? c[accepted].t : tUpper;
-                if(!SlabExact(reinterpret_cast<const float*>(a.boxes + ni), o, invD, tMin, tcur))
-                {
-                    if(usePrior) reach = false; else full = true;
-                    break;
-                }
-                // a box that passes with tUpper is enclosed by every remaining ancestor, which therefore pass too
-                // (edge hits make the flat leaf boxes marginal, not the boxes above them)
-                if(!usePrior) break;
-                ni = a.nodes[ni].parent;
-            }
-            if(!full && reach && (accepted < 0 || z.t < c[accepted].t)) accepted = (s == 0 ? first : 1 - first);
-        }
-        if(full || accepted < 0) fallbackList[atomicAdd(counters + 4, 1u)] = r;
-        else WriteHit(a, accelKey, r, c[accepted], hitKeys, metaHits, rays);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Two-level scenes
 // ------------------------------------------------------------------------------------------------
 // Matrix3x4::TransformRay (Core/Matrix.hpp:L905-912) with Math::Dot's FMA chains: dir' = M dir,
@@ -625,16 +630,106 @@ __device__ __forceinline__ bool CertifyLeaf2(const InstanceRec& in, uint32_t lea
     return SlabExact(box, lo, linv, tMin, tUpper);
 }
 
+// Exact two-level traversal of ONE ray (audit path and fallback): KCIntersectBaseLBVH semantics on the top level
+// (internal boxes and the instance leaf AABB slab-tested with the current tMax, left-first), the
+// bottom-level ClosestHit / FirstHit in local space, tMax shrinking across instances.
+template<bool ANY_HIT>
+__device__ __forceinline__ void TraceBinary2RayBody(const SceneData& sc,
+                                                    mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
+                                                    uint32_t* __restrict__ visibleBits, mrb_ray_gmem* rays, uint32_t r)
+{
+    const float4 r0 = reinterpret_cast<const float4*>(rays + r)[0];
+    const float4 r1 = reinterpret_cast<const float4*>(rays + r)[1];
+    const float wo[3] = {r0.x, r0.y, r0.z}, wd[3] = {r1.x, r1.y, r1.z};
+    const float winv[3] = {__fdiv_rn(1.0f, wd[0]), __fdiv_rn(1.0f, wd[1]), __fdiv_rn(1.0f, wd[2])};
+    const float tMin = r0.w; float tMax = r1.w;
+    HitRecord best; best.t = tMax; best.rank = 0u; best.leaf = INVALID_U32; best.u = best.v = 0.f; best.flags = 0u;
+    uint32_t bestInst = 0; bool done = false;
+    uint32_t tstack[96]; int tsp = 0;
+    tstack[tsp++] = 0u;
+    while(tsp > 0 && !done)
+    {
+        uint32_t tn = tstack[--tsp];
+        if(tn == INVALID_U32) continue;
+        if(!(tn & LEAF_FLAG))
+        {
+            if(SlabExact(reinterpret_cast<const float*>(sc.tlas.boxes + tn), wo, winv, tMin, tMax))
+            {
+                LBVHNode nd = sc.tlas.nodes[tn];
+                tstack[tsp++] = nd.right; tstack[tsp++] = nd.left;
+            }
+            continue;
+        }
+        const uint32_t ii = tn & ~LEAF_FLAG;
+        const InstanceRec& in = sc.instances[ii];
+        if(!SlabExact(in.worldAABB, wo, winv, tMin, tMax)) continue;
+        float o[3] = {wo[0], wo[1], wo[2]}, d[3] = {wd[0], wd[1], wd[2]};
+        if(!in.identity) TransformRayExact(in.invTransform, wo[0], wo[1], wo[2], wd[0], wd[1], wd[2], o, d);
+        const float invD[3] = {__fdiv_rn(1.0f, d[0]), __fdiv_rn(1.0f, d[1]), __fdiv_rn(1.0f, d[2])};
+        uint32_t stack[128]; int sp = 0;
+        stack[sp++] = 0u;
+        while(sp > 0)
+        {
+            uint32_t ni = stack[--sp];
+            if(ni == INVALID_U32) continue;
+            if(ni & LEAF_FLAG)
+            {
+                uint32_t leaf = ni & ~LEAF_FLAG;
+                const uint32_t ri = (in.ranges.count == 1u) ? 0u : FindRange(in.ranges, leaf);
+                uint32_t prim = in.ranges.primBegin[ri] + (leaf - in.ranges.leafStart[ri]);
+                uint32_t i0 = in.indices[3 * size_t(prim)], i1 = in.indices[3 * size_t(prim) + 1], i2 = in.indices[3 * size_t(prim) + 2];
+                const float* p0 = in.positions + 3 * size_t(i0);
+                const float* p1 = in.positions + 3 * size_t(i1);
+                const float* p2 = in.positions + 3 * size_t(i2);
+                float4 v0 = make_float4(p0[0], p0[1], p0[2], 0.f);
+                float4 e0 = make_float4(__fsub_rn(p1[0], p0[0]), __fsub_rn(p1[1], p0[1]), __fsub_rn(p1[2], p0[2]), 0.f);
+                float4 e1 = make_float4(__fsub_rn(p2[0], p0[0]), __fsub_rn(p2[1], p0[1]), __fsub_rn(p2[2], p0[2]), 0.f);
+                float t, u, v;
+                if(!RayTriangle(o[0], o[1], o[2], d[0], d[1], d[2], v0, e0, e1, in.ranges.cull[ri] != 0u, t, u, v)) continue;
+                if(!(t >= tMin && t < tMax)) continue;
+                best.t = t; best.u = u; best.v = v; best.leaf = leaf; best.flags = ri << 8; bestInst = ii;
+                tMax = t;
+                if(ANY_HIT) { done = true; break; }
+            }
+            else if(SlabExact(reinterpret_cast<const float*>(in.boxes + ni), o, invD, tMin, tMax))
+            {
+                LBVHNode nd = in.nodes[ni];
+                stack[sp++] = nd.right; stack[sp++] = nd.left;
+            }
+        }
+    }
+    if(best.leaf != INVALID_U32)
+    {
+        if(ANY_HIT) atomicAnd(&visibleBits[r >> 5], ~(1u << (r & 31u)));
+        else WriteHit2(sc.instances[bestInst], r, best, hitKeys, metaHits, rays);
+    }
+}
+__device__ __noinline__ void TraceBinary2RayClosest(const SceneData& sc, mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, mrb_ray_gmem* rays, uint32_t r)
+{ TraceBinary2RayBody<false>(sc, hitKeys, metaHits, nullptr, rays, r); }
+__device__ __noinline__ void TraceBinary2RayAny(const SceneData& sc, uint32_t* visibleBits, mrb_ray_gmem* rays, uint32_t r)
+{ TraceBinary2RayBody<true>(sc, nullptr, nullptr, visibleBits, rays, r); }
+
+template<bool ANY_HIT>
+__global__ void __launch_bounds__(TRACE_TPB)
+KTraceBinary2(const __grid_constant__ SceneData sc,
+              mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
+              uint32_t* __restrict__ visibleBits,
+              mrb_ray_gmem* rays, const uint32_t* __restrict__ rayIndices, uint32_t rayCount)
+{
+    for(uint32_t i = blockIdx.x * TRACE_TPB + threadIdx.x; i < rayCount; i += gridDim.x * TRACE_TPB)
+        TraceBinary2RayBody<ANY_HIT>(sc, hitKeys, metaHits, visibleBits, rays, rayIndices ? rayIndices[i] : i);
+}
+
 // Same phase-uniform persistent loop as KTraceWide with one more kind of leaf: in the top-level tree a
 // leaf record is an instance; entering it pushes the pending top-level groups and a sentinel, switches the
 // lane to the instance's local ray / node arrays, and the sentinel pop switches back.
 template<bool ANY_HIT>
 __global__ void __launch_bounds__(TRACE_TPB)
-KTraceWide2(SceneData sc,
+KTraceWide2(const __grid_constant__ SceneData sc,
             mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
             uint32_t* __restrict__ visibleBits,
             mrb_ray_gmem* rays, const uint32_t* __restrict__ rayIndices, uint32_t rayCount,
-            uint32_t* __restrict__ counters, uint32_t* __restrict__ fallbackList, TraceParams prm)
+            uint32_t* __restrict__ counters, TraceParams prm)
 {
     constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
@@ -674,7 +769,11 @@ KTraceWide2(SceneData sc,
             if(ANY_HIT)
             {
                 if(done) atomicAnd(&visibleBits[r >> 5], ~(1u << (r & 31u)));
-                else if(uncertified) { fallbackList[atomicAdd(counters + 4, 1u)] = r; atomicAdd(counters, 1u); atomicAdd(counters + 2, 1u); }
+                else if(uncertified)
+                {
+                    atomicAdd(counters, 1u); atomicAdd(counters + 2, 1u); atomicAdd(counters + 4, 1u);
+                    TraceBinary2RayAny(sc, visibleBits, rays, r);
+                }
             }
             else if(best.leaf != INVALID_U32)
             {
@@ -684,9 +783,10 @@ KTraceWide2(SceneData sc,
                     WriteHit2(in, r, best, hitKeys, metaHits, rays);
                 else
                 {
-                    fallbackList[atomicAdd(counters + 4, 1u)] = r;
-                    atomicAdd(counters, 1u);
+                    // near tie or uncertified leaf: the reference's two-level algorithm decides (out of line, rare)
+                    atomicAdd(counters, 1u); atomicAdd(counters + 4, 1u);
                     atomicAdd(counters + ((secondSeen || overflow) ? 1 : 2), 1u);
+                    TraceBinary2RayClosest(sc, hitKeys, metaHits, rays, r);
                 }
             }
         }
@@ -879,89 +979,6 @@ KTraceWide2(SceneData sc,
     }
 }
 
-// Exact two-level traversal (audit path and fallback): KCIntersectBaseLBVH semantics on the top level
-// (internal boxes and the instance leaf AABB slab-tested with the current tMax, left-first), the
-// bottom-level ClosestHit / FirstHit in local space, tMax shrinking across instances.
-template<bool ANY_HIT>
-__global__ void __launch_bounds__(TRACE_TPB)
-KTraceBinary2(SceneData sc,
-              mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
-              uint32_t* __restrict__ visibleBits,
-              mrb_ray_gmem* rays, const uint32_t* __restrict__ rayIndices, uint32_t rayCount,
-              const uint32_t* __restrict__ deviceRayCount)
-{
-    if(deviceRayCount) rayCount = *deviceRayCount;
-    for(uint32_t i = blockIdx.x * TRACE_TPB + threadIdx.x; i < rayCount; i += gridDim.x * TRACE_TPB)
-    {
-        const uint32_t r = rayIndices ? rayIndices[i] : i;
-        const float4 r0 = reinterpret_cast<const float4*>(rays + r)[0];
-        const float4 r1 = reinterpret_cast<const float4*>(rays + r)[1];
-        const float wo[3] = {r0.x, r0.y, r0.z}, wd[3] = {r1.x, r1.y, r1.z};
-        const float winv[3] = {__fdiv_rn(1.0f, wd[0]), __fdiv_rn(1.0f, wd[1]), __fdiv_rn(1.0f, wd[2])};
-        const float tMin = r0.w; float tMax = r1.w;
-        HitRecord best; best.t = tMax; best.rank = 0u; best.leaf = INVALID_U32; best.u = best.v = 0.f; best.flags = 0u;
-        uint32_t bestInst = 0; bool done = false;
-        uint32_t tstack[96]; int tsp = 0;
-        tstack[tsp++] = 0u;
-        while(tsp > 0 && !done)
-        {
-            uint32_t tn = tstack[--tsp];
-            if(tn == INVALID_U32) continue;
-            if(!(tn & LEAF_FLAG))
-            {
-                if(SlabExact(reinterpret_cast<const float*>(sc.tlas.boxes + tn), wo, winv, tMin, tMax))
-                {
-                    LBVHNode nd = sc.tlas.nodes[tn];
-                    tstack[tsp++] = nd.right; tstack[tsp++] = nd.left;
-                }
-                continue;
-            }
-            const uint32_t ii = tn & ~LEAF_FLAG;
-            const InstanceRec& in = sc.instances[ii];
-            if(!SlabExact(in.worldAABB, wo, winv, tMin, tMax)) continue;
-            float o[3] = {wo[0], wo[1], wo[2]}, d[3] = {wd[0], wd[1], wd[2]};
-            if(!in.identity) TransformRayExact(in.invTransform, wo[0], wo[1], wo[2], wd[0], wd[1], wd[2], o, d);
-            const float invD[3] = {__fdiv_rn(1.0f, d[0]), __fdiv_rn(1.0f, d[1]), __fdiv_rn(1.0f, d[2])};
-            uint32_t stack[128]; int sp = 0;
-            stack[sp++] = 0u;
-            while(sp > 0)
-            {
-                uint32_t ni = stack[--sp];
-                if(ni == INVALID_U32) continue;
-                if(ni & LEAF_FLAG)
-                {
-                    uint32_t leaf = ni & ~LEAF_FLAG;
-                    const uint32_t ri = (in.ranges.count == 1u) ? 0u : FindRange(in.ranges, leaf);
-                    uint32_t prim = in.ranges.primBegin[ri] + (leaf - in.ranges.leafStart[ri]);
-                    uint32_t i0 = in.indices[3 * size_t(prim)], i1 = in.indices[3 * size_t(prim) + 1], i2 = in.indices[3 * size_t(prim) + 2];
-                    const float* p0 = in.positions + 3 * size_t(i0);
-                    const float* p1 = in.positions + 3 * size_t(i1);
-                    const float* p2 = in.positions + 3 * size_t(i2);
-                    float4 v0 = make_float4(p0[0], p0[1], p0[2], 0.f);
-                    float4 e0 = make_float4(__fsub_rn(p1[0], p0[0]), __fsub_rn(p1[1], p0[1]), __fsub_rn(p1[2], p0[2]), 0.f);
-                    float4 e1 = make_float4(__fsub_rn(p2[0], p0[0]), __fsub_rn(p2[1], p0[1]), __fsub_rn(p2[2], p0[2]), 0.f);
-                    float t, u, v;
-                    if(!RayTriangle(o[0], o[1], o[2], d[0], d[1], d[2], v0, e0, e1, in.ranges.cull[ri] != 0u, t, u, v)) continue;
-                    if(!(t >= tMin && t < tMax)) continue;
-                    best.t = t; best.u = u; best.v = v; best.leaf = leaf; best.flags = ri << 8; bestInst = ii;
-                    tMax = t;
-                    if(ANY_HIT) { done = true; break; }
-                }
-                else if(SlabExact(reinterpret_cast<const float*>(in.boxes + ni), o, invD, tMin, tMax))
-                {
-                    LBVHNode nd = in.nodes[ni];
-                    stack[sp++] = nd.right; stack[sp++] = nd.left;
-                }
-            }
-        }
-        if(best.leaf != INVALID_U32)
-        {
-            if(ANY_HIT) atomicAnd(&visibleBits[r >> 5], ~(1u << (r & 31u)));
-            else WriteHit2(sc.instances[bestInst], r, best, hitKeys, metaHits, rays);
-        }
-    }
-}
-
 // Scheduling knobs of the wide kernels, shared by single-accelerator and scene casts (MRB_TRI_DIV / MRB_FETCH_THR
 // override them for parameter sweeps)
 const TraceParams& WideTraceParams()
@@ -978,6 +995,31 @@ const TraceParams& WideTraceParams()
 
 } // namespace
 
+// L2 residency hint: nodes + triangle records of the accelerator being traced (20 MB at 264 K triangles) are marked
+// persisting in the stream's access-policy window, so the ~130 MB ray / hit stream of a cast cannot evict them.
+static void SetPersistingWindow(Context& ctx, const void* base, size_t bytes)
+{
+    if(ctx.persistBase == base && ctx.persistStream == ctx.stream) return;
+    static const bool enabled = []{ const char* e = getenv("MRB_L2_PERSIST"); return !(e && e[0] == '0'); }();
+    if(!enabled) return;
+    int maxWindow = 0, maxPersist = 0;
+    cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, ctx.device);
+    cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, ctx.device);
+    ctx.persistBase = base; ctx.persistStream = ctx.stream;
+    if(maxWindow <= 0 || maxPersist <= 0) return;
+    const size_t win = bytes < size_t(maxWindow) ? bytes : size_t(maxWindow);
+    const size_t carve = win < size_t(maxPersist) ? win : size_t(maxPersist);
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+    cudaStreamAttrValue attr = {};
+    attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+    attr.accessPolicyWindow.num_bytes = win;
+    attr.accessPolicyWindow.hitRatio = win <= carve ? 1.0f : float(double(carve) / double(win));
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(ctx.stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaGetLastError();   // a hint: never fatal
+}
+
 void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode mode,
                mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, uint32_t* visibleBits,
                mrb_ray_gmem* rays, const uint32_t* rayIndices, uint32_t rayCount)
@@ -986,14 +1028,10 @@ void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode
     const uint32_t grid = DivUp(rayCount, TRACE_TPB);
     if(mode == MRB_TRACE_WIDE)
     {
-        // trace scratch: [counters (64 words)][resolve records][full-fallback ray list]
-        MultiAlloc sz(nullptr);
-        sz.Take<uint32_t>(64); sz.Take<uint4>(size_t(RESOLVE_CAPACITY) * 4); sz.Take<uint32_t>(rayCount);
-        ctx.traceScratch.Reserve(sz.Total());
-        MultiAlloc ma(ctx.traceScratch.Base());
-        uint32_t* counters = ma.Take<uint32_t>(64);
-        uint4* records = ma.Take<uint4>(size_t(RESOLVE_CAPACITY) * 4);
-        uint32_t* fbList = ma.Take<uint32_t>(rayCount);
+        // counters of the cast: [0] uncertified rays, [1] near ties, [2] uncertified leaves, [3] fetch cursor,
+        // [4] rays re-traced by the reference's binary algorithm
+        ctx.traceScratch.Reserve(sizeof(uint32_t) * 64);
+        uint32_t* counters = static_cast<uint32_t*>(ctx.traceScratch.Base());
 #ifdef MRB_TRACE_STATS
         MRB_CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 16, ctx.stream));
 #else
@@ -1004,23 +1042,14 @@ void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode
             MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx.occWide[0], KTraceWide<false>, TRACE_TPB, 0));
             MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx.occWide[1], KTraceWide<true>, TRACE_TPB, 0));
         }
+        if(acc.d.wideNodes && acc.d.tris)
+            SetPersistingWindow(ctx, acc.d.wideNodes, size_t(reinterpret_cast<const char*>(acc.d.tris + acc.d.leafCount) - reinterpret_cast<const char*>(acc.d.wideNodes)));
         const TraceParams prm = WideTraceParams();
         const uint32_t pgrid = min(grid, uint32_t(ctx.smCount) * uint32_t(ctx.occWide[anyHit ? 1 : 0]));
-        const uint32_t fbGrid = uint32_t(ctx.smCount);
-        if(anyHit)
         {
-            { ProfileScope ps(ctx, PROF_TRACE_ANY);
-              MRB_LAUNCH(ctx, KTraceWide<true>, pgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, fbList, records, prm); }
-            ProfileScope pt(ctx, PROF_TRACE_TAIL);
-            MRB_LAUNCH(ctx, KTraceBinary<true>, fbGrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, fbList, 0u, counters + 4);
-        }
-        else
-        {
-            { ProfileScope ps(ctx, PROF_TRACE_CLOSEST);
-              MRB_LAUNCH(ctx, KTraceWide<false>, pgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, fbList, records, prm); }
-            ProfileScope pt(ctx, PROF_TRACE_TAIL);
-            MRB_LAUNCH(ctx, KResolveExact, fbGrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, rays, counters, fbList, records);
-            MRB_LAUNCH(ctx, KTraceBinary<false>, fbGrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, fbList, 0u, counters + 4);
+            ProfileScope ps(ctx, anyHit ? PROF_TRACE_ANY : PROF_TRACE_CLOSEST);
+            if(anyHit) MRB_LAUNCH(ctx, KTraceWide<true>, pgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, prm);
+            else       MRB_LAUNCH(ctx, KTraceWide<false>, pgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, prm);
         }
         ctx.lastFallbackCount = counters;
 #ifdef MRB_TRACE_STATS
@@ -1037,8 +1066,8 @@ void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode
     else
     {
         const uint32_t bgrid = min(grid, uint32_t(ctx.smCount) * 16u);
-        if(anyHit) MRB_LAUNCH(ctx, KTraceBinary<true>, bgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, nullptr);
-        else       MRB_LAUNCH(ctx, KTraceBinary<false>, bgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, nullptr);
+        if(anyHit) MRB_LAUNCH(ctx, KTraceBinary<true>, bgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount);
+        else       MRB_LAUNCH(ctx, KTraceBinary<false>, bgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount);
         ctx.lastFallbackCount = nullptr;
     }
 }
@@ -1052,13 +1081,8 @@ void TraceScene(Context& ctx, const SceneData& scnData, bool anyHit, mrb_trace_m
     const uint32_t grid = DivUp(rayCount, TRACE_TPB);
     if(mode == MRB_TRACE_WIDE)
     {
-        MultiAlloc sz(nullptr);
-        sz.Take<uint32_t>(64); sz.Take<uint4>(size_t(RESOLVE_CAPACITY) * 4); sz.Take<uint32_t>(rayCount);
-        ctx.traceScratch.Reserve(sz.Total());
-        MultiAlloc ma(ctx.traceScratch.Base());
-        uint32_t* counters = ma.Take<uint32_t>(64);
-        ma.Take<uint4>(size_t(RESOLVE_CAPACITY) * 4);
-        uint32_t* fbList = ma.Take<uint32_t>(rayCount);
+        ctx.traceScratch.Reserve(sizeof(uint32_t) * 64);
+        uint32_t* counters = static_cast<uint32_t*>(ctx.traceScratch.Base());
         MRB_CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 8, ctx.stream));
         if(!ctx.occWide2[0])
         {
@@ -1067,28 +1091,18 @@ void TraceScene(Context& ctx, const SceneData& scnData, bool anyHit, mrb_trace_m
         }
         const TraceParams prm = WideTraceParams();
         const uint32_t pgrid = min(grid, uint32_t(ctx.smCount) * uint32_t(ctx.occWide2[anyHit ? 1 : 0]));
-        const uint32_t fbGrid = uint32_t(ctx.smCount);
-        if(anyHit)
         {
-            { ProfileScope ps(ctx, PROF_TRACE_ANY);
-              MRB_LAUNCH(ctx, KTraceWide2<true>, pgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, fbList, prm); }
-            ProfileScope pt(ctx, PROF_TRACE_TAIL);
-            MRB_LAUNCH(ctx, KTraceBinary2<true>, fbGrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, fbList, 0u, counters + 4);
-        }
-        else
-        {
-            { ProfileScope ps(ctx, PROF_TRACE_CLOSEST);
-              MRB_LAUNCH(ctx, KTraceWide2<false>, pgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, fbList, prm); }
-            ProfileScope pt(ctx, PROF_TRACE_TAIL);
-            MRB_LAUNCH(ctx, KTraceBinary2<false>, fbGrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, fbList, 0u, counters + 4);
+            ProfileScope ps(ctx, anyHit ? PROF_TRACE_ANY : PROF_TRACE_CLOSEST);
+            if(anyHit) MRB_LAUNCH(ctx, KTraceWide2<true>, pgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, prm);
+            else       MRB_LAUNCH(ctx, KTraceWide2<false>, pgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, prm);
         }
         ctx.lastFallbackCount = counters;
     }
     else
     {
         const uint32_t bgrid = min(grid, uint32_t(ctx.smCount) * 16u);
-        if(anyHit) MRB_LAUNCH(ctx, KTraceBinary2<true>, bgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, nullptr);
-        else       MRB_LAUNCH(ctx, KTraceBinary2<false>, bgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, nullptr);
+        if(anyHit) MRB_LAUNCH(ctx, KTraceBinary2<true>, bgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount);
+        else       MRB_LAUNCH(ctx, KTraceBinary2<false>, bgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount);
         ctx.lastFallbackCount = nullptr;
     }
 }
