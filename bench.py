@@ -145,7 +145,13 @@ def run_ours(args):
     if world > 1:
         # NCCL writes its version / debug lines to stdout by default; stdout carries exactly one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # ... and its "NCCL version" banner goes to fd 1 whatever that says: park stdout on stderr until the communicator exists
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.all_reduce(torch.zeros(1024, device="cuda")); torch.cuda.synchronize()
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1); os.close(saved_stdout)
     if not spectral.available():
         raise SystemExit("bench.py: mray_b200/data/ACES_CG.mrspectra is missing (run __graft_entry__.build() where /root/reference exists)")
     ctx = mray_b200.Context(local)
@@ -384,22 +390,26 @@ def e2e_plugin(sc, spp, rank, world, local, rays_per_step, barrier, max_over_ran
     steps = max(2, min(args.steps, 3))
 
     def once():
-        t0 = time.perf_counter()
+        """One render through TracerI. Timed: everything the call does to produce the image on the host — scene upload
+        calls, CommitSurfaces, StartRender, the DoRenderWork loop with every hand-off and the caller's accumulation, and
+        (N > 1) the sum of the ranks' host images on rank 0. Not timed: tracer tear-down after the image exists."""
         img, w, st = O.driver_render(plugin, bsc, alb, len(sc["palb"]), sc["prad"], scenes.ARCADE_CAMERA, W, H, spp,
                                      renderer=RENDERER, sample_mode=SAMPLE_MODE, rr_range=RR, seed=0, burst_size=BURST)
+        sec = st["scene_s"] + st["commit_s"] + st["start_s"] + st["render_s"]
         if world > 1:
+            t0 = time.perf_counter()
             t = torch.from_numpy(np.concatenate([img * w[..., None], w[..., None]], axis=-1)).cuda()
             dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
             h = t.cpu().numpy()
             img, w = h[..., :3] / np.maximum(h[..., 3:], 1e-20), h[..., 3]
-        else:
-            _ = float(img[0, 0, 0])   # the result is on the host already
-        return time.perf_counter() - t0, st, w
+            sec += time.perf_counter() - t0
+        return sec, st, w
 
     once()                                           # warm: library load, allocations, page-locking
     barrier()
     tt, st, w = 0.0, None, None
     for _ in range(steps):
+        barrier()
         dt, st, w = once()
         tt += dt
     barrier()

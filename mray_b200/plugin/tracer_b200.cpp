@@ -23,6 +23,7 @@
 #include <filesystem>
 #include <fstream>
 #include <cstdlib>
+#include <cstdio>
 
 #include <algorithm>
 #include <cmath>
@@ -260,8 +261,20 @@ class TracerB200 final : public TracerI
         }
         throw MRayError("Unable to open the Sobol generator matrices (sobol_matrices.bin)");
     }
+    // MRB_PLUGIN_TIMING=1: wall time of the tear-down steps on stderr
+    struct ScopeTimer
+    {
+        const char* what; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+        explicit ScopeTimer(const char* w) : what(w) {}
+        ~ScopeTimer()
+        {
+            static const bool on = std::getenv("MRB_PLUGIN_TIMING") != nullptr;
+            if(on) std::fprintf(stderr, "[mray_b200 plugin] %s: %.2f ms\n", what, 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+        }
+    };
     void ReleaseRenderers()
     {
+        ScopeTimer t("ReleaseRenderers");
         for(DeviceB200& d : devs) if(d.renderer) { mrb_renderer_destroy(d.ctx, d.renderer); d.renderer = nullptr; }
     }
     void ReleaseAccels()
@@ -278,10 +291,10 @@ class TracerB200 final : public TracerI
     ~TracerB200() override
     {
         ReleaseRenderers();
-        if(staging) mrb_host_free(ctx, staging);
-        for(DeviceB200& d : devs) if(d.spectrum) mrb_spectrum_destroy(d.ctx, d.spectrum);
-        ReleaseAccels();
-        for(DeviceB200& d : devs) mrb_context_destroy(d.ctx);
+        { ScopeTimer t("free staging"); if(staging) mrb_host_free(ctx, staging); }
+        { ScopeTimer t("free spectrum"); for(DeviceB200& d : devs) if(d.spectrum) mrb_spectrum_destroy(d.ctx, d.spectrum); }
+        { ScopeTimer t("ReleaseAccels"); ReleaseAccels(); }
+        { ScopeTimer t("context destroy"); for(DeviceB200& d : devs) mrb_context_destroy(d.ctx); }
     }
 
     // ------------------------------- generic -------------------------------
