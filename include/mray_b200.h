@@ -334,7 +334,10 @@ typedef enum mrb_sample_mode
  * bit 31 = light flag, bits 0..20 = index into albedo[] (material) or lightRadiance[] (light).
  * Scope: (R)PathTracerRGB / Spectral, (Mt)Lambert (constant or textured albedo), (Mt)Reflect, (L)Prim(P)Triangle with
  * constant radiance, (L)Null boundary, (C)Pinhole, the four film filters, Independent / Sobol / ZSobol samplers. */
-typedef enum mrb_material_type { MRB_MATERIAL_LAMBERT = 0, MRB_MATERIAL_REFLECT = 1 } mrb_material_type;
+typedef enum mrb_material_type
+{   /* MatGroupLambert / Reflect / Refract / Unreal (Tracer/MaterialsDefault.h) */
+    MRB_MATERIAL_LAMBERT = 0, MRB_MATERIAL_REFLECT = 1, MRB_MATERIAL_REFRACT = 2, MRB_MATERIAL_UNREAL = 3
+} mrb_material_type;
 /* FilterType::E (Core/TracerEnums.h:L162-173) */
 typedef enum mrb_film_filter { MRB_FILTER_BOX = 0, MRB_FILTER_TENT = 1, MRB_FILTER_GAUSSIAN = 2, MRB_FILTER_MITCHELL_NETRAVALI = 3 } mrb_film_filter;
 
@@ -413,8 +416,9 @@ typedef struct mrb_render_desc
     uint32_t        fullResolution[2];
     uint32_t        regionMin[2];
     /* NULL (every material is (Mt)Lambert), or host u8 per material: mrb_material_type. (Mt)Reflect
-     * (Tracer/MaterialsDefault.hpp:L132-215) is a perfect mirror: no NEE shadow ray, no Russian roulette, the next ray is
-     * a SPECULAR_RAY (PathTracerRendererShaders.h:L245-262,L415-424); its `albedo` entry is ignored. */
+     * (Tracer/MaterialsDefault.hpp:L132-215) and (Mt)Refract are perfectly specular: no NEE shadow ray, no Russian
+     * roulette, the next ray is a SPECULAR_RAY (PathTracerRendererShaders.h:L245-262,L415-424); their `albedo` entries are
+     * ignored. (Mt)Unreal behaves the same way once its specularity (1 - diffuse lobe probability) reaches 0.95. */
     const uint8_t*  materialType;
     /* TracerParameters.filmFilter.type (FilterType::E, Core/TracerEnums.h:L162-173; Tracer/Filters.h): the sampler of the
      * camera sample's sub-pixel offset and its film weight Evaluate / pdf. filmFilterRadius above is its radius. */
@@ -426,6 +430,21 @@ typedef struct mrb_render_desc
      * 0 = sampleOffset + totalSPP. */
     uint32_t        sampleOffset;
     uint32_t        jobSPP;
+    /* NULL, or host materialCount * 8 floats — the constant attributes of the non-Lambert materials:
+     *   (Mt)Refract (Tracer/MaterialsDefault.hpp:L232-312): [0..2] cauchyFront, [4..6] cauchyBack — Cauchy coefficients of
+     *     the media in front of / behind the surface (index of refraction = c0 + c1 / l^2 + c2 / l^4, l in micrometres, at the
+     *     path's first wavelength; c0 alone in the RGB renderer). Refraction disperses a spectral path to that wavelength.
+     *   (Mt)Unreal (L466-760): [0] roughness, [1] specular, [2] metallic (constants; `albedo` as for Lambert, may be textured).
+     * Other entries are ignored. */
+    const float*    materialParams;
+    /* PrimGroupTriangle's NORMAL attribute as the scene loader delivers it (Tracer/PrimitiveDefaultTriangle.cu:L169-184): one
+     * world -> tangent-space rotation quaternion (w, x, y, z) per vertex. The hit's frame is Quaternion::BarySLerp of the
+     * three vertex quaternions and the shading normal its Z axis (Triangle::GenerateSurface,
+     * PrimitiveDefaultTriangle.hpp:L463-470) — takes precedence over vertexNormals / instanceVertexNormals, which interpolate
+     * plain normals linearly. vertexTBN: host, vertexCount * 4 (single accelerator); instanceVertexTBN: one host pointer per
+     * instance or NULL entries (two-level scenes). */
+    const float*    vertexTBN;
+    const float* const* instanceVertexTBN;
 } mrb_render_desc;
 
 typedef struct mrb_render_stats

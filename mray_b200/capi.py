@@ -79,7 +79,8 @@ class RenderDesc(C.Structure):
                 ("textureCount", C.c_uint32), ("textures", C.c_void_p), ("albedoTexture", C.c_void_p),
                 ("vertexUVs", C.c_void_p), ("instanceVertexUVs", C.POINTER(C.c_void_p)),
                 ("fullResolution", C.c_uint32 * 2), ("regionMin", C.c_uint32 * 2), ("materialType", C.c_void_p),
-                ("filmFilterType", C.c_uint32), ("sampleOffset", C.c_uint32), ("jobSPP", C.c_uint32)]
+                ("filmFilterType", C.c_uint32), ("sampleOffset", C.c_uint32), ("jobSPP", C.c_uint32), ("materialParams", C.c_void_p),
+                ("vertexTBN", C.c_void_p), ("instanceVertexTBN", C.POINTER(C.c_void_p))]
 
 
 class TextureDesc(C.Structure):
@@ -481,7 +482,7 @@ class Renderer:
                  max_path_count=0, partition_rays=False, instance_vertex_normals=None, spectrum=None, sampler="Independent",
                  textures=None, albedo_texture=None, vertex_uvs=None, instance_vertex_uvs=None,
                  full_resolution=None, region_min=(0, 0), material_type=None, film_filter="Gaussian",
-                 sample_offset=0, job_spp=0):
+                 sample_offset=0, job_spp=0, material_params=None, vertex_tbn=None):
         """`accel` is an Accelerator, or a Scene (two-level; vertex_count / triangle_count / vertex_normals
         are then ignored and instance_vertex_normals may hold one array or None per instance).
         textures: list of dict(data=[h, w, 3|4] float32 or uint8 array, interp="Linear"|"Nearest",
@@ -512,6 +513,10 @@ class Renderer:
         else:
             d.accel = accel.handle
             d.vertexCount, d.triangleCount = vertex_count, triangle_count
+            if vertex_tbn is not None:   # [V, 4] world -> tangent-space quaternions (w, x, y, z): Quaternion::BarySLerp shading frames
+                tq = np.ascontiguousarray(vertex_tbn, np.float32).reshape(-1, 4)
+                self._keep.append(tq)
+                d.vertexTBN = tq.ctypes.data
 
         def host(a, dt):
             if a is None:
@@ -541,7 +546,11 @@ class Renderer:
         d.seed = seed
         d.maxPathCount = max_path_count
         d.partitionRays = 1 if partition_rays else 0
-        d.materialType = host(material_type, np.uint8)   # per material: 0 (Mt)Lambert, 1 (Mt)Reflect
+        d.materialType = host(material_type, np.uint8)   # per material: 0 (Mt)Lambert, 1 (Mt)Reflect, 2 (Mt)Refract, 3 (Mt)Unreal
+        if material_params is not None:                  # [material, 8]: Refract cauchyFront / cauchyBack, Unreal roughness / specular / metallic
+            mp = np.ascontiguousarray(material_params, np.float32).reshape(-1, 8)
+            assert mp.shape[0] == alb.shape[0], "material_params needs one row of 8 floats per material"
+            d.materialParams = host(mp, np.float32)
         if full_resolution is not None:   # width x height is a region of a larger image
             d.fullResolution = (C.c_uint32 * 2)(*full_resolution)
             d.regionMin = (C.c_uint32 * 2)(*region_min)

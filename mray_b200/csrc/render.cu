@@ -185,7 +185,7 @@ __device__ __forceinline__ float LerpU(float a, float b, float t) { return __fad
 __device__ __forceinline__ float TentSample(float xi, float r, float& pdf)
 {   // Distribution::Common::SampleTent(xi, -r, r) (DistributionFunctions.h:L785-805) over BisectSample2 + SampleLine(., 1, 0)
     const float a = -r, b = r;
-    if(b - a < 1.0e-5f) { pdf = 1.0f / (b - a); return 0.0f; }
+    if(b - a < 1.0e-4f) { pdf = 1.0f / (b - a); return 0.0f; }   // MathConstants::LargeEpsilon
     const float w = r / (r + r);                                  // weights[0] / weights.Sum()
     const bool left = xi < w;
     float lxi = left ? xi / w : (xi - w) / (1.0f - w);
@@ -276,13 +276,13 @@ struct RenderInstance
 {
     const float*    positions;
     const uint32_t* indices;
-    const float4*   vertexNormals;   // optional (xyz), nullptr = geometric
+    const float4*   vertexNormals;   // optional: shading normals (xyz), or to-tangent-space quaternions (w, x, y, z) when `tbn` is set; nullptr = geometric
     const uint32_t* lightOfPrim;     // prim index -> emissive triangle index or INVALID
     const float2*   vertexUVs;       // optional UV0 per vertex, nullptr = (0, 0)
     float           transform[12];   // local -> world, row-major 3x4
     float           invTransform[12];
     uint32_t        identity;
-    uint32_t        pad[1];
+    uint32_t        tbn;             // vertexNormals holds quaternions (PrimGroupTriangle's NORMAL attribute as the loader delivers it)
 };
 
 struct RenderData
@@ -292,7 +292,8 @@ struct RenderData
     uint32_t          sceneMode;       // 1 = hitKeys.accelKey holds the instance index
     const TexRec*     textures;        // textured albedo (ParamVaryingData): texture table ...
     const int32_t*    albedoTex;       // ... and per material index: texture or -1; nullptr = no material is textured
-    const uint8_t*    materialType;    // per material index: 0 (Mt)Lambert, 1 (Mt)Reflect; nullptr = all Lambert
+    const uint8_t*    materialType;    // per material index: mrb_material_type; nullptr = all Lambert
+    const float4*     matParams;       // per material index 2 x float4: Refract (cauchyFront xyz, cauchyBack xyz), Unreal (roughness, specular, metallic)
     const float4*     albedo;          // per material index: (r, g, b, 0), or Jakob coefficients (c0, c1, c2, -) when spectral
     // hero-wavelength spectral transport ((R)PathTracerSpectral); lights carry (c0, c1, c2, scale) in .radiance
     SpectrumData      spec;
@@ -522,6 +523,230 @@ __device__ __forceinline__ Spec RadianceAt(const RenderData& d, float4 r, float4
     return S4(EvalRadiance(d.spec, r, w.x), EvalRadiance(d.spec, r, w.y), EvalRadiance(d.spec, r, w.z), EvalRadiance(d.spec, r, w.w));
 }
 
+// ---- (Mt)Refract and (Mt)Unreal building blocks (Tracer/DistributionFunctions.h, Core/GraphicsFunctions.h) ----
+enum : uint32_t { MAT_LAMBERT = 0u, MAT_REFLECT = 1u, MAT_REFRACT = 2u, MAT_UNREAL = 3u };   // mrb_material_type
+constexpr float SPECULAR_THRESHOLD = 0.95f;   // MaterialCommon::SpecularThreshold (Tracer/MaterialC.h:L11)
+
+__device__ __forceinline__ float SqrtMax(float x) { return sqrtf(fmaxf(x, 0.0f)); }
+// Common::PDFCosDirection (DistributionFunctions.h:L882-889): cos / pi, zero at or below MathConstants::Epsilon
+__device__ __forceinline__ float PdfCosDirection(float cosTheta) { const float p = cosTheta * INV_PI_F; return (p <= 1.0e-5f) ? 0.0f : p; }
+// BxDF::FresnelDielectric (DistributionFunctions.h:L382-403)
+__device__ __forceinline__ float FresnelDielectric(float cosFront, float etaFront, float etaBack)
+{
+    const float sinFront = SqrtMax(1.0f - cosFront * cosFront);
+    const float sinBack = etaFront / etaBack * sinFront;
+    if(sinFront >= 1.0f) return 1.0f;
+    const float cosBack = SqrtMax(1.0f - sinBack * sinBack);
+    float parallel = (etaBack * cosFront - etaFront * cosBack) / (etaBack * cosFront + etaFront * cosBack);
+    parallel = parallel * parallel;
+    float perpendicular = (etaFront * cosFront - etaBack * cosBack) / (etaFront * cosFront + etaBack * cosBack);
+    perpendicular = perpendicular * perpendicular;
+    return (parallel + perpendicular) * 0.5f;
+}
+// Graphics::Reflect / Refract (GraphicsFunctions.h:L157-203): v points away from the surface, on the normal's side
+__device__ __forceinline__ Float3 ReflectAbout(Float3 n, Float3 v) { return n * (2.0f * Dot(v, n)) - v; }
+__device__ __forceinline__ bool RefractThrough(Float3 n, Float3 v, float etaFrom, float etaTo, Float3& out)
+{
+    const float etaRatio = etaFrom / etaTo;
+    const float cosIn = Dot(n, v);
+    const float sinInSqr = fmaxf(0.0f, 1.0f - cosIn * cosIn);
+    const float sinOutSqr = etaRatio * etaRatio * sinInSqr;
+    const float cosOut = SqrtMax(1.0f - sinOutSqr);
+    if(sinOutSqr >= 1.0f) return false;
+    out = v * -etaRatio + n * (etaRatio * cosIn - cosOut);
+    return true;
+}
+// Medium::WavelengthToIoRCauchy (DistributionFunctions.h:L978-986)
+__device__ __forceinline__ float CauchyIoR(float wavelengthNm, float4 c)
+{
+    const float w = wavelengthNm * 1.0e-3f, w2 = w * w, w4 = w2 * w2;
+    return c.x + c.y / w2 + c.z / w4;
+}
+// GGX microfacet terms in tangent space, Z = shading normal (DistributionFunctions.h:L431-590)
+__device__ __forceinline__ float DGGX(float NdH, float alpha)
+{
+    const float a2 = alpha * alpha;
+    float denom = NdH * NdH * (a2 - 1.0f) + 1.0f;
+    denom = denom * denom * PI_F;
+    return a2 / denom;
+}
+__device__ __forceinline__ float LambdaSmith(Float3 v, float alpha)
+{
+    const float inner = alpha * alpha * (v.x * v.x + v.y * v.y) / (v.z * v.z);
+    return (sqrtf(1.0f + inner) - 1.0f) * 0.5f;
+}
+__device__ __forceinline__ float GSmithSingle(Float3 v, float alpha) { return 1.0f / (1.0f + LambdaSmith(v, alpha)); }
+__device__ __forceinline__ float GSmithCorrelated(Float3 wO, Float3 wI, float alpha) { return 1.0f / (LambdaSmith(wO, alpha) + LambdaSmith(wI, alpha) + 1.0f); }
+__device__ __forceinline__ float VNDFGGXSmithPDF(Float3 V, Float3 H, float alpha)
+{
+    const float VdH = fmaxf(0.0f, Dot(H, V)), NdH = fmaxf(0.0f, H.z), NdV = fmaxf(0.0f, V.z);
+    const float D = DGGX(NdH, alpha), G1 = GSmithSingle(V, alpha);
+    if(NdV == 0.0f) return 0.0f;
+    return VdH * D * G1 / NdV;
+}
+__device__ __forceinline__ Float3 VNDFGGXSmithSample(Float3 V, float alpha, float xi0, float xi1, float& pdf)
+{   // Heitz 2018, "Sampling the GGX Distribution of Visible Normals" (DistributionFunctions.h:L528-575)
+    const Float3 VHemi = Normalize(F3(alpha * V.x, alpha * V.y, V.z));
+    const float len2 = VHemi.x * VHemi.x + VHemi.y * VHemi.y;
+    const Float3 T1 = (len2 > 0.0f) ? F3(-VHemi.y, VHemi.x, 0.0f) * rsqrtf(len2) : F3(1.f, 0.f, 0.f);
+    const Float3 T2 = Cross(VHemi, T1);
+    const float r = sqrtf(xi0), phi = 2.0f * PI_F * xi1;
+    float sinPhi, cosPhi; sincosf(phi, &sinPhi, &cosPhi);
+    const float t1 = r * cosPhi;
+    float t2 = r * sinPhi;
+    const float s = 0.5f * (1.0f + VHemi.z);
+    t2 = (1.0f - s) * sqrtf(1.0f - t1 * t1) + s * t2;
+    const float val = 1.0f - t1 * t1 - t2 * t2;
+    const Float3 NHemi = T1 * t1 + T2 * t2 + VHemi * SqrtMax(val);
+    Float3 N = F3(alpha * NHemi.x, alpha * NHemi.y, SqrtMax(NHemi.z));
+    const float nLen2 = Dot(N, N);
+    if(nLen2 < 1.0e-5f) N = F3(0.f, 0.f, 1.f); else N = N * rsqrtf(nLen2);   // MathConstants::Epsilon
+    pdf = VNDFGGXSmithPDF(V, N, alpha);
+    return N;
+}
+__device__ __forceinline__ float BurleyDiffuseCorrection(float NdL, float NdV, float LdH, float roughness)
+{
+    const float Fd90 = 0.5f + 2.0f * roughness * LdH * LdH;
+    auto F = [Fd90](float dot) { const float pw = 1.0f - dot, pw2 = pw * pw; return 1.0f + (Fd90 - 1.0f) * (pw2 * pw2 * pw); };
+    return F(NdL) * F(NdV);
+}
+// UnrealMaterial (MaterialsDefault.hpp:L466-760) with constant roughness / specular / metallic; everything in tangent space
+struct UnrealBxDF
+{
+    Spec  albedo;      // at the path's wavelengths (or rgb, 0)
+    float roughness, specular, metallic;
+    __device__ __forceinline__ float AvgAlbedo() const { return (albedo.x + albedo.y + albedo.z + albedo.w) * 0.3333f; }
+    __device__ __forceinline__ float MISRatio() const
+    {   // probability of the diffuse lobe
+        const float avg = AvgAlbedo();
+        const float integralDiffuse = 2.0f * PI_F * avg * (1.0f - metallic);
+        const float specularRatio = specular * (1.0f - metallic) + avg * metallic;
+        const float total = specularRatio + integralDiffuse;
+        return (total == 0.0f) ? 0.0f : integralDiffuse / total;
+    }
+    __device__ __forceinline__ float Specularity() const { return 1.0f - MISRatio(); }
+    __device__ __forceinline__ Spec F0() const
+    {
+        const float specOut = specular * 0.08f, om = 1.0f - metallic;
+        return S4(specOut * om + albedo.x * metallic, specOut * om + albedo.y * metallic, specOut * om + albedo.z * metallic, specOut * om + albedo.w * metallic);
+    }
+    __device__ __forceinline__ Spec FSchlick(float VdH) const
+    {
+        const Spec f0 = F0();
+        const float pw = 1.0f - VdH, pw2 = pw * pw, pw5 = pw2 * pw2 * pw;
+        return S4((1.0f - f0.x) * pw5 + f0.x, (1.0f - f0.y) * pw5 + f0.y, (1.0f - f0.z) * pw5 + f0.z, (1.0f - f0.w) * pw5 + f0.w);
+    }
+    __device__ __forceinline__ Spec Diffuse(float NdL, float NdV, float LdH) const
+    {
+        const float k = NdL * INV_PI_F * (1.0f - metallic) * BurleyDiffuseCorrection(NdL, NdV, LdH, roughness);
+        return albedo * k;
+    }
+    // Evaluate (L760+): reflectance of tangent-space directions V (out) and L (in)
+    __device__ __forceinline__ Spec Evaluate(Float3 V, Float3 L) const
+    {
+        const float alpha = roughness * roughness;
+        const Float3 H = Normalize(L + V);
+        const float LdH = fmaxf(0.f, Dot(L, H)), VdH = fmaxf(0.f, Dot(V, H)), NdH = fmaxf(0.f, H.z), NdV = fmaxf(0.f, V.z);
+        float D = DGGX(NdH, alpha);
+        D = (isnan(D) || isinf(D)) ? 0.0f : D;
+        float G = GSmithCorrelated(V, L, alpha);
+        G = (LdH == 0.0f) ? 0.0f : G;
+        G = (VdH == 0.0f) ? 0.0f : G;
+        Spec specularTerm = FSchlick(VdH) * (D * G * 0.25f / NdV);
+        if(NdV == 0.0f) specularTerm = S4(0.f, 0.f, 0.f, 0.f);
+        const float NdL = fmaxf(0.f, L.z);
+        return Diffuse(NdL, NdV, LdH) + specularTerm;
+    }
+    __device__ __forceinline__ float Pdf(Float3 V, Float3 L) const
+    {
+        const float alpha = roughness * roughness;
+        const Float3 H = Normalize(L + V);
+        const float mis = MISRatio();
+        const float pdfD = PdfCosDirection(L.z);
+        const float NdH = fmaxf(0.f, H.z), VdH = fmaxf(0.f, Dot(V, H));
+        const float D = DGGX(NdH, alpha);
+        float pdfS = VNDFGGXSmithPDF(V, H, alpha);
+        pdfS = (isnan(D) || isinf(D)) ? 0.0f : pdfS;
+        pdfS = (VdH == 0.0f) ? 0.0f : pdfS / (4.0f * VdH);
+        return pdfD * mis + pdfS * (1.0f - mis);
+    }
+    // SampleBxDF (L536-640): sXi picks the lobe, (xi0, xi1) samples it; returns L, reflectance and the mixture pdf
+    __device__ __forceinline__ Float3 Sample(Float3 V, float sXi, float xi0, float xi1, Spec& reflectance, float& pdfOut) const
+    {
+        const float alpha = roughness * roughness;
+        const float mis = MISRatio();
+        Float3 L, H; float pdfD, pdfS;
+        if(sXi < mis)
+        {   // Common::SampleCosDirection
+            const float phi = 2.0f * PI_F * xi1, su = sqrtf(xi0);
+            float sn, cs; sincosf(phi, &sn, &cs);
+            const float lx = su * cs, ly = su * sn;
+            L = F3(lx, ly, sqrtf(fmaxf(0.0f, 1.0f - (lx * lx + ly * ly))));
+            pdfD = L.z * INV_PI_F;                               // the sample's own pdf (SampleCosDirection)
+            H = Normalize(L + V);
+            const float VdH = fmaxf(0.f, Dot(V, H));
+            pdfS = VNDFGGXSmithPDF(V, H, alpha);
+            pdfS = (VdH == 0.0f) ? 0.0f : pdfS / (4.0f * VdH);
+        }
+        else
+        {
+            float pdfH;
+            H = VNDFGGXSmithSample(V, alpha, xi0, xi1, pdfH);
+            L = ReflectAbout(H, V);
+            const float VdH = fmaxf(0.f, Dot(V, H));
+            pdfS = (VdH == 0.0f) ? 0.0f : pdfH / (4.0f * VdH);
+            pdfD = PdfCosDirection(L.z);
+        }
+        const float VdH = fmaxf(0.f, Dot(V, H)), LdH = fmaxf(0.f, Dot(L, H)), NdH = fmaxf(0.f, H.z), NdV = fmaxf(0.f, V.z);
+        const float D = DGGX(NdH, alpha);
+        float G = GSmithCorrelated(V, L, alpha);
+        G = (LdH == 0.0f) ? 0.0f : G;
+        G = (VdH == 0.0f) ? 0.0f : G;
+        const Spec F = FSchlick(VdH);
+        Spec specularTerm = F * (D * G * 0.25f / NdV);
+        if(NdV == 0.0f) specularTerm = S4(0.f, 0.f, 0.f, 0.f);
+        if(isinf(D) || isnan(D))
+        {   // alpha ~ 0: the cancelled form
+            specularTerm = F * (G / GSmithSingle(V, alpha));
+            pdfS = 1.0f;
+        }
+        const float NdL = fmaxf(0.f, L.z);
+        reflectance = Diffuse(NdL, NdV, LdH) + specularTerm;
+        pdfOut = pdfD * mis + pdfS * (1.0f - mis);
+        return L;
+    }
+};
+
+// Shading frame of a triangle hit as the reference builds it (Triangle::GenerateSurface, PrimitiveDefaultTriangle.hpp:L463-470):
+// the three vertex quaternions (world -> tangent space rotations, (w, x, y, z)) are blended with Quaternion::BarySLerp
+// (Core/Quaternion.hpp:L289-353: slerp(q1, q0, a / (a + b)) then slerp(., q2, 1 - a - b), shortest arc, lerp when nearly
+// parallel), normalised, and the shading normal is the frame's Z axis (OrthoBasisZ, L256-270).
+__device__ __forceinline__ float4 QuatSLerp(float4 s, float4 e, float t)
+{
+    const float cosTheta = s.x * e.x + s.y * e.y + s.z * e.z + s.w * e.w;
+    const float cosFlipped = (cosTheta >= 0.0f) ? cosTheta : -cosTheta;
+    float s0, s1;
+    if(cosFlipped < (1.0f - 1.0e-5f))
+    {
+        const float angle = acosf(cosFlipped), sinRecip = 1.0f / sinf(angle);
+        s0 = sinf(angle * (1.0f - t)) * sinRecip;
+        s1 = sinf(angle * t) * sinRecip;
+    }
+    else { s0 = 1.0f - t; s1 = t; }
+    s1 = (cosTheta >= 0.0f) ? s1 : -s1;
+    return make_float4(s.x * s0 + e.x * s1, s.y * s0 + e.y * s1, s.z * s0 + e.z * s1, s.w * s0 + e.w * s1);
+}
+__device__ __forceinline__ Float3 ShadingNormalFromTBN(float4 q0, float4 q1, float4 q2, float a, float b)
+{
+    const float c = 1.0f - a - b;
+    float4 q;
+    if(fabsf(a + b) < 1.0e-5f) q = q2;
+    else q = QuatSLerp(QuatSLerp(q1, q0, a / (a + b)), q2, c);
+    const float inv = rsqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    const float w = q.x * inv, x = q.y * inv, y = q.z * inv, z = q.w * inv;       // stored (w, x, y, z)
+    return F3(2.0f * (x * z - w * y), 2.0f * (y * z + w * x), w * w - x * x - y * y + z * z);
+}
+
 // LightPrim::EmitViaHit / EmitViaSurfacePoint for a constant radiance (LightsDefault.hpp:L129-168)
 __device__ __forceinline__ Spec Emit(const RenderData& d, const EmissiveTri& l, Float3 n, Float3 wO, float4 waves)
 {
@@ -550,6 +775,8 @@ __global__ void __launch_bounds__(RTPB) KGenWorkKeys(RenderData d)
 
 // Shading of one slot. Returns true when the slot held a live path (= one closest-hit ray was cast for it
 // this bounce); castShadow reports an NEE shadow ray.
+// GLOSSY: the scene has (Mt)Refract / (Mt)Unreal materials (their code costs 16 registers, so scenes without them run the lean kernel)
+template<bool GLOSSY>
 __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool& castShadow, bool& neeSample)
 {
     // every per-slot input is requested before the first use, so one round trip covers them all
@@ -617,7 +844,7 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
         return true;
     }
 
-    // ------------------------------- Lambert surface -------------------------------
+    // ------------------------------- material surface -------------------------------
     SlotSampler rng = LoadSampler(d.samplerType, rngState, d.samplerType != SAMPLER_INDEPENDENT ? d.sampleState[i] : make_uint2(0u, 0u),
                                   meta.y % d.width + d.regionX, meta.y / d.width + d.regionY, d.sobolMatrices, d.zsobol);
     const bool backSide = Dot(geoN, Normalize(rd)) > 0.0f;
@@ -625,28 +852,68 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
     if(in.vertexNormals)
     {
         const float4 n0 = in.vertexNormals[vi[0]], n1 = in.vertexNormals[vi[1]], n2 = in.vertexNormals[vi[2]];
-        shadeN = F3(n0.x, n0.y, n0.z) * a + F3(n1.x, n1.y, n1.z) * b + F3(n2.x, n2.y, n2.z) * c;
+        if(in.tbn) shadeN = ShadingNormalFromTBN(n0, n1, n2, a, b);
+        else shadeN = F3(n0.x, n0.y, n0.z) * a + F3(n1.x, n1.y, n1.z) * b + F3(n2.x, n2.y, n2.z) * c;
+        // (the reference leaves the tangent frame in the primitive's local space under a (T)Single transform — "we can't
+        // apply a transform to tbn", PrimitiveDefaultTriangle.hpp:L612 — which tilts its shading normals by the instance's
+        // rotation; here the normal follows the instance like the geometry does)
         if(!in.identity) shadeN = ApplyN(in.invTransform, shadeN);
         shadeN = Normalize(shadeN);
     }
     if(backSide) { geoN = geoN * -1.0f; shadeN = shadeN * -1.0f; }
     const uint32_t matIndex = lmKey & 0x1FFFFFu;
-    if(d.materialType && d.materialType[matIndex] == 1u)
+    const uint32_t matType = d.materialType ? uint32_t(d.materialType[matIndex]) : MAT_LAMBERT;
+    const Float3 wO = Normalize(rd) * -1.0f;
+    if(matType == MAT_REFLECT || (GLOSSY && matType == MAT_REFRACT))
     {
-        // (Mt)Reflect (MaterialsDefault.hpp:L132-215): WorkFunctionNEE draws its light sample but casts no shadow ray for a
-        // specular material; WorkFunction reflects wO about the shading normal (reflectance 1, pdf 1), skips the
-        // roulette and marks the next ray SPECULAR_RAY, so a light it hits counts in full
+        // Perfectly specular materials. WorkFunctionNEE draws its light sample but casts no shadow ray for them
+        // (PathTracerRendererShaders.h:L415-424); WorkFunction samples the BxDF, skips the roulette and marks the next ray
+        // SPECULAR_RAY, so a light it hits counts in full in every sample mode (L245-262).
         if(d.sampleMode != 0u) { float skip[3]; rng.Next<3>(skip); }
-        const Float3 wO = Normalize(rd) * -1.0f;
-        const Float3 wIr = Normalize(shadeN * (2.0f * Dot(wO, shadeN)) - wO);
+        Float3 wIr; float pdfS = 1.0f; bool passedThrough = false;
+        Float3 originBase = pos;
+        if(!GLOSSY || matType == MAT_REFLECT)
+        {   // (Mt)Reflect (MaterialsDefault.hpp:L132-215): wO about the shading normal, reflectance 1, pdf 1
+            wIr = Normalize(ReflectAbout(shadeN, wO));
+        }
+        else
+        {   // (Mt)Refract (MaterialsDefault.hpp:L246-312): Fresnel-weighted choice between reflection and refraction
+            const float4 cf = d.matParams[2 * matIndex], cb = d.matParams[2 * matIndex + 1];
+            float fromEta = d.spectral ? CauchyIoR(waves.x, cf) : cf.x;
+            float toEta = d.spectral ? CauchyIoR(waves.x, cb) : cb.x;
+            if(backSide) { const float t = fromEta; fromEta = toEta; toEta = t; }
+            const float cosTheta = fabsf(Dot(wO, shadeN));
+            const float f = FresnelDielectric(cosTheta, fromEta, toEta);
+            float xiF[1]; rng.Next<1>(xiF);
+            const bool doReflection = xiF[0] < f;
+            Float3 refr = wO * -1.0f;
+            if(!doReflection) RefractThrough(shadeN, wO, fromEta, toEta, refr);   // f = 1 under total internal reflection: never taken then
+            wIr = Normalize(doReflection ? ReflectAbout(shadeN, wO) : refr);
+            pdfS = doReflection ? f : (1.0f - f);
+            passedThrough = !doReflection;
+            // BxDFSample.wI is nudged along the shading normal by the material itself (L296), before the work function
+            // nudges it again along the (flipped) geometric normal
+            originBase = NudgePos(pos, shadeN);
+            // reflectance = Spectrum(pdf): cancels against the division by the pdf below
+            throughput = throughput * pdfS;
+            if(passedThrough && d.spectral)
+            {   // DisperseWaves + StoreWaves (L229-238): the path keeps its first wavelength only
+                d.waves[i] = make_float4(waves.x, -1.0f, -1.0f, -1.0f);
+            }
+        }
         d.shadowRadiance[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         depth += 1u;
         if(d.samplerType == SAMPLER_INDEPENDENT) d.rng[i] = rng.state;
         else d.sampleState[i].y = rng.dim;
         if(depth < d.rrHi)
         {
-            d.meta[i].w = __float_as_uint(1.0f);
-            const Float3 no = NudgePos(pos, geoN);
+            if(GLOSSY && matType == MAT_REFRACT)
+            {
+                throughput = (pdfS == 0.0f) ? S4(0, 0, 0, 0) : throughput * (1.0f / pdfS);
+                d.throughput[i] = F4(throughput);
+            }
+            d.meta[i].w = __float_as_uint(pdfS);
+            const Float3 no = NudgePos(originBase, passedThrough ? geoN * -1.0f : geoN);
             float4* rp = reinterpret_cast<float4*>(d.rays + i);
             rp[0] = make_float4(no.x, no.y, no.z, 1.0e-4f);
             rp[1] = make_float4(wIr.x, wIr.y, wIr.z, FLT_MAX);
@@ -675,10 +942,16 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
         else albedoRaw = make_float4(rgb.x, rgb.y, rgb.z, 0.f);
     }
     const Spec albedo = AlbedoAt(d, albedoRaw, waves);
-    // orthonormal frame about the shading normal
+    // (Mt)Unreal (MaterialsDefault.hpp:L466-760): GGX + Burley diffuse; specular enough (>= 0.95) it is treated like a mirror
+    const bool unreal = GLOSSY && matType == MAT_UNREAL;
+    UnrealBxDF ub; ub.albedo = albedo; ub.roughness = ub.specular = ub.metallic = 0.0f;
+    if(unreal) { const float4 mp = d.matParams[2 * matIndex]; ub.roughness = mp.x; ub.specular = mp.y; ub.metallic = mp.z; }
+    const bool specularMat = unreal && ub.Specularity() >= SPECULAR_THRESHOLD;
+    // orthonormal frame about the shading normal (any frame does: both BxDFs are isotropic)
     const Float3 hlp = (fabsf(shadeN.x) > 0.9f) ? F3(0, 1, 0) : F3(1, 0, 0);
     const Float3 tX = Normalize(Cross(hlp, shadeN));
     const Float3 tY = Cross(shadeN, tX);
+    const Float3 V = F3(Dot(wO, tX), Dot(wO, tY), Dot(wO, shadeN));
 
     // ---- NEE (WorkFunctionNEE::Call) ----
     uint32_t newType = type;
@@ -690,8 +963,8 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
         const uint32_t nLights = d.lightCount + 1u; // + boundary light
         uint32_t li = min(uint32_t(xs * float(nLights)), nLights - 1u);
         newType = RAY_SHADOW;
-        neeSample = true;
-        if(li < d.lightCount)
+        neeSample = !specularMat;
+        if(li < d.lightCount && !specularMat)
         {
             const EmissiveTri l = d.lights[li];
             // Triangle::SampleSurface (Osada)
@@ -714,11 +987,21 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
             const Float3 wI = Normalize(lpos - pos);
             const Float3 lposN = NudgePos(lpos, wI * -1.0f);
             const float len = Length(lposN - pos);
-            // Lambert Evaluate / Pdf
-            const float nDotL = fmaxf(Dot(shadeN, wI), 0.0f);
-            const Spec refl = albedo * (nDotL * INV_PI_F);
+            // Material::Evaluate / Pdf
+            Spec refl; float pdfBx;
+            if(unreal)
+            {
+                const Float3 Lt = F3(Dot(wI, tX), Dot(wI, tY), Dot(wI, shadeN));
+                refl = ub.Evaluate(V, Lt); pdfBx = ub.Pdf(V, Lt);
+            }
+            else
+            {
+                const float nDotL = fmaxf(Dot(shadeN, wI), 0.0f);
+                refl = albedo * (nDotL * INV_PI_F);
+                pdfBx = fmaxf(PdfCosDirection(Dot(shadeN, wI)), 0.0f);
+            }
             float pdf = pdfL;
-            if(d.sampleMode == 2u) pdf = fmaxf(nDotL * INV_PI_F, 0.0f) + pdfL;
+            if(d.sampleMode == 2u) pdf = pdfBx + pdfL;
             Spec sr = throughput * refl * em;
             sr = (pdf == 0.0f) ? S4(0, 0, 0, 0) : sr * (1.0f / pdf);
             // +2: depth is not incremented yet (KCAccumulateShadowRaysPT)
@@ -741,18 +1024,29 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
     d.shadowRadiance[i] = shadowRad;
 
     // ---- BxDF sample + Russian roulette (WorkFunction::Call) ----
-    float xiB[2]; rng.Next<2>(xiB);
-    const float u0 = xiB[0], u1 = xiB[1];
-    const float phi = 2.0f * PI_F * u1, su = sqrtf(u0);
-    float sn, cs; sincosf(phi, &sn, &cs);
-    const float lx = su * cs, ly = su * sn;
-    const float lz = sqrtf(fmaxf(0.0f, 1.0f - (lx * lx + ly * ly)));
-    const float pdfB = lz * INV_PI_F;
-    const Float3 wIw = Normalize(tX * lx + tY * ly + shadeN * lz);
-    throughput = throughput * (albedo * (fmaxf(lz, 0.0f) * INV_PI_F));
+    Float3 Lt; float pdfB; Spec reflS;
+    if(unreal)
+    {
+        float xiS[1]; rng.Next<1>(xiS);
+        float xiB[2]; rng.Next<2>(xiB);
+        Lt = ub.Sample(V, xiS[0], xiB[0], xiB[1], reflS, pdfB);
+    }
+    else
+    {   // LambertMaterial::SampleBxDF: cosine-weighted hemisphere
+        float xiB[2]; rng.Next<2>(xiB);
+        const float phi = 2.0f * PI_F * xiB[1], su = sqrtf(xiB[0]);
+        float sn, cs; sincosf(phi, &sn, &cs);
+        const float lx = su * cs, ly = su * sn;
+        const float lz = sqrtf(fmaxf(0.0f, 1.0f - (lx * lx + ly * ly)));
+        Lt = F3(lx, ly, lz);
+        pdfB = lz * INV_PI_F;
+        reflS = albedo * (fmaxf(lz, 0.0f) * INV_PI_F);
+    }
+    const Float3 wIw = Normalize(tX * Lt.x + tY * Lt.y + shadeN * Lt.z);
+    throughput = throughput * reflS;
     depth += 1u;
     bool dead = depth >= d.rrHi;
-    if(!dead && depth >= d.rrLo)
+    if(!dead && depth >= d.rrLo && !specularMat)
     {
         float xiR[1]; rng.Next<1>(xiR);
         const float rrXi = xiR[0];
@@ -764,6 +1058,8 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
     }
     if(d.samplerType == SAMPLER_INDEPENDENT) d.rng[i] = rng.state;
     else d.sampleState[i].y = rng.dim;
+    // the NEXT hit's MIS decision: PATH_RAY, or SPECULAR_RAY after a near-mirror; the shadow flag only lives until the finish kernel
+    const uint32_t nextType = (specularMat ? RAY_SPECULAR : RAY_PATH) | ((newType == RAY_SHADOW && castShadow) ? 0x80u : 0u);
     if(!dead)
     {
         throughput = (pdfB == 0.0f) ? S4(0, 0, 0, 0) : throughput * (1.0f / pdfB);
@@ -773,22 +1069,22 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
         float4* rp = reinterpret_cast<float4*>(d.rays + i);
         rp[0] = make_float4(no.x, no.y, no.z, 1.0e-4f);
         rp[1] = make_float4(wIw.x, wIw.y, wIw.z, FLT_MAX);
-        // type of the NEXT hit's MIS decision is PATH_RAY; the shadow flag only lives until KFinish
-        d.meta[i].x = PackPD(depth, ST_ALIVE, (newType == RAY_SHADOW) ? (RAY_PATH | 0x80u) : RAY_PATH);
+        d.meta[i].x = PackPD(depth, ST_ALIVE, nextType);
     }
     else
     {
         d.rays[i].tMin = 1.0f; d.rays[i].tMax = -1.0f;
-        d.meta[i].x = PackPD(depth, ST_DEAD, (newType == RAY_SHADOW) ? (RAY_PATH | 0x80u) : RAY_PATH);
+        d.meta[i].x = PackPD(depth, ST_DEAD, nextType);
     }
     return true;
 }
 
+template<bool GLOSSY>
 __global__ void __launch_bounds__(RTPB) KShade(RenderData d)
 {
     const uint32_t tidx = blockIdx.x * RTPB + threadIdx.x;
     bool alive = false, castShadow = false, neeSample = false;
-    if(tidx < d.slots) alive = ShadeSlot(d, d.partitionRays ? d.workIndices[tidx] : tidx, castShadow, neeSample);
+    if(tidx < d.slots) alive = ShadeSlot<GLOSSY>(d, d.partitionRays ? d.workIndices[tidx] : tidx, castShadow, neeSample);
     // ray statistics: one atomic per block per counter
     const int nAlive = __syncthreads_count(alive), nShadow = __syncthreads_count(castShadow), nNee = __syncthreads_count(neeSample);
     if(threadIdx.x == 0)
@@ -902,6 +1198,7 @@ struct mrb_renderer_t
     mrb::SceneData   sceneData;        // scene->d with the renderer's instance records (accelKey = instance index)
     uint64_t         iterations = 0;
     bool             needReload = true;   // the next iteration starts with KReload (first one, or a pass has just begun)
+    bool             glossy = false;      // any (Mt)Refract / (Mt)Unreal material: KShade<true>
     // passes: samples [sampleBase, sampleBase + passSamples) of every pixel of the current region
     uint32_t         maxWidth = 0, maxHeight = 0;      // the film allocation (the largest region a pass may take)
     uint32_t         totalSPP = 0, sampleOffset = 0;
@@ -976,7 +1273,7 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
     d.cam.tNear = desc.nearFar[0]; d.cam.tFar = desc.nearFar[1];
 
     // instance list: the scene's instances, or one identity instance of the single accelerator
-    struct HostInst { const mrb_accel_t* acc; const float* m; const float* inv; bool identity; const float* normals; const float* uvs; };
+    struct HostInst { const mrb_accel_t* acc; const float* m; const float* inv; bool identity; const float* normals; const float* uvs; const float* tbn; };
     static const float IDENTITY[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
     std::vector<HostInst> hinst;
     if(desc.scene)
@@ -985,9 +1282,10 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
             const mrb_instance_desc& id = desc.scene->hInstances[k];
             hinst.push_back({id.accel, id.transform, id.invTransform, id.isIdentity != 0,
                              desc.instanceVertexNormals ? desc.instanceVertexNormals[k] : nullptr,
-                             desc.instanceVertexUVs ? desc.instanceVertexUVs[k] : nullptr});
+                             desc.instanceVertexUVs ? desc.instanceVertexUVs[k] : nullptr,
+                             desc.instanceVertexTBN ? desc.instanceVertexTBN[k] : nullptr});
         }
-    else hinst.push_back({desc.accel, IDENTITY, IDENTITY, true, desc.vertexNormals, desc.vertexUVs});
+    else hinst.push_back({desc.accel, IDENTITY, IDENTITY, true, desc.vertexNormals, desc.vertexUVs, desc.vertexTBN});
     const uint32_t instCount = uint32_t(hinst.size());
 
     // emissive triangle list (MetaLightArrayT::Construct: one meta light per emissive triangle of every
@@ -1090,12 +1388,13 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
         for(uint32_t k = 0; k < instCount; k++)
         {
             hri[k].lightOfPrim = ma.Take<uint32_t>(hinst[k].acc->triangleCount);
-            hri[k].vertexNormals = hinst[k].normals ? ma.Take<float4>(hinst[k].acc->vertexCount) : nullptr;
+            hri[k].vertexNormals = (hinst[k].normals || hinst[k].tbn) ? ma.Take<float4>(hinst[k].acc->vertexCount) : nullptr;
             hri[k].vertexUVs = hinst[k].uvs ? ma.Take<float2>(hinst[k].acc->vertexCount) : nullptr;
         }
         d.workKeys = ma.Take<uint32_t>(P); d.workIndices = ma.Take<uint32_t>(P); d.partTable = ma.Take<uint32_t>(32);
         d.albedoTex = desc.albedoTexture ? ma.Take<int32_t>(desc.materialCount ? desc.materialCount : 1) : nullptr;
         d.materialType = desc.materialType ? ma.Take<uint8_t>(desc.materialCount ? desc.materialCount : 1) : nullptr;
+        d.matParams = desc.materialParams ? ma.Take<float4>(2 * size_t(desc.materialCount ? desc.materialCount : 1)) : nullptr;
         d.textures = desc.textureCount ? ma.Take<TexRec>(desc.textureCount) : nullptr;
         for(uint32_t t = 0; t < desc.textureCount; t++)
             htex[t].data = ma.Take<char>(size_t(desc.textures[t].width) * desc.textures[t].height * desc.textures[t].channels *
@@ -1113,7 +1412,17 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
         halb[m] = make_float4(desc.albedo[3 * m], desc.albedo[3 * m + 1], desc.albedo[3 * m + 2], 0.f);
     MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<float4*>(d.albedo), halb.data(), halb.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx.stream));
     if(desc.materialType)
+    {
+        for(uint32_t m = 0; m < desc.materialCount; m++)
+        {
+            if(desc.materialType[m] > MAT_UNREAL) throw std::runtime_error("unknown material type");
+            if(desc.materialType[m] >= MAT_REFRACT && !desc.materialParams) throw std::runtime_error("(Mt)Refract / (Mt)Unreal need materialParams");
+            if(desc.materialType[m] >= MAT_REFRACT) r.glossy = true;
+        }
         MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<uint8_t*>(d.materialType), desc.materialType, desc.materialCount, cudaMemcpyHostToDevice, ctx.stream));
+    }
+    if(desc.materialParams)
+        MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<float4*>(d.matParams), desc.materialParams, sizeof(float4) * 2 * desc.materialCount, cudaMemcpyHostToDevice, ctx.stream));
     if(desc.albedoTexture)
         MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<int32_t*>(d.albedoTex), desc.albedoTexture, sizeof(int32_t) * desc.materialCount, cudaMemcpyHostToDevice, ctx.stream));
     for(uint32_t t = 0; t < desc.textureCount; t++)
@@ -1143,7 +1452,13 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
         MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<uint32_t*>(ri.lightOfPrim), lightOfPrim[k].data(), lightOfPrim[k].size() * 4, cudaMemcpyHostToDevice, ctx.stream));
         if(hinst[k].uvs)
             MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<float2*>(ri.vertexUVs), hinst[k].uvs, size_t(hacc.vertexCount) * sizeof(float2), cudaMemcpyHostToDevice, ctx.stream));
-        if(hinst[k].normals)
+        ri.tbn = hinst[k].tbn ? 1u : 0u;
+        if(hinst[k].tbn)
+        {
+            MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<float4*>(ri.vertexNormals), hinst[k].tbn, size_t(hacc.vertexCount) * sizeof(float4), cudaMemcpyHostToDevice, ctx.stream));
+            MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
+        }
+        else if(hinst[k].normals)
         {
             hn.resize(hacc.vertexCount);
             for(uint32_t v = 0; v < hacc.vertexCount; v++)
@@ -1208,7 +1523,10 @@ void RenderIterate(Context& ctx, mrb_renderer_t& r, uint32_t iterations)
             MultiPartition(ctx, d.workKeys, d.workIndices, d.slots, dataBits, batchBits, false, 4,
                            d.partTable, d.partTable + 1, d.partTable + 8, ctx.scratch.Base());
         }
-        { ProfileScope ps(ctx, PROF_SHADE); MRB_LAUNCH(ctx, KShade, grid, RTPB, 0, d); }
+        {
+            ProfileScope ps(ctx, PROF_SHADE);
+            if(r.glossy) MRB_LAUNCH(ctx, KShade<true>, grid, RTPB, 0, d); else MRB_LAUNCH(ctx, KShade<false>, grid, RTPB, 0, d);
+        }
         if(d.sampleMode != 0u)
         {
             MRB_CUDA_TRY(cudaMemsetAsync(d.visible, 0xFF, sizeof(uint32_t) * ((d.slots + 31) / 32), ctx.stream));

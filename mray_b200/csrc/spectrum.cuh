@@ -177,20 +177,25 @@ __device__ __forceinline__ float EvalRadiance(const SpectrumData& s, float4 c, f
     return v * c.w;
 }
 
-// ConvertSpectraToRGBSingle (non-dispersed waves)
+// ConvertSpectraToRGBSingle. A path that went through a dispersive interface ((Mt)Refract) carries ONE wavelength:
+// its secondary waves are SpectrumWaves::DISPERSED_WAVE (-1), only sample 0 counts and the 1/4 weight becomes 1
+// (Tracer/SpectrumContext.cu:L137-171, Tracer/TracerTypes.h:L114,L386-401).
 __device__ __forceinline__ float3 SpectraToRGB(const SpectrumData& s, const float value[4], const float w[4], const float p[4])
 {
     float X = 0.f, Y = 0.f, Z = 0.f;
+    const bool dispersed = w[1] == -1.0f;
     #pragma unroll
     for(int i = 0; i < 4; i++)
     {
+        if(dispersed && i > 0) break;
         int a, b; float f;
         SpecInterp1(w[i] + (0.5f - float(CIE_START)), CIE_N, a, b, f);
         const float4 oa = __ldg(s.observer + a), ob = __ldg(s.observer + b);
         const float val = (p[i] == 0.0f) ? 0.0f : value[i] / p[i];
         X += SpecLerp(oa.x, ob.x, f) * val; Y += SpecLerp(oa.y, ob.y, f) * val; Z += SpecLerp(oa.z, ob.z, f) * val;
     }
-    X *= 0.25f; Y *= 0.25f; Z *= 0.25f;
+    const float weight = dispersed ? 1.0f : 0.25f;
+    X *= weight; Y *= weight; Z *= weight;
     return make_float3(s.xyzToRGB[0] * X + s.xyzToRGB[1] * Y + s.xyzToRGB[2] * Z,
                        s.xyzToRGB[3] * X + s.xyzToRGB[4] * Y + s.xyzToRGB[5] * Z,
                        s.xyzToRGB[6] * X + s.xyzToRGB[7] * Y + s.xyzToRGB[8] * Z);

@@ -49,10 +49,17 @@ struct PrimGroupB200
 {
     std::string type; bool committed = false;
     std::vector<PrimBatch> batches;
-    std::vector<Vector3> positions; std::vector<Vector3> normals; std::vector<Vector2> uvs; std::vector<Vector3ui> indices;
+    std::vector<Vector3> positions; std::vector<Vector2> uvs; std::vector<Vector3ui> indices;
+    std::vector<std::array<float, 4>> tbn;   // NORMAL attribute: world -> tangent-space quaternions (w, x, y, z); all zero = not pushed
+    bool hasTBN = false;
     uint32_t primTotal = 0, vertexTotal = 0;
 };
-struct MatGroupB200 { std::string type; bool committed = false; std::vector<Vector3> albedo; std::vector<int32_t> albedoTex; /* TextureId or -1 */ };
+struct MatGroupB200
+{
+    std::string type; bool committed = false; std::vector<Vector3> albedo; std::vector<int32_t> albedoTex; /* TextureId or -1 */
+    // constant attributes of (Mt)Refract {cauchyFront xyz, -, cauchyBack xyz, -} and (Mt)Unreal {roughness, specular, metallic, ...}
+    std::vector<std::array<float, 8>> params;
+};
 // One 2-D texture as TracerI::CreateTexture2D / PushTextureData deliver it (first slice: one mip level, 4-channel
 // fp32 or unorm8 pixels, already in the global colour space)
 struct TextureB200
@@ -132,6 +139,7 @@ class TracerB200 final : public TracerI
     uint32_t flatPrimGroup = 0; std::vector<float> flatLightRadiance; std::vector<uint8_t> flatLightTwoSided;
     std::vector<float> flatAlbedo;
     std::vector<uint8_t> flatMaterialType;          // per flat material: mrb_material_type
+    std::vector<float> flatMaterialParams;          // per flat material: 8 floats (mrb_render_desc.materialParams)
     std::vector<int32_t> flatAlbedoTex;             // per flat material: index into flatTextures or -1
     std::vector<uint32_t> flatTextures;             // TextureIds in use, in first-use order
     std::vector<TextureB200> textures;              // TextureId = index + 1 (0 = InvalidTexture)
@@ -299,7 +307,7 @@ class TracerB200 final : public TracerI
 
     // ------------------------------- generic -------------------------------
     TypeNameList PrimitiveGroups() const override { return {"(P)Triangle"sv, "(P)Empty"sv}; }
-    TypeNameList MaterialGroups() const override { return {"(Mt)Lambert"sv, "(Mt)Passthrough"sv, "(Mt)Reflect"sv}; }
+    TypeNameList MaterialGroups() const override { return {"(Mt)Lambert"sv, "(Mt)Passthrough"sv, "(Mt)Reflect"sv, "(Mt)Refract"sv, "(Mt)Unreal"sv}; }
     TypeNameList TransformGroups() const override { return {"(T)Identity"sv, "(T)Single"sv}; }
     TypeNameList CameraGroups() const override { return {"(C)Pinhole"sv}; }
     TypeNameList MediumGroups() const override { return {"(Md)Vacuum"sv}; }
@@ -323,6 +331,21 @@ class TracerB200 final : public TracerI
     MatAttributeInfoList AttributeInfoMat(std::string_view name) const override
     {
         using enum MRayDataEnum; using enum AttributeIsArray; using enum AttributeOptionality; using enum AttributeTexturable; using enum AttributeIsColor;
+        if(name == "(Mt)Refract"sv)   // Tracer/MaterialsDefault.cpp:L236-251
+            return MatAttributeInfoList
+            {
+                MatAttributeInfo("cauchyBack", MRayDataTypeRT(MR_VECTOR_3), IS_SCALAR, MR_MANDATORY, MR_CONSTANT_ONLY, IS_PURE_DATA),
+                MatAttributeInfo("cauchyFront", MRayDataTypeRT(MR_VECTOR_3), IS_SCALAR, MR_MANDATORY, MR_CONSTANT_ONLY, IS_PURE_DATA)
+            };
+        if(name == "(Mt)Unreal"sv)    // Tracer/MaterialsDefault.cpp:L382-403
+            return MatAttributeInfoList
+            {
+                MatAttributeInfo("albedo", MRayDataTypeRT(MR_VECTOR_3), IS_SCALAR, MR_MANDATORY, MR_TEXTURE_OR_CONSTANT, IS_COLOR),
+                MatAttributeInfo("normalMap", MRayDataTypeRT(MR_VECTOR_3), IS_SCALAR, MR_OPTIONAL, MR_TEXTURE_ONLY, IS_PURE_DATA),
+                MatAttributeInfo("roughness", MRayDataTypeRT(MR_FLOAT), IS_SCALAR, MR_MANDATORY, MR_TEXTURE_OR_CONSTANT, IS_PURE_DATA),
+                MatAttributeInfo("specular", MRayDataTypeRT(MR_FLOAT), IS_SCALAR, MR_MANDATORY, MR_TEXTURE_OR_CONSTANT, IS_PURE_DATA),
+                MatAttributeInfo("metallic", MRayDataTypeRT(MR_FLOAT), IS_SCALAR, MR_MANDATORY, MR_TEXTURE_OR_CONSTANT, IS_PURE_DATA)
+            };
         if(name != "(Mt)Lambert"sv) return {};
         return MatAttributeInfoList
         {
@@ -417,7 +440,7 @@ class TracerB200 final : public TracerI
         std::lock_guard lk(mtx);
         PrimGroupB200& pg = Get(prims, Raw(g), "PrimitiveGroup");
         pg.positions.assign(pg.vertexTotal, Vector3::Zero());
-        pg.normals.assign(pg.vertexTotal, Vector3::Zero());
+        pg.tbn.assign(pg.vertexTotal, std::array<float, 4>{1.f, 0.f, 0.f, 0.f});
         pg.uvs.assign(pg.vertexTotal, Vector2::Zero());
         pg.indices.assign(pg.primTotal, Vector3ui::Zero());
         pg.committed = true;
@@ -434,8 +457,11 @@ class TracerB200 final : public TracerI
             case 0: { auto s = data.AccessAs<const Vector3>(); if(s.size() != pb.vertexCount) throw MRayError("position count mismatch");
                       std::copy(s.begin(), s.end(), pg.positions.begin() + pb.vertexOffset); break; }
             case 1: { auto s = data.AccessAs<const Quaternion>(); if(s.size() != pb.vertexCount) throw MRayError("normal count mismatch");
-                      // the attribute is the to-tangent-space rotation; its Z basis is the shading normal
-                      for(size_t i = 0; i < s.size(); i++) pg.normals[pb.vertexOffset + i] = s[i].OrthoBasisZ(); break; }
+                      // the attribute is the to-tangent-space rotation; the renderer blends the three vertex quaternions of a
+                      // hit (Quaternion::BarySLerp) and takes the frame's Z axis as the shading normal
+                      for(size_t i = 0; i < s.size(); i++)
+                      { const Quaternion& q = s[i]; pg.tbn[pb.vertexOffset + i] = {q[0], q[1], q[2], q[3]}; }
+                      pg.hasTBN = true; break; }
             case 2: { auto s = data.AccessAs<const Vector2>(); if(s.size() != pb.vertexCount) throw MRayError("uv count mismatch");
                       std::copy(s.begin(), s.end(), pg.uvs.begin() + pb.vertexOffset); break; }
             case 3: { auto s = data.AccessAs<const Vector3ui>(); if(s.size() != pb.primCount) throw MRayError("index count mismatch");
@@ -454,7 +480,8 @@ class TracerB200 final : public TracerI
     {
         std::lock_guard lk(mtx);
         // (Mt)Reflect has no attributes (MatGroupReflect::AttributeInfo returns an empty list, MaterialsDefault.cpp:L161-164)
-        if(typeName != "(Mt)Lambert" && typeName != "(Mt)Reflect") throw MRayError("Unable to find generator for {}", typeName);
+        if(typeName != "(Mt)Lambert" && typeName != "(Mt)Reflect" && typeName != "(Mt)Refract" && typeName != "(Mt)Unreal")
+            throw MRayError("Unable to find generator for {}", typeName);
         mats.push_back(MatGroupB200{typeName});
         return MatGroupId(uint32_t(mats.size() - 1));
     }
@@ -466,20 +493,41 @@ class TracerB200 final : public TracerI
         MaterialIdList out;
         for(size_t i = 0; i < counts.size(); i++)
         {
-            mg.albedo.push_back(Vector3::Zero()); mg.albedoTex.push_back(-1);
+            mg.albedo.push_back(Vector3::Zero()); mg.albedoTex.push_back(-1); mg.params.push_back(std::array<float, 8>{});
             out.push_back(MaterialId((Raw(g) << MAT_ID_BITS) | uint32_t(mg.albedo.size() - 1)));
         }
         return out;
     }
     void CommitMatReservations(MatGroupId g) override { Get(mats, Raw(g), "MaterialGroup").committed = true; }
     bool IsMatCommitted(MatGroupId g) const override { return Get(mats, Raw(g), "MaterialGroup").committed; }
-    void PushMatAttribute(MatGroupId, CommonIdRange, uint32_t attributeIndex, TransientData) override
-    { throw MRayError("(Mt)Lambert: Attribute {:d} is not \"ConstantOnly\", wrong function is called", attributeIndex); }
+    void PushMatAttribute(MatGroupId g, CommonIdRange range, uint32_t attributeIndex, TransientData data) override
+    {
+        MatGroupB200& mg = Get(mats, Raw(g), "MaterialGroup");
+        if(mg.type != "(Mt)Refract") throw MRayError("{}: Attribute {:d} is not \"ConstantOnly\", wrong function is called", mg.type, attributeIndex);
+        // MatGroupRefract::PushAttribute (Tracer/MaterialsDefault.cpp:L295-314): 0 = cauchyBack, 1 = cauchyFront
+        if(attributeIndex > 1) throw MRayError("{:s}: Unkown attribute index {:d}", mg.type, attributeIndex);
+        uint32_t lo = range[0] & ((1u << MAT_ID_BITS) - 1u), hi = range[1] & ((1u << MAT_ID_BITS) - 1u);
+        auto s = data.AccessAs<const Vector3>();
+        if(hi >= mg.params.size() || s.size() != hi - lo + 1) throw MRayError("{}: cauchy coefficient range mismatch", mg.type);
+        for(size_t k = 0; k < s.size(); k++)
+            for(unsigned c = 0; c < 3; c++) mg.params[lo + k][(attributeIndex == 1 ? 0 : 4) + c] = s[k][c];
+    }
     void PushMatAttribute(MatGroupId g, CommonIdRange range, uint32_t attributeIndex, TransientData data,
                           std::vector<Optional<TextureId>> tex) override
     {
         MatGroupB200& mg = Get(mats, Raw(g), "MaterialGroup");
         if(mg.type == "(Mt)Reflect") throw MRayError("{} group does not have any attributes!", mg.type);
+        if(mg.type == "(Mt)Refract") throw MRayError("{}: Attribute {:d} is \"ConstantOnly\", wrong function is called", mg.type, attributeIndex);
+        if(mg.type == "(Mt)Unreal" && attributeIndex >= 2 && !data.IsEmpty())
+        {   // roughness / specular / metallic: ParamVaryingData<2, Float> (MatGroupUnreal::PushTexAttribute, MaterialsDefault.cpp:L433-454)
+            if(attributeIndex > 4) throw MRayError("{:s}: Attribute {:d} is not \"ParamVarying\", wrong function is called", mg.type, attributeIndex);
+            for(const auto& t : tex) if(t.has_value()) throw MRayError("{}: textured roughness / specular / metallic are not supported yet", mg.type);
+            uint32_t lo = range[0] & ((1u << MAT_ID_BITS) - 1u), hi = range[1] & ((1u << MAT_ID_BITS) - 1u);
+            auto s = data.AccessAs<const Float>();
+            if(hi >= mg.params.size() || s.size() != hi - lo + 1 || tex.size() != s.size()) throw MRayError("{}: attribute range mismatch", mg.type);
+            for(size_t k = 0; k < s.size(); k++) mg.params[lo + k][attributeIndex - 2] = s[k];
+            return;
+        }
         // An EMPTY TransientData routes to the optional texture-only overload (TracerBase.cpp:L843-867): the
         // scene loader always pushes Lambert's optional `normalMap` this way, with nullopt where a material has none.
         if(data.IsEmpty())
@@ -710,7 +758,8 @@ class TracerB200 final : public TracerI
             groups.push_back(Group{Raw(t), {}, {}, {}});
             return groups.back();
         };
-        flatAlbedo.clear(); flatAlbedoTex.clear(); flatMaterialType.clear(); flatTextures.clear(); flatLightRadiance.clear(); flatLightTwoSided.clear();
+        flatAlbedo.clear(); flatAlbedoTex.clear(); flatMaterialType.clear(); flatMaterialParams.clear(); flatTextures.clear();
+        flatLightRadiance.clear(); flatLightTwoSided.clear();
         int32_t pgUsed = -1;
         auto UsePrimGroup = [&](uint32_t g)
         {
@@ -737,7 +786,9 @@ class TracerB200 final : public TracerI
                 if(it == flatTextures.end()) flatTextures.push_back(tid);
             }
             flatAlbedoTex.push_back(ft);
-            flatMaterialType.push_back(mg.type == "(Mt)Reflect" ? uint8_t(MRB_MATERIAL_REFLECT) : uint8_t(MRB_MATERIAL_LAMBERT));
+            flatMaterialType.push_back(mg.type == "(Mt)Reflect" ? uint8_t(MRB_MATERIAL_REFLECT) : mg.type == "(Mt)Refract" ? uint8_t(MRB_MATERIAL_REFRACT)
+                                       : mg.type == "(Mt)Unreal" ? uint8_t(MRB_MATERIAL_UNREAL) : uint8_t(MRB_MATERIAL_LAMBERT));
+            flatMaterialParams.insert(flatMaterialParams.end(), mg.params[idx].begin(), mg.params[idx].end());
             return uint32_t(matKeyOf.size() - 1);
         };
         for(const SurfaceParams& s : surfaces)
@@ -953,11 +1004,10 @@ class TracerB200 final : public TracerI
         saveImage = true; completedPaths = 0; primed = false;
 
         mrb_render_desc d = {};
-        bool hasNormals = std::any_of(pg.normals.begin(), pg.normals.end(), [](const Vector3& n) { return n != Vector3::Zero(); });
-        const float* normals = hasNormals ? reinterpret_cast<const float*>(pg.normals.data()) : nullptr;
-        std::vector<const float*> instNormals(twoLevel ? sceneInstanceCount : 1u, normals);
+        const float* tbn = pg.hasTBN ? reinterpret_cast<const float*>(pg.tbn.data()) : nullptr;
+        std::vector<const float*> instTBN(twoLevel ? sceneInstanceCount : 1u, tbn);
         d.materialCount = uint32_t(flatAlbedo.size() / 3); d.albedo = flatAlbedo.data();
-        d.materialType = flatMaterialType.data();
+        d.materialType = flatMaterialType.data(); d.materialParams = flatMaterialParams.data();
         std::vector<mrb_texture_desc> texDescs(flatTextures.size());
         std::vector<const float*> instUVs(twoLevel ? sceneInstanceCount : 1u, reinterpret_cast<const float*>(pg.uvs.data()));
         if(!flatTextures.empty())
@@ -1006,8 +1056,8 @@ class TracerB200 final : public TracerI
         for(uint32_t k = 0; k < nDev; k++)
         {
             DeviceB200& dv = devs[k];
-            if(twoLevel) { d.scene = dv.scene; d.accel = nullptr; d.instanceVertexNormals = instNormals.data(); if(!flatTextures.empty()) d.instanceVertexUVs = instUVs.data(); }
-            else { d.accel = dv.accel; d.vertexCount = pg.vertexTotal; d.triangleCount = pg.primTotal; d.vertexNormals = normals; if(!flatTextures.empty()) d.vertexUVs = instUVs[0]; }
+            if(twoLevel) { d.scene = dv.scene; d.accel = nullptr; d.instanceVertexTBN = instTBN.data(); if(!flatTextures.empty()) d.instanceVertexUVs = instUVs.data(); }
+            else { d.accel = dv.accel; d.vertexCount = pg.vertexTotal; d.triangleCount = pg.primTotal; d.vertexTBN = tbn; if(!flatTextures.empty()) d.vertexUVs = instUVs[0]; }
             d.spectrum = (r.type == "(R)PathTracerSpectral") ? dv.spectrum : nullptr;
             // throughput mode: the renderer's initial pass is this device's share of the job's samples; pass modes
             // (re)define the range with every pass
@@ -1207,7 +1257,7 @@ class TracerB200 final : public TracerI
         surfaces.clear(); lightSurfaces.clear(); camSurfaces.clear(); volumes.clear(); textures.clear();
         boundary = LightSurfaceParams{};
         flatPrimGroup = 0; flatLightRadiance.clear(); flatLightTwoSided.clear(); flatAlbedo.clear();
-        flatMaterialType.clear(); flatAlbedoTex.clear(); flatTextures.clear();
+        flatMaterialType.clear(); flatMaterialParams.clear(); flatAlbedoTex.clear(); flatTextures.clear();
         lastStart.reset(); camOverride.reset(); pendingCam.reset(); tileSPPs.clear(); currentTile = 0;
     }
     void Flush() const override { for(const DeviceB200& d : devs) mrb_context_synchronize(d.ctx); }

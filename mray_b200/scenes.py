@@ -374,3 +374,67 @@ def cornell_mirror():
     c["albedo"] = np.concatenate([c["albedo"], np.zeros((1, 3), np.float32)])
     c["material_type"] = np.array([0, 0, 0, 0, 1], np.uint8)
     return c
+
+
+def cornell_glossy():
+    """``cornell_box`` with the tall box made of (Mt)Unreal (a rough gold-like metal) and the short box of (Mt)Refract
+    (glass, air outside): material 4 = Unreal (triangles 12..23), material 5 = Refract (triangles 24..35). Returns the
+    cornell dict with `material` updated, a 6-row albedo table, `material_type` (mrb_material_type per material id; id 3 is
+    the light) and `material_params` [6, 8] (Unreal: roughness, specular, metallic; Refract: cauchyFront xyz, -, cauchyBack xyz)."""
+    c = cornell_box()
+    m = c["material"].copy()
+    m[12:24] = 4
+    m[24:36] = 5
+    c["material"] = m
+    c["albedo"] = np.concatenate([c["albedo"], np.array([[0.95, 0.64, 0.30], [0, 0, 0]], np.float32)])
+    c["material_type"] = np.array([0, 0, 0, 0, 3, 2], np.uint8)
+    mp = np.zeros((6, 8), np.float32)
+    mp[4, :3] = [0.35, 0.5, 0.8]                 # roughness, specular, metallic
+    mp[5, :3] = [1.0, 0.0, 0.0]                  # cauchyFront: air
+    mp[5, 4:7] = [1.5046, 0.0042, 0.0]           # cauchyBack: BK7-like glass
+    c["material_params"] = mp
+    return c
+
+
+def icosphere(subdivisions: int = 1):
+    """Unit icosphere: (positions [V, 3] float64, indices [T, 3]); 20 * 4^subdivisions triangles, shared vertices."""
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    v = [[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t], [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1]]
+    f = [[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4], [11, 10, 2], [10, 7, 6], [7, 1, 8],
+         [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9], [4, 9, 5], [2, 4, 11], [6, 2, 10], [8, 6, 7], [9, 8, 1]]
+    v = [np.array(p, np.float64) / np.linalg.norm(p) for p in v]
+    for _ in range(subdivisions):
+        cache, nf = {}, []
+        def mid(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in cache:
+                m = v[a] + v[b]; v.append(m / np.linalg.norm(m)); cache[key] = len(v) - 1
+            return cache[key]
+        for a, b, c in f:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [[a, ab, ca], [b, bc, ab], [c, ca, bc], [ab, bc, ca]]
+        f = nf
+    return np.array(v), np.array(f, np.uint32)
+
+
+def cornell_sphere():
+    """``cornell_box`` with the short box replaced by an 80-triangle sphere with SMOOTH vertex normals (the only fixture
+    whose shading normals differ from the geometric ones: Triangle::GenerateSurface's interpolated tangent frames).
+    Returns the cornell dict plus `normals` [V, 3] (face normals on the quads, radial on the sphere)."""
+    c = cornell_box()
+    keep = np.ones(c["indices"].shape[0], bool); keep[24:36] = False
+    idx = c["indices"][keep]; mat = c["material"][keep]
+    pos = c["positions"].astype(np.float64)
+    fn = np.cross(pos[c["indices"][:, 1]] - pos[c["indices"][:, 0]], pos[c["indices"][:, 2]] - pos[c["indices"][:, 0]])
+    fn /= np.linalg.norm(fn, axis=1, keepdims=True)
+    nrm = np.zeros_like(pos)
+    for k in range(3):
+        nrm[c["indices"][:, k]] = fn                      # quads: unshared vertices, every corner takes its face's normal
+    sv, sf = icosphere(1)
+    centre, radius = np.array([0.4, 0.35, 0.35]), 0.35
+    base = pos.shape[0]
+    pos = np.concatenate([pos, centre + radius * sv]); nrm = np.concatenate([nrm, sv])
+    idx = np.concatenate([idx, sf + base]); mat = np.concatenate([mat, np.zeros(sf.shape[0], np.uint32)])
+    c["positions"] = np.ascontiguousarray(pos, np.float32); c["indices"] = np.ascontiguousarray(idx, np.uint32)
+    c["material"] = mat.astype(np.uint32); c["normals"] = np.ascontiguousarray(nrm, np.float32)
+    return c

@@ -62,6 +62,12 @@ ITEMS = {
     "cornell64_box_spp16384":      (64, 16384, 21, "WithNEEAndMIS", (2, 20), ("filter", "Box", 1.0), np.float32, RGB),
     "cornell64_tent_spp16384":     (64, 16384, 22, "WithNEEAndMIS", (2, 20), ("filter", "Tent", 1.5), np.float32, RGB),
     "cornell64_mitchell_spp16384": (64, 16384, 23, "WithNEEAndMIS", (2, 20), ("filter", "Mitchell-Netravali", 2.0), np.float32, RGB),
+    # (Mt)Unreal + (Mt)Refract (scenes.cornell_glossy): a rough metal box and a glass box; the spectral render disperses
+    "cornell64_glossy_spp16384": (64, 16384, 24, "WithNEEAndMIS", (2, 20), "glossy", np.float32, RGB),
+    "cornell64_glossy_spectral_spp16384": (64, 16384, 25, "WithNEEAndMIS", (2, 20), "glossy", np.float32, SPECTRAL),
+    # smooth shading normals: an 80-triangle sphere with radial vertex normals (scenes.cornell_sphere) — the interpolated
+    # tangent frames of Triangle::GenerateSurface (every other fixture has flat normals)
+    "cornell64_sphere_spp16384": (64, 16384, 26, "WithNEEAndMIS", (2, 20), "sphere", np.float32, RGB),
     # two-level scene: every batch in its own local space under a (T)Single transform
     "cornell64_single_spp16384": (64, 16384, 6, "WithNEEAndMIS", (2, 20), True, np.float32, RGB),
 }
@@ -101,7 +107,8 @@ def localise(b, seed=17):
 
 def render(name):
     res, spp, seed, mode, rr, single, dt, renderer = ITEMS[name]
-    c = scenes.cornell_mirror() if single == "mirror" else scenes.cornell_box()
+    c = (scenes.cornell_mirror() if single == "mirror" else scenes.cornell_glossy() if single == "glossy"
+         else scenes.cornell_sphere() if single == "sphere" else scenes.cornell_box())
     kw = {}
     if single == "twosided":
         b = O.batched_scene(c["positions"], c["indices"], c["material"])
@@ -110,6 +117,13 @@ def render(name):
     elif single in ("Sobol", "ZSobol"):
         b = O.batched_scene(c["positions"], c["indices"], c["material"])
         kw = dict(sampler=single)
+        bt = None
+    elif single == "sphere":
+        b = O.batched_scene(c["positions"], c["indices"], c["material"], normals=c["normals"])
+        bt = None
+    elif single == "glossy":
+        b = O.batched_scene(c["positions"], c["indices"], c["material"])
+        kw = dict(material_kind=c["material_type"], material_params=c["material_params"])
         bt = None
     elif single == "mirror":
         b = O.batched_scene(c["positions"], c["indices"], c["material"])

@@ -91,6 +91,12 @@ typedef struct
     /* TracerParameters.filmFilter.type: 0 = the default (Gaussian), else FilterType::E + 1 (1 Box, 2 Tent, 3 Gaussian,
      * 4 Mitchell-Netravali); the radius is filterRadius */
     uint32_t filmFilter;
+    /* per material 8 floats (NULL = none): materialType 2 = (Mt)Refract {cauchyFront xyz, -, cauchyBack xyz, -},
+     * 3 = (Mt)Unreal {roughness, specular, metallic, ...} */
+    const float* materialParams;
+    /* per vertex world -> tangent-space quaternion (w, x, y, z), the triangle group's NORMAL attribute; NULL = geometric
+     * normals */
+    const float* vertexTBN;
 } pt_scene;
 
 /* One single-level 2-D texture as the reference's host-backend view reads it (Device/CPU/TextureViewCPU.h):
@@ -384,6 +390,142 @@ void orc_pt_light_sample(const float* triv, int twoSided, float x0, float x1, co
     out[4] = light_pdf(q, twoSided, hit, from, dir);
 }
 
+/* ---- (Mt)Refract / (Mt)Unreal (Tracer/MaterialsDefault.hpp:L232-760, Tracer/DistributionFunctions.h:L382-590) ---- */
+static float sqrt_max(float x) { return x > 0 ? sqrtf(x) : 0.0f; }
+static float pdf_cos_direction(float cosT) { float p = cosT * 0.31830988618f; return p <= 1.0e-5f ? 0.0f : p; }   /* Common::PDFCosDirection */
+static float fresnel_dielectric(float cosFront, float etaFront, float etaBack)
+{
+    float sinFront = sqrt_max(1.0f - cosFront * cosFront), sinBack = etaFront / etaBack * sinFront;
+    if(sinFront >= 1.0f) return 1.0f;
+    float cosBack = sqrt_max(1.0f - sinBack * sinBack);
+    float par = (etaBack * cosFront - etaFront * cosBack) / (etaBack * cosFront + etaFront * cosBack);
+    float per = (etaFront * cosFront - etaBack * cosBack) / (etaFront * cosFront + etaBack * cosBack);
+    return (par * par + per * per) * 0.5f;
+}
+static float cauchy_ior(float wavelengthNm, const float* c) { float w = wavelengthNm * 1.0e-3f, w2 = w * w; return c[0] + c[1] / w2 + c[2] / (w2 * w2); }
+static float d_ggx(float NdH, float alpha) { float a2 = alpha * alpha, den = NdH * NdH * (a2 - 1.0f) + 1.0f; return a2 / (den * den * 3.14159265358979f); }
+static float lambda_smith(v3 v, float alpha) { return (sqrtf(1.0f + alpha * alpha * (v.x * v.x + v.y * v.y) / (v.z * v.z)) - 1.0f) * 0.5f; }
+static float g_smith_single(v3 v, float alpha) { return 1.0f / (1.0f + lambda_smith(v, alpha)); }
+static float g_smith_correlated(v3 a, v3 b, float alpha) { return 1.0f / (lambda_smith(a, alpha) + lambda_smith(b, alpha) + 1.0f); }
+static float vndf_pdf(v3 Vv, v3 H, float alpha)
+{
+    float VdH = dot(H, Vv); if(VdH < 0) VdH = 0;
+    float NdH = H.z > 0 ? H.z : 0, NdV = Vv.z > 0 ? Vv.z : 0;
+    if(NdV == 0.0f) return 0.0f;
+    return VdH * d_ggx(NdH, alpha) * g_smith_single(Vv, alpha) / NdV;
+}
+static v3 vndf_sample(v3 Vv, float alpha, float xi0, float xi1, float* pdf)
+{
+    v3 VH = nrm(V(alpha * Vv.x, alpha * Vv.y, Vv.z));
+    float len2 = VH.x * VH.x + VH.y * VH.y;
+    v3 T1 = len2 > 0 ? mul(V(-VH.y, VH.x, 0), 1.0f / sqrtf(len2)) : V(1, 0, 0);
+    v3 T2 = cross(VH, T1);
+    float r = sqrtf(xi0), phi = 6.28318530718f * xi1;
+    float t1 = r * cosf(phi), t2 = r * sinf(phi), sh = 0.5f * (1.0f + VH.z);
+    t2 = (1.0f - sh) * sqrtf(1.0f - t1 * t1) + sh * t2;
+    v3 NH = add(add(mul(T1, t1), mul(T2, t2)), mul(VH, sqrt_max(1.0f - t1 * t1 - t2 * t2)));
+    v3 N = V(alpha * NH.x, alpha * NH.y, sqrt_max(NH.z));
+    float nl2 = dot(N, N);
+    N = nl2 < 1.0e-5f ? V(0, 0, 1) : mul(N, 1.0f / sqrtf(nl2));
+    *pdf = vndf_pdf(Vv, N, alpha);
+    return N;
+}
+typedef struct { s4 albedo; float roughness, specular, metallic; } unreal_mat;
+static float unreal_mis_ratio(const unreal_mat* u)
+{
+    float avg = (u->albedo.v[0] + u->albedo.v[1] + u->albedo.v[2] + u->albedo.v[3]) * 0.3333f;
+    float integralDiffuse = 2.0f * 3.14159265358979f * avg * (1.0f - u->metallic);
+    float specularRatio = u->specular * (1.0f - u->metallic) + avg * u->metallic;
+    float total = specularRatio + integralDiffuse;
+    return total == 0.0f ? 0.0f : integralDiffuse / total;
+}
+static s4 unreal_fschlick(const unreal_mat* u, float VdH)
+{
+    float specOut = u->specular * 0.08f, pw = 1.0f - VdH, pw5 = pw * pw * pw * pw * pw; s4 o;
+    for(int k = 0; k < 4; k++) { float f0 = specOut * (1.0f - u->metallic) + u->albedo.v[k] * u->metallic; o.v[k] = (1.0f - f0) * pw5 + f0; }
+    return o;
+}
+static float burley(float NdL, float NdV, float LdH, float roughness)
+{
+    float fd90 = 0.5f + 2.0f * roughness * LdH * LdH;
+    float a = 1.0f - NdL, b = 1.0f - NdV;
+    return (1.0f + (fd90 - 1.0f) * a * a * a * a * a) * (1.0f + (fd90 - 1.0f) * b * b * b * b * b);
+}
+static s4 unreal_terms(const unreal_mat* u, v3 Vt, v3 L, v3 H, int cancelOnBadD, float* pdfSpecOverride)
+{
+    float alpha = u->roughness * u->roughness;
+    float LdH = dot(L, H), VdH = dot(Vt, H); if(LdH < 0) LdH = 0; if(VdH < 0) VdH = 0;
+    float NdH = H.z > 0 ? H.z : 0, NdV = Vt.z > 0 ? Vt.z : 0, NdL = L.z > 0 ? L.z : 0;
+    float D = d_ggx(NdH, alpha);
+    int badD = isnan(D) || isinf(D);
+    float G = g_smith_correlated(Vt, L, alpha);
+    if(LdH == 0.0f || VdH == 0.0f) G = 0.0f;
+    s4 F = unreal_fschlick(u, VdH), spec;
+    if(badD && cancelOnBadD) { spec = s_mul(F, G / g_smith_single(Vt, alpha)); if(pdfSpecOverride) *pdfSpecOverride = 1.0f; }
+    else
+    {
+        if(badD) D = 0.0f;
+        spec = (NdV == 0.0f) ? S(0, 0, 0, 0) : s_mul(F, D * G * 0.25f / NdV);
+    }
+    s4 diff = s_mul(u->albedo, NdL * 0.31830988618f * (1.0f - u->metallic) * burley(NdL, NdV, LdH, u->roughness));
+    return s_add(diff, spec);
+}
+static s4 unreal_evaluate(const unreal_mat* u, v3 Vt, v3 L) { return unreal_terms(u, Vt, L, nrm(add(L, Vt)), 0, NULL); }
+static float unreal_pdf(const unreal_mat* u, v3 Vt, v3 L)
+{
+    float alpha = u->roughness * u->roughness, mis = unreal_mis_ratio(u);
+    v3 H = nrm(add(L, Vt));
+    float NdH = H.z > 0 ? H.z : 0, VdH = dot(Vt, H); if(VdH < 0) VdH = 0;
+    float D = d_ggx(NdH, alpha), ps = vndf_pdf(Vt, H, alpha);
+    if(isnan(D) || isinf(D)) ps = 0.0f;
+    ps = VdH == 0.0f ? 0.0f : ps / (4.0f * VdH);
+    return pdf_cos_direction(L.z) * mis + ps * (1.0f - mis);
+}
+static v3 unreal_sample(const unreal_mat* u, v3 Vt, float sXi, float xi0, float xi1, s4* refl, float* pdfOut)
+{
+    float alpha = u->roughness * u->roughness, mis = unreal_mis_ratio(u), pd, ps;
+    v3 L, H;
+    if(sXi < mis)
+    {
+        float cd[4]; cos_direction(xi0, xi1, cd);
+        L = V(cd[0], cd[1], cd[2]); pd = cd[3];
+        H = nrm(add(L, Vt));
+        float VdH = dot(Vt, H); if(VdH < 0) VdH = 0;
+        ps = vndf_pdf(Vt, H, alpha); ps = VdH == 0.0f ? 0.0f : ps / (4.0f * VdH);
+    }
+    else
+    {
+        float ph; H = vndf_sample(Vt, alpha, xi0, xi1, &ph);
+        L = sub(mul(H, 2.0f * dot(Vt, H)), Vt);
+        float VdH = dot(Vt, H); if(VdH < 0) VdH = 0;
+        ps = VdH == 0.0f ? 0.0f : ph / (4.0f * VdH);
+        pd = pdf_cos_direction(L.z);
+    }
+    *refl = unreal_terms(u, Vt, L, H, 1, &ps);
+    *pdfOut = pd * mis + ps * (1.0f - mis);
+    return L;
+}
+
+/* Quaternion::SLerp / BarySLerp / OrthoBasisZ (Core/Quaternion.hpp:L256-353): the shading normal of a hit is the Z axis of
+ * the barycentric blend of the three vertex frames (Triangle::GenerateSurface, PrimitiveDefaultTriangle.hpp:L463-470) */
+static void quat_slerp(const float* a, const float* b, float t, float* o)
+{
+    float cosT = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3], cf = cosT >= 0 ? cosT : -cosT, s0, s1;
+    if(cf < 1.0f - 1.0e-5f) { float ang = acosf(cf), sr = 1.0f / sinf(ang); s0 = sinf(ang * (1.0f - t)) * sr; s1 = sinf(ang * t) * sr; }
+    else { s0 = 1.0f - t; s1 = t; }
+    if(cosT < 0) s1 = -s1;
+    for(int k = 0; k < 4; k++) o[k] = a[k] * s0 + b[k] * s1;
+}
+static v3 tbn_normal(const float* q0, const float* q1, const float* q2, float a, float b)
+{
+    float q[4], qab[4];
+    if(fabsf(a + b) < 1.0e-5f) memcpy(q, q2, sizeof(q));
+    else { quat_slerp(q1, q0, a / (a + b), qab); quat_slerp(qab, q2, 1.0f - a - b, q); }
+    float inv = 1.0f / sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    float w = q[0] * inv, x = q[1] * inv, y = q[2] * inv, z = q[3] * inv;
+    return V(2.0f * (x * z - w * y), 2.0f * (y * z + w * x), w * w - x * x - y * y + z * z);
+}
+
 static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, float* filmW, float waves[4], float wavePdf[4]);
 static v3 path(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, float* filmW)
 {
@@ -460,7 +602,14 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
             }
             break;
         }
-        if(dot(gN, nrm(d)) > 0) gN = mul(gN, -1.0f);
+        const int backSide = dot(gN, nrm(d)) > 0;
+        v3 sN = gN;   /* shading normal: the interpolated tangent frame's Z axis when the group has a NORMAL attribute */
+        if(s->vertexTBN)
+        {
+            const uint32_t* vi = s->idx + 3 * (size_t)prim;
+            sN = tbn_normal(s->vertexTBN + 4 * (size_t)vi[0], s->vertexTBN + 4 * (size_t)vi[1], s->vertexTBN + 4 * (size_t)vi[2], a, b);
+        }
+        if(backSide) { gN = mul(gN, -1.0f); sN = mul(sN, -1.0f); }
         if(s->materialType && s->materialType[m] == 1u)
         {   /* (Mt)Reflect (MaterialsDefault.hpp:L132-215): a perfect mirror, Specularity() = 1. WorkFunctionNEE samples
              * a light (three random numbers) but casts no shadow ray for a specular material; WorkFunction reflects
@@ -468,23 +617,60 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
              * and marks the ray SPECULAR_RAY so that a light it hits counts in full (no MIS, counted under pure NEE). */
             if(s->sampleMode != 0u) { pcg_float(rng); pcg_float(rng); pcg_float(rng); }
             v3 wO = mul(nrm(d), -1.0f);
-            v3 wI = nrm(sub(mul(gN, 2.0f * dot(wO, gN)), wO));
+            v3 wI = nrm(sub(mul(sN, 2.0f * dot(wO, sN)), wO));
             depth += 1;
             if(depth >= s->rrHi) break;
             prevPdf = 1.0f; type = 1; /* SPECULAR_RAY */
             o = nudge(hitPos, gN); d = wI; tMin = 1.0e-4f; tMax = FLT_MAX;
             continue;
         }
-        /* Lambert */
+        if(s->materialType && s->materialType[m] == 2u)
+        {   /* (Mt)Refract (MaterialsDefault.hpp:L246-312): Fresnel-weighted reflection / refraction, reflectance = pdf (cancels),
+             * Specularity() = 1 like the mirror; a refraction disperses a spectral path to its first wavelength. The BxDF sample
+             * is nudged along the shading normal by the material and again along the (flipped) geometric normal by the
+             * work function (PathTracerRendererShaders.h:L277-283). */
+            if(s->sampleMode != 0u) { pcg_float(rng); pcg_float(rng); pcg_float(rng); }
+            const float* mp = s->materialParams + 8 * (size_t)m;
+            int back = backSide;
+            float fromEta = s->spectrum ? cauchy_ior(waves[0], mp) : mp[0], toEta = s->spectrum ? cauchy_ior(waves[0], mp + 4) : mp[4];
+            if(back) { float tt = fromEta; fromEta = toEta; toEta = tt; }
+            v3 wO = mul(nrm(d), -1.0f);
+            float cosT = fabsf(dot(wO, sN));
+            float f = fresnel_dielectric(cosT, fromEta, toEta);
+            int refl = pcg_float(rng) < f;
+            v3 wI;
+            if(refl) wI = sub(mul(sN, 2.0f * dot(wO, sN)), wO);
+            else
+            {
+                float er = fromEta / toEta, cosIn = dot(sN, wO), sinIn2 = 1.0f - cosIn * cosIn; if(sinIn2 < 0) sinIn2 = 0;
+                float cosOut = sqrt_max(1.0f - er * er * sinIn2);
+                wI = add(mul(wO, -er), mul(sN, er * cosIn - cosOut));
+                if(s->spectrum) { waves[1] = waves[2] = waves[3] = -1.0f; }
+            }
+            float pdfS = refl ? f : 1.0f - f;
+            depth += 1;
+            if(depth >= s->rrHi) break;
+            throughput = (pdfS == 0) ? S(0, 0, 0, 0) : s_mul(s_mul(throughput, pdfS), 1.0f / pdfS);
+            prevPdf = pdfS; type = 1; /* SPECULAR_RAY */
+            o = nudge(nudge(hitPos, sN), refl ? gN : mul(gN, -1.0f)); d = nrm(wI); tMin = 1.0e-4f; tMax = FLT_MAX;
+            continue;
+        }
+        /* Lambert / Unreal */
         s4 alb = albedo_at(s, (uint32_t)m, waves, prim, a, b, c);
-        v3 hlp = fabsf(gN.x) > 0.9f ? V(0, 1, 0) : V(1, 0, 0);
-        v3 tX = nrm(cross(hlp, gN)), tY = cross(gN, tX);
+        v3 hlp = fabsf(sN.x) > 0.9f ? V(0, 1, 0) : V(1, 0, 0);
+        v3 tX = nrm(cross(hlp, sN)), tY = cross(sN, tX);
+        const int unreal = s->materialType && s->materialType[m] == 3u;
+        unreal_mat um; um.albedo = alb; um.roughness = um.specular = um.metallic = 0;
+        if(unreal) { const float* mp = s->materialParams + 8 * (size_t)m; um.roughness = mp[0]; um.specular = mp[1]; um.metallic = mp[2]; }
+        const int specularMat = unreal && (1.0f - unreal_mis_ratio(&um)) >= 0.95f;   /* MaterialCommon::IsSpecular */
+        v3 wOw = mul(nrm(d), -1.0f);
+        v3 Vt = V(dot(wOw, tX), dot(wOw, tY), dot(wOw, sN));
         if(s->sampleMode != 0u)
         {   /* NEE */
             float x0 = pcg_float(rng), x1 = pcg_float(rng), xs = pcg_float(rng);
             uint32_t li = (uint32_t)(xs * (float)nLights);
             if(li > nLights - 1u) li = nLights - 1u;
-            if(li < s->nLightTris)
+            if(li < s->nLightTris && !specularMat)
             {
                 uint32_t lt = s->lightTris[li]; uint32_t lightIdx = (uint32_t)(-1 - s->triMaterial[lt]);
                 v3 q[3]; tri(s, lt, q);
@@ -495,10 +681,16 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
                 v3 wI = nrm(sub(lpos, hitPos));
                 v3 lposN = nudge(lpos, mul(wI, -1.0f));
                 float length = len(sub(lposN, hitPos));
-                float nDotL = dot(gN, wI); if(nDotL < 0) nDotL = 0;
+                float nDotL = dot(sN, wI); if(nDotL < 0) nDotL = 0;
                 s4 refl = s_mul(alb, nDotL * 0.31830988618f);
+                float pdfBx = pdf_cos_direction(dot(sN, wI));
+                if(unreal)
+                {
+                    v3 Lt = V(dot(wI, tX), dot(wI, tY), dot(wI, sN));
+                    refl = unreal_evaluate(&um, Vt, Lt); pdfBx = unreal_pdf(&um, Vt, Lt);
+                }
                 float pdf = pdfL;
-                if(s->sampleMode == 2u) pdf = nDotL * 0.31830988618f + pdfL;
+                if(s->sampleMode == 2u) pdf = pdfBx + pdfL;
                 s4 sr = s_mulv(s_mulv(throughput, refl), em);
                 sr = (pdf == 0) ? S(0, 0, 0, 0) : s_mul(sr, 1.0f / pdf);
                 if(depth + 2u <= s->rrHi && (sr.v[0] > 0 || sr.v[1] > 0 || sr.v[2] > 0 || sr.v[3] > 0))
@@ -510,14 +702,25 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
             }
         }
         /* BxDF sample + RR */
-        float u0 = pcg_float(rng), u1 = pcg_float(rng);
-        float cd[4]; cos_direction(u0, u1, cd);
-        float lx = cd[0], ly = cd[1], lz = cd[2], pdfB = cd[3];
-        v3 wI = nrm(add(add(mul(tX, lx), mul(tY, ly)), mul(gN, lz)));
-        throughput = s_mulv(throughput, s_mul(alb, lz * 0.31830988618f));
+        float lx, ly, lz, pdfB; s4 reflS;
+        if(unreal)
+        {
+            float sXi = pcg_float(rng), u0 = pcg_float(rng), u1 = pcg_float(rng);
+            v3 L = unreal_sample(&um, Vt, sXi, u0, u1, &reflS, &pdfB);
+            lx = L.x; ly = L.y; lz = L.z;
+        }
+        else
+        {
+            float u0 = pcg_float(rng), u1 = pcg_float(rng);
+            float cd[4]; cos_direction(u0, u1, cd);
+            lx = cd[0]; ly = cd[1]; lz = cd[2]; pdfB = cd[3];
+            reflS = s_mul(alb, lz * 0.31830988618f);
+        }
+        v3 wI = nrm(add(add(mul(tX, lx), mul(tY, ly)), mul(sN, lz)));
+        throughput = s_mulv(throughput, reflS);
         depth += 1;
         int dead = depth >= s->rrHi;
-        if(!dead && depth >= s->rrLo)
+        if(!dead && depth >= s->rrLo && !specularMat)
         {
             float xi = pcg_float(rng);
             float prob = (throughput.v[0] + throughput.v[1] + throughput.v[2] + throughput.v[3]) * (s->spectrum ? 0.25f : 0.33333333f);
@@ -526,7 +729,7 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
         }
         if(dead) break;
         throughput = (pdfB == 0) ? S(0, 0, 0, 0) : s_mul(throughput, 1.0f / pdfB);
-        prevPdf = pdfB; type = 2; /* PATH_RAY */
+        prevPdf = pdfB; type = specularMat ? 1 : 2; /* SPECULAR_RAY after a near-mirror, else PATH_RAY */
         o = nudge(hitPos, gN); d = wI; tMin = 1.0e-4f; tMax = FLT_MAX;
     }
     return radiance;

@@ -26,7 +26,7 @@ struct DriverScene
     uint32_t materialCount; const float* albedo; uint32_t lightCount; const float* radiance;
     float camPos[3], camGaze[3], camUp[3]; float fovXY[2]; float nearFar[2];
     const float* batchTransforms; const int32_t* batchInstanceOf;
-    uint32_t textureCount; const uint32_t* textureInfo; const uint8_t* textureBytes; const int32_t* materialTexture; const float* uvs; const uint8_t* materialKind; const uint8_t* lightTwoSided;
+    uint32_t textureCount; const uint32_t* textureInfo; const uint8_t* textureBytes; const int32_t* materialTexture; const float* uvs; const uint8_t* materialKind; const uint8_t* lightTwoSided; const float* materialParams;
 };
 struct DriverRender
 {
@@ -43,7 +43,7 @@ int main(int argc, char** argv)
     FILE* f = std::fopen(argv[1], "rb");
     if(!f) { std::perror("blob"); return 65; }
     uint64_t n = 0;
-    if(std::fread(&n, 8, 1, f) != 1 || n != 23) { std::fprintf(stderr, "bad blob\n"); return 66; }
+    if(std::fread(&n, 8, 1, f) != 1 || (n != 23 && n != 24)) { std::fprintf(stderr, "bad blob\n"); return 66; }
     std::vector<std::vector<uint64_t>> sec(n);     // 8-byte aligned storage
     std::vector<uint64_t> bytes(n);
     for(uint64_t i = 0; i < n; i++)
@@ -74,6 +74,7 @@ int main(int argc, char** argv)
     sc.textureBytes = static_cast<const uint8_t*>(P(18)); sc.materialTexture = static_cast<const int32_t*>(P(19));
     sc.uvs = static_cast<const float*>(P(20)); sc.materialKind = static_cast<const uint8_t*>(P(21));
     sc.lightTwoSided = static_cast<const uint8_t*>(P(22));
+    if(n > 23) sc.materialParams = static_cast<const float*>(P(23));   // 23 materialParams (8 floats per material; may be empty)
     std::memcpy(sc.camPos, cam, 12); std::memcpy(sc.camGaze, cam + 3, 12); std::memcpy(sc.camUp, cam + 6, 12);
     std::memcpy(sc.fovXY, cam + 9, 8); std::memcpy(sc.nearFar, cam + 11, 8);
     DriverRender rd{};

@@ -64,6 +64,9 @@ struct DriverScene
     const uint8_t*  materialKind;
     // optional: per light the isTwoSided attribute of (L)Prim(P)Triangle; NULL = one-sided
     const uint8_t*  lightTwoSided;
+    // optional: per material 8 floats. materialKind 2 = (Mt)Refract {cauchyFront xyz, -, cauchyBack xyz, -},
+    // 3 = (Mt)Unreal {roughness, specular, metallic, ...} (albedo from `albedo`, constant)
+    const float*    materialParams;
 };
 
 struct DriverRender
@@ -278,9 +281,12 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
             }
         }
         // ---- materials: (Mt)Lambert (constant or textured albedo) and, where materialKind says so, (Mt)Reflect ----
-        std::vector<uint32_t> lambertOf, reflectOf;                 // scene material index per group entry
+        std::vector<uint32_t> lambertOf, reflectOf, refractOf, unrealOf;   // scene material index per group entry
         for(uint32_t m = 0; m < sc->materialCount; m++)
-            ((sc->materialKind && sc->materialKind[m] == 1) ? reflectOf : lambertOf).push_back(m);
+        {
+            const uint32_t kind = sc->materialKind ? sc->materialKind[m] : 0u;
+            (kind == 1 ? reflectOf : kind == 2 ? refractOf : kind == 3 ? unrealOf : lambertOf).push_back(m);
+        }
         MaterialIdList mats(sc->materialCount);
         if(!lambertOf.empty())
         {
@@ -324,6 +330,71 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
             MaterialIdList ids = tracer->ReserveMaterials(rg, rCounts);
             tracer->CommitMatReservations(rg);
             for(size_t k = 0; k < reflectOf.size(); k++) mats[reflectOf[k]] = ids[k];
+        }
+        if(!refractOf.empty())
+        {   // (Mt)Refract: constant-only Cauchy coefficients, attribute 0 = cauchyBack, 1 = cauchyFront
+            const uint32_t n = uint32_t(refractOf.size());
+            MatGroupId g = tracer->CreateMaterialGroup("(Mt)Refract");
+            MatAttributeInfoList info = tracer->AttributeInfo(g);
+            std::vector<AttributeCountList> counts(n);
+            for(auto& c : counts) { c = AttributeCountList(StaticVecSize(info.size())); for(size_t k = 0; k < info.size(); k++) c[k] = 1; }
+            MaterialIdList ids = tracer->ReserveMaterials(g, counts);
+            tracer->CommitMatReservations(g);
+            auto range = CommonIdRange(std::bit_cast<CommonId>(ids.front()), std::bit_cast<CommonId>(ids.back()));
+            for(uint32_t a = 0; a < 2; a++)
+            {
+                std::vector<Vector3> v(n);
+                for(uint32_t k = 0; k < n; k++)
+                {
+                    const float* mp = sc->materialParams + 8 * size_t(refractOf[k]) + (info[a].name == "cauchyFront" ? 0 : 4);
+                    v[k] = Vector3(mp[0], mp[1], mp[2]); mats[refractOf[k]] = ids[k];
+                }
+                TransientData d(std::in_place_type_t<Vector3>{}, n);
+                d.Push(Span<const Vector3>(v.data(), n));
+                tracer->PushMatAttribute(g, range, a, std::move(d));
+            }
+        }
+        if(!unrealOf.empty())
+        {   // (Mt)Unreal: albedo / roughness / specular / metallic as constants (ParamVarying, no textures), normalMap absent
+            const uint32_t n = uint32_t(unrealOf.size());
+            MatGroupId g = tracer->CreateMaterialGroup("(Mt)Unreal");
+            MatAttributeInfoList info = tracer->AttributeInfo(g);
+            std::vector<AttributeCountList> counts(n);
+            for(auto& c : counts)
+            {
+                c = AttributeCountList(StaticVecSize(info.size()));
+                for(size_t k = 0; k < info.size(); k++) c[k] = (info[k].isOptional == AttributeOptionality::MR_OPTIONAL) ? 0 : 1;
+            }
+            MaterialIdList ids = tracer->ReserveMaterials(g, counts);
+            tracer->CommitMatReservations(g);
+            for(uint32_t k = 0; k < n; k++) mats[unrealOf[k]] = ids[k];
+            auto range = CommonIdRange(std::bit_cast<CommonId>(ids.front()), std::bit_cast<CommonId>(ids.back()));
+            for(uint32_t a = 0; a < info.size(); a++)
+            {
+                std::vector<Optional<TextureId>> noTex(n, std::nullopt);
+                if(info[a].isTexturable == AttributeTexturable::MR_TEXTURE_ONLY)
+                {
+                    TransientData e(std::in_place_type_t<Vector3>{}, 0);
+                    tracer->PushMatAttribute(g, range, a, std::move(e), std::move(noTex));
+                }
+                else if(info[a].dataType.Name() == MRayDataEnum::MR_VECTOR_3)
+                {
+                    std::vector<Vector3> v(n);
+                    for(uint32_t k = 0; k < n; k++) v[k] = reinterpret_cast<const Vector3*>(sc->albedo)[unrealOf[k]];
+                    TransientData d(std::in_place_type_t<Vector3>{}, n);
+                    d.Push(Span<const Vector3>(v.data(), n));
+                    tracer->PushMatAttribute(g, range, a, std::move(d), std::move(noTex));
+                }
+                else
+                {
+                    const uint32_t slot = info[a].name == "roughness" ? 0u : info[a].name == "specular" ? 1u : 2u;
+                    std::vector<Float> v(n);
+                    for(uint32_t k = 0; k < n; k++) v[k] = sc->materialParams[8 * size_t(unrealOf[k]) + slot];
+                    TransientData d(std::in_place_type_t<Float>{}, n);
+                    d.Push(Span<const Float>(v.data(), n));
+                    tracer->PushMatAttribute(g, range, a, std::move(d), std::move(noTex));
+                }
+            }
         }
         // ---- lights (prim backed) ----
         LightGroupId lg = sc->lightCount ? tracer->CreateLightGroup("(L)Prim(P)Triangle", pg) : LightGroupId(0);

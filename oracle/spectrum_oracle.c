@@ -227,14 +227,17 @@ void orc_spectra_to_rgb(const orc_spectrum_tables* t, const float value[4], cons
 {
     const float OFFSET = 0.5f - (float)CIE_START;
     float xyz[3] = {0.f, 0.f, 0.f};
-    for(int i = 0; i < 4; i++)
+    /* a dispersed path ((Mt)Refract) keeps its first wavelength only: secondary waves are DISPERSED_WAVE = -1, one
+     * sample counts and the 1/4 weight becomes 1 (SpectrumContext.cu:L148-157, TracerTypes.h:L114,L386-401) */
+    const int dispersed = waves[1] == -1.0f;
+    for(int i = 0; i < (dispersed ? 1 : 4); i++)
     {
         int a, b; float f; interp1(waves[i] + OFFSET, CIE_N, &a, &b, &f);
         float val = (pdf[i] == 0.0f) ? 0.0f : value[i] / pdf[i];
         for(int c = 0; c < 3; c++)
             xyz[c] += lerpf(t->observer[3 * a + c], t->observer[3 * b + c], f) * val;
     }
-    for(int c = 0; c < 3; c++) xyz[c] *= 0.25f;
+    for(int c = 0; c < 3; c++) xyz[c] *= dispersed ? 1.0f : 0.25f;
     for(int r = 0; r < 3; r++)
         out[r] = t->xyzToRGB[3 * r] * xyz[0] + t->xyzToRGB[3 * r + 1] * xyz[1] + t->xyzToRGB[3 * r + 2] * xyz[2];
     out[3] = 0.0f;

@@ -166,7 +166,8 @@ class _DriverScene(C.Structure):
                 ("fovXY", C.c_float * 2), ("nearFar", C.c_float * 2), ("batchTransforms", C.c_void_p),
                 ("batchInstanceOf", C.c_void_p),
                 ("textureCount", C.c_uint32), ("textureInfo", C.c_void_p), ("textureBytes", C.c_void_p),
-                ("materialTexture", C.c_void_p), ("uvs", C.c_void_p), ("materialKind", C.c_void_p), ("lightTwoSided", C.c_void_p)]
+                ("materialTexture", C.c_void_p), ("uvs", C.c_void_p), ("materialKind", C.c_void_p), ("lightTwoSided", C.c_void_p),
+                ("materialParams", C.c_void_p)]
 
 
 class _DriverRender(C.Structure):
@@ -219,7 +220,8 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
                   accel_mode=1, threads=0, parallel_hint=0, near_far=(0.01, 1000.0), driver_flavour="",
                   batch_transforms=None, sampler="Independent", host_exe=False, instance_of=None,
                   textures=None, material_texture=None, region=None, material_kind=None,
-                  latency=False, burst_size=1, cam_switch=None, light_two_sided=False, film_filter=None, film_filter_radius=0.0):
+                  latency=False, burst_size=1, cam_switch=None, light_two_sided=False, film_filter=None, film_filter_radius=0.0,
+                  material_params=None):
     """Renders through TracerI. `light_material`: material id whose batch is the prim-backed light.
     batch_transforms: optional [batch, 3, 4] local->world matrices ((T)Single per batch; positions local).
     textures: list of dict(data=[h, w, 4] float32 / uint8 (RGBA), interp=, edge=); material_texture: per material id
@@ -248,6 +250,8 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
     tinfo = tbytes = mtex = None
     lts = np.array([1 if light_two_sided else 0], np.uint8)
     mkind = None if material_kind is None else np.ascontiguousarray(np.asarray(material_kind, np.uint8)[lambert])
+    # per material id 8 floats: kind 2 (Mt)Refract {cauchyFront xyz, -, cauchyBack xyz, -}, kind 3 (Mt)Unreal {roughness, specular, metallic}
+    mparams = None if material_params is None else np.ascontiguousarray(np.asarray(material_params, np.float32).reshape(-1, 8)[lambert])
     uvs = None if batched.get("uvs") is None else np.ascontiguousarray(batched["uvs"], np.float32)
     if textures:
         info, blobs, off = [], [], 0
@@ -281,7 +285,8 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
                 b"" if bt is None else bt.tobytes(), b"" if io is None else io.tobytes(),
                 b"" if tinfo is None else tinfo.tobytes(), b"" if tbytes is None else tbytes.tobytes(),
                 b"" if mtex is None else mtex.tobytes(), b"" if uvs is None else uvs.tobytes(),
-                b"" if mkind is None else mkind.tobytes(), lts.tobytes() if light_two_sided else b""]
+                b"" if mkind is None else mkind.tobytes(), lts.tobytes() if light_two_sided else b"",
+                b"" if mparams is None else mparams.tobytes()]
         with tempfile.TemporaryDirectory() as td:
             with open(os.path.join(td, "in.blob"), "wb") as f:
                 f.write(np.uint64(len(secs)).tobytes())
@@ -325,6 +330,8 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
         keep.append(mkind); sc.materialKind = mkind.ctypes.data
     if light_two_sided:
         keep.append(lts); sc.lightTwoSided = lts.ctypes.data
+    if mparams is not None:
+        keep.append(mparams); sc.materialParams = mparams.ctypes.data
     rd = _DriverRender(renderer.encode(), width, height, spp, sample_mode.encode(), (C.c_uint32 * 2)(*rr_range), seed,
                        accel_mode, parallel_hint, threads, sampler_id, (C.c_uint32 * 4)(*(region or (0, 0, 0, 0))),
                        1 if latency else 0, burst_size, cam_switch[0] if cam_switch else 0,
@@ -357,7 +364,7 @@ class _PtScene(C.Structure):
                 ("rrLo", C.c_uint32), ("rrHi", C.c_uint32), ("filterRadius", C.c_float), ("seed", C.c_uint64),
                 ("spectrum", C.c_void_p), ("wavelengthMode", C.c_uint32),
                 ("uv", C.c_void_p), ("textures", C.c_void_p), ("albedoTexture", C.c_void_p), ("nTextures", C.c_uint32),
-                ("materialType", C.c_void_p), ("filmFilter", C.c_uint32)]
+                ("materialType", C.c_void_p), ("filmFilter", C.c_uint32), ("materialParams", C.c_void_p), ("vertexTBN", C.c_void_p)]
 
 
 class _OrcTexture(C.Structure):
@@ -398,10 +405,43 @@ def oracle_texture_sample(texture, uv):
     return out
 
 
+def normals_to_tbn(normals):
+    """Per-vertex shading normals -> world -> tangent-space quaternions (w, x, y, z) the way the scene loader / the TracerI
+    driver builds them (SceneLoaderMRay.cpp:L395-436): bitangent = Graphics::OrthogonalVector(n)
+    (Core/GraphicsFunctions.h:L212-222), tangent = bitangent x n, TransformGen::ToSpaceQuat(t, b, n) (Core/Quaternion.hpp:L413-470,
+    Mike Day's matrix-to-quaternion, then conjugated)."""
+    n = np.asarray(normals, np.float32)
+    n = n / np.linalg.norm(n, axis=1, keepdims=True)
+    out = np.zeros((n.shape[0], 4), np.float32)
+    for k in range(n.shape[0]):
+        v = n[k].astype(np.float32)
+        if abs(v[0]) > abs(v[1]):
+            bt = np.array([-v[2], 0, v[0]], np.float32) / np.float32(np.sqrt(v[0] * v[0] + v[2] * v[2]))
+        else:
+            bt = np.array([0, v[2], -v[1]], np.float32) / np.float32(np.sqrt(v[1] * v[1] + v[2] * v[2]))
+        x = np.cross(bt, v).astype(np.float32); y = bt; z = v
+        if np.any(np.abs(np.cross(x, y) - z) > 0.1):
+            x = -x
+        if z[2] < 0:
+            if x[0] > y[1]:
+                t = 1 + x[0] - y[1] - z[2]; q = [y[2] - z[1], t, x[1] + y[0], z[0] + x[2]]
+            else:
+                t = 1 - x[0] + y[1] - z[2]; q = [z[0] - x[2], x[1] + y[0], t, y[2] + z[1]]
+        else:
+            if x[0] < -y[1]:
+                t = 1 - x[0] - y[1] + z[2]; q = [x[1] - y[0], z[0] + x[2], y[2] + z[1], t]
+            else:
+                t = 1 + x[0] + y[1] + z[2]; q = [t, y[2] - z[1], z[0] - x[2], x[1] - y[0]]
+        q = np.array(q, np.float64) * 0.5 / np.sqrt(max(t, 1e-30))
+        q /= np.linalg.norm(q)
+        out[k] = [q[0], -q[1], -q[2], -q[3]]          # Conjugate
+    return np.ascontiguousarray(out)
+
+
 def oracle_render(positions, indices, tri_material, albedo, radiance, camera, width, height, spp,
                   sample_mode=2, rr_range=(2, 20), seed=0, near_far=(0.01, 1000.0), threads=None,
                   spectral_data=None, wavelength_mode=2, textures=None, albedo_texture=None, vertex_uvs=None,
-                  material_type=None, light_two_sided=None, film_filter=None, film_filter_radius=1.0):
+                  material_type=None, light_two_sided=None, film_filter=None, film_filter_radius=1.0, material_params=None, vertex_normals=None):
     """tri_material: per triangle, >= 0 Lambert material index, -1 - k for light k. Returns image[h,w,3]
     (row 0 = bottom) resolved as sum radiance / sum weight. spectral_data (mray_b200.spectral.load())
     switches to the hero-wavelength spectral estimator."""
@@ -436,9 +476,15 @@ def oracle_render(positions, indices, tri_material, albedo, radiance, camera, wi
         uvs = None if vertex_uvs is None else np.ascontiguousarray(vertex_uvs, np.float32)
         s.textures, s.nTextures, s.albedoTexture = C.addressof(tarr), len(textures), at.ctypes.data
         s.uv = None if uvs is None else uvs.ctypes.data
-    if material_type is not None:     # per material: 0 (Mt)Lambert, 1 (Mt)Reflect
+    if material_type is not None:     # per material: 0 (Mt)Lambert, 1 (Mt)Reflect, 2 (Mt)Refract, 3 (Mt)Unreal
         mt = np.ascontiguousarray(material_type, np.uint8)
         s.materialType = mt.ctypes.data
+    if vertex_normals is not None:    # smooth shading: per-vertex tangent frames as the loader builds them from normals
+        tq = normals_to_tbn(vertex_normals)
+        s.vertexTBN = tq.ctypes.data
+    if material_params is not None:   # [material, 8]: Refract cauchyFront / cauchyBack, Unreal roughness / specular / metallic
+        mp = np.ascontiguousarray(material_params, np.float32).reshape(-1, 8)
+        s.materialParams = mp.ctypes.data
     out = np.zeros((4, height, width), np.float32)
     threads = threads or min(16, os.cpu_count() or 1)
     rows = np.linspace(0, height, threads * 4 + 1).astype(int)

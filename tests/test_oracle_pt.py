@@ -192,3 +192,68 @@ def test_two_sided_light_oracle_matches_reference_render():
     assert np.allclose(img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=5e-3), (img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)))
     # the attribute matters: brighter than the one-sided image
     assert ref.mean() > 1.02 * ref_image("cornell64_spp16384").mean()
+
+
+def glossy():
+    """scenes.cornell_glossy() in oracle shape: flat material table without the light row."""
+    from mray_b200 import scenes
+    c = scenes.cornell_glossy()
+    order = {0: 0, 1: 1, 2: 2, 4: 3, 5: 4}
+    tm = np.array([-1 if m == 3 else order[int(m)] for m in c["material"]], np.int32)
+    rows = [0, 1, 2, 4, 5]
+    return c, tm, c["albedo"][rows], c["material_type"][rows], c["material_params"][rows]
+
+
+def test_refract_closed_forms():
+    """(Mt)Refract: equal indices of refraction on both sides make the interface invisible (Fresnel 0, straight-through
+    refraction): a camera looking at a one-sided light through two such panes sees exactly its radiance."""
+    L = 3.0
+    pane1 = np.array([[-5, -5, 1], [5, -5, 1], [5, 5, 1], [-5, 5, 1]], np.float32)
+    pane2 = pane1 + np.array([0, 0, -1], np.float32)
+    light = np.array([[-30, -30, -3], [30, -30, -3], [30, 30, -3], [-30, 30, -3]], np.float32)   # faces +z
+    pos = np.concatenate([pane1, pane2, light])
+    idx = np.array([[0, 1, 2], [0, 2, 3], [4, 5, 6], [4, 6, 7], [8, 9, 10], [8, 10, 11]], np.uint32)
+    tm = np.array([0, 0, 0, 0, -1, -1], np.int32)
+    cam = dict(eye=(0.0, 0.0, 4.0), gaze=(0.0, 0.0, 0.0), up=(0.0, 1.0, 0.0), fov_y_deg=20.0)
+    mp = np.zeros((1, 8), np.float32); mp[0, 0] = 1.3; mp[0, 4] = 1.3
+    for mode in (0, 1, 2):
+        img = O.oracle_render(pos, idx, tm, [[0.5, 0.5, 0.5]], [L, L, L], cam, 8, 8, 16, sample_mode=mode, material_type=[2], material_params=mp)
+        assert np.allclose(img, L, rtol=1e-5), (mode, img.min(), img.max())
+
+
+def test_glossy_oracle_matches_reference_render():
+    """(Mt)Unreal + (Mt)Refract against the reference's render of scenes.cornell_glossy (RGB renderer). The glass box
+    makes the scene noisy (caustic paths): 8x8 block means carry the converged comparison."""
+    path = os.path.join(GOLDEN, "render_cornell64_glossy_spp16384.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden image was not generated")
+    c, tm, alb, mtype, mparams = glossy()
+    ref = ref_image("cornell64_glossy_spp16384")
+    img = O.oracle_render(c["positions"], c["indices"], tm, alb, c["radiance"], c["camera"], 64, 64, 1024,
+                          sample_mode=2, seed=47, material_type=mtype, material_params=mparams)
+    err = rel_mse(block_mean(img, 8), block_mean(ref, 8))
+    assert err <= 2e-3, err
+    assert np.allclose(img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=0.02), (img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)))
+    assert rel_mse(block_mean(ref, 8), block_mean(ref_image("cornell64_spp16384"), 8)) > 5e-3     # the materials are visible
+
+
+def test_smooth_normals_oracle_matches_reference_render():
+    """Shading normals that differ from the geometric ones: the 80-triangle sphere with radial vertex normals
+    (scenes.cornell_sphere) against the reference's render — the interpolated tangent frames of Triangle::GenerateSurface
+    (Quaternion::BarySLerp of the vertex quaternions, Z axis as the shading normal)."""
+    path = os.path.join(GOLDEN, "render_cornell64_sphere_spp16384.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden image was not generated")
+    from mray_b200 import scenes
+    c = scenes.cornell_sphere()
+    tm = np.where(c["material"] == 3, -1, c["material"]).astype(np.int32)
+    ref = ref_image("cornell64_sphere_spp16384")
+    img = O.oracle_render(c["positions"], c["indices"], tm, c["albedo"][:3], c["radiance"], c["camera"], 64, 64, 1024,
+                          sample_mode=2, seed=48, vertex_normals=c["normals"])
+    err = rel_mse(block_mean(img, 4), block_mean(ref, 4))
+    assert err <= 1e-3, err
+    assert np.allclose(img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=0.01), (img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)))
+    # the smooth normals matter: the same mesh shaded with its face normals is visibly different on the sphere
+    flat = O.oracle_render(c["positions"], c["indices"], tm, c["albedo"][:3], c["radiance"], c["camera"], 64, 64, 1024, sample_mode=2, seed=49)
+    sphere = (slice(4, 24), slice(36, 60))          # rows / columns covering the sphere (row 0 = bottom)
+    assert rel_mse(img[sphere], ref[sphere]) < 0.5 * rel_mse(flat[sphere], ref[sphere])
