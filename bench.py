@@ -304,7 +304,9 @@ def run_ours(args):
                      "traffic": TRAFFIC_CLOSEST, "algorithmic_bytes_per_launch": round(rays_per_launch * BYTES_CLOSEST),
                      "rays_per_launch": round(rays_per_launch), "mean_launch_ms": round(mean_launch_ms, 4),
                      "launch_samples": tc_n, "bytes_per_ray": BYTES_CLOSEST, "peak_source": peak_src,
-                     "issue": ISSUE_ROOFLINE},
+                     # second roofline (the kernel is issue-bound, not byte-bound): warp-instructions per second against
+                     # 148 SMs x 4 schedulers x SM clock, one warp-instruction per scheduler per cycle
+                     "issue": issue_roofline(rays_per_launch, mean_launch_ms, clocks)},
     }
     if rank == 0:
         if world == 1 and os.environ.get("MRB_BENCH_SKIP_CPU") is None:
@@ -317,9 +319,21 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-# filled from the ncu captures under profiles/ (see profiles/r2_*.md); None until a capture of this round exists
-TRAFFIC_CLOSEST = None
-ISSUE_ROOFLINE = None
+# From the ncu --set full capture of one mid-render KTraceWide<closest> launch (profiles/r2_pt_kernels.md, launch 0):
+# dram__bytes_read.sum 93.0 MB + dram__bytes_write.sum 69.6 MB (rays in, hits out: the BVH itself stays in L2), and
+# smsp__inst_executed.sum 774.2 M warp-instructions for the 2.06 M rays of that launch.
+TRAFFIC_CLOSEST = 93_007_872 + 69_567_744
+WARP_INST_PER_CLOSEST_RAY = 774_216_416 / 2_064_000
+
+
+def issue_roofline(rays_per_launch, mean_launch_ms, clocks):
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    peak = 148 * 4 * sm_mhz * 1e6 / 1e9                              # G warp-instructions / s
+    achieved = WARP_INST_PER_CLOSEST_RAY * rays_per_launch / (mean_launch_ms * 1e-3) / 1e9
+    return {"bound": "issue", "achieved": round(achieved, 1), "peak": round(peak, 1), "unit": "Gwarp-inst/s",
+            "frac": round(achieved / peak, 4), "warp_inst_per_ray": round(WARP_INST_PER_CLOSEST_RAY, 1),
+            "lanes_per_inst": 20.0, "source": "profiles/r2_pt_kernels.md (ncu smsp__inst_executed.sum, "
+            "smsp__thread_inst_executed_per_inst_executed.ratio)"}
 
 
 def config2_leg(ctx, acc, sc, stream, rank, peak):
