@@ -62,7 +62,7 @@ typedef struct mrb_meta_hit { float a, b; } mrb_meta_hit;
 /* ---- library / context ------------------------------------------------------------------ */
 
 /* ABI version of this header (major<<16 | minor); the descriptor struct layouts are part of it. */
-#define MRB_ABI_VERSION ((0u << 16) | 3u)
+#define MRB_ABI_VERSION ((0u << 16) | 4u)
 MRB_API uint32_t mrb_abi_version(void);
 
 /* Replaces GPUSystem + GPUQueue ownership inside TracerBase (Device/CUDA/GPUSystemCUDA.cpp:L249-405:
@@ -339,6 +339,7 @@ typedef enum mrb_material_type
     MRB_MATERIAL_LAMBERT = 0, MRB_MATERIAL_REFLECT = 1, MRB_MATERIAL_REFRACT = 2, MRB_MATERIAL_UNREAL = 3
 } mrb_material_type;
 /* FilterType::E (Core/TracerEnums.h:L162-173) */
+typedef enum mrb_boundary_type { MRB_BOUNDARY_NULL = 0, MRB_BOUNDARY_SKYSPHERE_SPHERICAL = 1, MRB_BOUNDARY_SKYSPHERE_COOCTA = 2 } mrb_boundary_type;
 typedef enum mrb_film_filter { MRB_FILTER_BOX = 0, MRB_FILTER_TENT = 1, MRB_FILTER_GAUSSIAN = 2, MRB_FILTER_MITCHELL_NETRAVALI = 3 } mrb_film_filter;
 
 /* One 2-D texture of the renderer (first slice): what TracerI::CreateTexture2D +
@@ -445,6 +446,22 @@ typedef struct mrb_render_desc
      * instance or NULL entries (two-level scenes). */
     const float*    vertexTBN;
     const float* const* instanceVertexTBN;
+    /* The boundary light surface (TracerI::SetBoundarySurface): what a ray that leaves the scene sees, and one more entry
+     * (the last) of the uniform light sampler. MRB_BOUNDARY_NULL = (L)Null. The skyspheres (LightGroupSkysphere<
+     * SphericalCoordConverter / CoOctaCoordConverter>, Tracer/LightsDefault.hpp:L173-443) map the Y-up direction to a uv
+     * on a latitude-longitude or concentric-octahedral map; boundaryTexture < 0: constant boundaryRadiance (sampled uniformly
+     * in uv), else an index into `textures` holding the radiance map, importance-sampled through the piecewise-constant
+     * 2-D distribution of its luminance (built at create time, see mrb_dist2d_build). boundaryTransform: NULL = (T)Identity,
+     * else the row-major 3x4 local -> world matrix of the light surface's (T)Single transform (directions use its linear
+     * part). sceneDiameter: how far away NEE places the sampled point; 0 = the reference's choice, the length of the XZ
+     * span of the scene AABB (Tracer/TracerBase.cpp:L1653-1664). luminanceRow: the Y row of the global texture colour
+     * space's RGB -> XYZ matrix (KCExtractLuminance, Tracer/ColorConverter.cu:L405-476); all zero = ACES_CG. */
+    uint32_t        boundaryType;        /* mrb_boundary_type */
+    int32_t         boundaryTexture;
+    float           boundaryRadiance[3];
+    const float*    boundaryTransform;
+    float           sceneDiameter;
+    float           luminanceRow[3];
 } mrb_render_desc;
 
 typedef struct mrb_render_stats
@@ -518,6 +535,27 @@ MRB_API float*     mrb_renderer_film_device_ptr(mrb_renderer r);
  * single-level texture (Tracer/TextureView.hpp:L70-85 -> Device/CPU/TextureViewCPU.h:L397-470). Host pointers:
  * uv[count*2] -> rgbOut[count*3]. */
 MRB_API mrb_status mrb_texture_sample(mrb_context ctx, const mrb_texture_desc* texture, const float* uv, uint32_t count, float* rgbOut);
+
+/* ---- piecewise-constant 2-D distribution + skysphere maps ---------------------------------- */
+
+/* DistributionGroupPwC2D::Construct (Tracer/Distributions.cu:L437-503): function = height rows of width values (a
+ * texture's luminance) -> cdfX (width*height: the normalised inclusive CDF of |f| along every row) and cdfY (height: the
+ * normalised CDF of the row sums). Row sums accumulate in fp64 and are stored as fp32, the marginal accumulates in fp32 in
+ * row order, both are normalised by 1 / last in fp64 — the arithmetic of the reference's host-backend kernels. */
+MRB_API mrb_status mrb_dist2d_build(mrb_context ctx, const float* function, uint32_t width, uint32_t height,
+                                    float* cdfX, float* cdfY, mrb_memspace memspace);
+/* DistributionPwC<2>::SampleUV + PdfUV (Tracer/Distributions.h:L183-239) for `count` random pairs xi[count*2]:
+ * out[count*4] = {u, v, pdf of the sample, PdfUV(u, v)}. (Tests/Tracer/T_Distributions.cu:L17-44 KCSampleDist) */
+MRB_API mrb_status mrb_dist2d_sample(mrb_context ctx, const float* cdfX, const float* cdfY, uint32_t width, uint32_t height,
+                                     const float* xi, uint32_t count, float* out, mrb_memspace memspace);
+/* Parity tap of the skysphere coordinate converters (Tracer/LightsDefault.hpp:L173-310): per unit Y-up direction
+ * dirs[count*3] -> out[count*8] = {DirToUV u, v, ToSolidAnglePdf(1, dir), UVToDir(DirToUV(dir)) xyz, ToSolidAnglePdf(1, uv), 0}.
+ * converter: MRB_BOUNDARY_SKYSPHERE_SPHERICAL or _COOCTA. */
+MRB_API mrb_status mrb_skysphere_convert(mrb_context ctx, uint32_t converter, const float* dirs, uint32_t count, float* out,
+                                         mrb_memspace memspace);
+/* KCExtractLuminance (Tracer/ColorConverter.cu:L405-476) of a single-level texture: out[width*height] (host) =
+ * luminanceRow . rgb of every texel. Host pointers. */
+MRB_API mrb_status mrb_texture_luminance(mrb_context ctx, const mrb_texture_desc* texture, const float luminanceRow[3], float* out);
 
 /* ---- device algorithms (Device/GPUAlgRadixSort.h, exposed for parity tests) -------------- */
 

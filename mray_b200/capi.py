@@ -80,7 +80,9 @@ class RenderDesc(C.Structure):
                 ("vertexUVs", C.c_void_p), ("instanceVertexUVs", C.POINTER(C.c_void_p)),
                 ("fullResolution", C.c_uint32 * 2), ("regionMin", C.c_uint32 * 2), ("materialType", C.c_void_p),
                 ("filmFilterType", C.c_uint32), ("sampleOffset", C.c_uint32), ("jobSPP", C.c_uint32), ("materialParams", C.c_void_p),
-                ("vertexTBN", C.c_void_p), ("instanceVertexTBN", C.POINTER(C.c_void_p))]
+                ("vertexTBN", C.c_void_p), ("instanceVertexTBN", C.POINTER(C.c_void_p)),
+                ("boundaryType", C.c_uint32), ("boundaryTexture", C.c_int32), ("boundaryRadiance", C.c_float * 3),
+                ("boundaryTransform", C.c_void_p), ("sceneDiameter", C.c_float), ("luminanceRow", C.c_float * 3)]
 
 
 class TextureDesc(C.Structure):
@@ -103,10 +105,11 @@ class KernelProfile(C.Structure):
 
 PROFILE_KINDS = ["trace_closest", "shade", "trace_any", "finish_reload", "trace_tail"]
 SAMPLE_MODES = {"Pure": 0, "WithNextEventEstimation": 1, "WithNEEAndMIS": 2}
+BOUNDARY_TYPES = {"Null": 0, "Skysphere_Spherical": 1, "Skysphere_CoOcta": 2}   # (L)Null / LightGroupSkysphere<...>
 FILM_FILTERS = {"Box": 0, "Tent": 1, "Gaussian": 2, "Mitchell-Netravali": 3}   # FilterType::E (Core/TracerEnums.h:L162-173)
 HOST_FN = C.CFUNCTYPE(None, C.c_void_p)
 # the descriptor mirrors above are written for this ABI (include/mray_b200.h: MRB_ABI_VERSION)
-MRB_ABI_VERSION = (0 << 16) | 3
+MRB_ABI_VERSION = (0 << 16) | 4
 
 # every symbol include/mray_b200.h declares (tests/test_capi_symbols.py checks the header against this)
 _PROTOTYPES = {
@@ -161,6 +164,10 @@ _PROTOTYPES = {
     "mrb_host_free": (None, [C.c_void_p, C.c_void_p]),
     "mrb_filter_sample": (C.c_int, [C.c_void_p, C.c_uint32, C.c_float, C.c_void_p, C.c_uint32, C.c_void_p]),
     "mrb_texture_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "mrb_dist2d_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]),
+    "mrb_dist2d_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]),
+    "mrb_skysphere_convert": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]),
+    "mrb_texture_luminance": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]),
     "mrb_multi_partition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                       C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "mrb_binary_partition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]),
@@ -482,12 +489,14 @@ class Renderer:
                  max_path_count=0, partition_rays=False, instance_vertex_normals=None, spectrum=None, sampler="Independent",
                  textures=None, albedo_texture=None, vertex_uvs=None, instance_vertex_uvs=None,
                  full_resolution=None, region_min=(0, 0), material_type=None, film_filter="Gaussian",
-                 sample_offset=0, job_spp=0, material_params=None, vertex_tbn=None):
+                 sample_offset=0, job_spp=0, material_params=None, vertex_tbn=None, boundary=None):
         """`accel` is an Accelerator, or a Scene (two-level; vertex_count / triangle_count / vertex_normals
         are then ignored and instance_vertex_normals may hold one array or None per instance).
         textures: list of dict(data=[h, w, 3|4] float32 or uint8 array, interp="Linear"|"Nearest",
         edge="Wrap"|"Clamp"|"Mirror"); albedo_texture: per material, -1 or an index into `textures`;
-        vertex_uvs [V, 2] (instance_vertex_uvs: one array or None per instance of a Scene)."""
+        vertex_uvs [V, 2] (instance_vertex_uvs: one array or None per instance of a Scene).
+        boundary: None = (L)Null, or dict(type="Skysphere_Spherical"|"Skysphere_CoOcta", radiance=(r, g, b) | texture=index into
+        `textures`, transform=[3, 4] local -> world or None, scene_diameter=0 (the reference's XZ diagonal))."""
         self.ctx, self.accel, self.spectrum = ctx, accel, spectrum
         self.width, self.height = width, height
         d = RenderDesc()
@@ -579,6 +588,15 @@ class Renderer:
                 d.instanceVertexUVs = C.cast(uptrs, C.POINTER(C.c_void_p))
         else:
             d.vertexUVs = host(vertex_uvs, np.float32)
+        d.boundaryTexture = -1
+        if boundary is not None:
+            d.boundaryType = BOUNDARY_TYPES[boundary["type"]]
+            d.boundaryTexture = int(boundary.get("texture", -1))
+            d.boundaryRadiance = (C.c_float * 3)(*boundary.get("radiance", (0.0, 0.0, 0.0)))
+            d.boundaryTransform = host(boundary.get("transform"), np.float32)
+            d.sceneDiameter = float(boundary.get("scene_diameter", 0.0))
+            if "luminance_row" in boundary:
+                d.luminanceRow = (C.c_float * 3)(*boundary["luminance_row"])
         h = C.c_void_p()
         ctx.check(ctx.lib.mrb_renderer_create(ctx.handle, C.byref(d), C.byref(h)))
         self.handle = h
@@ -738,6 +756,57 @@ def texture_sample(ctx: Context, texture, uv):
     uv = np.ascontiguousarray(uv, np.float32)
     out = np.zeros((uv.shape[0], 3), np.float32)
     ctx.check(ctx.lib.mrb_texture_sample(ctx.handle, C.byref(t), uv.ctypes.data, uv.shape[0], out.ctypes.data))
+    return out
+
+
+def _texture_desc(texture):
+    a = np.ascontiguousarray(texture["data"])
+    if a.dtype != np.uint8:
+        a = np.ascontiguousarray(a, np.float32)
+    t = TextureDesc()
+    t.data = a.ctypes.data
+    t.height, t.width, t.channels = a.shape
+    t.format = 1 if a.dtype == np.uint8 else 0
+    t.interp, t.edge = TEX_INTERP[texture.get("interp", "Linear")], TEX_EDGE[texture.get("edge", "Wrap")]
+    return t, a
+
+
+ACES_CG_LUMINANCE_ROW = (float.fromhex("0x1.1614ep-2"), float.fromhex("0x1.58e6fep-1"), float.fromhex("0x1.d946e6p-5"))
+
+
+def texture_luminance(ctx: Context, texture, luminance_row=ACES_CG_LUMINANCE_ROW):
+    """mrb_texture_luminance (KCExtractLuminance): -> [h, w] float32."""
+    t, keep = _texture_desc(texture)
+    out = np.zeros((t.height, t.width), np.float32)
+    ctx.check(ctx.lib.mrb_texture_luminance(ctx.handle, C.byref(t), (C.c_float * 3)(*luminance_row), out.ctypes.data))
+    return out
+
+
+def dist2d_build(ctx: Context, function):
+    """mrb_dist2d_build (DistributionGroupPwC2D::Construct): function [h, w] -> (cdf_x [h, w], cdf_y [h])."""
+    f = np.ascontiguousarray(function, np.float32)
+    h, w = f.shape
+    cx, cy = np.zeros((h, w), np.float32), np.zeros(h, np.float32)
+    ctx.check(ctx.lib.mrb_dist2d_build(ctx.handle, f.ctypes.data, w, h, cx.ctypes.data, cy.ctypes.data, MRB_MEM_HOST))
+    return cx, cy
+
+
+def dist2d_sample(ctx: Context, cdf_x, cdf_y, xi):
+    """mrb_dist2d_sample: xi [n, 2] -> [n, 4] = (u, v, SampleUV pdf, PdfUV(u, v))."""
+    cx, cy = np.ascontiguousarray(cdf_x, np.float32), np.ascontiguousarray(cdf_y, np.float32)
+    xi = np.ascontiguousarray(xi, np.float32).reshape(-1, 2)
+    out = np.zeros((xi.shape[0], 4), np.float32)
+    ctx.check(ctx.lib.mrb_dist2d_sample(ctx.handle, cx.ctypes.data, cy.ctypes.data, cx.shape[1], cx.shape[0], xi.ctypes.data, xi.shape[0],
+                                        out.ctypes.data, MRB_MEM_HOST))
+    return out
+
+
+def skysphere_convert(ctx: Context, converter, dirs):
+    """mrb_skysphere_convert: unit Y-up dirs [n, 3] -> [n, 8] (see the header)."""
+    dirs = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+    out = np.zeros((dirs.shape[0], 8), np.float32)
+    c = BOUNDARY_TYPES[converter] if isinstance(converter, str) else int(converter)
+    ctx.check(ctx.lib.mrb_skysphere_convert(ctx.handle, c, dirs.ctypes.data, dirs.shape[0], out.ctypes.data, MRB_MEM_HOST))
     return out
 
 

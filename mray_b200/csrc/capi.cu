@@ -2,6 +2,7 @@
 // MRB_MEM_HOST variants, exception -> status translation. No CPU fallback anywhere.
 #include "accel.cuh"
 #include "spectrum.cuh"
+#include "dist2d.cuh"
 #include <cstring>
 #include <initializer_list>
 #include <vector>
@@ -96,7 +97,7 @@ static mrb_status Fail(mrb::Context& c, mrb_status s, const char* msg) { c.error
 extern "C"
 {
 
-uint32_t mrb_abi_version(void) { return MRB_ABI_VERSION; }   // 3: film filter type, sample offsets, passes, NEE sample counter
+uint32_t mrb_abi_version(void) { return MRB_ABI_VERSION; }   // 4: boundary light (skysphere) fields of mrb_render_desc, mrb_dist2d_*
 
 mrb_status mrb_context_create(int device, mrb_context* out)
 {
@@ -800,6 +801,75 @@ mrb_status mrb_texture_sample(mrb_context ctx, const mrb_texture_desc* texture, 
     });
 }
 
+
+mrb_status mrb_dist2d_build(mrb_context ctx, const float* function, uint32_t width, uint32_t height, float* cdfX, float* cdfY, mrb_memspace memspace)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!function || !cdfX || !cdfY) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        if(width == 0 || height == 0) return Fail(c, MRB_ERR_INVALID_ARG, "empty distribution");
+        const size_t n = size_t(width) * height;
+        if(n > 0xFFFFFFFFull / 4) return Fail(c, MRB_ERR_INVALID_ARG, "distribution too large");
+        return Staged(c, memspace, {{const_cast<float*>(function), n * 4, true, false, nullptr}, {cdfX, n * 4, false, true, nullptr},
+                                    {cdfY, size_t(height) * 4, false, true, nullptr}, {nullptr, 0, false, false, nullptr}},
+                      [&](std::vector<StagedArray>& a)
+                      {
+                          // row totals: scratch of the build (the staging block when staged, the trace scratch for device arrays)
+                          c.traceScratch.Reserve(size_t(height) * 4);
+                          mrb::Dist2DBuild(c, static_cast<const float*>(a[0].dev), width, height, static_cast<float*>(a[1].dev),
+                                           static_cast<float*>(a[2].dev), static_cast<float*>(c.traceScratch.Base()));
+                      });
+    });
+}
+
+mrb_status mrb_dist2d_sample(mrb_context ctx, const float* cdfX, const float* cdfY, uint32_t width, uint32_t height,
+                             const float* xi, uint32_t count, float* out, mrb_memspace memspace)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!cdfX || !cdfY || (count && (!xi || !out))) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        if(width == 0 || height == 0) return Fail(c, MRB_ERR_INVALID_ARG, "empty distribution");
+        if(count == 0) return MRB_OK;
+        const size_t n = size_t(width) * height;
+        return Staged(c, memspace, {{const_cast<float*>(cdfX), n * 4, true, false, nullptr}, {const_cast<float*>(cdfY), size_t(height) * 4, true, false, nullptr},
+                                    {const_cast<float*>(xi), size_t(count) * 8, true, false, nullptr}, {out, size_t(count) * 16, false, true, nullptr}},
+                      [&](std::vector<StagedArray>& a)
+                      {
+                          const mrb::Dist2D d{static_cast<const float*>(a[0].dev), static_cast<const float*>(a[1].dev), width, height};
+                          mrb::Dist2DSample(c, d, static_cast<const float*>(a[2].dev), count, static_cast<float*>(a[3].dev));
+                      });
+    });
+}
+
+mrb_status mrb_skysphere_convert(mrb_context ctx, uint32_t converter, const float* dirs, uint32_t count, float* out, mrb_memspace memspace)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(converter != MRB_BOUNDARY_SKYSPHERE_SPHERICAL && converter != MRB_BOUNDARY_SKYSPHERE_COOCTA)
+            return Fail(c, MRB_ERR_INVALID_ARG, "converter must be one of the skysphere types");
+        if(count && (!dirs || !out)) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        if(count == 0) return MRB_OK;
+        return Staged(c, memspace, {{const_cast<float*>(dirs), size_t(count) * 12, true, false, nullptr}, {out, size_t(count) * 32, false, true, nullptr}},
+                      [&](std::vector<StagedArray>& a)
+                      { mrb::SkyConverters(c, converter, static_cast<const float*>(a[0].dev), count, static_cast<float*>(a[1].dev)); });
+    });
+}
+
+mrb_status mrb_texture_luminance(mrb_context ctx, const mrb_texture_desc* texture, const float luminanceRow[3], float* out)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!texture || !luminanceRow || !out || !texture->data) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        if(texture->width == 0 || texture->height == 0 || (texture->channels != 3 && texture->channels != 4) || texture->format > 1u)
+            return Fail(c, MRB_ERR_INVALID_ARG, "bad texture descriptor");
+        const size_t n = size_t(texture->width) * texture->height;
+        const size_t texBytes = n * texture->channels * (texture->format == 0u ? 4u : 1u);
+        return Staged(c, MRB_MEM_HOST, {{const_cast<void*>(texture->data), texBytes, true, false, nullptr}, {out, n * 4, false, true, nullptr}},
+                      [&](std::vector<StagedArray>& a)
+                      { mrb::TextureLuminance(c, a[0].dev, texture->width, texture->height, texture->channels, texture->format, luminanceRow,
+                                              static_cast<float*>(a[1].dev)); });
+    });
+}
 
 mrb_status mrb_multi_partition(mrb_context ctx, uint32_t* keys, uint32_t* indices, uint32_t count,
                                const uint32_t dataBitRange[2], const uint32_t batchBitRange[2],

@@ -22,6 +22,7 @@
 #include "accel.cuh"
 #include "spectrum.cuh"
 #include "sampler.cuh"
+#include "dist2d.cuh"
 #include <cfloat>
 #include <stdexcept>
 #include <cstring>
@@ -302,6 +303,14 @@ struct RenderData
     float4*           wavePdf;         // per slot: their pdfs
     const EmissiveTri* lights;         // one per emissive triangle (MetaLight list), world space
     uint32_t          lightCount;      // emissive triangles (+1 boundary light in the sampler)
+    // boundary light: 0 = (L)Null, 1 = (L)Skysphere_Spherical, 2 = (L)Skysphere_CoOcta (Tracer/LightsDefault.hpp:L310-443)
+    uint32_t          boundaryType;
+    int32_t           boundaryTex;     // radiance texture (index into textures) or -1 = constant
+    float4            boundaryRadiance;// constant radiance: rgb, or Jakob coefficients + scale when spectral
+    Dist2D            boundaryDist;    // luminance distribution of the radiance texture (textured skysphere only)
+    float             boundaryM[9], boundaryInvM[9]; // linear part of the light surface's transform and its inverse (ApplyV / InvApplyV)
+    uint32_t          boundaryIdentity;
+    float             sceneDiameter;
     Camera            cam;
     uint32_t          width, height;   // the tile (region) of the current pass
     uint32_t          fullWidth, fullHeight, regionX, regionY; // the image it is a region of
@@ -747,6 +756,39 @@ __device__ __forceinline__ Float3 ShadingNormalFromTBN(float4 q0, float4 q1, flo
     return F3(2.0f * (x * z - w * y), 2.0f * (y * z + w * x), w * w - x * x - y * y + z * z);
 }
 
+// ---- LightSkysphere (Tracer/LightsDefault.hpp:L310-443): the boundary light as an environment sphere ----
+// TransformContext::ApplyV / InvApplyV of the light surface's transform (the linear part only: directions)
+__device__ __forceinline__ Float3 SkyApply(const float* m, Float3 v)
+{
+    return F3(Dot(F3(m[0], m[1], m[2]), v), Dot(F3(m[3], m[4], m[5]), v), Dot(F3(m[6], m[7], m[8]), v));
+}
+// radiance(uv) converted to the path's wavelengths (ParamVaryingData<2, Vector3> behind the SpectrumConverter)
+__device__ __forceinline__ Spec SkyRadiance(const RenderData& d, float2 uv, float4 waves)
+{
+    if(d.boundaryTex < 0) return RadianceAt(d, d.boundaryRadiance, waves);
+    const Float3 rgb = SampleTexture(d.textures[d.boundaryTex], uv.x, uv.y);
+    if(d.spectral) return RadianceAt(d, FetchRadianceCoeffs(d.spec, rgb.x, rgb.y, rgb.z), waves);
+    return S4(rgb.x, rgb.y, rgb.z, 0.0f);
+}
+// EmitViaHit / EmitViaSurfacePoint (L408-443): the direction alone decides
+__device__ __forceinline__ Spec SkyEmit(const RenderData& d, Float3 wO, float4 waves)
+{
+    Float3 dir = wO * -1.0f;
+    if(!d.boundaryIdentity) dir = SkyApply(d.boundaryInvM, dir);
+    dir = Normalize(dir);
+    const float2 uv = (d.boundaryTex < 0) ? make_float2(0.f, 0.f) : SkyDirToUV(d.boundaryType, dir.x, dir.y, dir.z);
+    return SkyRadiance(d, uv, waves);
+}
+// PdfSolidAngle (L359-370)
+__device__ __forceinline__ float SkyPdfSolidAngle(const RenderData& d, Float3 dirWorld)
+{
+    const Float3 dirYUp = d.boundaryIdentity ? dirWorld : SkyApply(d.boundaryInvM, dirWorld);
+    const Float3 n = Normalize(dirYUp);
+    const float2 uv = SkyDirToUV(d.boundaryType, n.x, n.y, n.z);
+    const float pdf = (d.boundaryTex < 0) ? 1.0f : DistPdfUV(d.boundaryDist, uv.x, uv.y);
+    return SkyPdfFromDir(d.boundaryType, pdf, dirYUp.y);
+}
+
 // LightPrim::EmitViaHit / EmitViaSurfacePoint for a constant radiance (LightsDefault.hpp:L129-168)
 __device__ __forceinline__ Spec Emit(const RenderData& d, const EmissiveTri& l, Float3 n, Float3 wO, float4 waves)
 {
@@ -775,7 +817,8 @@ __global__ void __launch_bounds__(RTPB) KGenWorkKeys(RenderData d)
 
 // Shading of one slot. Returns true when the slot held a live path (= one closest-hit ray was cast for it
 // this bounce); castShadow reports an NEE shadow ray.
-// GLOSSY: the scene has (Mt)Refract / (Mt)Unreal materials (their code costs 16 registers, so scenes without them run the lean kernel)
+// GLOSSY (the full-featured kernel): the scene has (Mt)Refract / (Mt)Unreal materials or a skysphere boundary light (their code
+// costs 16-30 registers, so scenes without them run the lean kernel)
 template<bool GLOSSY>
 __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool& castShadow, bool& neeSample)
 {
@@ -798,7 +841,27 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
 
     if(keys.x == INVALID_U32)
     {
-        // boundary light (Null): no emission; path ends (LightWorkFunction[WithNEE]::Call)
+        // boundary light (LightWorkFunction[WithNEE]::Call for a light that is not primitive backed). (L)Null emits
+        // nothing; a skysphere emits along the ray's direction, MIS-weighted against its own solid-angle pdf.
+        if(GLOSSY && d.boundaryType != 0u)
+        {
+            bool count = true;
+            if(d.sampleMode == 1u && type != RAY_CAMERA && type != RAY_SPECULAR) count = false;
+            if(count)
+            {
+                if(d.sampleMode == 2u && type == RAY_PATH)
+                {
+                    const float pdfB = __uint_as_float(meta.w);
+                    const float pdfL = SkyPdfSolidAngle(d, rd) * (1.0f / float(d.lightCount + 1u));
+                    const float mis = pdfB + pdfL;
+                    throughput = throughput * pdfB;
+                    throughput = (mis == 0.0f) ? S4(0, 0, 0, 0) : throughput * (1.0f / mis);
+                }
+                const Spec em = SkyEmit(d, rd * -1.0f, waves);
+                if(depth + 1u <= d.rrHi)
+                    d.radiance[i] = F4(S4(d.radiance[i]) + em * throughput);
+            }
+        }
         d.meta[i].x = PackPD(depth, ST_DEAD, type);
         return true;
     }
@@ -964,25 +1027,43 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
         uint32_t li = min(uint32_t(xs * float(nLights)), nLights - 1u);
         newType = RAY_SHADOW;
         neeSample = !specularMat;
-        if(li < d.lightCount && !specularMat)
+        if((li < d.lightCount || (GLOSSY && d.boundaryType != 0u)) && !specularMat)
         {
-            const EmissiveTri l = d.lights[li];
-            // Triangle::SampleSurface (Osada)
-            const float r1s = sqrtf(x0), r2s = x1;
-            const float la = 1.0f - r1s, lb = (1.0f - r2s) * r1s, lc = r1s * r2s;
-            const Float3 lp0 = F3(l.p0.x, l.p0.y, l.p0.z), le0 = F3(l.e0.x, l.e0.y, l.e0.z), le1 = F3(l.e1.x, l.e1.y, l.e1.z);
-            const Float3 lpos = lp0 * la + (lp0 + le0) * lb + (lp0 + le1) * lc;
-            const Float3 lN = Normalize(Cross(le0, le1));
-            // LightPrim::SampleSolidAngle
-            Float3 sdir = pos - lpos;
-            const float distSqr = Dot(sdir, sdir);
-            sdir = Normalize(sdir);
-            float NdL = Dot(lN, sdir);
-            NdL = (l.e0.w != 0.0f) ? fabsf(NdL) : fmaxf(0.0f, NdL);
-            float pdfL = (NdL == 0.0f) ? 0.0f : (1.0f / l.p0.w) / NdL;
-            pdfL *= distSqr;
-            pdfL *= 1.0f / float(nLights);
-            const Spec em = Emit(d, l, lN, sdir, waves);
+            Float3 lpos; float pdfL; Spec em;
+            if(!GLOSSY || li < d.lightCount)
+            {
+                const EmissiveTri l = d.lights[li];
+                // Triangle::SampleSurface (Osada)
+                const float r1s = sqrtf(x0), r2s = x1;
+                const float la = 1.0f - r1s, lb = (1.0f - r2s) * r1s, lc = r1s * r2s;
+                const Float3 lp0 = F3(l.p0.x, l.p0.y, l.p0.z), le0 = F3(l.e0.x, l.e0.y, l.e0.z), le1 = F3(l.e1.x, l.e1.y, l.e1.z);
+                lpos = lp0 * la + (lp0 + le0) * lb + (lp0 + le1) * lc;
+                const Float3 lN = Normalize(Cross(le0, le1));
+                // LightPrim::SampleSolidAngle
+                Float3 sdir = pos - lpos;
+                const float distSqr = Dot(sdir, sdir);
+                sdir = Normalize(sdir);
+                float NdL = Dot(lN, sdir);
+                NdL = (l.e0.w != 0.0f) ? fabsf(NdL) : fmaxf(0.0f, NdL);
+                pdfL = (NdL == 0.0f) ? 0.0f : (1.0f / l.p0.w) / NdL;
+                pdfL *= distSqr;
+                pdfL *= 1.0f / float(nLights);
+                em = Emit(d, l, lN, sdir, waves);
+            }
+            else
+            {
+                // LightSkysphere::SampleSolidAngle (LightsDefault.hpp:L338-357): a direction from the luminance distribution
+                // (uniform in uv for a constant radiance), a point one scene diameter away along it
+                const float3 suv = (d.boundaryTex < 0) ? make_float3(x0, x1, 1.0f) : DistSampleUV(d.boundaryDist, x0, x1);
+                const float3 dl = SkyUVToDir(d.boundaryType, suv.x, suv.y);
+                Float3 worldDir = F3(dl.x, dl.y, dl.z);
+                if(!d.boundaryIdentity) worldDir = SkyApply(d.boundaryM, worldDir);
+                pdfL = SkyPdfFromUV(d.boundaryType, suv.z, suv.y);
+                lpos = pos + worldDir * d.sceneDiameter;
+                pdfL *= 1.0f / float(nLights);
+                // DirectLightSamplerUniform::SampleLight: EmitViaSurfacePoint(wO = towards the surface)
+                em = SkyEmit(d, Normalize(pos - lpos), waves);
+            }
             // LightSampleOutput::SampledRay
             const Float3 wI = Normalize(lpos - pos);
             const Float3 lposN = NudgePos(lpos, wI * -1.0f);
@@ -1096,9 +1177,11 @@ __global__ void __launch_bounds__(RTPB) KShade(RenderData d)
 }
 
 // Converter::ConvertAlbedo / ConvertRadiance, LUT half: RGB attributes -> Jakob coefficients, once per render
-__global__ void KPrepareSpectral(SpectrumData s, float4* albedo, uint32_t materialCount, EmissiveTri* lights, uint32_t lightCount)
+__global__ void KPrepareSpectral(SpectrumData s, float4* albedo, uint32_t materialCount, EmissiveTri* lights, uint32_t lightCount,
+                                 float4 boundaryRGB, float4* boundaryOut)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i == 0u && boundaryOut) *boundaryOut = FetchRadianceCoeffs(s, boundaryRGB.x, boundaryRGB.y, boundaryRGB.z);
     if(i < materialCount)
     {
         const float4 a = albedo[i];
@@ -1198,7 +1281,7 @@ struct mrb_renderer_t
     mrb::SceneData   sceneData;        // scene->d with the renderer's instance records (accelKey = instance index)
     uint64_t         iterations = 0;
     bool             needReload = true;   // the next iteration starts with KReload (first one, or a pass has just begun)
-    bool             glossy = false;      // any (Mt)Refract / (Mt)Unreal material: KShade<true>
+    bool             glossy = false;      // any (Mt)Refract / (Mt)Unreal material, or a skysphere boundary: KShade<true>
     // passes: samples [sampleBase, sampleBase + passSamples) of every pixel of the current region
     uint32_t         maxWidth = 0, maxHeight = 0;      // the film allocation (the largest region a pass may take)
     uint32_t         totalSPP = 0, sampleOffset = 0;
@@ -1356,6 +1439,38 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
     }
     d.lightCount = uint32_t(lights.size());
 
+    // boundary light surface (SetBoundarySurface): (L)Null or one of the skyspheres
+    if(desc.boundaryType > 2u) throw std::runtime_error("unknown boundaryType");
+    d.boundaryType = desc.boundaryType;
+    if(desc.boundaryType != 0u) r.glossy = true;
+    d.boundaryTex = -1;
+    d.boundaryIdentity = 1u;
+    uint32_t skyW = 0, skyH = 0;
+    if(desc.boundaryType != 0u)
+    {
+        if(desc.boundaryTexture >= int32_t(desc.textureCount)) throw std::runtime_error("boundaryTexture index exceeds textureCount");
+        d.boundaryTex = desc.boundaryTexture < 0 ? -1 : desc.boundaryTexture;
+        if(d.boundaryTex >= 0) { skyW = desc.textures[d.boundaryTex].width; skyH = desc.textures[d.boundaryTex].height; }
+        d.boundaryRadiance = make_float4(desc.boundaryRadiance[0], desc.boundaryRadiance[1], desc.boundaryRadiance[2], 0.0f);
+        if(desc.boundaryTransform)
+        {
+            const float* m = desc.boundaryTransform;
+            const double a[9] = {m[0], m[1], m[2], m[4], m[5], m[6], m[8], m[9], m[10]};
+            const double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+            if(det == 0.0) throw std::runtime_error("boundaryTransform is singular");
+            const double inv[9] = {(a[4] * a[8] - a[5] * a[7]) / det, (a[2] * a[7] - a[1] * a[8]) / det, (a[1] * a[5] - a[2] * a[4]) / det,
+                                   (a[5] * a[6] - a[3] * a[8]) / det, (a[0] * a[8] - a[2] * a[6]) / det, (a[2] * a[3] - a[0] * a[5]) / det,
+                                   (a[3] * a[7] - a[4] * a[6]) / det, (a[1] * a[6] - a[0] * a[7]) / det, (a[0] * a[4] - a[1] * a[3]) / det};
+            bool ident = true;
+            for(int k = 0; k < 9; k++) { d.boundaryM[k] = float(a[k]); d.boundaryInvM[k] = float(inv[k]); ident = ident && a[k] == ((k % 4 == 0) ? 1.0 : 0.0); }
+            d.boundaryIdentity = ident ? 1u : 0u;
+        }
+        // TracerBase::CommitSurfaces (Tracer/TracerBase.cpp:L1653-1664): the diameter over the XZ plane of the scene AABB
+        const float* bb = desc.scene ? desc.scene->aabb : desc.accel->info.aabb;
+        const float sx = bb[3] - bb[0], sz = bb[5] - bb[2];
+        d.sceneDiameter = desc.sceneDiameter > 0.0f ? desc.sceneDiameter : sqrtf(sx * sx + sz * sz);
+    }
+
     std::vector<RenderInstance> hri(instCount);
     std::vector<TexRec> htex(desc.textureCount);
     for(uint32_t t = 0; t < desc.textureCount; t++)
@@ -1369,6 +1484,7 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
         for(uint32_t m = 0; m < desc.materialCount; m++)
             if(desc.albedoTexture[m] >= int32_t(desc.textureCount)) throw std::runtime_error("albedoTexture index exceeds textureCount");
     InstanceRec* dSceneInst = nullptr;
+    float* skyLuminance = nullptr; float* skyRowTotals = nullptr; float4* dBoundaryCoeffs = nullptr;
     auto Layout = [&](MultiAlloc& ma)
     {
         const uint32_t P = d.slots;
@@ -1400,6 +1516,12 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
             htex[t].data = ma.Take<char>(size_t(desc.textures[t].width) * desc.textures[t].height * desc.textures[t].channels *
                                          (desc.textures[t].format == 0u ? 4u : 1u));
         d.waves = desc.spectrum ? ma.Take<float4>(P) : nullptr; d.wavePdf = desc.spectrum ? ma.Take<float4>(P) : nullptr;
+        // textured skysphere: the luminance distribution (row CDFs + marginal) and the scratch of its construction
+        d.boundaryDist.cdfX = skyW ? ma.Take<float>(size_t(skyW) * skyH) : nullptr;
+        d.boundaryDist.cdfY = skyW ? ma.Take<float>(skyH) : nullptr;
+        skyLuminance = skyW ? ma.Take<float>(size_t(skyW) * skyH) : nullptr;
+        skyRowTotals = skyW ? ma.Take<float>(skyH) : nullptr;
+        dBoundaryCoeffs = (desc.spectrum && desc.boundaryType != 0u) ? ma.Take<float4>(1) : nullptr;
     };
     MultiAlloc sz(nullptr); Layout(sz);
     r.mem.Reserve(sz.Total());
@@ -1437,8 +1559,23 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
     {
         d.spec = desc.spectrum->d;
         const uint32_t total = desc.materialCount + uint32_t(lights.size());
-        if(total) MRB_LAUNCH(ctx, KPrepareSpectral, DivUp(total, 128u), 128, 0, d.spec, const_cast<float4*>(d.albedo), desc.materialCount,
-                             const_cast<EmissiveTri*>(d.lights), uint32_t(lights.size()));
+        if(total || dBoundaryCoeffs)
+            MRB_LAUNCH(ctx, KPrepareSpectral, DivUp(total ? total : 1u, 128u), 128, 0, d.spec, const_cast<float4*>(d.albedo), desc.materialCount,
+                       const_cast<EmissiveTri*>(d.lights), uint32_t(lights.size()), d.boundaryRadiance, dBoundaryCoeffs);
+        if(dBoundaryCoeffs)
+        {   // the constant skysphere radiance as Jakob coefficients + scale, back into the by-value kernel parameters
+            MRB_CUDA_TRY(cudaMemcpyAsync(&d.boundaryRadiance, dBoundaryCoeffs, sizeof(float4), cudaMemcpyDeviceToHost, ctx.stream));
+            MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
+        }
+    }
+    if(skyW)
+    {   // LightGroupSkysphere::Finalize (Tracer/LightsDefault.hpp:L848-893): luminance of the radiance map -> PwC 2-D distribution
+        static const float ACES_CG_Y[3] = {0x1.1614ep-2f, 0x1.58e6fep-1f, 0x1.d946e6p-5f};   // Color::Colorspace<MR_ACES_CG>::ToXYZMatrix row 1
+        const bool given = desc.luminanceRow[0] != 0.0f || desc.luminanceRow[1] != 0.0f || desc.luminanceRow[2] != 0.0f;
+        const TexRec& st = htex[d.boundaryTex];
+        TextureLuminance(ctx, st.data, st.w, st.h, st.channels, st.format, given ? desc.luminanceRow : ACES_CG_Y, skyLuminance);
+        Dist2DBuild(ctx, skyLuminance, skyW, skyH, const_cast<float*>(d.boundaryDist.cdfX), const_cast<float*>(d.boundaryDist.cdfY), skyRowTotals);
+        d.boundaryDist.w = skyW; d.boundaryDist.h = skyH;
     }
     std::vector<float4> hn;
     for(uint32_t k = 0; k < instCount; k++)

@@ -71,6 +71,8 @@ struct LightGroupB200
 {
     std::string type; bool committed = false; uint32_t primGroup = 0;
     std::vector<Vector3> radiance; std::vector<uint8_t> twoSided; std::vector<uint32_t> primBatch;
+    std::vector<int32_t> radianceTex;   // skyspheres: TextureId of the radiance map or -1 (constant)
+    bool IsSkysphere() const { return type == "(L)Skysphere_Spherical" || type == "(L)Skysphere_CoOcta"; }
 };
 struct TransGroupB200 { std::string type; bool committed = false; std::vector<Matrix3x4> matrices; };
 struct CamGroupB200 { std::string type; bool committed = false; std::vector<Vector4> fovPlanes; std::vector<Vector3> gaze, position, up; };
@@ -80,6 +82,23 @@ struct RendererB200
     uint32_t totalSPP = 16384, burstSize = 1, sampleMode = 0; Vector2ui rrRange = Vector2ui(4, 20);
     bool latency = false;      // renderMode "Latency": every DoRenderWork finishes burstSize samples per pixel
 };
+
+// Color::Colorspace<E>::ToXYZMatrix of the tracer's global texture colour space (KCExtractLuminance's InvokeAt over the
+// ColorspaceList, Tracer/ColorConverter.cu:L70-78,L459-468)
+Matrix3x3 LuminanceMatrix(MRayColorSpaceEnum e)
+{
+    using enum MRayColorSpaceEnum;
+    switch(e)
+    {
+        case MR_ACES2065_1: return Color::Colorspace<MR_ACES2065_1>::ToXYZMatrix;
+        case MR_ACES_CG:    return Color::Colorspace<MR_ACES_CG>::ToXYZMatrix;
+        case MR_REC_709:    return Color::Colorspace<MR_REC_709>::ToXYZMatrix;
+        case MR_REC_2020:   return Color::Colorspace<MR_REC_2020>::ToXYZMatrix;
+        case MR_DCI_P3:     return Color::Colorspace<MR_DCI_P3>::ToXYZMatrix;
+        case MR_ADOBE_RGB:  return Color::Colorspace<MR_ADOBE_RGB>::ToXYZMatrix;
+        default: throw MRayError("skysphere luminance: unsupported global texture colour space");
+    }
+}
 
 // Inverse of an affine 3x4 matrix by Laplace expansion, the arithmetic of Matrix3x4T::Inverse
 // (Core/Matrix.hpp:L853-903) term for term, EXCEPT element (1,2): the reference writes +s1 where the
@@ -127,6 +146,7 @@ class TracerB200 final : public TracerI
     std::vector<DeviceB200> devs;        // devs[0] owns the film hand-off
     mrb_context ctx = nullptr;           // = devs[0].ctx
     uint32_t sceneInstanceCount = 0, uniqueAccelCount = 0;
+    float sceneDiameter = 0.0f;          // what TracerBase hands to LightGroup::SetSceneDiameter at CommitSurfaces
     bool committed = false, twoLevel = false;
     std::mutex mtx; // scene-loading calls arrive concurrently from pool threads (TracerBase.h:L97-130)
 
@@ -356,6 +376,11 @@ class TracerB200 final : public TracerI
     LightAttributeInfoList AttributeInfoLight(std::string_view name) const override
     {
         using enum MRayDataEnum; using enum AttributeIsArray; using enum AttributeOptionality; using enum AttributeTexturable; using enum AttributeIsColor;
+        if(name == "(L)Skysphere_Spherical"sv || name == "(L)Skysphere_CoOcta"sv)
+            return LightAttributeInfoList // Tracer/LightsDefault.hpp:L724-738
+            {
+                LightAttributeInfo("radiance", MRayDataTypeRT(MR_VECTOR_3), IS_SCALAR, MR_MANDATORY, MR_TEXTURE_OR_CONSTANT, IS_COLOR)
+            };
         if(name != "(L)Prim(P)Triangle"sv) return {};
         return LightAttributeInfoList // Tracer/LightsDefault.hpp:L547-562
         {
@@ -643,7 +668,8 @@ class TracerB200 final : public TracerI
     LightGroupId CreateLightGroup(std::string typeName, PrimGroupId pg) override
     {
         std::lock_guard lk(mtx);
-        if(typeName != "(L)Prim(P)Triangle") throw MRayError("Unable to find generator for {}", typeName);
+        if(typeName != "(L)Prim(P)Triangle" && typeName != "(L)Skysphere_Spherical" && typeName != "(L)Skysphere_CoOcta")
+            throw MRayError("Unable to find generator for {}", typeName);
         lights.push_back(LightGroupB200{typeName, false, Raw(pg)});
         return LightGroupId(uint32_t(lights.size() - 1));
     }
@@ -652,12 +678,12 @@ class TracerB200 final : public TracerI
     {
         std::lock_guard lk(mtx);
         LightGroupB200& lg = Get(lights, Raw(g), "LightGroup");
-        if(batches.size() != counts.size()) throw MRayError("{}: prim-backed lights need one prim batch each", lg.type);
+        if(!lg.IsSkysphere() && batches.size() != counts.size()) throw MRayError("{}: prim-backed lights need one prim batch each", lg.type);
         LightIdList out;
         for(size_t i = 0; i < counts.size(); i++)
         {
-            lg.radiance.push_back(Vector3::Zero()); lg.twoSided.push_back(0);
-            lg.primBatch.push_back(Raw(batches[i]) & ((1u << PRIM_ID_BITS) - 1u));
+            lg.radiance.push_back(Vector3::Zero()); lg.twoSided.push_back(0); lg.radianceTex.push_back(-1);
+            lg.primBatch.push_back(i < batches.size() ? (Raw(batches[i]) & ((1u << PRIM_ID_BITS) - 1u)) : 0u);
             out.push_back(LightId((Raw(g) << MAT_ID_BITS) | uint32_t(lg.radiance.size() - 1)));
         }
         return out;
@@ -678,11 +704,19 @@ class TracerB200 final : public TracerI
     {
         LightGroupB200& lg = Get(lights, Raw(g), "LightGroup");
         if(attributeIndex != 0) throw MRayError("{}: Attribute {:d} is not \"ParamVarying\", wrong function is called", lg.type, attributeIndex);
-        for(const auto& t : tex) if(t.has_value()) throw MRayError("{}: textured radiance is not supported yet", lg.type);
         uint32_t lo = range[0] & ((1u << MAT_ID_BITS) - 1u), hi = range[1] & ((1u << MAT_ID_BITS) - 1u);
         auto s = data.AccessAs<const Vector3>();
         if(hi >= lg.radiance.size() || s.size() != hi - lo + 1) throw MRayError("{}: radiance range mismatch", lg.type);
         std::copy(s.begin(), s.end(), lg.radiance.begin() + lo);
+        for(size_t i = 0; i < tex.size() && lo + i <= hi; i++)
+        {
+            if(!tex[i].has_value()) continue;
+            // LightGroupSkysphere::PushTexAttribute (Tracer/LightsDefault.hpp:L779-816): the radiance field of an environment map
+            if(!lg.IsSkysphere()) throw MRayError("{}: textured radiance is not supported yet", lg.type);
+            const uint32_t tid = Raw(*tex[i]);
+            if(tid == 0 || tid > textures.size()) throw MRayError("{:s}: Given texture({:d}) is not found", lg.type, tid);
+            lg.radianceTex[lo + i] = int32_t(tid);
+        }
     }
     void PushLightAttribute(LightGroupId, CommonIdRange, uint32_t, std::vector<TextureId>) override
     { throw MRayError("textured lights are not supported yet"); }
@@ -747,7 +781,12 @@ class TracerB200 final : public TracerI
         // TracerBase::CommitSurfaces (Tracer/TracerBase.cpp:L1529-1674) + BaseAccelerator::Construct:
         // surfaces sharing a transform become the prim ranges of one accelerator; (T)Identity-only scenes
         // are a single accelerator, anything else a two-level scene with one instance per transform.
-        if(Raw(boundary.lightId) != 0) throw MRayError("boundary lights other than (L)Null are not supported yet");
+        if(Raw(boundary.lightId) != 0)
+        {   // RendererCommon.cu:L337-345: the boundary light cannot be primitive backed; here it is (L)Null or a skysphere
+            const LightGroupB200& blg = Get(lights, Raw(boundary.lightId) >> MAT_ID_BITS, "LightGroup");
+            if(!blg.IsSkysphere()) throw MRayError("Primitive-backed light ({}) is requested as a boundary material!", blg.type);
+            if((Raw(boundary.lightId) & ((1u << MAT_ID_BITS) - 1u)) >= blg.radiance.size()) throw MRayError("Unable to find Light({})", Raw(boundary.lightId));
+        }
         struct Group { uint32_t transformId; std::vector<uint32_t> ranges, lmKeys; std::vector<uint8_t> cull; };
         std::vector<Group> groups;
         auto GroupOf = [&](TransformId t) -> Group&
@@ -878,6 +917,10 @@ class TracerB200 final : public TracerI
             aabb = AABB3(Vector3(box[0], box[1], box[2]), Vector3(box[3], box[4], box[5]));
         }
         committed = true;
+        {   // TracerBase::CommitSurfaces (Tracer/TracerBase.cpp:L1653-1664): the lights learn the scene's diameter over the XZ plane
+            const Vector3 span = aabb.GeomSpan();
+            sceneDiameter = Math::Length(Vector2(span[0], span[2]));
+        }
         return SurfaceCommitResult
         {
             .aabb = aabb,
@@ -1019,6 +1062,44 @@ class TracerB200 final : public TracerI
                                                uint32_t(t.params.interpolation), uint32_t(t.params.edgeResolve)};
             }
             d.textureCount = uint32_t(texDescs.size()); d.textures = texDescs.data(); d.albedoTexture = flatAlbedoTex.data();
+        }
+        // boundary light surface: (L)Null (nothing to do) or a skysphere (LightGroupSkysphere, Tracer/LightsDefault.hpp:L704-893)
+        d.boundaryTexture = -1;
+        std::array<float, 12> skyMatrix{};
+        if(Raw(boundary.lightId) != 0)
+        {
+            const LightGroupB200& blg = Get(lights, Raw(boundary.lightId) >> MAT_ID_BITS, "LightGroup");
+            const uint32_t bi = Raw(boundary.lightId) & ((1u << MAT_ID_BITS) - 1u);
+            d.boundaryType = blg.type == "(L)Skysphere_Spherical" ? MRB_BOUNDARY_SKYSPHERE_SPHERICAL : MRB_BOUNDARY_SKYSPHERE_COOCTA;
+            for(int k = 0; k < 3; k++) d.boundaryRadiance[k] = blg.radiance[bi][k];
+            if(blg.radianceTex[bi] >= 0)
+            {
+                const uint32_t tid = uint32_t(blg.radianceTex[bi]);
+                const TextureB200& t = textures[tid - 1];
+                if(!t.loaded) throw MRayError("texture({}) has no data", tid);
+                auto it = std::find(flatTextures.begin(), flatTextures.end(), tid);
+                if(it != flatTextures.end()) d.boundaryTexture = int32_t(it - flatTextures.begin());
+                else
+                {   // the radiance map is not an albedo texture of any material: append it to this render's table
+                    texDescs.push_back(mrb_texture_desc{t.pixels.data(), t.size[0], t.size[1], t.channels, t.format,
+                                                        uint32_t(t.params.interpolation), uint32_t(t.params.edgeResolve)});
+                    d.boundaryTexture = int32_t(texDescs.size() - 1);
+                    d.textureCount = uint32_t(texDescs.size()); d.textures = texDescs.data();
+                    if(flatTextures.empty()) d.albedoTexture = nullptr;
+                }
+            }
+            if(Raw(boundary.transformId) != Raw(TracerConstants::IdentityTransformId))
+            {
+                const TransGroupB200& tg = Get(transforms, Raw(boundary.transformId) >> TRANS_ID_BITS, "TransformGroup");
+                const uint32_t ti = Raw(boundary.transformId) & ((1u << TRANS_ID_BITS) - 1u);
+                if(ti >= tg.matrices.size()) throw MRayError("Unable to find Transform({})", Raw(boundary.transformId));
+                for(unsigned rr = 0; rr < 3; rr++) for(unsigned cc = 0; cc < 4; cc++) skyMatrix[4 * rr + cc] = tg.matrices[ti](rr, cc);
+                d.boundaryTransform = skyMatrix.data();
+            }
+            // KCExtractLuminance weighs the texel with the Y row of the global texture colour space's RGB -> XYZ matrix
+            const Matrix3x3 toXYZ = LuminanceMatrix(params.globalTextureColorSpace);
+            for(int k = 0; k < 3; k++) d.luminanceRow[k] = toXYZ(1, k);
+            d.sceneDiameter = sceneDiameter;
         }
         d.lightCount = uint32_t(flatLightTwoSided.size()); d.lightRadiance = flatLightRadiance.data(); d.lightTwoSided = flatLightTwoSided.data();
         for(int k = 0; k < 3; k++) { d.camPosition[k] = cg.position[ci][k]; d.camGaze[k] = cg.gaze[ci][k]; d.camUp[k] = cg.up[ci][k]; }

@@ -438,3 +438,33 @@ def cornell_sphere():
     c["positions"] = np.ascontiguousarray(pos, np.float32); c["indices"] = np.ascontiguousarray(idx, np.uint32)
     c["material"] = mat.astype(np.uint32); c["normals"] = np.ascontiguousarray(nrm, np.float32)
     return c
+
+
+def cornell_open(keep_light: bool = False):
+    """``cornell_box`` with the ceiling removed (and, unless keep_light, the area light too): the room is lit through the
+    opening by the BOUNDARY light — the skysphere test scene. Same dict layout as cornell_box."""
+    c = cornell_box()
+    keep = np.ones(c["indices"].shape[0], bool)
+    keep[2:4] = False                  # ceiling quad = triangles 2, 3
+    if not keep_light:
+        keep[10:12] = False            # light quad = triangles 10, 11
+    c["indices"] = np.ascontiguousarray(c["indices"][keep])
+    c["material"] = np.ascontiguousarray(c["material"][keep])
+    return c
+
+
+def sky_texture(width: int = 32, height: int = 16, seed: int = 9):
+    """A small HDR environment map (RGBA fp32, bilinear, wrap): a blue-ish gradient brighter towards the top rows, low-
+    amplitude noise, and a 2x2-texel "sun" three orders of magnitude brighter — so that importance sampling of the
+    luminance distribution matters. Row 0 is v = 0 (towards -Y on the latitude-longitude map)."""
+    rng = np.random.default_rng(seed)
+    v = (np.arange(height, dtype=np.float32) + 0.5) / height
+    t = np.zeros((height, width, 4), np.float32)
+    t[..., 0] = (0.15 + 0.6 * v)[:, None]
+    t[..., 1] = (0.2 + 0.9 * v)[:, None]
+    t[..., 2] = (0.3 + 1.6 * v)[:, None]
+    t[..., :3] *= (0.85 + 0.3 * rng.random((height, width, 1))).astype(np.float32)
+    sy, sx = int(height * 0.8), int(width * 0.3)
+    t[sy:sy + 2, sx:sx + 2, :3] = np.array([900.0, 800.0, 600.0], np.float32)
+    t[..., 3] = 1.0
+    return dict(data=np.ascontiguousarray(t), interp="Linear", edge="Wrap")

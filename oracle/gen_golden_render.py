@@ -68,6 +68,13 @@ ITEMS = {
     # smooth shading normals: an 80-triangle sphere with radial vertex normals (scenes.cornell_sphere) — the interpolated
     # tangent frames of Triangle::GenerateSurface (every other fixture has flat normals)
     "cornell64_sphere_spp16384": (64, 16384, 26, "WithNEEAndMIS", (2, 20), "sphere", np.float32, RGB),
+    # skysphere boundary lights (scenes.cornell_open: the box without its ceiling): a constant sky on the latitude-longitude
+    # map; an HDR map with a "sun" on the same map under a (T)Single rotation about Y (from the transform family the
+    # reference inverts correctly); the same map on the concentric-octahedral map next to the area light, spectral
+    "cornell64_sky_const_spp16384": (64, 16384, 31, "WithNEEAndMIS", (2, 20), ("sky", "Skysphere_Spherical", "const"), np.float32, RGB),
+    "cornell64_sky_tex_spp16384": (64, 16384, 32, "WithNEEAndMIS", (2, 20), ("sky", "Skysphere_Spherical", "tex"), np.float32, RGB),
+    "cornell64_sky_nee_spp16384": (64, 16384, 34, "WithNextEventEstimation", (2, 20), ("sky", "Skysphere_Spherical", "tex"), np.float32, RGB),
+    "cornell64_sky_coocta_spectral_spp16384": (64, 16384, 33, "WithNEEAndMIS", (2, 20), ("sky", "Skysphere_CoOcta", "tex+light"), np.float32, SPECTRAL),
     # two-level scene: every batch in its own local space under a (T)Single transform
     "cornell64_single_spp16384": (64, 16384, 6, "WithNEEAndMIS", (2, 20), True, np.float32, RGB),
 }
@@ -105,9 +112,25 @@ def localise(b, seed=17):
     return mats34
 
 
+SKY_CONSTANT = (1.5, 1.8, 2.5)
+SKY_ROTATION = [[0.0, 0.0, 1.0, 0.0], [0.0, 1.0, 0.0, 0.0], [-1.0, 0.0, 0.0, 0.0]]   # 90 degrees about Y; m00 m12 - m02 m10 = 0
+
+
+def sky_kwargs(single):
+    """driver_render keywords of a ("sky", type, flavour) item (tests/test_gpu_sky.py builds the same scenes)."""
+    _, kind, flavour = single
+    if flavour == "const":
+        return dict(boundary=dict(type=kind, radiance=SKY_CONSTANT))
+    b = dict(type=kind, texture=0)
+    if flavour == "tex":
+        b["transform"] = SKY_ROTATION
+    return dict(textures=[scenes.sky_texture()], boundary=b)
+
+
 def render(name):
     res, spp, seed, mode, rr, single, dt, renderer = ITEMS[name]
-    c = (scenes.cornell_mirror() if single == "mirror" else scenes.cornell_glossy() if single == "glossy"
+    sky = isinstance(single, tuple) and single[0] == "sky"
+    c = (scenes.cornell_open(keep_light=single[2] == "tex+light") if sky else scenes.cornell_mirror() if single == "mirror" else scenes.cornell_glossy() if single == "glossy"
          else scenes.cornell_sphere() if single == "sphere" else scenes.cornell_box())
     kw = {}
     if single == "twosided":
@@ -129,6 +152,10 @@ def render(name):
         b = O.batched_scene(c["positions"], c["indices"], c["material"])
         kw = dict(material_kind=c["material_type"])
         bt = None
+    elif sky:
+        b = O.batched_scene(c["positions"], c["indices"], c["material"])
+        kw = sky_kwargs(single)
+        bt = None
     elif isinstance(single, tuple) and single[0] == "filter":
         b = O.batched_scene(c["positions"], c["indices"], c["material"])
         kw = dict(film_filter=single[1], film_filter_radius=single[2])
@@ -146,6 +173,8 @@ def render(name):
                                  sample_mode=mode, rr_range=rr, seed=seed, threads=0, batch_transforms=bt,
                                  renderer=renderer, host_exe=True, **kw)
     extra = {}
+    if sky:
+        extra = dict(boundary_type=single[1], flavour=single[2], scene_aabb=np.array(st["aabb"], np.float32))
     if isinstance(single, tuple) and single[0] == "filter":
         extra = dict(weight=w.astype(np.float32), film_filter=single[1], film_filter_radius=single[2])
         if single[1] != "Mitchell-Netravali":

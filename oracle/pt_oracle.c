@@ -97,6 +97,13 @@ typedef struct
     /* per vertex world -> tangent-space quaternion (w, x, y, z), the triangle group's NORMAL attribute; NULL = geometric
      * normals */
     const float* vertexTBN;
+    /* boundary light surface: 0 = (L)Null, 1 = (L)Skysphere_Spherical, 2 = (L)Skysphere_CoOcta (LightsDefault.hpp:L310-443).
+     * boundaryTexture: -1 = constant boundaryRadiance, else an index into `textures` (the radiance map) whose luminance
+     * distribution is boundaryCdfX / boundaryCdfY (dist_oracle.c: orc_dist2d_build of orc_luminance). boundaryM / boundaryInvM:
+     * linear part of the light surface's transform and its inverse (row-major 3x3). */
+    uint32_t boundaryType; int32_t boundaryTexture; float boundaryRadiance[3];
+    const float* boundaryCdfX; const float* boundaryCdfY;
+    float boundaryM[9], boundaryInvM[9]; float sceneDiameter;
 } pt_scene;
 
 /* One single-level 2-D texture as the reference's host-backend view reads it (Device/CPU/TextureViewCPU.h):
@@ -202,6 +209,53 @@ static int trace(const pt_scene* s, v3 o, v3 d, float tMin, float tMax, int any,
     uint8_t back;
     orc_lbvh_trace(s->pos, s->idx, s->nodes, s->boxes, ray, 1, any, 0, prim, t, bary, &back);
     return *prim != 0xFFFFFFFFu;
+}
+
+/* dist_oracle.c */
+void orc_dist2d_sample_uv(const float* cdfX, const float* cdfY, uint32_t w, uint32_t h, float xi0, float xi1, float out[3]);
+float orc_dist2d_pdf_uv(const float* cdfX, const float* cdfY, uint32_t w, uint32_t h, float u, float v);
+void orc_sky_dir_to_uv(int mode, const float d[3], float uv[2]);
+void orc_sky_uv_to_dir(int mode, const float uv[2], float d[3]);
+float orc_sky_pdf_from_dir(int mode, float pdf, const float d[3]);
+float orc_sky_pdf_from_uv(int mode, float pdf, const float uv[2]);
+
+static v3 mul33(const float* m, v3 v) { return V(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z); }
+/* LightSkysphere::EmitViaHit / EmitViaSurfacePoint (LightsDefault.hpp:L408-443) */
+static s4 sky_emit(const pt_scene* s, v3 wO, const float waves[4])
+{
+    v3 dir = nrm(mul33(s->boundaryInvM, mul(wO, -1.0f)));
+    float rgb[3] = {s->boundaryRadiance[0], s->boundaryRadiance[1], s->boundaryRadiance[2]};
+    if(s->boundaryTexture >= 0)
+    {
+        float dv[3] = {dir.x, dir.y, dir.z}, uv[2];
+        orc_sky_dir_to_uv((int)s->boundaryType, dv, uv);
+        orc_texture_sample(&s->textures[s->boundaryTexture], uv[0], uv[1], rgb);
+    }
+    if(!s->spectrum) return S(rgb[0], rgb[1], rgb[2], 0.0f);
+    s4 o; orc_convert_radiance(s->spectrum, rgb, waves, o.v); return o;
+}
+/* LightSkysphere::PdfSolidAngle (L359-370) */
+static float sky_pdf(const pt_scene* s, v3 dirWorld)
+{
+    v3 dY = mul33(s->boundaryInvM, dirWorld), n = nrm(dY);
+    float nv[3] = {n.x, n.y, n.z}, dv[3] = {dY.x, dY.y, dY.z}, uv[2];
+    orc_sky_dir_to_uv((int)s->boundaryType, nv, uv);
+    float pdf = 1.0f;
+    if(s->boundaryTexture >= 0)
+        pdf = orc_dist2d_pdf_uv(s->boundaryCdfX, s->boundaryCdfY, s->textures[s->boundaryTexture].w, s->textures[s->boundaryTexture].h, uv[0], uv[1]);
+    return orc_sky_pdf_from_dir((int)s->boundaryType, pdf, dv);
+}
+/* LightSkysphere::SampleSolidAngle (L338-357): -> sampled point, solid-angle pdf (not yet divided by the light count) */
+static float sky_sample(const pt_scene* s, float x0, float x1, v3 from, v3* lposOut)
+{
+    float suv[3] = {x0, x1, 1.0f};
+    if(s->boundaryTexture >= 0)
+        orc_dist2d_sample_uv(s->boundaryCdfX, s->boundaryCdfY, s->textures[s->boundaryTexture].w, s->textures[s->boundaryTexture].h, x0, x1, suv);
+    float d[3]; orc_sky_uv_to_dir((int)s->boundaryType, suv, d);
+    float pdf = orc_sky_pdf_from_uv((int)s->boundaryType, suv[2], suv);
+    v3 worldDir = mul33(s->boundaryM, V(d[0], d[1], d[2]));
+    *lposOut = add(from, mul(worldDir, s->sceneDiameter));
+    return pdf;
 }
 
 static s4 light_emit(const pt_scene* s, uint32_t li, v3 n, v3 wO, const float waves[4])
@@ -576,7 +630,22 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
     for(;;)
     {
         uint32_t prim; float t, bary[2];
-        if(!trace(s, o, d, tMin, tMax, 0, &prim, &t, bary)) break; /* boundary Null light: nothing, path dead */
+        if(!trace(s, o, d, tMin, tMax, 0, &prim, &t, bary))
+        {   /* boundary light (LightWorkFunction[WithNEE] for a light without primitives): (L)Null adds nothing */
+            if(s->boundaryType != 0u && !(s->sampleMode == 1u && type != 3 && type != 1))
+            {
+                s4 thr = throughput;
+                if(s->sampleMode == 2u && type == 2)
+                {
+                    float pdfL = sky_pdf(s, d) * (1.0f / (float)nLights);
+                    float mis = prevPdf + pdfL;
+                    thr = s_mul(thr, prevPdf);
+                    thr = (mis == 0) ? S(0, 0, 0, 0) : s_mul(thr, 1.0f / mis);
+                }
+                if(depth + 1u <= s->rrHi) radiance = s_add(radiance, s_mulv(sky_emit(s, mul(d, -1.0f), waves), thr));
+            }
+            break;
+        }
         v3 p[3]; tri(s, prim, p);
         float a = bary[0], b = bary[1], c = 1.0f - a - b;
         v3 hitPos = add(add(mul(p[0], a), mul(p[1], b)), mul(p[2], c));
@@ -670,14 +739,24 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
             float x0 = pcg_float(rng), x1 = pcg_float(rng), xs = pcg_float(rng);
             uint32_t li = (uint32_t)(xs * (float)nLights);
             if(li > nLights - 1u) li = nLights - 1u;
-            if(li < s->nLightTris && !specularMat)
+            if((li < s->nLightTris || s->boundaryType != 0u) && !specularMat)
             {
-                uint32_t lt = s->lightTris[li]; uint32_t lightIdx = (uint32_t)(-1 - s->triMaterial[lt]);
-                v3 q[3]; tri(s, lt, q);
-                v3 lpos, lN, sd;
-                float pdfL = light_sample(q, s->twoSided && s->twoSided[lightIdx], x0, x1, hitPos, &lpos, &lN, &sd);
-                pdfL *= 1.0f / (float)nLights;
-                s4 em = light_emit(s, lightIdx, lN, sd, waves);
+                v3 lpos; float pdfL; s4 em;
+                if(li < s->nLightTris)
+                {
+                    uint32_t lt = s->lightTris[li]; uint32_t lightIdx = (uint32_t)(-1 - s->triMaterial[lt]);
+                    v3 q[3]; tri(s, lt, q);
+                    v3 lN, sd;
+                    pdfL = light_sample(q, s->twoSided && s->twoSided[lightIdx], x0, x1, hitPos, &lpos, &lN, &sd);
+                    pdfL *= 1.0f / (float)nLights;
+                    em = light_emit(s, lightIdx, lN, sd, waves);
+                }
+                else
+                {   /* the skysphere is the last meta light (MetaLight.hpp:L512-518) */
+                    pdfL = sky_sample(s, x0, x1, hitPos, &lpos);
+                    pdfL *= 1.0f / (float)nLights;
+                    em = sky_emit(s, nrm(sub(hitPos, lpos)), waves);
+                }
                 v3 wI = nrm(sub(lpos, hitPos));
                 v3 lposN = nudge(lpos, mul(wI, -1.0f));
                 float length = len(sub(lposN, hitPos));

@@ -27,6 +27,7 @@ struct DriverScene
     float camPos[3], camGaze[3], camUp[3]; float fovXY[2]; float nearFar[2];
     const float* batchTransforms; const int32_t* batchInstanceOf;
     uint32_t textureCount; const uint32_t* textureInfo; const uint8_t* textureBytes; const int32_t* materialTexture; const float* uvs; const uint8_t* materialKind; const uint8_t* lightTwoSided; const float* materialParams;
+    uint32_t boundaryType; float boundaryRadiance[3]; int32_t boundaryTexture; const float* boundaryTransform;
 };
 struct DriverRender
 {
@@ -43,7 +44,7 @@ int main(int argc, char** argv)
     FILE* f = std::fopen(argv[1], "rb");
     if(!f) { std::perror("blob"); return 65; }
     uint64_t n = 0;
-    if(std::fread(&n, 8, 1, f) != 1 || (n != 23 && n != 24)) { std::fprintf(stderr, "bad blob\n"); return 66; }
+    if(std::fread(&n, 8, 1, f) != 1 || (n < 23 || n > 25)) { std::fprintf(stderr, "bad blob\n"); return 66; }
     std::vector<std::vector<uint64_t>> sec(n);     // 8-byte aligned storage
     std::vector<uint64_t> bytes(n);
     for(uint64_t i = 0; i < n; i++)
@@ -75,6 +76,12 @@ int main(int argc, char** argv)
     sc.uvs = static_cast<const float*>(P(20)); sc.materialKind = static_cast<const uint8_t*>(P(21));
     sc.lightTwoSided = static_cast<const uint8_t*>(P(22));
     if(n > 23) sc.materialParams = static_cast<const float*>(P(23));   // 23 materialParams (8 floats per material; may be empty)
+    if(n > 24 && bytes[24] >= 20)
+    {   // 24 boundary light: u32 type, f32 radiance[3], i32 texture, then (optional) f32[12] transform
+        const uint32_t* b = static_cast<const uint32_t*>(P(24));
+        sc.boundaryType = b[0]; std::memcpy(sc.boundaryRadiance, b + 1, 12); std::memcpy(&sc.boundaryTexture, b + 4, 4);
+        if(bytes[24] >= 20 + 48) sc.boundaryTransform = reinterpret_cast<const float*>(b + 5);
+    }
     std::memcpy(sc.camPos, cam, 12); std::memcpy(sc.camGaze, cam + 3, 12); std::memcpy(sc.camUp, cam + 6, 12);
     std::memcpy(sc.fovXY, cam + 9, 8); std::memcpy(sc.nearFar, cam + 11, 8);
     DriverRender rd{};

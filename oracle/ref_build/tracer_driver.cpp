@@ -67,6 +67,13 @@ struct DriverScene
     // optional: per material 8 floats. materialKind 2 = (Mt)Refract {cauchyFront xyz, -, cauchyBack xyz, -},
     // 3 = (Mt)Unreal {roughness, specular, metallic, ...} (albedo from `albedo`, constant)
     const float*    materialParams;
+    // optional boundary light surface: 0 = (L)Null, 1 = (L)Skysphere_Spherical, 2 = (L)Skysphere_CoOcta; radiance constant, or
+    // (boundaryTexture >= 0) the texture of that index as the radiance map; boundaryTransform: NULL = (T)Identity, else one
+    // row-major 3x4 matrix pushed as a (T)Single transform for the light surface
+    uint32_t        boundaryType;
+    float           boundaryRadiance[3];
+    int32_t         boundaryTexture;
+    const float*    boundaryTransform;
 };
 
 struct DriverRender
@@ -453,19 +460,28 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
         }
         // ---- transforms ----
         std::vector<TransformId> batchTrans(sc->batchCount, TracerConstants::IdentityTransformId);
-        if(sc->batchTransforms)
+        TransformId skyT = TracerConstants::IdentityTransformId;   // transform of the boundary light surface
+        const bool skyTransform = sc->boundaryType != 0u && sc->boundaryTransform;
+        if(sc->batchTransforms || skyTransform)
         {
             TransGroupId tg = tracer->CreateTransformGroup("(T)Single");
-            std::vector<AttributeCountList> tCounts(sc->batchCount);
+            const uint32_t nBatchT = sc->batchTransforms ? sc->batchCount : 0u;
+            std::vector<AttributeCountList> tCounts(nBatchT + (skyTransform ? 1u : 0u));
             for(auto& c : tCounts) { c = AttributeCountList(StaticVecSize(1)); c[0] = 1; }
             TransformIdList tids = tracer->ReserveTransformations(tg, tCounts);
             tracer->CommitTransReservations(tg);
             std::vector<Matrix3x4> ms;
-            for(uint32_t b = 0; b < sc->batchCount; b++)
+            for(uint32_t b = 0; b < nBatchT; b++)
             {
                 const float* m = sc->batchTransforms + 12 * size_t(b);
                 ms.push_back(Matrix3x4(Vector4(m[0], m[1], m[2], m[3]), Vector4(m[4], m[5], m[6], m[7]), Vector4(m[8], m[9], m[10], m[11])));
                 batchTrans[b] = tids[b];
+            }
+            if(skyTransform)
+            {
+                const float* m = sc->boundaryTransform;
+                ms.push_back(Matrix3x4(Vector4(m[0], m[1], m[2], m[3]), Vector4(m[4], m[5], m[6], m[7]), Vector4(m[8], m[9], m[10], m[11])));
+                skyT = tids[nBatchT];
             }
             TransientData d(std::in_place_type_t<Matrix3x4>{}, ms.size());
             d.Push(Span<const Matrix3x4>(ms.data(), ms.size()));
@@ -488,7 +504,26 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
             if(sc->batchLight[b] >= 0)
                 tracer->CreateLightSurface(LightSurfaceParams{lights[size_t(sc->batchLight[b])], batchTrans[b], {}});
         CamSurfaceId camSurf = tracer->CreateCameraSurface(CameraSurfaceParams{cam, TracerConstants::IdentityTransformId, {}});
-        tracer->SetBoundarySurface(TracerConstants::NullLightId, TracerConstants::IdentityTransformId);
+        if(sc->boundaryType == 0u)
+            tracer->SetBoundarySurface(TracerConstants::NullLightId, TracerConstants::IdentityTransformId);
+        else
+        {   // the skysphere as the scene loader creates it (SceneLoaderMRay.cpp:L1590-1660,L2210-2222): a light group over the
+            // empty primitive group, ONE light whose "radiance" is a constant or a texture
+            LightGroupId sg = tracer->CreateLightGroup(sc->boundaryType == 1u ? "(L)Skysphere_Spherical" : "(L)Skysphere_CoOcta");
+            LightAttributeInfoList sInfo = tracer->AttributeInfo(sg);
+            AttributeCountList sCount(StaticVecSize(sInfo.size()));
+            for(size_t k = 0; k < sInfo.size(); k++) sCount[k] = 1;
+            LightId sky = tracer->ReserveLight(sg, sCount);
+            tracer->CommitLightReservations(sg);
+            auto range = CommonIdRange(std::bit_cast<CommonId>(sky), std::bit_cast<CommonId>(sky));
+            Vector3 rad(sc->boundaryRadiance[0], sc->boundaryRadiance[1], sc->boundaryRadiance[2]);
+            TransientData d(std::in_place_type_t<Vector3>{}, 1);
+            d.Push(Span<const Vector3>(&rad, 1));
+            std::vector<Optional<TextureId>> tex(1, std::nullopt);
+            if(sc->boundaryTexture >= 0) tex[0] = texIds[size_t(sc->boundaryTexture)];
+            tracer->PushLightAttribute(sg, range, 0, std::move(d), std::move(tex));
+            tracer->SetBoundarySurface(sky, skyT);
+        }
         VolumeId bVol = tracer->RegisterVolume(VolumeParams{TracerConstants::VacuumMediumId,
                                                             TracerConstants::IdentityTransformId, 0});
         tracer->SetBoundaryVolume(bVol);

@@ -21,7 +21,7 @@ _u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 
 
 def build_oracle():
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("mray_oracle.c", "pt_oracle.c", "spectrum_oracle.c", "sobol_oracle.c")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("mray_oracle.c", "pt_oracle.c", "spectrum_oracle.c", "sobol_oracle.c", "dist_oracle.c")]
     so = os.path.join(ORACLE_DIR, "liboracle.so")
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(x) for x in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
@@ -167,7 +167,9 @@ class _DriverScene(C.Structure):
                 ("batchInstanceOf", C.c_void_p),
                 ("textureCount", C.c_uint32), ("textureInfo", C.c_void_p), ("textureBytes", C.c_void_p),
                 ("materialTexture", C.c_void_p), ("uvs", C.c_void_p), ("materialKind", C.c_void_p), ("lightTwoSided", C.c_void_p),
-                ("materialParams", C.c_void_p)]
+                ("materialParams", C.c_void_p),
+                ("boundaryType", C.c_uint32), ("boundaryRadiance", C.c_float * 3), ("boundaryTexture", C.c_int32),
+                ("boundaryTransform", C.c_void_p)]
 
 
 class _DriverRender(C.Structure):
@@ -221,8 +223,9 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
                   batch_transforms=None, sampler="Independent", host_exe=False, instance_of=None,
                   textures=None, material_texture=None, region=None, material_kind=None,
                   latency=False, burst_size=1, cam_switch=None, light_two_sided=False, film_filter=None, film_filter_radius=0.0,
-                  material_params=None):
-    """Renders through TracerI. `light_material`: material id whose batch is the prim-backed light.
+                  material_params=None, boundary=None):
+    """Renders through TracerI. boundary: None = (L)Null boundary, or dict(type="Skysphere_Spherical"|"Skysphere_CoOcta",
+    radiance=(r, g, b) | texture=index into `textures`, transform=[3, 4] or None). `light_material`: material id whose batch is the prim-backed light.
     batch_transforms: optional [batch, 3, 4] local->world matrices ((T)Single per batch; positions local).
     textures: list of dict(data=[h, w, 4] float32 / uint8 (RGBA), interp=, edge=); material_texture: per material id
     (an index into `albedo`) -1 or a texture index; UV0 comes from batched["uvs"] (zeros when absent).
@@ -265,8 +268,14 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
             blobs.append(a.tobytes()); off += len(blobs[-1]) + (-len(blobs[-1]) % 16)
             blobs[-1] += b"\0" * (-len(blobs[-1]) % 16)
         tinfo = np.array(info, np.uint32); tbytes = np.frombuffer(b"".join(blobs), np.uint8).copy()
-        mtex = np.ascontiguousarray(np.asarray(material_texture, np.int32)[lambert])
+        mtex = None if material_texture is None else np.ascontiguousarray(np.asarray(material_texture, np.int32)[lambert])
     n_lights = 1 if light_material in mats else 0
+    b_type = 0 if boundary is None else {"Skysphere_Spherical": 1, "Skysphere_CoOcta": 2}[boundary["type"]]
+    b_rad = np.asarray((boundary or {}).get("radiance", (0.0, 0.0, 0.0)), np.float32)
+    b_tex = int((boundary or {}).get("texture", -1))
+    b_xf = None if (boundary or {}).get("transform") is None else np.ascontiguousarray(boundary["transform"], np.float32).reshape(12)
+    if textures and mtex is None:
+        mtex = np.full(len(lambert), -1, np.int32)
     if host_exe:
         import subprocess
         import tempfile
@@ -286,7 +295,9 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
                 b"" if tinfo is None else tinfo.tobytes(), b"" if tbytes is None else tbytes.tobytes(),
                 b"" if mtex is None else mtex.tobytes(), b"" if uvs is None else uvs.tobytes(),
                 b"" if mkind is None else mkind.tobytes(), lts.tobytes() if light_two_sided else b"",
-                b"" if mparams is None else mparams.tobytes()]
+                b"" if mparams is None else mparams.tobytes(),
+                b"" if b_type == 0 else (np.uint32(b_type).tobytes() + b_rad.tobytes() + np.int32(b_tex).tobytes() +
+                                         (b"" if b_xf is None else b_xf.tobytes()))]
         with tempfile.TemporaryDirectory() as td:
             with open(os.path.join(td, "in.blob"), "wb") as f:
                 f.write(np.uint64(len(secs)).tobytes())
@@ -332,6 +343,9 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
         keep.append(lts); sc.lightTwoSided = lts.ctypes.data
     if mparams is not None:
         keep.append(mparams); sc.materialParams = mparams.ctypes.data
+    sc.boundaryType, sc.boundaryRadiance, sc.boundaryTexture = b_type, (C.c_float * 3)(*b_rad), b_tex
+    if b_xf is not None:
+        keep.append(b_xf); sc.boundaryTransform = b_xf.ctypes.data
     rd = _DriverRender(renderer.encode(), width, height, spp, sample_mode.encode(), (C.c_uint32 * 2)(*rr_range), seed,
                        accel_mode, parallel_hint, threads, sampler_id, (C.c_uint32 * 4)(*(region or (0, 0, 0, 0))),
                        1 if latency else 0, burst_size, cam_switch[0] if cam_switch else 0,
@@ -364,7 +378,10 @@ class _PtScene(C.Structure):
                 ("rrLo", C.c_uint32), ("rrHi", C.c_uint32), ("filterRadius", C.c_float), ("seed", C.c_uint64),
                 ("spectrum", C.c_void_p), ("wavelengthMode", C.c_uint32),
                 ("uv", C.c_void_p), ("textures", C.c_void_p), ("albedoTexture", C.c_void_p), ("nTextures", C.c_uint32),
-                ("materialType", C.c_void_p), ("filmFilter", C.c_uint32), ("materialParams", C.c_void_p), ("vertexTBN", C.c_void_p)]
+                ("materialType", C.c_void_p), ("filmFilter", C.c_uint32), ("materialParams", C.c_void_p), ("vertexTBN", C.c_void_p),
+                ("boundaryType", C.c_uint32), ("boundaryTexture", C.c_int32), ("boundaryRadiance", C.c_float * 3),
+                ("boundaryCdfX", C.c_void_p), ("boundaryCdfY", C.c_void_p), ("boundaryM", C.c_float * 9), ("boundaryInvM", C.c_float * 9),
+                ("sceneDiameter", C.c_float)]
 
 
 class _OrcTexture(C.Structure):
@@ -438,11 +455,21 @@ def normals_to_tbn(normals):
     return np.ascontiguousarray(out)
 
 
+ACES_CG_LUMINANCE_ROW = (float.fromhex("0x1.1614ep-2"), float.fromhex("0x1.58e6fep-1"), float.fromhex("0x1.d946e6p-5"))
+
+
+def _texel_floats(data):
+    a = np.asarray(data)
+    return (a.astype(np.float32) * np.float32(1.0 / 255.0)) if a.dtype == np.uint8 else a.astype(np.float32)
+
+
 def oracle_render(positions, indices, tri_material, albedo, radiance, camera, width, height, spp,
                   sample_mode=2, rr_range=(2, 20), seed=0, near_far=(0.01, 1000.0), threads=None,
                   spectral_data=None, wavelength_mode=2, textures=None, albedo_texture=None, vertex_uvs=None,
-                  material_type=None, light_two_sided=None, film_filter=None, film_filter_radius=1.0, material_params=None, vertex_normals=None):
-    """tri_material: per triangle, >= 0 Lambert material index, -1 - k for light k. Returns image[h,w,3]
+                  material_type=None, light_two_sided=None, film_filter=None, film_filter_radius=1.0, material_params=None, vertex_normals=None,
+                  boundary=None):
+    """boundary: None = (L)Null, or dict(type="Skysphere_Spherical"|"Skysphere_CoOcta", radiance=(r, g, b) | texture=index, transform=[3, 4],
+    scene_diameter=0, luminance_row=ACES_CG). tri_material: per triangle, >= 0 Lambert material index, -1 - k for light k. Returns image[h,w,3]
     (row 0 = bottom) resolved as sum radiance / sum weight. spectral_data (mray_b200.spectral.load())
     switches to the hero-wavelength spectral estimator."""
     from concurrent.futures import ThreadPoolExecutor
@@ -485,6 +512,25 @@ def oracle_render(positions, indices, tri_material, albedo, radiance, camera, wi
     if material_params is not None:   # [material, 8]: Refract cauchyFront / cauchyBack, Unreal roughness / specular / metallic
         mp = np.ascontiguousarray(material_params, np.float32).reshape(-1, 8)
         s.materialParams = mp.ctypes.data
+    s.boundaryTexture = -1
+    s.boundaryM = (C.c_float * 9)(1, 0, 0, 0, 1, 0, 0, 0, 1); s.boundaryInvM = (C.c_float * 9)(1, 0, 0, 0, 1, 0, 0, 0, 1)
+    if boundary is not None:
+        s.boundaryType = {"Skysphere_Spherical": 1, "Skysphere_CoOcta": 2}[boundary["type"]]
+        s.boundaryRadiance = (C.c_float * 3)(*boundary.get("radiance", (0.0, 0.0, 0.0)))
+        if boundary.get("transform") is not None:
+            m = np.asarray(boundary["transform"], np.float64).reshape(3, 4)[:, :3]
+            s.boundaryM = (C.c_float * 9)(*m.reshape(-1)); s.boundaryInvM = (C.c_float * 9)(*np.linalg.inv(m).reshape(-1))
+        if boundary.get("texture", -1) >= 0:
+            s.boundaryTexture = int(boundary["texture"])
+            lum = oracle_luminance(np.asarray(_texel_floats(textures[s.boundaryTexture]["data"])), boundary.get("luminance_row", ACES_CG_LUMINANCE_ROW))
+            sky_cx, sky_cy = oracle_dist2d_build(lum)
+            s.boundaryCdfX, s.boundaryCdfY = sky_cx.ctypes.data, sky_cy.ctypes.data
+        dia = float(boundary.get("scene_diameter", 0.0))
+        if dia <= 0.0:   # TracerBase::CommitSurfaces: the XZ diagonal of the scene AABB
+            used = positions[np.unique(indices)]
+            span = used.max(axis=0) - used.min(axis=0)
+            dia = float(np.sqrt(np.float32(span[0]) ** 2 + np.float32(span[2]) ** 2))
+        s.sceneDiameter = dia
     out = np.zeros((4, height, width), np.float32)
     threads = threads or min(16, os.cpu_count() or 1)
     rows = np.linspace(0, height, threads * 4 + 1).astype(int)
@@ -584,3 +630,51 @@ def oracle_rng_generate(kind, matrices, seeds, sample_index, width, height, init
                        C.c_uint32(width), C.c_uint32(height), C.c_uint32(initial_max_spp), C.c_uint32(dim_start), req,
                        C.c_int(len(requests)), out.ctypes.data_as(C.c_void_p))
     return out
+
+
+# ---- piecewise-constant 2-D distribution + skysphere converters (oracle/dist_oracle.c) ----
+def oracle_dist2d_build(function):
+    f = np.ascontiguousarray(function, np.float32)
+    h, w = f.shape
+    L = lib()
+    L.orc_dist2d_build.argtypes = [_f32p, C.c_uint32, C.c_uint32, _f32p, _f32p]
+    cx, cy = np.zeros((h, w), np.float32), np.zeros(h, np.float32)
+    L.orc_dist2d_build(f, w, h, cx, cy)
+    return cx, cy
+
+
+def oracle_dist2d_sample(cdf_x, cdf_y, xi):
+    """-> (n, 4): u, v, SampleUV pdf, PdfUV(u, v)"""
+    L = lib()
+    L.orc_dist2d_sample_many.argtypes = [_f32p, _f32p, C.c_uint32, C.c_uint32, _f32p, C.c_uint32, _f32p]
+    xi = np.ascontiguousarray(xi, np.float32)
+    out = np.zeros((xi.shape[0], 4), np.float32)
+    h, w = cdf_x.shape
+    L.orc_dist2d_sample_many(np.ascontiguousarray(cdf_x), np.ascontiguousarray(cdf_y), w, h, xi, xi.shape[0], out)
+    return out
+
+
+def oracle_sky_converters(mode, dirs):
+    """-> (n, 8): DirToUV u, v, ToSolidAnglePdf(1, dir), UVToDir(DirToUV) xyz, ToSolidAnglePdf(1, uv), 0 (the tap's layout)"""
+    L = lib()
+    f3, f2 = C.c_float * 3, C.c_float * 2
+    L.orc_sky_dir_to_uv.argtypes = [C.c_int, f3, f2]
+    L.orc_sky_uv_to_dir.argtypes = [C.c_int, f2, f3]
+    L.orc_sky_pdf_from_dir.argtypes = [C.c_int, C.c_float, f3]; L.orc_sky_pdf_from_dir.restype = C.c_float
+    L.orc_sky_pdf_from_uv.argtypes = [C.c_int, C.c_float, f2]; L.orc_sky_pdf_from_uv.restype = C.c_float
+    out = np.zeros((dirs.shape[0], 8), np.float32)
+    for i, d in enumerate(np.asarray(dirs, np.float32)):
+        dd, uv, back = f3(*d), f2(), f3()
+        L.orc_sky_dir_to_uv(mode, dd, uv)
+        L.orc_sky_uv_to_dir(mode, uv, back)
+        out[i] = [uv[0], uv[1], L.orc_sky_pdf_from_dir(mode, 1.0, dd), back[0], back[1], back[2], L.orc_sky_pdf_from_uv(mode, 1.0, uv), 0.0]
+    return out
+
+
+def oracle_luminance(rgb, y_row):
+    L = lib()
+    L.orc_luminance.argtypes = [_f32p, C.c_uint32, C.c_uint32, _f32p, _f32p]
+    p = np.ascontiguousarray(rgb, np.float32).reshape(-1, rgb.shape[-1])
+    out = np.zeros(p.shape[0], np.float32)
+    L.orc_luminance(p, p.shape[0], p.shape[1], np.asarray(y_row, np.float32), out)
+    return out.reshape(rgb.shape[:-1])
