@@ -62,7 +62,7 @@ typedef struct mrb_meta_hit { float a, b; } mrb_meta_hit;
 /* ---- library / context ------------------------------------------------------------------ */
 
 /* ABI version of this header (major<<16 | minor); the descriptor struct layouts are part of it. */
-#define MRB_ABI_VERSION ((0u << 16) | 4u)
+#define MRB_ABI_VERSION ((0u << 16) | 5u)
 MRB_API uint32_t mrb_abi_version(void);
 
 /* Replaces GPUSystem + GPUQueue ownership inside TracerBase (Device/CUDA/GPUSystemCUDA.cpp:L249-405:
@@ -94,6 +94,11 @@ MRB_API const char* mrb_last_error(mrb_context ctx); /* ctx may be NULL: last cr
  * [0] wide closest-hit traversal kernel, [1] shading kernel, [2] wide any-hit traversal kernel, [3] finish + reload kernel,
  * [4] the exact-resolution tail of a cast (KResolveExact + KTraceBinary). The reference's counterpart is its NVTX ranges. */
 typedef struct mrb_kernel_profile { double ms[5]; uint64_t samples[5]; } mrb_kernel_profile;
+/* Seed of the stochastic alpha test of the NEXT casts on this context (see mrb_accel_desc.rangeAlphaMap): every cast
+ * hashes (seed, ray index, leaf) and then advances the context's seed by one, so consecutive casts decorrelate and a
+ * caller that sets the seed replays the same decisions. Renderers derive it from TracerParameters.seed and their
+ * iteration counter. */
+MRB_API mrb_status mrb_context_set_alpha_seed(mrb_context ctx, uint32_t seed);
 MRB_API mrb_status mrb_context_set_profiling(mrb_context ctx, int enabled, uint32_t iterationStride);
 MRB_API mrb_status mrb_context_get_profile(mrb_context ctx, mrb_kernel_profile* out);
 
@@ -141,6 +146,18 @@ typedef struct mrb_accel_desc
     const uint32_t* lightOrMatKeys;/* rangeCount ; host ; NULL = 0                                 */
     const uint8_t*  cullBackface; /* rangeCount ; host ; NULL = 0 (two sided)                      */
     uint32_t        flags;        /* mrb_build_flags                                               */
+    /* Alpha maps (SurfaceParams.alphaMaps, Core/TracerI.h; AcceleratorLBVH::IntersectionCheck,
+     * Tracer/AcceleratorLBVH.hpp:L263-282): rangeAlphaMap[r] = -1, or an index into alphaTextures. A triangle hit of
+     * such a range is kept with probability alpha(uv) — uv = the hit's interpolated UV0, alpha = channel 0 of the
+     * texture — both in closest-hit and in visibility casts ("stochastic alpha culling"). The reference draws the
+     * deciding number from its per-ray backup PCG32; here it is a hash of (cast seed, ray index, leaf), so one
+     * (ray, triangle) pair gets one decision however often and in whatever order the traversal meets it.
+     * alphaTextures: single-mip textures, 1..4 channels of fp32 / unorm8 (host data, mrb_texture_desc is declared
+     * below); vertexUVs: vertexCount * 2 floats in `memspace`. All NULL / 0 = no alpha maps. */
+    const float*    vertexUVs;
+    uint32_t        alphaTextureCount;
+    const struct mrb_texture_desc* alphaTextures;
+    const int32_t*  rangeAlphaMap; /* rangeCount ; host ; NULL = none */
 } mrb_accel_desc;
 
 MRB_API mrb_status mrb_accel_build(mrb_context ctx, const mrb_accel_desc* desc, mrb_accel* out);
@@ -350,7 +367,7 @@ typedef enum mrb_film_filter { MRB_FILTER_BOX = 0, MRB_FILTER_TENT = 1, MRB_FILT
  * +0.5, nearest or bilinear with unfused lerps, wrap / clamp / mirror edge resolve; with one mip level the
  * ray-cone gradient of TracerTexView::operator()(uv, dpdx, dpdy) clamps to level 0. */
 typedef struct mrb_texture_desc
-{
+{   /* (channels: 3 or 4 for colour reads; an alpha map may also have 1 or 2 and only its first channel is read) */
     const void* data;        /* host; row-major, width*height texels, `channels` values each */
     uint32_t    width, height;
     uint32_t    channels;    /* 3 or 4 (a 4th channel is ignored by Vector3 reads) */

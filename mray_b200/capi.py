@@ -45,7 +45,8 @@ class AccelDesc(C.Structure):
                 ("memspace", C.c_int), ("primGroupId", C.c_uint32),
                 ("rangeCount", C.c_uint32), ("primRanges", C.c_void_p),
                 ("lightOrMatKeys", C.c_void_p), ("cullBackface", C.c_void_p),
-                ("flags", C.c_uint32)]
+                ("flags", C.c_uint32), ("vertexUVs", C.c_void_p), ("alphaTextureCount", C.c_uint32),
+                ("alphaTextures", C.c_void_p), ("rangeAlphaMap", C.c_void_p)]
 
 
 class AccelInfo(C.Structure):
@@ -109,7 +110,7 @@ BOUNDARY_TYPES = {"Null": 0, "Skysphere_Spherical": 1, "Skysphere_CoOcta": 2}   
 FILM_FILTERS = {"Box": 0, "Tent": 1, "Gaussian": 2, "Mitchell-Netravali": 3}   # FilterType::E (Core/TracerEnums.h:L162-173)
 HOST_FN = C.CFUNCTYPE(None, C.c_void_p)
 # the descriptor mirrors above are written for this ABI (include/mray_b200.h: MRB_ABI_VERSION)
-MRB_ABI_VERSION = (0 << 16) | 4
+MRB_ABI_VERSION = (0 << 16) | 5
 
 # every symbol include/mray_b200.h declares (tests/test_capi_symbols.py checks the header against this)
 _PROTOTYPES = {
@@ -123,6 +124,7 @@ _PROTOTYPES = {
     "mrb_context_launch_count": (C.c_uint64, [C.c_void_p]),
     "mrb_context_last_fallback_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "mrb_last_error": (C.c_char_p, [C.c_void_p]),
+    "mrb_context_set_alpha_seed": (C.c_int, [C.c_void_p, C.c_uint32]),
     "mrb_context_set_profiling": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32]),
     "mrb_context_get_profile": (C.c_int, [C.c_void_p, C.POINTER(KernelProfile)]),
     "mrb_accel_build": (C.c_int, [C.c_void_p, C.POINTER(AccelDesc), C.POINTER(C.c_void_p)]),
@@ -275,6 +277,10 @@ class Context:
         self.check(self.lib.mrb_context_last_fallback_count(self.handle, out))
         return tuple(int(x) for x in out)
 
+    def set_alpha_seed(self, seed: int):
+        """Seed of the stochastic alpha test of the next casts (mrb_context_set_alpha_seed); advances by one per cast."""
+        self.check(self.lib.mrb_context_set_alpha_seed(self.handle, seed & 0xFFFFFFFF))
+
     def set_profiling(self, enabled: bool, iteration_stride: int = 16):
         """Sampled CUDA-event timing of the renderer's kernels (mrb_context_set_profiling)."""
         self.check(self.lib.mrb_context_set_profiling(self.handle, 1 if enabled else 0, iteration_stride))
@@ -344,7 +350,10 @@ class Accelerator:
     identity-transform instance (Tracer/AcceleratorLBVH.hpp:L433-899)."""
 
     def __init__(self, ctx: Context, positions, indices, prim_ranges=None, light_or_mat_keys=None,
-                 cull_backface=None, prim_group_id: int = 0, flags: int = MRB_BUILD_DEFAULT):
+                 cull_backface=None, prim_group_id: int = 0, flags: int = MRB_BUILD_DEFAULT,
+                 vertex_uvs=None, alpha_textures=None, range_alpha_map=None):
+        """alpha maps (SurfaceParams.alphaMaps): alpha_textures = list of dict(data=[h, w] or [h, w, c] float32 / uint8, interp=,
+        edge=) read through their first channel, range_alpha_map = per prim range -1 or a texture index, vertex_uvs [V, 2]."""
         self.ctx = ctx
         d = AccelDesc()
         d.positions = _ptr(positions)
@@ -368,6 +377,29 @@ class Accelerator:
             d.cullBackface = cb.ctypes.data
             self._keep.append(cb)
         d.flags = flags
+        if range_alpha_map is not None:
+            ram = np.ascontiguousarray(range_alpha_map, np.int32)
+            self._keep.append(ram)
+            d.rangeAlphaMap = ram.ctypes.data
+            if vertex_uvs is not None:
+                uv = vertex_uvs if not isinstance(vertex_uvs, np.ndarray) else np.ascontiguousarray(vertex_uvs, np.float32)
+                self._keep.append(uv)
+                d.vertexUVs = _ptr(uv)
+            tarr = (TextureDesc * max(1, len(alpha_textures or [])))()
+            for k, t in enumerate(alpha_textures or []):
+                a = np.ascontiguousarray(t["data"])
+                if a.dtype != np.uint8:
+                    a = np.ascontiguousarray(a, np.float32)
+                if a.ndim == 2:
+                    a = a[..., None]
+                self._keep.append(a)
+                tarr[k].data = a.ctypes.data
+                tarr[k].height, tarr[k].width, tarr[k].channels = a.shape
+                tarr[k].format = 1 if a.dtype == np.uint8 else 0
+                tarr[k].interp = TEX_INTERP[t.get("interp", "Linear")]
+                tarr[k].edge = TEX_EDGE[t.get("edge", "Wrap")]
+            self._keep.append(tarr)
+            d.alphaTextureCount, d.alphaTextures = len(alpha_textures or []), C.cast(tarr, C.c_void_p)
         h = C.c_void_p()
         ctx.check(ctx.lib.mrb_accel_build(ctx.handle, C.byref(d), C.byref(h)))
         self.handle = h

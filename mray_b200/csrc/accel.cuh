@@ -17,6 +17,10 @@ struct LBVHBox  { float min[3], max[3]; };
 // (the reference allows <= 8 per surface, AcceleratorC.h:L281-301; surfaces that share the identity
 // transform may be flattened into one accelerator here, so the list lives in device memory and is
 // searched by bisection).
+// One single-channel 2-D texture read as an alpha map (AlphaMap = TracerTexView<2, Float>, Tracer/AcceleratorC.h:L123):
+// channel 0 of `channels`, fp32 or unorm8, one mip level, filtered like every other texture of this library.
+struct AlphaTex { const void* data; uint32_t w, h, channels, format, interp, edge, pad; };
+
 struct PrimRanges
 {
     uint32_t        count;
@@ -25,6 +29,10 @@ struct PrimRanges
     const uint32_t* primBegin; // count
     const uint32_t* lmKey;     // count
     const uint32_t* cull;      // count
+    // alpha maps (SurfaceParams.alphaMaps, one Optional<TextureId> per prim batch): nullptr = none in this accelerator
+    const int32_t*  alphaMap;  // count: index into alphaTex, or -1
+    const AlphaTex* alphaTex;
+    const float*    uvs;       // vertex UV0 (2 floats per vertex of the primitive group)
 };
 
 __host__ __device__ __forceinline__ uint32_t FindRange(const PrimRanges& r, uint32_t leaf)
@@ -54,7 +62,7 @@ struct alignas(16) WideNode { uint4 q[5]; };
 // arithmetic stays bit-identical to the reference.
 //   v0 : p0.xyz, leaf index (position in the accelerator's leaf list)
 //   v1 : e0.xyz, rank (position after the Morton sort = the reference's visit order; tie-break)
-//   v2 : e1.xyz, flags (bit0 = cull back face) | range index << 8
+//   v2 : e1.xyz, flags (bit0 = cull back face, bit1 = the range has an alpha map) | range index << 8
 struct alignas(16) TriRecord { float4 v0, v1, v2; };
 
 struct AccelData
@@ -106,6 +114,7 @@ struct SceneData
     AccelData          tlas;              // leaves = instances (leafAABB = world AABBs)
     const InstanceRec* instances = nullptr;
     uint32_t           instanceCount = 0;
+    uint32_t           hasAlpha = 0;      // any instance's accelerator carries alpha maps: the ALPHA kernels run
 };
 
 } // namespace mrb
@@ -115,6 +124,7 @@ struct mrb_accel_t
     mrb::AccelData   d;
     // host copies of the prim-range table (d.ranges points at the device copy)
     std::vector<uint32_t> hLeafStart, hPrimBegin, hLmKey, hCull;
+    std::vector<int32_t> hAlphaMap;        // per range: alpha texture index or -1 (empty = no alpha maps)
     mrb::DeviceBlock mem;
     mrb_accel_info   info = {};
     uint32_t         flags = 0;

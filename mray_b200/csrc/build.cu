@@ -11,6 +11,7 @@
 // Floating point: every expression that feeds an integer artefact (Morton code) is written with
 // explicit round-to-nearest intrinsics so that nvcc cannot contract it into an FMA.
 #include "accel.cuh"
+#include <stdexcept>
 #include <cfloat>
 #include <cstring>
 #include <cooperative_groups.h>
@@ -531,7 +532,7 @@ KFillTris(AccelData a, const uint32_t* __restrict__ triRank)
         t.v1 = make_float4(__fsub_rn(p[1][0], p[0][0]), __fsub_rn(p[1][1], p[0][1]), __fsub_rn(p[1][2], p[0][2]),
                            __uint_as_float(rank));
         t.v2 = make_float4(__fsub_rn(p[2][0], p[0][0]), __fsub_rn(p[2][1], p[0][1]), __fsub_rn(p[2][2], p[0][2]),
-                           __uint_as_float((a.ranges.cull[ri] ? 1u : 0u) | (ri << 8)));
+                           __uint_as_float((a.ranges.cull[ri] ? 1u : 0u) | ((a.ranges.alphaMap && a.ranges.alphaMap[ri] >= 0) ? 2u : 0u) | (ri << 8)));
         a.tris[s] = t;
     }
 }
@@ -685,6 +686,7 @@ void BuildScene(Context& ctx, mrb_scene_t& sc, const mrb_instance_desc* inst, ui
         memcpy(r.invTransform, inst[i].invTransform, sizeof(r.invTransform));
         r.wideNodes = a.d.wideNodes; r.tris = a.d.tris; r.leafAABB = a.d.leafAABB;
         r.positions = a.d.positions; r.indices = a.d.indices; r.nodes = a.d.nodes; r.boxes = a.d.boxes;
+        if(a.d.ranges.alphaMap) s.hasAlpha = 1u;
         r.ranges = a.d.ranges; r.accelKey = inst[i].accelKey; r.transKey = inst[i].transformKey;
         r.identity = inst[i].isIdentity ? 1u : 0u; r.leafCount = a.d.leafCount;
         if(inst[i].lightOrMatKeys)
@@ -755,8 +757,21 @@ void BuildScene(Context& ctx, mrb_scene_t& sc, const mrb_instance_desc* inst, ui
 }
 
 // Sizes the persistent block of one accelerator (sub-arrays are 256-byte aligned).
-static void LayoutAccel(MultiAlloc& ma, AccelData& d, uint32_t vertexCount, uint32_t triCount, bool ownInputs, bool wide)
+static void LayoutAccel(MultiAlloc& ma, AccelData& d, uint32_t vertexCount, uint32_t triCount, bool ownInputs, bool wide,
+                        const mrb_accel_desc* alphaDesc = nullptr, std::vector<AlphaTex>* alphaTex = nullptr)
 {
+    if(alphaDesc)
+    {   // alpha maps: per-range table, texture records + texels, vertex UVs
+        d.ranges.alphaMap = ma.Take<int32_t>(d.ranges.count);
+        d.ranges.alphaTex = ma.Take<AlphaTex>(alphaDesc->alphaTextureCount);
+        d.ranges.uvs = ma.Take<float>(size_t(vertexCount) * 2);
+        for(uint32_t t = 0; t < alphaDesc->alphaTextureCount; t++)
+        {
+            const mrb_texture_desc& td = alphaDesc->alphaTextures[t];
+            (*alphaTex)[t] = AlphaTex{ma.Take<char>(size_t(td.width) * td.height * td.channels * (td.format == 0u ? 4u : 1u)),
+                                      td.width, td.height, td.channels, td.format, td.interp, td.edge, 0u};
+        }
+    }
     if(ownInputs)
     {
         d.positions = ma.Take<float>(size_t(vertexCount) * 3);
@@ -807,12 +822,31 @@ void BuildAccel(Context& ctx, mrb_accel_t& acc, const mrb_accel_desc& desc)
     }
     d.leafCount = acc.hLeafStart[r.count];
     d.nodeCount = d.leafCount > 1 ? d.leafCount - 1 : 1;
+    // alpha maps (SurfaceParams.alphaMaps): validated here, uploaded below
+    acc.hAlphaMap.clear();
+    bool anyAlpha = false;
+    if(desc.rangeAlphaMap)
+        for(uint32_t i = 0; i < r.count; i++) anyAlpha = anyAlpha || desc.rangeAlphaMap[i] >= 0;
+    std::vector<AlphaTex> alphaTex(anyAlpha ? desc.alphaTextureCount : 0u);
+    if(anyAlpha)
+    {
+        if(!desc.vertexUVs || !desc.alphaTextures) throw std::runtime_error("alpha maps need vertexUVs and alphaTextures");
+        acc.hAlphaMap.assign(desc.rangeAlphaMap, desc.rangeAlphaMap + r.count);
+        for(int32_t m : acc.hAlphaMap) if(m >= int32_t(desc.alphaTextureCount)) throw std::runtime_error("rangeAlphaMap index exceeds alphaTextureCount");
+        for(uint32_t t = 0; t < desc.alphaTextureCount; t++)
+        {
+            const mrb_texture_desc& td = desc.alphaTextures[t];
+            if(!td.data || td.width == 0 || td.height == 0 || td.channels < 1 || td.channels > 4 || td.format > 1u || td.interp > 1u || td.edge > 2u)
+                throw std::runtime_error("bad alpha texture descriptor");
+        }
+    }
+    const mrb_accel_desc* alphaDesc = anyAlpha ? &desc : nullptr;
 
     MultiAlloc sizing(nullptr);
-    LayoutAccel(sizing, d, desc.vertexCount, desc.triangleCount, true, wide);
+    LayoutAccel(sizing, d, desc.vertexCount, desc.triangleCount, true, wide, alphaDesc, &alphaTex);
     acc.mem.Reserve(sizing.Total());
     MultiAlloc ma(acc.mem.Base());
-    LayoutAccel(ma, d, desc.vertexCount, desc.triangleCount, true, wide);
+    LayoutAccel(ma, d, desc.vertexCount, desc.triangleCount, true, wide, alphaDesc, &alphaTex);
     ctx.persistentBytes += acc.mem.Capacity();
 
     MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<uint32_t*>(r.leafStart), acc.hLeafStart.data(), 4 * (r.count + 1), cudaMemcpyHostToDevice, ctx.stream));
@@ -820,6 +854,17 @@ void BuildAccel(Context& ctx, mrb_accel_t& acc, const mrb_accel_desc& desc)
     MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<uint32_t*>(r.lmKey), acc.hLmKey.data(), 4 * r.count, cudaMemcpyHostToDevice, ctx.stream));
     MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<uint32_t*>(r.cull), acc.hCull.data(), 4 * r.count, cudaMemcpyHostToDevice, ctx.stream));
     cudaMemcpyKind kind = (desc.memspace == MRB_MEM_HOST) ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    if(anyAlpha)
+    {
+        MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<int32_t*>(r.alphaMap), acc.hAlphaMap.data(), 4 * r.count, cudaMemcpyHostToDevice, ctx.stream));
+        MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<float*>(r.uvs), desc.vertexUVs, sizeof(float) * 2 * size_t(desc.vertexCount), kind, ctx.stream));
+        for(uint32_t t = 0; t < desc.alphaTextureCount; t++)
+            MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<void*>(alphaTex[t].data), desc.alphaTextures[t].data,
+                                         size_t(alphaTex[t].w) * alphaTex[t].h * alphaTex[t].channels * (alphaTex[t].format == 0u ? 4u : 1u),
+                                         cudaMemcpyHostToDevice, ctx.stream));
+        MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<AlphaTex*>(r.alphaTex), alphaTex.data(), sizeof(AlphaTex) * alphaTex.size(), cudaMemcpyHostToDevice, ctx.stream));
+        MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));   // alphaTex (host vector) is read by the copy above
+    }
     MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<float*>(d.positions), desc.positions,
                                  sizeof(float) * 3 * size_t(desc.vertexCount), kind, ctx.stream));
     MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<uint32_t*>(d.indices), desc.indices,

@@ -97,7 +97,7 @@ static mrb_status Fail(mrb::Context& c, mrb_status s, const char* msg) { c.error
 extern "C"
 {
 
-uint32_t mrb_abi_version(void) { return MRB_ABI_VERSION; }   // 4: boundary light (skysphere) fields of mrb_render_desc, mrb_dist2d_*
+uint32_t mrb_abi_version(void) { return MRB_ABI_VERSION; }   // 5: alpha maps in mrb_accel_desc; 4: boundary light (skysphere) fields of mrb_render_desc, mrb_dist2d_*
 
 mrb_status mrb_context_create(int device, mrb_context* out)
 {
@@ -193,6 +193,11 @@ mrb_status mrb_context_last_fallback_count(mrb_context ctx, uint32_t* out)
 }
 
 const char* mrb_last_error(mrb_context ctx) { return ctx ? ctx->c.error.c_str() : gCreateError.c_str(); }
+
+mrb_status mrb_context_set_alpha_seed(mrb_context ctx, uint32_t seed)
+{
+    return Guard(ctx, [&](mrb::Context& c) { c.alphaSeed = seed; return MRB_OK; });
+}
 
 mrb_status mrb_context_set_profiling(mrb_context ctx, int enabled, uint32_t iterationStride)
 {

@@ -90,6 +90,7 @@ struct Context
     DeviceBlock  traceScratch;        // exact-fallback ray list of the wide traversal
     const uint32_t* lastFallbackCount = nullptr; // device counter of the last wide cast
     uint64_t     launches = 0;
+    uint32_t     alphaSeed = 0x9E3779B9u; // seed of the next cast's stochastic alpha test (advances per cast)
     std::string  error;
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
     // host-pointer casts: upload / trace / download of consecutive ray chunks overlap on three streams
@@ -99,7 +100,7 @@ struct Context
     cudaEvent_t  evStart = nullptr;
     KernelProfile prof;
     // occupancy of the persistent traversal kernels on THIS device (blocks per SM), filled on first use
-    int          occWide[2] = {0, 0}, occWide2[2] = {0, 0};
+    int          occWide[4] = {0, 0, 0, 0}, occWide2[4] = {0, 0, 0, 0};   // [anyHit + 2 * alphaMaps]
     const void*  persistBase = nullptr;   // accelerator the stream's L2 access-policy window currently covers
     cudaStream_t persistStream = nullptr;
 };

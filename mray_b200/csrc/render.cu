@@ -1650,6 +1650,13 @@ void RenderIterate(Context& ctx, mrb_renderer_t& r, uint32_t iterations)
     {
         ctx.prof.sampleNow = ctx.prof.enabled && (r.iterations % ctx.prof.stride) == 0;
         if(r.needReload) { MRB_LAUNCH(ctx, KReload, grid, RTPB, 0, d); r.needReload = false; }
+        // stochastic alpha decisions of this iteration's two casts: a function of (seed, iteration) like every other random
+        // number of the renderer, so a fixed seed still gives a fixed image
+        {
+            uint64_t z = d.seed + 0x9E3779B97F4A7C15ull * (r.iterations + 1ull);
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+            ctx.alphaSeed = uint32_t(z) & ~1u;
+        }
         if(r.scene) TraceScene(ctx, r.sceneData, false, MRB_TRACE_WIDE, d.hitKeys, d.hits, nullptr, d.rays, nullptr, d.slots);
         else TraceRays(ctx, *r.accel, false, MRB_TRACE_WIDE, d.hitKeys, d.hits, nullptr, d.rays, nullptr, d.slots);
         if(d.partitionRays)

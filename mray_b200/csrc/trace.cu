@@ -101,6 +101,91 @@ __device__ __forceinline__ void WriteHit(const AccelData& a, uint32_t accelKey, 
 __device__ __forceinline__ float StdMax(float a, float b) { return (a < b) ? b : a; }
 __device__ __forceinline__ float StdMin(float a, float b) { return (b < a) ? b : a; }
 
+
+// ------------------------------------------------------------------------------------------------
+// Stochastic alpha test (AcceleratorLBVH::IntersectionCheck, Tracer/AcceleratorLBVH.hpp:L263-282)
+// ------------------------------------------------------------------------------------------------
+// The alpha map's texture view, restating the reference's host-backend view for ONE channel
+// (Device/CPU/TextureViewCPU.h: texel centres at +0.5, nearest or bilinear with unfused lerps, wrap / clamp / mirror).
+__device__ __forceinline__ int AlphaEdge(int i, int n, uint32_t edge)
+{
+    if(edge == 1u) return min(max(i, 0), n - 1);
+    if(edge == 2u)
+    {
+        const int dim = i / n;
+        i = i % n;
+        if(i < 0) i += n;
+        if((dim & 1) == 1) i = n - i;
+        return min(i, n - 1);
+    }
+    i = i % n;
+    if(i < 0) i += n;
+    return i;
+}
+__device__ __forceinline__ float AlphaTexel(const AlphaTex& t, int x, int y)
+{
+    const size_t o = (size_t(y) * t.w + size_t(x)) * t.channels;
+    if(t.format == 0u) return __ldg(static_cast<const float*>(t.data) + o);
+    return __fmul_rn(float(__ldg(static_cast<const uint8_t*>(t.data) + o)), 1.0f / 255.0f);
+}
+__device__ __forceinline__ float AlphaLerp(float a, float b, float t) { return __fadd_rn(__fmul_rn(a, __fsub_rn(1.0f, t)), __fmul_rn(b, t)); }
+__device__ __forceinline__ float SampleAlpha(const AlphaTex& t, float u, float v)
+{
+    const float tu = __fmul_rn(u, float(t.w)), tv = __fmul_rn(v, float(t.h));
+    if(t.interp == 0u)
+    {
+        const int x = int(roundf(tu - 0.5f)), y = int(roundf(tv - 0.5f));
+        return AlphaTexel(t, AlphaEdge(x, int(t.w), t.edge), AlphaEdge(y, int(t.h), t.edge));
+    }
+    float bx, by;
+    float fx = modff(tu - 0.5f, &bx), fy = modff(tv - 0.5f, &by);
+    int x0 = int(bx), y0 = int(by);
+    if(fx < 0.0f) { x0 -= 1; fx = fabsf(fx); }
+    if(fy < 0.0f) { y0 -= 1; fy = fabsf(fy); }
+    const int xa = AlphaEdge(x0, int(t.w), t.edge), xb = AlphaEdge(x0 + 1, int(t.w), t.edge);
+    const int ya = AlphaEdge(y0, int(t.h), t.edge), yb = AlphaEdge(y0 + 1, int(t.h), t.edge);
+    const float p0 = AlphaLerp(AlphaTexel(t, xa, ya), AlphaTexel(t, xb, ya), fx);
+    const float p1 = AlphaLerp(AlphaTexel(t, xa, yb), AlphaTexel(t, xb, yb), fx);
+    return AlphaLerp(p0, p1, fy);
+}
+// Does the hit (u, v = Moller-Trumbore coordinates) on `leaf` of range `ri` survive its alpha map? uv = the hit's
+// interpolated UV0 (Triangle::SurfaceParametrization: uv0 a + uv1 b + uv2 c with (a, b) = (1 - u - v, u)); the hit is
+// dropped when xi >= alpha. xi: the reference takes the next float of the ray's backup PCG32; here one hash of
+// (cast seed, the ray's bits, leaf), so a (ray, triangle) pair always gets the same answer — the wide kernels, the exact
+// resolution and the binary fallback may each meet the same triangle. Out of line: only alpha-mapped triangles pay.
+__device__ __noinline__ bool AlphaKeepsHit(const PrimRanges& rg, const uint32_t* __restrict__ indices, uint32_t leaf, uint32_t ri,
+                                           float u, float v, const mrb_ray_gmem* ray, uint32_t seed)
+{
+    const AlphaTex t = rg.alphaTex[rg.alphaMap[ri]];
+    const uint32_t prim = rg.primBegin[ri] + (leaf - rg.leafStart[ri]);
+    const uint32_t i0 = indices[3 * size_t(prim)], i1 = indices[3 * size_t(prim) + 1], i2 = indices[3 * size_t(prim) + 2];
+    const float2 t0 = *reinterpret_cast<const float2*>(rg.uvs + 2 * size_t(i0));
+    const float2 t1 = *reinterpret_cast<const float2*>(rg.uvs + 2 * size_t(i1));
+    const float2 t2 = *reinterpret_cast<const float2*>(rg.uvs + 2 * size_t(i2));
+    const float a = __fsub_rn(__fsub_rn(1.0f, u), v), b = u, c = __fsub_rn(__fsub_rn(1.0f, a), b);
+    const float tu = __fadd_rn(__fadd_rn(__fmul_rn(t0.x, a), __fmul_rn(t1.x, b)), __fmul_rn(t2.x, c));
+    const float tv = __fadd_rn(__fadd_rn(__fmul_rn(t0.y, a), __fmul_rn(t1.y, b)), __fmul_rn(t2.y, c));
+    const float alpha = SampleAlpha(t, tu, tv);
+    // the "ray" half of the key is the WORLD ray's own bits (as stored in the ray buffer, which no kernel rewrites except
+    // tMax): independent of slot assignment and of ray-index indirection, identical in every kernel that meets the pair
+    const uint4 w0 = *reinterpret_cast<const uint4*>(ray);
+    const uint4 w1 = *(reinterpret_cast<const uint4*>(ray) + 1);
+    uint32_t h = seed ^ (leaf * 0x85EBCA6Bu);
+    h = (h ^ w0.x) * 0x9E3779B1u; h = (h ^ (h >> 15) ^ w0.y) * 0x85EBCA77u; h = (h ^ (h >> 13) ^ w0.z) * 0xC2B2AE3Du;
+    h = (h ^ (h >> 16) ^ w1.x) * 0x27D4EB2Fu; h = (h ^ (h >> 15) ^ w1.y) * 0x165667B1u; h ^= w1.z;
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    const float xi = float(h >> 8) * 5.9604644775390625e-08f;   // [0, 1)
+    return xi < alpha;
+}
+
+template<bool ALPHA>
+__device__ __forceinline__ bool AlphaGate(const PrimRanges& rg, const uint32_t* __restrict__ indices, uint32_t flags, uint32_t leaf,
+                                          float u, float v, const mrb_ray_gmem* ray, uint32_t seed)
+{
+    if constexpr(ALPHA) return !(flags & 2u) || AlphaKeepsHit(rg, indices, leaf, flags >> 8, u, v, ray, seed);
+    else return true;
+}
+
 // Ray::IntersectsAABB (Core/Ray.hpp:L192-219), identical arithmetic (IEEE div / sub / mul, host
 // std::min / std::max semantics).
 __device__ __forceinline__ bool SlabExact(const float* __restrict__ b, const float o[3], const float invD[3],
@@ -141,10 +226,10 @@ constexpr float NEAR_TIE = 1.0000152587890625f; // 1 + 2^-16
 // ------------------------------------------------------------------------------------------------
 // One ray through the reference's own algorithm: binary LBVH, left-first stack traversal
 // (TraverseLBVHStack, AcceleratorLBVH.hpp:L109-167), Ray::IntersectsAABB arithmetic.
-template<bool ANY_HIT>
+template<bool ANY_HIT, bool ALPHA>
 __device__ __forceinline__ void TraceBinaryRayBody(const AccelData& a, uint32_t accelKey,
                                                    mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
-                                                   uint32_t* __restrict__ visibleBits, mrb_ray_gmem* rays, uint32_t r)
+                                                   uint32_t* __restrict__ visibleBits, mrb_ray_gmem* rays, uint32_t r, uint32_t alphaSeed)
 {
     const float4 r0 = reinterpret_cast<const float4*>(rays + r)[0];
     const float4 r1 = reinterpret_cast<const float4*>(rays + r)[1];
@@ -178,6 +263,7 @@ __device__ __forceinline__ void TraceBinaryRayBody(const AccelData& a, uint32_t 
             float t, u, v;
             if(!RayTriangle(o[0], o[1], o[2], d[0], d[1], d[2], v0, e0, e1, a.ranges.cull[ri] != 0u, t, u, v)) continue;
             if(!(t >= tMin && t < tMax)) continue;
+            if(ALPHA && a.ranges.alphaMap && a.ranges.alphaMap[ri] >= 0 && !AlphaKeepsHit(a.ranges, a.indices, leaf, ri, u, v, rays + r, alphaSeed)) continue;
             best.t = t; best.u = u; best.v = v; best.leaf = leaf; best.flags = ri << 8;
             tMax = t;
             if(ANY_HIT) break;
@@ -216,19 +302,26 @@ __device__ __forceinline__ void TraceBinaryRayBody(const AccelData& a, uint32_t 
 // and keeps the 160-entry stack and the registers of this code out of the hot loop.
 __device__ __noinline__ void TraceBinaryRayClosest(const AccelData& a, uint32_t accelKey, mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits,
                                                    mrb_ray_gmem* rays, uint32_t r)
-{ TraceBinaryRayBody<false>(a, accelKey, hitKeys, metaHits, nullptr, rays, r); }
+{ TraceBinaryRayBody<false, false>(a, accelKey, hitKeys, metaHits, nullptr, rays, r, 0u); }
 __device__ __noinline__ void TraceBinaryRayAny(const AccelData& a, uint32_t* visibleBits, mrb_ray_gmem* rays, uint32_t r)
-{ TraceBinaryRayBody<true>(a, 0u, nullptr, nullptr, visibleBits, rays, r); }
+{ TraceBinaryRayBody<true, false>(a, 0u, nullptr, nullptr, visibleBits, rays, r, 0u); }
+// ... and for accelerators with alpha maps (their own copies, so the kernels of scenes without alpha maps compile to exactly
+// what they were before alpha maps existed)
+__device__ __noinline__ void TraceBinaryRayClosestAlpha(const AccelData& a, uint32_t accelKey, mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits,
+                                                        mrb_ray_gmem* rays, uint32_t r, uint32_t alphaSeed)
+{ TraceBinaryRayBody<false, true>(a, accelKey, hitKeys, metaHits, nullptr, rays, r, alphaSeed); }
+__device__ __noinline__ void TraceBinaryRayAnyAlpha(const AccelData& a, uint32_t* visibleBits, mrb_ray_gmem* rays, uint32_t r, uint32_t alphaSeed)
+{ TraceBinaryRayBody<true, true>(a, 0u, nullptr, nullptr, visibleBits, rays, r, alphaSeed); }
 
 template<bool ANY_HIT>
 __global__ void __launch_bounds__(TRACE_TPB)
 KTraceBinary(const __grid_constant__ AccelData a, uint32_t accelKey,
              mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
              uint32_t* __restrict__ visibleBits,
-             mrb_ray_gmem* rays, const uint32_t* __restrict__ rayIndices, uint32_t rayCount)
+             mrb_ray_gmem* rays, const uint32_t* __restrict__ rayIndices, uint32_t rayCount, uint32_t alphaSeed)
 {
     for(uint32_t i = blockIdx.x * TRACE_TPB + threadIdx.x; i < rayCount; i += gridDim.x * TRACE_TPB)
-        TraceBinaryRayBody<ANY_HIT>(a, accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices ? rayIndices[i] : i);
+        TraceBinaryRayBody<ANY_HIT, true>(a, accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices ? rayIndices[i] : i, alphaSeed);
 }
 
 // Exact resolution of a ray the wide path could not certify, WITHOUT a full re-traversal: the
@@ -240,9 +333,11 @@ KTraceBinary(const __grid_constant__ AccelData a, uint32_t accelKey,
 // the ray goes to the full binary traversal (TraceBinaryRay), as do rays with three or more
 // candidates in the window. Called by the lane that owns the ray, straight from the wide kernel's epilogue
 // (round 1 ran this and the binary fallback as two more launches per cast: ~17 us of fixed cost each).
-__device__ __noinline__ void ResolveExactRay(const AccelData& a, uint32_t accelKey,
+template<bool ALPHA>
+__device__ __forceinline__ void ResolveExactRayBody(const AccelData& a, uint32_t accelKey,
                                              mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, mrb_ray_gmem* rays,
-                                             uint32_t* counters, uint32_t r, bool full, HitRecord c0, HitRecord c1, bool hasSecond)
+                                             uint32_t* counters, uint32_t r, bool full, HitRecord c0, HitRecord c1, bool hasSecond,
+                                             uint32_t alphaSeed)
 {
     HitRecord c[2] = {c0, c1};   // by value: the caller's records must stay in registers
     const int n = hasSecond ? 2 : 1;
@@ -286,10 +381,20 @@ __device__ __noinline__ void ResolveExactRay(const AccelData& a, uint32_t accelK
     if(full || accepted < 0)
     {
         atomicAdd(counters + 4, 1u);
-        TraceBinaryRayClosest(a, accelKey, hitKeys, metaHits, rays, r);
+        if constexpr(ALPHA) TraceBinaryRayClosestAlpha(a, accelKey, hitKeys, metaHits, rays, r, alphaSeed);
+        else TraceBinaryRayClosest(a, accelKey, hitKeys, metaHits, rays, r);
     }
     else WriteHit(a, accelKey, r, c[accepted], hitKeys, metaHits, rays);
 }
+
+__device__ __noinline__ void ResolveExactRay(const AccelData& a, uint32_t accelKey,
+                                             mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, mrb_ray_gmem* rays,
+                                             uint32_t* counters, uint32_t r, bool full, HitRecord c0, HitRecord c1, bool hasSecond)
+{ ResolveExactRayBody<false>(a, accelKey, hitKeys, metaHits, rays, counters, r, full, c0, c1, hasSecond, 0u); }
+__device__ __noinline__ void ResolveExactRayAlpha(const AccelData& a, uint32_t accelKey,
+                                                  mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, mrb_ray_gmem* rays,
+                                                  uint32_t* counters, uint32_t r, bool full, HitRecord c0, HitRecord c1, bool hasSecond, uint32_t alphaSeed)
+{ ResolveExactRayBody<true>(a, accelKey, hitKeys, metaHits, rays, counters, r, full, c0, c1, hasSecond, alphaSeed); }
 
 // ------------------------------------------------------------------------------------------------
 // Wide traversal
@@ -320,6 +425,7 @@ struct TraceParams
     uint32_t triDiv;    // triangle phase runs when lanesWithTriangles * triDiv >= liveLanes (or no lane has node work)
     uint32_t fetchThr;  // refill idle lanes with new rays when fewer than this many lanes are live
     uint32_t magic;     // 0x47000000 (float 32768): see QF
+    uint32_t alphaSeed; // seed of this cast's stochastic alpha decisions (AlphaKeepsHit)
 };
 
 // Persistent warps: every lane owns one ray at a time; finished lanes are refilled from a global
@@ -327,7 +433,9 @@ struct TraceParams
 // one node step per iteration, each executed by all lanes that have that kind of work — so the
 // 200-instruction node step and the 60-instruction triangle test always run with as many lanes as
 // possible; triangle groups are postponed (kept / pushed on the stack) until enough lanes have one.
-template<bool ANY_HIT>
+// ALPHA: the accelerator has alpha maps. Scenes without them run the instantiation that contains no trace of the alpha test
+// (its call sites, live ranges and seed argument cost the 72-register closest-hit kernel 1-3 % otherwise).
+template<bool ANY_HIT, bool ALPHA>
 __global__ void __launch_bounds__(TRACE_TPB, ANY_HIT ? MRB_WIDE_BLOCKS_ANY : MRB_WIDE_BLOCKS_CLOSEST)
 KTraceWide(const __grid_constant__ AccelData a, uint32_t accelKey,
            mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
@@ -366,7 +474,8 @@ KTraceWide(const __grid_constant__ AccelData a, uint32_t accelKey,
                 else if(uncertified)
                 {   // a hit whose leaf box the reference's own slab test might reject: ask the reference's algorithm
                     atomicAdd(counters, 1u); atomicAdd(counters + 2, 1u); atomicAdd(counters + 4, 1u);
-                    TraceBinaryRayAny(a, visibleBits, rays, r);
+                    if constexpr(ALPHA) TraceBinaryRayAnyAlpha(a, visibleBits, rays, r, prm.alphaSeed);
+                    else TraceBinaryRayAny(a, visibleBits, rays, r);
                 }
             }
             else if(best.leaf != INVALID_U32)
@@ -380,7 +489,8 @@ KTraceWide(const __grid_constant__ AccelData a, uint32_t accelKey,
                     // settle it here and now with the reference's own box arithmetic (out of line, ~1e-4 of the rays)
                     atomicAdd(counters, 1u);
                     atomicAdd(counters + ((hasSecond || overflow) ? 1 : 2), 1u); // [1] near ties, [2] uncertified leaf
-                    ResolveExactRay(a, accelKey, hitKeys, metaHits, rays, counters, r, overflow, best, second, hasSecond);
+                    if constexpr(ALPHA) ResolveExactRayAlpha(a, accelKey, hitKeys, metaHits, rays, counters, r, overflow, best, second, hasSecond, prm.alphaSeed);
+                    else ResolveExactRay(a, accelKey, hitKeys, metaHits, rays, counters, r, overflow, best, second, hasSecond);
                 }
             }
         }
@@ -449,7 +559,8 @@ KTraceWide(const __grid_constant__ AccelData a, uint32_t accelKey,
                     const uint32_t flags = __float_as_uint(e1.w);
                     float t, u, v;
                     if(RayTriangle(ox, oy, oz, dx, dy, dz, v0, e0, e1, (flags & 1u) != 0u, t, u, v) &&
-                       (t >= tMin && t < tMaxOrig)) // IsInRange (AcceleratorLBVH.hpp:L233-236)
+                       (t >= tMin && t < tMaxOrig) && // IsInRange (AcceleratorLBVH.hpp:L233-236)
+                       AlphaGate<ALPHA>(a.ranges, a.indices, flags, __float_as_uint(v0.w), u, v, rays + r, prm.alphaSeed))
                     {
                         const uint32_t rank = __float_as_uint(e0.w);
                         if(ANY_HIT)
@@ -633,10 +744,10 @@ __device__ __forceinline__ bool CertifyLeaf2(const InstanceRec& in, uint32_t lea
 // Exact two-level traversal of ONE ray (audit path and fallback): KCIntersectBaseLBVH semantics on the top level
 // (internal boxes and the instance leaf AABB slab-tested with the current tMax, left-first), the
 // bottom-level ClosestHit / FirstHit in local space, tMax shrinking across instances.
-template<bool ANY_HIT>
+template<bool ANY_HIT, bool ALPHA>
 __device__ __forceinline__ void TraceBinary2RayBody(const SceneData& sc,
                                                     mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
-                                                    uint32_t* __restrict__ visibleBits, mrb_ray_gmem* rays, uint32_t r)
+                                                    uint32_t* __restrict__ visibleBits, mrb_ray_gmem* rays, uint32_t r, uint32_t alphaSeed)
 {
     const float4 r0 = reinterpret_cast<const float4*>(rays + r)[0];
     const float4 r1 = reinterpret_cast<const float4*>(rays + r)[1];
@@ -687,6 +798,8 @@ __device__ __forceinline__ void TraceBinary2RayBody(const SceneData& sc,
                 float t, u, v;
                 if(!RayTriangle(o[0], o[1], o[2], d[0], d[1], d[2], v0, e0, e1, in.ranges.cull[ri] != 0u, t, u, v)) continue;
                 if(!(t >= tMin && t < tMax)) continue;
+                // (the instance index joins the seed: instances of one accelerator decide independently)
+                if(ALPHA && in.ranges.alphaMap && in.ranges.alphaMap[ri] >= 0 && !AlphaKeepsHit(in.ranges, in.indices, leaf, ri, u, v, rays + r, alphaSeed ^ (ii * 0xC2B2AE35u))) continue;
                 best.t = t; best.u = u; best.v = v; best.leaf = leaf; best.flags = ri << 8; bestInst = ii;
                 tMax = t;
                 if(ANY_HIT) { done = true; break; }
@@ -705,25 +818,29 @@ __device__ __forceinline__ void TraceBinary2RayBody(const SceneData& sc,
     }
 }
 __device__ __noinline__ void TraceBinary2RayClosest(const SceneData& sc, mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, mrb_ray_gmem* rays, uint32_t r)
-{ TraceBinary2RayBody<false>(sc, hitKeys, metaHits, nullptr, rays, r); }
+{ TraceBinary2RayBody<false, false>(sc, hitKeys, metaHits, nullptr, rays, r, 0u); }
 __device__ __noinline__ void TraceBinary2RayAny(const SceneData& sc, uint32_t* visibleBits, mrb_ray_gmem* rays, uint32_t r)
-{ TraceBinary2RayBody<true>(sc, nullptr, nullptr, visibleBits, rays, r); }
+{ TraceBinary2RayBody<true, false>(sc, nullptr, nullptr, visibleBits, rays, r, 0u); }
+__device__ __noinline__ void TraceBinary2RayClosestAlpha(const SceneData& sc, mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, mrb_ray_gmem* rays, uint32_t r, uint32_t alphaSeed)
+{ TraceBinary2RayBody<false, true>(sc, hitKeys, metaHits, nullptr, rays, r, alphaSeed); }
+__device__ __noinline__ void TraceBinary2RayAnyAlpha(const SceneData& sc, uint32_t* visibleBits, mrb_ray_gmem* rays, uint32_t r, uint32_t alphaSeed)
+{ TraceBinary2RayBody<true, true>(sc, nullptr, nullptr, visibleBits, rays, r, alphaSeed); }
 
 template<bool ANY_HIT>
 __global__ void __launch_bounds__(TRACE_TPB)
 KTraceBinary2(const __grid_constant__ SceneData sc,
               mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
               uint32_t* __restrict__ visibleBits,
-              mrb_ray_gmem* rays, const uint32_t* __restrict__ rayIndices, uint32_t rayCount)
+              mrb_ray_gmem* rays, const uint32_t* __restrict__ rayIndices, uint32_t rayCount, uint32_t alphaSeed)
 {
     for(uint32_t i = blockIdx.x * TRACE_TPB + threadIdx.x; i < rayCount; i += gridDim.x * TRACE_TPB)
-        TraceBinary2RayBody<ANY_HIT>(sc, hitKeys, metaHits, visibleBits, rays, rayIndices ? rayIndices[i] : i);
+        TraceBinary2RayBody<ANY_HIT, true>(sc, hitKeys, metaHits, visibleBits, rays, rayIndices ? rayIndices[i] : i, alphaSeed);
 }
 
 // Same phase-uniform persistent loop as KTraceWide with one more kind of leaf: in the top-level tree a
 // leaf record is an instance; entering it pushes the pending top-level groups and a sentinel, switches the
 // lane to the instance's local ray / node arrays, and the sentinel pop switches back.
-template<bool ANY_HIT>
+template<bool ANY_HIT, bool ALPHA>
 __global__ void __launch_bounds__(TRACE_TPB)
 KTraceWide2(const __grid_constant__ SceneData sc,
             mrb_hit_key_pack* __restrict__ hitKeys, mrb_meta_hit* __restrict__ metaHits,
@@ -772,7 +889,8 @@ KTraceWide2(const __grid_constant__ SceneData sc,
                 else if(uncertified)
                 {
                     atomicAdd(counters, 1u); atomicAdd(counters + 2, 1u); atomicAdd(counters + 4, 1u);
-                    TraceBinary2RayAny(sc, visibleBits, rays, r);
+                    if constexpr(ALPHA) TraceBinary2RayAnyAlpha(sc, visibleBits, rays, r, prm.alphaSeed);
+                    else TraceBinary2RayAny(sc, visibleBits, rays, r);
                 }
             }
             else if(best.leaf != INVALID_U32)
@@ -786,7 +904,8 @@ KTraceWide2(const __grid_constant__ SceneData sc,
                     // near tie or uncertified leaf: the reference's two-level algorithm decides (out of line, rare)
                     atomicAdd(counters, 1u); atomicAdd(counters + 4, 1u);
                     atomicAdd(counters + ((secondSeen || overflow) ? 1 : 2), 1u);
-                    TraceBinary2RayClosest(sc, hitKeys, metaHits, rays, r);
+                    if constexpr(ALPHA) TraceBinary2RayClosestAlpha(sc, hitKeys, metaHits, rays, r, prm.alphaSeed);
+                    else TraceBinary2RayClosest(sc, hitKeys, metaHits, rays, r);
                 }
             }
         }
@@ -859,7 +978,9 @@ KTraceWide2(const __grid_constant__ SceneData sc,
                         const uint32_t flags = __float_as_uint(e1.w);
                         float t, u, v;
                         if(RayTriangle(ox, oy, oz, dx, dy, dz, v0, e0, e1, (flags & 1u) != 0u, t, u, v) &&
-                           (t >= tMin && t < tMaxOrig))
+                           (t >= tMin && t < tMaxOrig) &&
+                           AlphaGate<ALPHA>(sc.instances[inst].ranges, sc.instances[inst].indices, flags, __float_as_uint(v0.w), u, v, rays + r,
+                                            prm.alphaSeed ^ (inst * 0xC2B2AE35u)))
                         {
                             const uint32_t rank = __float_as_uint(e0.w);
                             if(ANY_HIT)
@@ -985,7 +1106,7 @@ const TraceParams& WideTraceParams()
 {
     static const TraceParams prm = []
     {
-        TraceParams p{8u, 24u, 0x47000000u};
+        TraceParams p{8u, 24u, 0x47000000u, 0u};
         if(const char* e = getenv("MRB_TRI_DIV")) p.triDiv = uint32_t(atoi(e));
         if(const char* e = getenv("MRB_FETCH_THR")) p.fetchThr = uint32_t(atoi(e));
         return p;
@@ -1025,6 +1146,7 @@ void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode
                mrb_ray_gmem* rays, const uint32_t* rayIndices, uint32_t rayCount)
 {
     if(rayCount == 0) return;
+    const uint32_t alphaSeed = ctx.alphaSeed++;   // one seed per cast: consecutive casts decide independently
     const uint32_t grid = DivUp(rayCount, TRACE_TPB);
     if(mode == MRB_TRACE_WIDE)
     {
@@ -1037,19 +1159,28 @@ void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode
 #else
         MRB_CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 8, ctx.stream));
 #endif
+        const bool alpha = acc.d.ranges.alphaMap != nullptr;
         if(!ctx.occWide[0])   // per context: a process may drive several devices
         {
-            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx.occWide[0], KTraceWide<false>, TRACE_TPB, 0));
-            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx.occWide[1], KTraceWide<true>, TRACE_TPB, 0));
+            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx.occWide[0], KTraceWide<false, false>, TRACE_TPB, 0));
+            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx.occWide[1], KTraceWide<true, false>, TRACE_TPB, 0));
+            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx.occWide[2], KTraceWide<false, true>, TRACE_TPB, 0));
+            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx.occWide[3], KTraceWide<true, true>, TRACE_TPB, 0));
         }
         if(acc.d.wideNodes && acc.d.tris)
             SetPersistingWindow(ctx, acc.d.wideNodes, size_t(reinterpret_cast<const char*>(acc.d.tris + acc.d.leafCount) - reinterpret_cast<const char*>(acc.d.wideNodes)));
-        const TraceParams prm = WideTraceParams();
-        const uint32_t pgrid = min(grid, uint32_t(ctx.smCount) * uint32_t(ctx.occWide[anyHit ? 1 : 0]));
+        TraceParams prm = WideTraceParams();
+        prm.alphaSeed = alphaSeed;
+        const uint32_t pgrid = min(grid, uint32_t(ctx.smCount) * uint32_t(ctx.occWide[(anyHit ? 1 : 0) + (alpha ? 2 : 0)]));
         {
             ProfileScope ps(ctx, anyHit ? PROF_TRACE_ANY : PROF_TRACE_CLOSEST);
-            if(anyHit) MRB_LAUNCH(ctx, KTraceWide<true>, pgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, prm);
-            else       MRB_LAUNCH(ctx, KTraceWide<false>, pgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, prm);
+            if(alpha)
+            {
+                if(anyHit) MRB_LAUNCH(ctx, (KTraceWide<true, true>), pgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, prm);
+                else       MRB_LAUNCH(ctx, (KTraceWide<false, true>), pgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, prm);
+            }
+            else if(anyHit) MRB_LAUNCH(ctx, (KTraceWide<true, false>), pgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, prm);
+            else            MRB_LAUNCH(ctx, (KTraceWide<false, false>), pgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, prm);
         }
         ctx.lastFallbackCount = counters;
 #ifdef MRB_TRACE_STATS
@@ -1066,8 +1197,8 @@ void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode
     else
     {
         const uint32_t bgrid = min(grid, uint32_t(ctx.smCount) * 16u);
-        if(anyHit) MRB_LAUNCH(ctx, KTraceBinary<true>, bgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount);
-        else       MRB_LAUNCH(ctx, KTraceBinary<false>, bgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount);
+        if(anyHit) MRB_LAUNCH(ctx, KTraceBinary<true>, bgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, alphaSeed);
+        else       MRB_LAUNCH(ctx, KTraceBinary<false>, bgrid, TRACE_TPB, 0, acc.d, acc.accelKey, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, alphaSeed);
         ctx.lastFallbackCount = nullptr;
     }
 }
@@ -1078,31 +1209,41 @@ void TraceScene(Context& ctx, const SceneData& scnData, bool anyHit, mrb_trace_m
                 mrb_ray_gmem* rays, const uint32_t* rayIndices, uint32_t rayCount)
 {
     if(rayCount == 0) return;
+    const uint32_t alphaSeed = ctx.alphaSeed++;
     const uint32_t grid = DivUp(rayCount, TRACE_TPB);
     if(mode == MRB_TRACE_WIDE)
     {
         ctx.traceScratch.Reserve(sizeof(uint32_t) * 64);
         uint32_t* counters = static_cast<uint32_t*>(ctx.traceScratch.Base());
         MRB_CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 8, ctx.stream));
+        const bool alpha = scnData.hasAlpha != 0u;
         if(!ctx.occWide2[0])
         {
-            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx.occWide2[0], KTraceWide2<false>, TRACE_TPB, 0));
-            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx.occWide2[1], KTraceWide2<true>, TRACE_TPB, 0));
+            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx.occWide2[0], KTraceWide2<false, false>, TRACE_TPB, 0));
+            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx.occWide2[1], KTraceWide2<true, false>, TRACE_TPB, 0));
+            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx.occWide2[2], KTraceWide2<false, true>, TRACE_TPB, 0));
+            MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx.occWide2[3], KTraceWide2<true, true>, TRACE_TPB, 0));
         }
-        const TraceParams prm = WideTraceParams();
-        const uint32_t pgrid = min(grid, uint32_t(ctx.smCount) * uint32_t(ctx.occWide2[anyHit ? 1 : 0]));
+        TraceParams prm = WideTraceParams();
+        prm.alphaSeed = alphaSeed;
+        const uint32_t pgrid = min(grid, uint32_t(ctx.smCount) * uint32_t(ctx.occWide2[(anyHit ? 1 : 0) + (alpha ? 2 : 0)]));
         {
             ProfileScope ps(ctx, anyHit ? PROF_TRACE_ANY : PROF_TRACE_CLOSEST);
-            if(anyHit) MRB_LAUNCH(ctx, KTraceWide2<true>, pgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, prm);
-            else       MRB_LAUNCH(ctx, KTraceWide2<false>, pgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, prm);
+            if(alpha)
+            {
+                if(anyHit) MRB_LAUNCH(ctx, (KTraceWide2<true, true>), pgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, prm);
+                else       MRB_LAUNCH(ctx, (KTraceWide2<false, true>), pgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, prm);
+            }
+            else if(anyHit) MRB_LAUNCH(ctx, (KTraceWide2<true, false>), pgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, prm);
+            else            MRB_LAUNCH(ctx, (KTraceWide2<false, false>), pgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, counters, prm);
         }
         ctx.lastFallbackCount = counters;
     }
     else
     {
         const uint32_t bgrid = min(grid, uint32_t(ctx.smCount) * 16u);
-        if(anyHit) MRB_LAUNCH(ctx, KTraceBinary2<true>, bgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount);
-        else       MRB_LAUNCH(ctx, KTraceBinary2<false>, bgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount);
+        if(anyHit) MRB_LAUNCH(ctx, KTraceBinary2<true>, bgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, alphaSeed);
+        else       MRB_LAUNCH(ctx, KTraceBinary2<false>, bgrid, TRACE_TPB, 0, scnData, hitKeys, metaHits, visibleBits, rays, rayIndices, rayCount, alphaSeed);
         ctx.lastFallbackCount = nullptr;
     }
 }

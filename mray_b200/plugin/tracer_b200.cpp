@@ -597,7 +597,9 @@ class TracerB200 final : public TracerI
         {
             case MRayPixelEnum::MR_RGBA_FLOAT:  t.channels = 4; t.format = 0; break;
             case MRayPixelEnum::MR_RGBA8_UNORM: t.channels = 4; t.format = 1; break;
-            default: throw MRayError("textures: only MR_RGBA_FLOAT and MR_RGBA8_UNORM pixels are supported yet");
+            case MRayPixelEnum::MR_R_FLOAT:     t.channels = 1; t.format = 0; break;   // alpha maps (TracerTexView<2, Float>)
+            case MRayPixelEnum::MR_R8_UNORM:    t.channels = 1; t.format = 1; break;
+            default: throw MRayError("textures: only MR_RGBA_FLOAT / MR_RGBA8_UNORM / MR_R_FLOAT / MR_R8_UNORM pixels are supported yet");
         }
         // TextureMemory::ConvertColorspaces leaves a texture alone when it is not a colour, or already global + linear
         const bool needsConversion = p.isColor == AttributeIsColor::IS_COLOR &&
@@ -622,7 +624,9 @@ class TracerB200 final : public TracerI
         // the TransientData is typed by the pixel (MRayPixelType<E>::Type): Vector4 / Vector4uc here
         const size_t pixels = size_t(t.size[0]) * t.size[1];
         const Byte* src = nullptr; size_t got = 0;
-        if(t.format == 0) { auto s = data.AccessAs<const Vector4>(); src = reinterpret_cast<const Byte*>(s.data()); got = s.size(); }
+        if(t.channels == 1 && t.format == 0) { auto s = data.AccessAs<const Float>(); src = reinterpret_cast<const Byte*>(s.data()); got = s.size(); }
+        else if(t.channels == 1) { auto s = data.AccessAs<const uint8_t>(); src = reinterpret_cast<const Byte*>(s.data()); got = s.size(); }
+        else if(t.format == 0) { auto s = data.AccessAs<const Vector4>(); src = reinterpret_cast<const Byte*>(s.data()); got = s.size(); }
         else { auto s = data.AccessAs<const Vector4uc>(); src = reinterpret_cast<const Byte*>(s.data()); got = s.size(); }
         if(got != pixels) throw MRayError("textures: {} pixels pushed, {} expected", got, pixels);
         t.pixels.assign(src, src + pixels * t.channels * (t.format == 0 ? 4u : 1u));
@@ -787,14 +791,14 @@ class TracerB200 final : public TracerI
             if(!blg.IsSkysphere()) throw MRayError("Primitive-backed light ({}) is requested as a boundary material!", blg.type);
             if((Raw(boundary.lightId) & ((1u << MAT_ID_BITS) - 1u)) >= blg.radiance.size()) throw MRayError("Unable to find Light({})", Raw(boundary.lightId));
         }
-        struct Group { uint32_t transformId; std::vector<uint32_t> ranges, lmKeys; std::vector<uint8_t> cull; };
+        struct Group { uint32_t transformId; std::vector<uint32_t> ranges, lmKeys; std::vector<uint8_t> cull; std::vector<int32_t> alpha; };   // alpha: TextureId or -1
         std::vector<Group> groups;
         auto GroupOf = [&](TransformId t) -> Group&
         {
             for(Group& g : groups) if(g.transformId == Raw(t)) return g;
             const TransGroupB200& tg = Get(transforms, Raw(t) >> TRANS_ID_BITS, "TransformGroup");
             if((Raw(t) & ((1u << TRANS_ID_BITS) - 1u)) >= tg.matrices.size()) throw MRayError("Unable to find Transform({})", Raw(t));
-            groups.push_back(Group{Raw(t), {}, {}, {}});
+            groups.push_back(Group{Raw(t), {}, {}, {}, {}});
             return groups.back();
         };
         flatAlbedo.clear(); flatAlbedoTex.clear(); flatMaterialType.clear(); flatMaterialParams.clear(); flatTextures.clear();
@@ -841,6 +845,16 @@ class TracerB200 final : public TracerI
                 grp.ranges.insert(grp.ranges.end(), {pb.primOffset, pb.primOffset + pb.primCount});
                 grp.lmKeys.push_back(FlatMat(s.materials[k]));
                 grp.cull.push_back(s.cullFaceFlags[k] ? 1 : 0);
+                int32_t am = -1;
+                if(k < s.alphaMaps.size() && s.alphaMaps[k].has_value())
+                {   // AcceleratorCommon.cu:L293-311: the alpha map must be a single-channel texture (a TracerTexView<2, Float>)
+                    const uint32_t tid = Raw(*s.alphaMaps[k]);
+                    if(tid == 0 || tid > textures.size()) throw MRayError("Alpha map texture({}) is not found", tid);
+                    if(textures[tid - 1].channels != 1) throw MRayError("Alpha map texture({}) is not a single channel texture!", tid);
+                    if(!textures[tid - 1].loaded) throw MRayError("texture({}) has no data", tid);
+                    am = int32_t(tid);
+                }
+                grp.alpha.push_back(am);
             }
         }
         for(const LightSurfaceParams& ls : lightSurfaces)
@@ -853,7 +867,7 @@ class TracerB200 final : public TracerI
             const PrimBatch& pb = Get(Get(prims, lg.primGroup, "PrimitiveGroup").batches, lg.primBatch[li], "PrimitiveBatch");
             grp.ranges.insert(grp.ranges.end(), {pb.primOffset, pb.primOffset + pb.primCount});
             grp.lmKeys.push_back(0x80000000u | uint32_t(flatLightTwoSided.size()));
-            grp.cull.push_back(0);
+            grp.cull.push_back(0); grp.alpha.push_back(-1);
             flatLightRadiance.insert(flatLightRadiance.end(), {lg.radiance[li][0], lg.radiance[li][1], lg.radiance[li][2]});
             flatLightTwoSided.push_back(lg.twoSided[li]);
         }
@@ -870,6 +884,24 @@ class TracerB200 final : public TracerI
             d.memspace = MRB_MEM_HOST; d.primGroupId = flatPrimGroup;
             d.rangeCount = uint32_t(g.lmKeys.size()); d.primRanges = g.ranges.data();
             d.lightOrMatKeys = g.lmKeys.data(); d.cullBackface = g.cull.data(); d.flags = MRB_BUILD_DEFAULT;
+            // alpha maps of this accelerator: its own compact texture table
+            std::vector<uint32_t> used; std::vector<int32_t> rangeAlpha(g.alpha.size(), -1); std::vector<mrb_texture_desc> atex;
+            for(size_t k = 0; k < g.alpha.size(); k++)
+            {
+                if(g.alpha[k] < 0) continue;
+                auto it = std::find(used.begin(), used.end(), uint32_t(g.alpha[k]));
+                rangeAlpha[k] = int32_t(it - used.begin());
+                if(it != used.end()) continue;
+                used.push_back(uint32_t(g.alpha[k]));
+                const TextureB200& t = textures[size_t(g.alpha[k]) - 1];
+                atex.push_back(mrb_texture_desc{t.pixels.data(), t.size[0], t.size[1], t.channels, t.format,
+                                                uint32_t(t.params.interpolation), uint32_t(t.params.edgeResolve)});
+            }
+            if(!used.empty())
+            {
+                d.vertexUVs = reinterpret_cast<const float*>(pg.uvs.data());
+                d.alphaTextureCount = uint32_t(atex.size()); d.alphaTextures = atex.data(); d.rangeAlphaMap = rangeAlpha.data();
+            }
             mrb_accel a = nullptr;
             CheckOn(dv, mrb_accel_build(dv.ctx, &d, &a));
             return a;
@@ -894,7 +926,8 @@ class TracerB200 final : public TracerI
                 {
                     mrb_accel a = nullptr;
                     for(size_t u = 0; u < builtFor.size() && !a; u++)
-                        if(groups[builtFor[u]].ranges == groups[k].ranges && groups[builtFor[u]].cull == groups[k].cull) a = dv.instAccels[u];
+                        if(groups[builtFor[u]].ranges == groups[k].ranges && groups[builtFor[u]].cull == groups[k].cull &&
+                           groups[builtFor[u]].alpha == groups[k].alpha) a = dv.instAccels[u];
                     if(!a) { a = BuildGroup(dv, groups[k]); dv.instAccels.push_back(a); builtFor.push_back(k); }
                     const uint32_t tid = groups[k].transformId;
                     const Matrix3x4& m = transforms[tid >> TRANS_ID_BITS].matrices[tid & ((1u << TRANS_ID_BITS) - 1u)];

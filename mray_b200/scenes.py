@@ -468,3 +468,26 @@ def sky_texture(width: int = 32, height: int = 16, seed: int = 9):
     t[sy:sy + 2, sx:sx + 2, :3] = np.array([900.0, 800.0, 600.0], np.float32)
     t[..., 3] = 1.0
     return dict(data=np.ascontiguousarray(t), interp="Linear", edge="Wrap")
+
+
+def cornell_alpha(seed: int = 21):
+    """``cornell_box`` plus a pane (material 4, bluish Lambert) standing in front of the boxes whose surface carries an ALPHA
+    MAP: an 8x8 single-channel fp32 texture (nearest, clamp) with fully transparent, fully opaque and fractional texels, so
+    camera rays, bounce rays and NEE shadow rays all meet the stochastic alpha test. Returns the cornell dict with
+    `material` / `albedo` extended, `uvs` [V, 2] (the pane spans uv [0, 1]^2, everything else (0, 0)), `alpha_texture`
+    and `alpha_map` (per material id: -1 or 0)."""
+    rng = np.random.default_rng(seed)
+    c = cornell_box()
+    pane = np.array([[-0.8, 0.2, 0.6], [0.8, 0.2, 0.6], [0.8, 1.6, 0.6], [-0.8, 1.6, 0.6]], np.float32)
+    nv = c["positions"].shape[0]
+    c["positions"] = np.ascontiguousarray(np.concatenate([c["positions"], pane]))
+    c["indices"] = np.ascontiguousarray(np.concatenate([c["indices"], np.array([[nv, nv + 1, nv + 2], [nv, nv + 2, nv + 3]], np.uint32)]))
+    c["material"] = np.concatenate([c["material"], np.array([4, 4], np.uint32)])
+    c["albedo"] = np.concatenate([c["albedo"], np.array([[0.15, 0.25, 0.7]], np.float32)])
+    uvs = np.zeros((nv + 4, 2), np.float32)
+    uvs[nv:] = [[0, 0], [1, 0], [1, 1], [0, 1]]
+    a = rng.choice(np.array([0.0, 0.0, 1.0, 1.0, 0.25, 0.5, 0.75], np.float32), size=(8, 8)).astype(np.float32)
+    c["uvs"] = uvs
+    c["alpha_texture"] = dict(data=np.ascontiguousarray(a), interp="Nearest", edge="Clamp")
+    c["alpha_map"] = np.array([-1, -1, -1, -1, 0], np.int32)
+    return c

@@ -75,6 +75,9 @@ ITEMS = {
     "cornell64_sky_tex_spp16384": (64, 16384, 32, "WithNEEAndMIS", (2, 20), ("sky", "Skysphere_Spherical", "tex"), np.float32, RGB),
     "cornell64_sky_nee_spp16384": (64, 16384, 34, "WithNextEventEstimation", (2, 20), ("sky", "Skysphere_Spherical", "tex"), np.float32, RGB),
     "cornell64_sky_coocta_spectral_spp16384": (64, 16384, 33, "WithNEEAndMIS", (2, 20), ("sky", "Skysphere_CoOcta", "tex+light"), np.float32, SPECTRAL),
+    # alpha maps (SurfaceParams.alphaMaps -> the stochastic test inside IntersectionCheck): scenes.cornell_alpha, a pane with
+    # transparent / opaque / fractional texels in front of the boxes
+    "cornell64_alpha_spp16384": (64, 16384, 41, "WithNEEAndMIS", (2, 20), "alpha", np.float32, RGB),
     # two-level scene: every batch in its own local space under a (T)Single transform
     "cornell64_single_spp16384": (64, 16384, 6, "WithNEEAndMIS", (2, 20), True, np.float32, RGB),
 }
@@ -130,7 +133,8 @@ def sky_kwargs(single):
 def render(name):
     res, spp, seed, mode, rr, single, dt, renderer = ITEMS[name]
     sky = isinstance(single, tuple) and single[0] == "sky"
-    c = (scenes.cornell_open(keep_light=single[2] == "tex+light") if sky else scenes.cornell_mirror() if single == "mirror" else scenes.cornell_glossy() if single == "glossy"
+    c = (scenes.cornell_open(keep_light=single[2] == "tex+light") if sky else scenes.cornell_alpha() if single == "alpha"
+         else scenes.cornell_mirror() if single == "mirror" else scenes.cornell_glossy() if single == "glossy"
          else scenes.cornell_sphere() if single == "sphere" else scenes.cornell_box())
     kw = {}
     if single == "twosided":
@@ -155,6 +159,10 @@ def render(name):
     elif sky:
         b = O.batched_scene(c["positions"], c["indices"], c["material"])
         kw = sky_kwargs(single)
+        bt = None
+    elif single == "alpha":
+        b = O.batched_scene(c["positions"], c["indices"], c["material"], uvs=c["uvs"])
+        kw = dict(textures=[c["alpha_texture"]], alpha_map=c["alpha_map"])
         bt = None
     elif isinstance(single, tuple) and single[0] == "filter":
         b = O.batched_scene(c["positions"], c["indices"], c["material"])

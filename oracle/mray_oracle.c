@@ -379,10 +379,14 @@ int orc_ray_triangle(const float pos[3], const float dir[3],
 /* Closest / first hit over one accelerator — TraverseLBVHStack (AcceleratorLBVH.hpp:L109-167)
  * with the leaf functors of ClosestHit / FirstHit (hpp:L327-410) and IntersectionCheck's range
  * test (hpp:L233-236,L270-271). rays: n*8 floats in RayGMem order (pos,tMin,dir,tMax). */
-void orc_lbvh_trace(const float* pos, const uint32_t* idx,
-                    const uint32_t* nodes, const float* boxes,
-                    const float* rays, uint32_t nRays, int mode, int cullFace,
-                    uint32_t* outPrim, float* outT, float* outBary, uint8_t* outBack)
+/* leafFilter (may be NULL): IntersectionCheck's stochastic alpha test (hpp:L263-282) — called for a leaf whose triangle was
+ * hit inside the range with the hit's barycentrics; returning 0 drops the hit. */
+typedef int (*orc_leaf_filter)(void* user, uint32_t leaf, const float bary[2]);
+void orc_lbvh_trace_filtered(const float* pos, const uint32_t* idx,
+                             const uint32_t* nodes, const float* boxes,
+                             const float* rays, uint32_t nRays, int mode, int cullFace,
+                             uint32_t* outPrim, float* outT, float* outBary, uint8_t* outBack,
+                             orc_leaf_filter leafFilter, void* user)
 {
     for(uint32_t r = 0; r < nRays; r++)
     {
@@ -405,6 +409,7 @@ void orc_lbvh_trace(const float* pos, const uint32_t* idx,
                 float t, b2[2]; int back;
                 if(!orc_ray_triangle(rp, rd, p0, p1, p2, cullFace, &t, b2, &back)) continue;
                 if(!(t >= tMin && t < tMax)) continue;
+                if(leafFilter && !leafFilter(user, leaf, b2)) continue;
                 best = leaf; tMax = t; bb[0] = b2[0]; bb[1] = b2[1]; bback = back;
                 if(mode == 1) break;
             }
@@ -417,6 +422,14 @@ void orc_lbvh_trace(const float* pos, const uint32_t* idx,
         outPrim[r] = best; outT[r] = tMax;
         outBary[2 * r] = bb[0]; outBary[2 * r + 1] = bb[1]; outBack[r] = (uint8_t)bback;
     }
+}
+
+void orc_lbvh_trace(const float* pos, const uint32_t* idx,
+                    const uint32_t* nodes, const float* boxes,
+                    const float* rays, uint32_t nRays, int mode, int cullFace,
+                    uint32_t* outPrim, float* outT, float* outBary, uint8_t* outBack)
+{
+    orc_lbvh_trace_filtered(pos, idx, nodes, boxes, rays, nRays, mode, cullFace, outPrim, outT, outBary, outBack, NULL, NULL);
 }
 
 /* Topology-independent closest hit: brute force over all triangles, winner = min (t, rank) where

@@ -104,6 +104,9 @@ typedef struct
     uint32_t boundaryType; int32_t boundaryTexture; float boundaryRadiance[3];
     const float* boundaryCdfX; const float* boundaryCdfY;
     float boundaryM[9], boundaryInvM[9]; float sceneDiameter;
+    /* alpha maps (SurfaceParams.alphaMaps): per triangle -1 or an index into `textures` whose first channel is the alpha
+     * (NULL = none); uv = the per-vertex UV0 above */
+    const int32_t* triAlpha;
 } pt_scene;
 
 /* One single-level 2-D texture as the reference's host-backend view reads it (Device/CPU/TextureViewCPU.h):
@@ -130,10 +133,12 @@ static int tex_edge(int i, int n, uint32_t edge)
 static void tex_pixel(const struct orc_texture* t, int x, int y, float out[3])
 {
     size_t o = ((size_t)y * t->w + (size_t)x) * t->channels;
-    if(t->format == 0u) { const float* f = (const float*)t->data + o; out[0] = f[0]; out[1] = f[1]; out[2] = f[2]; return; }
+    const uint32_t nc = t->channels < 3u ? t->channels : 3u;   /* alpha maps are single-channel: missing channels read 0 */
+    out[0] = out[1] = out[2] = 0.0f;
+    if(t->format == 0u) { const float* f = (const float*)t->data + o; for(uint32_t k = 0; k < nc; k++) out[k] = f[k]; return; }
     const uint8_t* b = (const uint8_t*)t->data + o;
     const float DELTA = 1.0f / 255.0f;
-    for(int k = 0; k < 3; k++) out[k] = (float)b[k] * DELTA;
+    for(uint32_t k = 0; k < nc; k++) out[k] = (float)b[k] * DELTA;
 }
 /* Math::Lerp (Core/Math.h): a * (1 - t) + b * t, unfused */
 static float tex_lerp(float a, float b, float t) { volatile float x = a * (1.0f - t); volatile float y = b * t; return x + y; }
@@ -203,11 +208,34 @@ static void tri(const pt_scene* s, uint32_t t, v3 p[3])
     }
 }
 
-static int trace(const pt_scene* s, v3 o, v3 d, float tMin, float tMax, int any, uint32_t* prim, float* t, float bary[2])
+typedef int (*orc_leaf_filter)(void* user, uint32_t leaf, const float bary[2]);
+void orc_lbvh_trace_filtered(const float* pos, const uint32_t* idx, const uint32_t* nodes, const float* boxes,
+                             const float* rays, uint32_t nRays, int mode, int cullFace,
+                             uint32_t* outPrim, float* outT, float* outBary, uint8_t* outBack, orc_leaf_filter f, void* user);
+void orc_texture_sample(const struct orc_texture* t, float u, float v, float out[3]);
+/* IntersectionCheck's stochastic alpha culling (AcceleratorLBVH.hpp:L263-282): alpha = alphaMap(SurfaceParametrization(hit)),
+ * the hit is dropped when xi >= alpha; xi comes from the ray's backup generator (here: the path's) */
+struct alpha_ctx { const pt_scene* s; pcg* rng; };
+static int alpha_filter(void* user, uint32_t leaf, const float bary[2])
+{
+    struct alpha_ctx* c = (struct alpha_ctx*)user;
+    const pt_scene* s = c->s;
+    int32_t ti = s->triAlpha[leaf];
+    if(ti < 0) return 1;
+    const uint32_t* vi = s->idx + 3 * (size_t)leaf;
+    float a = bary[0], b = bary[1], cc = 1.0f - a - b;
+    float u = s->uv[2 * vi[0]] * a + s->uv[2 * vi[1]] * b + s->uv[2 * vi[2]] * cc;
+    float v = s->uv[2 * vi[0] + 1] * a + s->uv[2 * vi[1] + 1] * b + s->uv[2 * vi[2] + 1] * cc;
+    float px[3]; orc_texture_sample(&s->textures[ti], u, v, px);
+    return pcg_float(c->rng) < px[0];
+}
+static int trace_rng(const pt_scene* s, pcg* rng, v3 o, v3 d, float tMin, float tMax, int any, uint32_t* prim, float* t, float bary[2])
 {
     float ray[8] = {o.x, o.y, o.z, tMin, d.x, d.y, d.z, tMax};
     uint8_t back;
-    orc_lbvh_trace(s->pos, s->idx, s->nodes, s->boxes, ray, 1, any, 0, prim, t, bary, &back);
+    struct alpha_ctx ctx = {s, rng};
+    if(s->triAlpha) orc_lbvh_trace_filtered(s->pos, s->idx, s->nodes, s->boxes, ray, 1, any, 0, prim, t, bary, &back, alpha_filter, &ctx);
+    else orc_lbvh_trace(s->pos, s->idx, s->nodes, s->boxes, ray, 1, any, 0, prim, t, bary, &back);
     return *prim != 0xFFFFFFFFu;
 }
 
@@ -630,7 +658,7 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
     for(;;)
     {
         uint32_t prim; float t, bary[2];
-        if(!trace(s, o, d, tMin, tMax, 0, &prim, &t, bary))
+        if(!trace_rng(s, rng, o, d, tMin, tMax, 0, &prim, &t, bary))
         {   /* boundary light (LightWorkFunction[WithNEE] for a light without primitives): (L)Null adds nothing */
             if(s->boundaryType != 0u && !(s->sampleMode == 1u && type != 3 && type != 1))
             {
@@ -776,7 +804,7 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
                 {
                     v3 so = nudge(hitPos, gN);
                     uint32_t sp; float st, sb[2];
-                    if(!trace(s, so, wI, 1.0e-5f, length * (1.0f - 1.0e-4f), 1, &sp, &st, sb)) radiance = s_add(radiance, sr);
+                    if(!trace_rng(s, rng, so, wI, 1.0e-5f, length * (1.0f - 1.0e-4f), 1, &sp, &st, sb)) radiance = s_add(radiance, sr);
                 }
             }
         }

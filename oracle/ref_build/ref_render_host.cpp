@@ -28,6 +28,7 @@ struct DriverScene
     const float* batchTransforms; const int32_t* batchInstanceOf;
     uint32_t textureCount; const uint32_t* textureInfo; const uint8_t* textureBytes; const int32_t* materialTexture; const float* uvs; const uint8_t* materialKind; const uint8_t* lightTwoSided; const float* materialParams;
     uint32_t boundaryType; float boundaryRadiance[3]; int32_t boundaryTexture; const float* boundaryTransform;
+    const int32_t* batchAlphaMap;
 };
 struct DriverRender
 {
@@ -44,7 +45,7 @@ int main(int argc, char** argv)
     FILE* f = std::fopen(argv[1], "rb");
     if(!f) { std::perror("blob"); return 65; }
     uint64_t n = 0;
-    if(std::fread(&n, 8, 1, f) != 1 || (n < 23 || n > 25)) { std::fprintf(stderr, "bad blob\n"); return 66; }
+    if(std::fread(&n, 8, 1, f) != 1 || (n < 23 || n > 26)) { std::fprintf(stderr, "bad blob\n"); return 66; }
     std::vector<std::vector<uint64_t>> sec(n);     // 8-byte aligned storage
     std::vector<uint64_t> bytes(n);
     for(uint64_t i = 0; i < n; i++)
@@ -82,6 +83,7 @@ int main(int argc, char** argv)
         sc.boundaryType = b[0]; std::memcpy(sc.boundaryRadiance, b + 1, 12); std::memcpy(&sc.boundaryTexture, b + 4, 4);
         if(bytes[24] >= 20 + 48) sc.boundaryTransform = reinterpret_cast<const float*>(b + 5);
     }
+    if(n > 25) sc.batchAlphaMap = static_cast<const int32_t*>(P(25));   // 25 batchAlphaMap (i32 per batch; may be empty)
     std::memcpy(sc.camPos, cam, 12); std::memcpy(sc.camGaze, cam + 3, 12); std::memcpy(sc.camUp, cam + 6, 12);
     std::memcpy(sc.fovXY, cam + 9, 8); std::memcpy(sc.nearFar, cam + 11, 8);
     DriverRender rd{};

@@ -74,6 +74,9 @@ struct DriverScene
     float           boundaryRadiance[3];
     int32_t         boundaryTexture;
     const float*    boundaryTransform;
+    // optional alpha maps (SurfaceParams.alphaMaps): per batch -1 or a texture index; such textures have format 2
+    // (MR_R_FLOAT) or 3 (MR_R8_UNORM) in textureInfo: single-channel pure data, read as Float (AlphaMap = TracerTexView<2, Float>)
+    const int32_t*  batchAlphaMap;
 };
 
 struct DriverRender
@@ -261,10 +264,12 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
         {
             const uint32_t* ti = sc->textureInfo + 6 * size_t(t);
             MRayTextureParameters tp;
-            tp.pixelType = MRayPixelTypeRT(ti[2] == 0 ? MRayPixelEnum::MR_RGBA_FLOAT : MRayPixelEnum::MR_RGBA8_UNORM);
+            tp.pixelType = MRayPixelTypeRT(ti[2] == 0 ? MRayPixelEnum::MR_RGBA_FLOAT : ti[2] == 1 ? MRayPixelEnum::MR_RGBA8_UNORM
+                                           : ti[2] == 2 ? MRayPixelEnum::MR_R_FLOAT : MRayPixelEnum::MR_R8_UNORM);
             tp.colorSpace = MRayColorSpaceEnum::MR_DEFAULT; tp.gamma = Float(1);
             tp.interpolation = MRayTextureInterpEnum(ti[3]); tp.edgeResolve = MRayTextureEdgeResolveEnum(ti[4]);
-            tp.readMode = MRayTextureReadMode::MR_DROP_1;   // RGBA pixels read as Vector3 (TextureReadMode::TO_3C_FROM_4C): the albedo's view type
+            if(ti[2] < 2) tp.readMode = MRayTextureReadMode::MR_DROP_1;   // RGBA pixels read as Vector3 (TextureReadMode::TO_3C_FROM_4C): the albedo's view type
+            else { tp.readMode = MRayTextureReadMode::MR_PASSTHROUGH; tp.isColor = AttributeIsColor::IS_PURE_DATA; }   // alpha maps
             texIds.push_back(tracer->CreateTexture2D(Vector2ui(ti[0], ti[1]), 1, tp));
         }
         tracer->CommitTextures();
@@ -278,6 +283,18 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
             {
                 TransientData d(std::in_place_type_t<Vector4>{}, pixels);
                 d.Push(Span<const Vector4>(reinterpret_cast<const Vector4*>(src), pixels));
+                tracer->PushTextureData(texIds[t], 0, std::move(d));
+            }
+            else if(ti[2] == 2)
+            {
+                TransientData d(std::in_place_type_t<Float>{}, pixels);
+                d.Push(Span<const Float>(reinterpret_cast<const Float*>(src), pixels));
+                tracer->PushTextureData(texIds[t], 0, std::move(d));
+            }
+            else if(ti[2] == 3)
+            {
+                TransientData d(std::in_place_type_t<uint8_t>{}, pixels);
+                d.Push(Span<const uint8_t>(reinterpret_cast<const uint8_t*>(src), pixels));
                 tracer->PushTextureData(texIds[t], 0, std::move(d));
             }
             else
@@ -495,7 +512,8 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
             sp.primBatches.push_back(batches[(sc->batchInstanceOf && sc->batchInstanceOf[b] >= 0) ? uint32_t(sc->batchInstanceOf[b]) : b]);
             sp.materials.push_back(mats[size_t(sc->batchMaterial[b])]);
             sp.transformId = batchTrans[b];
-            sp.alphaMaps.push_back(std::nullopt);
+            if(sc->batchAlphaMap && sc->batchAlphaMap[b] >= 0) sp.alphaMaps.push_back(texIds[size_t(sc->batchAlphaMap[b])]);
+            else sp.alphaMaps.push_back(std::nullopt);
             sp.cullFaceFlags.push_back(false);
             sp.volumes.push_back(TracerConstants::InvalidVolume);
             tracer->CreateSurface(sp);

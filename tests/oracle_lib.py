@@ -169,7 +169,7 @@ class _DriverScene(C.Structure):
                 ("materialTexture", C.c_void_p), ("uvs", C.c_void_p), ("materialKind", C.c_void_p), ("lightTwoSided", C.c_void_p),
                 ("materialParams", C.c_void_p),
                 ("boundaryType", C.c_uint32), ("boundaryRadiance", C.c_float * 3), ("boundaryTexture", C.c_int32),
-                ("boundaryTransform", C.c_void_p)]
+                ("boundaryTransform", C.c_void_p), ("batchAlphaMap", C.c_void_p)]
 
 
 class _DriverRender(C.Structure):
@@ -223,8 +223,9 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
                   batch_transforms=None, sampler="Independent", host_exe=False, instance_of=None,
                   textures=None, material_texture=None, region=None, material_kind=None,
                   latency=False, burst_size=1, cam_switch=None, light_two_sided=False, film_filter=None, film_filter_radius=0.0,
-                  material_params=None, boundary=None):
-    """Renders through TracerI. boundary: None = (L)Null boundary, or dict(type="Skysphere_Spherical"|"Skysphere_CoOcta",
+                  material_params=None, boundary=None, alpha_map=None):
+    """Renders through TracerI. alpha_map: per material id (an index into `albedo`) -1 or a texture index: the batches of
+    that material get SurfaceParams.alphaMaps (such textures are [h, w] or [h, w, 1] arrays: single-channel pure data). boundary: None = (L)Null boundary, or dict(type="Skysphere_Spherical"|"Skysphere_CoOcta",
     radiance=(r, g, b) | texture=index into `textures`, transform=[3, 4] or None). `light_material`: material id whose batch is the prim-backed light.
     batch_transforms: optional [batch, 3, 4] local->world matrices ((T)Single per batch; positions local).
     textures: list of dict(data=[h, w, 4] float32 / uint8 (RGBA), interp=, edge=); material_texture: per material id
@@ -262,8 +263,9 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
             a = np.ascontiguousarray(t["data"])
             if a.dtype != np.uint8:
                 a = np.ascontiguousarray(a, np.float32)
-            assert a.shape[2] == 4, "the TracerI driver pushes RGBA pixels"
-            info.append([a.shape[1], a.shape[0], 1 if a.dtype == np.uint8 else 0, _TEX_INTERP[t.get("interp", "Linear")],
+            single = a.ndim == 2 or a.shape[2] == 1
+            assert single or a.shape[2] == 4, "the TracerI driver pushes RGBA (colour) or single-channel (alpha) pixels"
+            info.append([a.shape[1], a.shape[0], (1 if a.dtype == np.uint8 else 0) + (2 if single else 0), _TEX_INTERP[t.get("interp", "Linear")],
                          _TEX_EDGE[t.get("edge", "Wrap")], off])
             blobs.append(a.tobytes()); off += len(blobs[-1]) + (-len(blobs[-1]) % 16)
             blobs[-1] += b"\0" * (-len(blobs[-1]) % 16)
@@ -276,6 +278,7 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
     b_xf = None if (boundary or {}).get("transform") is None else np.ascontiguousarray(boundary["transform"], np.float32).reshape(12)
     if textures and mtex is None:
         mtex = np.full(len(lambert), -1, np.int32)
+    b_alpha = None if alpha_map is None else np.ascontiguousarray([-1 if m == light_material else int(alpha_map[m]) for m in mats], np.int32)
     if host_exe:
         import subprocess
         import tempfile
@@ -297,7 +300,8 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
                 b"" if mkind is None else mkind.tobytes(), lts.tobytes() if light_two_sided else b"",
                 b"" if mparams is None else mparams.tobytes(),
                 b"" if b_type == 0 else (np.uint32(b_type).tobytes() + b_rad.tobytes() + np.int32(b_tex).tobytes() +
-                                         (b"" if b_xf is None else b_xf.tobytes()))]
+                                         (b"" if b_xf is None else b_xf.tobytes())),
+                b"" if b_alpha is None else b_alpha.tobytes()]
         with tempfile.TemporaryDirectory() as td:
             with open(os.path.join(td, "in.blob"), "wb") as f:
                 f.write(np.uint64(len(secs)).tobytes())
@@ -346,6 +350,8 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
     sc.boundaryType, sc.boundaryRadiance, sc.boundaryTexture = b_type, (C.c_float * 3)(*b_rad), b_tex
     if b_xf is not None:
         keep.append(b_xf); sc.boundaryTransform = b_xf.ctypes.data
+    if b_alpha is not None:
+        keep.append(b_alpha); sc.batchAlphaMap = b_alpha.ctypes.data
     rd = _DriverRender(renderer.encode(), width, height, spp, sample_mode.encode(), (C.c_uint32 * 2)(*rr_range), seed,
                        accel_mode, parallel_hint, threads, sampler_id, (C.c_uint32 * 4)(*(region or (0, 0, 0, 0))),
                        1 if latency else 0, burst_size, cam_switch[0] if cam_switch else 0,
@@ -381,7 +387,7 @@ class _PtScene(C.Structure):
                 ("materialType", C.c_void_p), ("filmFilter", C.c_uint32), ("materialParams", C.c_void_p), ("vertexTBN", C.c_void_p),
                 ("boundaryType", C.c_uint32), ("boundaryTexture", C.c_int32), ("boundaryRadiance", C.c_float * 3),
                 ("boundaryCdfX", C.c_void_p), ("boundaryCdfY", C.c_void_p), ("boundaryM", C.c_float * 9), ("boundaryInvM", C.c_float * 9),
-                ("sceneDiameter", C.c_float)]
+                ("sceneDiameter", C.c_float), ("triAlpha", C.c_void_p)]
 
 
 class _OrcTexture(C.Structure):
@@ -401,6 +407,8 @@ def _orc_textures(textures):
         a = np.ascontiguousarray(t["data"])
         if a.dtype != np.uint8:
             a = np.ascontiguousarray(a, np.float32)
+        if a.ndim == 2:       # single-channel (alpha map)
+            a = a[..., None]
         keep.append(a)
         arr[k].data = a.ctypes.data
         arr[k].h, arr[k].w, arr[k].channels = a.shape
@@ -467,8 +475,9 @@ def oracle_render(positions, indices, tri_material, albedo, radiance, camera, wi
                   sample_mode=2, rr_range=(2, 20), seed=0, near_far=(0.01, 1000.0), threads=None,
                   spectral_data=None, wavelength_mode=2, textures=None, albedo_texture=None, vertex_uvs=None,
                   material_type=None, light_two_sided=None, film_filter=None, film_filter_radius=1.0, material_params=None, vertex_normals=None,
-                  boundary=None):
-    """boundary: None = (L)Null, or dict(type="Skysphere_Spherical"|"Skysphere_CoOcta", radiance=(r, g, b) | texture=index, transform=[3, 4],
+                  boundary=None, tri_alpha=None):
+    """tri_alpha: per triangle -1 or an index into `textures` (an alpha map read through its first channel).
+    boundary: None = (L)Null, or dict(type="Skysphere_Spherical"|"Skysphere_CoOcta", radiance=(r, g, b) | texture=index, transform=[3, 4],
     scene_diameter=0, luminance_row=ACES_CG). tri_material: per triangle, >= 0 Lambert material index, -1 - k for light k. Returns image[h,w,3]
     (row 0 = bottom) resolved as sum radiance / sum weight. spectral_data (mray_b200.spectral.load())
     switches to the hero-wavelength spectral estimator."""
@@ -497,9 +506,12 @@ def oracle_render(positions, indices, tri_material, albedo, radiance, camera, wi
     if spectral_data is not None:
         tables, keep_tables = spectrum_tables(spectral_data)
         s.spectrum, s.wavelengthMode = C.addressof(tables), wavelength_mode
+    if tri_alpha is not None:
+        ta = np.ascontiguousarray(tri_alpha, np.int32)
+        s.triAlpha = ta.ctypes.data
     if textures:
         tarr, keep_tex = _orc_textures(textures)
-        at = np.ascontiguousarray(albedo_texture, np.int32)
+        at = np.ascontiguousarray(albedo_texture if albedo_texture is not None else np.full(alb.shape[0], -1), np.int32)
         uvs = None if vertex_uvs is None else np.ascontiguousarray(vertex_uvs, np.float32)
         s.textures, s.nTextures, s.albedoTexture = C.addressof(tarr), len(textures), at.ctypes.data
         s.uv = None if uvs is None else uvs.ctypes.data

@@ -291,3 +291,23 @@ def test_oracle_skysphere_matches_reference_render(name, mode, spp, kw):
     e = rel_mse(block_mean(img, 8), block_mean(ref, 8))
     # NEE-only under a "sun" is the noisiest estimator here: measured 1.9e-3 at 1024 spp, 7.8e-4 at 4096 spp (means within 0.05 %)
     assert e <= (3e-3 if mode == 1 else 1e-3), e
+
+
+def test_oracle_alpha_map_matches_reference_render():
+    """SurfaceParams.alphaMaps: the stochastic alpha test of IntersectionCheck (AcceleratorLBVH.hpp:L263-282) on a pane with
+    transparent / opaque / fractional texels (scenes.cornell_alpha), closest-hit and shadow rays alike."""
+    path = os.path.join(GOLDEN, "render_cornell64_alpha_spp16384.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden image was not generated")
+    ref = np.load(path)["img"].astype(np.float32)
+    c = scenes.cornell_alpha()
+    tm = np.where(c["material"] == 3, -1, np.where(c["material"] == 4, 3, c["material"])).astype(np.int32)
+    tri_alpha = np.where(c["material"] == 4, 0, -1).astype(np.int32)
+    img = O.oracle_render(c["positions"], c["indices"], tm, c["albedo"][[0, 1, 2, 4]], c["radiance"], c["camera"], 64, 64, 1024,
+                          sample_mode=2, seed=9, textures=[c["alpha_texture"]], vertex_uvs=c["uvs"], tri_alpha=tri_alpha)
+    assert np.allclose(img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=0.01), (img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)))
+    e = rel_mse(block_mean(img, 4), block_mean(ref, 4))
+    assert e <= 1e-3, e
+    # and the alpha map matters: without it the pane is opaque and the image differs by far more than the noise
+    opaque = O.oracle_render(c["positions"], c["indices"], tm, c["albedo"][[0, 1, 2, 4]], c["radiance"], c["camera"], 64, 64, 256, sample_mode=2, seed=9)
+    assert rel_mse(block_mean(opaque, 4), block_mean(ref, 4)) > 20 * e
