@@ -491,3 +491,74 @@ def cornell_alpha(seed: int = 21):
     c["alpha_texture"] = dict(data=np.ascontiguousarray(a), interp="Nearest", edge="Clamp")
     c["alpha_map"] = np.array([-1, -1, -1, -1, 0], np.int32)
     return c
+
+
+def mray_scene_json(c, width: int, height: int, near_far=(0.01, 1000.0), light_material: int = 3, material_types=None,
+                    boundary=None, textures=None, alpha_map=None, uvs=None, cull_back_face: bool = False) -> str:
+    """A scene dict (cornell_box layout: positions, indices, per-triangle material id, albedo, radiance, camera) as a scene file
+    of the reference's JSON format (Docs/markdown/scene/mrayScene.md): one in-node indexed triangle primitive per material id,
+    one surface each, the `light_material` batch as a Primitive light. boundary: None (Null light) or dict(type=
+    "Skysphere_Spherical"|"Skysphere_CoOcta", radiance=[r, g, b] | texture=scene texture id); textures: list of
+    dict(id=, file=, ...) texture nodes; alpha_map: per material id a scene texture id or None."""
+    import json
+    pos, idx, mat = c["positions"], c["indices"], c["material"]
+    prims, mats, surfaces = [], [], []
+    for m in np.unique(mat):
+        tris = idx[mat == m]
+        used, inv = np.unique(tris.ravel(), return_inverse=True)
+        node = {"id": int(m), "type": "Triangle", "tag": "nodeTriangleIndexed",
+                "position": pos[used].astype(float).round(9).tolist(), "index": inv.reshape(-1, 3).astype(int).tolist()}
+        if c.get("normals") is not None:
+            node["normal"] = np.asarray(c["normals"])[used].astype(float).tolist()
+        if uvs is not None:
+            node["uv"] = np.asarray(uvs)[used].astype(float).tolist()
+        prims.append(node)
+        if int(m) == light_material:
+            continue
+        kind = "Lambert" if material_types is None else material_types[int(m)]
+        mnode = {"id": int(m), "type": kind}
+        if kind in ("Lambert", "Unreal"):
+            mnode["albedo"] = [float(x) for x in c["albedo"][int(m)]]
+        mats.append(mnode)
+        s = {"transform": 0, "material": int(m), "primitive": int(m), "cullBackFace": bool(cull_back_face)}
+        if alpha_map is not None and alpha_map[int(m)] is not None:
+            s["alphaMap"] = {"texture": int(alpha_map[int(m)])}
+        surfaces.append(s)
+    cam = c["camera"]
+    lights = [{"id": 0, "type": "Null"}]
+    light_surfaces = []
+    if light_material in np.unique(mat):
+        lights.append({"id": 1, "type": "Primitive", "primitive": int(light_material), "radiance": [float(x) for x in c["radiance"]]})
+        light_surfaces.append({"light": 1, "transform": 0})
+    b_light = 0
+    if boundary is not None:
+        node = {"id": 2, "type": boundary["type"]}
+        node["radiance"] = {"texture": int(boundary["texture"])} if "texture" in boundary else [float(x) for x in boundary["radiance"]]
+        lights.append(node); b_light = 2
+    scene = {
+        "Cameras": [{"id": 0, "type": "Pinhole", "isFovX": False, "fov": float(cam["fov_y_deg"]), "aspect": width / height,
+                     "planes": [float(near_far[0]), float(near_far[1])], "gaze": list(map(float, cam["gaze"])),
+                     "position": list(map(float, cam["eye"])), "up": list(map(float, cam["up"]))}],
+        "Lights": lights, "Mediums": [{"id": 0, "type": "Vacuum"}], "Transforms": [{"id": 0, "type": "Identity"}],
+        "Materials": mats, "Primitives": prims, "Textures": textures or [],
+        "Boundary": {"medium": 0, "light": b_light, "transform": 0},
+        "Surfaces": surfaces, "LightSurfaces": light_surfaces, "CameraSurfaces": [{"camera": 0}],
+    }
+    return json.dumps(scene, indent=1)
+
+
+def write_pfm(path: str, image) -> None:
+    """[h, w] or [h, w, 3] float image -> PFM ("Pf" / "PF", little endian, row 0 first = the bottom row of the format)."""
+    a = np.ascontiguousarray(image, np.float32)
+    with open(path, "wb") as f:
+        f.write(("Pf" if a.ndim == 2 else "PF").encode() + f"\n{a.shape[1]} {a.shape[0]}\n-1.0\n".encode())
+        f.write(a.tobytes())
+
+
+def read_pfm(path: str):
+    with open(path, "rb") as f:
+        magic = f.readline().strip().decode()
+        w, h = map(int, f.readline().split())
+        scale = float(f.readline())
+        a = np.frombuffer(f.read(), "<f4" if scale < 0 else ">f4")
+    return a.reshape(h, w, 3).astype(np.float32) if magic == "PF" else a.reshape(h, w).astype(np.float32)
