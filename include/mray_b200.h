@@ -62,7 +62,7 @@ typedef struct mrb_meta_hit { float a, b; } mrb_meta_hit;
 /* ---- library / context ------------------------------------------------------------------ */
 
 /* ABI version of this header (major<<16 | minor); the descriptor struct layouts are part of it. */
-#define MRB_ABI_VERSION ((0u << 16) | 5u)
+#define MRB_ABI_VERSION ((0u << 16) | 7u)
 MRB_API uint32_t mrb_abi_version(void);
 
 /* Replaces GPUSystem + GPUQueue ownership inside TracerBase (Device/CUDA/GPUSystemCUDA.cpp:L249-405:
@@ -374,6 +374,13 @@ typedef struct mrb_texture_desc
     uint32_t    format;      /* 0 = fp32, 1 = unorm8 (NormConversion::FromUNorm: v * (1/255)) */
     uint32_t    interp;      /* MRayTextureInterpEnum: 0 NEAREST, 1 LINEAR */
     uint32_t    edge;        /* MRayTextureEdgeResolveEnum: 0 WRAP, 1 CLAMP, 2 MIRROR */
+    /* TextureMemory::ConvertColorspaces (Tracer/TextureMemory.cpp:L434-487) -> KCConvertColor (Tracer/ColorConverter.cu:L306-398),
+     * applied to the texels once, on upload: rgb <- pow(rgb, gamma) (OpticalTransferGamma::ToLinear; 0 or 1 = no gamma), then
+     * rgb <- colorMatrix . rgb (ColorspaceTransfer<from, global>::RGBToRGBMatrix = FromXYZ(global) ToXYZ(from), row-major 3x3;
+     * NULL = the texture is already in the global colour space). unorm8 texels are de-normalised, converted and rounded back
+     * (ToUNorm). Needs >= 3 channels. */
+    float       gamma;
+    const float* colorMatrix;
 } mrb_texture_desc;
 
 typedef struct mrb_render_desc
@@ -479,6 +486,11 @@ typedef struct mrb_render_desc
     const float*    boundaryTransform;
     float           sceneDiameter;
     float           luminanceRow[3];
+    /* Normal maps (the optional "normalMap" attribute of (Mt)Lambert / (Mt)Unreal; Triangle::GenerateSurface,
+     * Tracer/PrimitiveDefaultTriangle.hpp:L478-491,L571-575): NULL, or host int32 per material: -1, or an index into `textures`
+     * whose rgb is the TANGENT-SPACE normal (used as is, then normalised). The hit's interpolated tangent frame is re-aimed so
+     * that its Z axis is that normal; needs vertexTBN / instanceVertexTBN and the UVs. */
+    const int32_t*  normalTexture;
 } mrb_render_desc;
 
 typedef struct mrb_render_stats
@@ -552,6 +564,30 @@ MRB_API float*     mrb_renderer_film_device_ptr(mrb_renderer r);
  * single-level texture (Tracer/TextureView.hpp:L70-85 -> Device/CPU/TextureViewCPU.h:L397-470). Host pointers:
  * uv[count*2] -> rgbOut[count*3]. */
 MRB_API mrb_status mrb_texture_sample(mrb_context ctx, const mrb_texture_desc* texture, const float* uv, uint32_t count, float* rgbOut);
+/* Parity tap: the upload-time colour conversion of a texture on its own (KCConvertColor): texelsOut (host) receives the texels of
+ * `texture` after its gamma / colorMatrix have been applied, in the texture's own format. */
+MRB_API mrb_status mrb_texture_convert(mrb_context ctx, const mrb_texture_desc* texture, void* texelsOut);
+
+/* ---- spectral LUT generation --------------------------------------------------------------- */
+
+/* GenerateSpectraLUT of the reference's SpectraLUTGen tool (Source/SpectraLUTGen/main.cpp:L81-537, after Jakob & Hanika 2019 /
+ * rgb2spec): the payload of SpectraLUT/<COLORSPACE>.mrspectra, computed on the device (one thread per (table, y, x) column,
+ * Gauss-Newton in fp64 on the CIELab residual). Host pointers, exactly what the reference's tool reads from Core/ColorFunctions:
+ * cieXYZ[471*3] (CIE 1931 observer, 360..830 nm), illuminantSPD[471] with its normalisation factor, the colour space's
+ * RGB -> XYZ matrix without white-point adaptation (Color::GenRGBToXYZ(Primaries)) and its inverse (row-major 3x3).
+ * lutOut: 9 * resolution^3 floats laid out [table l][coefficient][z][y][x]; whitepointOut (may be NULL): the XYZ white point
+ * the residual is measured against. optimizePassCount: the tool uses 15. */
+typedef struct mrb_spectra_lut_desc
+{
+    const float* cieXYZ;
+    const float* illuminantSPD;
+    float        illuminantNormFactor;
+    float        rgbToXYZ[9];
+    float        xyzToRGB[9];
+    uint32_t     resolution;
+    uint32_t     optimizePassCount;
+} mrb_spectra_lut_desc;
+MRB_API mrb_status mrb_spectra_lut_generate(mrb_context ctx, const mrb_spectra_lut_desc* desc, float* lutOut, double whitepointOut[3]);
 
 /* ---- piecewise-constant 2-D distribution + skysphere maps ---------------------------------- */
 

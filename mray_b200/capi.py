@@ -83,12 +83,18 @@ class RenderDesc(C.Structure):
                 ("filmFilterType", C.c_uint32), ("sampleOffset", C.c_uint32), ("jobSPP", C.c_uint32), ("materialParams", C.c_void_p),
                 ("vertexTBN", C.c_void_p), ("instanceVertexTBN", C.POINTER(C.c_void_p)),
                 ("boundaryType", C.c_uint32), ("boundaryTexture", C.c_int32), ("boundaryRadiance", C.c_float * 3),
-                ("boundaryTransform", C.c_void_p), ("sceneDiameter", C.c_float), ("luminanceRow", C.c_float * 3)]
+                ("boundaryTransform", C.c_void_p), ("sceneDiameter", C.c_float), ("luminanceRow", C.c_float * 3),
+                ("normalTexture", C.c_void_p)]
+
+
+class SpectraLutDesc(C.Structure):
+    _fields_ = [("cieXYZ", C.c_void_p), ("illuminantSPD", C.c_void_p), ("illuminantNormFactor", C.c_float),
+                ("rgbToXYZ", C.c_float * 9), ("xyzToRGB", C.c_float * 9), ("resolution", C.c_uint32), ("optimizePassCount", C.c_uint32)]
 
 
 class TextureDesc(C.Structure):
     _fields_ = [("data", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("channels", C.c_uint32),
-                ("format", C.c_uint32), ("interp", C.c_uint32), ("edge", C.c_uint32)]
+                ("format", C.c_uint32), ("interp", C.c_uint32), ("edge", C.c_uint32), ("gamma", C.c_float), ("colorMatrix", C.c_void_p)]
 
 
 TEX_INTERP = {"Nearest": 0, "Linear": 1}
@@ -110,7 +116,7 @@ BOUNDARY_TYPES = {"Null": 0, "Skysphere_Spherical": 1, "Skysphere_CoOcta": 2}   
 FILM_FILTERS = {"Box": 0, "Tent": 1, "Gaussian": 2, "Mitchell-Netravali": 3}   # FilterType::E (Core/TracerEnums.h:L162-173)
 HOST_FN = C.CFUNCTYPE(None, C.c_void_p)
 # the descriptor mirrors above are written for this ABI (include/mray_b200.h: MRB_ABI_VERSION)
-MRB_ABI_VERSION = (0 << 16) | 5
+MRB_ABI_VERSION = (0 << 16) | 7
 
 # every symbol include/mray_b200.h declares (tests/test_capi_symbols.py checks the header against this)
 _PROTOTYPES = {
@@ -170,6 +176,8 @@ _PROTOTYPES = {
     "mrb_dist2d_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]),
     "mrb_skysphere_convert": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]),
     "mrb_texture_luminance": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]),
+    "mrb_texture_convert": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mrb_spectra_lut_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mrb_multi_partition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                       C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "mrb_binary_partition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]),
@@ -521,7 +529,7 @@ class Renderer:
                  max_path_count=0, partition_rays=False, instance_vertex_normals=None, spectrum=None, sampler="Independent",
                  textures=None, albedo_texture=None, vertex_uvs=None, instance_vertex_uvs=None,
                  full_resolution=None, region_min=(0, 0), material_type=None, film_filter="Gaussian",
-                 sample_offset=0, job_spp=0, material_params=None, vertex_tbn=None, boundary=None):
+                 sample_offset=0, job_spp=0, material_params=None, vertex_tbn=None, boundary=None, normal_texture=None):
         """`accel` is an Accelerator, or a Scene (two-level; vertex_count / triangle_count / vertex_normals
         are then ignored and instance_vertex_normals may hold one array or None per instance).
         textures: list of dict(data=[h, w, 3|4] float32 or uint8 array, interp="Linear"|"Nearest",
@@ -607,9 +615,14 @@ class Renderer:
                 tarr[k].format = 1 if a.dtype == np.uint8 else 0
                 tarr[k].interp = TEX_INTERP[t.get("interp", "Linear")]
                 tarr[k].edge = TEX_EDGE[t.get("edge", "Wrap")]
+                tarr[k].gamma = float(t.get("gamma", 1.0))
+                if t.get("color_matrix") is not None:
+                    cm = np.ascontiguousarray(t["color_matrix"], np.float32).reshape(9)
+                    self._keep.append(cm); tarr[k].colorMatrix = cm.ctypes.data
             self._keep.append(tarr)
             d.textureCount, d.textures = len(textures), C.cast(tarr, C.c_void_p)
             d.albedoTexture = host(albedo_texture, np.int32)
+            d.normalTexture = host(normal_texture, np.int32)    # per material: -1 or a texture holding tangent-space normals
         if isinstance(accel, Scene):
             if instance_vertex_uvs is not None:
                 uptrs = (C.c_void_p * accel.count)()
@@ -800,7 +813,20 @@ def _texture_desc(texture):
     t.height, t.width, t.channels = a.shape
     t.format = 1 if a.dtype == np.uint8 else 0
     t.interp, t.edge = TEX_INTERP[texture.get("interp", "Linear")], TEX_EDGE[texture.get("edge", "Wrap")]
-    return t, a
+    keep = [a]
+    t.gamma = float(texture.get("gamma", 1.0))
+    if texture.get("color_matrix") is not None:     # RGB -> RGB matrix into the global colour space (row-major 3x3)
+        m = np.ascontiguousarray(texture["color_matrix"], np.float32).reshape(9)
+        keep.append(m); t.colorMatrix = m.ctypes.data
+    return t, keep
+
+
+def texture_convert(ctx: Context, texture):
+    """mrb_texture_convert: the texels after the upload-time gamma / colour-space conversion, same shape and dtype."""
+    t, keep = _texture_desc(texture)
+    out = np.zeros_like(keep[0])
+    ctx.check(ctx.lib.mrb_texture_convert(ctx.handle, C.byref(t), out.ctypes.data))
+    return out
 
 
 ACES_CG_LUMINANCE_ROW = (float.fromhex("0x1.1614ep-2"), float.fromhex("0x1.58e6fep-1"), float.fromhex("0x1.d946e6p-5"))
@@ -840,6 +866,19 @@ def skysphere_convert(ctx: Context, converter, dirs):
     c = BOUNDARY_TYPES[converter] if isinstance(converter, str) else int(converter)
     ctx.check(ctx.lib.mrb_skysphere_convert(ctx.handle, c, dirs.ctypes.data, dirs.shape[0], out.ctypes.data, MRB_MEM_HOST))
     return out
+
+
+def spectra_lut_generate(ctx: Context, cie_xyz, illuminant_spd, illuminant_norm, rgb_to_xyz, xyz_to_rgb, resolution=64, passes=15):
+    """mrb_spectra_lut_generate (the reference's SpectraLUTGen on the device): -> (lut float32 [9 * res^3], whitepoint float64 [3])."""
+    cie = np.ascontiguousarray(cie_xyz, np.float32).reshape(-1, 3); spd = np.ascontiguousarray(illuminant_spd, np.float32)
+    assert cie.shape[0] == 471 and spd.shape[0] == 471
+    d = SpectraLutDesc()
+    d.cieXYZ, d.illuminantSPD, d.illuminantNormFactor = cie.ctypes.data, spd.ctypes.data, float(illuminant_norm)
+    d.rgbToXYZ = (C.c_float * 9)(*np.asarray(rgb_to_xyz, np.float32).ravel()); d.xyzToRGB = (C.c_float * 9)(*np.asarray(xyz_to_rgb, np.float32).ravel())
+    d.resolution, d.optimizePassCount = resolution, passes
+    lut = np.zeros(9 * resolution ** 3, np.float32); wp = np.zeros(3, np.float64)
+    ctx.check(ctx.lib.mrb_spectra_lut_generate(ctx.handle, C.byref(d), lut.ctypes.data, wp.ctypes.data))
+    return lut, wp
 
 
 def filter_sample(ctx: Context, film_filter, radius, xi):

@@ -61,6 +61,9 @@ void SpectrumSampleWavelengths(Context& ctx, const mrb_spectrum_t& sp, const uin
 void SpectrumToRGB(Context& ctx, const mrb_spectrum_t& sp, float* values, const float* waves, const float* pdfs, uint32_t n);
 void SpectrumUpsample(Context& ctx, const mrb_spectrum_t& sp, const float* rgb, uint32_t rgbStride, const float* waves, uint32_t n,
                       bool isRadiance, float* out);
+void TextureConvertHost(Context& ctx, const mrb_texture_desc& td, void* texelsOut);
+void GenerateSpectraLUT(Context& ctx, const float* cieXYZ, const float* illuminantSPD, float illuminantNorm, const float rgbToXYZ[9],
+                        const float xyzToRGB[9], uint32_t res, uint32_t passes, float* lutOut, double whitepointOut[3]);
 void TraceScene(Context& ctx, const SceneData& scn, bool anyHit, mrb_trace_mode mode,
                 mrb_hit_key_pack* hitKeys, mrb_meta_hit* metaHits, uint32_t* visibleBits,
                 mrb_ray_gmem* rays, const uint32_t* rayIndices, uint32_t rayCount);
@@ -97,7 +100,7 @@ static mrb_status Fail(mrb::Context& c, mrb_status s, const char* msg) { c.error
 extern "C"
 {
 
-uint32_t mrb_abi_version(void) { return MRB_ABI_VERSION; }   // 5: alpha maps in mrb_accel_desc; 4: boundary light (skysphere) fields of mrb_render_desc, mrb_dist2d_*
+uint32_t mrb_abi_version(void) { return MRB_ABI_VERSION; }   // 7: texture colour conversion fields; 6: normal maps; 5: alpha maps in mrb_accel_desc; 4: boundary light (skysphere) fields of mrb_render_desc, mrb_dist2d_*
 
 mrb_status mrb_context_create(int device, mrb_context* out)
 {
@@ -873,6 +876,28 @@ mrb_status mrb_texture_luminance(mrb_context ctx, const mrb_texture_desc* textur
                       [&](std::vector<StagedArray>& a)
                       { mrb::TextureLuminance(c, a[0].dev, texture->width, texture->height, texture->channels, texture->format, luminanceRow,
                                               static_cast<float*>(a[1].dev)); });
+    });
+}
+
+mrb_status mrb_spectra_lut_generate(mrb_context ctx, const mrb_spectra_lut_desc* desc, float* lutOut, double whitepointOut[3])
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!desc || !lutOut || !desc->cieXYZ || !desc->illuminantSPD) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        if(!(desc->illuminantNormFactor > 0.0f)) return Fail(c, MRB_ERR_INVALID_ARG, "illuminantNormFactor must be positive");
+        mrb::GenerateSpectraLUT(c, desc->cieXYZ, desc->illuminantSPD, desc->illuminantNormFactor, desc->rgbToXYZ, desc->xyzToRGB,
+                                desc->resolution, desc->optimizePassCount ? desc->optimizePassCount : 15u, lutOut, whitepointOut);
+        return MRB_OK;
+    });
+}
+
+mrb_status mrb_texture_convert(mrb_context ctx, const mrb_texture_desc* texture, void* texelsOut)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!texture || !texelsOut) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        mrb::TextureConvertHost(c, *texture, texelsOut);
+        return MRB_OK;
     });
 }
 

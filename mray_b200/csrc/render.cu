@@ -293,6 +293,7 @@ struct RenderData
     uint32_t          sceneMode;       // 1 = hitKeys.accelKey holds the instance index
     const TexRec*     textures;        // textured albedo (ParamVaryingData): texture table ...
     const int32_t*    albedoTex;       // ... and per material index: texture or -1; nullptr = no material is textured
+    const int32_t*    normalTex;       // per material index: tangent-space normal map (texture index) or -1; nullptr = none
     const uint8_t*    materialType;    // per material index: mrb_material_type; nullptr = all Lambert
     const float4*     matParams;       // per material index 2 x float4: Refract (cauchyFront xyz, cauchyBack xyz), Unreal (roughness, specular, metallic)
     const float4*     albedo;          // per material index: (r, g, b, 0), or Jakob coefficients (c0, c1, c2, -) when spectral
@@ -756,6 +757,21 @@ __device__ __forceinline__ Float3 ShadingNormalFromTBN(float4 q0, float4 q1, flo
     return F3(2.0f * (x * z - w * y), 2.0f * (y * z + w * x), w * w - x * x - y * y + z * z);
 }
 
+// The interpolated world -> tangent rotation of a hit as the three rows of its matrix (row 2 = the shading normal above);
+// a tangent-space vector v goes back to the world as v.x row0 + v.y row1 + v.z row2 (Quaternion::ApplyInvRotation).
+__device__ __forceinline__ void TBNRows(float4 q0, float4 q1, float4 q2, float a, float b, Float3 rows[3])
+{
+    const float c = 1.0f - a - b;
+    float4 q;
+    if(fabsf(a + b) < 1.0e-5f) q = q2;
+    else q = QuatSLerp(QuatSLerp(q1, q0, a / (a + b)), q2, c);
+    const float inv = rsqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    const float w = q.x * inv, x = q.y * inv, y = q.z * inv, z = q.w * inv;
+    rows[0] = F3(w * w + x * x - y * y - z * z, 2.0f * (x * y - w * z), 2.0f * (x * z + w * y));
+    rows[1] = F3(2.0f * (x * y + w * z), w * w - x * x + y * y - z * z, 2.0f * (y * z - w * x));
+    rows[2] = F3(2.0f * (x * z - w * y), 2.0f * (y * z + w * x), w * w - x * x - y * y + z * z);
+}
+
 // ---- LightSkysphere (Tracer/LightsDefault.hpp:L310-443): the boundary light as an environment sphere ----
 // TransformContext::ApplyV / InvApplyV of the light surface's transform (the linear part only: directions)
 __device__ __forceinline__ Float3 SkyApply(const float* m, Float3 v)
@@ -912,10 +928,30 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
                                   meta.y % d.width + d.regionX, meta.y / d.width + d.regionY, d.sobolMatrices, d.zsobol);
     const bool backSide = Dot(geoN, Normalize(rd)) > 0.0f;
     Float3 shadeN = geoN;
+    bool normalMapped = false;
+    const uint32_t matIndex = lmKey & 0x1FFFFFu;
     if(in.vertexNormals)
     {
         const float4 n0 = in.vertexNormals[vi[0]], n1 = in.vertexNormals[vi[1]], n2 = in.vertexNormals[vi[2]];
-        if(in.tbn) shadeN = ShadingNormalFromTBN(n0, n1, n2, a, b);
+        const int32_t normalTex = (GLOSSY && d.normalTex && in.tbn) ? d.normalTex[matIndex] : -1;
+        if(GLOSSY && normalTex >= 0)
+        {
+            // normal map (Triangle::GenerateSurface, PrimitiveDefaultTriangle.hpp:L478-491,L571-575): the hit's frame — turned half
+            // a turn about its tangent axis on a back-side hit — is re-aimed so that its Z axis is the texture's normal:
+            // tbn' = RotationBetweenZAxis(n).Conjugate() * tbn, i.e. the shading normal is tbn^-1 (n)
+            float2 uv = make_float2(0.f, 0.f);
+            if(in.vertexUVs)
+            {
+                const float2 t0 = in.vertexUVs[vi[0]], t1 = in.vertexUVs[vi[1]], t2 = in.vertexUVs[vi[2]];
+                uv = make_float2(t0.x * a + t1.x * b + t2.x * c, t0.y * a + t1.y * b + t2.y * c);
+            }
+            const Float3 nt = Normalize(SampleTexture(d.textures[normalTex], uv.x, uv.y));
+            Float3 rows[3]; TBNRows(n0, n1, n2, a, b, rows);
+            const float sgn = backSide ? -1.0f : 1.0f;
+            shadeN = rows[0] * nt.x + (rows[1] * nt.y + rows[2] * nt.z) * sgn;
+            normalMapped = true;
+        }
+        else if(in.tbn) shadeN = ShadingNormalFromTBN(n0, n1, n2, a, b);
         else shadeN = F3(n0.x, n0.y, n0.z) * a + F3(n1.x, n1.y, n1.z) * b + F3(n2.x, n2.y, n2.z) * c;
         // (the reference leaves the tangent frame in the primitive's local space under a (T)Single transform — "we can't
         // apply a transform to tbn", PrimitiveDefaultTriangle.hpp:L612 — which tilts its shading normals by the instance's
@@ -923,8 +959,7 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
         if(!in.identity) shadeN = ApplyN(in.invTransform, shadeN);
         shadeN = Normalize(shadeN);
     }
-    if(backSide) { geoN = geoN * -1.0f; shadeN = shadeN * -1.0f; }
-    const uint32_t matIndex = lmKey & 0x1FFFFFu;
+    if(backSide) { geoN = geoN * -1.0f; if(!normalMapped) shadeN = shadeN * -1.0f; }
     const uint32_t matType = d.materialType ? uint32_t(d.materialType[matIndex]) : MAT_LAMBERT;
     const Float3 wO = Normalize(rd) * -1.0f;
     if(matType == MAT_REFLECT || (GLOSSY && matType == MAT_REFRACT))
@@ -1174,6 +1209,50 @@ __global__ void __launch_bounds__(RTPB) KShade(RenderData d)
         if(nShadow) atomicAdd(&d.counters[3], (unsigned long long)nShadow);
         if(nNee) atomicAdd(&d.counters[4], (unsigned long long)nNee);
     }
+}
+
+// KCConvertColor (Tracer/ColorConverter.cu:L306-398): gamma to linear, then the RGB -> RGB matrix into the global colour space
+// (Matrix * Vector = Math::Dot FMA chains), in place on the uploaded texels; unorm8 goes through FromUNorm / ToUNorm.
+struct ColorConv { float gamma; float m[9]; uint32_t hasMatrix; };
+__global__ void __launch_bounds__(256) KConvertTextureColor(TexRec t, ColorConv cc)
+{
+    const size_t n = size_t(t.w) * t.h;
+    for(size_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += size_t(gridDim.x) * 256ull)
+    {
+        float c[3];
+        if(t.format == 0u) { const float* f = static_cast<const float*>(t.data) + i * t.channels; c[0] = f[0]; c[1] = f[1]; c[2] = f[2]; }
+        else { const uint8_t* b = static_cast<const uint8_t*>(t.data) + i * t.channels; for(int k = 0; k < 3; k++) c[k] = __fmul_rn(float(b[k]), 1.0f / 255.0f); }
+        if(cc.gamma != 1.0f) { c[0] = powf(c[0], cc.gamma); c[1] = powf(c[1], cc.gamma); c[2] = powf(c[2], cc.gamma); }
+        if(cc.hasMatrix)
+        {
+            float o[3];
+            #pragma unroll
+            for(int r = 0; r < 3; r++)
+            {
+                float d = __fmaf_rn(cc.m[3 * r], c[0], 0.0f);
+                d = __fmaf_rn(cc.m[3 * r + 1], c[1], d);
+                o[r] = __fmaf_rn(cc.m[3 * r + 2], c[2], d);
+            }
+            c[0] = o[0]; c[1] = o[1]; c[2] = o[2];
+        }
+        if(t.format == 0u) { float* f = const_cast<float*>(static_cast<const float*>(t.data)) + i * t.channels; f[0] = c[0]; f[1] = c[1]; f[2] = c[2]; }
+        else
+        {
+            uint8_t* b = const_cast<uint8_t*>(static_cast<const uint8_t*>(t.data)) + i * t.channels;
+            for(int k = 0; k < 3; k++) b[k] = uint8_t(fminf(fmaxf(roundf(__fmul_rn(c[k], 255.0f)), 0.0f), 255.0f));   // ToUNorm (clamped: it asserts [0, 1])
+        }
+    }
+}
+static bool NeedsColorConversion(const mrb_texture_desc& td) { return (td.gamma != 0.0f && td.gamma != 1.0f) || td.colorMatrix != nullptr; }
+static void ConvertTextureColor(Context& ctx, const TexRec& t, const mrb_texture_desc& td)
+{
+    if(!NeedsColorConversion(td)) return;
+    if(t.channels < 3u) throw std::runtime_error("colour conversion needs a texture with at least 3 channels");
+    ColorConv cc = {};
+    cc.gamma = (td.gamma == 0.0f) ? 1.0f : td.gamma;
+    cc.hasMatrix = td.colorMatrix ? 1u : 0u;
+    if(td.colorMatrix) memcpy(cc.m, td.colorMatrix, sizeof(cc.m));
+    MRB_LAUNCH(ctx, KConvertTextureColor, GridFor(ctx, t.w * t.h, 256u), 256, 0, t, cc);
 }
 
 // Converter::ConvertAlbedo / ConvertRadiance, LUT half: RGB attributes -> Jakob coefficients, once per render
@@ -1483,6 +1562,13 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
     if(desc.albedoTexture)
         for(uint32_t m = 0; m < desc.materialCount; m++)
             if(desc.albedoTexture[m] >= int32_t(desc.textureCount)) throw std::runtime_error("albedoTexture index exceeds textureCount");
+    if(desc.normalTexture)
+        for(uint32_t m = 0; m < desc.materialCount; m++)
+        {
+            if(desc.normalTexture[m] >= int32_t(desc.textureCount)) throw std::runtime_error("normalTexture index exceeds textureCount");
+            if(desc.normalTexture[m] >= 0 && !(desc.scene ? desc.instanceVertexTBN != nullptr : desc.vertexTBN != nullptr))
+                throw std::runtime_error("normal maps need the per-vertex tangent frames (vertexTBN / instanceVertexTBN)");
+        }
     InstanceRec* dSceneInst = nullptr;
     float* skyLuminance = nullptr; float* skyRowTotals = nullptr; float4* dBoundaryCoeffs = nullptr;
     auto Layout = [&](MultiAlloc& ma)
@@ -1509,6 +1595,7 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
         }
         d.workKeys = ma.Take<uint32_t>(P); d.workIndices = ma.Take<uint32_t>(P); d.partTable = ma.Take<uint32_t>(32);
         d.albedoTex = desc.albedoTexture ? ma.Take<int32_t>(desc.materialCount ? desc.materialCount : 1) : nullptr;
+        d.normalTex = desc.normalTexture ? ma.Take<int32_t>(desc.materialCount ? desc.materialCount : 1) : nullptr;
         d.materialType = desc.materialType ? ma.Take<uint8_t>(desc.materialCount ? desc.materialCount : 1) : nullptr;
         d.matParams = desc.materialParams ? ma.Take<float4>(2 * size_t(desc.materialCount ? desc.materialCount : 1)) : nullptr;
         d.textures = desc.textureCount ? ma.Take<TexRec>(desc.textureCount) : nullptr;
@@ -1547,9 +1634,15 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
         MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<float4*>(d.matParams), desc.materialParams, sizeof(float4) * 2 * desc.materialCount, cudaMemcpyHostToDevice, ctx.stream));
     if(desc.albedoTexture)
         MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<int32_t*>(d.albedoTex), desc.albedoTexture, sizeof(int32_t) * desc.materialCount, cudaMemcpyHostToDevice, ctx.stream));
+    if(desc.normalTexture)
+    {
+        MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<int32_t*>(d.normalTex), desc.normalTexture, sizeof(int32_t) * desc.materialCount, cudaMemcpyHostToDevice, ctx.stream));
+        for(uint32_t m = 0; m < desc.materialCount; m++) if(desc.normalTexture[m] >= 0) r.glossy = true;   // normal maps live in the full shading kernel
+    }
     for(uint32_t t = 0; t < desc.textureCount; t++)
         MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<void*>(htex[t].data), desc.textures[t].data,
                                      size_t(htex[t].w) * htex[t].h * htex[t].channels * (htex[t].format == 0u ? 4u : 1u), cudaMemcpyHostToDevice, ctx.stream));
+    for(uint32_t t = 0; t < desc.textureCount; t++) ConvertTextureColor(ctx, htex[t], desc.textures[t]);   // TextureMemory::ConvertColorspaces
     if(desc.textureCount)
         MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<TexRec*>(d.textures), htex.data(), htex.size() * sizeof(TexRec), cudaMemcpyHostToDevice, ctx.stream));
     if(!lights.empty())
@@ -1938,8 +2031,23 @@ void TextureSampleHost(Context& ctx, const mrb_texture_desc& td, const float* uv
     MRB_CUDA_TRY(cudaMemcpyAsync(dTex, td.data, texBytes, cudaMemcpyHostToDevice, ctx.stream));
     MRB_CUDA_TRY(cudaMemcpyAsync(dUV, uv, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx.stream));
     const TexRec t{dTex, td.width, td.height, td.channels, td.format, td.interp, td.edge, 0u};
+    ConvertTextureColor(ctx, t, td);
     if(n) MRB_LAUNCH(ctx, KSampleTexture, DivUp(n, 256u), 256, 0, t, dUV, n, dOut);
     MRB_CUDA_TRY(cudaMemcpyAsync(rgbOut, dOut, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx.stream));
+    MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
+}
+
+void TextureConvertHost(Context& ctx, const mrb_texture_desc& td, void* texelsOut)
+{
+    if(!td.data || td.width == 0 || td.height == 0 || (td.channels != 3 && td.channels != 4) || td.format > 1u)
+        throw std::runtime_error("bad texture descriptor");
+    const size_t texBytes = size_t(td.width) * td.height * td.channels * (td.format == 0u ? 4u : 1u);
+    ctx.scratch.Reserve(texBytes);
+    char* dTex = static_cast<char*>(ctx.scratch.Base());
+    MRB_CUDA_TRY(cudaMemcpyAsync(dTex, td.data, texBytes, cudaMemcpyHostToDevice, ctx.stream));
+    const TexRec t{dTex, td.width, td.height, td.channels, td.format, td.interp, td.edge, 0u};
+    ConvertTextureColor(ctx, t, td);
+    MRB_CUDA_TRY(cudaMemcpyAsync(texelsOut, dTex, texBytes, cudaMemcpyDeviceToHost, ctx.stream));
     MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
 }
 

@@ -56,7 +56,7 @@ struct PrimGroupB200
 };
 struct MatGroupB200
 {
-    std::string type; bool committed = false; std::vector<Vector3> albedo; std::vector<int32_t> albedoTex; /* TextureId or -1 */
+    std::string type; bool committed = false; std::vector<Vector3> albedo; std::vector<int32_t> albedoTex; /* TextureId or -1 */ std::vector<int32_t> normalTex; /* TextureId or -1 */
     // constant attributes of (Mt)Refract {cauchyFront xyz, -, cauchyBack xyz, -} and (Mt)Unreal {roughness, specular, metallic, ...}
     std::vector<std::array<float, 8>> params;
 };
@@ -66,6 +66,7 @@ struct TextureB200
 {
     Vector2ui size; MRayTextureParameters params; uint32_t channels = 4, format = 0;
     std::vector<Byte> pixels; bool loaded = false;
+    float gamma = 1.0f; bool hasColorMatrix = false; float colorMatrix[9] = {};   // TextureMemory::ConvertColorspaces, done on upload
 };
 struct LightGroupB200
 {
@@ -161,6 +162,7 @@ class TracerB200 final : public TracerI
     std::vector<uint8_t> flatMaterialType;          // per flat material: mrb_material_type
     std::vector<float> flatMaterialParams;          // per flat material: 8 floats (mrb_render_desc.materialParams)
     std::vector<int32_t> flatAlbedoTex;             // per flat material: index into flatTextures or -1
+    std::vector<int32_t> flatNormalTex;             // per flat material: normal map (index into flatTextures) or -1
     std::vector<uint32_t> flatTextures;             // TextureIds in use, in first-use order
     std::vector<TextureB200> textures;              // TextureId = index + 1 (0 = InvalidTexture)
     // render hand-off: pinned staging the caller reads between semaphore acquire / release
@@ -518,7 +520,7 @@ class TracerB200 final : public TracerI
         MaterialIdList out;
         for(size_t i = 0; i < counts.size(); i++)
         {
-            mg.albedo.push_back(Vector3::Zero()); mg.albedoTex.push_back(-1); mg.params.push_back(std::array<float, 8>{});
+            mg.albedo.push_back(Vector3::Zero()); mg.albedoTex.push_back(-1); mg.normalTex.push_back(-1); mg.params.push_back(std::array<float, 8>{});
             out.push_back(MaterialId((Raw(g) << MAT_ID_BITS) | uint32_t(mg.albedo.size() - 1)));
         }
         return out;
@@ -558,7 +560,19 @@ class TracerB200 final : public TracerI
         if(data.IsEmpty())
         {
             if(attributeIndex != 1) throw MRayError("{}: Attribute {:d} is not \"Optional Texture\"", mg.type, attributeIndex);
-            for(const auto& t : tex) if(t.has_value()) throw MRayError("{}: normal maps are not supported yet", mg.type);
+            uint32_t lo = range[0] & ((1u << MAT_ID_BITS) - 1u), hi = range[1] & ((1u << MAT_ID_BITS) - 1u);
+            if(hi >= mg.normalTex.size() || tex.size() != hi - lo + 1) throw MRayError("{}: normalMap range mismatch", mg.type);
+            for(size_t k = 0; k < tex.size(); k++)
+            {
+                mg.normalTex[lo + k] = -1;
+                if(!tex[k].has_value()) continue;
+                const uint32_t tid = Raw(*tex[k]);
+                if(tid == 0 || tid > textures.size()) throw MRayError("{}: Given texture({}) is not found", mg.type, tid);
+                // the normal map wants a TracerTexView<2, Vector3> (MaterialsDefault.h:L14)
+                if(textures[tid - 1].channels != 4 || textures[tid - 1].params.readMode != MRayTextureReadMode::MR_DROP_1)
+                    throw MRayError("{}: Given texture({}) does not have a correct type for, Attribute {}", mg.type, tid, attributeIndex);
+                mg.normalTex[lo + k] = int32_t(tid);
+            }
             return;
         }
         if(attributeIndex != 0) throw MRayError("{}: Attribute {:d} is not \"ParamVarying\"", mg.type, attributeIndex);
@@ -604,7 +618,18 @@ class TracerB200 final : public TracerI
         // TextureMemory::ConvertColorspaces leaves a texture alone when it is not a colour, or already global + linear
         const bool needsConversion = p.isColor == AttributeIsColor::IS_COLOR &&
             ((p.colorSpace != MRayColorSpaceEnum::MR_DEFAULT && p.colorSpace != params.globalTextureColorSpace) || p.gamma != Float(1));
-        if(needsConversion) throw MRayError("textures: colour space / gamma conversion is not supported yet");
+        if(needsConversion)
+        {   // converted on upload by libmray_b200 (KCConvertColor): gamma to linear, then the RGB -> RGB matrix into the global space
+            if(t.channels < 3) throw MRayError("textures: colour conversion of a {}-channel texture is not supported yet", t.channels);
+            t.gamma = float(p.gamma);
+            if(p.colorSpace != MRayColorSpaceEnum::MR_DEFAULT && p.colorSpace != params.globalTextureColorSpace)
+            {
+                // ColorspaceTransfer<from, global>::RGBToRGBMatrix = FromXYZ(global) * ToXYZ(from) (Core/ColorFunctions.h:L147-153)
+                const Matrix3x3 m = LuminanceMatrix(params.globalTextureColorSpace).Inverse() * LuminanceMatrix(p.colorSpace);
+                for(unsigned r = 0; r < 3; r++) for(unsigned c = 0; c < 3; c++) t.colorMatrix[3 * r + c] = m(r, c);
+                t.hasColorMatrix = true;
+            }
+        }
         // the view type follows DetermineReadMode (Tracer/TextureMemory.cpp:L329-396): 4 channels + MR_DROP_1 read as Vector3
         if(p.readMode != MRayTextureReadMode::MR_PASSTHROUGH && p.readMode != MRayTextureReadMode::MR_DROP_1)
             throw MRayError("textures: only MR_PASSTHROUGH / MR_DROP_1 reads are supported yet");
@@ -801,7 +826,7 @@ class TracerB200 final : public TracerI
             groups.push_back(Group{Raw(t), {}, {}, {}, {}});
             return groups.back();
         };
-        flatAlbedo.clear(); flatAlbedoTex.clear(); flatMaterialType.clear(); flatMaterialParams.clear(); flatTextures.clear();
+        flatAlbedo.clear(); flatAlbedoTex.clear(); flatNormalTex.clear(); flatMaterialType.clear(); flatMaterialParams.clear(); flatTextures.clear();
         flatLightRadiance.clear(); flatLightTwoSided.clear();
         int32_t pgUsed = -1;
         auto UsePrimGroup = [&](uint32_t g)
@@ -829,6 +854,16 @@ class TracerB200 final : public TracerI
                 if(it == flatTextures.end()) flatTextures.push_back(tid);
             }
             flatAlbedoTex.push_back(ft);
+            int32_t fn = -1;
+            if(mg.normalTex[idx] >= 0)
+            {
+                const uint32_t tid = uint32_t(mg.normalTex[idx]);
+                if(!textures[tid - 1].loaded) throw MRayError("texture({}) has no data", tid);
+                auto it = std::find(flatTextures.begin(), flatTextures.end(), tid);
+                fn = int32_t(it - flatTextures.begin());
+                if(it == flatTextures.end()) flatTextures.push_back(tid);
+            }
+            flatNormalTex.push_back(fn);
             flatMaterialType.push_back(mg.type == "(Mt)Reflect" ? uint8_t(MRB_MATERIAL_REFLECT) : mg.type == "(Mt)Refract" ? uint8_t(MRB_MATERIAL_REFRACT)
                                        : mg.type == "(Mt)Unreal" ? uint8_t(MRB_MATERIAL_UNREAL) : uint8_t(MRB_MATERIAL_LAMBERT));
             flatMaterialParams.insert(flatMaterialParams.end(), mg.params[idx].begin(), mg.params[idx].end());
@@ -895,7 +930,7 @@ class TracerB200 final : public TracerI
                 used.push_back(uint32_t(g.alpha[k]));
                 const TextureB200& t = textures[size_t(g.alpha[k]) - 1];
                 atex.push_back(mrb_texture_desc{t.pixels.data(), t.size[0], t.size[1], t.channels, t.format,
-                                                uint32_t(t.params.interpolation), uint32_t(t.params.edgeResolve)});
+                                                uint32_t(t.params.interpolation), uint32_t(t.params.edgeResolve), 1.0f, nullptr});
             }
             if(!used.empty())
             {
@@ -1092,9 +1127,11 @@ class TracerB200 final : public TracerI
             {
                 const TextureB200& t = textures[flatTextures[k] - 1];
                 texDescs[k] = mrb_texture_desc{t.pixels.data(), t.size[0], t.size[1], t.channels, t.format,
-                                               uint32_t(t.params.interpolation), uint32_t(t.params.edgeResolve)};
+                                               uint32_t(t.params.interpolation), uint32_t(t.params.edgeResolve),
+                                               t.gamma, t.hasColorMatrix ? t.colorMatrix : nullptr};
             }
             d.textureCount = uint32_t(texDescs.size()); d.textures = texDescs.data(); d.albedoTexture = flatAlbedoTex.data();
+            if(std::any_of(flatNormalTex.begin(), flatNormalTex.end(), [](int32_t t) { return t >= 0; })) d.normalTexture = flatNormalTex.data();
         }
         // boundary light surface: (L)Null (nothing to do) or a skysphere (LightGroupSkysphere, Tracer/LightsDefault.hpp:L704-893)
         d.boundaryTexture = -1;
@@ -1115,7 +1152,8 @@ class TracerB200 final : public TracerI
                 else
                 {   // the radiance map is not an albedo texture of any material: append it to this render's table
                     texDescs.push_back(mrb_texture_desc{t.pixels.data(), t.size[0], t.size[1], t.channels, t.format,
-                                                        uint32_t(t.params.interpolation), uint32_t(t.params.edgeResolve)});
+                                                        uint32_t(t.params.interpolation), uint32_t(t.params.edgeResolve),
+                                                        t.gamma, t.hasColorMatrix ? t.colorMatrix : nullptr});
                     d.boundaryTexture = int32_t(texDescs.size() - 1);
                     d.textureCount = uint32_t(texDescs.size()); d.textures = texDescs.data();
                     if(flatTextures.empty()) d.albedoTexture = nullptr;
@@ -1371,7 +1409,7 @@ class TracerB200 final : public TracerI
         surfaces.clear(); lightSurfaces.clear(); camSurfaces.clear(); volumes.clear(); textures.clear();
         boundary = LightSurfaceParams{};
         flatPrimGroup = 0; flatLightRadiance.clear(); flatLightTwoSided.clear(); flatAlbedo.clear();
-        flatMaterialType.clear(); flatMaterialParams.clear(); flatAlbedoTex.clear(); flatTextures.clear();
+        flatMaterialType.clear(); flatMaterialParams.clear(); flatAlbedoTex.clear(); flatNormalTex.clear(); flatTextures.clear();
         lastStart.reset(); camOverride.reset(); pendingCam.reset(); tileSPPs.clear(); currentTile = 0;
     }
     void Flush() const override { for(const DeviceB200& d : devs) mrb_context_synchronize(d.ctx); }

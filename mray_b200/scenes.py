@@ -562,3 +562,27 @@ def read_pfm(path: str):
         scale = float(f.readline())
         a = np.frombuffer(f.read(), "<f4" if scale < 0 else ">f4")
     return a.reshape(h, w, 3).astype(np.float32) if magic == "PF" else a.reshape(h, w).astype(np.float32)
+
+
+def cornell_normal_map(size: int = 16):
+    """``cornell_box`` whose white material (id 0: floor, ceiling, back wall, boxes) carries a NORMAL MAP: a size x size fp32
+    RGBA texture of tangent-space normals (a smooth egg-crate bump, tilted up to ~35 degrees; bilinear, wrap) addressed by
+    per-quad UVs that tile it twice. Returns the cornell dict with `uvs` [V, 2], `normals` (flat per-vertex normals: every
+    quad owns its vertices), `normal_texture` and `normal_map` (per material id: -1 or 0)."""
+    c = cornell_box()
+    nq = c["positions"].shape[0] // 4
+    c["uvs"] = np.tile(np.array([[0, 0], [2, 0], [2, 2], [0, 2]], np.float32), (nq, 1))
+    p, i = c["positions"], c["indices"]
+    fn = np.cross(p[i[:, 1]] - p[i[:, 0]], p[i[:, 2]] - p[i[:, 0]])
+    fn /= np.linalg.norm(fn, axis=1, keepdims=True)
+    nrm = np.zeros_like(p)
+    nrm[i[:, 0]] = fn; nrm[i[:, 1]] = fn; nrm[i[:, 2]] = fn
+    c["normals"] = nrm.astype(np.float32)
+    g = (np.arange(size, dtype=np.float32) + 0.5) / size * 2.0 * np.pi
+    x, y = np.meshgrid(g, g)
+    n = np.stack([0.7 * np.cos(x), 0.7 * np.cos(y), np.ones_like(x)], axis=-1)
+    n /= np.linalg.norm(n, axis=-1, keepdims=True)
+    t = np.concatenate([n, np.ones((size, size, 1))], axis=-1).astype(np.float32)
+    c["normal_texture"] = dict(data=np.ascontiguousarray(t), interp="Linear", edge="Wrap")
+    c["normal_map"] = np.array([0, -1, -1, -1], np.int32)
+    return c

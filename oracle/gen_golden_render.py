@@ -78,6 +78,12 @@ ITEMS = {
     # alpha maps (SurfaceParams.alphaMaps -> the stochastic test inside IntersectionCheck): scenes.cornell_alpha, a pane with
     # transparent / opaque / fractional texels in front of the boxes
     "cornell64_alpha_spp16384": (64, 16384, 41, "WithNEEAndMIS", (2, 20), "alpha", np.float32, RGB),
+    # normal maps (the optional "normalMap" attribute of (Mt)Lambert): scenes.cornell_normal_map, an egg-crate bump on the white
+    # material, through the tangent frames the loader derives from the vertex normals
+    "cornell64_normalmap_spp16384": (64, 16384, 42, "WithNEEAndMIS", (2, 20), "normalmap", np.float32, RGB),
+    # texture colour conversion at load (TextureMemory::ConvertColorspaces): the textured-albedo scene again, with the fp32
+    # texture declared REC_709 + gamma 2.2 and the unorm8 one gamma 2.2, under the tracer's ACES_CG global colour space
+    "cornell64_srgbtex_spp16384": (64, 16384, 43, "WithNEEAndMIS", (2, 20), "srgbtex", np.float32, RGB),
     # two-level scene: every batch in its own local space under a (T)Single transform
     "cornell64_single_spp16384": (64, 16384, 6, "WithNEEAndMIS", (2, 20), True, np.float32, RGB),
 }
@@ -134,6 +140,7 @@ def render(name):
     res, spp, seed, mode, rr, single, dt, renderer = ITEMS[name]
     sky = isinstance(single, tuple) and single[0] == "sky"
     c = (scenes.cornell_open(keep_light=single[2] == "tex+light") if sky else scenes.cornell_alpha() if single == "alpha"
+         else scenes.cornell_normal_map() if single == "normalmap"
          else scenes.cornell_mirror() if single == "mirror" else scenes.cornell_glossy() if single == "glossy"
          else scenes.cornell_sphere() if single == "sphere" else scenes.cornell_box())
     kw = {}
@@ -160,6 +167,10 @@ def render(name):
         b = O.batched_scene(c["positions"], c["indices"], c["material"])
         kw = sky_kwargs(single)
         bt = None
+    elif single == "normalmap":
+        b = O.batched_scene(c["positions"], c["indices"], c["material"], normals=c["normals"], uvs=c["uvs"])
+        kw = dict(textures=[c["normal_texture"]], normal_map=c["normal_map"])
+        bt = None
     elif single == "alpha":
         b = O.batched_scene(c["positions"], c["indices"], c["material"], uvs=c["uvs"])
         kw = dict(textures=[c["alpha_texture"]], alpha_map=c["alpha_map"])
@@ -167,6 +178,13 @@ def render(name):
     elif isinstance(single, tuple) and single[0] == "filter":
         b = O.batched_scene(c["positions"], c["indices"], c["material"])
         kw = dict(film_filter=single[1], film_filter_radius=single[2])
+        bt = None
+    elif single == "srgbtex":
+        uvs, textures, at = scenes.cornell_textures()
+        textures[0] = dict(textures[0], color_space="REC_709", gamma=2.2)
+        textures[1] = dict(textures[1], gamma=2.2)
+        b = O.batched_scene(c["positions"], c["indices"], c["material"], uvs=uvs)
+        kw = dict(textures=textures, material_texture=at)
         bt = None
     elif single == "textured":
         uvs, textures, at = scenes.cornell_textures()

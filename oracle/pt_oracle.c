@@ -107,6 +107,8 @@ typedef struct
     /* alpha maps (SurfaceParams.alphaMaps): per triangle -1 or an index into `textures` whose first channel is the alpha
      * (NULL = none); uv = the per-vertex UV0 above */
     const int32_t* triAlpha;
+    /* normal maps: per material -1 or an index into `textures` holding tangent-space normals (NULL = none); needs vertexTBN */
+    const int32_t* normalTexture;
 } pt_scene;
 
 /* One single-level 2-D texture as the reference's host-backend view reads it (Device/CPU/TextureViewCPU.h):
@@ -608,6 +610,23 @@ static v3 tbn_normal(const float* q0, const float* q1, const float* q2, float a,
     return V(2.0f * (x * z - w * y), 2.0f * (y * z + w * x), w * w - x * x - y * y + z * z);
 }
 
+/* Shading normal under a normal map (Triangle::GenerateSurface, PrimitiveDefaultTriangle.hpp:L478-491,L571-575): the frame
+ * (turned 180 degrees about its tangent on a back-side hit: TANGENT_ROT * tbn) is re-aimed with
+ * RotationBetweenZAxis(n).Conjugate() * tbn, so its Z axis in the world is tbn^-1 (n) */
+static v3 tbn_normal_mapped(const float* q0, const float* q1, const float* q2, float a, float b, v3 nTS, int backSide)
+{
+    float q[4], qab[4];
+    if(fabsf(a + b) < 1.0e-5f) memcpy(q, q2, sizeof(q));
+    else { quat_slerp(q1, q0, a / (a + b), qab); quat_slerp(qab, q2, 1.0f - a - b, q); }
+    float inv = 1.0f / sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    float w = q[0] * inv, x = q[1] * inv, y = q[2] * inv, z = q[3] * inv;
+    v3 r0 = V(w * w + x * x - y * y - z * z, 2.0f * (x * y - w * z), 2.0f * (x * z + w * y));
+    v3 r1 = V(2.0f * (x * y + w * z), w * w - x * x + y * y - z * z, 2.0f * (y * z - w * x));
+    v3 r2 = V(2.0f * (x * z - w * y), 2.0f * (y * z + w * x), w * w - x * x - y * y + z * z);
+    float sg = backSide ? -1.0f : 1.0f;
+    return add(mul(r0, nTS.x), mul(add(mul(r1, nTS.y), mul(r2, nTS.z)), sg));
+}
+
 static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, float* filmW, float waves[4], float wavePdf[4]);
 static v3 path(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, float* filmW)
 {
@@ -701,12 +720,22 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
         }
         const int backSide = dot(gN, nrm(d)) > 0;
         v3 sN = gN;   /* shading normal: the interpolated tangent frame's Z axis when the group has a NORMAL attribute */
+        int normalMapped = 0;
         if(s->vertexTBN)
         {
             const uint32_t* vi = s->idx + 3 * (size_t)prim;
-            sN = tbn_normal(s->vertexTBN + 4 * (size_t)vi[0], s->vertexTBN + 4 * (size_t)vi[1], s->vertexTBN + 4 * (size_t)vi[2], a, b);
+            const float* q0 = s->vertexTBN + 4 * (size_t)vi[0]; const float* q1 = s->vertexTBN + 4 * (size_t)vi[1]; const float* q2 = s->vertexTBN + 4 * (size_t)vi[2];
+            if(s->normalTexture && s->normalTexture[m] >= 0)
+            {
+                float u = 0, v = 0, px3[3];
+                if(s->uv) { u = s->uv[2 * vi[0]] * a + s->uv[2 * vi[1]] * b + s->uv[2 * vi[2]] * c; v = s->uv[2 * vi[0] + 1] * a + s->uv[2 * vi[1] + 1] * b + s->uv[2 * vi[2] + 1] * c; }
+                orc_texture_sample(&s->textures[s->normalTexture[m]], u, v, px3);
+                sN = nrm(tbn_normal_mapped(q0, q1, q2, a, b, nrm(V(px3[0], px3[1], px3[2])), backSide));
+                normalMapped = 1;
+            }
+            else sN = tbn_normal(q0, q1, q2, a, b);
         }
-        if(backSide) { gN = mul(gN, -1.0f); sN = mul(sN, -1.0f); }
+        if(backSide) { gN = mul(gN, -1.0f); if(!normalMapped) sN = mul(sN, -1.0f); }
         if(s->materialType && s->materialType[m] == 1u)
         {   /* (Mt)Reflect (MaterialsDefault.hpp:L132-215): a perfect mirror, Specularity() = 1. WorkFunctionNEE samples
              * a light (three random numbers) but casts no shadow ray for a specular material; WorkFunction reflects

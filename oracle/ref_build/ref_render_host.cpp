@@ -28,7 +28,7 @@ struct DriverScene
     const float* batchTransforms; const int32_t* batchInstanceOf;
     uint32_t textureCount; const uint32_t* textureInfo; const uint8_t* textureBytes; const int32_t* materialTexture; const float* uvs; const uint8_t* materialKind; const uint8_t* lightTwoSided; const float* materialParams;
     uint32_t boundaryType; float boundaryRadiance[3]; int32_t boundaryTexture; const float* boundaryTransform;
-    const int32_t* batchAlphaMap;
+    const int32_t* batchAlphaMap; const int32_t* materialNormalMap;
 };
 struct DriverRender
 {
@@ -45,7 +45,7 @@ int main(int argc, char** argv)
     FILE* f = std::fopen(argv[1], "rb");
     if(!f) { std::perror("blob"); return 65; }
     uint64_t n = 0;
-    if(std::fread(&n, 8, 1, f) != 1 || (n < 23 || n > 26)) { std::fprintf(stderr, "bad blob\n"); return 66; }
+    if(std::fread(&n, 8, 1, f) != 1 || (n < 23 || n > 27)) { std::fprintf(stderr, "bad blob\n"); return 66; }
     std::vector<std::vector<uint64_t>> sec(n);     // 8-byte aligned storage
     std::vector<uint64_t> bytes(n);
     for(uint64_t i = 0; i < n; i++)
@@ -61,7 +61,7 @@ int main(int argc, char** argv)
     //   latency, burstSize, camSwitchAfter, camSwitch[9] (float bits)},
     // 4 u64 seed, 5 f32[13] camera {pos, gaze, up, fovXY, nearFar}, 6 vertexOffsets, 7 triOffsets, 8 positions,
     // 9 normals, 10 indices, 11 batchMaterial, 12 batchLight, 13 albedo, 14 radiance, 15 batchTransforms (may be empty), 16 batchInstanceOf (may be empty),
-    // 17 textureInfo (6 u32 per texture; may be empty), 18 textureBytes, 19 materialTexture, 20 uvs (may be empty), 21 materialKind (may be empty), 22 lightTwoSided (may be empty)
+    // 17 textureInfo (8 u32 per texture; may be empty), 18 textureBytes, 19 materialTexture, 20 uvs (may be empty), 21 materialKind (may be empty), 22 lightTwoSided (may be empty)
     const uint32_t* u = static_cast<const uint32_t*>(P(3));
     const float* cam = static_cast<const float*>(P(5));
     DriverScene sc{};
@@ -72,7 +72,7 @@ int main(int argc, char** argv)
     sc.batchMaterial = static_cast<const int32_t*>(P(11)); sc.batchLight = static_cast<const int32_t*>(P(12));
     sc.albedo = static_cast<const float*>(P(13)); sc.radiance = static_cast<const float*>(P(14));
     sc.batchTransforms = static_cast<const float*>(P(15)); sc.batchInstanceOf = static_cast<const int32_t*>(P(16));
-    sc.textureCount = uint32_t(bytes[17] / 24); sc.textureInfo = static_cast<const uint32_t*>(P(17));
+    sc.textureCount = uint32_t(bytes[17] / 32); sc.textureInfo = static_cast<const uint32_t*>(P(17));
     sc.textureBytes = static_cast<const uint8_t*>(P(18)); sc.materialTexture = static_cast<const int32_t*>(P(19));
     sc.uvs = static_cast<const float*>(P(20)); sc.materialKind = static_cast<const uint8_t*>(P(21));
     sc.lightTwoSided = static_cast<const uint8_t*>(P(22));
@@ -84,6 +84,7 @@ int main(int argc, char** argv)
         if(bytes[24] >= 20 + 48) sc.boundaryTransform = reinterpret_cast<const float*>(b + 5);
     }
     if(n > 25) sc.batchAlphaMap = static_cast<const int32_t*>(P(25));   // 25 batchAlphaMap (i32 per batch; may be empty)
+    if(n > 26) sc.materialNormalMap = static_cast<const int32_t*>(P(26));   // 26 materialNormalMap (i32 per material; may be empty)
     std::memcpy(sc.camPos, cam, 12); std::memcpy(sc.camGaze, cam + 3, 12); std::memcpy(sc.camUp, cam + 6, 12);
     std::memcpy(sc.fovXY, cam + 9, 8); std::memcpy(sc.nearFar, cam + 11, 8);
     DriverRender rd{};

@@ -52,8 +52,9 @@ struct DriverScene
     // optional: batchCount entries; batchInstanceOf[b] = a >= 0 makes the SURFACE of batch b use the primitive batch
     // of batch a (instancing: same geometry, own material and transform; b's own geometry stays unused). -1 = itself.
     const int32_t*  batchInstanceOf;
-    // optional textured albedo: per texture 6 x u32 {width, height, format (0 = MR_RGBA_FLOAT, 1 = MR_RGBA8_UNORM),
-    // MRayTextureInterpEnum, MRayTextureEdgeResolveEnum, byte offset into textureBytes}; materialTexture: per material
+    // optional textured albedo: per texture 8 x u32 {width, height, format (0 = MR_RGBA_FLOAT, 1 = MR_RGBA8_UNORM),
+    // MRayTextureInterpEnum, MRayTextureEdgeResolveEnum, byte offset into textureBytes, MRayColorSpaceEnum + 1 (0 = MR_DEFAULT),
+    // gamma as float bits (0 = 1.0)}; materialTexture: per material
     // -1 or a texture index; uvs: V * 2 (UV0), NULL = zeros
     uint32_t        textureCount;
     const uint32_t* textureInfo;
@@ -77,6 +78,9 @@ struct DriverScene
     // optional alpha maps (SurfaceParams.alphaMaps): per batch -1 or a texture index; such textures have format 2
     // (MR_R_FLOAT) or 3 (MR_R8_UNORM) in textureInfo: single-channel pure data, read as Float (AlphaMap = TracerTexView<2, Float>)
     const int32_t*  batchAlphaMap;
+    // optional normal maps: per material -1 or a texture index (RGBA texture read as Vector3): the optional texture-only
+    // "normalMap" attribute of (Mt)Lambert / (Mt)Unreal
+    const int32_t*  materialNormalMap;
 };
 
 struct DriverRender
@@ -262,11 +266,13 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
         std::vector<TextureId> texIds;
         for(uint32_t t = 0; t < sc->textureCount; t++)
         {
-            const uint32_t* ti = sc->textureInfo + 6 * size_t(t);
+            const uint32_t* ti = sc->textureInfo + 8 * size_t(t);
             MRayTextureParameters tp;
             tp.pixelType = MRayPixelTypeRT(ti[2] == 0 ? MRayPixelEnum::MR_RGBA_FLOAT : ti[2] == 1 ? MRayPixelEnum::MR_RGBA8_UNORM
                                            : ti[2] == 2 ? MRayPixelEnum::MR_R_FLOAT : MRayPixelEnum::MR_R8_UNORM);
-            tp.colorSpace = MRayColorSpaceEnum::MR_DEFAULT; tp.gamma = Float(1);
+            tp.colorSpace = ti[6] ? MRayColorSpaceEnum(ti[6] - 1u) : MRayColorSpaceEnum::MR_DEFAULT;
+            tp.gamma = Float(1);
+            if(ti[7]) { float g; std::memcpy(&g, &ti[7], 4); tp.gamma = g; }
             tp.interpolation = MRayTextureInterpEnum(ti[3]); tp.edgeResolve = MRayTextureEdgeResolveEnum(ti[4]);
             if(ti[2] < 2) tp.readMode = MRayTextureReadMode::MR_DROP_1;   // RGBA pixels read as Vector3 (TextureReadMode::TO_3C_FROM_4C): the albedo's view type
             else { tp.readMode = MRayTextureReadMode::MR_PASSTHROUGH; tp.isColor = AttributeIsColor::IS_PURE_DATA; }   // alpha maps
@@ -275,7 +281,7 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
         tracer->CommitTextures();
         for(uint32_t t = 0; t < sc->textureCount; t++)
         {
-            const uint32_t* ti = sc->textureInfo + 6 * size_t(t);
+            const uint32_t* ti = sc->textureInfo + 8 * size_t(t);
             const Byte* src = reinterpret_cast<const Byte*>(sc->textureBytes) + ti[5];
             size_t pixels = size_t(ti[0]) * ti[1];
             // TransientData is typed by the pixel (the reference reads it back with AccessAs<PixelType>)
@@ -343,7 +349,11 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
                    mInfo[a].isOptional == AttributeOptionality::MR_OPTIONAL)
                 {
                     TransientData e(std::in_place_type_t<Vector3>{}, 0);
-                    tracer->PushMatAttribute(mg, range, a, std::move(e), std::vector<Optional<TextureId>>(n, std::nullopt));
+                    std::vector<Optional<TextureId>> nm(n, std::nullopt);
+                    if(sc->materialNormalMap && mInfo[a].name == "normalMap")
+                        for(uint32_t k = 0; k < n; k++)
+                            if(sc->materialNormalMap[lambertOf[k]] >= 0) nm[k] = texIds[size_t(sc->materialNormalMap[lambertOf[k]])];
+                    tracer->PushMatAttribute(mg, range, a, std::move(e), std::move(nm));
                 }
         }
         if(!reflectOf.empty())

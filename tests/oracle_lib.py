@@ -21,7 +21,7 @@ _u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 
 
 def build_oracle():
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("mray_oracle.c", "pt_oracle.c", "spectrum_oracle.c", "sobol_oracle.c", "dist_oracle.c")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("mray_oracle.c", "pt_oracle.c", "spectrum_oracle.c", "sobol_oracle.c", "dist_oracle.c", "spectra_lut_oracle.c")]
     so = os.path.join(ORACLE_DIR, "liboracle.so")
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(x) for x in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
@@ -169,7 +169,7 @@ class _DriverScene(C.Structure):
                 ("materialTexture", C.c_void_p), ("uvs", C.c_void_p), ("materialKind", C.c_void_p), ("lightTwoSided", C.c_void_p),
                 ("materialParams", C.c_void_p),
                 ("boundaryType", C.c_uint32), ("boundaryRadiance", C.c_float * 3), ("boundaryTexture", C.c_int32),
-                ("boundaryTransform", C.c_void_p), ("batchAlphaMap", C.c_void_p)]
+                ("boundaryTransform", C.c_void_p), ("batchAlphaMap", C.c_void_p), ("materialNormalMap", C.c_void_p)]
 
 
 class _DriverRender(C.Structure):
@@ -185,6 +185,34 @@ class _DriverStats(C.Structure):
     _fields_ = [("commitSeconds", C.c_double), ("renderSeconds", C.c_double), ("totalPaths", C.c_double),
                 ("iterations", C.c_uint32), ("sceneAABB", C.c_float * 6), ("startSeconds", C.c_double),
                 ("sceneSeconds", C.c_double), ("closeSeconds", C.c_double), ("totalSeconds", C.c_double)]
+
+
+COLOR_SPACES = ["ACES2065_1", "ACES_CG", "REC_709", "REC_2020", "DCI_P3", "ADOBE_RGB"]     # MRayColorSpaceEnum order
+# Color::Colorspace<E>::ToXYZMatrix of the reference (printed from its own headers, Core/ColorFunctions.h), row-major
+TO_XYZ = {
+    "ACES_CG": [0.66094172, 0.132851541, 0.169431195, 0.271564007, 0.673637331, 0.0577730648, -0.00545531698, 0.00124250283, 1.0903964],
+    "REC_709": [0.412407905, 0.357589543, 0.180432633, 0.21264784, 0.715179145, 0.0721730441, 0.0193316191, 0.119196467, 0.950278521],
+    "ADOBE_RGB": [0.576688468, 0.185560912, 0.188180566, 0.297355026, 0.627372682, 0.0752722174, 0.027032271, 0.0706899166, 0.991084278],
+}
+
+
+def rgb_to_rgb_matrix(from_space, to_space="ACES_CG"):
+    """ColorspaceTransfer<from, to>::RGBToRGBMatrix = FromXYZ(to) ToXYZ(from), float32"""
+    a, b = np.array(TO_XYZ[to_space], np.float64).reshape(3, 3), np.array(TO_XYZ[from_space], np.float64).reshape(3, 3)
+    return (np.linalg.inv(a) @ b).astype(np.float32)
+
+
+def convert_texture_color(data, gamma=1.0, color_matrix=None):
+    """KCConvertColor restated in numpy: texels [h, w, c >= 3] float32 / uint8 -> same dtype after pow(gamma) and the matrix."""
+    a = np.asarray(data)
+    rgb = (a[..., :3].astype(np.float32) * np.float32(1.0 / 255.0)) if a.dtype == np.uint8 else a[..., :3].astype(np.float32)
+    if gamma != 1.0:
+        rgb = np.power(rgb, np.float32(gamma), dtype=np.float32)
+    if color_matrix is not None:
+        rgb = (rgb.astype(np.float64) @ np.asarray(color_matrix, np.float64).reshape(3, 3).T).astype(np.float32)
+    out = a.copy()
+    out[..., :3] = np.clip(np.round(rgb * np.float32(255.0)), 0, 255).astype(np.uint8) if a.dtype == np.uint8 else rgb
+    return out
 
 
 def driver_available():
@@ -223,7 +251,7 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
                   batch_transforms=None, sampler="Independent", host_exe=False, instance_of=None,
                   textures=None, material_texture=None, region=None, material_kind=None,
                   latency=False, burst_size=1, cam_switch=None, light_two_sided=False, film_filter=None, film_filter_radius=0.0,
-                  material_params=None, boundary=None, alpha_map=None):
+                  material_params=None, boundary=None, alpha_map=None, normal_map=None):
     """Renders through TracerI. alpha_map: per material id (an index into `albedo`) -1 or a texture index: the batches of
     that material get SurfaceParams.alphaMaps (such textures are [h, w] or [h, w, 1] arrays: single-channel pure data). boundary: None = (L)Null boundary, or dict(type="Skysphere_Spherical"|"Skysphere_CoOcta",
     radiance=(r, g, b) | texture=index into `textures`, transform=[3, 4] or None). `light_material`: material id whose batch is the prim-backed light.
@@ -266,7 +294,8 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
             single = a.ndim == 2 or a.shape[2] == 1
             assert single or a.shape[2] == 4, "the TracerI driver pushes RGBA (colour) or single-channel (alpha) pixels"
             info.append([a.shape[1], a.shape[0], (1 if a.dtype == np.uint8 else 0) + (2 if single else 0), _TEX_INTERP[t.get("interp", "Linear")],
-                         _TEX_EDGE[t.get("edge", "Wrap")], off])
+                         _TEX_EDGE[t.get("edge", "Wrap")], off, (COLOR_SPACES.index(t["color_space"]) + 1) if t.get("color_space") else 0,
+                         int(np.float32(t["gamma"]).view(np.uint32)) if t.get("gamma") else 0])
             blobs.append(a.tobytes()); off += len(blobs[-1]) + (-len(blobs[-1]) % 16)
             blobs[-1] += b"\0" * (-len(blobs[-1]) % 16)
         tinfo = np.array(info, np.uint32); tbytes = np.frombuffer(b"".join(blobs), np.uint8).copy()
@@ -278,6 +307,7 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
     b_xf = None if (boundary or {}).get("transform") is None else np.ascontiguousarray(boundary["transform"], np.float32).reshape(12)
     if textures and mtex is None:
         mtex = np.full(len(lambert), -1, np.int32)
+    m_normal = None if normal_map is None else np.ascontiguousarray(np.asarray(normal_map, np.int32)[lambert])   # per material id: -1 or a texture index
     b_alpha = None if alpha_map is None else np.ascontiguousarray([-1 if m == light_material else int(alpha_map[m]) for m in mats], np.int32)
     if host_exe:
         import subprocess
@@ -301,7 +331,8 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
                 b"" if mparams is None else mparams.tobytes(),
                 b"" if b_type == 0 else (np.uint32(b_type).tobytes() + b_rad.tobytes() + np.int32(b_tex).tobytes() +
                                          (b"" if b_xf is None else b_xf.tobytes())),
-                b"" if b_alpha is None else b_alpha.tobytes()]
+                b"" if b_alpha is None else b_alpha.tobytes(),
+                b"" if m_normal is None else m_normal.tobytes()]
         with tempfile.TemporaryDirectory() as td:
             with open(os.path.join(td, "in.blob"), "wb") as f:
                 f.write(np.uint64(len(secs)).tobytes())
@@ -352,6 +383,8 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
         keep.append(b_xf); sc.boundaryTransform = b_xf.ctypes.data
     if b_alpha is not None:
         keep.append(b_alpha); sc.batchAlphaMap = b_alpha.ctypes.data
+    if m_normal is not None:
+        keep.append(m_normal); sc.materialNormalMap = m_normal.ctypes.data
     rd = _DriverRender(renderer.encode(), width, height, spp, sample_mode.encode(), (C.c_uint32 * 2)(*rr_range), seed,
                        accel_mode, parallel_hint, threads, sampler_id, (C.c_uint32 * 4)(*(region or (0, 0, 0, 0))),
                        1 if latency else 0, burst_size, cam_switch[0] if cam_switch else 0,
@@ -387,7 +420,7 @@ class _PtScene(C.Structure):
                 ("materialType", C.c_void_p), ("filmFilter", C.c_uint32), ("materialParams", C.c_void_p), ("vertexTBN", C.c_void_p),
                 ("boundaryType", C.c_uint32), ("boundaryTexture", C.c_int32), ("boundaryRadiance", C.c_float * 3),
                 ("boundaryCdfX", C.c_void_p), ("boundaryCdfY", C.c_void_p), ("boundaryM", C.c_float * 9), ("boundaryInvM", C.c_float * 9),
-                ("sceneDiameter", C.c_float), ("triAlpha", C.c_void_p)]
+                ("sceneDiameter", C.c_float), ("triAlpha", C.c_void_p), ("normalTexture", C.c_void_p)]
 
 
 class _OrcTexture(C.Structure):
@@ -475,7 +508,7 @@ def oracle_render(positions, indices, tri_material, albedo, radiance, camera, wi
                   sample_mode=2, rr_range=(2, 20), seed=0, near_far=(0.01, 1000.0), threads=None,
                   spectral_data=None, wavelength_mode=2, textures=None, albedo_texture=None, vertex_uvs=None,
                   material_type=None, light_two_sided=None, film_filter=None, film_filter_radius=1.0, material_params=None, vertex_normals=None,
-                  boundary=None, tri_alpha=None):
+                  boundary=None, tri_alpha=None, normal_texture=None):
     """tri_alpha: per triangle -1 or an index into `textures` (an alpha map read through its first channel).
     boundary: None = (L)Null, or dict(type="Skysphere_Spherical"|"Skysphere_CoOcta", radiance=(r, g, b) | texture=index, transform=[3, 4],
     scene_diameter=0, luminance_row=ACES_CG). tri_material: per triangle, >= 0 Lambert material index, -1 - k for light k. Returns image[h,w,3]
@@ -509,6 +542,9 @@ def oracle_render(positions, indices, tri_material, albedo, radiance, camera, wi
     if tri_alpha is not None:
         ta = np.ascontiguousarray(tri_alpha, np.int32)
         s.triAlpha = ta.ctypes.data
+    if normal_texture is not None:     # per material: -1 or a texture of tangent-space normals (needs vertex_normals -> tangent frames)
+        ntx = np.ascontiguousarray(normal_texture, np.int32)
+        s.normalTexture = ntx.ctypes.data
     if textures:
         tarr, keep_tex = _orc_textures(textures)
         at = np.ascontiguousarray(albedo_texture if albedo_texture is not None else np.full(alb.shape[0], -1), np.int32)
@@ -690,3 +726,12 @@ def oracle_luminance(rgb, y_row):
     out = np.zeros(p.shape[0], np.float32)
     L.orc_luminance(p, p.shape[0], p.shape[1], np.asarray(y_row, np.float32), out)
     return out.reshape(rgb.shape[:-1])
+
+
+def oracle_spectra_lut_column(inputs, l, j, i, res=64, passes=15):
+    """oracle/spectra_lut_oracle.c: the three stored coefficients of cells k = 0 .. res-1 of column (l, j, i) -> [res, 3]."""
+    L = lib()
+    L.orc_spectra_lut_column.argtypes = [_f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _f32p]
+    out = np.zeros((res, 3), np.float32)
+    L.orc_spectra_lut_column(np.ascontiguousarray(inputs, np.float32), res, passes, l, j, i, out)
+    return out

@@ -119,3 +119,39 @@ def test_smooth_normals_against_reference(gpu_ctx):
         assert np.allclose(w, 16384, rtol=1e-3)
         assert rel(bm(img, 2), bm(ref, 2)) <= 1e-3, rel(bm(img, 2), bm(ref, 2))
         assert np.allclose(img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=0.01)
+
+
+def test_normal_map_against_reference(gpu_ctx):
+    """Normal maps (mrb_render_desc.normalTexture; through TracerI the optional "normalMap" attribute of (Mt)Lambert) against the
+    reference's render of scenes.cornell_normal_map."""
+    path = os.path.join(ROOT, "tests", "golden", "render_cornell64_normalmap_spp16384.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden image was not generated")
+    ref = np.load(path)["img"].astype(np.float32)
+    c = scenes.cornell_normal_map()
+    order = np.argsort(c["material"], kind="stable")
+    idx = np.ascontiguousarray(c["indices"][order]); mat = c["material"][order]
+    ranges, keys = [], []
+    for m in np.unique(mat):
+        w = np.nonzero(mat == m)[0]
+        ranges.append([w[0], w[-1] + 1]); keys.append(capi.light_key(0) if m == 3 else int(m))
+    acc = capi.Accelerator(gpu_ctx, c["positions"], idx, prim_ranges=ranges, light_or_mat_keys=keys)
+    args = (gpu_ctx, acc, c["positions"].shape[0], idx.shape[0], c["albedo"][:3], c["radiance"], c["camera"], 64, 64)
+    kw = dict(textures=[c["normal_texture"]], albedo_texture=[-1, -1, -1], vertex_uvs=c["uvs"], vertex_tbn=O.normals_to_tbn(c["normals"]))
+    r = capi.Renderer(*args, 16384, seed=61, normal_texture=c["normal_map"][:3], **kw)
+    img, st = r.render(batch=32); r.close()
+    assert rel(bm(img, 2), bm(ref, 2)) <= 1e-3, rel(bm(img, 2), bm(ref, 2))
+    assert np.allclose(img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=0.01)
+    r = capi.Renderer(*args, 1024, seed=62, **kw)           # the same scene without the map is a visibly different image
+    flat, _ = r.render(batch=32); r.close()
+    assert rel(bm(flat, 4), bm(ref, 4)) > 5 * rel(bm(img, 4), bm(ref, 4))
+    with pytest.raises(capi.MrbError):                      # a normal map needs the tangent frames
+        capi.Renderer(*args, 1, normal_texture=c["normal_map"][:3], textures=[c["normal_texture"]], albedo_texture=[-1, -1, -1], vertex_uvs=c["uvs"])
+    acc.close()
+    if os.path.exists(PLUGIN) and O.driver_available():
+        b = O.batched_scene(c["positions"], c["indices"], c["material"], normals=c["normals"], uvs=c["uvs"])
+        pimg, w, pst = O.driver_render(PLUGIN, b, c["albedo"], 3, c["radiance"], c["camera"], 64, 64, 16384, seed=63, burst_size=64,
+                                       textures=[c["normal_texture"]], normal_map=c["normal_map"])
+        assert np.allclose(w, 16384, rtol=1e-3)
+        assert rel(bm(pimg, 2), bm(ref, 2)) <= 1e-3, rel(bm(pimg, 2), bm(ref, 2))
+        assert np.allclose(pimg.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=0.01)

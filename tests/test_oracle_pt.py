@@ -311,3 +311,43 @@ def test_oracle_alpha_map_matches_reference_render():
     # and the alpha map matters: without it the pane is opaque and the image differs by far more than the noise
     opaque = O.oracle_render(c["positions"], c["indices"], tm, c["albedo"][[0, 1, 2, 4]], c["radiance"], c["camera"], 64, 64, 256, sample_mode=2, seed=9)
     assert rel_mse(block_mean(opaque, 4), block_mean(ref, 4)) > 20 * e
+
+
+def test_oracle_normal_map_matches_reference_render():
+    """The optional "normalMap" of (Mt)Lambert: Triangle::GenerateSurface re-aims the hit's tangent frame at the texture's
+    tangent-space normal (PrimitiveDefaultTriangle.hpp:L571-575). scenes.cornell_normal_map, vs the reference's render."""
+    path = os.path.join(GOLDEN, "render_cornell64_normalmap_spp16384.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden image was not generated")
+    ref = np.load(path)["img"].astype(np.float32)
+    c = scenes.cornell_normal_map()
+    tm = np.where(c["material"] == 3, -1, c["material"]).astype(np.int32)
+    kw = dict(sample_mode=2, seed=4, textures=[c["normal_texture"]], vertex_uvs=c["uvs"], vertex_normals=c["normals"])
+    img = O.oracle_render(c["positions"], c["indices"], tm, c["albedo"][:3], c["radiance"], c["camera"], 64, 64, 1024,
+                          normal_texture=c["normal_map"][:3], **kw)
+    assert np.allclose(img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=0.01), (img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)))
+    e = rel_mse(block_mean(img, 4), block_mean(ref, 4))
+    assert e <= 1e-3, e
+    flat = O.oracle_render(c["positions"], c["indices"], tm, c["albedo"][:3], c["radiance"], c["camera"], 64, 64, 256, **kw)
+    assert rel_mse(block_mean(flat, 4), block_mean(ref, 4)) > 5 * e      # the bump is visible: without the map the image differs
+
+
+def test_oracle_converted_textures_match_reference_render():
+    """TextureMemory::ConvertColorspaces: textures declared REC_709 + gamma 2.2 (fp32) and gamma 2.2 (unorm8) are converted to the
+    tracer's ACES_CG space at load; the oracle renders with the numpy restatement of that conversion (oracle_lib.convert_texture_color)."""
+    path = os.path.join(GOLDEN, "render_cornell64_srgbtex_spp16384.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden image was not generated")
+    ref = np.load(path)["img"].astype(np.float32)
+    c, tm = cornell()
+    uvs, textures, at = scenes.cornell_textures()
+    conv = [dict(textures[0], data=O.convert_texture_color(textures[0]["data"], 2.2, O.rgb_to_rgb_matrix("REC_709", "ACES_CG"))),
+            dict(textures[1], data=O.convert_texture_color(textures[1]["data"], 2.2, None))]
+    img = O.oracle_render(c["positions"], c["indices"], tm, c["albedo"][:3], c["radiance"], c["camera"], 64, 64, 1024, sample_mode=2, seed=6,
+                          textures=conv, albedo_texture=at[:3], vertex_uvs=uvs)
+    assert np.allclose(img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=0.01), (img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)))
+    e = rel_mse(block_mean(img, 4), block_mean(ref, 4))
+    assert e <= 1e-3, e
+    plain = O.oracle_render(c["positions"], c["indices"], tm, c["albedo"][:3], c["radiance"], c["camera"], 64, 64, 256, sample_mode=2, seed=6,
+                            textures=textures, albedo_texture=at[:3], vertex_uvs=uvs)
+    assert rel_mse(block_mean(plain, 4), block_mean(ref, 4)) > 5 * e    # unconverted textures give a visibly different image

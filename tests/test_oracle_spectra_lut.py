@@ -1,0 +1,37 @@
+"""CPU: the SpectraLUTGen restatement (oracle/spectra_lut_oracle.c) against the ACES_CG.mrspectra file the UNMODIFIED reference
+tool wrote in the authoring container (mray_b200/data/, installed by oracle/ref_build/build_spectral_data.sh). Coefficients of
+near-black cells are ill-conditioned (any very negative polynomial gives the same ~0 spectrum), so cells are compared through
+the SPECTRA they encode as well as bit for bit."""
+import os
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from mray_b200 import spectral
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+INPUTS = os.path.join(GOLDEN, "spectra_lut_inputs_ACES_CG.bin")      # mray_b200_spectra_lut_gen 64 ACES_CG . --dump-inputs
+pytestmark = pytest.mark.skipif(not os.path.exists(spectral.lut_path()), reason="mray_b200/data/ACES_CG.mrspectra was not generated")
+
+
+def spectra(coeffs, lambdas=np.arange(360.0, 831.0, 10.0)):
+    c = coeffs.astype(np.float64)[..., None, :]
+    x = (c[..., 0] * lambdas + c[..., 1]) * lambdas + c[..., 2]
+    return 0.5 * x / np.sqrt(1.0 + x * x) + 0.5
+
+
+def test_columns_match_the_reference_tools_file():
+    inp = np.fromfile(INPUTS, np.float32)
+    assert inp.size == 471 * 4 + 1 + 18
+    lut = spectral.read_mrspectra(spectral.lut_path()).reshape(3, 3, 64, 64, 64)     # table, coefficient, z, y, x
+    rng = np.random.default_rng(0)
+    exact = []
+    for _ in range(48):
+        l, j, i = int(rng.integers(3)), int(rng.integers(64)), int(rng.integers(64))
+        col = O.oracle_spectra_lut_column(inp, l, j, i)
+        ref = lut[l, :, :, j, i].T
+        assert np.isfinite(col).all()
+        # one fp32 ulp of a stored constant term (|c2| up to ~300) moves the spectrum by ~1.5e-5
+        assert np.abs(spectra(col) - spectra(ref)).max() < 1e-4, (l, j, i)
+        exact.append((col.view(np.uint32) == ref.view(np.uint32)).mean())
+    assert np.mean(exact) > 0.95, np.mean(exact)     # the rest differs in the last bits (cbrt, white-point summation order)
