@@ -15,6 +15,7 @@ pytestmark = pytest.mark.skipif(not os.path.exists(spectral.lut_path()), reason=
 
 
 def spectra(coeffs, lambdas=np.arange(360.0, 831.0, 10.0)):
+    lambdas = np.asarray(lambdas, np.float64)
     c = coeffs.astype(np.float64)[..., None, :]
     x = (c[..., 0] * lambdas + c[..., 1]) * lambdas + c[..., 2]
     return 0.5 * x / np.sqrt(1.0 + x * x) + 0.5
