@@ -183,6 +183,10 @@ MRB_API mrb_status mrb_accel_export_lbvh(mrb_context ctx, mrb_accel accel,
                                          uint64_t* morton, uint64_t* sortedMorton, uint32_t* sortedLeaf,
                                          uint32_t* nodes, uint32_t* leafParent,
                                          float* nodeBoxes, float* leafAABBs);
+/* Audit export of the product traversal structure (no reference counterpart: the reference traverses the binary tree):
+ * wideNodes = mrb_accel_info.wideNodeCount x 80-byte nodes, triRecords = leafCount x 48-byte records (either may be NULL);
+ * layouts in mray_b200/csrc/accel.cuh. Node ORDER inside a level depends on the order of the builder's allocations. */
+MRB_API mrb_status mrb_accel_export_wide(mrb_context ctx, mrb_accel accel, void* wideNodes, void* triRecords);
 
 /* ---- ray casting ------------------------------------------------------------------------ */
 

@@ -130,6 +130,7 @@ _PROTOTYPES = {
     "mrb_context_launch_count": (C.c_uint64, [C.c_void_p]),
     "mrb_context_last_fallback_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "mrb_last_error": (C.c_char_p, [C.c_void_p]),
+    "mrb_accel_export_wide": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mrb_context_set_alpha_seed": (C.c_int, [C.c_void_p, C.c_uint32]),
     "mrb_context_set_profiling": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32]),
     "mrb_context_get_profile": (C.c_int, [C.c_void_p, C.POINTER(KernelProfile)]),
@@ -436,6 +437,13 @@ class Accelerator:
             out["boxes"].ctypes.data, out["leaf_aabb"].ctypes.data))
         out["accel_aabb"] = np.array(list(self.info.aabb), np.float32)
         return out
+
+    def export_wide(self):
+        """The 8-wide tree as the kernels read it: (nodes uint32 [W, 20], triangle records float32 [N, 12])."""
+        nodes = np.zeros((int(self.info.wideNodeCount), 20), np.uint32)
+        tris = np.zeros((self.leaf_count, 12), np.float32)
+        self.ctx.check(self.ctx.lib.mrb_accel_export_wide(self.ctx.handle, self.handle, nodes.ctypes.data, tris.ctypes.data))
+        return nodes, tris
 
     def cast_rays(self, hit_keys, meta_hits, rays, ray_indices=None, mode=MRB_TRACE_WIDE):
         """BaseAcceleratorLBVH::CastRays (Tracer/AcceleratorLBVH.cu:L760-896): closest hit; writes

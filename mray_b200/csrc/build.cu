@@ -11,6 +11,8 @@
 // Floating point: every expression that feeds an integer artefact (Morton code) is written with
 // explicit round-to-nearest intrinsics so that nvcc cannot contract it into an FMA.
 #include "accel.cuh"
+#include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <cfloat>
 #include <cstring>
@@ -493,6 +495,8 @@ __device__ void CollapseNode(const AccelData& a, CollapseState* st, unsigned lon
     atomicMax(&st->maxDepth, depth);
 }
 
+#include "collapse_group.cuh"   // CollapseNodeGroup + KCollapseGroups: the same node built by eight lanes (the product path)
+
 // Level-synchronous collapse in ONE cooperative launch: wide nodes [begin,end) form the current
 // level, their internal children are appended behind `end` (atomic bump of st->created), a grid-wide
 // barrier separates levels. No spinning, no inter-thread waiting other than the barrier.
@@ -734,10 +738,15 @@ void BuildScene(Context& ctx, mrb_scene_t& sc, const mrb_instance_desc* inst, ui
         unsigned long long rootItem = 0ull;
         MRB_CUDA_TRY(cudaMemcpyAsync(queue, &rootItem, sizeof(rootItem), cudaMemcpyHostToDevice, ctx.stream));
         int perSM = 0;
-        MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, KCollapse, 64, 0));
-        uint32_t cgrid = min(uint32_t(ctx.smCount) * uint32_t(max(1, min(perSM, 16))), max(1u, DivUp(d.wideNodeCapacity, 64u)));
+        // eight lanes per node (KCollapseGroups); MRB_COLLAPSE_SERIAL=1 keeps the one-thread-per-node kernel as the audit path
+        static const bool serialCollapse = []{ const char* e = getenv("MRB_COLLAPSE_SERIAL"); return e && e[0] == '1'; }();
+        const void* ck = serialCollapse ? (const void*)KCollapse : (const void*)KCollapseGroups;
+        const uint32_t ctpb = serialCollapse ? 64u : COLLAPSE_TPB;
+        MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, ck, int(ctpb), 0));
+        uint32_t cgrid = min(uint32_t(ctx.smCount) * uint32_t(max(1, min(perSM, serialCollapse ? 16 : 4))),
+                             max(1u, DivUp(d.wideNodeCapacity, serialCollapse ? 64u : COLLAPSE_TPB / 8u)));
         void* cargs[] = {(void*)&d, (void*)&cst, (void*)&queue, (void*)&slotRank};
-        MRB_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)KCollapse, dim3(cgrid), dim3(64), cargs, 0, ctx.stream));
+        MRB_CUDA_TRY(cudaLaunchCooperativeKernel(ck, dim3(cgrid), dim3(ctpb), cargs, 0, ctx.stream));
         ctx.launches++;
         MRB_LAUNCH(ctx, KFillInstanceSlots, grid, TPB, 0, d, slotRank);
     }
@@ -902,10 +911,15 @@ void BuildAccel(Context& ctx, mrb_accel_t& acc, const mrb_accel_desc& desc)
         unsigned long long rootItem = 0ull; // binary node 0, depth 0
         MRB_CUDA_TRY(cudaMemcpyAsync(queue, &rootItem, sizeof(rootItem), cudaMemcpyHostToDevice, ctx.stream));
         int perSM = 0;
-        MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, KCollapse, 64, 0));
-        uint32_t cgrid = min(uint32_t(ctx.smCount) * uint32_t(max(1, min(perSM, 16))), max(1u, DivUp(d.wideNodeCapacity, 64u)));
+        // eight lanes per node (KCollapseGroups); MRB_COLLAPSE_SERIAL=1 keeps the one-thread-per-node kernel as the audit path
+        static const bool serialCollapse = []{ const char* e = getenv("MRB_COLLAPSE_SERIAL"); return e && e[0] == '1'; }();
+        const void* ck = serialCollapse ? (const void*)KCollapse : (const void*)KCollapseGroups;
+        const uint32_t ctpb = serialCollapse ? 64u : COLLAPSE_TPB;
+        MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, ck, int(ctpb), 0));
+        uint32_t cgrid = min(uint32_t(ctx.smCount) * uint32_t(max(1, min(perSM, serialCollapse ? 16 : 4))),
+                             max(1u, DivUp(d.wideNodeCapacity, serialCollapse ? 64u : COLLAPSE_TPB / 8u)));
         void* cargs[] = {(void*)&d, (void*)&cst, (void*)&queue, (void*)&triRank};
-        MRB_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)KCollapse, dim3(cgrid), dim3(64), cargs, 0, ctx.stream));
+        MRB_CUDA_TRY(cudaLaunchCooperativeKernel(ck, dim3(cgrid), dim3(ctpb), cargs, 0, ctx.stream));
         ctx.launches++;
         MRB_LAUNCH(ctx, KFillTris, grid, TPB, 0, d, triRank);
     }

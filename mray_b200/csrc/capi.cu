@@ -308,6 +308,20 @@ mrb_status mrb_accel_export_lbvh(mrb_context ctx, mrb_accel accel,
     });
 }
 
+mrb_status mrb_accel_export_wide(mrb_context ctx, mrb_accel accel, void* wideNodes, void* triRecords)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!accel) return Fail(c, MRB_ERR_INVALID_ARG, "null accelerator");
+        const mrb::AccelData& d = accel->d;
+        if(!d.wideNodes) return Fail(c, MRB_ERR_UNSUPPORTED, "accelerator was built BINARY_ONLY");
+        if(wideNodes) MRB_CUDA_TRY(cudaMemcpyAsync(wideNodes, d.wideNodes, sizeof(mrb::WideNode) * d.wideNodeCount, cudaMemcpyDeviceToHost, c.stream));
+        if(triRecords) MRB_CUDA_TRY(cudaMemcpyAsync(triRecords, d.tris, sizeof(mrb::TriRecord) * d.leafCount, cudaMemcpyDeviceToHost, c.stream));
+        MRB_CUDA_TRY(cudaStreamSynchronize(c.stream));
+        return MRB_OK;
+    });
+}
+
 } // extern "C"
 
 // Host-pointer casts (the boundary a TracerI host uses before its buffers live on the device): the rays are
