@@ -62,7 +62,7 @@ typedef struct mrb_meta_hit { float a, b; } mrb_meta_hit;
 /* ---- library / context ------------------------------------------------------------------ */
 
 /* ABI version of this header (major<<16 | minor); the descriptor struct layouts are part of it. */
-#define MRB_ABI_VERSION ((0u << 16) | 7u)
+#define MRB_ABI_VERSION ((0u << 16) | 8u)
 MRB_API uint32_t mrb_abi_version(void);
 
 /* Replaces GPUSystem + GPUQueue ownership inside TracerBase (Device/CUDA/GPUSystemCUDA.cpp:L249-405:
@@ -116,7 +116,10 @@ typedef enum mrb_build_flags
      * node for node. */
     MRB_BUILD_REFERENCE_DELTA = 1,
     /* keep only the binary LBVH (skip the wide-BVH collapse) */
-    MRB_BUILD_BINARY_ONLY = 2
+    MRB_BUILD_BINARY_ONLY = 2,
+    /* Audit mode: collapse with the one-thread-per-node kernel instead of the eight-lanes-per-node one. Both build the same
+     * tree (same nodes and records; only the order of allocations inside a level differs). */
+    MRB_BUILD_SERIAL_COLLAPSE = 4
 } mrb_build_flags;
 
 /* One concrete accelerator over a triangle primitive group.
@@ -364,8 +367,7 @@ typedef enum mrb_boundary_type { MRB_BOUNDARY_NULL = 0, MRB_BOUNDARY_SKYSPHERE_S
 typedef enum mrb_film_filter { MRB_FILTER_BOX = 0, MRB_FILTER_TENT = 1, MRB_FILTER_GAUSSIAN = 2, MRB_FILTER_MITCHELL_NETRAVALI = 3 } mrb_film_filter;
 
 /* One 2-D texture of the renderer (first slice): what TracerI::CreateTexture2D +
- * PushTextureData + CommitTextures hand to TextureMemory (Tracer/TextureMemory.cpp), restricted to ONE mip
- * level, 3 / 4 channels of fp32 or unorm8, already in the global colour space (MRayTextureParameters.colorSpace
+ * PushTextureData + CommitTextures hand to TextureMemory (Tracer/TextureMemory.cpp): 3 / 4 channels of fp32 or unorm8, one or more mip levels, already in the global colour space (MRayTextureParameters.colorSpace
  * = MR_DEFAULT, gamma 1: TextureMemory::ConvertColorspaces skips such textures). Sampling restates the reference's
  * host-backend texture view (Device/CPU/TextureViewCPU.h:L172-470): normalised coordinates, texel centres at
  * +0.5, nearest or bilinear with unfused lerps, wrap / clamp / mirror edge resolve; with one mip level the
@@ -385,6 +387,19 @@ typedef struct mrb_texture_desc
      * (ToUNorm). Needs >= 3 channels. */
     float       gamma;
     const float* colorMatrix;
+    /* Mip chain (TracerI::CreateTexture2D(size, mipCount, ...) + PushTextureData(id, mipLevel, ...)): `data` holds mipCount levels
+     * (0 reads as 1) back to back, level k = max(width >> k, 1) x max(height >> k, 1) texels (Graphics::TextureMipSize,
+     * Core/GraphicsFunctions.h:L474-490). generateMips != 0 = TracerParameters.genMips: the chain is completed down to 1 x 1
+     * (TextureMemory::CreateTexture, Tracer/TextureMemory.cpp:L588-591) and the missing levels are filtered from their parents after the
+     * colour conversion (TextureMemory::Finalize L809-833 -> KCGenerateMipmaps, Tracer/TextureFilter.cu:L126-198) with
+     * TracerParameters.mipGenFilter = {mipFilterType (mrb_film_filter), mipFilterRadius}; the reference's default is Gaussian, 2.
+     * A renderer with any multi-level texture carries a ray cone per path (Tracer/TracerTypes.h:L48-69) and reads albedo / normal
+     * textures at the level its footprint selects (trilinear under MR_LINEAR). Alpha maps and skysphere radiance are read at
+     * level 0, as the reference reads them (no gradients at those call sites). */
+    uint32_t    mipCount;
+    uint32_t    generateMips;
+    uint32_t    mipFilterType;
+    float       mipFilterRadius;
 } mrb_texture_desc;
 
 typedef struct mrb_render_desc
@@ -495,6 +510,11 @@ typedef struct mrb_render_desc
      * whose rgb is the TANGENT-SPACE normal (used as is, then normalised). The hit's interpolated tangent frame is re-aimed so
      * that its Z axis is that normal; needs vertexTBN / instanceVertexTBN and the UVs. */
     const int32_t*  normalTexture;
+    /* How a textured read turns the ray cone's UV gradients into a mip level (TracerTexView::operator()(uv, dpdx, dpdy)):
+     * 0 = level = log2 of the longer gradient in UV units — what the reference's host backend computes for normalised-coordinate
+     * textures (Device/CPU/TextureViewCPU.h:L405-420; the mode the parity goldens pin);
+     * 1 = gradients scaled by the texture size first — what tex2DGrad does on the reference's device backends. */
+    uint32_t        textureLodMode;
 } mrb_render_desc;
 
 typedef struct mrb_render_stats
@@ -571,6 +591,15 @@ MRB_API mrb_status mrb_texture_sample(mrb_context ctx, const mrb_texture_desc* t
 /* Parity tap: the upload-time colour conversion of a texture on its own (KCConvertColor): texelsOut (host) receives the texels of
  * `texture` after its gamma / colorMatrix have been applied, in the texture's own format. */
 MRB_API mrb_status mrb_texture_convert(mrb_context ctx, const mrb_texture_desc* texture, void* texelsOut);
+/* Parity taps of the mip path. mrb_texture_mip_chain: the whole chain of `texture` as the renderer stores it (supplied levels colour
+ * converted, generated levels after them), chainOut (host) sized for mrb_texture_chain_texels(...) texels in the texture's own format;
+ * *mipCountOut = levels. mrb_texture_sample_lod: TextureViewCPU::operator()(uv, mipLevel) (lod != NULL) or operator()(uv, dpdx, dpdy)
+ * (grads = count * 4 floats {dpdx.xy, dpdy.xy}; lodMode as mrb_render_desc.textureLodMode) on that chain. Host pointers. */
+MRB_API size_t     mrb_texture_chain_texels(uint32_t width, uint32_t height, uint32_t mipCount);
+MRB_API uint32_t   mrb_texture_full_mip_count(uint32_t width, uint32_t height);
+MRB_API mrb_status mrb_texture_mip_chain(mrb_context ctx, const mrb_texture_desc* texture, void* chainOut, uint32_t* mipCountOut);
+MRB_API mrb_status mrb_texture_sample_lod(mrb_context ctx, const mrb_texture_desc* texture, const float* uv, const float* lod, const float* grads,
+                                          uint32_t lodMode, uint32_t count, float* rgbOut);
 
 /* ---- spectral LUT generation --------------------------------------------------------------- */
 

@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmray_b200.so")
 MRB_MEM_HOST, MRB_MEM_DEVICE = 0, 1
 MRB_TRACE_WIDE, MRB_TRACE_BINARY_EXACT = 0, 1
 MRB_TRACE_FRESH_OUTPUTS = 0x100   # OR-ed flag: outputs need not be read, misses get INVALID keys / zero hits / set bits
-MRB_BUILD_DEFAULT, MRB_BUILD_REFERENCE_DELTA, MRB_BUILD_BINARY_ONLY = 0, 1, 2
+MRB_BUILD_DEFAULT, MRB_BUILD_REFERENCE_DELTA, MRB_BUILD_BINARY_ONLY, MRB_BUILD_SERIAL_COLLAPSE = 0, 1, 2, 4
 INVALID_KEY = 0xFFFFFFFF
 
 STATUS = {0: "MRB_OK", -1: "MRB_ERR_NO_DEVICE", -2: "MRB_ERR_INVALID_ARG", -3: "MRB_ERR_CUDA",
@@ -84,7 +84,7 @@ class RenderDesc(C.Structure):
                 ("vertexTBN", C.c_void_p), ("instanceVertexTBN", C.POINTER(C.c_void_p)),
                 ("boundaryType", C.c_uint32), ("boundaryTexture", C.c_int32), ("boundaryRadiance", C.c_float * 3),
                 ("boundaryTransform", C.c_void_p), ("sceneDiameter", C.c_float), ("luminanceRow", C.c_float * 3),
-                ("normalTexture", C.c_void_p)]
+                ("normalTexture", C.c_void_p), ("textureLodMode", C.c_uint32)]
 
 
 class SpectraLutDesc(C.Structure):
@@ -94,11 +94,49 @@ class SpectraLutDesc(C.Structure):
 
 class TextureDesc(C.Structure):
     _fields_ = [("data", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("channels", C.c_uint32),
-                ("format", C.c_uint32), ("interp", C.c_uint32), ("edge", C.c_uint32), ("gamma", C.c_float), ("colorMatrix", C.c_void_p)]
+                ("format", C.c_uint32), ("interp", C.c_uint32), ("edge", C.c_uint32), ("gamma", C.c_float), ("colorMatrix", C.c_void_p),
+                ("mipCount", C.c_uint32), ("generateMips", C.c_uint32), ("mipFilterType", C.c_uint32), ("mipFilterRadius", C.c_float)]
 
 
 TEX_INTERP = {"Nearest": 0, "Linear": 1}
 TEX_EDGE = {"Wrap": 0, "Clamp": 1, "Mirror": 2}
+
+
+def _fill_texture_desc(t, texture, keep):
+    """texture = dict(data=[h, w, C] float32 / uint8 (level 0), interp=, edge=, gamma=, color_matrix=, mips=[level 1, level 2, ...]
+    (explicit levels, each [max(h >> k, 1), max(w >> k, 1), C]), gen_mips=(filter name, radius) (TracerParameters.genMips + mipGenFilter))"""
+    a = np.ascontiguousarray(texture["data"])
+    if a.dtype != np.uint8:
+        a = np.ascontiguousarray(a, np.float32)
+    if a.ndim == 2:
+        a = a[..., None]
+    t.height, t.width, t.channels = a.shape
+    t.format = 1 if a.dtype == np.uint8 else 0
+    t.interp, t.edge = TEX_INTERP[texture.get("interp", "Linear")], TEX_EDGE[texture.get("edge", "Wrap")]
+    t.gamma = float(texture.get("gamma", 1.0))
+    t.mipCount = 1
+    if texture.get("mips"):
+        levels = [a.reshape(-1, t.channels)]
+        for k, m in enumerate(texture["mips"]):
+            m = np.ascontiguousarray(m, a.dtype)
+            assert m.size == max(t.height >> (k + 1), 1) * max(t.width >> (k + 1), 1) * t.channels, "mip level has the wrong size"
+            levels.append(m.reshape(-1, t.channels))
+        a = np.ascontiguousarray(np.concatenate(levels, axis=0))
+        t.mipCount = len(levels)
+    if texture.get("gen_mips"):
+        t.generateMips, t.mipFilterType, t.mipFilterRadius = 1, FILM_FILTERS[texture["gen_mips"][0]], float(texture["gen_mips"][1])
+    keep.append(a)
+    t.data = a.ctypes.data
+    if texture.get("color_matrix") is not None:     # RGB -> RGB matrix into the global colour space (row-major 3x3)
+        m = np.ascontiguousarray(texture["color_matrix"], np.float32).reshape(9)
+        keep.append(m); t.colorMatrix = m.ctypes.data
+    return a
+
+
+def _texture_desc(texture):
+    t, keep = TextureDesc(), []
+    _fill_texture_desc(t, texture, keep)
+    return t, keep
 
 
 class RenderStats(C.Structure):
@@ -116,7 +154,7 @@ BOUNDARY_TYPES = {"Null": 0, "Skysphere_Spherical": 1, "Skysphere_CoOcta": 2}   
 FILM_FILTERS = {"Box": 0, "Tent": 1, "Gaussian": 2, "Mitchell-Netravali": 3}   # FilterType::E (Core/TracerEnums.h:L162-173)
 HOST_FN = C.CFUNCTYPE(None, C.c_void_p)
 # the descriptor mirrors above are written for this ABI (include/mray_b200.h: MRB_ABI_VERSION)
-MRB_ABI_VERSION = (0 << 16) | 7
+MRB_ABI_VERSION = (0 << 16) | 8
 
 # every symbol include/mray_b200.h declares (tests/test_capi_symbols.py checks the header against this)
 _PROTOTYPES = {
@@ -178,6 +216,10 @@ _PROTOTYPES = {
     "mrb_skysphere_convert": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]),
     "mrb_texture_luminance": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]),
     "mrb_texture_convert": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mrb_texture_chain_texels": (C.c_size_t, [C.c_uint32, C.c_uint32, C.c_uint32]),
+    "mrb_texture_full_mip_count": (C.c_uint32, [C.c_uint32, C.c_uint32]),
+    "mrb_texture_mip_chain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]),
+    "mrb_texture_sample_lod": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "mrb_spectra_lut_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mrb_multi_partition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                       C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
@@ -396,17 +438,7 @@ class Accelerator:
                 d.vertexUVs = _ptr(uv)
             tarr = (TextureDesc * max(1, len(alpha_textures or [])))()
             for k, t in enumerate(alpha_textures or []):
-                a = np.ascontiguousarray(t["data"])
-                if a.dtype != np.uint8:
-                    a = np.ascontiguousarray(a, np.float32)
-                if a.ndim == 2:
-                    a = a[..., None]
-                self._keep.append(a)
-                tarr[k].data = a.ctypes.data
-                tarr[k].height, tarr[k].width, tarr[k].channels = a.shape
-                tarr[k].format = 1 if a.dtype == np.uint8 else 0
-                tarr[k].interp = TEX_INTERP[t.get("interp", "Linear")]
-                tarr[k].edge = TEX_EDGE[t.get("edge", "Wrap")]
+                _fill_texture_desc(tarr[k], t, self._keep)
             self._keep.append(tarr)
             d.alphaTextureCount, d.alphaTextures = len(alpha_textures or []), C.cast(tarr, C.c_void_p)
         h = C.c_void_p()
@@ -537,7 +569,7 @@ class Renderer:
                  max_path_count=0, partition_rays=False, instance_vertex_normals=None, spectrum=None, sampler="Independent",
                  textures=None, albedo_texture=None, vertex_uvs=None, instance_vertex_uvs=None,
                  full_resolution=None, region_min=(0, 0), material_type=None, film_filter="Gaussian",
-                 sample_offset=0, job_spp=0, material_params=None, vertex_tbn=None, boundary=None, normal_texture=None):
+                 sample_offset=0, job_spp=0, material_params=None, vertex_tbn=None, boundary=None, normal_texture=None, texture_lod_mode=0):
         """`accel` is an Accelerator, or a Scene (two-level; vertex_count / triangle_count / vertex_normals
         are then ignored and instance_vertex_normals may hold one array or None per instance).
         textures: list of dict(data=[h, w, 3|4] float32 or uint8 array, interp="Linear"|"Nearest",
@@ -614,23 +646,12 @@ class Renderer:
         if textures:
             tarr = (TextureDesc * len(textures))()
             for k, t in enumerate(textures):
-                a = np.ascontiguousarray(t["data"])
-                if a.dtype != np.uint8:
-                    a = np.ascontiguousarray(a, np.float32)
-                self._keep.append(a)
-                tarr[k].data = a.ctypes.data
-                tarr[k].height, tarr[k].width, tarr[k].channels = a.shape
-                tarr[k].format = 1 if a.dtype == np.uint8 else 0
-                tarr[k].interp = TEX_INTERP[t.get("interp", "Linear")]
-                tarr[k].edge = TEX_EDGE[t.get("edge", "Wrap")]
-                tarr[k].gamma = float(t.get("gamma", 1.0))
-                if t.get("color_matrix") is not None:
-                    cm = np.ascontiguousarray(t["color_matrix"], np.float32).reshape(9)
-                    self._keep.append(cm); tarr[k].colorMatrix = cm.ctypes.data
+                _fill_texture_desc(tarr[k], t, self._keep)
             self._keep.append(tarr)
             d.textureCount, d.textures = len(textures), C.cast(tarr, C.c_void_p)
             d.albedoTexture = host(albedo_texture, np.int32)
             d.normalTexture = host(normal_texture, np.int32)    # per material: -1 or a texture holding tangent-space normals
+            d.textureLodMode = texture_lod_mode   # 0 = mip level from UV-space gradients (reference host backend), 1 = texel-space (tex2DGrad)
         if isinstance(accel, Scene):
             if instance_vertex_uvs is not None:
                 uptrs = (C.c_void_p * accel.count)()
@@ -798,35 +819,39 @@ class Scene:
 
 def texture_sample(ctx: Context, texture, uv):
     """mrb_texture_sample: texture = dict(data=[h, w, 3|4] float32 / uint8, interp=, edge=), uv[n, 2] -> rgb[n, 3]."""
-    a = np.ascontiguousarray(texture["data"])
-    if a.dtype != np.uint8:
-        a = np.ascontiguousarray(a, np.float32)
-    t = TextureDesc()
-    t.data = a.ctypes.data
-    t.height, t.width, t.channels = a.shape
-    t.format = 1 if a.dtype == np.uint8 else 0
-    t.interp, t.edge = TEX_INTERP[texture.get("interp", "Linear")], TEX_EDGE[texture.get("edge", "Wrap")]
+    t, keep = _texture_desc(texture)
     uv = np.ascontiguousarray(uv, np.float32)
     out = np.zeros((uv.shape[0], 3), np.float32)
     ctx.check(ctx.lib.mrb_texture_sample(ctx.handle, C.byref(t), uv.ctypes.data, uv.shape[0], out.ctypes.data))
     return out
 
 
-def _texture_desc(texture):
-    a = np.ascontiguousarray(texture["data"])
-    if a.dtype != np.uint8:
-        a = np.ascontiguousarray(a, np.float32)
-    t = TextureDesc()
-    t.data = a.ctypes.data
-    t.height, t.width, t.channels = a.shape
-    t.format = 1 if a.dtype == np.uint8 else 0
-    t.interp, t.edge = TEX_INTERP[texture.get("interp", "Linear")], TEX_EDGE[texture.get("edge", "Wrap")]
-    keep = [a]
-    t.gamma = float(texture.get("gamma", 1.0))
-    if texture.get("color_matrix") is not None:     # RGB -> RGB matrix into the global colour space (row-major 3x3)
-        m = np.ascontiguousarray(texture["color_matrix"], np.float32).reshape(9)
-        keep.append(m); t.colorMatrix = m.ctypes.data
-    return t, keep
+def texture_mip_chain(ctx: Context, texture):
+    """mrb_texture_mip_chain: (chain [total texels, C] in the texture's dtype, mip count) — supplied levels colour converted,
+    generated levels after them."""
+    t, keep = _texture_desc(texture)
+    full = ctx.lib.mrb_texture_full_mip_count(t.width, t.height)
+    count = max(t.mipCount, full) if t.generateMips else t.mipCount
+    texels = ctx.lib.mrb_texture_chain_texels(t.width, t.height, count)
+    out = np.zeros((texels, t.channels), keep[0].dtype)
+    got = C.c_uint32(0)
+    ctx.check(ctx.lib.mrb_texture_mip_chain(ctx.handle, C.byref(t), out.ctypes.data, C.byref(got)))
+    assert got.value == count
+    return out, count
+
+
+def texture_sample_lod(ctx: Context, texture, uv, lod=None, dpdx=None, dpdy=None, lod_mode=0):
+    """mrb_texture_sample_lod: uv[n, 2] with lod[n], or with gradients dpdx / dpdy [n, 2] -> rgb[n, 3]."""
+    t, keep = _texture_desc(texture)
+    uv = np.ascontiguousarray(uv, np.float32)
+    out = np.zeros((uv.shape[0], 3), np.float32)
+    lp = gp = None
+    if lod is not None:
+        la = np.ascontiguousarray(lod, np.float32); lp = la.ctypes.data
+    else:
+        ga = np.ascontiguousarray(np.concatenate([np.asarray(dpdx, np.float32), np.asarray(dpdy, np.float32)], axis=1)); gp = ga.ctypes.data
+    ctx.check(ctx.lib.mrb_texture_sample_lod(ctx.handle, C.byref(t), uv.ctypes.data, C.c_void_p(lp), C.c_void_p(gp), lod_mode, uv.shape[0], out.ctypes.data))
+    return out
 
 
 def texture_convert(ctx: Context, texture):

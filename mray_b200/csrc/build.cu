@@ -738,7 +738,7 @@ void BuildScene(Context& ctx, mrb_scene_t& sc, const mrb_instance_desc* inst, ui
         unsigned long long rootItem = 0ull;
         MRB_CUDA_TRY(cudaMemcpyAsync(queue, &rootItem, sizeof(rootItem), cudaMemcpyHostToDevice, ctx.stream));
         int perSM = 0;
-        // eight lanes per node (KCollapseGroups); MRB_COLLAPSE_SERIAL=1 keeps the one-thread-per-node kernel as the audit path
+        // eight lanes per node (KCollapseGroups); MRB_COLLAPSE_SERIAL=1 / MRB_BUILD_SERIAL_COLLAPSE select the one-thread-per-node audit kernel
         static const bool serialCollapse = []{ const char* e = getenv("MRB_COLLAPSE_SERIAL"); return e && e[0] == '1'; }();
         const void* ck = serialCollapse ? (const void*)KCollapse : (const void*)KCollapseGroups;
         const uint32_t ctpb = serialCollapse ? 64u : COLLAPSE_TPB;
@@ -911,8 +911,9 @@ void BuildAccel(Context& ctx, mrb_accel_t& acc, const mrb_accel_desc& desc)
         unsigned long long rootItem = 0ull; // binary node 0, depth 0
         MRB_CUDA_TRY(cudaMemcpyAsync(queue, &rootItem, sizeof(rootItem), cudaMemcpyHostToDevice, ctx.stream));
         int perSM = 0;
-        // eight lanes per node (KCollapseGroups); MRB_COLLAPSE_SERIAL=1 keeps the one-thread-per-node kernel as the audit path
-        static const bool serialCollapse = []{ const char* e = getenv("MRB_COLLAPSE_SERIAL"); return e && e[0] == '1'; }();
+        // eight lanes per node (KCollapseGroups); MRB_COLLAPSE_SERIAL=1 / MRB_BUILD_SERIAL_COLLAPSE select the one-thread-per-node audit kernel
+        static const bool serialEnv = []{ const char* e = getenv("MRB_COLLAPSE_SERIAL"); return e && e[0] == '1'; }();
+        const bool serialCollapse = serialEnv || (desc.flags & MRB_BUILD_SERIAL_COLLAPSE);
         const void* ck = serialCollapse ? (const void*)KCollapse : (const void*)KCollapseGroups;
         const uint32_t ctpb = serialCollapse ? 64u : COLLAPSE_TPB;
         MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, ck, int(ctpb), 0));

@@ -62,6 +62,10 @@ void SpectrumToRGB(Context& ctx, const mrb_spectrum_t& sp, float* values, const 
 void SpectrumUpsample(Context& ctx, const mrb_spectrum_t& sp, const float* rgb, uint32_t rgbStride, const float* waves, uint32_t n,
                       bool isRadiance, float* out);
 void TextureConvertHost(Context& ctx, const mrb_texture_desc& td, void* texelsOut);
+void TextureMipChainHost(Context& ctx, const mrb_texture_desc& td, void* chainOut, uint32_t* mipCountOut);
+void TextureSampleLodHost(Context& ctx, const mrb_texture_desc& td, const float* uv, const float* lod, const float* grads, uint32_t lodMode, uint32_t n, float* rgbOut);
+size_t TextureChainTexels(uint32_t w, uint32_t h, uint32_t mips);
+uint32_t TextureFullMipCount(uint32_t w, uint32_t h);
 void GenerateSpectraLUT(Context& ctx, const float* cieXYZ, const float* illuminantSPD, float illuminantNorm, const float rgbToXYZ[9],
                         const float xyzToRGB[9], uint32_t res, uint32_t passes, float* lutOut, double whitepointOut[3]);
 void TraceScene(Context& ctx, const SceneData& scn, bool anyHit, mrb_trace_mode mode,
@@ -100,7 +104,7 @@ static mrb_status Fail(mrb::Context& c, mrb_status s, const char* msg) { c.error
 extern "C"
 {
 
-uint32_t mrb_abi_version(void) { return MRB_ABI_VERSION; }   // 7: texture colour conversion fields; 6: normal maps; 5: alpha maps in mrb_accel_desc; 4: boundary light (skysphere) fields of mrb_render_desc, mrb_dist2d_*
+uint32_t mrb_abi_version(void) { return MRB_ABI_VERSION; }   // 8: texture mip chains + ray cones (mrb_texture_desc / mrb_render_desc fields); 7: texture colour conversion fields; 6: normal maps; 5: alpha maps in mrb_accel_desc; 4: boundary light (skysphere) fields of mrb_render_desc, mrb_dist2d_*
 
 mrb_status mrb_context_create(int device, mrb_context* out)
 {
@@ -911,6 +915,29 @@ mrb_status mrb_texture_convert(mrb_context ctx, const mrb_texture_desc* texture,
     {
         if(!texture || !texelsOut) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
         mrb::TextureConvertHost(c, *texture, texelsOut);
+        return MRB_OK;
+    });
+}
+
+size_t mrb_texture_chain_texels(uint32_t width, uint32_t height, uint32_t mipCount) { return mrb::TextureChainTexels(width, height, mipCount); }
+uint32_t mrb_texture_full_mip_count(uint32_t width, uint32_t height) { return mrb::TextureFullMipCount(width, height); }
+mrb_status mrb_texture_mip_chain(mrb_context ctx, const mrb_texture_desc* texture, void* chainOut, uint32_t* mipCountOut)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!texture || !chainOut) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        mrb::TextureMipChainHost(c, *texture, chainOut, mipCountOut);
+        return MRB_OK;
+    });
+}
+mrb_status mrb_texture_sample_lod(mrb_context ctx, const mrb_texture_desc* texture, const float* uv, const float* lod, const float* grads,
+                                  uint32_t lodMode, uint32_t count, float* rgbOut)
+{
+    return Guard(ctx, [&](mrb::Context& c)
+    {
+        if(!texture || (count && (!uv || !rgbOut || (!lod && !grads)))) return Fail(c, MRB_ERR_INVALID_ARG, "null argument");
+        if(lodMode > 1u) return Fail(c, MRB_ERR_INVALID_ARG, "unknown lodMode");
+        mrb::TextureSampleLodHost(c, *texture, uv, lod, grads, lodMode, count, rgbOut);
         return MRB_OK;
     });
 }

@@ -172,7 +172,7 @@ constexpr float PREV_ONE = 0.99999994f;
 __device__ __forceinline__ float GaussPdf(float x, float sigma, float mu = 0.0f)
 {   // Math::Gaussian (Core/Math.h:L1032-1042)
     const float si = 1.0f / sigma, p = (x - mu) * si;
-    return 0.3989422804f * si * expf(-0.5f * p * p);
+    return 0x1.988452p-2f * si * expf(-0.5f * p * p);   // InvSqrt2Pi = (1 / Sqrt2<float>) * (1 / SqrtPi<float>) as the reference's constexpr evaluates it
 }
 __device__ __forceinline__ float GaussSample(float xi, float sigma, float mu, float& pdf)
 {   // Distribution::Common::SampleGaussian (DistributionFunctions.h:L686-705)
@@ -200,12 +200,14 @@ __device__ __forceinline__ float TentSample(float xi, float r, float& pdf)
 __device__ __forceinline__ float Mitchell1D(float x, float radiusRecip)
 {   // MitchellNetravaliFilter::Evaluate, b = c = 0.33333 (Filters.h:L258-300)
     const float B = 0.33333f, C = 0.33333f, F = 1.0f / 6.0f;
-    x = fabsf(2.0f * x * radiusRecip);
-    const float x2 = x * x, x3 = x2 * x;
+    x = fabsf(__fmul_rn(__fmul_rn(2.0f, x), radiusRecip));
+    const float x2 = __fmul_rn(x, x), x3 = __fmul_rn(x2, x);
     float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
     if(x < 1.0f) { c0 = F * (12.0f - 9.0f * B - 6.0f * C); c1 = F * (-18.0f + 12.0f * B + 6.0f * C); c3 = F * (6.0f - 2.0f * B); }
     else if(x < 2.0f) { c0 = F * (-B - 6.0f * C); c1 = F * (6.0f * B + 30.0f * C); c2 = F * (-12.0f * B - 48.0f * C); c3 = F * (8.0f * B + 24.0f * C); }
-    return (c0 * x3 + c1 * x2 + c2 * x + c3) * 2.0f * radiusRecip;
+    // unfused, left to right, as the reference's host build evaluates it (mip levels filtered with this kernel match bit for bit)
+    const float poly = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(c0, x3), __fmul_rn(c1, x2)), __fmul_rn(c2, x)), c3);
+    return __fmul_rn(__fmul_rn(poly, 2.0f), radiusRecip);
 }
 __device__ __forceinline__ float MitchellSampleDim(float xi, float r, float& pdf)
 {   // MitchellNetravaliFilter::Sample, one axis (Filters.h:L302-346): balance-heuristic mixture of three Gaussians
@@ -267,7 +269,13 @@ struct Camera // CameraPinhole members (CamerasDefault.hpp:L8-36), tile-local
 };
 
 // One 2-D texture (single mip level) as the reference's host-backend view sees it (Device/CPU/TextureViewCPU.h)
-struct TexRec { const void* data; uint32_t w, h, channels, format, interp, edge, pad; };
+// `data` holds mipCount levels back to back: level k at texel offset MipStart(k), MipDim(w, k) x MipDim(h, k) texels
+// (Graphics::TextureMipSize / TextureMipPixelStart, Core/GraphicsFunctions.h:L474-525 — the layout of the reference's host texture)
+struct TexRec { const void* data; uint32_t w, h, channels, format, interp, edge, mipCount; };
+__host__ __device__ __forceinline__ uint32_t MipDim(uint32_t n, uint32_t level) { const uint32_t v = n >> level; return v ? v : 1u; }
+__host__ __device__ __forceinline__ size_t MipStart(uint32_t w, uint32_t h, uint32_t level)
+{ size_t o = 0; for(uint32_t i = 0; i < level; i++) o += size_t(MipDim(w, i)) * MipDim(h, i); return o; }
+static uint32_t FullMipCount(uint32_t w, uint32_t h) { uint32_t m = max(w, h), c = 0; while(m) { c++; m >>= 1; } return c; }   // Graphics::TextureMipCount
 
 struct EmissiveTri { float4 p0, e0, e1; float4 radiance; }; // p0.w = area, e0.w = twoSided, radiance.w unused
 
@@ -294,6 +302,8 @@ struct RenderData
     const TexRec*     textures;        // textured albedo (ParamVaryingData): texture table ...
     const int32_t*    albedoTex;       // ... and per material index: texture or -1; nullptr = no material is textured
     const int32_t*    normalTex;       // per material index: tangent-space normal map (texture index) or -1; nullptr = none
+    float2*           cones;           // per slot ray cone (aperture, width); nullptr unless a texture has more than one mip level
+    uint32_t          textureLodMode;  // SampleTextureGrad: 0 = UV-space gradients (reference host backend), 1 = texel-space (tex2DGrad)
     const uint8_t*    materialType;    // per material index: mrb_material_type; nullptr = all Lambert
     const float4*     matParams;       // per material index 2 x float4: Refract (cauchyFront xyz, cauchyBack xyz), Unreal (roughness, specular, metallic)
     const float4*     albedo;          // per material index: (r, g, b, 0), or Jakob coefficients (c0, c1, c2, -) when spectral
@@ -424,6 +434,8 @@ __device__ __forceinline__ void ReloadSlot(const RenderData& d, uint32_t i, bool
     d.radiance[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     d.shadowRadiance[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     d.meta[i] = make_uint4(PackPD(0, ST_ALIVE, RAY_CAMERA), pix, __float_as_uint(weight), __float_as_uint(0.0f));
+    // CameraPinhole::EvaluateRay (CamerasDefault.hpp:L134-139): aperture = 2 tan(fovY / 2) / resolution.y, width 0
+    if(d.cones) d.cones[i] = make_float2(d.cam.planeH / d.cam.tNear / float(d.fullHeight), 0.0f);
     if(d.spectral)
     {
         // one more dimension after the camera sample (PathTracerRendererBase.cu:L139-168)
@@ -485,9 +497,9 @@ __device__ __forceinline__ int TexResolveEdge(int i, int n, uint32_t edge)
     if(i < 0) i += n;
     return i;
 }
-__device__ __forceinline__ Float3 TexReadPixel(const TexRec& t, int x, int y)
+__device__ __forceinline__ Float3 TexReadPixel(const TexRec& t, size_t levelStart, uint32_t levelW, int x, int y)
 {
-    const size_t o = (size_t(y) * t.w + size_t(x)) * t.channels;
+    const size_t o = (levelStart + size_t(y) * levelW + size_t(x)) * t.channels;
     if(t.format == 0u)
     {
         const float* f = static_cast<const float*>(t.data) + o;
@@ -499,24 +511,51 @@ __device__ __forceinline__ Float3 TexReadPixel(const TexRec& t, int x, int y)
 }
 __device__ __forceinline__ Float3 TexLerp(Float3 a, Float3 b, float t)
 { return F3(SpecLerp(a.x, b.x, t), SpecLerp(a.y, b.y, t), SpecLerp(a.z, b.z, t)); }
-__device__ __forceinline__ Float3 SampleTexture(const TexRec& t, float u, float v)
+__device__ __forceinline__ Float3 SampleTextureLevel(const TexRec& t, uint32_t level, float u, float v)
 {
-    const float tu = __fmul_rn(u, float(t.w)), tv = __fmul_rn(v, float(t.h));
+    const uint32_t w = MipDim(t.w, level), h = MipDim(t.h, level);
+    const size_t start = level ? MipStart(t.w, t.h, level) : 0;
+    const float tu = __fmul_rn(u, float(w)), tv = __fmul_rn(v, float(h));
     if(t.interp == 0u)
     {
         const int x = int(roundf(tu - 0.5f)), y = int(roundf(tv - 0.5f));
-        return TexReadPixel(t, TexResolveEdge(x, int(t.w), t.edge), TexResolveEdge(y, int(t.h), t.edge));
+        return TexReadPixel(t, start, w, TexResolveEdge(x, int(w), t.edge), TexResolveEdge(y, int(h), t.edge));
     }
     float bx, by;
     float fx = modff(tu - 0.5f, &bx), fy = modff(tv - 0.5f, &by);
     int x0 = int(bx), y0 = int(by);
     if(fx < 0.0f) { x0 -= 1; fx = fabsf(fx); }
     if(fy < 0.0f) { y0 -= 1; fy = fabsf(fy); }
-    const int xa = TexResolveEdge(x0, int(t.w), t.edge), xb = TexResolveEdge(x0 + 1, int(t.w), t.edge);
-    const int ya = TexResolveEdge(y0, int(t.h), t.edge), yb = TexResolveEdge(y0 + 1, int(t.h), t.edge);
-    const Float3 p0 = TexLerp(TexReadPixel(t, xa, ya), TexReadPixel(t, xb, ya), fx);
-    const Float3 p1 = TexLerp(TexReadPixel(t, xa, yb), TexReadPixel(t, xb, yb), fx);
+    const int xa = TexResolveEdge(x0, int(w), t.edge), xb = TexResolveEdge(x0 + 1, int(w), t.edge);
+    const int ya = TexResolveEdge(y0, int(h), t.edge), yb = TexResolveEdge(y0 + 1, int(h), t.edge);
+    const Float3 p0 = TexLerp(TexReadPixel(t, start, w, xa, ya), TexReadPixel(t, start, w, xb, ya), fx);
+    const Float3 p1 = TexLerp(TexReadPixel(t, start, w, xa, yb), TexReadPixel(t, start, w, xb, yb), fx);
     return TexLerp(p0, p1, fy);
+}
+__device__ __forceinline__ Float3 SampleTexture(const TexRec& t, float u, float v) { return SampleTextureLevel(t, 0u, u, v); }
+// TextureViewCPU::operator()(uv, mipLevel) (Device/CPU/TextureViewCPU.h:L422-470): the level clamped to [0, mipCount - 1] and split
+// by ModFInt; LINEAR = Math::Lerp of the two levels' bilinear reads, NEAREST = the nearer level's nearest texel (the reference
+// resolves the edge of that read against the BASE size, L446 — an out-of-range index; here against the level's own size).
+__device__ __noinline__ Float3 SampleTextureLod(const TexRec& t, float u, float v, float mipLevel)
+{
+    const uint32_t mc = t.mipCount ? t.mipCount : 1u;
+    mipLevel = fminf(fmaxf(mipLevel, 0.0f), float(mc - 1u));   // fmaxf(NaN, 0) = 0
+    float ip; const float frac = modff(mipLevel, &ip);
+    const uint32_t m0 = uint32_t(ip), m1 = min(m0 + 1u, mc - 1u);
+    if(t.interp == 0u) return SampleTextureLevel(t, frac < 0.5f ? m0 : m1, u, v);
+    const Float3 a = SampleTextureLevel(t, m0, u, v);
+    if(m0 == m1) return a;
+    return TexLerp(a, SampleTextureLevel(t, m1, u, v), frac);
+}
+// TextureViewCPU::operator()(uv, dpdx, dpdy) (L405-420): level = 0.5 log2(max |gradient|^2). lodMode 0 keeps the gradients in UV
+// units, as the reference's host backend reads a normalised-coordinate texture; 1 scales them by the base size first, which is
+// what tex2DGrad does on the reference's device backends.
+__device__ __forceinline__ Float3 SampleTextureGrad(const TexRec& t, float u, float v, float2 dpdx, float2 dpdy, uint32_t lodMode)
+{
+    if(t.mipCount <= 1u) return SampleTextureLevel(t, 0u, u, v);
+    if(lodMode == 1u) { dpdx.x *= float(t.w); dpdx.y *= float(t.h); dpdy.x *= float(t.w); dpdy.y *= float(t.h); }
+    const float la = __fmaf_rn(dpdx.y, dpdx.y, __fmul_rn(dpdx.x, dpdx.x)), lb = __fmaf_rn(dpdy.y, dpdy.y, __fmul_rn(dpdy.x, dpdy.x));   // Math::LengthSqr = Dot: an FMA chain
+    return SampleTextureLod(t, u, v, 0.5f * log2f(fmaxf(la, lb)));
 }
 
 // Material / light colour at the path's wavelengths: Converter::ConvertAlbedo / ConvertRadiance with the
@@ -772,6 +811,105 @@ __device__ __forceinline__ void TBNRows(float4 q0, float4 q1, float4 q2, float a
     rows[2] = F3(2.0f * (x * z - w * y), 2.0f * (y * z + w * x), w * w - x * x - y * y + z * z);
 }
 
+// ---- ray cones (Tracer/TracerTypes.h:L48-69,L323-383; RT Gems I ch. 20, Akenine-Moller et al. JCGT 10(1)): the footprint a path
+// carries so that textured reads can pick a mip level. x = aperture, y = width. ----
+struct ConeSurf { float2 front, back; float betaN; };
+__device__ __forceinline__ float2 ConeAdvance(float2 c, float t)
+{   // RayCone::Advance: width + aperture * t, clamped to [Epsilon, 1e6]
+    return make_float2(c.x, fminf(fmaxf(c.y + c.x * t, 1.0e-5f), 1.0e6f));
+}
+// The ray-cone half of Triangle::GenerateSurface (PrimitiveDefaultTriangle.hpp:L495-569): RayCone::Project gives the two axes of the
+// footprint ellipse on the hit plane, the vertex normals along the triangle's edges a curvature estimate (JCGT eq. 6) that will
+// widen or narrow the cone at the bounce (betaN), and the UVs one axis away from the hit the texture gradients (listing 1).
+// gN = geometric normal flipped towards the ray, dDotN = dot(unflipped normal, dir), dirN = normalised ray direction.
+__device__ __noinline__ void ConeSurface(const Float3* p, const Float3* vn, bool hasNormals, float2 t0, float2 t1, float2 t2, float a, float b, Float3 pos,
+                                         Float3 gN, float dDotN, Float3 dirN, float2 cone, ConeSurf& out, float2& dpdx, float2& dpdy)
+{
+    const float EPS = 1.0e-5f;
+    Float3 dd = dirN;
+    const float fd = Dot(gN, dd);
+    if(fabsf(fd + 1.0f) < EPS) dd = dd + F3(EPS, EPS, EPS);
+    const Float3 h1 = dd - gN * fd, h2 = Cross(gN, h1);
+    const float r = cone.y * 0.5f;
+    const Float3 a1 = h1 * (r / fmaxf(EPS, Length(h1 - dd * Dot(dd, h1)))), a2 = h2 * (r / fmaxf(EPS, Length(h2 - dd * Dot(dd, h2))));
+    const Float3 r0 = Normalize(a1), r1 = Normalize(a2);
+    const Float3 e[3] = {p[1] - p[0], p[2] - p[0], p[2] - p[1]};
+    float k[3] = {0.f, 0.f, 0.f};
+    if(hasNormals)
+    {
+        k[0] = Dot(vn[1] - vn[0], e[0]) / Dot(e[0], e[0]);
+        k[1] = Dot(vn[2] - vn[0], e[1]) / Dot(e[1], e[1]);
+        k[2] = Dot(vn[2] - vn[1], e[2]) / Dot(e[2], e[2]);
+    }
+    // Vector3::Minimum / Maximum: index of the first smallest / largest
+    const uint32_t mn = (k[1] < k[0]) ? ((k[2] < k[1]) ? 2u : 1u) : ((k[2] < k[0]) ? 2u : 0u);
+    const uint32_t mx = (k[1] > k[0]) ? ((k[2] > k[1]) ? 2u : 1u) : ((k[2] > k[0]) ? 2u : 0u);
+    const Float3 eMn = (mn == 0u) ? e[0] : (mn == 1u ? e[1] : e[2]), eMx = (mx == 0u) ? e[0] : (mx == 1u ? e[1] : e[2]);
+    const float kMn = (mn == 0u) ? k[0] : (mn == 1u ? k[1] : k[2]), kMx = (mx == 0u) ? k[0] : (mx == 1u ? k[1] : k[2]);
+    const float a1L = Length(a1), a2L = Length(a2), a1S = a1L * a1L, a2S = a2L * a2L, a12 = a1L * a2L;
+    const float mnx = Dot(r0, eMn), mny = Dot(r1, eMn), mxx = Dot(r0, eMx), mxy = Dot(r1, eMx);
+    const float l0 = a12 * (1.0f / sqrtf(a1S * mnx * mnx + a2S * mny * mny));
+    const float l1 = a12 * (1.0f / sqrtf(a1S * mxx * mxx + a2S * mxy * mxy));
+    const float lMaxRecip = 1.0f / fmaxf(l0, l1);
+    const float beta0 = -1.0f * (kMn * l0 * lMaxRecip) * fabsf(cone.y) / dDotN, beta1 = -1.0f * (kMx * l1 * lMaxRecip) * fabsf(cone.y) / dDotN;
+    out.front = cone; out.back = cone;
+    out.betaN = (fabsf(cone.x + beta0) >= fabsf(cone.x + beta1)) ? beta0 : beta1;
+    const float areaRecip = 1.0f / Dot(gN, Cross(e[0], e[1]));
+    const float c = 1.0f - a - b;
+    const float u = t0.x * a + t1.x * b + t2.x * c, v = t0.y * a + t1.y * b + t2.y * c;
+    #pragma unroll
+    for(int i = 0; i < 2; i++)
+    {
+        const Float3 eP = pos - p[0] + (i == 0 ? a1 : a2);
+        const float ba = Dot(gN, Cross(eP, e[1]) * areaRecip), bb = Dot(gN, Cross(e[0], eP) * areaRecip), bc = 1.0f - ba - bb;
+        const float2 g = make_float2((t0.x * bc + t1.x * ba + t2.x * bb) - u, (t0.y * bc + t1.y * ba + t2.y * bb) - v);
+        if(i == 0) dpdx = g; else dpdy = g;
+    }
+}
+// RayConeSurface::ConeAfterScatter: a reflected cone widens by twice the curvature term, a transmitted one takes the back cone
+__device__ __forceinline__ float2 ConeAfterScatter(const ConeSurf& cs, Float3 wI, Float3 n)
+{
+    return (Dot(wI, n) > 0.0f) ? make_float2(cs.front.x + 2.0f * cs.betaN, cs.front.y) : make_float2(cs.back.x - cs.betaN, cs.back.y);
+}
+__device__ __forceinline__ float2 Refract2D(float2 v, float2 n, float fromEta, float toEta)
+{   // Graphics::Refract(n, -v) in the plane of incidence; under total internal reflection the tangential direction
+    const float er = fromEta / toEta, cosIn = -(n.x * v.x + n.y * v.y);
+    const float sinOut2 = er * er * fmaxf(0.0f, 1.0f - cosIn * cosIn);
+    if(sinOut2 >= 1.0f)
+    {
+        const float nd = n.x * v.x + n.y * v.y;
+        const float tx = v.x - n.x * nd, ty = v.y - n.y * nd, l = 1.0f / sqrtf(tx * tx + ty * ty);
+        return make_float2(tx * l, ty * l);
+    }
+    const float k = er * cosIn - sqrtf(fmaxf(0.0f, 1.0f - sinOut2));
+    return make_float2(er * v.x + k * n.x, er * v.y + k * n.y);
+}
+// RefractMaterial::RefractRayCone (MaterialsDefault.hpp:L355-462, after RT Gems II ch. 10 / Falcor): the upper and lower edge rays
+// of the cone refracted in the plane of incidence through normals tilted by the curvature term give the back cone's aperture and
+// width. fromEta / toEta already swapped for a back-side hit; gN flipped towards wO.
+__device__ __noinline__ void RefractRayCone(ConeSurf& cs, Float3 wO, Float3 gN, float fromEta, float toEta)
+{
+    const float er = fromEta / toEta, cosIn3 = Dot(gN, wO);
+    if(er * er * fmaxf(0.0f, 1.0f - cosIn3 * cosIn3) >= 1.0f) return;
+    const Float3 d3 = wO * -1.0f;
+    const Float3 x = Normalize(d3 - gN * Dot(d3, gN));
+    const float2 d = make_float2(Dot(x, d3), Dot(gN, d3));
+    const float aperture = cs.front.x, width = cs.front.y;
+    float sn, co; sincosf(((width > 0.0f) ? 1.0f : 0.0f) * aperture * 0.5f, &sn, &co);
+    const float2 du = make_float2(d.x * co - d.y * sn, d.x * sn + d.y * co), dl = make_float2(d.x * co + d.y * sn, d.x * -sn + d.y * co);
+    const float2 od = make_float2(-d.y * width * 0.5f, d.x * width * 0.5f);
+    const float uHitX = +od.x + du.x * (-od.y / du.y), lHitX = -od.x + dl.x * (+od.y / dl.y);
+    const float nSign = (uHitX > lHitX) ? 1.0f : -1.0f;
+    sincosf(-cs.betaN * nSign * 0.5f, &sn, &co);
+    const float2 nu = make_float2(-sn, co), nl = make_float2(sn, co);   // Rotate2D_UL((0, 1), alpha)
+    const float2 tu = Refract2D(du, nu, fromEta, toEta), tl = Refract2D(dl, nl, fromEta, toEta);
+    const float2 o1 = make_float2(-d.y, d.x);
+    const float wl = (-uHitX * tu.y) / (o1.x * -tu.y + o1.y * tu.x), wu = (+lHitX * tl.y) / (o1.x * -tl.y + o1.y * tl.x);
+    const float sign = copysignf(1.0f, tu.x * tl.y - tu.y * tl.x);
+    const float ap = fmaxf(acosf(fminf(fmaxf(tu.x * tl.x + tu.y * tl.y, -1.0f), 1.0f)) * sign, 1.0e-5f);
+    cs.back = make_float2(ap + cs.betaN, wu + wl);
+}
+
 // ---- LightSkysphere (Tracer/LightsDefault.hpp:L310-443): the boundary light as an environment sphere ----
 // TransformContext::ApplyV / InvApplyV of the light surface's transform (the linear part only: directions)
 __device__ __forceinline__ Float3 SkyApply(const float* m, Float3 v)
@@ -927,6 +1065,31 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
     SlotSampler rng = LoadSampler(d.samplerType, rngState, d.samplerType != SAMPLER_INDEPENDENT ? d.sampleState[i] : make_uint2(0u, 0u),
                                   meta.y % d.width + d.regionX, meta.y / d.width + d.regionY, d.sobolMatrices, d.zsobol);
     const bool backSide = Dot(geoN, Normalize(rd)) > 0.0f;
+    // ray cone at the hit (KCRenderWork, RenderWork.kt.h:L65-85: the cone arrives advanced by the hit distance); only tracked when a
+    // texture has more than one mip level (the full kernel)
+    float2 dpdx = make_float2(0.f, 0.f), dpdy = make_float2(0.f, 0.f);
+    ConeSurf cs; cs.front = cs.back = make_float2(0.f, 0.f); cs.betaN = 0.0f;
+    const bool useCones = GLOSSY && d.cones != nullptr;
+    if(GLOSSY && useCones)
+    {
+        const Float3 dirN = Normalize(rd);
+        Float3 pw[3] = {p[0], p[1], p[2]}, vn[3] = {geoN, geoN, geoN};
+        if(!in.identity) { pw[0] = ApplyP(in.transform, p[0]); pw[1] = ApplyP(in.transform, p[1]); pw[2] = ApplyP(in.transform, p[2]); }
+        if(in.vertexNormals)
+        {   // Quaternion::OrthoBasisZ of the vertex frames (left in the primitive's local space, as the reference does)
+            #pragma unroll
+            for(int k = 0; k < 3; k++)
+            {
+                const float4 q = in.vertexNormals[vi[k]];
+                vn[k] = in.tbn ? F3(q.y * q.w - q.x * q.z + q.y * q.w - q.x * q.z, q.z * q.w + q.x * q.y + q.z * q.w + q.x * q.y, q.x * q.x - q.y * q.y - q.z * q.z + q.w * q.w)
+                               : F3(q.x, q.y, q.z);
+            }
+        }
+        float2 t0 = make_float2(0.f, 0.f), t1 = t0, t2 = t0;
+        if(in.vertexUVs) { t0 = in.vertexUVs[vi[0]]; t1 = in.vertexUVs[vi[1]]; t2 = in.vertexUVs[vi[2]]; }
+        ConeSurface(pw, vn, in.vertexNormals != nullptr, t0, t1, t2, a, b, pos, backSide ? geoN * -1.0f : geoN, Dot(geoN, dirN), dirN,
+                    ConeAdvance(d.cones[i], r1.w), cs, dpdx, dpdy);
+    }
     Float3 shadeN = geoN;
     bool normalMapped = false;
     const uint32_t matIndex = lmKey & 0x1FFFFFu;
@@ -945,7 +1108,7 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
                 const float2 t0 = in.vertexUVs[vi[0]], t1 = in.vertexUVs[vi[1]], t2 = in.vertexUVs[vi[2]];
                 uv = make_float2(t0.x * a + t1.x * b + t2.x * c, t0.y * a + t1.y * b + t2.y * c);
             }
-            const Float3 nt = Normalize(SampleTexture(d.textures[normalTex], uv.x, uv.y));
+            const Float3 nt = Normalize(SampleTextureGrad(d.textures[normalTex], uv.x, uv.y, dpdx, dpdy, d.textureLodMode));
             Float3 rows[3]; TBNRows(n0, n1, n2, a, b, rows);
             const float sgn = backSide ? -1.0f : 1.0f;
             shadeN = rows[0] * nt.x + (rows[1] * nt.y + rows[2] * nt.z) * sgn;
@@ -994,6 +1157,7 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
             originBase = NudgePos(pos, shadeN);
             // reflectance = Spectrum(pdf): cancels against the division by the pdf below
             throughput = throughput * pdfS;
+            if(useCones) RefractRayCone(cs, wO, geoN, fromEta, toEta);
             if(passedThrough && d.spectral)
             {   // DisperseWaves + StoreWaves (L229-238): the path keeps its first wavelength only
                 d.waves[i] = make_float4(waves.x, -1.0f, -1.0f, -1.0f);
@@ -1015,6 +1179,7 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
             float4* rp = reinterpret_cast<float4*>(d.rays + i);
             rp[0] = make_float4(no.x, no.y, no.z, 1.0e-4f);
             rp[1] = make_float4(wIr.x, wIr.y, wIr.z, FLT_MAX);
+            if(GLOSSY && useCones) d.cones[i] = ConeAfterScatter(cs, wIr, geoN);
             d.meta[i].x = PackPD(depth, ST_ALIVE, RAY_SPECULAR);
         }
         else
@@ -1035,7 +1200,7 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
             const float2 t0 = in.vertexUVs[vi[0]], t1 = in.vertexUVs[vi[1]], t2 = in.vertexUVs[vi[2]];
             uv = make_float2(t0.x * a + t1.x * b + t2.x * c, t0.y * a + t1.y * b + t2.y * c);
         }
-        const Float3 rgb = SampleTexture(d.textures[texIndex], uv.x, uv.y);
+        const Float3 rgb = GLOSSY ? SampleTextureGrad(d.textures[texIndex], uv.x, uv.y, dpdx, dpdy, d.textureLodMode) : SampleTexture(d.textures[texIndex], uv.x, uv.y);
         if(d.spectral) { const float3 cf = FetchAlbedoCoeffs(d.spec, rgb.x, rgb.y, rgb.z); albedoRaw = make_float4(cf.x, cf.y, cf.z, 0.f); }
         else albedoRaw = make_float4(rgb.x, rgb.y, rgb.z, 0.f);
     }
@@ -1185,6 +1350,7 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
         float4* rp = reinterpret_cast<float4*>(d.rays + i);
         rp[0] = make_float4(no.x, no.y, no.z, 1.0e-4f);
         rp[1] = make_float4(wIw.x, wIw.y, wIw.z, FLT_MAX);
+        if(GLOSSY && useCones) d.cones[i] = ConeAfterScatter(cs, wIw, geoN);
         d.meta[i].x = PackPD(depth, ST_ALIVE, nextType);
     }
     else
@@ -1216,7 +1382,7 @@ __global__ void __launch_bounds__(RTPB) KShade(RenderData d)
 struct ColorConv { float gamma; float m[9]; uint32_t hasMatrix; };
 __global__ void __launch_bounds__(256) KConvertTextureColor(TexRec t, ColorConv cc)
 {
-    const size_t n = size_t(t.w) * t.h;
+    const size_t n = MipStart(t.w, t.h, t.mipCount ? t.mipCount : 1u);   // every supplied level (ColorConvParams.validMips)
     for(size_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += size_t(gridDim.x) * 256ull)
     {
         float c[3];
@@ -1253,6 +1419,79 @@ static void ConvertTextureColor(Context& ctx, const TexRec& t, const mrb_texture
     cc.hasMatrix = td.colorMatrix ? 1u : 0u;
     if(td.colorMatrix) memcpy(cc.m, td.colorMatrix, sizeof(cc.m));
     MRB_LAUNCH(ctx, KConvertTextureColor, GridFor(ctx, t.w * t.h, 256u), 256, 0, t, cc);
+}
+
+// <Filter>::Evaluate(duv) of Tracer/Filters.h (L110-117 Box, L153-164 Tent, L202-206 Gaussian, L257-278 Mitchell-Netravali)
+__device__ __forceinline__ float FilterEvaluate(uint32_t type, float r, float x, float y)
+{
+    if(type == FILTER_BOX) { const float rr = 1.0f / r; return (fabsf(x) <= r && fabsf(y) <= r) ? 0.25f * rr * rr : 0.0f; }
+    if(type == FILTER_TENT) { const float rcp = 1.0f / r; return LerpU(rcp, 0.0f, fabsf(x * rcp)) * LerpU(rcp, 0.0f, fabsf(y * rcp)); }
+    if(type == FILTER_MITCHELL) { const float rcp = 1.0f / r; return Mitchell1D(x, rcp) * Mitchell1D(y, rcp); }
+    const float sigma = r * 0.285714f;
+    return GaussPdf(x, sigma) * GaussPdf(y, sigma);
+}
+// TextureMemory::GenerateMipmaps -> KCGenerateMipmaps (Tracer/TextureFilter.cu:L55-118,L126-198,L1064-1096): one level from its parent.
+// Per texel 8 x 8 stratified offsets over [-r, r]^2 (FilterMode::ACCUMULATE), weight = Evaluate(offset), the parent texel nearest
+// to the offset pixel centre (ConvertPixelIndices + RoundInt), sum / weight sum; unorm8 texels are filtered as their 0..255 integer
+// values, rounded and clamped (GenericRead / GenericWrite). One thread per texel: the 64 parent reads of neighbouring texels overlap
+// in L1, and a full chain is 1/3 of the base level, so the kernel is a small fraction of the upload it follows.
+__global__ void __launch_bounds__(256) KGenerateMipLevel(TexRec t, uint32_t level, uint32_t filterType, float radius)
+{
+    const uint32_t mw = MipDim(t.w, level), mh = MipDim(t.h, level), pw = MipDim(t.w, level - 1u), ph = MipDim(t.h, level - 1u);
+    const size_t dst = MipStart(t.w, t.h, level), src = MipStart(t.w, t.h, level - 1u);
+    const uint32_t n = mw * mh;
+    for(uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u)
+    {
+        const uint32_t x = i % mw, y = i / mw;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f}, wsum = 0.0f;
+        const float ratioX = float(pw) / float(mw), ratioY = float(ph) / float(mh);
+        for(uint32_t sy = 0; sy < 8u; sy++)
+        for(uint32_t sx = 0; sx < 8u; sx++)
+        {
+            const float dxy = 1.0f / 8.0f;
+            const float xi0 = __fadd_rn(dxy * 0.5f, __fmul_rn(dxy, float(sx))), xi1 = __fadd_rn(dxy * 0.5f, __fmul_rn(dxy, float(sy)));
+            const float ox = __fsub_rn(__fmul_rn(__fmul_rn(xi0, 2.0f), radius), radius), oy = __fsub_rn(__fmul_rn(__fmul_rn(xi1, 2.0f), radius), radius);
+            const float wgt = FilterEvaluate(filterType, radius, ox, oy);
+            float rx = __fsub_rn(__fmul_rn(__fadd_rn(__fadd_rn(float(x), ox), 0.5f), ratioX), 0.5f);
+            float ry = __fsub_rn(__fmul_rn(__fadd_rn(__fadd_rn(float(y), oy), 0.5f), ratioY), 0.5f);
+            rx = fminf(fmaxf(rx, 0.0f), float(pw) - 1.0f); ry = fminf(fmaxf(ry, 0.0f), float(ph) - 1.0f);
+            const size_t o = (src + size_t(lroundf(ry)) * pw + size_t(lroundf(rx))) * t.channels;
+            for(uint32_t c = 0; c < t.channels; c++)
+            {
+                const float px = (t.format == 0u) ? static_cast<const float*>(t.data)[o + c] : float(static_cast<const uint8_t*>(t.data)[o + c]);
+                acc[c] = __fadd_rn(acc[c], __fmul_rn(wgt, px));
+            }
+            wsum = __fadd_rn(wsum, wgt);
+        }
+        const size_t o = (dst + size_t(y) * mw + x) * t.channels;
+        for(uint32_t c = 0; c < t.channels; c++)
+        {
+            const float v = __fdiv_rn(acc[c], wsum);
+            if(t.format == 0u) const_cast<float*>(static_cast<const float*>(t.data))[o + c] = v;
+            else const_cast<uint8_t*>(static_cast<const uint8_t*>(t.data))[o + c] = uint8_t(fminf(fmaxf(roundf(v), 0.0f), 255.0f));
+        }
+    }
+}
+// levels a texture ends up with: the supplied ones, or the full chain when mips are generated (TextureMemory::CreateTexture, L588-591)
+static uint32_t SuppliedMips(const mrb_texture_desc& td) { return td.mipCount ? td.mipCount : 1u; }
+static uint32_t FinalMips(const mrb_texture_desc& td) { return td.generateMips ? max(SuppliedMips(td), FullMipCount(td.width, td.height)) : SuppliedMips(td); }
+static size_t ChainTexels(uint32_t w, uint32_t h, uint32_t mips) { return MipStart(w, h, mips); }
+static void ValidateMips(const mrb_texture_desc& td)
+{
+    if(SuppliedMips(td) > FullMipCount(td.width, td.height)) throw std::runtime_error("texture mipCount exceeds the full chain of its size");
+    if(td.generateMips && (td.mipFilterType > FILTER_MITCHELL || !(td.mipFilterRadius > 0.0f))) throw std::runtime_error("bad mip generation filter");
+}
+// upload + TextureMemory::Finalize (L809-833): colour conversion of the supplied levels, then the missing levels of the chain
+static void UploadTexture(Context& ctx, TexRec& t, const mrb_texture_desc& td)
+{
+    const size_t texel = size_t(t.channels) * (t.format == 0u ? 4u : 1u);
+    const uint32_t supplied = SuppliedMips(td);
+    MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<void*>(t.data), td.data, ChainTexels(t.w, t.h, supplied) * texel, cudaMemcpyHostToDevice, ctx.stream));
+    t.mipCount = supplied;
+    ConvertTextureColor(ctx, t, td);
+    t.mipCount = FinalMips(td);
+    for(uint32_t level = supplied; level < t.mipCount; level++)
+        MRB_LAUNCH(ctx, KGenerateMipLevel, GridFor(ctx, MipDim(t.w, level) * MipDim(t.h, level), 256u), 256, 0, t, level, td.mipFilterType, td.mipFilterRadius);
 }
 
 // Converter::ConvertAlbedo / ConvertRadiance, LUT half: RGB attributes -> Jakob coefficients, once per render
@@ -1552,13 +1791,18 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
 
     std::vector<RenderInstance> hri(instCount);
     std::vector<TexRec> htex(desc.textureCount);
+    bool anyMips = false;
     for(uint32_t t = 0; t < desc.textureCount; t++)
     {
         const mrb_texture_desc& td = desc.textures[t];
         if(!td.data || td.width == 0 || td.height == 0 || (td.channels != 3 && td.channels != 4) || td.format > 1u || td.interp > 1u || td.edge > 2u)
             throw std::runtime_error("bad texture descriptor");
-        htex[t] = TexRec{nullptr, td.width, td.height, td.channels, td.format, td.interp, td.edge, 0u};
+        ValidateMips(td);
+        htex[t] = TexRec{nullptr, td.width, td.height, td.channels, td.format, td.interp, td.edge, FinalMips(td)};
+        if(FinalMips(td) > 1u) { anyMips = true; r.glossy = true; }   // ray cones + level selection live in the full shading kernel
     }
+    if(desc.textureLodMode > 1u) throw std::runtime_error("unknown textureLodMode");
+    d.textureLodMode = desc.textureLodMode;
     if(desc.albedoTexture)
         for(uint32_t m = 0; m < desc.materialCount; m++)
             if(desc.albedoTexture[m] >= int32_t(desc.textureCount)) throw std::runtime_error("albedoTexture index exceeds textureCount");
@@ -1600,8 +1844,8 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
         d.matParams = desc.materialParams ? ma.Take<float4>(2 * size_t(desc.materialCount ? desc.materialCount : 1)) : nullptr;
         d.textures = desc.textureCount ? ma.Take<TexRec>(desc.textureCount) : nullptr;
         for(uint32_t t = 0; t < desc.textureCount; t++)
-            htex[t].data = ma.Take<char>(size_t(desc.textures[t].width) * desc.textures[t].height * desc.textures[t].channels *
-                                         (desc.textures[t].format == 0u ? 4u : 1u));
+            htex[t].data = ma.Take<char>(ChainTexels(htex[t].w, htex[t].h, htex[t].mipCount) * htex[t].channels * (htex[t].format == 0u ? 4u : 1u));
+        d.cones = anyMips ? ma.Take<float2>(P) : nullptr;
         d.waves = desc.spectrum ? ma.Take<float4>(P) : nullptr; d.wavePdf = desc.spectrum ? ma.Take<float4>(P) : nullptr;
         // textured skysphere: the luminance distribution (row CDFs + marginal) and the scratch of its construction
         d.boundaryDist.cdfX = skyW ? ma.Take<float>(size_t(skyW) * skyH) : nullptr;
@@ -1639,10 +1883,7 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
         MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<int32_t*>(d.normalTex), desc.normalTexture, sizeof(int32_t) * desc.materialCount, cudaMemcpyHostToDevice, ctx.stream));
         for(uint32_t m = 0; m < desc.materialCount; m++) if(desc.normalTexture[m] >= 0) r.glossy = true;   // normal maps live in the full shading kernel
     }
-    for(uint32_t t = 0; t < desc.textureCount; t++)
-        MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<void*>(htex[t].data), desc.textures[t].data,
-                                     size_t(htex[t].w) * htex[t].h * htex[t].channels * (htex[t].format == 0u ? 4u : 1u), cudaMemcpyHostToDevice, ctx.stream));
-    for(uint32_t t = 0; t < desc.textureCount; t++) ConvertTextureColor(ctx, htex[t], desc.textures[t]);   // TextureMemory::ConvertColorspaces
+    for(uint32_t t = 0; t < desc.textureCount; t++) UploadTexture(ctx, htex[t], desc.textures[t]);   // + ConvertColorspaces + GenerateMipmaps
     if(desc.textureCount)
         MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<TexRec*>(d.textures), htex.data(), htex.size() * sizeof(TexRec), cudaMemcpyHostToDevice, ctx.stream));
     if(!lights.empty())
@@ -2019,35 +2260,79 @@ __global__ void KSampleTexture(TexRec t, const float2* __restrict__ uv, uint32_t
     out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z;
 }
 
-void TextureSampleHost(Context& ctx, const mrb_texture_desc& td, const float* uv, uint32_t n, float* rgbOut)
+static void ValidateTapTexture(const mrb_texture_desc& td)
 {
     if(!td.data || td.width == 0 || td.height == 0 || (td.channels != 3 && td.channels != 4) || td.format > 1u || td.interp > 1u || td.edge > 2u)
         throw std::runtime_error("bad texture descriptor");
-    const size_t texBytes = size_t(td.width) * td.height * td.channels * (td.format == 0u ? 4u : 1u);
-    MultiAlloc sz(nullptr); sz.Take<char>(texBytes); sz.Take<float2>(n); sz.Take<float>(size_t(n) * 3);
+    ValidateMips(td);
+}
+// the texture as the renderer would hold it, in the context's scratch block (followed by `extra` bytes for the caller)
+static TexRec StageTexture(Context& ctx, const mrb_texture_desc& td, size_t extra, char** extraOut)
+{
+    ValidateTapTexture(td);
+    const size_t texBytes = ChainTexels(td.width, td.height, FinalMips(td)) * td.channels * (td.format == 0u ? 4u : 1u);
+    MultiAlloc sz(nullptr); sz.Take<char>(texBytes); sz.Take<char>(extra);
     ctx.scratch.Reserve(sz.Total());
     MultiAlloc ma(ctx.scratch.Base());
-    char* dTex = ma.Take<char>(texBytes); float2* dUV = ma.Take<float2>(n); float* dOut = ma.Take<float>(size_t(n) * 3);
-    MRB_CUDA_TRY(cudaMemcpyAsync(dTex, td.data, texBytes, cudaMemcpyHostToDevice, ctx.stream));
+    char* dTex = ma.Take<char>(texBytes); char* dExtra = ma.Take<char>(extra);
+    if(extraOut) *extraOut = dExtra;
+    TexRec t{dTex, td.width, td.height, td.channels, td.format, td.interp, td.edge, 0u};
+    UploadTexture(ctx, t, td);
+    return t;
+}
+size_t TextureChainTexels(uint32_t w, uint32_t h, uint32_t mips) { return ChainTexels(w, h, mips); }
+uint32_t TextureFullMipCount(uint32_t w, uint32_t h) { return FullMipCount(w, h); }
+
+void TextureSampleHost(Context& ctx, const mrb_texture_desc& td, const float* uv, uint32_t n, float* rgbOut)
+{
+    char* extra = nullptr;
+    const TexRec t = StageTexture(ctx, td, sizeof(float2) * n + 256 + sizeof(float) * 3 * size_t(n), &extra);
+    float2* dUV = reinterpret_cast<float2*>(extra); float* dOut = reinterpret_cast<float*>(extra + ((sizeof(float2) * n + 255) / 256) * 256);
     MRB_CUDA_TRY(cudaMemcpyAsync(dUV, uv, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx.stream));
-    const TexRec t{dTex, td.width, td.height, td.channels, td.format, td.interp, td.edge, 0u};
-    ConvertTextureColor(ctx, t, td);
     if(n) MRB_LAUNCH(ctx, KSampleTexture, DivUp(n, 256u), 256, 0, t, dUV, n, dOut);
     MRB_CUDA_TRY(cudaMemcpyAsync(rgbOut, dOut, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx.stream));
     MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
 }
 
-void TextureConvertHost(Context& ctx, const mrb_texture_desc& td, void* texelsOut)
+// mrb_texture_sample_lod: SampleTextureLod / SampleTextureGrad on their own
+__global__ void KSampleTextureLod(TexRec t, const float2* __restrict__ uv, const float* __restrict__ lod, const float4* __restrict__ grads,
+                                  uint32_t lodMode, uint32_t n, float* __restrict__ out)
 {
-    if(!td.data || td.width == 0 || td.height == 0 || (td.channels != 3 && td.channels != 4) || td.format > 1u)
-        throw std::runtime_error("bad texture descriptor");
-    const size_t texBytes = size_t(td.width) * td.height * td.channels * (td.format == 0u ? 4u : 1u);
-    ctx.scratch.Reserve(texBytes);
-    char* dTex = static_cast<char*>(ctx.scratch.Base());
-    MRB_CUDA_TRY(cudaMemcpyAsync(dTex, td.data, texBytes, cudaMemcpyHostToDevice, ctx.stream));
-    const TexRec t{dTex, td.width, td.height, td.channels, td.format, td.interp, td.edge, 0u};
-    ConvertTextureColor(ctx, t, td);
-    MRB_CUDA_TRY(cudaMemcpyAsync(texelsOut, dTex, texBytes, cudaMemcpyDeviceToHost, ctx.stream));
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const Float3 c = lod ? SampleTextureLod(t, uv[i].x, uv[i].y, lod[i])
+                         : SampleTextureGrad(t, uv[i].x, uv[i].y, make_float2(grads[i].x, grads[i].y), make_float2(grads[i].z, grads[i].w), lodMode);
+    out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z;
+}
+void TextureSampleLodHost(Context& ctx, const mrb_texture_desc& td, const float* uv, const float* lod, const float* grads, uint32_t lodMode, uint32_t n, float* rgbOut)
+{
+    char* extra = nullptr;
+    const size_t slot = ((sizeof(float4) * size_t(n) + 255) / 256) * 256;
+    const TexRec t = StageTexture(ctx, td, 4 * slot + 256, &extra);
+    float2* dUV = reinterpret_cast<float2*>(extra); float* dLod = reinterpret_cast<float*>(extra + slot);
+    float4* dGrad = reinterpret_cast<float4*>(extra + 2 * slot); float* dOut = reinterpret_cast<float*>(extra + 3 * slot);
+    MRB_CUDA_TRY(cudaMemcpyAsync(dUV, uv, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx.stream));
+    if(lod) MRB_CUDA_TRY(cudaMemcpyAsync(dLod, lod, sizeof(float) * n, cudaMemcpyHostToDevice, ctx.stream));
+    else MRB_CUDA_TRY(cudaMemcpyAsync(dGrad, grads, sizeof(float4) * n, cudaMemcpyHostToDevice, ctx.stream));
+    if(n) MRB_LAUNCH(ctx, KSampleTextureLod, DivUp(n, 256u), 256, 0, t, dUV, lod ? dLod : nullptr, lod ? nullptr : dGrad, lodMode, n, dOut);
+    MRB_CUDA_TRY(cudaMemcpyAsync(rgbOut, dOut, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx.stream));
+    MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
+}
+
+void TextureMipChainHost(Context& ctx, const mrb_texture_desc& td, void* chainOut, uint32_t* mipCountOut)
+{
+    const TexRec t = StageTexture(ctx, td, 0, nullptr);
+    const size_t texBytes = ChainTexels(t.w, t.h, t.mipCount) * t.channels * (t.format == 0u ? 4u : 1u);
+    MRB_CUDA_TRY(cudaMemcpyAsync(chainOut, t.data, texBytes, cudaMemcpyDeviceToHost, ctx.stream));
+    MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
+    if(mipCountOut) *mipCountOut = t.mipCount;
+}
+
+void TextureConvertHost(Context& ctx, const mrb_texture_desc& td, void* texelsOut)
+{   // level 0 only: the supplied levels after TextureMemory::ConvertColorspaces
+    const TexRec t = StageTexture(ctx, td, 0, nullptr);
+    const size_t texBytes = size_t(t.w) * t.h * t.channels * (t.format == 0u ? 4u : 1u);
+    MRB_CUDA_TRY(cudaMemcpyAsync(texelsOut, t.data, texBytes, cudaMemcpyDeviceToHost, ctx.stream));
     MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));
 }
 

@@ -9,7 +9,7 @@
 //   mray_b200_run --tracer libTracerDLL_B200.so --loader libSceneLoaderB200.so --scene scene.json -r 512x512 --spp 64
 //                 [--renderer PathTracerRGB|PathTracerSpectral] [--sampleMode Pure|WithNextEventEstimation|WithNEEAndMIS]
 //                 [--rr 3,8] [--seed 0] [--sampler Independent|Sobol|ZSobol] [--renderMode Throughput|Latency] [--burst 1]
-//                 [--filter Gaussian,1.0] [--hint 2097152] [-t threads] [--camera 0] --out image.pfm
+//                 [--filter Gaussian,1.0] [--genMips [Gaussian,2.0]] [--hint 2097152] [-t threads] [--camera 0] --out image.pfm
 #include "Core/TracerI.h"
 #include "Core/SceneLoaderI.h"
 #include "Core/ThreadPool.h"
@@ -38,6 +38,7 @@ struct Options
     uint32_t width = 512, height = 512, spp = 64, rrLo = 3, rrHi = 8, burst = 1, threads = 0, hint = 0, camera = 0;
     float filterRadius = 1.0f;
     uint64_t seed = 0;
+    bool genMips = false; std::string mipFilter = "Gaussian"; float mipFilterRadius = 2.0f;   // tracer config "genMipmaps" / "mipGenFilter"
 };
 
 bool Parse(int argc, char** argv, Options& o, std::string& err)
@@ -69,6 +70,16 @@ bool Parse(int argc, char** argv, Options& o, std::string& err)
             std::string s = v; size_t c = s.find(',');
             o.filter = s.substr(0, c);
             if(c != std::string::npos) o.filterRadius = std::strtof(s.c_str() + c + 1, nullptr);
+        }
+        else if(a == "--genMips")
+        {   // TracerParameters.genMips, optionally with mipGenFilter as NAME,RADIUS (default Gaussian,2 as the reference)
+            o.genMips = true;
+            if(i + 1 < argc && argv[i + 1][0] != '-')
+            {
+                std::string s = argv[++i]; size_t c = s.find(',');
+                o.mipFilter = s.substr(0, c);
+                if(c != std::string::npos) o.mipFilterRadius = std::strtof(s.c_str() + c + 1, nullptr);
+            }
         }
         else { err = "unknown option " + a; return false; }
     }
@@ -128,6 +139,7 @@ int main(int argc, char** argv)
         if(!filters.count(o.filter)) throw MRayError("unknown film filter \"{}\"", o.filter);
         tp.samplerType = samplers.at(o.sampler);
         tp.filmFilter.type = filters.at(o.filter); tp.filmFilter.radius = o.filterRadius;
+        tp.genMips = o.genMips; tp.mipGenFilter.type = filters.at(o.mipFilter); tp.mipGenFilter.radius = o.mipFilterRadius;
         tracer = constructT(tp);
         ThreadPool pool;
         auto threadInit = tracer->GetThreadInitFunction();

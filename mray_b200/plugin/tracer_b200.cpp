@@ -65,8 +65,30 @@ struct MatGroupB200
 struct TextureB200
 {
     Vector2ui size; MRayTextureParameters params; uint32_t channels = 4, format = 0;
-    std::vector<Byte> pixels; bool loaded = false;
+    std::vector<Byte> pixels; bool loaded = false;   // all levels back to back (Graphics::TextureMipPixelStart order); loaded = level 0 arrived
     float gamma = 1.0f; bool hasColorMatrix = false; float colorMatrix[9] = {};   // TextureMemory::ConvertColorspaces, done on upload
+    uint32_t mipCount = 1; std::vector<uint8_t> levelLoaded;   // levels the caller reserved (CreateTexture2D) and pushed so far
+    bool genMips = false; uint32_t mipFilterType = 2; float mipFilterRadius = 2.0f;   // TracerParameters.genMips / mipGenFilter
+    size_t TexelBytes() const { return size_t(channels) * (format == 0 ? 4u : 1u); }
+    static uint32_t LevelDim(uint32_t n, uint32_t level) { return std::max(n >> level, 1u); }
+    size_t LevelStart(uint32_t level) const
+    { size_t o = 0; for(uint32_t i = 0; i < level; i++) o += size_t(LevelDim(size[0], i)) * LevelDim(size[1], i); return o; }
+    // the leading run of pushed levels is what the library is given; with genMips it filters the rest itself (KCGenerateMipmaps
+    // skips the levels that arrived, Tracer/TextureFilter.cu:L158-167)
+    uint32_t SuppliedLevels() const { uint32_t n = 0; while(n < mipCount && levelLoaded[n]) n++; return n; }
+    mrb_texture_desc Desc(bool convertColor = true) const
+    {
+        const uint32_t supplied = SuppliedLevels();
+        for(uint32_t l = supplied; l < mipCount; l++)
+            if(levelLoaded[l]) throw MRayError("textures: mip level {} was pushed but level {} was not", l, supplied);
+        if(!genMips && supplied != mipCount) throw MRayError("textures: {} of {} mip levels have no data", mipCount - supplied, mipCount);
+        mrb_texture_desc d = {};
+        d.data = pixels.data(); d.width = size[0]; d.height = size[1]; d.channels = channels; d.format = format;
+        d.interp = uint32_t(params.interpolation); d.edge = uint32_t(params.edgeResolve);
+        d.gamma = convertColor ? gamma : 1.0f; d.colorMatrix = (convertColor && hasColorMatrix) ? colorMatrix : nullptr;
+        d.mipCount = supplied; d.generateMips = genMips ? 1u : 0u; d.mipFilterType = mipFilterType; d.mipFilterRadius = mipFilterRadius;
+        return d;
+    }
 };
 struct LightGroupB200
 {
@@ -604,9 +626,10 @@ class TracerB200 final : public TracerI
     TextureId CreateTexture2D(Vector2ui size, uint32_t mipCount, MRayTextureParameters p) override
     {
         std::lock_guard lk(mtx);
-        if(mipCount != 1) throw MRayError("textures: mip chains are not supported yet (mipCount {})", mipCount);
         if(size[0] == 0 || size[1] == 0) throw MRayError("textures: empty texture");
-        TextureB200 t; t.size = size; t.params = p;
+        uint32_t fullMips = 0; for(uint32_t m = std::max(size[0], size[1]); m; m >>= 1) fullMips++;   // Graphics::TextureMipCount
+        if(mipCount == 0 || mipCount > fullMips) throw MRayError("textures: mipCount {} of a {}x{} texture", mipCount, size[0], size[1]);
+        TextureB200 t; t.size = size; t.params = p; t.mipCount = mipCount; t.levelLoaded.assign(mipCount, 0);
         switch(p.pixelType.Name())
         {
             case MRayPixelEnum::MR_RGBA_FLOAT:  t.channels = 4; t.format = 0; break;
@@ -633,7 +656,10 @@ class TracerB200 final : public TracerI
         // the view type follows DetermineReadMode (Tracer/TextureMemory.cpp:L329-396): 4 channels + MR_DROP_1 read as Vector3
         if(p.readMode != MRayTextureReadMode::MR_PASSTHROUGH && p.readMode != MRayTextureReadMode::MR_DROP_1)
             throw MRayError("textures: only MR_PASSTHROUGH / MR_DROP_1 reads are supported yet");
-        if(params.genMips) throw MRayError("textures: genMips is not supported yet");
+        // TracerParameters.genMips: every (non block-compressed) texture gets its full chain (TextureMemory::CreateTexture L588-591),
+        // filtered on upload by libmray_b200 with TracerParameters.mipGenFilter
+        t.genMips = params.genMips; t.mipFilterType = uint32_t(params.mipGenFilter.type); t.mipFilterRadius = float(params.mipGenFilter.radius);
+        t.pixels.resize(t.LevelStart(mipCount) * t.TexelBytes());
         if(!p.ignoreResClamp && std::max(size[0], size[1]) > params.clampedTexRes) throw MRayError("textures: clampedTexRes is not supported yet");
         textures.push_back(std::move(t));
         return TextureId(uint32_t(textures.size()));
@@ -645,16 +671,18 @@ class TracerB200 final : public TracerI
         const uint32_t tid = Raw(id);
         if(tid == 0 || tid > textures.size()) throw MRayError("Unable to find texture({})", tid);
         TextureB200& t = textures[tid - 1];
-        if(mipLevel != 0) throw MRayError("textures: mip level {} of a single-level texture", mipLevel);
+        if(mipLevel >= t.mipCount) throw MRayError("textures: mip level {} of a texture with {} levels", mipLevel, t.mipCount);
         // the TransientData is typed by the pixel (MRayPixelType<E>::Type): Vector4 / Vector4uc here
-        const size_t pixels = size_t(t.size[0]) * t.size[1];
+        const size_t pixels = size_t(TextureB200::LevelDim(t.size[0], mipLevel)) * TextureB200::LevelDim(t.size[1], mipLevel);
         const Byte* src = nullptr; size_t got = 0;
         if(t.channels == 1 && t.format == 0) { auto s = data.AccessAs<const Float>(); src = reinterpret_cast<const Byte*>(s.data()); got = s.size(); }
         else if(t.channels == 1) { auto s = data.AccessAs<const uint8_t>(); src = reinterpret_cast<const Byte*>(s.data()); got = s.size(); }
         else if(t.format == 0) { auto s = data.AccessAs<const Vector4>(); src = reinterpret_cast<const Byte*>(s.data()); got = s.size(); }
         else { auto s = data.AccessAs<const Vector4uc>(); src = reinterpret_cast<const Byte*>(s.data()); got = s.size(); }
         if(got != pixels) throw MRayError("textures: {} pixels pushed, {} expected", got, pixels);
-        t.pixels.assign(src, src + pixels * t.channels * (t.format == 0 ? 4u : 1u));
+        std::copy(src, src + pixels * t.TexelBytes(), t.pixels.begin() + ptrdiff_t(t.LevelStart(mipLevel) * t.TexelBytes()));
+        t.levelLoaded[mipLevel] = 1;
+        if(mipLevel != 0) return;
         t.loaded = true;
     }
 
@@ -929,8 +957,8 @@ class TracerB200 final : public TracerI
                 if(it != used.end()) continue;
                 used.push_back(uint32_t(g.alpha[k]));
                 const TextureB200& t = textures[size_t(g.alpha[k]) - 1];
-                atex.push_back(mrb_texture_desc{t.pixels.data(), t.size[0], t.size[1], t.channels, t.format,
-                                                uint32_t(t.params.interpolation), uint32_t(t.params.edgeResolve), 1.0f, nullptr});
+                atex.push_back(t.Desc(false));   // pure data: no colour conversion; read at level 0 (IntersectionCheck has no gradients)
+                atex.back().mipCount = 1; atex.back().generateMips = 0;
             }
             if(!used.empty())
             {
@@ -1126,11 +1154,12 @@ class TracerB200 final : public TracerI
             for(size_t k = 0; k < flatTextures.size(); k++)
             {
                 const TextureB200& t = textures[flatTextures[k] - 1];
-                texDescs[k] = mrb_texture_desc{t.pixels.data(), t.size[0], t.size[1], t.channels, t.format,
-                                               uint32_t(t.params.interpolation), uint32_t(t.params.edgeResolve),
-                                               t.gamma, t.hasColorMatrix ? t.colorMatrix : nullptr};
+                texDescs[k] = t.Desc();
             }
             d.textureCount = uint32_t(texDescs.size()); d.textures = texDescs.data(); d.albedoTexture = flatAlbedoTex.data();
+            // mip level from the ray cone's gradients: as the reference's host backend computes it (the mode the goldens pin), or
+            // MRB_TEXTURE_LOD=device for what tex2DGrad does on its device backends (gradients scaled by the texture size)
+            if(const char* e = std::getenv("MRB_TEXTURE_LOD")) d.textureLodMode = (std::string(e) == "device") ? 1u : 0u;
             if(std::any_of(flatNormalTex.begin(), flatNormalTex.end(), [](int32_t t) { return t >= 0; })) d.normalTexture = flatNormalTex.data();
         }
         // boundary light surface: (L)Null (nothing to do) or a skysphere (LightGroupSkysphere, Tracer/LightsDefault.hpp:L704-893)
@@ -1151,9 +1180,7 @@ class TracerB200 final : public TracerI
                 if(it != flatTextures.end()) d.boundaryTexture = int32_t(it - flatTextures.begin());
                 else
                 {   // the radiance map is not an albedo texture of any material: append it to this render's table
-                    texDescs.push_back(mrb_texture_desc{t.pixels.data(), t.size[0], t.size[1], t.channels, t.format,
-                                                        uint32_t(t.params.interpolation), uint32_t(t.params.edgeResolve),
-                                                        t.gamma, t.hasColorMatrix ? t.colorMatrix : nullptr});
+                    texDescs.push_back(t.Desc());
                     d.boundaryTexture = int32_t(texDescs.size() - 1);
                     d.textureCount = uint32_t(texDescs.size()); d.textures = texDescs.data();
                     if(flatTextures.empty()) d.albedoTexture = nullptr;

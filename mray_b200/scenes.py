@@ -586,3 +586,68 @@ def cornell_normal_map(size: int = 16):
     c["normal_texture"] = dict(data=np.ascontiguousarray(t), interp="Linear", edge="Wrap")
     c["normal_map"] = np.array([0, -1, -1, -1], np.int32)
     return c
+
+
+MIP_LEVEL_COLOURS = np.array([[0.80, 0.80, 0.80], [0.85, 0.25, 0.20], [0.20, 0.80, 0.25], [0.20, 0.30, 0.85], [0.85, 0.80, 0.15], [0.80, 0.20, 0.80]],
+                             np.float32)
+
+
+def mip_debug_texture(size: int = 32, seed: int = 9):
+    """An fp32 RGBA texture with EXPLICIT mip levels down to 1 x 1, every level its own colour (MIP_LEVEL_COLOURS) under +-0.1 of
+    per-texel noise: which level a read takes — and how two levels blend — shows in the image, which a filtered chain (whose
+    levels all average to the same colour) would hide. Bilinear, wrap."""
+    rng = np.random.default_rng(seed)
+    levels = []
+    k = 0
+    while True:
+        n = max(size >> k, 1)
+        lv = np.ones((n, n, 4), np.float32)
+        lv[..., :3] = MIP_LEVEL_COLOURS[k % len(MIP_LEVEL_COLOURS)] + (rng.random((n, n, 3), dtype=np.float32) - 0.5) * 0.2
+        levels.append(np.clip(lv, 0.02, 0.98).astype(np.float32))
+        if n == 1:
+            break
+        k += 1
+    return dict(data=levels[0], mips=levels[1:], interp="Linear", edge="Wrap")
+
+
+def cornell_mips(kind: str = "explicit", tile: float = 96.0):
+    """Mip-mapped albedo on the white material of a Cornell box (floor, ceiling, back wall, tall / short box), UV0 tiling the texture
+    `tile` times across every quad so that the ray cone's footprint spans several texels (the reference's host backend takes the mip
+    level from the gradient in UV units, so only a strongly tiled texture leaves level 0 there).
+      "explicit"      : cornell_box + mip_debug_texture (explicit levels, distinct colours)
+      "gen_glossy"    : cornell_glossy (a (Mt)Refract and a (Mt)Unreal box: refracted / reflected cones) + a 64 x 64 unorm8 noise
+                        texture whose chain is GENERATED (TracerParameters.genMips, Gaussian radius 2)
+      "sphere_mirror" : cornell_sphere with the smooth-normal sphere made a (Mt)Reflect mirror (curvature widens the reflected cone)
+                        + mip_debug_texture
+    Returns the scene dict with `uvs`, `textures`, `albedo_texture` (per material id) and, for "gen_glossy", `gen_mips`."""
+    if kind == "gen_glossy":
+        c = cornell_glossy()
+    elif kind == "sphere_mirror":
+        c = cornell_sphere()
+        m = c["material"].copy()
+        sphere = np.arange(m.shape[0]) >= 24          # the sphere's triangles follow the 24 kept box triangles
+        m[sphere] = 4
+        c["material"] = m
+        c["albedo"] = np.concatenate([c["albedo"], np.zeros((1, 3), np.float32)])
+        c["material_type"] = np.array([0, 0, 0, 0, 1], np.uint8)
+    else:
+        c = cornell_box()
+    nq = 18                                            # cornell_box: 18 quads own its 72 vertices (a sphere's vertices follow them)
+    uv = np.zeros((c["positions"].shape[0], 2), np.float32)
+    uv[:4 * nq] = np.tile(np.array([[0, 0], [tile, 0], [tile, tile], [0, tile]], np.float32), (nq, 1))
+    c["uvs"] = uv
+    if kind == "gen_glossy":
+        rng = np.random.default_rng(12)
+        t = rng.integers(0, 256, size=(64, 64, 4), dtype=np.uint8)
+        # low-frequency structure, so that coarse levels differ from each other (pure noise filters to flat grey)
+        g = (np.arange(64) // 16)
+        t[..., 0] = np.clip(t[..., 0] // 2 + 40 * ((g[:, None] + g[None, :]) % 3), 0, 255)
+        t[..., 1] = np.clip(t[..., 1] // 2 + 50 * ((g[:, None] * 2 + g[None, :]) % 3), 0, 255)
+        t[..., 3] = 255
+        c["textures"] = [dict(data=np.ascontiguousarray(t), interp="Linear", edge="Wrap")]
+        c["gen_mips"] = ("Gaussian", 2.0)
+    else:
+        c["textures"] = [mip_debug_texture()]
+    at = np.full(c["albedo"].shape[0], -1, np.int32); at[0] = 0
+    c["albedo_texture"] = at
+    return c

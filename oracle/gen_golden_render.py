@@ -84,6 +84,12 @@ ITEMS = {
     # texture colour conversion at load (TextureMemory::ConvertColorspaces): the textured-albedo scene again, with the fp32
     # texture declared REC_709 + gamma 2.2 and the unorm8 one gamma 2.2, under the tracer's ACES_CG global colour space
     "cornell64_srgbtex_spp16384": (64, 16384, 43, "WithNEEAndMIS", (2, 20), "srgbtex", np.float32, RGB),
+    # mip chains + ray cones (scenes.cornell_mips): explicit levels of distinct colours on strongly tiled UVs — the level every read
+    # takes shows in the image —, the same seen in a smooth-normal MIRROR sphere (curvature term of the reflected cone), and a chain
+    # GENERATED by the tracer (TracerParameters.genMips, Gaussian radius 2) next to a (Mt)Refract / (Mt)Unreal box (refracted cones)
+    "cornell64_mips_explicit_spp16384": (64, 16384, 51, "WithNEEAndMIS", (2, 20), ("mips", "explicit"), np.float32, RGB),
+    "cornell64_mips_sphere_mirror_spp16384": (64, 16384, 52, "WithNEEAndMIS", (2, 20), ("mips", "sphere_mirror"), np.float32, RGB),
+    "cornell64_mips_gen_glossy_spp16384": (64, 16384, 53, "WithNEEAndMIS", (2, 20), ("mips", "gen_glossy"), np.float32, RGB),
     # two-level scene: every batch in its own local space under a (T)Single transform
     "cornell64_single_spp16384": (64, 16384, 6, "WithNEEAndMIS", (2, 20), True, np.float32, RGB),
 }
@@ -139,12 +145,21 @@ def sky_kwargs(single):
 def render(name):
     res, spp, seed, mode, rr, single, dt, renderer = ITEMS[name]
     sky = isinstance(single, tuple) and single[0] == "sky"
-    c = (scenes.cornell_open(keep_light=single[2] == "tex+light") if sky else scenes.cornell_alpha() if single == "alpha"
+    mips = isinstance(single, tuple) and single[0] == "mips"
+    c = (scenes.cornell_mips(single[1]) if mips else scenes.cornell_open(keep_light=single[2] == "tex+light") if sky else scenes.cornell_alpha() if single == "alpha"
          else scenes.cornell_normal_map() if single == "normalmap"
          else scenes.cornell_mirror() if single == "mirror" else scenes.cornell_glossy() if single == "glossy"
          else scenes.cornell_sphere() if single == "sphere" else scenes.cornell_box())
     kw = {}
-    if single == "twosided":
+    if mips:
+        b = O.batched_scene(c["positions"], c["indices"], c["material"], normals=c.get("normals"), uvs=c["uvs"])
+        kw = dict(textures=c["textures"], material_texture=c["albedo_texture"], gen_mips=c.get("gen_mips"))
+        if "material_type" in c:
+            kw["material_kind"] = c["material_type"]
+        if "material_params" in c:
+            kw["material_params"] = c["material_params"]
+        bt = None
+    elif single == "twosided":
         b = O.batched_scene(c["positions"], c["indices"], c["material"])
         kw = dict(light_two_sided=True)
         bt = None

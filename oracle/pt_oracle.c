@@ -109,11 +109,21 @@ typedef struct
     const int32_t* triAlpha;
     /* normal maps: per material -1 or an index into `textures` holding tangent-space normals (NULL = none); needs vertexTBN */
     const int32_t* normalTexture;
+    /* how a textured read turns ray-cone gradients into a mip level (orc_texture_sample_grad): 0 = host backend, 1 = tex2DGrad */
+    uint32_t textureLodMode;
 } pt_scene;
 
 /* One single-level 2-D texture as the reference's host-backend view reads it (Device/CPU/TextureViewCPU.h):
  * format 0 = fp32, 1 = unorm8; interp 0 = nearest, 1 = linear; edge 0 = wrap, 1 = clamp, 2 = mirror. */
-struct orc_texture { const void* data; uint32_t w, h, channels, format, interp, edge; };
+struct orc_texture { const void* data; uint32_t w, h, channels, format, interp, edge, mipCount; };
+/* `data` holds mipCount (0 reads as 1) levels back to back, level k at pixel offset TextureMipPixelStart(size, k) with
+ * TextureMipSize(size, k) = max(size >> k, 1) texels per axis (Core/GraphicsFunctions.h:L474-525): the layout of the
+ * reference's host-backend texture. */
+static uint32_t mip_dim(uint32_t n, uint32_t level) { uint32_t v = n >> level; return v ? v : 1u; }
+static size_t mip_start(uint32_t w, uint32_t h, uint32_t level)
+{ size_t o = 0; for(uint32_t i = 0; i < level; i++) o += (size_t)mip_dim(w, i) * mip_dim(h, i); return o; }
+uint32_t orc_texture_mip_count(uint32_t w, uint32_t h)
+{ uint32_t m = w > h ? w : h, c = 0; while(m) { c++; m >>= 1; } return c; }   /* Bit::RequiredBitsToRepresent(max dim) */
 
 /* TextureViewCPU::ResolveEdge (TextureViewCPU.h:L196-246); C's / and % truncate like the reference's */
 static int tex_edge(int i, int n, uint32_t edge)
@@ -132,9 +142,9 @@ static int tex_edge(int i, int n, uint32_t edge)
     return i;
 }
 /* ReadPixel + Convert (L120-170,L305-340): FromUNorm = v * (1 / 255) */
-static void tex_pixel(const struct orc_texture* t, int x, int y, float out[3])
+static void tex_pixel_level(const struct orc_texture* t, uint32_t level, int x, int y, float out[3])
 {
-    size_t o = ((size_t)y * t->w + (size_t)x) * t->channels;
+    size_t o = (mip_start(t->w, t->h, level) + (size_t)y * mip_dim(t->w, level) + (size_t)x) * t->channels;
     const uint32_t nc = t->channels < 3u ? t->channels : 3u;   /* alpha maps are single-channel: missing channels read 0 */
     out[0] = out[1] = out[2] = 0.0f;
     if(t->format == 0u) { const float* f = (const float*)t->data + o; for(uint32_t k = 0; k < nc; k++) out[k] = f[k]; return; }
@@ -147,13 +157,14 @@ static float tex_lerp(float a, float b, float t) { volatile float x = a * (1.0f 
 /* TracerTexView<2, Vector3>::operator()(uv, dpdx, dpdy) for a texture with ONE mip level: the mip level computed
  * from the gradients clamps to 0 (L429-470), leaving NearestPixel (L248-260) or FindInterpolants +
  * ReadInterpolatedPixel (L262-300,L352-385) on the base level. */
-void orc_texture_sample(const struct orc_texture* t, float u, float v, float out[3])
+static void texture_sample_level(const struct orc_texture* t, uint32_t level, float u, float v, float out[3])
 {
-    float tu = u * (float)t->w, tv = v * (float)t->h;
+    const uint32_t w = mip_dim(t->w, level), h = mip_dim(t->h, level);
+    float tu = u * (float)w, tv = v * (float)h;
     if(t->interp == 0u)
     {
         int x = (int)roundf(tu - 0.5f), y = (int)roundf(tv - 0.5f);
-        tex_pixel(t, tex_edge(x, (int)t->w, t->edge), tex_edge(y, (int)t->h, t->edge), out);
+        tex_pixel_level(t, level, tex_edge(x, (int)w, t->edge), tex_edge(y, (int)h, t->edge), out);
         return;
     }
     float bx, by;
@@ -161,12 +172,99 @@ void orc_texture_sample(const struct orc_texture* t, float u, float v, float out
     int x0 = (int)bx, y0 = (int)by;
     if(fx < 0.0f) { x0 -= 1; fx = fabsf(fx); }   /* as the reference: |frac|, not 1 - |frac| */
     if(fy < 0.0f) { y0 -= 1; fy = fabsf(fy); }
-    int xa = tex_edge(x0, (int)t->w, t->edge), xb = tex_edge(x0 + 1, (int)t->w, t->edge);
-    int ya = tex_edge(y0, (int)t->h, t->edge), yb = tex_edge(y0 + 1, (int)t->h, t->edge);
+    int xa = tex_edge(x0, (int)w, t->edge), xb = tex_edge(x0 + 1, (int)w, t->edge);
+    int ya = tex_edge(y0, (int)h, t->edge), yb = tex_edge(y0 + 1, (int)h, t->edge);
     float p00[3], p10[3], p01[3], p11[3];
-    tex_pixel(t, xa, ya, p00); tex_pixel(t, xb, ya, p10); tex_pixel(t, xa, yb, p01); tex_pixel(t, xb, yb, p11);
+    tex_pixel_level(t, level, xa, ya, p00); tex_pixel_level(t, level, xb, ya, p10);
+    tex_pixel_level(t, level, xa, yb, p01); tex_pixel_level(t, level, xb, yb, p11);
     for(int k = 0; k < 3; k++)
         out[k] = tex_lerp(tex_lerp(p00[k], p10[k], fx), tex_lerp(p01[k], p11[k], fx), fy);
+}
+void orc_texture_sample(const struct orc_texture* t, float u, float v, float out[3]) { texture_sample_level(t, 0u, u, v, out); }
+/* TextureViewCPU::operator()(uv, mipLevel) (TextureViewCPU.h:L422-470): level clamped to [0, mipCount - 1], ModFInt; LINEAR =
+ * Math::Lerp of the two levels' bilinear reads; NEAREST = the nearer level's nearest texel (the reference resolves the edge
+ * of that read against the BASE size, L446 — an out-of-range index there; here the level's own size). */
+void orc_texture_sample_lod(const struct orc_texture* t, float u, float v, float mipLevel, float out[3])
+{
+    const uint32_t mc = t->mipCount ? t->mipCount : 1u;
+    const float top = (float)(mc - 1u);
+    mipLevel = mipLevel < 0.0f ? 0.0f : (mipLevel > top ? top : mipLevel);   /* Math::Clamp; NaN (log2 of 0 * ...) cannot occur: -inf clamps */
+    if(!(mipLevel >= 0.0f)) mipLevel = 0.0f;
+    float ip; const float frac = modff(mipLevel, &ip);
+    const uint32_t m0 = (uint32_t)ip, m1 = (m0 + 1u > mc - 1u) ? mc - 1u : m0 + 1u;
+    if(t->interp == 0u) { texture_sample_level(t, frac < 0.5f ? m0 : m1, u, v, out); return; }
+    float a[3]; texture_sample_level(t, m0, u, v, a);
+    if(m0 == m1) { out[0] = a[0]; out[1] = a[1]; out[2] = a[2]; return; }
+    float b[3]; texture_sample_level(t, m1, u, v, b);
+    for(int k = 0; k < 3; k++) out[k] = tex_lerp(a[k], b[k], frac);
+}
+/* TextureViewCPU::operator()(uv, dpdx, dpdy) (L405-420): level = 0.5 log2(max |gradient|^2). lodMode 0 = as the reference's host
+ * backend reads a normalised-coordinate texture (the gradients stay in UV units); 1 = as the device backends' tex2DGrad
+ * (gradients scaled by the base size first). */
+void orc_texture_sample_grad(const struct orc_texture* t, float u, float v, const float dpdx[2], const float dpdy[2], uint32_t lodMode, float out[3])
+{
+    float ax = dpdx[0], ay = dpdx[1], bx = dpdy[0], by = dpdy[1];
+    if(lodMode == 1u) { ax *= (float)t->w; ay *= (float)t->h; bx *= (float)t->w; by *= (float)t->h; }
+    const float la = fmaf(ay, ay, ax * ax), lb = fmaf(by, by, bx * bx);   /* Math::LengthSqr = Dot: an FMA chain (Core/Math.h:L1586-1596) */
+    const float m = la > lb ? la : lb;
+    orc_texture_sample_lod(t, u, v, 0.5f * log2f(m), out);
+}
+
+static float gauss_pdf_mu(float x, float sig, float mu);
+static float lerp_u(float a, float b, float t);
+static float mitchell_1d(float x, float rr);
+/* <Filter>::Evaluate(duv) of Tracer/Filters.h (L110-117 Box, L153-164 Tent, L202-206 Gaussian, L257-278 Mitchell-Netravali) */
+static float filter_evaluate(uint32_t type, float r, float x, float y)
+{
+    if(type == 0u) { float rr = 1.0f / r; return (fabsf(x) <= r && fabsf(y) <= r) ? 0.25f * rr * rr : 0.0f; }
+    if(type == 1u) { float rcp = 1.0f / r, cap = 1.0f / r; return lerp_u(cap, 0.0f, fabsf(x * rcp)) * lerp_u(cap, 0.0f, fabsf(y * rcp)); }
+    if(type == 3u) { float rcp = 1.0f / r; return mitchell_1d(x, rcp) * mitchell_1d(y, rcp); }
+    const float sigma = r * 0.285714f;
+    return gauss_pdf_mu(x, sigma, 0.0f) * gauss_pdf_mu(y, sigma, 0.0f);
+}
+/* TextureMemory::GenerateMipmaps -> KCGenerateMipmaps (Tracer/TextureFilter.cu:L55-118,L126-198,L1064-1096): every level k >=
+ * firstLevel of `chain` (a full chain buffer whose levels < firstLevel are valid) is filtered from level k - 1: 8 x 8 stratified
+ * offsets over [-r, r]^2 (FilterMode::ACCUMULATE), weight = Evaluate(offset), the parent texel nearest to the offset pixel centre
+ * (ConvertPixelIndices + RoundInt), sum / weight sum. fp32 texels are written as they are, unorm8 texels — filtered as their
+ * 0..255 integer values — are rounded and clamped (GenericWrite). */
+void orc_texture_generate_mips(void* chain, uint32_t w, uint32_t h, uint32_t channels, uint32_t format, uint32_t firstLevel,
+                               uint32_t mipCount, uint32_t filterType, float radius)
+{
+    for(uint32_t level = firstLevel ? firstLevel : 1u; level < mipCount; level++)
+    {
+        const uint32_t mw = mip_dim(w, level), mh = mip_dim(h, level), pw = mip_dim(w, level - 1u), ph = mip_dim(h, level - 1u);
+        const size_t dst = mip_start(w, h, level), src = mip_start(w, h, level - 1u);
+        for(uint32_t y = 0; y < mh; y++) for(uint32_t x = 0; x < mw; x++)
+        {
+            float acc[4] = {0, 0, 0, 0}, wsum = 0.0f;
+            for(uint32_t sy = 0; sy < 8u; sy++) for(uint32_t sx = 0; sx < 8u; sx++)
+            {
+                const float dxy = 1.0f / 8.0f;
+                const float xi0 = dxy * 0.5f + dxy * (float)sx, xi1 = dxy * 0.5f + dxy * (float)sy;
+                const float ox = xi0 * 2.0f * radius - radius, oy = xi1 * 2.0f * radius - radius;
+                const float wgt = filter_evaluate(filterType, radius, ox, oy);
+                /* ConvertPixelIndices(pix + offset, parentRes, mipRes) */
+                float rx = ((float)x + ox + 0.5f) * ((float)pw / (float)mw) - 0.5f, ry = ((float)y + oy + 0.5f) * ((float)ph / (float)mh) - 0.5f;
+                rx = rx < 0.0f ? 0.0f : (rx > (float)pw - 1.0f ? (float)pw - 1.0f : rx);
+                ry = ry < 0.0f ? 0.0f : (ry > (float)ph - 1.0f ? (float)ph - 1.0f : ry);
+                const size_t o = (src + (size_t)lroundf(ry) * pw + (size_t)lroundf(rx)) * channels;
+                for(uint32_t c = 0; c < channels; c++)
+                {
+                    const float px = format == 0u ? ((const float*)chain)[o + c] : (float)((const uint8_t*)chain)[o + c];
+                    volatile float term = wgt * px;
+                    acc[c] += term;
+                }
+                wsum += wgt;
+            }
+            const size_t o = (dst + (size_t)y * mw + x) * channels;
+            for(uint32_t c = 0; c < channels; c++)
+            {
+                const float v = acc[c] / wsum;
+                if(format == 0u) ((float*)chain)[o + c] = v;
+                else { float r = roundf(v); r = r < 0.0f ? 0.0f : (r > 255.0f ? 255.0f : r); ((uint8_t*)chain)[o + c] = (uint8_t)r; }
+            }
+        }
+    }
 }
 
 /* spectrum_oracle.c */
@@ -183,7 +281,8 @@ static s4 s_mul(s4 a, float k) { return S(a.v[0] * k, a.v[1] * k, a.v[2] * k, a.
 static s4 s_mulv(s4 a, s4 b) { return S(a.v[0] * b.v[0], a.v[1] * b.v[1], a.v[2] * b.v[2], a.v[3] * b.v[3]); }
 static s4 s_add(s4 a, s4 b) { return S(a.v[0] + b.v[0], a.v[1] + b.v[1], a.v[2] + b.v[2], a.v[3] + b.v[3]); }
 /* LambertMaterial ctor (MaterialsDefault.hpp:L17-25): albedo = ConvertAlbedo(albedoMap(uv, dpdx, dpdy)) */
-static s4 albedo_at(const pt_scene* s, uint32_t m, const float waves[4], uint32_t prim, float a, float b, float c)
+void orc_texture_sample_grad(const struct orc_texture* t, float u, float v, const float dpdx[2], const float dpdy[2], uint32_t lodMode, float out[3]);
+static s4 albedo_at(const pt_scene* s, uint32_t m, const float waves[4], uint32_t prim, float a, float b, float c, const float dpdx[2], const float dpdy[2])
 {
     float rgb[3] = {s->albedo[3 * m], s->albedo[3 * m + 1], s->albedo[3 * m + 2]};
     if(s->albedoTexture && s->albedoTexture[m] >= 0)
@@ -195,7 +294,7 @@ static s4 albedo_at(const pt_scene* s, uint32_t m, const float waves[4], uint32_
             u = s->uv[2 * ix[0]] * a + s->uv[2 * ix[1]] * b + s->uv[2 * ix[2]] * c;
             v = s->uv[2 * ix[0] + 1] * a + s->uv[2 * ix[1] + 1] * b + s->uv[2 * ix[2] + 1] * c;
         }
-        orc_texture_sample(s->textures + s->albedoTexture[m], u, v, rgb);
+        orc_texture_sample_grad(s->textures + s->albedoTexture[m], u, v, dpdx, dpdy, s->textureLodMode, rgb);
     }
     if(!s->spectrum) return S(rgb[0], rgb[1], rgb[2], 0.0f);
     s4 o; orc_convert_albedo(s->spectrum, rgb, waves, o.v); return o;
@@ -323,7 +422,8 @@ void orc_pt_filter_sample(float radius, float xi0, float xi1, float out[5])
 }
 
 /* ---- the four film filters of Tracer/Filters.h ---- */
-static float gauss_pdf_mu(float x, float sig, float mu) { float si = 1.0f / sig, p = (x - mu) * si; return 0.3989422804f * si * expf(-0.5f * p * p); }
+/* Math::Gaussian (Core/Math.h:L1032-1042); InvSqrt2Pi = (1 / Sqrt2<float>) * (1 / SqrtPi<float>) evaluated in float = 0x1.988452p-2 (one ulp under 1 / sqrt(2 pi)) */
+static float gauss_pdf_mu(float x, float sig, float mu) { float si = 1.0f / sig, p = (x - mu) * si; return 0x1.988452p-2f * si * expf(-0.5f * p * p); }
 static float gauss_sample_mu(float xi, float sig, float mu, float* pdf)
 {   /* Common::SampleGaussian(xi, sigma, mu) (DistributionFunctions.h:L686-705) */
     double e, y = 2.0 * xi - 1.0;
@@ -627,6 +727,133 @@ static v3 tbn_normal_mapped(const float* q0, const float* q1, const float* q2, f
     return add(mul(r0, nTS.x), mul(add(mul(r1, nTS.y), mul(r2, nTS.z)), sg));
 }
 
+/* ---- ray cones (Tracer/TracerTypes.h:L48-69,L323-383; RT Gems I ch. 20, Akenine-Moller et al. JCGT 10(1)) ---- */
+typedef struct { float aperture, width; } cone_t;
+typedef struct { cone_t front, back; float betaN; } cone_surf;
+static cone_t cone_advance(cone_t c, float t)
+{   /* RayCone::Advance: width + aperture * t, clamped to [Epsilon, 1e6] */
+    float w = c.width + c.aperture * t;
+    w = w < 1.0e-5f ? 1.0e-5f : (w > 1.0e6f ? 1.0e6f : w);
+    cone_t r = {c.aperture, w}; return r;
+}
+static void cone_project(cone_t c, v3 f, v3 d, v3* a1, v3* a2)
+{   /* RayCone::Project (JCGT eq. 8, 9): the two axes of the cone's footprint ellipse on the plane with normal f */
+    const float EPS = 1.0e-5f;
+    const float fd = dot(f, d);
+    if(fabsf(fd + 1.0f) < EPS) d = add(d, V(EPS, EPS, EPS));
+    v3 h1 = sub(d, mul(f, fd)), h2 = cross(f, h1);
+    const float r = c.width * 0.5f;
+    float den1 = len(sub(h1, mul(d, dot(d, h1)))); if(den1 < EPS) den1 = EPS;
+    float den2 = len(sub(h2, mul(d, dot(d, h2)))); if(den2 < EPS) den2 = EPS;
+    *a1 = mul(h1, r / den1); *a2 = mul(h2, r / den2);
+}
+static v3 quat_z(const float* q)
+{   /* Quaternion::OrthoBasisZ (Core/Quaternion.hpp:L256-270), q = (w, x, y, z) */
+    const float v00 = q[0] * q[0], v01 = q[0] * q[1], v02 = q[0] * q[2], v11 = q[1] * q[1], v13 = q[1] * q[3], v22 = q[2] * q[2], v23 = q[2] * q[3], v33 = q[3] * q[3];
+    return V(v13 - v02 + v13 - v02, v23 + v01 + v23 + v01, v00 - v11 - v22 + v33);
+}
+/* The ray-cone half of Triangle::GenerateSurface (PrimitiveDefaultTriangle.hpp:L495-569): curvature estimate betaN from the
+ * vertex normals along the triangle's edges (JCGT eq. 6), and the UV differences dpdx / dpdy over the footprint's axes
+ * (listing 1). gN = the geometric normal already flipped towards the ray, dDotN = dot(unflipped normal, dir). */
+static void cone_surface(const v3 p[3], const float* q0, const float* q1, const float* q2, const float* uv0, const float* uv1, const float* uv2,
+                         float a, float b, v3 pos, v3 gN, float dDotN, v3 dirN, cone_t cone, cone_surf* out, float dpdx[2], float dpdy[2])
+{
+    v3 a1, a2; cone_project(cone, gN, dirN, &a1, &a2);
+    const v3 r0 = nrm(a1), r1 = nrm(a2);
+    const v3 e[3] = {sub(p[1], p[0]), sub(p[2], p[0]), sub(p[2], p[1])};
+    float k[3] = {0, 0, 0};
+    if(q0)
+    {
+        const v3 n0 = quat_z(q0), n1 = quat_z(q1), n2 = quat_z(q2);
+        k[0] = dot(sub(n1, n0), e[0]) / dot(e[0], e[0]);
+        k[1] = dot(sub(n2, n0), e[1]) / dot(e[1], e[1]);
+        k[2] = dot(sub(n2, n1), e[2]) / dot(e[2], e[2]);
+    }
+    uint32_t mn = 0, mx = 0;
+    for(uint32_t i = 1; i < 3; i++) { if(k[i] < k[mn]) mn = i; if(k[i] > k[mx]) mx = i; }
+    const float eMin[2] = {dot(r0, e[mn]), dot(r1, e[mn])}, eMax[2] = {dot(r0, e[mx]), dot(r1, e[mx])};
+    const float a1L = len(a1), a2L = len(a2), a1S = a1L * a1L, a2S = a2L * a2L, a12 = a1L * a2L;
+    const float l0 = a12 * (1.0f / sqrtf(a1S * eMin[0] * eMin[0] + a2S * eMin[1] * eMin[1]));
+    const float l1 = a12 * (1.0f / sqrtf(a1S * eMax[0] * eMax[0] + a2S * eMax[1] * eMax[1]));
+    const float lMaxRecip = 1.0f / (l0 > l1 ? l0 : l1);
+    const float k0 = k[mn] * l0 * lMaxRecip, k1 = k[mx] * l1 * lMaxRecip;
+    const float beta0 = -1.0f * k0 * fabsf(cone.width) / dDotN, beta1 = -1.0f * k1 * fabsf(cone.width) / dDotN;
+    out->front = cone; out->back = cone;
+    out->betaN = (fabsf(cone.aperture + beta0) >= fabsf(cone.aperture + beta1)) ? beta0 : beta1;
+    /* texture gradients: barycentrics of pos + axis, UV there minus UV here */
+    const float areaRecip = 1.0f / dot(gN, cross(e[0], e[1]));
+    const float c = 1.0f - a - b;
+    const float u = uv0[0] * a + uv1[0] * b + uv2[0] * c, v = uv0[1] * a + uv1[1] * b + uv2[1] * c;
+    const v3 axes[2] = {a1, a2};
+    float* outs[2] = {dpdx, dpdy};
+    for(int i = 0; i < 2; i++)
+    {
+        const v3 eP = add(sub(pos, p[0]), axes[i]);
+        const float ba = dot(gN, mul(cross(eP, e[1]), areaRecip)), bb = dot(gN, mul(cross(e[0], eP), areaRecip)), bc = 1.0f - ba - bb;
+        outs[i][0] = (uv0[0] * bc + uv1[0] * ba + uv2[0] * bb) - u;
+        outs[i][1] = (uv0[1] * bc + uv1[1] * ba + uv2[1] * bb) - v;
+    }
+}
+static cone_t cone_after_scatter(const cone_surf* cs, v3 wI, v3 n)
+{   /* RayConeSurface::ConeAfterScatter: reflected cones widen by twice the curvature term, refracted ones take the back cone */
+    cone_t f = {cs->front.aperture + 2.0f * cs->betaN, cs->front.width}, b = {cs->back.aperture - cs->betaN, cs->back.width};
+    return dot(wI, n) > 0.0f ? f : b;
+}
+static void rot2(float vx, float vy, float alpha, float u[2], float l[2])
+{   /* Rotate2D_UL: v turned by +alpha and by -alpha */
+    const float sn = sinf(alpha), cs = cosf(alpha);
+    u[0] = vx * cs - vy * sn; u[1] = vx * sn + vy * cs;
+    l[0] = vx * cs + vy * sn; l[1] = vx * -sn + vy * cs;
+}
+static void refract2(const float v[2], const float n[2], float fromEta, float toEta, float out[2])
+{   /* Refract2D: Graphics::Refract(n, -v) in the plane; under total internal reflection the tangential direction */
+    const float er = fromEta / toEta, cosIn = -(n[0] * v[0] + n[1] * v[1]);
+    float sinIn2 = 1.0f - cosIn * cosIn; if(sinIn2 < 0) sinIn2 = 0;
+    const float sinOut2 = er * er * sinIn2;
+    if(sinOut2 >= 1.0f)
+    {
+        const float nd = n[0] * v[0] + n[1] * v[1];
+        float tx = v[0] - n[0] * nd, ty = v[1] - n[1] * nd; const float l = sqrtf(tx * tx + ty * ty);
+        out[0] = tx / l; out[1] = ty / l; return;
+    }
+    const float cosOut = sqrt_max(1.0f - sinOut2);
+    out[0] = er * v[0] + (er * cosIn - cosOut) * n[0]; out[1] = er * v[1] + (er * cosIn - cosOut) * n[1];
+}
+/* RefractMaterial::RefractRayCone (MaterialsDefault.hpp:L355-462, after RT Gems II ch. 10 / Falcor): the back cone of a surface
+ * whose refraction exists — the upper and lower edge rays of the cone refracted in the plane of incidence through normals
+ * tilted by the curvature term. fromEta / toEta already swapped for a back-side hit; gN flipped towards wO. */
+static cone_surf refract_ray_cone(cone_surf in, v3 wO, v3 gN, float fromEta, float toEta)
+{
+    const float er = fromEta / toEta, cosIn3 = dot(gN, wO);
+    float sinIn2 = 1.0f - cosIn3 * cosIn3; if(sinIn2 < 0) sinIn2 = 0;
+    if(er * er * sinIn2 >= 1.0f) return in;
+    const float cosOut3 = sqrt_max(1.0f - er * er * sinIn2);
+    const v3 t3 = add(mul(wO, -er), mul(gN, er * cosIn3 - cosOut3)), d3 = mul(wO, -1.0f);
+    const v3 x = nrm(sub(d3, mul(gN, dot(d3, gN)))), y = gN;
+    const float d[2] = {dot(x, d3), dot(y, d3)};
+    (void)t3;
+    const float aperture = in.front.aperture, width = in.front.width;
+    const float wSign = width > 0.0f ? 1.0f : 0.0f;
+    float du[2], dl[2]; rot2(d[0], d[1], wSign * aperture * 0.5f, du, dl);
+    float od[2] = {-d[1] * width * 0.5f, d[0] * width * 0.5f};
+    const float uHitX = +od[0] + du[0] * (-od[1] / du[1]), lHitX = -od[0] + dl[0] * (+od[1] / dl[1]);
+    const float nSign = uHitX > lHitX ? 1.0f : -1.0f;
+    const float dN = -in.betaN * nSign * 0.5f;
+    float nu[2], nl[2]; rot2(0.0f, 1.0f, dN, nu, nl);
+    float tu[2], tl[2]; refract2(du, nu, fromEta, toEta, tu); refract2(dl, nl, fromEta, toEta, tl);
+    od[0] = -d[1]; od[1] = d[0];
+    float wl = -uHitX * tu[1]; wl /= od[0] * -tu[1] + od[1] * tu[0];
+    float wu = +lHitX * tl[1]; wu /= od[0] * -tl[1] + od[1] * tl[0];
+    const float sign = copysignf(1.0f, tu[0] * tl[1] - tu[1] * tl[0]);
+    float ct = tu[0] * tl[0] + tu[1] * tl[1]; ct = ct < -1.0f ? -1.0f : (ct > 1.0f ? 1.0f : ct);
+    float ap = acosf(ct) * sign; if(ap < 1.0e-5f) ap = 1.0e-5f;
+    cone_surf r = in;
+    r.back.aperture = ap + in.betaN; r.back.width = wu + wl;
+    return r;
+}
+static int scene_has_mips(const pt_scene* s)
+{ for(uint32_t t = 0; t < s->nTextures; t++) if(s->textures[t].mipCount > 1u) return 1; return 0; }
+
 static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, float* filmW, float waves[4], float wavePdf[4]);
 static v3 path(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, float* filmW)
 {
@@ -671,6 +898,10 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
         orc_sample_wavelengths((int)s->wavelengthMode, &rn, 1, waves, wavePdf);
     }
     s4 throughput = S(1, 1, 1, 1), radiance = S(0, 0, 0, 0);
+    /* CameraPinhole::EvaluateRay (CamerasDefault.hpp:L134-139): aperture = 2 tan(fovY / 2) / resolution.y, width 0. The cone only
+     * matters to textures with more than one mip level, so it is tracked only then. */
+    const int useCones = scene_has_mips(s);
+    cone_t cone = {2.0f * tanf(s->fovXY[1] * 0.5f) / (float)s->height, 0.0f};
     uint32_t depth = 0; int type = 3; /* CAMERA_RAY */
     float prevPdf = 0;
     const uint32_t nLights = s->nLightTris + 1u; /* + boundary (Null) light, MetaLight.hpp:L514-516 */
@@ -718,7 +949,18 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
             }
             break;
         }
-        const int backSide = dot(gN, nrm(d)) > 0;
+        const float dDotN = dot(gN, nrm(d));
+        const int backSide = dDotN > 0;
+        cone_surf cs = {cone, cone, 0.0f}; float dpdx[2] = {0, 0}, dpdy[2] = {0, 0};
+        if(useCones)
+        {   /* KCRenderWork (RenderWork.kt.h:L65): the cone arrives advanced by the hit distance */
+            const uint32_t* vi = s->idx + 3 * (size_t)prim;
+            static const float zero2[2] = {0, 0};
+            const float* q0 = s->vertexTBN ? s->vertexTBN + 4 * (size_t)vi[0] : NULL; const float* q1 = s->vertexTBN ? s->vertexTBN + 4 * (size_t)vi[1] : NULL;
+            const float* q2 = s->vertexTBN ? s->vertexTBN + 4 * (size_t)vi[2] : NULL;
+            cone_surface(p, q0, q1, q2, s->uv ? s->uv + 2 * (size_t)vi[0] : zero2, s->uv ? s->uv + 2 * (size_t)vi[1] : zero2, s->uv ? s->uv + 2 * (size_t)vi[2] : zero2,
+                         a, b, hitPos, backSide ? mul(gN, -1.0f) : gN, dDotN, nrm(d), cone_advance(cone, t), &cs, dpdx, dpdy);
+        }
         v3 sN = gN;   /* shading normal: the interpolated tangent frame's Z axis when the group has a NORMAL attribute */
         int normalMapped = 0;
         if(s->vertexTBN)
@@ -729,7 +971,7 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
             {
                 float u = 0, v = 0, px3[3];
                 if(s->uv) { u = s->uv[2 * vi[0]] * a + s->uv[2 * vi[1]] * b + s->uv[2 * vi[2]] * c; v = s->uv[2 * vi[0] + 1] * a + s->uv[2 * vi[1] + 1] * b + s->uv[2 * vi[2] + 1] * c; }
-                orc_texture_sample(&s->textures[s->normalTexture[m]], u, v, px3);
+                orc_texture_sample_grad(&s->textures[s->normalTexture[m]], u, v, dpdx, dpdy, s->textureLodMode, px3);
                 sN = nrm(tbn_normal_mapped(q0, q1, q2, a, b, nrm(V(px3[0], px3[1], px3[2])), backSide));
                 normalMapped = 1;
             }
@@ -747,6 +989,7 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
             depth += 1;
             if(depth >= s->rrHi) break;
             prevPdf = 1.0f; type = 1; /* SPECULAR_RAY */
+            cone = cone_after_scatter(&cs, wI, gN);
             o = nudge(hitPos, gN); d = wI; tMin = 1.0e-4f; tMax = FLT_MAX;
             continue;
         }
@@ -778,11 +1021,12 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
             if(depth >= s->rrHi) break;
             throughput = (pdfS == 0) ? S(0, 0, 0, 0) : s_mul(s_mul(throughput, pdfS), 1.0f / pdfS);
             prevPdf = pdfS; type = 1; /* SPECULAR_RAY */
+            if(useCones) { cone_surf cr = refract_ray_cone(cs, wO, gN, fromEta, toEta); cone = cone_after_scatter(&cr, nrm(wI), gN); }
             o = nudge(nudge(hitPos, sN), refl ? gN : mul(gN, -1.0f)); d = nrm(wI); tMin = 1.0e-4f; tMax = FLT_MAX;
             continue;
         }
         /* Lambert / Unreal */
-        s4 alb = albedo_at(s, (uint32_t)m, waves, prim, a, b, c);
+        s4 alb = albedo_at(s, (uint32_t)m, waves, prim, a, b, c, dpdx, dpdy);
         v3 hlp = fabsf(sN.x) > 0.9f ? V(0, 1, 0) : V(1, 0, 0);
         v3 tX = nrm(cross(hlp, sN)), tY = cross(sN, tX);
         const int unreal = s->materialType && s->materialType[m] == 3u;
@@ -866,6 +1110,7 @@ static s4 path_spectrum(const pt_scene* s, pcg* rng, uint32_t px, uint32_t py, f
         if(dead) break;
         throughput = (pdfB == 0) ? S(0, 0, 0, 0) : s_mul(throughput, 1.0f / pdfB);
         prevPdf = pdfB; type = specularMat ? 1 : 2; /* SPECULAR_RAY after a near-mirror, else PATH_RAY */
+        cone = cone_after_scatter(&cs, wI, gN);
         o = nudge(hitPos, gN); d = wI; tMin = 1.0e-4f; tMax = FLT_MAX;
     }
     return radiance;

@@ -28,13 +28,13 @@ struct DriverScene
     const float* batchTransforms; const int32_t* batchInstanceOf;
     uint32_t textureCount; const uint32_t* textureInfo; const uint8_t* textureBytes; const int32_t* materialTexture; const float* uvs; const uint8_t* materialKind; const uint8_t* lightTwoSided; const float* materialParams;
     uint32_t boundaryType; float boundaryRadiance[3]; int32_t boundaryTexture; const float* boundaryTransform;
-    const int32_t* batchAlphaMap; const int32_t* materialNormalMap;
+    const int32_t* batchAlphaMap; const int32_t* materialNormalMap; const uint32_t* textureMipCounts;
 };
 struct DriverRender
 {
     const char* rendererName; uint32_t width, height; uint32_t totalSPP; const char* sampleMode;
     uint32_t rrRange[2]; uint64_t seed; uint32_t accelMode; uint32_t parallelHint; uint32_t threads; uint32_t samplerType; uint32_t region[4]; uint32_t latency; uint32_t burstSize; uint32_t camSwitchAfter; float camSwitch[9];
-    uint32_t filmFilter; float filmFilterRadius;
+    uint32_t filmFilter; float filmFilterRadius; uint32_t genMips; uint32_t mipGenFilter; float mipGenFilterRadius;
 };
 struct DriverStats { double commitSeconds, renderSeconds, totalPaths; uint32_t iterations; float sceneAABB[6]; double startSeconds, sceneSeconds, closeSeconds, totalSeconds; };
 using RenderF = int (*)(const char*, const DriverScene*, const DriverRender*, float*, float*, DriverStats*, char*, size_t);
@@ -45,7 +45,7 @@ int main(int argc, char** argv)
     FILE* f = std::fopen(argv[1], "rb");
     if(!f) { std::perror("blob"); return 65; }
     uint64_t n = 0;
-    if(std::fread(&n, 8, 1, f) != 1 || (n < 23 || n > 27)) { std::fprintf(stderr, "bad blob\n"); return 66; }
+    if(std::fread(&n, 8, 1, f) != 1 || (n < 23 || n > 28)) { std::fprintf(stderr, "bad blob\n"); return 66; }
     std::vector<std::vector<uint64_t>> sec(n);     // 8-byte aligned storage
     std::vector<uint64_t> bytes(n);
     for(uint64_t i = 0; i < n; i++)
@@ -85,6 +85,7 @@ int main(int argc, char** argv)
     }
     if(n > 25) sc.batchAlphaMap = static_cast<const int32_t*>(P(25));   // 25 batchAlphaMap (i32 per batch; may be empty)
     if(n > 26) sc.materialNormalMap = static_cast<const int32_t*>(P(26));   // 26 materialNormalMap (i32 per material; may be empty)
+    if(n > 27) sc.textureMipCounts = static_cast<const uint32_t*>(P(27));   // 27 textureMipCounts (u32 per texture; may be empty)
     std::memcpy(sc.camPos, cam, 12); std::memcpy(sc.camGaze, cam + 3, 12); std::memcpy(sc.camUp, cam + 6, 12);
     std::memcpy(sc.fovXY, cam + 9, 8); std::memcpy(sc.nearFar, cam + 11, 8);
     DriverRender rd{};
@@ -96,6 +97,7 @@ int main(int argc, char** argv)
     rd.latency = u[16]; rd.burstSize = u[17]; rd.camSwitchAfter = u[18];
     std::memcpy(rd.camSwitch, u + 19, sizeof(rd.camSwitch));
     if(bytes[3] >= 30 * 4) { rd.filmFilter = u[28]; std::memcpy(&rd.filmFilterRadius, u + 29, 4); }
+    if(bytes[3] >= 33 * 4) { rd.genMips = u[30]; rd.mipGenFilter = u[31]; std::memcpy(&rd.mipGenFilterRadius, u + 32, 4); }   // TracerParameters.genMips / mipGenFilter
 
     char self[PATH_MAX]; ssize_t k = readlink("/proc/self/exe", self, sizeof(self) - 1);
     if(k <= 0) return 67;

@@ -16,6 +16,9 @@
 //                  (AcceleratorLBVH.hpp:L109-167, Core/Ray.hpp:L121-219); the leaf functor mirrors
 //                  AcceleratorLBVH::ClosestHit / FirstHit / IntersectionCheck (hpp:L225-410)
 //                  for a triangle group without alpha maps.
+//   texture     -> TextureMemory (CreateTexture2D / PushTextureData per level / Finalize = ConvertColorspaces + GenerateMipmaps,
+//                  Tracer/TextureMemory.cpp) and the resulting TracerTexView<2, Vector3>::operator()(uv, mipLevel | dpdx, dpdy)
+//                  (Tracer/TextureView.hpp -> Device/CPU/TextureViewCPU.h)
 #include "Tracer/AcceleratorLBVH.h"
 #include "Tracer/AcceleratorLBVH.hpp"
 #include "Tracer/PrimitiveDefaultTriangle.h"
@@ -26,6 +29,12 @@
 #include "Device/GPUAlgRadixSort.h"
 #include "Device/GPUAlgGeneric.h"
 #include "Core/GraphicsFunctions.h"
+#include "Core/TracerI.h"
+#include "Tracer/TextureMemory.h"
+#include "Tracer/TextureFilter.h"
+#include "Tracer/TextureView.h"
+#include "Tracer/TextureView.hpp"
+#include "Tracer/GenericGroup.h"
 
 #include <memory>
 #include <vector>
@@ -273,6 +282,69 @@ void ref_linear_trace(const float* positions, uint32_t nVerts,
         }
         outPrim[r] = best; outT[r] = tMM[1];
     }
+}
+
+// One RGBA texture through the reference's TextureMemory, then `n` reads of its view. format 0 = MR_RGBA_FLOAT, 1 = MR_RGBA8_UNORM;
+// `chain` holds suppliedMips levels back to back; genMips = TracerParameters.genMips with mipGenFilter {filterType, filterRadius};
+// lod != NULL: view(uv, lod[i]); else view(uv, grads[4 i .. 4 i + 1], grads[4 i + 2 .. 4 i + 3]). Returns 0, or -1 on an exception.
+int ref_texture_sample(const void* chain, uint32_t w, uint32_t h, uint32_t format, uint32_t interp, uint32_t edge,
+                       uint32_t suppliedMips, uint32_t genMips, uint32_t filterType, float filterRadius,
+                       const float* uv, const float* lod, const float* grads, uint32_t n, float* out)
+{
+    try
+    {
+        Queue();
+        TracerParameters tp;
+        tp.genMips = genMips != 0;
+        tp.mipGenFilter = FilterType{FilterType::E(filterType), filterRadius};
+        FilterGeneratorMap fmap;
+        fmap.emplace(TextureFilterBox::TypeName, &GenerateType<TextureFilterI, TextureFilterBox, const GPUSystem&, Float>);
+        fmap.emplace(TextureFilterTent::TypeName, &GenerateType<TextureFilterI, TextureFilterTent, const GPUSystem&, Float>);
+        fmap.emplace(TextureFilterGaussian::TypeName, &GenerateType<TextureFilterI, TextureFilterGaussian, const GPUSystem&, Float>);
+        fmap.emplace(TextureFilterMitchellNetravali::TypeName, &GenerateType<TextureFilterI, TextureFilterMitchellNetravali, const GPUSystem&, Float>);
+        TextureMemory tm(*gSystem, tp, fmap);
+        MRayTextureParameters p;
+        p.pixelType = MRayPixelTypeRT(format == 0 ? MRayPixelEnum::MR_RGBA_FLOAT : MRayPixelEnum::MR_RGBA8_UNORM);
+        p.colorSpace = MRayColorSpaceEnum::MR_DEFAULT;
+        p.gamma = Float(1);
+        p.interpolation = MRayTextureInterpEnum(interp); p.edgeResolve = MRayTextureEdgeResolveEnum(edge);
+        p.readMode = MRayTextureReadMode::MR_DROP_1;
+        TextureId id = tm.CreateTexture2D(Vector2ui(w, h), suppliedMips, p);
+        tm.CommitTextures();
+        const Byte* src = reinterpret_cast<const Byte*>(chain);
+        for(uint32_t level = 0; level < suppliedMips; level++)
+        {
+            const size_t pixels = size_t(std::max(w >> level, 1u)) * std::max(h >> level, 1u);
+            if(format == 0)
+            {
+                TransientData d(std::in_place_type_t<Vector4>{}, pixels);
+                d.Push(Span<const Vector4>(reinterpret_cast<const Vector4*>(src), pixels));
+                tm.PushTextureData(id, level, std::move(d));
+                src += pixels * sizeof(Vector4);
+            }
+            else
+            {
+                TransientData d(std::in_place_type_t<Vector4uc>{}, pixels);
+                d.Push(Span<const Vector4uc>(reinterpret_cast<const Vector4uc*>(src), pixels));
+                tm.PushTextureData(id, level, std::move(d));
+                src += pixels * 4;
+            }
+        }
+        tm.Finalize();
+        gSystem->SyncAll();
+        const GenericTextureView& gv = tm.TextureViews().at(id).value().get();
+        const auto& view = std::get<TracerTexView<2, Vector3>>(gv);
+        for(uint32_t i = 0; i < n; i++)
+        {
+            Vector2 q(uv[2 * i], uv[2 * i + 1]);
+            Vector3 r = lod ? view(q, lod[i])
+                            : view(q, Vector2(grads[4 * i], grads[4 * i + 1]), Vector2(grads[4 * i + 2], grads[4 * i + 3]));
+            out[3 * i] = r[0]; out[3 * i + 1] = r[1]; out[3 * i + 2] = r[2];
+        }
+        return 0;
+    }
+    catch(const MRayError& e) { fprintf(stderr, "ref_texture_sample: %s\n", e.GetError().c_str()); return -1; }
+    catch(const std::exception& e) { fprintf(stderr, "ref_texture_sample: %s\n", e.what()); return -1; }
 }
 
 } // extern "C"

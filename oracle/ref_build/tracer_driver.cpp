@@ -81,6 +81,9 @@ struct DriverScene
     // optional normal maps: per material -1 or a texture index (RGBA texture read as Vector3): the optional texture-only
     // "normalMap" attribute of (Mt)Lambert / (Mt)Unreal
     const int32_t*  materialNormalMap;
+    // optional: per texture the number of mip levels supplied (NULL = 1 each): CreateTexture2D(size, mipCount, ...) and one
+    // PushTextureData per level; the levels lie back to back from the texture's byte offset, level k = max(size >> k, 1) texels
+    const uint32_t* textureMipCounts;
 };
 
 struct DriverRender
@@ -106,6 +109,11 @@ struct DriverRender
     // (1 Box, 2 Tent, 3 Gaussian, 4 Mitchell-Netravali); filmFilterRadius = 0 keeps the default radius
     uint32_t    filmFilter;
     float       filmFilterRadius;
+    // TracerParameters.genMips / mipGenFilter: genMips = 1 completes every texture's chain by filtering; mipGenFilter = 0 keeps the
+    // default (Gaussian, radius 2), else FilterType::E + 1 with mipGenFilterRadius
+    uint32_t    genMips;
+    uint32_t    mipGenFilter;
+    float       mipGenFilterRadius;
 };
 
 struct DriverStats
@@ -193,6 +201,9 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
         tp.samplerType = SamplerType::E(rd->samplerType);
         if(rd->filmFilter) tp.filmFilter.type = FilterType::E(rd->filmFilter - 1u);
         if(rd->filmFilterRadius > 0.0f) tp.filmFilter.radius = rd->filmFilterRadius;
+        tp.genMips = rd->genMips != 0;
+        if(rd->mipGenFilter) tp.mipGenFilter.type = FilterType::E(rd->mipGenFilter - 1u);
+        if(rd->mipGenFilterRadius > 0.0f) tp.mipGenFilter.radius = rd->mipGenFilterRadius;
         tracer = construct(tp);
         // as MRay/RunCommand.cpp:L1015-1025: worker threads run the tracer's device-init function
         ThreadPool pool;
@@ -276,38 +287,47 @@ int tracer_driver_render(const char* dllPath, const DriverScene* sc, const Drive
             tp.interpolation = MRayTextureInterpEnum(ti[3]); tp.edgeResolve = MRayTextureEdgeResolveEnum(ti[4]);
             if(ti[2] < 2) tp.readMode = MRayTextureReadMode::MR_DROP_1;   // RGBA pixels read as Vector3 (TextureReadMode::TO_3C_FROM_4C): the albedo's view type
             else { tp.readMode = MRayTextureReadMode::MR_PASSTHROUGH; tp.isColor = AttributeIsColor::IS_PURE_DATA; }   // alpha maps
-            texIds.push_back(tracer->CreateTexture2D(Vector2ui(ti[0], ti[1]), 1, tp));
+            texIds.push_back(tracer->CreateTexture2D(Vector2ui(ti[0], ti[1]), sc->textureMipCounts ? sc->textureMipCounts[t] : 1u, tp));
         }
         tracer->CommitTextures();
         for(uint32_t t = 0; t < sc->textureCount; t++)
         {
             const uint32_t* ti = sc->textureInfo + 8 * size_t(t);
             const Byte* src = reinterpret_cast<const Byte*>(sc->textureBytes) + ti[5];
-            size_t pixels = size_t(ti[0]) * ti[1];
-            // TransientData is typed by the pixel (the reference reads it back with AccessAs<PixelType>)
-            if(ti[2] == 0)
+            const uint32_t levels = sc->textureMipCounts ? sc->textureMipCounts[t] : 1u;
+            for(uint32_t level = 0; level < levels; level++)
             {
-                TransientData d(std::in_place_type_t<Vector4>{}, pixels);
-                d.Push(Span<const Vector4>(reinterpret_cast<const Vector4*>(src), pixels));
-                tracer->PushTextureData(texIds[t], 0, std::move(d));
-            }
-            else if(ti[2] == 2)
-            {
-                TransientData d(std::in_place_type_t<Float>{}, pixels);
-                d.Push(Span<const Float>(reinterpret_cast<const Float*>(src), pixels));
-                tracer->PushTextureData(texIds[t], 0, std::move(d));
-            }
-            else if(ti[2] == 3)
-            {
-                TransientData d(std::in_place_type_t<uint8_t>{}, pixels);
-                d.Push(Span<const uint8_t>(reinterpret_cast<const uint8_t*>(src), pixels));
-                tracer->PushTextureData(texIds[t], 0, std::move(d));
-            }
-            else
-            {
-                TransientData d(std::in_place_type_t<Vector4uc>{}, pixels);
-                d.Push(Span<const Vector4uc>(reinterpret_cast<const Vector4uc*>(src), pixels));
-                tracer->PushTextureData(texIds[t], 0, std::move(d));
+                const uint32_t lw = std::max(ti[0] >> level, 1u), lh = std::max(ti[1] >> level, 1u);
+                size_t pixels = size_t(lw) * lh;
+                // TransientData is typed by the pixel (the reference reads it back with AccessAs<PixelType>)
+                if(ti[2] == 0)
+                {
+                    TransientData d(std::in_place_type_t<Vector4>{}, pixels);
+                    d.Push(Span<const Vector4>(reinterpret_cast<const Vector4*>(src), pixels));
+                    tracer->PushTextureData(texIds[t], level, std::move(d));
+                    src += pixels * sizeof(Vector4);
+                }
+                else if(ti[2] == 2)
+                {
+                    TransientData d(std::in_place_type_t<Float>{}, pixels);
+                    d.Push(Span<const Float>(reinterpret_cast<const Float*>(src), pixels));
+                    tracer->PushTextureData(texIds[t], level, std::move(d));
+                    src += pixels * sizeof(Float);
+                }
+                else if(ti[2] == 3)
+                {
+                    TransientData d(std::in_place_type_t<uint8_t>{}, pixels);
+                    d.Push(Span<const uint8_t>(reinterpret_cast<const uint8_t*>(src), pixels));
+                    tracer->PushTextureData(texIds[t], level, std::move(d));
+                    src += pixels;
+                }
+                else
+                {
+                    TransientData d(std::in_place_type_t<Vector4uc>{}, pixels);
+                    d.Push(Span<const Vector4uc>(reinterpret_cast<const Vector4uc*>(src), pixels));
+                    tracer->PushTextureData(texIds[t], level, std::move(d));
+                    src += pixels * 4;
+                }
             }
         }
         // ---- materials: (Mt)Lambert (constant or textured albedo) and, where materialKind says so, (Mt)Reflect ----

@@ -128,6 +128,34 @@ def ref():
     return _ref
 
 
+def ref_texture_sample(texture, uv, lod=None, dpdx=None, dpdy=None):
+    """The reference's own TextureMemory + TracerTexView (oracle/ref_build/ref_taps.cpp::ref_texture_sample): texture = dict(data=RGBA
+    level 0, mips=[...] explicit levels, gen_mips=(filter, radius), interp=, edge=) -> rgb[n, 3] at uv with lod[n] or gradients."""
+    a = np.ascontiguousarray(texture["data"])
+    if a.dtype != np.uint8:
+        a = np.ascontiguousarray(a, np.float32)
+    h, w, ch = a.shape
+    assert ch == 4, "the tap creates MR_RGBA_FLOAT / MR_RGBA8_UNORM textures"
+    levels = [a.reshape(-1, 4)] + [np.ascontiguousarray(m, a.dtype).reshape(-1, 4) for m in (texture.get("mips") or [])]
+    chain = np.ascontiguousarray(np.concatenate(levels, axis=0))
+    gen = texture.get("gen_mips")
+    uv = np.ascontiguousarray(uv, np.float32)
+    out = np.zeros((uv.shape[0], 3), np.float32)
+    lp = gp = None
+    if lod is not None:
+        la = np.ascontiguousarray(lod, np.float32); lp = la.ctypes.data
+    else:
+        ga = np.ascontiguousarray(np.concatenate([np.asarray(dpdx, np.float32), np.asarray(dpdy, np.float32)], axis=1)); gp = ga.ctypes.data
+    L = ref()
+    L.ref_texture_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    rc = L.ref_texture_sample(chain.ctypes.data, w, h, 1 if a.dtype == np.uint8 else 0, _TEX_INTERP[texture.get("interp", "Linear")],
+                              _TEX_EDGE[texture.get("edge", "Wrap")], len(levels), 1 if gen else 0, _MIP_FILTERS[gen[0]] if gen else 2,
+                              float(gen[1]) if gen else 2.0, uv.ctypes.data, C.c_void_p(lp), C.c_void_p(gp), uv.shape[0], out.ctypes.data)
+    assert rc == 0, "reference texture tap failed"
+    return out
+
+
 def ref_build(positions, indices) -> LBVH:
     n = indices.shape[0]
     b = LBVH(n)
@@ -169,7 +197,8 @@ class _DriverScene(C.Structure):
                 ("materialTexture", C.c_void_p), ("uvs", C.c_void_p), ("materialKind", C.c_void_p), ("lightTwoSided", C.c_void_p),
                 ("materialParams", C.c_void_p),
                 ("boundaryType", C.c_uint32), ("boundaryRadiance", C.c_float * 3), ("boundaryTexture", C.c_int32),
-                ("boundaryTransform", C.c_void_p), ("batchAlphaMap", C.c_void_p), ("materialNormalMap", C.c_void_p)]
+                ("boundaryTransform", C.c_void_p), ("batchAlphaMap", C.c_void_p), ("materialNormalMap", C.c_void_p),
+                ("textureMipCounts", C.c_void_p)]
 
 
 class _DriverRender(C.Structure):
@@ -178,7 +207,8 @@ class _DriverRender(C.Structure):
                 ("accelMode", C.c_uint32), ("parallelHint", C.c_uint32), ("threads", C.c_uint32), ("samplerType", C.c_uint32),
                 ("region", C.c_uint32 * 4), ("latency", C.c_uint32), ("burstSize", C.c_uint32),
                 ("camSwitchAfter", C.c_uint32), ("camSwitch", C.c_float * 9),
-                ("filmFilter", C.c_uint32), ("filmFilterRadius", C.c_float)]
+                ("filmFilter", C.c_uint32), ("filmFilterRadius", C.c_float),
+                ("genMips", C.c_uint32), ("mipGenFilter", C.c_uint32), ("mipGenFilterRadius", C.c_float)]
 
 
 class _DriverStats(C.Structure):
@@ -251,8 +281,9 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
                   batch_transforms=None, sampler="Independent", host_exe=False, instance_of=None,
                   textures=None, material_texture=None, region=None, material_kind=None,
                   latency=False, burst_size=1, cam_switch=None, light_two_sided=False, film_filter=None, film_filter_radius=0.0,
-                  material_params=None, boundary=None, alpha_map=None, normal_map=None):
-    """Renders through TracerI. alpha_map: per material id (an index into `albedo`) -1 or a texture index: the batches of
+                  material_params=None, boundary=None, alpha_map=None, normal_map=None, gen_mips=None):
+    """Renders through TracerI. gen_mips: None, or (filter name, radius) = TracerParameters.genMips with that mipGenFilter; a texture
+    dict may carry mips=[level 1, ...] (explicit levels pushed with PushTextureData(id, level, ...)). alpha_map: per material id (an index into `albedo`) -1 or a texture index: the batches of
     that material get SurfaceParams.alphaMaps (such textures are [h, w] or [h, w, 1] arrays: single-channel pure data). boundary: None = (L)Null boundary, or dict(type="Skysphere_Spherical"|"Skysphere_CoOcta",
     radiance=(r, g, b) | texture=index into `textures`, transform=[3, 4] or None). `light_material`: material id whose batch is the prim-backed light.
     batch_transforms: optional [batch, 3, 4] local->world matrices ((T)Single per batch; positions local).
@@ -279,14 +310,16 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
     # TracerParameters.filmFilter: None keeps the default (Gaussian, radius 1)
     filter_id = 0 if film_filter is None else 1 + {"Box": 0, "Tent": 1, "Gaussian": 2, "Mitchell-Netravali": 3}[film_filter]
     io = None if instance_of is None else np.ascontiguousarray(instance_of, np.int32)
-    tinfo = tbytes = mtex = None
+    tinfo = tbytes = mtex = tmips = None
+    mip_filter_id = 0 if not gen_mips else 1 + _MIP_FILTERS[gen_mips[0]]
+    mip_filter_radius = float(gen_mips[1]) if gen_mips else 0.0
     lts = np.array([1 if light_two_sided else 0], np.uint8)
     mkind = None if material_kind is None else np.ascontiguousarray(np.asarray(material_kind, np.uint8)[lambert])
     # per material id 8 floats: kind 2 (Mt)Refract {cauchyFront xyz, -, cauchyBack xyz, -}, kind 3 (Mt)Unreal {roughness, specular, metallic}
     mparams = None if material_params is None else np.ascontiguousarray(np.asarray(material_params, np.float32).reshape(-1, 8)[lambert])
     uvs = None if batched.get("uvs") is None else np.ascontiguousarray(batched["uvs"], np.float32)
     if textures:
-        info, blobs, off = [], [], 0
+        info, blobs, off, mip_counts = [], [], 0, []
         for t in textures:
             a = np.ascontiguousarray(t["data"])
             if a.dtype != np.uint8:
@@ -296,9 +329,12 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
             info.append([a.shape[1], a.shape[0], (1 if a.dtype == np.uint8 else 0) + (2 if single else 0), _TEX_INTERP[t.get("interp", "Linear")],
                          _TEX_EDGE[t.get("edge", "Wrap")], off, (COLOR_SPACES.index(t["color_space"]) + 1) if t.get("color_space") else 0,
                          int(np.float32(t["gamma"]).view(np.uint32)) if t.get("gamma") else 0])
-            blobs.append(a.tobytes()); off += len(blobs[-1]) + (-len(blobs[-1]) % 16)
+            levels = [a] + [np.ascontiguousarray(m, a.dtype) for m in (t.get("mips") or [])]
+            mip_counts.append(len(levels))
+            blobs.append(b"".join(lv.tobytes() for lv in levels)); off += len(blobs[-1]) + (-len(blobs[-1]) % 16)
             blobs[-1] += b"\0" * (-len(blobs[-1]) % 16)
         tinfo = np.array(info, np.uint32); tbytes = np.frombuffer(b"".join(blobs), np.uint8).copy()
+        tmips = np.array(mip_counts, np.uint32)
         mtex = None if material_texture is None else np.ascontiguousarray(np.asarray(material_texture, np.int32)[lambert])
     n_lights = 1 if light_material in mats else 0
     b_type = 0 if boundary is None else {"Skysphere_Spherical": 1, "Skysphere_CoOcta": 2}[boundary["type"]]
@@ -318,7 +354,8 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
         cs = np.zeros(9, np.float32)
         if cam_switch:
             cs[:] = list(cam_switch[1]["eye"]) + list(cam_switch[1]["gaze"]) + list(cam_switch[1]["up"])
-        u = np.concatenate([u, cs.view(np.uint32), np.array([filter_id], np.uint32), np.array([film_filter_radius], np.float32).view(np.uint32)])
+        u = np.concatenate([u, cs.view(np.uint32), np.array([filter_id], np.uint32), np.array([film_filter_radius], np.float32).view(np.uint32),
+                            np.array([1 if gen_mips else 0, mip_filter_id], np.uint32), np.array([mip_filter_radius], np.float32).view(np.uint32)])
         cam = np.array(list(camera["eye"]) + list(camera["gaze"]) + list(camera["up"]) + [fx, fy] + list(near_far), np.float32)
         secs = [dll_path.encode(), renderer.encode(), sample_mode.encode(), u.tobytes(), np.uint64(seed).tobytes(),
                 cam.tobytes(), batched["vertex_offsets"].astype(np.uint32).tobytes(), batched["tri_offsets"].astype(np.uint32).tobytes(),
@@ -332,7 +369,8 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
                 b"" if b_type == 0 else (np.uint32(b_type).tobytes() + b_rad.tobytes() + np.int32(b_tex).tobytes() +
                                          (b"" if b_xf is None else b_xf.tobytes())),
                 b"" if b_alpha is None else b_alpha.tobytes(),
-                b"" if m_normal is None else m_normal.tobytes()]
+                b"" if m_normal is None else m_normal.tobytes(),
+                b"" if tmips is None else tmips.tobytes()]
         with tempfile.TemporaryDirectory() as td:
             with open(os.path.join(td, "in.blob"), "wb") as f:
                 f.write(np.uint64(len(secs)).tobytes())
@@ -368,7 +406,8 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
     if io is not None:
         keep.append(io); sc.batchInstanceOf = io.ctypes.data
     if tinfo is not None:
-        keep += [tinfo, tbytes, mtex]
+        keep += [tinfo, tbytes, mtex, tmips]
+        sc.textureMipCounts = tmips.ctypes.data
         sc.textureCount, sc.textureInfo, sc.textureBytes, sc.materialTexture = len(textures), tinfo.ctypes.data, tbytes.ctypes.data, mtex.ctypes.data
     if uvs is not None:
         keep.append(uvs); sc.uvs = uvs.ctypes.data
@@ -389,7 +428,7 @@ def driver_render(dll_path, batched, albedo, light_material, radiance, camera, w
                        accel_mode, parallel_hint, threads, sampler_id, (C.c_uint32 * 4)(*(region or (0, 0, 0, 0))),
                        1 if latency else 0, burst_size, cam_switch[0] if cam_switch else 0,
                        (C.c_float * 9)(*((list(cam_switch[1]["eye"]) + list(cam_switch[1]["gaze"]) + list(cam_switch[1]["up"])) if cam_switch else [0.0] * 9)),
-                       filter_id, float(film_filter_radius))
+                       filter_id, float(film_filter_radius), 1 if gen_mips else 0, mip_filter_id, mip_filter_radius)
     img = np.zeros((height, width, 3), np.float32)
     wgt = np.zeros((height, width), np.float32)
     st = _DriverStats()
@@ -420,12 +459,59 @@ class _PtScene(C.Structure):
                 ("materialType", C.c_void_p), ("filmFilter", C.c_uint32), ("materialParams", C.c_void_p), ("vertexTBN", C.c_void_p),
                 ("boundaryType", C.c_uint32), ("boundaryTexture", C.c_int32), ("boundaryRadiance", C.c_float * 3),
                 ("boundaryCdfX", C.c_void_p), ("boundaryCdfY", C.c_void_p), ("boundaryM", C.c_float * 9), ("boundaryInvM", C.c_float * 9),
-                ("sceneDiameter", C.c_float), ("triAlpha", C.c_void_p), ("normalTexture", C.c_void_p)]
+                ("sceneDiameter", C.c_float), ("triAlpha", C.c_void_p), ("normalTexture", C.c_void_p), ("textureLodMode", C.c_uint32)]
 
 
 class _OrcTexture(C.Structure):
     _fields_ = [("data", C.c_void_p), ("w", C.c_uint32), ("h", C.c_uint32), ("channels", C.c_uint32),
-                ("format", C.c_uint32), ("interp", C.c_uint32), ("edge", C.c_uint32)]
+                ("format", C.c_uint32), ("interp", C.c_uint32), ("edge", C.c_uint32), ("mipCount", C.c_uint32)]
+
+
+_MIP_FILTERS = {"Box": 0, "Tent": 1, "Gaussian": 2, "Mitchell-Netravali": 3}
+
+
+def mip_dims(w, h, level):
+    """Graphics::TextureMipSize (Core/GraphicsFunctions.h:L479-490)"""
+    return max(w >> level, 1), max(h >> level, 1)
+
+
+def full_mip_count(w, h):
+    """Graphics::TextureMipCount: bits needed for the larger dimension"""
+    return int(max(w, h)).bit_length()
+
+
+def mip_chain(texture):
+    """dict(data=level 0 [h, w, C], mips=[level 1, ...] (optional, explicit), gen_mips=None | (filter name, radius)) ->
+    (chain [total texels, C] in the reference's host layout, mip count). Explicit levels are kept; gen_mips fills the rest of
+    the full chain with the oracle's restatement of KCGenerateMipmaps."""
+    a = np.ascontiguousarray(texture["data"])
+    if a.dtype != np.uint8:
+        a = np.ascontiguousarray(a, np.float32)
+    if a.ndim == 2:
+        a = a[..., None]
+    h, w, ch = a.shape
+    levels = [a] + [np.ascontiguousarray(m, a.dtype).reshape(*mip_dims(w, h, k + 1)[::-1], ch) for k, m in enumerate(texture.get("mips") or [])]
+    count = len(levels)
+    gen = texture.get("gen_mips")
+    if gen:
+        count = full_mip_count(w, h)
+    total = sum(mip_dims(w, h, k)[0] * mip_dims(w, h, k)[1] for k in range(count))
+    chain = np.zeros((total, ch), a.dtype)
+    o = 0
+    for lv in levels:
+        n = lv.shape[0] * lv.shape[1]
+        chain[o:o + n] = lv.reshape(n, ch); o += n
+    if gen and count > len(levels):
+        L = lib()
+        L.orc_texture_generate_mips.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float]
+        L.orc_texture_generate_mips(chain.ctypes.data, w, h, ch, 1 if a.dtype == np.uint8 else 0, len(levels), count, _MIP_FILTERS[gen[0]], float(gen[1]))
+    return chain, count
+
+
+def mip_level(chain, w, h, level):
+    o = sum(mip_dims(w, h, k)[0] * mip_dims(w, h, k)[1] for k in range(level))
+    mw, mh = mip_dims(w, h, level)
+    return chain[o:o + mw * mh].reshape(mh, mw, -1)
 
 
 _TEX_INTERP = {"Nearest": 0, "Linear": 1}
@@ -442,9 +528,12 @@ def _orc_textures(textures):
             a = np.ascontiguousarray(a, np.float32)
         if a.ndim == 2:       # single-channel (alpha map)
             a = a[..., None]
+        arr[k].h, arr[k].w, arr[k].channels = a.shape
+        arr[k].mipCount = 1
+        if t.get("mips") or t.get("gen_mips"):
+            a, arr[k].mipCount = mip_chain(t)
         keep.append(a)
         arr[k].data = a.ctypes.data
-        arr[k].h, arr[k].w, arr[k].channels = a.shape
         arr[k].format = 1 if a.dtype == np.uint8 else 0
         arr[k].interp = _TEX_INTERP[t.get("interp", "Linear")]
         arr[k].edge = _TEX_EDGE[t.get("edge", "Wrap")]
@@ -460,6 +549,23 @@ def oracle_texture_sample(texture, uv):
     L.orc_texture_sample.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p]
     for k in range(uv.shape[0]):
         L.orc_texture_sample(C.addressof(arr), float(uv[k, 0]), float(uv[k, 1]), out[k].ctypes.data)
+    return out
+
+
+def oracle_texture_sample_lod(texture, uv, lod=None, dpdx=None, dpdy=None, lod_mode=0):
+    """TextureViewCPU::operator()(uv, mipLevel) / (uv, dpdx, dpdy) restated: uv[n, 2] with lod[n] or gradients [n, 2] -> rgb[n, 3]."""
+    L = lib()
+    arr, keep = _orc_textures([texture])
+    uv = np.ascontiguousarray(uv, np.float32)
+    out = np.zeros((uv.shape[0], 3), np.float32)
+    L.orc_texture_sample_lod.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    L.orc_texture_sample_grad.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    for k in range(uv.shape[0]):
+        if lod is not None:
+            L.orc_texture_sample_lod(C.addressof(arr), float(uv[k, 0]), float(uv[k, 1]), float(lod[k]), out[k].ctypes.data)
+        else:
+            gx = np.ascontiguousarray(dpdx[k], np.float32); gy = np.ascontiguousarray(dpdy[k], np.float32)
+            L.orc_texture_sample_grad(C.addressof(arr), float(uv[k, 0]), float(uv[k, 1]), gx.ctypes.data, gy.ctypes.data, lod_mode, out[k].ctypes.data)
     return out
 
 
@@ -508,8 +614,9 @@ def oracle_render(positions, indices, tri_material, albedo, radiance, camera, wi
                   sample_mode=2, rr_range=(2, 20), seed=0, near_far=(0.01, 1000.0), threads=None,
                   spectral_data=None, wavelength_mode=2, textures=None, albedo_texture=None, vertex_uvs=None,
                   material_type=None, light_two_sided=None, film_filter=None, film_filter_radius=1.0, material_params=None, vertex_normals=None,
-                  boundary=None, tri_alpha=None, normal_texture=None):
-    """tri_alpha: per triangle -1 or an index into `textures` (an alpha map read through its first channel).
+                  boundary=None, tri_alpha=None, normal_texture=None, texture_lod_mode=0):
+    """texture_lod_mode: 0 = mip level from UV-space gradients (the reference's host backend), 1 = from texel-space gradients (tex2DGrad).
+    tri_alpha: per triangle -1 or an index into `textures` (an alpha map read through its first channel).
     boundary: None = (L)Null, or dict(type="Skysphere_Spherical"|"Skysphere_CoOcta", radiance=(r, g, b) | texture=index, transform=[3, 4],
     scene_diameter=0, luminance_row=ACES_CG). tri_material: per triangle, >= 0 Lambert material index, -1 - k for light k. Returns image[h,w,3]
     (row 0 = bottom) resolved as sum radiance / sum weight. spectral_data (mray_b200.spectral.load())
@@ -535,6 +642,7 @@ def oracle_render(positions, indices, tri_material, albedo, radiance, camera, wi
     s.fovXY = (C.c_float * 2)(fx, fy); s.nearFar = (C.c_float * 2)(*near_far)
     s.width, s.height, s.spp, s.sampleMode = width, height, spp, sample_mode
     s.rrLo, s.rrHi, s.filterRadius, s.seed = rr_range[0], rr_range[1], float(film_filter_radius), seed
+    s.textureLodMode = texture_lod_mode
     s.filmFilter = 0 if film_filter is None else 1 + {"Box": 0, "Tent": 1, "Gaussian": 2, "Mitchell-Netravali": 3}[film_filter]
     if spectral_data is not None:
         tables, keep_tables = spectrum_tables(spectral_data)

@@ -177,6 +177,38 @@ def test_build_large_soup_matches_oracle(gpu_ctx):
     acc.close()
 
 
+def _wide_signature(acc):
+    """The wide tree without what depends on allocation order inside a level (child / triangle base offsets, node order)."""
+    nodes, tris = acc.export_wide()
+    sig = nodes.copy(); sig[:, 4] = 0; sig[:, 5] = 0                 # q1.x = childBase, q1.y = triBase
+    sig = sig[np.lexsort(sig.T[::-1])]
+    t = tris.view(np.uint32)[:, [3, 7, 11]]                           # leaf, rank, flags | range
+    return sig, t[np.lexsort(t.T[::-1])]
+
+
+@pytest.mark.parametrize("mesh", ["cornell", "arcade20k", "arcade264k", "soup300k", "duplicates"])
+def test_group_collapse_builds_the_serial_tree(gpu_ctx, mesh):
+    """KCollapseGroups (eight lanes per wide node, the default) against the one-thread-per-node audit kernel: same nodes, same
+    triangle records, and the same hits through the wide traversal."""
+    if mesh == "cornell":
+        c = scenes.cornell_box(); p, i = c["positions"], c["indices"]
+    elif mesh == "arcade20k": p, i = scenes.arcade_mesh(20000)
+    elif mesh == "arcade264k": p, i = scenes.arcade_mesh()
+    elif mesh == "soup300k": p, i = scenes.random_soup(300_000, seed=11)
+    else:
+        p, i = scenes.arcade_mesh(3000); i = np.ascontiguousarray(np.concatenate([i, i, i]))
+    a = capi.Accelerator(gpu_ctx, p, i)
+    b = capi.Accelerator(gpu_ctx, p, i, flags=capi.MRB_BUILD_SERIAL_COLLAPSE)
+    assert a.info.wideNodeCount == b.info.wideNodeCount > 0
+    (na, ta), (nb, tb) = _wide_signature(a), _wide_signature(b)
+    assert np.array_equal(na, nb) and np.array_equal(ta, tb)
+    rays = scenes.pinhole_rays(160, 90, **scenes.ARCADE_CAMERA)
+    ka, _, ra = gpu_cast(a, rays, capi.MRB_TRACE_WIDE)
+    kb, _, rb = gpu_cast(b, rays, capi.MRB_TRACE_WIDE)
+    assert np.array_equal(ka, kb) and np.array_equal(ra, rb)
+    a.close(); b.close()
+
+
 def test_build_duplicate_codes_reference_delta_audit(gpu_ctx):
     """Repeated codes: REFERENCE_DELTA reproduces the reference's (possibly ill-formed) node list node
     for node; the default build uses the augmented key and still traces correctly."""

@@ -1,0 +1,124 @@
+"""Mip chains and level-of-detail reads: the C restatement (oracle/pt_oracle.c: orc_texture_generate_mips,
+orc_texture_sample_lod / _grad) against golden vectors produced by the reference's own TextureMemory + TracerTexView on its CPU backend
+(oracle/gen_golden_texture.py -> tests/golden/texture_mips.npz). CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "texture_mips.npz")
+
+
+def load_cases():
+    z = np.load(GOLDEN)
+    for name in z["names"]:
+        interp, edge, filt, radius, nmips = z[name + "_params"]
+        t = dict(data=z[name + "_data"], interp=str(interp), edge=str(edge))
+        if int(nmips):
+            t["mips"] = [z[f"{name}_mip{k + 1}"] for k in range(int(nmips))]
+        if str(filt):
+            t["gen_mips"] = (str(filt), float(radius))
+        yield str(name), t, {k: z[f"{name}_{k}"] for k in ["uv", "lod", "dpdx", "dpdy", "rgb_lod", "rgb_grad"]}
+
+
+CASES = {name: (t, v) for name, t, v in load_cases()}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_lod_reads_match_the_reference_bit_for_bit(name):
+    t, v = CASES[name]
+    got = O.oracle_texture_sample_lod(t, v["uv"], lod=v["lod"])
+    assert np.array_equal(got, v["rgb_lod"])
+    got = O.oracle_texture_sample_lod(t, v["uv"], dpdx=v["dpdx"], dpdy=v["dpdy"], lod_mode=0)
+    assert np.array_equal(got, v["rgb_grad"])
+
+
+def test_mip_chain_layout_and_counts():
+    assert [O.full_mip_count(w, h) for w, h in [(1, 1), (2, 1), (32, 16), (20, 12), (64, 64), (65, 3)]] == [1, 2, 6, 5, 7, 7]
+    assert O.mip_dims(20, 12, 3) == (2, 1) and O.mip_dims(20, 12, 4) == (1, 1)
+    t = CASES["gauss2_u8_npot"][0]
+    chain, count = O.mip_chain(t)
+    assert count == 5 and chain.shape == (20 * 12 + 10 * 6 + 5 * 3 + 2 * 1 + 1, 4) and chain.dtype == np.uint8
+    assert np.array_equal(O.mip_level(chain, 12, 20, 0), t["data"])     # (w, h) = (12, 20): data is [h, w, C]
+
+
+def test_box_half_radius_is_the_2x2_average():
+    """A known answer: Box with radius 0.5 weighs the four parents of an even-sized level equally."""
+    rng = np.random.default_rng(3)
+    base = rng.random((8, 8, 4), dtype=np.float32)
+    chain, count = O.mip_chain(dict(data=base, gen_mips=("Box", 0.5)))
+    lvl1 = O.mip_level(chain, 8, 8, 1)
+    expect = base.reshape(4, 2, 4, 2, 4).mean(axis=(1, 3))
+    assert count == 4 and np.allclose(lvl1, expect, rtol=0, atol=2e-6)   # 64 weighted terms per texel
+
+
+def test_constant_texture_stays_constant_through_the_chain():
+    base = np.full((16, 16, 4), 0.37, np.float32)
+    for filt in [("Gaussian", 2.0), ("Tent", 1.5), ("Mitchell-Netravali", 2.0), ("Box", 1.0)]:
+        chain, _ = O.mip_chain(dict(data=base, gen_mips=filt))
+        assert np.allclose(chain, 0.37, rtol=0, atol=1e-6), filt
+
+
+def test_device_lod_mode_is_the_host_mode_with_texel_space_gradients():
+    t, v = CASES["gauss2_f32"]
+    h, w, _ = t["data"].shape
+    size = np.array([w, h], np.float32)
+    host = O.oracle_texture_sample_lod(t, v["uv"], dpdx=v["dpdx"] * size, dpdy=v["dpdy"] * size, lod_mode=0)
+    dev = O.oracle_texture_sample_lod(t, v["uv"], dpdx=v["dpdx"], dpdy=v["dpdy"], lod_mode=1)
+    assert np.array_equal(host, dev)
+
+
+def test_single_level_reads_ignore_the_gradients():
+    t, v = CASES["gauss2_f32"]
+    single = dict(data=t["data"])
+    assert np.array_equal(O.oracle_texture_sample_lod(single, v["uv"], dpdx=v["dpdx"], dpdy=v["dpdy"]), O.oracle_texture_sample(single, v["uv"]))
+    assert np.array_equal(O.oracle_texture_sample_lod(single, v["uv"], lod=v["lod"]), O.oracle_texture_sample(single, v["uv"]))
+
+
+# ---- the estimator oracle with ray cones against the reference's renders of scenes.cornell_mips ----
+from mray_b200 import scenes  # noqa: E402
+
+
+def _rel(a, b):
+    return float(((a - b) ** 2).mean() / (b ** 2).mean())
+
+
+def _bm(img, k):
+    h, w, c = img.shape
+    return img.reshape(h // k, k, w // k, k, c).mean(axis=(1, 3))
+
+
+def _oracle_mip_render(kind, spp, seed, strip=False):
+    c = scenes.cornell_mips(kind)
+    tm = np.where(c["material"] == 3, -1, c["material"].astype(np.int32))
+    textures = [dict(t, gen_mips=c.get("gen_mips")) for t in c["textures"]]
+    if strip:
+        textures = [dict(t, mips=None, gen_mips=None) for t in textures]
+    kw = {}
+    if "material_type" in c:
+        kw["material_type"] = c["material_type"]
+    if "material_params" in c:
+        kw["material_params"] = c["material_params"]
+    if "normals" in c:
+        kw["vertex_normals"] = c["normals"]
+    return O.oracle_render(c["positions"], c["indices"], tm, c["albedo"], c["radiance"], c["camera"], 64, 64, spp, seed=seed,
+                           textures=textures, albedo_texture=c["albedo_texture"], vertex_uvs=c["uvs"], **kw)
+
+
+@pytest.mark.parametrize("kind", ["explicit", "sphere_mirror", "gen_glossy"])
+def test_oracle_ray_cones_match_reference_render(kind):
+    """RayCone::Advance / Project, the curvature and texture-gradient half of Triangle::GenerateSurface, ConeAfterScatter and
+    RefractMaterial::RefractRayCone restated in pt_oracle.c: the level every textured read takes decides the colours of these images."""
+    path = os.path.join(os.path.dirname(__file__), "golden", f"render_cornell64_mips_{kind}_spp16384.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden image was not generated")
+    ref = np.load(path)["img"].astype(np.float32)
+    img = _oracle_mip_render(kind, 1024, 3)
+    assert np.allclose(img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=0.01), (img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)))
+    e = _rel(_bm(img, 4), _bm(ref, 4))
+    assert e <= 1e-3, e
+    if kind != "gen_glossy":
+        flat = _oracle_mip_render(kind, 256, 4, strip=True)
+        assert _rel(_bm(flat, 4), _bm(ref, 4)) > 20 * e
