@@ -400,6 +400,12 @@ typedef struct mrb_texture_desc
     uint32_t    generateMips;
     uint32_t    mipFilterType;
     float       mipFilterRadius;
+    /* TracerParameters.clampedTexRes (0 = none; pass 0 for MRayTextureParameters.ignoreResClamp): a texture whose larger side exceeds it
+     * loses ceil(log2(ceil(maxDim / clamp))) levels (TextureMemory::CreateTexture, Tracer/TextureMemory.cpp:L544-583). With fewer levels
+     * supplied than that, the last supplied level is filtered down to the new level 0 at upload (ClampImageFromBuffer -> KCClampImage,
+     * Tracer/TextureFilter.cu:L206-262: 4 x 4 samples of the mip filter; mipFilterRadius 0 = the default Gaussian, 2); otherwise the
+     * levels that fit are kept. Sizes reported by the taps are the clamped ones. */
+    uint32_t    clampResolution;
 } mrb_texture_desc;
 
 typedef struct mrb_render_desc
@@ -598,6 +604,8 @@ MRB_API mrb_status mrb_texture_convert(mrb_context ctx, const mrb_texture_desc* 
 MRB_API size_t     mrb_texture_chain_texels(uint32_t width, uint32_t height, uint32_t mipCount);
 MRB_API uint32_t   mrb_texture_full_mip_count(uint32_t width, uint32_t height);
 MRB_API mrb_status mrb_texture_mip_chain(mrb_context ctx, const mrb_texture_desc* texture, void* chainOut, uint32_t* mipCountOut);
+/* {width, height, mip count} the renderer will hold `texture` with (clampResolution / generateMips applied); no device work */
+MRB_API mrb_status mrb_texture_final_extent(const mrb_texture_desc* texture, uint32_t extentOut[3]);
 MRB_API mrb_status mrb_texture_sample_lod(mrb_context ctx, const mrb_texture_desc* texture, const float* uv, const float* lod, const float* grads,
                                           uint32_t lodMode, uint32_t count, float* rgbOut);
 

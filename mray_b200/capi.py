@@ -95,7 +95,8 @@ class SpectraLutDesc(C.Structure):
 class TextureDesc(C.Structure):
     _fields_ = [("data", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("channels", C.c_uint32),
                 ("format", C.c_uint32), ("interp", C.c_uint32), ("edge", C.c_uint32), ("gamma", C.c_float), ("colorMatrix", C.c_void_p),
-                ("mipCount", C.c_uint32), ("generateMips", C.c_uint32), ("mipFilterType", C.c_uint32), ("mipFilterRadius", C.c_float)]
+                ("mipCount", C.c_uint32), ("generateMips", C.c_uint32), ("mipFilterType", C.c_uint32), ("mipFilterRadius", C.c_float),
+                ("clampResolution", C.c_uint32)]
 
 
 TEX_INTERP = {"Nearest": 0, "Linear": 1}
@@ -125,6 +126,10 @@ def _fill_texture_desc(t, texture, keep):
         t.mipCount = len(levels)
     if texture.get("gen_mips"):
         t.generateMips, t.mipFilterType, t.mipFilterRadius = 1, FILM_FILTERS[texture["gen_mips"][0]], float(texture["gen_mips"][1])
+    if texture.get("clamp_res"):      # TracerParameters.clampedTexRes; filtered with gen_mips' filter (or clamp_filter, default Gaussian 2)
+        t.clampResolution = int(texture["clamp_res"])
+        if not texture.get("gen_mips") and texture.get("clamp_filter"):
+            t.mipFilterType, t.mipFilterRadius = FILM_FILTERS[texture["clamp_filter"][0]], float(texture["clamp_filter"][1])
     keep.append(a)
     t.data = a.ctypes.data
     if texture.get("color_matrix") is not None:     # RGB -> RGB matrix into the global colour space (row-major 3x3)
@@ -218,6 +223,7 @@ _PROTOTYPES = {
     "mrb_texture_convert": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mrb_texture_chain_texels": (C.c_size_t, [C.c_uint32, C.c_uint32, C.c_uint32]),
     "mrb_texture_full_mip_count": (C.c_uint32, [C.c_uint32, C.c_uint32]),
+    "mrb_texture_final_extent": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "mrb_texture_mip_chain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]),
     "mrb_texture_sample_lod": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "mrb_spectra_lut_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -826,13 +832,20 @@ def texture_sample(ctx: Context, texture, uv):
     return out
 
 
-def texture_mip_chain(ctx: Context, texture):
-    """mrb_texture_mip_chain: (chain [total texels, C] in the texture's dtype, mip count) — supplied levels colour converted,
-    generated levels after them."""
+def texture_final_extent(ctx: Context, texture):
+    """mrb_texture_final_extent: (width, height, mip count) after clampResolution / generateMips."""
     t, keep = _texture_desc(texture)
-    full = ctx.lib.mrb_texture_full_mip_count(t.width, t.height)
-    count = max(t.mipCount, full) if t.generateMips else t.mipCount
-    texels = ctx.lib.mrb_texture_chain_texels(t.width, t.height, count)
+    e = (C.c_uint32 * 3)()
+    ctx.check(ctx.lib.mrb_texture_final_extent(C.byref(t), e))
+    return int(e[0]), int(e[1]), int(e[2])
+
+
+def texture_mip_chain(ctx: Context, texture):
+    """mrb_texture_mip_chain: (chain [total texels, C] in the texture's dtype, mip count, (width, height)) — resolution clamp applied,
+    kept levels colour converted, generated levels after them."""
+    t, keep = _texture_desc(texture)
+    w, h, count = texture_final_extent(ctx, texture)
+    texels = ctx.lib.mrb_texture_chain_texels(w, h, count)
     out = np.zeros((texels, t.channels), keep[0].dtype)
     got = C.c_uint32(0)
     ctx.check(ctx.lib.mrb_texture_mip_chain(ctx.handle, C.byref(t), out.ctypes.data, C.byref(got)))
@@ -855,9 +868,10 @@ def texture_sample_lod(ctx: Context, texture, uv, lod=None, dpdx=None, dpdy=None
 
 
 def texture_convert(ctx: Context, texture):
-    """mrb_texture_convert: the texels after the upload-time gamma / colour-space conversion, same shape and dtype."""
+    """mrb_texture_convert: level 0 after the upload-time gamma / colour-space conversion (and resolution clamp), same dtype."""
     t, keep = _texture_desc(texture)
-    out = np.zeros_like(keep[0])
+    w, h, _ = texture_final_extent(ctx, texture)
+    out = np.zeros((h, w, t.channels), keep[0].dtype)
     ctx.check(ctx.lib.mrb_texture_convert(ctx.handle, C.byref(t), out.ctypes.data))
     return out
 

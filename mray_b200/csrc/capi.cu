@@ -66,6 +66,7 @@ void TextureMipChainHost(Context& ctx, const mrb_texture_desc& td, void* chainOu
 void TextureSampleLodHost(Context& ctx, const mrb_texture_desc& td, const float* uv, const float* lod, const float* grads, uint32_t lodMode, uint32_t n, float* rgbOut);
 size_t TextureChainTexels(uint32_t w, uint32_t h, uint32_t mips);
 uint32_t TextureFullMipCount(uint32_t w, uint32_t h);
+void TextureFinalExtent(const mrb_texture_desc& td, uint32_t out[3]);
 void GenerateSpectraLUT(Context& ctx, const float* cieXYZ, const float* illuminantSPD, float illuminantNorm, const float rgbToXYZ[9],
                         const float xyzToRGB[9], uint32_t res, uint32_t passes, float* lutOut, double whitepointOut[3]);
 void TraceScene(Context& ctx, const SceneData& scn, bool anyHit, mrb_trace_mode mode,
@@ -921,6 +922,12 @@ mrb_status mrb_texture_convert(mrb_context ctx, const mrb_texture_desc* texture,
 
 size_t mrb_texture_chain_texels(uint32_t width, uint32_t height, uint32_t mipCount) { return mrb::TextureChainTexels(width, height, mipCount); }
 uint32_t mrb_texture_full_mip_count(uint32_t width, uint32_t height) { return mrb::TextureFullMipCount(width, height); }
+mrb_status mrb_texture_final_extent(const mrb_texture_desc* texture, uint32_t extentOut[3])
+{
+    if(!texture || !extentOut || texture->width == 0 || texture->height == 0) return MRB_ERR_INVALID_ARG;
+    mrb::TextureFinalExtent(*texture, extentOut);
+    return MRB_OK;
+}
 mrb_status mrb_texture_mip_chain(mrb_context ctx, const mrb_texture_desc* texture, void* chainOut, uint32_t* mipCountOut)
 {
     return Guard(ctx, [&](mrb::Context& c)

@@ -1472,25 +1472,94 @@ __global__ void __launch_bounds__(256) KGenerateMipLevel(TexRec t, uint32_t leve
         }
     }
 }
-// levels a texture ends up with: the supplied ones, or the full chain when mips are generated (TextureMemory::CreateTexture, L588-591)
+// ClampImageFromBuffer -> KCClampImage (Tracer/TextureFilter.cu:L206-262,L1100-1150), TracerParameters.clampedTexRes: the pushed image
+// `src` (sw x sh, the texture's texel format) filtered down to level 0 of t. Per texel 4 x 4 stratified numbers through the mip filter's
+// Sample() (FilterMode::SAMPLING), weight = Evaluate / pdf / 16, the source texel nearest to the offset pixel centre
+// (ConvertPixelIndices + Math::Round), sum / weight sum.
+__global__ void __launch_bounds__(256) KClampImage(TexRec t, const void* __restrict__ src, uint32_t sw, uint32_t sh, uint32_t filterType, float radius)
+{
+    const uint32_t n = t.w * t.h;
+    const float ratioX = float(sw) / float(t.w), ratioY = float(sh) / float(t.h);
+    for(uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u)
+    {
+        const uint32_t x = i % t.w, y = i / t.w;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f}, wsum = 0.0f;
+        for(uint32_t sy = 0; sy < 4u; sy++)
+        for(uint32_t sx = 0; sx < 4u; sx++)
+        {
+            const float dxy = 0.25f, inv = 0.0625f;
+            const float xi0 = __fadd_rn(dxy * 0.5f, __fmul_rn(dxy, float(sx))), xi1 = __fadd_rn(dxy * 0.5f, __fmul_rn(dxy, float(sy)));
+            float ox, oy, pdf, wgt;
+            FilterSample(filterType, radius, xi0, xi1, ox, oy, pdf, wgt);
+            float rx = __fsub_rn(__fmul_rn(__fadd_rn(__fadd_rn(float(x), ox), 0.5f), ratioX), 0.5f);
+            float ry = __fsub_rn(__fmul_rn(__fadd_rn(__fadd_rn(float(y), oy), 0.5f), ratioY), 0.5f);
+            rx = fminf(fmaxf(rx, 0.0f), float(sw) - 1.0f); ry = fminf(fmaxf(ry, 0.0f), float(sh) - 1.0f);
+            const size_t o = (size_t(uint32_t(roundf(ry))) * sw + size_t(uint32_t(roundf(rx)))) * t.channels;
+            for(uint32_t c = 0; c < t.channels; c++)
+            {
+                const float px = (t.format == 0u) ? static_cast<const float*>(src)[o + c] : float(static_cast<const uint8_t*>(src)[o + c]);
+                acc[c] = __fadd_rn(acc[c], __fdiv_rn(__fmul_rn(__fmul_rn(wgt, px), inv), pdf));
+            }
+            wsum = __fadd_rn(wsum, __fdiv_rn(__fmul_rn(wgt, inv), pdf));
+        }
+        const size_t o = size_t(i) * t.channels;
+        for(uint32_t c = 0; c < t.channels; c++)
+        {
+            const float v = __fdiv_rn(acc[c], wsum);
+            if(t.format == 0u) const_cast<float*>(static_cast<const float*>(t.data))[o + c] = v;
+            else const_cast<uint8_t*>(static_cast<const uint8_t*>(t.data))[o + c] = uint8_t(fminf(fmaxf(roundf(v), 0.0f), 255.0f));
+        }
+    }
+}
+// TracerParameters.clampedTexRes (TextureMemory::CreateTexture, Tracer/TextureMemory.cpp:L544-583): the number of levels dropped so that
+// the larger side fits clampResolution = ceil(log2(ceil(maxDim / min(clamp, maxDim)))); 0 = no clamp
+static uint32_t ClampLevels(const mrb_texture_desc& td)
+{
+    if(td.clampResolution == 0u) return 0u;
+    const uint32_t maxDim = max(td.width, td.height), c = min(td.clampResolution, maxDim);
+    return uint32_t(int32_t(ceilf(log2f(float((maxDim + c - 1u) / c)))));
+}
+// levels a texture ends up with: the supplied ones (less the levels the clamp drops, never below one), or the full chain of the final
+// size when mips are generated (TextureMemory::CreateTexture, L556,L588-591)
 static uint32_t SuppliedMips(const mrb_texture_desc& td) { return td.mipCount ? td.mipCount : 1u; }
-static uint32_t FinalMips(const mrb_texture_desc& td) { return td.generateMips ? max(SuppliedMips(td), FullMipCount(td.width, td.height)) : SuppliedMips(td); }
+static uint32_t KeptMips(const mrb_texture_desc& td) { const uint32_t s = SuppliedMips(td), r = ClampLevels(td); return r >= s ? 1u : s - r; }
+static uint32_t FinalWidth(const mrb_texture_desc& td) { return MipDim(td.width, ClampLevels(td)); }
+static uint32_t FinalHeight(const mrb_texture_desc& td) { return MipDim(td.height, ClampLevels(td)); }
+static uint32_t FinalMips(const mrb_texture_desc& td) { return td.generateMips ? max(KeptMips(td), FullMipCount(FinalWidth(td), FinalHeight(td))) : KeptMips(td); }
 static size_t ChainTexels(uint32_t w, uint32_t h, uint32_t mips) { return MipStart(w, h, mips); }
 static void ValidateMips(const mrb_texture_desc& td)
 {
     if(SuppliedMips(td) > FullMipCount(td.width, td.height)) throw std::runtime_error("texture mipCount exceeds the full chain of its size");
-    if(td.generateMips && (td.mipFilterType > FILTER_MITCHELL || !(td.mipFilterRadius > 0.0f))) throw std::runtime_error("bad mip generation filter");
+    if((td.generateMips || (td.clampResolution && td.mipFilterRadius != 0.0f)) && (td.mipFilterType > FILTER_MITCHELL || !(td.mipFilterRadius > 0.0f)))
+        throw std::runtime_error("bad mip generation filter");
 }
-// upload + TextureMemory::Finalize (L809-833): colour conversion of the supplied levels, then the missing levels of the chain
+// upload + TextureMemory::Finalize (L809-833): resolution clamp at load, colour conversion of the kept levels, then the missing levels
+// of the chain. t = the texture at its FINAL size (FinalWidth x FinalHeight, FinalMips levels allocated).
 static void UploadTexture(Context& ctx, TexRec& t, const mrb_texture_desc& td)
 {
     const size_t texel = size_t(t.channels) * (t.format == 0u ? 4u : 1u);
-    const uint32_t supplied = SuppliedMips(td);
-    MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<void*>(t.data), td.data, ChainTexels(t.w, t.h, supplied) * texel, cudaMemcpyHostToDevice, ctx.stream));
-    t.mipCount = supplied;
+    const uint32_t supplied = SuppliedMips(td), drop = ClampLevels(td), kept = KeptMips(td);
+    const char* src = static_cast<const char*>(td.data);
+    if(drop >= supplied && drop > 0u)
+    {   // fewer levels supplied than the clamp drops: the last supplied level is filtered down to the new level 0 (KCClampImage)
+        const uint32_t sl = supplied - 1u, sw = MipDim(td.width, sl), sh = MipDim(td.height, sl);
+        const size_t bytes = size_t(sw) * sh * texel;
+        DeviceBlock stage; stage.Reserve(bytes);
+        MRB_CUDA_TRY(cudaMemcpyAsync(stage.Base(), src + MipStart(td.width, td.height, sl) * texel, bytes, cudaMemcpyHostToDevice, ctx.stream));
+        MRB_LAUNCH(ctx, KClampImage, GridFor(ctx, t.w * t.h, 256u), 256, 0, t, stage.Base(), sw, sh, td.mipFilterRadius > 0.0f ? td.mipFilterType : uint32_t(FILTER_GAUSSIAN),
+                   td.mipFilterRadius > 0.0f ? td.mipFilterRadius : 2.0f);
+        MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream));   // the staging block dies with this scope
+    }
+    else
+    {   // enough levels supplied: levels drop .. supplied - 1 become levels 0 .. kept - 1 (the reference copies the un-shifted levels
+        // here, TextureMemory.cpp:L785-794, which reads the wrong texels; the levels that fit are used instead)
+        MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<void*>(t.data), src + MipStart(td.width, td.height, drop) * texel, ChainTexels(t.w, t.h, kept) * texel,
+                                     cudaMemcpyHostToDevice, ctx.stream));
+    }
+    t.mipCount = kept;
     ConvertTextureColor(ctx, t, td);
     t.mipCount = FinalMips(td);
-    for(uint32_t level = supplied; level < t.mipCount; level++)
+    for(uint32_t level = kept; level < t.mipCount; level++)
         MRB_LAUNCH(ctx, KGenerateMipLevel, GridFor(ctx, MipDim(t.w, level) * MipDim(t.h, level), 256u), 256, 0, t, level, td.mipFilterType, td.mipFilterRadius);
 }
 
@@ -1768,7 +1837,7 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
     {
         if(desc.boundaryTexture >= int32_t(desc.textureCount)) throw std::runtime_error("boundaryTexture index exceeds textureCount");
         d.boundaryTex = desc.boundaryTexture < 0 ? -1 : desc.boundaryTexture;
-        if(d.boundaryTex >= 0) { skyW = desc.textures[d.boundaryTex].width; skyH = desc.textures[d.boundaryTex].height; }
+        if(d.boundaryTex >= 0) { skyW = FinalWidth(desc.textures[d.boundaryTex]); skyH = FinalHeight(desc.textures[d.boundaryTex]); }
         d.boundaryRadiance = make_float4(desc.boundaryRadiance[0], desc.boundaryRadiance[1], desc.boundaryRadiance[2], 0.0f);
         if(desc.boundaryTransform)
         {
@@ -1798,7 +1867,7 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
         if(!td.data || td.width == 0 || td.height == 0 || (td.channels != 3 && td.channels != 4) || td.format > 1u || td.interp > 1u || td.edge > 2u)
             throw std::runtime_error("bad texture descriptor");
         ValidateMips(td);
-        htex[t] = TexRec{nullptr, td.width, td.height, td.channels, td.format, td.interp, td.edge, FinalMips(td)};
+        htex[t] = TexRec{nullptr, FinalWidth(td), FinalHeight(td), td.channels, td.format, td.interp, td.edge, FinalMips(td)};
         if(FinalMips(td) > 1u) { anyMips = true; r.glossy = true; }   // ray cones + level selection live in the full shading kernel
     }
     if(desc.textureLodMode > 1u) throw std::runtime_error("unknown textureLodMode");
@@ -2270,18 +2339,19 @@ static void ValidateTapTexture(const mrb_texture_desc& td)
 static TexRec StageTexture(Context& ctx, const mrb_texture_desc& td, size_t extra, char** extraOut)
 {
     ValidateTapTexture(td);
-    const size_t texBytes = ChainTexels(td.width, td.height, FinalMips(td)) * td.channels * (td.format == 0u ? 4u : 1u);
+    const size_t texBytes = ChainTexels(FinalWidth(td), FinalHeight(td), FinalMips(td)) * td.channels * (td.format == 0u ? 4u : 1u);
     MultiAlloc sz(nullptr); sz.Take<char>(texBytes); sz.Take<char>(extra);
     ctx.scratch.Reserve(sz.Total());
     MultiAlloc ma(ctx.scratch.Base());
     char* dTex = ma.Take<char>(texBytes); char* dExtra = ma.Take<char>(extra);
     if(extraOut) *extraOut = dExtra;
-    TexRec t{dTex, td.width, td.height, td.channels, td.format, td.interp, td.edge, 0u};
+    TexRec t{dTex, FinalWidth(td), FinalHeight(td), td.channels, td.format, td.interp, td.edge, 0u};
     UploadTexture(ctx, t, td);
     return t;
 }
 size_t TextureChainTexels(uint32_t w, uint32_t h, uint32_t mips) { return ChainTexels(w, h, mips); }
 uint32_t TextureFullMipCount(uint32_t w, uint32_t h) { return FullMipCount(w, h); }
+void TextureFinalExtent(const mrb_texture_desc& td, uint32_t out[3]) { out[0] = FinalWidth(td); out[1] = FinalHeight(td); out[2] = FinalMips(td); }
 
 void TextureSampleHost(Context& ctx, const mrb_texture_desc& td, const float* uv, uint32_t n, float* rgbOut)
 {

@@ -69,6 +69,7 @@ struct TextureB200
     float gamma = 1.0f; bool hasColorMatrix = false; float colorMatrix[9] = {};   // TextureMemory::ConvertColorspaces, done on upload
     uint32_t mipCount = 1; std::vector<uint8_t> levelLoaded;   // levels the caller reserved (CreateTexture2D) and pushed so far
     bool genMips = false; uint32_t mipFilterType = 2; float mipFilterRadius = 2.0f;   // TracerParameters.genMips / mipGenFilter
+    uint32_t clampRes = 0;                                                             // TracerParameters.clampedTexRes (0 = ignoreResClamp)
     size_t TexelBytes() const { return size_t(channels) * (format == 0 ? 4u : 1u); }
     static uint32_t LevelDim(uint32_t n, uint32_t level) { return std::max(n >> level, 1u); }
     size_t LevelStart(uint32_t level) const
@@ -87,6 +88,7 @@ struct TextureB200
         d.interp = uint32_t(params.interpolation); d.edge = uint32_t(params.edgeResolve);
         d.gamma = convertColor ? gamma : 1.0f; d.colorMatrix = (convertColor && hasColorMatrix) ? colorMatrix : nullptr;
         d.mipCount = supplied; d.generateMips = genMips ? 1u : 0u; d.mipFilterType = mipFilterType; d.mipFilterRadius = mipFilterRadius;
+        d.clampResolution = clampRes;
         return d;
     }
 };
@@ -660,7 +662,8 @@ class TracerB200 final : public TracerI
         // filtered on upload by libmray_b200 with TracerParameters.mipGenFilter
         t.genMips = params.genMips; t.mipFilterType = uint32_t(params.mipGenFilter.type); t.mipFilterRadius = float(params.mipGenFilter.radius);
         t.pixels.resize(t.LevelStart(mipCount) * t.TexelBytes());
-        if(!p.ignoreResClamp && std::max(size[0], size[1]) > params.clampedTexRes) throw MRayError("textures: clampedTexRes is not supported yet");
+        // TracerParameters.clampedTexRes: applied on upload by libmray_b200 (levels dropped, or the pushed image filtered down)
+        t.clampRes = p.ignoreResClamp ? 0u : params.clampedTexRes;
         textures.push_back(std::move(t));
         return TextureId(uint32_t(textures.size()));
     }
@@ -958,7 +961,7 @@ class TracerB200 final : public TracerI
                 used.push_back(uint32_t(g.alpha[k]));
                 const TextureB200& t = textures[size_t(g.alpha[k]) - 1];
                 atex.push_back(t.Desc(false));   // pure data: no colour conversion; read at level 0 (IntersectionCheck has no gradients)
-                atex.back().mipCount = 1; atex.back().generateMips = 0;
+                atex.back().mipCount = 1; atex.back().generateMips = 0; atex.back().clampResolution = 0;   // alpha maps stay at full resolution
             }
             if(!used.empty())
             {

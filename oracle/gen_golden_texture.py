@@ -26,11 +26,21 @@ def cases():
     yield "explicit3_f32", dict(data=f, mips=explicit)                                # levels pushed by the caller, none generated
     yield "explicit2_then_gen", dict(data=f, mips=explicit[:1], gen_mips=("Gaussian", 2.0))   # level 1 supplied, 2.. generated from it
     yield "nearest_f32", dict(data=f, gen_mips=("Gaussian", 2.0), interp="Nearest")
+    # TracerParameters.clampedTexRes: the pushed image filtered down at load (KCClampImage), then (optionally) a generated chain
+    g = rng.random((40, 64, 4), dtype=np.float32)
+    yield "clamp16_f32", dict(data=g, clamp_res=16)                                    # 64x40 -> 16x10, one level, default Gaussian 2
+    yield "clamp16_gen_f32", dict(data=g, clamp_res=16, gen_mips=("Gaussian", 2.0))
+    yield "clamp20_tent_f32", dict(data=g, clamp_res=20, gen_mips=("Tent", 1.5))      # 20 does not divide 64: still 2 levels dropped
+    yield "clamp8_u8", dict(data=(g * 255).astype(np.uint8), clamp_res=8, gen_mips=("Gaussian", 2.0))
+    yield "clamp100_noop_f32", dict(data=g, clamp_res=100)
+    yield "clamp8_box_f32", dict(data=g, clamp_res=8, gen_mips=("Box", 1.0))
+    # (Mitchell-Netravali's sampler — a three-Gaussian mixture — matches the restatement to 2e-7, not bit for bit: it is checked
+    #  against the oracle on the GPU only)
 
 
 def main():
     rng = np.random.default_rng(5)
-    n = 600
+    n = 400
     out = {}
     names = []
     for name, t in cases():
@@ -48,7 +58,7 @@ def main():
         for k, m in enumerate(t.get("mips") or []):
             out[f"{name}_mip{k + 1}"] = m
         out[name + "_params"] = np.array([t.get("interp", "Linear"), t.get("edge", "Wrap"), (t.get("gen_mips") or ("", 0))[0],
-                                          str((t.get("gen_mips") or ("", 0))[1]), str(len(t.get("mips") or []))])
+                                          str((t.get("gen_mips") or ("", 0))[1]), str(len(t.get("mips") or [])), str(int(t.get("clamp_res") or 0))])
         out[name + "_uv"], out[name + "_lod"], out[name + "_dpdx"], out[name + "_dpdy"] = uv, lod, dpdx, dpdy
         out[name + "_rgb_lod"] = O.ref_texture_sample(t, uv, lod=lod)
         out[name + "_rgb_grad"] = O.ref_texture_sample(t, uv, dpdx=dpdx, dpdy=dpdy)

@@ -267,6 +267,54 @@ void orc_texture_generate_mips(void* chain, uint32_t w, uint32_t h, uint32_t cha
     }
 }
 
+void orc_pt_filter_sample_typed(uint32_t type, float radius, float xi0, float xi1, float out[5]);
+/* TracerParameters.clampedTexRes (TextureMemory::CreateTexture, Tracer/TextureMemory.cpp:L544-583): levels dropped so that the larger
+ * side fits `clampRes` = ceil(log2(ceil(maxDim / min(clampRes, maxDim)))) */
+uint32_t orc_texture_clamp_levels(uint32_t w, uint32_t h, uint32_t clampRes)
+{
+    const uint32_t maxDim = w > h ? w : h, c = clampRes < maxDim ? clampRes : maxDim;
+    if(c == 0u) return 0u;
+    const uint32_t ratio = (maxDim + c - 1u) / c;
+    return (uint32_t)(int32_t)ceilf(log2f((float)ratio));
+}
+/* ClampImageFromBuffer -> KCClampImage (Tracer/TextureFilter.cu:L206-262,L1100-1150): the image `src` (sw x sh) filtered down to
+ * dw x dh: per texel 4 x 4 stratified numbers through the mip filter's Sample() (FilterMode::SAMPLING), weight = Evaluate / pdf / 16,
+ * the source texel nearest to the offset pixel centre (ConvertPixelIndices + Math::Round), sum / weight sum. */
+void orc_texture_clamp(const void* src, uint32_t sw, uint32_t sh, void* dst, uint32_t dw, uint32_t dh, uint32_t channels, uint32_t format,
+                       uint32_t filterType, float radius)
+{
+    for(uint32_t y = 0; y < dh; y++) for(uint32_t x = 0; x < dw; x++)
+    {
+        float acc[4] = {0, 0, 0, 0}, wsum = 0.0f;
+        for(uint32_t sy = 0; sy < 4u; sy++) for(uint32_t sx = 0; sx < 4u; sx++)
+        {
+            const float dxy = 1.0f / 4.0f, inv = dxy * dxy;
+            const float xi0 = dxy * 0.5f + dxy * (float)sx, xi1 = dxy * 0.5f + dxy * (float)sy;
+            float fo[5]; orc_pt_filter_sample_typed(filterType, radius, xi0, xi1, fo);
+            const float wgt = fo[4], pdf = fo[2];
+            float rx = ((float)x + fo[0] + 0.5f) * ((float)sw / (float)dw) - 0.5f, ry = ((float)y + fo[1] + 0.5f) * ((float)sh / (float)dh) - 0.5f;
+            rx = rx < 0.0f ? 0.0f : (rx > (float)sw - 1.0f ? (float)sw - 1.0f : rx);
+            ry = ry < 0.0f ? 0.0f : (ry > (float)sh - 1.0f ? (float)sh - 1.0f : ry);
+            const size_t o = ((size_t)(uint32_t)roundf(ry) * sw + (size_t)(uint32_t)roundf(rx)) * channels;
+            for(uint32_t c = 0; c < channels; c++)
+            {
+                const float px = format == 0u ? ((const float*)src)[o + c] : (float)((const uint8_t*)src)[o + c];
+                volatile float t0 = wgt * px; volatile float t1 = t0 * inv; volatile float t2 = t1 / pdf;
+                acc[c] += t2;
+            }
+            volatile float w0 = wgt * inv; volatile float w1 = w0 / pdf;
+            wsum += w1;
+        }
+        const size_t o = ((size_t)y * dw + x) * channels;
+        for(uint32_t c = 0; c < channels; c++)
+        {
+            const float v = acc[c] / wsum;
+            if(format == 0u) ((float*)dst)[o + c] = v;
+            else { float r = roundf(v); r = r < 0.0f ? 0.0f : (r > 255.0f ? 255.0f : r); ((uint8_t*)dst)[o + c] = (uint8_t)r; }
+        }
+    }
+}
+
 /* spectrum_oracle.c */
 struct orc_spectrum_tables;
 void orc_sample_wavelengths(int mode, const uint32_t* randoms, uint32_t n, float* waves, float* pdfs);
@@ -410,7 +458,8 @@ static float gauss_sample(float xi, float sig)
     return x;
 }
 /* Math::Gaussian(x, sigma) = PDFGaussian = GaussianFilter::Evaluate per axis (Filters.h:L195-227) */
-static float gauss_pdf(float x, float sig) { float p = x / sig; return 0.3989422804f / sig * expf(-0.5f * p * p); }
+static float gauss_pdf_mu(float x, float sig, float mu);
+static float gauss_pdf(float x, float sig) { return gauss_pdf_mu(x, sig, 0.0f); }
 /* GaussianFilter(radius): out = {offset x, offset y, Sample().pdf, Pdf(offset), Evaluate(offset)} */
 void orc_pt_filter_sample(float radius, float xi0, float xi1, float out[5])
 {

@@ -286,15 +286,18 @@ void ref_linear_trace(const float* positions, uint32_t nVerts,
 
 // One RGBA texture through the reference's TextureMemory, then `n` reads of its view. format 0 = MR_RGBA_FLOAT, 1 = MR_RGBA8_UNORM;
 // `chain` holds suppliedMips levels back to back; genMips = TracerParameters.genMips with mipGenFilter {filterType, filterRadius};
-// lod != NULL: view(uv, lod[i]); else view(uv, grads[4 i .. 4 i + 1], grads[4 i + 2 .. 4 i + 3]). Returns 0, or -1 on an exception.
+// lod != NULL: view(uv, lod[i]); else view(uv, grads[4 i .. 4 i + 1], grads[4 i + 2 .. 4 i + 3]). clampedTexRes = 0 keeps the default (no
+// clamp); sizeOut (optional) receives the texture's final {width, height, mip count}. Returns 0, or -1 on an exception.
 int ref_texture_sample(const void* chain, uint32_t w, uint32_t h, uint32_t format, uint32_t interp, uint32_t edge,
                        uint32_t suppliedMips, uint32_t genMips, uint32_t filterType, float filterRadius,
-                       const float* uv, const float* lod, const float* grads, uint32_t n, float* out)
+                       const float* uv, const float* lod, const float* grads, uint32_t n, float* out, uint32_t clampedTexRes,
+                       uint32_t* sizeOut)
 {
     try
     {
         Queue();
         TracerParameters tp;
+        if(clampedTexRes) tp.clampedTexRes = clampedTexRes;   // TextureMemory::CreateTexture drops levels / filters the pushed image down
         tp.genMips = genMips != 0;
         tp.mipGenFilter = FilterType{FilterType::E(filterType), filterRadius};
         FilterGeneratorMap fmap;
@@ -330,8 +333,14 @@ int ref_texture_sample(const void* chain, uint32_t w, uint32_t h, uint32_t forma
                 src += pixels * 4;
             }
         }
+        gSystem->SyncAll();   // the clamp filter of PushTextureData runs asynchronously and Finalize releases its staging buffer
         tm.Finalize();
         gSystem->SyncAll();
+        if(sizeOut)
+        {
+            const GenericTexture& gt = tm.Textures().at(id).value().get();
+            sizeOut[0] = gt.Extents()[0]; sizeOut[1] = gt.Extents()[1]; sizeOut[2] = gt.MipCount();
+        }
         const GenericTextureView& gv = tm.TextureViews().at(id).value().get();
         const auto& view = std::get<TracerTexView<2, Vector3>>(gv);
         for(uint32_t i = 0; i < n; i++)

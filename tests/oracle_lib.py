@@ -128,7 +128,7 @@ def ref():
     return _ref
 
 
-def ref_texture_sample(texture, uv, lod=None, dpdx=None, dpdy=None):
+def ref_texture_sample(texture, uv, lod=None, dpdx=None, dpdy=None, return_size=False):
     """The reference's own TextureMemory + TracerTexView (oracle/ref_build/ref_taps.cpp::ref_texture_sample): texture = dict(data=RGBA
     level 0, mips=[...] explicit levels, gen_mips=(filter, radius), interp=, edge=) -> rgb[n, 3] at uv with lod[n] or gradients."""
     a = np.ascontiguousarray(texture["data"])
@@ -146,14 +146,16 @@ def ref_texture_sample(texture, uv, lod=None, dpdx=None, dpdy=None):
         la = np.ascontiguousarray(lod, np.float32); lp = la.ctypes.data
     else:
         ga = np.ascontiguousarray(np.concatenate([np.asarray(dpdx, np.float32), np.asarray(dpdy, np.float32)], axis=1)); gp = ga.ctypes.data
+    size = np.zeros(3, np.uint32)
     L = ref()
     L.ref_texture_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
-                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
     rc = L.ref_texture_sample(chain.ctypes.data, w, h, 1 if a.dtype == np.uint8 else 0, _TEX_INTERP[texture.get("interp", "Linear")],
                               _TEX_EDGE[texture.get("edge", "Wrap")], len(levels), 1 if gen else 0, _MIP_FILTERS[gen[0]] if gen else 2,
-                              float(gen[1]) if gen else 2.0, uv.ctypes.data, C.c_void_p(lp), C.c_void_p(gp), uv.shape[0], out.ctypes.data)
+                              float(gen[1]) if gen else 2.0, uv.ctypes.data, C.c_void_p(lp), C.c_void_p(gp), uv.shape[0], out.ctypes.data,
+                              int(texture.get("clamp_res") or 0), size.ctypes.data)
     assert rc == 0, "reference texture tap failed"
-    return out
+    return (out, tuple(int(x) for x in size)) if return_size else out
 
 
 def ref_build(positions, indices) -> LBVH:
@@ -480,6 +482,13 @@ def full_mip_count(w, h):
     return int(max(w, h)).bit_length()
 
 
+def clamped_size(w, h, clamp_res):
+    """Size of a texture under TracerParameters.clampedTexRes (TextureMemory::CreateTexture)"""
+    L = lib()
+    L.orc_texture_clamp_levels.restype = C.c_uint32
+    return mip_dims(w, h, L.orc_texture_clamp_levels(w, h, int(clamp_res)))
+
+
 def mip_chain(texture):
     """dict(data=level 0 [h, w, C], mips=[level 1, ...] (optional, explicit), gen_mips=None | (filter name, radius)) ->
     (chain [total texels, C] in the reference's host layout, mip count). Explicit levels are kept; gen_mips fills the rest of
@@ -491,6 +500,24 @@ def mip_chain(texture):
         a = a[..., None]
     h, w, ch = a.shape
     levels = [a] + [np.ascontiguousarray(m, a.dtype).reshape(*mip_dims(w, h, k + 1)[::-1], ch) for k, m in enumerate(texture.get("mips") or [])]
+    if texture.get("clamp_res"):
+        # TracerParameters.clampedTexRes: drop `reduce` levels; with fewer levels supplied, filter the last one down (KCClampImage)
+        L = lib()
+        L.orc_texture_clamp_levels.restype = C.c_uint32
+        reduce = L.orc_texture_clamp_levels(w, h, int(texture["clamp_res"]))
+        if reduce > 0:
+            nw, nh = mip_dims(w, h, reduce)
+            if reduce > len(levels) - 1:
+                src = levels[-1]
+                dst = np.zeros((nh, nw, ch), a.dtype)
+                gen0 = texture.get("gen_mips") or texture.get("clamp_filter") or ("Gaussian", 2.0)
+                L.orc_texture_clamp.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float]
+                L.orc_texture_clamp(src.ctypes.data, src.shape[1], src.shape[0], dst.ctypes.data, nw, nh, ch, 1 if a.dtype == np.uint8 else 0,
+                                    _MIP_FILTERS[gen0[0]], float(gen0[1]))
+                levels = [dst]
+            else:
+                levels = levels[reduce:]
+            a = levels[0]; h, w, ch = a.shape
     count = len(levels)
     gen = texture.get("gen_mips")
     if gen:
@@ -530,8 +557,10 @@ def _orc_textures(textures):
             a = a[..., None]
         arr[k].h, arr[k].w, arr[k].channels = a.shape
         arr[k].mipCount = 1
-        if t.get("mips") or t.get("gen_mips"):
+        if t.get("mips") or t.get("gen_mips") or t.get("clamp_res"):
             a, arr[k].mipCount = mip_chain(t)
+            if t.get("clamp_res"):
+                arr[k].w, arr[k].h = clamped_size(arr[k].w, arr[k].h, t["clamp_res"])
         keep.append(a)
         arr[k].data = a.ctypes.data
         arr[k].format = 1 if a.dtype == np.uint8 else 0

@@ -57,6 +57,25 @@ def test_device_lod_mode_scales_the_gradients_by_the_texture_size(gpu_ctx):
     assert np.allclose(dev, ref, rtol=0, atol=1e-6) and (dev == ref).mean() > 0.9
 
 
+def test_resolution_clamp(gpu_ctx):
+    """TracerParameters.clampedTexRes: final sizes, the filtered level 0 against the oracle (Mitchell-Netravali too), kept levels."""
+    rng = np.random.default_rng(4)
+    g = rng.random((40, 64, 4), dtype=np.float32)
+    assert capi.texture_final_extent(gpu_ctx, dict(data=g, clamp_res=16)) == (16, 10, 1)
+    assert capi.texture_final_extent(gpu_ctx, dict(data=g, clamp_res=20, gen_mips=("Tent", 1.0))) == (16, 10, 5)
+    assert capi.texture_final_extent(gpu_ctx, dict(data=g, clamp_res=4096)) == (64, 40, 1)
+    for filt in [("Mitchell-Netravali", 2.0), ("Tent", 1.0), ("Box", 0.75)]:
+        t = dict(data=g, clamp_res=16, gen_mips=filt)
+        chain, count = capi.texture_mip_chain(gpu_ctx, t)
+        ref, ref_count = O.mip_chain(t)
+        assert count == ref_count == 5 and np.allclose(chain, ref, rtol=0, atol=2e-6), filt
+    lv = [rng.random((8, 8, 4), dtype=np.float32), rng.random((4, 4, 4), dtype=np.float32), rng.random((2, 2, 4), dtype=np.float32)]
+    chain, count = capi.texture_mip_chain(gpu_ctx, dict(data=lv[0], mips=lv[1:], clamp_res=4))     # the levels that fit are kept
+    assert count == 2 and np.array_equal(chain[:16].reshape(4, 4, 4), lv[1]) and np.array_equal(chain[16:].reshape(2, 2, 4), lv[2])
+    conv = capi.texture_convert(gpu_ctx, dict(data=g, clamp_res=16))
+    assert conv.shape == (10, 16, 4) and np.array_equal(conv.reshape(-1, 4), O.mip_chain(dict(data=g, clamp_res=16))[0])
+
+
 def test_large_chain_generation(gpu_ctx):
     """A 1024 x 512 RGBA8 texture: 11 levels, every one equal to the oracle's on all but a stray texel."""
     rng = np.random.default_rng(8)

@@ -14,8 +14,10 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "texture_mips.npz")
 def load_cases():
     z = np.load(GOLDEN)
     for name in z["names"]:
-        interp, edge, filt, radius, nmips = z[name + "_params"]
+        interp, edge, filt, radius, nmips, clamp = z[name + "_params"]
         t = dict(data=z[name + "_data"], interp=str(interp), edge=str(edge))
+        if int(clamp):
+            t["clamp_res"] = int(clamp)
         if int(nmips):
             t["mips"] = [z[f"{name}_mip{k + 1}"] for k in range(int(nmips))]
         if str(filt):
@@ -42,6 +44,19 @@ def test_mip_chain_layout_and_counts():
     chain, count = O.mip_chain(t)
     assert count == 5 and chain.shape == (20 * 12 + 10 * 6 + 5 * 3 + 2 * 1 + 1, 4) and chain.dtype == np.uint8
     assert np.array_equal(O.mip_level(chain, 12, 20, 0), t["data"])     # (w, h) = (12, 20): data is [h, w, C]
+
+
+def test_clamped_sizes_follow_the_reference_rule():
+    """ceil(log2(ceil(maxDim / clamp))) levels dropped (TextureMemory::CreateTexture)"""
+    assert O.clamped_size(64, 40, 16) == (16, 10) and O.clamped_size(64, 40, 20) == (16, 10) and O.clamped_size(64, 40, 32) == (32, 20)
+    assert O.clamped_size(64, 40, 64) == (64, 40) and O.clamped_size(64, 40, 1000) == (64, 40) and O.clamped_size(64, 40, 1) == (1, 1)
+    chain, count = O.mip_chain(CASES["clamp16_gen_f32"][0])
+    assert count == 5 and chain.shape[0] == 16 * 10 + 8 * 5 + 4 * 2 + 2 * 1 + 1
+    # enough levels supplied: the ones that fit are kept as they are (no filtering)
+    rng = np.random.default_rng(1)
+    lv = [rng.random((8, 8, 4), dtype=np.float32), rng.random((4, 4, 4), dtype=np.float32), rng.random((2, 2, 4), dtype=np.float32)]
+    chain, count = O.mip_chain(dict(data=lv[0], mips=lv[1:], clamp_res=4))
+    assert count == 2 and np.array_equal(chain[:16].reshape(4, 4, 4), lv[1]) and np.array_equal(chain[16:].reshape(2, 2, 4), lv[2])
 
 
 def test_box_half_radius_is_the_2x2_average():
