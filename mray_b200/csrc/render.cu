@@ -369,6 +369,7 @@ __device__ __forceinline__ uint32_t PackPD(uint32_t depth, uint32_t status, uint
 
 // Reload of one slot; must be called by all 32 lanes of a warp (warp-aggregated claim). `isFree`: the slot
 // holds no path (its meta.x status is INVALID).
+__device__ __forceinline__ void ReloadClaimed(const RenderData& d, uint32_t i, unsigned long long g);
 __device__ __forceinline__ void ReloadSlot(const RenderData& d, uint32_t i, bool inRange, bool isFree)
 {
     // block-aggregated claim of new path indices: ONE atomic per block on the global counter (same-address
@@ -395,7 +396,12 @@ __device__ __forceinline__ void ReloadSlot(const RenderData& d, uint32_t i, bool
         d.hitKeys[i].primKey = INVALID_U32; // default: boundary (KCSetBoundaryWorkKeysIndirect)
         return;
     }
-    const unsigned long long g = base + __popc(want & ((1u << lane) - 1u));
+    ReloadClaimed(d, i, base + __popc(want & ((1u << lane) - 1u)));
+}
+
+// The slot's next path: camera path `g` of the pass (or nothing once the pass has handed out all its paths)
+__device__ __forceinline__ void ReloadClaimed(const RenderData& d, uint32_t i, unsigned long long g)
+{
     if(g >= d.pathLimit)
     {
         // surplus slot: never traced (KCWriteInvalidRaysIndirect)
@@ -1591,7 +1597,9 @@ __global__ void KIndexInstances(InstanceRec* inst, uint32_t n)
 // End of a bounce for one slot: add the NEE estimate of an unoccluded shadow ray, put finished paths on the
 // film. All inputs are requested up front (one memory round trip). Returns true when the slot is free
 // afterwards; `died` reports a path that finished in this call.
-__device__ __forceinline__ bool FinishSlot(const RenderData& d, uint32_t i, bool& died)
+// A dead path leaves the pool: its last shadow contribution, ConvertSpectrumToRGBIndirect (PathTracerRendererBase.cu:L228-241),
+// ConvertNaNsToColor and the atomic add into the film (planar R,G,B,W).
+__device__ __forceinline__ void FilmDeadPath(const RenderData& d, uint32_t i)
 {
     const uint4 meta = d.meta[i];
     float4 rad = d.radiance[i];
@@ -1599,31 +1607,11 @@ __device__ __forceinline__ bool FinishSlot(const RenderData& d, uint32_t i, bool
     const float4 sr = d.shadowRadiance[i];
     float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f), p4 = w4;
     if(d.spectral) { w4 = d.waves[i]; p4 = d.wavePdf[i]; }
-    const uint32_t pd = meta.x;
-    const uint32_t status = (pd >> 8) & 0xFFu;
-    if(status == ST_INVALID) return true;
-    uint32_t type = (pd >> 16) & 0xFFu;
-    if(type & 0x80u)
-    {
-        // shadow ray of this bounce: add the pre-multiplied NEE estimate when unoccluded
-        if((visWord >> (i & 31u)) & 1u)
-        {
-            rad.x += sr.x; rad.y += sr.y; rad.z += sr.z; rad.w += sr.w;
-            if(status != ST_DEAD) d.radiance[i] = rad;
-        }
-        type &= 0x7Fu;
-    }
-    if(status != ST_DEAD)
-    {
-        d.meta[i].x = PackPD(pd & 0xFFu, ST_ALIVE, type);
-        return false;
-    }
-    // film: ConvertNaNsToColor + atomic add (planar R,G,B,W)
+    if((((meta.x >> 16) & 0xFFu) & 0x80u) && ((visWord >> (i & 31u)) & 1u)) { rad.x += sr.x; rad.y += sr.y; rad.z += sr.z; rad.w += sr.w; }
     float w = __uint_as_float(meta.z);
     Float3 v = F3(rad.x, rad.y, rad.z);
     if(d.spectral)
     {
-        // ConvertSpectrumToRGBIndirect on the dead paths (PathTracerRendererBase.cu:L228-241)
         const float val[4] = {rad.x, rad.y, rad.z, rad.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w}, pp[4] = {p4.x, p4.y, p4.z, p4.w};
         const float3 rgb = SpectraToRGB(d.spec, val, wv, pp);
         v = F3(rgb.x, rgb.y, rgb.z);
@@ -1635,22 +1623,74 @@ __device__ __forceinline__ bool FinishSlot(const RenderData& d, uint32_t i, bool
     atomicAdd(d.film + plane + pix, v.y);
     atomicAdd(d.film + 2 * plane + pix, v.z);
     atomicAdd(d.film + 3 * plane + pix, w);
-    died = true;
     d.meta[i].x = PackPD(0, ST_INVALID, 0);
     d.rays[i].tMin = 1.0f; d.rays[i].tMax = -1.0f;
-    return true;
 }
 
 // The end of bounce k (shadow accumulate, film) fused with the reload of bounce k+1: the slot a path just left is refilled in the same pass
+// Finish + reload of one block of slots. The expensive branch — a dead path's spectrum -> RGB conversion, its four film atomics and
+// the whole camera-ray generation of the slot's next path — concerns about a third of the slots, scattered over the warps (6.7 of 32
+// lanes active per instruction when every thread handled its own slot). So the block first settles the live paths, compacts the
+// indices of the slots to refill into shared memory (ballot order: the same slot <-> path assignment as before) and then lets
+// consecutive threads work through that list with full warps.
 __global__ void __launch_bounds__(RTPB) KFinishReload(RenderData d)
 {
-    const uint32_t i = blockIdx.x * RTPB + threadIdx.x;
+    __shared__ uint16_t sList[RTPB];
+    __shared__ uint32_t sWarpBase[RTPB / 32];
+    __shared__ uint32_t sTotal, sDied;
+    __shared__ unsigned long long sBase;
+    const uint32_t blockBase = blockIdx.x * RTPB, i = blockBase + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const bool inRange = i < d.slots;
-    bool died = false;
-    const bool isFree = inRange ? FinishSlot(d, i, died) : false;
-    const int nDied = __syncthreads_count(died);
-    if(threadIdx.x == 0 && nDied) atomicAdd(&d.counters[1], (unsigned long long)nDied);
-    ReloadSlot(d, i, inRange, isFree);
+    // phase A: live paths take their shadow contribution; dead / empty slots are only classified
+    bool isFree = false, died = false;
+    if(inRange)
+    {
+        const uint32_t pd = d.meta[i].x;
+        const uint32_t status = (pd >> 8) & 0xFFu;
+        uint32_t type = (pd >> 16) & 0xFFu;
+        if(status == ST_INVALID) isFree = true;
+        else if(status == ST_DEAD) { isFree = true; died = true; }
+        else
+        {
+            if(type & 0x80u)
+            {   // shadow ray of this bounce: add the pre-multiplied NEE estimate when unoccluded
+                if((d.visible[i >> 5] >> (i & 31u)) & 1u)
+                {
+                    float4 rad = d.radiance[i]; const float4 sr = d.shadowRadiance[i];
+                    rad.x += sr.x; rad.y += sr.y; rad.z += sr.z; rad.w += sr.w;
+                    d.radiance[i] = rad;
+                }
+                type &= 0x7Fu;
+            }
+            d.meta[i].x = PackPD(pd & 0xFFu, ST_ALIVE, type);
+            d.hitKeys[i].primKey = INVALID_U32;   // default: boundary (KCSetBoundaryWorkKeysIndirect)
+        }
+    }
+    const uint32_t want = __ballot_sync(0xffffffffu, isFree), dead = __ballot_sync(0xffffffffu, died);
+    if(lane == 0) sWarpBase[warp] = uint32_t(__popc(want)) | (uint32_t(__popc(dead)) << 16);
+    __syncthreads();
+    if(threadIdx.x == 0)
+    {
+        uint32_t total = 0, nDied = 0;
+        #pragma unroll
+        for(int k = 0; k < RTPB / 32; k++) { const uint32_t c = sWarpBase[k]; sWarpBase[k] = total; total += c & 0xFFFFu; nDied += c >> 16; }
+        sTotal = total; sDied = nDied;
+        // block-aggregated claim of new path indices: ONE atomic per block on the global counter
+        sBase = total ? atomicAdd(&d.counters[0], (unsigned long long)total) : 0ull;
+        if(nDied) atomicAdd(&d.counters[1], (unsigned long long)nDied);
+    }
+    __syncthreads();
+    if(isFree) sList[sWarpBase[warp] + __popc(want & ((1u << lane) - 1u))] = uint16_t(threadIdx.x | (died ? 0x8000u : 0u));
+    __syncthreads();
+    // phase B: thread k refills the k-th free slot of the block
+    const uint32_t total = sTotal;
+    for(uint32_t k = threadIdx.x; k < total; k += RTPB)
+    {
+        const uint32_t e = sList[k], slot = blockBase + (e & 0x7FFFu);
+        if(e & 0x8000u) FilmDeadPath(d, slot);
+        ReloadClaimed(d, slot, sBase + k);
+    }
 }
 
 } // namespace
