@@ -1367,8 +1367,18 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
     return true;
 }
 
+// resident blocks per SM the shading kernels are compiled for: both are bound by the latency of the path-state loads, so occupancy
+// pays until the spills start to (lean: 4 blocks = 64 registers, no spills, 0.196 -> 0.158 ms per iteration against 3 blocks / 76
+// registers; 5 blocks = 48 registers + spills: 0.167. full: 3 blocks = 80 registers + 58 B of spills, 23.6 ms/spp on the config-4
+// material mix; 2 blocks / 125 registers 24.1; unconstrained 130 registers = ONE block: 26.6) — profiles/r2_experiments.md
+#ifndef MRB_SHADE_MINBLOCKS
+#define MRB_SHADE_MINBLOCKS 4
+#endif
+#ifndef MRB_GLOSSY_MINBLOCKS
+#define MRB_GLOSSY_MINBLOCKS 3
+#endif
 template<bool GLOSSY>
-__global__ void __launch_bounds__(RTPB) KShade(RenderData d)
+__global__ void __launch_bounds__(RTPB, GLOSSY ? MRB_GLOSSY_MINBLOCKS : MRB_SHADE_MINBLOCKS) KShade(RenderData d)
 {
     const uint32_t tidx = blockIdx.x * RTPB + threadIdx.x;
     bool alive = false, castShadow = false, neeSample = false;
@@ -1633,7 +1643,10 @@ __device__ __forceinline__ void FilmDeadPath(const RenderData& d, uint32_t i)
 // lanes active per instruction when every thread handled its own slot). So the block first settles the live paths, compacts the
 // indices of the slots to refill into shared memory (ballot order: the same slot <-> path assignment as before) and then lets
 // consecutive threads work through that list with full warps.
-__global__ void __launch_bounds__(RTPB) KFinishReload(RenderData d)
+#ifndef MRB_FINISH_MINBLOCKS
+#define MRB_FINISH_MINBLOCKS 6   // 40 registers; 8 blocks (32 registers + spills) measured slower: 0.129 -> 0.143 ms
+#endif
+__global__ void __launch_bounds__(RTPB, MRB_FINISH_MINBLOCKS) KFinishReload(RenderData d)
 {
     __shared__ uint16_t sList[RTPB];
     __shared__ uint32_t sWarpBase[RTPB / 32];
