@@ -193,3 +193,58 @@ def test_mip_mapped_render_through_tracer_interface(kind, tol):
     e = rel(bm(img, 2), bm(ref, 2))
     assert e <= tol, e
     assert np.allclose(img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=0.012)
+
+
+def test_mip_mapped_two_level_scene_matches_flat(gpu_ctx):
+    """The same mip-mapped scene as instances under rigid (T)Single transforms: the ray cone's footprint, curvature and texture
+    gradients are formed from world-space positions, so the levels — hence the image — do not move with the instances' local frames."""
+    from test_gpu_render import _rigid
+    c = scenes.cornell_mips("explicit")
+    ref = golden("explicit")
+    rng = np.random.default_rng(15)
+    mat = c["material"]
+    instances, accels, uvs = [], [], []
+    for k, m in enumerate(np.unique(mat)):
+        tri = c["indices"][mat == m]
+        wpos = c["positions"][tri.reshape(-1)].astype(np.float64)            # unwelded world-space vertices
+        M = None if k == 1 else _rigid(rng)
+        if M is None:
+            lpos = wpos
+        else:
+            inv = np.linalg.inv(np.vstack([M, [0, 0, 0, 1]]))
+            lpos = wpos @ inv[:3, :3].T + inv[:3, 3]
+        lpos = np.ascontiguousarray(lpos, np.float32)
+        lidx = np.arange(lpos.shape[0], dtype=np.uint32).reshape(-1, 3)
+        key = capi.light_key(0) if m == 3 else int(m)
+        a = capi.Accelerator(gpu_ctx, lpos, lidx, prim_ranges=[[0, lidx.shape[0]]], light_or_mat_keys=[key])
+        accels.append(a); instances.append((a, M)); uvs.append(np.ascontiguousarray(c["uvs"][tri.reshape(-1)], np.float32))
+    scene = capi.Scene(gpu_ctx, instances)
+    r = capi.Renderer(gpu_ctx, scene, 0, 0, c["albedo"], c["radiance"], c["camera"], 64, 64, 32768, seed=81,
+                      textures=c["textures"], albedo_texture=c["albedo_texture"], instance_vertex_uvs=uvs)
+    img, st = r.render(batch=64)
+    assert st.finished
+    r.close(); scene.close()
+    for a in accels:
+        a.close()
+    e = rel(bm(img, 2), bm(ref, 2))
+    assert e <= 1e-3, e
+    assert np.allclose(img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=0.012), (img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)))
+
+
+def test_mip_mapped_spectral_render_matches_oracle(gpu_ctx):
+    """Ray cones under (R)PathTracerSpectral (the refracted cone uses the first wavelength's indices of refraction)."""
+    from mray_b200 import spectral
+    if not spectral.available():
+        pytest.skip("spectral LUT was not generated")
+    sp = capi.Spectrum(gpu_ctx, spectral.load(), "HyperbolicPBRT")
+    img = mip_scene_renderer(gpu_ctx, "gen_glossy", 32, 32768, seed=91, spectrum=sp)
+    sp.close()
+    c = scenes.cornell_mips("gen_glossy")
+    tm = np.where(c["material"] == 3, -1, c["material"].astype(np.int32))
+    textures = [dict(t, gen_mips=c["gen_mips"]) for t in c["textures"]]
+    ref = O.oracle_render(c["positions"], c["indices"], tm, c["albedo"], c["radiance"], c["camera"], 32, 32, 8192, seed=92, textures=textures,
+                          albedo_texture=c["albedo_texture"], vertex_uvs=c["uvs"], material_type=c["material_type"], material_params=c["material_params"],
+                          spectral_data=spectral.load())
+    e = rel(bm(img, 2), bm(ref, 2))
+    assert e <= 3e-3, e
+    assert np.allclose(img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=0.02), (img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)))
