@@ -494,12 +494,12 @@ def cornell_alpha(seed: int = 21):
 
 
 def mray_scene_json(c, width: int, height: int, near_far=(0.01, 1000.0), light_material: int = 3, material_types=None,
-                    boundary=None, textures=None, alpha_map=None, uvs=None, cull_back_face: bool = False) -> str:
+                    boundary=None, textures=None, alpha_map=None, uvs=None, cull_back_face: bool = False, albedo_texture=None) -> str:
     """A scene dict (cornell_box layout: positions, indices, per-triangle material id, albedo, radiance, camera) as a scene file
     of the reference's JSON format (Docs/markdown/scene/mrayScene.md): one in-node indexed triangle primitive per material id,
     one surface each, the `light_material` batch as a Primitive light. boundary: None (Null light) or dict(type=
     "Skysphere_Spherical"|"Skysphere_CoOcta", radiance=[r, g, b] | texture=scene texture id); textures: list of
-    dict(id=, file=, ...) texture nodes; alpha_map: per material id a scene texture id or None."""
+    dict(id=, file=, ...) texture nodes; alpha_map / albedo_texture: per material id a scene texture id or None."""
     import json
     pos, idx, mat = c["positions"], c["indices"], c["material"]
     prims, mats, surfaces = [], [], []
@@ -519,6 +519,8 @@ def mray_scene_json(c, width: int, height: int, near_far=(0.01, 1000.0), light_m
         mnode = {"id": int(m), "type": kind}
         if kind in ("Lambert", "Unreal"):
             mnode["albedo"] = [float(x) for x in c["albedo"][int(m)]]
+            if albedo_texture is not None and albedo_texture[int(m)] is not None:
+                mnode["albedo"] = {"texture": int(albedo_texture[int(m)])}
         mats.append(mnode)
         s = {"transform": 0, "material": int(m), "primitive": int(m), "cullBackFace": bool(cull_back_face)}
         if alpha_map is not None and alpha_map[int(m)] is not None:

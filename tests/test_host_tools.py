@@ -206,3 +206,51 @@ def test_textures_alpha_maps_and_skysphere_through_the_loader(tmp_path):
     img = scenes.read_pfm(op)
     assert rel(bm(img, 4), bm(ref, 4)) <= 1e-3
     assert np.allclose(img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=0.01)
+
+
+@needs_plugin
+@pytest.mark.gpu
+def test_generated_mips_through_the_loader_and_run_command(tmp_path):
+    """`--genMips` (TracerParameters.genMips + mipGenFilter) on a scene file whose white material reads a strongly tiled PFM texture:
+    the plugin completes the chain at upload and the path's ray cones pick the levels — the same image as the C-ABI renderer given
+    the same texture with gen_mips, and not the image of the single-level texture."""
+    import mray_b200
+    from mray_b200 import capi
+    c = scenes.cornell_box()
+    rng = np.random.default_rng(21)
+    tex = rng.random((64, 64, 3)).astype(np.float32)
+    g = np.arange(64) // 16
+    tex[..., 0] = 0.5 * tex[..., 0] + 0.15 * ((g[:, None] + g[None, :]) % 3)        # low-frequency structure: coarse levels differ
+    tex[..., 1] = 0.5 * tex[..., 1] + 0.2 * ((2 * g[:, None] + g[None, :]) % 3)
+    uvs = np.tile(np.array([[0, 0], [96, 0], [96, 96], [0, 96]], np.float32), (c["positions"].shape[0] // 4, 1))
+    scenes.write_pfm(str(tmp_path / "albedo.pfm"), tex)
+    nodes = [dict(id=7, file="albedo.pfm", interpolation="Linear", edgeResolve="Wrap")]
+    sp, op = str(tmp_path / "mips.json"), str(tmp_path / "mips_out.pfm")
+    open(sp, "w").write(scenes.mray_scene_json(c, 64, 64, textures=nodes, albedo_texture=[7, None, None, None], uvs=uvs))
+    r, st = run(PLUGIN, sp, op, spp=16384, extra=("--seed", "5", "--burst", "64", "--genMips", "Gaussian,2"))
+    assert r.returncode == 0, r.stderr[-800:]
+    img = scenes.read_pfm(op)
+    # the same through the C-ABI
+    ctx = mray_b200.Context(0)
+    order = np.argsort(c["material"], kind="stable")
+    idx = np.ascontiguousarray(c["indices"][order]); mat = c["material"][order]
+    ranges, keys = [], []
+    for m in np.unique(mat):
+        w = np.nonzero(mat == m)[0]
+        ranges.append([w[0], w[-1] + 1]); keys.append(capi.light_key(0) if m == 3 else int(m))
+    acc = capi.Accelerator(ctx, c["positions"], idx, prim_ranges=ranges, light_or_mat_keys=keys)
+    rgba = np.concatenate([tex, np.ones((64, 64, 1), np.float32)], axis=-1)
+    imgs = {}
+    for name, t in (("mips", dict(data=rgba, gen_mips=("Gaussian", 2.0))), ("flat", dict(data=rgba))):
+        rr = capi.Renderer(ctx, acc, c["positions"].shape[0], idx.shape[0], c["albedo"][:3], c["radiance"], c["camera"], 64, 64, 16384, seed=6,
+                           rr_range=(2, 20), textures=[t], albedo_texture=[0, -1, -1], vertex_uvs=uvs)
+        imgs[name], s2 = rr.render(batch=64); rr.close()
+    acc.close(); ctx.close()
+    e = rel(bm(img, 2), bm(imgs["mips"], 2))
+    assert e <= 1e-3, e
+    assert np.allclose(img.mean(axis=(0, 1)), imgs["mips"].mean(axis=(0, 1)), rtol=0.01)
+    # without --genMips the run command renders the single-level image
+    r, st = run(PLUGIN, sp, op, spp=4096, extra=("--seed", "7", "--burst", "64"))
+    assert r.returncode == 0, r.stderr[-800:]
+    flat = scenes.read_pfm(op)
+    assert rel(bm(flat, 2), bm(imgs["flat"], 2)) <= 1.5e-3
