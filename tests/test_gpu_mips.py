@@ -248,3 +248,18 @@ def test_mip_mapped_spectral_render_matches_oracle(gpu_ctx):
     e = rel(bm(img, 2), bm(ref, 2))
     assert e <= 3e-3, e
     assert np.allclose(img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=0.02), (img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)))
+
+
+def test_degenerate_sizes_and_empty_reads(gpu_ctx):
+    one = dict(data=np.full((1, 1, 4), 0.25, np.float32), gen_mips=("Gaussian", 2.0))
+    chain, count = capi.texture_mip_chain(gpu_ctx, one)
+    assert count == 1 and np.array_equal(chain, O.mip_chain(one)[0])
+    strip = dict(data=np.arange(7 * 4, dtype=np.float32).reshape(7, 1, 4) / 28.0, gen_mips=("Box", 0.5))
+    chain, count = capi.texture_mip_chain(gpu_ctx, strip)
+    ref, ref_count = O.mip_chain(strip)
+    assert count == ref_count == 3 and np.array_equal(chain, ref)
+    assert capi.texture_final_extent(gpu_ctx, strip) == (1, 7, 3)
+    uv = np.array([[0.5, 0.5], [0.1, 0.9], [-3.25, 7.5]], np.float32)
+    lod = np.array([0.0, 1.5, 2.0], np.float32)
+    assert np.array_equal(capi.texture_sample_lod(gpu_ctx, strip, uv, lod=lod), O.oracle_texture_sample_lod(strip, uv, lod=lod))
+    assert capi.texture_sample_lod(gpu_ctx, strip, np.zeros((0, 2), np.float32), lod=np.zeros(0, np.float32)).shape == (0, 3)

@@ -137,3 +137,18 @@ def test_oracle_ray_cones_match_reference_render(kind):
     if kind != "gen_glossy":
         flat = _oracle_mip_render(kind, 256, 4, strip=True)
         assert _rel(_bm(flat, 4), _bm(ref, 4)) > 20 * e
+
+
+def test_degenerate_sizes():
+    """1 x 1 and 1 x N textures: the chain stops at 1 x 1 and a level never drops below one texel per axis."""
+    one = dict(data=np.full((1, 1, 4), 0.25, np.float32), gen_mips=("Gaussian", 2.0))
+    chain, count = O.mip_chain(one)
+    assert count == 1 and chain.shape == (1, 4)
+    strip = dict(data=np.arange(7 * 4, dtype=np.float32).reshape(7, 1, 4) / 28.0, gen_mips=("Box", 0.5))
+    chain, count = O.mip_chain(strip)
+    assert count == 3 and chain.shape == (7 + 3 + 1, 4)
+    assert [O.mip_dims(1, 7, k) for k in range(3)] == [(1, 7), (1, 3), (1, 1)]
+    uv = np.array([[0.5, 0.5], [0.1, 0.9]], np.float32)
+    assert np.allclose(O.oracle_texture_sample_lod(one, uv, lod=[0.0, 5.0]), 0.25)
+    top = O.oracle_texture_sample_lod(strip, uv, lod=[2.0, 2.0])
+    assert np.allclose(top[0], top[1])           # the 1 x 1 level is one colour everywhere
