@@ -247,12 +247,16 @@ KUnionBoxes(AccelData a, uint32_t* counters, const uint32_t* __restrict__ sorted
     for(uint32_t i = blockIdx.x * TPB + threadIdx.x; i < totalLeafs; i += gridDim.x * TPB)
     {
         uint32_t ni = sortedLeafParent[i];
+        // the node record of a level is fetched one level ahead (the topology is read-only here), so a level of the walk costs the
+        // counter's round trip + the two child boxes', not a third one for the record
+        LBVHNode nd = a.nodes[ni];
         while(ni != INVALID_U32)
         {
             uint32_t prev = atomicAdd(&counters[ni], 1u);
             if(prev != 1u) break;
             __threadfence();
-            LBVHNode nd = a.nodes[ni];
+            LBVHNode up = nd;
+            if(nd.parent != INVALID_U32) up = a.nodes[nd.parent];
             float l[6], r[6];
             const float* lp = (nd.left & LEAF_FLAG) ? a.leafAABB + 6 * size_t(nd.left & ~LEAF_FLAG)
                                                     : reinterpret_cast<const float*>(a.boxes + nd.left);
@@ -268,7 +272,7 @@ KUnionBoxes(AccelData a, uint32_t* counters, const uint32_t* __restrict__ sorted
                 __stcg(bp + 3 + k, (l[3 + k] < r[3 + k]) ? r[3 + k] : l[3 + k]); // Math::Max(l, r)
             }
             __threadfence();
-            ni = nd.parent;
+            ni = nd.parent; nd = up;
         }
     }
 }
