@@ -168,16 +168,27 @@ KOnesweepPass(const K* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
         {
             int32_t t = int32_t(tile) - 1;
             uint32_t spins = 0;
-            while(true)
+            // the predecessors' words are fetched LOOK at a time (independent loads, one round trip) and consumed in order: at small
+            // sizes every tile of a pass runs at once and tile t walks back through up to t aggregates before it meets a prefix
+            constexpr int LOOK = 4;
+            bool doneLook = false;
+            while(!doneLook)
             {
-                uint32_t v = status[size_t(t) * RADIX + d];
-                uint32_t f = v & FLAG_MASK;
-                // predecessor tiles hold smaller dynamic ids, so they are already running; the cap
-                // only turns a would-be device hang (a bug) into a wrong answer the tests catch
-                if(f == 0) { if(++spins > (1u << 28)) break; continue; }
-                excl += v & COUNT_MASK;
-                if(f == FLAG_PREFIX) break;
-                t--;
+                uint32_t v[LOOK];
+                #pragma unroll
+                for(int k = 0; k < LOOK; k++) { v[k] = 2u << 30; if(t - k >= 0) v[k] = status[size_t(t - k) * RADIX + d]; }   // past tile 0: an empty prefix
+                #pragma unroll
+                for(int k = 0; k < LOOK; k++)
+                {
+                    if(doneLook) break;
+                    const uint32_t f = v[k] & FLAG_MASK;
+                    // predecessor tiles hold smaller dynamic ids, so they are already running; the cap
+                    // only turns a would-be device hang (a bug) into a wrong answer the tests catch
+                    if(f == 0) { if(++spins > (1u << 28)) doneLook = true; break; }   // not published yet: fetch again from this tile
+                    excl += v[k] & COUNT_MASK;
+                    t--;
+                    if(f == FLAG_PREFIX) doneLook = true;
+                }
             }
             status[size_t(tile) * RADIX + d] = FLAG_PREFIX | (excl + total);
         }
