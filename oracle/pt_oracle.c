@@ -796,6 +796,13 @@ static void cone_project(cone_t c, v3 f, v3 d, v3* a1, v3* a2)
     float den2 = len(sub(h2, mul(d, dot(d, h2)))); if(den2 < EPS) den2 = EPS;
     *a1 = mul(h1, r / den1); *a2 = mul(h2, r / den2);
 }
+/* test tap of cone_project (the inputs of the reference's Tests/Tracer/T_RayCone.cu) */
+void orc_ray_cone_project(float aperture, float width, const float f[3], const float d[3], float out[6])
+{
+    cone_t c = {aperture, width}; v3 a1, a2;
+    cone_project(c, V(f[0], f[1], f[2]), V(d[0], d[1], d[2]), &a1, &a2);
+    out[0] = a1.x; out[1] = a1.y; out[2] = a1.z; out[3] = a2.x; out[4] = a2.y; out[5] = a2.z;
+}
 static v3 quat_z(const float* q)
 {   /* Quaternion::OrthoBasisZ (Core/Quaternion.hpp:L256-270), q = (w, x, y, z) */
     const float v00 = q[0] * q[0], v01 = q[0] * q[1], v02 = q[0] * q[2], v11 = q[1] * q[1], v13 = q[1] * q[3], v22 = q[2] * q[2], v23 = q[2] * q[3], v33 = q[3] * q[3];

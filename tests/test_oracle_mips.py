@@ -152,3 +152,26 @@ def test_degenerate_sizes():
     assert np.allclose(O.oracle_texture_sample_lod(one, uv, lod=[0.0, 5.0]), 0.25)
     top = O.oracle_texture_sample_lod(strip, uv, lod=[2.0, 2.0])
     assert np.allclose(top[0], top[1])           # the 1 x 1 level is one colour everywhere
+
+
+def test_ray_cone_projection_edge_cases():
+    """The two inputs the reference keeps in Tests/Tracer/T_RayCone.cu ("value from an assert"): a ray exactly against the normal
+    (h1 would vanish: RayCone::Project nudges d) and a runaway negative width. The footprint axes stay finite; for a regular cone
+    they are perpendicular to the normal and, head-on, as long as the cone's radius."""
+    L = O.lib()
+    L.orc_ray_cone_project.argtypes = [O.C.c_float, O.C.c_float, O.C.c_void_p, O.C.c_void_p, O.C.c_void_p]
+
+    def project(aperture, width, f, d):
+        f = np.asarray(f, np.float32); d = np.asarray(d, np.float32); out = np.zeros(6, np.float32)
+        L.orc_ray_cone_project(aperture, width, f.ctypes.data, d.ctypes.data, out.ctypes.data)
+        return out[:3], out[3:]
+    a1, a2 = project(0.000318206352, 0.00251944619, [-0.0, -0.0, -1.0], [-0.0, -0.0, 1.0])
+    assert np.isfinite(a1).all() and np.isfinite(a2).all()
+    a1, a2 = project(0.0, -5.33283590e+19, [-0.867630541, -0.418694645, 0.268164247], [-0.167027116, -0.138377547, -0.976193428])
+    assert np.isfinite(a1).all() and np.isfinite(a2).all()
+    f = np.array([0.0, 1.0, 0.0], np.float32)
+    d = np.array([0.6, -0.8, 0.0], np.float32)                  # 53 degrees off the normal
+    a1, a2 = project(0.01, 0.2, f, d)
+    assert abs(float(a1 @ f)) < 1e-6 and abs(float(a2 @ f)) < 1e-6 and abs(float(a1 @ a2)) < 1e-6
+    assert np.isclose(np.linalg.norm(a2), 0.1, rtol=1e-5)       # across the plane of incidence: the cone's radius
+    assert np.isclose(np.linalg.norm(a1), 0.1 / 0.8, rtol=1e-5)  # along it: stretched by 1 / cos(theta)
