@@ -1102,7 +1102,7 @@ KTraceWide2(const __grid_constant__ SceneData sc,
 
 // Scheduling knobs of the wide kernels, shared by single-accelerator and scene casts (MRB_TRI_DIV / MRB_FETCH_THR
 // override them for parameter sweeps)
-const TraceParams& WideTraceParams()
+const TraceParams& WideTraceParams(bool anyHit = false)
 {
     static const TraceParams prm = []
     {
@@ -1111,7 +1111,16 @@ const TraceParams& WideTraceParams()
         if(const char* e = getenv("MRB_FETCH_THR")) p.fetchThr = uint32_t(atoi(e));
         return p;
     }();
-    return prm;
+    // the any-hit kernel may take its own knobs (MRB_TRI_DIV_ANY / MRB_FETCH_THR_ANY); unset = the closest-hit kernel's
+    static const TraceParams prmAny = []
+    {
+        TraceParams p = prm;
+        p.fetchThr = 28u;   // shadow rays end at their first hit, so lanes free up faster: refilling a little earlier pays (PT 6.72 -> 6.67 ms/spp)
+        if(const char* e = getenv("MRB_TRI_DIV_ANY")) p.triDiv = uint32_t(atoi(e));
+        if(const char* e = getenv("MRB_FETCH_THR_ANY")) p.fetchThr = uint32_t(atoi(e));
+        return p;
+    }();
+    return anyHit ? prmAny : prm;
 }
 
 } // namespace
@@ -1169,7 +1178,7 @@ void TraceRays(Context& ctx, const mrb_accel_t& acc, bool anyHit, mrb_trace_mode
         }
         if(acc.d.wideNodes && acc.d.tris)
             SetPersistingWindow(ctx, acc.d.wideNodes, size_t(reinterpret_cast<const char*>(acc.d.tris + acc.d.leafCount) - reinterpret_cast<const char*>(acc.d.wideNodes)));
-        TraceParams prm = WideTraceParams();
+        TraceParams prm = WideTraceParams(anyHit);
         prm.alphaSeed = alphaSeed;
         const uint32_t pgrid = min(grid, uint32_t(ctx.smCount) * uint32_t(ctx.occWide[(anyHit ? 1 : 0) + (alpha ? 2 : 0)]));
         {
@@ -1224,7 +1233,7 @@ void TraceScene(Context& ctx, const SceneData& scnData, bool anyHit, mrb_trace_m
             MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx.occWide2[2], KTraceWide2<false, true>, TRACE_TPB, 0));
             MRB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx.occWide2[3], KTraceWide2<true, true>, TRACE_TPB, 0));
         }
-        TraceParams prm = WideTraceParams();
+        TraceParams prm = WideTraceParams(anyHit);
         prm.alphaSeed = alphaSeed;
         const uint32_t pgrid = min(grid, uint32_t(ctx.smCount) * uint32_t(ctx.occWide2[(anyHit ? 1 : 0) + (alpha ? 2 : 0)]));
         {
