@@ -288,6 +288,8 @@ struct RenderInstance
     const float*    positions;
     const uint32_t* indices;
     const float4*   triPos;          // 3 x float4 per primitive: its vertex positions gathered once per renderer (one load instead of index -> position)
+    const float4*   triNrm;          // ... and, where the instance has them, its three vertex normals / tangent frames
+    const float2*   triUV;           // ... and UVs
     const float4*   vertexNormals;   // optional: shading normals (xyz), or to-tangent-space quaternions (w, x, y, z) when `tbn` is set; nullptr = geometric
     const uint32_t* lightOfPrim;     // prim index -> emissive triangle index or INVALID
     const float2*   vertexUVs;       // optional UV0 per vertex, nullptr = (0, 0)
@@ -477,10 +479,14 @@ __device__ __forceinline__ void LoadTriangle(const RenderInstance& in, uint32_t 
     // positions come from the renderer's gathered copy (the same floats); the vertex indices are only needed for per-vertex attributes
     const float4* tp = in.triPos + 3 * size_t(prim);
     const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);   // (nine scalar loads of the same words: shade 0.142 -> 0.151 ms)
-    vi[0] = vi[1] = vi[2] = 0u;
-    if(in.vertexNormals || in.vertexUVs)
-    { vi[0] = in.indices[3 * size_t(prim)]; vi[1] = in.indices[3 * size_t(prim) + 1]; vi[2] = in.indices[3 * size_t(prim) + 2]; }
+    vi[0] = vi[1] = vi[2] = 0u;   // (per-vertex attributes come from the gathered triNrm / triUV copies too)
     p[0] = F3(a.x, a.y, a.z); p[1] = F3(b.x, b.y, b.z); p[2] = F3(c.x, c.y, c.z);
+}
+
+template<class T>
+__global__ void __launch_bounds__(256) KGatherTriAttribute(const T* __restrict__ perVertex, const uint32_t* __restrict__ indices, uint32_t tris, T* __restrict__ out)
+{
+    for(uint32_t j = blockIdx.x * 256u + threadIdx.x; j < 3u * tris; j += gridDim.x * 256u) out[j] = perVertex[indices[j]];
 }
 
 // renderer creation: triPos of one accelerator's primitive group
@@ -1106,13 +1112,13 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
             #pragma unroll
             for(int k = 0; k < 3; k++)
             {
-                const float4 q = in.vertexNormals[vi[k]];
+                const float4 q = in.triNrm[3 * size_t(prim) + k];
                 vn[k] = in.tbn ? F3(q.y * q.w - q.x * q.z + q.y * q.w - q.x * q.z, q.z * q.w + q.x * q.y + q.z * q.w + q.x * q.y, q.x * q.x - q.y * q.y - q.z * q.z + q.w * q.w)
                                : F3(q.x, q.y, q.z);
             }
         }
         float2 t0 = make_float2(0.f, 0.f), t1 = t0, t2 = t0;
-        if(in.vertexUVs) { t0 = in.vertexUVs[vi[0]]; t1 = in.vertexUVs[vi[1]]; t2 = in.vertexUVs[vi[2]]; }
+        if(in.vertexUVs) { t0 = in.triUV[3 * size_t(prim) + 0]; t1 = in.triUV[3 * size_t(prim) + 1]; t2 = in.triUV[3 * size_t(prim) + 2]; }
         ConeSurface(pw, vn, in.vertexNormals != nullptr, t0, t1, t2, a, b, pos, backSide ? geoN * -1.0f : geoN, Dot(geoN, dirN), dirN,
                     ConeAdvance(d.cones[i], r1.w), cs, dpdx, dpdy);
     }
@@ -1121,7 +1127,7 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
     const uint32_t matIndex = lmKey & 0x1FFFFFu;
     if(in.vertexNormals)
     {
-        const float4 n0 = in.vertexNormals[vi[0]], n1 = in.vertexNormals[vi[1]], n2 = in.vertexNormals[vi[2]];
+        const float4 n0 = in.triNrm[3 * size_t(prim) + 0], n1 = in.triNrm[3 * size_t(prim) + 1], n2 = in.triNrm[3 * size_t(prim) + 2];
         const int32_t normalTex = (GLOSSY && d.normalTex && in.tbn) ? d.normalTex[matIndex] : -1;
         if(GLOSSY && normalTex >= 0)
         {
@@ -1131,7 +1137,7 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
             float2 uv = make_float2(0.f, 0.f);
             if(in.vertexUVs)
             {
-                const float2 t0 = in.vertexUVs[vi[0]], t1 = in.vertexUVs[vi[1]], t2 = in.vertexUVs[vi[2]];
+                const float2 t0 = in.triUV[3 * size_t(prim) + 0], t1 = in.triUV[3 * size_t(prim) + 1], t2 = in.triUV[3 * size_t(prim) + 2];
                 uv = make_float2(t0.x * a + t1.x * b + t2.x * c, t0.y * a + t1.y * b + t2.y * c);
             }
             const Float3 nt = Normalize(SampleTextureGrad(d.textures[normalTex], uv.x, uv.y, dpdx, dpdy, d.textureLodMode));
@@ -1223,7 +1229,7 @@ __device__ __forceinline__ bool ShadeSlot(const RenderData& d, uint32_t i, bool&
         float2 uv = make_float2(0.f, 0.f);
         if(in.vertexUVs)
         {
-            const float2 t0 = in.vertexUVs[vi[0]], t1 = in.vertexUVs[vi[1]], t2 = in.vertexUVs[vi[2]];
+            const float2 t0 = in.triUV[3 * size_t(prim) + 0], t1 = in.triUV[3 * size_t(prim) + 1], t2 = in.triUV[3 * size_t(prim) + 2];
             uv = make_float2(t0.x * a + t1.x * b + t2.x * c, t0.y * a + t1.y * b + t2.y * c);
         }
         const Float3 rgb = GLOSSY ? SampleTextureGrad(d.textures[texIndex], uv.x, uv.y, dpdx, dpdy, d.textureLodMode) : SampleTexture(d.textures[texIndex], uv.x, uv.y);
@@ -1982,6 +1988,8 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
             hri[k].lightOfPrim = ma.Take<uint32_t>(hinst[k].acc->triangleCount);
             hri[k].vertexNormals = (hinst[k].normals || hinst[k].tbn) ? ma.Take<float4>(hinst[k].acc->vertexCount) : nullptr;
             hri[k].vertexUVs = hinst[k].uvs ? ma.Take<float2>(hinst[k].acc->vertexCount) : nullptr;
+            hri[k].triNrm = hri[k].vertexNormals ? ma.Take<float4>(3 * size_t(hinst[k].acc->triangleCount)) : nullptr;
+            hri[k].triUV = hri[k].vertexUVs ? ma.Take<float2>(3 * size_t(hinst[k].acc->triangleCount)) : nullptr;
         }
         d.workKeys = ma.Take<uint32_t>(P); d.workIndices = ma.Take<uint32_t>(P); d.partTable = ma.Take<uint32_t>(32);
         d.albedoTex = desc.albedoTexture ? ma.Take<int32_t>(desc.materialCount ? desc.materialCount : 1) : nullptr;
@@ -2087,6 +2095,13 @@ void CreateRenderer(Context& ctx, mrb_renderer_t& r, const mrb_render_desc& desc
             MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<float4*>(ri.vertexNormals), hn.data(), hn.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx.stream));
             MRB_CUDA_TRY(cudaStreamSynchronize(ctx.stream)); // hn is reused
         }
+        // per-triangle copies of the per-vertex attributes (stream order: after their uploads above)
+        if(ri.triNrm && hacc.triangleCount)
+            MRB_LAUNCH(ctx, KGatherTriAttribute<float4>, GridFor(ctx, 3u * hacc.triangleCount, 256u), 256, 0, ri.vertexNormals, hacc.d.indices, hacc.triangleCount,
+                       const_cast<float4*>(ri.triNrm));
+        if(ri.triUV && hacc.triangleCount)
+            MRB_LAUNCH(ctx, KGatherTriAttribute<float2>, GridFor(ctx, 3u * hacc.triangleCount, 256u), 256, 0, ri.vertexUVs, hacc.d.indices, hacc.triangleCount,
+                       const_cast<float2*>(ri.triUV));
     }
     MRB_CUDA_TRY(cudaMemcpyAsync(const_cast<RenderInstance*>(d.instances), hri.data(), hri.size() * sizeof(RenderInstance), cudaMemcpyHostToDevice, ctx.stream));
     if(desc.scene)
