@@ -863,7 +863,7 @@ static void rot2(float vx, float vy, float alpha, float u[2], float l[2])
 }
 static void refract2(const float v[2], const float n[2], float fromEta, float toEta, float out[2])
 {   /* Refract2D: Graphics::Refract(n, -v) in the plane; under total internal reflection the tangential direction */
-    const float er = fromEta / toEta, cosIn = -(n[0] * v[0] + n[1] * v[1]);
+    const float er = fromEta / toEta, cosIn = fmaf(n[1], -v[1], n[0] * -v[0]);   /* Math::Dot(normal, -v): an FMA chain */
     float sinIn2 = 1.0f - cosIn * cosIn; if(sinIn2 < 0) sinIn2 = 0;
     const float sinOut2 = er * er * sinIn2;
     if(sinOut2 >= 1.0f)
@@ -901,11 +901,20 @@ static cone_surf refract_ray_cone(cone_surf in, v3 wO, v3 gN, float fromEta, flo
     float wl = -uHitX * tu[1]; wl /= od[0] * -tu[1] + od[1] * tu[0];
     float wu = +lHitX * tl[1]; wu /= od[0] * -tl[1] + od[1] * tl[0];
     const float sign = copysignf(1.0f, tu[0] * tl[1] - tu[1] * tl[0]);
-    float ct = tu[0] * tl[0] + tu[1] * tl[1]; ct = ct < -1.0f ? -1.0f : (ct > 1.0f ? 1.0f : ct);
+    float ct = fmaf(tu[1], tl[1], tu[0] * tl[0]); ct = ct < -1.0f ? -1.0f : (ct > 1.0f ? 1.0f : ct);   /* Math::Dot: FMA chain; acos near 1 is ill-conditioned */
     float ap = acosf(ct) * sign; if(ap < 1.0e-5f) ap = 1.0e-5f;
     cone_surf r = in;
     r.back.aperture = ap + in.betaN; r.back.width = wu + wl;
     return r;
+}
+/* test tap of refract_ray_cone + cone_after_scatter for a transmitted ray: out = {aperture, width} of the cone that continues */
+void orc_refract_ray_cone(float aperture, float width, float betaN, const float wO[3], const float n[3], float fromEta, float toEta, float out[2])
+{
+    cone_surf cs; cs.front.aperture = aperture; cs.front.width = width; cs.back = cs.front; cs.betaN = betaN;
+    const v3 o = V(wO[0], wO[1], wO[2]), nn = V(n[0], n[1], n[2]);
+    const cone_surf r = refract_ray_cone(cs, o, nn, fromEta, toEta);
+    const cone_t c = cone_after_scatter(&r, mul(nn, -1.0f), nn);   /* any direction below the surface selects the back cone */
+    out[0] = c.aperture; out[1] = c.width;
 }
 static int scene_has_mips(const pt_scene* s)
 { for(uint32_t t = 0; t < s->nTextures; t++) if(s->textures[t].mipCount > 1u) return 1; return 0; }

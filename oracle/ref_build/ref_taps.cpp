@@ -35,6 +35,9 @@
 #include "Tracer/TextureView.h"
 #include "Tracer/TextureView.hpp"
 #include "Tracer/GenericGroup.h"
+#include "Tracer/SpectrumC.h"
+#include "Tracer/MaterialsDefault.h"
+#include "Tracer/MaterialsDefault.hpp"
 
 #include <memory>
 #include <vector>
@@ -354,6 +357,31 @@ int ref_texture_sample(const void* chain, uint32_t w, uint32_t h, uint32_t forma
     }
     catch(const MRayError& e) { fprintf(stderr, "ref_texture_sample: %s\n", e.GetError().c_str()); return -1; }
     catch(const std::exception& e) { fprintf(stderr, "ref_texture_sample: %s\n", e.what()); return -1; }
+}
+
+// RefractMaterial::RefractRayCone + RayConeSurface::ConeAfterScatter of the reference (Tracer/MaterialsDefault.hpp:L355-462,
+// Tracer/TracerTypes.h:L339-352) for n inputs: in[i] = {aperture, width, betaN, wO xyz, geoNormal xyz (already flipped towards wO),
+// frontIoR, backIoR, backSide (0 / 1)} (12 floats); out[i] = {aperture, width} of the cone that continues along a TRANSMITTED ray.
+void ref_refract_ray_cone(const float* in, uint32_t n, float* out)
+{
+    using Mat = RefractMatDetail::RefractMaterial<SpectrumContextIdentity>;
+    for(uint32_t i = 0; i < n; i++)
+    {
+        const float* v = in + 12 * size_t(i);
+        const Vector3 front(v[9], 0, 0), back(v[10], 0, 0);
+        RefractMatDetail::RefractMatData soa{Span<const Vector3>(&front, 1), Span<const Vector3>(&back, 1)};
+        DefaultSurface surf{};
+        surf.geoNormal = Vector3(v[6], v[7], v[8]);
+        surf.shadingTBN = Quaternion::Identity();
+        surf.backSide = v[11] != 0.0f;
+        SpectrumConverterIdentity conv;
+        Mat mat(conv, surf, soa, MaterialKey::CombinedKey(0, 0));
+        RayConeSurface rcs{RayCone{v[0], v[1]}, RayCone{v[0], v[1]}, v[2]};
+        const Vector3 wO(v[3], v[4], v[5]);
+        const RayConeSurface r = mat.RefractRayCone(rcs, wO);
+        const RayCone c = r.ConeAfterScatter(-surf.geoNormal, surf.geoNormal);
+        out[2 * i] = c.aperture; out[2 * i + 1] = c.width;
+    }
 }
 
 } // extern "C"

@@ -175,3 +175,44 @@ def test_ray_cone_projection_edge_cases():
     assert abs(float(a1 @ f)) < 1e-6 and abs(float(a2 @ f)) < 1e-6 and abs(float(a1 @ a2)) < 1e-6
     assert np.isclose(np.linalg.norm(a2), 0.1, rtol=1e-5)       # across the plane of incidence: the cone's radius
     assert np.isclose(np.linalg.norm(a1), 0.1 / 0.8, rtol=1e-5)  # along it: stretched by 1 / cos(theta)
+
+
+def _oracle_refract_cone(aperture, width, beta, wo, n, e0, e1):
+    L = O.lib()
+    L.orc_refract_ray_cone.argtypes = [O.C.c_float] * 3 + [O.C.c_void_p, O.C.c_void_p, O.C.c_float, O.C.c_float, O.C.c_void_p]
+    wo = np.ascontiguousarray(wo, np.float32); n = np.ascontiguousarray(n, np.float32); out = np.zeros(2, np.float32)
+    L.orc_refract_ray_cone(aperture, width, beta, wo.ctypes.data, n.ctypes.data, e0, e1, out.ctypes.data)
+    return out
+
+
+def test_refracted_ray_cone_matches_the_reference():
+    """pt_oracle.c::refract_ray_cone + cone_after_scatter against RefractMaterial::RefractRayCone + ConeAfterScatter run by the
+    reference itself (oracle/gen_golden_raycone.py -> tests/golden/refract_ray_cone.npz, 3 000 random surface cones / directions /
+    index pairs). Widths agree to rounding; apertures come out of acos(dot) of two nearly parallel unit vectors — ill-conditioned
+    near 1, where one ulp of the dot is ~1e-4 rad — so they are compared at that resolution."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "refract_ray_cone.npz"))
+    inp, ref = z["inputs"], z["cones"]
+    got = np.zeros_like(ref)
+    for i in range(inp.shape[0]):
+        e0, e1 = (inp[i, 9], inp[i, 10]) if inp[i, 11] == 0 else (inp[i, 10], inp[i, 9])
+        got[i] = _oracle_refract_cone(inp[i, 0], inp[i, 1], inp[i, 2], inp[i, 3:6], inp[i, 6:9], e0, e1)
+    assert np.isfinite(got).all()
+    assert np.allclose(got[:, 1], ref[:, 1], rtol=1e-3, atol=1e-6)      # measured: 99.9 % within 1e-5, worst (a grazing ray) 2.7e-4
+    assert np.allclose(got[:, 0], ref[:, 0], rtol=0, atol=1e-3)         # measured: worst 5.9e-4
+    assert (np.abs(got[:, 0] - ref[:, 0]) <= 2e-5).mean() > 0.95 and (got == ref).all(axis=1).mean() > 0.5
+    # what the reference does with a diverging cone on a FLAT surface: its 2-D frame keeps y along the normal, the signed angle between the refracted
+    # edge rays is negative, and the aperture falls to the Epsilon clamp (+ betaN, minus betaN again in ConeAfterScatter)
+    diverging = (inp[:, 0] > 1e-3) & (inp[:, 1] > 1e-3) & (inp[:, 2] == 0) & (np.abs(ref[:, 0] - inp[:, 0]) > 1e-9)   # flat surface, refraction exists
+    assert (np.abs(ref[diverging, 0] - 1.0e-5) < 1e-6).mean() > 0.95
+
+
+def test_refracted_ray_cone_closed_forms():
+    """Widths: kept at (near-)normal incidence and for equal indices; under total internal reflection the surface cone comes back
+    untouched (ConeAfterScatter then subtracts betaN from the back cone)."""
+    n = [0.0, 1.0, 0.0]
+    unit = lambda v: np.asarray(v, np.float32) / np.linalg.norm(v)
+    assert np.isclose(_oracle_refract_cone(0.02, 0.3, 0.0, unit([1e-4, 1.0, 0.0]), n, 1.0, 1.5)[1], 0.3, rtol=2e-3)
+    assert np.isclose(_oracle_refract_cone(0.02, 0.3, 0.0, unit([0.5, 0.8, 0.0]), n, 1.3, 1.3)[1], 0.3, rtol=2e-3)
+    assert _oracle_refract_cone(0.02, 0.3, 0.0, unit([0.8, 0.6, 0.0]), n, 1.0, 1.5)[1] > 0.3     # oblique into the denser medium: wider
+    ap, w = _oracle_refract_cone(0.02, 0.3, 0.004, unit([0.8, 0.6, 0.0]), n, 1.5, 1.0)     # sin(theta_t) would be 1.2
+    assert np.isclose(ap, 0.02 - 0.004, atol=1e-7) and np.isclose(w, 0.3)
